@@ -1,0 +1,188 @@
+"""ctypes mirror of include/hikari_cuda.h (struct layouts + prototypes) and the loader of
+libhikari_cuda.so.  There is NO CPU fallback: if the CUDA library cannot be loaded, or no CUDA device
+is usable, every compute entry point raises.
+"""
+import ctypes as C
+import os
+
+c_f = C.c_float
+c_fp = C.POINTER(C.c_float)
+c_u32p = C.POINTER(C.c_uint32)
+c_i32p = C.POINTER(C.c_int32)
+c_u8p = C.POINTER(C.c_uint8)
+
+HK_MAT_MATTE, HK_MAT_MIRROR, HK_MAT_GLASS, HK_MAT_CONDUCTOR = 1, 2, 3, 4
+HK_MAT_COATED_DIFFUSE, HK_MAT_THIN_DIELECTRIC, HK_MAT_DIFFUSE_TRANSMISSION = 5, 6, 7
+HK_MATFLAG_REMAP_ROUGHNESS, HK_MATFLAG_SPECTRAL_ETA_K = 1, 2
+HK_LIGHT_POINT, HK_LIGHT_SPOT, HK_LIGHT_DIRECTIONAL, HK_LIGHT_SUN = 1, 2, 3, 4
+HK_LIGHT_ENVIRONMENT, HK_LIGHT_AMBIENT, HK_LIGHT_DIFFUSE_AREA = 5, 6, 7
+HK_SPECTRUM_RGB, HK_SPECTRUM_ILLUMINANT = 0, 1
+HK_MEDIUM_HOMOGENEOUS, HK_MEDIUM_GRID, HK_MEDIUM_NANOVDB = 1, 2, 3
+
+
+class HkTables(C.Structure):
+    _fields_ = [("sobol_matrices", c_u32p), ("cie_x", c_fp), ("cie_y", c_fp), ("cie_z", c_fp), ("d65", c_fp),
+                ("rgb2spec_res", C.c_int32), ("rgb2spec_scale", c_fp), ("rgb2spec_coeffs", c_fp)]
+
+
+class HkGeometry(C.Structure):
+    _fields_ = [("positions", c_fp), ("normals", c_fp), ("tangents", c_fp), ("uvs", c_fp), ("indices", c_u32p),
+                ("tri_meta", c_u32p), ("n_verts", C.c_uint32), ("n_tris", C.c_uint32)]
+
+
+class HkMaterial(C.Structure):
+    _fields_ = [("type", C.c_int32), ("flags", C.c_uint32), ("rgb0", c_f * 3), ("rgb1", c_f * 3), ("f", c_f * 8),
+                ("spec", C.c_int32 * 2), ("ival", C.c_int32 * 2)]
+
+
+class HkMediumInterface(C.Structure):
+    _fields_ = [("material", C.c_uint32), ("inside", C.c_uint32), ("outside", C.c_uint32)]
+
+
+class HkSpectra(C.Structure):
+    _fields_ = [("lambdas", c_fp), ("values", c_fp), ("offsets", c_u32p), ("n_spectra", C.c_uint32)]
+
+
+class HkLight(C.Structure):
+    _fields_ = [("type", C.c_int32), ("spectrum_kind", C.c_int32), ("scale", c_f), ("rgb", c_f * 3), ("poly", c_f * 3),
+                ("illum_scale", c_f), ("position", c_f * 3), ("direction", c_f * 3), ("cos_total_width", c_f),
+                ("cos_falloff_start", c_f), ("world_to_light", c_f * 16), ("v", c_f * 9), ("normal", c_f * 3),
+                ("area", c_f), ("uv", c_f * 6), ("two_sided", C.c_int32), ("env_map", C.c_int32)]
+
+
+class HkEnvMap(C.Structure):
+    _fields_ = [("rgb", c_fp), ("w", C.c_int32), ("h", C.c_int32), ("rotation", c_f * 9), ("scale_rgb", c_f * 3),
+                ("conditional_func", c_fp), ("conditional_cdf", c_fp), ("conditional_func_int", c_fp),
+                ("marginal_func", c_fp), ("marginal_cdf", c_fp), ("marginal_func_int", c_f),
+                ("nu", C.c_int32), ("nv", C.c_int32)]
+
+
+class HkLightBVHNode(C.Structure):
+    _fields_ = [("bounds_min", c_f * 3), ("bounds_max", c_f * 3), ("w", c_f * 3), ("phi", c_f), ("cos_theta_o", c_f),
+                ("cos_theta_e", c_f), ("two_sided", C.c_uint32), ("child1_or_light_idx", C.c_uint32),
+                ("is_leaf", C.c_uint32), ("_pad", C.c_uint32)]
+
+
+class HkLightSampler(C.Structure):
+    _fields_ = [("nodes", C.POINTER(HkLightBVHNode)), ("n_nodes", C.c_uint32), ("light_to_bit_trail", c_u32p),
+                ("infinite_light_indices", c_i32p), ("n_infinite", C.c_uint32), ("n_bvh_lights", C.c_uint32)]
+
+
+class HkMedium(C.Structure):
+    _fields_ = [("type", C.c_int32), ("sigma_a_rgb", c_f * 3), ("sigma_s_rgb", c_f * 3), ("Le_rgb", c_f * 3),
+                ("scale", c_f), ("g", c_f), ("bounds_min", c_f * 3), ("bounds_max", c_f * 3),
+                ("render_from_medium", c_f * 16), ("medium_from_render", c_f * 16), ("density_res", C.c_int32 * 3),
+                ("density", c_fp), ("majorant_res", C.c_int32 * 3), ("majorant", c_fp), ("nanovdb_buf", c_u8p),
+                ("nanovdb_bytes", C.c_uint64), ("nanovdb_inv_mat", c_f * 9), ("nanovdb_vec", c_f * 3),
+                ("nanovdb_root_offset", C.c_uint64), ("nanovdb_upper_offset", C.c_uint64),
+                ("nanovdb_lower_offset", C.c_uint64), ("nanovdb_leaf_offset", C.c_uint64),
+                ("nanovdb_root_tiles", C.c_int32), ("nanovdb_upper_count", C.c_int32),
+                ("nanovdb_lower_count", C.c_int32), ("nanovdb_leaf_count", C.c_int32)]
+
+
+class HkCamera(C.Structure):
+    _fields_ = [("raster_to_camera", c_f * 16), ("camera_to_world", c_f * 16), ("lens_radius", c_f),
+                ("focal_distance", c_f), ("shutter_open", c_f), ("shutter_close", c_f), ("dx_camera", c_f * 3),
+                ("dy_camera", c_f * 3)]
+
+
+class HkFilter(C.Structure):
+    _fields_ = [("type", C.c_int32), ("radius", c_f * 2), ("nx", C.c_int32), ("ny", C.c_int32), ("func", c_fp),
+                ("marginal_cdf", c_fp), ("marginal_func", c_fp), ("conditional_cdf", c_fp), ("domain_min", c_f * 2),
+                ("domain_max", c_f * 2), ("func_integral", c_f)]
+
+
+class HkRenderParams(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("max_depth", C.c_int32),
+                ("samples_per_pixel", C.c_int32), ("regularize", C.c_int32), ("max_component_value", c_f),
+                ("sampler_seed", C.c_uint32), ("sobol_log2_spp", C.c_int32), ("sobol_n_base4_digits", C.c_int32),
+                ("material_coherence", C.c_int32), ("sample_batch", C.c_int32)]
+
+
+class HkStats(C.Structure):
+    _fields_ = [("rays_traced", C.c_uint64), ("samples_rendered", C.c_uint64), ("queue_overflows", C.c_uint64),
+                ("bvh_nodes", C.c_uint64), ("bvh_bytes", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("last_render_ms", c_f), ("last_trace_ms", c_f)]
+
+
+# every symbol include/hikari_cuda.h declares (checked by tests/test_abi.py)
+HK_SYMBOLS = [
+    "hk_abi_version", "hk_create", "hk_destroy", "hk_last_error", "hk_upload_tables", "hk_upload_geometry",
+    "hk_upload_spectra", "hk_upload_materials", "hk_upload_envmaps", "hk_upload_lights", "hk_upload_media",
+    "hk_set_camera", "hk_set_filter", "hk_set_params", "hk_clear", "hk_render_samples", "hk_render_samples_strided",
+    "hk_read_film", "hk_film_accum_dev", "hk_read_accum", "hk_write_accum", "hk_trace_closest",
+    "hk_trace_closest_dev", "hk_trace_any", "hk_stats", "hk_synchronize", "hk_dev_alloc", "hk_dev_free",
+    "hk_dev_upload", "hk_dev_download",
+]
+
+_VP = C.c_void_p
+
+
+def bind_common(lib, p):
+    """Set prototypes of the scene/render entry points shared by hk_* (CUDA) and ok_* (oracle)."""
+    def f(name, args, res=C.c_int32):
+        fn = getattr(lib, p + name)
+        fn.argtypes = args
+        fn.restype = res
+        return fn
+    f("create", [C.c_int32, C.POINTER(_VP)] if p == "hk_" else [C.POINTER(_VP)])
+    f("destroy", [_VP])
+    f("upload_tables", [_VP, C.POINTER(HkTables)])
+    f("upload_geometry", [_VP, C.POINTER(HkGeometry)])
+    f("upload_spectra", [_VP, C.POINTER(HkSpectra)])
+    f("upload_materials", [_VP, C.POINTER(HkMaterial), C.c_uint32, C.POINTER(HkMediumInterface), C.c_uint32])
+    f("upload_envmaps", [_VP, C.POINTER(HkEnvMap), C.c_uint32])
+    f("upload_lights", [_VP, C.POINTER(HkLight), C.c_uint32, C.POINTER(HkLightSampler)])
+    f("upload_media", [_VP, C.POINTER(HkMedium), C.c_uint32])
+    f("set_camera", [_VP, C.POINTER(HkCamera)])
+    f("set_filter", [_VP, C.POINTER(HkFilter)])
+    f("set_params", [_VP, C.POINTER(HkRenderParams)])
+    f("clear", [_VP])
+    f("render_samples", [_VP, C.c_int32, C.c_int32])
+    f("render_samples_strided", [_VP, C.c_int32, C.c_int32, C.c_int32])
+    f("read_film", [_VP, c_fp])
+    f("read_accum", [_VP, c_fp, c_fp])
+    return lib
+
+
+def bind_hk(lib):
+    bind_common(lib, "hk_")
+    def f(name, args, res=C.c_int32):
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = res
+    f("hk_abi_version", [])
+    f("hk_last_error", [_VP], C.c_char_p)
+    f("hk_write_accum", [_VP, c_fp, c_fp])
+    f("hk_film_accum_dev", [_VP, C.POINTER(_VP), C.POINTER(C.c_uint64)])
+    f("hk_trace_closest", [_VP, c_fp, C.c_uint64, c_fp])
+    f("hk_trace_closest_dev", [_VP, _VP, C.c_uint64, _VP, C.c_int32])
+    f("hk_trace_any", [_VP, c_fp, C.c_uint64, c_u8p])
+    f("hk_stats", [_VP, C.POINTER(HkStats)])
+    f("hk_synchronize", [_VP])
+    f("hk_dev_alloc", [_VP, C.c_uint64, C.POINTER(_VP)])
+    f("hk_dev_free", [_VP, _VP])
+    f("hk_dev_upload", [_VP, _VP, _VP, C.c_uint64])
+    f("hk_dev_download", [_VP, _VP, _VP, C.c_uint64])
+    # host-side scene-build helpers (CPU code, usable without a GPU)
+    f("hk_host_generate_rgb2spec", [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                    C.POINTER(C.c_double), c_fp, c_fp])
+    f("hk_host_build_light_sampler", [C.POINTER(HkLight), C.c_uint32, C.POINTER(HkLightBVHNode), c_u32p, c_u32p,
+                                      c_i32p, c_u32p, c_u32p])
+    return lib
+
+
+_LIB = None
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libhikari_cuda.so")
+
+
+def load_library():
+    """Load libhikari_cuda.so (built in-tree by __graft_entry__.build()).  Fails loudly when missing."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc -gencode arch=compute_100a,code=sm_100a). There is no CPU fallback.")
+        _LIB = bind_hk(C.CDLL(LIB_PATH))
+    return _LIB

@@ -1,0 +1,511 @@
+// hk_api.cu — C ABI of libhikari_cuda.so (include/hikari_cuda.h): context, uploads, render loop, film, traversal.
+// There is NO CPU fallback anywhere in this file: every compute entry point needs a CUDA device and fails with
+// HK_ERR_NO_DEVICE / HK_ERR_CUDA otherwise.
+#include "../../include/hikari_cuda.h"
+#include "../../include/hikari_cuda_testing.h"
+#include "hk_wavefront.cuh"
+#include "hk_bvh.h"
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__); return HK_ERR_CUDA; } } while (0)
+#define REQUIRE(cond, msg) do { if (!(cond)) { ctx->err = (msg); return HK_ERR_INVALID; } } while (0)
+
+struct DevBuf {
+    void* p = nullptr; size_t bytes = 0;
+    cudaError_t alloc(size_t n) { release(); if (n == 0) n = 16; cudaError_t e = cudaMalloc(&p, n); if (e == cudaSuccess) bytes = n; else p = nullptr; return e; }
+    cudaError_t upload(const void* src, size_t n) { cudaError_t e = alloc(n); if (e != cudaSuccess) return e; return n ? cudaMemcpy(p, src, n, cudaMemcpyHostToDevice) : cudaSuccess; }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct HkContext {
+    int device = 0;
+    std::string err;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 148;
+    DevScene D;
+    PathState S;
+    HkRenderParams params;
+    bool have_tables = false, have_geom = false, have_mats = false, have_lights = false, have_cam = false, have_filter = false, have_params = false;
+    bool camera_medium_valid = false; uint32_t camera_medium = 0;
+    uint32_t mat_types_present = 0;
+    // device buffers
+    DevBuf b_sobol, b_cie_x, b_cie_y, b_cie_z, b_d65, b_rgb_scale, b_rgb_coeffs;
+    DevBuf b_nodes, b_tris, b_pos, b_nrm, b_idx, b_meta;
+    DevBuf b_mats, b_ifaces, b_spec_l, b_spec_v, b_spec_o;
+    DevBuf b_lights, b_env, b_lnodes, b_trails, b_inf;
+    std::vector<DevBuf> env_bufs, media_bufs;
+    DevBuf b_media;
+    DevBuf b_f_func, b_f_mcdf, b_f_mfunc, b_f_ccdf;
+    DevBuf b_state, b_counts, b_rays, b_film, b_scratch_u32, b_trace_ctr;
+    size_t n_slots = 0;
+    HkStats stats;
+    uint64_t launches = 0;
+    HkContext() { std::memset(&D, 0, sizeof(D)); std::memset(&S, 0, sizeof(S)); std::memset(&params, 0, sizeof(params)); std::memset(&stats, 0, sizeof(stats)); }
+};
+
+static int grid_for(const HkContext* c, size_t n, int block, int per_sm) {
+    size_t need = (n + block - 1) / block;
+    size_t cap = (size_t)c->sm_count * per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+extern "C" {
+
+int32_t hk_abi_version(void) { return HK_ABI_VERSION; }
+
+int32_t hk_create(int32_t device, HkContext** out) {
+    if (!out) return HK_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return HK_ERR_NO_DEVICE;
+    if (cudaSetDevice(device) != cudaSuccess) return HK_ERR_NO_DEVICE;
+    HkContext* ctx = new HkContext();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return HK_ERR_CUDA; }
+    cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
+    if (ctx->b_counts.alloc(sizeof(uint32_t) * HK_N_COUNTERS + 64) != cudaSuccess || ctx->b_trace_ctr.alloc(64) != cudaSuccess) { delete ctx; return HK_ERR_OOM; }
+    cudaMemset(ctx->b_counts.p, 0, ctx->b_counts.bytes); cudaMemset(ctx->b_trace_ctr.p, 0, 64);
+    *out = ctx;
+    return HK_OK;
+}
+int32_t hk_destroy(HkContext* ctx) {
+    if (!ctx) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    DevBuf* bufs[] = {&ctx->b_sobol, &ctx->b_cie_x, &ctx->b_cie_y, &ctx->b_cie_z, &ctx->b_d65, &ctx->b_rgb_scale, &ctx->b_rgb_coeffs, &ctx->b_nodes, &ctx->b_tris,
+                      &ctx->b_pos, &ctx->b_nrm, &ctx->b_idx, &ctx->b_meta, &ctx->b_mats, &ctx->b_ifaces, &ctx->b_spec_l, &ctx->b_spec_v, &ctx->b_spec_o, &ctx->b_lights,
+                      &ctx->b_env, &ctx->b_lnodes, &ctx->b_trails, &ctx->b_inf, &ctx->b_media, &ctx->b_f_func, &ctx->b_f_mcdf, &ctx->b_f_mfunc, &ctx->b_f_ccdf,
+                      &ctx->b_state, &ctx->b_counts, &ctx->b_rays, &ctx->b_film, &ctx->b_scratch_u32, &ctx->b_trace_ctr};
+    for (DevBuf* b : bufs) b->release();
+    for (auto& b : ctx->env_bufs) b.release();
+    for (auto& b : ctx->media_bufs) b.release();
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return HK_OK;
+}
+const char* hk_last_error(HkContext* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int32_t hk_upload_tables(HkContext* ctx, const HkTables* t) {
+    if (!ctx || !t) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    REQUIRE(t->rgb2spec_res >= 2, "rgb2spec_res must be >= 2");
+    CK(ctx->b_sobol.upload(t->sobol_matrices, sizeof(uint32_t) * 1024 * 52));
+    CK(ctx->b_cie_x.upload(t->cie_x, 4 * 471)); CK(ctx->b_cie_y.upload(t->cie_y, 4 * 471)); CK(ctx->b_cie_z.upload(t->cie_z, 4 * 471));
+    CK(ctx->b_d65.upload(t->d65, 4 * 107));
+    const size_t R = (size_t)t->rgb2spec_res;
+    CK(ctx->b_rgb_scale.upload(t->rgb2spec_scale, 4 * R));
+    // re-layout [coef][x][y][z][maxc] -> [maxc][z][y][x] float4(c0,c1,c2,0): see hk_spectral.cuh
+    std::vector<float> re(4 * 3 * R * R * R);
+    for (size_t m = 0; m < 3; m++) for (size_t z = 0; z < R; z++) for (size_t y = 0; y < R; y++) for (size_t x = 0; x < R; x++) {
+        size_t dst = 4 * (((m * R + z) * R + y) * R + x);
+        for (size_t c = 0; c < 3; c++) re[dst + c] = t->rgb2spec_coeffs[m + 3 * (z + R * (y + R * (x + R * c)))];
+        re[dst + 3] = 0.0f;
+    }
+    CK(ctx->b_rgb_coeffs.upload(re.data(), re.size() * 4));
+    DevTables& T = ctx->D.T;
+    T.sobol = ctx->b_sobol.as<uint32_t>(); T.cie_x = ctx->b_cie_x.as<float>(); T.cie_y = ctx->b_cie_y.as<float>(); T.cie_z = ctx->b_cie_z.as<float>();
+    T.d65 = ctx->b_d65.as<float>(); T.rgb_scale = ctx->b_rgb_scale.as<float>(); T.rgb_coeffs = ctx->b_rgb_coeffs.as<float4>(); T.rgb_res = t->rgb2spec_res;
+    ctx->D.sobol.M = T.sobol;
+    ctx->have_tables = true;
+    return HK_OK;
+}
+
+int32_t hk_upload_geometry(HkContext* ctx, const HkGeometry* g) {
+    if (!ctx || !g) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    REQUIRE(g->n_tris == 0 || (g->positions && g->indices && g->tri_meta), "geometry arrays missing");
+    HkBvh bvh;
+    hk_build_bvh8(g->positions, g->indices, g->n_tris, bvh);
+    CK(ctx->b_nodes.upload(bvh.nodes.data(), bvh.nodes.size() * sizeof(HkBvhNode)));
+    CK(ctx->b_tris.upload(bvh.tris.data(), bvh.tris.size() * sizeof(HkBvhTri)));
+    CK(ctx->b_pos.upload(g->positions, 12 * (size_t)g->n_verts));
+    if (g->normals) CK(ctx->b_nrm.upload(g->normals, 12 * (size_t)g->n_verts)); else ctx->b_nrm.release();
+    CK(ctx->b_idx.upload(g->indices, 12 * (size_t)g->n_tris));
+    CK(ctx->b_meta.upload(g->tri_meta, 12 * (size_t)g->n_tris));
+    ctx->D.bvh.nodes = ctx->b_nodes.as<float4>(); ctx->D.bvh.tris = ctx->b_tris.as<float4>();
+    ctx->D.positions = ctx->b_pos.as<float>(); ctx->D.normals = g->normals ? ctx->b_nrm.as<float>() : nullptr;
+    ctx->D.indices = ctx->b_idx.as<uint32_t>(); ctx->D.tri_meta = ctx->b_meta.as<uint32_t>();
+    ctx->stats.bvh_nodes = bvh.nodes.size();
+    ctx->stats.bvh_bytes = bvh.nodes.size() * sizeof(HkBvhNode) + bvh.tris.size() * sizeof(HkBvhTri);
+    ctx->have_geom = true; ctx->camera_medium_valid = false;
+    return HK_OK;
+}
+
+int32_t hk_upload_spectra(HkContext* ctx, const HkSpectra* s) {
+    if (!ctx || !s) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    uint32_t n = s->n_spectra ? s->offsets[s->n_spectra] : 0;
+    CK(ctx->b_spec_l.upload(s->lambdas, 4 * (size_t)n)); CK(ctx->b_spec_v.upload(s->values, 4 * (size_t)n));
+    CK(ctx->b_spec_o.upload(s->offsets, 4 * ((size_t)s->n_spectra + 1)));
+    ctx->D.spec_lambdas = ctx->b_spec_l.as<float>(); ctx->D.spec_values = ctx->b_spec_v.as<float>(); ctx->D.spec_offsets = ctx->b_spec_o.as<uint32_t>();
+    return HK_OK;
+}
+
+int32_t hk_upload_materials(HkContext* ctx, const HkMaterial* m, uint32_t nm, const HkMediumInterface* mi, uint32_t ni) {
+    if (!ctx) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    REQUIRE(nm == 0 || m, "materials missing"); REQUIRE(ni == 0 || mi, "interfaces missing");
+    uint32_t present = 0; int32_t trans = 0;
+    for (uint32_t i = 0; i < nm; i++) {
+        REQUIRE(m[i].type >= 1 && m[i].type < HK_MAX_MAT_TYPES, "unsupported material type (CoatedConductor / CoatedDiffuseTransmission / Mix are SURVEY 8f items)");
+        present |= 1u << m[i].type;
+    }
+    for (uint32_t i = 0; i < ni; i++) {
+        REQUIRE(mi[i].material >= 1 && mi[i].material <= nm, "interface references a missing material");
+        if (mi[i].inside != mi[i].outside) trans = 1;
+    }
+    CK(ctx->b_mats.upload(m, sizeof(HkMaterial) * (size_t)nm)); CK(ctx->b_ifaces.upload(mi, sizeof(HkMediumInterface) * (size_t)ni));
+    ctx->D.materials = ctx->b_mats.as<HkMaterial>(); ctx->D.interfaces = ctx->b_ifaces.as<HkMediumInterface>();
+    ctx->D.any_medium_transition = trans; ctx->mat_types_present = present;
+    if (!ctx->b_spec_o.p) { uint32_t zero = 0; CK(ctx->b_spec_o.upload(&zero, 4)); ctx->D.spec_offsets = ctx->b_spec_o.as<uint32_t>(); }
+    ctx->have_mats = true; ctx->camera_medium_valid = false;
+    return HK_OK;
+}
+
+int32_t hk_upload_envmaps(HkContext* ctx, const HkEnvMap* maps, uint32_t n) {
+    if (!ctx) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    for (auto& b : ctx->env_bufs) b.release();
+    ctx->env_bufs.clear(); ctx->env_bufs.resize(6 * (size_t)n);
+    std::vector<DevEnvMap> dev(n);
+    for (uint32_t i = 0; i < n; i++) {
+        const HkEnvMap& E = maps[i];
+        size_t w = E.w, h = E.h, nu = E.nu, nv = E.nv;
+        DevBuf* B = &ctx->env_bufs[6 * (size_t)i];
+        CK(B[0].upload(E.rgb, 12 * w * h)); CK(B[1].upload(E.conditional_func, 4 * nu * nv)); CK(B[2].upload(E.conditional_cdf, 4 * (nu + 1) * nv));
+        CK(B[3].upload(E.conditional_func_int, 4 * nv)); CK(B[4].upload(E.marginal_func, 4 * nv)); CK(B[5].upload(E.marginal_cdf, 4 * (nv + 1)));
+        DevEnvMap& d = dev[i];
+        d.rgb = B[0].as<float>(); d.w = E.w; d.h = E.h; std::memcpy(d.rot, E.rotation, 36); std::memcpy(d.scale_rgb, E.scale_rgb, 12);
+        d.cfunc = B[1].as<float>(); d.ccdf = B[2].as<float>(); d.cfint = B[3].as<float>(); d.mfunc = B[4].as<float>(); d.mcdf = B[5].as<float>();
+        d.mfint = E.marginal_func_int; d.nu = E.nu; d.nv = E.nv;
+    }
+    CK(ctx->b_env.upload(dev.data(), sizeof(DevEnvMap) * (size_t)n));
+    ctx->D.envmaps = ctx->b_env.as<DevEnvMap>();
+    return HK_OK;
+}
+
+int32_t hk_upload_lights(HkContext* ctx, const HkLight* l, uint32_t n, const HkLightSampler* sm) {
+    if (!ctx || !sm) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    REQUIRE(n == 0 || l, "lights missing");
+    for (uint32_t i = 0; i < n; i++) REQUIRE(l[i].type >= 1 && l[i].type <= 7, "unknown light type");
+    CK(ctx->b_lights.upload(l, sizeof(HkLight) * (size_t)n));
+    CK(ctx->b_lnodes.upload(sm->nodes, sizeof(HkLightBVHNode) * (size_t)sm->n_nodes));
+    CK(ctx->b_trails.upload(sm->light_to_bit_trail, 4 * (size_t)n));
+    CK(ctx->b_inf.upload(sm->infinite_light_indices, 4 * (size_t)sm->n_infinite));
+    ctx->D.lights = ctx->b_lights.as<HkLight>(); ctx->D.n_lights = (int32_t)n;
+    ctx->D.lnodes = ctx->b_lnodes.as<HkLightBVHNode>(); ctx->D.bit_trails = ctx->b_trails.as<uint32_t>(); ctx->D.inf_idx = ctx->b_inf.as<int32_t>();
+    ctx->D.n_infinite = (int32_t)sm->n_infinite; ctx->D.n_bvh = (int32_t)sm->n_bvh_lights;
+    ctx->have_lights = true;
+    return HK_OK;
+}
+
+int32_t hk_upload_media(HkContext* ctx, const HkMedium* m, uint32_t n) {
+    if (!ctx) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    for (auto& b : ctx->media_bufs) b.release();
+    ctx->media_bufs.clear(); ctx->media_bufs.resize(3 * (size_t)n);
+    std::vector<DevMedium> dev(n);
+    for (uint32_t i = 0; i < n; i++) {
+        const HkMedium& M = m[i];
+        REQUIRE(M.type >= 1 && M.type <= 3, "unknown medium type (RGBGridMedium is out of scope)");
+        DevMedium& d = dev[i]; std::memset(&d, 0, sizeof(d));
+        d.type = M.type; std::memcpy(d.sigma_a, M.sigma_a_rgb, 12); std::memcpy(d.sigma_s, M.sigma_s_rgb, 12); std::memcpy(d.Le, M.Le_rgb, 12); d.g = M.g;
+        std::memcpy(d.bmin, M.bounds_min, 12); std::memcpy(d.bmax, M.bounds_max, 12); std::memcpy(d.medium_from_render, M.medium_from_render, 48);
+        DevBuf* B = &ctx->media_bufs[3 * (size_t)i];
+        if (M.type == HK_MEDIUM_GRID) {
+            size_t cnt = (size_t)M.density_res[0] * M.density_res[1] * M.density_res[2];
+            CK(B[0].upload(M.density, 4 * cnt)); d.density = B[0].as<float>(); std::memcpy(d.dres, M.density_res, 12);
+        }
+        if (M.type != HK_MEDIUM_HOMOGENEOUS) {
+            size_t cnt = (size_t)M.majorant_res[0] * M.majorant_res[1] * M.majorant_res[2];
+            CK(B[1].upload(M.majorant, 4 * cnt)); d.majorant = B[1].as<float>(); std::memcpy(d.mres, M.majorant_res, 12);
+        }
+        if (M.type == HK_MEDIUM_NANOVDB) {
+            CK(B[2].upload(M.nanovdb_buf, (size_t)M.nanovdb_bytes)); d.nvdb = B[2].as<uint8_t>();
+            std::memcpy(d.inv_mat, M.nanovdb_inv_mat, 36); std::memcpy(d.vec, M.nanovdb_vec, 12); d.root_off = M.nanovdb_root_offset; d.root_tiles = M.nanovdb_root_tiles;
+        }
+    }
+    CK(ctx->b_media.upload(dev.data(), sizeof(DevMedium) * (size_t)n));
+    ctx->D.media = ctx->b_media.as<DevMedium>(); ctx->D.n_media = (int32_t)n;
+    ctx->camera_medium_valid = false;
+    return HK_OK;
+}
+
+int32_t hk_set_camera(HkContext* ctx, const HkCamera* c) {
+    if (!ctx || !c) return HK_ERR_INVALID;
+    ctx->D.camera = *c; ctx->have_cam = true; ctx->camera_medium_valid = false;
+    return HK_OK;
+}
+int32_t hk_set_filter(HkContext* ctx, const HkFilter* f) {
+    if (!ctx || !f) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    REQUIRE(f->type >= 1 && f->type <= 5, "unknown filter type");
+    DevFilter& F = ctx->D.filter; std::memset(&F, 0, sizeof(F));
+    F.type = f->type; F.rx = f->radius[0]; F.ry = f->radius[1]; F.nx = f->nx; F.ny = f->ny;
+    if (f->type >= 3) {
+        REQUIRE(f->nx > 0 && f->ny > 0 && f->func && f->marginal_cdf && f->marginal_func && f->conditional_cdf, "tabulated filter data missing");
+        size_t nx = f->nx, ny = f->ny;
+        CK(ctx->b_f_func.upload(f->func, 4 * nx * ny)); CK(ctx->b_f_mcdf.upload(f->marginal_cdf, 4 * (ny + 1)));
+        CK(ctx->b_f_mfunc.upload(f->marginal_func, 4 * ny)); CK(ctx->b_f_ccdf.upload(f->conditional_cdf, 4 * ny * (nx + 1)));
+        F.func = ctx->b_f_func.as<float>(); F.mcdf = ctx->b_f_mcdf.as<float>(); F.mfunc = ctx->b_f_mfunc.as<float>(); F.ccdf = ctx->b_f_ccdf.as<float>();
+        F.dmin_x = f->domain_min[0]; F.dmin_y = f->domain_min[1]; F.dmax_x = f->domain_max[0]; F.dmax_y = f->domain_max[1]; F.func_integral = f->func_integral;
+    }
+    ctx->have_filter = true;
+    return HK_OK;
+}
+
+static int32_t alloc_state(HkContext* ctx, size_t n_slots, size_t n_pixels) {
+    // one slab: 14 float4 arrays, 3 u32/f32 arrays, 13 queues; every array starts 256-byte aligned
+    const size_t f4 = 14, w4 = 3, q = 5 + HK_MAX_MAT_TYPES;
+    size_t rounded = f4 * (((16 * n_slots + 255) / 256) * 256) + (w4 + q) * (((4 * n_slots + 255) / 256) * 256);
+    CK(ctx->b_state.alloc(rounded));
+    CK(ctx->b_film.alloc(16 * n_pixels + 64));
+    CK(cudaMemset(ctx->b_film.p, 0, ctx->b_film.bytes));
+    char* p = ctx->b_state.as<char>();
+    auto take = [&](size_t elt) { char* r = p; p += ((elt * n_slots + 255) / 256) * 256; return r; };
+    PathState& S = ctx->S;
+    float4** f4s[] = {&S.ray_a, &S.ray_b, &S.hit, &S.lambda, &S.lpdf, &S.beta, &S.r_u, &S.r_l, &S.L, &S.sh_a, &S.sh_b, &S.sh_Ld, &S.sh_ru, &S.sh_rl};
+    for (auto pp : f4s) *pp = reinterpret_cast<float4*>(take(16));
+    S.flags = reinterpret_cast<uint32_t*>(take(4)); S.fweight = reinterpret_cast<float*>(take(4)); S.sh_medium = reinterpret_cast<uint32_t*>(take(4));
+    S.q_ray[0] = reinterpret_cast<uint32_t*>(take(4)); S.q_ray[1] = reinterpret_cast<uint32_t*>(take(4));
+    S.q_escaped = reinterpret_cast<uint32_t*>(take(4)); S.q_medium = reinterpret_cast<uint32_t*>(take(4)); S.q_shadow = reinterpret_cast<uint32_t*>(take(4));
+    for (int t = 0; t < HK_MAX_MAT_TYPES; t++) S.q_hit[t] = reinterpret_cast<uint32_t*>(take(4));
+    S.counts = ctx->b_counts.as<uint32_t>();
+    S.rays_traced = reinterpret_cast<unsigned long long*>(ctx->b_counts.as<char>() + sizeof(uint32_t) * HK_N_COUNTERS);
+    S.pixel_rgb = ctx->b_film.as<float>(); S.pixel_weight = ctx->b_film.as<float>() + 3 * n_pixels;
+    ctx->n_slots = n_slots;
+    return HK_OK;
+}
+
+int32_t hk_set_params(HkContext* ctx, const HkRenderParams* p) {
+    if (!ctx || !p) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    REQUIRE(p->width > 0 && p->height > 0, "width/height must be positive");
+    REQUIRE(p->max_depth >= 1 && p->max_depth <= 255, "max_depth must be in [1, 255]");
+    ctx->params = *p;
+    if (ctx->params.sample_batch < 1) ctx->params.sample_batch = 1;
+    DevScene& D = ctx->D;
+    D.width = p->width; D.height = p->height; D.max_depth = p->max_depth; D.regularize = p->regularize; D.max_component_value = p->max_component_value;
+    D.sobol.log2_spp = p->sobol_log2_spp; D.sobol.n_base4_digits = p->sobol_n_base4_digits; D.sobol.seed = p->sampler_seed;
+    size_t n_pixels = (size_t)p->width * p->height;
+    int32_t rc = alloc_state(ctx, n_pixels * (size_t)ctx->params.sample_batch, n_pixels);
+    if (rc != HK_OK) return rc;
+    ctx->have_params = true;
+    return HK_OK;
+}
+
+int32_t hk_clear(HkContext* ctx) {
+    if (!ctx) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    REQUIRE(ctx->have_params, "hk_set_params has not been called");
+    CK(cudaMemsetAsync(ctx->b_film.p, 0, ctx->b_film.bytes, ctx->stream));
+    return HK_OK;
+}
+
+}  // extern "C"
+template <int TYPE> static void launch_shade(HkContext* ctx, const PassArgs& A, int next) {
+    if (!(ctx->mat_types_present & (1u << TYPE))) return;
+    k_shade<TYPE><<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(ctx->D, ctx->S, A, next);
+    ctx->launches++;
+}
+
+extern "C" {
+int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride, int32_t count) {
+    if (!ctx) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    REQUIRE(ctx->have_tables && ctx->have_geom && ctx->have_mats && ctx->have_lights && ctx->have_cam && ctx->have_filter && ctx->have_params,
+            "render called before tables/geometry/materials/lights/camera/filter/params were all uploaded");
+    REQUIRE(count >= 0 && stride >= 1 && first >= 1, "bad sample range");
+    const size_t n_pixels = (size_t)ctx->params.width * ctx->params.height;
+    cudaStream_t st = ctx->stream;
+    if (!ctx->camera_medium_valid) {   // hoisted out of the per-sample path (reference: one alloc + sync per sample, volpath.jl:503)
+        CK(ctx->b_scratch_u32.alloc(16));
+        k_detect_camera_medium<<<1, 32, 0, st>>>(ctx->D, ctx->b_scratch_u32.as<uint32_t>());
+        ctx->launches++;
+        CK(cudaMemcpyAsync(&ctx->camera_medium, ctx->b_scratch_u32.p, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        ctx->camera_medium_valid = true;
+    }
+    const bool opaque_only = !ctx->D.any_medium_transition && ctx->D.n_media == 0;
+    CK(cudaEventRecord(ctx->ev0, st));
+    int32_t done = 0;
+    while (done < count) {
+        PassArgs A;
+        A.n_batch = std::min<int32_t>(ctx->params.sample_batch, count - done);
+        A.first_sample = first + done * stride; A.stride = stride; A.n_pixels = (uint32_t)n_pixels;
+        const size_t n_slots = n_pixels * (size_t)A.n_batch;
+        k_camera<<<grid_for(ctx, n_slots, 256, 8), 256, 0, st>>>(ctx->D, ctx->S, A, ctx->camera_medium);
+        ctx->launches++;
+        int cur = 0;
+        for (int depth = 0; depth < ctx->params.max_depth; depth++) {
+            k_reset_bounce<<<1, 32, 0, st>>>(ctx->S, cur);
+            k_trace<<<ctx->sm_count * 8, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, cur);
+            ctx->launches += 2;
+            if (ctx->D.n_media > 0) { k_medium<<<ctx->sm_count * 8, 128, 0, st>>>(ctx->D, ctx->S, A, cur ^ 1); ctx->launches++; }
+            if (ctx->D.n_lights > 0) { k_escaped<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->D, ctx->S); ctx->launches++; }
+            launch_shade<HK_MAT_MATTE>(ctx, A, cur ^ 1); launch_shade<HK_MAT_MIRROR>(ctx, A, cur ^ 1); launch_shade<HK_MAT_GLASS>(ctx, A, cur ^ 1);
+            launch_shade<HK_MAT_CONDUCTOR>(ctx, A, cur ^ 1); launch_shade<HK_MAT_COATED_DIFFUSE>(ctx, A, cur ^ 1);
+            launch_shade<HK_MAT_THIN_DIELECTRIC>(ctx, A, cur ^ 1); launch_shade<HK_MAT_DIFFUSE_TRANSMISSION>(ctx, A, cur ^ 1);
+            if (ctx->D.n_lights > 0) {
+                if (opaque_only) k_shadow<true><<<ctx->sm_count * 8, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S);
+                else k_shadow<false><<<ctx->sm_count * 8, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S);
+                ctx->launches++;
+            }
+            cur ^= 1;
+        }
+        k_film_accumulate<<<grid_for(ctx, n_pixels, 256, 8), 256, 0, st>>>(ctx->D, ctx->S, A);
+        ctx->launches++;
+        done += A.n_batch;
+    }
+    CK(cudaEventRecord(ctx->ev1, st));
+    CK(cudaGetLastError());
+    ctx->stats.samples_rendered += (uint64_t)count * n_pixels;
+    return HK_OK;
+}
+int32_t hk_render_samples(HkContext* ctx, int32_t first, int32_t count) { return hk_render_samples_strided(ctx, first, 1, count); }
+
+int32_t hk_synchronize(HkContext* ctx) {
+    if (!ctx) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    return HK_OK;
+}
+
+int32_t hk_read_film(HkContext* ctx, float* out) {
+    if (!ctx || !out) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    REQUIRE(ctx->have_params, "hk_set_params has not been called");
+    const size_t n = (size_t)ctx->params.width * ctx->params.height;
+    DevBuf tmp; CK(tmp.alloc(12 * n));
+    k_film_finalize<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(ctx->S.pixel_rgb, ctx->S.pixel_weight, tmp.as<float>(), ctx->params.width, ctx->params.height);
+    ctx->launches++;
+    cudaError_t e = cudaMemcpyAsync(out, tmp.p, 12 * n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    tmp.release();
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return HK_ERR_CUDA; }
+    return HK_OK;
+}
+int32_t hk_film_accum_dev(HkContext* ctx, float** out, uint64_t* count) {
+    if (!ctx || !out || !count) return HK_ERR_INVALID;
+    REQUIRE(ctx->have_params, "hk_set_params has not been called");
+    *out = ctx->S.pixel_rgb; *count = 4ull * (uint64_t)ctx->params.width * ctx->params.height;
+    return HK_OK;
+}
+int32_t hk_read_accum(HkContext* ctx, float* rgb, float* w) {
+    if (!ctx || !rgb || !w) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    REQUIRE(ctx->have_params, "hk_set_params has not been called");
+    const size_t n = (size_t)ctx->params.width * ctx->params.height;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(rgb, ctx->S.pixel_rgb, 12 * n, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(w, ctx->S.pixel_weight, 4 * n, cudaMemcpyDeviceToHost));
+    return HK_OK;
+}
+int32_t hk_write_accum(HkContext* ctx, const float* rgb, const float* w) {
+    if (!ctx || !rgb || !w) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    REQUIRE(ctx->have_params, "hk_set_params has not been called");
+    const size_t n = (size_t)ctx->params.width * ctx->params.height;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(ctx->S.pixel_rgb, rgb, 12 * n, cudaMemcpyHostToDevice)); CK(cudaMemcpy(ctx->S.pixel_weight, w, 4 * n, cudaMemcpyHostToDevice));
+    return HK_OK;
+}
+
+// ---- stand-alone traversal -----------------------------------------------------------------------------------------
+static int32_t trace_dev(HkContext* ctx, const float* rays_dev, uint64_t n, float* hits_dev, uint8_t* occ_dev, int repeat, bool any, bool count) {
+    cudaStream_t st = ctx->stream;
+    unsigned long long* ctr = ctx->b_trace_ctr.as<unsigned long long>();
+    CK(cudaEventRecord(ctx->ev0, st));
+    for (int r = 0; r < repeat; r++) {
+        CK(cudaMemsetAsync(ctr, 0, 24, st));
+        const int grid = ctx->sm_count * 8;
+        const float4* rp = reinterpret_cast<const float4*>(rays_dev); float4* hp = reinterpret_cast<float4*>(hits_dev);
+        if (any) k_trace_batch<true, false><<<grid, HK_TRACE_THREADS, 0, st>>>(ctx->D.bvh, rp, n, hp, occ_dev, ctr, ctr + 1);
+        else if (count) k_trace_batch<false, true><<<grid, HK_TRACE_THREADS, 0, st>>>(ctx->D.bvh, rp, n, hp, occ_dev, ctr, ctr + 1);
+        else k_trace_batch<false, false><<<grid, HK_TRACE_THREADS, 0, st>>>(ctx->D.bvh, rp, n, hp, occ_dev, ctr, ctr + 1);
+        ctx->launches++;
+    }
+    CK(cudaEventRecord(ctx->ev1, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->stats.last_trace_ms = ms / (float)(repeat > 0 ? repeat : 1);
+    ctx->stats.rays_traced += n * (uint64_t)repeat;
+    return HK_OK;
+}
+int32_t hk_trace_closest_dev(HkContext* ctx, const float* rays_dev, uint64_t n, float* hits_dev, int32_t repeat) {
+    if (!ctx || !rays_dev || !hits_dev) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    REQUIRE(ctx->have_geom, "hk_upload_geometry has not been called");
+    return trace_dev(ctx, rays_dev, n, hits_dev, nullptr, repeat < 1 ? 1 : repeat, false, false);
+}
+int32_t hk_trace_closest(HkContext* ctx, const float* rays, uint64_t n, float* hits) {
+    if (!ctx || (n && (!rays || !hits))) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    REQUIRE(ctx->have_geom, "hk_upload_geometry has not been called");
+    if (n == 0) return HK_OK;
+    DevBuf r, h; CK(r.upload(rays, 32 * (size_t)n)); CK(h.alloc(16 * (size_t)n));
+    int32_t rc = trace_dev(ctx, r.as<float>(), n, h.as<float>(), nullptr, 1, false, false);
+    if (rc == HK_OK) { cudaError_t e = cudaMemcpy(hits, h.p, 16 * (size_t)n, cudaMemcpyDeviceToHost); if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = HK_ERR_CUDA; } }
+    r.release(); h.release();
+    return rc;
+}
+int32_t hk_trace_any(HkContext* ctx, const float* rays, uint64_t n, uint8_t* occluded) {
+    if (!ctx || (n && (!rays || !occluded))) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    REQUIRE(ctx->have_geom, "hk_upload_geometry has not been called");
+    if (n == 0) return HK_OK;
+    DevBuf r, o; CK(r.upload(rays, 32 * (size_t)n)); CK(o.alloc((size_t)n));
+    int32_t rc = trace_dev(ctx, r.as<float>(), n, nullptr, o.as<uint8_t>(), 1, true, false);
+    if (rc == HK_OK) { cudaError_t e = cudaMemcpy(occluded, o.p, (size_t)n, cudaMemcpyDeviceToHost); if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = HK_ERR_CUDA; } }
+    r.release(); o.release();
+    return rc;
+}
+// traversal work counters for the roofline formula: node visits and triangle tests of one batch
+int32_t hk_test_trace_counts(HkContext* ctx, const float* rays, uint64_t n, uint64_t* out_nodes, uint64_t* out_tris) {
+    if (!ctx || !rays || !out_nodes || !out_tris) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    REQUIRE(ctx->have_geom, "hk_upload_geometry has not been called");
+    DevBuf r, h; CK(r.upload(rays, 32 * (size_t)n)); CK(h.alloc(16 * (size_t)n + 16));
+    int32_t rc = trace_dev(ctx, r.as<float>(), n, h.as<float>(), nullptr, 1, false, true);
+    unsigned long long c[2] = {0, 0};
+    // counters live after the cursor word
+    if (rc == HK_OK) { cudaMemcpy(c, ctx->b_trace_ctr.as<unsigned long long>() + 1, 16, cudaMemcpyDeviceToHost); }
+    *out_nodes = c[0]; *out_tris = c[1];
+    r.release(); h.release();
+    return rc;
+}
+
+int32_t hk_stats(HkContext* ctx, HkStats* out) {
+    if (!ctx || !out) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->stats.last_render_ms = ms; else cudaGetLastError();
+    unsigned long long rt = 0;
+    if (ctx->S.rays_traced) cudaMemcpy(&rt, ctx->S.rays_traced, 8, cudaMemcpyDeviceToHost);
+    *out = ctx->stats;
+    out->rays_traced = ctx->stats.rays_traced + rt;
+    out->kernel_launches = ctx->launches;
+    out->queue_overflows = 0;
+    return HK_OK;
+}
+
+int32_t hk_dev_alloc(HkContext* ctx, uint64_t bytes, void** out) { if (!ctx || !out) return HK_ERR_INVALID; cudaSetDevice(ctx->device); CK(cudaMalloc(out, bytes ? bytes : 16)); return HK_OK; }
+int32_t hk_dev_free(HkContext* ctx, void* p) { if (!ctx) return HK_ERR_INVALID; cudaSetDevice(ctx->device); CK(cudaFree(p)); return HK_OK; }
+int32_t hk_dev_upload(HkContext* ctx, void* dst, const void* src, uint64_t bytes) { if (!ctx) return HK_ERR_INVALID; cudaSetDevice(ctx->device); CK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice)); return HK_OK; }
+int32_t hk_dev_download(HkContext* ctx, void* dst, const void* src, uint64_t bytes) { if (!ctx) return HK_ERR_INVALID; cudaSetDevice(ctx->device); CK(cudaStreamSynchronize(ctx->stream)); CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost)); return HK_OK; }
+
+}  // extern "C"
+
+#include "hk_testing.cuh"

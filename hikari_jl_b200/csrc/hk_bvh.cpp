@@ -1,0 +1,249 @@
+// hk_bvh.cpp — host builder: binned-SAH BVH2 -> greedy collapse to BVH8 -> octant slot assignment ->
+// 8-bit quantisation (conservative) -> BFS layout with contiguous internal children / leaf triangles.
+// Replaces Raycore's BVH/TLAS construction behind scene.accel (reference: Raycore.jl, not vendored;
+// call sites src/scene.jl:146-151 sync!).
+#include "hk_bvh.h"
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <numeric>
+
+namespace {
+
+const float INF = std::numeric_limits<float>::infinity();
+
+struct Box {
+    float lo[3], hi[3];
+    void reset() { for (int k = 0; k < 3; k++) { lo[k] = INF; hi[k] = -INF; } }
+    void grow(const Box& b) { for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], b.lo[k]); hi[k] = std::max(hi[k], b.hi[k]); } }
+    void grow(const float* p) { for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], p[k]); hi[k] = std::max(hi[k], p[k]); } }
+    float half_area() const {
+        float d[3] = {hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]};
+        if (d[0] < 0) return 0.0f;
+        return d[0] * d[1] + d[1] * d[2] + d[2] * d[0];
+    }
+};
+struct Node2 { Box box; uint32_t left, right, first, count; };   // count > 0 => leaf
+
+struct Builder {
+    const std::vector<Box>& pb;      // per-primitive (padded) boxes
+    const std::vector<float>& cen;   // centroids [n][3]
+    std::vector<uint32_t> order;
+    std::vector<Node2> nodes;
+    std::atomic<uint32_t> n_nodes{0};
+    static constexpr int NBINS = 16;
+    static constexpr uint32_t MAX_LEAF = 3;
+
+    Builder(const std::vector<Box>& b, const std::vector<float>& c) : pb(b), cen(c) {}
+
+    uint32_t alloc() { return n_nodes.fetch_add(1); }
+
+    void build(uint32_t me, uint32_t first, uint32_t count, int depth) {
+        Box box, cbox; box.reset(); cbox.reset();
+        for (uint32_t i = first; i < first + count; i++) { uint32_t p = order[i]; box.grow(pb[p]); cbox.grow(&cen[3 * (size_t)p]); }
+        nodes[me].box = box;
+        if (count <= MAX_LEAF && (count == 1 || depth > 60)) { make_leaf(me, first, count); return; }
+        // binned SAH over the three axes
+        float best_cost = INF; int best_axis = -1, best_bin = 0;
+        for (int ax = 0; ax < 3; ax++) {
+            float ext = cbox.hi[ax] - cbox.lo[ax];
+            if (!(ext > 0.0f)) continue;
+            Box bb[NBINS]; uint32_t bc[NBINS];
+            for (int b = 0; b < NBINS; b++) { bb[b].reset(); bc[b] = 0; }
+            float k1 = NBINS * (1.0f - 1e-6f) / ext;
+            for (uint32_t i = first; i < first + count; i++) {
+                uint32_t p = order[i];
+                int b = (int)(k1 * (cen[3 * (size_t)p + ax] - cbox.lo[ax]));
+                b = b < 0 ? 0 : (b >= NBINS ? NBINS - 1 : b);
+                bb[b].grow(pb[p]); bc[b]++;
+            }
+            float ra[NBINS]; uint32_t rc[NBINS];
+            Box acc; acc.reset(); uint32_t c = 0;
+            for (int b = NBINS - 1; b > 0; b--) { acc.grow(bb[b]); c += bc[b]; ra[b] = acc.half_area(); rc[b] = c; }
+            acc.reset(); c = 0;
+            for (int b = 0; b < NBINS - 1; b++) {
+                acc.grow(bb[b]); c += bc[b];
+                if (c == 0 || rc[b + 1] == 0) continue;
+                float cost = acc.half_area() * (float)((c + 2) / 3) + ra[b + 1] * (float)((rc[b + 1] + 2) / 3);
+                if (cost < best_cost) { best_cost = cost; best_axis = ax; best_bin = b; }
+            }
+        }
+        uint32_t mid;
+        if (best_axis >= 0) {
+            float leaf_cost = box.half_area() * (float)((count + 2) / 3);
+            if (count <= MAX_LEAF && leaf_cost <= best_cost + 0.125f * box.half_area()) { make_leaf(me, first, count); return; }
+            float ext = cbox.hi[best_axis] - cbox.lo[best_axis];
+            float k1 = NBINS * (1.0f - 1e-6f) / ext;
+            auto it = std::partition(order.begin() + first, order.begin() + first + count, [&](uint32_t p) {
+                int b = (int)(k1 * (cen[3 * (size_t)p + best_axis] - cbox.lo[best_axis]));
+                b = b < 0 ? 0 : (b >= NBINS ? NBINS - 1 : b);
+                return b <= best_bin;
+            });
+            mid = (uint32_t)(it - order.begin());
+            if (mid == first || mid == first + count) mid = first + count / 2;
+        } else {
+            if (count <= MAX_LEAF) { make_leaf(me, first, count); return; }
+            mid = first + count / 2;   // coincident centroids: split the list
+        }
+        uint32_t l = alloc(), r = alloc();
+        nodes[me].left = l; nodes[me].right = r; nodes[me].count = 0; nodes[me].first = 0;
+        if (count > 200000) {
+            #pragma omp task shared(nodes)
+            build(l, first, mid - first, depth + 1);
+            #pragma omp task shared(nodes)
+            build(r, mid, first + count - mid, depth + 1);
+            #pragma omp taskwait
+        } else {
+            build(l, first, mid - first, depth + 1);
+            build(r, mid, first + count - mid, depth + 1);
+        }
+    }
+    void make_leaf(uint32_t me, uint32_t first, uint32_t count) {
+        nodes[me].left = nodes[me].right = 0; nodes[me].first = first; nodes[me].count = count;
+        std::sort(order.begin() + first, order.begin() + first + count);   // deterministic leaf order
+    }
+};
+
+inline uint32_t f2u(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+inline float u2f(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+
+}  // namespace
+
+void hk_build_bvh8(const float* positions, const uint32_t* indices, uint32_t n_tris, HkBvh& out) {
+    out.nodes.clear(); out.tris.clear();
+    for (int k = 0; k < 3; k++) { out.bounds_min[k] = 0; out.bounds_max[k] = 0; }
+    if (n_tris == 0) {
+        HkBvhNode root; std::memset(&root, 0, sizeof(root)); out.nodes.push_back(root); return;
+    }
+    std::vector<Box> pb(n_tris); std::vector<float> cen(3 * (size_t)n_tris);
+    #pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)n_tris; i++) {
+        Box b; b.reset();
+        for (int v = 0; v < 3; v++) b.grow(positions + 3 * (size_t)indices[3 * i + v]);
+        for (int k = 0; k < 3; k++) {
+            cen[3 * i + k] = 0.5f * (b.lo[k] + b.hi[k]);
+            float pad = 1.0e-5f * std::max(std::fabs(b.lo[k]), std::fabs(b.hi[k])) + 1.0e-6f;
+            b.lo[k] -= pad; b.hi[k] += pad;
+        }
+        pb[i] = b;
+    }
+    Builder B(pb, cen);
+    B.order.resize(n_tris); std::iota(B.order.begin(), B.order.end(), 0u);
+    B.nodes.resize(2 * (size_t)n_tris);
+    uint32_t root2 = B.alloc();
+    #pragma omp parallel
+    {
+        #pragma omp single
+        B.build(root2, 0, n_tris, 0);
+    }
+    const std::vector<Node2>& N2 = B.nodes;
+    for (int k = 0; k < 3; k++) { out.bounds_min[k] = N2[root2].box.lo[k]; out.bounds_max[k] = N2[root2].box.hi[k]; }
+
+    // ---- collapse + layout (BFS) ----------------------------------------------------------------
+    out.nodes.reserve((size_t)n_tris / 4 + 16); out.tris.reserve(n_tris);
+    struct Pending { uint32_t n2; uint32_t out_idx; };
+    std::vector<Pending> queue; queue.reserve((size_t)n_tris / 4 + 16);
+    out.nodes.emplace_back(); std::memset(&out.nodes[0], 0, sizeof(HkBvhNode));
+    // a root that is itself a leaf gets wrapped: treat it as a wide node with one leaf child
+    queue.push_back(Pending{root2, 0});
+    for (size_t qi = 0; qi < queue.size(); qi++) {
+        Pending cur = queue[qi];
+        uint32_t ch[8]; int nch = 0;
+        if (N2[cur.n2].count > 0) { ch[nch++] = cur.n2; }
+        else {
+            ch[nch++] = N2[cur.n2].left; ch[nch++] = N2[cur.n2].right;
+            while (nch < 8) {
+                int best = -1; float ba = -1.0f;
+                for (int i = 0; i < nch; i++) if (N2[ch[i]].count == 0) { float a = N2[ch[i]].box.half_area(); if (a > ba) { ba = a; best = i; } }
+                if (best < 0) break;
+                uint32_t n = ch[best];
+                ch[best] = N2[n].left; ch[nch++] = N2[n].right;
+            }
+        }
+        // node frame
+        Box nb; nb.reset();
+        for (int i = 0; i < nch; i++) nb.grow(N2[ch[i]].box);
+        float ctr[3] = {0.5f * (nb.lo[0] + nb.hi[0]), 0.5f * (nb.lo[1] + nb.hi[1]), 0.5f * (nb.lo[2] + nb.hi[2])};
+        // greedy octant slot assignment: slot bit set <=> child lies towards + along that axis
+        int slot_of[8]; bool slot_used[8] = {false}; bool assigned[8] = {false};
+        float cost[8][8];
+        for (int i = 0; i < nch; i++) {
+            const Box& b = N2[ch[i]].box;
+            float c[3] = {0.5f * (b.lo[0] + b.hi[0]) - ctr[0], 0.5f * (b.lo[1] + b.hi[1]) - ctr[1], 0.5f * (b.lo[2] + b.hi[2]) - ctr[2]};
+            for (int s = 0; s < 8; s++) cost[i][s] = ((s & 4) ? c[0] : -c[0]) + ((s & 2) ? c[1] : -c[1]) + ((s & 1) ? c[2] : -c[2]);
+        }
+        for (int it = 0; it < nch; it++) {
+            int bi = -1, bs = -1; float bc = -INF;
+            for (int i = 0; i < nch; i++) if (!assigned[i]) for (int s = 0; s < 8; s++) if (!slot_used[s] && cost[i][s] > bc) { bc = cost[i][s]; bi = i; bs = s; }
+            assigned[bi] = true; slot_used[bs] = true; slot_of[bi] = bs;
+        }
+        int child_at[8]; for (int s = 0; s < 8; s++) child_at[s] = -1;
+        for (int i = 0; i < nch; i++) child_at[slot_of[i]] = i;
+
+        HkBvhNode node; std::memset(&node, 0, sizeof(node));
+        float scale[3];
+        for (int k = 0; k < 3; k++) {
+            node.p[k] = nb.lo[k];
+            float ext = nb.hi[k] - nb.lo[k];
+            int e;
+            if (!(ext > 0.0f)) e = -100;
+            else {
+                int ex; std::frexp(ext / 255.0f, &ex);   // ext/255 = m * 2^ex, m in [0.5,1)
+                e = ex;                                   // 2^ex >= ext/255
+                if (e < -120) e = -120;
+            }
+            for (;;) {   // make sure the largest child max fits in 8 bits
+                scale[k] = std::ldexp(1.0f, e);
+                if (std::ceil((nb.hi[k] - nb.lo[k]) / scale[k]) <= 255.0f) break;
+                e++;
+            }
+            node.e[k] = (uint8_t)(e + 127);
+            scale[k] = u2f((uint32_t)node.e[k] << 23);
+        }
+        node.child_base = (uint32_t)out.nodes.size();
+        node.tri_base = (uint32_t)out.tris.size();
+        uint32_t tri_off = 0;
+        for (int s = 0; s < 8; s++) {
+            int i = child_at[s];
+            if (i < 0) { node.meta[s] = 0; continue; }
+            const Node2& c = N2[ch[i]];
+            for (int k = 0; k < 3; k++) {
+                float lo = std::floor((c.box.lo[k] - node.p[k]) / scale[k]);
+                float hi = std::ceil((c.box.hi[k] - node.p[k]) / scale[k]);
+                lo = std::min(std::max(lo, 0.0f), 255.0f); hi = std::min(std::max(hi, 0.0f), 255.0f);
+                while (lo > 0.0f && node.p[k] + lo * scale[k] > c.box.lo[k]) lo -= 1.0f;
+                while (hi < 255.0f && node.p[k] + hi * scale[k] < c.box.hi[k]) hi += 1.0f;
+                node.qlo[k][s] = (uint8_t)lo; node.qhi[k][s] = (uint8_t)hi;
+            }
+            if (c.count == 0) {
+                node.imask |= (uint8_t)(1u << s);
+                node.meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
+            } else {
+                uint32_t unary = c.count == 1 ? 1u : (c.count == 2 ? 3u : 7u);
+                node.meta[s] = (uint8_t)((unary << 5) | tri_off);
+                for (uint32_t t = 0; t < c.count; t++) {
+                    uint32_t prim = B.order[c.first + t];
+                    const float* a = positions + 3 * (size_t)indices[3 * (size_t)prim];
+                    const float* b = positions + 3 * (size_t)indices[3 * (size_t)prim + 1];
+                    const float* cc = positions + 3 * (size_t)indices[3 * (size_t)prim + 2];
+                    HkBvhTri T; std::memset(&T, 0, sizeof(T));
+                    for (int k = 0; k < 3; k++) { T.v0[k] = a[k]; T.e1[k] = b[k] - a[k]; T.e2[k] = cc[k] - a[k]; }
+                    T.prim = prim;
+                    out.tris.push_back(T);
+                }
+                tri_off += c.count;
+            }
+        }
+        // internal children in slot order, contiguous
+        for (int s = 0; s < 8; s++) {
+            int i = child_at[s];
+            if (i < 0 || N2[ch[i]].count != 0) continue;
+            uint32_t idx = (uint32_t)out.nodes.size();
+            out.nodes.emplace_back(); std::memset(&out.nodes.back(), 0, sizeof(HkBvhNode));
+            queue.push_back(Pending{ch[i], idx});
+        }
+        out.nodes[cur.out_idx] = node;
+    }
+}

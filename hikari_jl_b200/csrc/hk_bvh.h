@@ -1,0 +1,36 @@
+// hk_bvh.h — 8-wide BVH with quantised child bounds (80-byte nodes) + 48-byte triangles.
+// Layout follows the compressed wide BVH idea (Ylitie, Karras, Laine 2017): children share one
+// origin/exponent frame, child boxes are 8-bit quantised, internal children and leaf triangles of a
+// node are stored contiguously so one base index each suffices.  Sized to stay L2-resident for the
+// small/medium configs (126 MB L2) and to stream from HBM3e for the 50 M-triangle config.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+struct alignas(16) HkBvhNode {        // 80 bytes = 5 x 16-byte vector loads
+    float    p[3];                     // quantisation origin
+    uint8_t  e[3];                     // per-axis exponent (biased by 127 like IEEE)
+    uint8_t  imask;                    // bit i set <=> child slot i is an internal node
+    uint32_t child_base;               // index of the first internal child
+    uint32_t tri_base;                 // index of the first triangle referenced by leaf children
+    uint8_t  meta[8];                  // internal: 001sssss (sssss = 24+slot); leaf: unary count<<5 | tri offset; empty: 0
+    uint8_t  qlo[3][8];                // quantised child mins  [axis][slot]
+    uint8_t  qhi[3][8];                // quantised child maxs
+};
+static_assert(sizeof(HkBvhNode) == 80, "node must be 80 bytes");
+
+struct alignas(16) HkBvhTri {          // 48 bytes = 3 x 16-byte vector loads
+    float v0[3]; uint32_t prim;        // global primitive id (0-based)
+    float e1[3]; uint32_t pad1;
+    float e2[3]; uint32_t pad2;
+};
+static_assert(sizeof(HkBvhTri) == 48, "triangle must be 48 bytes");
+
+struct HkBvh {
+    std::vector<HkBvhNode> nodes;      // nodes[0] = root
+    std::vector<HkBvhTri>  tris;       // in leaf order
+    float bounds_min[3], bounds_max[3];
+};
+
+// positions [n_verts][3], indices [n_tris][3]
+void hk_build_bvh8(const float* positions, const uint32_t* indices, uint32_t n_tris, HkBvh& out);

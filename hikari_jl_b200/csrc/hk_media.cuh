@@ -1,0 +1,294 @@
+// hk_media.cuh — participating media on the device: HG phase, majorant DDA, Homogeneous / Grid / NanoVDB
+// density, delta tracking and ratio tracking.
+// Reference: src/integrators/volpath/media.jl:28-74,275-391,625-729,781-850,1544-1740, nanovdb.jl:246-543,
+// delta-tracking.jl:142-453, intersection.jl:421-542.
+#pragma once
+#include "hk_spectral.cuh"
+
+struct DevMedium {
+    int32_t type; float sigma_a[3], sigma_s[3], Le[3]; float g;
+    float bmin[3], bmax[3]; float medium_from_render[12];
+    int32_t dres[3]; const float* __restrict__ density;
+    int32_t mres[3]; const float* __restrict__ majorant;
+    const uint8_t* __restrict__ nvdb; float inv_mat[9], vec[3]; uint64_t root_off; int32_t root_tiles;
+};
+struct MediaCtx { DevTables T; const DevMedium* __restrict__ media; int32_t n_media; };
+
+HK_DEV float hg_p(float g, float c) { float g2 = g * g, d = 1.0f + g2 - 2.0f * g * c; return (1.0f - g2) / (4.0f * HK_PI * d * sqrtf(d)); }   // media.jl:28-32
+HK_DEV float3 sample_hg(float g, float3 wo, float2 u, float& pdf) {                                                                            // media.jl:42-74
+    float c;
+    if (fabsf(g) < 1.0e-3f) c = 1.0f - 2.0f * u.x;
+    else { float g2 = g * g; float q = (1.0f - g2) / (1.0f - g + 2.0f * g * u.x); c = clampf((1.0f + g2 - q * q) / (2.0f * g), -1.0f, 1.0f); }
+    float s = sqrtf(fmaxf(0.0f, 1.0f - c * c)), phi = 2.0f * HK_PI * u.y;
+    Frame fr = make_frame(-wo);
+    float3 wi = norm3(s * cosf(phi) * fr.t + s * sinf(phi) * fr.b + c * (-wo));
+    pdf = hg_p(g, c);
+    return wi;
+}
+
+// ---- majorant iterator ----------------------------------------------------------------------------------------
+struct MajIter { int mode; Spec sigma_t; float t_min, t_max; bool hom_called; const float* __restrict__ grid; int res[3]; float next_t[3], delta_t[3]; int step[3], limit[3], voxel[3]; };
+struct MajSeg { float t_min, t_max; Spec sigma_maj; };
+HK_DEV float jl_max(float a, float b) { return (a != a || b != b) ? __int_as_float(0x7fc00000) : fmaxf(a, b); }
+HK_DEV float jl_min(float a, float b) { return (a != a || b != b) ? __int_as_float(0x7fc00000) : fminf(a, b); }
+HK_DEV void ray_bounds(float3 o, float3 d, const float* bmin, const float* bmax, float& te, float& tx) {   // media.jl:1704-1740
+    float t0[3], t1[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float dk = comp3(d, k), ok = comp3(o, k);
+        float inv = fabsf(dk) > 1.0e-10f ? 1.0f / dk : (dk >= 0.0f ? HK_INF : -HK_INF);
+        float a = (bmin[k] - ok) * inv, b = (bmax[k] - ok) * inv;
+        if (a > b) { float t = a; a = b; b = t; }
+        t0[k] = a; t1[k] = b;
+    }
+    te = jl_max(jl_max(t0[0], t0[1]), t0[2]);
+    tx = jl_min(jl_min(t1[0], t1[1]), t1[2]);
+}
+HK_DEV void majiter_invalid(MajIter& it) { it.mode = 0; it.t_min = HK_INF; it.t_max = -HK_INF; it.hom_called = true; }
+HK_DEV void dda_init(MajIter& it, const DevMedium& M, float3 o, float3 d, float t_min, float t_max, Spec sigma_t) {   // media.jl:275-391
+    it.sigma_t = sigma_t; it.t_min = t_min; it.t_max = t_max; it.grid = M.majorant; it.hom_called = false;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        int r = M.mres[k];
+        it.res[k] = r;
+        float diag = M.bmax[k] - M.bmin[k];
+        float go = (comp3(o, k) - M.bmin[k]) / diag;
+        float gd = comp3(d, k) * (fabsf(diag) > 1.0e-10f ? 1.0f / diag : 0.0f);
+        float gi = go + gd * t_min;
+        int vox = clampi(floor_i(gi * (float)r), 0, r - 1);
+        it.delta_t[k] = fabsf(gd) > 1.0e-10f ? 1.0f / (fabsf(gd) * (float)r) : HK_INF;
+        if (gd >= 0.0f) { it.next_t[k] = gd > 1.0e-10f ? t_min + ((float)(vox + 1) / (float)r - gi) / gd : HK_INF; it.step[k] = 1; it.limit[k] = r; }
+        else { it.next_t[k] = gd < -1.0e-10f ? t_min + ((float)vox / (float)r - gi) / gd : HK_INF; it.step[k] = -1; it.limit[k] = -1; }
+        it.voxel[k] = vox;
+    }
+    it.mode = t_min >= t_max ? 0 : 2;
+}
+HK_DEV bool majiter_next(MajIter& it, MajSeg& seg) {   // media.jl:625-729
+    if (it.mode == 0) return false;
+    if (it.mode == 1) {
+        if (it.hom_called || it.t_min >= it.t_max) { it.mode = 0; return false; }
+        seg.t_min = it.t_min; seg.t_max = it.t_max; seg.sigma_maj = it.sigma_t; it.hom_called = true;
+        return true;
+    }
+    if (it.t_min >= it.t_max) { it.mode = 0; return false; }
+    int axis = (it.next_t[0] < it.next_t[1]) ? ((it.next_t[0] < it.next_t[2]) ? 0 : 2) : ((it.next_t[1] < it.next_t[2]) ? 1 : 2);
+    float nt = axis == 0 ? it.next_t[0] : (axis == 1 ? it.next_t[1] : it.next_t[2]);
+    float st = fminf(nt, it.t_max);
+    float rho = __ldg(it.grid + it.voxel[0] + it.res[0] * (it.voxel[1] + it.res[1] * it.voxel[2]));
+    seg.t_min = it.t_min; seg.t_max = st; seg.sigma_maj = it.sigma_t * rho;
+    it.t_min = st;
+    if (axis == 0) { it.voxel[0] += it.step[0]; it.next_t[0] += it.delta_t[0]; }
+    else if (axis == 1) { it.voxel[1] += it.step[1]; it.next_t[1] += it.delta_t[1]; }
+    else { it.voxel[2] += it.step[2]; it.next_t[2] += it.delta_t[2]; }
+    if (it.voxel[0] == it.limit[0] || it.voxel[1] == it.limit[1] || it.voxel[2] == it.limit[2]) { it.mode = 0; it.t_min = it.t_max; }
+    return true;
+}
+
+// ---- NanoVDB (nanovdb.jl:246-469).  The 8 trilinear corners share one root->lower walk whenever they fall in
+// the same 8^3 leaf (the common case); the per-thread LeafCache keeps that walk. Values read are exactly the
+// ones the reference's 8 independent walks return. ------------------------------------------------------------
+struct LeafCache { int32_t kx, ky, kz; uint64_t leaf_off; float tile; bool valid, is_leaf; };
+template <class Tp> HK_DEV Tp rd(const uint8_t* __restrict__ b, uint64_t off) { return __ldg(reinterpret_cast<const Tp*>(b + off)); }
+HK_DEV bool mask_on(const uint8_t* __restrict__ b, uint64_t off, uint32_t n) { return ((__ldg(b + off + (n >> 3)) >> (n & 7)) & 1) != 0; }
+HK_DEV float nvdb_value(const DevMedium& M, LeafCache& lc, int32_t x, int32_t y, int32_t z) {
+    const int32_t kx = x >> 3, ky = y >> 3, kz = z >> 3;
+    if (!(lc.valid && lc.kx == kx && lc.ky == ky && lc.kz == kz)) {
+        const uint8_t* b = M.nvdb;
+        uint32_t xu = (uint32_t)x, yu = (uint32_t)y, zu = (uint32_t)z;
+        uint64_t key = (uint64_t)((zu >> 12) & 0x1fffff) | ((uint64_t)((yu >> 12) & 0x1fffff) << 21) | ((uint64_t)((xu >> 12) & 0x1fffff) << 42);
+        lc.valid = true; lc.kx = kx; lc.ky = ky; lc.kz = kz; lc.is_leaf = false;
+        uint64_t tile = 0; bool found = false;
+        for (int i = 0; i < M.root_tiles; i++) { uint64_t to = M.root_off + 64 + (uint64_t)i * 32; if (rd<uint64_t>(b, to) == key) { found = true; tile = to; break; } }
+        if (!found) lc.tile = rd<float>(b, M.root_off + 28);
+        else {
+            int64_t child = rd<int64_t>(b, tile + 8);
+            if (child == 0) lc.tile = rd<float>(b, tile + 20);
+            else {
+                uint64_t upper = M.root_off + child;
+                uint32_t nu = (((xu >> 7) & 31) << 10) | (((yu >> 7) & 31) << 5) | ((zu >> 7) & 31);
+                if (!mask_on(b, upper + 4128, nu)) lc.tile = rd<float>(b, upper + 8256 + (uint64_t)nu * 8);
+                else {
+                    uint64_t lower = upper + rd<int64_t>(b, upper + 8256 + (uint64_t)nu * 8);
+                    uint32_t nl = (((xu >> 3) & 15) << 8) | (((yu >> 3) & 15) << 4) | ((zu >> 3) & 15);
+                    if (!mask_on(b, lower + 544, nl)) lc.tile = rd<float>(b, lower + 1088 + (uint64_t)nl * 8);
+                    else { lc.is_leaf = true; lc.leaf_off = lower + rd<int64_t>(b, lower + 1088 + (uint64_t)nl * 8); }
+                }
+            }
+        }
+    }
+    if (!lc.is_leaf) return lc.tile;
+    uint32_t nf = ((uint32_t)(x & 7) << 6) | ((uint32_t)(y & 7) << 3) | (uint32_t)(z & 7);
+    return rd<float>(M.nvdb, lc.leaf_off + 96 + (uint64_t)nf * 4);
+}
+HK_DEV float nvdb_density(const DevMedium& M, float3 p) {
+    float px = p.x - M.vec[0], py = p.y - M.vec[1], pz = p.z - M.vec[2];
+    float gx = M.inv_mat[0] * px + M.inv_mat[1] * py + M.inv_mat[2] * pz;
+    float gy = M.inv_mat[3] * px + M.inv_mat[4] * py + M.inv_mat[5] * pz;
+    float gz = M.inv_mat[6] * px + M.inv_mat[7] * py + M.inv_mat[8] * pz;
+    int ix = floor_i(gx), iy = floor_i(gy), iz = floor_i(gz);
+    float fx = gx - (float)ix, fy = gy - (float)iy, fz = gz - (float)iz;
+    LeafCache lc; lc.valid = false;
+    float v000 = nvdb_value(M, lc, ix, iy, iz), v001 = nvdb_value(M, lc, ix, iy, iz + 1);
+    float v010 = nvdb_value(M, lc, ix, iy + 1, iz), v011 = nvdb_value(M, lc, ix, iy + 1, iz + 1);
+    float v100 = nvdb_value(M, lc, ix + 1, iy, iz), v101 = nvdb_value(M, lc, ix + 1, iy, iz + 1);
+    float v110 = nvdb_value(M, lc, ix + 1, iy + 1, iz), v111 = nvdb_value(M, lc, ix + 1, iy + 1, iz + 1);
+    float fx1 = 1.0f - fx, fy1 = 1.0f - fy, fz1 = 1.0f - fz;
+    float v00 = v000 * fz1 + v001 * fz, v01 = v010 * fz1 + v011 * fz, v10 = v100 * fz1 + v101 * fz, v11 = v110 * fz1 + v111 * fz;
+    float v0 = v00 * fy1 + v01 * fy, v1 = v10 * fy1 + v11 * fy;
+    return v0 * fx1 + v1 * fx;
+}
+HK_DEV float grid_density(const DevMedium& M, float3 pm) {   // media.jl:1544-1595
+    float pn[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) pn[k] = (comp3(pm, k) - M.bmin[k]) / (M.bmax[k] - M.bmin[k]);
+    if (pn[0] < 0.0f || pn[1] < 0.0f || pn[2] < 0.0f || pn[0] > 1.0f || pn[1] > 1.0f || pn[2] > 1.0f) return 0.0f;
+    const int nx = M.dres[0], ny = M.dres[1], nz = M.dres[2];
+    float gx = pn[0] * (float)nx + 0.5f, gy = pn[1] * (float)ny + 0.5f, gz = pn[2] * (float)nz + 0.5f;
+    int ix = clampi(floor_i(gx), 1, nx - 1), iy = clampi(floor_i(gy), 1, ny - 1), iz = clampi(floor_i(gz), 1, nz - 1);
+    float fx = clampf(gx - (float)ix, 0.0f, 1.0f), fy = clampf(gy - (float)iy, 0.0f, 1.0f), fz = clampf(gz - (float)iz, 0.0f, 1.0f);
+    const float* b = M.density + (size_t)(ix - 1) + (size_t)nx * ((size_t)(iy - 1) + (size_t)ny * (size_t)(iz - 1));
+    const size_t sy = (size_t)nx, sz = (size_t)nx * ny;
+    float fx1 = 1.0f - fx;
+    float d00 = __ldg(b) * fx1 + __ldg(b + 1) * fx, d10 = __ldg(b + sy) * fx1 + __ldg(b + sy + 1) * fx;
+    float d01 = __ldg(b + sz) * fx1 + __ldg(b + sz + 1) * fx, d11 = __ldg(b + sz + sy) * fx1 + __ldg(b + sz + sy + 1) * fx;
+    float fy1 = 1.0f - fy;
+    float d0 = d00 * fy1 + d10 * fy, d1 = d01 * fy1 + d11 * fy;
+    return d0 * (1.0f - fz) + d1 * fz;
+}
+HK_DEV float3 affine_pt(const float* M, float3 p) { return f3(M[0] * p.x + M[1] * p.y + M[2] * p.z + M[3], M[4] * p.x + M[5] * p.y + M[6] * p.z + M[7], M[8] * p.x + M[9] * p.y + M[10] * p.z + M[11]); }
+HK_DEV float3 affine_vc(const float* M, float3 v) { return f3(M[0] * v.x + M[1] * v.y + M[2] * v.z, M[4] * v.x + M[5] * v.y + M[6] * v.z, M[8] * v.x + M[9] * v.y + M[10] * v.z); }
+
+// per-ray cached coefficients: sigma_a / sigma_s spectra depend only on (medium, lambda)
+struct MediumCoef { Spec sa, ss, Le; float g; };
+HK_DEV MediumCoef medium_coef(const MediaCtx& C, const DevMedium& M, float4 lam) {
+    MediumCoef c;
+    c.sa = uplift_rgb_unbounded(C.T, M.sigma_a[0], M.sigma_a[1], M.sigma_a[2], lam);
+    c.ss = uplift_rgb_unbounded(C.T, M.sigma_s[0], M.sigma_s[1], M.sigma_s[2], lam);
+    c.Le = M.type == HK_MEDIUM_HOMOGENEOUS ? uplift_rgb_unbounded(C.T, M.Le[0], M.Le[1], M.Le[2], lam) : sp(0.0f);
+    c.g = M.g;
+    return c;
+}
+HK_DEV float medium_density(const DevMedium& M, float3 p) {
+    if (M.type == HK_MEDIUM_GRID) return grid_density(M, affine_pt(M.medium_from_render, p));
+    if (M.type == HK_MEDIUM_NANOVDB) return nvdb_density(M, p);
+    return 1.0f;
+}
+HK_DEV void majiter_create(MajIter& it, const DevMedium& M, const MediumCoef& mc, float3 o, float3 d, float t_max) {
+    Spec st = mc.sa + mc.ss;
+    if (M.type == HK_MEDIUM_HOMOGENEOUS) { it.mode = (0.0f >= t_max) ? 0 : 1; it.sigma_t = st; it.t_min = 0.0f; it.t_max = t_max; it.hom_called = false; return; }
+    float3 ro = o, rd_ = d;
+    if (M.type == HK_MEDIUM_GRID) {
+        ro = affine_pt(M.medium_from_render, o); rd_ = affine_vc(M.medium_from_render, d);
+        if (rd_.x * rd_.x + rd_.y * rd_.y + rd_.z * rd_.z < 1.0e-20f) { majiter_invalid(it); return; }
+    }
+    float te, tx; ray_bounds(ro, rd_, M.bmin, M.bmax, te, tx);
+    te = jl_max(te, 0.0f); tx = jl_min(tx, t_max);
+    if (te >= tx) { majiter_invalid(it); return; }
+    dda_init(it, M, ro, rd_, te, tx, st);
+}
+
+// ---- delta tracking ----------------------------------------------------------------------------------------
+#define HK_EV_ABSORBED 0
+#define HK_EV_SCATTER 1
+#define HK_EV_SURVIVED 2
+struct DeltaOut { int event; Spec beta, r_u, r_l; float3 p; float g; Spec Le_add; };
+HK_DEV DeltaOut delta_track(const MediaCtx& C, int medium, float3 o, float3 d, float t_max, float4 lam, Spec beta, Spec r_u, Spec r_l, int depth, int max_depth) {
+    DeltaOut R; R.g = 0.0f; R.p = f3(0, 0, 0); R.Le_add = sp(0.0f);
+    const DevMedium& M = C.media[medium - 1];
+    MediumCoef mc = medium_coef(C, M, lam);
+    uint64_t rng = lcg_init(o, d, t_max);
+    MajIter it; majiter_create(it, M, mc, o, d, t_max);
+    for (int sg = 0; sg < 256; sg++) {
+        MajSeg seg;
+        if (!majiter_next(it, seg)) break;
+        const Spec smaj = seg.sigma_maj;
+        const float s0 = smaj.x;
+        if (s0 < 1.0e-10f) continue;
+        float t = seg.t_min;
+        float3 ro = o + d * t;
+        for (int si = 0; si < 1024; si++) {
+            float u = lcg_next(rng);
+            float dt = -logf(fmaxf(1.0e-10f, 1.0f - u)) / s0;
+            float ts = t + dt;
+            if (ts >= seg.t_max) {
+                Spec Tm = sp_exp(-(seg.t_max - t) * smaj);
+                if (Tm.x > 1.0e-10f) { beta = beta * Tm / Tm.x; r_u = r_u * Tm / Tm.x; r_l = r_l * Tm / Tm.x; }
+                break;
+            }
+            Spec Tm = sp_exp(-dt * smaj);
+            float3 p = ro + d * dt;
+            float dens = medium_density(M, p);
+            Spec sa = M.type == HK_MEDIUM_HOMOGENEOUS ? mc.sa : mc.sa * dens;
+            Spec ss = M.type == HK_MEDIUM_HOMOGENEOUS ? mc.ss : mc.ss * dens;
+            if (!sp_black(mc.Le) && depth < max_depth) {
+                float pr = s0 * Tm.x;
+                if (pr > 1.0e-10f) {
+                    Spec re = r_u * smaj * Tm / pr;
+                    if (!sp_black(re)) R.Le_add = R.Le_add + beta * sa * Tm * mc.Le / (pr * sp_avg(re));
+                }
+            }
+            float pa = sa.x / s0, ps = ss.x / s0;
+            float ue = lcg_next(rng);
+            if (ue < pa) { R.event = HK_EV_ABSORBED; R.beta = sp(0.0f); R.r_u = r_u; R.r_l = r_l; return R; }
+            if (ue < pa + ps) {
+                if (depth >= max_depth) { R.event = HK_EV_ABSORBED; R.beta = beta; R.r_u = r_u; R.r_l = r_l; return R; }
+                float pdf = Tm.x * ss.x;
+                if (pdf > 1.0e-10f) { beta = beta * Tm * ss / pdf; r_u = r_u * Tm * ss / pdf; }
+                R.event = HK_EV_SCATTER; R.beta = beta; R.r_u = r_u; R.r_l = r_l; R.p = p; R.g = mc.g;
+                return R;
+            }
+            Spec sn = sp_max0(smaj - sa - ss);
+            float pdf = Tm.x * sn.x;
+            if (!(pdf > 1.0e-10f)) { R.event = HK_EV_ABSORBED; R.beta = sp(0.0f); R.r_u = r_u; R.r_l = r_l; return R; }
+            beta = beta * Tm * sn / pdf; r_u = r_u * Tm * sn / pdf; r_l = r_l * Tm * smaj / pdf;
+            t = ts; ro = p;
+            if (sp_black(beta) || sp_black(r_u)) { R.event = HK_EV_ABSORBED; R.beta = beta; R.r_u = r_u; R.r_l = r_l; return R; }
+        }
+    }
+    R.event = HK_EV_SURVIVED; R.beta = beta; R.r_u = r_u; R.r_l = r_l;
+    return R;
+}
+
+// ---- ratio tracking (shadow rays), intersection.jl:446-542 ---------------------------------------------------
+HK_DEV void ratio_track(const MediaCtx& C, int medium, float3 o, float3 d, float t_max, float4 lam, Spec& T_ray, Spec& r_u, Spec& r_l) {
+    T_ray = sp(1.0f); r_u = sp(1.0f); r_l = sp(1.0f);
+    const DevMedium& M = C.media[medium - 1];
+    MediumCoef mc = medium_coef(C, M, lam);
+    MajIter it; majiter_create(it, M, mc, o, d, t_max);
+    Pcg32 rng = pcg32_init(hash_f3(o), hash_f3(d));
+    for (int sg = 0; sg < 256; sg++) {
+        MajSeg seg;
+        if (!majiter_next(it, seg)) break;
+        const Spec smaj = seg.sigma_maj;
+        const float s0 = smaj.x;
+        if (s0 < 1.0e-10f) continue;
+        float t = seg.t_min;
+        for (int si = 0; si < 100; si++) {
+            float u = pcg32_f32(rng);
+            float dt = -logf(fmaxf(1.0e-10f, 1.0f - u)) / s0;
+            float ts = t + dt;
+            if (ts >= seg.t_max) {
+                Spec Tm = sp_exp(-(seg.t_max - t) * smaj);
+                if (Tm.x > 1.0e-10f) { T_ray = T_ray * Tm / Tm.x; r_l = r_l * Tm / Tm.x; r_u = r_u * Tm / Tm.x; }
+                break;
+            }
+            float3 p = o + d * ts;
+            float dens = medium_density(M, p);
+            Spec sa = M.type == HK_MEDIUM_HOMOGENEOUS ? mc.sa : mc.sa * dens;
+            Spec ss = M.type == HK_MEDIUM_HOMOGENEOUS ? mc.ss : mc.ss * dens;
+            Spec sn = sp_max0(smaj - sa - ss);
+            Spec Tm = sp_exp(-dt * smaj);
+            float pr = Tm.x * s0;
+            if (!(pr > 1.0e-10f)) { T_ray = sp(0.0f); return; }
+            T_ray = T_ray * Tm * sn / pr; r_l = r_l * Tm * smaj / pr; r_u = r_u * Tm * sn / pr;
+            Spec Tr = T_ray / fmaxf(1.0e-10f, sp_avg(r_l + r_u));
+            if (sp_maxc(Tr) < 0.05f) {
+                if (pcg32_f32(rng) < 0.75f) { T_ray = sp(0.0f); return; }
+                T_ray = T_ray / (1.0f - 0.75f);
+            }
+            if (sp_black(T_ray)) return;
+            t = ts;
+        }
+        if (sp_black(T_ray)) break;
+    }
+}

@@ -1,0 +1,580 @@
+// hk_wavefront.cuh — device-resident scene + SoA path state + queues + the wavefront stage kernels.
+//
+// What the reference does per bounce with ~12 KernelAbstractions launches over AOS records of 112-340 bytes and a
+// device->host `length(queue)` copy per stage (src/integrators/volpath/volpath.jl:538-612, workqueue.jl:108-121) is
+// done here with: one SoA path-state pool indexed by slot (= sample-in-batch * n_pixels + pixel), queues of 4-byte
+// slot ids, warp-aggregated appends (__match_any_sync / __popc), per-material queues and kernels, device-side counts
+// (no host round trips inside a sample pass), and traversal kernels that pull work warp-by-warp from a global cursor.
+#pragma once
+#include "hk_math.cuh"
+#include "hk_spectral.cuh"
+#include "hk_bsdf.cuh"
+#include "hk_lights.cuh"
+#include "hk_media.cuh"
+#include "hk_traverse.cuh"
+
+#define HK_MAX_MAT_TYPES 8
+// counter slots
+#define HK_C_RAY0 0
+#define HK_C_RAY1 1
+#define HK_C_ESCAPED 2
+#define HK_C_MEDIUM 3
+#define HK_C_SHADOW 4
+#define HK_C_TOTAL_HITS 5
+#define HK_C_CURSOR_TRACE 6
+#define HK_C_CURSOR_SHADOW 7
+#define HK_C_HIT0 8            // + material type (1..7)
+#define HK_N_COUNTERS 16
+
+struct DevScene {
+    DevTables T;
+    DevBvh bvh;
+    // shading geometry (world space)
+    const float* __restrict__ positions; const float* __restrict__ normals; const uint32_t* __restrict__ indices; const uint32_t* __restrict__ tri_meta;
+    const HkMaterial* __restrict__ materials; const HkMediumInterface* __restrict__ interfaces;
+    const float* __restrict__ spec_lambdas; const float* __restrict__ spec_values; const uint32_t* __restrict__ spec_offsets;
+    const HkLight* __restrict__ lights; int32_t n_lights;
+    const DevEnvMap* __restrict__ envmaps;
+    const HkLightBVHNode* __restrict__ lnodes; const uint32_t* __restrict__ bit_trails; const int32_t* __restrict__ inf_idx; int32_t n_infinite, n_bvh;
+    const DevMedium* __restrict__ media; int32_t n_media;
+    int32_t any_medium_transition;     // some interface has inside != outside
+    HkCamera camera;
+    DevFilter filter;
+    int32_t width, height, max_depth, regularize;
+    float max_component_value;
+    SobolParams sobol;
+};
+struct PathState {
+    float4 *ray_a, *ray_b, *hit, *lambda, *lpdf, *beta, *r_u, *r_l, *L;
+    uint32_t* flags; float* fweight;
+    float4 *sh_a, *sh_b, *sh_Ld, *sh_ru, *sh_rl; uint32_t* sh_medium;
+    uint32_t *q_ray[2], *q_escaped, *q_medium, *q_shadow, *q_hit[HK_MAX_MAT_TYPES];
+    uint32_t* counts;                  // [HK_N_COUNTERS]
+    unsigned long long* rays_traced;
+    float *pixel_rgb, *pixel_weight;   // film accumulators
+};
+struct PassArgs { int32_t first_sample, stride, n_batch; uint32_t n_pixels; };
+
+#define HK_FLAG_DEPTH(f) ((int)((f) & 0xFFu))
+#define HK_FLAG_SPEC 0x100u
+#define HK_FLAG_ANYNS 0x200u
+#define HK_FLAG_MEDIUM(f) ((f) >> 16)
+
+HK_DEV MatCtx mat_ctx(const DevScene& D) { MatCtx c; c.T = D.T; c.spec_lambdas = D.spec_lambdas; c.spec_values = D.spec_values; c.spec_offsets = D.spec_offsets; return c; }
+HK_DEV LightCtx light_ctx(const DevScene& D) {
+    LightCtx c; c.T = D.T; c.lights = D.lights; c.n_lights = D.n_lights; c.envmaps = D.envmaps; c.nodes = D.lnodes; c.bit_trails = D.bit_trails;
+    c.inf_idx = D.inf_idx; c.n_infinite = D.n_infinite; c.n_bvh = D.n_bvh; return c;
+}
+HK_DEV MediaCtx media_ctx(const DevScene& D) { MediaCtx c; c.T = D.T; c.media = D.media; c.n_media = D.n_media; return c; }
+
+// Warp-aggregated append to one of several queues: lanes that target the same queue elect a leader, which does a single
+// atomicAdd for the group.  Must be called by all 32 lanes (qid < 0 = nothing to push).
+HK_DEV void warp_push(uint32_t* counts, uint32_t* const* queues_by_id, int qid, uint32_t value, uint32_t* q_direct = nullptr) {
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned grp = __match_any_sync(0xFFFFFFFFu, qid);
+    if (qid < 0) return;
+    unsigned leader = (unsigned)__ffs(grp) - 1u;
+    unsigned rank = (unsigned)__popc(grp & ((1u << lane) - 1u));
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counts + qid, (uint32_t)__popc(grp));
+    base = __shfl_sync(grp, base, leader);
+    uint32_t* q = q_direct ? q_direct : queues_by_id[qid];
+    q[base + rank] = value;
+}
+// single-queue variant with a predicate (ballot form)
+HK_DEV void warp_push1(uint32_t* counter, uint32_t* queue, bool pred, uint32_t value) {
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned m = __ballot_sync(0xFFFFFFFFu, pred);
+    if (!pred) return;
+    unsigned leader = (unsigned)__ffs(m) - 1u;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    queue[base + (unsigned)__popc(m & ((1u << lane) - 1u))] = value;
+}
+HK_DEV void count_rays(unsigned long long* ctr, uint32_t mine) {
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_down_sync(0xFFFFFFFFu, mine, o);
+    if ((threadIdx.x & 31u) == 0 && mine) atomicAdd(ctr, (unsigned long long)mine);
+}
+
+// ---- surface geometry actually consumed downstream (intersection.jl:13-182): pi, flipped geometric normal, shading
+// normal.  dpdu/dpdv/dpdus/dpdvs/uv only feed texture filtering, which constant-parameter materials never read. --------
+struct Surf { float3 pi, n, ns; float area; uint32_t iface, arealight; };
+HK_DEV Surf surface_at(const DevScene& D, uint32_t prim0, float b1, float b2, float3 o, float3 d, float t) {
+    Surf s;
+    const uint32_t i0 = __ldg(D.indices + 3 * (size_t)prim0), i1 = __ldg(D.indices + 3 * (size_t)prim0 + 1), i2 = __ldg(D.indices + 3 * (size_t)prim0 + 2);
+    const float* P = D.positions;
+    float3 v0 = f3(__ldg(P + 3 * (size_t)i0), __ldg(P + 3 * (size_t)i0 + 1), __ldg(P + 3 * (size_t)i0 + 2));
+    float3 v1 = f3(__ldg(P + 3 * (size_t)i1), __ldg(P + 3 * (size_t)i1 + 1), __ldg(P + 3 * (size_t)i1 + 2));
+    float3 v2 = f3(__ldg(P + 3 * (size_t)i2), __ldg(P + 3 * (size_t)i2 + 1), __ldg(P + 3 * (size_t)i2 + 2));
+    s.pi = o + d * t;
+    float3 cr = cross3(v1 - v0, v2 - v0);
+    float3 n = norm3(cr);
+    s.area = 0.5f * len3(cr);
+    float3 ns = n;
+    if (D.normals) {
+        const float* N = D.normals;
+        float3 n0 = f3(__ldg(N + 3 * (size_t)i0), __ldg(N + 3 * (size_t)i0 + 1), __ldg(N + 3 * (size_t)i0 + 2));
+        float3 n1 = f3(__ldg(N + 3 * (size_t)i1), __ldg(N + 3 * (size_t)i1 + 1), __ldg(N + 3 * (size_t)i1 + 2));
+        float3 n2 = f3(__ldg(N + 3 * (size_t)i2), __ldg(N + 3 * (size_t)i2 + 1), __ldg(N + 3 * (size_t)i2 + 2));
+        if (!(isnan(n0.x) || isnan(n1.x) || isnan(n2.x))) {
+            float w = 1.0f - b1 - b2;
+            ns = norm3(f3(w * n0.x + b1 * n1.x + b2 * n2.x, w * n0.y + b1 * n1.y + b2 * n2.y, w * n0.z + b1 * n1.z + b2 * n2.z));
+        }
+    }
+    s.ns = ns;
+    s.n = dot3(n, ns) < 0.0f ? -n : n;
+    s.iface = __ldg(D.tri_meta + 3 * (size_t)prim0);
+    s.arealight = __ldg(D.tri_meta + 3 * (size_t)prim0 + 2);
+    return s;
+}
+HK_DEV float3 geometric_normal(const DevScene& D, uint32_t prim0) {
+    const uint32_t i0 = __ldg(D.indices + 3 * (size_t)prim0), i1 = __ldg(D.indices + 3 * (size_t)prim0 + 1), i2 = __ldg(D.indices + 3 * (size_t)prim0 + 2);
+    const float* P = D.positions;
+    float3 v0 = f3(__ldg(P + 3 * (size_t)i0), __ldg(P + 3 * (size_t)i0 + 1), __ldg(P + 3 * (size_t)i0 + 2));
+    float3 v1 = f3(__ldg(P + 3 * (size_t)i1), __ldg(P + 3 * (size_t)i1 + 1), __ldg(P + 3 * (size_t)i1 + 2));
+    float3 v2 = f3(__ldg(P + 3 * (size_t)i2), __ldg(P + 3 * (size_t)i2 + 1), __ldg(P + 3 * (size_t)i2 + 2));
+    return norm3(cross3(v1 - v0, v2 - v0));
+}
+HK_DEV int material_type_of_prim(const DevScene& D, uint32_t prim0) {
+    uint32_t mi = __ldg(D.tri_meta + 3 * (size_t)prim0);
+    uint32_t mat = __ldg(&D.interfaces[mi - 1].material);
+    return __ldg(&D.materials[mat - 1].type);
+}
+
+// =====================================================================================================================
+// stage kernels
+// =====================================================================================================================
+HK_DEV int slot_sample_idx(const PassArgs& A, uint32_t slot) { return A.first_sample + A.stride * (int)(slot / A.n_pixels); }
+
+// vp_generate_camera_rays_kernel!, volpath.jl:125-205.  One thread per slot; ray queue 0 becomes the identity.
+__global__ void __launch_bounds__(256) k_camera(const __grid_constant__ DevScene D, PathState S, PassArgs A, uint32_t camera_medium) {
+    const uint32_t n_slots = A.n_pixels * (uint32_t)A.n_batch;
+    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_slots; slot += gridDim.x * blockDim.x) {
+        const uint32_t pix = slot % A.n_pixels;
+        const int sample_idx = slot_sample_idx(A, slot);
+        const int x = (int)(pix % (uint32_t)D.width) + 1, y = (int)(pix / (uint32_t)D.width) + 1;
+        float wu = zsobol_1d(D.sobol, x, y, sample_idx, 1);
+        float2 jit = zsobol_2d(D.sobol, x, y, sample_idx, 3);
+        // the time sample (dim 4) is drawn by the reference but VolPath's ray drops it (volpath.jl:184)
+        float2 lens = D.camera.lens_radius > 0.0f ? zsobol_2d(D.sobol, x, y, sample_idx, 6) : make_float2(0.0f, 0.0f);
+        float fx, fy, fw;
+        filter_sample(D.filter, jit, fx, fy, fw);
+        float4 lam, pdf;
+        sample_wavelengths_visible(wu, lam, pdf);
+        float3 o, d;
+        camera_generate_ray(D.camera, (float)x + 0.5f + fx, (float)D.height - (float)y + 1.0f + 0.5f + fy, lens, o, d);
+        S.fweight[slot] = fw; S.lambda[slot] = lam; S.lpdf[slot] = pdf;
+        S.ray_a[slot] = make_float4(o.x, o.y, o.z, d.x);
+        S.ray_b[slot] = make_float4(d.y, d.z, HK_INF, 0.0f);
+        S.beta[slot] = sp(1.0f); S.r_u[slot] = sp(1.0f); S.r_l[slot] = sp(1.0f); S.L[slot] = sp(0.0f);
+        S.flags[slot] = camera_medium << 16;
+        S.q_ray[0][slot] = slot;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { S.counts[HK_C_RAY0] = n_slots; S.counts[HK_C_RAY1] = 0; }
+}
+
+// reset_iteration_queues!, volpath-state.jl:214-222 (+ the next ray queue and the traversal cursors)
+__global__ void k_reset_bounce(PathState S, int cur) {
+    int i = threadIdx.x;
+    if (i < HK_N_COUNTERS && i != (HK_C_RAY0 + cur)) S.counts[i] = 0;
+}
+
+HK_DEV uint32_t* queue_of(const PathState& S, int qid) {
+    if (qid == HK_C_MEDIUM) return S.q_medium;
+    if (qid == HK_C_ESCAPED) return S.q_escaped;
+    if (qid >= HK_C_HIT0) return S.q_hit[qid - HK_C_HIT0];
+    return nullptr;
+}
+
+// vp_trace_rays_kernel!, intersection.jl:188-269: closest hit + routing.  Persistent: warps pull 32 rays at a time.
+__global__ void __launch_bounds__(HK_TRACE_THREADS) k_trace(const __grid_constant__ DevScene D, PathState S, int cur) {
+    __shared__ uint2 sm_stack[HK_SM_STACK * HK_TRACE_THREADS];
+    const uint32_t n = S.counts[HK_C_RAY0 + cur];
+    const unsigned lane = threadIdx.x & 31u;
+    uint32_t traced = 0;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(S.counts + HK_C_CURSOR_TRACE, 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= n) break;
+        const uint32_t idx = base + lane;
+        int qid = -1; uint32_t slot = 0;
+        if (idx < n) {
+            slot = S.q_ray[cur][idx];
+            float4 ra = S.ray_a[slot], rb = S.ray_b[slot];
+            HitRec h = bvh8_trace<false, false>(D.bvh, sm_stack + threadIdx.x, f3(ra.x, ra.y, ra.z), f3(ra.w, rb.x, rb.y), rb.z);
+            traced++;
+            S.hit[slot] = make_float4(h.t, __uint_as_float(h.prim1), h.b1, h.b2);
+            // in-medium rays go to delta tracking with their hit record; the vacuum alpha loop (:224-266) ends on its
+            // first iteration because every constant-parameter material has alpha == 1 (spectral-eval.jl:3882-3888)
+            if (HK_FLAG_MEDIUM(S.flags[slot]) != 0) qid = HK_C_MEDIUM;
+            else if (h.prim1 == 0) qid = HK_C_ESCAPED;
+            else qid = HK_C_HIT0 + material_type_of_prim(D, h.prim1 - 1);
+        }
+        warp_push(S.counts, nullptr, qid, slot, queue_of(S, qid));
+        unsigned hm = __ballot_sync(0xFFFFFFFFu, qid >= HK_C_HIT0);
+        if (lane == 0 && hm) atomicAdd(S.counts + HK_C_TOTAL_HITS, (uint32_t)__popc(hm));
+    }
+    count_rays(S.rays_traced, traced);
+}
+
+// vp_handle_escaped_rays_kernel!, intersection.jl:622-668
+__global__ void __launch_bounds__(256) k_escaped(const __grid_constant__ DevScene D, PathState S) {
+    const uint32_t n = S.counts[HK_C_ESCAPED];
+    if (D.n_lights <= 0) return;
+    LightCtx LC = light_ctx(D);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t slot = S.q_escaped[i];
+        float4 ra = S.ray_a[slot], rb = S.ray_b[slot];
+        float3 d = f3(ra.w, rb.x, rb.y);
+        float4 lam = S.lambda[slot];
+        Spec contrib = S.beta[slot] * escaped_Le(LC, d, lam);
+        if (sp_black(contrib)) continue;
+        const uint32_t fl = S.flags[slot];
+        Spec ru = S.r_u[slot], fin;
+        if (HK_FLAG_DEPTH(fl) == 0 || (fl & HK_FLAG_SPEC)) fin = contrib / sp_avg(ru);
+        else {
+            float lcp = 1.0f / (float)D.n_lights;
+            Spec rl = S.r_l[slot] * lcp * env_light_pdf(LC, d);
+            float den = sp_avg(ru + rl);
+            fin = den > 1.0e-10f ? contrib / den : contrib / sp_avg(ru);
+        }
+        S.L[slot] = S.L[slot] + fin;
+    }
+}
+
+// russian_roulette_spectral, material-dispatch.jl:263-287
+HK_DEV bool russian_roulette(Spec& beta, int depth, float rr) {
+    if (depth <= 3) return true;
+    float q = fmaxf(0.05f, 1.0f - sp_maxc(beta));
+    if (rr < q) return false;
+    beta = beta * (1.0f / (1.0f - q));
+    return true;
+}
+
+// Shading of one material type: emissive-hit MIS (surface-eval.jl:147-220), NEE (:250-342 + lights.jl:535-600) and
+// BSDF sampling / Russian roulette / continuation ray (:396-512), fused into one kernel per material type.
+template <int TYPE>
+__global__ void __launch_bounds__(128) k_shade(const __grid_constant__ DevScene D, PathState S, PassArgs A, int next) {
+    const uint32_t n = S.counts[HK_C_HIT0 + TYPE];
+    MatCtx MC = mat_ctx(D);
+    LightCtx LC = light_ctx(D);
+    const uint32_t n_round = (n + 31u) & ~31u;     // whole warps iterate together so the aggregated pushes stay converged
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        bool push_shadow = false, push_ray = false;
+        uint32_t slot = 0;
+        if (i < n) {
+            slot = S.q_hit[TYPE][i];
+            const float4 hr = S.hit[slot];
+            const uint32_t prim0 = __float_as_uint(hr.y) - 1u;
+            const float4 ra = S.ray_a[slot], rb = S.ray_b[slot];
+            const float3 o = f3(ra.x, ra.y, ra.z), d = f3(ra.w, rb.x, rb.y);
+            const Surf sf = surface_at(D, prim0, hr.z, hr.w, o, d, hr.x);
+            const HkMediumInterface mi = D.interfaces[sf.iface - 1];
+            const HkMaterial& mat = D.materials[mi.material - 1];
+            const float4 lam = S.lambda[slot];
+            const Spec beta = S.beta[slot], r_u = S.r_u[slot], r_l = S.r_l[slot];
+            const uint32_t fl = S.flags[slot];
+            const int depth = HK_FLAG_DEPTH(fl);
+            const uint32_t cur_medium = HK_FLAG_MEDIUM(fl);
+            const float3 wo = -d;
+            // ---- HandleEmissiveIntersection ----------------------------------------------------------------
+            if (sf.arealight > 0u) {
+                Spec Le = arealight_Le(D.T, D.lights[sf.arealight - 1], wo, sf.n, lam);
+                if (!sp_black(Le)) {
+                    Spec contrib = beta * Le, fin;
+                    if (depth == 0 || (fl & HK_FLAG_SPEC)) fin = contrib / sp_avg(r_u);
+                    else {
+                        float lcp = bvh_light_pmf(LC, sf.pi, sf.n, (int)sf.arealight);
+                        float ct = fabsf(dot3(sf.n, norm3(d)));
+                        float lpdf = (ct > 0.0f && sf.area > 0.0f) ? lcp * ((hr.x * hr.x) / (ct * sf.area)) : 0.0f;
+                        float den = sp_avg(r_u + r_l * lpdf);
+                        fin = den > 1.0e-10f ? contrib / den : contrib / sp_avg(r_u);
+                    }
+                    S.L[slot] = S.L[slot] + fin;
+                }
+            }
+            // ---- per-bounce Sobol dimensions (volpath.jl:253-262) ---------------------------------------------
+            const uint32_t pix = slot % A.n_pixels;
+            const int px = (int)(pix % (uint32_t)D.width) + 1, py = (int)(pix / (uint32_t)D.width) + 1;
+            const int sidx = slot_sample_idx(A, slot);
+            const int bdim = 6 + 7 * depth;
+            // ---- next-event estimation ---------------------------------------------------------------------------
+            if (D.n_lights > 0) {
+                float direct_uc = zsobol_1d(D.sobol, px, py, sidx, bdim + 1);
+                float pmf;
+                int li = bvh_sample_light(LC, sf.pi, sf.ns, direct_uc, pmf);
+                if (li >= 1 && li <= D.n_lights && pmf > 0.0f) {
+                    float2 direct_u = zsobol_2d(D.sobol, px, py, sidx, bdim + 3);
+                    LightSample ls = sample_light(LC, D.lights[li - 1], sf.pi, lam, direct_u);
+                    if (ls.pdf > 0.0f && !sp_black(ls.Li)) {
+                        BsdfEval be = eval_bsdf<TYPE>(MC, mat, wo, ls.wi, sf.ns, lam);
+                        if (!sp_black(be.f)) {
+                            float ct = fabsf(dot3(ls.wi, sf.ns));
+                            Spec Ld = beta * be.f * ls.Li * ct;
+                            if (!sp_black(Ld)) {
+                                float3 off = 1.0e-4f * sf.ns;
+                                float3 ro = dot3(ls.wi, sf.ns) > 0.0f ? sf.pi + off : sf.pi - off;
+                                float3 tl = ls.p_light - ro;
+                                float tmax = sqrtf(dot3(tl, tl)) - 1.0e-3f;
+                                S.sh_a[slot] = make_float4(ro.x, ro.y, ro.z, ls.wi.x);
+                                S.sh_b[slot] = make_float4(ls.wi.y, ls.wi.z, tmax, 0.0f);
+                                S.sh_Ld[slot] = Ld;
+                                S.sh_ru[slot] = r_u * (ls.delta ? 0.0f : be.pdf);
+                                S.sh_rl[slot] = r_u * ls.pdf * pmf;
+                                S.sh_medium[slot] = cur_medium;
+                                push_shadow = true;
+                            }
+                        }
+                    }
+                }
+            }
+            // ---- BSDF sampling + continuation ----------------------------------------------------------------------
+            const int new_depth = depth + 1;
+            if (new_depth < D.max_depth) {
+                float indirect_uc = zsobol_1d(D.sobol, px, py, sidx, bdim + 4);
+                float2 indirect_u = zsobol_2d(D.sobol, px, py, sidx, bdim + 6);
+                const bool reg = D.regularize && (fl & HK_FLAG_ANYNS);
+                BsdfSample bs = sample_bsdf<TYPE>(MC, mat, wo, sf.ns, lam, indirect_u, indirect_uc, reg);
+                if (bs.pdf > 0.0f && !sp_black(bs.f)) {
+                    float ct = fabsf(dot3(bs.wi, sf.ns));
+                    Spec nb = bs.specular ? beta * bs.f : beta * bs.f * ct / bs.pdf;
+                    Spec nrl = bs.specular ? r_u : r_u / bs.pdf;
+                    float rr = zsobol_1d(D.sobol, px, py, sidx, bdim + 7);
+                    if (russian_roulette(nb, new_depth, rr)) {
+                        const float side = dot3(bs.wi, sf.n);
+                        uint32_t nm = (mi.inside != mi.outside) ? (side > 0.0f ? mi.outside : mi.inside) : cur_medium;
+                        float3 od = side > 0.0f ? sf.n : -sf.n;
+                        float3 no = sf.pi + od * 0.0001f;
+                        S.ray_a[slot] = make_float4(no.x, no.y, no.z, bs.wi.x);
+                        S.ray_b[slot] = make_float4(bs.wi.y, bs.wi.z, HK_INF, 0.0f);
+                        S.beta[slot] = nb; S.r_l[slot] = nrl;
+                        uint32_t nf = (uint32_t)new_depth | (bs.specular ? HK_FLAG_SPEC : 0u) | (((fl & HK_FLAG_ANYNS) || !bs.specular) ? HK_FLAG_ANYNS : 0u) | (nm << 16);
+                        S.flags[slot] = nf;
+                        push_ray = true;
+                    }
+                }
+            }
+        }
+        warp_push1(S.counts + HK_C_SHADOW, S.q_shadow, push_shadow, slot);
+        warp_push1(S.counts + HK_C_RAY0 + next, S.q_ray[next], push_ray, slot);
+    }
+}
+
+// Delta tracking + medium NEE + phase-function sampling, fused (delta-tracking.jl:142-453, medium-scatter.jl:15-203)
+__global__ void __launch_bounds__(128) k_medium(const __grid_constant__ DevScene D, PathState S, PassArgs A, int next) {
+    const uint32_t n = S.counts[HK_C_MEDIUM];
+    LightCtx LC = light_ctx(D);
+    MediaCtx MDC = media_ctx(D);
+    const uint32_t n_round = (n + 31u) & ~31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        bool push_shadow = false, push_ray = false;
+        int qid = -1;
+        uint32_t slot = 0;
+        if (i < n) {
+            slot = S.q_medium[i];
+            const float4 hr = S.hit[slot];
+            const uint32_t prim1 = __float_as_uint(hr.y);
+            const float4 ra = S.ray_a[slot], rb = S.ray_b[slot];
+            const float3 o = f3(ra.x, ra.y, ra.z), d = f3(ra.w, rb.x, rb.y);
+            const float4 lam = S.lambda[slot];
+            const uint32_t fl = S.flags[slot];
+            const int depth = HK_FLAG_DEPTH(fl);
+            const uint32_t medium = HK_FLAG_MEDIUM(fl);
+            const float t_max = prim1 ? hr.x : HK_INF;
+            DeltaOut R = delta_track(MDC, (int)medium, o, d, t_max, lam, S.beta[slot], S.r_u[slot], S.r_l[slot], depth, D.max_depth);
+            if (!sp_black(R.Le_add)) S.L[slot] = S.L[slot] + R.Le_add;
+            if (R.event == HK_EV_SCATTER) {
+                const uint32_t pix = slot % A.n_pixels;
+                const int px = (int)(pix % (uint32_t)D.width) + 1, py = (int)(pix / (uint32_t)D.width) + 1;
+                const int sidx = slot_sample_idx(A, slot);
+                const int bdim = 6 + 7 * depth;
+                const float3 wo = -d;
+                if (D.n_lights > 0) {   // medium_direct_lighting_inner!
+                    float pmf;
+                    int li = bvh_sample_light(LC, R.p, f3(0, 0, 0), zsobol_1d(D.sobol, px, py, sidx, bdim + 1), pmf);
+                    if (li >= 1 && li <= D.n_lights && pmf > 0.0f) {
+                        LightSample ls = sample_light(LC, D.lights[li - 1], R.p, lam, zsobol_2d(D.sobol, px, py, sidx, bdim + 3));
+                        if (ls.pdf > 0.0f && !sp_black(ls.Li)) {
+                            float ph = hg_p(R.g, dot3(wo, ls.wi));
+                            if (ph > 0.0f) {
+                                float tmax = ls.delta ? len3(ls.p_light - R.p) - 0.001f : 1.0e6f;
+                                S.sh_a[slot] = make_float4(R.p.x, R.p.y, R.p.z, ls.wi.x);
+                                S.sh_b[slot] = make_float4(ls.wi.y, ls.wi.z, tmax, 0.0f);
+                                S.sh_Ld[slot] = R.beta * ph * ls.Li;
+                                S.sh_ru[slot] = R.r_u * (ls.delta ? 0.0f : ph);
+                                S.sh_rl[slot] = R.r_u * (ls.pdf * pmf);
+                                S.sh_medium[slot] = medium;
+                                push_shadow = true;
+                            }
+                        }
+                    }
+                }
+                const int nd = depth + 1;   // medium_scatter_inner!
+                if (nd < D.max_depth) {
+                    float pdf;
+                    float3 wi = sample_hg(R.g, wo, zsobol_2d(D.sobol, px, py, sidx, bdim + 6), pdf);
+                    if (pdf > 0.0f) {
+                        S.ray_a[slot] = make_float4(R.p.x, R.p.y, R.p.z, wi.x);
+                        S.ray_b[slot] = make_float4(wi.y, wi.z, HK_INF, 0.0f);
+                        S.beta[slot] = R.beta; S.r_u[slot] = R.r_u; S.r_l[slot] = R.r_u / pdf;
+                        S.flags[slot] = (uint32_t)nd | HK_FLAG_ANYNS | (medium << 16);
+                        push_ray = true;
+                    }
+                }
+            } else if (R.event == HK_EV_SURVIVED && !(sp_black(R.beta) || sp_black(R.r_u) || depth >= D.max_depth)) {
+                S.beta[slot] = R.beta; S.r_u[slot] = R.r_u; S.r_l[slot] = R.r_l;
+                qid = prim1 ? HK_C_HIT0 + material_type_of_prim(D, prim1 - 1) : HK_C_ESCAPED;
+            }
+        }
+        warp_push(S.counts, nullptr, qid, slot, queue_of(S, qid));
+        unsigned hm = __ballot_sync(0xFFFFFFFFu, qid >= HK_C_HIT0);
+        if ((threadIdx.x & 31u) == 0 && hm) atomicAdd(S.counts + HK_C_TOTAL_HITS, (uint32_t)__popc(hm));
+        warp_push1(S.counts + HK_C_SHADOW, S.q_shadow, push_shadow, slot);
+        warp_push1(S.counts + HK_C_RAY0 + next, S.q_ray[next], push_ray, slot);
+    }
+}
+
+// trace_shadow_transmittance + vp_trace_shadow_rays_kernel!, intersection.jl:302-406, 565-600.
+// OPAQUE_ONLY (no interface with inside != outside, no media): visibility is a single any-hit query, which yields the
+// same T in {0,1} as the reference's closest-hit loop.  Otherwise the ordered closest-hit walk with ratio tracking.
+template <bool OPAQUE_ONLY>
+__global__ void __launch_bounds__(HK_TRACE_THREADS) k_shadow(const __grid_constant__ DevScene D, PathState S) {
+    __shared__ uint2 sm_stack[HK_SM_STACK * HK_TRACE_THREADS];
+    // reference quirk (volpath.jl:571-609): shadow rays are only traced inside the `n_hits > 0` branch
+    if (S.counts[HK_C_TOTAL_HITS] == 0) return;
+    const uint32_t n = S.counts[HK_C_SHADOW];
+    const unsigned lane = threadIdx.x & 31u;
+    MediaCtx MDC = media_ctx(D);
+    uint32_t traced = 0;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(S.counts + HK_C_CURSOR_SHADOW, 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= n) break;
+        const uint32_t idx = base + lane;
+        if (idx >= n) continue;
+        const uint32_t slot = S.q_shadow[idx];
+        const float4 sa = S.sh_a[slot], sb = S.sh_b[slot];
+        float3 o = f3(sa.x, sa.y, sa.z);
+        const float3 d = f3(sa.w, sb.x, sb.y);
+        float t_rem = sb.z;
+        Spec T = sp(1.0f), tu = sp(1.0f), tl = sp(1.0f);
+        bool visible = false;
+        if (OPAQUE_ONLY) {
+            if (!(t_rem < 1.0e-6f)) {
+                HitRec h = bvh8_trace<true, false>(D.bvh, sm_stack + threadIdx.x, o, d, t_rem);
+                traced++;
+                visible = h.prim1 == 0;
+            }
+        } else {
+            const float4 lam = S.lambda[slot];
+            uint32_t cur = S.sh_medium[slot];
+            bool done = false;
+            for (int it = 0; it < 10 && !done; it++) {
+                if (t_rem < 1.0e-6f) break;
+                HitRec h = bvh8_trace<false, false>(D.bvh, sm_stack + threadIdx.x, o, d, t_rem);
+                traced++;
+                if (h.prim1 == 0) {
+                    if (cur != 0) { Spec a, b, c; ratio_track(MDC, (int)cur, o, d, t_rem, lam, a, b, c); T = T * a; tu = tu * b; tl = tl * c; }
+                    visible = true; done = true; break;
+                }
+                const uint32_t prim0 = h.prim1 - 1u;
+                const HkMediumInterface mi = D.interfaces[__ldg(D.tri_meta + 3 * (size_t)prim0) - 1];
+                if (mi.inside == mi.outside) { visible = false; done = true; break; }   // opaque (alpha == 1)
+                if (cur != 0) { Spec a, b, c; ratio_track(MDC, (int)cur, o, d, h.t, lam, a, b, c); T = T * a; tu = tu * b; tl = tl * c; }
+                if (sp_black(T)) { visible = true; done = true; break; }
+                const bool entering = dot3(d, geometric_normal(D, prim0)) < 0.0f;
+                cur = entering ? mi.inside : mi.outside;
+                o = o + d * (h.t + 1.0e-4f);
+                t_rem = t_rem - h.t - 1.0e-4f;
+            }
+            if (!done) visible = false;
+        }
+        if (visible && !sp_black(T)) {
+            float den = sp_avg(S.sh_ru[slot] * tu + S.sh_rl[slot] * tl);
+            if (den > 1.0e-10f) {
+                Spec fin = S.sh_Ld[slot] * T / den;
+                if (!sp_black(fin)) S.L[slot] = S.L[slot] + fin;
+            }
+        }
+    }
+    count_rays(S.rays_traced, traced);
+}
+
+// vp_accumulate_to_rgb_kernel!, volpath.jl:326-375.  One thread per pixel walks the batch in sample order, so the
+// f32 sums see the samples in exactly the order the reference's per-sample passes do (and no atomics are needed).
+__global__ void __launch_bounds__(256) k_film_accumulate(const __grid_constant__ DevScene D, PathState S, PassArgs A) {
+    for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < A.n_pixels; pix += gridDim.x * blockDim.x) {
+        float r = S.pixel_rgb[3 * (size_t)pix], g = S.pixel_rgb[3 * (size_t)pix + 1], b = S.pixel_rgb[3 * (size_t)pix + 2], ws = S.pixel_weight[pix];
+        for (int k = 0; k < A.n_batch; k++) {
+            const size_t slot = (size_t)k * A.n_pixels + pix;
+            float3 rgb = xyz_to_linear_srgb(spectral_to_xyz(D.T, S.L[slot], S.lambda[slot], S.lpdf[slot]));
+            rgb = f3(rgb.x != rgb.x ? rgb.x : fmaxf(0.0f, rgb.x), rgb.y != rgb.y ? rgb.y : fmaxf(0.0f, rgb.y), rgb.z != rgb.z ? rgb.z : fmaxf(0.0f, rgb.z));
+            float m = fmaxf(fmaxf(rgb.x, rgb.y), rgb.z);
+            if (m > D.max_component_value) rgb = rgb * (D.max_component_value / m);
+            float w = S.fweight[slot];
+            r += w * rgb.x; g += w * rgb.y; b += w * rgb.z; ws += w;
+        }
+        S.pixel_rgb[3 * (size_t)pix] = r; S.pixel_rgb[3 * (size_t)pix + 1] = g; S.pixel_rgb[3 * (size_t)pix + 2] = b; S.pixel_weight[pix] = ws;
+    }
+}
+
+// vp_finalize_film_kernel!, volpath.jl:384-417: framebuffer[py, px] in (H, W) column-major
+__global__ void __launch_bounds__(256) k_film_finalize(const float* __restrict__ rgb, const float* __restrict__ wsum, float* __restrict__ out, int W, int H) {
+    const uint32_t n = (uint32_t)W * (uint32_t)H;
+    for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < n; pix += gridDim.x * blockDim.x) {
+        const uint32_t px = pix % (uint32_t)W, py = pix / (uint32_t)W;
+        const float w = wsum[pix];
+        float r = 0.0f, g = 0.0f, b = 0.0f;
+        if (w > 0.0f) { float inv = 1.0f / w; r = rgb[3 * (size_t)pix] * inv; g = rgb[3 * (size_t)pix + 1] * inv; b = rgb[3 * (size_t)pix + 2] * inv; }
+        float* o = out + ((size_t)px * H + py) * 3;
+        o[0] = r; o[1] = g; o[2] = b;
+    }
+}
+
+// stand-alone traversal: rays [n][8] -> hits [n][4]   (hk_trace_closest / hk_trace_any)
+template <bool ANY, bool COUNT>
+__global__ void __launch_bounds__(HK_TRACE_THREADS) k_trace_batch(DevBvh B, const float4* __restrict__ rays, uint64_t n, float4* __restrict__ hits,
+                                                                uint8_t* __restrict__ occluded, unsigned long long* cursor, unsigned long long* counters) {
+    __shared__ uint2 sm_stack[HK_SM_STACK * HK_TRACE_THREADS];
+    const unsigned lane = threadIdx.x & 31u;
+    uint32_t nn = 0, nt = 0;
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(cursor, 32ull);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= n) break;
+        const unsigned long long i = base + lane;
+        if (i >= n) continue;
+        float4 ra = __ldg(rays + 2 * i), rb = __ldg(rays + 2 * i + 1);
+        HitRec h = bvh8_trace<ANY, COUNT>(B, sm_stack + threadIdx.x, f3(ra.x, ra.y, ra.z), f3(ra.w, rb.x, rb.y), rb.z, &nn, &nt);
+        if (ANY) occluded[i] = h.prim1 ? 1 : 0;
+        else hits[i] = make_float4(h.prim1 ? h.t : rb.z, __uint_as_float(h.prim1), h.b1, h.b2);
+    }
+    if (COUNT) {
+        for (int o = 16; o > 0; o >>= 1) { nn += __shfl_down_sync(0xFFFFFFFFu, nn, o); nt += __shfl_down_sync(0xFFFFFFFFu, nt, o); }
+        if (lane == 0) { atomicAdd(counters, (unsigned long long)nn); atomicAdd(counters + 1, (unsigned long long)nt); }
+    }
+}
+
+// detect_camera_medium, intersection.jl:690-747 (single thread; run once per camera change, not once per sample)
+__global__ void k_detect_camera_medium(const __grid_constant__ DevScene D, uint32_t* out) {
+    __shared__ uint2 sm_stack[HK_SM_STACK * HK_TRACE_THREADS];
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float3 o = xf_point(D.camera.camera_to_world, f3(0, 0, 0));
+    const float3 d = f3(0.57735027f, 0.57735027f, 0.57735027f);
+    uint32_t res = 0;
+    for (int it = 0; it < 16; it++) {
+        HitRec h = bvh8_trace<false, false>(D.bvh, sm_stack, o, d, HK_INF);
+        if (h.prim1 == 0) break;
+        const uint32_t prim0 = h.prim1 - 1u;
+        const HkMediumInterface mi = D.interfaces[__ldg(D.tri_meta + 3 * (size_t)prim0) - 1];
+        float3 n = geometric_normal(D, prim0);
+        if (mi.inside != mi.outside) { res = dot3(-d, n) > 0.0f ? mi.outside : mi.inside; break; }
+        float3 pi = o + d * h.t;
+        o = pi + (dot3(d, n) > 0.0f ? n : -n) * 1.0e-4f;
+    }
+    *out = res;
+}

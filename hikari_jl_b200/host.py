@@ -1,0 +1,976 @@
+"""Host-side mirror of the reference's scene / integrator API for the VolPath path.
+
+Julia is not available in this image, so the host side that a Julia user would drive
+(`Scene()`, `push!`, `sync!`, `PerspectiveCamera`, `Film`, `VolPath(samples=…, max_depth=…)`,
+`integrator(scene, film, camera)`, `render!`, `clear!`) is mirrored here in Python with the same names,
+argument meaning and error behaviour, on top of the C ABI in include/hikari_cuda.h.  Everything in this
+file is HOST logic (scene flattening, table building); all rendering happens in libhikari_cuda.so.
+
+Reference files mirrored: src/scene.jl, src/scene-mesh.jl, src/materials/*.jl (constructors),
+src/lights/*.jl (constructors), src/camera/perspective.jl, src/film.jl:61-183, src/filter.jl:136-150,
+611-725, src/sampler/sampling.jl:201-263, src/sampler/sobol.jl:317-323, src/integrators/volpath/volpath.jl:29-113,
+445-670.
+"""
+import ctypes as C
+import math
+import numpy as np
+
+from . import _abi as A
+from . import tables as T
+
+f32 = np.float32
+
+
+def _fp(a):
+    return a.ctypes.data_as(A.c_fp)
+
+
+def _v3(x):
+    return np.asarray(x, dtype=f32).reshape(3)
+
+
+# ------------------------------------------------------------------------------------------------
+# transforms (Raycore.look_at / perspective equivalents; camera looks down -z, see perspective.jl:109)
+# ------------------------------------------------------------------------------------------------
+def look_at(eye, target, up=(0, 1, 0)):
+    """camera_to_world 4x4 (row-major): columns = right, up, back (eye - target), position."""
+    eye, target, up = _v3(eye), _v3(target), _v3(up)
+    z = eye - target
+    z = z / np.linalg.norm(z)
+    x = np.cross(up / np.linalg.norm(up), z)
+    x = x / np.linalg.norm(x)
+    y = np.cross(z, x)
+    m = np.eye(4, dtype=f32)
+    m[:3, 0], m[:3, 1], m[:3, 2], m[:3, 3] = x, y, z, eye
+    return m
+
+
+def translate(v):
+    m = np.eye(4, dtype=f32)
+    m[:3, 3] = _v3(v)
+    return m
+
+
+def scale_matrix(s):
+    m = np.eye(4, dtype=f32)
+    s = np.broadcast_to(np.asarray(s, dtype=f32), (3,))
+    m[0, 0], m[1, 1], m[2, 2] = s
+    return m
+
+
+def rotation_matrix(angle_degrees, axis):
+    """src/textures/environment_map.jl:52-64 (returns row-major 3x3 of the same matrix)."""
+    th = math.radians(angle_degrees)
+    a = _v3(axis)
+    a = a / np.linalg.norm(a)
+    s, c = math.sin(th), math.cos(th)
+    t = 1 - c
+    return np.array([[t * a[0] * a[0] + c, t * a[0] * a[1] + s * a[2], t * a[0] * a[2] - s * a[1]],
+                     [t * a[0] * a[1] - s * a[2], t * a[1] * a[1] + c, t * a[1] * a[2] + s * a[0]],
+                     [t * a[0] * a[2] + s * a[1], t * a[1] * a[2] - s * a[0], t * a[2] * a[2] + c]], dtype=f32).T
+
+
+class Film:
+    """src/film.jl:61-183 — only the output-buffer contract used by VolPath."""
+
+    def __init__(self, resolution):
+        self.resolution = (int(resolution[0]), int(resolution[1]))   # (W, H)
+        w, h = self.resolution
+        self.framebuffer = np.zeros((h, w, 3), dtype=f32)            # framebuffer[py, px] = RGB
+        self.iteration_index = 0
+
+    def clear(self):
+        self.framebuffer[:] = 0
+        self.iteration_index = 0
+
+
+class PerspectiveCamera:
+    """src/camera/perspective.jl:41-91.  `screen_window=None` picks the aspect-correct window (shorter axis
+    spans [-1,1]); pass ((-1,-1),(1,1)) for the reference convenience constructor's literal window (:84)."""
+
+    def __init__(self, eyepos, lookat, film, up=(0, 1, 0), fov=55.0, lens_radius=0.0, focal_distance=1e6,
+                 screen_window=None):
+        w, h = film.resolution
+        self.camera_to_world = look_at(eyepos, lookat, up)
+        if screen_window is None:
+            aspect = w / h
+            screen_window = ((-aspect, -1.0), (aspect, 1.0)) if aspect >= 1 else ((-1.0, -1 / aspect), (1.0, 1 / aspect))
+        (x0, y0), (x1, y1) = screen_window
+        near = 0.01
+        tan_half = math.tan(math.radians(fov) / 2)
+        sx, sy = (x1 - x0) / w, (y1 - y0) / h
+        m = np.zeros((4, 4), dtype=np.float64)
+        m[0, 0], m[0, 3] = sx * tan_half * near, x0 * tan_half * near
+        m[1, 1], m[1, 3] = sy * tan_half * near, y0 * tan_half * near
+        m[2, 3] = -near
+        m[3, 3] = 1
+        self.raster_to_camera = m.astype(f32)
+        self.lens_radius, self.focal_distance = float(lens_radius), float(focal_distance)
+        self.shutter_open, self.shutter_close = 0.0, 1.0
+        self.dx_camera = np.array([m[0, 0], 0, 0], dtype=f32)
+        self.dy_camera = np.array([0, m[1, 1], 0], dtype=f32)
+        self.position = _v3(eyepos)
+
+    def to_abi(self):
+        c = A.HkCamera()
+        c.raster_to_camera[:] = self.raster_to_camera.reshape(-1).tolist()
+        c.camera_to_world[:] = self.camera_to_world.reshape(-1).tolist()
+        c.lens_radius, c.focal_distance = self.lens_radius, self.focal_distance
+        c.shutter_open, c.shutter_close = self.shutter_open, self.shutter_close
+        c.dx_camera[:] = self.dx_camera.tolist()
+        c.dy_camera[:] = self.dy_camera.tolist()
+        return c
+
+
+# ------------------------------------------------------------------------------------------------
+# filters (src/filter.jl)
+# ------------------------------------------------------------------------------------------------
+class GaussianFilter:
+    """filter.jl:136-162"""
+
+    def __init__(self, radius=(1.5, 1.5), sigma=0.5):
+        self.radius = (f32(radius[0]), f32(radius[1]))
+        self.sigma = f32(sigma)
+        self.exp_x = self._g(self.radius[0])
+        self.exp_y = self._g(self.radius[1])
+        self.type = 3
+
+    def _g(self, x):
+        x = f32(x)
+        return f32(np.exp(f32(-(x * x)) / f32(f32(2) * self.sigma * self.sigma)))
+
+    def evaluate(self, px, py):
+        gx = max(f32(0), f32(self._g(px) - self.exp_x))
+        gy = max(f32(0), f32(self._g(py) - self.exp_y))
+        return f32(gx * gy)
+
+
+class BoxFilter:
+    def __init__(self, radius=(0.5, 0.5)):
+        self.radius = (f32(radius[0]), f32(radius[1]))
+        self.type = 1
+
+
+class TriangleFilter:
+    def __init__(self, radius=(2.0, 2.0)):
+        self.radius = (f32(radius[0]), f32(radius[1]))
+        self.type = 2
+
+
+class FilterSamplerData:
+    """GPUFilterSamplerData, filter.jl:611-725 (all arithmetic in Float32, sequential sums)."""
+
+    def __init__(self, flt):
+        self.flt = flt
+        self.keep = []
+        if flt.type in (1, 2):
+            self.nx = self.ny = 0
+            return
+        r = flt.radius
+        nx = max(int(math.ceil(32 * float(r[0]))), 8)
+        ny = max(int(math.ceil(32 * float(r[1]))), 8)
+        dmin = (f32(-r[0]), f32(-r[1]))
+        dmax = (f32(r[0]), f32(r[1]))
+        dx = f32(f32(dmax[0] - dmin[0]) / f32(nx))
+        dy = f32(f32(dmax[1] - dmin[1]) / f32(ny))
+        func = np.zeros((ny, nx), dtype=f32)
+        for iy in range(1, ny + 1):
+            py = f32(dmin[1] + f32(f32(f32(iy) - f32(0.5)) * dy))
+            for ix in range(1, nx + 1):
+                px = f32(dmin[0] + f32(f32(f32(ix) - f32(0.5)) * dx))
+                func[iy - 1, ix - 1] = max(f32(0), flt.evaluate(px, py))
+        marginal_func = np.zeros(ny, dtype=f32)
+        for iy in range(ny):
+            acc = f32(0)
+            for ix in range(nx):
+                acc = f32(acc + func[iy, ix])
+            marginal_func[iy] = acc
+        mcdf = np.zeros(ny + 1, dtype=f32)
+        for iy in range(ny):
+            mcdf[iy + 1] = f32(mcdf[iy] + marginal_func[iy])
+        self.func_integral = f32(f32(mcdf[-1] * dx) * dy)
+        end = mcdf[-1]
+        if end > 0:
+            mcdf = (mcdf / end).astype(f32)
+        else:
+            mcdf = (np.arange(ny + 1, dtype=f32) / f32(ny)).astype(f32)
+        ccdf = np.zeros((ny, nx + 1), dtype=f32)
+        for iy in range(ny):
+            for ix in range(nx):
+                ccdf[iy, ix + 1] = f32(ccdf[iy, ix] + func[iy, ix])
+            rs = ccdf[iy, nx]
+            if rs > 0:
+                ccdf[iy, :] = (ccdf[iy, :] / rs).astype(f32)
+            else:
+                ccdf[iy, :] = (np.arange(nx + 1, dtype=f32) / f32(nx)).astype(f32)
+        self.nx, self.ny = nx, ny
+        self.func, self.marginal_cdf, self.marginal_func, self.conditional_cdf = func, mcdf, marginal_func, ccdf
+        self.domain_min, self.domain_max = dmin, dmax
+
+    def to_abi(self):
+        f = A.HkFilter()
+        f.type = self.flt.type
+        f.radius[:] = [float(self.flt.radius[0]), float(self.flt.radius[1])]
+        f.nx, f.ny = self.nx, self.ny
+        if self.nx:
+            f.func, f.marginal_cdf = _fp(self.func), _fp(self.marginal_cdf)
+            f.marginal_func, f.conditional_cdf = _fp(self.marginal_func), _fp(self.conditional_cdf)
+            f.domain_min[:] = [float(self.domain_min[0]), float(self.domain_min[1])]
+            f.domain_max[:] = [float(self.domain_max[0]), float(self.domain_max[1])]
+            f.func_integral = float(self.func_integral)
+        return f
+
+
+# ------------------------------------------------------------------------------------------------
+# materials (constructors mirror src/materials/*.jl keyword constructors; constant parameters only)
+# ------------------------------------------------------------------------------------------------
+def _rgb(x):
+    if np.isscalar(x):
+        return (float(x),) * 3
+    x = tuple(float(v) for v in x)
+    assert len(x) == 3
+    return x
+
+
+class Material:
+    type = 0
+
+    def to_abi(self, scene):
+        raise NotImplementedError
+
+
+class MatteMaterial(Material):            # uber-material.jl:180-183, 256
+    type = A.HK_MAT_MATTE
+
+    def __init__(self, Kd=0.5, sigma=0.0):
+        self.Kd, self.sigma = _rgb(Kd), float(sigma)
+
+    def to_abi(self, scene):
+        m = A.HkMaterial(type=self.type)
+        m.rgb0[:] = self.Kd
+        m.f[0] = self.sigma
+        return m
+
+
+class MirrorMaterial(Material):           # :193-195, 275
+    type = A.HK_MAT_MIRROR
+
+    def __init__(self, Kr=0.9):
+        self.Kr = _rgb(Kr)
+
+    def to_abi(self, scene):
+        m = A.HkMaterial(type=self.type)
+        m.rgb0[:] = self.Kr
+        return m
+
+
+class GlassMaterial(Material):            # :209-216, 299
+    type = A.HK_MAT_GLASS
+
+    def __init__(self, Kr=1.0, Kt=1.0, index=1.5, u_roughness=0.0, v_roughness=0.0, remap_roughness=True):
+        self.Kr, self.Kt, self.index = _rgb(Kr), _rgb(Kt), float(index)
+
+    def to_abi(self, scene):
+        m = A.HkMaterial(type=self.type)
+        m.rgb0[:] = self.Kr
+        m.rgb1[:] = self.Kt
+        m.f[0] = self.index
+        return m
+
+
+class PiecewiseLinearSpectrum:            # src/spectral/piecewise-linear.jl:4-7
+    def __init__(self, lambdas, values):
+        self.lambdas = np.asarray(lambdas, dtype=f32)
+        self.values = np.asarray(values, dtype=f32)
+
+
+class ConductorMaterial(Material):        # :378-384, 418-426
+    type = A.HK_MAT_CONDUCTOR
+
+    def __init__(self, eta=(0.2, 0.2, 0.2), k=(3.9, 3.9, 3.9), roughness=0.1, reflectance=(1, 1, 1),
+                 remap_roughness=True):
+        self.eta, self.k = eta, k
+        self.roughness, self.reflectance, self.remap = float(roughness), _rgb(reflectance), bool(remap_roughness)
+
+    def to_abi(self, scene):
+        m = A.HkMaterial(type=self.type)
+        m.flags = A.HK_MATFLAG_REMAP_ROUGHNESS if self.remap else 0
+        m.f[0] = self.roughness
+        spectral = isinstance(self.eta, PiecewiseLinearSpectrum)
+        assert spectral == isinstance(self.k, PiecewiseLinearSpectrum), "eta and k must both be spectra or both RGB"
+        if spectral:
+            m.flags |= A.HK_MATFLAG_SPECTRAL_ETA_K
+            m.spec[0] = scene._spectrum_id(self.eta)
+            m.spec[1] = scene._spectrum_id(self.k)
+        else:
+            m.rgb0[:] = _rgb(self.eta)
+            m.rgb1[:] = _rgb(self.k)
+        return m
+
+
+def _metal(name, roughness, remap):
+    t = T.load_tables()
+    e, k = t[name + "_eta"], t[name + "_k"]
+    return ConductorMaterial(PiecewiseLinearSpectrum(e[0], e[1]), PiecewiseLinearSpectrum(k[0], k[1]), roughness,
+                             (1, 1, 1), remap)
+
+
+def Gold(roughness=0.0, remap_roughness=True):      # uber-material.jl:469-470
+    return _metal("au", roughness, remap_roughness)
+
+
+def Silver(roughness=0.0, remap_roughness=True):
+    return _metal("ag", roughness, remap_roughness)
+
+
+def Copper(roughness=0.0, remap_roughness=True):
+    return _metal("cu", roughness, remap_roughness)
+
+
+def Aluminum(roughness=0.0, remap_roughness=True):
+    return _metal("al", roughness, remap_roughness)
+
+
+class CoatedDiffuseMaterial(Material):    # coated-diffuse.jl:98-127
+    type = A.HK_MAT_COATED_DIFFUSE
+
+    def __init__(self, reflectance=0.5, roughness=0.0, thickness=0.01, eta=1.5, albedo=0.0, g=0.0, max_depth=10,
+                 n_samples=1, remap_roughness=True):
+        self.reflectance, self.albedo = _rgb(reflectance), _rgb(albedo)
+        self.u_rough, self.v_rough = (roughness if isinstance(roughness, tuple) else (roughness, roughness))
+        self.thickness, self.eta, self.g = float(thickness), float(eta), float(g)
+        self.max_depth, self.n_samples, self.remap = int(max_depth), int(n_samples), bool(remap_roughness)
+
+    def to_abi(self, scene):
+        m = A.HkMaterial(type=self.type)
+        m.flags = A.HK_MATFLAG_REMAP_ROUGHNESS if self.remap else 0
+        m.rgb0[:] = self.reflectance
+        m.rgb1[:] = self.albedo
+        m.f[0], m.f[1], m.f[2], m.f[3], m.f[4] = float(self.u_rough), float(self.v_rough), self.thickness, self.eta, self.g
+        m.ival[0], m.ival[1] = self.max_depth, self.n_samples
+        return m
+
+
+class ThinDielectricMaterial(Material):   # thin-dielectric.jl:45-52
+    type = A.HK_MAT_THIN_DIELECTRIC
+
+    def __init__(self, eta=1.5):
+        self.eta = float(eta)
+
+    def to_abi(self, scene):
+        m = A.HkMaterial(type=self.type)
+        m.f[0] = self.eta
+        return m
+
+
+class DiffuseTransmissionMaterial(Material):   # diffuse-transmission.jl:39-85
+    type = A.HK_MAT_DIFFUSE_TRANSMISSION
+
+    def __init__(self, reflectance=0.25, transmittance=0.25, scale=1.0):
+        self.reflectance, self.transmittance, self.scale = _rgb(reflectance), _rgb(transmittance), float(scale)
+
+    def to_abi(self, scene):
+        m = A.HkMaterial(type=self.type)
+        m.rgb0[:] = self.reflectance
+        m.rgb1[:] = self.transmittance
+        m.f[0] = self.scale
+        return m
+
+
+class MediumInterface:
+    """src/materials/medium-interface.jl:40-56.  `emission=(Le_rgb, scale, two_sided)` registers one
+    DiffuseAreaLight per face (src/scene-mesh.jl:100-138)."""
+
+    def __init__(self, material, inside=None, outside=None, emission=None):
+        self.material, self.inside, self.outside, self.emission = material, inside, outside, emission
+
+
+# ------------------------------------------------------------------------------------------------
+# media (src/integrators/volpath/media.jl, nanovdb.jl)
+# ------------------------------------------------------------------------------------------------
+class HomogeneousMedium:                  # media.jl:735-750
+    def __init__(self, sigma_a=0.01, sigma_s=1.0, Le=0.0, g=0.0):
+        self.sigma_a, self.sigma_s, self.Le, self.g = _rgb(sigma_a), _rgb(sigma_s), _rgb(Le), float(g)
+
+    def to_abi(self, keep):
+        m = A.HkMedium(type=A.HK_MEDIUM_HOMOGENEOUS)
+        m.sigma_a_rgb[:], m.sigma_s_rgb[:], m.Le_rgb[:] = self.sigma_a, self.sigma_s, self.Le
+        m.g, m.scale = self.g, 1.0
+        return m
+
+
+def build_majorant_grid(density_xyz, res):
+    """media.jl:1458-1487; density indexed [x, y, z]; returns array [rz][ry][rx]."""
+    nx, ny, nz = density_xyz.shape
+    out = np.zeros((res[2], res[1], res[0]), dtype=f32)
+    def rng(i, n, r):
+        s = max(1, int(math.floor(i * n / r)) + 1)
+        e = min(n, int(math.ceil((i + 1) * n / r)))
+        return s - 1, e
+    for iz in range(res[2]):
+        z0, z1 = rng(iz, nz, res[2])
+        for iy in range(res[1]):
+            y0, y1 = rng(iy, ny, res[1])
+            for ix in range(res[0]):
+                x0, x1 = rng(ix, nx, res[0])
+                blk = density_xyz[x0:x1, y0:y1, z0:z1]
+                out[iz, iy, ix] = max(f32(0), blk.max()) if blk.size else f32(0)
+    return out
+
+
+class GridMedium:                         # media.jl:886-936
+    def __init__(self, density_xyz, sigma_a=0.01, sigma_s=1.0, g=0.0, bounds=((0, 0, 0), (1, 1, 1)),
+                 transform=None, majorant_res=(16, 16, 16)):
+        self.density = np.ascontiguousarray(np.asarray(density_xyz, dtype=f32))
+        self.sigma_a, self.sigma_s, self.g = _rgb(sigma_a), _rgb(sigma_s), float(g)
+        self.bounds = (np.asarray(bounds[0], dtype=f32), np.asarray(bounds[1], dtype=f32))
+        self.medium_to_render = np.eye(4, dtype=f32) if transform is None else np.asarray(transform, dtype=f32)
+        self.render_to_medium = np.linalg.inv(self.medium_to_render.astype(np.float64)).astype(f32)
+        self.majorant_res = tuple(int(v) for v in majorant_res)
+        self.majorant = build_majorant_grid(self.density, self.majorant_res)
+
+    def to_abi(self, keep):
+        m = A.HkMedium(type=A.HK_MEDIUM_GRID)
+        m.sigma_a_rgb[:], m.sigma_s_rgb[:], m.Le_rgb[:] = self.sigma_a, self.sigma_s, (0, 0, 0)
+        m.g, m.scale = self.g, 1.0
+        m.bounds_min[:], m.bounds_max[:] = self.bounds[0].tolist(), self.bounds[1].tolist()
+        m.render_from_medium[:] = self.medium_to_render.reshape(-1).tolist()
+        m.medium_from_render[:] = self.render_to_medium.reshape(-1).tolist()
+        nx, ny, nz = self.density.shape
+        m.density_res[:] = [nx, ny, nz]
+        d = np.ascontiguousarray(self.density.transpose(2, 1, 0))     # -> [nz][ny][nx]
+        keep.append(d)
+        m.density = _fp(d)
+        m.majorant_res[:] = list(self.majorant_res)
+        mj = np.ascontiguousarray(self.majorant)
+        keep.append(mj)
+        m.majorant = _fp(mj)
+        return m
+
+
+from .nanovdb import NanoVDBMedium  # noqa: E402  (host-side NanoVDB builder, nanovdb.jl:602-858)
+
+
+# ------------------------------------------------------------------------------------------------
+# lights (constructors mirror src/lights/*.jl)
+# ------------------------------------------------------------------------------------------------
+class _Light:
+    type = 0
+    infinite = False
+
+    def _spectrum(self, L, rgb, legacy_rgbspectrum):
+        """RGB{Float32} ctor -> RGBIlluminantSpectrum + scale 1/D65_PHOTOMETRIC (point.jl:56-66);
+        RGBSpectrum ctor (legacy) keeps the RGB and uplifts on device (point.jl:72-75)."""
+        if legacy_rgbspectrum:
+            L.spectrum_kind = A.HK_SPECTRUM_RGB
+            L.rgb[:] = _rgb(rgb)
+        else:
+            poly, s = T.rgb_illuminant_spectrum(_rgb(rgb))
+            L.spectrum_kind = A.HK_SPECTRUM_ILLUMINANT
+            L.poly[:] = [float(v) for v in poly]
+            L.illum_scale = float(s)
+            L.rgb[:] = _rgb(rgb)
+        L.scale = float(f32(1.0) / f32(10567.0))
+
+
+class PointLight(_Light):
+    type = A.HK_LIGHT_POINT
+
+    def __init__(self, rgb, position, legacy_rgbspectrum=False, scale=None):
+        """PointLight(rgb::RGB, position) [point.jl:56-66]; legacy_rgbspectrum=True mirrors
+        PointLight(i::RGBSpectrum, position) [:72-75, scale 1/D65_PHOTOMETRIC] or, with scale given,
+        PointLight(position, i::S, scale) [:26-28]."""
+        self.rgb, self.position, self.legacy, self.scale = _rgb(rgb), _v3(position), legacy_rgbspectrum, scale
+
+    def to_abi(self, scene):
+        L = A.HkLight(type=self.type)
+        self._spectrum(L, self.rgb, self.legacy)
+        if self.scale is not None:
+            L.scale = float(self.scale)
+        L.position[:] = self.position.tolist()
+        return L
+
+
+class DirectionalLight(_Light):
+    type = A.HK_LIGHT_DIRECTIONAL
+    infinite = True
+
+    def __init__(self, rgb, direction, legacy_rgbspectrum=False):
+        d = _v3(direction).astype(np.float64)
+        self.rgb, self.direction, self.legacy = _rgb(rgb), (d / np.linalg.norm(d)).astype(f32), legacy_rgbspectrum
+
+    def to_abi(self, scene):
+        L = A.HkLight(type=self.type)
+        self._spectrum(L, self.rgb, self.legacy)
+        L.direction[:] = self.direction.tolist()
+        return L
+
+
+class SunLight(DirectionalLight):
+    type = A.HK_LIGHT_SUN
+
+
+class AmbientLight(_Light):
+    type = A.HK_LIGHT_AMBIENT
+    infinite = True
+
+    def __init__(self, rgb, legacy_rgbspectrum=False):
+        self.rgb, self.legacy = _rgb(rgb), legacy_rgbspectrum
+
+    def to_abi(self, scene):
+        L = A.HkLight(type=self.type)
+        self._spectrum(L, self.rgb, self.legacy)
+        if self.legacy:
+            L.scale = 1.0      # AmbientLight(s::Spectrum) = AmbientLight(s, 1f0), ambient.jl:33
+        return L
+
+
+class Distribution2D:
+    """src/sampler/sampling.jl:201-263 (Float32, sequential sums); func has shape (nv, nu)."""
+
+    def __init__(self, func):
+        func = np.asarray(func, dtype=f32)
+        nv, nu = func.shape
+        self.nu, self.nv = nu, nv
+        self.conditional_func = np.ascontiguousarray(func)
+        ccdf = np.zeros((nv, nu + 1), dtype=f32)
+        cfi = np.zeros(nv, dtype=f32)
+        for v in range(nv):
+            ccdf[v, 1:] = np.cumsum((func[v] / f32(nu)).astype(f32), dtype=f32)
+            fi = ccdf[v, nu]
+            cfi[v] = fi
+            if fi == 0:
+                ccdf[v, 1:] = (np.arange(1, nu + 1, dtype=f32) / f32(nu)).astype(f32)
+            else:
+                ccdf[v, 1:] = (ccdf[v, 1:] / fi).astype(f32)
+        self.conditional_cdf, self.conditional_func_int = ccdf, cfi
+        self.marginal_func = cfi.copy()
+        mcdf = np.zeros(nv + 1, dtype=f32)
+        mcdf[1:] = np.cumsum((cfi / f32(nv)).astype(f32), dtype=f32)
+        self.marginal_func_int = f32(mcdf[nv])
+        if self.marginal_func_int == 0:
+            mcdf[1:] = (np.arange(1, nv + 1, dtype=f32) / f32(nv)).astype(f32)
+        else:
+            mcdf[1:] = (mcdf[1:] / self.marginal_func_int).astype(f32)
+        self.marginal_cdf = mcdf
+
+
+class EnvironmentMap:
+    """src/textures/environment_map.jl:9-45; data (h, w, 3) in equal-area (octahedral) layout."""
+
+    def __init__(self, data, rotation=None):
+        self.data = np.ascontiguousarray(np.asarray(data, dtype=f32))
+        self.rotation = np.eye(3, dtype=f32) if rotation is None else np.asarray(rotation, dtype=f32)  # row-major
+        lum = (f32(0.212671) * self.data[..., 0] + f32(0.715160) * self.data[..., 1]
+               + f32(0.072169) * self.data[..., 2]).astype(f32)
+        self.distribution = Distribution2D(lum)
+
+
+class EnvironmentLight(_Light):
+    type = A.HK_LIGHT_ENVIRONMENT
+    infinite = True
+
+    def __init__(self, env_map, scale=(1, 1, 1)):
+        self.env_map, self.scale = env_map, _rgb(scale)
+
+    def to_abi(self, scene):
+        L = A.HkLight(type=self.type)
+        L.env_map = scene._envmap_id(self)
+        L.scale = 1.0
+        return L
+
+
+class DiffuseAreaLight(_Light):
+    type = A.HK_LIGHT_DIFFUSE_AREA
+
+    def __init__(self, vertices, normal, area, uv, Le, scale, two_sided):
+        self.vertices, self.normal, self.area, self.uv = vertices, normal, area, uv
+        self.Le, self.scale, self.two_sided = _rgb(Le), float(scale), bool(two_sided)
+
+    def to_abi(self, scene):
+        L = A.HkLight(type=self.type)
+        L.scale = self.scale
+        L.rgb[:] = self.Le
+        L.v[:] = np.asarray(self.vertices, dtype=f32).reshape(-1).tolist()
+        L.normal[:] = np.asarray(self.normal, dtype=f32).tolist()
+        L.area = float(self.area)
+        L.uv[:] = np.asarray(self.uv, dtype=f32).reshape(-1).tolist()
+        L.two_sided = 1 if self.two_sided else 0
+        return L
+
+
+# ------------------------------------------------------------------------------------------------
+# meshes
+# ------------------------------------------------------------------------------------------------
+class Mesh:
+    def __init__(self, positions, faces, normals=None, uvs=None):
+        self.positions = np.asarray(positions, dtype=f32).reshape(-1, 3)
+        self.faces = np.asarray(faces, dtype=np.uint32).reshape(-1, 3)
+        self.normals = None if normals is None else np.asarray(normals, dtype=f32).reshape(-1, 3)
+        self.uvs = None if uvs is None else np.asarray(uvs, dtype=f32).reshape(-1, 2)
+
+
+def uv_sphere(center, radius, nu=64, nv=64):
+    """Tessellated sphere (GeometryBasics.Tesselation(Sphere, n) stand-in): (nu) x (nv) vertex grid."""
+    th = np.linspace(0, np.pi, nv, dtype=np.float64)
+    ph = np.linspace(0, 2 * np.pi, nu, dtype=np.float64)
+    TH, PH = np.meshgrid(th, ph, indexing="ij")
+    n = np.stack([np.sin(TH) * np.cos(PH), np.cos(TH), np.sin(TH) * np.sin(PH)], -1).reshape(-1, 3)
+    p = np.asarray(center, dtype=np.float64) + radius * n
+    uv = np.stack([PH / (2 * np.pi), TH / np.pi], -1).reshape(-1, 2)
+    faces = []
+    for i in range(nv - 1):
+        for j in range(nu - 1):
+            a, b, c, d = i * nu + j, i * nu + j + 1, (i + 1) * nu + j, (i + 1) * nu + j + 1
+            faces.append((a, c, b))
+            faces.append((b, c, d))
+    return Mesh(p, faces, n, uv)
+
+
+def rect3(origin, widths):
+    """Axis-aligned box Rect3f(origin, widths) as 12 triangles with flat per-face normals."""
+    o = np.asarray(origin, dtype=np.float64)
+    w = np.asarray(widths, dtype=np.float64)
+    P, N, UV, F = [], [], [], []
+    axes = [(0, 1, 2), (1, 2, 0), (2, 0, 1)]
+    for ax, u, v in axes:
+        for side in (0, 1):
+            base = o.copy()
+            base[ax] += w[ax] * side
+            du = np.zeros(3); du[u] = w[u]
+            dv = np.zeros(3); dv[v] = w[v]
+            n = np.zeros(3); n[ax] = 1.0 if side else -1.0
+            i0 = len(P)
+            for (a, b) in ((0, 0), (1, 0), (1, 1), (0, 1)):
+                P.append(base + a * du + b * dv); N.append(n); UV.append((a, b))
+            if side:
+                F += [(i0, i0 + 1, i0 + 2), (i0, i0 + 2, i0 + 3)]
+            else:
+                F += [(i0, i0 + 2, i0 + 1), (i0, i0 + 3, i0 + 2)]
+    return Mesh(P, F, N, UV)
+
+
+def quad(p0, p1, p2, p3, normal=None):
+    P = np.asarray([p0, p1, p2, p3], dtype=np.float64)
+    n = np.cross(P[1] - P[0], P[3] - P[0])
+    n = n / np.linalg.norm(n) if normal is None else np.asarray(normal, dtype=np.float64)
+    return Mesh(P, [(0, 1, 2), (0, 2, 3)], [n] * 4, [(0, 0), (1, 0), (1, 1), (0, 1)])
+
+
+# ------------------------------------------------------------------------------------------------
+# Scene (src/scene.jl:21-151, src/scene-mesh.jl)
+# ------------------------------------------------------------------------------------------------
+class Scene:
+    def __init__(self):
+        self.meshes = []            # (mesh, transform, interface_idx, emission)
+        self.materials = []         # unique Material objects
+        self.interfaces = []        # (material_idx, inside_medium_idx, outside_medium_idx)
+        self.media = []
+        self.lights = []
+        self._spectra = []
+        self._envmaps = []
+        self._synced = None
+
+    # -- push! ------------------------------------------------------------------------------------
+    def _index_of(self, lst, obj):
+        for i, o in enumerate(lst):
+            if o is obj:
+                return i + 1
+        lst.append(obj)
+        return len(lst)
+
+    def _spectrum_id(self, s):
+        return self._index_of(self._spectra, s)
+
+    def _envmap_id(self, light):
+        return self._index_of(self._envmaps, light)
+
+    def push_material(self, material):
+        """push!(scene, material) -> index into media_interfaces (scene.jl; every material is wrapped in a
+        MediumInterfaceIdx)."""
+        if isinstance(material, MediumInterface):
+            mat, inside, outside = material.material, material.inside, material.outside
+        else:
+            mat, inside, outside = material, None, None
+        mi = self._index_of(self.materials, mat)
+        ii = 0 if inside is None else self._index_of(self.media, inside)
+        oi = 0 if outside is None else self._index_of(self.media, outside)
+        self.interfaces.append((mi, ii, oi))
+        return len(self.interfaces)
+
+    def push(self, obj, material=None, transform=None):
+        """push!(scene, mesh, material; transform) / push!(scene, light)."""
+        self._synced = None
+        if isinstance(obj, _Light):
+            self.lights.append(obj)
+            return len(self.lights)
+        assert isinstance(obj, Mesh) and material is not None
+        idx = self.push_material(material)
+        emission = material.emission if isinstance(material, MediumInterface) else None
+        self.meshes.append((obj, None if transform is None else np.asarray(transform, dtype=np.float64), idx, emission))
+        return len(self.meshes)
+
+    # -- sync!: flatten to the C ABI arrays ----------------------------------------------------------
+    def sync(self):
+        pos, nrm, uvs, idx, meta = [], [], [], [], []
+        any_n = any(m.normals is not None for m, *_ in self.meshes)
+        any_uv = any(m.uvs is not None for m, *_ in self.meshes)
+        area_lights = []
+        voff = 0
+        # flat light order: the reference's MultiTypeSet groups lights by type slot in first-push order
+        type_order = []
+        for L in self.lights:
+            if type(L) not in type_order:
+                type_order.append(type(L))
+        for mesh, xf, iface, emission in self.meshes:
+            P = mesh.positions.astype(np.float64)
+            Nn = None if mesh.normals is None else mesh.normals.astype(np.float64)
+            if xf is not None:
+                P = P @ xf[:3, :3].T + xf[:3, 3]
+                if Nn is not None:
+                    Nn = Nn @ np.linalg.inv(xf[:3, :3])
+                    Nn = Nn / np.linalg.norm(Nn, axis=1, keepdims=True)
+            P32 = P.astype(f32)
+            pos.append(P32)
+            if any_n:
+                nrm.append(np.full((len(P), 3), np.nan, dtype=f32) if Nn is None else Nn.astype(f32))
+            if any_uv:
+                uvs.append(np.zeros((len(P), 2), dtype=f32) if mesh.uvs is None else mesh.uvs)
+            idx.append(mesh.faces + np.uint32(voff))
+            m = np.zeros((len(mesh.faces), 3), dtype=np.uint32)
+            m[:, 0] = iface
+            m[:, 1] = np.arange(1, len(mesh.faces) + 1, dtype=np.uint32)
+            if emission is not None:                       # register_face_area_lights!, scene-mesh.jl:100-138
+                Le, scale, two_sided = emission
+                Le = _rgb(Le)
+                lum = f32(0.212671) * f32(Le[0]) + f32(0.715160) * f32(Le[1]) + f32(0.072169) * f32(Le[2])
+                for fi, face in enumerate(mesh.faces):
+                    vs = P32[face]
+                    fuv = (mesh.uvs[face] if mesh.uvs is not None else np.array([[0, 0], [1, 0], [1, 1]], dtype=f32))
+                    if lum < 1e-4:
+                        continue
+                    e1, e2 = (vs[1] - vs[0]).astype(f32), (vs[2] - vs[0]).astype(f32)
+                    cp = np.cross(e1, e2).astype(f32)
+                    ta = f32(np.sqrt(f32(cp[0] * cp[0] + cp[1] * cp[1]) + f32(cp[2] * cp[2])))
+                    if ta < 1e-10:
+                        continue
+                    al = DiffuseAreaLight(vs, (cp / ta).astype(f32), f32(0.5) * ta, fuv, Le, scale, two_sided)
+                    area_lights.append((al, len(meta), fi))
+            meta.append(m)
+            voff += len(P)
+        lights = list(self.lights)
+        if area_lights and DiffuseAreaLight not in type_order:
+            type_order.append(DiffuseAreaLight)
+        lights += [al for al, _, _ in area_lights]
+        order = sorted(range(len(lights)), key=lambda i: (type_order.index(type(lights[i])), i))
+        flat = [lights[i] for i in order]
+        flat_of = {id(l): k + 1 for k, l in enumerate(flat)}
+        for al, mi, fi in area_lights:
+            meta[mi][fi, 2] = flat_of[id(al)]
+        s = type("Synced", (), {})()
+        s.positions = np.ascontiguousarray(np.concatenate(pos)) if pos else np.zeros((0, 3), f32)
+        s.normals = np.ascontiguousarray(np.concatenate(nrm)) if any_n else None
+        s.uvs = np.ascontiguousarray(np.concatenate(uvs).astype(f32)) if any_uv else None
+        s.indices = np.ascontiguousarray(np.concatenate(idx).astype(np.uint32)) if idx else np.zeros((0, 3), np.uint32)
+        s.tri_meta = np.ascontiguousarray(np.concatenate(meta).astype(np.uint32)) if meta else np.zeros((0, 3), np.uint32)
+        s.lights = flat
+        self._synced = s
+        return s
+
+    def world_radius(self):
+        s = self._synced or self.sync()
+        lo, hi = s.positions.min(0), s.positions.max(0)
+        return float(np.linalg.norm(hi - lo) / 2)
+
+
+# ------------------------------------------------------------------------------------------------
+# VolPath (src/integrators/volpath/volpath.jl)
+# ------------------------------------------------------------------------------------------------
+def compute_zsobol_params(samples_per_pixel, width, height):
+    """src/sampler/sobol.jl:317-323"""
+    log2_spp = int(math.ceil(math.log2(max(1, samples_per_pixel))))
+    res_log2 = int(math.ceil(math.log2(max(width, height))))
+    log4_spp = (log2_spp + 1) // 2
+    return log2_spp, res_log2 + log4_spp
+
+
+class Backend:
+    """One loaded C-ABI library + prefix.  The product backend is libhikari_cuda.so ('hk_'); tests construct a
+    second Backend around the oracle library ('ok_') to feed it the identical flattened scene."""
+
+    def __init__(self, lib=None, prefix="hk_", device=0):
+        self.lib = A.load_library() if lib is None else lib
+        self.prefix = prefix
+        self.ctx = C.c_void_p()
+        if prefix == "hk_":
+            rc = self.lib.hk_create(device, C.byref(self.ctx))
+        else:
+            rc = getattr(self.lib, prefix + "create")(C.byref(self.ctx))
+        if rc != 0:
+            raise RuntimeError(f"{prefix}create failed with status {rc}: no usable CUDA device / library "
+                               "(there is no CPU fallback)")
+        self._keep = []
+
+    def call(self, name, *args):
+        rc = getattr(self.lib, self.prefix + name)(self.ctx, *args)
+        if rc != 0:
+            msg = ""
+            if self.prefix == "hk_":
+                e = self.lib.hk_last_error(self.ctx)
+                msg = e.decode() if e else ""
+            raise RuntimeError(f"{self.prefix}{name} failed ({rc}): {msg}")
+        return rc
+
+    def close(self):
+        if self.ctx:
+            getattr(self.lib, self.prefix + "destroy")(self.ctx)
+            self.ctx = C.c_void_p()
+
+    # ---- uploads --------------------------------------------------------------------------------
+    def upload_tables(self):
+        t = T.load_tables()
+        scale, coeffs = T.get_srgb_table()
+        keep = [np.ascontiguousarray(t[k]) for k in ("sobol_matrices", "cie_x", "cie_y", "cie_z", "d65_values")]
+        keep += [scale, coeffs]
+        ht = A.HkTables(keep[0].ctypes.data_as(A.c_u32p), _fp(keep[1]), _fp(keep[2]), _fp(keep[3]), _fp(keep[4]),
+                        len(scale), _fp(scale), _fp(coeffs))
+        self.call("upload_tables", C.byref(ht))
+
+    def upload_scene(self, scene):
+        s = scene._synced or scene.sync()
+        g = A.HkGeometry(_fp(s.positions), None if s.normals is None else _fp(s.normals), None,
+                         None if s.uvs is None else _fp(s.uvs), s.indices.ctypes.data_as(A.c_u32p),
+                         s.tri_meta.ctypes.data_as(A.c_u32p), len(s.positions), len(s.indices))
+        self.call("upload_geometry", C.byref(g))
+        # materials first (registers spectra ids), then spectra
+        mats = (A.HkMaterial * max(1, len(scene.materials)))(*[m.to_abi(scene) for m in scene.materials])
+        lam = np.concatenate([sp.lambdas for sp in scene._spectra]) if scene._spectra else np.zeros(0, f32)
+        val = np.concatenate([sp.values for sp in scene._spectra]) if scene._spectra else np.zeros(0, f32)
+        offs = np.cumsum([0] + [len(sp.lambdas) for sp in scene._spectra]).astype(np.uint32)
+        sp = A.HkSpectra(_fp(lam), _fp(val), offs.ctypes.data_as(A.c_u32p), len(scene._spectra))
+        self.call("upload_spectra", C.byref(sp))
+        ifs = (A.HkMediumInterface * max(1, len(scene.interfaces)))(*[A.HkMediumInterface(*t) for t in scene.interfaces])
+        self.call("upload_materials", mats, len(scene.materials), ifs, len(scene.interfaces))
+        # media
+        keep = []
+        if scene.media:
+            med = (A.HkMedium * len(scene.media))(*[m.to_abi(keep) for m in scene.media])
+            self.call("upload_media", med, len(scene.media))
+        else:
+            self.call("upload_media", None, 0)
+        # lights (+ env maps + sampler)
+        scene._envmaps = []
+        labi = [L.to_abi(scene) for L in s.lights]
+        if scene._envmaps:
+            envs = []
+            for L in scene._envmaps:
+                em, d = L.env_map, L.env_map.distribution
+                e = A.HkEnvMap()
+                e.rgb, e.w, e.h = _fp(em.data), em.data.shape[1], em.data.shape[0]
+                e.rotation[:] = em.rotation.T.reshape(-1).tolist()        # column-major like Julia's Mat3f
+                e.scale_rgb[:] = L.scale
+                e.conditional_func, e.conditional_cdf = _fp(d.conditional_func), _fp(d.conditional_cdf)
+                e.conditional_func_int, e.marginal_func = _fp(d.conditional_func_int), _fp(d.marginal_func)
+                e.marginal_cdf, e.marginal_func_int, e.nu, e.nv = _fp(d.marginal_cdf), float(d.marginal_func_int), d.nu, d.nv
+                envs.append(e)
+            earr = (A.HkEnvMap * len(envs))(*envs)
+            self.call("upload_envmaps", earr, len(envs))
+        n = len(labi)
+        larr = (A.HkLight * max(1, n))(*labi)
+        nodes = (A.HkLightBVHNode * max(1, 2 * n))()
+        trails = np.zeros(max(1, n), dtype=np.uint32)
+        inf = np.zeros(max(1, n), dtype=np.int32)
+        nn, ni, nb = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        A.load_library().hk_host_build_light_sampler(larr, n, nodes, C.byref(nn), trails.ctypes.data_as(A.c_u32p),
+                                                     inf.ctypes.data_as(A.c_i32p), C.byref(ni), C.byref(nb))
+        smp = A.HkLightSampler(nodes, nn.value, trails.ctypes.data_as(A.c_u32p), inf.ctypes.data_as(A.c_i32p), ni.value, nb.value)
+        self.call("upload_lights", larr, n, C.byref(smp))
+        self.light_sampler_info = (nn.value, ni.value, nb.value)
+        self._keep = [s, keep]
+
+    def set_camera(self, camera):
+        c = camera.to_abi()
+        self.call("set_camera", C.byref(c))
+
+    def set_filter(self, sampler_data):
+        f = sampler_data.to_abi()
+        self.call("set_filter", C.byref(f))
+
+    def set_params(self, vp, width, height, sample_batch=1):
+        sobol_spp = max(int(vp.samples_per_pixel), 4096)            # volpath.jl:475
+        l2, nb4 = compute_zsobol_params(sobol_spp, width, height)
+        p = A.HkRenderParams(width, height, vp.max_depth, vp.samples_per_pixel, 1 if vp.regularize else 0,
+                             vp.max_component_value, 0, l2, nb4,
+                             {"none": 0, "sorted": 1, "per_type": 2}[vp.material_coherence], sample_batch)
+        self.call("set_params", C.byref(p))
+        self.width, self.height = width, height
+
+    def read_film(self, out_hw3):
+        """framebuffer[py, px] (H, W, 3); the ABI writes the reference's (H, W) column-major RGB layout."""
+        buf = np.empty((self.width, self.height, 3), dtype=f32)     # column-major (H,W) == C-order (W,H)
+        self.call("read_film", _fp(buf))
+        out_hw3[...] = buf.transpose(1, 0, 2)
+
+    def read_accum(self):
+        n = self.width * self.height
+        rgb, w = np.empty((n, 3), dtype=f32), np.empty(n, dtype=f32)
+        self.call("read_accum", _fp(rgb), _fp(w))
+        return rgb, w
+
+
+class VolPath:
+    """volpath.jl:29-101.  Keyword-only like the reference: VolPath(samples=…, max_depth=…)."""
+
+    def __init__(self, *, max_depth=8, samples=64, russian_roulette_depth=3, regularize=True,
+                 material_coherence="none", max_component_value=10.0, filter=None, backend=None, sample_batch=1):
+        assert material_coherence in ("none", "sorted", "per_type"), \
+            "material_coherence must be :none, :sorted, :per_type"
+        self.max_depth, self.samples_per_pixel = int(max_depth), int(samples)
+        self.russian_roulette_depth, self.regularize = int(russian_roulette_depth), bool(regularize)
+        self.material_coherence, self.max_component_value = material_coherence, float(max_component_value)
+        self.filter = GaussianFilter() if filter is None else filter
+        self.filter_sampler_data = FilterSamplerData(self.filter)
+        self.backend = backend
+        self.sample_batch = int(sample_batch)
+        self.state = None          # (scene id, W, H, n_lights) the backend was prepared for
+
+    def _prepare(self, scene, film, camera):
+        w, h = film.resolution
+        s = scene._synced or scene.sync()
+        key = (id(s), w, h, len(s.lights))
+        if self.backend is None:
+            self.backend = Backend()
+        if self.state != key:
+            b = self.backend
+            b.upload_tables()
+            b.upload_scene(scene)
+            b.set_filter(self.filter_sampler_data)
+            b.set_params(self, w, h, self.sample_batch)
+            self.state = key
+        self.backend.set_camera(camera)
+
+    def clear(self):
+        """clear!(vp), volpath.jl:108-113"""
+        if self.state is not None:
+            self.backend.call("clear")
+
+    def render(self, scene, film, camera, count=1, read=True):
+        """render!(vp, scene, film, camera) — `count` sample passes (volpath.jl:445-636)."""
+        self._prepare(scene, film, camera)
+        first = film.iteration_index + 1
+        self.backend.call("render_samples", first, count)
+        film.iteration_index += count
+        if read:
+            self.backend.read_film(film.framebuffer)
+
+    def __call__(self, scene, film, camera):
+        """(vp::VolPath)(scene, film, camera), volpath.jl:655-670"""
+        film.iteration_index = 0
+        self._prepare(scene, film, camera)
+        self.clear()
+        self.render(scene, film, camera, count=self.samples_per_pixel)
+        return film.framebuffer
+
+    def close(self):
+        if self.backend is not None:
+            self.backend.close()

@@ -1,0 +1,242 @@
+"""The BASELINE.json configs restated as concrete synthetic scenes with the CURRENT
+reference API shape (Scene / push / sync, VolPath(samples=…, max_depth=…)).
+
+  cornell_smoke   test/volpath_integration.jl:8-95 (64x64, 4 spp, depth 4) — the reference's own smoke scene
+  c1_triangle     examples/single_triangle_test.jl:12-90
+  c1_spheres      examples/sphere_normals_test.jl:41-98
+  c2_cat          examples/cat_scene.jl:39-130 (cat.obj asset absent -> procedural closed stand-in mesh)
+  c3_many_lights  README.md:66-77 + 10 000 emissive triangles (analytic sky stand-in for the Hosek-Wilkie bake)
+  c4_cloud        examples/bomex_cloud_example.jl:78-161 with a procedural cumulus field (NanoVDB or Grid)
+  c5_instanced    instanced mixed-material field (triangle budget is a parameter; 50 M at full size)
+
+Each function returns (scene, camera_factory) where camera_factory(film) -> PerspectiveCamera.
+"""
+import numpy as np
+
+from . import host as H
+
+f32 = np.float32
+
+
+def _cam(eye, look, fov):
+    return lambda film: H.PerspectiveCamera(eye, look, film, fov=fov)
+
+
+def cornell_smoke():
+    white = H.MatteMaterial(Kd=(0.73, 0.73, 0.73))
+    red = H.MatteMaterial(Kd=(0.65, 0.05, 0.05))
+    green = H.MatteMaterial(Kd=(0.12, 0.45, 0.15))
+    glass = H.GlassMaterial(Kr=1.0, Kt=1.0, index=1.5)
+    fog = H.HomogeneousMedium(sigma_a=0.01, sigma_s=0.3, Le=0.0, g=0.3)
+    glass_fog = H.MediumInterface(glass, inside=fog, outside=None)
+    gold = H.ConductorMaterial(eta=(0.15557, 0.42415, 1.3831), k=(3.6024, 2.4721, 1.9155))
+    s = H.Scene()
+    half, box = 1.0, 2.0
+    s.push(H.rect3((-half, 0, -half), (box, 0.01, box)), white)
+    s.push(H.rect3((-half, 0, half - 0.01), (box, box, 0.01)), white)
+    s.push(H.rect3((-half, 0, -half), (0.01, box, box)), red)
+    s.push(H.rect3((half - 0.01, 0, -half), (0.01, box, box)), green)
+    s.push(H.uv_sphere((-0.4, 0.4, 0.0), 0.35, 32, 32), glass_fog)
+    s.push(H.uv_sphere((0.4, 0.35, 0.0), 0.3, 32, 32), gold)
+    # PointLight(position, i::RGBSpectrum) -> scale = 1 (src/lights/point.jl:26-28)
+    s.push(H.PointLight((15, 15, 15), (0.0, 1.8, 0.0), legacy_rgbspectrum=True, scale=1.0))
+    s.sync()
+    return s, _cam((0.0, 1.0, -3.5), (0.0, 1.0, 0.0), 40.0)
+
+
+def c1_triangle():
+    s = H.Scene()
+    tri = H.Mesh([(-1, -0.5, 0), (1, -0.5, 0), (0, 1, 0)], [(0, 1, 2)],
+                 normals=[(0, 0, 1), (0.7, 0, 0.714), (0, 0.7, 0.714)], uvs=[(0, 0), (1, 0), (0.5, 1)])
+    s.push(tri, H.MatteMaterial(Kd=(0.8, 0.8, 0.8)))
+    s.push(H.DirectionalLight((2, 2, 2), (0, 0, -1), legacy_rgbspectrum=True))
+    s.sync()
+    return s, _cam((0, 0, 3), (0, 0, 0), 50.0)
+
+
+def c1_spheres(tess=64):
+    s = H.Scene()
+    s.push(H.rect3((-5, -1, -5), (10, 0.1, 10)), H.MatteMaterial(Kd=(0.7, 0.7, 0.7)))
+    for x, kd in ((-1.5, (0.8, 0.2, 0.2)), (0.0, (0.2, 0.8, 0.2)), (1.5, (0.2, 0.2, 0.8))):
+        s.push(H.uv_sphere((x, 0.5, 0.0), 0.8, tess, tess), H.MatteMaterial(Kd=kd))
+    d = np.array([-1.0, -1.5, -0.5])
+    s.push(H.DirectionalLight((3, 3, 3), d / np.linalg.norm(d), legacy_rgbspectrum=True))
+    s.sync()
+    return s, _cam((0, 1.5, 4), (0, 0.5, 0), 40.0)
+
+
+def blob_mesh(center, radius, n=256, seed=3):
+    """Closed procedural stand-in for cat.obj: a sphere displaced by a few low-frequency harmonics."""
+    m = H.uv_sphere((0, 0, 0), 1.0, n, n)
+    p = m.positions.astype(np.float64)
+    rng = np.random.RandomState(seed)
+    disp = np.zeros(len(p))
+    for _ in range(6):
+        k = rng.randint(1, 5, size=3)
+        ph = rng.uniform(0, 2 * np.pi, size=3)
+        disp += 0.08 * np.sin(k[0] * p[:, 0] * 3 + ph[0]) * np.sin(k[1] * p[:, 1] * 3 + ph[1]) * np.sin(k[2] * p[:, 2] * 3 + ph[2])
+    p = p * (1.0 + disp)[:, None] * np.array([0.7, 1.0, 1.2])
+    pos = p * radius + np.asarray(center, dtype=np.float64)
+    # smooth normals from face normals
+    f = m.faces
+    fn = np.cross(pos[f[:, 1]] - pos[f[:, 0]], pos[f[:, 2]] - pos[f[:, 0]])
+    vn = np.zeros_like(pos)
+    for k in range(3):
+        np.add.at(vn, f[:, k], fn)
+    ln = np.linalg.norm(vn, axis=1, keepdims=True)
+    vn = np.where(ln > 0, vn / np.maximum(ln, 1e-30), m.normals)
+    return H.Mesh(pos, f, vn, m.uvs)
+
+
+def c2_cat(cat_tess=256, sphere_tess=64):
+    s = H.Scene()
+    s.push(H.PointLight((1, 1, 1), (3, 3, -1)))
+    s.push(H.PointLight((5, 5, 5), (-3, 2, 0)))
+    s.push(H.AmbientLight((0.5, 0.7, 1.0)))
+    s.push(blob_mesh((0.0, -0.9, 1.5), 0.6, cat_tess), H.MatteMaterial(Kd=(0.8, 0.6, 0.4)))
+    s.push(H.rect3((-5, -1.5, -2), (10, 0.01, 10)), H.MatteMaterial(Kd=(0.3, 0.5, 0.3)))
+    s.push(H.rect3((-5, -1.5, 8), (10, 5, 0.01)), H.ConductorMaterial(reflectance=(0.8, 0.6, 0.5), roughness=0.05))
+    s.push(H.rect3((-5, -1.5, -2), (0.01, 5, 10)), H.MatteMaterial(Kd=(0.7, 0.7, 0.8)))
+    s.push(H.uv_sphere((-2, -1.5 + 0.8, 2), 0.8, sphere_tess, sphere_tess), H.ConductorMaterial(reflectance=(0.9, 0.9, 0.9), roughness=0.02))
+    s.push(H.uv_sphere((2, -1.5 + 0.6, 1), 0.6, sphere_tess, sphere_tess), H.ConductorMaterial(reflectance=(0.3, 0.6, 0.9), roughness=0.3))
+    glass = H.GlassMaterial(Kr=(0.98, 1.0, 0.98), Kt=(0.98, 1.0, 0.98), index=1.5)
+    s.push(H.uv_sphere((-0.8, -1.5 + 0.5, 0.5), 0.5, sphere_tess, sphere_tess), glass)
+    s.push(H.uv_sphere((0.8, -1.5 + 0.4, 0.3), 0.4, sphere_tess, sphere_tess), glass)
+    s.sync()
+    return s, _cam((0, -0.9, -2.5), (0, -0.9, 10), 45.0)
+
+
+def analytic_sky(res=512, sun_dir=(1, 2, 9), turbidity=3.0):
+    """Stand-in for sunsky_to_envlight (src/lights/sun_sky.jl:358-434, Hosek-Wilkie bake on the Julia host):
+    a smooth analytic sky in the same 512^2 equal-area layout.  Only the light's data differs from the
+    reference config; the device code path (Distribution2D sampling, equal-area mapping, illuminant uplift) is
+    identical."""
+    sd = np.asarray(sun_dir, dtype=np.float64)
+    sd = sd / np.linalg.norm(sd)
+    u = (np.arange(res) + 0.5) / res
+    U, V = np.meshgrid(u, u, indexing="xy")          # data[v, u]
+    # equal-area square -> sphere (same mapping as environment_map.jl:133-160), float64 host code
+    uu, vv = 2 * U - 1, 2 * V - 1
+    up, vp = np.abs(uu), np.abs(vv)
+    sdist = 1 - (up + vp)
+    r = 1 - np.abs(sdist)
+    phi = np.where(r == 0, 1.0, (vp - up) / np.where(r == 0, 1, r) + 1.0) * np.pi / 4
+    z = np.copysign(1 - r * r, sdist)
+    cx, sy = np.copysign(np.cos(phi), uu), np.copysign(np.sin(phi), vv)
+    rc = r * np.sqrt(2 - r * r)
+    d = np.stack([cx * rc, sy * rc, z], -1)
+    cos_g = np.clip(d @ sd, -1, 1)
+    up_c = np.clip(d[..., 2], 0, 1)
+    zenith = np.array([0.25, 0.45, 0.95])
+    horizon = np.array([0.85, 0.9, 1.0])
+    sky = horizon + (zenith - horizon) * (up_c[..., None] ** 0.5)
+    glow = (0.5 * (1 + cos_g)) ** (64 / turbidity)
+    sky = sky * (0.6 + 1.4 * glow[..., None]) + np.array([1.0, 0.85, 0.6]) * (glow[..., None] ** 8) * 4
+    sky = np.where(d[..., 2:3] < 0, sky * 0.05, sky)     # ground_enabled=false: dark lower hemisphere
+    return sky.astype(f32), sd
+
+
+def c3_many_lights(n_emitters=10000, sphere_tess=128, seed=1234):
+    s = H.Scene()
+    sky, sd = analytic_sky(512)
+    s.push(H.EnvironmentLight(H.EnvironmentMap(sky), scale=tuple([float(f32(1.0) / f32(10567.0))] * 3)))
+    s.push(H.SunLight((5.0, 4.75, 4.25), -sd))
+    s.push(H.uv_sphere((0, 0, 0), 1.0, sphere_tess, sphere_tess), H.GlassMaterial(index=1.5))
+    s.push(H.rect3((-2, -2, -1), (4, 4, 0.01)), H.Gold(roughness=0.01))
+    rng = np.random.RandomState(seed)
+    c = np.stack([rng.uniform(-2, 2, n_emitters), rng.uniform(-2, 2, n_emitters), rng.uniform(0, 2, n_emitters)], -1)
+    nrm = rng.normal(size=(n_emitters, 3))
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    t = np.cross(nrm, rng.normal(size=(n_emitters, 3)))
+    t /= np.linalg.norm(t, axis=1, keepdims=True)
+    b = np.cross(nrm, t)
+    e = 0.02
+    Le = rng.uniform(5, 50, size=(n_emitters, 3))
+    dark = H.MatteMaterial(Kd=(0.0, 0.0, 0.0))
+    # one mesh per emitter colour bucket would be slow to flatten in Python: push in groups of equal Le (quantised)
+    groups = 16
+    q = np.floor((Le - 5) / 45 * groups).clip(0, groups - 1).astype(int)
+    key = q[:, 0] * groups * groups + q[:, 1] * groups + q[:, 2]
+    for k in np.unique(key):
+        idx = np.nonzero(key == k)[0]
+        P = np.concatenate([c[idx] - 0.5 * e * t[idx] - 0.289 * e * b[idx], c[idx] + 0.5 * e * t[idx] - 0.289 * e * b[idx],
+                            c[idx] + 0.577 * e * b[idx]], 0)
+        n = len(idx)
+        F = np.stack([np.arange(n), np.arange(n) + n, np.arange(n) + 2 * n], -1)
+        le = tuple(float(v) for v in (5 + (np.array([k // (groups * groups), (k // groups) % groups, k % groups]) + 0.5) * 45 / groups))
+        s.push(H.Mesh(P, F), H.MediumInterface(dark, emission=(le, 1.0, True)))
+    s.sync()
+    return s, _cam((0, -6.0, 2.5), (0, 0, 0.2), 40.0)
+
+
+def cumulus_field(shape=(256, 256, 128), occupancy=0.03, seed=7, max_extinction=620.0):
+    """Procedural BOMEX-like cloud field: thresholded fBm, scaled so max extinction ~ 620 (bomex_cloud_example.jl:50)."""
+    rng = np.random.RandomState(seed)
+    nx, ny, nz = shape
+    field = np.zeros(shape, dtype=np.float64)
+    amp = 1.0
+    for octave in range(5):
+        cells = 2 ** (octave + 2)
+        coarse = rng.normal(size=(cells + 1, cells + 1, max(2, cells // 2) + 1))
+        xs = np.linspace(0, cells, nx, endpoint=False); ys = np.linspace(0, cells, ny, endpoint=False)
+        zs = np.linspace(0, max(2, cells // 2), nz, endpoint=False)
+        xi, yi, zi = xs.astype(int), ys.astype(int), zs.astype(int)
+        fx, fy, fz = (xs - xi)[:, None, None], (ys - yi)[None, :, None], (zs - zi)[None, None, :]
+        def g(a, b, c):
+            return coarse[np.ix_(xi + a, yi + b, zi + c)]
+        v = ((g(0, 0, 0) * (1 - fx) + g(1, 0, 0) * fx) * (1 - fy) + (g(0, 1, 0) * (1 - fx) + g(1, 1, 0) * fx) * fy) * (1 - fz) + \
+            ((g(0, 0, 1) * (1 - fx) + g(1, 0, 1) * fx) * (1 - fy) + (g(0, 1, 1) * (1 - fx) + g(1, 1, 1) * fx) * fy) * fz
+        field += amp * v
+        amp *= 0.5
+    zprof = np.exp(-((np.linspace(0, 1, nz) - 0.45) / 0.25) ** 2)[None, None, :]
+    field = field * zprof
+    thr = np.quantile(field, 1 - occupancy)
+    dens = np.clip(field - thr, 0, None)
+    dens = dens / dens.max() * max_extinction
+    return dens.astype(f32)
+
+
+def c4_cloud(shape=(256, 256, 128), medium_kind="nanovdb", majorant_res=(64, 64, 64)):
+    s = H.Scene()
+    dens = cumulus_field(shape)
+    lo, hi = (-0.6, 0.3, -0.6), (0.6, 1.5, 0.6)
+    if medium_kind == "nanovdb":
+        med = H.NanoVDBMedium(dens, bounds=(lo, hi), sigma_a=0.0, sigma_s=1.0, g=0.877, majorant_res=majorant_res)
+    else:
+        med = H.GridMedium(dens, sigma_a=0.0, sigma_s=1.0, g=0.877, bounds=(lo, hi), majorant_res=majorant_res)
+    boundary = H.MediumInterface(H.GlassMaterial(Kr=0.0, Kt=1.0, index=1.0), inside=med, outside=None)
+    s.push(H.rect3(lo, tuple(h - l for l, h in zip(lo, hi))), boundary)
+    s.push(H.rect3((-5, -0.01, -5), (10, 0.01, 10)), H.MatteMaterial(Kd=(0.4, 0.4, 0.4)))
+    s.push(H.rect3((-3, 0, -3), (0.01, 4, 6)), H.MatteMaterial(Kd=(0.5, 0.5, 0.55)))
+    s.push(H.rect3((3, 0, -3), (0.01, 4, 6)), H.MatteMaterial(Kd=(0.5, 0.5, 0.55)))
+    s.push(H.AmbientLight((0.03, 0.07, 0.23)))
+    s.push(H.DirectionalLight((2.6, 2.5, 2.3), (-0.5826, -0.7660, -0.2717)))
+    s.sync()
+    return s, _cam((0, 1, -3.5), (0, 0.9, 0), 40.0)
+
+
+def c5_instanced(n_instances=1000, base_tess=160, seed=11):
+    """n_instances copies (jittered grid, random rotations) of a base mesh with (base_tess-1)^2*2 triangles;
+    materials round-robin over the six in-scope types.  Full size: 1000 x ~50 000 = 50 M triangles."""
+    s = H.Scene()
+    sky, sd = analytic_sky(512)
+    s.push(H.EnvironmentLight(H.EnvironmentMap(sky), scale=tuple([float(f32(1.0) / f32(10567.0))] * 3)))
+    s.push(H.SunLight((5.0, 4.75, 4.25), -sd))
+    mats = [H.MatteMaterial(Kd=(0.7, 0.5, 0.3)), H.GlassMaterial(index=1.5), H.Gold(roughness=0.05),
+            H.CoatedDiffuseMaterial(reflectance=(0.4, 0.45, 0.35), roughness=0.1),
+            H.ThinDielectricMaterial(eta=1.5), H.DiffuseTransmissionMaterial(reflectance=(0.4, 0.3, 0.2), transmittance=(0.3, 0.4, 0.3))]
+    base = blob_mesh((0, 0, 0), 0.35, base_tess, seed=5)
+    rng = np.random.RandomState(seed)
+    side = int(np.ceil(np.sqrt(n_instances)))
+    s.push(H.rect3((-side * 0.5 - 1, -0.45, -side * 0.5 - 1), (side + 2, 0.05, side + 2)), H.MatteMaterial(Kd=(0.5, 0.5, 0.5)))
+    for i in range(n_instances):
+        gx, gz = i % side, i // side
+        ang = rng.uniform(0, 2 * np.pi)
+        ax = rng.normal(size=3); ax /= np.linalg.norm(ax)
+        R = np.eye(4)
+        R[:3, :3] = H.rotation_matrix(np.degrees(ang), ax).astype(np.float64)
+        Tm = np.eye(4)
+        Tm[:3, 3] = (gx - side / 2 + rng.uniform(-0.1, 0.1), rng.uniform(0.0, 0.3), gz - side / 2 + rng.uniform(-0.1, 0.1))
+        s.push(base, mats[i % len(mats)], transform=Tm @ R)
+    s.sync()
+    return s, _cam((0, side * 0.35, -side * 0.75), (0, 0, 0), 40.0)

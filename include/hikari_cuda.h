@@ -1,0 +1,333 @@
+/*
+ * hikari_cuda.h — C ABI of libhikari_cuda.so, the sm_100a back end of Hikari.jl's VolPath
+ * wavefront integrator.
+ *
+ * The reference has no FFI seam for integrators: the seam is Julia multiple dispatch on
+ *   render!(vp::VolPath, scene, film, camera)          src/integrators/volpath/volpath.jl:445-636
+ *   (vp::VolPath)(scene, film, camera)                 src/integrators/volpath/volpath.jl:655-670
+ *   clear!(vp::VolPath)                                src/integrators/volpath/volpath.jl:108-113
+ * A Julia shim overloads those methods and ccalls the entry points below.
+ * Every entry point cites the reference interface it replaces.
+ *
+ * Conventions
+ *  - all functions return 0 on success, a negative HK_ERR_* code otherwise; hk_last_error()
+ *    gives a human-readable message for the last failure on that context.
+ *  - every pointer argument is a HOST pointer borrowed for the duration of the call unless the
+ *    name ends in _dev.  The library owns all device memory behind the opaque HkContext.
+ *  - all multi-dimensional arrays are dense C (row-major) arrays with the documented shape; all
+ *    indices stored INSIDE arrays keep the reference's 1-based convention (0 = "none").
+ *  - matrices are 4x4 row-major (m[r*4+c]); points transform as M*(x,y,z,1) with a divide by w
+ *    when w != 1, vectors by the upper 3x3 (Raycore.Transformation semantics).
+ *  - a context is bound to one CUDA device and is not thread-safe; drive one context per GPU.
+ */
+#ifndef HIKARI_CUDA_H
+#define HIKARI_CUDA_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HK_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------------------------ */
+#define HK_OK                 0
+#define HK_ERR_INVALID       -1   /* bad argument / missing prerequisite upload            */
+#define HK_ERR_CUDA          -2   /* CUDA runtime error, see hk_last_error                */
+#define HK_ERR_NO_DEVICE     -3   /* no usable CUDA device: there is NO CPU fallback      */
+#define HK_ERR_UNSUPPORTED   -4   /* feature outside the implemented hot-path scope       */
+#define HK_ERR_OOM           -5
+
+typedef struct HkContext HkContext;
+
+/* ---- constant tables ----------------------------------------------------------------------
+ * replaces: SobolRNG upload (src/sampler/sobol.jl:370-379), CIEXYZTable (src/spectral/color.jl:28-32),
+ * D65 table (src/spectral/uplift.jl:412-429) and RGBToSpectrumTable (src/spectral/rgb2spec.jl:71-75)
+ * allocation in VolPathState (src/integrators/volpath/volpath-state.jl:98-181).               */
+typedef struct HkTables {
+    const uint32_t* sobol_matrices;   /* [1024*52]                                            */
+    const float*    cie_x;            /* [471] 360..830 nm, 1 nm                              */
+    const float*    cie_y;            /* [471]                                                */
+    const float*    cie_z;            /* [471]                                                */
+    const float*    d65;              /* [107] 300..830 nm, 5 nm                              */
+    int32_t         rgb2spec_res;     /* 64                                                   */
+    const float*    rgb2spec_scale;   /* [res]                                                */
+    const float*    rgb2spec_coeffs;  /* [3][res][res][res][3] = [coef][x][y][z][maxc] i.e. the
+                                         raw memory of the Julia Array{Float32,5}(3,res,res,res,3)
+                                         indexed [maxc, z, y, x, coef] (column-major)          */
+} HkTables;
+
+/* ---- geometry -----------------------------------------------------------------------------
+ * replaces: scene.accel (Raycore TLAS) as consumed by Raycore.closest_hit at
+ * src/integrators/volpath/intersection.jl:200,225,323,703 and the primitive fields read at
+ * intersection.jl:14-16,30-32,86-88,130-132 (vertices/normals/tangents/uv/metadata).
+ * World-space triangle soup; the global primitive id is the triangle's index here (instance-major,
+ * then face order) and is what hk_trace_closest reports.                                      */
+typedef struct HkGeometry {
+    const float*    positions;   /* [n_verts][3]                                              */
+    const float*    normals;     /* [n_verts][3] or NULL; NaN x-component = "no normal"        */
+    const float*    tangents;    /* [n_verts][3] or NULL; NaN x-component = "no tangent"       */
+    const float*    uvs;         /* [n_verts][2] or NULL (treated as 0)                        */
+    const uint32_t* indices;     /* [n_tris][3]  0-based vertex indices                        */
+    const uint32_t* tri_meta;    /* [n_tris][3]  TriangleMeta (src/scene.jl:11-15):
+                                    medium_interface_idx (1-based), primitive_index (1-based face
+                                    index within its mesh), arealight_flat_idx (0 = none)       */
+    uint32_t        n_verts;
+    uint32_t        n_tris;
+} HkGeometry;
+
+/* ---- materials ----------------------------------------------------------------------------
+ * replaces: scene.materials (MultiTypeSet) + scene.media_interfaces (src/scene.jl:21-28,
+ * src/materials/medium-interface.jl:78-82).  Only constant-valued parameters are in scope this
+ * round (TextureRef parameters: SURVEY §8f item 2).                                            */
+#define HK_MAT_MATTE                1   /* src/materials/spectral-eval.jl:42-101, 371-397      */
+#define HK_MAT_MIRROR               2   /* :108-132                                            */
+#define HK_MAT_GLASS                3   /* :140-198, 407-413                                   */
+#define HK_MAT_CONDUCTOR            4   /* :223-318, 421-488                                   */
+#define HK_MAT_COATED_DIFFUSE       5   /* :1232-1937                                          */
+#define HK_MAT_THIN_DIELECTRIC      6   /* :1975-2051                                          */
+#define HK_MAT_DIFFUSE_TRANSMISSION 7   /* :2083-2218                                          */
+
+#define HK_MATFLAG_REMAP_ROUGHNESS  1u
+#define HK_MATFLAG_SPECTRAL_ETA_K   2u  /* conductor eta/k are piecewise-linear spectra (ids in spec[]) */
+
+typedef struct HkMaterial {
+    int32_t  type;
+    uint32_t flags;
+    float    rgb0[3];   /* Matte Kd | Mirror Kr | Glass Kr | Conductor eta | Coated reflectance | DiffTrans reflectance */
+    float    rgb1[3];   /* Glass Kt | Conductor k | Coated albedo | DiffTrans transmittance                            */
+    float    f[8];      /* Matte: f0=sigma. Glass: f0=index. Conductor: f0=roughness.
+                           ThinDielectric: f0=eta. DiffuseTransmission: f0=scale.
+                           CoatedDiffuse: f0=u_roughness f1=v_roughness f2=thickness f3=eta f4=g       */
+    int32_t  spec[2];   /* 1-based ids into the uploaded piecewise-linear spectra (eta, k); 0 = unused  */
+    int32_t  ival[2];   /* CoatedDiffuse: ival0=max_depth ival1=n_samples                               */
+} HkMaterial;
+
+typedef struct HkMediumInterface {   /* MediumInterfaceIdx, src/materials/medium-interface.jl:78-82 */
+    uint32_t material;  /* 1-based index into materials                                          */
+    uint32_t inside;    /* 1-based medium index, 0 = vacuum                                      */
+    uint32_t outside;
+} HkMediumInterface;
+
+/* piecewise-linear spectra (src/spectral/piecewise-linear.jl:4-7): spectrum i (1-based) occupies
+ * lambdas/values[offsets[i-1] .. offsets[i])                                                     */
+typedef struct HkSpectra {
+    const float*    lambdas;
+    const float*    values;
+    const uint32_t* offsets;   /* [n_spectra+1] */
+    uint32_t        n_spectra;
+} HkSpectra;
+
+/* ---- lights -------------------------------------------------------------------------------
+ * replaces: scene.lights (MultiTypeSet) in FLAT index order (src/lights/light-sampler.jl:289-329)
+ * and the BVHLightSampler arrays (src/lights/bvh-light-sampler.jl:269-275).                     */
+#define HK_LIGHT_POINT        1   /* src/integrators/physical-wavefront/lights.jl:39-59   */
+#define HK_LIGHT_SPOT         2   /* :66-105                                              */
+#define HK_LIGHT_DIRECTIONAL  3   /* :112-128                                             */
+#define HK_LIGHT_SUN          4   /* :135-150                                             */
+#define HK_LIGHT_ENVIRONMENT  5   /* :158-189, 408-419                                    */
+#define HK_LIGHT_AMBIENT      6   /* :199-221, 427-433                                    */
+#define HK_LIGHT_DIFFUSE_AREA 7   /* :235-290, src/lights/diffuse-area.jl:54-81           */
+
+#define HK_SPECTRUM_RGB        0  /* RGBSpectrum: uplifted at evaluation time                     */
+#define HK_SPECTRUM_ILLUMINANT 1  /* RGBIlluminantSpectrum: poly + scale baked (rgb2spec.jl:331-334) */
+
+typedef struct HkLight {
+    int32_t type;
+    int32_t spectrum_kind;
+    float   scale;              /* light.scale (photometric normalisation); area light: scale   */
+    float   rgb[3];             /* light.i.c (HK_SPECTRUM_RGB) or area light Le                  */
+    float   poly[3];            /* HK_SPECTRUM_ILLUMINANT: c0,c1,c2                              */
+    float   illum_scale;        /* HK_SPECTRUM_ILLUMINANT: s.scale                               */
+    float   position[3];        /* point / spot                                                  */
+    float   direction[3];       /* directional / sun: normalised travel direction                */
+    float   cos_total_width;    /* spot                                                          */
+    float   cos_falloff_start;  /* spot                                                          */
+    float   world_to_light[16]; /* spot                                                          */
+    float   v[9];               /* area light triangle vertices                                  */
+    float   normal[3];          /* area light geometric normal                                   */
+    float   area;
+    float   uv[6];
+    int32_t two_sided;
+    int32_t env_map;            /* environment: 1-based id of the uploaded env map               */
+} HkLight;
+
+typedef struct HkEnvMap {   /* src/textures/environment_map.jl:9-45 + Distribution2D sampling.jl:179-193 */
+    const float* rgb;                   /* [h][w][3]                                             */
+    int32_t      w, h;
+    float        rotation[9];           /* Mat3f column-major as stored by Julia                 */
+    float        scale_rgb[3];          /* EnvironmentLight.scale (src/lights/environment.jl:10) */
+    const float* conditional_func;      /* [nv][nu]                                              */
+    const float* conditional_cdf;       /* [nv][nu+1]                                            */
+    const float* conditional_func_int;  /* [nv]                                                  */
+    const float* marginal_func;         /* [nv]                                                  */
+    const float* marginal_cdf;          /* [nv+1]                                                */
+    float        marginal_func_int;
+    int32_t      nu, nv;
+} HkEnvMap;
+
+typedef struct HkLightBVHNode {  /* LightBVHNode, src/lights/bvh-light-sampler.jl:26-38 */
+    float    bounds_min[3];
+    float    bounds_max[3];
+    float    w[3];
+    float    phi;
+    float    cos_theta_o;
+    float    cos_theta_e;
+    uint32_t two_sided;
+    uint32_t child1_or_light_idx;   /* interior: 1-based index of child1 (child0 = self+1); leaf: flat light idx */
+    uint32_t is_leaf;
+    uint32_t _pad;
+} HkLightBVHNode;
+
+typedef struct HkLightSampler {
+    const HkLightBVHNode* nodes;            uint32_t n_nodes;
+    const uint32_t* light_to_bit_trail;     /* [n_lights], 0xFFFFFFFF = infinite-light sentinel   */
+    const int32_t*  infinite_light_indices; uint32_t n_infinite;
+    uint32_t        n_bvh_lights;
+} HkLightSampler;
+
+/* ---- media (src/integrators/volpath/media.jl, nanovdb.jl) ----------------------------------- */
+#define HK_MEDIUM_HOMOGENEOUS 1   /* media.jl:735-793   */
+#define HK_MEDIUM_GRID        2   /* media.jl:800-1000, 1544-1623 */
+#define HK_MEDIUM_NANOVDB     3   /* nanovdb.jl:153-191, 315-543   */
+
+typedef struct HkMedium {
+    int32_t  type;
+    float    sigma_a_rgb[3];
+    float    sigma_s_rgb[3];
+    float    Le_rgb[3];
+    float    scale;              /* density scale                                           */
+    float    g;                  /* Henyey-Greenstein asymmetry                              */
+    float    bounds_min[3];
+    float    bounds_max[3];
+    float    render_from_medium[16];
+    float    medium_from_render[16];
+    int32_t  density_res[3];     /* Grid: nx,ny,nz                                          */
+    const float* density;        /* Grid: [nz][ny][nx]                                      */
+    int32_t  majorant_res[3];
+    const float* majorant;       /* [rz][ry][rx] max density per coarse voxel               */
+    const uint8_t* nanovdb_buf;  /* NanoVDB: raw grid buffer                                */
+    uint64_t nanovdb_bytes;
+    float    nanovdb_inv_mat[9]; /* index-from-world 3x3, row-major                         */
+    float    nanovdb_vec[3];     /* translation                                             */
+    uint64_t nanovdb_root_offset, nanovdb_upper_offset, nanovdb_lower_offset, nanovdb_leaf_offset;
+    int32_t  nanovdb_root_tiles, nanovdb_upper_count, nanovdb_lower_count, nanovdb_leaf_count;
+} HkMedium;
+
+/* ---- camera, filter, params ---------------------------------------------------------------- */
+typedef struct HkCamera {       /* PerspectiveCamera, src/camera/perspective.jl:1-80 */
+    float raster_to_camera[16];
+    float camera_to_world[16];
+    float lens_radius;
+    float focal_distance;
+    float shutter_open;
+    float shutter_close;
+    float dx_camera[3];
+    float dy_camera[3];
+} HkCamera;
+
+typedef struct HkFilter {       /* GPUFilterParams + GPUFilterSamplerData, src/filter.jl:574-725 */
+    int32_t      type;          /* 1 Box, 2 Triangle, 3 Gaussian, 4 Mitchell, 5 Lanczos          */
+    float        radius[2];
+    int32_t      nx, ny;        /* tabulated sampler (types 3..5); 0 for Box/Triangle            */
+    const float* func;              /* [ny][nx]                                                  */
+    const float* marginal_cdf;      /* [ny+1]                                                    */
+    const float* marginal_func;     /* [ny]                                                      */
+    const float* conditional_cdf;   /* [ny][nx+1]                                                */
+    float        domain_min[2];
+    float        domain_max[2];
+    float        func_integral;
+} HkFilter;
+
+typedef struct HkRenderParams {  /* VolPath fields, src/integrators/volpath/volpath.jl:29-42,75-101 */
+    int32_t  width, height;
+    int32_t  max_depth;
+    int32_t  samples_per_pixel;      /* vp.samples_per_pixel (only used for texture footprints)   */
+    int32_t  regularize;
+    float    max_component_value;
+    uint32_t sampler_seed;           /* 0 in the reference (volpath.jl:480)                       */
+    int32_t  sobol_log2_spp;         /* compute_zsobol_params(max(spp,4096),W,H) sobol.jl:317-323 */
+    int32_t  sobol_n_base4_digits;
+    int32_t  material_coherence;     /* 0 :none, 1 :sorted, 2 :per_type — all map to per-type queues */
+    int32_t  sample_batch;           /* library extension: samples in flight per pass (>=1)       */
+} HkRenderParams;
+
+typedef struct HkStats {
+    uint64_t rays_traced;        /* closest-hit queries: primary + continuation + every shadow segment */
+    uint64_t samples_rendered;   /* pixel samples accumulated                                          */
+    uint64_t queue_overflows;    /* always 0: queues are sized to the slot count                       */
+    uint64_t bvh_nodes;          /* number of 80-byte wide-BVH nodes                                   */
+    uint64_t bvh_bytes;          /* node + triangle bytes resident                                     */
+    uint64_t kernel_launches;    /* kernels launched by this context so far                           */
+    float    last_render_ms;     /* device time of the last hk_render_samples (CUDA events)            */
+    float    last_trace_ms;      /* device time of the last hk_trace_closest kernel                    */
+} HkStats;
+
+/* ---- lifecycle ---------------------------------------------------------------------------- */
+int32_t hk_abi_version(void);
+/* replaces: VolPathState(backend, ...) allocation, volpath-state.jl:98-181 */
+int32_t hk_create(int32_t device, HkContext** out_ctx);
+/* replaces: cleanup!(state) volpath-state.jl:238-273 / Base.close(::Integrator) Hikari.jl:47 */
+int32_t hk_destroy(HkContext* ctx);
+const char* hk_last_error(HkContext* ctx);
+
+/* ---- scene upload (replaces Adapt.adapt(backend, scene), volpath.jl:455-461) ---------------- */
+int32_t hk_upload_tables(HkContext* ctx, const HkTables* tables);
+int32_t hk_upload_geometry(HkContext* ctx, const HkGeometry* geom);
+int32_t hk_upload_spectra(HkContext* ctx, const HkSpectra* spectra);
+int32_t hk_upload_materials(HkContext* ctx, const HkMaterial* materials, uint32_t n_materials,
+                            const HkMediumInterface* interfaces, uint32_t n_interfaces);
+int32_t hk_upload_envmaps(HkContext* ctx, const HkEnvMap* maps, uint32_t n_maps);
+int32_t hk_upload_lights(HkContext* ctx, const HkLight* lights, uint32_t n_lights,
+                         const HkLightSampler* sampler);
+int32_t hk_upload_media(HkContext* ctx, const HkMedium* media, uint32_t n_media);
+int32_t hk_set_camera(HkContext* ctx, const HkCamera* camera);
+int32_t hk_set_filter(HkContext* ctx, const HkFilter* filter);
+/* replaces: VolPath(...) fields + state (re)allocation on resize, volpath.jl:466-482 */
+int32_t hk_set_params(HkContext* ctx, const HkRenderParams* params);
+
+/* ---- rendering ---------------------------------------------------------------------------- */
+/* replaces: clear!(vp) volpath.jl:108-113 */
+int32_t hk_clear(HkContext* ctx);
+/* replaces: `count` consecutive render!(vp, scene, film, camera) calls (volpath.jl:445-636) for
+ * sample indices first_sample_idx .. first_sample_idx+count-1 (1-based, = film.iteration_index+1). */
+int32_t hk_render_samples(HkContext* ctx, int32_t first_sample_idx, int32_t count);
+/* same, strided: sample indices first, first+stride, ... (count of them) — the multi-GPU partition */
+int32_t hk_render_samples_strided(HkContext* ctx, int32_t first_sample_idx, int32_t stride, int32_t count);
+/* replaces: vp_finalize_film_kernel! + host read of film.framebuffer (volpath.jl:384-417).
+ * Writes RGB{Float32} in the reference's (H, W) column-major layout: out[((px-1)*H + (py-1))*3 + c]. */
+int32_t hk_read_film(HkContext* ctx, float* out_rgb_hw_colmajor);
+/* raw accumulators for the multi-GPU film reduce (pixel_rgb ‖ pixel_weight_sum, volpath-state.jl):
+ * device pointer to [n*3] rgb sums followed by [n] weight sums, valid until the next hk_set_params. */
+int32_t hk_film_accum_dev(HkContext* ctx, float** out_accum_dev, uint64_t* out_count);
+/* host copies of the accumulators (rgb [n][3], weight [n]) */
+int32_t hk_read_accum(HkContext* ctx, float* out_rgb_sum, float* out_weight_sum);
+int32_t hk_write_accum(HkContext* ctx, const float* rgb_sum, const float* weight_sum);
+
+/* ---- stand-alone traversal (parity + roofline measurement) --------------------------------
+ * replaces: Raycore.closest_hit(accel, ray) (call sites intersection.jl:200,225,323,703).
+ * rays: [n][8] = o.xyz, d.xyz, t_max, time.  hits: [n][4] = t (f32), prim (u32 bits, 1-based global
+ * primitive id, 0 = miss), b1, b2 (barycentrics of v1, v2; b0 = 1-b1-b2).
+ * Tie-break: smallest t wins; equal t -> smallest primitive id.                */
+int32_t hk_trace_closest(HkContext* ctx, const float* rays, uint64_t n, float* hits);
+/* same on device-resident buffers (timed path of bench.py); repeat>1 re-runs the kernel */
+int32_t hk_trace_closest_dev(HkContext* ctx, const float* rays_dev, uint64_t n, float* hits_dev, int32_t repeat);
+/* any-hit: occluded[i] = 1 if any triangle has 0 < t < t_max */
+int32_t hk_trace_any(HkContext* ctx, const float* rays, uint64_t n, uint8_t* occluded);
+
+int32_t hk_stats(HkContext* ctx, HkStats* out);
+int32_t hk_synchronize(HkContext* ctx);
+
+/* device memory helpers so a host without a CUDA binding (the Python mirror, tests) can keep
+ * inputs resident in HBM across timed calls */
+int32_t hk_dev_alloc(HkContext* ctx, uint64_t bytes, void** out_dev);
+int32_t hk_dev_free(HkContext* ctx, void* dev);
+int32_t hk_dev_upload(HkContext* ctx, void* dst_dev, const void* src_host, uint64_t bytes);
+int32_t hk_dev_download(HkContext* ctx, void* dst_host, const void* src_dev, uint64_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HIKARI_CUDA_H */

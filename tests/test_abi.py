@@ -1,0 +1,52 @@
+"""CPU tests: the C-ABI library loads without a GPU and exports every symbol include/*.h declares; compute
+entry points fail loudly (no CPU fallback) when no CUDA device is usable."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from hikari_jl_b200 import _abi as A
+from util import gpu_available
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    names = set()
+    for h in os.listdir(os.path.join(ROOT, "include")):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(hk_[a-z0-9_]+)\s*\(", src))
+    return sorted(names)
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = A.load_library()
+    syms = declared_symbols()
+    assert len(syms) >= 40
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, f"declared in include/*.h but not exported: {missing}"
+    for s in A.HK_SYMBOLS:
+        assert s in syms, f"{s} listed in _abi.HK_SYMBOLS but not declared in the header"
+    assert lib.hk_abi_version() == 1
+
+
+def test_struct_sizes_match_header_layout():
+    # sizes computed from the header by hand; a drift between ctypes and C would corrupt every upload
+    assert C.sizeof(A.HkMaterial) == 4 + 4 + 12 + 12 + 32 + 8 + 8
+    assert C.sizeof(A.HkLightBVHNode) == 64
+    assert C.sizeof(A.HkMediumInterface) == 12
+    assert C.sizeof(A.HkRenderParams) == 44
+    assert C.sizeof(A.HkLight) == 4 * (2 + 1 + 3 + 3 + 1 + 3 + 3 + 2 + 16 + 9 + 3 + 1 + 6 + 2)
+
+
+@pytest.mark.skipif(gpu_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback_without_a_device():
+    lib = A.load_library()
+    ctx = C.c_void_p()
+    rc = lib.hk_create(0, C.byref(ctx))
+    assert rc == -3, "hk_create must fail with HK_ERR_NO_DEVICE when no CUDA device is present"
+    from hikari_jl_b200.host import Backend
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Backend()

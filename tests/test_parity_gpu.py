@@ -1,0 +1,346 @@
+"""GPU parity tests (run on the B200 box): every stage of the CUDA path vs the CPU oracle on identical inputs,
+through the C ABI.  Bit-exact for integer / index work; stated tolerances for floating point."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from hikari_jl_b200 import _abi as A
+from hikari_jl_b200 import host as H
+from hikari_jl_b200 import scenes
+from util import Pair, fp, f32, image_close, random_rays, trace_both
+
+pytestmark = pytest.mark.gpu
+U64P = C.POINTER(C.c_uint64)
+
+
+@pytest.fixture(scope="module")
+def bare():
+    p = Pair()
+    yield p
+    p.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# integer-exact primitives
+# ---------------------------------------------------------------------------------------------------------
+def test_sobol_bit_exact(bare):
+    rng = np.random.RandomState(0)
+    n = 20000
+    q = np.stack([rng.randint(1, 3841, n), rng.randint(1, 2161, n), rng.randint(1, 4097, n), rng.randint(0, 100, n)], -1).astype(np.int32)
+    q[:8] = [[1, 1, 1, 1], [3840, 2160, 4096, 90], [1, 1, 4096, 0], [512, 512, 64, 13], [1920, 1080, 256, 6], [7, 9, 1, 89], [2, 1, 2, 3], [1, 2, 3, 4]]
+    for (l2, nb4) in ((12, 18), (12, 15), (5, 12)):
+        a1 = np.zeros(n, f32); a2 = np.zeros((n, 2), f32); b1 = np.zeros(n, f32); b2 = np.zeros((n, 2), f32)
+        assert bare.lib.hk_test_sobol(bare.cu.ctx, q.ctypes.data_as(A.c_i32p), n, l2, nb4, 0, fp(a1), fp(a2)) == 0
+        bare.olib.ok_test_sobol(bare.ok.ctx, q.ctypes.data_as(A.c_i32p), n, l2, nb4, 0, fp(b1), fp(b2))
+        assert np.array_equal(a1.view(np.uint32), b1.view(np.uint32))
+        assert np.array_equal(a2.view(np.uint32), b2.view(np.uint32))
+        assert (a1 >= 0).all() and (a1 < 1).all()
+
+
+def test_hashes_and_pcg_bit_exact(bare):
+    rng = np.random.RandomState(1)
+    n = 10000
+    v = rng.normal(size=(n, 3)).astype(f32)
+    v[0] = 0; v[1] = [1, -0.0, np.inf]
+    h1 = np.zeros(n, np.uint64); m1 = np.zeros(n, np.uint64); p1 = np.zeros((n, 2), f32)
+    h2 = np.zeros(n, np.uint64); m2 = np.zeros(n, np.uint64); p2 = np.zeros((n, 2), f32)
+    assert bare.lib.hk_test_hashes(bare.cu.ctx, fp(v), n, h1.ctypes.data_as(U64P), m1.ctypes.data_as(U64P), fp(p1)) == 0
+    bare.olib.ok_test_hashes(fp(v), n, h2.ctypes.data_as(U64P), m2.ctypes.data_as(U64P), fp(p2))
+    assert np.array_equal(h1, h2) and np.array_equal(m1, m2) and np.array_equal(p1.view(np.uint32), p2.view(np.uint32))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# floating-point primitives: tolerance = a few ulp of libm difference (glibc vs CUDA)
+# ---------------------------------------------------------------------------------------------------------
+def test_wavelengths(bare):
+    u = np.linspace(0, 0.99999994, 4097).astype(f32)
+    l1 = np.zeros((len(u), 4), f32); p1 = np.zeros_like(l1); l2 = np.zeros_like(l1); p2 = np.zeros_like(l1)
+    assert bare.lib.hk_test_wavelengths(bare.cu.ctx, fp(u), len(u), fp(l1), fp(p1)) == 0
+    bare.olib.ok_test_wavelengths(fp(u), len(u), fp(l2), fp(p2))
+    np.testing.assert_allclose(l1, l2, rtol=2e-6)
+    np.testing.assert_allclose(p1, p2, rtol=2e-5, atol=1e-9)
+
+
+def test_uplift_and_cie(bare):
+    rng = np.random.RandomState(2)
+    n = 20000
+    rgb = rng.uniform(0, 1, size=(n, 3)).astype(f32)
+    rgb[:6] = [[0.5, 0.5, 0.5], [0, 0, 0], [1, 1, 1], [1, 0, 0], [0, 1, 0], [0.2, 0.2, 0.9]]
+    lam = rng.uniform(360, 830, size=(n, 4)).astype(f32)
+    for kind, scale in ((0, 1.0), (1, 7.0), (2, 30.0)):
+        r = (rgb * scale).astype(f32)
+        o1 = np.zeros((n, 4), f32); c1 = np.zeros((n, 3), f32); o2 = np.zeros((n, 4), f32); c2 = np.zeros((n, 3), f32)
+        assert bare.lib.hk_test_uplift(bare.cu.ctx, kind, fp(r), fp(lam), n, fp(o1), fp(c1)) == 0
+        bare.olib.ok_test_uplift(bare.ok.ctx, kind, fp(r), fp(lam), n, fp(o2), fp(c2))
+        assert np.array_equal(c1.view(np.uint32), c2.view(np.uint32)), "rgb_to_spectrum coefficients must be bit-exact (no libm involved)"
+        np.testing.assert_allclose(o1, o2, rtol=1e-5, atol=1e-7)
+    L = rng.uniform(0, 5, size=(n, 4)).astype(f32)
+    pdf = rng.uniform(1e-3, 4e-3, size=(n, 4)).astype(f32); pdf[::7, 1:] = 0
+    x1 = np.zeros((n, 3), f32); r1 = np.zeros((n, 3), f32); x2 = np.zeros((n, 3), f32); r2 = np.zeros((n, 3), f32)
+    assert bare.lib.hk_test_spectral_to_rgb(bare.cu.ctx, fp(L), fp(lam), fp(pdf), n, fp(x1), fp(r1)) == 0
+    bare.olib.ok_test_spectral_to_rgb(bare.ok.ctx, fp(L), fp(lam), fp(pdf), n, fp(x2), fp(r2))
+    assert np.array_equal(x1.view(np.uint32), x2.view(np.uint32)) and np.array_equal(r1.view(np.uint32), r2.view(np.uint32))
+
+
+def test_filter_bit_exact(bare):
+    rng = np.random.RandomState(3)
+    u = rng.uniform(0, 1, size=(20000, 2)).astype(f32)
+    u[:4] = [[0, 0], [0.99999994, 0.99999994], [0.5, 0.5], [0, 0.99999994]]
+    a = np.zeros((len(u), 3), f32); b = np.zeros_like(a)
+    assert bare.lib.hk_test_filter(bare.cu.ctx, fp(u), len(u), fp(a)) == 0
+    bare.olib.ok_test_filter(bare.ok.ctx, fp(u), len(u), fp(b))
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# closest hit: primitive ids, t and barycentrics bit-exact vs BOTH the oracle BVH and brute force
+# ---------------------------------------------------------------------------------------------------------
+def _soup(n_tris, seed, span=2.0, size=0.3):
+    rng = np.random.RandomState(seed)
+    c = rng.uniform(-span, span, size=(n_tris, 1, 3))
+    p = (c + rng.normal(scale=size, size=(n_tris, 3, 3))).reshape(-1, 3)
+    return H.Mesh(p, np.arange(3 * n_tris).reshape(-1, 3))
+
+
+@pytest.mark.parametrize("which", ["soup", "spheres", "boxes", "single", "degenerate"])
+def test_closest_hit_bit_exact(which):
+    s = H.Scene()
+    mat = H.MatteMaterial()
+    if which == "soup":
+        s.push(_soup(5000, 5), mat)
+    elif which == "spheres":
+        for x in (-1.5, 0.0, 1.5):
+            s.push(H.uv_sphere((x, 0.5, 0), 0.8, 48, 48), mat)
+        s.push(H.rect3((-5, -1, -5), (10, 0.1, 10)), mat)
+    elif which == "boxes":      # axis-aligned faces, shared edges, coincident duplicate geometry (exercises the t tie-break)
+        s.push(H.rect3((-1, -1, -1), (2, 2, 2)), mat)
+        s.push(H.rect3((-1, -1, -1), (2, 2, 2)), mat)
+        s.push(H.rect3((-0.5, -0.5, -0.5), (1, 1, 1)), mat)
+    elif which == "single":
+        s.push(H.Mesh([(-1, -0.5, 0), (1, -0.5, 0), (0, 1, 0)], [(0, 1, 2)]), mat)
+    else:
+        s.push(H.Mesh([(0, 0, 0), (1, 0, 0), (2, 0, 0), (0, 1, 0), (0, 0, 0), (0, 0, 0)], [(0, 1, 2), (0, 1, 3), (4, 4, 5)]), mat)
+    s.push(H.PointLight((1, 1, 1), (0, 5, 0)))
+    s.sync()
+    p = Pair(scene=s)
+    try:
+        rays = random_rays(40000, 11)
+        # axis-parallel rays, rays starting on geometry, finite t_max cuts
+        rays[:3000, 3:6] = np.eye(3, dtype=f32)[np.arange(3000) % 3] * np.where(np.arange(3000) % 2, 1, -1)[:, None]
+        rays[3000:6000, 6] = np.random.RandomState(2).uniform(0.1, 4.0, 3000)
+        rays[6000:6100, 0:3] = 0
+        h_cu, h_bvh = trace_both(p, rays, brute=False)
+        _, h_brute = trace_both(p, rays, brute=True)
+        assert np.array_equal(h_bvh.view(np.uint32), h_brute.view(np.uint32)), "oracle BVH and brute force disagree"
+        prim_cu, prim_ok = h_cu.view(np.uint32)[:, 1], h_brute.view(np.uint32)[:, 1]
+        assert np.array_equal(prim_cu, prim_ok), f"{(prim_cu != prim_ok).sum()} primitive ids differ"
+        assert np.array_equal(h_cu.view(np.uint32), h_brute.view(np.uint32)), "t / barycentrics differ bitwise"
+        if which != "degenerate":
+            assert (prim_cu > 0).sum() > 100
+        # any-hit agrees with closest-hit occupancy
+        occ = np.zeros(len(rays), np.uint8)
+        assert p.lib.hk_trace_any(p.cu.ctx, fp(rays), len(rays), occ.ctypes.data_as(A.c_u8p)) == 0
+        assert np.array_equal(occ != 0, prim_ok != 0)
+    finally:
+        p.close()
+
+
+def test_trace_empty_inputs():
+    s = H.Scene()
+    s.push(H.Mesh([(0, 0, 0), (1, 0, 0), (0, 1, 0)], [(0, 1, 2)]), H.MatteMaterial())
+    s.push(H.PointLight((1, 1, 1), (0, 5, 0)))
+    s.sync()
+    p = Pair(scene=s)
+    try:
+        assert p.lib.hk_trace_closest(p.cu.ctx, None, 0, None) == 0        # n = 0 is a no-op
+        rays = random_rays(33, 1)                                           # ragged: not a multiple of the warp size
+        h_cu, h_ok = trace_both(p, rays, brute=True)
+        assert np.array_equal(h_cu.view(np.uint32), h_ok.view(np.uint32))
+    finally:
+        p.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BSDFs, lights
+# ---------------------------------------------------------------------------------------------------------
+def _bsdf_inputs(n, seed):
+    rng = np.random.RandomState(seed)
+    x = np.zeros((n, 17), f32)
+    def unit(k):
+        v = rng.normal(size=(k, 3)); return v / np.linalg.norm(v, axis=1, keepdims=True)
+    x[:, 0:3] = unit(n); x[:, 3:6] = unit(n)
+    x[:, 6:10] = rng.uniform(380, 780, size=(n, 4))
+    x[:, 10:13] = rng.uniform(0, 1, size=(n, 3))
+    x[:, 13] = rng.randint(0, 2, n)
+    x[:, 14:17] = unit(n)
+    return x
+
+
+MATERIALS = [
+    ("matte", H.MatteMaterial(Kd=(0.8, 0.6, 0.4))), ("matte_sigma", H.MatteMaterial(Kd=(0.3, 0.5, 0.3), sigma=20.0)),
+    ("mirror", H.MirrorMaterial()), ("glass", H.GlassMaterial(Kr=(0.98, 1, 0.98), Kt=(0.98, 1, 0.98), index=1.5)),
+    ("conductor_rgb", H.ConductorMaterial(roughness=0.05)), ("conductor_smooth", H.ConductorMaterial(roughness=0.0)),
+    ("gold_rough", None), ("coated_smooth", H.CoatedDiffuseMaterial(reflectance=(0.4, 0.45, 0.35), roughness=0.0)),
+    ("coated_rough", H.CoatedDiffuseMaterial(reflectance=(0.8, 0.2, 0.2), roughness=0.3)),
+    ("coated_medium", H.CoatedDiffuseMaterial(reflectance=(0.9, 0.9, 0.9), albedo=(0.8, 0.4, 0.2), g=0.3, roughness=0.1, thickness=0.1)),
+    ("thin", H.ThinDielectricMaterial(eta=1.5)), ("difftrans", H.DiffuseTransmissionMaterial(reflectance=(0.4, 0.3, 0.2), transmittance=(0.3, 0.4, 0.3))),
+]
+
+
+@pytest.mark.parametrize("name,mat", MATERIALS, ids=[m[0] for m in MATERIALS])
+def test_bsdf_sample_and_eval(name, mat):
+    if mat is None:
+        mat = H.Gold(roughness=0.1)
+    s = H.Scene()
+    s.push(H.Mesh([(0, 0, 0), (1, 0, 0), (0, 1, 0)], [(0, 1, 2)]), mat)
+    s.push(H.PointLight((1, 1, 1), (0, 5, 0)))
+    s.sync()
+    p = Pair(scene=s)
+    try:
+        n = 20000
+        x = _bsdf_inputs(n, 7)
+        a = np.zeros((n, 16), f32); b = np.zeros((n, 16), f32)
+        assert p.lib.hk_test_bsdf(p.cu.ctx, 1, fp(x), n, fp(a)) == 0
+        p.olib.ok_test_bsdf(p.ok.ctx, 1, fp(x), n, fp(b))
+        # discrete outcome (valid / specular flag) may flip where a libm ulp moves a threshold: allow <= 0.2 %
+        same_kind = (a[:, 8] == b[:, 8]) & ((a[:, 7] > 0) == (b[:, 7] > 0))
+        assert same_kind.mean() >= 0.998, f"sample kind differs for {(~same_kind).sum()} of {n}"
+        close = np.isclose(a, b, rtol=2e-3, atol=1e-5).all(axis=1)
+        assert (close | ~same_kind).mean() >= 0.995, f"{(~close).sum()} of {n} BSDF records differ beyond rtol 2e-3"
+        assert np.isfinite(a[:, :15]).all() == np.isfinite(b[:, :15]).all()
+    finally:
+        p.close()
+
+
+def _lights_scene(kind):
+    s = H.Scene()
+    s.push(H.rect3((-2, -0.1, -2), (4, 0.1, 4)), H.MatteMaterial())
+    if kind == "mixed":
+        s.push(H.PointLight((1, 1, 1), (3, 3, -1))); s.push(H.PointLight((5, 5, 5), (-3, 2, 0)))
+        s.push(H.AmbientLight((0.5, 0.7, 1.0))); s.push(H.DirectionalLight((2, 2, 2), (0, -1, 0.2), legacy_rgbspectrum=True))
+    else:
+        sky, sd = scenes.analytic_sky(64)
+        s.push(H.EnvironmentLight(H.EnvironmentMap(sky), scale=(1e-4, 1e-4, 1e-4))); s.push(H.SunLight((5, 4.75, 4.25), -sd))
+        rng = np.random.RandomState(4)
+        for k in range(40):
+            c = rng.uniform(-1.5, 1.5, 3) + (0, 1.5, 0)
+            s.push(H.Mesh(c + rng.normal(scale=0.1, size=(3, 3)), [(0, 1, 2)]),
+                   H.MediumInterface(H.MatteMaterial(Kd=0.0), emission=(tuple(rng.uniform(5, 50, 3)), 1.0, k % 2 == 0)))
+    s.sync()
+    return s
+
+
+@pytest.mark.parametrize("kind", ["mixed", "env_area"])
+def test_light_sampling(kind):
+    s = _lights_scene(kind)
+    p = Pair(scene=s)
+    try:
+        rng = np.random.RandomState(9)
+        n = 20000
+        x = np.zeros((n, 10), f32)
+        x[:, 0:3] = rng.uniform(-1.5, 1.5, size=(n, 3)); x[:, 1] = np.abs(x[:, 1])
+        nn = rng.normal(size=(n, 3)); x[:, 3:6] = nn / np.linalg.norm(nn, axis=1, keepdims=True)
+        x[::5, 3:6] = 0                      # medium vertices pass n = 0
+        x[:, 6:10] = rng.uniform(0, 1, size=(n, 4))
+        a = np.zeros((n, 16), f32); b = np.zeros((n, 16), f32)
+        assert p.lib.hk_test_lights(p.cu.ctx, fp(x), n, fp(a)) == 0
+        p.olib.ok_test_lights(p.ok.ctx, fp(x), n, fp(b))
+        same = a[:, 0] == b[:, 0]
+        assert same.mean() >= 0.999, f"light choice differs for {(~same).sum()} of {n}"
+        close = np.isclose(a, b, rtol=1e-3, atol=1e-6).all(axis=1)
+        assert (close | ~same).mean() >= 0.998
+        # escaped rays
+        e = np.zeros((n, 4), f32); e[:, :3] = x[:, 3:6]; e[::5, :3] = [0, 1, 0]; e[:, 3] = x[:, 6]
+        ea = np.zeros((n, 5), f32); eb = np.zeros((n, 5), f32)
+        assert p.lib.hk_test_escaped(p.cu.ctx, fp(e), n, fp(ea)) == 0
+        p.olib.ok_test_escaped(p.ok.ctx, fp(e), n, fp(eb))
+        assert np.isclose(ea, eb, rtol=1e-4, atol=1e-9).all(axis=1).mean() >= 0.999
+    finally:
+        p.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# camera rays and whole images
+# ---------------------------------------------------------------------------------------------------------
+def _render_pair(scene, camf, res, spp, depth, batch=1, **kw):
+    film_c, film_o = H.Film(res), H.Film(res)
+    vp_c = H.VolPath(samples=spp, max_depth=depth, sample_batch=batch, **kw)
+    import oracle_backend
+    vp_o = H.VolPath(samples=spp, max_depth=depth, backend=oracle_backend.make_backend(), **kw)
+    a = vp_c(scene, film_c, camf(film_c)).copy()
+    b = vp_o(scene, film_o, camf(film_o)).copy()
+    stats = A.HkStats(); vp_c.backend.lib.hk_stats(vp_c.backend.ctx, C.byref(stats))
+    rays_o = oracle_backend.lib().ok_rays_traced(vp_o.backend.ctx)
+    vp_c.close(); vp_o.close()
+    return a, b, stats.rays_traced, rays_o
+
+
+def test_camera_rays():
+    scene, camf = scenes.c1_spheres(16)
+    film = H.Film((96, 64))
+    p = Pair(scene=scene, film=film, camera=camf(film))
+    try:
+        n = 96 * 64
+        a = np.zeros((n, 8), f32); b = np.zeros((n, 8), f32)
+        assert p.lib.hk_test_camera_rays(p.cu.ctx, 3, fp(a)) == 0
+        p.olib.ok_test_camera_rays(p.ok.ctx, 3, fp(b))
+        assert np.array_equal(a[:, :6].view(np.uint32), b[:, :6].view(np.uint32)), "camera rays must be bit-exact (no libm beyond sqrt/div)"
+        assert np.array_equal(a[:, 7].view(np.uint32), b[:, 7].view(np.uint32))
+        np.testing.assert_allclose(a[:, 6], b[:, 6], rtol=2e-6)
+    finally:
+        p.close()
+
+
+IMAGE_CASES = [
+    ("cornell_smoke", lambda: scenes.cornell_smoke(), (64, 64), 4, 4),
+    ("c1_triangle", lambda: scenes.c1_triangle(), (96, 96), 4, 5),
+    ("c1_spheres", lambda: scenes.c1_spheres(32), (128, 128), 4, 5),
+    ("c2_cat_small", lambda: scenes.c2_cat(48, 24), (160, 90), 4, 8),
+]
+
+
+@pytest.mark.parametrize("name,make,res,spp,depth", IMAGE_CASES, ids=[c[0] for c in IMAGE_CASES])
+def test_image_parity(name, make, res, spp, depth):
+    scene, camf = make()
+    a, b, rays_c, rays_o = _render_pair(scene, camf, res, spp, depth)
+    assert np.isfinite(a).all() and a.max() > 0
+    frac, rrmse = image_close(a, b)
+    print(f"{name}: within_tol={frac:.5f} rrmse={rrmse:.5f} mean_cuda={a.mean():.5f} mean_oracle={b.mean():.5f} rays {rays_c} vs {rays_o}")
+    # >= 99.9 % of values within |a-b| <= 1e-3 + 2e-2*max(a,b) and relative RMSE <= 1 % at equal sample streams.
+    # Glass/specular scenes can flip a stochastic reflect/refract branch on a libm ulp: per-pixel bound relaxed to 99.5 %.
+    assert frac >= 0.995, f"{name}: only {frac:.5f} of pixel values within tolerance"
+    assert rrmse <= 0.02, f"{name}: relative RMSE {rrmse:.4f}"
+    assert abs(rays_c - rays_o) <= 0.002 * rays_o + 8, "ray counts differ: the two paths are not tracing the same work"
+
+
+def test_sample_batching_is_bitwise_invariant():
+    scene, camf = scenes.c1_spheres(16)
+    outs = []
+    for batch in (1, 3):
+        film = H.Film((64, 48))
+        vp = H.VolPath(samples=6, max_depth=4, sample_batch=batch)
+        outs.append(vp(scene, film, camf(film)).copy())
+        vp.close()
+    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+
+
+def test_strided_partition_sums_to_the_full_render():
+    """The multi-GPU partition (hk_render_samples_strided): two contexts render disjoint sample indices;
+    the summed accumulators equal the single-context film within f32 summation-order tolerance."""
+    scene, camf = scenes.c1_spheres(16)
+    res = (64, 48)
+    film = H.Film(res)
+    vp = H.VolPath(samples=8, max_depth=4)
+    full = vp(scene, film, camf(film)).copy()
+    acc = []
+    for r in range(2):
+        f2 = H.Film(res)
+        v2 = H.VolPath(samples=8, max_depth=4)
+        v2._prepare(scene, f2, camf(f2)); v2.clear()
+        v2.backend.call("render_samples_strided", r + 1, 2, 4)
+        acc.append(v2.backend.read_accum()); v2.close()
+    rgb = acc[0][0] + acc[1][0]; w = acc[0][1] + acc[1][1]
+    img = (rgb / np.maximum(w, 1e-30)[:, None]).reshape(res[1], res[0], 3)
+    np.testing.assert_allclose(img, full, rtol=1e-4, atol=1e-6)
+    vp.close()
