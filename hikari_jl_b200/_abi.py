@@ -112,7 +112,7 @@ HK_SYMBOLS = [
     "hk_set_camera", "hk_set_filter", "hk_set_params", "hk_clear", "hk_render_samples", "hk_render_samples_strided",
     "hk_read_film", "hk_film_accum_dev", "hk_read_accum", "hk_write_accum", "hk_trace_closest",
     "hk_trace_closest_dev", "hk_trace_any", "hk_stats", "hk_synchronize", "hk_dev_alloc", "hk_dev_free",
-    "hk_dev_upload", "hk_dev_download",
+    "hk_dev_upload", "hk_dev_download", "hk_set_profiling", "hk_stage_times", "hk_pinned_alloc", "hk_pinned_free",
 ]
 
 _VP = C.c_void_p
@@ -164,6 +164,11 @@ def bind_hk(lib):
     f("hk_dev_free", [_VP, _VP])
     f("hk_dev_upload", [_VP, _VP, _VP, C.c_uint64])
     f("hk_dev_download", [_VP, _VP, _VP, C.c_uint64])
+    f("hk_pinned_alloc", [C.c_uint64, C.POINTER(_VP)])
+    f("hk_pinned_free", [_VP])
+    f("hk_set_profiling", [_VP, C.c_int32])
+    f("hk_stage_times", [_VP, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)])
+    f("hk_test_trace_counts", [_VP, c_fp, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)])
     # host-side scene-build helpers (CPU code, usable without a GPU)
     f("hk_host_generate_rgb2spec", [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                     C.POINTER(C.c_double), c_fp, c_fp])

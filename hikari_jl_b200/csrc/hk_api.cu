@@ -5,6 +5,7 @@
 #include "../../include/hikari_cuda_testing.h"
 #include "hk_wavefront.cuh"
 #include "hk_bvh.h"
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -41,10 +42,16 @@ struct HkContext {
     std::vector<DevBuf> env_bufs, media_bufs;
     DevBuf b_media;
     DevBuf b_f_func, b_f_mcdf, b_f_mfunc, b_f_ccdf;
-    DevBuf b_state, b_counts, b_rays, b_film, b_scratch_u32, b_trace_ctr;
+    DevBuf b_state, b_counts, b_rays, b_film, b_scratch_u32, b_trace_ctr, b_readback;
     size_t n_slots = 0;
     HkStats stats;
     uint64_t launches = 0;
+    // optional per-stage profiling (hk_set_profiling): CUDA events around every stage launch on the launching stream
+    int profiling = 0;
+    struct StageEv { int stage; cudaEvent_t a, b; };
+    std::vector<StageEv> stage_events; size_t stage_ev_used = 0;
+    double stage_ms[HK_N_STAGES]; uint64_t stage_launches[HK_N_STAGES];
+    DevBuf b_work_ctr;
     HkContext() { std::memset(&D, 0, sizeof(D)); std::memset(&S, 0, sizeof(S)); std::memset(&params, 0, sizeof(params)); std::memset(&stats, 0, sizeof(stats)); }
 };
 
@@ -53,6 +60,26 @@ static int grid_for(const HkContext* c, size_t n, int block, int per_sm) {
     size_t cap = (size_t)c->sm_count * per_sm;
     if (need < 1) need = 1;
     return (int)(need < cap ? need : cap);
+}
+
+struct StageScope {
+    HkContext* c; int stage; HkContext::StageEv* ev = nullptr;
+    StageScope(HkContext* ctx, int st) : c(ctx), stage(st) {
+        if (!(c->profiling & 1)) return;
+        if (c->stage_ev_used == c->stage_events.size()) {
+            HkContext::StageEv e; e.stage = st; cudaEventCreate(&e.a); cudaEventCreate(&e.b); c->stage_events.push_back(e);
+        }
+        ev = &c->stage_events[c->stage_ev_used++]; ev->stage = st;
+        cudaEventRecord(ev->a, c->stream);
+    }
+    ~StageScope() { if (ev) cudaEventRecord(ev->b, c->stream); c->launches++; }
+};
+static void collect_stage_times(HkContext* c) {
+    cudaStreamSynchronize(c->stream);
+    for (size_t i = 0; i < c->stage_ev_used; i++) {
+        float ms = 0; if (cudaEventElapsedTime(&ms, c->stage_events[i].a, c->stage_events[i].b) == cudaSuccess) { c->stage_ms[c->stage_events[i].stage] += ms; c->stage_launches[c->stage_events[i].stage]++; }
+    }
+    c->stage_ev_used = 0;
 }
 
 extern "C" {
@@ -71,8 +98,9 @@ int32_t hk_create(int32_t device, HkContext** out) {
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return HK_ERR_CUDA; }
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
-    if (ctx->b_counts.alloc(sizeof(uint32_t) * HK_N_COUNTERS + 64) != cudaSuccess || ctx->b_trace_ctr.alloc(64) != cudaSuccess) { delete ctx; return HK_ERR_OOM; }
-    cudaMemset(ctx->b_counts.p, 0, ctx->b_counts.bytes); cudaMemset(ctx->b_trace_ctr.p, 0, 64);
+    if (ctx->b_counts.alloc(sizeof(uint32_t) * HK_N_COUNTERS + 64) != cudaSuccess || ctx->b_trace_ctr.alloc(64) != cudaSuccess || ctx->b_work_ctr.alloc(64) != cudaSuccess) { delete ctx; return HK_ERR_OOM; }
+    cudaMemset(ctx->b_counts.p, 0, ctx->b_counts.bytes); cudaMemset(ctx->b_trace_ctr.p, 0, 64); cudaMemset(ctx->b_work_ctr.p, 0, 64);
+    for (int i = 0; i < HK_N_STAGES; i++) { ctx->stage_ms[i] = 0; ctx->stage_launches[i] = 0; }
     *out = ctx;
     return HK_OK;
 }
@@ -83,7 +111,8 @@ int32_t hk_destroy(HkContext* ctx) {
     DevBuf* bufs[] = {&ctx->b_sobol, &ctx->b_cie_x, &ctx->b_cie_y, &ctx->b_cie_z, &ctx->b_d65, &ctx->b_rgb_scale, &ctx->b_rgb_coeffs, &ctx->b_nodes, &ctx->b_tris,
                       &ctx->b_pos, &ctx->b_nrm, &ctx->b_idx, &ctx->b_meta, &ctx->b_mats, &ctx->b_ifaces, &ctx->b_spec_l, &ctx->b_spec_v, &ctx->b_spec_o, &ctx->b_lights,
                       &ctx->b_env, &ctx->b_lnodes, &ctx->b_trails, &ctx->b_inf, &ctx->b_media, &ctx->b_f_func, &ctx->b_f_mcdf, &ctx->b_f_mfunc, &ctx->b_f_ccdf,
-                      &ctx->b_state, &ctx->b_counts, &ctx->b_rays, &ctx->b_film, &ctx->b_scratch_u32, &ctx->b_trace_ctr};
+                      &ctx->b_state, &ctx->b_counts, &ctx->b_rays, &ctx->b_film, &ctx->b_scratch_u32, &ctx->b_trace_ctr, &ctx->b_work_ctr, &ctx->b_readback};
+    for (auto& e : ctx->stage_events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (DevBuf* b : bufs) b->release();
     for (auto& b : ctx->env_bufs) b.release();
     for (auto& b : ctx->media_bufs) b.release();
@@ -316,10 +345,9 @@ int32_t hk_clear(HkContext* ctx) {
 }  // extern "C"
 template <int TYPE> static void launch_shade(HkContext* ctx, const PassArgs& A, int next) {
     if (!(ctx->mat_types_present & (1u << TYPE))) return;
+    StageScope sc(ctx, HK_STAGE_SHADE);
     k_shade<TYPE><<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(ctx->D, ctx->S, A, next);
-    ctx->launches++;
 }
-
 extern "C" {
 int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride, int32_t count) {
     if (!ctx) return HK_ERR_INVALID;
@@ -338,6 +366,9 @@ int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride,
         ctx->camera_medium_valid = true;
     }
     const bool opaque_only = !ctx->D.any_medium_transition && ctx->D.n_media == 0;
+    const bool cnt = (ctx->profiling & 2) != 0;
+    unsigned long long* work = ctx->b_work_ctr.as<unsigned long long>();
+    const int tgrid = ctx->sm_count * 8;
     CK(cudaEventRecord(ctx->ev0, st));
     int32_t done = 0;
     while (done < count) {
@@ -345,32 +376,51 @@ int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride,
         A.n_batch = std::min<int32_t>(ctx->params.sample_batch, count - done);
         A.first_sample = first + done * stride; A.stride = stride; A.n_pixels = (uint32_t)n_pixels;
         const size_t n_slots = n_pixels * (size_t)A.n_batch;
-        k_camera<<<grid_for(ctx, n_slots, 256, 8), 256, 0, st>>>(ctx->D, ctx->S, A, ctx->camera_medium);
-        ctx->launches++;
+        { StageScope sc(ctx, HK_STAGE_CAMERA); k_camera<<<grid_for(ctx, n_slots, 256, 8), 256, 0, st>>>(ctx->D, ctx->S, A, ctx->camera_medium); }
         int cur = 0;
         for (int depth = 0; depth < ctx->params.max_depth; depth++) {
-            k_reset_bounce<<<1, 32, 0, st>>>(ctx->S, cur);
-            k_trace<<<ctx->sm_count * 8, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, cur);
-            ctx->launches += 2;
-            if (ctx->D.n_media > 0) { k_medium<<<ctx->sm_count * 8, 128, 0, st>>>(ctx->D, ctx->S, A, cur ^ 1); ctx->launches++; }
-            if (ctx->D.n_lights > 0) { k_escaped<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->D, ctx->S); ctx->launches++; }
+            k_reset_bounce<<<1, 32, 0, st>>>(ctx->S, cur); ctx->launches++;
+            {
+                StageScope sc(ctx, HK_STAGE_TRACE);
+                if (cnt) k_trace<true><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, cur, work);
+                else k_trace<false><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, cur, work);
+            }
+            if (ctx->D.n_media > 0) { StageScope sc(ctx, HK_STAGE_MEDIUM); k_medium<<<ctx->sm_count * 8, 128, 0, st>>>(ctx->D, ctx->S, A, cur ^ 1); }
+            if (ctx->D.n_lights > 0) { StageScope sc(ctx, HK_STAGE_ESCAPED); k_escaped<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->D, ctx->S); }
             launch_shade<HK_MAT_MATTE>(ctx, A, cur ^ 1); launch_shade<HK_MAT_MIRROR>(ctx, A, cur ^ 1); launch_shade<HK_MAT_GLASS>(ctx, A, cur ^ 1);
             launch_shade<HK_MAT_CONDUCTOR>(ctx, A, cur ^ 1); launch_shade<HK_MAT_COATED_DIFFUSE>(ctx, A, cur ^ 1);
             launch_shade<HK_MAT_THIN_DIELECTRIC>(ctx, A, cur ^ 1); launch_shade<HK_MAT_DIFFUSE_TRANSMISSION>(ctx, A, cur ^ 1);
             if (ctx->D.n_lights > 0) {
-                if (opaque_only) k_shadow<true><<<ctx->sm_count * 8, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S);
-                else k_shadow<false><<<ctx->sm_count * 8, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S);
-                ctx->launches++;
+                StageScope sc(ctx, HK_STAGE_SHADOW);
+                if (opaque_only) { if (cnt) k_shadow<true, true><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, work); else k_shadow<true, false><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, work); }
+                else { if (cnt) k_shadow<false, true><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, work); else k_shadow<false, false><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, work); }
             }
             cur ^= 1;
         }
-        k_film_accumulate<<<grid_for(ctx, n_pixels, 256, 8), 256, 0, st>>>(ctx->D, ctx->S, A);
-        ctx->launches++;
+        { StageScope sc(ctx, HK_STAGE_FILM); k_film_accumulate<<<grid_for(ctx, n_pixels, 256, 8), 256, 0, st>>>(ctx->D, ctx->S, A); }
         done += A.n_batch;
+        if (ctx->profiling & 1) collect_stage_times(ctx);
     }
     CK(cudaEventRecord(ctx->ev1, st));
     CK(cudaGetLastError());
     ctx->stats.samples_rendered += (uint64_t)count * n_pixels;
+    return HK_OK;
+}
+// profiling: bit 0 = time every stage launch with CUDA events, bit 1 = count traversal node visits / triangle tests
+int32_t hk_set_profiling(HkContext* ctx, int32_t mode) {
+    if (!ctx) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    ctx->profiling = mode;
+    for (int i = 0; i < HK_N_STAGES; i++) { ctx->stage_ms[i] = 0; ctx->stage_launches[i] = 0; }
+    CK(cudaMemset(ctx->b_work_ctr.p, 0, 64));
+    return HK_OK;
+}
+int32_t hk_stage_times(HkContext* ctx, double* out_ms, uint64_t* out_launches, uint64_t* out_work) {
+    if (!ctx || !out_ms || !out_launches || !out_work) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    collect_stage_times(ctx);
+    for (int i = 0; i < HK_N_STAGES; i++) { out_ms[i] = ctx->stage_ms[i]; out_launches[i] = ctx->stage_launches[i]; }
+    CK(cudaMemcpy(out_work, ctx->b_work_ctr.p, 48, cudaMemcpyDeviceToHost));
     return HK_OK;
 }
 int32_t hk_render_samples(HkContext* ctx, int32_t first, int32_t count) { return hk_render_samples_strided(ctx, first, 1, count); }
@@ -387,15 +437,20 @@ int32_t hk_read_film(HkContext* ctx, float* out) {
     cudaSetDevice(ctx->device);
     REQUIRE(ctx->have_params, "hk_set_params has not been called");
     const size_t n = (size_t)ctx->params.width * ctx->params.height;
-    DevBuf tmp; CK(tmp.alloc(12 * n));
-    k_film_finalize<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(ctx->S.pixel_rgb, ctx->S.pixel_weight, tmp.as<float>(), ctx->params.width, ctx->params.height);
+    if (ctx->b_readback.bytes < 12 * n) CK(ctx->b_readback.alloc(12 * n));
+    k_film_finalize<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(ctx->S.pixel_rgb, ctx->S.pixel_weight, ctx->b_readback.as<float>(), ctx->params.width, ctx->params.height);
     ctx->launches++;
-    cudaError_t e = cudaMemcpyAsync(out, tmp.p, 12 * n, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    tmp.release();
-    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return HK_ERR_CUDA; }
+    CK(cudaMemcpyAsync(out, ctx->b_readback.p, 12 * n, cudaMemcpyDeviceToHost, ctx->stream));   // true async DMA when `out` is pinned
+    CK(cudaStreamSynchronize(ctx->stream));
     return HK_OK;
 }
+// pinned host memory for film.framebuffer (the Julia shim would use CUDA.pin / cudaHostRegister on the Film's array)
+int32_t hk_pinned_alloc(uint64_t bytes, void** out) {
+    if (!out) return HK_ERR_INVALID;
+    *out = nullptr;
+    return cudaHostAlloc(out, bytes ? bytes : 16, cudaHostAllocDefault) == cudaSuccess ? HK_OK : HK_ERR_CUDA;
+}
+int32_t hk_pinned_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? HK_OK : HK_ERR_CUDA; }
 int32_t hk_film_accum_dev(HkContext* ctx, float** out, uint64_t* count) {
     if (!ctx || !out || !count) return HK_ERR_INVALID;
     REQUIRE(ctx->have_params, "hk_set_params has not been called");

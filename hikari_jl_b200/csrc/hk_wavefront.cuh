@@ -188,11 +188,12 @@ HK_DEV uint32_t* queue_of(const PathState& S, int qid) {
 }
 
 // vp_trace_rays_kernel!, intersection.jl:188-269: closest hit + routing.  Persistent: warps pull 32 rays at a time.
-__global__ void __launch_bounds__(HK_TRACE_THREADS) k_trace(const __grid_constant__ DevScene D, PathState S, int cur) {
+template <bool COUNT>
+__global__ void __launch_bounds__(HK_TRACE_THREADS) k_trace(const __grid_constant__ DevScene D, PathState S, int cur, unsigned long long* work) {
     __shared__ uint2 sm_stack[HK_SM_STACK * HK_TRACE_THREADS];
     const uint32_t n = S.counts[HK_C_RAY0 + cur];
     const unsigned lane = threadIdx.x & 31u;
-    uint32_t traced = 0;
+    uint32_t traced = 0, wn = 0, wt = 0;
     for (;;) {
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(S.counts + HK_C_CURSOR_TRACE, 32u);
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(HK_TRACE_THREADS) k_trace(const __grid_constan
         if (idx < n) {
             slot = S.q_ray[cur][idx];
             float4 ra = S.ray_a[slot], rb = S.ray_b[slot];
-            HitRec h = bvh8_trace<false, false>(D.bvh, sm_stack + threadIdx.x, f3(ra.x, ra.y, ra.z), f3(ra.w, rb.x, rb.y), rb.z);
+            HitRec h = bvh8_trace<false, COUNT>(D.bvh, sm_stack + threadIdx.x, f3(ra.x, ra.y, ra.z), f3(ra.w, rb.x, rb.y), rb.z, &wn, &wt);
             traced++;
             S.hit[slot] = make_float4(h.t, __uint_as_float(h.prim1), h.b1, h.b2);
             // in-medium rays go to delta tracking with their hit record; the vacuum alpha loop (:224-266) ends on its
@@ -217,6 +218,7 @@ __global__ void __launch_bounds__(HK_TRACE_THREADS) k_trace(const __grid_constan
         if (lane == 0 && hm) atomicAdd(S.counts + HK_C_TOTAL_HITS, (uint32_t)__popc(hm));
     }
     count_rays(S.rays_traced, traced);
+    if (COUNT) { count_rays(work, traced); count_rays(work + 1, wn); count_rays(work + 2, wt); }
 }
 
 // vp_handle_escaped_rays_kernel!, intersection.jl:622-668
@@ -439,15 +441,15 @@ __global__ void __launch_bounds__(128) k_medium(const __grid_constant__ DevScene
 // trace_shadow_transmittance + vp_trace_shadow_rays_kernel!, intersection.jl:302-406, 565-600.
 // OPAQUE_ONLY (no interface with inside != outside, no media): visibility is a single any-hit query, which yields the
 // same T in {0,1} as the reference's closest-hit loop.  Otherwise the ordered closest-hit walk with ratio tracking.
-template <bool OPAQUE_ONLY>
-__global__ void __launch_bounds__(HK_TRACE_THREADS) k_shadow(const __grid_constant__ DevScene D, PathState S) {
+template <bool OPAQUE_ONLY, bool COUNT>
+__global__ void __launch_bounds__(HK_TRACE_THREADS) k_shadow(const __grid_constant__ DevScene D, PathState S, unsigned long long* work) {
     __shared__ uint2 sm_stack[HK_SM_STACK * HK_TRACE_THREADS];
     // reference quirk (volpath.jl:571-609): shadow rays are only traced inside the `n_hits > 0` branch
     if (S.counts[HK_C_TOTAL_HITS] == 0) return;
     const uint32_t n = S.counts[HK_C_SHADOW];
     const unsigned lane = threadIdx.x & 31u;
     MediaCtx MDC = media_ctx(D);
-    uint32_t traced = 0;
+    uint32_t traced = 0, wn = 0, wt = 0;
     for (;;) {
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(S.counts + HK_C_CURSOR_SHADOW, 32u);
@@ -464,7 +466,7 @@ __global__ void __launch_bounds__(HK_TRACE_THREADS) k_shadow(const __grid_consta
         bool visible = false;
         if (OPAQUE_ONLY) {
             if (!(t_rem < 1.0e-6f)) {
-                HitRec h = bvh8_trace<true, false>(D.bvh, sm_stack + threadIdx.x, o, d, t_rem);
+                HitRec h = bvh8_trace<true, COUNT>(D.bvh, sm_stack + threadIdx.x, o, d, t_rem, &wn, &wt);
                 traced++;
                 visible = h.prim1 == 0;
             }
@@ -474,7 +476,7 @@ __global__ void __launch_bounds__(HK_TRACE_THREADS) k_shadow(const __grid_consta
             bool done = false;
             for (int it = 0; it < 10 && !done; it++) {
                 if (t_rem < 1.0e-6f) break;
-                HitRec h = bvh8_trace<false, false>(D.bvh, sm_stack + threadIdx.x, o, d, t_rem);
+                HitRec h = bvh8_trace<false, COUNT>(D.bvh, sm_stack + threadIdx.x, o, d, t_rem, &wn, &wt);
                 traced++;
                 if (h.prim1 == 0) {
                     if (cur != 0) { Spec a, b, c; ratio_track(MDC, (int)cur, o, d, t_rem, lam, a, b, c); T = T * a; tu = tu * b; tl = tl * c; }
@@ -501,6 +503,7 @@ __global__ void __launch_bounds__(HK_TRACE_THREADS) k_shadow(const __grid_consta
         }
     }
     count_rays(S.rays_traced, traced);
+    if (COUNT) { count_rays(work + 3, traced); count_rays(work + 4, wn); count_rays(work + 5, wt); }
 }
 
 // vp_accumulate_to_rgb_kernel!, volpath.jl:326-375.  One thread per pixel walks the batch in sample order, so the

@@ -76,8 +76,31 @@ class Film:
     def __init__(self, resolution):
         self.resolution = (int(resolution[0]), int(resolution[1]))   # (W, H)
         w, h = self.resolution
-        self.framebuffer = np.zeros((h, w, 3), dtype=f32)            # framebuffer[py, px] = RGB
+        # The reference's framebuffer is an (H, W) COLUMN-major RGB{Float32} matrix (film.jl:61-106): linear index
+        # (px-1)*H + py.  The same bytes are a C-order (W, H, 3) array; `framebuffer` is the [py, px] view of it, so
+        # hk_read_film writes straight into it.  The storage is page-locked when a CUDA device is present.
+        self._pinned = None
+        self._store = None
+        try:
+            lib = A.load_library()
+            p = C.c_void_p()
+            if lib.hk_pinned_alloc(12 * w * h, C.byref(p)) == 0 and p.value:
+                self._pinned = (lib, p)
+                self._store = np.ctypeslib.as_array(C.cast(p, A.c_fp), shape=(w, h, 3))
+        except Exception:
+            self._pinned = None
+        if self._store is None:
+            self._store = np.empty((w, h, 3), dtype=f32)
+        self._store[...] = 0
+        self.framebuffer = self._store.transpose(1, 0, 2)            # framebuffer[py, px] = RGB (a view)
         self.iteration_index = 0
+
+    def __del__(self):
+        if getattr(self, "_pinned", None):
+            lib, p = self._pinned
+            self.framebuffer = None; self._store = None
+            lib.hk_pinned_free(p)
+            self._pinned = None
 
     def clear(self):
         self.framebuffer[:] = 0
@@ -907,6 +930,10 @@ class Backend:
 
     def read_film(self, out_hw3):
         """framebuffer[py, px] (H, W, 3); the ABI writes the reference's (H, W) column-major RGB layout."""
+        if isinstance(out_hw3, Film):                                # zero-copy: the film's storage is already (H,W) col-major
+            assert out_hw3.resolution == (self.width, self.height)
+            self.call("read_film", _fp(out_hw3._store))
+            return
         buf = np.empty((self.width, self.height, 3), dtype=f32)     # column-major (H,W) == C-order (W,H)
         self.call("read_film", _fp(buf))
         out_hw3[...] = buf.transpose(1, 0, 2)
@@ -961,7 +988,7 @@ class VolPath:
         self.backend.call("render_samples", first, count)
         film.iteration_index += count
         if read:
-            self.backend.read_film(film.framebuffer)
+            self.backend.read_film(film)
 
     def __call__(self, scene, film, camera):
         """(vp::VolPath)(scene, film, camera), volpath.jl:655-670"""

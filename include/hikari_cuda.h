@@ -318,10 +318,27 @@ int32_t hk_trace_closest_dev(HkContext* ctx, const float* rays_dev, uint64_t n, 
 int32_t hk_trace_any(HkContext* ctx, const float* rays, uint64_t n, uint8_t* occluded);
 
 int32_t hk_stats(HkContext* ctx, HkStats* out);
+
+/* per-stage device timing (CUDA events on the launching stream) and traversal work counters, for the roofline
+ * line of bench.py.  mode bit 0: time every stage launch; bit 1: count node visits / triangle tests.
+ * hk_stage_times: out_ms[HK_N_STAGES], out_launches[HK_N_STAGES], out_work[6] = closest-hit {rays, node visits,
+ * triangle tests}, shadow {rays, node visits, triangle tests} accumulated since hk_set_profiling.          */
+#define HK_STAGE_CAMERA  0
+#define HK_STAGE_TRACE   1
+#define HK_STAGE_MEDIUM  2
+#define HK_STAGE_ESCAPED 3
+#define HK_STAGE_SHADE   4
+#define HK_STAGE_SHADOW  5
+#define HK_STAGE_FILM    6
+#define HK_N_STAGES      7
+int32_t hk_set_profiling(HkContext* ctx, int32_t mode);
+int32_t hk_stage_times(HkContext* ctx, double* out_ms, uint64_t* out_launches, uint64_t* out_work);
 int32_t hk_synchronize(HkContext* ctx);
 
 /* device memory helpers so a host without a CUDA binding (the Python mirror, tests) can keep
  * inputs resident in HBM across timed calls */
+int32_t hk_pinned_alloc(uint64_t bytes, void** out_host);   /* page-locked host memory for film.framebuffer */
+int32_t hk_pinned_free(void* host);
 int32_t hk_dev_alloc(HkContext* ctx, uint64_t bytes, void** out_dev);
 int32_t hk_dev_free(HkContext* ctx, void* dev);
 int32_t hk_dev_upload(HkContext* ctx, void* dst_dev, const void* src_host, uint64_t bytes);

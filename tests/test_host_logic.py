@@ -1,0 +1,148 @@
+"""CPU tests of the host-side logic: scene flattening, BVH light sampler construction, Distribution2D, NanoVDB builder,
+ZSobol parameters, the oracle's two closest-hit implementations, and the sample-index partition."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from hikari_jl_b200 import _abi as A, host as H, scenes
+from hikari_jl_b200.nanovdb import build_nanovdb_from_dense
+import oracle_backend
+from util import Pair, fp, f32, random_rays
+
+OL = oracle_backend.lib
+
+
+def test_zsobol_params_match_reference_formula():
+    # sobol.jl:317-323 with volpath.jl:475 (sobol_spp = max(spp, 4096))
+    assert H.compute_zsobol_params(4096, 512, 512) == (12, 9 + 6)
+    assert H.compute_zsobol_params(4096, 1920, 1080) == (12, 11 + 6)
+    assert H.compute_zsobol_params(4096, 3840, 2160) == (12, 12 + 6)
+    assert H.compute_zsobol_params(1, 64, 64) == (0, 6)
+
+
+def test_scene_flattening_and_area_light_registration():
+    s = H.Scene()
+    s.push(H.rect3((0, 0, 0), (1, 1, 1)), H.MatteMaterial())
+    s.push(H.PointLight((1, 1, 1), (0, 3, 0)))
+    tri = H.Mesh([(0, 2, 0), (1, 2, 0), (0, 2, 1), (5, 5, 5), (5, 5, 5), (5, 5, 5)], [(0, 1, 2), (3, 4, 5)])
+    s.push(tri, H.MediumInterface(H.MatteMaterial(Kd=0.0), emission=((10, 10, 10), 2.0, False)))
+    s.push(H.AmbientLight((0.1, 0.1, 0.1)))
+    f = s.sync()
+    assert len(f.indices) == 12 + 2 and f.tri_meta.shape == (14, 3)
+    assert (f.tri_meta[:12, 0] == 1).all() and (f.tri_meta[12:, 0] == 2).all()
+    assert list(f.tri_meta[:3, 1]) == [1, 2, 3]                      # primitive_index is the 1-based face index within its mesh
+    assert [type(l).__name__ for l in f.lights] == ["PointLight", "AmbientLight", "DiffuseAreaLight"]
+    assert f.tri_meta[12, 2] == 3 and f.tri_meta[13, 2] == 0          # degenerate face registers no light (scene-mesh.jl:118-121)
+    al = f.lights[2]
+    assert abs(al.area - 0.5) < 1e-6 and np.allclose(np.abs(al.normal), [0, 1, 0])
+
+
+def test_light_sampler_pmf_is_a_distribution():
+    """bvh_sample_light / bvh_pmf consistency (bvh-light-sampler.jl:105-232): sampling returns pmf == bvh_pmf replay, and
+    stratified u covers the lights with frequencies matching the pmf."""
+    scene, _ = scenes.c3_many_lights(200, 8)
+    p = Pair(scene=scene, need_gpu=False)
+    try:
+        n_nodes, n_inf, n_bvh = p.ok.light_sampler_info
+        assert n_bvh == 200 and n_inf == 2 and n_nodes == 2 * 200 - 1
+        n = 4096
+        x = np.zeros((n, 10), f32)
+        x[:, 0:3] = (0.3, -0.2, 0.4); x[:, 3:6] = (0, 0, 1); x[:, 6] = 0.3
+        x[:, 7] = (np.arange(n) + 0.5) / n
+        out = np.zeros((n, 16), f32)
+        OL().ok_test_lights(p.ok.ctx, fp(x), n, fp(out))
+        idx, pmf, replay = out[:, 0].astype(int), out[:, 1], out[:, 14]
+        ok = idx > 0
+        assert ok.mean() > 0.99
+        np.testing.assert_allclose(pmf[ok], replay[ok], rtol=1e-5)
+        # total probability over distinct lights ~ 1
+        first = {}
+        for i, pm in zip(idx[ok], pmf[ok]):
+            first.setdefault(i, pm)
+        assert abs(sum(first.values()) - 1.0) < 0.05
+        # empirical frequency ~ pmf for the most likely lights
+        for i, pm in sorted(first.items(), key=lambda kv: -kv[1])[:5]:
+            assert abs((idx == i).mean() - pm) < 0.02 + 0.2 * pm
+    finally:
+        p.close()
+
+
+def test_distribution2d_matches_reference_construction():
+    rng = np.random.RandomState(0)
+    f = rng.uniform(0, 1, size=(6, 9)).astype(f32)
+    f[2, :] = 0
+    d = H.Distribution2D(f)
+    assert d.nu == 9 and d.nv == 6
+    np.testing.assert_allclose(d.conditional_cdf[:, -1], 1.0, rtol=1e-6)
+    np.testing.assert_allclose(d.conditional_cdf[2], np.arange(10) / 9, rtol=1e-6)   # zero row -> uniform fallback (sampling.jl:227-230)
+    np.testing.assert_allclose(d.marginal_cdf[-1], 1.0, rtol=1e-6)
+    np.testing.assert_allclose(d.marginal_func_int, f.mean(), rtol=1e-5)
+
+
+def test_nanovdb_builder_round_trips_through_the_oracle_reader():
+    rng = np.random.RandomState(1)
+    dens = np.zeros((20, 17, 9), f32)                      # not multiples of 8: partially filled leaves
+    dens[3:12, 2:9, 1:8] = rng.uniform(0.5, 2, size=(9, 7, 7))
+    dens[18, 16, 8] = 7.0
+    buf, meta = build_nanovdb_from_dense(dens, (0, 0, 0), (2.0, 1.7, 0.9))
+    assert meta["leaf_count"] == int(((np.add.reduceat(np.add.reduceat(np.add.reduceat(np.pad(dens, ((0, 4), (0, 7), (0, 7))), np.arange(0, 24, 8), 0), np.arange(0, 24, 8), 1), np.arange(0, 16, 8), 2)) > 0).sum())
+    med = H.NanoVDBMedium(dens, bounds=((0, 0, 0), (2.0, 1.7, 0.9)), majorant_res=(4, 4, 4))
+    s = H.Scene()
+    s.push(H.rect3((0, 0, 0), (2.0, 1.7, 0.9)), H.MediumInterface(H.GlassMaterial(Kr=0, Kt=1, index=1), inside=med))
+    s.push(H.PointLight((1, 1, 1), (0, 5, 0)))
+    s.sync()
+    p = Pair(scene=s, need_gpu=False)
+    try:
+        ii = np.stack(np.meshgrid(np.arange(20), np.arange(17), np.arange(9), indexing="ij"), -1).reshape(-1, 3)
+        pts = ((ii + 0.5) * 0.1).astype(f32)               # voxel centres -> index-space integers
+        out = np.zeros(len(pts), f32)
+        OL().ok_test_density(p.ok.ctx, 1, fp(pts), len(pts), fp(out))
+        np.testing.assert_allclose(out, dens.reshape(-1), rtol=1e-4, atol=1e-4)
+        assert (med.majorant.max() >= dens.max() - 1e-6) and med.majorant.shape == (4, 4, 4)
+        # every voxel's density is bounded by the majorant cell that contains it
+        cell = np.minimum((ii / np.array([20, 17, 9]) * 4).astype(int), 3)
+        assert (dens.reshape(-1) <= med.majorant[cell[:, 2], cell[:, 1], cell[:, 0]] + 1e-6).all()
+    finally:
+        p.close()
+
+
+def test_oracle_bvh_equals_brute_force_with_tie_break():
+    s = H.Scene()
+    s.push(H.rect3((-1, -1, -1), (2, 2, 2)), H.MatteMaterial())
+    s.push(H.rect3((-1, -1, -1), (2, 2, 2)), H.MatteMaterial())       # coincident duplicate: every hit is a t tie
+    s.push(H.uv_sphere((0, 0, 0), 0.7, 24, 24), H.MatteMaterial())
+    s.push(H.PointLight((1, 1, 1), (0, 5, 0)))
+    s.sync()
+    p = Pair(scene=s, need_gpu=False)
+    try:
+        rays = random_rays(20000, 3)
+        a = np.zeros((len(rays), 4), f32); b = np.zeros_like(a)
+        OL().ok_trace_closest(p.ok.ctx, fp(rays), len(rays), fp(a), 0)
+        OL().ok_trace_closest(p.ok.ctx, fp(rays), len(rays), fp(b), 1)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        prim = a.view(np.uint32)[:, 1]
+        assert (prim > 0).mean() > 0.05
+        box_hits = prim[(prim > 0) & (prim <= 24)]
+        assert (box_hits <= 12).all(), "equal-t ties must resolve to the smallest primitive id"
+    finally:
+        p.close()
+
+
+def test_strided_partition_on_the_oracle():
+    """rank g renders sample indices g+1, g+1+G, ...; summed accumulators == single-process film."""
+    scene, camf = scenes.c1_spheres(8)
+    res = (32, 24)
+    film = H.Film(res)
+    vp = H.VolPath(samples=4, max_depth=3, backend=oracle_backend.make_backend())
+    full = vp(scene, film, camf(film)).copy()
+    accs = []
+    for r in range(2):
+        f2 = H.Film(res); v2 = H.VolPath(samples=4, max_depth=3, backend=oracle_backend.make_backend())
+        v2._prepare(scene, f2, camf(f2)); v2.clear()
+        v2.backend.call("render_samples_strided", r + 1, 2, 2)
+        accs.append(v2.backend.read_accum()); v2.close()
+    rgb = accs[0][0] + accs[1][0]; w = accs[0][1] + accs[1][1]
+    img = (rgb / np.maximum(w, 1e-30)[:, None]).reshape(res[1], res[0], 3)
+    np.testing.assert_allclose(img, full, rtol=1e-4, atol=1e-6)
+    vp.close()

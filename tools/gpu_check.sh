@@ -1,7 +1,14 @@
 #!/bin/bash
-# first-contact GPU run: parity tests + tiny bench (called through gpurun)
+# GPU run: parity tests + bench + ncu launch list + one full capture of the traversal kernel (called through gpurun)
 set -x
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
-timeout 1500 python -m pytest tests -m gpu -x -q -s 2>&1 | tail -60 > gpurun_out/pytest_gpu.log
+timeout 1500 python -m pytest tests -m gpu -q -s 2>&1 | tail -80 > gpurun_out/pytest_gpu.log
 cat gpurun_out/pytest_gpu.log
+timeout 900 python bench.py --steps 8 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
+tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
+if [ "$1" == "ncu" ]; then
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_bench.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_trace -s 14 -c 3 -o gpurun_out/prof_trace python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_full.log 2>&1
+  ls -la gpurun_out
+fi
