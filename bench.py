@@ -220,7 +220,7 @@ def run_cuda(args):
         # ---- roofline of the dominant kernel (k_trace): per-launch device time + traversal work counters, measured live ----
         lib.hk_set_profiling(ctx, 1)
         B.call("render_samples_strided", sample_of(args.warmup), world, 2)
-        ms = (C.c_double * 7)(); ln = (C.c_uint64 * 7)(); wk = (C.c_uint64 * 6)()
+        ms = (C.c_double * 8)(); ln = (C.c_uint64 * 8)(); wk = (C.c_uint64 * 6)()
         lib.hk_stage_times(ctx, ms, ln, wk)
         stage_ms = list(ms); stage_ln = list(ln)
         lib.hk_set_profiling(ctx, 2)
@@ -232,7 +232,7 @@ def run_cuda(args):
         trace_bytes = work[0] * 48 + work[1] * 80 + work[2] * 48          # 32 B ray + 16 B hit + 80 B/node + 48 B/tri
         trace_ms = stage_ms[1]
         achieved = trace_bytes / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else 0.0
-        names = ["camera", "trace", "medium", "escaped", "shade", "shadow", "film"]
+        names = ["camera", "trace", "medium", "escaped", "shade", "shadow", "film", "route"]
         total_ms = sum(stage_ms) or 1.0
         roofline = {"kernel": "k_trace (closest-hit BVH8 traversal + queue routing)", "bound": "hbm", "achieved": achieved, "peak": peak,
                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,

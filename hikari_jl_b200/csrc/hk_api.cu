@@ -385,6 +385,7 @@ int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride,
                 if (cnt) k_trace<true><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, cur, work);
                 else k_trace<false><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, cur, work);
             }
+            { StageScope sc(ctx, HK_STAGE_ROUTE); k_route<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->D, ctx->S, cur); }
             if (ctx->D.n_media > 0) { StageScope sc(ctx, HK_STAGE_MEDIUM); k_medium<<<ctx->sm_count * 8, 128, 0, st>>>(ctx->D, ctx->S, A, cur ^ 1); }
             if (ctx->D.n_lights > 0) { StageScope sc(ctx, HK_STAGE_ESCAPED); k_escaped<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->D, ctx->S); }
             launch_shade<HK_MAT_MATTE>(ctx, A, cur ^ 1); launch_shade<HK_MAT_MIRROR>(ctx, A, cur ^ 1); launch_shade<HK_MAT_GLASS>(ctx, A, cur ^ 1);
@@ -392,8 +393,8 @@ int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride,
             launch_shade<HK_MAT_THIN_DIELECTRIC>(ctx, A, cur ^ 1); launch_shade<HK_MAT_DIFFUSE_TRANSMISSION>(ctx, A, cur ^ 1);
             if (ctx->D.n_lights > 0) {
                 StageScope sc(ctx, HK_STAGE_SHADOW);
-                if (opaque_only) { if (cnt) k_shadow<true, true><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, work); else k_shadow<true, false><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, work); }
-                else { if (cnt) k_shadow<false, true><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, work); else k_shadow<false, false><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, work); }
+                if (opaque_only) { if (cnt) k_shadow_opaque<true><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, work); else k_shadow_opaque<false><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, work); }
+                else { if (cnt) k_shadow_general<true><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, work); else k_shadow_general<false><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, work); }
             }
             cur ^= 1;
         }
@@ -477,17 +478,19 @@ int32_t hk_write_accum(HkContext* ctx, const float* rgb, const float* w) {
 }
 
 // ---- stand-alone traversal -----------------------------------------------------------------------------------------
-static int32_t trace_dev(HkContext* ctx, const float* rays_dev, uint64_t n, float* hits_dev, uint8_t* occ_dev, int repeat, bool any, bool count) {
+static int32_t trace_dev(HkContext* ctx, const float* rays_dev, uint64_t n64, float* hits_dev, uint8_t* occ_dev, int repeat, bool any, bool count) {
     cudaStream_t st = ctx->stream;
+    REQUIRE(n64 < 0xFFFFFF00ull, "at most 2^32-256 rays per call");
+    const uint32_t n = (uint32_t)n64;
     unsigned long long* ctr = ctx->b_trace_ctr.as<unsigned long long>();
     CK(cudaEventRecord(ctx->ev0, st));
     for (int r = 0; r < repeat; r++) {
         CK(cudaMemsetAsync(ctr, 0, 24, st));
         const int grid = ctx->sm_count * 8;
         const float4* rp = reinterpret_cast<const float4*>(rays_dev); float4* hp = reinterpret_cast<float4*>(hits_dev);
-        if (any) k_trace_batch<true, false><<<grid, HK_TRACE_THREADS, 0, st>>>(ctx->D.bvh, rp, n, hp, occ_dev, ctr, ctr + 1);
-        else if (count) k_trace_batch<false, true><<<grid, HK_TRACE_THREADS, 0, st>>>(ctx->D.bvh, rp, n, hp, occ_dev, ctr, ctr + 1);
-        else k_trace_batch<false, false><<<grid, HK_TRACE_THREADS, 0, st>>>(ctx->D.bvh, rp, n, hp, occ_dev, ctr, ctr + 1);
+        if (any) k_trace_batch<true, false><<<grid, HK_TRACE_THREADS, 0, st>>>(ctx->D.bvh, rp, n, hp, occ_dev, reinterpret_cast<uint32_t*>(ctr), ctr + 1);
+        else if (count) k_trace_batch<false, true><<<grid, HK_TRACE_THREADS, 0, st>>>(ctx->D.bvh, rp, n, hp, occ_dev, reinterpret_cast<uint32_t*>(ctr), ctr + 1);
+        else k_trace_batch<false, false><<<grid, HK_TRACE_THREADS, 0, st>>>(ctx->D.bvh, rp, n, hp, occ_dev, reinterpret_cast<uint32_t*>(ctr), ctr + 1);
         ctx->launches++;
     }
     CK(cudaEventRecord(ctx->ev1, st));
@@ -495,7 +498,7 @@ static int32_t trace_dev(HkContext* ctx, const float* rays_dev, uint64_t n, floa
     CK(cudaGetLastError());
     float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->stats.last_trace_ms = ms / (float)(repeat > 0 ? repeat : 1);
-    ctx->stats.rays_traced += n * (uint64_t)repeat;
+    ctx->stats.rays_traced += (uint64_t)n * (uint64_t)repeat;
     return HK_OK;
 }
 int32_t hk_trace_closest_dev(HkContext* ctx, const float* rays_dev, uint64_t n, float* hits_dev, int32_t repeat) {

@@ -41,91 +41,139 @@ struct TravStack {
     HK_DEV uint2 pop() { n--; return n < HK_SM_STACK ? sm[n * HK_TRACE_THREADS] : lm[n - HK_SM_STACK]; }
 };
 
+// Traversal state machine.  One call of step() either expands the nearest pending internal node of the current node
+// group (one 80-byte node fetch + 8 slab tests) or hands the group to the triangle loop, tests all pending triangles and
+// pops the next group.  Persistent kernels interleave step() with per-lane refill so that a finished lane takes a new ray
+// instead of idling until the slowest ray of its warp is done (hk_wavefront.cuh::trace_queue).
 // COUNT: accumulate node visits / triangle tests (roofline accounting).  ANY: stop at the first accepted hit.
 template <bool ANY, bool COUNT>
-HK_DEV HitRec bvh8_trace(const DevBvh& B, uint2* sm_stack, float3 o, float3 d, float t_max, uint32_t* n_nodes = nullptr, uint32_t* n_tris = nullptr) {
-    HitRec best; best.t = t_max; best.prim1 = 0; best.b1 = 0.0f; best.b2 = 0.0f;
-    const float3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-    // octant: bit set <=> direction component is non-negative (near children then sit at the - side)
-    const uint32_t oct_inv = (d.x >= 0.0f ? 4u : 0u) | (d.y >= 0.0f ? 2u : 0u) | (d.z >= 0.0f ? 1u : 0u);
-    TravStack st; st.sm = sm_stack; st.n = 0;
-    uint2 ngroup = make_uint2(0u, 0x80000000u);   // root: node base 0, "child bit 31" set, imask irrelevant (relative index 0)
-    uint2 tgroup = make_uint2(0u, 0u);
-    bool root = true;
-    for (;;) {
+struct Bvh8Walker {
+    float3 o, d, inv;
+    float t_max;
+    uint32_t oct_inv;
+    uint2 ngroup, tgroup;
+    TravStack st;
+    HitRec best;
+    bool root;
+
+    HK_DEV void begin(uint2* sm_stack, float3 o_, float3 d_, float t_max_) {
+        o = o_; d = d_; t_max = t_max_;
+        inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+        // octant: bit set <=> direction component is non-negative (near children then sit at the - side)
+        oct_inv = (d.x >= 0.0f ? 4u : 0u) | (d.y >= 0.0f ? 2u : 0u) | (d.z >= 0.0f ? 1u : 0u);
+        st.sm = sm_stack; st.n = 0;
+        ngroup = make_uint2(0u, 0x80000000u);   // root: node base 0, "child bit 31" set
+        tgroup = make_uint2(0u, 0u);
+        best.t = t_max; best.prim1 = 0; best.b1 = 0.0f; best.b2 = 0.0f;
+        root = true;
+    }
+    // returns true when the traversal is finished
+    HK_DEV bool step(const DevBvh& B, uint32_t* n_nodes, uint32_t* n_tris) {
         if (ngroup.y > 0x00FFFFFFu) {
             // ---- pop the nearest pending internal child of this group -------------------------------------
-            uint32_t hits = ngroup.y;
-            uint32_t bit = 31u - (uint32_t)__clz(hits);
+            const uint32_t hits = ngroup.y;
+            const uint32_t bit = 31u - (uint32_t)__clz(hits);
             ngroup.y &= ~(1u << bit);
             if (ngroup.y > 0x00FFFFFFu) st.push(ngroup);
             uint32_t node_idx;
             if (root) { node_idx = 0; root = false; }
             else {
-                uint32_t slot = (bit - 24u) ^ oct_inv;
-                uint32_t imask = hits & 0xFFu;
-                node_idx = ngroup.x + (uint32_t)__popc(imask & ((1u << slot) - 1u));
+                const uint32_t slot = (bit - 24u) ^ oct_inv;
+                node_idx = ngroup.x + (uint32_t)__popc((hits & 0xFFu) & ((1u << slot) - 1u));
             }
             // ---- fetch the 80-byte node as five 16-byte loads --------------------------------------------
             const float4* np = B.nodes + (size_t)node_idx * 5;
-            float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+            const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
             if (COUNT) (*n_nodes)++;
-            uint32_t ex = __float_as_uint(n0.w);
-            float sx = __uint_as_float((ex & 0xFFu) << 23), sy = __uint_as_float(((ex >> 8) & 0xFFu) << 23), sz = __uint_as_float(((ex >> 16) & 0xFFu) << 23);
-            uint32_t imask = ex >> 24;
-            uint32_t child_base = __float_as_uint(n1.x), tri_base = __float_as_uint(n1.y);
-            uint32_t meta_lo = __float_as_uint(n1.z), meta_hi = __float_as_uint(n1.w);
-            // quantised planes: qlo x/y/z = n2.xy, n2.zw, n3.xy ; qhi x/y/z = n3.zw, n4.xy, n4.zw
-            uint32_t q[12] = {__float_as_uint(n2.x), __float_as_uint(n2.y), __float_as_uint(n2.z), __float_as_uint(n2.w),
-                              __float_as_uint(n3.x), __float_as_uint(n3.y), __float_as_uint(n3.z), __float_as_uint(n3.w),
-                              __float_as_uint(n4.x), __float_as_uint(n4.y), __float_as_uint(n4.z), __float_as_uint(n4.w)};
-            const float ax = sx * inv.x, ay = sy * inv.y, az = sz * inv.z;
+            const uint32_t ex = __float_as_uint(n0.w);
+            // slab coefficients: t = q * (2^e / d) + (p - o) / d.  Node culling only has to be conservative, so FMA is fine
+            // here (the exact, contraction-free arithmetic is reserved for the triangle test).
+            const float ax = __uint_as_float((ex & 0xFFu) << 23) * inv.x, ay = __uint_as_float(((ex >> 8) & 0xFFu) << 23) * inv.y, az = __uint_as_float(((ex >> 16) & 0xFFu) << 23) * inv.z;
             const float bx = (n0.x - o.x) * inv.x, by = (n0.y - o.y) * inv.y, bz = (n0.z - o.z) * inv.z;
+            const uint32_t meta_lo = __float_as_uint(n1.z), meta_hi = __float_as_uint(n1.w);
+            // near/far plane words per axis, selected once per node by the ray octant:
+            // qlo x/y/z = n2.xy, n2.zw, n3.xy ; qhi x/y/z = n3.zw, n4.xy, n4.zw
+            const bool px = d.x >= 0.0f, py = d.y >= 0.0f, pz = d.z >= 0.0f;
+            const uint32_t nx0 = __float_as_uint(px ? n2.x : n3.z), nx1 = __float_as_uint(px ? n2.y : n3.w), fx0 = __float_as_uint(px ? n3.z : n2.x), fx1 = __float_as_uint(px ? n3.w : n2.y);
+            const uint32_t ny0 = __float_as_uint(py ? n2.z : n4.x), ny1 = __float_as_uint(py ? n2.w : n4.y), fy0 = __float_as_uint(py ? n4.x : n2.z), fy1 = __float_as_uint(py ? n4.y : n2.w);
+            const uint32_t nz0 = __float_as_uint(pz ? n3.x : n4.z), nz1 = __float_as_uint(pz ? n3.y : n4.w), fz0 = __float_as_uint(pz ? n4.z : n3.x), fz1 = __float_as_uint(pz ? n4.w : n3.y);
             const float tlim = best.t;
             uint32_t hitmask = 0;
 #pragma unroll
             for (int i = 0; i < 8; i++) {
-                const uint32_t meta = ((i < 4 ? meta_lo : meta_hi) >> (8 * (i & 3))) & 0xFFu;
-                if (meta == 0) continue;
-                const int w = i >> 2, sh = 8 * (i & 3);
-                float lox = (float)((q[0 + w] >> sh) & 0xFFu), loy = (float)((q[2 + w] >> sh) & 0xFFu), loz = (float)((q[4 + w] >> sh) & 0xFFu);
-                float hix = (float)((q[6 + w] >> sh) & 0xFFu), hiy = (float)((q[8 + w] >> sh) & 0xFFu), hiz = (float)((q[10 + w] >> sh) & 0xFFu);
-                float tx0 = (d.x >= 0.0f ? lox : hix) * ax + bx, tx1 = (d.x >= 0.0f ? hix : lox) * ax + bx;
-                float ty0 = (d.y >= 0.0f ? loy : hiy) * ay + by, ty1 = (d.y >= 0.0f ? hiy : loy) * ay + by;
-                float tz0 = (d.z >= 0.0f ? loz : hiz) * az + bz, tz1 = (d.z >= 0.0f ? hiz : loz) * az + bz;
+                const int sh = 8 * (i & 3);
+                const uint32_t meta = ((i < 4 ? meta_lo : meta_hi) >> sh) & 0xFFu;
+                const float tx0 = __fmaf_rn((float)(((i < 4 ? nx0 : nx1) >> sh) & 0xFFu), ax, bx), tx1 = __fmaf_rn((float)(((i < 4 ? fx0 : fx1) >> sh) & 0xFFu), ax, bx);
+                const float ty0 = __fmaf_rn((float)(((i < 4 ? ny0 : ny1) >> sh) & 0xFFu), ay, by), ty1 = __fmaf_rn((float)(((i < 4 ? fy0 : fy1) >> sh) & 0xFFu), ay, by);
+                const float tz0 = __fmaf_rn((float)(((i < 4 ? nz0 : nz1) >> sh) & 0xFFu), az, bz), tz1 = __fmaf_rn((float)(((i < 4 ? fz0 : fz1) >> sh) & 0xFFu), az, bz);
                 // fmaxf/fminf drop NaNs (0*inf when the origin lies in a slab plane of a zero direction): conservative
-                float tn = fmaxf(fmaxf(tx0, ty0), fmaxf(tz0, 0.0f));
-                float tf = fminf(fminf(tx1, ty1), fminf(tz1, tlim)) * 1.0000004f;
-                if (tn <= tf) {
-                    uint32_t inner = (meta & (meta << 1)) & 0x10u;             // bits 3 and 4 both set <=> internal child
-                    uint32_t bit_index = (meta ^ (inner ? oct_inv : 0u)) & 0x1Fu;
-                    hitmask |= (meta >> 5) << bit_index;
+                const float tn = fmaxf(fmaxf(tx0, ty0), fmaxf(tz0, 0.0f));
+                const float tf = fminf(fminf(tx1, ty1), fminf(tz1, tlim)) * 1.0000004f;
+                if (meta != 0u && tn <= tf) {
+                    const uint32_t inner = (meta & (meta << 1)) & 0x10u;             // bits 3 and 4 both set <=> internal child
+                    hitmask |= (meta >> 5) << ((meta ^ (inner ? oct_inv : 0u)) & 0x1Fu);
                 }
             }
-            ngroup = make_uint2(child_base, (hitmask & 0xFF000000u) | imask);
-            tgroup = make_uint2(tri_base, hitmask & 0x00FFFFFFu);
+            ngroup = make_uint2(__float_as_uint(n1.x), (hitmask & 0xFF000000u) | (ex >> 24));
+            tgroup = make_uint2(__float_as_uint(n1.y), hitmask & 0x00FFFFFFu);
         } else {
             tgroup = ngroup;
             ngroup = make_uint2(0u, 0u);
         }
         // ---- triangles of this node ----------------------------------------------------------------------
         while (tgroup.y != 0u) {
-            uint32_t ti = (uint32_t)__ffs(tgroup.y) - 1u;
+            const uint32_t ti = (uint32_t)__ffs(tgroup.y) - 1u;
             tgroup.y &= tgroup.y - 1u;
             const float4* tp = B.tris + (size_t)(tgroup.x + ti) * 3;
-            float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+            const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
             if (COUNT) (*n_tris)++;
             float t, u, v;
             if (tri_test(o, d, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), t_max, t, u, v)) {
-                uint32_t prim1 = __float_as_uint(a.w) + 1u;
-                if (ANY) { best.t = t; best.prim1 = prim1; best.b1 = u; best.b2 = v; return best; }
+                const uint32_t prim1 = __float_as_uint(a.w) + 1u;
+                if (ANY) { best.t = t; best.prim1 = prim1; best.b1 = u; best.b2 = v; return true; }
                 if (best.prim1 == 0u || t < best.t || (t == best.t && prim1 < best.prim1)) { best.t = t; best.prim1 = prim1; best.b1 = u; best.b2 = v; }
             }
         }
         if (ngroup.y <= 0x00FFFFFFu) {
-            if (st.n == 0) break;
+            if (st.n == 0) return true;
             ngroup = st.pop();
         }
+        return false;
     }
-    return best;
+};
+
+// blocking form (one ray, run to completion)
+template <bool ANY, bool COUNT>
+HK_DEV HitRec bvh8_trace(const DevBvh& B, uint2* sm_stack, float3 o, float3 d, float t_max, uint32_t* n_nodes = nullptr, uint32_t* n_tris = nullptr) {
+    Bvh8Walker<ANY, COUNT> w;
+    w.begin(sm_stack, o, d, t_max);
+    while (!w.step(B, n_nodes, n_tris)) {}
+    return w.best;
+}
+
+// Persistent per-lane refill loop: every lane owns one in-flight ray; a lane whose ray finishes immediately claims the
+// next queue entry (claims of the lanes that are idle at the same time are aggregated into one atomicAdd).
+// IO supplies  bool load(idx, o, d, t_max)  and  void store(idx, hit).
+template <bool ANY, bool COUNT, class IO>
+HK_DEV void trace_queue(const DevBvh& B, uint2* sm_stack, uint32_t n, uint32_t* cursor, IO& io, uint32_t& traced, uint32_t& wn, uint32_t& wt) {
+    Bvh8Walker<ANY, COUNT> w;
+    bool busy = false;
+    uint32_t idx = 0;
+    const unsigned lane = threadIdx.x & 31u;
+    for (;;) {
+        if (!busy) {
+            const unsigned m = __activemask();
+            const unsigned leader = (unsigned)__ffs(m) - 1u;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(cursor, (uint32_t)__popc(m));
+            base = __shfl_sync(m, base, leader);
+            idx = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+            if (idx >= n) break;
+            float3 o, d; float tm;
+            io.load(idx, o, d, tm);
+            w.begin(sm_stack, o, d, tm);
+            busy = true; traced++;
+        }
+        if (w.step(B, &wn, &wt)) { io.store(idx, w.best); busy = false; }
+    }
 }

@@ -187,38 +187,45 @@ HK_DEV uint32_t* queue_of(const PathState& S, int qid) {
     return nullptr;
 }
 
-// vp_trace_rays_kernel!, intersection.jl:188-269: closest hit + routing.  Persistent: warps pull 32 rays at a time.
+// vp_trace_rays_kernel!, intersection.jl:188-269, split in two: k_trace = closest hit for every queued ray
+// (persistent, per-lane refill), k_route = classification into the medium / escaped / per-material queues.
+struct QueueRayIO {
+    const PathState& S; const uint32_t* __restrict__ q;
+    HK_DEV void load(uint32_t idx, float3& o, float3& d, float& tm) const {
+        const uint32_t slot = q[idx];
+        const float4 ra = S.ray_a[slot], rb = S.ray_b[slot];
+        o = f3(ra.x, ra.y, ra.z); d = f3(ra.w, rb.x, rb.y); tm = rb.z;
+    }
+    HK_DEV void store(uint32_t idx, const HitRec& h) const { S.hit[q[idx]] = make_float4(h.t, __uint_as_float(h.prim1), h.b1, h.b2); }
+};
 template <bool COUNT>
 __global__ void __launch_bounds__(HK_TRACE_THREADS) k_trace(const __grid_constant__ DevScene D, PathState S, int cur, unsigned long long* work) {
     __shared__ uint2 sm_stack[HK_SM_STACK * HK_TRACE_THREADS];
     const uint32_t n = S.counts[HK_C_RAY0 + cur];
-    const unsigned lane = threadIdx.x & 31u;
     uint32_t traced = 0, wn = 0, wt = 0;
-    for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(S.counts + HK_C_CURSOR_TRACE, 32u);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (base >= n) break;
-        const uint32_t idx = base + lane;
+    QueueRayIO io{S, S.q_ray[cur]};
+    trace_queue<false, COUNT>(D.bvh, sm_stack + threadIdx.x, n, S.counts + HK_C_CURSOR_TRACE, io, traced, wn, wt);
+    count_rays(S.rays_traced, traced);
+    if (COUNT) { count_rays(work, traced); count_rays(work + 1, wn); count_rays(work + 2, wt); }
+}
+// in-medium rays go to delta tracking with their hit record; the vacuum alpha loop (:224-266) ends on its first iteration
+// because every constant-parameter material has alpha == 1 (spectral-eval.jl:3882-3888)
+__global__ void __launch_bounds__(256) k_route(const __grid_constant__ DevScene D, PathState S, int cur) {
+    const uint32_t n = S.counts[HK_C_RAY0 + cur];
+    const uint32_t n_round = (n + 31u) & ~31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
         int qid = -1; uint32_t slot = 0;
-        if (idx < n) {
-            slot = S.q_ray[cur][idx];
-            float4 ra = S.ray_a[slot], rb = S.ray_b[slot];
-            HitRec h = bvh8_trace<false, COUNT>(D.bvh, sm_stack + threadIdx.x, f3(ra.x, ra.y, ra.z), f3(ra.w, rb.x, rb.y), rb.z, &wn, &wt);
-            traced++;
-            S.hit[slot] = make_float4(h.t, __uint_as_float(h.prim1), h.b1, h.b2);
-            // in-medium rays go to delta tracking with their hit record; the vacuum alpha loop (:224-266) ends on its
-            // first iteration because every constant-parameter material has alpha == 1 (spectral-eval.jl:3882-3888)
+        if (i < n) {
+            slot = S.q_ray[cur][i];
+            const uint32_t prim1 = __float_as_uint(S.hit[slot].y);
             if (HK_FLAG_MEDIUM(S.flags[slot]) != 0) qid = HK_C_MEDIUM;
-            else if (h.prim1 == 0) qid = HK_C_ESCAPED;
-            else qid = HK_C_HIT0 + material_type_of_prim(D, h.prim1 - 1);
+            else if (prim1 == 0) qid = HK_C_ESCAPED;
+            else qid = HK_C_HIT0 + material_type_of_prim(D, prim1 - 1);
         }
         warp_push(S.counts, nullptr, qid, slot, queue_of(S, qid));
         unsigned hm = __ballot_sync(0xFFFFFFFFu, qid >= HK_C_HIT0);
-        if (lane == 0 && hm) atomicAdd(S.counts + HK_C_TOTAL_HITS, (uint32_t)__popc(hm));
+        if ((threadIdx.x & 31u) == 0 && hm) atomicAdd(S.counts + HK_C_TOTAL_HITS, (uint32_t)__popc(hm));
     }
-    count_rays(S.rays_traced, traced);
-    if (COUNT) { count_rays(work, traced); count_rays(work + 1, wn); count_rays(work + 2, wt); }
 }
 
 // vp_handle_escaped_rays_kernel!, intersection.jl:622-668
@@ -439,12 +446,41 @@ __global__ void __launch_bounds__(128) k_medium(const __grid_constant__ DevScene
 }
 
 // trace_shadow_transmittance + vp_trace_shadow_rays_kernel!, intersection.jl:302-406, 565-600.
-// OPAQUE_ONLY (no interface with inside != outside, no media): visibility is a single any-hit query, which yields the
-// same T in {0,1} as the reference's closest-hit loop.  Otherwise the ordered closest-hit walk with ratio tracking.
-template <bool OPAQUE_ONLY, bool COUNT>
-__global__ void __launch_bounds__(HK_TRACE_THREADS) k_shadow(const __grid_constant__ DevScene D, PathState S, unsigned long long* work) {
+// Opaque-only scenes (no interface with inside != outside, no media): visibility is a single any-hit query, which yields
+// the same T in {0,1} as the reference's closest-hit loop.  Otherwise the ordered closest-hit walk with ratio tracking.
+struct ShadowRayIO {
+    const PathState& S;
+    HK_DEV void load(uint32_t idx, float3& o, float3& d, float& tm) const {
+        const uint32_t slot = S.q_shadow[idx];
+        const float4 sa = S.sh_a[slot], sb = S.sh_b[slot];
+        o = f3(sa.x, sa.y, sa.z); d = f3(sa.w, sb.x, sb.y);
+        tm = sb.z < 1.0e-6f ? -1.0f : sb.z;          // t_remaining < 1e-6: the reference's loop breaks => treated as occluded
+    }
+    HK_DEV void store(uint32_t idx, const HitRec& h) const {
+        const uint32_t slot = S.q_shadow[idx];
+        if (h.prim1 != 0u || S.sh_b[slot].z < 1.0e-6f) return;      // blocked
+        const float den = sp_avg(S.sh_ru[slot] + S.sh_rl[slot]);     // T = tr_u = tr_l = 1
+        if (den > 1.0e-10f) {
+            const Spec fin = S.sh_Ld[slot] / den;
+            if (!sp_black(fin)) S.L[slot] = S.L[slot] + fin;
+        }
+    }
+};
+template <bool COUNT>
+__global__ void __launch_bounds__(HK_TRACE_THREADS) k_shadow_opaque(const __grid_constant__ DevScene D, PathState S, unsigned long long* work) {
     __shared__ uint2 sm_stack[HK_SM_STACK * HK_TRACE_THREADS];
     // reference quirk (volpath.jl:571-609): shadow rays are only traced inside the `n_hits > 0` branch
+    if (S.counts[HK_C_TOTAL_HITS] == 0) return;
+    const uint32_t n = S.counts[HK_C_SHADOW];
+    uint32_t traced = 0, wn = 0, wt = 0;
+    ShadowRayIO io{S};
+    trace_queue<true, COUNT>(D.bvh, sm_stack + threadIdx.x, n, S.counts + HK_C_CURSOR_SHADOW, io, traced, wn, wt);
+    count_rays(S.rays_traced, traced);
+    if (COUNT) { count_rays(work + 3, traced); count_rays(work + 4, wn); count_rays(work + 5, wt); }
+}
+template <bool COUNT>
+__global__ void __launch_bounds__(HK_TRACE_THREADS) k_shadow_general(const __grid_constant__ DevScene D, PathState S, unsigned long long* work) {
+    __shared__ uint2 sm_stack[HK_SM_STACK * HK_TRACE_THREADS];
     if (S.counts[HK_C_TOTAL_HITS] == 0) return;
     const uint32_t n = S.counts[HK_C_SHADOW];
     const unsigned lane = threadIdx.x & 31u;
@@ -463,37 +499,28 @@ __global__ void __launch_bounds__(HK_TRACE_THREADS) k_shadow(const __grid_consta
         const float3 d = f3(sa.w, sb.x, sb.y);
         float t_rem = sb.z;
         Spec T = sp(1.0f), tu = sp(1.0f), tl = sp(1.0f);
-        bool visible = false;
-        if (OPAQUE_ONLY) {
-            if (!(t_rem < 1.0e-6f)) {
-                HitRec h = bvh8_trace<true, COUNT>(D.bvh, sm_stack + threadIdx.x, o, d, t_rem, &wn, &wt);
-                traced++;
-                visible = h.prim1 == 0;
+        bool visible = false, done = false;
+        const float4 lam = S.lambda[slot];
+        uint32_t cur = S.sh_medium[slot];
+        for (int it = 0; it < 10 && !done; it++) {
+            if (t_rem < 1.0e-6f) break;
+            HitRec h = bvh8_trace<false, COUNT>(D.bvh, sm_stack + threadIdx.x, o, d, t_rem, &wn, &wt);
+            traced++;
+            if (h.prim1 == 0) {
+                if (cur != 0) { Spec a, b, c; ratio_track(MDC, (int)cur, o, d, t_rem, lam, a, b, c); T = T * a; tu = tu * b; tl = tl * c; }
+                visible = true; done = true; break;
             }
-        } else {
-            const float4 lam = S.lambda[slot];
-            uint32_t cur = S.sh_medium[slot];
-            bool done = false;
-            for (int it = 0; it < 10 && !done; it++) {
-                if (t_rem < 1.0e-6f) break;
-                HitRec h = bvh8_trace<false, COUNT>(D.bvh, sm_stack + threadIdx.x, o, d, t_rem, &wn, &wt);
-                traced++;
-                if (h.prim1 == 0) {
-                    if (cur != 0) { Spec a, b, c; ratio_track(MDC, (int)cur, o, d, t_rem, lam, a, b, c); T = T * a; tu = tu * b; tl = tl * c; }
-                    visible = true; done = true; break;
-                }
-                const uint32_t prim0 = h.prim1 - 1u;
-                const HkMediumInterface mi = D.interfaces[__ldg(D.tri_meta + 3 * (size_t)prim0) - 1];
-                if (mi.inside == mi.outside) { visible = false; done = true; break; }   // opaque (alpha == 1)
-                if (cur != 0) { Spec a, b, c; ratio_track(MDC, (int)cur, o, d, h.t, lam, a, b, c); T = T * a; tu = tu * b; tl = tl * c; }
-                if (sp_black(T)) { visible = true; done = true; break; }
-                const bool entering = dot3(d, geometric_normal(D, prim0)) < 0.0f;
-                cur = entering ? mi.inside : mi.outside;
-                o = o + d * (h.t + 1.0e-4f);
-                t_rem = t_rem - h.t - 1.0e-4f;
-            }
-            if (!done) visible = false;
+            const uint32_t prim0 = h.prim1 - 1u;
+            const HkMediumInterface mi = D.interfaces[__ldg(D.tri_meta + 3 * (size_t)prim0) - 1];
+            if (mi.inside == mi.outside) { visible = false; done = true; break; }   // opaque (alpha == 1)
+            if (cur != 0) { Spec a, b, c; ratio_track(MDC, (int)cur, o, d, h.t, lam, a, b, c); T = T * a; tu = tu * b; tl = tl * c; }
+            if (sp_black(T)) { visible = true; done = true; break; }
+            const bool entering = dot3(d, geometric_normal(D, prim0)) < 0.0f;
+            cur = entering ? mi.inside : mi.outside;
+            o = o + d * (h.t + 1.0e-4f);
+            t_rem = t_rem - h.t - 1.0e-4f;
         }
+        if (!done) visible = false;
         if (visible && !sp_black(T)) {
             float den = sp_avg(S.sh_ru[slot] * tu + S.sh_rl[slot] * tl);
             if (den > 1.0e-10f) {
@@ -538,28 +565,26 @@ __global__ void __launch_bounds__(256) k_film_finalize(const float* __restrict__
 }
 
 // stand-alone traversal: rays [n][8] -> hits [n][4]   (hk_trace_closest / hk_trace_any)
-template <bool ANY, bool COUNT>
-__global__ void __launch_bounds__(HK_TRACE_THREADS) k_trace_batch(DevBvh B, const float4* __restrict__ rays, uint64_t n, float4* __restrict__ hits,
-                                                                uint8_t* __restrict__ occluded, unsigned long long* cursor, unsigned long long* counters) {
-    __shared__ uint2 sm_stack[HK_SM_STACK * HK_TRACE_THREADS];
-    const unsigned lane = threadIdx.x & 31u;
-    uint32_t nn = 0, nt = 0;
-    for (;;) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(cursor, 32ull);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (base >= n) break;
-        const unsigned long long i = base + lane;
-        if (i >= n) continue;
-        float4 ra = __ldg(rays + 2 * i), rb = __ldg(rays + 2 * i + 1);
-        HitRec h = bvh8_trace<ANY, COUNT>(B, sm_stack + threadIdx.x, f3(ra.x, ra.y, ra.z), f3(ra.w, rb.x, rb.y), rb.z, &nn, &nt);
+template <bool ANY>
+struct BatchRayIO {
+    const float4* __restrict__ rays; float4* __restrict__ hits; uint8_t* __restrict__ occluded;
+    HK_DEV void load(uint32_t i, float3& o, float3& d, float& tm) const {
+        const float4 ra = __ldg(rays + 2 * (size_t)i), rb = __ldg(rays + 2 * (size_t)i + 1);
+        o = f3(ra.x, ra.y, ra.z); d = f3(ra.w, rb.x, rb.y); tm = rb.z;
+    }
+    HK_DEV void store(uint32_t i, const HitRec& h) const {
         if (ANY) occluded[i] = h.prim1 ? 1 : 0;
-        else hits[i] = make_float4(h.prim1 ? h.t : rb.z, __uint_as_float(h.prim1), h.b1, h.b2);
+        else hits[i] = make_float4(h.prim1 ? h.t : __ldg(rays + 2 * (size_t)i + 1).z, __uint_as_float(h.prim1), h.b1, h.b2);
     }
-    if (COUNT) {
-        for (int o = 16; o > 0; o >>= 1) { nn += __shfl_down_sync(0xFFFFFFFFu, nn, o); nt += __shfl_down_sync(0xFFFFFFFFu, nt, o); }
-        if (lane == 0) { atomicAdd(counters, (unsigned long long)nn); atomicAdd(counters + 1, (unsigned long long)nt); }
-    }
+};
+template <bool ANY, bool COUNT>
+__global__ void __launch_bounds__(HK_TRACE_THREADS) k_trace_batch(DevBvh B, const float4* __restrict__ rays, uint32_t n, float4* __restrict__ hits,
+                                                                uint8_t* __restrict__ occluded, uint32_t* cursor, unsigned long long* counters) {
+    __shared__ uint2 sm_stack[HK_SM_STACK * HK_TRACE_THREADS];
+    uint32_t traced = 0, nn = 0, nt = 0;
+    BatchRayIO<ANY> io{rays, hits, occluded};
+    trace_queue<ANY, COUNT>(B, sm_stack + threadIdx.x, n, cursor, io, traced, nn, nt);
+    if (COUNT) { count_rays(counters, nn); count_rays(counters + 1, nt); }
 }
 
 // detect_camera_medium, intersection.jl:690-747 (single thread; run once per camera change, not once per sample)

@@ -330,7 +330,8 @@ int32_t hk_stats(HkContext* ctx, HkStats* out);
 #define HK_STAGE_SHADE   4
 #define HK_STAGE_SHADOW  5
 #define HK_STAGE_FILM    6
-#define HK_N_STAGES      7
+#define HK_STAGE_ROUTE   7
+#define HK_N_STAGES      8
 int32_t hk_set_profiling(HkContext* ctx, int32_t mode);
 int32_t hk_stage_times(HkContext* ctx, double* out_ms, uint64_t* out_launches, uint64_t* out_work);
 int32_t hk_synchronize(HkContext* ctx);
