@@ -241,7 +241,7 @@ def run_cuda(args):
                     "stage_share": {nm: stage_ms[i] / total_ms for i, nm in enumerate(names)},
                     "shadow": {"rays": work[3], "node_visits_per_ray": work[4] / max(1, work[3]), "tri_tests_per_ray": work[5] / max(1, work[3]),
                                "achieved": (work[3] * 48 + work[4] * 80 + work[5] * 48) / max(1e-9, stage_ms[5] * 1e-3) / 1e9}}
-        cpu = cpu_baseline_leg()
+        cpu = None if args.quick else cpu_baseline_leg()
         line = {
             "metric": "VolPath throughput", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -253,6 +253,7 @@ def run_cuda(args):
                     "scene_upload_s": t_upload},
             "gpu_launches": int(launches), "wall_s": wall, "film_reduce_ms": red_ms, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         }
+        line["roofline"]["stage_ms_per_step"] = {nm: stage_ms[i] / 2.0 for i, nm in enumerate(names)}
     vp.close()
     if dist:
         dist.barrier(); dist.destroy_process_group()
@@ -266,6 +267,7 @@ def main():
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--quick", action="store_true", help="development: skip the CPU baseline leg (tuning-variant sweeps, tools/variants.py)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else max(args.warmup, 1)
     if args.impl == "reference":

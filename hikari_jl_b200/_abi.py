@@ -179,6 +179,8 @@ def bind_hk(lib):
 
 _LIB = None
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libhikari_cuda.so")
+if os.environ.get("HK_CUDA_LIB"):      # development only: a tuning variant of the same CUDA library (tools/variants.sh)
+    LIB_PATH = os.path.abspath(os.environ["HK_CUDA_LIB"])
 
 
 def load_library():

@@ -145,6 +145,16 @@ int32_t hk_upload_tables(HkContext* ctx, const HkTables* t) {
     T.sobol = ctx->b_sobol.as<uint32_t>(); T.cie_x = ctx->b_cie_x.as<float>(); T.cie_y = ctx->b_cie_y.as<float>(); T.cie_z = ctx->b_cie_z.as<float>();
     T.d65 = ctx->b_d65.as<float>(); T.rgb_scale = ctx->b_rgb_scale.as<float>(); T.rgb_coeffs = ctx->b_rgb_coeffs.as<float4>(); T.rgb_res = t->rgb2spec_res;
     ctx->D.sobol.M = T.sobol;
+    {   // closed forms for Sobol' dimensions 0 and 1 are only used when the uploaded table really has that structure
+        const uint32_t* M = t->sobol_matrices;
+        auto pascal_col = [](int j) { uint32_t r = 0; for (int i = 0; i <= j && i < 32; i++) if ((j & i) == i) r |= 0x80000000u >> i; return r; };   // C(j,i) odd <=> i subset of j
+        bool ok = true;
+        for (int j = 0; j < 52 && ok; j++) {
+            ok = M[j] == (j < 32 ? 0x80000000u >> j : 0u);
+            if (ok) ok = M[52 + j] == pascal_col(j & 31) && (j < 32 || j - 32 < 32);
+        }
+        ctx->D.sobol.fast = ok ? 1 : 0;
+    }
     ctx->have_tables = true;
     return HK_OK;
 }
@@ -368,7 +378,7 @@ int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride,
     const bool opaque_only = !ctx->D.any_medium_transition && ctx->D.n_media == 0;
     const bool cnt = (ctx->profiling & 2) != 0;
     unsigned long long* work = ctx->b_work_ctr.as<unsigned long long>();
-    const int tgrid = ctx->sm_count * 8;
+    const int tgrid = ctx->sm_count * HK_TRACE_BLOCKS_PER_SM;
     CK(cudaEventRecord(ctx->ev0, st));
     int32_t done = 0;
     while (done < count) {
@@ -486,7 +496,7 @@ static int32_t trace_dev(HkContext* ctx, const float* rays_dev, uint64_t n64, fl
     CK(cudaEventRecord(ctx->ev0, st));
     for (int r = 0; r < repeat; r++) {
         CK(cudaMemsetAsync(ctr, 0, 24, st));
-        const int grid = ctx->sm_count * 8;
+        const int grid = ctx->sm_count * HK_TRACE_BLOCKS_PER_SM;
         const float4* rp = reinterpret_cast<const float4*>(rays_dev); float4* hp = reinterpret_cast<float4*>(hits_dev);
         if (any) k_trace_batch<true, false><<<grid, HK_TRACE_THREADS, 0, st>>>(ctx->D.bvh, rp, n, hp, occ_dev, reinterpret_cast<uint32_t*>(ctr), ctr + 1);
         else if (count) k_trace_batch<false, true><<<grid, HK_TRACE_THREADS, 0, st>>>(ctx->D.bvh, rp, n, hp, occ_dev, reinterpret_cast<uint32_t*>(ctr), ctr + 1);

@@ -143,7 +143,11 @@ HK_DEV float lcg_next(uint64_t& s) {                           // delta-tracking
 // ---- ZSobol, sobol.jl:17-309.  Integer-exact; loops are trimmed to the iterations that can contribute
 // (digits i in [last_digit, n_base4_digits) and index bits below 2*n_base4_digits), which leaves every
 // output bit identical to the reference's fixed 32 / 52 iteration loops. ----------------------------------
-struct SobolParams { const uint32_t* __restrict__ M; int32_t log2_spp, n_base4_digits; uint32_t seed; };
+// `fast` != 0: the uploaded matrices for dimensions 0 and 1 were verified on the host (hk_upload_tables) to be the
+// standard ones -- dimension 0 = bit reversal, dimension 1 = bit-reversed Pascal triangle mod 2 with columns 32.. repeating
+// columns 0.. -- so sobol_bits() can use their closed forms (a GF(2)-linear map applied as a 5-level butterfly) instead of
+// one dependent table load per set index bit.  Same output bits either way.
+struct SobolParams { const uint32_t* __restrict__ M; int32_t log2_spp, n_base4_digits; uint32_t seed; int32_t fast; };
 
 HK_DEV uint64_t left_shift2(uint64_t x) {
     x &= 0xffffffffull;
@@ -164,11 +168,26 @@ HK_DEV uint32_t fast_owen_scramble(uint32_t v, uint32_t seed) {
     v ^= v * 0x53a22864u;
     return __brev(v);
 }
-// the 24 permutations of (0,1,2,3), 2 bits per entry packed into one byte each (sobol.jl:155-180)
-__device__ __constant__ uint8_t c_perm4[24] = {
-    0xE4, 0xB4, 0xD8, 0x78, 0x6C, 0x9C, 0xE1, 0xB1, 0xC9, 0x39, 0x2D, 0x8D,
-    0xC6, 0x36, 0xD2, 0x72, 0x4E, 0x1E, 0x27, 0x87, 0x1B, 0x4B, 0x63, 0x93};
-HK_DEV uint64_t zsobol_sample_index(uint64_t morton, int32_t dim, int32_t log2_spp, int32_t nb4) {
+// the 24 permutations of (0,1,2,3), 2 bits per entry packed into one byte each (sobol.jl:155-180), held as six words in
+// registers and indexed with PRMT: a per-lane index into __constant__ memory serialises over the distinct addresses of a
+// warp (it was the top stall line of k_shade in ncu), three byte-permutes and two selects do not.
+HK_DEV uint32_t perm4_byte(uint32_t p) {   // p in [0, 24)
+    const uint32_t a = __byte_perm(0x78D8B4E4u, 0xB1E19C6Cu, p & 7u);      // entries 0..7   (selector uses the low 3 bits)
+    const uint32_t b = __byte_perm(0x8D2D39C9u, 0x72D236C6u, p & 7u);      // entries 8..15
+    const uint32_t c = __byte_perm(0x87271E4Eu, 0x93634B1Bu, p & 7u);      // entries 16..23
+    return (p < 8u ? a : (p < 16u ? b : c)) & 0xFFu;
+}
+// not inlined: the digit loop is ~600 instructions and has five call sites per shading kernel; inlining all of them made
+// the kernels instruction-fetch bound (stall_no_instruction was the top stall reason)
+#ifndef HK_SOBOL_NOINLINE
+#define HK_SOBOL_NOINLINE 1
+#endif
+#if HK_SOBOL_NOINLINE
+__device__ __noinline__
+#else
+HK_DEV
+#endif
+uint64_t zsobol_sample_index(uint64_t morton, int32_t dim, int32_t log2_spp, int32_t nb4) {
     uint64_t idx = 0;
     const int pow2 = log2_spp & 1;
     const uint64_t dmix = 0x55555555ull * (uint64_t)(int64_t)dim;
@@ -177,8 +196,11 @@ HK_DEV uint64_t zsobol_sample_index(uint64_t morton, int32_t dim, int32_t log2_s
         uint32_t digit = (uint32_t)(morton >> shift) & 3u;
         int hs = shift + 2;
         uint64_t higher = hs >= 64 ? 0ull : (morton >> hs);
-        uint32_t p = (uint32_t)((mix_bits(higher ^ dmix) >> 24) % 24ull);
-        uint64_t pd = (c_perm4[p] >> (2 * digit)) & 3u;
+        // (h >> 24) % 24 for the 40-bit value h >> 24, in 32-bit arithmetic: 2^24 mod 24 = 16, so
+        // h>>24 = top16 * 2^24 + low24  ==  top16 * 16 + low24  (mod 24), which is < 2^25
+        const uint64_t hm = mix_bits(higher ^ dmix);
+        const uint32_t p = ((uint32_t)(hm >> 48) * 16u + ((uint32_t)(hm >> 24) & 0xFFFFFFu)) % 24u;
+        const uint64_t pd = (perm4_byte(p) >> (2 * digit)) & 3u;
         idx |= pd << shift;
     }
     if (pow2) {
@@ -193,19 +215,28 @@ HK_DEV uint32_t sobol_bits(uint64_t a, int32_t dimension, const uint32_t* __rest
     for (int bit = 0; a != 0; ++bit, a >>= 1) if (a & 1) v ^= __ldg(m + bit);
     return v;
 }
+HK_DEV uint32_t pascal_butterfly(uint32_t x) {   // y_i = XOR_{j >= i} C(j, i) x_j  (Kronecker power of [[1,1],[0,1]])
+    x ^= (x >> 1) & 0x55555555u; x ^= (x >> 2) & 0x33333333u; x ^= (x >> 4) & 0x0f0f0f0fu;
+    x ^= (x >> 8) & 0x00ff00ffu; x ^= (x >> 16) & 0x0000ffffu;
+    return x;
+}
+HK_DEV uint32_t sobol_bits0(const SobolParams& S, uint64_t a) { return S.fast ? __brev((uint32_t)a) : sobol_bits(a, 0, S.M); }
+HK_DEV uint32_t sobol_bits1(const SobolParams& S, uint64_t a) {
+    return S.fast ? __brev(pascal_butterfly((uint32_t)a) ^ pascal_butterfly((uint32_t)(a >> 32))) : sobol_bits(a, 1, S.M);
+}
 HK_DEV float sobol_to_float(uint32_t v) { return fminf((float)v * 2.3283064365386963e-10f, HK_ONE_MINUS_EPS); }
 HK_DEV float zsobol_1d(const SobolParams& S, int32_t px, int32_t py, int32_t sample_idx, int32_t dim) {
     uint64_t morton = (encode_morton2((uint32_t)px, (uint32_t)py) << S.log2_spp) | (uint64_t)(int64_t)sample_idx;
     uint64_t si = zsobol_sample_index(morton, dim, S.log2_spp, S.n_base4_digits);
     uint32_t h = (uint32_t)hash_dim_seed(dim + 1, S.seed);
-    return sobol_to_float(fast_owen_scramble(sobol_bits(si, 0, S.M), h));
+    return sobol_to_float(fast_owen_scramble(sobol_bits0(S, si), h));
 }
 HK_DEV float2 zsobol_2d(const SobolParams& S, int32_t px, int32_t py, int32_t sample_idx, int32_t dim) {
     uint64_t morton = (encode_morton2((uint32_t)px, (uint32_t)py) << S.log2_spp) | (uint64_t)(int64_t)sample_idx;
     uint64_t si = zsobol_sample_index(morton, dim, S.log2_spp, S.n_base4_digits);
     uint64_t bits = hash_dim_seed(dim + 2, S.seed);
-    return make_float2(sobol_to_float(fast_owen_scramble(sobol_bits(si, 0, S.M), (uint32_t)bits)),
-                       sobol_to_float(fast_owen_scramble(sobol_bits(si, 1, S.M), (uint32_t)(bits >> 32))));
+    return make_float2(sobol_to_float(fast_owen_scramble(sobol_bits0(S, si), (uint32_t)bits)),
+                       sobol_to_float(fast_owen_scramble(sobol_bits1(S, si), (uint32_t)(bits >> 32))));
 }
 
 // ---- sampling primitives, sampling.jl:5-33, spectral-eval.jl:3514-3533 ------------------------------------

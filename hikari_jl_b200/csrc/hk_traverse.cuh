@@ -11,13 +11,34 @@
 #include "hk_math.cuh"
 #include "hk_bvh.h"
 
+#ifndef HK_SM_STACK
 #define HK_SM_STACK 8
+#endif
 #define HK_LM_STACK 24
+#ifndef HK_TRACE_THREADS
 #define HK_TRACE_THREADS 128
+#endif
+// tuning switches (tools/variants.sh builds and times the alternatives on the GPU; defaults = the measured best)
+#ifndef HK_QF_PRMT
+#define HK_QF_PRMT 1          // 1: byte -> float by PRMT (ALU pipe), 0: by I2F (XU pipe)
+#endif
+#ifndef HK_REFILL_MIN
+#define HK_REFILL_MIN 8       // idle lanes of a warp needed before the warp fetches new rays
+#endif
+#ifndef HK_NODE_PREFETCH
+#define HK_NODE_PREFETCH 0    // 1: L1-prefetch the node that will be visited next while this node's triangles are tested
+#endif
+#ifndef HK_RCP_APPROX
+#define HK_RCP_APPROX 0       // 1: MUFU.RCP for the inverse direction (slab tests only)
+#endif
+#ifndef HK_TRACE_BLOCKS_PER_SM
+#define HK_TRACE_BLOCKS_PER_SM 8
+#endif
 
 struct DevBvh { const float4* __restrict__ nodes; const float4* __restrict__ tris; };
 struct HitRec { float t; uint32_t prim1; float b1, b2; };   // prim1: 1-based global id, 0 = miss
 
+HK_DEV float __frcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 HK_DEV bool tri_test(float3 o, float3 d, float3 v0, float3 e1, float3 e2, float t_max, float& t, float& u, float& v) {
     float3 pvec = cross3(d, e2);
     float det = dot3(e1, pvec);
@@ -35,16 +56,21 @@ HK_DEV bool tri_test(float3 o, float3 d, float3 v0, float3 e1, float3 e2, float 
 
 struct TravStack {
     uint2* sm;          // shared column base for this thread (stride HK_TRACE_THREADS)
-    uint2 lm[HK_LM_STACK];
+    uint2* lm;          // overflow entries: a local-memory array owned by the caller (kept OUT of the walker struct --
+                        // a dynamically indexed member array pins the whole struct, n and the node groups included,
+                        // in local memory, which showed up as ~20 M local-store sectors per launch in ncu)
     int n;
     HK_DEV void push(uint2 v) { if (n < HK_SM_STACK) sm[n * HK_TRACE_THREADS] = v; else lm[n - HK_SM_STACK] = v; n++; }
     HK_DEV uint2 pop() { n--; return n < HK_SM_STACK ? sm[n * HK_TRACE_THREADS] : lm[n - HK_SM_STACK]; }
 };
 
-// Traversal state machine.  One call of step() either expands the nearest pending internal node of the current node
-// group (one 80-byte node fetch + 8 slab tests) or hands the group to the triangle loop, tests all pending triangles and
-// pops the next group.  Persistent kernels interleave step() with per-lane refill so that a finished lane takes a new ray
-// instead of idling until the slowest ray of its warp is done (hk_wavefront.cuh::trace_queue).
+// Traversal state machine, split into two kinds of unit work so that a warp can interleave them lane by lane:
+//   node_step(): pop the nearest pending internal child (from the current node group or the stack), fetch that 80-byte
+//                node, slab-test its 8 quantised children -> new node group + the triangles of the leaf children hit;
+//   tri_step():  test ONE pending triangle.
+// The persistent loop (trace_queue) runs "node_step for lanes without pending triangles, then tri_step for lanes with
+// pending triangles" per iteration: a lane whose leaf has several triangles keeps testing them in the following iterations
+// while its neighbours already expand their next node, instead of the whole warp waiting for the longest triangle list.
 // COUNT: accumulate node visits / triangle tests (roofline accounting).  ANY: stop at the first accepted hit.
 template <bool ANY, bool COUNT>
 struct Bvh8Walker {
@@ -54,89 +80,110 @@ struct Bvh8Walker {
     uint2 ngroup, tgroup;
     TravStack st;
     HitRec best;
-    bool root;
 
-    HK_DEV void begin(uint2* sm_stack, float3 o_, float3 d_, float t_max_) {
+    HK_DEV void begin(uint2* sm_stack, uint2* lm_stack, float3 o_, float3 d_, float t_max_) {
         o = o_; d = d_; t_max = t_max_;
-        inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+#if HK_RCP_APPROX
+        inv = f3(__frcp_approx(d.x), __frcp_approx(d.y), __frcp_approx(d.z));
+#else
+        inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);   // feeds the (conservative) slab tests only
+#endif
         // octant: bit set <=> direction component is non-negative (near children then sit at the - side)
         oct_inv = (d.x >= 0.0f ? 4u : 0u) | (d.y >= 0.0f ? 2u : 0u) | (d.z >= 0.0f ? 1u : 0u);
-        st.sm = sm_stack; st.n = 0;
-        ngroup = make_uint2(0u, 0x80000000u);   // root: node base 0, "child bit 31" set
+        st.sm = sm_stack; st.lm = lm_stack; st.n = 0;
+        ngroup = make_uint2(0u, 0x80000000u);   // root: base 0 and an empty internal mask => child index 0 whatever the octant
         tgroup = make_uint2(0u, 0u);
         best.t = t_max; best.prim1 = 0; best.b1 = 0.0f; best.b2 = 0.0f;
-        root = true;
     }
-    // returns true when the traversal is finished
-    HK_DEV bool step(const DevBvh& B, uint32_t* n_nodes, uint32_t* n_tris) {
-        if (ngroup.y > 0x00FFFFFFu) {
-            // ---- pop the nearest pending internal child of this group -------------------------------------
-            const uint32_t hits = ngroup.y;
-            const uint32_t bit = 31u - (uint32_t)__clz(hits);
-            ngroup.y &= ~(1u << bit);
-            if (ngroup.y > 0x00FFFFFFu) st.push(ngroup);
-            uint32_t node_idx;
-            if (root) { node_idx = 0; root = false; }
-            else {
-                const uint32_t slot = (bit - 24u) ^ oct_inv;
-                node_idx = ngroup.x + (uint32_t)__popc((hits & 0xFFu) & ((1u << slot) - 1u));
-            }
-            // ---- fetch the 80-byte node as five 16-byte loads --------------------------------------------
-            const float4* np = B.nodes + (size_t)node_idx * 5;
-            const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
-            if (COUNT) (*n_nodes)++;
-            const uint32_t ex = __float_as_uint(n0.w);
-            // slab coefficients: t = q * (2^e / d) + (p - o) / d.  Node culling only has to be conservative, so FMA is fine
-            // here (the exact, contraction-free arithmetic is reserved for the triangle test).
-            const float ax = __uint_as_float((ex & 0xFFu) << 23) * inv.x, ay = __uint_as_float(((ex >> 8) & 0xFFu) << 23) * inv.y, az = __uint_as_float(((ex >> 16) & 0xFFu) << 23) * inv.z;
-            const float bx = (n0.x - o.x) * inv.x, by = (n0.y - o.y) * inv.y, bz = (n0.z - o.z) * inv.z;
-            const uint32_t meta_lo = __float_as_uint(n1.z), meta_hi = __float_as_uint(n1.w);
-            // near/far plane words per axis, selected once per node by the ray octant:
-            // qlo x/y/z = n2.xy, n2.zw, n3.xy ; qhi x/y/z = n3.zw, n4.xy, n4.zw
-            const bool px = d.x >= 0.0f, py = d.y >= 0.0f, pz = d.z >= 0.0f;
-            const uint32_t nx0 = __float_as_uint(px ? n2.x : n3.z), nx1 = __float_as_uint(px ? n2.y : n3.w), fx0 = __float_as_uint(px ? n3.z : n2.x), fx1 = __float_as_uint(px ? n3.w : n2.y);
-            const uint32_t ny0 = __float_as_uint(py ? n2.z : n4.x), ny1 = __float_as_uint(py ? n2.w : n4.y), fy0 = __float_as_uint(py ? n4.x : n2.z), fy1 = __float_as_uint(py ? n4.y : n2.w);
-            const uint32_t nz0 = __float_as_uint(pz ? n3.x : n4.z), nz1 = __float_as_uint(pz ? n3.y : n4.w), fz0 = __float_as_uint(pz ? n4.z : n3.x), fz1 = __float_as_uint(pz ? n4.w : n3.y);
-            const float tlim = best.t;
-            uint32_t hitmask = 0;
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int sh = 8 * (i & 3);
-                const uint32_t meta = ((i < 4 ? meta_lo : meta_hi) >> sh) & 0xFFu;
-                const float tx0 = __fmaf_rn((float)(((i < 4 ? nx0 : nx1) >> sh) & 0xFFu), ax, bx), tx1 = __fmaf_rn((float)(((i < 4 ? fx0 : fx1) >> sh) & 0xFFu), ax, bx);
-                const float ty0 = __fmaf_rn((float)(((i < 4 ? ny0 : ny1) >> sh) & 0xFFu), ay, by), ty1 = __fmaf_rn((float)(((i < 4 ? fy0 : fy1) >> sh) & 0xFFu), ay, by);
-                const float tz0 = __fmaf_rn((float)(((i < 4 ? nz0 : nz1) >> sh) & 0xFFu), az, bz), tz1 = __fmaf_rn((float)(((i < 4 ? fz0 : fz1) >> sh) & 0xFFu), az, bz);
-                // fmaxf/fminf drop NaNs (0*inf when the origin lies in a slab plane of a zero direction): conservative
-                const float tn = fmaxf(fmaxf(tx0, ty0), fmaxf(tz0, 0.0f));
-                const float tf = fminf(fminf(tx1, ty1), fminf(tz1, tlim)) * 1.0000004f;
-                if (meta != 0u && tn <= tf) {
-                    const uint32_t inner = (meta & (meta << 1)) & 0x10u;             // bits 3 and 4 both set <=> internal child
-                    hitmask |= (meta >> 5) << ((meta ^ (inner ? oct_inv : 0u)) & 0x1Fu);
-                }
-            }
-            ngroup = make_uint2(__float_as_uint(n1.x), (hitmask & 0xFF000000u) | (ex >> 24));
-            tgroup = make_uint2(__float_as_uint(n1.y), hitmask & 0x00FFFFFFu);
-        } else {
-            tgroup = ngroup;
-            ngroup = make_uint2(0u, 0u);
-        }
-        // ---- triangles of this node ----------------------------------------------------------------------
-        while (tgroup.y != 0u) {
-            const uint32_t ti = (uint32_t)__ffs(tgroup.y) - 1u;
-            tgroup.y &= tgroup.y - 1u;
-            const float4* tp = B.tris + (size_t)(tgroup.x + ti) * 3;
-            const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-            if (COUNT) (*n_tris)++;
-            float t, u, v;
-            if (tri_test(o, d, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), t_max, t, u, v)) {
-                const uint32_t prim1 = __float_as_uint(a.w) + 1u;
-                if (ANY) { best.t = t; best.prim1 = prim1; best.b1 = u; best.b2 = v; return true; }
-                if (best.prim1 == 0u || t < best.t || (t == best.t && prim1 < best.prim1)) { best.t = t; best.prim1 = prim1; best.b1 = u; best.b2 = v; }
-            }
-        }
+    // precondition: no pending triangles.  Returns true when the traversal is finished (nothing left to visit).
+    HK_DEV bool node_step(const DevBvh& B, uint32_t* n_nodes) {
         if (ngroup.y <= 0x00FFFFFFu) {
             if (st.n == 0) return true;
             ngroup = st.pop();
+        }
+        // ---- pop the nearest pending internal child of this group -------------------------------------
+        const uint32_t hits = ngroup.y;
+        const uint32_t bit = 31u - (uint32_t)__clz(hits);
+        ngroup.y &= ~(1u << bit);
+        if (ngroup.y > 0x00FFFFFFu) st.push(ngroup);
+        const uint32_t slot = (bit - 24u) ^ oct_inv;
+        const uint32_t node_idx = ngroup.x + (uint32_t)__popc((hits & 0xFFu) & ((1u << slot) - 1u));
+        // ---- fetch the 80-byte node as five 16-byte loads --------------------------------------------
+        const float4* np = B.nodes + (size_t)node_idx * 5;
+        const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+        if (COUNT) (*n_nodes)++;
+        const uint32_t ex = __float_as_uint(n0.w);
+        // Slab test of the 8 quantised child boxes: t = q * (2^e / d) + (p - o) / d.  Node culling only has to be
+        // conservative (the exact, contraction-free arithmetic is reserved for the triangle test), so:
+        //  * a quantised byte q becomes a float with one PRMT instead of an I2F (quarter-rate XU pipe, which ncu showed
+        //    as the busiest pipe of this kernel): bytes [3F 80 q 00] = 1 + q * 2^-15, and
+        //    t = (1 + q 2^-15) * A + (b - A) with A = 2^15 * 2^e / d;
+        //  * b - A is rounded down for the entry planes and up for the exit planes, so the extra rounding can only
+        //    widen a box; the remaining FMA rounding is covered by the relative slack on the exit distance.
+        const float Ax = __uint_as_float(((ex & 0xFFu) + 15u) << 23) * inv.x, Ay = __uint_as_float((((ex >> 8) & 0xFFu) + 15u) << 23) * inv.y,
+                    Az = __uint_as_float((((ex >> 16) & 0xFFu) + 15u) << 23) * inv.z;
+        const float bx = (n0.x - o.x) * inv.x, by = (n0.y - o.y) * inv.y, bz = (n0.z - o.z) * inv.z;
+        const float bxn = __fsub_rd(bx, Ax), byn = __fsub_rd(by, Ay), bzn = __fsub_rd(bz, Az);
+        const float bxf = __fsub_ru(bx, Ax), byf = __fsub_ru(by, Ay), bzf = __fsub_ru(bz, Az);
+        const uint32_t meta_lo = __float_as_uint(n1.z), meta_hi = __float_as_uint(n1.w);
+        // near/far plane words per axis, selected once per node by the ray octant:
+        // qlo x/y/z = n2.xy, n2.zw, n3.xy ; qhi x/y/z = n3.zw, n4.xy, n4.zw
+        const bool px = d.x >= 0.0f, py = d.y >= 0.0f, pz = d.z >= 0.0f;
+        const uint32_t nx0 = __float_as_uint(px ? n2.x : n3.z), nx1 = __float_as_uint(px ? n2.y : n3.w), fx0 = __float_as_uint(px ? n3.z : n2.x), fx1 = __float_as_uint(px ? n3.w : n2.y);
+        const uint32_t ny0 = __float_as_uint(py ? n2.z : n4.x), ny1 = __float_as_uint(py ? n2.w : n4.y), fy0 = __float_as_uint(py ? n4.x : n2.z), fy1 = __float_as_uint(py ? n4.y : n2.w);
+        const uint32_t nz0 = __float_as_uint(pz ? n3.x : n4.z), nz1 = __float_as_uint(pz ? n3.y : n4.w), fz0 = __float_as_uint(pz ? n4.z : n3.x), fz1 = __float_as_uint(pz ? n4.w : n3.y);
+        const float tlim = best.t;
+        uint32_t hitmask = 0;
+#if HK_QF_PRMT
+#define HK_QF(word, k) __uint_as_float(__byte_perm((word), 0x3F800000u, 0x7604u | ((k) << 4)))
+#else
+#define HK_QF(word, k) __fmaf_rn((float)(((word) >> (8 * (k))) & 0xFFu), 3.0517578125e-05f, 1.0f)
+#endif
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int k = i & 3;
+            const uint32_t meta = ((i < 4 ? meta_lo : meta_hi) >> (8 * k)) & 0xFFu;
+            const float tx0 = __fmaf_rn(HK_QF(i < 4 ? nx0 : nx1, k), Ax, bxn), tx1 = __fmaf_rn(HK_QF(i < 4 ? fx0 : fx1, k), Ax, bxf);
+            const float ty0 = __fmaf_rn(HK_QF(i < 4 ? ny0 : ny1, k), Ay, byn), ty1 = __fmaf_rn(HK_QF(i < 4 ? fy0 : fy1, k), Ay, byf);
+            const float tz0 = __fmaf_rn(HK_QF(i < 4 ? nz0 : nz1, k), Az, bzn), tz1 = __fmaf_rn(HK_QF(i < 4 ? fz0 : fz1, k), Az, bzf);
+            // fmaxf/fminf drop NaNs (inf - inf when a direction component is zero): that axis is left unconstrained
+            const float tn = fmaxf(fmaxf(tx0, ty0), fmaxf(tz0, 0.0f));
+            const float tf = fminf(fminf(tx1, ty1), fminf(tz1, tlim)) * 1.0000007f;
+            if (meta != 0u && tn <= tf) {
+                const uint32_t inner = (meta & (meta << 1)) & 0x10u;             // bits 3 and 4 both set <=> internal child
+                hitmask |= (meta >> 5) << ((meta ^ (inner ? oct_inv : 0u)) & 0x1Fu);
+            }
+        }
+#undef HK_QF
+        ngroup = make_uint2(__float_as_uint(n1.x), (hitmask & 0xFF000000u) | (ex >> 24));
+        tgroup = make_uint2(__float_as_uint(n1.y), hitmask & 0x00FFFFFFu);
+#if HK_NODE_PREFETCH
+        if (tgroup.y != 0u) {   // the next node is already decided (nearest pending child, else the stack top): overlap its fetch with the triangle tests
+            uint2 g = ngroup;
+            if (g.y <= 0x00FFFFFFu && st.n > 0) g = st.n <= HK_SM_STACK ? st.sm[(st.n - 1) * HK_TRACE_THREADS] : st.lm[st.n - 1 - HK_SM_STACK];
+            if (g.y > 0x00FFFFFFu) {
+                const uint32_t b2 = 31u - (uint32_t)__clz(g.y);
+                const uint32_t s2 = (b2 - 24u) ^ oct_inv;
+                const char* np2 = (const char*)(B.nodes + (size_t)(g.x + (uint32_t)__popc((g.y & 0xFFu) & ((1u << s2) - 1u))) * 5);
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(np2));
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(np2 + 64));
+            }
+        }
+#endif
+        return false;
+    }
+    // precondition: tgroup.y != 0.  Tests one pending triangle; returns true only for ANY when a hit was accepted.
+    HK_DEV bool tri_step(const DevBvh& B, uint32_t* n_tris) {
+        const uint32_t ti = (uint32_t)__ffs(tgroup.y) - 1u;
+        tgroup.y &= tgroup.y - 1u;
+        const float4* tp = B.tris + (size_t)(tgroup.x + ti) * 3;
+        const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+        if (COUNT) (*n_tris)++;
+        float t, u, v;
+        if (tri_test(o, d, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), t_max, t, u, v)) {
+            const uint32_t prim1 = __float_as_uint(a.w) + 1u;
+            if (ANY) { best.t = t; best.prim1 = prim1; best.b1 = u; best.b2 = v; return true; }
+            if (best.prim1 == 0u || t < best.t || (t == best.t && prim1 < best.prim1)) { best.t = t; best.prim1 = prim1; best.b1 = u; best.b2 = v; }
         }
         return false;
     }
@@ -146,34 +193,53 @@ struct Bvh8Walker {
 template <bool ANY, bool COUNT>
 HK_DEV HitRec bvh8_trace(const DevBvh& B, uint2* sm_stack, float3 o, float3 d, float t_max, uint32_t* n_nodes = nullptr, uint32_t* n_tris = nullptr) {
     Bvh8Walker<ANY, COUNT> w;
-    w.begin(sm_stack, o, d, t_max);
-    while (!w.step(B, n_nodes, n_tris)) {}
+    uint2 lm_stack[HK_LM_STACK];
+    w.begin(sm_stack, lm_stack, o, d, t_max);
+    for (;;) {
+        if (w.node_step(B, n_nodes)) break;
+        bool hit = false;
+        while (w.tgroup.y != 0u && !hit) hit = w.tri_step(B, n_tris);
+        if (hit) break;
+    }
     return w.best;
 }
 
-// Persistent per-lane refill loop: every lane owns one in-flight ray; a lane whose ray finishes immediately claims the
-// next queue entry (claims of the lanes that are idle at the same time are aggregated into one atomicAdd).
-// IO supplies  bool load(idx, o, d, t_max)  and  void store(idx, hit).
+// Persistent per-lane refill loop: every lane owns one in-flight ray.  Finished lanes claim new queue entries together
+// (one atomicAdd per refill) once at least HK_REFILL_MIN lanes of the warp are idle -- the ray set-up is a divergent
+// region of its own, so it is batched instead of being run for single lanes in almost every iteration.
+// IO supplies  uint32_t load(idx, o, d, t_max) -> token  and  void store(token, hit).
 template <bool ANY, bool COUNT, class IO>
 HK_DEV void trace_queue(const DevBvh& B, uint2* sm_stack, uint32_t n, uint32_t* cursor, IO& io, uint32_t& traced, uint32_t& wn, uint32_t& wt) {
     Bvh8Walker<ANY, COUNT> w;
-    bool busy = false;
-    uint32_t idx = 0;
+    uint2 lm_stack[HK_LM_STACK];
+    bool busy = false, exhausted = false;
+    uint32_t token = 0;
     const unsigned lane = threadIdx.x & 31u;
     for (;;) {
-        if (!busy) {
-            const unsigned m = __activemask();
-            const unsigned leader = (unsigned)__ffs(m) - 1u;
-            uint32_t base = 0;
-            if (lane == leader) base = atomicAdd(cursor, (uint32_t)__popc(m));
-            base = __shfl_sync(m, base, leader);
-            idx = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
-            if (idx >= n) break;
-            float3 o, d; float tm;
-            io.load(idx, o, d, tm);
-            w.begin(sm_stack, o, d, tm);
-            busy = true; traced++;
+        unsigned idle = __ballot_sync(0xFFFFFFFFu, !busy);
+        if (!exhausted && (uint32_t)__popc(idle) >= (uint32_t)HK_REFILL_MIN) {
+            if (!busy) {
+                const unsigned leader = (unsigned)__ffs(idle) - 1u;
+                uint32_t base = 0;
+                if (lane == leader) base = atomicAdd(cursor, (uint32_t)__popc(idle));
+                base = __shfl_sync(idle, base, leader);
+                const uint32_t idx = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
+                if (idx < n) {
+                    float3 o, d; float tm;
+                    token = io.load(idx, o, d, tm);
+                    w.begin(sm_stack, lm_stack, o, d, tm);
+                    busy = true; traced++;
+                }
+            }
+            idle = __ballot_sync(0xFFFFFFFFu, !busy);
+            exhausted = idle != 0u;          // a lane that found the queue empty
         }
-        if (w.step(B, &wn, &wt)) { io.store(idx, w.best); busy = false; }
+        if (idle == 0xFFFFFFFFu) break;      // only reachable once the queue is exhausted
+        if (busy) {
+            bool fin = false;
+            if (w.tgroup.y == 0u) fin = w.node_step(B, &wn);
+            if (!fin && w.tgroup.y != 0u) fin = w.tri_step(B, &wt);
+            if (fin) { io.store(token, w.best); busy = false; }
+        }
     }
 }

@@ -191,15 +191,16 @@ HK_DEV uint32_t* queue_of(const PathState& S, int qid) {
 // (persistent, per-lane refill), k_route = classification into the medium / escaped / per-material queues.
 struct QueueRayIO {
     const PathState& S; const uint32_t* __restrict__ q;
-    HK_DEV void load(uint32_t idx, float3& o, float3& d, float& tm) const {
+    HK_DEV uint32_t load(uint32_t idx, float3& o, float3& d, float& tm) const {
         const uint32_t slot = q[idx];
         const float4 ra = S.ray_a[slot], rb = S.ray_b[slot];
         o = f3(ra.x, ra.y, ra.z); d = f3(ra.w, rb.x, rb.y); tm = rb.z;
+        return slot;
     }
-    HK_DEV void store(uint32_t idx, const HitRec& h) const { S.hit[q[idx]] = make_float4(h.t, __uint_as_float(h.prim1), h.b1, h.b2); }
+    HK_DEV void store(uint32_t slot, const HitRec& h) const { S.hit[slot] = make_float4(h.t, __uint_as_float(h.prim1), h.b1, h.b2); }
 };
 template <bool COUNT>
-__global__ void __launch_bounds__(HK_TRACE_THREADS) k_trace(const __grid_constant__ DevScene D, PathState S, int cur, unsigned long long* work) {
+__global__ void __launch_bounds__(HK_TRACE_THREADS, HK_TRACE_BLOCKS_PER_SM) k_trace(const __grid_constant__ DevScene D, PathState S, int cur, unsigned long long* work) {
     __shared__ uint2 sm_stack[HK_SM_STACK * HK_TRACE_THREADS];
     const uint32_t n = S.counts[HK_C_RAY0 + cur];
     uint32_t traced = 0, wn = 0, wt = 0;
@@ -264,8 +265,11 @@ HK_DEV bool russian_roulette(Spec& beta, int depth, float rr) {
 
 // Shading of one material type: emissive-hit MIS (surface-eval.jl:147-220), NEE (:250-342 + lights.jl:535-600) and
 // BSDF sampling / Russian roulette / continuation ray (:396-512), fused into one kernel per material type.
+#ifndef HK_SHADE_MIN_BLOCKS
+#define HK_SHADE_MIN_BLOCKS 1
+#endif
 template <int TYPE>
-__global__ void __launch_bounds__(128) k_shade(const __grid_constant__ DevScene D, PathState S, PassArgs A, int next) {
+__global__ void __launch_bounds__(128, HK_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DevScene D, PathState S, PassArgs A, int next) {
     const uint32_t n = S.counts[HK_C_HIT0 + TYPE];
     MatCtx MC = mat_ctx(D);
     LightCtx LC = light_ctx(D);
@@ -450,14 +454,14 @@ __global__ void __launch_bounds__(128) k_medium(const __grid_constant__ DevScene
 // the same T in {0,1} as the reference's closest-hit loop.  Otherwise the ordered closest-hit walk with ratio tracking.
 struct ShadowRayIO {
     const PathState& S;
-    HK_DEV void load(uint32_t idx, float3& o, float3& d, float& tm) const {
+    HK_DEV uint32_t load(uint32_t idx, float3& o, float3& d, float& tm) const {
         const uint32_t slot = S.q_shadow[idx];
         const float4 sa = S.sh_a[slot], sb = S.sh_b[slot];
         o = f3(sa.x, sa.y, sa.z); d = f3(sa.w, sb.x, sb.y);
         tm = sb.z < 1.0e-6f ? -1.0f : sb.z;          // t_remaining < 1e-6: the reference's loop breaks => treated as occluded
+        return slot;
     }
-    HK_DEV void store(uint32_t idx, const HitRec& h) const {
-        const uint32_t slot = S.q_shadow[idx];
+    HK_DEV void store(uint32_t slot, const HitRec& h) const {
         if (h.prim1 != 0u || S.sh_b[slot].z < 1.0e-6f) return;      // blocked
         const float den = sp_avg(S.sh_ru[slot] + S.sh_rl[slot]);     // T = tr_u = tr_l = 1
         if (den > 1.0e-10f) {
@@ -467,7 +471,7 @@ struct ShadowRayIO {
     }
 };
 template <bool COUNT>
-__global__ void __launch_bounds__(HK_TRACE_THREADS) k_shadow_opaque(const __grid_constant__ DevScene D, PathState S, unsigned long long* work) {
+__global__ void __launch_bounds__(HK_TRACE_THREADS, HK_TRACE_BLOCKS_PER_SM) k_shadow_opaque(const __grid_constant__ DevScene D, PathState S, unsigned long long* work) {
     __shared__ uint2 sm_stack[HK_SM_STACK * HK_TRACE_THREADS];
     // reference quirk (volpath.jl:571-609): shadow rays are only traced inside the `n_hits > 0` branch
     if (S.counts[HK_C_TOTAL_HITS] == 0) return;
@@ -568,9 +572,10 @@ __global__ void __launch_bounds__(256) k_film_finalize(const float* __restrict__
 template <bool ANY>
 struct BatchRayIO {
     const float4* __restrict__ rays; float4* __restrict__ hits; uint8_t* __restrict__ occluded;
-    HK_DEV void load(uint32_t i, float3& o, float3& d, float& tm) const {
+    HK_DEV uint32_t load(uint32_t i, float3& o, float3& d, float& tm) const {
         const float4 ra = __ldg(rays + 2 * (size_t)i), rb = __ldg(rays + 2 * (size_t)i + 1);
         o = f3(ra.x, ra.y, ra.z); d = f3(ra.w, rb.x, rb.y); tm = rb.z;
+        return i;
     }
     HK_DEV void store(uint32_t i, const HitRec& h) const {
         if (ANY) occluded[i] = h.prim1 ? 1 : 0;
@@ -578,7 +583,7 @@ struct BatchRayIO {
     }
 };
 template <bool ANY, bool COUNT>
-__global__ void __launch_bounds__(HK_TRACE_THREADS) k_trace_batch(DevBvh B, const float4* __restrict__ rays, uint32_t n, float4* __restrict__ hits,
+__global__ void __launch_bounds__(HK_TRACE_THREADS, HK_TRACE_BLOCKS_PER_SM) k_trace_batch(DevBvh B, const float4* __restrict__ rays, uint32_t n, float4* __restrict__ hits,
                                                                 uint8_t* __restrict__ occluded, uint32_t* cursor, unsigned long long* counters) {
     __shared__ uint2 sm_stack[HK_SM_STACK * HK_TRACE_THREADS];
     uint32_t traced = 0, nn = 0, nt = 0;

@@ -13,6 +13,9 @@ extern "C" {
 
 /* q[n][4] = (px, py, sample_idx, dim) -> zsobol_sample_1d / _2d (src/sampler/sobol.jl:269-309) */
 int32_t hk_test_sobol(HkContext* ctx, const int32_t* q, uint64_t n, int32_t log2_spp, int32_t n_base4_digits, uint32_t seed, float* out1d, float* out2d);
+/* select the Sobol' evaluation: 0 = generic matrix loop, 1 = closed forms for dimensions 0/1 (only valid when
+ * hk_upload_tables verified the table structure); returns the previous mode */
+int32_t hk_test_sobol_mode(HkContext* ctx, int32_t fast);
 /* v[n][3] -> pbrt_hash(Vec3f), mix_bits(hash), two pcg32 floats seeded (hash, mix) (spectral-eval.jl:575-815) */
 int32_t hk_test_hashes(HkContext* ctx, const float* v3, uint64_t n, uint64_t* out_hash, uint64_t* out_mix, float* out_pcg);
 /* u[n] -> lambda[n][4], pdf[n][4] (src/spectral/spectral.jl:221-249) */

@@ -29,13 +29,16 @@ def test_sobol_bit_exact(bare):
     n = 20000
     q = np.stack([rng.randint(1, 3841, n), rng.randint(1, 2161, n), rng.randint(1, 4097, n), rng.randint(0, 100, n)], -1).astype(np.int32)
     q[:8] = [[1, 1, 1, 1], [3840, 2160, 4096, 90], [1, 1, 4096, 0], [512, 512, 64, 13], [1920, 1080, 256, 6], [7, 9, 1, 89], [2, 1, 2, 3], [1, 2, 3, 4]]
-    for (l2, nb4) in ((12, 18), (12, 15), (5, 12)):
+    assert bare.lib.hk_test_sobol_mode(bare.cu.ctx, 1) == 1, "standard Sobol' table must select the closed-form path"
+    for (l2, nb4, fast) in ((12, 18, 1), (12, 15, 1), (5, 12, 1), (12, 18, 0), (5, 12, 0), (11, 16, 1), (11, 16, 0)):
+        bare.lib.hk_test_sobol_mode(bare.cu.ctx, fast)
         a1 = np.zeros(n, f32); a2 = np.zeros((n, 2), f32); b1 = np.zeros(n, f32); b2 = np.zeros((n, 2), f32)
         assert bare.lib.hk_test_sobol(bare.cu.ctx, q.ctypes.data_as(A.c_i32p), n, l2, nb4, 0, fp(a1), fp(a2)) == 0
         bare.olib.ok_test_sobol(bare.ok.ctx, q.ctypes.data_as(A.c_i32p), n, l2, nb4, 0, fp(b1), fp(b2))
         assert np.array_equal(a1.view(np.uint32), b1.view(np.uint32))
         assert np.array_equal(a2.view(np.uint32), b2.view(np.uint32))
         assert (a1 >= 0).all() and (a1 < 1).all()
+    bare.lib.hk_test_sobol_mode(bare.cu.ctx, 1)
 
 
 def test_hashes_and_pcg_bit_exact(bare):

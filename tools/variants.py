@@ -1,0 +1,56 @@
+#!/usr/bin/env python3
+"""Tuning-variant sweeps of libhikari_cuda.so (development tool).
+
+  python tools/variants.py build name1:-DHK_X=1,-DHK_Y=2 name2:...   # here (nvcc cross-compiles), into build/variants/
+  python tools/variants.py run [--steps K]                          # on the GPU box (through gpurun): bench.py --quick per variant
+  python tools/variants.py table                                    # here: summarise gpurun_out/var_*.json
+"""
+import glob, json, os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+VDIR = os.path.join(ROOT, "build", "variants")
+
+
+def build(specs):
+    import __graft_entry__ as g
+    os.makedirs(VDIR, exist_ok=True)
+    for f in glob.glob(os.path.join(VDIR, "*.so")): os.remove(f)
+    procs = []
+    for spec in specs:
+        name, _, defs = spec.partition(":")
+        out = os.path.join(VDIR, f"lib_{name}.so")
+        srcs = [os.path.join(g.CSRC, f) for f in ("hk_api.cu", "hk_bvh.cpp", "host_rgb2spec.cpp", "host_lightbvh.cpp")]
+        flags = [f for f in g.NVCC_FLAGS if f not in ("-v",)]
+        flags = [f for i, f in enumerate(flags) if not (f == "-Xptxas" and g.NVCC_FLAGS[i + 1] == "-v")]
+        cmd = [g.NVCC] + flags + [d for d in defs.split(",") if d] + ["-o", out] + srcs + ["-lgomp"]
+        procs.append((name, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for name, p in procs:
+        o, _ = p.communicate()
+        print(name, "OK" if p.returncode == 0 else "FAILED\n" + o[-2000:])
+
+
+def run(argv):
+    steps = argv[argv.index("--steps") + 1] if "--steps" in argv else "8"
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    for so in sorted(glob.glob(os.path.join(VDIR, "*.so"))):
+        name = os.path.basename(so)[4:-3]
+        env = dict(os.environ, HK_CUDA_LIB=so)
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--quick", "--steps", steps, "--warmup", "3"], env=env, capture_output=True, text=True, timeout=600)
+        open(os.path.join(ROOT, "gpurun_out", f"var_{name}.json"), "w").write(r.stdout if r.returncode == 0 else json.dumps({"error": r.stderr[-1500:]}))
+        print(name, r.stdout[:160] if r.returncode == 0 else r.stderr[-500:], flush=True)
+
+
+def table():
+    for f in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "var_*.json"))):
+        try: j = json.loads(open(f).read().strip().splitlines()[-1])
+        except Exception as e: print(os.path.basename(f), "unreadable", e); continue
+        if "error" in j: print(os.path.basename(f), "ERROR", j["error"][-300:]); continue
+        st = j["roofline"].get("stage_ms_per_step", {})
+        print(f"{os.path.basename(f)[4:-5]:28s} {j['value']:7.1f} Msamples/s  {j['ms_per_step']:6.3f} ms/step  " + "  ".join(f"{k}={v:.3f}" for k, v in st.items()) + f"  frac={j['roofline']['frac']:.3f}")
+
+
+if __name__ == "__main__":
+    cmd = sys.argv[1]
+    if cmd == "build": build(sys.argv[2:])
+    elif cmd == "run": run(sys.argv[2:])
+    else: table()
