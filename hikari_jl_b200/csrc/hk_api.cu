@@ -171,7 +171,7 @@ int32_t hk_upload_geometry(HkContext* ctx, const HkGeometry* g) {
     if (g->normals) CK(ctx->b_nrm.upload(g->normals, 12 * (size_t)g->n_verts)); else ctx->b_nrm.release();
     CK(ctx->b_idx.upload(g->indices, 12 * (size_t)g->n_tris));
     CK(ctx->b_meta.upload(g->tri_meta, 12 * (size_t)g->n_tris));
-    ctx->D.bvh.nodes = ctx->b_nodes.as<float4>(); ctx->D.bvh.tris = ctx->b_tris.as<float4>();
+    ctx->D.bvh.nodes = ctx->b_nodes.as<float4>(); ctx->D.bvh.tris = ctx->b_tris.as<float4>(); ctx->D.bvh.one_bits = 0x3F800000u;
     ctx->D.positions = ctx->b_pos.as<float>(); ctx->D.normals = g->normals ? ctx->b_nrm.as<float>() : nullptr;
     ctx->D.indices = ctx->b_idx.as<uint32_t>(); ctx->D.tri_meta = ctx->b_meta.as<uint32_t>();
     ctx->stats.bvh_nodes = bvh.nodes.size();

@@ -204,10 +204,9 @@ void hk_build_bvh8(const float* positions, const uint32_t* indices, uint32_t n_t
         }
         node.child_base = (uint32_t)out.nodes.size();
         node.tri_base = (uint32_t)out.tris.size();
-        uint32_t tri_off = 0;
         for (int s = 0; s < 8; s++) {
             int i = child_at[s];
-            if (i < 0) { node.meta[s] = 0; continue; }
+            if (i < 0) continue;
             const Node2& c = N2[ch[i]];
             for (int k = 0; k < 3; k++) {
                 float lo = std::floor((c.box.lo[k] - node.p[k]) / scale[k]);
@@ -219,10 +218,9 @@ void hk_build_bvh8(const float* positions, const uint32_t* indices, uint32_t n_t
             }
             if (c.count == 0) {
                 node.imask |= (uint8_t)(1u << s);
-                node.meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
             } else {
                 uint32_t unary = c.count == 1 ? 1u : (c.count == 2 ? 3u : 7u);
-                node.meta[s] = (uint8_t)((unary << 5) | tri_off);
+                node.trivalid |= unary << (3 * s);
                 for (uint32_t t = 0; t < c.count; t++) {
                     uint32_t prim = B.order[c.first + t];
                     const float* a = positions + 3 * (size_t)indices[3 * (size_t)prim];
@@ -233,7 +231,6 @@ void hk_build_bvh8(const float* positions, const uint32_t* indices, uint32_t n_t
                     T.prim = prim;
                     out.tris.push_back(T);
                 }
-                tri_off += c.count;
             }
         }
         // internal children in slot order, contiguous

@@ -13,7 +13,9 @@ struct alignas(16) HkBvhNode {        // 80 bytes = 5 x 16-byte vector loads
     uint8_t  imask;                    // bit i set <=> child slot i is an internal node
     uint32_t child_base;               // index of the first internal child
     uint32_t tri_base;                 // index of the first triangle referenced by leaf children
-    uint8_t  meta[8];                  // internal: 001sssss (sssss = 24+slot); leaf: unary count<<5 | tri offset; empty: 0
+    uint32_t trivalid;                 // bits 3s..3s+2 = unary triangle count of the leaf child in slot s (0 for internal / empty
+                                       // slots); triangle k of slot s lives at tri_base + popc(trivalid & ((1 << (3s+k)) - 1))
+    uint32_t pad;
     uint8_t  qlo[3][8];                // quantised child mins  [axis][slot]
     uint8_t  qhi[3][8];                // quantised child maxs
 };

@@ -180,7 +180,12 @@ HK_DEV uint32_t perm4_byte(uint32_t p) {   // p in [0, 24)
 // not inlined: the digit loop is ~600 instructions and has five call sites per shading kernel; inlining all of them made
 // the kernels instruction-fetch bound (stall_no_instruction was the top stall reason)
 #ifndef HK_SOBOL_NOINLINE
-#define HK_SOBOL_NOINLINE 1
+#define HK_SOBOL_NOINLINE 0
+#endif
+#define HK_PRAGMA_(x) _Pragma(#x)
+#define HK_UNROLL(n) HK_PRAGMA_(unroll n)
+#ifndef HK_SOBOL_UNROLL
+#define HK_SOBOL_UNROLL 1
 #endif
 #if HK_SOBOL_NOINLINE
 __device__ __noinline__
@@ -191,6 +196,9 @@ uint64_t zsobol_sample_index(uint64_t morton, int32_t dim, int32_t log2_spp, int
     uint64_t idx = 0;
     const int pow2 = log2_spp & 1;
     const uint64_t dmix = 0x55555555ull * (uint64_t)(int64_t)dim;
+    // iterations are independent (each digit hashes its own prefix): unrolling interleaves the serial 64-bit
+    // multiply / xor-shift chains of several digits, which is what bounds this loop (fixed-latency "wait" stalls)
+    HK_UNROLL(HK_SOBOL_UNROLL)
     for (int i = nb4 - 1; i >= pow2; --i) {
         int shift = 2 * i - pow2;
         uint32_t digit = (uint32_t)(morton >> shift) & 3u;

@@ -35,7 +35,8 @@
 #define HK_TRACE_BLOCKS_PER_SM 8
 #endif
 
-struct DevBvh { const float4* __restrict__ nodes; const float4* __restrict__ tris; };
+// one_bits = 0x3F800000, supplied by the host so that it reaches the kernels as a run-time value: see HK_QF in node_step()
+struct DevBvh { const float4* __restrict__ nodes; const float4* __restrict__ tris; uint32_t one_bits; };
 struct HitRec { float t; uint32_t prim1; float b1, b2; };   // prim1: 1-based global id, 0 = miss
 
 HK_DEV float __frcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
@@ -77,7 +78,8 @@ struct Bvh8Walker {
     float3 o, d, inv;
     float t_max;
     uint32_t oct_inv;
-    uint2 ngroup, tgroup;
+    uint2 ngroup, tgroup;      // ngroup: (first internal child, octant-ordered hit bits << 24 | imask); tgroup: (first triangle, pending triangle bits)
+    uint32_t tvalid;           // HkBvhNode::trivalid of the node tgroup came from
     TravStack st;
     HitRec best;
 
@@ -92,7 +94,7 @@ struct Bvh8Walker {
         oct_inv = (d.x >= 0.0f ? 4u : 0u) | (d.y >= 0.0f ? 2u : 0u) | (d.z >= 0.0f ? 1u : 0u);
         st.sm = sm_stack; st.lm = lm_stack; st.n = 0;
         ngroup = make_uint2(0u, 0x80000000u);   // root: base 0 and an empty internal mask => child index 0 whatever the octant
-        tgroup = make_uint2(0u, 0u);
+        tgroup = make_uint2(0u, 0u); tvalid = 0u;
         best.t = t_max; best.prim1 = 0; best.b1 = 0.0f; best.b2 = 0.0f;
     }
     // precondition: no pending triangles.  Returns true when the traversal is finished (nothing left to visit).
@@ -125,7 +127,6 @@ struct Bvh8Walker {
         const float bx = (n0.x - o.x) * inv.x, by = (n0.y - o.y) * inv.y, bz = (n0.z - o.z) * inv.z;
         const float bxn = __fsub_rd(bx, Ax), byn = __fsub_rd(by, Ay), bzn = __fsub_rd(bz, Az);
         const float bxf = __fsub_ru(bx, Ax), byf = __fsub_ru(by, Ay), bzf = __fsub_ru(bz, Az);
-        const uint32_t meta_lo = __float_as_uint(n1.z), meta_hi = __float_as_uint(n1.w);
         // near/far plane words per axis, selected once per node by the ray octant:
         // qlo x/y/z = n2.xy, n2.zw, n3.xy ; qhi x/y/z = n3.zw, n4.xy, n4.zw
         const bool px = d.x >= 0.0f, py = d.y >= 0.0f, pz = d.z >= 0.0f;
@@ -133,50 +134,49 @@ struct Bvh8Walker {
         const uint32_t ny0 = __float_as_uint(py ? n2.z : n4.x), ny1 = __float_as_uint(py ? n2.w : n4.y), fy0 = __float_as_uint(py ? n4.x : n2.z), fy1 = __float_as_uint(py ? n4.y : n2.w);
         const uint32_t nz0 = __float_as_uint(pz ? n3.x : n4.z), nz1 = __float_as_uint(pz ? n3.y : n4.w), fz0 = __float_as_uint(pz ? n4.z : n3.x), fz1 = __float_as_uint(pz ? n4.w : n3.y);
         const float tlim = best.t;
-        uint32_t hitmask = 0;
+        uint32_t hits8 = 0;                       // bit s: the ray overlaps the box of child slot s (empty slots may set bits; they are masked below)
 #if HK_QF_PRMT
-#define HK_QF(word, k) __uint_as_float(__byte_perm((word), 0x3F800000u, 0x7604u | ((k) << 4)))
+        // 0x3F800000 arrives as a run-time value (DevBvh::one_bits) so that it sits in ONE register and PRMT takes the byte
+        // selector as its immediate; with both compile-time constants ptxas put the float constant in the immediate slot and
+        // re-materialised the four selectors with ~40 extra moves per node
+        const uint32_t k_one = B.one_bits;
+#define HK_QF(word, k) __uint_as_float(__byte_perm((word), k_one, 0x7604u | ((k) << 4)))
 #else
 #define HK_QF(word, k) __fmaf_rn((float)(((word) >> (8 * (k))) & 0xFFu), 3.0517578125e-05f, 1.0f)
 #endif
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const int k = i & 3;
-            const uint32_t meta = ((i < 4 ? meta_lo : meta_hi) >> (8 * k)) & 0xFFu;
             const float tx0 = __fmaf_rn(HK_QF(i < 4 ? nx0 : nx1, k), Ax, bxn), tx1 = __fmaf_rn(HK_QF(i < 4 ? fx0 : fx1, k), Ax, bxf);
             const float ty0 = __fmaf_rn(HK_QF(i < 4 ? ny0 : ny1, k), Ay, byn), ty1 = __fmaf_rn(HK_QF(i < 4 ? fy0 : fy1, k), Ay, byf);
             const float tz0 = __fmaf_rn(HK_QF(i < 4 ? nz0 : nz1, k), Az, bzn), tz1 = __fmaf_rn(HK_QF(i < 4 ? fz0 : fz1, k), Az, bzf);
             // fmaxf/fminf drop NaNs (inf - inf when a direction component is zero): that axis is left unconstrained
             const float tn = fmaxf(fmaxf(tx0, ty0), fmaxf(tz0, 0.0f));
             const float tf = fminf(fminf(tx1, ty1), fminf(tz1, tlim)) * 1.0000007f;
-            if (meta != 0u && tn <= tf) {
-                const uint32_t inner = (meta & (meta << 1)) & 0x10u;             // bits 3 and 4 both set <=> internal child
-                hitmask |= (meta >> 5) << ((meta ^ (inner ? oct_inv : 0u)) & 0x1Fu);
-            }
+            if (tn <= tf) hits8 |= 1u << i;
         }
 #undef HK_QF
-        ngroup = make_uint2(__float_as_uint(n1.x), (hitmask & 0xFF000000u) | (ex >> 24));
-        tgroup = make_uint2(__float_as_uint(n1.y), hitmask & 0x00FFFFFFu);
-#if HK_NODE_PREFETCH
-        if (tgroup.y != 0u) {   // the next node is already decided (nearest pending child, else the stack top): overlap its fetch with the triangle tests
-            uint2 g = ngroup;
-            if (g.y <= 0x00FFFFFFu && st.n > 0) g = st.n <= HK_SM_STACK ? st.sm[(st.n - 1) * HK_TRACE_THREADS] : st.lm[st.n - 1 - HK_SM_STACK];
-            if (g.y > 0x00FFFFFFu) {
-                const uint32_t b2 = 31u - (uint32_t)__clz(g.y);
-                const uint32_t s2 = (b2 - 24u) ^ oct_inv;
-                const char* np2 = (const char*)(B.nodes + (size_t)(g.x + (uint32_t)__popc((g.y & 0xFFu) & ((1u << s2) - 1u))) * 5);
-                asm volatile("prefetch.global.L1 [%0];" :: "l"(np2));
-                asm volatile("prefetch.global.L1 [%0];" :: "l"(np2 + 64));
-            }
-        }
-#endif
+        // internal children: reorder the slot-indexed hit bits into octant traversal order (bit j <- bit j ^ oct_inv) with
+        // three conditional bit-group swaps, instead of one variable shift per child
+        const uint32_t imask = ex >> 24;
+        uint32_t ih = hits8 & imask;
+        { const uint32_t s1 = oct_inv & 1u, s2 = oct_inv & 2u, s4 = oct_inv & 4u;
+          ih = ((ih >> s1) & 0x55u) | ((ih << s1) & 0xAAu);
+          ih = ((ih >> s2) & 0x33u) | ((ih << s2) & 0xCCu);
+          ih = ((ih >> s4) & 0x0Fu) | ((ih << s4) & 0xF0u); }
+        // leaf children: slot s owns triangle bits 3s..3s+2; spread the hit bits to those positions and keep the valid ones
+        uint32_t th = hits8;
+        th = (th | (th << 8)) & 0x00F00Fu; th = (th | (th << 4)) & 0x0C30C3u; th = (th | (th << 2)) & 0x249249u;
+        tvalid = __float_as_uint(n1.z);
+        ngroup = make_uint2(__float_as_uint(n1.x), (ih << 24) | imask);
+        tgroup = make_uint2(__float_as_uint(n1.y), (th * 7u) & tvalid);
         return false;
     }
     // precondition: tgroup.y != 0.  Tests one pending triangle; returns true only for ANY when a hit was accepted.
     HK_DEV bool tri_step(const DevBvh& B, uint32_t* n_tris) {
-        const uint32_t ti = (uint32_t)__ffs(tgroup.y) - 1u;
+        const uint32_t tbit = (uint32_t)__ffs(tgroup.y) - 1u;
         tgroup.y &= tgroup.y - 1u;
-        const float4* tp = B.tris + (size_t)(tgroup.x + ti) * 3;
+        const float4* tp = B.tris + (size_t)(tgroup.x + (uint32_t)__popc(tvalid & ((1u << tbit) - 1u))) * 3;
         const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
         if (COUNT) (*n_tris)++;
         float t, u, v;
