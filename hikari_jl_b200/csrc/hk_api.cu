@@ -43,6 +43,9 @@ struct HkContext {
     DevBuf b_media;
     DevBuf b_f_func, b_f_mcdf, b_f_mfunc, b_f_ccdf;
     DevBuf b_state, b_counts, b_rays, b_film, b_scratch_u32, b_trace_ctr, b_readback;
+    DevBuf b_sobol_top, b_sobol_dims, b_sobol_dimhash;        // ZSobol prefix cache (SobolParams::top)
+    int32_t sobol_cache_key[6] = {0, 0, 0, 0, 0, -1};          // width, height, log2_spp, nb4, seed, cached depths
+    bool sobol_cache_enabled = true;
     size_t n_slots = 0;
     HkStats stats;
     uint64_t launches = 0;
@@ -109,7 +112,7 @@ int32_t hk_destroy(HkContext* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&ctx->b_sobol, &ctx->b_cie_x, &ctx->b_cie_y, &ctx->b_cie_z, &ctx->b_d65, &ctx->b_rgb_scale, &ctx->b_rgb_coeffs, &ctx->b_nodes, &ctx->b_tris,
-                      &ctx->b_pos, &ctx->b_nrm, &ctx->b_idx, &ctx->b_meta, &ctx->b_mats, &ctx->b_ifaces, &ctx->b_spec_l, &ctx->b_spec_v, &ctx->b_spec_o, &ctx->b_lights,
+                      &ctx->b_sobol_top, &ctx->b_sobol_dims, &ctx->b_sobol_dimhash, &ctx->b_pos, &ctx->b_nrm, &ctx->b_idx, &ctx->b_meta, &ctx->b_mats, &ctx->b_ifaces, &ctx->b_spec_l, &ctx->b_spec_v, &ctx->b_spec_o, &ctx->b_lights,
                       &ctx->b_env, &ctx->b_lnodes, &ctx->b_trails, &ctx->b_inf, &ctx->b_media, &ctx->b_f_func, &ctx->b_f_mcdf, &ctx->b_f_mfunc, &ctx->b_f_ccdf,
                       &ctx->b_state, &ctx->b_counts, &ctx->b_rays, &ctx->b_film, &ctx->b_scratch_u32, &ctx->b_trace_ctr, &ctx->b_work_ctr, &ctx->b_readback};
     for (auto& e : ctx->stage_events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -327,6 +330,46 @@ static int32_t alloc_state(HkContext* ctx, size_t n_slots, size_t n_pixels) {
     return HK_OK;
 }
 
+// (Re)build the ZSobol prefix cache when resolution / sampler parameters change: one k_sobol_prefix pass over
+// pixels x dimensions-in-use, amortised over every sample rendered afterwards (like the BVH build at geometry upload).
+// Capped at HK_SOBOL_CACHE_BYTES; bounces beyond the cached depth use the uncached evaluation (same bits).
+#ifndef HK_SOBOL_CACHE_BYTES
+#define HK_SOBOL_CACHE_BYTES (8ull << 30)
+#endif
+static int32_t build_sobol_cache(HkContext* ctx) {
+    const HkRenderParams& P = ctx->params;
+    SobolParams& SP = ctx->D.sobol;
+    const size_t n_pixels = (size_t)P.width * P.height;
+    int32_t depths = 0;
+    if (ctx->sobol_cache_enabled && P.sobol_log2_spp >= 0 && P.sobol_n_base4_digits - ((P.sobol_log2_spp + 1) >> 1) <= 16) {
+        const size_t max_slots = HK_SOBOL_CACHE_BYTES / (4 * n_pixels);
+        depths = max_slots >= 8 ? (int32_t)std::min<size_t>((size_t)P.max_depth, (max_slots - 3) / 5) : 0;
+    }
+    const int32_t key[6] = {P.width, P.height, P.sobol_log2_spp, P.sobol_n_base4_digits, (int32_t)P.sampler_seed, depths};
+    if (std::memcmp(key, ctx->sobol_cache_key, sizeof(key)) == 0 && (depths == 0 || ctx->b_sobol_top.p)) {
+        if (depths == 0) { SP.top = nullptr; SP.dimhash = nullptr; SP.n_top = 0; }
+        return HK_OK;
+    }
+    SP.top = nullptr; SP.dimhash = nullptr; SP.n_top = 0; SP.top_stride = (uint32_t)n_pixels;
+    std::memcpy(ctx->sobol_cache_key, key, sizeof(key));
+    if (depths == 0) { ctx->b_sobol_top.release(); return HK_OK; }
+    const int32_t n_slots = 3 + 5 * depths;
+    std::vector<int32_t> dims(n_slots);
+    dims[0] = 1; dims[1] = 3; dims[2] = 6;                       // volpath.jl:150-170
+    static const int off[5] = {1, 3, 4, 6, 7};                   // volpath.jl:253-262
+    for (int d = 0; d < depths; d++) for (int j = 0; j < 5; j++) dims[3 + 5 * d + j] = 6 + 7 * d + off[j];
+    CK(ctx->b_sobol_dims.upload(dims.data(), dims.size() * 4));
+    CK(ctx->b_sobol_dimhash.alloc(16 * (size_t)n_slots));
+    CK(ctx->b_sobol_top.alloc(4 * n_pixels * (size_t)n_slots));
+    k_sobol_prefix<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->b_sobol_top.as<uint32_t>(), ctx->b_sobol_dimhash.as<uint4>(), ctx->b_sobol_dims.as<int32_t>(), n_slots,
+                                                              (uint32_t)n_pixels, P.width, P.sobol_log2_spp, P.sobol_n_base4_digits, P.sampler_seed);
+    ctx->launches++;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    SP.top = ctx->b_sobol_top.as<uint32_t>(); SP.dimhash = ctx->b_sobol_dimhash.as<uint4>(); SP.n_top = n_slots;
+    return HK_OK;
+}
+
 int32_t hk_set_params(HkContext* ctx, const HkRenderParams* p) {
     if (!ctx || !p) return HK_ERR_INVALID;
     cudaSetDevice(ctx->device);
@@ -339,6 +382,8 @@ int32_t hk_set_params(HkContext* ctx, const HkRenderParams* p) {
     D.sobol.log2_spp = p->sobol_log2_spp; D.sobol.n_base4_digits = p->sobol_n_base4_digits; D.sobol.seed = p->sampler_seed;
     size_t n_pixels = (size_t)p->width * p->height;
     int32_t rc = alloc_state(ctx, n_pixels * (size_t)ctx->params.sample_batch, n_pixels);
+    if (rc != HK_OK) return rc;
+    rc = build_sobol_cache(ctx);
     if (rc != HK_OK) return rc;
     ctx->have_params = true;
     return HK_OK;

@@ -147,7 +147,20 @@ HK_DEV float lcg_next(uint64_t& s) {                           // delta-tracking
 // standard ones -- dimension 0 = bit reversal, dimension 1 = bit-reversed Pascal triangle mod 2 with columns 32.. repeating
 // columns 0.. -- so sobol_bits() can use their closed forms (a GF(2)-linear map applied as a 5-level butterfly) instead of
 // one dependent table load per set index bit.  Same output bits either way.
-struct SobolParams { const uint32_t* __restrict__ M; int32_t log2_spp, n_base4_digits; uint32_t seed; int32_t fast; };
+//
+// Prefix cache (`top`): the base-4 digits of the Morton-indexed sample number that lie above the sample bits are a function
+// of (pixel, dimension) only -- their permutations hash nothing but pixel bits -- so they are computed once per
+// (resolution, seed) by k_sobol_prefix (hk_wavefront.cuh) into top[cache_slot][pixel] (u32, 4 B x pixels x dimensions in
+// use; a few GB at 4K out of 180 GB HBM).  A sample then only walks the ceil(log2_spp/2) digits that depend on sample_idx
+// (6 of 17 at 1080p).  Cache slots: 0,1,2 = camera dimensions 1,3,6; 3+5*depth+{0..4} = 6+7*depth+{1,3,4,6,7}.
+// dimhash[cache_slot] = {u32(hash(dim+1, seed)), lo/hi of hash(dim+2, seed), 0}: the Owen-scramble seeds of zsobol_1d / _2d.
+// sample_idx >= 2^log2_spp aliases into the pixel bits (reference quirk, sobol.jl:274) and takes the uncached path.
+struct SobolParams {
+    const uint32_t* __restrict__ M; int32_t log2_spp, n_base4_digits; uint32_t seed; int32_t fast;
+    const uint32_t* __restrict__ top; const uint4* __restrict__ dimhash; uint32_t top_stride; int32_t n_top;
+};
+#define HK_SOBOL_SLOT_CAMERA(j) (j)                      /* j = 0,1,2 for dimensions 1,3,6 */
+#define HK_SOBOL_SLOT_BOUNCE(depth, j) (3 + 5 * (depth) + (j))   /* j = 0..4 for 6+7*depth + {1,3,4,6,7} */
 
 HK_DEV uint64_t left_shift2(uint64_t x) {
     x &= 0xffffffffull;
@@ -179,27 +192,10 @@ HK_DEV uint32_t perm4_byte(uint32_t p) {   // p in [0, 24)
 }
 // not inlined: the digit loop is ~600 instructions and has five call sites per shading kernel; inlining all of them made
 // the kernels instruction-fetch bound (stall_no_instruction was the top stall reason)
-#ifndef HK_SOBOL_NOINLINE
-#define HK_SOBOL_NOINLINE 0
-#endif
-#define HK_PRAGMA_(x) _Pragma(#x)
-#define HK_UNROLL(n) HK_PRAGMA_(unroll n)
-#ifndef HK_SOBOL_UNROLL
-#define HK_SOBOL_UNROLL 1
-#endif
-#if HK_SOBOL_NOINLINE
-__device__ __noinline__
-#else
-HK_DEV
-#endif
-uint64_t zsobol_sample_index(uint64_t morton, int32_t dim, int32_t log2_spp, int32_t nb4) {
+// digits i_hi .. i_lo (inclusive, i_lo >= log2_spp & 1) of zsobol_get_sample_index, sobol.jl:269-291
+HK_DEV uint64_t zsobol_digits(uint64_t morton, uint64_t dmix, int pow2, int i_hi, int i_lo) {
     uint64_t idx = 0;
-    const int pow2 = log2_spp & 1;
-    const uint64_t dmix = 0x55555555ull * (uint64_t)(int64_t)dim;
-    // iterations are independent (each digit hashes its own prefix): unrolling interleaves the serial 64-bit
-    // multiply / xor-shift chains of several digits, which is what bounds this loop (fixed-latency "wait" stalls)
-    HK_UNROLL(HK_SOBOL_UNROLL)
-    for (int i = nb4 - 1; i >= pow2; --i) {
+    for (int i = i_hi; i >= i_lo; --i) {
         int shift = 2 * i - pow2;
         uint32_t digit = (uint32_t)(morton >> shift) & 3u;
         int hs = shift + 2;
@@ -211,11 +207,26 @@ uint64_t zsobol_sample_index(uint64_t morton, int32_t dim, int32_t log2_spp, int
         const uint64_t pd = (perm4_byte(p) >> (2 * digit)) & 3u;
         idx |= pd << shift;
     }
+    return idx;
+}
+HK_DEV uint64_t zsobol_dmix(int32_t dim) { return 0x55555555ull * (uint64_t)(int64_t)dim; }
+HK_DEV uint64_t zsobol_sample_index(uint64_t morton, int32_t dim, int32_t log2_spp, int32_t nb4) {
+    const int pow2 = log2_spp & 1;
+    const uint64_t dmix = zsobol_dmix(dim);
+    uint64_t idx = zsobol_digits(morton, dmix, pow2, nb4 - 1, pow2);
     if (pow2) {
         uint64_t digit = morton & 1ull;
         idx |= digit ^ (mix_bits((morton >> 1) ^ dmix) & 1ull);
     }
     return idx;
+}
+// first digit whose permutation depends on pixel bits only
+HK_DEV int zsobol_first_pixel_digit(int32_t log2_spp) { return (log2_spp + 1) >> 1; }
+// value stored in the prefix cache for one (pixel, dimension)
+HK_DEV uint32_t zsobol_prefix(uint32_t px, uint32_t py, int32_t dim, int32_t log2_spp, int32_t nb4) {
+    const int pow2 = log2_spp & 1, ilo = zsobol_first_pixel_digit(log2_spp);
+    const uint64_t morton = encode_morton2(px, py) << log2_spp;
+    return (uint32_t)(zsobol_digits(morton, zsobol_dmix(dim), pow2, nb4 - 1, ilo) >> (2 * ilo - pow2));
 }
 HK_DEV uint32_t sobol_bits(uint64_t a, int32_t dimension, const uint32_t* __restrict__ M) {
     uint32_t v = 0;
@@ -233,18 +244,36 @@ HK_DEV uint32_t sobol_bits1(const SobolParams& S, uint64_t a) {
     return S.fast ? __brev(pascal_butterfly((uint32_t)a) ^ pascal_butterfly((uint32_t)(a >> 32))) : sobol_bits(a, 1, S.M);
 }
 HK_DEV float sobol_to_float(uint32_t v) { return fminf((float)v * 2.3283064365386963e-10f, HK_ONE_MINUS_EPS); }
-HK_DEV float zsobol_1d(const SobolParams& S, int32_t px, int32_t py, int32_t sample_idx, int32_t dim) {
-    uint64_t morton = (encode_morton2((uint32_t)px, (uint32_t)py) << S.log2_spp) | (uint64_t)(int64_t)sample_idx;
-    uint64_t si = zsobol_sample_index(morton, dim, S.log2_spp, S.n_base4_digits);
-    uint32_t h = (uint32_t)hash_dim_seed(dim + 1, S.seed);
-    return sobol_to_float(fast_owen_scramble(sobol_bits0(S, si), h));
+// Morton-indexed sample number of (pixel, sample_idx) in one dimension + the Owen-scramble seeds of that dimension.
+// cslot < 0 (or no cache uploaded): everything is computed from scratch -- same bits either way.
+struct ZSample { uint64_t si; uint32_t h1, h2lo, h2hi; };
+HK_DEV ZSample zsobol_index(const SobolParams& S, int32_t px, int32_t py, int32_t sample_idx, int32_t dim, int32_t cslot, uint32_t pix) {
+    ZSample z;
+    const uint64_t morton = (encode_morton2((uint32_t)px, (uint32_t)py) << S.log2_spp) | (uint64_t)(int64_t)sample_idx;
+    if (S.top != nullptr && cslot >= 0 && cslot < S.n_top && ((uint32_t)sample_idx >> S.log2_spp) == 0u) {
+        const int pow2 = S.log2_spp & 1, ilo = zsobol_first_pixel_digit(S.log2_spp);
+        const uint64_t dmix = zsobol_dmix(dim);
+        uint64_t idx = ((uint64_t)__ldg(S.top + (size_t)cslot * S.top_stride + pix) << (2 * ilo - pow2)) | zsobol_digits(morton, dmix, pow2, ilo - 1, pow2);
+        if (pow2) idx |= (morton & 1ull) ^ (mix_bits((morton >> 1) ^ dmix) & 1ull);
+        z.si = idx;
+        const uint4 h = __ldg(S.dimhash + cslot);
+        z.h1 = h.x; z.h2lo = h.y; z.h2hi = h.z;
+    } else {
+        z.si = zsobol_sample_index(morton, dim, S.log2_spp, S.n_base4_digits);
+        z.h1 = (uint32_t)hash_dim_seed(dim + 1, S.seed);
+        const uint64_t b2 = hash_dim_seed(dim + 2, S.seed);
+        z.h2lo = (uint32_t)b2; z.h2hi = (uint32_t)(b2 >> 32);
+    }
+    return z;
 }
-HK_DEV float2 zsobol_2d(const SobolParams& S, int32_t px, int32_t py, int32_t sample_idx, int32_t dim) {
-    uint64_t morton = (encode_morton2((uint32_t)px, (uint32_t)py) << S.log2_spp) | (uint64_t)(int64_t)sample_idx;
-    uint64_t si = zsobol_sample_index(morton, dim, S.log2_spp, S.n_base4_digits);
-    uint64_t bits = hash_dim_seed(dim + 2, S.seed);
-    return make_float2(sobol_to_float(fast_owen_scramble(sobol_bits0(S, si), (uint32_t)bits)),
-                       sobol_to_float(fast_owen_scramble(sobol_bits1(S, si), (uint32_t)(bits >> 32))));
+HK_DEV float zsobol_1d(const SobolParams& S, int32_t px, int32_t py, int32_t sample_idx, int32_t dim, int32_t cslot = -1, uint32_t pix = 0) {
+    const ZSample z = zsobol_index(S, px, py, sample_idx, dim, cslot, pix);
+    return sobol_to_float(fast_owen_scramble(sobol_bits0(S, z.si), z.h1));
+}
+HK_DEV float2 zsobol_2d(const SobolParams& S, int32_t px, int32_t py, int32_t sample_idx, int32_t dim, int32_t cslot = -1, uint32_t pix = 0) {
+    const ZSample z = zsobol_index(S, px, py, sample_idx, dim, cslot, pix);
+    return make_float2(sobol_to_float(fast_owen_scramble(sobol_bits0(S, z.si), z.h2lo)),
+                       sobol_to_float(fast_owen_scramble(sobol_bits1(S, z.si), z.h2hi)));
 }
 
 // ---- sampling primitives, sampling.jl:5-33, spectral-eval.jl:3514-3533 ------------------------------------

@@ -158,7 +158,7 @@ extern "C" {
 int32_t hk_test_sobol(HkContext* ctx, const int32_t* q, uint64_t n, int32_t l2, int32_t nb4, uint32_t seed, float* o1, float* o2) {
     if (!ctx || !ctx->have_tables) return HK_ERR_INVALID;
     cudaSetDevice(ctx->device); TkIO io(ctx);
-    SobolParams P{ctx->D.T.sobol, l2, nb4, seed, ctx->D.sobol.fast};
+    SobolParams P{ctx->D.T.sobol, l2, nb4, seed, ctx->D.sobol.fast, nullptr, nullptr, 0u, 0};
     void* dq = io.in(q, 16 * n); float* d1 = (float*)io.out(4 * n); float* d2 = (float*)io.out(8 * n);
     if (io.rc) return io.rc;
     tk_sobol<<<TK_GRID(n)>>>(P, (const int32_t*)dq, n, d1, d2); ctx->launches++;
@@ -166,6 +166,8 @@ int32_t hk_test_sobol(HkContext* ctx, const int32_t* q, uint64_t n, int32_t l2, 
 }
 // 0: generic table loop, 1: closed forms for dimensions 0/1; returns the previous mode (tests run both)
 int32_t hk_test_sobol_mode(HkContext* ctx, int32_t fast) { if (!ctx) return HK_ERR_INVALID; int32_t old = ctx->D.sobol.fast; ctx->D.sobol.fast = fast ? 1 : 0; return old; }
+// 0 / 1: disable / enable the ZSobol prefix cache (takes effect at the next hk_set_params); returns the previous setting
+int32_t hk_test_sobol_cache(HkContext* ctx, int32_t on) { if (!ctx) return HK_ERR_INVALID; int32_t old = ctx->sobol_cache_enabled ? 1 : 0; ctx->sobol_cache_enabled = on != 0; ctx->sobol_cache_key[5] = -1; return old; }
 int32_t hk_test_hashes(HkContext* ctx, const float* v, uint64_t n, uint64_t* oh, uint64_t* om, float* op) {
     if (!ctx) return HK_ERR_INVALID;
     cudaSetDevice(ctx->device); TkIO io(ctx);

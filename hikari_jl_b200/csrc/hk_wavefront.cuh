@@ -154,10 +154,10 @@ __global__ void __launch_bounds__(256) k_camera(const __grid_constant__ DevScene
         const uint32_t pix = slot % A.n_pixels;
         const int sample_idx = slot_sample_idx(A, slot);
         const int x = (int)(pix % (uint32_t)D.width) + 1, y = (int)(pix / (uint32_t)D.width) + 1;
-        float wu = zsobol_1d(D.sobol, x, y, sample_idx, 1);
-        float2 jit = zsobol_2d(D.sobol, x, y, sample_idx, 3);
+        float wu = zsobol_1d(D.sobol, x, y, sample_idx, 1, HK_SOBOL_SLOT_CAMERA(0), pix);
+        float2 jit = zsobol_2d(D.sobol, x, y, sample_idx, 3, HK_SOBOL_SLOT_CAMERA(1), pix);
         // the time sample (dim 4) is drawn by the reference but VolPath's ray drops it (volpath.jl:184)
-        float2 lens = D.camera.lens_radius > 0.0f ? zsobol_2d(D.sobol, x, y, sample_idx, 6) : make_float2(0.0f, 0.0f);
+        float2 lens = D.camera.lens_radius > 0.0f ? zsobol_2d(D.sobol, x, y, sample_idx, 6, HK_SOBOL_SLOT_CAMERA(2), pix) : make_float2(0.0f, 0.0f);
         float fx, fy, fw;
         filter_sample(D.filter, jit, fx, fy, fw);
         float4 lam, pdf;
@@ -172,6 +172,22 @@ __global__ void __launch_bounds__(256) k_camera(const __grid_constant__ DevScene
         S.q_ray[0][slot] = slot;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) { S.counts[HK_C_RAY0] = n_slots; S.counts[HK_C_RAY1] = 0; }
+}
+
+// ZSobol prefix cache (SobolParams::top, hk_math.cuh): one pass per (resolution, seed), not per sample.
+// dims[slot] = the sampler dimension of cache slot `slot`.
+__global__ void __launch_bounds__(256) k_sobol_prefix(uint32_t* __restrict__ top, uint4* __restrict__ dimhash, const int32_t* __restrict__ dims, int32_t n_slots,
+                                                       uint32_t n_pixels, int32_t width, int32_t log2_spp, int32_t nb4, uint32_t seed) {
+    const size_t total = (size_t)n_slots * n_pixels;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t slot = (uint32_t)(i / n_pixels), pix = (uint32_t)(i % n_pixels);
+        const int32_t dim = __ldg(dims + slot);
+        top[i] = zsobol_prefix(pix % (uint32_t)width + 1u, pix / (uint32_t)width + 1u, dim, log2_spp, nb4);
+        if (pix == 0) {
+            const uint64_t b2 = hash_dim_seed(dim + 2, seed);
+            dimhash[slot] = make_uint4((uint32_t)hash_dim_seed(dim + 1, seed), (uint32_t)b2, (uint32_t)(b2 >> 32), 0u);
+        }
+    }
 }
 
 // reset_iteration_queues!, volpath-state.jl:214-222 (+ the next ray queue and the traversal cursors)
@@ -315,11 +331,11 @@ __global__ void __launch_bounds__(128, HK_SHADE_MIN_BLOCKS) k_shade(const __grid
             const int bdim = 6 + 7 * depth;
             // ---- next-event estimation ---------------------------------------------------------------------------
             if (D.n_lights > 0) {
-                float direct_uc = zsobol_1d(D.sobol, px, py, sidx, bdim + 1);
+                float direct_uc = zsobol_1d(D.sobol, px, py, sidx, bdim + 1, HK_SOBOL_SLOT_BOUNCE(depth, 0), pix);
                 float pmf;
                 int li = bvh_sample_light(LC, sf.pi, sf.ns, direct_uc, pmf);
                 if (li >= 1 && li <= D.n_lights && pmf > 0.0f) {
-                    float2 direct_u = zsobol_2d(D.sobol, px, py, sidx, bdim + 3);
+                    float2 direct_u = zsobol_2d(D.sobol, px, py, sidx, bdim + 3, HK_SOBOL_SLOT_BOUNCE(depth, 1), pix);
                     LightSample ls = sample_light(LC, D.lights[li - 1], sf.pi, lam, direct_u);
                     if (ls.pdf > 0.0f && !sp_black(ls.Li)) {
                         BsdfEval be = eval_bsdf<TYPE>(MC, mat, wo, ls.wi, sf.ns, lam);
@@ -346,15 +362,15 @@ __global__ void __launch_bounds__(128, HK_SHADE_MIN_BLOCKS) k_shade(const __grid
             // ---- BSDF sampling + continuation ----------------------------------------------------------------------
             const int new_depth = depth + 1;
             if (new_depth < D.max_depth) {
-                float indirect_uc = zsobol_1d(D.sobol, px, py, sidx, bdim + 4);
-                float2 indirect_u = zsobol_2d(D.sobol, px, py, sidx, bdim + 6);
+                float indirect_uc = zsobol_1d(D.sobol, px, py, sidx, bdim + 4, HK_SOBOL_SLOT_BOUNCE(depth, 2), pix);
+                float2 indirect_u = zsobol_2d(D.sobol, px, py, sidx, bdim + 6, HK_SOBOL_SLOT_BOUNCE(depth, 3), pix);
                 const bool reg = D.regularize && (fl & HK_FLAG_ANYNS);
                 BsdfSample bs = sample_bsdf<TYPE>(MC, mat, wo, sf.ns, lam, indirect_u, indirect_uc, reg);
                 if (bs.pdf > 0.0f && !sp_black(bs.f)) {
                     float ct = fabsf(dot3(bs.wi, sf.ns));
                     Spec nb = bs.specular ? beta * bs.f : beta * bs.f * ct / bs.pdf;
                     Spec nrl = bs.specular ? r_u : r_u / bs.pdf;
-                    float rr = zsobol_1d(D.sobol, px, py, sidx, bdim + 7);
+                    float rr = zsobol_1d(D.sobol, px, py, sidx, bdim + 7, HK_SOBOL_SLOT_BOUNCE(depth, 4), pix);
                     if (russian_roulette(nb, new_depth, rr)) {
                         const float side = dot3(bs.wi, sf.n);
                         uint32_t nm = (mi.inside != mi.outside) ? (side > 0.0f ? mi.outside : mi.inside) : cur_medium;
@@ -406,9 +422,9 @@ __global__ void __launch_bounds__(128) k_medium(const __grid_constant__ DevScene
                 const float3 wo = -d;
                 if (D.n_lights > 0) {   // medium_direct_lighting_inner!
                     float pmf;
-                    int li = bvh_sample_light(LC, R.p, f3(0, 0, 0), zsobol_1d(D.sobol, px, py, sidx, bdim + 1), pmf);
+                    int li = bvh_sample_light(LC, R.p, f3(0, 0, 0), zsobol_1d(D.sobol, px, py, sidx, bdim + 1, HK_SOBOL_SLOT_BOUNCE(depth, 0), pix), pmf);
                     if (li >= 1 && li <= D.n_lights && pmf > 0.0f) {
-                        LightSample ls = sample_light(LC, D.lights[li - 1], R.p, lam, zsobol_2d(D.sobol, px, py, sidx, bdim + 3));
+                        LightSample ls = sample_light(LC, D.lights[li - 1], R.p, lam, zsobol_2d(D.sobol, px, py, sidx, bdim + 3, HK_SOBOL_SLOT_BOUNCE(depth, 1), pix));
                         if (ls.pdf > 0.0f && !sp_black(ls.Li)) {
                             float ph = hg_p(R.g, dot3(wo, ls.wi));
                             if (ph > 0.0f) {
@@ -427,7 +443,7 @@ __global__ void __launch_bounds__(128) k_medium(const __grid_constant__ DevScene
                 const int nd = depth + 1;   // medium_scatter_inner!
                 if (nd < D.max_depth) {
                     float pdf;
-                    float3 wi = sample_hg(R.g, wo, zsobol_2d(D.sobol, px, py, sidx, bdim + 6), pdf);
+                    float3 wi = sample_hg(R.g, wo, zsobol_2d(D.sobol, px, py, sidx, bdim + 6, HK_SOBOL_SLOT_BOUNCE(depth, 3), pix), pdf);
                     if (pdf > 0.0f) {
                         S.ray_a[slot] = make_float4(R.p.x, R.p.y, R.p.z, wi.x);
                         S.ray_b[slot] = make_float4(wi.y, wi.z, HK_INF, 0.0f);

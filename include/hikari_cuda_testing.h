@@ -16,6 +16,9 @@ int32_t hk_test_sobol(HkContext* ctx, const int32_t* q, uint64_t n, int32_t log2
 /* select the Sobol' evaluation: 0 = generic matrix loop, 1 = closed forms for dimensions 0/1 (only valid when
  * hk_upload_tables verified the table structure); returns the previous mode */
 int32_t hk_test_sobol_mode(HkContext* ctx, int32_t fast);
+/* 0 / 1: disable / enable the per-pixel ZSobol prefix cache (applies at the next hk_set_params); returns the previous
+ * setting.  Images must be bit-identical either way (tests/test_parity_gpu.py). */
+int32_t hk_test_sobol_cache(HkContext* ctx, int32_t on);
 /* v[n][3] -> pbrt_hash(Vec3f), mix_bits(hash), two pcg32 floats seeded (hash, mix) (spectral-eval.jl:575-815) */
 int32_t hk_test_hashes(HkContext* ctx, const float* v3, uint64_t n, uint64_t* out_hash, uint64_t* out_mix, float* out_pcg);
 /* u[n] -> lambda[n][4], pdf[n][4] (src/spectral/spectral.jl:221-249) */

@@ -355,6 +355,28 @@ def test_sample_batching_is_bitwise_invariant():
     assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
 
 
+def test_sobol_prefix_cache_is_bitwise_invariant():
+    """The per-pixel ZSobol prefix cache (SobolParams::top) only moves work out of the sample loop: cached, uncached and
+    partially cached (sample_idx >= 2^log2_spp takes the uncached path, the reference's Morton aliasing quirk) renders
+    must agree bit for bit.  cornell_smoke covers the camera, surface and medium call sites."""
+    for make, res, depth in ((lambda: scenes.c1_spheres(16), (64, 48), 5), (scenes.cornell_smoke, (40, 40), 6)):
+        scene, camf = make()
+        outs = []
+        for cache in (1, 0):
+            film = H.Film(res)
+            vp = H.VolPath(samples=4, max_depth=depth)
+            vp.backend = H.Backend()
+            assert vp.backend.lib.hk_test_sobol_cache(vp.backend.ctx, cache) == 1
+            vp._prepare(scene, film, camf(film)); vp.clear()
+            vp.backend.call("render_samples", 1, 3)
+            vp.backend.call("render_samples", 4095, 3)        # 4095 cached, 4096 and 4097 alias into the pixel bits
+            vp.backend.read_film(film)
+            outs.append(film.framebuffer.copy())
+            vp.close()
+        assert np.isfinite(outs[0]).all() and outs[0].max() > 0
+        assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+
+
 def test_strided_partition_sums_to_the_full_render():
     """The multi-GPU partition (hk_render_samples_strided, SURVEY 8e): two contexts render disjoint sample indices;
     the summed accumulators equal the single-context film within f32 summation-order tolerance."""
