@@ -157,7 +157,7 @@ def run_cuda(args):
     scene, camf = build_scene()
     film = Film(RES)
     from hikari_jl_b200.host import Backend
-    vp = VolPath(samples=4096, max_depth=MAX_DEPTH, backend=Backend(device=local))
+    vp = VolPath(samples=4096, max_depth=MAX_DEPTH, backend=Backend(device=local), sample_batch=args.batch)
     cam = camf(film)
     t_up0 = time.perf_counter()
     vp._prepare(scene, film, cam)
@@ -203,6 +203,8 @@ def run_cuda(args):
         tsum = tt.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         t_ms, rays = float(tmax[0]), int(tsum[1])
     value = world * n * args.steps / (t_ms * 1e-3) / 1e6
+    auto_batch = max(1, min(64, (32 << 20) // n))                      # HK_AUTO_SLOTS in hk_api.cu
+    batch_used = min(args.batch if args.batch > 0 else auto_batch, args.steps)
     # ---- e2e: the interactive render! loop through the public API with HOST buffers: per step the camera is re-sent
     # (H2D), one sample pass runs and the framebuffer is read back (D2H) ------------------------------------------------
     e2e_steps = max(3, min(args.steps, 8))
@@ -219,12 +221,12 @@ def run_cuda(args):
     if rank == 0:
         # ---- roofline of the dominant kernel (k_trace): per-launch device time + traversal work counters, measured live ----
         lib.hk_set_profiling(ctx, 1)
-        B.call("render_samples_strided", sample_of(args.warmup), world, 2)
+        B.call("render_samples_strided", sample_of(args.warmup), world, args.steps)      # same passes as the timed region
         ms = (C.c_double * 8)(); ln = (C.c_uint64 * 8)(); wk = (C.c_uint64 * 6)()
         lib.hk_stage_times(ctx, ms, ln, wk)
         stage_ms = list(ms); stage_ln = list(ln)
         lib.hk_set_profiling(ctx, 2)
-        B.call("render_samples_strided", sample_of(args.warmup), world, 2)
+        B.call("render_samples_strided", sample_of(args.warmup), world, args.steps)
         lib.hk_stage_times(ctx, ms, ln, wk)
         lib.hk_set_profiling(ctx, 0)
         work = list(wk)
@@ -247,13 +249,14 @@ def run_cuda(args):
             "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "mrays_per_s": rays / (t_ms * 1e-3) / 1e6, "rays_per_sample": rays / (world * n * args.steps),
             "config": {"workload": WORKLOAD, "triangles": int(len(scene._synced.indices)), "max_depth": MAX_DEPTH, "partition": f"sample-index round-robin x{world}",
-                       "l2_note": "per-step working set (path state + queues, ~0.6 GB at 1080p) exceeds the 126 MB L2; no explicit flush"},
+                       "samples_in_flight": int(batch_used),
+                       "l2_note": "per-pass working set (path state + queues, ~0.6 GB per sample in flight at 1080p) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e_val, "unit": "Msamples/s", "h2d_bytes_per_step": C.sizeof(A.HkCamera), "d2h_bytes_per_step": 12 * n,
                     "steps": e2e_steps, "what": "render!(vp, scene, film, camera) + framebuffer read per step, host buffers",
                     "scene_upload_s": t_upload},
             "gpu_launches": int(launches), "wall_s": wall, "film_reduce_ms": red_ms, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         }
-        line["roofline"]["stage_ms_per_step"] = {nm: stage_ms[i] / 2.0 for i, nm in enumerate(names)}
+        line["roofline"]["stage_ms_per_step"] = {nm: stage_ms[i] / args.steps for i, nm in enumerate(names)}
     vp.close()
     if dist:
         dist.barrier(); dist.destroy_process_group()
@@ -267,6 +270,7 @@ def main():
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--batch", type=int, default=0, help="samples kept in flight per wavefront pass (HkRenderParams.sample_batch); 0 = the library's automatic choice")
     ap.add_argument("--quick", action="store_true", help="development: skip the CPU baseline leg (tuning-variant sweeps, tools/variants.py)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else max(args.warmup, 1)

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <array>
 #include <vector>
 
 #define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__); return HK_ERR_CUDA; } } while (0)
@@ -55,6 +56,9 @@ struct HkContext {
     std::vector<StageEv> stage_events; size_t stage_ev_used = 0;
     double stage_ms[HK_N_STAGES]; uint64_t stage_launches[HK_N_STAGES];
     DevBuf b_work_ctr;
+    // profiling bit 2: per-bounce queue counts and stage times of the most recent sample pass (host sync per bounce)
+    std::vector<std::array<uint32_t, HK_N_COUNTERS>> bounce_counts;
+    std::vector<std::array<double, HK_N_STAGES>> bounce_ms;
     HkContext() { std::memset(&D, 0, sizeof(D)); std::memset(&S, 0, sizeof(S)); std::memset(&params, 0, sizeof(params)); std::memset(&stats, 0, sizeof(stats)); }
 };
 
@@ -77,10 +81,14 @@ struct StageScope {
     }
     ~StageScope() { if (ev) cudaEventRecord(ev->b, c->stream); c->launches++; }
 };
-static void collect_stage_times(HkContext* c) {
+static void collect_stage_times(HkContext* c, double* also = nullptr) {
     cudaStreamSynchronize(c->stream);
     for (size_t i = 0; i < c->stage_ev_used; i++) {
-        float ms = 0; if (cudaEventElapsedTime(&ms, c->stage_events[i].a, c->stage_events[i].b) == cudaSuccess) { c->stage_ms[c->stage_events[i].stage] += ms; c->stage_launches[c->stage_events[i].stage]++; }
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c->stage_events[i].a, c->stage_events[i].b) == cudaSuccess) {
+            c->stage_ms[c->stage_events[i].stage] += ms; c->stage_launches[c->stage_events[i].stage]++;
+            if (also) also[c->stage_events[i].stage] += ms;
+        }
     }
     c->stage_ev_used = 0;
 }
@@ -307,13 +315,20 @@ int32_t hk_set_filter(HkContext* ctx, const HkFilter* f) {
     return HK_OK;
 }
 
-static int32_t alloc_state(HkContext* ctx, size_t n_slots, size_t n_pixels) {
+// Path-state pool for n_slots = (samples in flight) x n_pixels.  The film accumulators are separate (alloc_film) so that
+// the pool can grow when a later call renders more samples per pass without touching what was accumulated.
+static int32_t alloc_film(HkContext* ctx, size_t n_pixels) {
+    CK(ctx->b_film.alloc(16 * n_pixels + 64));
+    CK(cudaMemset(ctx->b_film.p, 0, ctx->b_film.bytes));
+    ctx->S.pixel_rgb = ctx->b_film.as<float>(); ctx->S.pixel_weight = ctx->b_film.as<float>() + 3 * n_pixels;
+    return HK_OK;
+}
+static int32_t alloc_state(HkContext* ctx, size_t n_slots) {
     // one slab: 14 float4 arrays, 3 u32/f32 arrays, 13 queues; every array starts 256-byte aligned
     const size_t f4 = 14, w4 = 3, q = 5 + HK_MAX_MAT_TYPES;
     size_t rounded = f4 * (((16 * n_slots + 255) / 256) * 256) + (w4 + q) * (((4 * n_slots + 255) / 256) * 256);
+    CK(cudaStreamSynchronize(ctx->stream));
     CK(ctx->b_state.alloc(rounded));
-    CK(ctx->b_film.alloc(16 * n_pixels + 64));
-    CK(cudaMemset(ctx->b_film.p, 0, ctx->b_film.bytes));
     char* p = ctx->b_state.as<char>();
     auto take = [&](size_t elt) { char* r = p; p += ((elt * n_slots + 255) / 256) * 256; return r; };
     PathState& S = ctx->S;
@@ -325,7 +340,6 @@ static int32_t alloc_state(HkContext* ctx, size_t n_slots, size_t n_pixels) {
     for (int t = 0; t < HK_MAX_MAT_TYPES; t++) S.q_hit[t] = reinterpret_cast<uint32_t*>(take(4));
     S.counts = ctx->b_counts.as<uint32_t>();
     S.rays_traced = reinterpret_cast<unsigned long long*>(ctx->b_counts.as<char>() + sizeof(uint32_t) * HK_N_COUNTERS);
-    S.pixel_rgb = ctx->b_film.as<float>(); S.pixel_weight = ctx->b_film.as<float>() + 3 * n_pixels;
     ctx->n_slots = n_slots;
     return HK_OK;
 }
@@ -333,6 +347,9 @@ static int32_t alloc_state(HkContext* ctx, size_t n_slots, size_t n_pixels) {
 // (Re)build the ZSobol prefix cache when resolution / sampler parameters change: one k_sobol_prefix pass over
 // pixels x dimensions-in-use, amortised over every sample rendered afterwards (like the BVH build at geometry upload).
 // Capped at HK_SOBOL_CACHE_BYTES; bounces beyond the cached depth use the uncached evaluation (same bits).
+#ifndef HK_AUTO_SLOTS
+#define HK_AUTO_SLOTS (32ull << 20)
+#endif
 #ifndef HK_SOBOL_CACHE_BYTES
 #define HK_SOBOL_CACHE_BYTES (8ull << 30)
 #endif
@@ -376,13 +393,22 @@ int32_t hk_set_params(HkContext* ctx, const HkRenderParams* p) {
     REQUIRE(p->width > 0 && p->height > 0, "width/height must be positive");
     REQUIRE(p->max_depth >= 1 && p->max_depth <= 255, "max_depth must be in [1, 255]");
     ctx->params = *p;
-    if (ctx->params.sample_batch < 1) ctx->params.sample_batch = 1;
+    if (ctx->params.sample_batch < 1) {
+        // auto: keep ~HK_AUTO_SLOTS path states in flight.  Deep bounces hold < 1 % of the rays but every stage still costs
+        // its latency floor (~0.1 ms: the longest single traversal / shading chain); several samples per pass share it.
+        // 1080p: 16 samples per pass (9.6 GB of path state), 4K: 4 -- memory is not the constraint on a 180 GB part.
+        const size_t auto_b = HK_AUTO_SLOTS / ((size_t)p->width * p->height);
+        ctx->params.sample_batch = (int32_t)std::min<size_t>(64, std::max<size_t>(1, auto_b));
+    }
     DevScene& D = ctx->D;
     D.width = p->width; D.height = p->height; D.max_depth = p->max_depth; D.regularize = p->regularize; D.max_component_value = p->max_component_value;
     D.sobol.log2_spp = p->sobol_log2_spp; D.sobol.n_base4_digits = p->sobol_n_base4_digits; D.sobol.seed = p->sampler_seed;
     size_t n_pixels = (size_t)p->width * p->height;
-    int32_t rc = alloc_state(ctx, n_pixels * (size_t)ctx->params.sample_batch, n_pixels);
+    // the pool itself is sized on demand by hk_render_samples* (a caller that renders one sample per call never
+    // allocates more than one sample's worth)
+    int32_t rc = alloc_film(ctx, n_pixels);
     if (rc != HK_OK) return rc;
+    ctx->b_state.release(); ctx->n_slots = 0;
     rc = build_sobol_cache(ctx);
     if (rc != HK_OK) return rc;
     ctx->have_params = true;
@@ -412,6 +438,10 @@ int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride,
     REQUIRE(count >= 0 && stride >= 1 && first >= 1, "bad sample range");
     const size_t n_pixels = (size_t)ctx->params.width * ctx->params.height;
     cudaStream_t st = ctx->stream;
+    {
+        const size_t need = n_pixels * (size_t)std::max<int32_t>(1, std::min<int32_t>(ctx->params.sample_batch, count));
+        if (ctx->n_slots < need) { int32_t rc = alloc_state(ctx, need); if (rc != HK_OK) return rc; }
+    }
     if (!ctx->camera_medium_valid) {   // hoisted out of the per-sample path (reference: one alloc + sync per sample, volpath.jl:503)
         CK(ctx->b_scratch_u32.alloc(16));
         k_detect_camera_medium<<<1, 32, 0, st>>>(ctx->D, ctx->b_scratch_u32.as<uint32_t>());
@@ -451,6 +481,12 @@ int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride,
                 if (opaque_only) { if (cnt) k_shadow_opaque<true><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, work); else k_shadow_opaque<false><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, work); }
                 else { if (cnt) k_shadow_general<true><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, work); else k_shadow_general<false><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, work); }
             }
+            if ((ctx->profiling & 5) == 5) {   // per-bounce record (debug): counts as left by this bounce + its stage times
+                if ((int)ctx->bounce_counts.size() <= depth) { ctx->bounce_counts.resize(depth + 1); ctx->bounce_ms.resize(depth + 1); }
+                ctx->bounce_ms[depth].fill(0.0);
+                collect_stage_times(ctx, ctx->bounce_ms[depth].data());
+                cudaMemcpy(ctx->bounce_counts[depth].data(), ctx->S.counts, sizeof(uint32_t) * HK_N_COUNTERS, cudaMemcpyDeviceToHost);
+            }
             cur ^= 1;
         }
         { StageScope sc(ctx, HK_STAGE_FILM); k_film_accumulate<<<grid_for(ctx, n_pixels, 256, 8), 256, 0, st>>>(ctx->D, ctx->S, A); }
@@ -477,6 +513,14 @@ int32_t hk_stage_times(HkContext* ctx, double* out_ms, uint64_t* out_launches, u
     collect_stage_times(ctx);
     for (int i = 0; i < HK_N_STAGES; i++) { out_ms[i] = ctx->stage_ms[i]; out_launches[i] = ctx->stage_launches[i]; }
     CK(cudaMemcpy(out_work, ctx->b_work_ctr.p, 48, cudaMemcpyDeviceToHost));
+    return HK_OK;
+}
+// per-bounce profile of the most recent sample pass rendered with hk_set_profiling(ctx, 5): counts[max_depth][16] (queue
+// counters after the bounce: ray0, ray1, escaped, medium, shadow, total hits, cursors, per-material hits) and ms[max_depth][8]
+int32_t hk_bounce_profile(HkContext* ctx, int32_t max_depth, uint32_t* counts, double* ms) {
+    if (!ctx || !counts || !ms) return HK_ERR_INVALID;
+    for (int d = 0; d < max_depth; d++) for (int i = 0; i < HK_N_COUNTERS; i++) counts[d * HK_N_COUNTERS + i] = d < (int)ctx->bounce_counts.size() ? ctx->bounce_counts[d][i] : 0u;
+    for (int d = 0; d < max_depth; d++) for (int i = 0; i < HK_N_STAGES; i++) ms[d * HK_N_STAGES + i] = d < (int)ctx->bounce_ms.size() ? ctx->bounce_ms[d][i] : 0.0;
     return HK_OK;
 }
 int32_t hk_render_samples(HkContext* ctx, int32_t first, int32_t count) { return hk_render_samples_strided(ctx, first, 1, count); }

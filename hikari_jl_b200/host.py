@@ -919,7 +919,7 @@ class Backend:
         f = sampler_data.to_abi()
         self.call("set_filter", C.byref(f))
 
-    def set_params(self, vp, width, height, sample_batch=1):
+    def set_params(self, vp, width, height, sample_batch=0):
         sobol_spp = max(int(vp.samples_per_pixel), 4096)            # volpath.jl:475
         l2, nb4 = compute_zsobol_params(sobol_spp, width, height)
         p = A.HkRenderParams(width, height, vp.max_depth, vp.samples_per_pixel, 1 if vp.regularize else 0,
@@ -949,7 +949,7 @@ class VolPath:
     """volpath.jl:29-101.  Keyword-only like the reference: VolPath(samples=…, max_depth=…)."""
 
     def __init__(self, *, max_depth=8, samples=64, russian_roulette_depth=3, regularize=True,
-                 material_coherence="none", max_component_value=10.0, filter=None, backend=None, sample_batch=1):
+                 material_coherence="none", max_component_value=10.0, filter=None, backend=None, sample_batch=0):
         assert material_coherence in ("none", "sorted", "per_type"), \
             "material_coherence must be :none, :sorted, :per_type"
         self.max_depth, self.samples_per_pixel = int(max_depth), int(samples)

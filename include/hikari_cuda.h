@@ -251,7 +251,9 @@ typedef struct HkRenderParams {  /* VolPath fields, src/integrators/volpath/volp
     int32_t  sobol_log2_spp;         /* compute_zsobol_params(max(spp,4096),W,H) sobol.jl:317-323 */
     int32_t  sobol_n_base4_digits;
     int32_t  material_coherence;     /* 0 :none, 1 :sorted, 2 :per_type — all map to per-type queues */
-    int32_t  sample_batch;           /* library extension: samples in flight per pass (>=1)       */
+    int32_t  sample_batch;           /* library extension: samples in flight per pass; <= 0 = auto
+                                      * (~32 M path states: 16 at 1080p, 4 at 4K).  Images are bitwise
+                                      * independent of it.                                          */
 } HkRenderParams;
 
 typedef struct HkStats {
@@ -334,6 +336,9 @@ int32_t hk_stats(HkContext* ctx, HkStats* out);
 #define HK_N_STAGES      8
 int32_t hk_set_profiling(HkContext* ctx, int32_t mode);
 int32_t hk_stage_times(HkContext* ctx, double* out_ms, uint64_t* out_launches, uint64_t* out_work);
+/* mode 5 additionally records, per bounce of the most recent sample pass, the 16 queue counters and the stage times
+ * (one host sync per bounce: diagnostics only).  counts[max_depth][16], ms[max_depth][HK_N_STAGES]. */
+int32_t hk_bounce_profile(HkContext* ctx, int32_t max_depth, uint32_t* counts, double* ms);
 int32_t hk_synchronize(HkContext* ctx);
 
 /* device memory helpers so a host without a CUDA binding (the Python mirror, tests) can keep

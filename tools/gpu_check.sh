@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 timeout 1500 python -m pytest tests -m gpu -q -s 2>&1 | tail -80 > gpurun_out/pytest_gpu.log
 cat gpurun_out/pytest_gpu.log
-timeout 900 python bench.py --steps 8 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
+timeout 900 python bench.py --steps 16 --warmup 16 > gpurun_out/bench.json 2> gpurun_out/bench.err
 tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
 if [ "$1" == "ncu" ]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_bench.log 2>&1
