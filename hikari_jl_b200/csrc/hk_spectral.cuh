@@ -18,12 +18,22 @@ struct DevTables {
 };
 
 struct Poly3 { float c0, c1, c2; };
+// HK_SPEC_FN: the uplift helpers are called from a dozen places per shading kernel; as real functions (not inlined)
+// the kernels shrink by a third, which matters because they were instruction-fetch bound (stall_no_instruction)
+#ifndef HK_NOINLINE_UPLIFT
+#define HK_NOINLINE_UPLIFT 1
+#endif
+#if HK_NOINLINE_UPLIFT
+#define HK_SPEC_FN __device__ __noinline__
+#else
+#define HK_SPEC_FN HK_DEV
+#endif
 HK_DEV float sigmoidf_(float x) {
     if (isinf(x)) return x > 0 ? 1.0f : 0.0f;
     return 0.5f + x / (2.0f * sqrtf(1.0f + x * x));
 }
 HK_DEV float poly_eval(const Poly3& p, float l) { return sigmoidf_(p.c0 * l * l + p.c1 * l + p.c2); }
-HK_DEV float poly_max_value(const Poly3& p) {
+HK_SPEC_FN float poly_max_value(Poly3 p) {
     float r = fmaxf(poly_eval(p, 360.0f), poly_eval(p, 830.0f));
     if (p.c0 != 0.0f) {
         float lc = -p.c1 / (2.0f * p.c0);
@@ -31,7 +41,8 @@ HK_DEV float poly_max_value(const Poly3& p) {
     }
     return r;
 }
-HK_DEV Poly3 rgb_to_spectrum(const DevTables& T, float r, float g, float b) {
+// (arguments by value: a reference parameter of a real function would push the caller's struct to local memory)
+HK_SPEC_FN Poly3 rgb_to_spectrum_tab(const float* __restrict__ rgb_scale, const float4* __restrict__ rgb_coeffs, int res, float r, float g, float b) {
     r = clampf(r, 0.0f, 1.0f); g = clampf(g, 0.0f, 1.0f); b = clampf(b, 0.0f, 1.0f);
     if (r == g && g == b) {
         float c2 = (r > 0.0f && r < 1.0f) ? (r - 0.5f) / sqrtf(r * (1.0f - r)) : (r <= 0.0f ? -1.0e10f : 1.0e10f);
@@ -41,18 +52,17 @@ HK_DEV Poly3 rgb_to_spectrum(const DevTables& T, float r, float g, float b) {
     float z = maxc == 0 ? r : (maxc == 1 ? g : b);
     float xc = maxc == 0 ? g : (maxc == 1 ? b : r);
     float yc = maxc == 0 ? b : (maxc == 1 ? r : g);
-    const int res = T.rgb_res;
     float x = xc * (float)(res - 1) / z;
     float y = yc * (float)(res - 1) / z;
     // last i in [1, res-1] with scale[i] < z (scale is increasing), 1 if none — same result as the linear scan
     int zi = 1;
-    { int lo = 1, hi = res - 1; while (lo <= hi) { int mid = (lo + hi) >> 1; if (__ldg(T.rgb_scale + mid - 1) < z) { zi = mid; lo = mid + 1; } else hi = mid - 1; } }
+    { int lo = 1, hi = res - 1; while (lo <= hi) { int mid = (lo + hi) >> 1; if (__ldg(rgb_scale + mid - 1) < z) { zi = mid; lo = mid + 1; } else hi = mid - 1; } }
     zi = min(zi, res - 1);
     int xi = min(trunc_i(x) + 1, res - 1), yi = min(trunc_i(y) + 1, res - 1);
     float dx = x - (float)(xi - 1), dy = y - (float)(yi - 1);
-    float s0 = __ldg(T.rgb_scale + zi - 1), s1 = __ldg(T.rgb_scale + zi);
+    float s0 = __ldg(rgb_scale + zi - 1), s1 = __ldg(rgb_scale + zi);
     float dz = (z - s0) / (s1 - s0);
-    const float4* base = T.rgb_coeffs + (((size_t)maxc * res + (zi - 1)) * res + (yi - 1)) * res + (xi - 1);
+    const float4* base = rgb_coeffs + (((size_t)maxc * res + (zi - 1)) * res + (yi - 1)) * res + (xi - 1);
     const size_t sy = (size_t)res, sz = (size_t)res * res;
     float4 c000 = __ldg(base), c001 = __ldg(base + 1), c010 = __ldg(base + sy), c011 = __ldg(base + sy + 1);
     float4 c100 = __ldg(base + sz), c101 = __ldg(base + sz + 1), c110 = __ldg(base + sz + sy), c111 = __ldg(base + sz + sy + 1);
@@ -62,28 +72,30 @@ HK_DEV Poly3 rgb_to_spectrum(const DevTables& T, float r, float g, float b) {
 #undef HK_TRI
     return p;
 }
-HK_DEV Spec poly_eval4(const Poly3& p, float4 l) { return sp4(poly_eval(p, l.x), poly_eval(p, l.y), poly_eval(p, l.z), poly_eval(p, l.w)); }
+HK_DEV Poly3 rgb_to_spectrum(const DevTables& T, float r, float g, float b) { return rgb_to_spectrum_tab(T.rgb_scale, T.rgb_coeffs, T.rgb_res, r, g, b); }
+HK_SPEC_FN Spec poly_eval4(Poly3 p, float4 l) { return sp4(poly_eval(p, l.x), poly_eval(p, l.y), poly_eval(p, l.z), poly_eval(p, l.w)); }
 HK_DEV Spec uplift_rgb(const DevTables& T, float r, float g, float b, float4 lambda) { return poly_eval4(rgb_to_spectrum(T, r, g, b), lambda); }
 HK_DEV Spec uplift_rgb_unbounded(const DevTables& T, float r, float g, float b, float4 lambda) {
     float m = fmaxf(fmaxf(r, g), b);
     if (m <= 0.0f) return sp(0.0f);
     Poly3 p = rgb_to_spectrum(T, r / m, g / m, b / m);
     float s = m / poly_max_value(p);
-    return sp4(s * poly_eval(p, lambda.x), s * poly_eval(p, lambda.y), s * poly_eval(p, lambda.z), s * poly_eval(p, lambda.w));
+    return poly_eval4(p, lambda) * s;
 }
-HK_DEV float sample_d65(const DevTables& T, float l) {
-    if (l <= 300.0f) return __ldg(T.d65);
-    if (l >= 830.0f) return __ldg(T.d65 + 106);
+HK_DEV float sample_d65(const float* __restrict__ d65, float l) {
+    if (l <= 300.0f) return __ldg(d65);
+    if (l >= 830.0f) return __ldg(d65 + 106);
     float t = (l - 300.0f) / 5.0f;
     int fl = floor_i(t);
     int idx = clampi(fl + 1, 1, 106);
     float fr = t - (float)fl;
-    return __ldg(T.d65 + idx - 1) * (1.0f - fr) + __ldg(T.d65 + idx) * fr;
+    return __ldg(d65 + idx - 1) * (1.0f - fr) + __ldg(d65 + idx) * fr;
 }
-HK_DEV Spec illuminant_eval(const DevTables& T, const Poly3& p, float scale, float4 l) {
-    return sp4(scale * poly_eval(p, l.x) * sample_d65(T, l.x), scale * poly_eval(p, l.y) * sample_d65(T, l.y),
-               scale * poly_eval(p, l.z) * sample_d65(T, l.z), scale * poly_eval(p, l.w) * sample_d65(T, l.w));
+HK_SPEC_FN Spec illuminant_eval_tab(const float* __restrict__ d65, Poly3 p, float scale, float4 l) {
+    return sp4(scale * poly_eval(p, l.x) * sample_d65(d65, l.x), scale * poly_eval(p, l.y) * sample_d65(d65, l.y),
+               scale * poly_eval(p, l.z) * sample_d65(d65, l.z), scale * poly_eval(p, l.w) * sample_d65(d65, l.w));
 }
+HK_DEV Spec illuminant_eval(const DevTables& T, const Poly3& p, float scale, float4 l) { return illuminant_eval_tab(T.d65, p, scale, l); }
 HK_DEV Spec uplift_rgb_illuminant(const DevTables& T, float r, float g, float b, float4 lambda) {
     float m = fmaxf(fmaxf(r, g), b);
     if (m <= 0.0f) return sp(0.0f);
