@@ -38,33 +38,58 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clocks + throttle reasons with nvidia-smi while the timed region runs."""
+    """Samples SM clocks + throttle reasons while the timed region runs: NVML in-process every ~2 ms (the timed region of
+    the default run is only tens of milliseconds), nvidia-smi as the fallback when pynvml is not importable."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz, self.stop_flag = index, [], set(), None, False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
-    def run(self):
+    def _sample_nvml(self):
+        n = self.nvml
+        self.samples.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for nm, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20)):
+            if r & bit:
+                self.reasons.add(nm)
+
+    def _sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+        self.samples.append(float(out[0])); self.max_mhz = float(out[1])
+        for nm, v in zip(names, out[2:]):
+            if v.strip().lower().startswith("active"):
+                self.reasons.add(nm)
+
+    def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(out[0])); self.max_mhz = float(out[1])
-                for nm, v in zip(names, out[2:]):
-                    if v.strip().lower().startswith("active"):
-                        self.reasons.add(nm)
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.002 if self.nvml is not None else 0.2)
 
     def result(self):
         self.stop_flag = True
         self.join(timeout=6)
         med = float(np.median(self.samples)) if self.samples else None
-        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "n_samples": len(self.samples)}
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "n_samples": len(self.samples),
+                "how": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def build_scene():
@@ -173,8 +198,8 @@ def run_cuda(args):
     def sample_of(k):      # rank-strided sample indices: the multi-GPU partition
         return rank + 1 + k * world
 
-    for w in range(args.warmup):
-        B.call("render_samples_strided", sample_of(w), world, 1)
+    if args.warmup > 0:      # W untimed steps, in one call like the timed region (same samples-in-flight, state pool allocated here)
+        B.call("render_samples_strided", sample_of(0), world, args.warmup)
     B.call("synchronize")
     # ---- timed region: K steps, device-timed (CUDA events on the library's launch stream), barrier + sync both sides ----
     if dist: dist.barrier()
@@ -236,8 +261,12 @@ def run_cuda(args):
         achieved = trace_bytes / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else 0.0
         names = ["camera", "trace", "medium", "escaped", "shade", "shadow", "film", "route"]
         total_ms = sum(stage_ms) or 1.0
-        roofline = {"kernel": "k_trace (closest-hit BVH8 traversal + queue routing)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                    "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r01_trace_traffic.json")     # dram__bytes_read+write per launch, one ncu --set full capture
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath)); traffic = tj["dram_bytes_per_launch"]; traffic_src = tj["source"]
+        roofline = {"kernel": "k_trace (closest-hit BVH8 traversal)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                    "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                     "bytes_per_launch": trace_bytes / max(1, stage_ln[1]), "ms_per_launch": trace_ms / max(1, stage_ln[1]),
                     "rays": work[0], "node_visits_per_ray": work[1] / max(1, work[0]), "tri_tests_per_ray": work[2] / max(1, work[0]),
                     "stage_share": {nm: stage_ms[i] / total_ms for i, nm in enumerate(names)},
