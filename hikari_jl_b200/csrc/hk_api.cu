@@ -35,6 +35,7 @@ struct HkContext {
     bool have_tables = false, have_geom = false, have_mats = false, have_lights = false, have_cam = false, have_filter = false, have_params = false;
     bool camera_medium_valid = false; uint32_t camera_medium = 0;
     uint32_t mat_types_present = 0;
+    uint32_t n_interfaces = 0, max_iface_in_geom = 0; bool tri_types_valid = false;
     // device buffers
     DevBuf b_sobol, b_cie_x, b_cie_y, b_cie_z, b_d65, b_rgb_scale, b_rgb_coeffs;
     DevBuf b_nodes, b_tris, b_pos, b_nrm, b_idx, b_meta;
@@ -170,10 +171,31 @@ int32_t hk_upload_tables(HkContext* ctx, const HkTables* t) {
     return HK_OK;
 }
 
+// material type per BVH triangle (HitRec): needs geometry and materials, runs after whichever is uploaded second
+static int32_t patch_tri_types(HkContext* ctx) {
+    ctx->tri_types_valid = false;
+    if (!ctx->have_geom || !ctx->have_mats) return HK_OK;
+    if (ctx->max_iface_in_geom > ctx->n_interfaces) return HK_OK;      // geometry and materials of different scenes: wait for the matching upload
+    const uint32_t n = (uint32_t)(ctx->b_tris.bytes / sizeof(HkBvhTri));
+    ctx->tri_types_valid = true;
+    if (n == 0 || !ctx->D.tri_meta) return HK_OK;
+    k_patch_tri_types<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(ctx->b_tris.as<float4>(), n, ctx->D.tri_meta, ctx->D.interfaces, ctx->D.materials);
+    ctx->launches++;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    return HK_OK;
+}
+
 int32_t hk_upload_geometry(HkContext* ctx, const HkGeometry* g) {
     if (!ctx || !g) return HK_ERR_INVALID;
     cudaSetDevice(ctx->device);
     REQUIRE(g->n_tris == 0 || (g->positions && g->indices && g->tri_meta), "geometry arrays missing");
+    REQUIRE(g->n_tris < HK_PRIM_MASK, "at most 2^28 - 2 triangles (the hit record keeps the material type in the top 4 bits)");
+    ctx->max_iface_in_geom = 0;
+    for (uint32_t i = 0; i < g->n_tris; i++) {
+        REQUIRE(g->tri_meta[3 * (size_t)i] >= 1, "TriangleMeta.medium_interface_idx is 1-based");
+        ctx->max_iface_in_geom = std::max(ctx->max_iface_in_geom, g->tri_meta[3 * (size_t)i]);
+    }
     HkBvh bvh;
     hk_build_bvh8(g->positions, g->indices, g->n_tris, bvh);
     CK(ctx->b_nodes.upload(bvh.nodes.data(), bvh.nodes.size() * sizeof(HkBvhNode)));
@@ -188,7 +210,7 @@ int32_t hk_upload_geometry(HkContext* ctx, const HkGeometry* g) {
     ctx->stats.bvh_nodes = bvh.nodes.size();
     ctx->stats.bvh_bytes = bvh.nodes.size() * sizeof(HkBvhNode) + bvh.tris.size() * sizeof(HkBvhTri);
     ctx->have_geom = true; ctx->camera_medium_valid = false;
-    return HK_OK;
+    return patch_tri_types(ctx);
 }
 
 int32_t hk_upload_spectra(HkContext* ctx, const HkSpectra* s) {
@@ -216,10 +238,10 @@ int32_t hk_upload_materials(HkContext* ctx, const HkMaterial* m, uint32_t nm, co
     }
     CK(ctx->b_mats.upload(m, sizeof(HkMaterial) * (size_t)nm)); CK(ctx->b_ifaces.upload(mi, sizeof(HkMediumInterface) * (size_t)ni));
     ctx->D.materials = ctx->b_mats.as<HkMaterial>(); ctx->D.interfaces = ctx->b_ifaces.as<HkMediumInterface>();
-    ctx->D.any_medium_transition = trans; ctx->mat_types_present = present;
+    ctx->D.any_medium_transition = trans; ctx->mat_types_present = present; ctx->n_interfaces = ni;
     if (!ctx->b_spec_o.p) { uint32_t zero = 0; CK(ctx->b_spec_o.upload(&zero, 4)); ctx->D.spec_offsets = ctx->b_spec_o.as<uint32_t>(); }
     ctx->have_mats = true; ctx->camera_medium_valid = false;
-    return HK_OK;
+    return patch_tri_types(ctx);
 }
 
 int32_t hk_upload_envmaps(HkContext* ctx, const HkEnvMap* maps, uint32_t n) {
@@ -435,6 +457,7 @@ int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride,
     cudaSetDevice(ctx->device);
     REQUIRE(ctx->have_tables && ctx->have_geom && ctx->have_mats && ctx->have_lights && ctx->have_cam && ctx->have_filter && ctx->have_params,
             "render called before tables/geometry/materials/lights/camera/filter/params were all uploaded");
+    REQUIRE(ctx->tri_types_valid, "geometry references medium interfaces that the uploaded material set does not have");
     REQUIRE(count >= 0 && stride >= 1 && first >= 1, "bad sample range");
     const size_t n_pixels = (size_t)ctx->params.width * ctx->params.height;
     cudaStream_t st = ctx->stream;

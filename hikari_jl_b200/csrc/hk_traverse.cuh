@@ -37,7 +37,14 @@
 
 // one_bits = 0x3F800000, supplied by the host so that it reaches the kernels as a run-time value: see HK_QF in node_step()
 struct DevBvh { const float4* __restrict__ nodes; const float4* __restrict__ tris; uint32_t one_bits; };
-struct HitRec { float t; uint32_t prim1; float b1, b2; };   // prim1: 1-based global id, 0 = miss
+// prim1: 1-based global primitive id in the low 28 bits (0 = miss) | material type of the triangle's interface << 28.
+// The type bits ride along for free (they sit in the spare word of the 48-byte triangle record, written by
+// k_patch_tri_types once geometry and materials are both uploaded) so that the routing kernel needs no
+// TriangleMeta -> interface -> material gather chain per ray.
+struct HitRec { float t; uint32_t prim1; float b1, b2; };
+#define HK_PRIM_MASK 0x0FFFFFFFu
+#define HK_HIT_PRIM1(bits) ((bits) & HK_PRIM_MASK)
+#define HK_HIT_MTYPE(bits) ((bits) >> 28)
 
 HK_DEV float __frcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 HK_DEV bool tri_test(float3 o, float3 d, float3 v0, float3 e1, float3 e2, float t_max, float& t, float& u, float& v) {
@@ -181,9 +188,9 @@ struct Bvh8Walker {
         if (COUNT) (*n_tris)++;
         float t, u, v;
         if (tri_test(o, d, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), t_max, t, u, v)) {
-            const uint32_t prim1 = __float_as_uint(a.w) + 1u;
+            const uint32_t prim1 = (__float_as_uint(a.w) + 1u) | (__float_as_uint(b.w) << 28);
             if (ANY) { best.t = t; best.prim1 = prim1; best.b1 = u; best.b2 = v; return true; }
-            if (best.prim1 == 0u || t < best.t || (t == best.t && prim1 < best.prim1)) { best.t = t; best.prim1 = prim1; best.b1 = u; best.b2 = v; }
+            if (best.prim1 == 0u || t < best.t || (t == best.t && HK_HIT_PRIM1(prim1) < HK_HIT_PRIM1(best.prim1))) { best.t = t; best.prim1 = prim1; best.b1 = u; best.b2 = v; }
         }
         return false;
     }

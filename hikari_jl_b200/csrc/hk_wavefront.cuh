@@ -92,6 +92,18 @@ HK_DEV void warp_push1(uint32_t* counter, uint32_t* queue, bool pred, uint32_t v
     base = __shfl_sync(m, base, leader);
     queue[base + (unsigned)__popc(m & ((1u << lane) - 1u))] = value;
 }
+// two predicated appends at once: both atomics are in flight before either result is used (one round trip, not two)
+HK_DEV void warp_push2(uint32_t* counter0, uint32_t* queue0, bool pred0, uint32_t* counter1, uint32_t* queue1, bool pred1, uint32_t value) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned m0 = __ballot_sync(0xFFFFFFFFu, pred0), m1 = __ballot_sync(0xFFFFFFFFu, pred1);
+    const unsigned l0 = m0 ? (unsigned)__ffs(m0) - 1u : 0u, l1 = m1 ? (unsigned)__ffs(m1) - 1u : 0u;
+    uint32_t b0 = 0, b1 = 0;
+    if (m0 && lane == l0) b0 = atomicAdd(counter0, (uint32_t)__popc(m0));
+    if (m1 && lane == l1) b1 = atomicAdd(counter1, (uint32_t)__popc(m1));
+    b0 = __shfl_sync(0xFFFFFFFFu, b0, l0); b1 = __shfl_sync(0xFFFFFFFFu, b1, l1);
+    if (pred0) queue0[b0 + (unsigned)__popc(m0 & ((1u << lane) - 1u))] = value;
+    if (pred1) queue1[b1 + (unsigned)__popc(m1 & ((1u << lane) - 1u))] = value;
+}
 HK_DEV void count_rays(unsigned long long* ctr, uint32_t mine) {
     for (int o = 16; o > 0; o >>= 1) mine += __shfl_down_sync(0xFFFFFFFFu, mine, o);
     if ((threadIdx.x & 31u) == 0 && mine) atomicAdd(ctr, (unsigned long long)mine);
@@ -227,21 +239,57 @@ __global__ void __launch_bounds__(HK_TRACE_THREADS, HK_TRACE_BLOCKS_PER_SM) k_tr
 }
 // in-medium rays go to delta tracking with their hit record; the vacuum alpha loop (:224-266) ends on its first iteration
 // because every constant-parameter material has alpha == 1 (spectral-eval.jl:3882-3888)
+// writes the material type (1..7) of every BVH triangle into the spare word of its record (HitRec)
+__global__ void __launch_bounds__(256) k_patch_tri_types(float4* __restrict__ tris, uint32_t n_tris, const uint32_t* __restrict__ tri_meta,
+                                                          const HkMediumInterface* __restrict__ interfaces, const HkMaterial* __restrict__ materials) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_tris; i += gridDim.x * blockDim.x) {
+        const uint32_t prim0 = __float_as_uint(tris[3 * (size_t)i].w);
+        const uint32_t mi = tri_meta[3 * (size_t)prim0];
+        const uint32_t type = (uint32_t)materials[interfaces[mi - 1].material - 1].type;
+        tris[3 * (size_t)i + 1].w = __uint_as_float(type & 0xFu);
+    }
+}
+// Appends are aggregated per BLOCK: every thread classifies HK_ROUTE_PER_THREAD rays, takes its positions from shared-memory
+// counters, and one thread per queue then reserves the block's range with a single global atomicAdd (1 per queue per 1024
+// rays).  With warp-level aggregation alone the ~0.5 M same-address atomics per sample were what the kernel waited for.
+#define HK_ROUTE_PER_THREAD 4
 __global__ void __launch_bounds__(256) k_route(const __grid_constant__ DevScene D, PathState S, int cur) {
+    __shared__ uint32_t s_cnt[HK_N_COUNTERS], s_base[HK_N_COUNTERS];
     const uint32_t n = S.counts[HK_C_RAY0 + cur];
-    const uint32_t n_round = (n + 31u) & ~31u;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
-        int qid = -1; uint32_t slot = 0;
-        if (i < n) {
-            slot = S.q_ray[cur][i];
-            const uint32_t prim1 = __float_as_uint(S.hit[slot].y);
-            if (HK_FLAG_MEDIUM(S.flags[slot]) != 0) qid = HK_C_MEDIUM;
-            else if (prim1 == 0) qid = HK_C_ESCAPED;
-            else qid = HK_C_HIT0 + material_type_of_prim(D, prim1 - 1);
+    const uint32_t chunk = 256u * HK_ROUTE_PER_THREAD;
+    const uint32_t* __restrict__ q = S.q_ray[cur];
+    for (uint32_t c0 = blockIdx.x * chunk; c0 < n; c0 += gridDim.x * chunk) {
+        if (threadIdx.x < HK_N_COUNTERS) s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        int qid[HK_ROUTE_PER_THREAD]; uint32_t slot[HK_ROUTE_PER_THREAD], pos[HK_ROUTE_PER_THREAD];
+#pragma unroll
+        for (int r = 0; r < HK_ROUTE_PER_THREAD; r++) {
+            const uint32_t i = c0 + r * 256u + threadIdx.x;
+            qid[r] = -1; slot[r] = 0; pos[r] = 0;
+            if (i < n) {
+                slot[r] = q[i];
+                const uint32_t hb = __float_as_uint(S.hit[slot[r]].y);
+                if (D.n_media > 0 && HK_FLAG_MEDIUM(S.flags[slot[r]]) != 0) qid[r] = HK_C_MEDIUM;
+                else if (HK_HIT_PRIM1(hb) == 0) qid[r] = HK_C_ESCAPED;
+                else qid[r] = HK_C_HIT0 + (int)HK_HIT_MTYPE(hb);
+            }
         }
-        warp_push(S.counts, nullptr, qid, slot, queue_of(S, qid));
-        unsigned hm = __ballot_sync(0xFFFFFFFFu, qid >= HK_C_HIT0);
-        if ((threadIdx.x & 31u) == 0 && hm) atomicAdd(S.counts + HK_C_TOTAL_HITS, (uint32_t)__popc(hm));
+#pragma unroll
+        for (int r = 0; r < HK_ROUTE_PER_THREAD; r++) if (qid[r] >= 0) pos[r] = atomicAdd(&s_cnt[qid[r]], 1u);
+        __syncthreads();
+        if (threadIdx.x < HK_N_COUNTERS) {
+            const uint32_t c = s_cnt[threadIdx.x];
+            if (c) s_base[threadIdx.x] = atomicAdd(S.counts + threadIdx.x, c);
+        }
+        if (threadIdx.x == 32) {   // total surface hits of the bounce (the reference's `n_hits > 0` shadow-pass condition)
+            uint32_t h = 0;
+            for (int t = 0; t < HK_MAX_MAT_TYPES; t++) h += s_cnt[HK_C_HIT0 + t];
+            if (h) atomicAdd(S.counts + HK_C_TOTAL_HITS, h);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < HK_ROUTE_PER_THREAD; r++) if (qid[r] >= 0) queue_of(S, qid[r])[s_base[qid[r]] + pos[r]] = slot[r];
+        __syncthreads();
     }
 }
 
@@ -296,7 +344,7 @@ __global__ void __launch_bounds__(128, HK_SHADE_MIN_BLOCKS) k_shade(const __grid
         if (i < n) {
             slot = S.q_hit[TYPE][i];
             const float4 hr = S.hit[slot];
-            const uint32_t prim0 = __float_as_uint(hr.y) - 1u;
+            const uint32_t prim0 = HK_HIT_PRIM1(__float_as_uint(hr.y)) - 1u;
             const float4 ra = S.ray_a[slot], rb = S.ray_b[slot];
             const float3 o = f3(ra.x, ra.y, ra.z), d = f3(ra.w, rb.x, rb.y);
             const Surf sf = surface_at(D, prim0, hr.z, hr.w, o, d, hr.x);
@@ -386,8 +434,7 @@ __global__ void __launch_bounds__(128, HK_SHADE_MIN_BLOCKS) k_shade(const __grid
                 }
             }
         }
-        warp_push1(S.counts + HK_C_SHADOW, S.q_shadow, push_shadow, slot);
-        warp_push1(S.counts + HK_C_RAY0 + next, S.q_ray[next], push_ray, slot);
+        warp_push2(S.counts + HK_C_SHADOW, S.q_shadow, push_shadow, S.counts + HK_C_RAY0 + next, S.q_ray[next], push_ray, slot);
     }
 }
 
@@ -404,7 +451,7 @@ __global__ void __launch_bounds__(128) k_medium(const __grid_constant__ DevScene
         if (i < n) {
             slot = S.q_medium[i];
             const float4 hr = S.hit[slot];
-            const uint32_t prim1 = __float_as_uint(hr.y);
+            const uint32_t prim1 = HK_HIT_PRIM1(__float_as_uint(hr.y));
             const float4 ra = S.ray_a[slot], rb = S.ray_b[slot];
             const float3 o = f3(ra.x, ra.y, ra.z), d = f3(ra.w, rb.x, rb.y);
             const float4 lam = S.lambda[slot];
@@ -454,14 +501,13 @@ __global__ void __launch_bounds__(128) k_medium(const __grid_constant__ DevScene
                 }
             } else if (R.event == HK_EV_SURVIVED && !(sp_black(R.beta) || sp_black(R.r_u) || depth >= D.max_depth)) {
                 S.beta[slot] = R.beta; S.r_u[slot] = R.r_u; S.r_l[slot] = R.r_l;
-                qid = prim1 ? HK_C_HIT0 + material_type_of_prim(D, prim1 - 1) : HK_C_ESCAPED;
+                qid = prim1 ? HK_C_HIT0 + (int)HK_HIT_MTYPE(__float_as_uint(hr.y)) : HK_C_ESCAPED;
             }
         }
         warp_push(S.counts, nullptr, qid, slot, queue_of(S, qid));
         unsigned hm = __ballot_sync(0xFFFFFFFFu, qid >= HK_C_HIT0);
         if ((threadIdx.x & 31u) == 0 && hm) atomicAdd(S.counts + HK_C_TOTAL_HITS, (uint32_t)__popc(hm));
-        warp_push1(S.counts + HK_C_SHADOW, S.q_shadow, push_shadow, slot);
-        warp_push1(S.counts + HK_C_RAY0 + next, S.q_ray[next], push_ray, slot);
+        warp_push2(S.counts + HK_C_SHADOW, S.q_shadow, push_shadow, S.counts + HK_C_RAY0 + next, S.q_ray[next], push_ray, slot);
     }
 }
 
@@ -530,7 +576,7 @@ __global__ void __launch_bounds__(HK_TRACE_THREADS) k_shadow_general(const __gri
                 if (cur != 0) { Spec a, b, c; ratio_track(MDC, (int)cur, o, d, t_rem, lam, a, b, c); T = T * a; tu = tu * b; tl = tl * c; }
                 visible = true; done = true; break;
             }
-            const uint32_t prim0 = h.prim1 - 1u;
+            const uint32_t prim0 = HK_HIT_PRIM1(h.prim1) - 1u;
             const HkMediumInterface mi = D.interfaces[__ldg(D.tri_meta + 3 * (size_t)prim0) - 1];
             if (mi.inside == mi.outside) { visible = false; done = true; break; }   // opaque (alpha == 1)
             if (cur != 0) { Spec a, b, c; ratio_track(MDC, (int)cur, o, d, h.t, lam, a, b, c); T = T * a; tu = tu * b; tl = tl * c; }
@@ -595,7 +641,7 @@ struct BatchRayIO {
     }
     HK_DEV void store(uint32_t i, const HitRec& h) const {
         if (ANY) occluded[i] = h.prim1 ? 1 : 0;
-        else hits[i] = make_float4(h.prim1 ? h.t : __ldg(rays + 2 * (size_t)i + 1).z, __uint_as_float(h.prim1), h.b1, h.b2);
+        else hits[i] = make_float4(h.prim1 ? h.t : __ldg(rays + 2 * (size_t)i + 1).z, __uint_as_float(HK_HIT_PRIM1(h.prim1)), h.b1, h.b2);
     }
 };
 template <bool ANY, bool COUNT>
@@ -618,7 +664,7 @@ __global__ void k_detect_camera_medium(const __grid_constant__ DevScene D, uint3
     for (int it = 0; it < 16; it++) {
         HitRec h = bvh8_trace<false, false>(D.bvh, sm_stack, o, d, HK_INF);
         if (h.prim1 == 0) break;
-        const uint32_t prim0 = h.prim1 - 1u;
+        const uint32_t prim0 = HK_HIT_PRIM1(h.prim1) - 1u;
         const HkMediumInterface mi = D.interfaces[__ldg(D.tri_meta + 3 * (size_t)prim0) - 1];
         float3 n = geometric_normal(D, prim0);
         if (mi.inside != mi.outside) { res = dot3(-d, n) > 0.0f ? mi.outside : mi.inside; break; }
