@@ -23,10 +23,28 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = "C2 cat scene (procedural stand-in mesh), 1920x1080, VolPath max_depth=12, 1 spp per step"
-RES = (1920, 1080)
-MAX_DEPTH = 12
-REF_RES = (480, 270)     # bounded CPU sample: same scene/camera/depth at 1/16 of the pixels
+# SURVEY 8d configs restated.  The default (and the configuration the driver's bench line is quoted on) is C2 =
+# BASELINE.json configs[1]; the others are selectable with --config for the per-config table in DESIGN.md.
+CONFIGS = {
+    "C1": dict(workload="C1 sphere-normals scene, 512x512, VolPath max_depth=5, 1 spp per step", res=(512, 512), depth=5, ref_res=(256, 256)),
+    "C2": dict(workload="C2 cat scene (procedural stand-in mesh), 1920x1080, VolPath max_depth=12, 1 spp per step", res=(1920, 1080), depth=12, ref_res=(480, 270)),
+    "C3": dict(workload="C3 glass sphere + gold plane, sun/sky env light + 10k emissive triangles (light BVH), 3840x2160, max_depth=12, 1 spp per step", res=(3840, 2160), depth=12, ref_res=(480, 270)),
+    "C4": dict(workload="C4 procedural cumulus NanoVDB cloud (256x256x128), delta tracking, 3840x2160, max_depth=32, 1 spp per step", res=(3840, 2160), depth=32, ref_res=(240, 135)),
+    "C5": dict(workload="C5 instanced blob meshes (mixed materials), sun/sky env light, 3840x2160, max_depth=8, 1 spp per step", res=(3840, 2160), depth=8, ref_res=(480, 270)),
+}
+WORKLOAD, RES, MAX_DEPTH, REF_RES = None, None, None, None
+C5_INSTANCES = 1000
+
+
+def select_config(name, c5_instances=1000):
+    global WORKLOAD, RES, MAX_DEPTH, REF_RES, CONFIG_NAME, C5_INSTANCES
+    c = CONFIGS[name]
+    CONFIG_NAME, WORKLOAD, RES, MAX_DEPTH, REF_RES, C5_INSTANCES = name, c["workload"], c["res"], c["depth"], c["ref_res"], c5_instances
+    if name == "C5":
+        WORKLOAD += f" ({c5_instances} instances)"
+
+
+select_config("C2")
 
 
 def load_peaks():
@@ -94,6 +112,14 @@ class ClockSampler(threading.Thread):
 
 def build_scene():
     from hikari_jl_b200 import scenes
+    if CONFIG_NAME == "C1":
+        return scenes.c1_spheres(64)
+    if CONFIG_NAME == "C3":
+        return scenes.c3_many_lights(10000, 128)
+    if CONFIG_NAME == "C4":
+        return scenes.c4_cloud((256, 256, 128), "nanovdb", (64, 64, 64))
+    if CONFIG_NAME == "C5":
+        return scenes.c5_instanced(C5_INSTANCES, 160)
     return scenes.c2_cat(256, 64)
 
 
@@ -124,7 +150,7 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     rays = oracle_backend.lib().ok_rays_traced(vp.backend.ctx) - r0
     val = n * args.steps / dt / 1e6
-    sample = f"same scene/camera/max_depth at {REF_RES[0]}x{REF_RES[1]} (1/16 of the pixels), 1 spp per step"
+    sample = f"same scene/camera/max_depth at {REF_RES[0]}x{REF_RES[1]} 1 spp per step"
     line = {
         "impl": "reference", "metric": "VolPath throughput", "value": val, "unit": "Msamples/s", "n_gpus": 0, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -153,7 +179,7 @@ def cpu_baseline_leg():
     cores = oracle_backend.lib().ok_num_threads()
     vp.close()
     return {"value": n * steps / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "port",
-            "sample": f"same scene/camera/max_depth at {REF_RES[0]}x{REF_RES[1]} (1/16 of the pixels), {steps} x 1 spp"}
+            "sample": f"same scene/camera/max_depth at {REF_RES[0]}x{REF_RES[1]} {steps} x 1 spp"}
 
 
 class _DevPtr:
@@ -279,7 +305,7 @@ def run_cuda(args):
             "data": "synthetic", "mrays_per_s": rays / (t_ms * 1e-3) / 1e6, "rays_per_sample": rays / (world * n * args.steps),
             "config": {"workload": WORKLOAD, "triangles": int(len(scene._synced.indices)), "max_depth": MAX_DEPTH, "partition": f"sample-index round-robin x{world}",
                        "samples_in_flight": int(batch_used),
-                       "l2_note": "per-pass working set (path state + queues, ~0.6 GB per sample in flight at 1080p) exceeds the 126 MB L2; no explicit flush"},
+                       "l2_note": f"per-pass working set (path state + queues, ~{288 * n / 1e9:.2f} GB per sample in flight) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e_val, "unit": "Msamples/s", "h2d_bytes_per_step": C.sizeof(A.HkCamera), "d2h_bytes_per_step": 12 * n,
                     "steps": e2e_steps, "what": "render!(vp, scene, film, camera) + framebuffer read per step, host buffers",
                     "scene_upload_s": t_upload},
@@ -300,8 +326,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="samples kept in flight per wavefront pass (HkRenderParams.sample_batch); 0 = the library's automatic choice")
+    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS), help="SURVEY 8d workload (default C2 = BASELINE.json configs[1])")
+    ap.add_argument("--c5-instances", type=int, default=1000, help="C5 only: instances of the ~50k-triangle base mesh (1000 = 50 M triangles)")
     ap.add_argument("--quick", action="store_true", help="development: skip the CPU baseline leg (tuning-variant sweeps, tools/variants.py)")
     args = ap.parse_args()
+    select_config(args.config, args.c5_instances)
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else max(args.warmup, 1)
     if args.impl == "reference":
         run_reference(args)

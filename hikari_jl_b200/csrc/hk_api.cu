@@ -40,7 +40,7 @@ struct HkContext {
     DevBuf b_sobol, b_cie_x, b_cie_y, b_cie_z, b_d65, b_rgb_scale, b_rgb_coeffs;
     DevBuf b_nodes, b_tris, b_pos, b_nrm, b_idx, b_meta;
     DevBuf b_mats, b_ifaces, b_spec_l, b_spec_v, b_spec_o;
-    DevBuf b_lights, b_env, b_lnodes, b_trails, b_inf;
+    DevBuf b_lights, b_env, b_lnodes, b_trails, b_inf, b_esc;
     std::vector<DevBuf> env_bufs, media_bufs;
     DevBuf b_media;
     DevBuf b_f_func, b_f_mcdf, b_f_mfunc, b_f_ccdf;
@@ -121,7 +121,7 @@ int32_t hk_destroy(HkContext* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&ctx->b_sobol, &ctx->b_cie_x, &ctx->b_cie_y, &ctx->b_cie_z, &ctx->b_d65, &ctx->b_rgb_scale, &ctx->b_rgb_coeffs, &ctx->b_nodes, &ctx->b_tris,
-                      &ctx->b_sobol_top, &ctx->b_sobol_dims, &ctx->b_sobol_dimhash, &ctx->b_pos, &ctx->b_nrm, &ctx->b_idx, &ctx->b_meta, &ctx->b_mats, &ctx->b_ifaces, &ctx->b_spec_l, &ctx->b_spec_v, &ctx->b_spec_o, &ctx->b_lights,
+                      &ctx->b_esc, &ctx->b_sobol_top, &ctx->b_sobol_dims, &ctx->b_sobol_dimhash, &ctx->b_pos, &ctx->b_nrm, &ctx->b_idx, &ctx->b_meta, &ctx->b_mats, &ctx->b_ifaces, &ctx->b_spec_l, &ctx->b_spec_v, &ctx->b_spec_o, &ctx->b_lights,
                       &ctx->b_env, &ctx->b_lnodes, &ctx->b_trails, &ctx->b_inf, &ctx->b_media, &ctx->b_f_func, &ctx->b_f_mcdf, &ctx->b_f_mfunc, &ctx->b_f_ccdf,
                       &ctx->b_state, &ctx->b_counts, &ctx->b_rays, &ctx->b_film, &ctx->b_scratch_u32, &ctx->b_trace_ctr, &ctx->b_work_ctr, &ctx->b_readback};
     for (auto& e : ctx->stage_events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -278,6 +278,10 @@ int32_t hk_upload_lights(HkContext* ctx, const HkLight* l, uint32_t n, const HkL
     ctx->D.lights = ctx->b_lights.as<HkLight>(); ctx->D.n_lights = (int32_t)n;
     ctx->D.lnodes = ctx->b_lnodes.as<HkLightBVHNode>(); ctx->D.bit_trails = ctx->b_trails.as<uint32_t>(); ctx->D.inf_idx = ctx->b_inf.as<int32_t>();
     ctx->D.n_infinite = (int32_t)sm->n_infinite; ctx->D.n_bvh = (int32_t)sm->n_bvh_lights;
+    std::vector<int32_t> esc;
+    for (uint32_t i = 0; i < n; i++) if (l[i].type == HK_LIGHT_ENVIRONMENT || l[i].type == HK_LIGHT_AMBIENT) esc.push_back((int32_t)i);
+    CK(ctx->b_esc.upload(esc.data(), 4 * esc.size()));
+    ctx->D.esc_idx = ctx->b_esc.as<int32_t>(); ctx->D.n_esc = (int32_t)esc.size();
     ctx->have_lights = true;
     return HK_OK;
 }

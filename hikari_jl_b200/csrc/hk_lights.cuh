@@ -16,6 +16,9 @@ struct LightCtx {
     const DevEnvMap* __restrict__ envmaps;
     const HkLightBVHNode* __restrict__ nodes; const uint32_t* __restrict__ bit_trails; const int32_t* __restrict__ inf_idx;
     int32_t n_infinite, n_bvh;
+    // ascending indices of the lights an escaped ray can see (Environment, Ambient): the reference walks the whole light
+    // tuple per escaped ray (lights.jl:408-467), which with 10 000 area lights (C3) is 10 002 type tests per ray
+    const int32_t* __restrict__ esc_idx; int32_t n_esc;
 };
 struct LightSample { Spec Li; float3 wi; float pdf; float3 p_light; bool delta; };
 HK_DEV LightSample ls_none() { LightSample s; s.Li = sp(0.0f); s.wi = f3(0, 0, 1); s.pdf = 0.0f; s.p_light = f3(0, 0, 0); s.delta = false; return s; }
@@ -172,8 +175,8 @@ HK_DEV LightSample sample_light(const LightCtx& C, const HkLight& L, float3 p, f
 }
 HK_DEV Spec escaped_Le(const LightCtx& C, float3 d, float4 lam) {   // lights.jl:408-448
     Spec sum = sp(0.0f);
-    for (int i = 0; i < C.n_lights; i++) {
-        const HkLight& L = C.lights[i];
+    for (int k = 0; k < C.n_esc; k++) {
+        const HkLight& L = C.lights[__ldg(C.esc_idx + k)];
         if (L.type == HK_LIGHT_ENVIRONMENT) {
             const DevEnvMap& E = C.envmaps[L.env_map - 1];
             float3 c = env_lookup_dir(E, d);
@@ -184,8 +187,8 @@ HK_DEV Spec escaped_Le(const LightCtx& C, float3 d, float4 lam) {   // lights.jl
 }
 HK_DEV float env_light_pdf(const LightCtx& C, float3 d) {   // lights.jl:452-467
     float sum = 0.0f;
-    for (int i = 0; i < C.n_lights; i++) {
-        const HkLight& L = C.lights[i];
+    for (int k = 0; k < C.n_esc; k++) {
+        const HkLight& L = C.lights[__ldg(C.esc_idx + k)];
         if (L.type == HK_LIGHT_ENVIRONMENT) {
             const DevEnvMap& E = C.envmaps[L.env_map - 1];
             sum = sum + env_pdf_uv(E, sphere_to_square(mat3_tmul(E.rot, d))) / (4.0f * HK_PI);

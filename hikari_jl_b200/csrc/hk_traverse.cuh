@@ -101,6 +101,13 @@ struct Bvh8Walker {
         oct_inv = (d.x >= 0.0f ? 4u : 0u) | (d.y >= 0.0f ? 2u : 0u) | (d.z >= 0.0f ? 1u : 0u);
         st.sm = sm_stack; st.lm = lm_stack; st.n = 0;
         ngroup = make_uint2(0u, 0x80000000u);   // root: base 0 and an empty internal mask => child index 0 whatever the octant
+        // A ray with a NaN / infinite component, a zero direction or a NaN t_max cannot pass the exact triangle test (every
+        // comparison fails), but its slab distances are NaN, which fminf/fmaxf drop: it would "hit" every box and walk the
+        // whole tree (measured: a handful of such rays from degenerate BSDF samples cost 0.8 s per pass at 10 M triangles).
+        // It is a miss by definition, so it never starts.
+        const bool finite = fabsf(o.x) <= 3.4e38f && fabsf(o.y) <= 3.4e38f && fabsf(o.z) <= 3.4e38f &&
+                            fabsf(d.x) <= 3.4e38f && fabsf(d.y) <= 3.4e38f && fabsf(d.z) <= 3.4e38f && t_max == t_max;
+        if (!finite || (d.x == 0.0f && d.y == 0.0f && d.z == 0.0f)) ngroup.y = 0u;
         tgroup = make_uint2(0u, 0u); tvalid = 0u;
         best.t = t_max; best.prim1 = 0; best.b1 = 0.0f; best.b2 = 0.0f;
     }

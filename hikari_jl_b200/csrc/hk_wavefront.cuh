@@ -36,6 +36,7 @@ struct DevScene {
     const HkLight* __restrict__ lights; int32_t n_lights;
     const DevEnvMap* __restrict__ envmaps;
     const HkLightBVHNode* __restrict__ lnodes; const uint32_t* __restrict__ bit_trails; const int32_t* __restrict__ inf_idx; int32_t n_infinite, n_bvh;
+    const int32_t* __restrict__ esc_idx; int32_t n_esc;
     const DevMedium* __restrict__ media; int32_t n_media;
     int32_t any_medium_transition;     // some interface has inside != outside
     HkCamera camera;
@@ -63,7 +64,7 @@ struct PassArgs { int32_t first_sample, stride, n_batch; uint32_t n_pixels; };
 HK_DEV MatCtx mat_ctx(const DevScene& D) { MatCtx c; c.T = D.T; c.spec_lambdas = D.spec_lambdas; c.spec_values = D.spec_values; c.spec_offsets = D.spec_offsets; return c; }
 HK_DEV LightCtx light_ctx(const DevScene& D) {
     LightCtx c; c.T = D.T; c.lights = D.lights; c.n_lights = D.n_lights; c.envmaps = D.envmaps; c.nodes = D.lnodes; c.bit_trails = D.bit_trails;
-    c.inf_idx = D.inf_idx; c.n_infinite = D.n_infinite; c.n_bvh = D.n_bvh; return c;
+    c.inf_idx = D.inf_idx; c.n_infinite = D.n_infinite; c.n_bvh = D.n_bvh; c.esc_idx = D.esc_idx; c.n_esc = D.n_esc; return c;
 }
 HK_DEV MediaCtx media_ctx(const DevScene& D) { MediaCtx c; c.T = D.T; c.media = D.media; c.n_media = D.n_media; return c; }
 

@@ -133,12 +133,21 @@ def test_closest_hit_bit_exact(which):
         rays[:3000, 3:6] = np.eye(3, dtype=f32)[np.arange(3000) % 3] * np.where(np.arange(3000) % 2, 1, -1)[:, None]
         rays[3000:6000, 6] = np.random.RandomState(2).uniform(0.1, 4.0, 3000)
         rays[6000:6100, 0:3] = 0
+        # invalid rays (NaN / inf components, zero direction, NaN t_max): a miss by definition on every path -- and the
+        # CUDA traversal must not walk the whole tree for them
+        bad = np.array([np.nan, np.inf, -np.inf], dtype=f32)
+        for k in range(6):
+            rays[6100 + 3 * k:6103 + 3 * k, k] = bad
+        rays[6118:6122, 3:6] = 0
+        rays[6122:6126, 6] = np.nan
         h_cu, h_bvh = trace_both(p, rays, brute=False)
         _, h_brute = trace_both(p, rays, brute=True)
         assert np.array_equal(h_bvh.view(np.uint32), h_brute.view(np.uint32)), "oracle BVH and brute force disagree"
         prim_cu, prim_ok = h_cu.view(np.uint32)[:, 1], h_brute.view(np.uint32)[:, 1]
         assert np.array_equal(prim_cu, prim_ok), f"{(prim_cu != prim_ok).sum()} primitive ids differ"
-        assert np.array_equal(h_cu.view(np.uint32), h_brute.view(np.uint32)), "t / barycentrics differ bitwise"
+        assert (prim_cu[6100:6126] == 0).all(), "invalid rays must miss"
+        valid = np.ones(len(rays), bool); valid[6100:6126] = False        # (the reported t of an invalid miss is its own t_max: may be NaN)
+        assert np.array_equal(h_cu.view(np.uint32)[valid], h_brute.view(np.uint32)[valid]), "t / barycentrics differ bitwise"
         if which != "degenerate":
             assert (prim_cu > 0).sum() > 100
         # any-hit agrees with closest-hit occupancy
