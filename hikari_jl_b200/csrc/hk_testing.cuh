@@ -265,6 +265,23 @@ int32_t hk_test_ratio_tracking(HkContext* ctx, uint32_t medium, const float* in,
     tk_ratio<<<TK_GRID(n)>>>(ctx->D, medium, (const float*)di, n, dout); ctx->launches++;
     return io.get(out, dout, 48 * n);
 }
+// rays [n_slots][8] = (o, d, t_max, 0) and hits [n_slots][4] = (t, prim1 bits, b1, b2) as the last pass left them: for
+// every slot the hit record is the closest hit of the LAST ray traced for that path (full-size traversal parity checks)
+int32_t hk_test_read_rays(HkContext* ctx, float* rays, float* hits, uint64_t n_slots) {
+    if (!ctx || !ctx->have_params || n_slots > ctx->n_slots || !rays || !hits) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<float4> a(n_slots), b(n_slots);
+    CK(cudaMemcpy(a.data(), ctx->S.ray_a, 16 * n_slots, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(b.data(), ctx->S.ray_b, 16 * n_slots, cudaMemcpyDeviceToHost));
+    for (uint64_t i = 0; i < n_slots; i++) {
+        float* r = rays + 8 * i;
+        r[0] = a[i].x; r[1] = a[i].y; r[2] = a[i].z; r[3] = a[i].w; r[4] = b[i].x; r[5] = b[i].y; r[6] = b[i].z; r[7] = 0.0f;
+    }
+    CK(cudaMemcpy(hits, ctx->S.hit, 16 * n_slots, cudaMemcpyDeviceToHost));
+    uint32_t* hb = reinterpret_cast<uint32_t*>(hits);
+    for (uint64_t i = 0; i < n_slots; i++) hb[4 * i + 1] &= HK_PRIM_MASK;
+    return HK_OK;
+}
 int32_t hk_test_read_pass(HkContext* ctx, float* L, float* lam, float* pdf, float* fw, uint64_t n_slots) {
     if (!ctx || !ctx->have_params || n_slots > ctx->n_slots) return HK_ERR_INVALID;
     cudaSetDevice(ctx->device);

@@ -13,6 +13,9 @@ extern "C" {
 
 /* q[n][4] = (px, py, sample_idx, dim) -> zsobol_sample_1d / _2d (src/sampler/sobol.jl:269-309) */
 int32_t hk_test_sobol(HkContext* ctx, const int32_t* q, uint64_t n, int32_t log2_spp, int32_t n_base4_digits, uint32_t seed, float* out1d, float* out2d);
+/* ray [n_slots][8] and hit [n_slots][4] (t, prim1, b1, b2) state after the last pass: per slot, the closest hit of the
+ * last ray traced for that path */
+int32_t hk_test_read_rays(HkContext* ctx, float* rays, float* hits, uint64_t n_slots);
 /* select the Sobol' evaluation: 0 = generic matrix loop, 1 = closed forms for dimensions 0/1 (only valid when
  * hk_upload_tables verified the table structure); returns the previous mode */
 int32_t hk_test_sobol_mode(HkContext* ctx, int32_t fast);
