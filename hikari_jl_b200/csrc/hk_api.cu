@@ -58,7 +58,7 @@ struct HkContext {
     double stage_ms[HK_N_STAGES]; uint64_t stage_launches[HK_N_STAGES];
     DevBuf b_work_ctr;
     // profiling bit 2: per-bounce queue counts and stage times of the most recent sample pass (host sync per bounce)
-    std::vector<std::array<uint32_t, HK_N_COUNTERS>> bounce_counts;
+    std::vector<std::array<uint32_t, HK_N_QUEUE_COUNTERS>> bounce_counts;
     std::vector<std::array<double, HK_N_STAGES>> bounce_ms;
     HkContext() { std::memset(&D, 0, sizeof(D)); std::memset(&S, 0, sizeof(S)); std::memset(&params, 0, sizeof(params)); std::memset(&stats, 0, sizeof(stats)); }
 };
@@ -350,19 +350,22 @@ static int32_t alloc_film(HkContext* ctx, size_t n_pixels) {
     return HK_OK;
 }
 static int32_t alloc_state(HkContext* ctx, size_t n_slots) {
-    // one slab: 14 float4 arrays, 3 u32/f32 arrays, 13 queues; every array starts 256-byte aligned
-    const size_t f4 = 14, w4 = 3, q = 5 + HK_MAX_MAT_TYPES;
+    // one slab: 19 float4 arrays, 4 u32/f32 arrays, 14 queues; every array starts 256-byte aligned
+    const size_t f4 = 19, w4 = 4, q = 6 + HK_MAX_MAT_TYPES;
     size_t rounded = f4 * (((16 * n_slots + 255) / 256) * 256) + (w4 + q) * (((4 * n_slots + 255) / 256) * 256);
     CK(cudaStreamSynchronize(ctx->stream));
     CK(ctx->b_state.alloc(rounded));
     char* p = ctx->b_state.as<char>();
     auto take = [&](size_t elt) { char* r = p; p += ((elt * n_slots + 255) / 256) * 256; return r; };
     PathState& S = ctx->S;
-    float4** f4s[] = {&S.ray_a, &S.ray_b, &S.hit, &S.lambda, &S.lpdf, &S.beta, &S.r_u, &S.r_l, &S.L, &S.sh_a, &S.sh_b, &S.sh_Ld, &S.sh_ru, &S.sh_rl};
+    float4** f4s[] = {&S.ray_a, &S.ray_b, &S.hit, &S.lambda, &S.lpdf, &S.beta, &S.r_u, &S.r_l, &S.L, &S.sh_a, &S.sh_b, &S.sh_Ld, &S.sh_ru, &S.sh_rl,
+                      &S.med, &S.sh_hit, &S.sh_T, &S.sh_tu, &S.sh_tl};
     for (auto pp : f4s) *pp = reinterpret_cast<float4*>(take(16));
     S.flags = reinterpret_cast<uint32_t*>(take(4)); S.fweight = reinterpret_cast<float*>(take(4)); S.sh_medium = reinterpret_cast<uint32_t*>(take(4));
+    S.med_ev = reinterpret_cast<uint32_t*>(take(4));
     S.q_ray[0] = reinterpret_cast<uint32_t*>(take(4)); S.q_ray[1] = reinterpret_cast<uint32_t*>(take(4));
     S.q_escaped = reinterpret_cast<uint32_t*>(take(4)); S.q_medium = reinterpret_cast<uint32_t*>(take(4)); S.q_shadow = reinterpret_cast<uint32_t*>(take(4));
+    S.q_shadow2 = reinterpret_cast<uint32_t*>(take(4));
     for (int t = 0; t < HK_MAX_MAT_TYPES; t++) S.q_hit[t] = reinterpret_cast<uint32_t*>(take(4));
     S.counts = ctx->b_counts.as<uint32_t>();
     S.rays_traced = reinterpret_cast<unsigned long long*>(ctx->b_counts.as<char>() + sizeof(uint32_t) * HK_N_COUNTERS);
@@ -491,14 +494,18 @@ int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride,
         { StageScope sc(ctx, HK_STAGE_CAMERA); k_camera<<<grid_for(ctx, n_slots, 256, 8), 256, 0, st>>>(ctx->D, ctx->S, A, ctx->camera_medium); }
         int cur = 0;
         for (int depth = 0; depth < ctx->params.max_depth; depth++) {
-            k_reset_bounce<<<1, 32, 0, st>>>(ctx->S, cur); ctx->launches++;
+            k_reset_bounce<<<1, HK_N_COUNTERS, 0, st>>>(ctx->S, cur); ctx->launches++;
             {
                 StageScope sc(ctx, HK_STAGE_TRACE);
                 if (cnt) k_trace<true><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, cur, work);
                 else k_trace<false><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, cur, work);
             }
             { StageScope sc(ctx, HK_STAGE_ROUTE); k_route<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->D, ctx->S, cur); }
-            if (ctx->D.n_media > 0) { StageScope sc(ctx, HK_STAGE_MEDIUM); k_medium<<<ctx->sm_count * 8, 128, 0, st>>>(ctx->D, ctx->S, A, cur ^ 1); }
+            if (ctx->D.n_media > 0) {
+                StageScope sc(ctx, HK_STAGE_MEDIUM);
+                k_medium_track<<<ctx->sm_count * 4, 128, 0, st>>>(ctx->D, ctx->S);
+                k_medium_finish<<<ctx->sm_count * 8, 128, 0, st>>>(ctx->D, ctx->S, A, cur ^ 1); ctx->launches++;
+            }
             if (ctx->D.n_lights > 0) { StageScope sc(ctx, HK_STAGE_ESCAPED); k_escaped<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->D, ctx->S); }
             launch_shade<HK_MAT_MATTE>(ctx, A, cur ^ 1); launch_shade<HK_MAT_MIRROR>(ctx, A, cur ^ 1); launch_shade<HK_MAT_GLASS>(ctx, A, cur ^ 1);
             launch_shade<HK_MAT_CONDUCTOR>(ctx, A, cur ^ 1); launch_shade<HK_MAT_COATED_DIFFUSE>(ctx, A, cur ^ 1);
@@ -506,13 +513,17 @@ int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride,
             if (ctx->D.n_lights > 0) {
                 StageScope sc(ctx, HK_STAGE_SHADOW);
                 if (opaque_only) { if (cnt) k_shadow_opaque<true><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, work); else k_shadow_opaque<false><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, work); }
-                else { if (cnt) k_shadow_general<true><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, work); else k_shadow_general<false><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, work); }
+                else for (int r = 0; r < HK_SHADOW_ROUNDS; r++) {      // one round per medium-boundary crossing; empty rounds exit at once
+                    if (cnt) k_shadow_seg_trace<true><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, r, work);
+                    else k_shadow_seg_trace<false><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, r, work);
+                    k_shadow_seg_ratio<<<ctx->sm_count * 4, 128, 0, st>>>(ctx->D, ctx->S, r); ctx->launches += r == 0 ? 1 : 2;
+                }
             }
             if ((ctx->profiling & 5) == 5) {   // per-bounce record (debug): counts as left by this bounce + its stage times
                 if ((int)ctx->bounce_counts.size() <= depth) { ctx->bounce_counts.resize(depth + 1); ctx->bounce_ms.resize(depth + 1); }
                 ctx->bounce_ms[depth].fill(0.0);
                 collect_stage_times(ctx, ctx->bounce_ms[depth].data());
-                cudaMemcpy(ctx->bounce_counts[depth].data(), ctx->S.counts, sizeof(uint32_t) * HK_N_COUNTERS, cudaMemcpyDeviceToHost);
+                cudaMemcpy(ctx->bounce_counts[depth].data(), ctx->S.counts, sizeof(uint32_t) * HK_N_QUEUE_COUNTERS, cudaMemcpyDeviceToHost);
             }
             cur ^= 1;
         }
@@ -546,7 +557,7 @@ int32_t hk_stage_times(HkContext* ctx, double* out_ms, uint64_t* out_launches, u
 // counters after the bounce: ray0, ray1, escaped, medium, shadow, total hits, cursors, per-material hits) and ms[max_depth][8]
 int32_t hk_bounce_profile(HkContext* ctx, int32_t max_depth, uint32_t* counts, double* ms) {
     if (!ctx || !counts || !ms) return HK_ERR_INVALID;
-    for (int d = 0; d < max_depth; d++) for (int i = 0; i < HK_N_COUNTERS; i++) counts[d * HK_N_COUNTERS + i] = d < (int)ctx->bounce_counts.size() ? ctx->bounce_counts[d][i] : 0u;
+    for (int d = 0; d < max_depth; d++) for (int i = 0; i < HK_N_QUEUE_COUNTERS; i++) counts[d * HK_N_QUEUE_COUNTERS + i] = d < (int)ctx->bounce_counts.size() ? ctx->bounce_counts[d][i] : 0u;
     for (int d = 0; d < max_depth; d++) for (int i = 0; i < HK_N_STAGES; i++) ms[d * HK_N_STAGES + i] = d < (int)ctx->bounce_ms.size() ? ctx->bounce_ms[d][i] : 0.0;
     return HK_OK;
 }

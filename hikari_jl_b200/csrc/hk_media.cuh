@@ -192,103 +192,148 @@ HK_DEV void majiter_create(MajIter& it, const DevMedium& M, const MediumCoef& mc
 #define HK_EV_SCATTER 1
 #define HK_EV_SURVIVED 2
 struct DeltaOut { int event; Spec beta, r_u, r_l; float3 p; float g; Spec Le_add; };
-HK_DEV DeltaOut delta_track(const MediaCtx& C, int medium, float3 o, float3 d, float t_max, float4 lam, Spec beta, Spec r_u, Spec r_l, int depth, int max_depth) {
-    DeltaOut R; R.g = 0.0f; R.p = f3(0, 0, 0); R.Le_add = sp(0.0f);
-    const DevMedium& M = C.media[medium - 1];
-    MediumCoef mc = medium_coef(C, M, lam);
-    uint64_t rng = lcg_init(o, d, t_max);
-    MajIter it; majiter_create(it, M, mc, o, d, t_max);
-    for (int sg = 0; sg < 256; sg++) {
-        MajSeg seg;
-        if (!majiter_next(it, seg)) break;
-        const Spec smaj = seg.sigma_maj;
-        const float s0 = smaj.x;
-        if (s0 < 1.0e-10f) continue;
-        float t = seg.t_min;
-        float3 ro = o + d * t;
-        for (int si = 0; si < 1024; si++) {
-            float u = lcg_next(rng);
-            float dt = -logf(fmaxf(1.0e-10f, 1.0f - u)) / s0;
-            float ts = t + dt;
-            if (ts >= seg.t_max) {
-                Spec Tm = sp_exp(-(seg.t_max - t) * smaj);
-                if (Tm.x > 1.0e-10f) { beta = beta * Tm / Tm.x; r_u = r_u * Tm / Tm.x; r_l = r_l * Tm / Tm.x; }
-                break;
-            }
-            Spec Tm = sp_exp(-dt * smaj);
-            float3 p = ro + d * dt;
-            float dens = medium_density(M, p);
-            Spec sa = M.type == HK_MEDIUM_HOMOGENEOUS ? mc.sa : mc.sa * dens;
-            Spec ss = M.type == HK_MEDIUM_HOMOGENEOUS ? mc.ss : mc.ss * dens;
-            if (!sp_black(mc.Le) && depth < max_depth) {
-                float pr = s0 * Tm.x;
-                if (pr > 1.0e-10f) {
-                    Spec re = r_u * smaj * Tm / pr;
-                    if (!sp_black(re)) R.Le_add = R.Le_add + beta * sa * Tm * mc.Le / (pr * sp_avg(re));
-                }
-            }
-            float pa = sa.x / s0, ps = ss.x / s0;
-            float ue = lcg_next(rng);
-            if (ue < pa) { R.event = HK_EV_ABSORBED; R.beta = sp(0.0f); R.r_u = r_u; R.r_l = r_l; return R; }
-            if (ue < pa + ps) {
-                if (depth >= max_depth) { R.event = HK_EV_ABSORBED; R.beta = beta; R.r_u = r_u; R.r_l = r_l; return R; }
-                float pdf = Tm.x * ss.x;
-                if (pdf > 1.0e-10f) { beta = beta * Tm * ss / pdf; r_u = r_u * Tm * ss / pdf; }
-                R.event = HK_EV_SCATTER; R.beta = beta; R.r_u = r_u; R.r_l = r_l; R.p = p; R.g = mc.g;
-                return R;
-            }
-            Spec sn = sp_max0(smaj - sa - ss);
-            float pdf = Tm.x * sn.x;
-            if (!(pdf > 1.0e-10f)) { R.event = HK_EV_ABSORBED; R.beta = sp(0.0f); R.r_u = r_u; R.r_l = r_l; return R; }
-            beta = beta * Tm * sn / pdf; r_u = r_u * Tm * sn / pdf; r_l = r_l * Tm * smaj / pdf;
-            t = ts; ro = p;
-            if (sp_black(beta) || sp_black(r_u)) { R.event = HK_EV_ABSORBED; R.beta = beta; R.r_u = r_u; R.r_l = r_l; return R; }
-        }
+// Delta tracking as a state machine: step() performs ONE unit of work -- advance the majorant DDA to the next non-empty
+// segment (skipping up to HK_TRACK_SKIP empty cells) or ONE tentative collision -- so a persistent warp can keep every lane
+// on its own ray and hand finished lanes a new one (k_medium_track) instead of idling until the longest walk of the warp
+// is done (ncu on C4: 7.9 of 32 lanes active in the one-ray-per-thread-to-completion form).  The arithmetic per ray, and
+// therefore every output bit, is that of the nested loops in delta-tracking.jl:142-453.
+#define HK_TRACK_SKIP 4
+struct DeltaTracker {
+    const DevMedium* M; MediumCoef mc; float3 o, d, ro; int depth, max_depth;
+    uint64_t rng; MajIter it; Spec smaj; float seg_t_max, t; int sg, si; bool in_seg;
+    Spec beta, r_u, r_l; DeltaOut R;
+    HK_DEV void init(const MediaCtx& C, int medium, float3 o_, float3 d_, float t_max, float4 lam, Spec beta_, Spec r_u_, Spec r_l_, int depth_, int max_depth_) {
+        R.g = 0.0f; R.p = f3(0, 0, 0); R.Le_add = sp(0.0f); R.event = HK_EV_SURVIVED;
+        M = &C.media[medium - 1];
+        mc = medium_coef(C, *M, lam);
+        o = o_; d = d_; depth = depth_; max_depth = max_depth_; beta = beta_; r_u = r_u_; r_l = r_l_;
+        rng = lcg_init(o, d, t_max);
+        majiter_create(it, *M, mc, o, d, t_max);
+        sg = 0; si = 0; in_seg = false; t = 0.0f; ro = o; smaj = sp(0.0f); seg_t_max = 0.0f;
     }
-    R.event = HK_EV_SURVIVED; R.beta = beta; R.r_u = r_u; R.r_l = r_l;
-    return R;
+    HK_DEV bool finish(int ev, Spec b) { R.event = ev; R.beta = b; R.r_u = r_u; R.r_l = r_l; return true; }
+    // returns true when the walk is over (R is final)
+    HK_DEV bool step() {
+        if (!in_seg) {
+            for (int k = 0; k < HK_TRACK_SKIP && !in_seg; k++) {
+                MajSeg seg;
+                if (sg >= 256 || !majiter_next(it, seg)) return finish(HK_EV_SURVIVED, beta);
+                sg++;
+                if (seg.sigma_maj.x < 1.0e-10f) continue;
+                smaj = seg.sigma_maj; seg_t_max = seg.t_max; t = seg.t_min; ro = o + d * t; si = 0; in_seg = true;
+            }
+            return false;
+        }
+        if (si >= 1024) { in_seg = false; return false; }
+        si++;
+        const float s0 = smaj.x;
+        float u = lcg_next(rng);
+        float dt = -logf(fmaxf(1.0e-10f, 1.0f - u)) / s0;
+        float ts = t + dt;
+        if (ts >= seg_t_max) {
+            Spec Tm = sp_exp(-(seg_t_max - t) * smaj);
+            if (Tm.x > 1.0e-10f) { beta = beta * Tm / Tm.x; r_u = r_u * Tm / Tm.x; r_l = r_l * Tm / Tm.x; }
+            in_seg = false;
+            return false;
+        }
+        Spec Tm = sp_exp(-dt * smaj);
+        float3 p = ro + d * dt;
+        float dens = medium_density(*M, p);
+        Spec sa = M->type == HK_MEDIUM_HOMOGENEOUS ? mc.sa : mc.sa * dens;
+        Spec ss = M->type == HK_MEDIUM_HOMOGENEOUS ? mc.ss : mc.ss * dens;
+        if (!sp_black(mc.Le) && depth < max_depth) {
+            float pr = s0 * Tm.x;
+            if (pr > 1.0e-10f) {
+                Spec re = r_u * smaj * Tm / pr;
+                if (!sp_black(re)) R.Le_add = R.Le_add + beta * sa * Tm * mc.Le / (pr * sp_avg(re));
+            }
+        }
+        float pa = sa.x / s0, ps = ss.x / s0;
+        float ue = lcg_next(rng);
+        if (ue < pa) return finish(HK_EV_ABSORBED, sp(0.0f));
+        if (ue < pa + ps) {
+            if (depth >= max_depth) return finish(HK_EV_ABSORBED, beta);
+            float pdf = Tm.x * ss.x;
+            if (pdf > 1.0e-10f) { beta = beta * Tm * ss / pdf; r_u = r_u * Tm * ss / pdf; }
+            R.p = p; R.g = mc.g;
+            return finish(HK_EV_SCATTER, beta);
+        }
+        Spec sn = sp_max0(smaj - sa - ss);
+        float pdf = Tm.x * sn.x;
+        if (!(pdf > 1.0e-10f)) return finish(HK_EV_ABSORBED, sp(0.0f));
+        beta = beta * Tm * sn / pdf; r_u = r_u * Tm * sn / pdf; r_l = r_l * Tm * smaj / pdf;
+        t = ts; ro = p;
+        if (sp_black(beta) || sp_black(r_u)) return finish(HK_EV_ABSORBED, beta);
+        return false;
+    }
+};
+// blocking form (stage-level parity tests, hk_test_delta_tracking)
+HK_DEV DeltaOut delta_track(const MediaCtx& C, int medium, float3 o, float3 d, float t_max, float4 lam, Spec beta, Spec r_u, Spec r_l, int depth, int max_depth) {
+    DeltaTracker T;
+    T.init(C, medium, o, d, t_max, lam, beta, r_u, r_l, depth, max_depth);
+    while (!T.step()) {}
+    return T.R;
 }
 
-// ---- ratio tracking (shadow rays), intersection.jl:446-542 ---------------------------------------------------
-HK_DEV void ratio_track(const MediaCtx& C, int medium, float3 o, float3 d, float t_max, float4 lam, Spec& T_ray, Spec& r_u, Spec& r_l) {
-    T_ray = sp(1.0f); r_u = sp(1.0f); r_l = sp(1.0f);
-    const DevMedium& M = C.media[medium - 1];
-    MediumCoef mc = medium_coef(C, M, lam);
-    MajIter it; majiter_create(it, M, mc, o, d, t_max);
-    Pcg32 rng = pcg32_init(hash_f3(o), hash_f3(d));
-    for (int sg = 0; sg < 256; sg++) {
-        MajSeg seg;
-        if (!majiter_next(it, seg)) break;
-        const Spec smaj = seg.sigma_maj;
-        const float s0 = smaj.x;
-        if (s0 < 1.0e-10f) continue;
-        float t = seg.t_min;
-        for (int si = 0; si < 100; si++) {
-            float u = pcg32_f32(rng);
-            float dt = -logf(fmaxf(1.0e-10f, 1.0f - u)) / s0;
-            float ts = t + dt;
-            if (ts >= seg.t_max) {
-                Spec Tm = sp_exp(-(seg.t_max - t) * smaj);
-                if (Tm.x > 1.0e-10f) { T_ray = T_ray * Tm / Tm.x; r_l = r_l * Tm / Tm.x; r_u = r_u * Tm / Tm.x; }
-                break;
-            }
-            float3 p = o + d * ts;
-            float dens = medium_density(M, p);
-            Spec sa = M.type == HK_MEDIUM_HOMOGENEOUS ? mc.sa : mc.sa * dens;
-            Spec ss = M.type == HK_MEDIUM_HOMOGENEOUS ? mc.ss : mc.ss * dens;
-            Spec sn = sp_max0(smaj - sa - ss);
-            Spec Tm = sp_exp(-dt * smaj);
-            float pr = Tm.x * s0;
-            if (!(pr > 1.0e-10f)) { T_ray = sp(0.0f); return; }
-            T_ray = T_ray * Tm * sn / pr; r_l = r_l * Tm * smaj / pr; r_u = r_u * Tm * sn / pr;
-            Spec Tr = T_ray / fmaxf(1.0e-10f, sp_avg(r_l + r_u));
-            if (sp_maxc(Tr) < 0.05f) {
-                if (pcg32_f32(rng) < 0.75f) { T_ray = sp(0.0f); return; }
-                T_ray = T_ray / (1.0f - 0.75f);
-            }
-            if (sp_black(T_ray)) return;
-            t = ts;
-        }
-        if (sp_black(T_ray)) break;
+// ---- ratio tracking (shadow rays), intersection.jl:446-542, same state-machine form ---------------------------
+struct RatioTracker {
+    const DevMedium* M; MediumCoef mc; float3 o, d;
+    Pcg32 rng; MajIter it; Spec smaj; float seg_t_max, t; int sg, si; bool in_seg;
+    Spec T_ray, r_u, r_l;
+    HK_DEV void init(const MediaCtx& C, int medium, float3 o_, float3 d_, float t_max, float4 lam) {
+        T_ray = sp(1.0f); r_u = sp(1.0f); r_l = sp(1.0f);
+        M = &C.media[medium - 1];
+        mc = medium_coef(C, *M, lam);
+        o = o_; d = d_;
+        majiter_create(it, *M, mc, o, d, t_max);
+        rng = pcg32_init(hash_f3(o), hash_f3(d));
+        sg = 0; si = 0; in_seg = false; t = 0.0f; smaj = sp(0.0f); seg_t_max = 0.0f;
     }
+    HK_DEV bool step() {
+        if (!in_seg) {
+            for (int k = 0; k < HK_TRACK_SKIP && !in_seg; k++) {
+                MajSeg seg;
+                if (sg >= 256 || !majiter_next(it, seg)) return true;
+                sg++;
+                if (seg.sigma_maj.x < 1.0e-10f) continue;
+                smaj = seg.sigma_maj; seg_t_max = seg.t_max; t = seg.t_min; si = 0; in_seg = true;
+            }
+            return false;
+        }
+        if (si >= 100) { in_seg = false; return sp_black(T_ray); }
+        si++;
+        const float s0 = smaj.x;
+        float u = pcg32_f32(rng);
+        float dt = -logf(fmaxf(1.0e-10f, 1.0f - u)) / s0;
+        float ts = t + dt;
+        if (ts >= seg_t_max) {
+            Spec Tm = sp_exp(-(seg_t_max - t) * smaj);
+            if (Tm.x > 1.0e-10f) { T_ray = T_ray * Tm / Tm.x; r_l = r_l * Tm / Tm.x; r_u = r_u * Tm / Tm.x; }
+            in_seg = false;
+            return sp_black(T_ray);
+        }
+        float3 p = o + d * ts;
+        float dens = medium_density(*M, p);
+        Spec sa = M->type == HK_MEDIUM_HOMOGENEOUS ? mc.sa : mc.sa * dens;
+        Spec ss = M->type == HK_MEDIUM_HOMOGENEOUS ? mc.ss : mc.ss * dens;
+        Spec sn = sp_max0(smaj - sa - ss);
+        Spec Tm = sp_exp(-dt * smaj);
+        float pr = Tm.x * s0;
+        if (!(pr > 1.0e-10f)) { T_ray = sp(0.0f); return true; }
+        T_ray = T_ray * Tm * sn / pr; r_l = r_l * Tm * smaj / pr; r_u = r_u * Tm * sn / pr;
+        Spec Tr = T_ray / fmaxf(1.0e-10f, sp_avg(r_l + r_u));
+        if (sp_maxc(Tr) < 0.05f) {
+            if (pcg32_f32(rng) < 0.75f) { T_ray = sp(0.0f); return true; }
+            T_ray = T_ray / (1.0f - 0.75f);
+        }
+        if (sp_black(T_ray)) return true;
+        t = ts;
+        return false;
+    }
+};
+HK_DEV void ratio_track(const MediaCtx& C, int medium, float3 o, float3 d, float t_max, float4 lam, Spec& T_ray, Spec& r_u, Spec& r_l) {
+    RatioTracker T;
+    T.init(C, medium, o, d, t_max, lam);
+    while (!T.step()) {}
+    T_ray = T.T_ray; r_u = T.r_u; r_l = T.r_l;
 }

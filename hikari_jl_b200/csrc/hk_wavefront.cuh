@@ -24,7 +24,13 @@
 #define HK_C_CURSOR_TRACE 6
 #define HK_C_CURSOR_SHADOW 7
 #define HK_C_HIT0 8            // + material type (1..7)
-#define HK_N_COUNTERS 16
+#define HK_N_QUEUE_COUNTERS 16 // the counters above (what hk_bounce_profile reports)
+#define HK_C_CURSOR_MEDIUM 16  // k_medium_track work cursor
+#define HK_C_SHROUND0 20       // + r (1..10): shadow rays still unresolved after r medium-boundary crossings (round 0 = HK_C_SHADOW)
+#define HK_C_SHCUR_TRACE 32    // + r: work cursor of the closest-hit pass of shadow round r
+#define HK_C_SHCUR_RATIO 44    // + r: work cursor of the ratio-tracking pass of shadow round r
+#define HK_SHADOW_ROUNDS 10    // trace_shadow_transmittance: at most 10 segments (intersection.jl:302-406)
+#define HK_N_COUNTERS 64
 
 struct DevScene {
     DevTables T;
@@ -49,7 +55,9 @@ struct PathState {
     float4 *ray_a, *ray_b, *hit, *lambda, *lpdf, *beta, *r_u, *r_l, *L;
     uint32_t* flags; float* fweight;
     float4 *sh_a, *sh_b, *sh_Ld, *sh_ru, *sh_rl; uint32_t* sh_medium;
-    uint32_t *q_ray[2], *q_escaped, *q_medium, *q_shadow, *q_hit[HK_MAX_MAT_TYPES];
+    float4 *med; uint32_t* med_ev;                 // delta-tracking result per slot: (scatter point, g), event
+    float4 *sh_hit, *sh_T, *sh_tu, *sh_tl;         // shadow rays through media: segment hit, running transmittance / MIS ratios
+    uint32_t *q_ray[2], *q_escaped, *q_medium, *q_shadow, *q_shadow2, *q_hit[HK_MAX_MAT_TYPES];
     uint32_t* counts;                  // [HK_N_COUNTERS]
     unsigned long long* rays_traced;
     float *pixel_rgb, *pixel_weight;   // film accumulators
@@ -204,9 +212,27 @@ __global__ void __launch_bounds__(256) k_sobol_prefix(uint32_t* __restrict__ top
 }
 
 // reset_iteration_queues!, volpath-state.jl:214-222 (+ the next ray queue and the traversal cursors)
-__global__ void k_reset_bounce(PathState S, int cur) {
+__global__ void k_reset_bounce(PathState S, int cur) {      // launched with HK_N_COUNTERS threads
     int i = threadIdx.x;
     if (i < HK_N_COUNTERS && i != (HK_C_RAY0 + cur)) S.counts[i] = 0;
+}
+// append from whichever lanes are here (a divergent region of a persistent loop): lanes that arrive together share one atomic
+HK_DEV void push_active(uint32_t* counter, uint32_t* queue, uint32_t value) {
+    const unsigned m = __activemask(), lane = threadIdx.x & 31u;
+    const unsigned leader = (unsigned)__ffs(m) - 1u;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    queue[base + (unsigned)__popc(m & ((1u << lane) - 1u))] = value;
+}
+// claim `popc(idle)` consecutive work items for the idle lanes of a warp; returns this lane's index (only meaningful for idle lanes)
+HK_DEV uint32_t claim_for_idle(uint32_t* cursor, unsigned idle) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned leader = (unsigned)__ffs(idle) - 1u;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(cursor, (uint32_t)__popc(idle));
+    base = __shfl_sync(idle, base, leader);
+    return base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
 }
 
 HK_DEV uint32_t* queue_of(const PathState& S, int qid) {
@@ -439,11 +465,51 @@ __global__ void __launch_bounds__(128, HK_SHADE_MIN_BLOCKS) k_shade(const __grid
     }
 }
 
-// Delta tracking + medium NEE + phase-function sampling, fused (delta-tracking.jl:142-453, medium-scatter.jl:15-203)
-__global__ void __launch_bounds__(128) k_medium(const __grid_constant__ DevScene D, PathState S, PassArgs A, int next) {
+// Delta tracking (delta-tracking.jl:142-453) runs as a persistent per-lane-refill loop over the DeltaTracker state machine
+// (hk_media.cuh); its per-slot result feeds k_medium_finish = medium NEE + phase-function sampling + routing
+// (medium-scatter.jl:15-203), a plain one-thread-per-entry pass where whole warps stay converged.
+#ifndef HK_MEDIUM_REFILL_MIN
+#define HK_MEDIUM_REFILL_MIN 4
+#endif
+__global__ void __launch_bounds__(128) k_medium_track(const __grid_constant__ DevScene D, PathState S) {
+    const uint32_t n = S.counts[HK_C_MEDIUM];
+    MediaCtx MDC = media_ctx(D);
+    DeltaTracker T;
+    bool busy = false, exhausted = false;
+    uint32_t slot = 0;
+    for (;;) {
+        unsigned idle = __ballot_sync(0xFFFFFFFFu, !busy);
+        if (!exhausted && (uint32_t)__popc(idle) >= (uint32_t)HK_MEDIUM_REFILL_MIN) {
+            if (!busy) {
+                const uint32_t idx = claim_for_idle(S.counts + HK_C_CURSOR_MEDIUM, idle);
+                if (idx < n) {
+                    slot = S.q_medium[idx];
+                    const float4 hr = S.hit[slot];
+                    const float4 ra = S.ray_a[slot], rb = S.ray_b[slot];
+                    const uint32_t fl = S.flags[slot];
+                    const float t_max = HK_HIT_PRIM1(__float_as_uint(hr.y)) ? hr.x : HK_INF;
+                    T.init(MDC, (int)HK_FLAG_MEDIUM(fl), f3(ra.x, ra.y, ra.z), f3(ra.w, rb.x, rb.y), t_max, S.lambda[slot], S.beta[slot], S.r_u[slot], S.r_l[slot],
+                           HK_FLAG_DEPTH(fl), D.max_depth);
+                    busy = true;
+                }
+            }
+            idle = __ballot_sync(0xFFFFFFFFu, !busy);
+            exhausted = idle != 0u;
+        }
+        if (idle == 0xFFFFFFFFu) break;
+        if (busy && T.step()) {
+            const DeltaOut& R = T.R;
+            if (!sp_black(R.Le_add)) S.L[slot] = S.L[slot] + R.Le_add;
+            S.beta[slot] = R.beta; S.r_u[slot] = R.r_u; S.r_l[slot] = R.r_l;
+            S.med[slot] = make_float4(R.p.x, R.p.y, R.p.z, R.g);
+            S.med_ev[slot] = (uint32_t)R.event;
+            busy = false;
+        }
+    }
+}
+__global__ void __launch_bounds__(128) k_medium_finish(const __grid_constant__ DevScene D, PathState S, PassArgs A, int next) {
     const uint32_t n = S.counts[HK_C_MEDIUM];
     LightCtx LC = light_ctx(D);
-    MediaCtx MDC = media_ctx(D);
     const uint32_t n_round = (n + 31u) & ~31u;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
         bool push_shadow = false, push_ray = false;
@@ -451,18 +517,17 @@ __global__ void __launch_bounds__(128) k_medium(const __grid_constant__ DevScene
         uint32_t slot = 0;
         if (i < n) {
             slot = S.q_medium[i];
-            const float4 hr = S.hit[slot];
-            const uint32_t prim1 = HK_HIT_PRIM1(__float_as_uint(hr.y));
-            const float4 ra = S.ray_a[slot], rb = S.ray_b[slot];
-            const float3 o = f3(ra.x, ra.y, ra.z), d = f3(ra.w, rb.x, rb.y);
-            const float4 lam = S.lambda[slot];
-            const uint32_t fl = S.flags[slot];
-            const int depth = HK_FLAG_DEPTH(fl);
-            const uint32_t medium = HK_FLAG_MEDIUM(fl);
-            const float t_max = prim1 ? hr.x : HK_INF;
-            DeltaOut R = delta_track(MDC, (int)medium, o, d, t_max, lam, S.beta[slot], S.r_u[slot], S.r_l[slot], depth, D.max_depth);
-            if (!sp_black(R.Le_add)) S.L[slot] = S.L[slot] + R.Le_add;
-            if (R.event == HK_EV_SCATTER) {
+            const uint32_t ev = S.med_ev[slot];
+            if (ev == HK_EV_SCATTER) {
+                const float4 md = S.med[slot];
+                const float3 Rp = f3(md.x, md.y, md.z); const float Rg = md.w;
+                const Spec Rbeta = S.beta[slot], Rru = S.r_u[slot];
+                const float4 ra = S.ray_a[slot], rb = S.ray_b[slot];
+                const float3 d = f3(ra.w, rb.x, rb.y);
+                const float4 lam = S.lambda[slot];
+                const uint32_t fl = S.flags[slot];
+                const int depth = HK_FLAG_DEPTH(fl);
+                const uint32_t medium = HK_FLAG_MEDIUM(fl);
                 const uint32_t pix = slot % A.n_pixels;
                 const int px = (int)(pix % (uint32_t)D.width) + 1, py = (int)(pix / (uint32_t)D.width) + 1;
                 const int sidx = slot_sample_idx(A, slot);
@@ -470,18 +535,18 @@ __global__ void __launch_bounds__(128) k_medium(const __grid_constant__ DevScene
                 const float3 wo = -d;
                 if (D.n_lights > 0) {   // medium_direct_lighting_inner!
                     float pmf;
-                    int li = bvh_sample_light(LC, R.p, f3(0, 0, 0), zsobol_1d(D.sobol, px, py, sidx, bdim + 1, HK_SOBOL_SLOT_BOUNCE(depth, 0), pix), pmf);
+                    int li = bvh_sample_light(LC, Rp, f3(0, 0, 0), zsobol_1d(D.sobol, px, py, sidx, bdim + 1, HK_SOBOL_SLOT_BOUNCE(depth, 0), pix), pmf);
                     if (li >= 1 && li <= D.n_lights && pmf > 0.0f) {
-                        LightSample ls = sample_light(LC, D.lights[li - 1], R.p, lam, zsobol_2d(D.sobol, px, py, sidx, bdim + 3, HK_SOBOL_SLOT_BOUNCE(depth, 1), pix));
+                        LightSample ls = sample_light(LC, D.lights[li - 1], Rp, lam, zsobol_2d(D.sobol, px, py, sidx, bdim + 3, HK_SOBOL_SLOT_BOUNCE(depth, 1), pix));
                         if (ls.pdf > 0.0f && !sp_black(ls.Li)) {
-                            float ph = hg_p(R.g, dot3(wo, ls.wi));
+                            float ph = hg_p(Rg, dot3(wo, ls.wi));
                             if (ph > 0.0f) {
-                                float tmax = ls.delta ? len3(ls.p_light - R.p) - 0.001f : 1.0e6f;
-                                S.sh_a[slot] = make_float4(R.p.x, R.p.y, R.p.z, ls.wi.x);
+                                float tmax = ls.delta ? len3(ls.p_light - Rp) - 0.001f : 1.0e6f;
+                                S.sh_a[slot] = make_float4(Rp.x, Rp.y, Rp.z, ls.wi.x);
                                 S.sh_b[slot] = make_float4(ls.wi.y, ls.wi.z, tmax, 0.0f);
-                                S.sh_Ld[slot] = R.beta * ph * ls.Li;
-                                S.sh_ru[slot] = R.r_u * (ls.delta ? 0.0f : ph);
-                                S.sh_rl[slot] = R.r_u * (ls.pdf * pmf);
+                                S.sh_Ld[slot] = Rbeta * ph * ls.Li;
+                                S.sh_ru[slot] = Rru * (ls.delta ? 0.0f : ph);
+                                S.sh_rl[slot] = Rru * (ls.pdf * pmf);
                                 S.sh_medium[slot] = medium;
                                 push_shadow = true;
                             }
@@ -491,18 +556,19 @@ __global__ void __launch_bounds__(128) k_medium(const __grid_constant__ DevScene
                 const int nd = depth + 1;   // medium_scatter_inner!
                 if (nd < D.max_depth) {
                     float pdf;
-                    float3 wi = sample_hg(R.g, wo, zsobol_2d(D.sobol, px, py, sidx, bdim + 6, HK_SOBOL_SLOT_BOUNCE(depth, 3), pix), pdf);
+                    float3 wi = sample_hg(Rg, wo, zsobol_2d(D.sobol, px, py, sidx, bdim + 6, HK_SOBOL_SLOT_BOUNCE(depth, 3), pix), pdf);
                     if (pdf > 0.0f) {
-                        S.ray_a[slot] = make_float4(R.p.x, R.p.y, R.p.z, wi.x);
+                        S.ray_a[slot] = make_float4(Rp.x, Rp.y, Rp.z, wi.x);
                         S.ray_b[slot] = make_float4(wi.y, wi.z, HK_INF, 0.0f);
-                        S.beta[slot] = R.beta; S.r_u[slot] = R.r_u; S.r_l[slot] = R.r_u / pdf;
+                        S.r_l[slot] = Rru / pdf;      // beta, r_u already hold the scattered values
                         S.flags[slot] = (uint32_t)nd | HK_FLAG_ANYNS | (medium << 16);
                         push_ray = true;
                     }
                 }
-            } else if (R.event == HK_EV_SURVIVED && !(sp_black(R.beta) || sp_black(R.r_u) || depth >= D.max_depth)) {
-                S.beta[slot] = R.beta; S.r_u[slot] = R.r_u; S.r_l[slot] = R.r_l;
-                qid = prim1 ? HK_C_HIT0 + (int)HK_HIT_MTYPE(__float_as_uint(hr.y)) : HK_C_ESCAPED;
+            } else if (ev == HK_EV_SURVIVED) {
+                const uint32_t hb = __float_as_uint(S.hit[slot].y);
+                if (!(sp_black(S.beta[slot]) || sp_black(S.r_u[slot]) || HK_FLAG_DEPTH(S.flags[slot]) >= D.max_depth))
+                    qid = HK_HIT_PRIM1(hb) ? HK_C_HIT0 + (int)HK_HIT_MTYPE(hb) : HK_C_ESCAPED;
             }
         }
         warp_push(S.counts, nullptr, qid, slot, queue_of(S, qid));
@@ -545,59 +611,108 @@ __global__ void __launch_bounds__(HK_TRACE_THREADS, HK_TRACE_BLOCKS_PER_SM) k_sh
     count_rays(S.rays_traced, traced);
     if (COUNT) { count_rays(work + 3, traced); count_rays(work + 4, wn); count_rays(work + 5, wt); }
 }
-template <bool COUNT>
-__global__ void __launch_bounds__(HK_TRACE_THREADS) k_shadow_general(const __grid_constant__ DevScene D, PathState S, unsigned long long* work) {
-    __shared__ uint2 sm_stack[HK_SM_STACK * HK_TRACE_THREADS];
-    if (S.counts[HK_C_TOTAL_HITS] == 0) return;
-    const uint32_t n = S.counts[HK_C_SHADOW];
-    const unsigned lane = threadIdx.x & 31u;
-    MediaCtx MDC = media_ctx(D);
-    uint32_t traced = 0, wn = 0, wt = 0;
-    for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(S.counts + HK_C_CURSOR_SHADOW, 32u);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (base >= n) break;
-        const uint32_t idx = base + lane;
-        if (idx >= n) continue;
-        const uint32_t slot = S.q_shadow[idx];
+// Scenes with media / medium interfaces: trace_shadow_transmittance (intersection.jl:302-406) walks the shadow ray segment
+// by segment -- closest hit, ratio tracking through the current medium up to it, cross the boundary, repeat (<= 10 times).
+// Here every segment is one wavefront ROUND of two persistent kernels over the still-unresolved shadow rays:
+//   k_shadow_seg_trace : closest hit of the segment, through the same per-lane-refill traversal loop as k_trace;
+//   k_shadow_seg_ratio : ratio tracking as a per-lane-refill loop over the RatioTracker state machine, then resolve
+//                        (visible -> add the contribution, blocked -> drop, boundary -> next round's queue).
+// The one-thread-per-ray-to-completion form this replaces ran with 4.5 of 32 lanes active on C4 (ncu, profiles/).
+struct ShadowSegIO {
+    const PathState& S; const uint32_t* __restrict__ q;
+    HK_DEV uint32_t load(uint32_t idx, float3& o, float3& d, float& tm) const {
+        const uint32_t slot = q[idx];
         const float4 sa = S.sh_a[slot], sb = S.sh_b[slot];
-        float3 o = f3(sa.x, sa.y, sa.z);
-        const float3 d = f3(sa.w, sb.x, sb.y);
-        float t_rem = sb.z;
-        Spec T = sp(1.0f), tu = sp(1.0f), tl = sp(1.0f);
-        bool visible = false, done = false;
-        const float4 lam = S.lambda[slot];
-        uint32_t cur = S.sh_medium[slot];
-        for (int it = 0; it < 10 && !done; it++) {
-            if (t_rem < 1.0e-6f) break;
-            HitRec h = bvh8_trace<false, COUNT>(D.bvh, sm_stack + threadIdx.x, o, d, t_rem, &wn, &wt);
-            traced++;
-            if (h.prim1 == 0) {
-                if (cur != 0) { Spec a, b, c; ratio_track(MDC, (int)cur, o, d, t_rem, lam, a, b, c); T = T * a; tu = tu * b; tl = tl * c; }
-                visible = true; done = true; break;
-            }
-            const uint32_t prim0 = HK_HIT_PRIM1(h.prim1) - 1u;
-            const HkMediumInterface mi = D.interfaces[__ldg(D.tri_meta + 3 * (size_t)prim0) - 1];
-            if (mi.inside == mi.outside) { visible = false; done = true; break; }   // opaque (alpha == 1)
-            if (cur != 0) { Spec a, b, c; ratio_track(MDC, (int)cur, o, d, h.t, lam, a, b, c); T = T * a; tu = tu * b; tl = tl * c; }
-            if (sp_black(T)) { visible = true; done = true; break; }
-            const bool entering = dot3(d, geometric_normal(D, prim0)) < 0.0f;
-            cur = entering ? mi.inside : mi.outside;
-            o = o + d * (h.t + 1.0e-4f);
-            t_rem = t_rem - h.t - 1.0e-4f;
-        }
-        if (!done) visible = false;
-        if (visible && !sp_black(T)) {
-            float den = sp_avg(S.sh_ru[slot] * tu + S.sh_rl[slot] * tl);
-            if (den > 1.0e-10f) {
-                Spec fin = S.sh_Ld[slot] * T / den;
-                if (!sp_black(fin)) S.L[slot] = S.L[slot] + fin;
-            }
-        }
+        o = f3(sa.x, sa.y, sa.z); d = f3(sa.w, sb.x, sb.y);
+        tm = sb.z < 1.0e-6f ? -1.0f : sb.z;          // t_remaining < 1e-6: the reference's loop breaks (ray dropped by the ratio pass)
+        return slot;
     }
+    HK_DEV void store(uint32_t slot, const HitRec& h) const { S.sh_hit[slot] = make_float4(h.t, __uint_as_float(h.prim1), h.b1, h.b2); }
+};
+template <bool COUNT>
+__global__ void __launch_bounds__(HK_TRACE_THREADS, HK_TRACE_BLOCKS_PER_SM) k_shadow_seg_trace(const __grid_constant__ DevScene D, PathState S, int round, unsigned long long* work) {
+    __shared__ uint2 sm_stack[HK_SM_STACK * HK_TRACE_THREADS];
+    if (S.counts[HK_C_TOTAL_HITS] == 0) return;      // reference quirk (volpath.jl:571-609): shadow pass only inside `n_hits > 0`
+    const uint32_t n = S.counts[round == 0 ? HK_C_SHADOW : HK_C_SHROUND0 + round];
+    uint32_t traced = 0, wn = 0, wt = 0;
+    ShadowSegIO io{S, (round & 1) ? S.q_shadow2 : S.q_shadow};
+    trace_queue<false, COUNT>(D.bvh, sm_stack + threadIdx.x, n, S.counts + HK_C_SHCUR_TRACE + round, io, traced, wn, wt);
     count_rays(S.rays_traced, traced);
     if (COUNT) { count_rays(work + 3, traced); count_rays(work + 4, wn); count_rays(work + 5, wt); }
+}
+__global__ void __launch_bounds__(128) k_shadow_seg_ratio(const __grid_constant__ DevScene D, PathState S, int round) {
+    if (S.counts[HK_C_TOTAL_HITS] == 0) return;
+    const uint32_t n = S.counts[round == 0 ? HK_C_SHADOW : HK_C_SHROUND0 + round];
+    const uint32_t* __restrict__ q = (round & 1) ? S.q_shadow2 : S.q_shadow;
+    uint32_t* q_next = (round & 1) ? S.q_shadow : S.q_shadow2;
+    MediaCtx MDC = media_ctx(D);
+    RatioTracker R;
+    bool busy = false, exhausted = false, tracking = false;
+    uint32_t slot = 0;
+    for (;;) {
+        unsigned idle = __ballot_sync(0xFFFFFFFFu, !busy);
+        if (!exhausted && (uint32_t)__popc(idle) >= (uint32_t)HK_MEDIUM_REFILL_MIN) {
+            if (!busy) {
+                const uint32_t idx = claim_for_idle(S.counts + HK_C_SHCUR_RATIO + round, idle);
+                if (idx < n) {
+                    slot = q[idx];
+                    const float4 sa = S.sh_a[slot], sb = S.sh_b[slot];
+                    const float4 h = S.sh_hit[slot];
+                    const uint32_t hp = HK_HIT_PRIM1(__float_as_uint(h.y));
+                    bool opaque = false;                          // an opaque surface (alpha == 1) blocks: no tracking needed
+                    if (hp != 0u) { const HkMediumInterface mi = D.interfaces[__ldg(D.tri_meta + 3 * (size_t)(hp - 1u)) - 1]; opaque = mi.inside == mi.outside; }
+                    if (!(sb.z < 1.0e-6f) && !opaque) {           // t_rem < 1e-6: dropped (the reference's loop ends without a visible ray)
+                        busy = true;
+                        const uint32_t cur = S.sh_medium[slot];
+                        tracking = cur != 0u;
+                        if (tracking) {
+                            const float t_seg = hp ? h.x : sb.z;
+                            R.init(MDC, (int)cur, f3(sa.x, sa.y, sa.z), f3(sa.w, sb.x, sb.y), t_seg, S.lambda[slot]);
+                        }
+                    }
+                }
+            }
+            idle = __ballot_sync(0xFFFFFFFFu, !busy);
+            exhausted = idle != 0u;
+        }
+        if (idle == 0xFFFFFFFFu) break;
+        if (busy && (!tracking || R.step())) {
+            // ---- the segment is done: fold its transmittance in and resolve ------------------------------------------
+            Spec T = sp(1.0f), tu = sp(1.0f), tl = sp(1.0f);
+            if (round > 0) { T = S.sh_T[slot]; tu = S.sh_tu[slot]; tl = S.sh_tl[slot]; }
+            if (tracking) { T = T * R.T_ray; tu = tu * R.r_u; tl = tl * R.r_l; }
+            const float4 h = S.sh_hit[slot];
+            const uint32_t prim1 = HK_HIT_PRIM1(__float_as_uint(h.y));
+            bool visible = false;
+            if (prim1 == 0u) visible = true;
+            else {
+                const uint32_t prim0 = prim1 - 1u;
+                const HkMediumInterface mi = D.interfaces[__ldg(D.tri_meta + 3 * (size_t)prim0) - 1];
+                if (mi.inside != mi.outside) {                     // (an opaque surface, alpha == 1, blocks: nothing to do)
+                    if (sp_black(T)) visible = true;               // reference: leaves the loop "visible" with T == 0 -> contributes nothing
+                    else if (round + 1 < HK_SHADOW_ROUNDS) {
+                        const float4 sa = S.sh_a[slot], sb = S.sh_b[slot];
+                        const float3 o = f3(sa.x, sa.y, sa.z), d = f3(sa.w, sb.x, sb.y);
+                        const bool entering = dot3(d, geometric_normal(D, prim0)) < 0.0f;
+                        const float3 no = o + d * (h.x + 1.0e-4f);
+                        S.sh_medium[slot] = entering ? mi.inside : mi.outside;
+                        S.sh_a[slot] = make_float4(no.x, no.y, no.z, d.x);
+                        S.sh_b[slot] = make_float4(sb.x, sb.y, sb.z - h.x - 1.0e-4f, 0.0f);
+                        S.sh_T[slot] = T; S.sh_tu[slot] = tu; S.sh_tl[slot] = tl;
+                        push_active(S.counts + HK_C_SHROUND0 + round + 1, q_next, slot);
+                    }
+                }
+            }
+            if (visible && !sp_black(T)) {
+                const float den = sp_avg(S.sh_ru[slot] * tu + S.sh_rl[slot] * tl);
+                if (den > 1.0e-10f) {
+                    const Spec fin = S.sh_Ld[slot] * T / den;
+                    if (!sp_black(fin)) S.L[slot] = S.L[slot] + fin;
+                }
+            }
+            busy = false;
+        }
+    }
 }
 
 // vp_accumulate_to_rgb_kernel!, volpath.jl:326-375.  One thread per pixel walks the batch in sample order, so the
