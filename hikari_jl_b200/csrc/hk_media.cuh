@@ -212,18 +212,21 @@ struct DeltaTracker {
         sg = 0; si = 0; in_seg = false; t = 0.0f; ro = o; smaj = sp(0.0f); seg_t_max = 0.0f;
     }
     HK_DEV bool finish(int ev, Spec b) { R.event = ev; R.beta = b; R.r_u = r_u; R.r_l = r_l; return true; }
-    // returns true when the walk is over (R is final)
-    HK_DEV bool step() {
-        if (!in_seg) {
-            for (int k = 0; k < HK_TRACK_SKIP && !in_seg; k++) {
-                MajSeg seg;
-                if (sg >= 256 || !majiter_next(it, seg)) return finish(HK_EV_SURVIVED, beta);
-                sg++;
-                if (seg.sigma_maj.x < 1.0e-10f) continue;
-                smaj = seg.sigma_maj; seg_t_max = seg.t_max; t = seg.t_min; ro = o + d * t; si = 0; in_seg = true;
-            }
-            return false;
+    // Both return true when the walk is over (R is final).  skip_step (precondition !in_seg): advance the DDA to the next
+    // non-empty segment; event_step (precondition in_seg): one tentative collision.  The persistent kernels vote per warp
+    // on which of the two to run, so the expensive event code executes with many lanes at once.
+    HK_DEV bool step() { return in_seg ? event_step() : skip_step(); }
+    HK_DEV bool skip_step() {
+        for (int k = 0; k < HK_TRACK_SKIP && !in_seg; k++) {
+            MajSeg seg;
+            if (sg >= 256 || !majiter_next(it, seg)) return finish(HK_EV_SURVIVED, beta);
+            sg++;
+            if (seg.sigma_maj.x < 1.0e-10f) continue;
+            smaj = seg.sigma_maj; seg_t_max = seg.t_max; t = seg.t_min; ro = o + d * t; si = 0; in_seg = true;
         }
+        return false;
+    }
+    HK_DEV bool event_step() {
         if (si >= 1024) { in_seg = false; return false; }
         si++;
         const float s0 = smaj.x;
@@ -289,17 +292,18 @@ struct RatioTracker {
         rng = pcg32_init(hash_f3(o), hash_f3(d));
         sg = 0; si = 0; in_seg = false; t = 0.0f; smaj = sp(0.0f); seg_t_max = 0.0f;
     }
-    HK_DEV bool step() {
-        if (!in_seg) {
-            for (int k = 0; k < HK_TRACK_SKIP && !in_seg; k++) {
-                MajSeg seg;
-                if (sg >= 256 || !majiter_next(it, seg)) return true;
-                sg++;
-                if (seg.sigma_maj.x < 1.0e-10f) continue;
-                smaj = seg.sigma_maj; seg_t_max = seg.t_max; t = seg.t_min; si = 0; in_seg = true;
-            }
-            return false;
+    HK_DEV bool step() { return in_seg ? event_step() : skip_step(); }
+    HK_DEV bool skip_step() {
+        for (int k = 0; k < HK_TRACK_SKIP && !in_seg; k++) {
+            MajSeg seg;
+            if (sg >= 256 || !majiter_next(it, seg)) return true;
+            sg++;
+            if (seg.sigma_maj.x < 1.0e-10f) continue;
+            smaj = seg.sigma_maj; seg_t_max = seg.t_max; t = seg.t_min; si = 0; in_seg = true;
         }
+        return false;
+    }
+    HK_DEV bool event_step() {
         if (si >= 100) { in_seg = false; return sp_black(T_ray); }
         si++;
         const float s0 = smaj.x;

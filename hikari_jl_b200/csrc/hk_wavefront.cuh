@@ -468,18 +468,26 @@ __global__ void __launch_bounds__(128, HK_SHADE_MIN_BLOCKS) k_shade(const __grid
 // Delta tracking (delta-tracking.jl:142-453) runs as a persistent per-lane-refill loop over the DeltaTracker state machine
 // (hk_media.cuh); its per-slot result feeds k_medium_finish = medium NEE + phase-function sampling + routing
 // (medium-scatter.jl:15-203), a plain one-thread-per-entry pass where whole warps stay converged.
-#ifndef HK_MEDIUM_REFILL_MIN
-#define HK_MEDIUM_REFILL_MIN 4
+#ifndef HK_PHASE_MIN
+#define HK_PHASE_MIN 16
 #endif
 __global__ void __launch_bounds__(128) k_medium_track(const __grid_constant__ DevScene D, PathState S) {
     const uint32_t n = S.counts[HK_C_MEDIUM];
     MediaCtx MDC = media_ctx(D);
     DeltaTracker T;
+    T.in_seg = false;
     bool busy = false, exhausted = false;
     uint32_t slot = 0;
     for (;;) {
-        unsigned idle = __ballot_sync(0xFFFFFFFFu, !busy);
-        if (!exhausted && (uint32_t)__popc(idle) >= (uint32_t)HK_MEDIUM_REFILL_MIN) {
+        // Phase vote: the warp runs ONE of {refill, event, skip} per iteration, chosen so that the two expensive ones (ray
+        // set-up and collision events) only run when at least HK_PHASE_MIN lanes want them or nothing else can progress.
+        // (Per-lane refill alone left 3 of 32 lanes active in the event code: at any time only a few lanes sit in a
+        // non-empty majorant cell while the rest skip empty ones.)
+        const unsigned idle = __ballot_sync(0xFFFFFFFFu, !busy);
+        const unsigned ev = __ballot_sync(0xFFFFFFFFu, busy && T.in_seg);
+        const unsigned sk = ~(idle | ev);
+        if (idle == 0xFFFFFFFFu && exhausted) break;
+        if (!exhausted && ((uint32_t)__popc(idle) >= (uint32_t)HK_PHASE_MIN || (ev | sk) == 0u)) {
             if (!busy) {
                 const uint32_t idx = claim_for_idle(S.counts + HK_C_CURSOR_MEDIUM, idle);
                 if (idx < n) {
@@ -493,17 +501,19 @@ __global__ void __launch_bounds__(128) k_medium_track(const __grid_constant__ De
                     busy = true;
                 }
             }
-            idle = __ballot_sync(0xFFFFFFFFu, !busy);
-            exhausted = idle != 0u;
+            exhausted = __any_sync(0xFFFFFFFFu, !busy);
+            continue;
         }
-        if (idle == 0xFFFFFFFFu) break;
-        if (busy && T.step()) {
+        bool fin = false;
+        if ((uint32_t)__popc(ev) >= (uint32_t)HK_PHASE_MIN || sk == 0u) { if (busy && T.in_seg) fin = T.event_step(); }
+        else if (busy && !T.in_seg) fin = T.skip_step();
+        if (fin) {
             const DeltaOut& R = T.R;
             if (!sp_black(R.Le_add)) S.L[slot] = S.L[slot] + R.Le_add;
             S.beta[slot] = R.beta; S.r_u[slot] = R.r_u; S.r_l[slot] = R.r_l;
             S.med[slot] = make_float4(R.p.x, R.p.y, R.p.z, R.g);
             S.med_ev[slot] = (uint32_t)R.event;
-            busy = false;
+            busy = false; T.in_seg = false;
         }
     }
 }
@@ -647,11 +657,16 @@ __global__ void __launch_bounds__(128) k_shadow_seg_ratio(const __grid_constant_
     uint32_t* q_next = (round & 1) ? S.q_shadow : S.q_shadow2;
     MediaCtx MDC = media_ctx(D);
     RatioTracker R;
+    R.in_seg = false;
     bool busy = false, exhausted = false, tracking = false;
     uint32_t slot = 0;
     for (;;) {
-        unsigned idle = __ballot_sync(0xFFFFFFFFu, !busy);
-        if (!exhausted && (uint32_t)__popc(idle) >= (uint32_t)HK_MEDIUM_REFILL_MIN) {
+        // same phase vote as k_medium_track; a lane whose segment needs no tracking (vacuum) resolves in the event phase
+        const unsigned idle = __ballot_sync(0xFFFFFFFFu, !busy);
+        const unsigned ev = __ballot_sync(0xFFFFFFFFu, busy && (!tracking || R.in_seg));
+        const unsigned sk = ~(idle | ev);
+        if (idle == 0xFFFFFFFFu && exhausted) break;
+        if (!exhausted && ((uint32_t)__popc(idle) >= (uint32_t)HK_PHASE_MIN || (ev | sk) == 0u)) {
             if (!busy) {
                 const uint32_t idx = claim_for_idle(S.counts + HK_C_SHCUR_RATIO + round, idle);
                 if (idx < n) {
@@ -665,6 +680,7 @@ __global__ void __launch_bounds__(128) k_shadow_seg_ratio(const __grid_constant_
                         busy = true;
                         const uint32_t cur = S.sh_medium[slot];
                         tracking = cur != 0u;
+                        R.in_seg = false;
                         if (tracking) {
                             const float t_seg = hp ? h.x : sb.z;
                             R.init(MDC, (int)cur, f3(sa.x, sa.y, sa.z), f3(sa.w, sb.x, sb.y), t_seg, S.lambda[slot]);
@@ -672,11 +688,13 @@ __global__ void __launch_bounds__(128) k_shadow_seg_ratio(const __grid_constant_
                     }
                 }
             }
-            idle = __ballot_sync(0xFFFFFFFFu, !busy);
-            exhausted = idle != 0u;
+            exhausted = __any_sync(0xFFFFFFFFu, !busy);
+            continue;
         }
-        if (idle == 0xFFFFFFFFu) break;
-        if (busy && (!tracking || R.step())) {
+        bool fin = false;
+        if ((uint32_t)__popc(ev) >= (uint32_t)HK_PHASE_MIN || sk == 0u) { if (busy) { if (!tracking) fin = true; else if (R.in_seg) fin = R.event_step(); } }
+        else if (busy && tracking && !R.in_seg) fin = R.skip_step();
+        if (fin) {
             // ---- the segment is done: fold its transmittance in and resolve ------------------------------------------
             Spec T = sp(1.0f), tu = sp(1.0f), tl = sp(1.0f);
             if (round > 0) { T = S.sh_T[slot]; tu = S.sh_tu[slot]; tl = S.sh_tl[slot]; }
@@ -706,8 +724,8 @@ __global__ void __launch_bounds__(128) k_shadow_seg_ratio(const __grid_constant_
             if (visible && !sp_black(T)) {
                 const float den = sp_avg(S.sh_ru[slot] * tu + S.sh_rl[slot] * tl);
                 if (den > 1.0e-10f) {
-                    const Spec fin = S.sh_Ld[slot] * T / den;
-                    if (!sp_black(fin)) S.L[slot] = S.L[slot] + fin;
+                    const Spec contrib = S.sh_Ld[slot] * T / den;
+                    if (!sp_black(contrib)) S.L[slot] = S.L[slot] + contrib;
                 }
             }
             busy = false;

@@ -20,4 +20,4 @@ byfile = collections.Counter()
 for (f, l), a in agg.items(): byfile[f] += a[1]
 print("samples by file:", ", ".join(f"{f}={v/ts*100:.1f}%" for f, v in byfile.most_common()))
 for (f, l), a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:topn]:
-    print(f"{a[1]/ts*100:5.1f}% samp {a[2]/te*100:5.1f}% inst  {f}:{l:>4}  {a[0].strip()[:105]}")
+    print(f"{a[1]/ts*100:5.1f}% samp {a[2]/te*100:5.1f}% inst {a[3]/max(1,a[2]):5.1f} lanes  {f}:{l:>4}  {a[0].strip()[:100]}")
