@@ -197,7 +197,9 @@ struct DeltaOut { int event; Spec beta, r_u, r_l; float3 p; float g; Spec Le_add
 // on its own ray and hand finished lanes a new one (k_medium_track) instead of idling until the longest walk of the warp
 // is done (ncu on C4: 7.9 of 32 lanes active in the one-ray-per-thread-to-completion form).  The arithmetic per ray, and
 // therefore every output bit, is that of the nested loops in delta-tracking.jl:142-453.
+#ifndef HK_TRACK_SKIP
 #define HK_TRACK_SKIP 4
+#endif
 struct DeltaTracker {
     const DevMedium* M; MediumCoef mc; float3 o, d, ro; int depth, max_depth;
     uint64_t rng; MajIter it; Spec smaj; float seg_t_max, t; int sg, si; bool in_seg;

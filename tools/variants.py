@@ -35,7 +35,8 @@ def run(argv):
     for so in sorted(glob.glob(os.path.join(VDIR, "*.so"))):
         name = os.path.basename(so)[4:-3]
         env = dict(os.environ, HK_CUDA_LIB=so)
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--quick", "--steps", steps, "--warmup", steps], env=env, capture_output=True, text=True, timeout=600)
+        extra = os.environ.get("HK_BENCH_ARGS", "").split()          # e.g. HK_BENCH_ARGS="--config C4"
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--quick", "--steps", steps, "--warmup", steps] + extra, env=env, capture_output=True, text=True, timeout=600)
         open(os.path.join(ROOT, "gpurun_out", f"var_{name}.json"), "w").write(r.stdout if r.returncode == 0 else json.dumps({"error": r.stderr[-1500:]}))
         print(name, r.stdout[:160] if r.returncode == 0 else r.stderr[-500:], flush=True)
 
