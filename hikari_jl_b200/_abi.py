@@ -13,6 +13,7 @@ c_u8p = C.POINTER(C.c_uint8)
 
 HK_MAT_MATTE, HK_MAT_MIRROR, HK_MAT_GLASS, HK_MAT_CONDUCTOR = 1, 2, 3, 4
 HK_MAT_COATED_DIFFUSE, HK_MAT_THIN_DIELECTRIC, HK_MAT_DIFFUSE_TRANSMISSION = 5, 6, 7
+HK_MAT_MIX = 8
 HK_MATFLAG_REMAP_ROUGHNESS, HK_MATFLAG_SPECTRAL_ETA_K = 1, 2
 HK_LIGHT_POINT, HK_LIGHT_SPOT, HK_LIGHT_DIRECTIONAL, HK_LIGHT_SUN = 1, 2, 3, 4
 HK_LIGHT_ENVIRONMENT, HK_LIGHT_AMBIENT, HK_LIGHT_DIFFUSE_AREA = 5, 6, 7

@@ -229,8 +229,9 @@ int32_t hk_upload_materials(HkContext* ctx, const HkMaterial* m, uint32_t nm, co
     REQUIRE(nm == 0 || m, "materials missing"); REQUIRE(ni == 0 || mi, "interfaces missing");
     uint32_t present = 0; int32_t trans = 0;
     for (uint32_t i = 0; i < nm; i++) {
-        REQUIRE(m[i].type >= 1 && m[i].type < HK_MAX_MAT_TYPES, "unsupported material type (CoatedConductor / CoatedDiffuseTransmission / Mix are SURVEY 8f items)");
-        present |= 1u << m[i].type;
+        REQUIRE((m[i].type >= 1 && m[i].type < HK_MAX_MAT_TYPES) || m[i].type == HK_MAT_MIX, "unsupported material type (CoatedConductor / CoatedDiffuseTransmission are SURVEY 8f items)");
+        if (m[i].type == HK_MAT_MIX) { REQUIRE(m[i].ival[0] >= 1 && (uint32_t)m[i].ival[0] <= nm && m[i].ival[1] >= 1 && (uint32_t)m[i].ival[1] <= nm, "MixMaterial references a missing material"); }
+        else present |= 1u << m[i].type;
     }
     for (uint32_t i = 0; i < ni; i++) {
         REQUIRE(mi[i].material >= 1 && mi[i].material <= nm, "interface references a missing material");
@@ -351,7 +352,7 @@ static int32_t alloc_film(HkContext* ctx, size_t n_pixels) {
 }
 static int32_t alloc_state(HkContext* ctx, size_t n_slots) {
     // one slab: 19 float4 arrays, 4 u32/f32 arrays, 14 queues; every array starts 256-byte aligned
-    const size_t f4 = 19, w4 = 4, q = 6 + HK_MAX_MAT_TYPES;
+    const size_t f4 = 19, w4 = 5, q = 6 + HK_MAX_MAT_TYPES;
     size_t rounded = f4 * (((16 * n_slots + 255) / 256) * 256) + (w4 + q) * (((4 * n_slots + 255) / 256) * 256);
     CK(cudaStreamSynchronize(ctx->stream));
     CK(ctx->b_state.alloc(rounded));
@@ -362,7 +363,7 @@ static int32_t alloc_state(HkContext* ctx, size_t n_slots) {
                       &S.med, &S.sh_hit, &S.sh_T, &S.sh_tu, &S.sh_tl};
     for (auto pp : f4s) *pp = reinterpret_cast<float4*>(take(16));
     S.flags = reinterpret_cast<uint32_t*>(take(4)); S.fweight = reinterpret_cast<float*>(take(4)); S.sh_medium = reinterpret_cast<uint32_t*>(take(4));
-    S.med_ev = reinterpret_cast<uint32_t*>(take(4));
+    S.med_ev = reinterpret_cast<uint32_t*>(take(4)); S.res_mat = reinterpret_cast<uint32_t*>(take(4));
     S.q_ray[0] = reinterpret_cast<uint32_t*>(take(4)); S.q_ray[1] = reinterpret_cast<uint32_t*>(take(4));
     S.q_escaped = reinterpret_cast<uint32_t*>(take(4)); S.q_medium = reinterpret_cast<uint32_t*>(take(4)); S.q_shadow = reinterpret_cast<uint32_t*>(take(4));
     S.q_shadow2 = reinterpret_cast<uint32_t*>(take(4));

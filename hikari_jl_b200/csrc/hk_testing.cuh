@@ -12,6 +12,12 @@ __global__ void tk_sobol(SobolParams P, const int32_t* __restrict__ q, uint64_t 
         o2[2 * i] = v.x; o2[2 * i + 1] = v.y;
     }
 }
+__global__ void tk_mix_hash(const float* __restrict__ in, uint64_t n, float* out) {
+    TK_LOOP(n) {
+        const float* e = in + 10 * i;
+        out[i] = mix_hash_float(f3(e[0], e[1], e[2]), f3(e[3], e[4], e[5]), (uint32_t)e[6], (uint32_t)e[7], (uint32_t)e[8], (uint32_t)e[9]);
+    }
+}
 __global__ void tk_hashes(const float* __restrict__ v, uint64_t n, uint64_t* oh, uint64_t* om, float* op) {
     TK_LOOP(n) {
         uint64_t h = hash_f3(f3(v[3 * i], v[3 * i + 1], v[3 * i + 2]));
@@ -168,6 +174,14 @@ int32_t hk_test_sobol(HkContext* ctx, const int32_t* q, uint64_t n, int32_t l2, 
 int32_t hk_test_sobol_mode(HkContext* ctx, int32_t fast) { if (!ctx) return HK_ERR_INVALID; int32_t old = ctx->D.sobol.fast; ctx->D.sobol.fast = fast ? 1 : 0; return old; }
 // 0 / 1: disable / enable the ZSobol prefix cache (takes effect at the next hk_set_params); returns the previous setting
 int32_t hk_test_sobol_cache(HkContext* ctx, int32_t on) { if (!ctx) return HK_ERR_INVALID; int32_t old = ctx->sobol_cache_enabled ? 1 : 0; ctx->sobol_cache_enabled = on != 0; ctx->sobol_cache_key[5] = -1; return old; }
+int32_t hk_test_mix_hash(HkContext* ctx, const float* in, uint64_t n, float* out) {
+    if (!ctx) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device); TkIO io(ctx);
+    void* di = io.in(in, 40 * n); float* dout = (float*)io.out(4 * n);
+    if (io.rc) return io.rc;
+    tk_mix_hash<<<TK_GRID(n)>>>((const float*)di, n, dout); ctx->launches++;
+    return io.get(out, dout, 4 * n);
+}
 int32_t hk_test_hashes(HkContext* ctx, const float* v, uint64_t n, uint64_t* oh, uint64_t* om, float* op) {
     if (!ctx) return HK_ERR_INVALID;
     cudaSetDevice(ctx->device); TkIO io(ctx);

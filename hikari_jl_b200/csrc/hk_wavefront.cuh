@@ -56,6 +56,7 @@ struct PathState {
     uint32_t* flags; float* fweight;
     float4 *sh_a, *sh_b, *sh_Ld, *sh_ru, *sh_rl; uint32_t* sh_medium;
     float4 *med; uint32_t* med_ev;                 // delta-tracking result per slot: (scatter point, g), event
+    uint32_t* res_mat;                             // material a MixMaterial hit resolved to (written by the routing, read by k_shade)
     float4 *sh_hit, *sh_T, *sh_tu, *sh_tl;         // shadow rays through media: segment hit, running transmittance / MIS ratios
     uint32_t *q_ray[2], *q_escaped, *q_medium, *q_shadow, *q_shadow2, *q_hit[HK_MAX_MAT_TYPES];
     uint32_t* counts;                  // [HK_N_COUNTERS]
@@ -266,6 +267,60 @@ __global__ void __launch_bounds__(HK_TRACE_THREADS, HK_TRACE_BLOCKS_PER_SM) k_tr
 }
 // in-medium rays go to delta tracking with their hit record; the vacuum alpha loop (:224-266) ends on its first iteration
 // because every constant-parameter material has alpha == 1 (spectral-eval.jl:3882-3888)
+// ---- MixMaterial, src/materials/mix-material.jl: mix_hash_float :114-158 (the UInt32 shifts truncate, the SetKey shifts
+// are 64-bit), choose_material :178-196 with a constant amount, resolve_mix_material :253-268 (<= 8 levels) ---------------
+HK_DEV float mix_hash_float(float3 p, float3 wo, uint32_t type1, uint32_t vec1, uint32_t type2, uint32_t vec2) {
+    uint64_t h = 0;
+    h ^= (uint64_t)__float_as_uint(p.x);
+    h *= 0xcc9e2d51ull;
+    h ^= (uint64_t)(uint32_t)(__float_as_uint(p.y) << 4);
+    h *= 0x1b873593ull;
+    h ^= (uint64_t)(uint32_t)(__float_as_uint(p.z) << 8);
+    h ^= (uint64_t)(uint32_t)(__float_as_uint(wo.x) << 16);
+    h *= 0xcc9e2d51ull;
+    h ^= (uint64_t)__float_as_uint(wo.y);
+    h *= 0x1b873593ull;
+    h ^= (uint64_t)(uint32_t)(__float_as_uint(wo.z) << 12);
+    h ^= (uint64_t)type1 << 24;
+    h ^= (uint64_t)vec1;
+    h *= 0xcc9e2d51ull;
+    h ^= (uint64_t)type2 << 28;
+    h ^= (uint64_t)vec2 << 4;
+    h *= 0x1b873593ull;
+    h = mix_bits(h);
+    return (float)(uint32_t)(h & 0xFFFFFFFFull) * 2.3283064365386963e-10f;
+}
+HK_DEV uint32_t resolve_mix_material(const HkMaterial* __restrict__ materials, uint32_t idx, float3 p, float3 wo) {
+    for (int it = 0; it < 8; it++) {
+        const HkMaterial& m = materials[idx - 1];
+        if (m.type != HK_MAT_MIX) return idx;
+        const float amt = m.f[0];
+        if (amt <= 0.0f) idx = (uint32_t)m.ival[0];
+        else if (amt >= 1.0f) idx = (uint32_t)m.ival[1];
+        else {
+            const float u = mix_hash_float(p, wo, m.flags & 0xFFu, (uint32_t)m.spec[0], (m.flags >> 8) & 0xFFu, (uint32_t)m.spec[1]);
+            idx = amt < u ? (uint32_t)m.ival[0] : (uint32_t)m.ival[1];
+        }
+    }
+    return idx;
+}
+// queue of a surface hit: the material type rides in the hit record; a MixMaterial is resolved here, at intersection time,
+// from the hit point and the outgoing direction (surface-eval.jl:162-168), and the chosen material is left for k_shade
+HK_DEV int hit_queue_id(const DevScene& D, const PathState& S, uint32_t slot, uint32_t hit_bits, float t_hit) {
+    uint32_t mtype = HK_HIT_MTYPE(hit_bits);
+    if (mtype == HK_MAT_MIX) {
+        const float4 ra = S.ray_a[slot], rb = S.ray_b[slot];
+        const float3 o = f3(ra.x, ra.y, ra.z), d = f3(ra.w, rb.x, rb.y);
+        const uint32_t prim0 = HK_HIT_PRIM1(hit_bits) - 1u;
+        const uint32_t mi = __ldg(D.tri_meta + 3 * (size_t)prim0);
+        const uint32_t res = resolve_mix_material(D.materials, D.interfaces[mi - 1].material, o + d * t_hit, -d);
+        S.res_mat[slot] = res;
+        mtype = (uint32_t)D.materials[res - 1].type;
+        if (mtype >= HK_MAX_MAT_TYPES) mtype = 0;      // a mix chain deeper than 8 levels: the reference would shade a MixMaterial (undefined); dropped
+    }
+    return HK_C_HIT0 + (int)mtype;
+}
+
 // writes the material type (1..7) of every BVH triangle into the spare word of its record (HitRec)
 __global__ void __launch_bounds__(256) k_patch_tri_types(float4* __restrict__ tris, uint32_t n_tris, const uint32_t* __restrict__ tri_meta,
                                                           const HkMediumInterface* __restrict__ interfaces, const HkMaterial* __restrict__ materials) {
@@ -295,10 +350,11 @@ __global__ void __launch_bounds__(256) k_route(const __grid_constant__ DevScene 
             qid[r] = -1; slot[r] = 0; pos[r] = 0;
             if (i < n) {
                 slot[r] = q[i];
-                const uint32_t hb = __float_as_uint(S.hit[slot[r]].y);
+                const float2 hty = *reinterpret_cast<const float2*>(&S.hit[slot[r]]);
+                const uint32_t hb = __float_as_uint(hty.y);
                 if (D.n_media > 0 && HK_FLAG_MEDIUM(S.flags[slot[r]]) != 0) qid[r] = HK_C_MEDIUM;
                 else if (HK_HIT_PRIM1(hb) == 0) qid[r] = HK_C_ESCAPED;
-                else qid[r] = HK_C_HIT0 + (int)HK_HIT_MTYPE(hb);
+                else qid[r] = hit_queue_id(D, S, slot[r], hb, hty.x);
             }
         }
 #pragma unroll
@@ -376,7 +432,7 @@ __global__ void __launch_bounds__(128, HK_SHADE_MIN_BLOCKS) k_shade(const __grid
             const float3 o = f3(ra.x, ra.y, ra.z), d = f3(ra.w, rb.x, rb.y);
             const Surf sf = surface_at(D, prim0, hr.z, hr.w, o, d, hr.x);
             const HkMediumInterface mi = D.interfaces[sf.iface - 1];
-            const HkMaterial& mat = D.materials[mi.material - 1];
+            const HkMaterial& mat = D.materials[(D.materials[mi.material - 1].type == HK_MAT_MIX ? S.res_mat[slot] : mi.material) - 1];
             const float4 lam = S.lambda[slot];
             const Spec beta = S.beta[slot], r_u = S.r_u[slot], r_l = S.r_l[slot];
             const uint32_t fl = S.flags[slot];
@@ -576,9 +632,10 @@ __global__ void __launch_bounds__(128) k_medium_finish(const __grid_constant__ D
                     }
                 }
             } else if (ev == HK_EV_SURVIVED) {
-                const uint32_t hb = __float_as_uint(S.hit[slot].y);
+                const float4 hr = S.hit[slot];
+                const uint32_t hb = __float_as_uint(hr.y);
                 if (!(sp_black(S.beta[slot]) || sp_black(S.r_u[slot]) || HK_FLAG_DEPTH(S.flags[slot]) >= D.max_depth))
-                    qid = HK_HIT_PRIM1(hb) ? HK_C_HIT0 + (int)HK_HIT_MTYPE(hb) : HK_C_ESCAPED;
+                    qid = HK_HIT_PRIM1(hb) ? hit_queue_id(D, S, slot, hb, hr.x) : HK_C_ESCAPED;
             }
         }
         warp_push(S.counts, nullptr, qid, slot, queue_of(S, qid));

@@ -262,6 +262,32 @@ class Material:
         raise NotImplementedError
 
 
+class MixMaterial(Material):
+    """src/materials/mix-material.jl:39-99: MixMaterial(materials=(m1, m2), amount=0.5).  Resolved to one of the two at
+    intersection time by a hash of (hit point, wo, SetKeys); `amount` is a constant here (textures: SURVEY 8f).
+    The reference takes the sub-materials' SetKeys explicitly (`material_indices`); the mirror derives them from the
+    scene: type_idx = position of the material's type in first-push order, vec_idx = position within that type."""
+    type = A.HK_MAT_MIX
+
+    def __init__(self, materials, amount=0.5):
+        assert len(materials) == 2 and all(isinstance(m, Material) for m in materials)
+        self.materials, self.amount = tuple(materials), float(amount)
+
+    def to_abi(self, scene):
+        m = A.HkMaterial(type=self.type)
+        m.f[0] = self.amount
+        keys = []
+        for k, sub in enumerate(self.materials):
+            m.ival[k] = scene._index_of(scene.materials, sub)
+            keys.append(scene.set_key(sub))
+        m.spec[0], m.spec[1] = keys[0][1], keys[1][1]
+        m.flags = keys[0][0] | (keys[1][0] << 8)
+        return m
+
+
+Mix = MixMaterial
+
+
 class MatteMaterial(Material):            # uber-material.jl:180-183, 256
     type = A.HK_MAT_MATTE
 
@@ -715,11 +741,28 @@ class Scene:
             mat, inside, outside = material.material, material.inside, material.outside
         else:
             mat, inside, outside = material, None, None
+        self._register_material(mat)
         mi = self._index_of(self.materials, mat)
         ii = 0 if inside is None else self._index_of(self.media, inside)
         oi = 0 if outside is None else self._index_of(self.media, outside)
         self.interfaces.append((mi, ii, oi))
         return len(self.interfaces)
+
+    def _register_material(self, mat):
+        """sub-materials of a MixMaterial are pushed before the mix itself (the reference needs their SetKeys first)"""
+        if isinstance(mat, MixMaterial):
+            for sub in mat.materials:
+                self._register_material(sub)
+        self._index_of(self.materials, mat)
+
+    def set_key(self, mat):
+        """SetKey (type_idx, vec_idx) of a pushed material, MultiTypeSet convention: type groups in first-push order"""
+        types = []
+        for m in self.materials:
+            if type(m) not in types:
+                types.append(type(m))
+        same = [m for m in self.materials if type(m) is type(mat)]
+        return types.index(type(mat)) + 1, [i for i, m in enumerate(same) if m is mat][0] + 1
 
     def push(self, obj, material=None, transform=None):
         """push!(scene, mesh, material; transform) / push!(scene, light)."""

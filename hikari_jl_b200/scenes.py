@@ -65,6 +65,24 @@ def c1_spheres(tess=64):
     return s, _cam((0, 1.5, 4), (0, 0.5, 0), 40.0)
 
 
+def mix_spheres(tess=32):
+    """c1_spheres with MixMaterials (mix-material.jl): a matte/mirror blend, a nested mix, and the amount = 0 / 1 ends."""
+    s = H.Scene()
+    red, green, blue = H.MatteMaterial(Kd=(0.8, 0.2, 0.2)), H.MatteMaterial(Kd=(0.2, 0.8, 0.2)), H.MatteMaterial(Kd=(0.2, 0.2, 0.8))
+    mirror, gold = H.MirrorMaterial(Kr=0.9), H.Gold(roughness=0.1)
+    inner = H.MixMaterial((green, gold), amount=0.35)
+    s.push(H.rect3((-5, -1, -5), (10, 0.1, 10)), H.MixMaterial((H.MatteMaterial(Kd=(0.7, 0.7, 0.7)), mirror), amount=0.25))
+    s.push(H.uv_sphere((-1.5, 0.5, 0.0), 0.8, tess, tess), H.MixMaterial((red, mirror), amount=0.5))
+    s.push(H.uv_sphere((0.0, 0.5, 0.0), 0.8, tess, tess), H.MixMaterial((inner, blue), amount=0.6))
+    s.push(H.uv_sphere((1.5, 0.5, 0.0), 0.8, tess, tess), H.MixMaterial((blue, red), amount=1.0))
+    s.push(H.uv_sphere((0.0, 1.9, 0.0), 0.4, tess, tess), H.MixMaterial((green, red), amount=0.0))
+    d = np.array([-1.0, -1.5, -0.5])
+    s.push(H.DirectionalLight((3, 3, 3), d / np.linalg.norm(d), legacy_rgbspectrum=True))
+    s.push(H.AmbientLight((0.2, 0.25, 0.3)))
+    s.sync()
+    return s, _cam((0, 1.5, 4), (0, 0.5, 0), 40.0)
+
+
 def blob_mesh(center, radius, n=256, seed=3):
     """Closed procedural stand-in for cat.obj: a sphere displaced by a few low-frequency harmonics."""
     m = H.uv_sphere((0, 0, 0), 1.0, n, n)

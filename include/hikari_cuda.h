@@ -89,6 +89,8 @@ typedef struct HkGeometry {
 #define HK_MAT_COATED_DIFFUSE       5   /* :1232-1937                                          */
 #define HK_MAT_THIN_DIELECTRIC      6   /* :1975-2051                                          */
 #define HK_MAT_DIFFUSE_TRANSMISSION 7   /* :2083-2218                                          */
+#define HK_MAT_MIX                  8   /* src/materials/mix-material.jl: resolved to one of its two sub-materials at
+                                           intersection time (resolve_mix_material :253-268), never shaded itself   */
 
 #define HK_MATFLAG_REMAP_ROUGHNESS  1u
 #define HK_MATFLAG_SPECTRAL_ETA_K   2u  /* conductor eta/k are piecewise-linear spectra (ids in spec[]) */
@@ -103,6 +105,9 @@ typedef struct HkMaterial {
                            CoatedDiffuse: f0=u_roughness f1=v_roughness f2=thickness f3=eta f4=g       */
     int32_t  spec[2];   /* 1-based ids into the uploaded piecewise-linear spectra (eta, k); 0 = unused  */
     int32_t  ival[2];   /* CoatedDiffuse: ival0=max_depth ival1=n_samples                               */
+                        /* Mix: f0 = amount (constant texture); ival0 / ival1 = 1-based material1 / material2;
+                           the SetKeys hashed by mix_hash_float (mix-material.jl:114-158): spec0 / spec1 = vec_idx of
+                           material1 / material2, flags = type_idx1 | type_idx2 << 8                             */
 } HkMaterial;
 
 typedef struct HkMediumInterface {   /* MediumInterfaceIdx, src/materials/medium-interface.jl:78-82 */

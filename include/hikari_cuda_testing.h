@@ -22,6 +22,8 @@ int32_t hk_test_sobol_mode(HkContext* ctx, int32_t fast);
 /* 0 / 1: disable / enable the per-pixel ZSobol prefix cache (applies at the next hk_set_params); returns the previous
  * setting.  Images must be bit-identical either way (tests/test_parity_gpu.py). */
 int32_t hk_test_sobol_cache(HkContext* ctx, int32_t on);
+/* in[n][10] = p, wo, type_idx1, vec_idx1, type_idx2, vec_idx2 -> mix_hash_float (src/materials/mix-material.jl:114-158) */
+int32_t hk_test_mix_hash(HkContext* ctx, const float* in, uint64_t n, float* out);
 /* v[n][3] -> pbrt_hash(Vec3f), mix_bits(hash), two pcg32 floats seeded (hash, mix) (spectral-eval.jl:575-815) */
 int32_t hk_test_hashes(HkContext* ctx, const float* v3, uint64_t n, uint64_t* out_hash, uint64_t* out_mix, float* out_pcg);
 /* u[n] -> lambda[n][4], pdf[n][4] (src/spectral/spectral.jl:221-249) */

@@ -375,5 +375,9 @@ int32_t ok_test_ratio_tracking(OkContext* c, uint32_t medium, const float* in, u
 }
 float ok_fresnel_dielectric(float c, float eta) { return fresnel_dielectric(c, eta); }
 float ok_fr_complex(float c, float eta, float k) { return fr_complex(c, eta, k); }
+// mix_hash_float, src/materials/mix-material.jl:114-158
+float ok_mix_hash_float(const float* p, const float* wo, uint32_t type1, uint32_t vec1, uint32_t type2, uint32_t vec2) {
+    return mix_hash_float(V3{p[0], p[1], p[2]}, V3{wo[0], wo[1], wo[2]}, type1, vec1, type2, vec2);
+}
 
 }  // extern "C"

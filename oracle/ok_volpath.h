@@ -10,6 +10,7 @@
 #include "ok_lights.h"
 #include "ok_accel.h"
 #include "ok_media.h"
+#include <cstring>
 #include <vector>
 #include <string>
 
@@ -223,6 +224,48 @@ struct Scene {
     void render_sample(int32_t sample_idx);   // render!, volpath.jl:445-636
     void trace_shadow(const ShadowWork& w);
 };
+
+// ---- MixMaterial, src/materials/mix-material.jl ------------------------------------------------------
+// mix_hash_float :114-158 (the UInt32 shifts truncate, the SetKey shifts are 64-bit), choose_material :178-196 with a
+// constant `amount`, resolve_mix_material :253-268 (at most 8 levels).
+inline float mix_hash_float(V3 p, V3 wo, uint32_t type1, uint32_t vec1, uint32_t type2, uint32_t vec2) {
+    auto fb = [](float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; };
+    uint64_t h = 0;
+    h ^= (uint64_t)fb(p.x);
+    h *= 0xcc9e2d51ull;
+    h ^= (uint64_t)(uint32_t)(fb(p.y) << 4);
+    h *= 0x1b873593ull;
+    h ^= (uint64_t)(uint32_t)(fb(p.z) << 8);
+    h ^= (uint64_t)(uint32_t)(fb(wo.x) << 16);
+    h *= 0xcc9e2d51ull;
+    h ^= (uint64_t)fb(wo.y);
+    h *= 0x1b873593ull;
+    h ^= (uint64_t)(uint32_t)(fb(wo.z) << 12);
+    h ^= (uint64_t)type1 << 24;
+    h ^= (uint64_t)vec1;
+    h *= 0xcc9e2d51ull;
+    h ^= (uint64_t)type2 << 28;
+    h ^= (uint64_t)vec2 << 4;
+    h *= 0x1b873593ull;
+    h ^= h >> 31; h *= 0x7fb5d329728ea185ull;
+    h ^= h >> 27; h *= 0x81dadef4bc2dd44dull;
+    h ^= h >> 33;
+    return (float)(uint32_t)(h & 0xFFFFFFFFull) * 2.3283064365386963e-10f;
+}
+inline uint32_t resolve_mix_material(const std::vector<HkMaterial>& materials, uint32_t idx, V3 p, V3 wo) {
+    for (int it = 0; it < 8; it++) {
+        const HkMaterial& m = materials[idx - 1];
+        if (m.type != HK_MAT_MIX) return idx;
+        const float amt = m.f[0];
+        if (amt <= 0.0f) idx = (uint32_t)m.ival[0];
+        else if (amt >= 1.0f) idx = (uint32_t)m.ival[1];
+        else {
+            const float u = mix_hash_float(p, wo, m.flags & 0xFFu, (uint32_t)m.spec[0], (m.flags >> 8) & 0xFFu, (uint32_t)m.spec[1]);
+            idx = amt < u ? (uint32_t)m.ival[0] : (uint32_t)m.ival[1];
+        }
+    }
+    return idx;
+}
 
 // ---- russian_roulette_spectral, material-dispatch.jl:263-287 ------------------------------------
 inline bool russian_roulette(Spec& beta, int32_t depth, float rr) {
@@ -478,7 +521,7 @@ inline void Scene::render_sample(int32_t sample_idx) {
             for (int64_t i = 0; i < n_hits; i++) {
                 const HitSurfaceWork& w = hit_surface_queue[i];
                 V3 wo = -w.ray.d;
-                uint32_t material_idx = w.material;   // resolve_mix_material: no MixMaterial in scope
+                uint32_t material_idx = resolve_mix_material(materials, w.material, w.g.pi, wo);   // mix-material.jl:253-268
                 if (w.arealight_flat_idx > 0) {
                     const HkLight& L = lights[w.arealight_flat_idx - 1];
                     Spec Le = arealight_Le(LC, L, wo, w.g.n, w.lambda);

