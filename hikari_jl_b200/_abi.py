@@ -109,7 +109,7 @@ class HkStats(C.Structure):
 # every symbol include/hikari_cuda.h declares (checked by tests/test_abi.py)
 HK_SYMBOLS = [
     "hk_abi_version", "hk_create", "hk_destroy", "hk_last_error", "hk_upload_tables", "hk_upload_geometry",
-    "hk_upload_spectra", "hk_upload_materials", "hk_upload_envmaps", "hk_upload_lights", "hk_upload_media",
+    "hk_upload_spectra", "hk_upload_materials", "hk_update_material", "hk_bounce_profile", "hk_upload_envmaps", "hk_upload_lights", "hk_upload_media",
     "hk_set_camera", "hk_set_filter", "hk_set_params", "hk_clear", "hk_render_samples", "hk_render_samples_strided",
     "hk_read_film", "hk_film_accum_dev", "hk_read_accum", "hk_write_accum", "hk_trace_closest",
     "hk_trace_closest_dev", "hk_trace_any", "hk_stats", "hk_synchronize", "hk_dev_alloc", "hk_dev_free",
@@ -132,6 +132,7 @@ def bind_common(lib, p):
     f("upload_geometry", [_VP, C.POINTER(HkGeometry)])
     f("upload_spectra", [_VP, C.POINTER(HkSpectra)])
     f("upload_materials", [_VP, C.POINTER(HkMaterial), C.c_uint32, C.POINTER(HkMediumInterface), C.c_uint32])
+    f("update_material", [_VP, C.c_uint32, C.POINTER(HkMaterial)])
     f("upload_envmaps", [_VP, C.POINTER(HkEnvMap), C.c_uint32])
     f("upload_lights", [_VP, C.POINTER(HkLight), C.c_uint32, C.POINTER(HkLightSampler)])
     f("upload_media", [_VP, C.POINTER(HkMedium), C.c_uint32])

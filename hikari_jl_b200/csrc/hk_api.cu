@@ -36,6 +36,7 @@ struct HkContext {
     bool camera_medium_valid = false; uint32_t camera_medium = 0;
     uint32_t mat_types_present = 0;
     uint32_t n_interfaces = 0, max_iface_in_geom = 0; bool tri_types_valid = false;
+    std::vector<int32_t> mat_types;                  // host copy of the material types (hk_update_material)
     // device buffers
     DevBuf b_sobol, b_cie_x, b_cie_y, b_cie_z, b_d65, b_rgb_scale, b_rgb_coeffs;
     DevBuf b_nodes, b_tris, b_pos, b_nrm, b_idx, b_meta;
@@ -240,9 +241,32 @@ int32_t hk_upload_materials(HkContext* ctx, const HkMaterial* m, uint32_t nm, co
     CK(ctx->b_mats.upload(m, sizeof(HkMaterial) * (size_t)nm)); CK(ctx->b_ifaces.upload(mi, sizeof(HkMediumInterface) * (size_t)ni));
     ctx->D.materials = ctx->b_mats.as<HkMaterial>(); ctx->D.interfaces = ctx->b_ifaces.as<HkMediumInterface>();
     ctx->D.any_medium_transition = trans; ctx->mat_types_present = present; ctx->n_interfaces = ni;
+    ctx->mat_types.resize(nm); for (uint32_t i = 0; i < nm; i++) ctx->mat_types[i] = m[i].type;
     if (!ctx->b_spec_o.p) { uint32_t zero = 0; CK(ctx->b_spec_o.upload(&zero, 4)); ctx->D.spec_offsets = ctx->b_spec_o.as<uint32_t>(); }
     ctx->have_mats = true; ctx->camera_medium_valid = false;
     return patch_tri_types(ctx);
+}
+
+// update_material!(scene, idx, new_material), src/scene.jl:109-112: replace ONE material in place (RayMakie's interactive
+// mode edits materials between frames); no re-upload of the scene.  index is 1-based into the uploaded material array.
+int32_t hk_update_material(HkContext* ctx, uint32_t index, const HkMaterial* m) {
+    if (!ctx || !m) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    REQUIRE(ctx->have_mats, "hk_upload_materials has not been called");
+    REQUIRE(index >= 1 && index <= ctx->mat_types.size(), "material index out of range");
+    REQUIRE((m->type >= 1 && m->type < HK_MAX_MAT_TYPES) || m->type == HK_MAT_MIX, "unsupported material type");
+    if (m->type == HK_MAT_MIX) REQUIRE(m->ival[0] >= 1 && (size_t)m->ival[0] <= ctx->mat_types.size() && m->ival[1] >= 1 && (size_t)m->ival[1] <= ctx->mat_types.size(), "MixMaterial references a missing material");
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(ctx->b_mats.as<HkMaterial>() + (index - 1), m, sizeof(HkMaterial), cudaMemcpyHostToDevice));
+    const bool type_changed = ctx->mat_types[index - 1] != m->type;
+    ctx->mat_types[index - 1] = m->type;
+    if (type_changed) {
+        uint32_t present = 0;
+        for (int32_t t : ctx->mat_types) if (t != HK_MAT_MIX) present |= 1u << t;
+        ctx->mat_types_present = present;
+        return patch_tri_types(ctx);      // the material type rides in the BVH triangle records
+    }
+    return HK_OK;
 }
 
 int32_t hk_upload_envmaps(HkContext* ctx, const HkEnvMap* maps, uint32_t n) {

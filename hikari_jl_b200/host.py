@@ -1019,6 +1019,16 @@ class VolPath:
             self.state = key
         self.backend.set_camera(camera)
 
+    def update_material(self, scene, interface_idx, new_material):
+        """update_material!(scene, idx, new_material), src/scene.jl:109-112: replace the material behind medium interface
+        `interface_idx` (what push! returned) in place; the prepared backend gets the one struct, not the scene."""
+        mi, _, _ = scene.interfaces[interface_idx - 1]
+        assert not isinstance(new_material, MixMaterial), "replace the sub-materials of a mix, not the mix slot"
+        scene.materials[mi - 1] = new_material
+        if self.backend is not None and self.state is not None:
+            abi = new_material.to_abi(scene)
+            self.backend.call("update_material", mi, C.byref(abi))
+
     def clear(self):
         """clear!(vp), volpath.jl:108-113"""
         if self.state is not None:

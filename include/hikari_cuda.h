@@ -286,6 +286,9 @@ int32_t hk_upload_geometry(HkContext* ctx, const HkGeometry* geom);
 int32_t hk_upload_spectra(HkContext* ctx, const HkSpectra* spectra);
 int32_t hk_upload_materials(HkContext* ctx, const HkMaterial* materials, uint32_t n_materials,
                             const HkMediumInterface* interfaces, uint32_t n_interfaces);
+/* update_material!(scene, idx, new_material), src/scene.jl:109-112: replace one uploaded material in place (1-based
+ * index into the material array); the scene is not re-uploaded.  A change of material type re-tags the BVH triangles. */
+int32_t hk_update_material(HkContext* ctx, uint32_t index, const HkMaterial* material);
 int32_t hk_upload_envmaps(HkContext* ctx, const HkEnvMap* maps, uint32_t n_maps);
 int32_t hk_upload_lights(HkContext* ctx, const HkLight* lights, uint32_t n_lights,
                          const HkLightSampler* sampler);

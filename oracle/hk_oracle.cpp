@@ -76,6 +76,11 @@ int32_t ok_upload_materials(OkContext* c, const HkMaterial* m, uint32_t nm, cons
     if (c->s.spec_offsets.empty()) { c->s.spec_offsets.assign(1, 0); c->s.spectra = HkSpectra{nullptr, nullptr, c->s.spec_offsets.data(), 0}; }
     return 0;
 }
+int32_t ok_update_material(OkContext* c, uint32_t index, const HkMaterial* m) {   // update_material!, scene.jl:109-112
+    if (index < 1 || index > c->s.materials.size()) return -1;
+    c->s.materials[index - 1] = *m;
+    return 0;
+}
 int32_t ok_upload_envmaps(OkContext* c, const HkEnvMap* maps, uint32_t n) {
     Scene& s = c->s;
     s.envmaps.assign(maps, maps + n); s.env_store.clear(); s.env_store.reserve(6 * (size_t)n);

@@ -403,6 +403,39 @@ def test_sobol_prefix_cache_is_bitwise_invariant():
         assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
 
 
+def test_update_material_in_place():
+    """update_material!(scene, idx, new_material) (scene.jl:109-112): one struct goes to the device, the BVH stays; the
+    next render must equal a fresh render of the scene built with the new material -- including a type change, which
+    re-tags the triangles' routing type, and on the oracle (ok_update_material) as well."""
+    import oracle_backend
+
+    def build(mat):
+        s = H.Scene()
+        s.push(H.rect3((-5, -1, -5), (10, 0.1, 10)), H.MatteMaterial(Kd=(0.7, 0.7, 0.7)))
+        handle = s.push_material(mat)
+        s.meshes.append((H.uv_sphere((0.0, 0.5, 0.0), 0.8, 16, 16), None, handle, None))
+        s.push(H.PointLight((8, 8, 8), (2, 4, 3)))
+        s.sync()
+        return s, handle
+
+    from hikari_jl_b200.scenes import _cam
+    camf = _cam((0, 1.5, 4), (0, 0.5, 0), 40.0)
+    res = (64, 48)
+    old, new_same_type, new_other_type = H.MatteMaterial(Kd=(0.8, 0.2, 0.2)), H.MatteMaterial(Kd=(0.1, 0.3, 0.9)), H.MirrorMaterial(Kr=0.9)
+    for new in (new_same_type, new_other_type):
+        for make_backend in (None, oracle_backend.make_backend):
+            fresh_scene, _ = build(new)
+            f0 = H.Film(res); v0 = H.VolPath(samples=3, max_depth=4, backend=make_backend() if make_backend else None)
+            want = v0(fresh_scene, f0, camf(f0)).copy(); v0.close()
+            scene, handle = build(old)
+            f1 = H.Film(res); v1 = H.VolPath(samples=3, max_depth=4, backend=make_backend() if make_backend else None)
+            before = v1(scene, f1, camf(f1)).copy()
+            assert not np.array_equal(before, want)
+            v1.update_material(scene, handle, new)
+            got = v1(scene, f1, camf(f1)).copy(); v1.close()
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
 def test_strided_partition_sums_to_the_full_render():
     """The multi-GPU partition (hk_render_samples_strided, SURVEY 8e): two contexts render disjoint sample indices;
     the summed accumulators equal the single-context film within f32 summation-order tolerance."""
