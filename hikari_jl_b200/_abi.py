@@ -26,6 +26,11 @@ class HkTables(C.Structure):
                 ("rgb2spec_res", C.c_int32), ("rgb2spec_scale", c_fp), ("rgb2spec_coeffs", c_fp)]
 
 
+class HkPostprocess(C.Structure):
+    _fields_ = [("exposure", c_f), ("tonemap_mode", C.c_int32), ("inv_gamma", c_f), ("apply_gamma", C.c_int32),
+                ("white_point", c_f), ("imaging_ratio", c_f), ("apply_wb", C.c_int32), ("wb", c_f * 9)]
+
+
 class HkGeometry(C.Structure):
     _fields_ = [("positions", c_fp), ("normals", c_fp), ("tangents", c_fp), ("uvs", c_fp), ("indices", c_u32p),
                 ("tri_meta", c_u32p), ("n_verts", C.c_uint32), ("n_tris", C.c_uint32)]
@@ -111,7 +116,7 @@ HK_SYMBOLS = [
     "hk_abi_version", "hk_create", "hk_destroy", "hk_last_error", "hk_upload_tables", "hk_upload_geometry",
     "hk_upload_spectra", "hk_upload_materials", "hk_update_material", "hk_bounce_profile", "hk_upload_envmaps", "hk_upload_lights", "hk_upload_media",
     "hk_set_camera", "hk_set_filter", "hk_set_params", "hk_clear", "hk_render_samples", "hk_render_samples_strided",
-    "hk_read_film", "hk_film_accum_dev", "hk_read_accum", "hk_write_accum", "hk_trace_closest",
+    "hk_read_film", "hk_postprocess", "hk_film_accum_dev", "hk_read_accum", "hk_write_accum", "hk_trace_closest",
     "hk_trace_closest_dev", "hk_trace_any", "hk_stats", "hk_synchronize", "hk_dev_alloc", "hk_dev_free",
     "hk_dev_upload", "hk_dev_download", "hk_set_profiling", "hk_stage_times", "hk_pinned_alloc", "hk_pinned_free",
 ]
@@ -133,6 +138,7 @@ def bind_common(lib, p):
     f("upload_spectra", [_VP, C.POINTER(HkSpectra)])
     f("upload_materials", [_VP, C.POINTER(HkMaterial), C.c_uint32, C.POINTER(HkMediumInterface), C.c_uint32])
     f("update_material", [_VP, C.c_uint32, C.POINTER(HkMaterial)])
+    f("postprocess", [_VP, C.POINTER(HkPostprocess), c_fp])
     f("upload_envmaps", [_VP, C.POINTER(HkEnvMap), C.c_uint32])
     f("upload_lights", [_VP, C.POINTER(HkLight), C.c_uint32, C.POINTER(HkLightSampler)])
     f("upload_media", [_VP, C.POINTER(HkMedium), C.c_uint32])

@@ -607,6 +607,19 @@ int32_t hk_read_film(HkContext* ctx, float* out) {
     CK(cudaStreamSynchronize(ctx->stream));
     return HK_OK;
 }
+int32_t hk_postprocess(HkContext* ctx, const HkPostprocess* p, float* out) {
+    if (!ctx || !p || !out) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    REQUIRE(ctx->have_params, "hk_set_params has not been called");
+    REQUIRE(p->tonemap_mode >= HK_TONEMAP_NONE && p->tonemap_mode <= HK_TONEMAP_FILMIC, "unknown tonemap mode");
+    const size_t n = (size_t)ctx->params.width * ctx->params.height;
+    if (ctx->b_readback.bytes < 12 * n) CK(ctx->b_readback.alloc(12 * n));
+    k_film_postprocess<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(ctx->S.pixel_rgb, ctx->S.pixel_weight, ctx->b_readback.as<float>(), ctx->params.width, ctx->params.height, *p);
+    ctx->launches++;
+    CK(cudaMemcpyAsync(out, ctx->b_readback.p, 12 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return HK_OK;
+}
 // pinned host memory for film.framebuffer (the Julia shim would use CUDA.pin / cudaHostRegister on the Film's array)
 int32_t hk_pinned_alloc(uint64_t bytes, void** out) {
     if (!out) return HK_ERR_INVALID;

@@ -821,6 +821,56 @@ __global__ void __launch_bounds__(256) k_film_finalize(const float* __restrict__
     }
 }
 
+
+// ---- postprocess!, src/postprocess.jl:55-182, 187-230 (per pixel) --------------------------------------------------------
+HK_DEV float pp_clamp01(float v) { return v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v); }
+HK_DEV float pp_uncharted2(float x) {
+    const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
+    return ((x * (A * x + C * B) + D * E) / (x * (A * x + B) + D * F)) - E / F;
+}
+HK_DEV float pp_filmic(float x) { x = fmaxf(0.0f, x - 0.004f); return (x * (6.2f * x + 0.5f)) / (x * (6.2f * x + 1.7f) + 0.06f); }
+HK_DEV float pp_aces(float x) { return pp_clamp01((x * (2.51f * x + 0.03f)) / (x * (2.43f * x + 0.59f) + 0.14f)); }
+HK_DEV float3 postprocess_pixel(const HkPostprocess& P, float3 c) {
+    float r = c.x * P.exposure, g = c.y * P.exposure, b = c.z * P.exposure;
+    if (P.apply_wb) {
+        const float ro = P.wb[0] * r + P.wb[1] * g + P.wb[2] * b, go = P.wb[3] * r + P.wb[4] * g + P.wb[5] * b, bo = P.wb[6] * r + P.wb[7] * g + P.wb[8] * b;
+        r = fmaxf(0.0f, ro); g = fmaxf(0.0f, go); b = fmaxf(0.0f, bo);
+    }
+    r = r * P.imaging_ratio; g = g * P.imaging_ratio; b = b * P.imaging_ratio;
+    switch (P.tonemap_mode) {
+        case HK_TONEMAP_REINHARD: {
+            const float lum = 0.2126f * r + 0.7152f * g + 0.0722f * b;
+            const float s = lum > 0.0f ? 1.0f / (1.0f + lum) : 1.0f;
+            r = pp_clamp01(r * s); g = pp_clamp01(g * s); b = pp_clamp01(b * s); break; }
+        case HK_TONEMAP_REINHARD_EXT: {
+            const float lum = 0.2126f * r + 0.7152f * g + 0.0722f * b;
+            const float lw2 = P.white_point * P.white_point;
+            const float s = lum > 0.0f ? (1.0f + lum / lw2) / (1.0f + lum) : 1.0f;
+            r = pp_clamp01(r * s); g = pp_clamp01(g * s); b = pp_clamp01(b * s); break; }
+        case HK_TONEMAP_ACES: r = pp_aces(r); g = pp_aces(g); b = pp_aces(b); break;
+        case HK_TONEMAP_UNCHARTED2: {
+            const float ws = 1.0f / pp_uncharted2(11.2f);
+            r = pp_clamp01(pp_uncharted2(r * 2.0f) * ws); g = pp_clamp01(pp_uncharted2(g * 2.0f) * ws); b = pp_clamp01(pp_uncharted2(b * 2.0f) * ws); break; }
+        case HK_TONEMAP_FILMIC: r = pp_filmic(r); g = pp_filmic(g); b = pp_filmic(b); break;
+        default: r = pp_clamp01(r); g = pp_clamp01(g); b = pp_clamp01(b); break;
+    }
+    if (P.apply_gamma) { r = powf(r, P.inv_gamma); g = powf(g, P.inv_gamma); b = powf(b, P.inv_gamma); }
+    return f3(r, g, b);
+}
+// framebuffer = sum / weight -> postprocess_pixel, same (H, W) column-major layout as k_film_finalize
+__global__ void __launch_bounds__(256) k_film_postprocess(const float* __restrict__ rgb, const float* __restrict__ wsum, float* __restrict__ out, int W, int H, HkPostprocess P) {
+    const uint32_t n = (uint32_t)W * (uint32_t)H;
+    for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < n; pix += gridDim.x * blockDim.x) {
+        const uint32_t px = pix % (uint32_t)W, py = pix / (uint32_t)W;
+        const float w = wsum[pix];
+        float3 c = f3(0.0f, 0.0f, 0.0f);
+        if (w > 0.0f) { float inv = 1.0f / w; c = f3(rgb[3 * (size_t)pix] * inv, rgb[3 * (size_t)pix + 1] * inv, rgb[3 * (size_t)pix + 2] * inv); }
+        c = postprocess_pixel(P, c);
+        float* o = out + ((size_t)px * H + py) * 3;
+        o[0] = c.x; o[1] = c.y; o[2] = c.z;
+    }
+}
+
 // stand-alone traversal: rays [n][8] -> hits [n][4]   (hk_trace_closest / hk_trace_any)
 template <bool ANY>
 struct BatchRayIO {

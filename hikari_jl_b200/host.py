@@ -107,6 +107,74 @@ class Film:
         self.iteration_index = 0
 
 
+class FilmSensor:
+    """src/postprocess.jl:37-47: FilmSensor(iso=100, exposure_time=1.0, white_balance=0)"""
+
+    def __init__(self, iso=100.0, exposure_time=1.0, white_balance=0.0):
+        self.iso, self.exposure_time, self.white_balance = f32(iso), f32(exposure_time), f32(white_balance)
+
+
+def planckian_xy(T):
+    """src/spectral/color.jl:469-493 (CIE 015:2004), Float32 arithmetic"""
+    T = f32(T); T2 = f32(T * T); T3 = f32(T2 * T)
+    if T <= f32(4000):
+        x = f32(f32(f32(f32(-0.2661239e9) / T3) - f32(f32(0.2343589e6) / T2)) + f32(f32(0.8776956e3) / T)) + f32(0.179910)
+    else:
+        x = f32(f32(f32(f32(-3.0258469e9) / T3) + f32(f32(2.1070379e6) / T2)) + f32(f32(0.2226347e3) / T)) + f32(0.240390)
+    x = f32(x); x2 = f32(x * x); x3 = f32(x2 * x)
+    if T <= f32(2222):
+        c = (-1.1063814, -1.34811020, 2.18555832, -0.20219683)
+    elif T <= f32(4000):
+        c = (-0.9549476, -1.37418593, 2.09137015, -0.16748867)
+    else:
+        c = (3.0817580, -5.87338670, 3.75112997, -0.37001483)
+    y = f32(f32(f32(f32(f32(c[0]) * x3) + f32(f32(c[1]) * x2)) + f32(f32(c[2]) * x)) + f32(c[3]))
+    return x, y
+
+
+def compute_white_balance_matrix(src_temp):
+    """src/spectral/color.jl:522-546: Bradford adaptation from a Planckian source at src_temp K to D65 (3x3, Float32)"""
+    lms_from_xyz = np.array([[0.8951, 0.2664, -0.1614], [-0.7502, 1.7135, 0.0367], [0.0389, -0.0685, 1.0296]], dtype=f32)
+    xyz_from_lms = np.array([[0.9869929, -0.1470543, 0.1599627], [0.4323053, 0.5183603, 0.0492912], [-0.0085287, 0.0400428, 0.9684867]], dtype=f32)
+
+    def xy_to_xyz(x, y):
+        return np.array([f32(x / y), f32(1.0), f32(f32(f32(f32(1.0) - x) - y) / y)], dtype=f32)
+
+    src = lms_from_xyz @ xy_to_xyz(*planckian_xy(src_temp))
+    dst = lms_from_xyz @ xy_to_xyz(f32(0.31272), f32(0.32903))
+    scale = np.diag((dst / src).astype(f32)).astype(f32)
+    return ((xyz_from_lms @ scale).astype(f32) @ lms_from_xyz).astype(f32)
+
+
+TONEMAP_MODES = {None: 0, "none": 0, "reinhard": 1, "reinhard_extended": 2, "aces": 3, "uncharted2": 4, "filmic": 5}
+
+
+def postprocess(film, vp, exposure=1.0, tonemap="aces", gamma=2.2, white_point=4.0, sensor=None, background=None):
+    """postprocess!(film; exposure, tonemap, gamma, white_point, sensor), src/postprocess.jl:281-357.  Non-destructive:
+    reads the accumulated film of `vp`'s backend, writes film.postprocess ([py, px] like film.framebuffer).  The reference
+    reads film.framebuffer; here the division by the weight sum is fused into the same pass (hk_postprocess)."""
+    if background is not None:
+        raise NotImplementedError("background masking needs the auxiliary depth buffer (fill_aux_buffers!, SURVEY 8f)")
+    if tonemap not in TONEMAP_MODES:
+        raise ValueError(f"unknown tonemap {tonemap!r}")
+    sensor = sensor if sensor is not None else FilmSensor()
+    p = A.HkPostprocess()
+    p.exposure = float(f32(exposure)); p.tonemap_mode = TONEMAP_MODES[tonemap]
+    p.apply_gamma = 0 if gamma is None else 1
+    p.inv_gamma = 1.0 if gamma is None else float(f32(1.0) / f32(gamma))
+    p.white_point = float(f32(white_point))
+    p.imaging_ratio = float(f32(f32(sensor.exposure_time * sensor.iso) / f32(100.0)))
+    p.apply_wb = 1 if sensor.white_balance > 0 else 0
+    wb = compute_white_balance_matrix(sensor.white_balance) if p.apply_wb else np.eye(3, dtype=f32)
+    p.wb[:] = [float(v) for v in wb.reshape(-1)]
+    w, h = film.resolution
+    if getattr(film, "_pp_store", None) is None:
+        film._pp_store = np.zeros((w, h, 3), dtype=f32)
+        film.postprocess = film._pp_store.transpose(1, 0, 2)
+    vp.backend.call("postprocess", C.byref(p), _fp(film._pp_store))
+    return film.postprocess
+
+
 class PerspectiveCamera:
     """src/camera/perspective.jl:41-91.  `screen_window=None` picks the aspect-correct window (shorter axis
     spans [-1,1]); pass ((-1,-1),(1,1)) for the reference convenience constructor's literal window (:84)."""

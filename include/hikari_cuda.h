@@ -309,6 +309,28 @@ int32_t hk_render_samples_strided(HkContext* ctx, int32_t first_sample_idx, int3
 /* replaces: vp_finalize_film_kernel! + host read of film.framebuffer (volpath.jl:384-417).
  * Writes RGB{Float32} in the reference's (H, W) column-major layout: out[((px-1)*H + (py-1))*3 + c]. */
 int32_t hk_read_film(HkContext* ctx, float* out_rgb_hw_colmajor);
+
+/* postprocess!(film; exposure, tonemap, gamma, white_point, sensor), src/postprocess.jl:187-357 -- fused into the film
+ * read-out: framebuffer = sum / weight, then exposure, Bradford white balance, sensor imaging ratio, tone map, gamma.
+ * Same (H, W) column-major RGB layout as hk_read_film.  The escaped-ray background mask needs the auxiliary depth
+ * buffer (fill_aux_buffers!) and is not offered.                                                         */
+#define HK_TONEMAP_NONE         0   /* linear clamp                          postprocess.jl:160-182 */
+#define HK_TONEMAP_REINHARD     1
+#define HK_TONEMAP_REINHARD_EXT 2
+#define HK_TONEMAP_ACES         3
+#define HK_TONEMAP_UNCHARTED2   4
+#define HK_TONEMAP_FILMIC       5
+typedef struct HkPostprocess {
+    float   exposure;
+    int32_t tonemap_mode;
+    float   inv_gamma;      /* 1 / gamma                                                             */
+    int32_t apply_gamma;    /* 0: gamma = nothing                                                    */
+    float   white_point;    /* extended Reinhard                                                     */
+    float   imaging_ratio;  /* sensor.exposure_time * sensor.iso / 100                               */
+    int32_t apply_wb;       /* sensor.white_balance > 0                                              */
+    float   wb[9];          /* compute_white_balance_matrix(T), row-major (spectral/color.jl:522-546) */
+} HkPostprocess;
+int32_t hk_postprocess(HkContext* ctx, const HkPostprocess* params, float* out_rgb_hw_colmajor);
 /* raw accumulators for the multi-GPU film reduce (pixel_rgb ‖ pixel_weight_sum, volpath-state.jl):
  * device pointer to [n*3] rgb sums followed by [n] weight sums, valid until the next hk_set_params. */
 int32_t hk_film_accum_dev(HkContext* ctx, float** out_accum_dev, uint64_t* out_count);

@@ -161,12 +161,62 @@ int32_t ok_read_film(OkContext* c, float* out) {
     }
     return 0;
 }
+// postprocess!, src/postprocess.jl:55-182 (tone maps), :187-230 (per-pixel kernel), fused with the film read-out like
+// hk_postprocess.  Plain scalar C++ restatement; libm powf for the gamma.
+static float pp_clamp01(float v) { return v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v); }
+static float pp_uncharted2(float x) {
+    const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
+    return ((x * (A * x + C * B) + D * E) / (x * (A * x + B) + D * F)) - E / F;
+}
+static float pp_filmic(float x) { x = std::max(0.0f, x - 0.004f); return (x * (6.2f * x + 0.5f)) / (x * (6.2f * x + 1.7f) + 0.06f); }
+static float pp_aces(float x) { return pp_clamp01((x * (2.51f * x + 0.03f)) / (x * (2.43f * x + 0.59f) + 0.14f)); }
+int32_t ok_postprocess(OkContext* c, const HkPostprocess* P, float* out) {
+    Scene& s = c->s;
+    const int W = s.params.width, H = s.params.height;
+    for (int64_t p = 0; p < (int64_t)W * H; p++) {
+        int px = (int)(p % W), py = (int)(p / W);
+        float ws = s.pixel_weight_sum[p];
+        float r = 0, g = 0, b = 0;
+        if (ws > 0.0f) { float inv = 1.0f / ws; r = s.pixel_rgb[3 * p] * inv; g = s.pixel_rgb[3 * p + 1] * inv; b = s.pixel_rgb[3 * p + 2] * inv; }
+        r *= P->exposure; g *= P->exposure; b *= P->exposure;
+        if (P->apply_wb) {
+            const float* m = P->wb;
+            float ro = m[0] * r + m[1] * g + m[2] * b, go = m[3] * r + m[4] * g + m[5] * b, bo = m[6] * r + m[7] * g + m[8] * b;
+            r = std::max(0.0f, ro); g = std::max(0.0f, go); b = std::max(0.0f, bo);
+        }
+        r *= P->imaging_ratio; g *= P->imaging_ratio; b *= P->imaging_ratio;
+        switch (P->tonemap_mode) {
+            case HK_TONEMAP_REINHARD: {
+                float lum = 0.2126f * r + 0.7152f * g + 0.0722f * b, sc = lum > 0.0f ? 1.0f / (1.0f + lum) : 1.0f;
+                r = pp_clamp01(r * sc); g = pp_clamp01(g * sc); b = pp_clamp01(b * sc); break; }
+            case HK_TONEMAP_REINHARD_EXT: {
+                float lum = 0.2126f * r + 0.7152f * g + 0.0722f * b, lw2 = P->white_point * P->white_point;
+                float sc = lum > 0.0f ? (1.0f + lum / lw2) / (1.0f + lum) : 1.0f;
+                r = pp_clamp01(r * sc); g = pp_clamp01(g * sc); b = pp_clamp01(b * sc); break; }
+            case HK_TONEMAP_ACES: r = pp_aces(r); g = pp_aces(g); b = pp_aces(b); break;
+            case HK_TONEMAP_UNCHARTED2: {
+                float wsc = 1.0f / pp_uncharted2(11.2f);
+                r = pp_clamp01(pp_uncharted2(r * 2.0f) * wsc); g = pp_clamp01(pp_uncharted2(g * 2.0f) * wsc); b = pp_clamp01(pp_uncharted2(b * 2.0f) * wsc); break; }
+            case HK_TONEMAP_FILMIC: r = pp_filmic(r); g = pp_filmic(g); b = pp_filmic(b); break;
+            default: r = pp_clamp01(r); g = pp_clamp01(g); b = pp_clamp01(b); break;
+        }
+        if (P->apply_gamma) { r = std::pow(r, P->inv_gamma); g = std::pow(g, P->inv_gamma); b = std::pow(b, P->inv_gamma); }
+        float* o = out + ((size_t)px * H + py) * 3;
+        o[0] = r; o[1] = g; o[2] = b;
+    }
+    return 0;
+}
 int32_t ok_read_accum(OkContext* c, float* rgb, float* w) {
     std::memcpy(rgb, c->s.pixel_rgb.data(), c->s.pixel_rgb.size() * 4);
     std::memcpy(w, c->s.pixel_weight_sum.data(), c->s.pixel_weight_sum.size() * 4);
     return 0;
 }
 // last sample pass' spectral buffer + per-pixel wavelengths (for stage-level parity checks)
+int32_t ok_write_accum(OkContext* c, const float* rgb, const float* w) {    // test hook: same film state on both paths
+    const size_t n = (size_t)c->s.params.width * c->s.params.height;
+    std::memcpy(c->s.pixel_rgb.data(), rgb, 12 * n); std::memcpy(c->s.pixel_weight_sum.data(), w, 4 * n);
+    return 0;
+}
 int32_t ok_read_pixel_L(OkContext* c, float* L, float* lambda, float* pdf, float* fw) {
     Scene& s = c->s;
     std::memcpy(L, s.pixel_L.data(), s.pixel_L.size() * 4); std::memcpy(lambda, s.wavelengths.data(), s.wavelengths.size() * 4);

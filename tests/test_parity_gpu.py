@@ -403,6 +403,37 @@ def test_sobol_prefix_cache_is_bitwise_invariant():
         assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
 
 
+def test_postprocess_matches_oracle():
+    """postprocess! (src/postprocess.jl) fused into the film read-out: every tone map, gamma on / off, sensor ISO and
+    Bradford white balance, on the SAME accumulated film (the CUDA render's accumulators are copied into the oracle).
+    Bit-exact without gamma (mul/add/div only); with gamma the two powf implementations may differ in the last bits
+    (tolerance 4e-6 absolute on [0,1] values)."""
+    import oracle_backend
+    scene, camf = scenes.c1_spheres(16)
+    res = (64, 48)
+    film = H.Film(res); vp = H.VolPath(samples=3, max_depth=4)
+    vp(scene, film, camf(film))
+    ofilm = H.Film(res); ovp = H.VolPath(samples=3, max_depth=4, backend=oracle_backend.make_backend())
+    ovp._prepare(scene, ofilm, camf(ofilm)); ovp.clear()
+    rgb, w = vp.backend.read_accum()
+    oracle_backend.lib().ok_write_accum(ovp.backend.ctx, fp(rgb), fp(w))
+    lin = H.postprocess(film, vp, exposure=1.0, tonemap=None, gamma=None).copy()
+    assert np.array_equal(lin, np.clip(film.framebuffer, 0.0, 1.0)), "tonemap=nothing, gamma=nothing is a linear clamp of the framebuffer"
+    for tm in (None, "reinhard", "reinhard_extended", "aces", "uncharted2", "filmic"):
+        for kw, atol in ((dict(exposure=1.7, gamma=None), 0.0),
+                         (dict(exposure=0.8, gamma=2.2, white_point=3.0, sensor=H.FilmSensor(iso=90, exposure_time=1.5, white_balance=5000)), 4e-6)):
+            a = H.postprocess(film, vp, tonemap=tm, **kw).copy()
+            b = H.postprocess(ofilm, ovp, tonemap=tm, **kw).copy()
+            assert np.isfinite(a).all() and a.min() >= 0.0 and a.max() <= 1.0 and a.max() > 0.05
+            if atol == 0.0:
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), f"tonemap {tm}"
+            else:
+                np.testing.assert_allclose(a, b, rtol=0, atol=atol)
+    vp.close(); ovp.close()
+    wb = H.compute_white_balance_matrix(6504.0)       # D65's correlated colour temperature -> (almost) the identity
+    assert np.abs(wb - np.eye(3)).max() < 5e-2
+
+
 def test_update_material_in_place():
     """update_material!(scene, idx, new_material) (scene.jl:109-112): one struct goes to the device, the BVH stays; the
     next render must equal a fresh render of the scene built with the new material -- including a type change, which
