@@ -226,6 +226,11 @@ def run_cuda(args):
 
     if args.warmup > 0:      # W untimed steps, in one call like the timed region (same samples-in-flight, state pool allocated here)
         B.call("render_samples_strided", sample_of(0), world, args.warmup)
+    if dist:                 # warm the collective too (NCCL sets up its channels on the first call of a given size); on a scratch
+        scratch = torch.zeros_like(acc_t)                            # buffer: the film accumulators are reduced exactly once
+        for _ in range(2):
+            dist.all_reduce(scratch)
+        del scratch
     B.call("synchronize")
     # ---- timed region: K steps, device-timed (CUDA events on the library's launch stream), barrier + sync both sides ----
     if dist: dist.barrier()
