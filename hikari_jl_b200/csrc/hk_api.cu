@@ -42,6 +42,8 @@ struct HkContext {
     DevBuf b_nodes, b_tris, b_pos, b_nrm, b_idx, b_meta;
     DevBuf b_mats, b_ifaces, b_spec_l, b_spec_v, b_spec_o;
     DevBuf b_lights, b_env, b_lnodes, b_trails, b_inf, b_esc;
+    DevBuf b_mat_pre, b_light_pre, b_med_pre;       // uplift cache (DevTables)
+    bool uplift_cache_enabled = true;
     std::vector<DevBuf> env_bufs, media_bufs;
     DevBuf b_media;
     DevBuf b_f_func, b_f_mcdf, b_f_mfunc, b_f_ccdf;
@@ -122,7 +124,7 @@ int32_t hk_destroy(HkContext* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&ctx->b_sobol, &ctx->b_cie_x, &ctx->b_cie_y, &ctx->b_cie_z, &ctx->b_d65, &ctx->b_rgb_scale, &ctx->b_rgb_coeffs, &ctx->b_nodes, &ctx->b_tris,
-                      &ctx->b_esc, &ctx->b_sobol_top, &ctx->b_sobol_dims, &ctx->b_sobol_dimhash, &ctx->b_pos, &ctx->b_nrm, &ctx->b_idx, &ctx->b_meta, &ctx->b_mats, &ctx->b_ifaces, &ctx->b_spec_l, &ctx->b_spec_v, &ctx->b_spec_o, &ctx->b_lights,
+                      &ctx->b_esc, &ctx->b_mat_pre, &ctx->b_light_pre, &ctx->b_med_pre, &ctx->b_sobol_top, &ctx->b_sobol_dims, &ctx->b_sobol_dimhash, &ctx->b_pos, &ctx->b_nrm, &ctx->b_idx, &ctx->b_meta, &ctx->b_mats, &ctx->b_ifaces, &ctx->b_spec_l, &ctx->b_spec_v, &ctx->b_spec_o, &ctx->b_lights,
                       &ctx->b_env, &ctx->b_lnodes, &ctx->b_trails, &ctx->b_inf, &ctx->b_media, &ctx->b_f_func, &ctx->b_f_mcdf, &ctx->b_f_mfunc, &ctx->b_f_ccdf,
                       &ctx->b_state, &ctx->b_counts, &ctx->b_rays, &ctx->b_film, &ctx->b_scratch_u32, &ctx->b_trace_ctr, &ctx->b_work_ctr, &ctx->b_readback};
     for (auto& e : ctx->stage_events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -137,6 +139,7 @@ int32_t hk_destroy(HkContext* ctx) {
 }
 const char* hk_last_error(HkContext* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
+static int32_t refresh_uplift_cache(HkContext* ctx);
 int32_t hk_upload_tables(HkContext* ctx, const HkTables* t) {
     if (!ctx || !t) return HK_ERR_INVALID;
     cudaSetDevice(ctx->device);
@@ -169,6 +172,28 @@ int32_t hk_upload_tables(HkContext* ctx, const HkTables* t) {
         ctx->D.sobol.fast = ok ? 1 : 0;
     }
     ctx->have_tables = true;
+    return refresh_uplift_cache(ctx);
+}
+
+// (Re)build the uplift cache for whatever is uploaded: needs the rgb2spec table; called after every upload that changes
+// a constant colour (tables, materials, lights, media, hk_update_material).
+static int32_t refresh_uplift_cache(HkContext* ctx) {
+    DevTables& T = ctx->D.T;
+    T.mat_pre = nullptr; T.light_pre = nullptr; T.med_pre = nullptr; T.mat_base = nullptr; T.light_base = nullptr; T.med_base = nullptr;
+    if (!ctx->have_tables || !ctx->uplift_cache_enabled) return HK_OK;
+    const uint32_t nm = ctx->have_mats ? (uint32_t)ctx->mat_types.size() : 0u;
+    const uint32_t nl = ctx->have_lights ? (uint32_t)ctx->D.n_lights : 0u;
+    const uint32_t nd = ctx->D.media ? (uint32_t)ctx->D.n_media : 0u;
+    if (nm + nl + nd == 0) return HK_OK;
+    CK(ctx->b_mat_pre.alloc(32 * (size_t)nm)); CK(ctx->b_light_pre.alloc(32 * (size_t)nl)); CK(ctx->b_med_pre.alloc(48 * (size_t)nd));
+    k_precompute_uplifts<<<grid_for(ctx, nm + nl + nd, 128, 8), 128, 0, ctx->stream>>>(T, ctx->D.materials, nm, ctx->b_mat_pre.as<float4>(), ctx->D.lights, nl,
+                                                                                ctx->b_light_pre.as<float4>(), ctx->D.media, nd, ctx->b_med_pre.as<float4>());
+    ctx->launches++;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    if (nm) { T.mat_pre = ctx->b_mat_pre.as<float4>(); T.mat_base = ctx->D.materials; }
+    if (nl) { T.light_pre = ctx->b_light_pre.as<float4>(); T.light_base = ctx->D.lights; }
+    if (nd) { T.med_pre = ctx->b_med_pre.as<float4>(); T.med_base = ctx->D.media; }
     return HK_OK;
 }
 
@@ -244,7 +269,8 @@ int32_t hk_upload_materials(HkContext* ctx, const HkMaterial* m, uint32_t nm, co
     ctx->mat_types.resize(nm); for (uint32_t i = 0; i < nm; i++) ctx->mat_types[i] = m[i].type;
     if (!ctx->b_spec_o.p) { uint32_t zero = 0; CK(ctx->b_spec_o.upload(&zero, 4)); ctx->D.spec_offsets = ctx->b_spec_o.as<uint32_t>(); }
     ctx->have_mats = true; ctx->camera_medium_valid = false;
-    return patch_tri_types(ctx);
+    int32_t rc = refresh_uplift_cache(ctx);
+    return rc != HK_OK ? rc : patch_tri_types(ctx);
 }
 
 // update_material!(scene, idx, new_material), src/scene.jl:109-112: replace ONE material in place (RayMakie's interactive
@@ -260,6 +286,7 @@ int32_t hk_update_material(HkContext* ctx, uint32_t index, const HkMaterial* m) 
     CK(cudaMemcpy(ctx->b_mats.as<HkMaterial>() + (index - 1), m, sizeof(HkMaterial), cudaMemcpyHostToDevice));
     const bool type_changed = ctx->mat_types[index - 1] != m->type;
     ctx->mat_types[index - 1] = m->type;
+    { int32_t rc = refresh_uplift_cache(ctx); if (rc != HK_OK) return rc; }
     if (type_changed) {
         uint32_t present = 0;
         for (int32_t t : ctx->mat_types) if (t != HK_MAT_MIX) present |= 1u << t;
@@ -308,7 +335,7 @@ int32_t hk_upload_lights(HkContext* ctx, const HkLight* l, uint32_t n, const HkL
     CK(ctx->b_esc.upload(esc.data(), 4 * esc.size()));
     ctx->D.esc_idx = ctx->b_esc.as<int32_t>(); ctx->D.n_esc = (int32_t)esc.size();
     ctx->have_lights = true;
-    return HK_OK;
+    return refresh_uplift_cache(ctx);
 }
 
 int32_t hk_upload_media(HkContext* ctx, const HkMedium* m, uint32_t n) {
@@ -340,7 +367,7 @@ int32_t hk_upload_media(HkContext* ctx, const HkMedium* m, uint32_t n) {
     CK(ctx->b_media.upload(dev.data(), sizeof(DevMedium) * (size_t)n));
     ctx->D.media = ctx->b_media.as<DevMedium>(); ctx->D.n_media = (int32_t)n;
     ctx->camera_medium_valid = false;
-    return HK_OK;
+    return refresh_uplift_cache(ctx);
 }
 
 int32_t hk_set_camera(HkContext* ctx, const HkCamera* c) {

@@ -92,21 +92,33 @@ HK_DEV float3 tr_sample_wm(float3 w, float2 u, float ax, float ay) {
     float3 nh = px * t1 + py * t2 + pz * wh;
     return norm3(f3(ax * nh.x, ay * nh.y, fmaxf(1.0e-6f, nh.z)));
 }
+// Uplift cache slots per material type (DevTables::mat_pre): the constant RGB a BSDF uplifts at every call.
+//   Matte / Mirror: A = rgb0.  Glass / CoatedDiffuse: A = rgb0, B = rgb1.  Conductor (RGB eta / k): A, B unbounded.
+//   DiffuseTransmission: A / B = clamp(rgb0 * scale) / clamp(rgb1 * scale).
+HK_DEV float4 mat_pre_compute(const DevTables& T, const HkMaterial& m, int which) {
+    const float* c = which == 0 ? m.rgb0 : m.rgb1;
+    if (m.type == HK_MAT_CONDUCTOR) return make_pre_unbounded(T, c[0], c[1], c[2]);
+    if (m.type == HK_MAT_DIFFUSE_TRANSMISSION) { const float s = m.f[0]; return make_pre_bounded(T, clampf(c[0] * s, 0.0f, 1.0f), clampf(c[1] * s, 0.0f, 1.0f), clampf(c[2] * s, 0.0f, 1.0f)); }
+    return make_pre_bounded(T, c[0], c[1], c[2]);      // (rgb_to_spectrum clamps to [0,1] itself)
+}
+HK_DEV Spec mat_spec(const MatCtx& C, const HkMaterial& m, int which, float4 lam) {
+    const float4 q = C.T.mat_pre ? __ldg(C.T.mat_pre + 2 * (&m - (const HkMaterial*)C.T.mat_base) + which) : mat_pre_compute(C.T, m, which);
+    return m.type == HK_MAT_CONDUCTOR ? pre_unbounded(q, lam) : pre_bounded(q, lam);
+}
 HK_DEV Spec ior_spectrum(const MatCtx& C, const HkMaterial& m, int which, float4 lambda) {   // :206-210
     if ((m.flags & HK_MATFLAG_SPECTRAL_ETA_K) && m.spec[which] > 0) {
         uint32_t a = __ldg(C.spec_offsets + m.spec[which] - 1), b = __ldg(C.spec_offsets + m.spec[which]);
         const float* l = C.spec_lambdas + a; const float* v = C.spec_values + a; int n = (int)(b - a);
         return sp4(pls_sample(l, v, n, lambda.x), pls_sample(l, v, n, lambda.y), pls_sample(l, v, n, lambda.z), pls_sample(l, v, n, lambda.w));
     }
-    const float* c = which == 0 ? m.rgb0 : m.rgb1;
-    return uplift_rgb_unbounded(C.T, c[0], c[1], c[2], lambda);
+    return mat_spec(C, m, which, lambda);
 }
 
 // ---- Matte :42-101 / :371-397 -----------------------------------------------------------------------------
 HK_DEV BsdfSample sample_matte(const MatCtx& C, const HkMaterial& m, float3 wo, float3 n, float4 lam, float2 u) {
     float wn = dot3(wo, n);
     if (fabsf(wn) < 1.0e-6f) return bsdf_none();
-    Spec kd = uplift_rgb(C.T, clampf(m.rgb0[0], 0.0f, 1.0f), clampf(m.rgb0[1], 0.0f, 1.0f), clampf(m.rgb0[2], 0.0f, 1.0f), lam);
+    Spec kd = mat_spec(C, m, 0, lam);
     Frame fr = make_frame(n);
     float3 lw = cosine_sample_hemisphere(u);
     float ct = lw.z;
@@ -122,21 +134,21 @@ HK_DEV BsdfEval eval_matte(const MatCtx& C, const HkMaterial& m, float3 wo, floa
     if (ci * co < 0.0f) return eval_none();
     float c = fabsf(ci);
     if (c < 1.0e-6f) return eval_none();
-    Spec kd = uplift_rgb(C.T, clampf(m.rgb0[0], 0.0f, 1.0f), clampf(m.rgb0[1], 0.0f, 1.0f), clampf(m.rgb0[2], 0.0f, 1.0f), lam);
+    Spec kd = mat_spec(C, m, 0, lam);
     return eval_make(kd / HK_PI, c / HK_PI);
 }
 // ---- Mirror :108-132 ---------------------------------------------------------------------------------------
 HK_DEV BsdfSample sample_mirror(const MatCtx& C, const HkMaterial& m, float3 wo, float3 n, float4 lam) {
     float wn = dot3(wo, n);
     if (fabsf(wn) < 1.0e-6f) return bsdf_none();
-    Spec kr = uplift_rgb(C.T, m.rgb0[0], m.rgb0[1], m.rgb0[2], lam);
+    Spec kr = mat_spec(C, m, 0, lam);
     return bsdf_make(reflect3(wo, wn < 0.0f ? -n : n), kr, 1.0f, true, 1.0f);
 }
 // ---- Glass :140-198 ----------------------------------------------------------------------------------------
 HK_DEV BsdfSample sample_glass(const MatCtx& C, const HkMaterial& m, float3 wo, float3 n, float4 lam, float uc) {
     float ior = m.f[0] == 0.0f ? 1.0f : m.f[0];
-    Spec kr = uplift_rgb(C.T, m.rgb0[0], m.rgb0[1], m.rgb0[2], lam);
-    Spec kt = uplift_rgb(C.T, m.rgb1[0], m.rgb1[1], m.rgb1[2], lam);
+    Spec kr = mat_spec(C, m, 0, lam);
+    Spec kt = mat_spec(C, m, 1, lam);
     float co = dot3(wo, n);
     bool entering = co > 0.0f;
     float3 no = entering ? n : -n;
@@ -224,7 +236,7 @@ HK_DEV BsdfSample sample_diffuse_transmission(const MatCtx& C, const HkMaterial&
     float wn = dot3(wo, n);
     if (fabsf(wn) < 1.0e-6f) return bsdf_none();
     float r[3], t[3]; difftrans_rgb(m, r, t);
-    Spec rs = uplift_rgb(C.T, r[0], r[1], r[2], lam), ts = uplift_rgb(C.T, t[0], t[1], t[2], lam);
+    Spec rs = mat_spec(C, m, 0, lam), ts = mat_spec(C, m, 1, lam);
     float pr = fmaxf(fmaxf(r[0], r[1]), r[2]), pt = fmaxf(fmaxf(t[0], t[1]), t[2]);
     if (pr + pt < 1.0e-10f) return bsdf_none();
     Frame fr = make_frame(n);
@@ -243,7 +255,7 @@ HK_DEV BsdfEval eval_diffuse_transmission(const MatCtx& C, const HkMaterial& m, 
     float ac = fabsf(ci);
     if (ac < 1.0e-6f) return eval_none();
     float r[3], t[3]; difftrans_rgb(m, r, t);
-    Spec rs = uplift_rgb(C.T, r[0], r[1], r[2], lam), ts = uplift_rgb(C.T, t[0], t[1], t[2], lam);
+    Spec rs = mat_spec(C, m, 0, lam), ts = mat_spec(C, m, 1, lam);
     float pr = fmaxf(fmaxf(r[0], r[1]), r[2]), pt = fmaxf(fmaxf(t[0], t[1]), t[2]);
     if (pr + pt < 1.0e-10f) return eval_none();
     if (ci * co > 0.0f) return eval_make(rs * (1.0f / HK_PI), pr / (pr + pt) * ac / HK_PI);

@@ -149,8 +149,8 @@ HK_DEV BsdfSample sample_coated_diffuse(const MatCtx& C, const HkMaterial& m, fl
     float wn = dot3(wo, n);
     if (fabsf(wn) < 1.0e-6f) return bsdf_none();
     CoatParams P = coat_params(m, regularize);
-    Spec refl = uplift_rgb(C.T, m.rgb0[0], m.rgb0[1], m.rgb0[2], lam);
-    Spec albedo = uplift_rgb(C.T, m.rgb1[0], m.rgb1[1], m.rgb1[2], lam);
+    Spec refl = mat_spec(C, m, 0, lam);
+    Spec albedo = mat_spec(C, m, 1, lam);
     Frame fr = make_frame(n);
     float3 wl = f3(dot3(wo, fr.t), dot3(wo, fr.b), wn);
     const bool flip = wl.z < 0.0f;
@@ -246,8 +246,8 @@ HK_DEV float coated_pdf(float3 wo, float3 wi, const CoatParams& P, Spec refl) {
 // eval: :1564-1840
 HK_DEV BsdfEval eval_coated_diffuse(const MatCtx& C, const HkMaterial& m, float3 wo_w, float3 wi_w, float3 n, float4 lam) {
     CoatParams P = coat_params(m, false);
-    Spec refl = uplift_rgb(C.T, m.rgb0[0], m.rgb0[1], m.rgb0[2], lam);
-    Spec albedo = uplift_rgb(C.T, m.rgb1[0], m.rgb1[1], m.rgb1[2], lam);
+    Spec refl = mat_spec(C, m, 0, lam);
+    Spec albedo = mat_spec(C, m, 1, lam);
     const float th = P.thickness, ax = P.ax, ay = P.ay, eta = P.eta, g = P.g;
     Frame fr = make_frame(n);
     float3 wo = f3(dot3(wo_w, fr.t), dot3(wo_w, fr.b), dot3(wo_w, n));

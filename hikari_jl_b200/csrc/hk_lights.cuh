@@ -101,12 +101,14 @@ HK_DEV float env_pdf_uv(const DevEnvMap& E, float2 uv) {   // sampling.jl:351-36
 
 HK_DEV Spec light_spectrum(const DevTables& T, const HkLight& L, float4 lam) {
     if (L.spectrum_kind == HK_SPECTRUM_ILLUMINANT) return illuminant_eval(T, Poly3{L.poly[0], L.poly[1], L.poly[2]}, L.illum_scale, lam);
-    return uplift_rgb_illuminant(T, L.rgb[0], L.rgb[1], L.rgb[2], lam);
+    const float4 q = T.light_pre ? __ldg(T.light_pre + 2 * (&L - (const HkLight*)T.light_base)) : make_pre_illuminant(T, L.rgb[0], L.rgb[1], L.rgb[2]);
+    return pre_illuminant(T, q, lam);
 }
 HK_DEV Spec arealight_Le(const DevTables& T, const HkLight& L, float3 wo, float3 n, float4 lam) {   // diffuse-area.jl:54-66
     if (L.type != HK_LIGHT_DIFFUSE_AREA) return sp(0.0f);
     if (!L.two_sided && dot3(wo, n) < 0.0f) return sp(0.0f);
-    return uplift_rgb(T, L.rgb[0] * L.scale, L.rgb[1] * L.scale, L.rgb[2] * L.scale, lam);
+    const float4 q = T.light_pre ? __ldg(T.light_pre + 2 * (&L - (const HkLight*)T.light_base) + 1) : make_pre_bounded(T, L.rgb[0] * L.scale, L.rgb[1] * L.scale, L.rgb[2] * L.scale);
+    return pre_bounded(q, lam);
 }
 HK_DEV LightSample sample_light(const LightCtx& C, const HkLight& L, float3 p, float4 lam, float2 u) {   // lights.jl:39-290
     LightSample s;

@@ -162,9 +162,15 @@ HK_DEV float3 affine_vc(const float* M, float3 v) { return f3(M[0] * v.x + M[1] 
 struct MediumCoef { Spec sa, ss, Le; float g; };
 HK_DEV MediumCoef medium_coef(const MediaCtx& C, const DevMedium& M, float4 lam) {
     MediumCoef c;
-    c.sa = uplift_rgb_unbounded(C.T, M.sigma_a[0], M.sigma_a[1], M.sigma_a[2], lam);
-    c.ss = uplift_rgb_unbounded(C.T, M.sigma_s[0], M.sigma_s[1], M.sigma_s[2], lam);
-    c.Le = M.type == HK_MEDIUM_HOMOGENEOUS ? uplift_rgb_unbounded(C.T, M.Le[0], M.Le[1], M.Le[2], lam) : sp(0.0f);
+    if (C.T.med_pre) {      // uplift cache (DevTables)
+        const float4* q = C.T.med_pre + 3 * (&M - (const DevMedium*)C.T.med_base);
+        c.sa = pre_unbounded(__ldg(q), lam); c.ss = pre_unbounded(__ldg(q + 1), lam);
+        c.Le = M.type == HK_MEDIUM_HOMOGENEOUS ? pre_unbounded(__ldg(q + 2), lam) : sp(0.0f);
+    } else {
+        c.sa = uplift_rgb_unbounded(C.T, M.sigma_a[0], M.sigma_a[1], M.sigma_a[2], lam);
+        c.ss = uplift_rgb_unbounded(C.T, M.sigma_s[0], M.sigma_s[1], M.sigma_s[2], lam);
+        c.Le = M.type == HK_MEDIUM_HOMOGENEOUS ? uplift_rgb_unbounded(C.T, M.Le[0], M.Le[1], M.Le[2], lam) : sp(0.0f);
+    }
     c.g = M.g;
     return c;
 }

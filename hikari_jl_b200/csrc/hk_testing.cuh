@@ -172,6 +172,14 @@ int32_t hk_test_sobol(HkContext* ctx, const int32_t* q, uint64_t n, int32_t l2, 
 }
 // 0: generic table loop, 1: closed forms for dimensions 0/1; returns the previous mode (tests run both)
 int32_t hk_test_sobol_mode(HkContext* ctx, int32_t fast) { if (!ctx) return HK_ERR_INVALID; int32_t old = ctx->D.sobol.fast; ctx->D.sobol.fast = fast ? 1 : 0; return old; }
+// 0 / 1: disable / enable the uplift cache (DevTables::mat_pre ...); returns the previous setting.  Takes effect at once.
+int32_t hk_test_uplift_cache(HkContext* ctx, int32_t on) {
+    if (!ctx) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    int32_t old = ctx->uplift_cache_enabled ? 1 : 0; ctx->uplift_cache_enabled = on != 0;
+    int32_t rc = refresh_uplift_cache(ctx);
+    return rc != HK_OK ? rc : old;
+}
 // 0 / 1: disable / enable the ZSobol prefix cache (takes effect at the next hk_set_params); returns the previous setting
 int32_t hk_test_sobol_cache(HkContext* ctx, int32_t on) { if (!ctx) return HK_ERR_INVALID; int32_t old = ctx->sobol_cache_enabled ? 1 : 0; ctx->sobol_cache_enabled = on != 0; ctx->sobol_cache_key[5] = -1; return old; }
 int32_t hk_test_mix_hash(HkContext* ctx, const float* in, uint64_t n, float* out) {

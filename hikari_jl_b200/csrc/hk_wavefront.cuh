@@ -196,6 +196,33 @@ __global__ void __launch_bounds__(256) k_camera(const __grid_constant__ DevScene
     if (blockIdx.x == 0 && threadIdx.x == 0) { S.counts[HK_C_RAY0] = n_slots; S.counts[HK_C_RAY1] = 0; }
 }
 
+// Uplift cache (DevTables::mat_pre / light_pre / med_pre): one thread per material / light / medium, run at upload.
+// T arrives with null cache pointers, so the make_* functions evaluate directly.
+__global__ void __launch_bounds__(128) k_precompute_uplifts(DevTables T, const HkMaterial* __restrict__ mats, uint32_t n_mats, float4* __restrict__ mat_pre,
+                                                             const HkLight* __restrict__ lights, uint32_t n_lights, float4* __restrict__ light_pre,
+                                                             const DevMedium* __restrict__ media, uint32_t n_media, float4* __restrict__ med_pre) {
+    const uint32_t n = n_mats + n_lights + n_media;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (i < n_mats) {
+            const HkMaterial& m = mats[i];
+            const bool rgb = m.type >= 1 && m.type < HK_MAX_MAT_TYPES && m.type != HK_MAT_THIN_DIELECTRIC;
+            mat_pre[2 * i] = rgb ? mat_pre_compute(T, m, 0) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            mat_pre[2 * i + 1] = rgb ? mat_pre_compute(T, m, 1) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        } else if (i < n_mats + n_lights) {
+            const uint32_t k = i - n_mats;
+            const HkLight& L = lights[k];
+            light_pre[2 * k] = make_pre_illuminant(T, L.rgb[0], L.rgb[1], L.rgb[2]);
+            light_pre[2 * k + 1] = make_pre_bounded(T, L.rgb[0] * L.scale, L.rgb[1] * L.scale, L.rgb[2] * L.scale);
+        } else {
+            const uint32_t k = i - n_mats - n_lights;
+            const DevMedium& M = media[k];
+            med_pre[3 * k] = make_pre_unbounded(T, M.sigma_a[0], M.sigma_a[1], M.sigma_a[2]);
+            med_pre[3 * k + 1] = make_pre_unbounded(T, M.sigma_s[0], M.sigma_s[1], M.sigma_s[2]);
+            med_pre[3 * k + 2] = make_pre_unbounded(T, M.Le[0], M.Le[1], M.Le[2]);
+        }
+    }
+}
+
 // ZSobol prefix cache (SobolParams::top, hk_math.cuh): one pass per (resolution, seed), not per sample.
 // dims[slot] = the sampler dimension of cache slot `slot`.
 __global__ void __launch_bounds__(256) k_sobol_prefix(uint32_t* __restrict__ top, uint4* __restrict__ dimhash, const int32_t* __restrict__ dims, int32_t n_slots,
@@ -413,7 +440,7 @@ HK_DEV bool russian_roulette(Spec& beta, int depth, float rr) {
 // Shading of one material type: emissive-hit MIS (surface-eval.jl:147-220), NEE (:250-342 + lights.jl:535-600) and
 // BSDF sampling / Russian roulette / continuation ray (:396-512), fused into one kernel per material type.
 #ifndef HK_SHADE_MIN_BLOCKS
-#define HK_SHADE_MIN_BLOCKS 1
+#define HK_SHADE_MIN_BLOCKS 4
 #endif
 template <int TYPE>
 __global__ void __launch_bounds__(128, HK_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DevScene D, PathState S, PassArgs A, int next) {

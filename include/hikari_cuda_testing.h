@@ -19,6 +19,9 @@ int32_t hk_test_read_rays(HkContext* ctx, float* rays, float* hits, uint64_t n_s
 /* select the Sobol' evaluation: 0 = generic matrix loop, 1 = closed forms for dimensions 0/1 (only valid when
  * hk_upload_tables verified the table structure); returns the previous mode */
 int32_t hk_test_sobol_mode(HkContext* ctx, int32_t fast);
+/* 0 / 1: disable / enable the upload-time uplift cache (rgb_to_spectrum of constant colours); returns the previous
+ * setting.  Images must be bit-identical either way. */
+int32_t hk_test_uplift_cache(HkContext* ctx, int32_t on);
 /* 0 / 1: disable / enable the per-pixel ZSobol prefix cache (applies at the next hk_set_params); returns the previous
  * setting.  Images must be bit-identical either way (tests/test_parity_gpu.py). */
 int32_t hk_test_sobol_cache(HkContext* ctx, int32_t on);
