@@ -33,7 +33,13 @@ struct Builder {
     std::vector<uint32_t> order;
     std::vector<Node2> nodes;
     std::atomic<uint32_t> n_nodes{0};
-    static constexpr int NBINS = 16;
+#ifndef HK_BVH_NBINS
+#define HK_BVH_NBINS 32
+#endif
+#ifndef HK_BVH_CT
+#define HK_BVH_CT 0.125f      // traversal-step cost relative to one leaf (<= 3 triangles) test in the SAH
+#endif
+    static constexpr int NBINS = HK_BVH_NBINS;
     static constexpr uint32_t MAX_LEAF = 3;
 
     Builder(const std::vector<Box>& b, const std::vector<float>& c) : pb(b), cen(c) {}
@@ -73,7 +79,7 @@ struct Builder {
         uint32_t mid;
         if (best_axis >= 0) {
             float leaf_cost = box.half_area() * (float)((count + 2) / 3);
-            if (count <= MAX_LEAF && leaf_cost <= best_cost + 0.125f * box.half_area()) { make_leaf(me, first, count); return; }
+            if (count <= MAX_LEAF && leaf_cost <= best_cost + HK_BVH_CT * box.half_area()) { make_leaf(me, first, count); return; }
             float ext = cbox.hi[best_axis] - cbox.lo[best_axis];
             float k1 = NBINS * (1.0f - 1e-6f) / ext;
             auto it = std::partition(order.begin() + first, order.begin() + first + count, [&](uint32_t p) {
