@@ -1,9 +1,14 @@
-// hk_bvh.cpp — host builder: binned-SAH BVH2 -> greedy collapse to BVH8 -> octant slot assignment ->
-// 8-bit quantisation (conservative) -> BFS layout with contiguous internal children / leaf triangles.
+// hk_bvh.cpp — host builder: binned-SAH BVH2 down to single triangles -> SAH-optimal collapse to BVH8 by dynamic
+// programming (Ylitie, Karras, Laine 2017, section 4: per BVH2 node the cheapest forest of <= i wide subtrees, i = 1..7;
+// leaves of <= 3 triangles are formed by the same optimisation) -> octant slot assignment -> 8-bit quantisation
+// (conservative) -> BFS layout with contiguous internal children / leaf triangles.
+// (The first version expanded the largest child greedily top-down: 3.9 children per 8-wide node on a tessellated mesh,
+// half of all nodes with only 2 -- every visit pays for 8 slab tests.)
 // Replaces Raycore's BVH/TLAS construction behind scene.accel (reference: Raycore.jl, not vendored;
 // call sites src/scene.jl:146-151 sync!).
 #include "hk_bvh.h"
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <cmath>
 #include <cstring>
@@ -25,7 +30,7 @@ struct Box {
         return d[0] * d[1] + d[1] * d[2] + d[2] * d[0];
     }
 };
-struct Node2 { Box box; uint32_t left, right, first, count; };   // count > 0 => leaf
+struct Node2 { Box box; uint32_t left, right, first, count; };   // [first, first+count) of `order` = the subtree's triangles; left == 0 => BVH2 leaf
 
 struct Builder {
     const std::vector<Box>& pb;      // per-primitive (padded) boxes
@@ -36,11 +41,14 @@ struct Builder {
 #ifndef HK_BVH_NBINS
 #define HK_BVH_NBINS 32
 #endif
+#ifndef HK_BVH_CPRIM
+#define HK_BVH_CPRIM 0.4f     // cost of one triangle test relative to one 8-wide node visit (~90 vs ~210 instructions)
+#endif
 #ifndef HK_BVH_CT
 #define HK_BVH_CT 0.125f      // traversal-step cost relative to one leaf (<= 3 triangles) test in the SAH
 #endif
     static constexpr int NBINS = HK_BVH_NBINS;
-    static constexpr uint32_t MAX_LEAF = 3;
+    static constexpr uint32_t MAX_LEAF = 3;       // triangles per BVH8 leaf child (unary count in 3 bits of trivalid)
 
     Builder(const std::vector<Box>& b, const std::vector<float>& c) : pb(b), cen(c) {}
 
@@ -49,8 +57,8 @@ struct Builder {
     void build(uint32_t me, uint32_t first, uint32_t count, int depth) {
         Box box, cbox; box.reset(); cbox.reset();
         for (uint32_t i = first; i < first + count; i++) { uint32_t p = order[i]; box.grow(pb[p]); cbox.grow(&cen[3 * (size_t)p]); }
-        nodes[me].box = box;
-        if (count <= MAX_LEAF && (count == 1 || depth > 60)) { make_leaf(me, first, count); return; }
+        nodes[me].box = box; nodes[me].first = first; nodes[me].count = count;
+        if (count == 1 || (count <= MAX_LEAF && depth > 60)) { make_leaf(me, first, count); return; }
         // binned SAH over the three axes
         float best_cost = INF; int best_axis = -1, best_bin = 0;
         for (int ax = 0; ax < 3; ax++) {
@@ -72,14 +80,12 @@ struct Builder {
             for (int b = 0; b < NBINS - 1; b++) {
                 acc.grow(bb[b]); c += bc[b];
                 if (c == 0 || rc[b + 1] == 0) continue;
-                float cost = acc.half_area() * (float)((c + 2) / 3) + ra[b + 1] * (float)((rc[b + 1] + 2) / 3);
+                float cost = acc.half_area() * (float)c + ra[b + 1] * (float)rc[b + 1];
                 if (cost < best_cost) { best_cost = cost; best_axis = ax; best_bin = b; }
             }
         }
         uint32_t mid;
         if (best_axis >= 0) {
-            float leaf_cost = box.half_area() * (float)((count + 2) / 3);
-            if (count <= MAX_LEAF && leaf_cost <= best_cost + HK_BVH_CT * box.half_area()) { make_leaf(me, first, count); return; }
             float ext = cbox.hi[best_axis] - cbox.lo[best_axis];
             float k1 = NBINS * (1.0f - 1e-6f) / ext;
             auto it = std::partition(order.begin() + first, order.begin() + first + count, [&](uint32_t p) {
@@ -94,7 +100,7 @@ struct Builder {
             mid = first + count / 2;   // coincident centroids: split the list
         }
         uint32_t l = alloc(), r = alloc();
-        nodes[me].left = l; nodes[me].right = r; nodes[me].count = 0; nodes[me].first = 0;
+        nodes[me].left = l; nodes[me].right = r;
         if (count > 200000) {
             #pragma omp task shared(nodes)
             build(l, first, mid - first, depth + 1);
@@ -107,8 +113,7 @@ struct Builder {
         }
     }
     void make_leaf(uint32_t me, uint32_t first, uint32_t count) {
-        nodes[me].left = nodes[me].right = 0; nodes[me].first = first; nodes[me].count = count;
-        std::sort(order.begin() + first, order.begin() + first + count);   // deterministic leaf order
+        nodes[me].left = nodes[me].right = 0;
     }
 };
 
@@ -147,42 +152,78 @@ void hk_build_bvh8(const float* positions, const uint32_t* indices, uint32_t n_t
     const std::vector<Node2>& N2 = B.nodes;
     for (int k = 0; k < 3; k++) { out.bounds_min[k] = N2[root2].box.lo[k]; out.bounds_max[k] = N2[root2].box.hi[k]; }
 
-    // ---- collapse + layout (BFS) ----------------------------------------------------------------
-    out.nodes.reserve((size_t)n_tris / 4 + 16); out.tris.reserve(n_tris);
+    // ---- SAH-optimal collapse: cost[n][i-1] = cheapest representation of BVH2 subtree n as a forest of <= i wide-BVH roots
+    // (a root = a leaf of <= MAX_LEAF triangles or an internal 8-wide node), i = 1..7.  Children carry larger indices than
+    // their parent (allocated later), so one sweep from the last node to the first visits children before parents. ---------
+    const uint32_t n2 = B.n_nodes.load();
+    const float C_NODE = 1.0f, C_PRIM = HK_BVH_CPRIM;
+    std::vector<std::array<float, 7>> cost(n2);
+    auto distribute = [&](uint32_t l, uint32_t r, int j, int* best_k) {       // min over 0 < k < j of cost[l][k] + cost[r][j-k]
+        float best = INF; int bk = 1;
+        for (int k = 1; k < j; k++) {
+            const int kl = std::min(k, 7), kr = std::min(j - k, 7);
+            const float c = cost[l][kl - 1] + cost[r][kr - 1];
+            if (c < best) { best = c; bk = k; }
+        }
+        if (best_k) *best_k = bk;
+        return best;
+    };
+    auto leaf_cost = [&](uint32_t n) { return N2[n].count <= Builder::MAX_LEAF ? N2[n].box.half_area() * (float)N2[n].count * C_PRIM : INF; };
+    for (int64_t n = (int64_t)n2 - 1; n >= 0; n--) {
+        const Node2& nd = N2[n];
+        if (nd.left == 0) { cost[n].fill(leaf_cost((uint32_t)n)); continue; }
+        const float c_internal = distribute(nd.left, nd.right, 8, nullptr) + nd.box.half_area() * C_NODE;
+        cost[n][0] = std::min(leaf_cost((uint32_t)n), c_internal);
+        for (int i = 2; i <= 7; i++) cost[n][i - 1] = std::min(distribute(nd.left, nd.right, i, nullptr), cost[n][i - 2]);
+    }
+    // the roots of the cheapest forest of <= i subtrees below BVH2 node n (decisions re-derived from the cost table)
+    struct Root { uint32_t n2; bool leaf; };
+    auto gather = [&](auto&& self, uint32_t n, int i, std::vector<Root>& out_roots) -> void {
+        const Node2& nd = N2[n];
+        if (nd.left == 0) { out_roots.push_back(Root{n, true}); return; }
+        while (i > 1 && cost[n][i - 1] == cost[n][i - 2]) i--;       // the extra roots bought nothing
+        if (i == 1) {
+            const float lc = leaf_cost(n);
+            out_roots.push_back(Root{n, lc <= cost[n][0] && lc < INF});
+            return;
+        }
+        int k; distribute(nd.left, nd.right, i, &k);
+        self(self, nd.left, std::min(k, 7), out_roots); self(self, nd.right, std::min(i - k, 7), out_roots);
+    };
+
+    // ---- layout (BFS) -----------------------------------------------------------------------------
+    out.nodes.reserve((size_t)n_tris / 6 + 16); out.tris.reserve(n_tris);
     struct Pending { uint32_t n2; uint32_t out_idx; };
-    std::vector<Pending> queue; queue.reserve((size_t)n_tris / 4 + 16);
+    std::vector<Pending> queue; queue.reserve((size_t)n_tris / 6 + 16);
     out.nodes.emplace_back(); std::memset(&out.nodes[0], 0, sizeof(HkBvhNode));
     // a root that is itself a leaf gets wrapped: treat it as a wide node with one leaf child
     queue.push_back(Pending{root2, 0});
+    std::vector<Root> roots;
     for (size_t qi = 0; qi < queue.size(); qi++) {
         Pending cur = queue[qi];
-        uint32_t ch[8]; int nch = 0;
-        if (N2[cur.n2].count > 0) { ch[nch++] = cur.n2; }
+        uint32_t ch[8]; bool ch_leaf[8]; int nch = 0;
+        roots.clear();
+        if (N2[cur.n2].left == 0) roots.push_back(Root{cur.n2, true});
         else {
-            ch[nch++] = N2[cur.n2].left; ch[nch++] = N2[cur.n2].right;
-            while (nch < 8) {
-                int best = -1; float ba = -1.0f;
-                for (int i = 0; i < nch; i++) if (N2[ch[i]].count == 0) { float a = N2[ch[i]].box.half_area(); if (a > ba) { ba = a; best = i; } }
-                if (best < 0) break;
-                uint32_t n = ch[best];
-                ch[best] = N2[n].left; ch[nch++] = N2[n].right;
-            }
+            int k; distribute(N2[cur.n2].left, N2[cur.n2].right, 8, &k);
+            gather(gather, N2[cur.n2].left, std::min(k, 7), roots); gather(gather, N2[cur.n2].right, std::min(8 - k, 7), roots);
         }
+        for (const Root& r : roots) { ch[nch] = r.n2; ch_leaf[nch] = r.leaf; nch++; }
         // node frame
         Box nb; nb.reset();
         for (int i = 0; i < nch; i++) nb.grow(N2[ch[i]].box);
         float ctr[3] = {0.5f * (nb.lo[0] + nb.hi[0]), 0.5f * (nb.lo[1] + nb.hi[1]), 0.5f * (nb.lo[2] + nb.hi[2])};
         // greedy octant slot assignment: slot bit set <=> child lies towards + along that axis
         int slot_of[8]; bool slot_used[8] = {false}; bool assigned[8] = {false};
-        float cost[8][8];
+        float scost[8][8];
         for (int i = 0; i < nch; i++) {
             const Box& b = N2[ch[i]].box;
             float c[3] = {0.5f * (b.lo[0] + b.hi[0]) - ctr[0], 0.5f * (b.lo[1] + b.hi[1]) - ctr[1], 0.5f * (b.lo[2] + b.hi[2]) - ctr[2]};
-            for (int s = 0; s < 8; s++) cost[i][s] = ((s & 4) ? c[0] : -c[0]) + ((s & 2) ? c[1] : -c[1]) + ((s & 1) ? c[2] : -c[2]);
+            for (int s = 0; s < 8; s++) scost[i][s] = ((s & 4) ? c[0] : -c[0]) + ((s & 2) ? c[1] : -c[1]) + ((s & 1) ? c[2] : -c[2]);
         }
         for (int it = 0; it < nch; it++) {
             int bi = -1, bs = -1; float bc = -INF;
-            for (int i = 0; i < nch; i++) if (!assigned[i]) for (int s = 0; s < 8; s++) if (!slot_used[s] && cost[i][s] > bc) { bc = cost[i][s]; bi = i; bs = s; }
+            for (int i = 0; i < nch; i++) if (!assigned[i]) for (int s = 0; s < 8; s++) if (!slot_used[s] && scost[i][s] > bc) { bc = scost[i][s]; bi = i; bs = s; }
             assigned[bi] = true; slot_used[bs] = true; slot_of[bi] = bs;
         }
         int child_at[8]; for (int s = 0; s < 8; s++) child_at[s] = -1;
@@ -222,13 +263,16 @@ void hk_build_bvh8(const float* positions, const uint32_t* indices, uint32_t n_t
                 while (hi < 255.0f && node.p[k] + hi * scale[k] < c.box.hi[k]) hi += 1.0f;
                 node.qlo[k][s] = (uint8_t)lo; node.qhi[k][s] = (uint8_t)hi;
             }
-            if (c.count == 0) {
+            if (!ch_leaf[i]) {
                 node.imask |= (uint8_t)(1u << s);
             } else {
                 uint32_t unary = c.count == 1 ? 1u : (c.count == 2 ? 3u : 7u);
                 node.trivalid |= unary << (3 * s);
+                uint32_t prims[3];
+                for (uint32_t t = 0; t < c.count; t++) prims[t] = B.order[c.first + t];
+                std::sort(prims, prims + c.count);                  // deterministic leaf order
                 for (uint32_t t = 0; t < c.count; t++) {
-                    uint32_t prim = B.order[c.first + t];
+                    uint32_t prim = prims[t];
                     const float* a = positions + 3 * (size_t)indices[3 * (size_t)prim];
                     const float* b = positions + 3 * (size_t)indices[3 * (size_t)prim + 1];
                     const float* cc = positions + 3 * (size_t)indices[3 * (size_t)prim + 2];
@@ -242,7 +286,7 @@ void hk_build_bvh8(const float* positions, const uint32_t* indices, uint32_t n_t
         // internal children in slot order, contiguous
         for (int s = 0; s < 8; s++) {
             int i = child_at[s];
-            if (i < 0 || N2[ch[i]].count != 0) continue;
+            if (i < 0 || ch_leaf[i]) continue;
             uint32_t idx = (uint32_t)out.nodes.size();
             out.nodes.emplace_back(); std::memset(&out.nodes.back(), 0, sizeof(HkBvhNode));
             queue.push_back(Pending{ch[i], idx});
