@@ -146,3 +146,48 @@ def test_strided_partition_on_the_oracle():
     img = (rgb / np.maximum(w, 1e-30)[:, None]).reshape(res[1], res[0], 3)
     np.testing.assert_allclose(img, full, rtol=1e-4, atol=1e-6)
     vp.close()
+
+
+def test_mix_material_setkeys_and_oracle_resolution():
+    """MixMaterial (mix-material.jl): sub-materials are registered before the mix, SetKeys follow the MultiTypeSet
+    convention (type groups in first-push order, 1-based position within the type), and the oracle's resolution obeys
+    amount = 0 / 1 exactly and amount = 0.5 statistically."""
+    s = H.Scene()
+    red, mirror, green = H.MatteMaterial(Kd=(0.8, 0.1, 0.1)), H.MirrorMaterial(), H.MatteMaterial(Kd=(0.1, 0.8, 0.1))
+    inner = H.MixMaterial((red, mirror), 0.3)
+    outer = H.MixMaterial((inner, green), 0.5)
+    s.push(H.rect3((0, 0, 0), (1, 1, 1)), outer)
+    assert [type(m).__name__ for m in s.materials] == ["MatteMaterial", "MirrorMaterial", "MixMaterial", "MatteMaterial", "MixMaterial"]
+    assert s.set_key(red) == (1, 1) and s.set_key(mirror) == (2, 1) and s.set_key(inner) == (3, 1) and s.set_key(green) == (1, 2)
+    m = outer.to_abi(s)
+    assert (m.type, m.ival[0], m.ival[1], m.spec[0], m.spec[1], m.flags) == (A.HK_MAT_MIX, 3, 4, 1, 2, 3 | (1 << 8))
+
+    def mean_image(amount):
+        sc = H.Scene()
+        sc.push(H.rect3((-2, -0.1, -2), (4, 0.1, 4)), H.MixMaterial((H.MatteMaterial(Kd=0.0), H.MatteMaterial(Kd=0.9)), amount))
+        sc.push(H.PointLight((8, 8, 8), (0, 3, 0)))
+        sc.sync()
+        film = H.Film((48, 32))
+        vp = H.VolPath(samples=4, max_depth=1, backend=oracle_backend.make_backend())
+        img = vp(sc, film, H.PerspectiveCamera((0, 3, 0.01), (0, 0, 0), film, fov=50)).copy()
+        vp.close()
+        return float(img.mean())
+
+    black, white, half = mean_image(0.0), mean_image(1.0), mean_image(0.5)
+    assert black == 0.0 and white > 0.0
+    assert 0.4 * white < half < 0.6 * white
+
+
+def test_white_balance_matrix_and_sensor_defaults():
+    """compute_white_balance_matrix (spectral/color.jl:522-546): rows map the source white to D65 in LMS space, so the
+    source white point itself must land on the D65 white point; FilmSensor defaults give imaging ratio 1."""
+    for T in (2000.0, 3200.0, 5000.0, 9000.0):
+        M = H.compute_white_balance_matrix(T).astype(np.float64)
+        x, y = [float(v) for v in H.planckian_xy(T)]
+        src = np.array([x / y, 1.0, (1 - x - y) / y])
+        dst = np.array([0.31272 / 0.32903, 1.0, (1 - 0.31272 - 0.32903) / 0.32903])
+        np.testing.assert_allclose(M @ src, dst, rtol=2e-4)
+    sensor = H.FilmSensor()
+    assert float(sensor.exposure_time * sensor.iso / 100) == 1.0 and sensor.white_balance == 0
+    with pytest.raises(ValueError):
+        H.postprocess(H.Film((4, 4)), None, tonemap="nope")
