@@ -95,7 +95,7 @@ __global__ void tk_lights(const __grid_constant__ DevScene D, const float* __res
         for (int k = 0; k < 16; k++) o[k] = 0.0f;
         float3 p = f3(e[0], e[1], e[2]), nn = f3(e[3], e[4], e[5]);
         float4 lam, pdf; sample_wavelengths_visible(e[6], lam, pdf);
-        float pmf; int li = bvh_sample_light(LC, p, nn, e[7], pmf);
+        float pmf; int li = bvh_sample_light_coop(LC, p, nn, e[7], pmf);      // the cooperative form the shading kernels use
         o[0] = (float)li; o[1] = pmf;
         if (li >= 1 && li <= D.n_lights) {
             LightSample ls = sample_light(LC, D.lights[li - 1], p, lam, make_float2(e[8], e[9]));

@@ -493,7 +493,7 @@ __global__ void __launch_bounds__(128, TYPE == HK_MAT_COATED_DIFFUSE ? HK_SHADE_
             if (D.n_lights > 0) {
                 float direct_uc = zsobol_1d(D.sobol, px, py, sidx, bdim + 1, HK_SOBOL_SLOT_BOUNCE(depth, 0), pix);
                 float pmf;
-                int li = bvh_sample_light(LC, sf.pi, sf.ns, direct_uc, pmf);
+                int li = bvh_sample_light_auto(LC, sf.pi, sf.ns, direct_uc, pmf);
                 if (li >= 1 && li <= D.n_lights && pmf > 0.0f) {
                     float2 direct_u = zsobol_2d(D.sobol, px, py, sidx, bdim + 3, HK_SOBOL_SLOT_BOUNCE(depth, 1), pix);
                     LightSample ls = sample_light(LC, D.lights[li - 1], sf.pi, lam, direct_u);
@@ -630,7 +630,7 @@ __global__ void __launch_bounds__(128) k_medium_finish(const __grid_constant__ D
                 const float3 wo = -d;
                 if (D.n_lights > 0) {   // medium_direct_lighting_inner!
                     float pmf;
-                    int li = bvh_sample_light(LC, Rp, f3(0, 0, 0), zsobol_1d(D.sobol, px, py, sidx, bdim + 1, HK_SOBOL_SLOT_BOUNCE(depth, 0), pix), pmf);
+                    int li = bvh_sample_light_auto(LC, Rp, f3(0, 0, 0), zsobol_1d(D.sobol, px, py, sidx, bdim + 1, HK_SOBOL_SLOT_BOUNCE(depth, 0), pix), pmf);
                     if (li >= 1 && li <= D.n_lights && pmf > 0.0f) {
                         LightSample ls = sample_light(LC, D.lights[li - 1], Rp, lam, zsobol_2d(D.sobol, px, py, sidx, bdim + 3, HK_SOBOL_SLOT_BOUNCE(depth, 1), pix));
                         if (ls.pdf > 0.0f && !sp_black(ls.Li)) {
