@@ -235,7 +235,7 @@ def run_cuda(args):
     # ---- timed region: K steps, device-timed (CUDA events on the library's launch stream), barrier + sync both sides ----
     if dist: dist.barrier()
     torch.cuda.synchronize()
-    lib.hk_stats(ctx, C.byref(stats)); rays0, launches0 = stats.rays_traced, stats.kernel_launches
+    lib.hk_stats(ctx, C.byref(stats)); rays0, launches0, verts0 = stats.rays_traced, stats.kernel_launches, stats.path_vertices
     sampler = ClockSampler(local); sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     wall0 = time.perf_counter()
@@ -251,6 +251,7 @@ def run_cuda(args):
     wall = time.perf_counter() - wall0
     clocks = sampler.result()
     rays = stats.rays_traced - rays0
+    verts = stats.path_vertices - verts0
     launches = stats.kernel_launches - launches0
     t_ms = dev_ms + red_ms
     if dist:
@@ -303,6 +304,13 @@ def run_cuda(args):
                     "stage_share": {nm: stage_ms[i] / total_ms for i, nm in enumerate(names)},
                     "shadow": {"rays": work[3], "node_visits_per_ray": work[4] / max(1, work[3]), "tri_tests_per_ray": work[5] / max(1, work[3]),
                                "achieved": (work[3] * 48 + work[4] * 80 + work[5] * 48) / max(1e-9, stage_ms[5] * 1e-3) / 1e9}}
+        # whole path, SURVEY 8d: per path vertex the reference moves 2 178 B of queue records; + the traversal bytes of every
+        # closest-hit and shadow query (counted by the COUNT pass over the same samples) + 84 B per pixel sample of film traffic
+        whole_bytes = verts * 2178 + trace_bytes + (work[3] * 48 + work[4] * 80 + work[5] * 48) + n * args.steps * 84
+        whole_achieved = whole_bytes / (dev_ms * 1e-3) / 1e9 if dev_ms > 0 else 0.0
+        roofline["whole_path"] = {"algorithmic_bytes_per_step": whole_bytes / args.steps, "path_vertices_per_sample": verts / (n * args.steps),
+                                  "achieved": whole_achieved, "peak": peak, "unit": "GB/s", "frac": whole_achieved / peak,
+                                  "note": "reference AOS record traffic (SURVEY 8d) for the work done, divided by this rank's device time"}
         cpu = None if args.quick else cpu_baseline_leg()
         line = {
             "metric": "VolPath throughput", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

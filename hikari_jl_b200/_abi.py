@@ -108,7 +108,7 @@ class HkRenderParams(C.Structure):
 class HkStats(C.Structure):
     _fields_ = [("rays_traced", C.c_uint64), ("samples_rendered", C.c_uint64), ("queue_overflows", C.c_uint64),
                 ("bvh_nodes", C.c_uint64), ("bvh_bytes", C.c_uint64), ("kernel_launches", C.c_uint64),
-                ("last_render_ms", c_f), ("last_trace_ms", c_f)]
+                ("last_render_ms", c_f), ("last_trace_ms", c_f), ("path_vertices", C.c_uint64)]
 
 
 # every symbol include/hikari_cuda.h declares (checked by tests/test_abi.py)

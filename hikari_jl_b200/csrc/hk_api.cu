@@ -421,6 +421,7 @@ static int32_t alloc_state(HkContext* ctx, size_t n_slots) {
     for (int t = 0; t < HK_MAX_MAT_TYPES; t++) S.q_hit[t] = reinterpret_cast<uint32_t*>(take(4));
     S.counts = ctx->b_counts.as<uint32_t>();
     S.rays_traced = reinterpret_cast<unsigned long long*>(ctx->b_counts.as<char>() + sizeof(uint32_t) * HK_N_COUNTERS);
+    S.path_vertices = S.rays_traced + 1;
     ctx->n_slots = n_slots;
     return HK_OK;
 }
@@ -756,6 +757,7 @@ int32_t hk_stats(HkContext* ctx, HkStats* out) {
     if (ctx->S.rays_traced) cudaMemcpy(&rt, ctx->S.rays_traced, 8, cudaMemcpyDeviceToHost);
     *out = ctx->stats;
     out->rays_traced = ctx->stats.rays_traced + rt;
+    { unsigned long long pv = 0; if (ctx->S.path_vertices) cudaMemcpy(&pv, ctx->S.path_vertices, 8, cudaMemcpyDeviceToHost); out->path_vertices = pv; }
     out->kernel_launches = ctx->launches;
     out->queue_overflows = 0;
     return HK_OK;

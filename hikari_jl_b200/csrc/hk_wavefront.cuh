@@ -61,6 +61,7 @@ struct PathState {
     uint32_t *q_ray[2], *q_escaped, *q_medium, *q_shadow, *q_shadow2, *q_hit[HK_MAX_MAT_TYPES];
     uint32_t* counts;                  // [HK_N_COUNTERS]
     unsigned long long* rays_traced;
+    unsigned long long* path_vertices;  // surface hits routed + medium scatter events (HkStats::path_vertices)
     float *pixel_rgb, *pixel_weight;   // film accumulators
 };
 struct PassArgs { int32_t first_sample, stride, n_batch; uint32_t n_pixels; };
@@ -394,7 +395,7 @@ __global__ void __launch_bounds__(256) k_route(const __grid_constant__ DevScene 
         if (threadIdx.x == 32) {   // total surface hits of the bounce (the reference's `n_hits > 0` shadow-pass condition)
             uint32_t h = 0;
             for (int t = 0; t < HK_MAX_MAT_TYPES; t++) h += s_cnt[HK_C_HIT0 + t];
-            if (h) atomicAdd(S.counts + HK_C_TOTAL_HITS, h);
+            if (h) { atomicAdd(S.counts + HK_C_TOTAL_HITS, h); atomicAdd(S.path_vertices, (unsigned long long)h); }
         }
         __syncthreads();
 #pragma unroll
@@ -670,6 +671,8 @@ __global__ void __launch_bounds__(128) k_medium_finish(const __grid_constant__ D
         warp_push(S.counts, nullptr, qid, slot, queue_of(S, qid));
         unsigned hm = __ballot_sync(0xFFFFFFFFu, qid >= HK_C_HIT0);
         if ((threadIdx.x & 31u) == 0 && hm) atomicAdd(S.counts + HK_C_TOTAL_HITS, (uint32_t)__popc(hm));
+        { const unsigned vm = hm | __ballot_sync(0xFFFFFFFFu, push_shadow || push_ray);      // surface vertices + medium scatter vertices
+          if ((threadIdx.x & 31u) == 0 && vm) atomicAdd(S.path_vertices, (unsigned long long)__popc(vm)); }
         warp_push2(S.counts + HK_C_SHADOW, S.q_shadow, push_shadow, S.counts + HK_C_RAY0 + next, S.q_ray[next], push_ray, slot);
     }
 }

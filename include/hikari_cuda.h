@@ -270,6 +270,8 @@ typedef struct HkStats {
     uint64_t kernel_launches;    /* kernels launched by this context so far                           */
     float    last_render_ms;     /* device time of the last hk_render_samples (CUDA events)            */
     float    last_trace_ms;      /* device time of the last hk_trace_closest kernel                    */
+    uint64_t path_vertices;      /* surface hits + medium scattering events shaded so far (the unit of the
+                                  * reference's per-vertex queue traffic)                   */
 } HkStats;
 
 /* ---- lifecycle ---------------------------------------------------------------------------- */
