@@ -579,3 +579,35 @@ def test_nanovdb_matches_dense_grid():
         np.testing.assert_allclose(a, dens.reshape(-1), rtol=2e-4, atol=2e-3)
     finally:
         p.close()
+
+
+def test_error_paths_return_status_codes_not_crashes():
+    """The C ABI never aborts: wrong call order, bad arguments and inconsistent scenes come back as negative status codes
+    with a message (include/hikari_cuda.h), and the context stays usable afterwards."""
+    b = H.Backend()
+    lib, ctx = b.lib, b.ctx
+    assert lib.hk_render_samples(ctx, 1, 1) < 0 and b"before" in lib.hk_last_error(ctx)            # nothing uploaded yet
+    assert lib.hk_clear(ctx) < 0
+    assert lib.hk_read_film(ctx, None) < 0
+    assert lib.hk_trace_closest(ctx, None, 5, None) < 0
+    bad = A.HkMaterial(type=99)
+    iface = A.HkMediumInterface(1, 0, 0)
+    assert lib.hk_upload_materials(ctx, C.byref(bad), 1, C.byref(iface), 1) < 0 and b"unsupported material" in lib.hk_last_error(ctx)
+    mix = A.HkMaterial(type=A.HK_MAT_MIX); mix.ival[0] = 1; mix.ival[1] = 7
+    assert lib.hk_upload_materials(ctx, C.byref(mix), 1, C.byref(iface), 1) < 0 and b"MixMaterial" in lib.hk_last_error(ctx)
+    p = A.HkRenderParams(0, 10, 5, 1, 1, 10.0, 0, 12, 15, 0, 1)
+    assert lib.hk_set_params(ctx, C.byref(p)) < 0
+    assert lib.hk_update_material(ctx, 1, C.byref(bad)) < 0
+    pp = A.HkPostprocess(); pp.tonemap_mode = 42
+    out = np.zeros(12, f32)
+    assert lib.hk_postprocess(ctx, C.byref(pp), fp(out)) < 0
+    b.close()
+    # after the failures a normal render on a fresh context of the same process still works
+    scene, camf = scenes.c1_triangle()
+    film = H.Film((32, 32)); vp = H.VolPath(samples=1, max_depth=2)
+    img = vp(scene, film, camf(film))
+    assert np.isfinite(img).all() and img.max() > 0
+    # sample range validation
+    assert vp.backend.lib.hk_render_samples(vp.backend.ctx, 0, 1) < 0            # sample indices are 1-based
+    assert vp.backend.lib.hk_render_samples_strided(vp.backend.ctx, 1, 0, 1) < 0
+    vp.close()
