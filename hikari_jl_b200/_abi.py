@@ -116,7 +116,7 @@ HK_SYMBOLS = [
     "hk_abi_version", "hk_create", "hk_destroy", "hk_last_error", "hk_upload_tables", "hk_upload_geometry",
     "hk_upload_spectra", "hk_upload_materials", "hk_update_material", "hk_bounce_profile", "hk_upload_envmaps", "hk_upload_lights", "hk_upload_media",
     "hk_set_camera", "hk_set_filter", "hk_set_params", "hk_clear", "hk_render_samples", "hk_render_samples_strided",
-    "hk_read_film", "hk_postprocess", "hk_film_accum_dev", "hk_read_accum", "hk_write_accum", "hk_trace_closest",
+    "hk_read_film", "hk_read_film_async", "hk_read_film_wait", "hk_postprocess", "hk_film_accum_dev", "hk_read_accum", "hk_write_accum", "hk_trace_closest",
     "hk_trace_closest_dev", "hk_trace_any", "hk_stats", "hk_synchronize", "hk_dev_alloc", "hk_dev_free",
     "hk_dev_upload", "hk_dev_download", "hk_set_profiling", "hk_stage_times", "hk_pinned_alloc", "hk_pinned_free",
 ]
@@ -139,6 +139,9 @@ def bind_common(lib, p):
     f("upload_materials", [_VP, C.POINTER(HkMaterial), C.c_uint32, C.POINTER(HkMediumInterface), C.c_uint32])
     f("update_material", [_VP, C.c_uint32, C.POINTER(HkMaterial)])
     f("postprocess", [_VP, C.POINTER(HkPostprocess), c_fp])
+    if p == "hk_":
+        f("read_film_async", [_VP, c_fp, C.POINTER(C.c_int32)])
+        f("read_film_wait", [_VP, C.c_int32])
     f("upload_envmaps", [_VP, C.POINTER(HkEnvMap), C.c_uint32])
     f("upload_lights", [_VP, C.POINTER(HkLight), C.c_uint32, C.POINTER(HkLightSampler)])
     f("upload_media", [_VP, C.POINTER(HkMedium), C.c_uint32])

@@ -48,6 +48,9 @@ struct HkContext {
     DevBuf b_media;
     DevBuf b_f_func, b_f_mcdf, b_f_mfunc, b_f_ccdf;
     DevBuf b_state, b_counts, b_rays, b_film, b_scratch_u32, b_trace_ctr, b_readback;
+    // pipelined read-out (hk_read_film_async): two device staging buffers, a copy stream, per-buffer events
+    DevBuf b_readback_async[2]; cudaStream_t copy_stream = nullptr; cudaEvent_t ev_final[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    int async_next = 0; bool async_used[2] = {false, false};
     DevBuf b_sobol_top, b_sobol_dims, b_sobol_dimhash;        // ZSobol prefix cache (SobolParams::top)
     int32_t sobol_cache_key[6] = {0, 0, 0, 0, 0, -1};          // width, height, log2_spp, nb4, seed, cached depths
     bool sobol_cache_enabled = true;
@@ -133,6 +136,8 @@ int32_t hk_destroy(HkContext* ctx) {
     for (auto& b : ctx->media_bufs) b.release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (int i = 0; i < 2; i++) { if (ctx->ev_final[i]) cudaEventDestroy(ctx->ev_final[i]); if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]); ctx->b_readback_async[i].release(); }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return HK_OK;
@@ -633,6 +638,38 @@ int32_t hk_read_film(HkContext* ctx, float* out) {
     ctx->launches++;
     CK(cudaMemcpyAsync(out, ctx->b_readback.p, 12 * n, cudaMemcpyDeviceToHost, ctx->stream));   // true async DMA when `out` is pinned
     CK(cudaStreamSynchronize(ctx->stream));
+    return HK_OK;
+}
+// Pipelined read-out for progressive display: finalize into one of two staging buffers on the render stream, copy it to the
+// (pinned) host buffer on a separate stream, and return at once -- the next hk_render_samples can be enqueued while the
+// DMA runs.  hk_read_film_wait(ticket) blocks until that frame has landed.  At most two frames in flight.
+int32_t hk_read_film_async(HkContext* ctx, float* out_pinned, int32_t* ticket) {
+    if (!ctx || !out_pinned || !ticket) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    REQUIRE(ctx->have_params, "hk_set_params has not been called");
+    const size_t n = (size_t)ctx->params.width * ctx->params.height;
+    if (!ctx->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) { CK(cudaEventCreateWithFlags(&ctx->ev_final[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming)); }
+    }
+    const int k = ctx->async_next;
+    if (ctx->b_readback_async[k].bytes < 12 * n) { CK(cudaStreamSynchronize(ctx->copy_stream)); CK(ctx->b_readback_async[k].alloc(12 * n)); ctx->async_used[k] = false; }
+    if (ctx->async_used[k]) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[k], 0));      // the staging buffer's previous copy must be done
+    k_film_finalize<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(ctx->S.pixel_rgb, ctx->S.pixel_weight, ctx->b_readback_async[k].as<float>(), ctx->params.width, ctx->params.height);
+    ctx->launches++;
+    CK(cudaEventRecord(ctx->ev_final[k], ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_final[k], 0));
+    CK(cudaMemcpyAsync(out_pinned, ctx->b_readback_async[k].p, 12 * n, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    CK(cudaEventRecord(ctx->ev_copied[k], ctx->copy_stream));
+    ctx->async_used[k] = true; ctx->async_next = k ^ 1;
+    *ticket = k;
+    return HK_OK;
+}
+int32_t hk_read_film_wait(HkContext* ctx, int32_t ticket) {
+    if (!ctx || ticket < 0 || ticket > 1) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    REQUIRE(ctx->copy_stream && ctx->async_used[ticket], "no asynchronous read-out with this ticket is in flight");
+    CK(cudaEventSynchronize(ctx->ev_copied[ticket]));
     return HK_OK;
 }
 int32_t hk_postprocess(HkContext* ctx, const HkPostprocess* p, float* out) {

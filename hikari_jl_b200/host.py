@@ -95,12 +95,39 @@ class Film:
         self.framebuffer = self._store.transpose(1, 0, 2)            # framebuffer[py, px] = RGB (a view)
         self.iteration_index = 0
 
+    def _other_store(self):
+        """second page-locked buffer for the pipelined read-out (Backend.read_film_async): the frame being displayed is
+        never the one being written"""
+        if getattr(self, "_store2", None) is None:
+            w, h = self.resolution
+            self._pinned2 = None
+            try:
+                lib = A.load_library()
+                p = C.c_void_p()
+                if lib.hk_pinned_alloc(12 * w * h, C.byref(p)) == 0 and p.value:
+                    self._pinned2 = (lib, p)
+                    self._store2 = np.ctypeslib.as_array(C.cast(p, A.c_fp), shape=(w, h, 3))
+            except Exception:
+                self._pinned2 = None
+            if getattr(self, "_store2", None) is None:
+                self._store2 = np.empty((w, h, 3), dtype=f32)
+            self._store2[...] = 0
+        return self._store2
+
+    def _show(self, store):
+        if store is not self._store:
+            self._store, self._store2 = store, self._store
+            if getattr(self, "_pinned2", None) is not None or getattr(self, "_pinned", None) is not None:
+                self._pinned, self._pinned2 = getattr(self, "_pinned2", None), getattr(self, "_pinned", None)
+            self.framebuffer = self._store.transpose(1, 0, 2)
+
     def __del__(self):
-        if getattr(self, "_pinned", None):
-            lib, p = self._pinned
-            self.framebuffer = None; self._store = None
-            lib.hk_pinned_free(p)
-            self._pinned = None
+        for name in ("_pinned", "_pinned2"):
+            if getattr(self, name, None):
+                lib, p = getattr(self, name)
+                lib.hk_pinned_free(p)
+                setattr(self, name, None)
+        self.framebuffer = None; self._store = None; self._store2 = None
 
     def clear(self):
         self.framebuffer[:] = 0
@@ -1049,6 +1076,20 @@ class Backend:
         self.call("read_film", _fp(buf))
         out_hw3[...] = buf.transpose(1, 0, 2)
 
+    def read_film_async(self, film):
+        """Enqueue finalize + device->host copy of the current film into the film's OTHER page-locked buffer and return a
+        handle at once (hk_read_film_async); wait_film(handle) makes that frame film.framebuffer."""
+        assert film.resolution == (self.width, self.height)
+        store = film._other_store()
+        ticket = C.c_int32(-1)
+        self.call("read_film_async", _fp(store), C.byref(ticket))
+        return (ticket.value, store)
+
+    def wait_film(self, film, handle):
+        ticket, store = handle
+        self.call("read_film_wait", ticket)
+        film._show(store)
+
     def read_accum(self):
         n = self.width * self.height
         rgb, w = np.empty((n, 3), dtype=f32), np.empty(n, dtype=f32)
@@ -1097,6 +1138,10 @@ class VolPath:
             abi = new_material.to_abi(scene)
             self.backend.call("update_material", mi, C.byref(abi))
 
+    def wait_film(self, film, handle):
+        """Block until the frame requested with render(..., read="async") is film.framebuffer."""
+        self.backend.wait_film(film, handle)
+
     def clear(self):
         """clear!(vp), volpath.jl:108-113"""
         if self.state is not None:
@@ -1108,6 +1153,8 @@ class VolPath:
         first = film.iteration_index + 1
         self.backend.call("render_samples", first, count)
         film.iteration_index += count
+        if read == "async":        # pipelined progressive display: returns a handle for wait_film()
+            return self.backend.read_film_async(film)
         if read:
             self.backend.read_film(film)
 

@@ -311,6 +311,12 @@ int32_t hk_render_samples_strided(HkContext* ctx, int32_t first_sample_idx, int3
 /* replaces: vp_finalize_film_kernel! + host read of film.framebuffer (volpath.jl:384-417).
  * Writes RGB{Float32} in the reference's (H, W) column-major layout: out[((px-1)*H + (py-1))*3 + c]. */
 int32_t hk_read_film(HkContext* ctx, float* out_rgb_hw_colmajor);
+/* Pipelined read-out for progressive display (library extension): finalize + device->host copy of the current film are
+ * enqueued (copy on its own stream) and the call returns a ticket at once, so the next hk_render_samples overlaps the
+ * DMA; hk_read_film_wait blocks until that frame is in `out` (page-locked memory: hk_pinned_alloc).  Two frames at
+ * most in flight; the caller alternates two host buffers.                                                         */
+int32_t hk_read_film_async(HkContext* ctx, float* out_rgb_hw_colmajor_pinned, int32_t* out_ticket);
+int32_t hk_read_film_wait(HkContext* ctx, int32_t ticket);
 
 /* postprocess!(film; exposure, tonemap, gamma, white_point, sensor), src/postprocess.jl:187-357 -- fused into the film
  * read-out: framebuffer = sum / weight, then exposure, Bradford white balance, sensor imaging ratio, tone map, gamma.

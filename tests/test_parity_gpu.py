@@ -611,3 +611,30 @@ def test_error_paths_return_status_codes_not_crashes():
     assert vp.backend.lib.hk_render_samples(vp.backend.ctx, 0, 1) < 0            # sample indices are 1-based
     assert vp.backend.lib.hk_render_samples_strided(vp.backend.ctx, 1, 0, 1) < 0
     vp.close()
+
+
+def test_pipelined_read_out_matches_blocking_read():
+    """hk_read_film_async / hk_read_film_wait (progressive display, one frame deep): every frame that lands equals the
+    frame a blocking hk_read_film returns after the same number of samples."""
+    scene, camf = scenes.c1_spheres(16)
+    res = (96, 64)
+    film_a, film_b = H.Film(res), H.Film(res)
+    va, vb = H.VolPath(samples=1, max_depth=4), H.VolPath(samples=1, max_depth=4)
+    cam_a, cam_b = camf(film_a), camf(film_b)
+    want = []
+    vb._prepare(scene, film_b, cam_b); vb.clear()
+    for k in range(5):
+        vb.render(scene, film_b, cam_b, count=1, read=True)
+        want.append(film_b.framebuffer.copy())
+    va._prepare(scene, film_a, cam_a); va.clear()
+    got, pending = [], None
+    for k in range(5):
+        h = va.render(scene, film_a, cam_a, count=1, read="async")
+        if pending is not None:
+            va.wait_film(film_a, pending); got.append(film_a.framebuffer.copy())
+        pending = h
+    va.wait_film(film_a, pending); got.append(film_a.framebuffer.copy())
+    for g, w in zip(got, want):
+        assert np.array_equal(g.view(np.uint32), w.view(np.uint32))
+    assert va.backend.lib.hk_read_film_wait(va.backend.ctx, 5) < 0          # bad ticket
+    va.close(); vb.close()
