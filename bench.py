@@ -224,8 +224,13 @@ def run_cuda(args):
     def sample_of(k):      # rank-strided sample indices: the multi-GPU partition
         return rank + 1 + k * world
 
-    if args.warmup > 0:      # W untimed steps, in one call like the timed region (same samples-in-flight, state pool allocated here)
-        B.call("render_samples_strided", sample_of(0), world, args.warmup)
+    # W untimed steps in one call like the timed region; if W is smaller than the number of samples the timed call keeps in
+    # flight, the warm-up is topped up to that number so that the path-state pool (allocated on demand) has its final size
+    # and has been touched before the timed region starts
+    n_pix = RES[0] * RES[1]
+    warm = max(args.warmup, min(args.steps, args.batch if args.batch > 0 else max(1, min(64, (32 << 20) // n_pix))))
+    if warm > 0:
+        B.call("render_samples_strided", sample_of(0), world, warm)
     if dist:                 # warm the collective too (NCCL sets up its channels on the first call of a given size); on a scratch
         scratch = torch.zeros_like(acc_t)                            # buffer: the film accumulators are reduced exactly once
         for _ in range(2):
