@@ -51,6 +51,9 @@ struct HkContext {
     // pipelined read-out (hk_read_film_async): two device staging buffers, a copy stream, per-buffer events
     DevBuf b_readback_async[2]; cudaStream_t copy_stream = nullptr; cudaEvent_t ev_final[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     int async_next = 0; bool async_used[2] = {false, false};
+    // fork / join of the per-material shading kernels of one bounce (independent queues) over side streams
+    cudaStream_t shade_streams[3] = {nullptr, nullptr, nullptr}; cudaEvent_t ev_fork = nullptr, ev_join[HK_MAX_MAT_TYPES] = {};
+    bool concurrent_shade = true; int shade_fork_slot = 0;
     DevBuf b_sobol_top, b_sobol_dims, b_sobol_dimhash;        // ZSobol prefix cache (SobolParams::top)
     int32_t sobol_cache_key[6] = {0, 0, 0, 0, 0, -1};          // width, height, log2_spp, nb4, seed, cached depths
     bool sobol_cache_enabled = true;
@@ -116,6 +119,10 @@ int32_t hk_create(int32_t device, HkContext** out) {
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return HK_ERR_CUDA; }
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
+    for (auto& s : ctx->shade_streams) if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { s = nullptr; ctx->concurrent_shade = false; }
+    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    for (auto& e : ctx->ev_join) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    if (std::getenv("HK_SERIAL_SHADE")) ctx->concurrent_shade = false;
     if (ctx->b_counts.alloc(sizeof(uint32_t) * HK_N_COUNTERS + 64) != cudaSuccess || ctx->b_trace_ctr.alloc(64) != cudaSuccess || ctx->b_work_ctr.alloc(64) != cudaSuccess) { delete ctx; return HK_ERR_OOM; }
     cudaMemset(ctx->b_counts.p, 0, ctx->b_counts.bytes); cudaMemset(ctx->b_trace_ctr.p, 0, 64); cudaMemset(ctx->b_work_ctr.p, 0, 64);
     for (int i = 0; i < HK_N_STAGES; i++) { ctx->stage_ms[i] = 0; ctx->stage_launches[i] = 0; }
@@ -136,6 +143,9 @@ int32_t hk_destroy(HkContext* ctx) {
     for (auto& b : ctx->media_bufs) b.release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (auto& s : ctx->shade_streams) if (s) cudaStreamDestroy(s);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    for (auto& e : ctx->ev_join) if (e) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) { if (ctx->ev_final[i]) cudaEventDestroy(ctx->ev_final[i]); if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]); ctx->b_readback_async[i].release(); }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -511,8 +521,21 @@ int32_t hk_clear(HkContext* ctx) {
 }
 
 }  // extern "C"
+// The shading kernels of one bounce work on disjoint slots (one queue per material type) and only share the atomic queue
+// counters, so they are forked over side streams between the routing and the shadow pass: in deep bounces each of them is a
+// latency floor of its own (~30-90 us for a handful of paths) and in early bounces one kernel's tail is filled by the next.
+// With stage timers on (hk_set_profiling) they stay on the render stream so that the timings remain attributable.
 template <int TYPE> static void launch_shade(HkContext* ctx, const PassArgs& A, int next) {
     if (!(ctx->mat_types_present & (1u << TYPE))) return;
+    if (ctx->concurrent_shade && ctx->profiling == 0) {
+        const int j = ctx->shade_fork_slot++;
+        cudaStream_t s = ctx->shade_streams[j % 3];
+        cudaStreamWaitEvent(s, ctx->ev_fork, 0);
+        k_shade<TYPE><<<ctx->sm_count * 8, 128, 0, s>>>(ctx->D, ctx->S, A, next);
+        cudaEventRecord(ctx->ev_join[j], s);
+        ctx->launches++;
+        return;
+    }
     StageScope sc(ctx, HK_STAGE_SHADE);
     k_shade<TYPE><<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(ctx->D, ctx->S, A, next);
 }
@@ -564,10 +587,13 @@ int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride,
                 k_medium_track<<<ctx->sm_count * 4, 128, 0, st>>>(ctx->D, ctx->S);
                 k_medium_finish<<<ctx->sm_count * 8, 128, 0, st>>>(ctx->D, ctx->S, A, cur ^ 1); ctx->launches++;
             }
+            const bool fork = ctx->concurrent_shade && ctx->profiling == 0;
+            if (fork) { ctx->shade_fork_slot = 0; cudaEventRecord(ctx->ev_fork, st); }      // (the escaped-ray kernel overlaps the shading kernels too)
             if (ctx->D.n_lights > 0) { StageScope sc(ctx, HK_STAGE_ESCAPED); k_escaped<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->D, ctx->S); }
             launch_shade<HK_MAT_MATTE>(ctx, A, cur ^ 1); launch_shade<HK_MAT_MIRROR>(ctx, A, cur ^ 1); launch_shade<HK_MAT_GLASS>(ctx, A, cur ^ 1);
             launch_shade<HK_MAT_CONDUCTOR>(ctx, A, cur ^ 1); launch_shade<HK_MAT_COATED_DIFFUSE>(ctx, A, cur ^ 1);
             launch_shade<HK_MAT_THIN_DIELECTRIC>(ctx, A, cur ^ 1); launch_shade<HK_MAT_DIFFUSE_TRANSMISSION>(ctx, A, cur ^ 1);
+            if (fork) for (int j = 0; j < ctx->shade_fork_slot; j++) cudaStreamWaitEvent(st, ctx->ev_join[j], 0);
             if (ctx->D.n_lights > 0) {
                 StageScope sc(ctx, HK_STAGE_SHADOW);
                 if (opaque_only) { if (cnt) k_shadow_opaque<true><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, work); else k_shadow_opaque<false><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, work); }
