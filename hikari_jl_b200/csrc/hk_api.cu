@@ -54,6 +54,8 @@ struct HkContext {
     // fork / join of the per-material shading kernels of one bounce (independent queues) over side streams
     cudaStream_t shade_streams[3] = {nullptr, nullptr, nullptr}; cudaEvent_t ev_fork = nullptr, ev_join[HK_MAX_MAT_TYPES] = {};
     bool concurrent_shade = true; int shade_fork_slot = 0;
+    // the shadow pass of bounce b on its own stream, overlapping trace + route of bounce b+1 (opaque-only scenes)
+    cudaStream_t shadow_stream = nullptr; cudaEvent_t ev_shaded = nullptr, ev_shadowed = nullptr; int bounce_par = 0;
     DevBuf b_sobol_top, b_sobol_dims, b_sobol_dimhash;        // ZSobol prefix cache (SobolParams::top)
     int32_t sobol_cache_key[6] = {0, 0, 0, 0, 0, -1};          // width, height, log2_spp, nb4, seed, cached depths
     bool sobol_cache_enabled = true;
@@ -123,6 +125,9 @@ int32_t hk_create(int32_t device, HkContext** out) {
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     for (auto& e : ctx->ev_join) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     if (std::getenv("HK_SERIAL_SHADE")) ctx->concurrent_shade = false;
+    if (cudaStreamCreateWithFlags(&ctx->shadow_stream, cudaStreamNonBlocking) != cudaSuccess) ctx->shadow_stream = nullptr;
+    cudaEventCreateWithFlags(&ctx->ev_shaded, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_shadowed, cudaEventDisableTiming);
+    if (std::getenv("HK_SERIAL_SHADOW") && ctx->shadow_stream) { cudaStreamDestroy(ctx->shadow_stream); ctx->shadow_stream = nullptr; }
     if (ctx->b_counts.alloc(sizeof(uint32_t) * HK_N_COUNTERS + 64) != cudaSuccess || ctx->b_trace_ctr.alloc(64) != cudaSuccess || ctx->b_work_ctr.alloc(64) != cudaSuccess) { delete ctx; return HK_ERR_OOM; }
     cudaMemset(ctx->b_counts.p, 0, ctx->b_counts.bytes); cudaMemset(ctx->b_trace_ctr.p, 0, 64); cudaMemset(ctx->b_work_ctr.p, 0, 64);
     for (int i = 0; i < HK_N_STAGES; i++) { ctx->stage_ms[i] = 0; ctx->stage_launches[i] = 0; }
@@ -145,6 +150,9 @@ int32_t hk_destroy(HkContext* ctx) {
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (auto& s : ctx->shade_streams) if (s) cudaStreamDestroy(s);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->shadow_stream) cudaStreamDestroy(ctx->shadow_stream);
+    if (ctx->ev_shaded) cudaEventDestroy(ctx->ev_shaded);
+    if (ctx->ev_shadowed) cudaEventDestroy(ctx->ev_shadowed);
     for (auto& e : ctx->ev_join) if (e) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) { if (ctx->ev_final[i]) cudaEventDestroy(ctx->ev_final[i]); if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]); ctx->b_readback_async[i].release(); }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -531,13 +539,13 @@ template <int TYPE> static void launch_shade(HkContext* ctx, const PassArgs& A, 
         const int j = ctx->shade_fork_slot++;
         cudaStream_t s = ctx->shade_streams[j % 3];
         cudaStreamWaitEvent(s, ctx->ev_fork, 0);
-        k_shade<TYPE><<<ctx->sm_count * 8, 128, 0, s>>>(ctx->D, ctx->S, A, next);
+        k_shade<TYPE><<<ctx->sm_count * 8, 128, 0, s>>>(ctx->D, ctx->S, A, next, ctx->bounce_par);
         cudaEventRecord(ctx->ev_join[j], s);
         ctx->launches++;
         return;
     }
     StageScope sc(ctx, HK_STAGE_SHADE);
-    k_shade<TYPE><<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(ctx->D, ctx->S, A, next);
+    k_shade<TYPE><<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(ctx->D, ctx->S, A, next, ctx->bounce_par);
 }
 extern "C" {
 int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride, int32_t count) {
@@ -574,19 +582,27 @@ int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride,
         const size_t n_slots = n_pixels * (size_t)A.n_batch;
         { StageScope sc(ctx, HK_STAGE_CAMERA); k_camera<<<grid_for(ctx, n_slots, 256, 8), 256, 0, st>>>(ctx->D, ctx->S, A, ctx->camera_medium); }
         int cur = 0;
+        // Opaque-only scenes, stage timers off: the shadow pass of bounce b runs on its own stream and overlaps reset / trace /
+        // route of bounce b+1 (it only reads the shadow records and adds to L; escaped / shading of b+1, which also add to L
+        // and rewrite the shadow records, wait for it).  Its three counters are double-buffered by bounce parity.
+        const bool overlap_shadow = opaque_only && ctx->shadow_stream != nullptr && ctx->profiling == 0 && ctx->D.n_lights > 0;
+        bool shadow_in_flight = false;
         for (int depth = 0; depth < ctx->params.max_depth; depth++) {
-            k_reset_bounce<<<1, HK_N_COUNTERS, 0, st>>>(ctx->S, cur); ctx->launches++;
+            const int par = overlap_shadow ? (depth & 1) : 0;
+            ctx->bounce_par = par;
+            k_reset_bounce<<<1, HK_N_COUNTERS, 0, st>>>(ctx->S, cur, overlap_shadow ? (par ^ 1) : -1); ctx->launches++;
             {
                 StageScope sc(ctx, HK_STAGE_TRACE);
                 if (cnt) k_trace<true><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, cur, work);
                 else k_trace<false><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, cur, work);
             }
-            { StageScope sc(ctx, HK_STAGE_ROUTE); k_route<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->D, ctx->S, cur); }
+            { StageScope sc(ctx, HK_STAGE_ROUTE); k_route<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->D, ctx->S, cur, par); }
             if (ctx->D.n_media > 0) {
                 StageScope sc(ctx, HK_STAGE_MEDIUM);
                 k_medium_track<<<ctx->sm_count * 4, 128, 0, st>>>(ctx->D, ctx->S);
                 k_medium_finish<<<ctx->sm_count * 8, 128, 0, st>>>(ctx->D, ctx->S, A, cur ^ 1); ctx->launches++;
             }
+            if (shadow_in_flight) { cudaStreamWaitEvent(st, ctx->ev_shadowed, 0); shadow_in_flight = false; }      // shadow(b-1) done before anything adds to L
             const bool fork = ctx->concurrent_shade && ctx->profiling == 0;
             if (fork) { ctx->shade_fork_slot = 0; cudaEventRecord(ctx->ev_fork, st); }      // (the escaped-ray kernel overlaps the shading kernels too)
             if (ctx->D.n_lights > 0) { StageScope sc(ctx, HK_STAGE_ESCAPED); k_escaped<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->D, ctx->S); }
@@ -595,12 +611,20 @@ int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride,
             launch_shade<HK_MAT_THIN_DIELECTRIC>(ctx, A, cur ^ 1); launch_shade<HK_MAT_DIFFUSE_TRANSMISSION>(ctx, A, cur ^ 1);
             if (fork) for (int j = 0; j < ctx->shade_fork_slot; j++) cudaStreamWaitEvent(st, ctx->ev_join[j], 0);
             if (ctx->D.n_lights > 0) {
-                StageScope sc(ctx, HK_STAGE_SHADOW);
-                if (opaque_only) { if (cnt) k_shadow_opaque<true><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, work); else k_shadow_opaque<false><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, work); }
-                else for (int r = 0; r < HK_SHADOW_ROUNDS; r++) {      // one round per medium-boundary crossing; empty rounds exit at once
-                    if (cnt) k_shadow_seg_trace<true><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, r, work);
-                    else k_shadow_seg_trace<false><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, r, work);
-                    k_shadow_seg_ratio<<<ctx->sm_count * 4, 128, 0, st>>>(ctx->D, ctx->S, r); ctx->launches += r == 0 ? 1 : 2;
+                if (overlap_shadow) {
+                    cudaEventRecord(ctx->ev_shaded, st);
+                    cudaStreamWaitEvent(ctx->shadow_stream, ctx->ev_shaded, 0);
+                    k_shadow_opaque<false><<<tgrid, HK_TRACE_THREADS, 0, ctx->shadow_stream>>>(ctx->D, ctx->S, work, par);
+                    cudaEventRecord(ctx->ev_shadowed, ctx->shadow_stream);
+                    ctx->launches++; shadow_in_flight = true;
+                } else {
+                    StageScope sc(ctx, HK_STAGE_SHADOW);
+                    if (opaque_only) { if (cnt) k_shadow_opaque<true><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, work, par); else k_shadow_opaque<false><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, work, par); }
+                    else for (int r = 0; r < HK_SHADOW_ROUNDS; r++) {      // one round per medium-boundary crossing; empty rounds exit at once
+                        if (cnt) k_shadow_seg_trace<true><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, r, work);
+                        else k_shadow_seg_trace<false><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, r, work);
+                        k_shadow_seg_ratio<<<ctx->sm_count * 4, 128, 0, st>>>(ctx->D, ctx->S, r); ctx->launches += r == 0 ? 1 : 2;
+                    }
                 }
             }
             if ((ctx->profiling & 5) == 5) {   // per-bounce record (debug): counts as left by this bounce + its stage times
@@ -611,6 +635,7 @@ int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride,
             }
             cur ^= 1;
         }
+        if (shadow_in_flight) cudaStreamWaitEvent(st, ctx->ev_shadowed, 0);      // the film pass reads L
         { StageScope sc(ctx, HK_STAGE_FILM); k_film_accumulate<<<grid_for(ctx, n_pixels, 256, 8), 256, 0, st>>>(ctx->D, ctx->S, A); }
         done += A.n_batch;
         if (ctx->profiling & 1) collect_stage_times(ctx);

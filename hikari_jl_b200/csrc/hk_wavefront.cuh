@@ -26,6 +26,14 @@
 #define HK_C_HIT0 8            // + material type (1..7)
 #define HK_N_QUEUE_COUNTERS 16 // the counters above (what hk_bounce_profile reports)
 #define HK_C_CURSOR_MEDIUM 16  // k_medium_track work cursor
+// second copies of the shadow-pass counters: in opaque-only scenes the shadow pass of bounce b runs on its own stream while
+// bounce b+1 is already being traced and routed, so bounces alternate between the two sets (parity = bounce & 1)
+#define HK_C_SHADOW_B 17
+#define HK_C_CURSOR_SHADOW_B 18
+#define HK_C_TOTAL_HITS_B 19
+#define HK_CI_SHADOW(par) ((par) ? HK_C_SHADOW_B : HK_C_SHADOW)
+#define HK_CI_CURSOR_SHADOW(par) ((par) ? HK_C_CURSOR_SHADOW_B : HK_C_CURSOR_SHADOW)
+#define HK_CI_TOTAL_HITS(par) ((par) ? HK_C_TOTAL_HITS_B : HK_C_TOTAL_HITS)
 #define HK_C_SHROUND0 20       // + r (1..10): shadow rays still unresolved after r medium-boundary crossings (round 0 = HK_C_SHADOW)
 #define HK_C_SHCUR_TRACE 32    // + r: work cursor of the closest-hit pass of shadow round r
 #define HK_C_SHCUR_RATIO 44    // + r: work cursor of the ratio-tracking pass of shadow round r
@@ -241,8 +249,11 @@ __global__ void __launch_bounds__(256) k_sobol_prefix(uint32_t* __restrict__ top
 }
 
 // reset_iteration_queues!, volpath-state.jl:214-222 (+ the next ray queue and the traversal cursors)
-__global__ void k_reset_bounce(PathState S, int cur) {      // launched with HK_N_COUNTERS threads
+// keep_par >= 0: the shadow-pass counters of that parity belong to the previous bounce's shadow kernel, which may still be
+// running on its own stream: leave them alone
+__global__ void k_reset_bounce(PathState S, int cur, int keep_par) {      // launched with HK_N_COUNTERS threads
     int i = threadIdx.x;
+    if (keep_par >= 0 && (i == HK_CI_SHADOW(keep_par) || i == HK_CI_CURSOR_SHADOW(keep_par) || i == HK_CI_TOTAL_HITS(keep_par))) return;
     if (i < HK_N_COUNTERS && i != (HK_C_RAY0 + cur)) S.counts[i] = 0;
 }
 // append from whichever lanes are here (a divergent region of a persistent loop): lanes that arrive together share one atomic
@@ -363,7 +374,7 @@ __global__ void __launch_bounds__(256) k_patch_tri_types(float4* __restrict__ tr
 // counters, and one thread per queue then reserves the block's range with a single global atomicAdd (1 per queue per 1024
 // rays).  With warp-level aggregation alone the ~0.5 M same-address atomics per sample were what the kernel waited for.
 #define HK_ROUTE_PER_THREAD 4
-__global__ void __launch_bounds__(256) k_route(const __grid_constant__ DevScene D, PathState S, int cur) {
+__global__ void __launch_bounds__(256) k_route(const __grid_constant__ DevScene D, PathState S, int cur, int par) {
     __shared__ uint32_t s_cnt[HK_N_COUNTERS], s_base[HK_N_COUNTERS];
     const uint32_t n = S.counts[HK_C_RAY0 + cur];
     const uint32_t chunk = 256u * HK_ROUTE_PER_THREAD;
@@ -395,7 +406,7 @@ __global__ void __launch_bounds__(256) k_route(const __grid_constant__ DevScene 
         if (threadIdx.x == 32) {   // total surface hits of the bounce (the reference's `n_hits > 0` shadow-pass condition)
             uint32_t h = 0;
             for (int t = 0; t < HK_MAX_MAT_TYPES; t++) h += s_cnt[HK_C_HIT0 + t];
-            if (h) { atomicAdd(S.counts + HK_C_TOTAL_HITS, h); atomicAdd(S.path_vertices, (unsigned long long)h); }
+            if (h) { atomicAdd(S.counts + HK_CI_TOTAL_HITS(par), h); atomicAdd(S.path_vertices, (unsigned long long)h); }
         }
         __syncthreads();
 #pragma unroll
@@ -446,7 +457,7 @@ HK_DEV bool russian_roulette(Spec& beta, int depth, float rr) {
 #define HK_SHADE_MIN_BLOCKS 4
 #endif
 template <int TYPE>
-__global__ void __launch_bounds__(128, TYPE == HK_MAT_COATED_DIFFUSE ? HK_SHADE_MIN_BLOCKS + 2 : HK_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DevScene D, PathState S, PassArgs A, int next) {
+__global__ void __launch_bounds__(128, TYPE == HK_MAT_COATED_DIFFUSE ? HK_SHADE_MIN_BLOCKS + 2 : HK_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DevScene D, PathState S, PassArgs A, int next, int par) {
     const uint32_t n = S.counts[HK_C_HIT0 + TYPE];
     MatCtx MC = mat_ctx(D);
     LightCtx LC = light_ctx(D);
@@ -547,7 +558,7 @@ __global__ void __launch_bounds__(128, TYPE == HK_MAT_COATED_DIFFUSE ? HK_SHADE_
                 }
             }
         }
-        warp_push2(S.counts + HK_C_SHADOW, S.q_shadow, push_shadow, S.counts + HK_C_RAY0 + next, S.q_ray[next], push_ray, slot);
+        warp_push2(S.counts + HK_CI_SHADOW(par), S.q_shadow, push_shadow, S.counts + HK_C_RAY0 + next, S.q_ray[next], push_ray, slot);
     }
 }
 
@@ -699,14 +710,14 @@ struct ShadowRayIO {
     }
 };
 template <bool COUNT>
-__global__ void __launch_bounds__(HK_TRACE_THREADS, HK_TRACE_BLOCKS_PER_SM) k_shadow_opaque(const __grid_constant__ DevScene D, PathState S, unsigned long long* work) {
+__global__ void __launch_bounds__(HK_TRACE_THREADS, HK_TRACE_BLOCKS_PER_SM) k_shadow_opaque(const __grid_constant__ DevScene D, PathState S, unsigned long long* work, int par) {
     __shared__ uint2 sm_stack[HK_SM_STACK * HK_TRACE_THREADS];
     // reference quirk (volpath.jl:571-609): shadow rays are only traced inside the `n_hits > 0` branch
-    if (S.counts[HK_C_TOTAL_HITS] == 0) return;
-    const uint32_t n = S.counts[HK_C_SHADOW];
+    if (S.counts[HK_CI_TOTAL_HITS(par)] == 0) return;
+    const uint32_t n = S.counts[HK_CI_SHADOW(par)];
     uint32_t traced = 0, wn = 0, wt = 0;
     ShadowRayIO io{S};
-    trace_queue<true, COUNT>(D.bvh, sm_stack + threadIdx.x, n, S.counts + HK_C_CURSOR_SHADOW, io, traced, wn, wt);
+    trace_queue<true, COUNT>(D.bvh, sm_stack + threadIdx.x, n, S.counts + HK_CI_CURSOR_SHADOW(par), io, traced, wn, wt);
     count_rays(S.rays_traced, traced);
     if (COUNT) { count_rays(work + 3, traced); count_rays(work + 4, wn); count_rays(work + 5, wt); }
 }
