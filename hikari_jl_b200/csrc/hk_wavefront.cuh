@@ -568,6 +568,9 @@ __global__ void __launch_bounds__(128, TYPE == HK_MAT_COATED_DIFFUSE ? HK_SHADE_
 #ifndef HK_PHASE_MIN
 #define HK_PHASE_MIN 16
 #endif
+#ifndef HK_MEDIUM_REFILL_MIN
+#define HK_MEDIUM_REFILL_MIN HK_PHASE_MIN     // idle lanes needed before the warp fetches new rays (32 = coherent groups, no mid-flight refill)
+#endif
 __global__ void __launch_bounds__(128) k_medium_track(const __grid_constant__ DevScene D, PathState S) {
     const uint32_t n = S.counts[HK_C_MEDIUM];
     MediaCtx MDC = media_ctx(D);
@@ -584,7 +587,7 @@ __global__ void __launch_bounds__(128) k_medium_track(const __grid_constant__ De
         const unsigned ev = __ballot_sync(0xFFFFFFFFu, busy && T.in_seg);
         const unsigned sk = ~(idle | ev);
         if (idle == 0xFFFFFFFFu && exhausted) break;
-        if (!exhausted && ((uint32_t)__popc(idle) >= (uint32_t)HK_PHASE_MIN || (ev | sk) == 0u)) {
+        if (!exhausted && ((uint32_t)__popc(idle) >= (uint32_t)HK_MEDIUM_REFILL_MIN || (ev | sk) == 0u)) {
             if (!busy) {
                 const uint32_t idx = claim_for_idle(S.counts + HK_C_CURSOR_MEDIUM, idle);
                 if (idx < n) {
@@ -766,7 +769,7 @@ __global__ void __launch_bounds__(128) k_shadow_seg_ratio(const __grid_constant_
         const unsigned ev = __ballot_sync(0xFFFFFFFFu, busy && (!tracking || R.in_seg));
         const unsigned sk = ~(idle | ev);
         if (idle == 0xFFFFFFFFu && exhausted) break;
-        if (!exhausted && ((uint32_t)__popc(idle) >= (uint32_t)HK_PHASE_MIN || (ev | sk) == 0u)) {
+        if (!exhausted && ((uint32_t)__popc(idle) >= (uint32_t)HK_MEDIUM_REFILL_MIN || (ev | sk) == 0u)) {
             if (!busy) {
                 const uint32_t idx = claim_for_idle(S.counts + HK_C_SHCUR_RATIO + round, idle);
                 if (idx < n) {
