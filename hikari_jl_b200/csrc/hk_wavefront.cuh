@@ -3,8 +3,14 @@
 // What the reference does per bounce with ~12 KernelAbstractions launches over AOS records of 112-340 bytes and a
 // device->host `length(queue)` copy per stage (src/integrators/volpath/volpath.jl:538-612, workqueue.jl:108-121) is
 // done here with: one SoA path-state pool indexed by slot (= sample-in-batch * n_pixels + pixel), queues of 4-byte
-// slot ids, warp-aggregated appends (__match_any_sync / __popc), per-material queues and kernels, device-side counts
-// (no host round trips inside a sample pass), and traversal kernels that pull work warp-by-warp from a global cursor.
+// slot ids, warp- / block-aggregated appends (__ballot_sync / __match_any_sync / __popc, shared-memory counters in the
+// routing kernel), per-material queues and kernels, device-side counts (no host round trips inside a sample pass), and
+// persistent kernels (traversal, delta / ratio tracking) whose lanes pull new work from a global cursor as they finish.
+// Kernels of one bounce:  k_reset_bounce -> k_trace -> k_route -> [k_medium_track -> k_medium_finish]
+//                         -> { k_escaped | k_shade<TYPE> ... }  (disjoint slots, forked over side streams by hk_api.cu)
+//                         -> k_shadow_opaque  or  { k_shadow_seg_trace -> k_shadow_seg_ratio } x rounds
+// once per pass: k_camera before, k_film_accumulate after; once per upload: k_sobol_prefix, k_precompute_uplifts,
+// k_patch_tri_types.
 #pragma once
 #include "hk_math.cuh"
 #include "hk_spectral.cuh"
