@@ -190,6 +190,10 @@ class _DevPtr:
 
 
 def run_cuda(args):
+    # torchrun exports OMP_NUM_THREADS=1; the host-side scene build (BVH of up to 50 M triangles, OpenMP) would then run on one
+    # core per rank.  Give every rank its share of the cores instead (must happen before the OpenMP runtime is loaded).
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.environ.get("OMP_NUM_THREADS", "1") == "1":
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 8) // int(os.environ["WORLD_SIZE"])))
     import torch
     import __graft_entry__ as g
     from hikari_jl_b200 import _abi as A
