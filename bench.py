@@ -140,6 +140,8 @@ def run_reference(args):
     cam = camf(film)
     vp._prepare(scene, film, cam); vp.clear()
     n = REF_RES[0] * REF_RES[1]
+    if os.environ.get("OMP_NUM_THREADS") == "1" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        oracle_backend.lib().ok_set_num_threads(os.cpu_count() or 1)      # torchrun pins OMP to 1 thread; rank 0 runs alone: use the box
     cores = oracle_backend.lib().ok_num_threads()
     for w in range(args.warmup):
         vp.backend.call("render_samples", w + 1, 1)
