@@ -332,7 +332,7 @@ def run_cuda(args):
         roofline["whole_path"] = {"algorithmic_bytes_per_step": whole_bytes / args.steps, "path_vertices_per_sample": verts / (n * args.steps),
                                   "achieved": whole_achieved, "peak": peak, "unit": "GB/s", "frac": whole_achieved / peak,
                                   "note": "reference AOS record traffic (SURVEY 8d) for the work done, divided by this rank's device time"}
-        cpu = None if args.quick else cpu_baseline_leg()
+        cpu = None if (args.quick or world > 1) else cpu_baseline_leg()       # the CPU baseline is reported at N=1 only
         line = {
             "metric": "VolPath throughput", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
