@@ -501,7 +501,7 @@ int32_t hk_set_params(HkContext* ctx, const HkRenderParams* p) {
     if (ctx->params.sample_batch < 1) {
         // auto: keep ~HK_AUTO_SLOTS path states in flight.  Deep bounces hold < 1 % of the rays but every stage still costs
         // its latency floor (~0.1 ms: the longest single traversal / shading chain); several samples per pass share it.
-        // 1080p: 16 samples per pass (9.6 GB of path state), 4K: 4 -- memory is not the constraint on a 180 GB part.
+        // 1080p: 16 samples per pass (12.6 GB of path state), 4K: 4 -- memory is not the constraint on a 180 GB part.
         const size_t auto_b = HK_AUTO_SLOTS / ((size_t)p->width * p->height);
         ctx->params.sample_batch = (int32_t)std::min<size_t>(64, std::max<size_t>(1, auto_b));
     }
