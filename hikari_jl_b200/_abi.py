@@ -14,7 +14,8 @@ c_u8p = C.POINTER(C.c_uint8)
 HK_MAT_MATTE, HK_MAT_MIRROR, HK_MAT_GLASS, HK_MAT_CONDUCTOR = 1, 2, 3, 4
 HK_MAT_COATED_DIFFUSE, HK_MAT_THIN_DIELECTRIC, HK_MAT_DIFFUSE_TRANSMISSION = 5, 6, 7
 HK_MAT_MIX = 8
-HK_MATFLAG_REMAP_ROUGHNESS, HK_MATFLAG_SPECTRAL_ETA_K = 1, 2
+HK_MAT_COATED_CONDUCTOR = 9
+HK_MATFLAG_REMAP_ROUGHNESS, HK_MATFLAG_SPECTRAL_ETA_K, HK_MATFLAG_USE_ETA_K = 1, 2, 4
 HK_LIGHT_POINT, HK_LIGHT_SPOT, HK_LIGHT_DIRECTIONAL, HK_LIGHT_SUN = 1, 2, 3, 4
 HK_LIGHT_ENVIRONMENT, HK_LIGHT_AMBIENT, HK_LIGHT_DIFFUSE_AREA = 5, 6, 7
 HK_SPECTRUM_RGB, HK_SPECTRUM_ILLUMINANT = 0, 1
@@ -37,7 +38,7 @@ class HkGeometry(C.Structure):
 
 
 class HkMaterial(C.Structure):
-    _fields_ = [("type", C.c_int32), ("flags", C.c_uint32), ("rgb0", c_f * 3), ("rgb1", c_f * 3), ("f", c_f * 8),
+    _fields_ = [("type", C.c_int32), ("flags", C.c_uint32), ("rgb0", c_f * 3), ("rgb1", c_f * 3), ("rgb2", c_f * 4), ("f", c_f * 8),
                 ("spec", C.c_int32 * 2), ("ival", C.c_int32 * 2)]
 
 

@@ -52,7 +52,7 @@ struct HkContext {
     DevBuf b_readback_async[2]; cudaStream_t copy_stream = nullptr; cudaEvent_t ev_final[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     int async_next = 0; bool async_used[2] = {false, false};
     // fork / join of the per-material shading kernels of one bounce (independent queues) over side streams
-    cudaStream_t shade_streams[3] = {nullptr, nullptr, nullptr}; cudaEvent_t ev_fork = nullptr, ev_join[HK_MAX_MAT_TYPES] = {};
+    cudaStream_t shade_streams[3] = {nullptr, nullptr, nullptr}; cudaEvent_t ev_fork = nullptr, ev_join[12] = {};
     bool concurrent_shade = true; int shade_fork_slot = 0;
     // the shadow pass of bounce b on its own stream, overlapping trace + route of bounce b+1 (opaque-only scenes)
     cudaStream_t shadow_stream = nullptr; cudaEvent_t ev_shaded = nullptr, ev_shadowed = nullptr; int bounce_par = 0;
@@ -272,13 +272,14 @@ int32_t hk_upload_spectra(HkContext* ctx, const HkSpectra* s) {
     return HK_OK;
 }
 
+static bool mat_type_supported(int32_t t) { return (t >= 1 && t < HK_MAX_MAT_TYPES) || t == HK_MAT_MIX || t == HK_MAT_COATED_CONDUCTOR; }
 int32_t hk_upload_materials(HkContext* ctx, const HkMaterial* m, uint32_t nm, const HkMediumInterface* mi, uint32_t ni) {
     if (!ctx) return HK_ERR_INVALID;
     cudaSetDevice(ctx->device);
     REQUIRE(nm == 0 || m, "materials missing"); REQUIRE(ni == 0 || mi, "interfaces missing");
     uint32_t present = 0; int32_t trans = 0;
     for (uint32_t i = 0; i < nm; i++) {
-        REQUIRE((m[i].type >= 1 && m[i].type < HK_MAX_MAT_TYPES) || m[i].type == HK_MAT_MIX, "unsupported material type (CoatedConductor / CoatedDiffuseTransmission are SURVEY 8f items)");
+        REQUIRE(mat_type_supported(m[i].type), "unsupported material type (CoatedDiffuseTransmission is a SURVEY 8f item)");
         if (m[i].type == HK_MAT_MIX) { REQUIRE(m[i].ival[0] >= 1 && (uint32_t)m[i].ival[0] <= nm && m[i].ival[1] >= 1 && (uint32_t)m[i].ival[1] <= nm, "MixMaterial references a missing material"); }
         else present |= 1u << m[i].type;
     }
@@ -303,7 +304,7 @@ int32_t hk_update_material(HkContext* ctx, uint32_t index, const HkMaterial* m) 
     cudaSetDevice(ctx->device);
     REQUIRE(ctx->have_mats, "hk_upload_materials has not been called");
     REQUIRE(index >= 1 && index <= ctx->mat_types.size(), "material index out of range");
-    REQUIRE((m->type >= 1 && m->type < HK_MAX_MAT_TYPES) || m->type == HK_MAT_MIX, "unsupported material type");
+    REQUIRE(mat_type_supported(m->type), "unsupported material type");
     if (m->type == HK_MAT_MIX) REQUIRE(m->ival[0] >= 1 && (size_t)m->ival[0] <= ctx->mat_types.size() && m->ival[1] >= 1 && (size_t)m->ival[1] <= ctx->mat_types.size(), "MixMaterial references a missing material");
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaMemcpy(ctx->b_mats.as<HkMaterial>() + (index - 1), m, sizeof(HkMaterial), cudaMemcpyHostToDevice));
@@ -609,6 +610,7 @@ int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride,
             launch_shade<HK_MAT_MATTE>(ctx, A, cur ^ 1); launch_shade<HK_MAT_MIRROR>(ctx, A, cur ^ 1); launch_shade<HK_MAT_GLASS>(ctx, A, cur ^ 1);
             launch_shade<HK_MAT_CONDUCTOR>(ctx, A, cur ^ 1); launch_shade<HK_MAT_COATED_DIFFUSE>(ctx, A, cur ^ 1);
             launch_shade<HK_MAT_THIN_DIELECTRIC>(ctx, A, cur ^ 1); launch_shade<HK_MAT_DIFFUSE_TRANSMISSION>(ctx, A, cur ^ 1);
+            launch_shade<HK_MAT_COATED_CONDUCTOR>(ctx, A, cur ^ 1);
             if (fork) for (int j = 0; j < ctx->shade_fork_slot; j++) cudaStreamWaitEvent(st, ctx->ev_join[j], 0);
             if (ctx->D.n_lights > 0) {
                 if (overlap_shadow) {

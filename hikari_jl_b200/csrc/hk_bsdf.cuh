@@ -95,15 +95,20 @@ HK_DEV float3 tr_sample_wm(float3 w, float2 u, float ax, float ay) {
 // Uplift cache slots per material type (DevTables::mat_pre): the constant RGB a BSDF uplifts at every call.
 //   Matte / Mirror: A = rgb0.  Glass / CoatedDiffuse: A = rgb0, B = rgb1.  Conductor (RGB eta / k): A, B unbounded.
 //   DiffuseTransmission: A / B = clamp(rgb0 * scale) / clamp(rgb1 * scale).
+//   CoatedConductor: A = eta (unbounded) or the reflectance clamped to [0, 0.9999]; B = k (unbounded).
+HK_DEV bool mat_pre_is_unbounded(const HkMaterial& m, int which) {
+    return m.type == HK_MAT_CONDUCTOR || (m.type == HK_MAT_COATED_CONDUCTOR && (which == 1 || (m.flags & HK_MATFLAG_USE_ETA_K)));
+}
 HK_DEV float4 mat_pre_compute(const DevTables& T, const HkMaterial& m, int which) {
     const float* c = which == 0 ? m.rgb0 : m.rgb1;
-    if (m.type == HK_MAT_CONDUCTOR) return make_pre_unbounded(T, c[0], c[1], c[2]);
+    if (mat_pre_is_unbounded(m, which)) return make_pre_unbounded(T, c[0], c[1], c[2]);
+    if (m.type == HK_MAT_COATED_CONDUCTOR) return make_pre_bounded(T, clampf(c[0], 0.0f, 0.9999f), clampf(c[1], 0.0f, 0.9999f), clampf(c[2], 0.0f, 0.9999f));
     if (m.type == HK_MAT_DIFFUSE_TRANSMISSION) { const float s = m.f[0]; return make_pre_bounded(T, clampf(c[0] * s, 0.0f, 1.0f), clampf(c[1] * s, 0.0f, 1.0f), clampf(c[2] * s, 0.0f, 1.0f)); }
     return make_pre_bounded(T, c[0], c[1], c[2]);      // (rgb_to_spectrum clamps to [0,1] itself)
 }
 HK_DEV Spec mat_spec(const MatCtx& C, const HkMaterial& m, int which, float4 lam) {
     const float4 q = C.T.mat_pre ? __ldg(C.T.mat_pre + 2 * (&m - (const HkMaterial*)C.T.mat_base) + which) : mat_pre_compute(C.T, m, which);
-    return m.type == HK_MAT_CONDUCTOR ? pre_unbounded(q, lam) : pre_bounded(q, lam);
+    return mat_pre_is_unbounded(m, which) ? pre_unbounded(q, lam) : pre_bounded(q, lam);
 }
 HK_DEV Spec ior_spectrum(const MatCtx& C, const HkMaterial& m, int which, float4 lambda) {   // :206-210
     if ((m.flags & HK_MATFLAG_SPECTRAL_ETA_K) && m.spec[which] > 0) {
@@ -263,6 +268,7 @@ HK_DEV BsdfEval eval_diffuse_transmission(const MatCtx& C, const HkMaterial& m, 
 }
 
 #include "hk_bsdf_layered.cuh"
+#include "hk_bsdf_coated_conductor.cuh"
 
 // ---- per-type dispatch used by the per-material-queue kernels (TYPE is a compile-time constant) ------------------
 template <int TYPE>
@@ -274,6 +280,7 @@ HK_DEV BsdfSample sample_bsdf(const MatCtx& C, const HkMaterial& m, float3 wo, f
     if (TYPE == HK_MAT_COATED_DIFFUSE) return sample_coated_diffuse(C, m, wo, ns, lam, u, uc, regularize);
     if (TYPE == HK_MAT_THIN_DIELECTRIC) return sample_thin_dielectric(m, wo, ns, uc);
     if (TYPE == HK_MAT_DIFFUSE_TRANSMISSION) return sample_diffuse_transmission(C, m, wo, ns, lam, u, uc);
+    if (TYPE == HK_MAT_COATED_CONDUCTOR) return sample_coated_conductor(C, m, wo, ns, lam, u, uc, regularize);
     return bsdf_none();
 }
 template <int TYPE>
@@ -282,5 +289,6 @@ HK_DEV BsdfEval eval_bsdf(const MatCtx& C, const HkMaterial& m, float3 wo, float
     if (TYPE == HK_MAT_CONDUCTOR) return eval_conductor(C, m, wo, wi, ns, lam);
     if (TYPE == HK_MAT_COATED_DIFFUSE) return eval_coated_diffuse(C, m, wo, wi, ns, lam);
     if (TYPE == HK_MAT_DIFFUSE_TRANSMISSION) return eval_diffuse_transmission(C, m, wo, wi, ns, lam);
+    if (TYPE == HK_MAT_COATED_CONDUCTOR) return eval_coated_conductor(C, m, wo, wi, ns, lam);
     return eval_none();   // Mirror / Glass / ThinDielectric are delta-only
 }

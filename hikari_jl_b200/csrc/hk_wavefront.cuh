@@ -29,7 +29,8 @@
 #define HK_C_TOTAL_HITS 5
 #define HK_C_CURSOR_TRACE 6
 #define HK_C_CURSOR_SHADOW 7
-#define HK_C_HIT0 8            // + material type (1..7)
+#define HK_C_HIT0 8            // + hit queue of the material type: types 1..7 use queue = type, CoatedConductor (9) the spare queue 0
+#define HK_TYPE_QUEUE(t) ((t) == HK_MAT_COATED_CONDUCTOR ? 0 : (t))
 #define HK_N_QUEUE_COUNTERS 16 // the counters above (what hk_bounce_profile reports)
 #define HK_C_CURSOR_MEDIUM 16  // k_medium_track work cursor
 // second copies of the shadow-pass counters: in opaque-only scenes the shadow pass of bounce b runs on its own stream while
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(128) k_precompute_uplifts(DevTables T, const H
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         if (i < n_mats) {
             const HkMaterial& m = mats[i];
-            const bool rgb = m.type >= 1 && m.type < HK_MAX_MAT_TYPES && m.type != HK_MAT_THIN_DIELECTRIC;
+            const bool rgb = (m.type >= 1 && m.type < HK_MAX_MAT_TYPES && m.type != HK_MAT_THIN_DIELECTRIC) || m.type == HK_MAT_COATED_CONDUCTOR;
             mat_pre[2 * i] = rgb ? mat_pre_compute(T, m, 0) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             mat_pre[2 * i + 1] = rgb ? mat_pre_compute(T, m, 1) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         } else if (i < n_mats + n_lights) {
@@ -361,9 +362,9 @@ HK_DEV int hit_queue_id(const DevScene& D, const PathState& S, uint32_t slot, ui
         const uint32_t res = resolve_mix_material(D.materials, D.interfaces[mi - 1].material, o + d * t_hit, -d);
         S.res_mat[slot] = res;
         mtype = (uint32_t)D.materials[res - 1].type;
-        if (mtype >= HK_MAX_MAT_TYPES) mtype = 0;      // a mix chain deeper than 8 levels: the reference would shade a MixMaterial (undefined); dropped
+        if (mtype == HK_MAT_MIX) return -1;            // a mix chain deeper than 8 levels: the reference would shade a MixMaterial (undefined); dropped
     }
-    return HK_C_HIT0 + (int)mtype;
+    return HK_C_HIT0 + (int)HK_TYPE_QUEUE(mtype);
 }
 
 // writes the material type (1..7) of every BVH triangle into the spare word of its record (HitRec)
@@ -464,7 +465,7 @@ HK_DEV bool russian_roulette(Spec& beta, int depth, float rr) {
 #endif
 template <int TYPE>
 __global__ void __launch_bounds__(128, TYPE == HK_MAT_COATED_DIFFUSE ? HK_SHADE_MIN_BLOCKS + 2 : HK_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DevScene D, PathState S, PassArgs A, int next, int par) {
-    const uint32_t n = S.counts[HK_C_HIT0 + TYPE];
+    const uint32_t n = S.counts[HK_C_HIT0 + HK_TYPE_QUEUE(TYPE)];
     MatCtx MC = mat_ctx(D);
     LightCtx LC = light_ctx(D);
     const uint32_t n_round = (n + 31u) & ~31u;     // whole warps iterate together so the aggregated pushes stay converged
@@ -472,7 +473,7 @@ __global__ void __launch_bounds__(128, TYPE == HK_MAT_COATED_DIFFUSE ? HK_SHADE_
         bool push_shadow = false, push_ray = false;
         uint32_t slot = 0;
         if (i < n) {
-            slot = S.q_hit[TYPE][i];
+            slot = S.q_hit[HK_TYPE_QUEUE(TYPE)][i];
             const float4 hr = S.hit[slot];
             const uint32_t prim0 = HK_HIT_PRIM1(__float_as_uint(hr.y)) - 1u;
             const float4 ra = S.ray_a[slot], rb = S.ray_b[slot];

@@ -495,6 +495,50 @@ class CoatedDiffuseMaterial(Material):    # coated-diffuse.jl:98-127
         return m
 
 
+class CoatedConductorMaterial(Material):  # coated-conductor.jl:48-105 (struct), 167-243 (keyword constructor)
+    """Dielectric coating over a conductor.  Give `conductor_eta` + `conductor_k` (RGB or PiecewiseLinearSpectrum) or the
+    artist `reflectance`; with neither, reflectance = 1 as in the reference."""
+    type = A.HK_MAT_COATED_CONDUCTOR
+
+    def __init__(self, interface_roughness=0.0, interface_eta=1.5, conductor_eta=None, conductor_k=None, reflectance=None,
+                 conductor_roughness=0.01, thickness=0.01, albedo=0.0, g=0.0, max_depth=10, n_samples=1,
+                 remap_roughness=True):
+        if conductor_eta is not None and conductor_k is None:
+            raise ValueError("conductor_k must be provided when using conductor_eta")     # coated-conductor.jl:203-205
+        pair = lambda r: tuple(float(v) for v in r) if isinstance(r, tuple) else (float(r), float(r))
+        self.i_rough, self.c_rough = pair(interface_roughness), pair(conductor_roughness)
+        self.interface_eta, self.thickness, self.g = float(interface_eta), float(thickness), float(g)
+        self.use_eta_k = conductor_eta is not None
+        self.conductor_eta, self.conductor_k = conductor_eta, conductor_k
+        self.reflectance = _rgb(1.0 if reflectance is None else reflectance)
+        self.albedo = _rgb(albedo)
+        self.max_depth, self.n_samples, self.remap = int(max_depth), int(n_samples), bool(remap_roughness)
+
+    def to_abi(self, scene):
+        m = A.HkMaterial(type=self.type)
+        m.flags = A.HK_MATFLAG_REMAP_ROUGHNESS if self.remap else 0
+        if self.use_eta_k:
+            m.flags |= A.HK_MATFLAG_USE_ETA_K
+            spectral = isinstance(self.conductor_eta, PiecewiseLinearSpectrum)
+            assert spectral == isinstance(self.conductor_k, PiecewiseLinearSpectrum), "eta and k must both be spectra or both RGB"
+            if spectral:
+                m.flags |= A.HK_MATFLAG_SPECTRAL_ETA_K
+                m.spec[0], m.spec[1] = scene._spectrum_id(self.conductor_eta), scene._spectrum_id(self.conductor_k)
+            else:
+                m.rgb0[:] = _rgb(self.conductor_eta)
+                m.rgb1[:] = _rgb(self.conductor_k)
+        else:
+            m.rgb0[:] = self.reflectance
+        m.rgb2[0:3] = self.albedo
+        m.f[0], m.f[1], m.f[2], m.f[3], m.f[4] = self.i_rough[0], self.i_rough[1], self.thickness, self.interface_eta, self.g
+        m.f[5], m.f[6] = self.c_rough
+        m.ival[0], m.ival[1] = self.max_depth, self.n_samples
+        return m
+
+
+CoatedConductor = CoatedConductorMaterial      # coated-conductor.jl:249
+
+
 class ThinDielectricMaterial(Material):   # thin-dielectric.jl:45-52
     type = A.HK_MAT_THIN_DIELECTRIC
 

@@ -83,6 +83,33 @@ def mix_spheres(tess=32):
     return s, _cam((0, 1.5, 4), (0, 0.5, 0), 40.0)
 
 
+def coated_conductor_spheres(tess=32):
+    """The four closed-form cases of CoatedConductorMaterial (spectral-eval.jl:2877-3418) side by side: coating smooth / rough
+    x conductor smooth / rough, in eta-k (RGB and measured-spectrum) and reflectance mode, one with an absorbing layer, and
+    one reached through a MixMaterial (amount = 1: always its second material)."""
+    s = H.Scene()
+    au = H.Gold()
+    s.push(H.rect3((-5, -1, -5), (10, 0.1, 10)), H.MatteMaterial(Kd=(0.7, 0.7, 0.7)))
+    s.push(H.uv_sphere((-2.1, 0.5, 0.0), 0.65, tess, tess),
+           H.CoatedConductorMaterial(interface_roughness=0.0, conductor_roughness=0.0, reflectance=(0.95, 0.64, 0.54)))
+    s.push(H.uv_sphere((-0.7, 0.5, 0.0), 0.65, tess, tess),
+           H.CoatedConductorMaterial(interface_roughness=0.0, conductor_roughness=0.15, conductor_eta=(0.143, 0.374, 1.442),
+                                     conductor_k=(3.983, 2.385, 1.603)))
+    s.push(H.uv_sphere((0.7, 0.5, 0.0), 0.65, tess, tess),
+           H.CoatedConductorMaterial(interface_roughness=0.3, conductor_roughness=0.0, conductor_eta=au.eta, conductor_k=au.k,
+                                     albedo=(0.6, 0.8, 0.6), thickness=0.2))
+    s.push(H.uv_sphere((2.1, 0.5, 0.0), 0.65, tess, tess),
+           H.MixMaterial((H.MatteMaterial(Kd=(0.8, 0.2, 0.2)),
+                          H.CoatedConductorMaterial(interface_roughness=(0.2, 0.05), conductor_roughness=(0.1, 0.3),
+                                                    reflectance=(0.9, 0.1, 0.1), interface_eta=1.33)), amount=1.0))
+    d = np.array([-1.0, -1.5, -0.5])
+    s.push(H.DirectionalLight((3, 3, 3), d / np.linalg.norm(d), legacy_rgbspectrum=True))
+    s.push(H.PointLight((40, 40, 40), (1.0, 3.0, 3.0)))
+    s.push(H.AmbientLight((0.4, 0.5, 0.6)))
+    s.sync()
+    return s, _cam((0, 1.5, 5), (0, 0.4, 0), 40.0)
+
+
 def blob_mesh(center, radius, n=256, seed=3):
     """Closed procedural stand-in for cat.obj: a sphere displaced by a few low-frequency harmonics."""
     m = H.uv_sphere((0, 0, 0), 1.0, n, n)

@@ -91,20 +91,27 @@ typedef struct HkGeometry {
 #define HK_MAT_DIFFUSE_TRANSMISSION 7   /* :2083-2218                                          */
 #define HK_MAT_MIX                  8   /* src/materials/mix-material.jl: resolved to one of its two sub-materials at
                                            intersection time (resolve_mix_material :253-268), never shaded itself   */
+#define HK_MAT_COATED_CONDUCTOR     9   /* src/materials/spectral-eval.jl:2877-3237 (sample), 3243-3418 (eval);
+                                           src/materials/coated-conductor.jl:48-105                                 */
 
 #define HK_MATFLAG_REMAP_ROUGHNESS  1u
 #define HK_MATFLAG_SPECTRAL_ETA_K   2u  /* conductor eta/k are piecewise-linear spectra (ids in spec[]) */
+#define HK_MATFLAG_USE_ETA_K        4u  /* CoatedConductor: rgb0 / rgb1 (or spec[]) are eta / k; clear = rgb0 is the
+                                           artist reflectance (use_eta_k, coated-conductor.jl:98)                   */
 
 typedef struct HkMaterial {
     int32_t  type;
     uint32_t flags;
     float    rgb0[3];   /* Matte Kd | Mirror Kr | Glass Kr | Conductor eta | Coated reflectance | DiffTrans reflectance */
     float    rgb1[3];   /* Glass Kt | Conductor k | Coated albedo | DiffTrans transmittance                            */
+    float    rgb2[4];   /* CoatedConductor: rgb0 = conductor eta (or reflectance), rgb1 = conductor k, rgb2 = albedo   */
     float    f[8];      /* Matte: f0=sigma. Glass: f0=index. Conductor: f0=roughness.
                            ThinDielectric: f0=eta. DiffuseTransmission: f0=scale.
-                           CoatedDiffuse: f0=u_roughness f1=v_roughness f2=thickness f3=eta f4=g       */
+                           CoatedDiffuse: f0=u_roughness f1=v_roughness f2=thickness f3=eta f4=g
+                           CoatedConductor: f0/f1=interface u/v roughness f2=thickness f3=interface_eta f4=g
+                                            f5/f6=conductor u/v roughness                              */
     int32_t  spec[2];   /* 1-based ids into the uploaded piecewise-linear spectra (eta, k); 0 = unused  */
-    int32_t  ival[2];   /* CoatedDiffuse: ival0=max_depth ival1=n_samples                               */
+    int32_t  ival[2];   /* CoatedDiffuse / CoatedConductor: ival0=max_depth ival1=n_samples             */
                         /* Mix: f0 = amount (constant texture); ival0 / ival1 = 1-based material1 / material2;
                            the SetKeys hashed by mix_hash_float (mix-material.jl:114-158): spec0 / spec1 = vec_idx of
                            material1 / material2, flags = type_idx1 | type_idx2 << 8                             */

@@ -223,3 +223,64 @@ def test_mix_material_hash_and_resolution():
         us.append(u)
     us = np.array(us)
     assert us.min() >= 0.0 and us.max() <= 1.0 and abs(us.mean() - 0.5) < 0.03      # a usable uniform variate
+
+
+def _oracle_bsdf(mats, x):
+    """ok_test_bsdf over one-triangle scenes: returns one (n, 16) record array per material"""
+    out = []
+    for mat in mats:
+        s = H.Scene()
+        s.push(H.Mesh([(0, 0, 0), (1, 0, 0), (0, 1, 0)], [(0, 1, 2)]), mat)
+        s.push(H.PointLight((1, 1, 1), (0, 5, 0)))
+        s.sync()
+        p = Pair(scene=s, need_gpu=False)
+        try:
+            o = np.zeros((len(x), 16), f32)
+            p.olib.ok_test_bsdf(p.ok.ctx, 1, fp(x), len(x), fp(o))
+            out.append(o)
+        finally:
+            p.close()
+    return out
+
+
+def test_coated_conductor_known_answers():
+    """CoatedConductorMaterial (spectral-eval.jl:2877-3418) has no golden vector upstream; the restatement is pinned by
+    the identities the reference's formulas imply: (1) a coating of IOR 1 has F = 0 and T = 1, so the material must
+    reduce to ConductorMaterial with the same eta / k / roughness (sample and eval); (2) in reflectance mode
+    k = 2 sqrt(r) / sqrt(1 - r) with eta = 1 gives a normal-incidence Fresnel reflectance of exactly r (pbrt-v4
+    materials.cpp:371-373), so a smooth/smooth gray 0.5 coated conductor seen head-on returns f = 0.5."""
+    rng = np.random.RandomState(5)
+    n = 4000
+    x = np.zeros((n, 17), f32)
+    nn = np.tile(np.array([0, 0, 1], f32), (n, 1))
+    def hemi(k):
+        v = rng.normal(size=(k, 3)); v[:, 2] = np.abs(v[:, 2]) + 0.05
+        return v / np.linalg.norm(v, axis=1, keepdims=True)
+    x[:, 0:3] = hemi(n); x[:, 3:6] = nn
+    x[:, 6:10] = rng.uniform(380, 780, size=(n, 4))
+    x[:, 10:13] = rng.uniform(0, 1, size=(n, 3))
+    x[:, 14:17] = hemi(n)
+    eta, k = (0.2, 0.9, 1.1), (3.9, 2.4, 1.6)
+    for rough in (0.2, 0.0):
+        cc, cd = _oracle_bsdf([H.CoatedConductorMaterial(interface_roughness=0.0, interface_eta=1.0, conductor_eta=eta,
+                                                         conductor_k=k, conductor_roughness=rough),
+                               H.ConductorMaterial(eta=eta, k=k, roughness=rough)], x)
+        valid = (cc[:, 7] > 0) & (cd[:, 7] > 0)
+        assert valid.mean() > 0.8 and ((cc[:, 7] > 0) == (cd[:, 7] > 0)).mean() > 0.999
+        # wi.z is rebuilt as sqrt(1 - x^2 - y^2) on the way out of the coating: absolute error ~1e-3 at grazing angles
+        assert np.allclose(cc[valid][:, 0:3], cd[valid][:, 0:3], atol=1e-3), rough
+        assert np.allclose(cc[valid][:, 3:15], cd[valid][:, 3:15], rtol=2e-3, atol=2e-5), rough
+    # (2) reflectance mode, normal incidence
+    x2 = x[:8].copy(); x2[:, 0:3] = (0, 0, 1)
+    (o,) = _oracle_bsdf([H.CoatedConductorMaterial(interface_roughness=0.0, interface_eta=1.0, reflectance=(0.5, 0.5, 0.5),
+                                                   conductor_roughness=0.0)], x2)
+    assert (o[:, 8] == 1).all() and np.allclose(o[:, 0:3], (0, 0, 1), atol=1e-6)
+    assert np.allclose(o[:, 3:7], 0.5, rtol=1e-3), o[0, 3:7]
+    # a real coating (IOR 1.5) over the same metal: every case finite, non-negative, never brighter than the bare metal bound
+    for ir, cr in ((0.0, 0.0), (0.0, 0.2), (0.3, 0.0), (0.3, 0.2)):
+        (o,) = _oracle_bsdf([H.CoatedConductorMaterial(interface_roughness=ir, conductor_roughness=cr, reflectance=(0.9, 0.6, 0.3),
+                                                       albedo=(0.5, 0.5, 0.5), thickness=0.05)], x)
+        assert np.isfinite(o).all() and (o[:, 3:7] >= 0).all() and (o[:, 10:14] >= 0).all() and (o[:, 7] >= 0).all()
+        assert (o[:, 7] > 0).mean() > 0.3, (ir, cr)      # rough conductor under IOR 1.5: reflections past the critical angle are dropped (:3063-3066)
+        if ir == 0.0 and cr == 0.0:
+            assert (o[:, 8] == 1).all() and (o[:, 10:15] == 0).all()      # both delta: eval == 0 (:3322-3325)

@@ -208,6 +208,14 @@ MATERIALS = [
     ("gold_rough", None), ("coated_smooth", H.CoatedDiffuseMaterial(reflectance=(0.4, 0.45, 0.35), roughness=0.0)),
     ("coated_rough", H.CoatedDiffuseMaterial(reflectance=(0.8, 0.2, 0.2), roughness=0.3)),
     ("coated_medium", H.CoatedDiffuseMaterial(reflectance=(0.9, 0.9, 0.9), albedo=(0.8, 0.4, 0.2), g=0.3, roughness=0.1, thickness=0.1)),
+    ("cc_smooth_smooth", H.CoatedConductorMaterial(interface_roughness=0.0, conductor_roughness=0.0, reflectance=(0.95, 0.64, 0.54))),
+    ("cc_smooth_rough", H.CoatedConductorMaterial(interface_roughness=0.0, conductor_roughness=0.15, conductor_eta=(0.143, 0.374, 1.442),
+                                                  conductor_k=(3.983, 2.385, 1.603))),
+    ("cc_rough_smooth", H.CoatedConductorMaterial(interface_roughness=0.3, conductor_roughness=0.0, reflectance=(0.2, 0.9, 0.4),
+                                                  albedo=(0.6, 0.8, 0.6), thickness=0.2)),
+    ("cc_rough_rough", H.CoatedConductorMaterial(interface_roughness=(0.2, 0.05), conductor_roughness=(0.1, 0.3), reflectance=(0.9, 0.1, 0.1),
+                                                 interface_eta=1.33, albedo=(0.5, 0.5, 0.9), thickness=0.05, remap_roughness=False)),
+    ("cc_gold", "cc_gold"),
     ("thin", H.ThinDielectricMaterial(eta=1.5)), ("difftrans", H.DiffuseTransmissionMaterial(reflectance=(0.4, 0.3, 0.2), transmittance=(0.3, 0.4, 0.3))),
 ]
 
@@ -216,6 +224,9 @@ MATERIALS = [
 def test_bsdf_sample_and_eval(name, mat):
     if mat is None:
         mat = H.Gold(roughness=0.1)
+    if mat == "cc_gold":
+        au = H.Gold()
+        mat = H.CoatedConductorMaterial(interface_roughness=0.1, conductor_roughness=0.2, conductor_eta=au.eta, conductor_k=au.k)
     s = H.Scene()
     s.push(H.Mesh([(0, 0, 0), (1, 0, 0), (0, 1, 0)], [(0, 1, 2)]), mat)
     s.push(H.PointLight((1, 1, 1), (0, 5, 0)))
@@ -340,6 +351,7 @@ IMAGE_CASES = [
     # on the inputs carry libm ulps (cos/sin of the BSDF sample), so choices can flip and only distributions agree
     ("mix_materials_primary", lambda: scenes.mix_spheres(24), (96, 72), 6, 1, "strict"),
     ("mix_materials", lambda: scenes.mix_spheres(24), (96, 72), 16, 6, "hashed:0.80"),
+    ("coated_conductor", lambda: scenes.coated_conductor_spheres(24), (128, 72), 6, 6, "strict"),
     ("c3_small", lambda: scenes.c3_many_lights(300, 24), (96, 54), 4, 6, "strict"),
     ("c4_cloud_small", lambda: scenes.c4_cloud((32, 32, 16), "nanovdb", (8, 8, 8)), (64, 36), 4, 8, "hashed"),
     ("c4_grid_small", lambda: scenes.c4_cloud((32, 32, 16), "grid", (8, 8, 8)), (64, 36), 4, 8, "hashed"),
