@@ -15,6 +15,7 @@ HK_MAT_MATTE, HK_MAT_MIRROR, HK_MAT_GLASS, HK_MAT_CONDUCTOR = 1, 2, 3, 4
 HK_MAT_COATED_DIFFUSE, HK_MAT_THIN_DIELECTRIC, HK_MAT_DIFFUSE_TRANSMISSION = 5, 6, 7
 HK_MAT_MIX = 8
 HK_MAT_COATED_CONDUCTOR = 9
+HK_MAT_COATED_DIFFUSE_TRANSMISSION = 10
 HK_MATFLAG_REMAP_ROUGHNESS, HK_MATFLAG_SPECTRAL_ETA_K, HK_MATFLAG_USE_ETA_K = 1, 2, 4
 HK_LIGHT_POINT, HK_LIGHT_SPOT, HK_LIGHT_DIRECTIONAL, HK_LIGHT_SUN = 1, 2, 3, 4
 HK_LIGHT_ENVIRONMENT, HK_LIGHT_AMBIENT, HK_LIGHT_DIFFUSE_AREA = 5, 6, 7
@@ -29,7 +30,8 @@ class HkTables(C.Structure):
 
 class HkPostprocess(C.Structure):
     _fields_ = [("exposure", c_f), ("tonemap_mode", C.c_int32), ("inv_gamma", c_f), ("apply_gamma", C.c_int32),
-                ("white_point", c_f), ("imaging_ratio", c_f), ("apply_wb", C.c_int32), ("wb", c_f * 9)]
+                ("white_point", c_f), ("imaging_ratio", c_f), ("apply_wb", C.c_int32), ("wb", c_f * 9),
+                ("mask_escaped", C.c_int32), ("background", c_f * 3)]
 
 
 class HkGeometry(C.Structure):
@@ -117,7 +119,7 @@ HK_SYMBOLS = [
     "hk_abi_version", "hk_create", "hk_destroy", "hk_last_error", "hk_upload_tables", "hk_upload_geometry",
     "hk_upload_spectra", "hk_upload_materials", "hk_update_material", "hk_bounce_profile", "hk_upload_envmaps", "hk_upload_lights", "hk_upload_media",
     "hk_set_camera", "hk_set_filter", "hk_set_params", "hk_clear", "hk_render_samples", "hk_render_samples_strided",
-    "hk_read_film", "hk_read_film_async", "hk_read_film_wait", "hk_postprocess", "hk_film_accum_dev", "hk_read_accum", "hk_write_accum", "hk_trace_closest",
+    "hk_read_film", "hk_read_film_async", "hk_read_film_wait", "hk_postprocess", "hk_fill_aux_buffers", "hk_read_aux_buffers", "hk_film_accum_dev", "hk_read_accum", "hk_write_accum", "hk_trace_closest",
     "hk_trace_closest_dev", "hk_trace_any", "hk_stats", "hk_synchronize", "hk_dev_alloc", "hk_dev_free",
     "hk_dev_upload", "hk_dev_download", "hk_set_profiling", "hk_stage_times", "hk_pinned_alloc", "hk_pinned_free",
 ]
@@ -140,6 +142,8 @@ def bind_common(lib, p):
     f("upload_materials", [_VP, C.POINTER(HkMaterial), C.c_uint32, C.POINTER(HkMediumInterface), C.c_uint32])
     f("update_material", [_VP, C.c_uint32, C.POINTER(HkMaterial)])
     f("postprocess", [_VP, C.POINTER(HkPostprocess), c_fp])
+    f("fill_aux_buffers", [_VP, C.c_int32])
+    f("read_aux_buffers", [_VP, c_fp, c_fp, c_fp])
     if p == "hk_":
         f("read_film_async", [_VP, c_fp, C.POINTER(C.c_int32)])
         f("read_film_wait", [_VP, C.c_int32])

@@ -48,6 +48,7 @@ struct HkContext {
     DevBuf b_media;
     DevBuf b_f_func, b_f_mcdf, b_f_mfunc, b_f_ccdf;
     DevBuf b_state, b_counts, b_rays, b_film, b_scratch_u32, b_trace_ctr, b_readback;
+    DevBuf b_aux; size_t aux_pixels = 0;     // film.albedo [3n] | film.normal [3n] | film.depth [n], (H, W) column-major
     // pipelined read-out (hk_read_film_async): two device staging buffers, a copy stream, per-buffer events
     DevBuf b_readback_async[2]; cudaStream_t copy_stream = nullptr; cudaEvent_t ev_final[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     int async_next = 0; bool async_used[2] = {false, false};
@@ -272,14 +273,14 @@ int32_t hk_upload_spectra(HkContext* ctx, const HkSpectra* s) {
     return HK_OK;
 }
 
-static bool mat_type_supported(int32_t t) { return (t >= 1 && t < HK_MAX_MAT_TYPES) || t == HK_MAT_MIX || t == HK_MAT_COATED_CONDUCTOR; }
+static bool mat_type_supported(int32_t t) { return (t >= 1 && t < HK_MAX_MAT_TYPES) || t == HK_MAT_MIX || t == HK_MAT_COATED_CONDUCTOR || t == HK_MAT_COATED_DIFFUSE_TRANSMISSION; }
 int32_t hk_upload_materials(HkContext* ctx, const HkMaterial* m, uint32_t nm, const HkMediumInterface* mi, uint32_t ni) {
     if (!ctx) return HK_ERR_INVALID;
     cudaSetDevice(ctx->device);
     REQUIRE(nm == 0 || m, "materials missing"); REQUIRE(ni == 0 || mi, "interfaces missing");
     uint32_t present = 0; int32_t trans = 0;
     for (uint32_t i = 0; i < nm; i++) {
-        REQUIRE(mat_type_supported(m[i].type), "unsupported material type (CoatedDiffuseTransmission is a SURVEY 8f item)");
+        REQUIRE(mat_type_supported(m[i].type), "unsupported material type");
         if (m[i].type == HK_MAT_MIX) { REQUIRE(m[i].ival[0] >= 1 && (uint32_t)m[i].ival[0] <= nm && m[i].ival[1] >= 1 && (uint32_t)m[i].ival[1] <= nm, "MixMaterial references a missing material"); }
         else present |= 1u << m[i].type;
     }
@@ -426,8 +427,8 @@ static int32_t alloc_film(HkContext* ctx, size_t n_pixels) {
     return HK_OK;
 }
 static int32_t alloc_state(HkContext* ctx, size_t n_slots) {
-    // one slab: 19 float4 arrays, 4 u32/f32 arrays, 14 queues; every array starts 256-byte aligned
-    const size_t f4 = 19, w4 = 5, q = 6 + HK_MAX_MAT_TYPES;
+    // one slab: 19 float4 arrays, 5 u32/f32 arrays, 15 queues; every array starts 256-byte aligned
+    const size_t f4 = 19, w4 = 5, q = 6 + HK_N_HIT_QUEUES;
     size_t rounded = f4 * (((16 * n_slots + 255) / 256) * 256) + (w4 + q) * (((4 * n_slots + 255) / 256) * 256);
     CK(cudaStreamSynchronize(ctx->stream));
     CK(ctx->b_state.alloc(rounded));
@@ -442,7 +443,7 @@ static int32_t alloc_state(HkContext* ctx, size_t n_slots) {
     S.q_ray[0] = reinterpret_cast<uint32_t*>(take(4)); S.q_ray[1] = reinterpret_cast<uint32_t*>(take(4));
     S.q_escaped = reinterpret_cast<uint32_t*>(take(4)); S.q_medium = reinterpret_cast<uint32_t*>(take(4)); S.q_shadow = reinterpret_cast<uint32_t*>(take(4));
     S.q_shadow2 = reinterpret_cast<uint32_t*>(take(4));
-    for (int t = 0; t < HK_MAX_MAT_TYPES; t++) S.q_hit[t] = reinterpret_cast<uint32_t*>(take(4));
+    for (int t = 0; t < HK_N_HIT_QUEUES; t++) S.q_hit[t] = reinterpret_cast<uint32_t*>(take(4));
     S.counts = ctx->b_counts.as<uint32_t>();
     S.rays_traced = reinterpret_cast<unsigned long long*>(ctx->b_counts.as<char>() + sizeof(uint32_t) * HK_N_COUNTERS);
     S.path_vertices = S.rays_traced + 1;
@@ -514,6 +515,7 @@ int32_t hk_set_params(HkContext* ctx, const HkRenderParams* p) {
     // allocates more than one sample's worth)
     int32_t rc = alloc_film(ctx, n_pixels);
     if (rc != HK_OK) return rc;
+    ctx->aux_pixels = 0;                 // film.albedo / normal / depth belong to the previous film
     ctx->b_state.release(); ctx->n_slots = 0;
     rc = build_sobol_cache(ctx);
     if (rc != HK_OK) return rc;
@@ -526,6 +528,7 @@ int32_t hk_clear(HkContext* ctx) {
     cudaSetDevice(ctx->device);
     REQUIRE(ctx->have_params, "hk_set_params has not been called");
     CK(cudaMemsetAsync(ctx->b_film.p, 0, ctx->b_film.bytes, ctx->stream));
+    if (ctx->b_aux.p) CK(cudaMemsetAsync(ctx->b_aux.p, 0, ctx->b_aux.bytes, ctx->stream));      // clear!(film) also resets albedo / normal / depth
     return HK_OK;
 }
 
@@ -610,7 +613,7 @@ int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride,
             launch_shade<HK_MAT_MATTE>(ctx, A, cur ^ 1); launch_shade<HK_MAT_MIRROR>(ctx, A, cur ^ 1); launch_shade<HK_MAT_GLASS>(ctx, A, cur ^ 1);
             launch_shade<HK_MAT_CONDUCTOR>(ctx, A, cur ^ 1); launch_shade<HK_MAT_COATED_DIFFUSE>(ctx, A, cur ^ 1);
             launch_shade<HK_MAT_THIN_DIELECTRIC>(ctx, A, cur ^ 1); launch_shade<HK_MAT_DIFFUSE_TRANSMISSION>(ctx, A, cur ^ 1);
-            launch_shade<HK_MAT_COATED_CONDUCTOR>(ctx, A, cur ^ 1);
+            launch_shade<HK_MAT_COATED_CONDUCTOR>(ctx, A, cur ^ 1); launch_shade<HK_MAT_COATED_DIFFUSE_TRANSMISSION>(ctx, A, cur ^ 1);
             if (fork) for (int j = 0; j < ctx->shade_fork_slot; j++) cudaStreamWaitEvent(st, ctx->ev_join[j], 0);
             if (ctx->D.n_lights > 0) {
                 if (overlap_shadow) {
@@ -732,9 +735,39 @@ int32_t hk_postprocess(HkContext* ctx, const HkPostprocess* p, float* out) {
     REQUIRE(p->tonemap_mode >= HK_TONEMAP_NONE && p->tonemap_mode <= HK_TONEMAP_FILMIC, "unknown tonemap mode");
     const size_t n = (size_t)ctx->params.width * ctx->params.height;
     if (ctx->b_readback.bytes < 12 * n) CK(ctx->b_readback.alloc(12 * n));
-    k_film_postprocess<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(ctx->S.pixel_rgb, ctx->S.pixel_weight, ctx->b_readback.as<float>(), ctx->params.width, ctx->params.height, *p);
+    REQUIRE(!p->mask_escaped || ctx->aux_pixels == n, "postprocess with a background needs film.depth: call hk_fill_aux_buffers first");
+    k_film_postprocess<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(ctx->S.pixel_rgb, ctx->S.pixel_weight, ctx->b_readback.as<float>(), ctx->params.width, ctx->params.height, *p,
+                                                                           p->mask_escaped ? ctx->b_aux.as<float>() + 6 * n : nullptr);
     ctx->launches++;
     CK(cudaMemcpyAsync(out, ctx->b_readback.p, 12 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return HK_OK;
+}
+// fill_aux_buffers!(film, scene, camera; has_infinite_lights), film.jl:410-431
+int32_t hk_fill_aux_buffers(HkContext* ctx, int32_t has_infinite_lights) {
+    if (!ctx) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    REQUIRE(ctx->have_params, "hk_set_params has not been called");
+    REQUIRE(ctx->have_geom && ctx->have_cam, "geometry and camera must be uploaded before hk_fill_aux_buffers");
+    const size_t n = (size_t)ctx->params.width * ctx->params.height;
+    if (ctx->b_aux.bytes != 28 * n) { CK(cudaStreamSynchronize(ctx->stream)); CK(ctx->b_aux.alloc(28 * n)); }
+    ctx->aux_pixels = n;
+    float* a = ctx->b_aux.as<float>();
+    k_aux_buffers<<<grid_for(ctx, n, HK_TRACE_THREADS, 8), HK_TRACE_THREADS, 0, ctx->stream>>>(ctx->D, a, a + 3 * n, a + 6 * n, has_infinite_lights ? 1.0e30f : HK_INF);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return HK_OK;
+}
+int32_t hk_read_aux_buffers(HkContext* ctx, float* albedo, float* normal, float* depth) {
+    if (!ctx) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    REQUIRE(ctx->have_params, "hk_set_params has not been called");
+    const size_t n = (size_t)ctx->params.width * ctx->params.height;
+    REQUIRE(ctx->aux_pixels == n, "hk_fill_aux_buffers has not been called for this film size");
+    const float* a = ctx->b_aux.as<float>();
+    if (albedo) CK(cudaMemcpyAsync(albedo, a, 12 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (normal) CK(cudaMemcpyAsync(normal, a + 3 * n, 12 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (depth) CK(cudaMemcpyAsync(depth, a + 6 * n, 4 * n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return HK_OK;
 }

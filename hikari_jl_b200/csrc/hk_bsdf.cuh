@@ -96,6 +96,7 @@ HK_DEV float3 tr_sample_wm(float3 w, float2 u, float ax, float ay) {
 //   Matte / Mirror: A = rgb0.  Glass / CoatedDiffuse: A = rgb0, B = rgb1.  Conductor (RGB eta / k): A, B unbounded.
 //   DiffuseTransmission: A / B = clamp(rgb0 * scale) / clamp(rgb1 * scale).
 //   CoatedConductor: A = eta (unbounded) or the reflectance clamped to [0, 0.9999]; B = k (unbounded).
+//   CoatedDiffuseTransmission: A = reflectance, B = albedo (as CoatedDiffuse); the transmittance (rgb2) is uplifted per call.
 HK_DEV bool mat_pre_is_unbounded(const HkMaterial& m, int which) {
     return m.type == HK_MAT_CONDUCTOR || (m.type == HK_MAT_COATED_CONDUCTOR && (which == 1 || (m.flags & HK_MATFLAG_USE_ETA_K)));
 }
@@ -269,6 +270,7 @@ HK_DEV BsdfEval eval_diffuse_transmission(const MatCtx& C, const HkMaterial& m, 
 
 #include "hk_bsdf_layered.cuh"
 #include "hk_bsdf_coated_conductor.cuh"
+#include "hk_bsdf_coated_difftrans.cuh"
 
 // ---- per-type dispatch used by the per-material-queue kernels (TYPE is a compile-time constant) ------------------
 template <int TYPE>
@@ -281,6 +283,7 @@ HK_DEV BsdfSample sample_bsdf(const MatCtx& C, const HkMaterial& m, float3 wo, f
     if (TYPE == HK_MAT_THIN_DIELECTRIC) return sample_thin_dielectric(m, wo, ns, uc);
     if (TYPE == HK_MAT_DIFFUSE_TRANSMISSION) return sample_diffuse_transmission(C, m, wo, ns, lam, u, uc);
     if (TYPE == HK_MAT_COATED_CONDUCTOR) return sample_coated_conductor(C, m, wo, ns, lam, u, uc, regularize);
+    if (TYPE == HK_MAT_COATED_DIFFUSE_TRANSMISSION) return sample_coated_difftrans(C, m, wo, ns, lam, u, uc, regularize);
     return bsdf_none();
 }
 template <int TYPE>
@@ -290,5 +293,6 @@ HK_DEV BsdfEval eval_bsdf(const MatCtx& C, const HkMaterial& m, float3 wo, float
     if (TYPE == HK_MAT_COATED_DIFFUSE) return eval_coated_diffuse(C, m, wo, wi, ns, lam);
     if (TYPE == HK_MAT_DIFFUSE_TRANSMISSION) return eval_diffuse_transmission(C, m, wo, wi, ns, lam);
     if (TYPE == HK_MAT_COATED_CONDUCTOR) return eval_coated_conductor(C, m, wo, wi, ns, lam);
+    if (TYPE == HK_MAT_COATED_DIFFUSE_TRANSMISSION) return eval_coated_difftrans(C, m, wo, wi, ns, lam);
     return eval_none();   // Mirror / Glass / ThinDielectric are delta-only
 }

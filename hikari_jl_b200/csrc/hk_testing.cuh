@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(128) tk_bsdf(const __grid_constant__ DevScene 
             case HK_MAT_THIN_DIELECTRIC: tk_bsdf_one<HK_MAT_THIN_DIELECTRIC>(MC, m, e, o); break;
             case HK_MAT_DIFFUSE_TRANSMISSION: tk_bsdf_one<HK_MAT_DIFFUSE_TRANSMISSION>(MC, m, e, o); break;
             case HK_MAT_COATED_CONDUCTOR: tk_bsdf_one<HK_MAT_COATED_CONDUCTOR>(MC, m, e, o); break;
+            case HK_MAT_COATED_DIFFUSE_TRANSMISSION: tk_bsdf_one<HK_MAT_COATED_DIFFUSE_TRANSMISSION>(MC, m, e, o); break;
         }
     }
 }

@@ -29,8 +29,11 @@
 #define HK_C_TOTAL_HITS 5
 #define HK_C_CURSOR_TRACE 6
 #define HK_C_CURSOR_SHADOW 7
-#define HK_C_HIT0 8            // + hit queue of the material type: types 1..7 use queue = type, CoatedConductor (9) the spare queue 0
-#define HK_TYPE_QUEUE(t) ((t) == HK_MAT_COATED_CONDUCTOR ? 0 : (t))
+#define HK_C_HIT0 8            // + hit queue 0..7 of the material type: types 1..7 use queue = type, CoatedConductor (9) the spare queue 0
+#define HK_C_HIT1 56           // + (hit queue - 8): second bank, CoatedDiffuseTransmission (10) = queue 8
+#define HK_N_HIT_QUEUES 9
+#define HK_TYPE_QUEUE(t) ((t) == HK_MAT_COATED_CONDUCTOR ? 0 : (t) == HK_MAT_COATED_DIFFUSE_TRANSMISSION ? 8 : (t))
+#define HK_HIT_COUNTER(q) ((q) < 8 ? HK_C_HIT0 + (q) : HK_C_HIT1 + (q) - 8)
 #define HK_N_QUEUE_COUNTERS 16 // the counters above (what hk_bounce_profile reports)
 #define HK_C_CURSOR_MEDIUM 16  // k_medium_track work cursor
 // second copies of the shadow-pass counters: in opaque-only scenes the shadow pass of bounce b runs on its own stream while
@@ -73,7 +76,7 @@ struct PathState {
     float4 *med; uint32_t* med_ev;                 // delta-tracking result per slot: (scatter point, g), event
     uint32_t* res_mat;                             // material a MixMaterial hit resolved to (written by the routing, read by k_shade)
     float4 *sh_hit, *sh_T, *sh_tu, *sh_tl;         // shadow rays through media: segment hit, running transmittance / MIS ratios
-    uint32_t *q_ray[2], *q_escaped, *q_medium, *q_shadow, *q_shadow2, *q_hit[HK_MAX_MAT_TYPES];
+    uint32_t *q_ray[2], *q_escaped, *q_medium, *q_shadow, *q_shadow2, *q_hit[HK_N_HIT_QUEUES];
     uint32_t* counts;                  // [HK_N_COUNTERS]
     unsigned long long* rays_traced;
     unsigned long long* path_vertices;  // surface hits routed + medium scatter events (HkStats::path_vertices)
@@ -221,7 +224,7 @@ __global__ void __launch_bounds__(128) k_precompute_uplifts(DevTables T, const H
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         if (i < n_mats) {
             const HkMaterial& m = mats[i];
-            const bool rgb = (m.type >= 1 && m.type < HK_MAX_MAT_TYPES && m.type != HK_MAT_THIN_DIELECTRIC) || m.type == HK_MAT_COATED_CONDUCTOR;
+            const bool rgb = (m.type >= 1 && m.type < HK_MAX_MAT_TYPES && m.type != HK_MAT_THIN_DIELECTRIC) || m.type == HK_MAT_COATED_CONDUCTOR || m.type == HK_MAT_COATED_DIFFUSE_TRANSMISSION;
             mat_pre[2 * i] = rgb ? mat_pre_compute(T, m, 0) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             mat_pre[2 * i + 1] = rgb ? mat_pre_compute(T, m, 1) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         } else if (i < n_mats + n_lights) {
@@ -285,6 +288,7 @@ HK_DEV uint32_t claim_for_idle(uint32_t* cursor, unsigned idle) {
 HK_DEV uint32_t* queue_of(const PathState& S, int qid) {
     if (qid == HK_C_MEDIUM) return S.q_medium;
     if (qid == HK_C_ESCAPED) return S.q_escaped;
+    if (qid >= HK_C_HIT1) return S.q_hit[8 + qid - HK_C_HIT1];
     if (qid >= HK_C_HIT0) return S.q_hit[qid - HK_C_HIT0];
     return nullptr;
 }
@@ -364,7 +368,7 @@ HK_DEV int hit_queue_id(const DevScene& D, const PathState& S, uint32_t slot, ui
         mtype = (uint32_t)D.materials[res - 1].type;
         if (mtype == HK_MAT_MIX) return -1;            // a mix chain deeper than 8 levels: the reference would shade a MixMaterial (undefined); dropped
     }
-    return HK_C_HIT0 + (int)HK_TYPE_QUEUE(mtype);
+    return HK_HIT_COUNTER((int)HK_TYPE_QUEUE(mtype));
 }
 
 // writes the material type (1..7) of every BVH triangle into the spare word of its record (HitRec)
@@ -412,7 +416,7 @@ __global__ void __launch_bounds__(256) k_route(const __grid_constant__ DevScene 
         }
         if (threadIdx.x == 32) {   // total surface hits of the bounce (the reference's `n_hits > 0` shadow-pass condition)
             uint32_t h = 0;
-            for (int t = 0; t < HK_MAX_MAT_TYPES; t++) h += s_cnt[HK_C_HIT0 + t];
+            for (int t = 0; t < HK_N_HIT_QUEUES; t++) h += s_cnt[HK_HIT_COUNTER(t)];
             if (h) { atomicAdd(S.counts + HK_CI_TOTAL_HITS(par), h); atomicAdd(S.path_vertices, (unsigned long long)h); }
         }
         __syncthreads();
@@ -464,8 +468,8 @@ HK_DEV bool russian_roulette(Spec& beta, int depth, float rr) {
 #define HK_SHADE_MIN_BLOCKS 4
 #endif
 template <int TYPE>
-__global__ void __launch_bounds__(128, TYPE == HK_MAT_COATED_DIFFUSE ? HK_SHADE_MIN_BLOCKS + 2 : HK_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DevScene D, PathState S, PassArgs A, int next, int par) {
-    const uint32_t n = S.counts[HK_C_HIT0 + HK_TYPE_QUEUE(TYPE)];
+__global__ void __launch_bounds__(128, (TYPE == HK_MAT_COATED_DIFFUSE || TYPE == HK_MAT_COATED_DIFFUSE_TRANSMISSION) ? HK_SHADE_MIN_BLOCKS + 2 : HK_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DevScene D, PathState S, PassArgs A, int next, int par) {
+    const uint32_t n = S.counts[HK_HIT_COUNTER(HK_TYPE_QUEUE(TYPE))];
     MatCtx MC = mat_ctx(D);
     LightCtx LC = light_ctx(D);
     const uint32_t n_round = (n + 31u) & ~31u;     // whole warps iterate together so the aggregated pushes stay converged
@@ -910,8 +914,10 @@ HK_DEV float3 postprocess_pixel(const HkPostprocess& P, float3 c) {
     if (P.apply_gamma) { r = powf(r, P.inv_gamma); g = powf(g, P.inv_gamma); b = powf(b, P.inv_gamma); }
     return f3(r, g, b);
 }
-// framebuffer = sum / weight -> postprocess_pixel, same (H, W) column-major layout as k_film_finalize
-__global__ void __launch_bounds__(256) k_film_postprocess(const float* __restrict__ rgb, const float* __restrict__ wsum, float* __restrict__ out, int W, int H, HkPostprocess P) {
+// framebuffer = sum / weight -> postprocess_pixel, same (H, W) column-major layout as k_film_finalize.
+// depth: film.depth for the escaped-ray mask (postprocess.jl:220-245), read with the reference's row flip.
+__global__ void __launch_bounds__(256) k_film_postprocess(const float* __restrict__ rgb, const float* __restrict__ wsum, float* __restrict__ out, int W, int H, HkPostprocess P,
+                                                           const float* __restrict__ depth) {
     const uint32_t n = (uint32_t)W * (uint32_t)H;
     for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < n; pix += gridDim.x * blockDim.x) {
         const uint32_t px = pix % (uint32_t)W, py = pix / (uint32_t)W;
@@ -919,8 +925,41 @@ __global__ void __launch_bounds__(256) k_film_postprocess(const float* __restric
         float3 c = f3(0.0f, 0.0f, 0.0f);
         if (w > 0.0f) { float inv = 1.0f / w; c = f3(rgb[3 * (size_t)pix] * inv, rgb[3 * (size_t)pix + 1] * inv, rgb[3 * (size_t)pix + 2] * inv); }
         c = postprocess_pixel(P, c);
+        if (P.mask_escaped) {
+            const int d_row = H - (int)py, col = (int)px + 1;      // 1-based (row, col) = (py + 1, px + 1); d_row = H - row + 1
+            int escaped = 0, total = 0;
+            for (int dr = -1; dr <= 1; dr++)
+                for (int dc = -1; dc <= 1; dc++) {
+                    const int nr = d_row + dr, nc = col + dc;
+                    if (nr >= 1 && nr <= H && nc >= 1 && nc <= W) { escaped += isinf(depth[(size_t)(nc - 1) * H + (nr - 1)]) ? 1 : 0; total++; }
+                }
+            const float alpha = (float)escaped / (float)total;
+            c = f3(c.x * (1.0f - alpha) + P.background[0] * alpha, c.y * (1.0f - alpha) + P.background[1] * alpha, c.z * (1.0f - alpha) + P.background[2] * alpha);
+        }
         float* o = out + ((size_t)px * H + py) * 3;
         o[0] = c.x; o[1] = c.y; o[2] = c.z;
+    }
+}
+
+// aux_buffer_kernel!, film.jl:433-488: one centre-of-pixel primary ray per pixel; idx runs over the (H, W) column-major buffers
+__global__ void __launch_bounds__(HK_TRACE_THREADS) k_aux_buffers(const __grid_constant__ DevScene D, float* __restrict__ albedo, float* __restrict__ normal,
+                                                                   float* __restrict__ depth, float miss_depth) {
+    __shared__ uint2 sm_stack[HK_SM_STACK * HK_TRACE_THREADS];
+    const uint32_t n = (uint32_t)D.width * (uint32_t)D.height, H = (uint32_t)D.height;
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+        const uint32_t row = idx % H + 1u, col = idx / H + 1u;
+        float3 o, d;
+        camera_generate_ray(D.camera, (float)col + 0.5f, (float)row + 0.5f, make_float2(0.5f, 0.5f), o, d);
+        const HitRec h = bvh8_trace<false, false>(D.bvh, sm_stack + threadIdx.x, o, d, HK_INF);
+        float3 nn = f3(0.0f, 0.0f, 0.0f); float dep = miss_depth, alb = 0.0f;
+        if (h.prim1) {
+            const Surf sf = surface_at(D, HK_HIT_PRIM1(h.prim1) - 1u, h.b1, h.b2, o, d, h.t);
+            const float3 v = sf.pi - o;
+            nn = sf.n; dep = sqrtf((v.x * v.x + v.y * v.y) + v.z * v.z); alb = 0.8f;
+        }
+        albedo[3 * (size_t)idx] = alb; albedo[3 * (size_t)idx + 1] = alb; albedo[3 * (size_t)idx + 2] = alb;
+        normal[3 * (size_t)idx] = nn.x; normal[3 * (size_t)idx + 1] = nn.y; normal[3 * (size_t)idx + 2] = nn.z;
+        depth[idx] = dep;
     }
 }
 

@@ -495,6 +495,24 @@ class CoatedDiffuseMaterial(Material):    # coated-diffuse.jl:98-127
         return m
 
 
+class CoatedDiffuseTransmissionMaterial(CoatedDiffuseMaterial):   # coated-diffuse-transmission.jl (keyword constructor)
+    """Dielectric coating over a Lambertian base that reflects (`reflectance`) and transmits (`transmittance`)."""
+    type = A.HK_MAT_COATED_DIFFUSE_TRANSMISSION
+
+    def __init__(self, reflectance=0.5, transmittance=0.25, roughness=0.0, thickness=0.01, eta=1.5, albedo=0.0, g=0.0,
+                 max_depth=10, n_samples=1, remap_roughness=True):
+        super().__init__(reflectance, roughness, thickness, eta, albedo, g, max_depth, n_samples, remap_roughness)
+        self.transmittance = _rgb(transmittance)
+
+    def to_abi(self, scene):
+        m = super().to_abi(scene)
+        m.rgb2[0:3] = self.transmittance
+        return m
+
+
+CoatedDiffuseTransmission = CoatedDiffuseTransmissionMaterial
+
+
 class CoatedConductorMaterial(Material):  # coated-conductor.jl:48-105 (struct), 167-243 (keyword constructor)
     """Dielectric coating over a conductor.  Give `conductor_eta` + `conductor_k` (RGB or PiecewiseLinearSpectrum) or the
     artist `reflectance`; with neither, reflectance = 1 as in the reference."""

@@ -110,6 +110,26 @@ def coated_conductor_spheres(tess=32):
     return s, _cam((0, 1.5, 5), (0, 0.4, 0), 40.0)
 
 
+def coated_difftrans_panels(tess=24):
+    """CoatedDiffuseTransmissionMaterial (spectral-eval.jl:2340-2840): three back-lit thin panels (smooth coating, rough
+    coating, rough coating + absorbing layer) and a sphere, over a matte floor."""
+    s = H.Scene()
+    s.push(H.rect3((-5, -1, -5), (10, 0.1, 10)), H.MatteMaterial(Kd=(0.7, 0.7, 0.7)))
+    kws = (dict(roughness=0.0), dict(roughness=0.3), dict(roughness=0.1, albedo=(0.8, 0.4, 0.2), g=0.3, thickness=0.1))
+    for k, kw in enumerate(kws):
+        x = -1.6 + 1.6 * k
+        s.push(H.rect3((x - 0.6, -0.9, 0.0), (1.2, 1.8, 0.02)),
+               H.CoatedDiffuseTransmissionMaterial(reflectance=(0.25, 0.5, 0.2), transmittance=(0.3, 0.6, 0.15), **kw))
+    s.push(H.uv_sphere((0.0, 1.6, 0.3), 0.5, tess, tess),
+           H.CoatedDiffuseTransmissionMaterial(reflectance=(0.6, 0.3, 0.3), transmittance=(0.3, 0.2, 0.5), roughness=0.05))
+    s.push(H.PointLight((60, 60, 60), (0.5, 2.0, -3.0)))        # behind the panels
+    d = np.array([-0.3, -1.0, -1.0])
+    s.push(H.DirectionalLight((2, 2, 2), d / np.linalg.norm(d), legacy_rgbspectrum=True))
+    s.push(H.AmbientLight((0.3, 0.35, 0.4)))
+    s.sync()
+    return s, _cam((0, 1.0, 5), (0, 0.3, 0), 40.0)
+
+
 def blob_mesh(center, radius, n=256, seed=3):
     """Closed procedural stand-in for cat.obj: a sphere displaced by a few low-frequency harmonics."""
     m = H.uv_sphere((0, 0, 0), 1.0, n, n)

@@ -93,6 +93,8 @@ typedef struct HkGeometry {
                                            intersection time (resolve_mix_material :253-268), never shaded itself   */
 #define HK_MAT_COATED_CONDUCTOR     9   /* src/materials/spectral-eval.jl:2877-3237 (sample), 3243-3418 (eval);
                                            src/materials/coated-conductor.jl:48-105                                 */
+#define HK_MAT_COATED_DIFFUSE_TRANSMISSION 10 /* :2340-2494 (sample), 2498-2763 (eval), 2767-2840 (pdf);
+                                           src/materials/coated-diffuse-transmission.jl                             */
 
 #define HK_MATFLAG_REMAP_ROUGHNESS  1u
 #define HK_MATFLAG_SPECTRAL_ETA_K   2u  /* conductor eta/k are piecewise-linear spectra (ids in spec[]) */
@@ -104,7 +106,9 @@ typedef struct HkMaterial {
     uint32_t flags;
     float    rgb0[3];   /* Matte Kd | Mirror Kr | Glass Kr | Conductor eta | Coated reflectance | DiffTrans reflectance */
     float    rgb1[3];   /* Glass Kt | Conductor k | Coated albedo | DiffTrans transmittance                            */
-    float    rgb2[4];   /* CoatedConductor: rgb0 = conductor eta (or reflectance), rgb1 = conductor k, rgb2 = albedo   */
+    float    rgb2[4];   /* CoatedConductor: rgb0 = conductor eta (or reflectance), rgb1 = conductor k, rgb2 = albedo.
+                           CoatedDiffuseTransmission: rgb0 = reflectance, rgb1 = albedo, rgb2 = transmittance; f[] and
+                           ival[] as CoatedDiffuse                                                                     */
     float    f[8];      /* Matte: f0=sigma. Glass: f0=index. Conductor: f0=roughness.
                            ThinDielectric: f0=eta. DiffuseTransmission: f0=scale.
                            CoatedDiffuse: f0=u_roughness f1=v_roughness f2=thickness f3=eta f4=g
@@ -344,8 +348,21 @@ typedef struct HkPostprocess {
     float   imaging_ratio;  /* sensor.exposure_time * sensor.iso / 100                               */
     int32_t apply_wb;       /* sensor.white_balance > 0                                              */
     float   wb[9];          /* compute_white_balance_matrix(T), row-major (spectral/color.jl:522-546) */
+    int32_t mask_escaped;   /* background !== nothing (postprocess.jl:339): blend towards `background` by the fraction
+                               of escaped (depth = Inf) pixels in the 3x3 neighbourhood of the depth buffer
+                               (:220-245); needs hk_fill_aux_buffers first                            */
+    float   background[3];
 } HkPostprocess;
 int32_t hk_postprocess(HkContext* ctx, const HkPostprocess* params, float* out_rgb_hw_colmajor);
+/* ---- auxiliary buffers ---------------------------------------------------------------------
+ * replaces: fill_aux_buffers!(film, scene, camera; has_infinite_lights) (src/film.jl:410-431, kernel :433-488):
+ * one primary ray per pixel through the pixel centre (lens sample (0.5, 0.5)); writes film.albedo (0.8 on a hit,
+ * 0 otherwise), film.normal (geometric normal on the shading-normal side, as vp_compute_surface_geometry
+ * intersection.jl:13-21,176; 0 on a miss) and film.depth (|hit - ray.o|; on a miss Inf, or 1e30 when
+ * has_infinite_lights).  All three are (H, W) column-major like the framebuffer; hk_clear zeroes them (film.jl:343-346).
+ * hk_read_aux_buffers: any pointer may be NULL.                                                                  */
+int32_t hk_fill_aux_buffers(HkContext* ctx, int32_t has_infinite_lights);
+int32_t hk_read_aux_buffers(HkContext* ctx, float* albedo_hw3, float* normal_hw3, float* depth_hw);
 /* raw accumulators for the multi-GPU film reduce (pixel_rgb ‖ pixel_weight_sum, volpath-state.jl):
  * device pointer to [n*3] rgb sums followed by [n] weight sums, valid until the next hk_set_params. */
 int32_t hk_film_accum_dev(HkContext* ctx, float** out_accum_dev, uint64_t* out_count);

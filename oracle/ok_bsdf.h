@@ -261,6 +261,7 @@ inline BSDFEval eval_conductor(const MatCtx& C, const HkMaterial& m, V3 wo_w, V3
 }  // namespace ok
 #include "ok_bsdf_layered.h"
 #include "ok_bsdf_coated_conductor.h"
+#include "ok_bsdf_coated_difftrans.h"
 namespace ok {
 
 // ---------------------------------------------------------------------------------------------
@@ -276,6 +277,7 @@ inline BSDFSample sample_material(const MatCtx& C, const HkMaterial& m, V3 wo, V
         case HK_MAT_THIN_DIELECTRIC: return sample_thin_dielectric(C, m, wo, ns, l, u, rng, regularize);
         case HK_MAT_DIFFUSE_TRANSMISSION: return sample_diffuse_transmission(C, m, wo, ns, l, u, rng, regularize);
         case HK_MAT_COATED_CONDUCTOR: return sample_coated_conductor(C, m, wo, ns, l, u, rng, regularize);
+        case HK_MAT_COATED_DIFFUSE_TRANSMISSION: return sample_coated_diffuse_transmission(C, m, wo, ns, l, u, rng, regularize);
     }
     return BSDFSample();
 }
@@ -286,6 +288,7 @@ inline BSDFEval eval_material(const MatCtx& C, const HkMaterial& m, V3 wo, V3 wi
         case HK_MAT_COATED_DIFFUSE: return eval_coated_diffuse(C, m, wo, wi, ns, l);
         case HK_MAT_DIFFUSE_TRANSMISSION: return eval_diffuse_transmission(C, m, wo, wi, ns, l);
         case HK_MAT_COATED_CONDUCTOR: return eval_coated_conductor(C, m, wo, wi, ns, l);
+        case HK_MAT_COATED_DIFFUSE_TRANSMISSION: return eval_coated_diffuse_transmission(C, m, wo, wi, ns, l);
         default: return BSDFEval();   // Mirror / Glass / ThinDielectric: specular, eval == 0
     }
 }

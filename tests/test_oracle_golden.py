@@ -284,3 +284,35 @@ def test_coated_conductor_known_answers():
         assert (o[:, 7] > 0).mean() > 0.3, (ir, cr)      # rough conductor under IOR 1.5: reflections past the critical angle are dropped (:3063-3066)
         if ir == 0.0 and cr == 0.0:
             assert (o[:, 8] == 1).all() and (o[:, 10:15] == 0).all()      # both delta: eval == 0 (:3322-3325)
+
+
+def test_coated_diffuse_transmission_known_answers():
+    """CoatedDiffuseTransmissionMaterial (spectral-eval.jl:2249-2840) has no golden vector upstream.  Pinned by the identity
+    its formulas imply: with transmittance = 0 the base never transmits (prob_reflect = 1) and, at n_samples = 1, consumes
+    the same random numbers as the Lambertian base of CoatedDiffuse, so sample and eval must reproduce CoatedDiffuse
+    exactly (same floats) — smooth and rough coating, with and without an absorbing layer.  With transmittance > 0 the
+    sampled directions must reach the far hemisphere and every record must be finite and non-negative."""
+    rng = np.random.RandomState(11)
+    n = 3000
+    x = np.zeros((n, 17), f32)
+    def unit(k):
+        v = rng.normal(size=(k, 3)); return v / np.linalg.norm(v, axis=1, keepdims=True)
+    x[:, 0:3] = unit(n); x[:, 3:6] = unit(n)
+    x[:, 6:10] = rng.uniform(380, 780, size=(n, 4))
+    x[:, 10:13] = rng.uniform(0, 1, size=(n, 3))
+    x[:, 13] = rng.randint(0, 2, n)
+    x[:, 14:17] = unit(n)
+    for kw in (dict(roughness=0.0), dict(roughness=0.3), dict(roughness=0.1, albedo=(0.8, 0.4, 0.2), g=0.3, thickness=0.1)):
+        a, b = _oracle_bsdf([H.CoatedDiffuseTransmissionMaterial(reflectance=(0.7, 0.5, 0.3), transmittance=0.0, **kw),
+                             H.CoatedDiffuseMaterial(reflectance=(0.7, 0.5, 0.3), **kw)], x)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), kw
+    for kw in (dict(roughness=0.0), dict(roughness=0.3), dict(roughness=0.1, albedo=(0.8, 0.4, 0.2), g=0.3, thickness=0.1)):
+        (o,) = _oracle_bsdf([H.CoatedDiffuseTransmissionMaterial(reflectance=(0.5, 0.4, 0.3), transmittance=(0.3, 0.4, 0.5), **kw)], x)
+        assert np.isfinite(o).all() and (o[:, 3:7] >= 0).all() and (o[:, 10:14] >= 0).all() and (o[:, 7] >= 0).all()
+        valid = o[:, 7] > 0
+        side_o = np.sign((x[:, 0:3] * x[:, 3:6]).sum(1)); side_i = np.sign((o[:, 0:3] * x[:, 3:6]).sum(1))
+        through = valid & (side_o != side_i)
+        assert valid.mean() > 0.5 and 0.1 < through.sum() / valid.sum() < 0.8, (kw, valid.mean(), through.sum() / valid.sum())
+        # the pdf estimate is the reference's literal lerp(0.9, 1/4pi, sum) = 0.9 (1 - sum) + sum / 4pi (:2839): mostly ~0.9
+        far = np.sign((x[:, 14:17] * x[:, 3:6]).sum(1)) != side_o
+        assert np.median(o[far, 14]) > 0.5
