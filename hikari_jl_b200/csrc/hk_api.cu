@@ -11,6 +11,7 @@
 #include <string>
 #include <array>
 #include <vector>
+#include <limits>
 
 #define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__); return HK_ERR_CUDA; } } while (0)
 #define REQUIRE(cond, msg) do { if (!(cond)) { ctx->err = (msg); return HK_ERR_INVALID; } } while (0)
@@ -753,7 +754,7 @@ int32_t hk_fill_aux_buffers(HkContext* ctx, int32_t has_infinite_lights) {
     if (ctx->b_aux.bytes != 28 * n) { CK(cudaStreamSynchronize(ctx->stream)); CK(ctx->b_aux.alloc(28 * n)); }
     ctx->aux_pixels = n;
     float* a = ctx->b_aux.as<float>();
-    k_aux_buffers<<<grid_for(ctx, n, HK_TRACE_THREADS, 8), HK_TRACE_THREADS, 0, ctx->stream>>>(ctx->D, a, a + 3 * n, a + 6 * n, has_infinite_lights ? 1.0e30f : HK_INF);
+    k_aux_buffers<<<grid_for(ctx, n, HK_TRACE_THREADS, 8), HK_TRACE_THREADS, 0, ctx->stream>>>(ctx->D, a, a + 3 * n, a + 6 * n, has_infinite_lights ? 1.0e30f : std::numeric_limits<float>::infinity());
     ctx->launches++;
     CK(cudaGetLastError());
     return HK_OK;

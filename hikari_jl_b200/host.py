@@ -180,8 +180,6 @@ def postprocess(film, vp, exposure=1.0, tonemap="aces", gamma=2.2, white_point=4
     """postprocess!(film; exposure, tonemap, gamma, white_point, sensor), src/postprocess.jl:281-357.  Non-destructive:
     reads the accumulated film of `vp`'s backend, writes film.postprocess ([py, px] like film.framebuffer).  The reference
     reads film.framebuffer; here the division by the weight sum is fused into the same pass (hk_postprocess)."""
-    if background is not None:
-        raise NotImplementedError("background masking needs the auxiliary depth buffer (fill_aux_buffers!, SURVEY 8f)")
     if tonemap not in TONEMAP_MODES:
         raise ValueError(f"unknown tonemap {tonemap!r}")
     sensor = sensor if sensor is not None else FilmSensor()
@@ -194,12 +192,28 @@ def postprocess(film, vp, exposure=1.0, tonemap="aces", gamma=2.2, white_point=4
     p.apply_wb = 1 if sensor.white_balance > 0 else 0
     wb = compute_white_balance_matrix(sensor.white_balance) if p.apply_wb else np.eye(3, dtype=f32)
     p.wb[:] = [float(v) for v in wb.reshape(-1)]
+    p.mask_escaped = 0 if background is None else 1      # escaped pixels (film.depth = Inf) fade to `background`, :339-342
+    p.background[:] = (0.0, 0.0, 0.0) if background is None else _rgb(background)
     w, h = film.resolution
     if getattr(film, "_pp_store", None) is None:
         film._pp_store = np.zeros((w, h, 3), dtype=f32)
         film.postprocess = film._pp_store.transpose(1, 0, 2)
     vp.backend.call("postprocess", C.byref(p), _fp(film._pp_store))
     return film.postprocess
+
+
+def fill_aux_buffers(film, vp, has_infinite_lights=False):
+    """fill_aux_buffers!(film, scene, camera; has_infinite_lights), src/film.jl:410-431: film.albedo / film.normal ([py, px, 3])
+    and film.depth ([py, px]) from one centre-of-pixel primary ray per pixel, traced by `vp`'s backend against the scene and
+    camera it last rendered (or was given through set_camera)."""
+    w, h = film.resolution
+    if getattr(film, "_aux_store", None) is None:
+        film._aux_store = (np.zeros((w, h, 3), dtype=f32), np.zeros((w, h, 3), dtype=f32), np.zeros((w, h), dtype=f32))
+        film.albedo, film.normal = film._aux_store[0].transpose(1, 0, 2), film._aux_store[1].transpose(1, 0, 2)
+        film.depth = film._aux_store[2].transpose(1, 0)
+    vp.backend.call("fill_aux_buffers", 1 if has_infinite_lights else 0)
+    vp.backend.call("read_aux_buffers", _fp(film._aux_store[0]), _fp(film._aux_store[1]), _fp(film._aux_store[2]))
+    return film
 
 
 class PerspectiveCamera:

@@ -140,6 +140,17 @@ int32_t ok_set_params(OkContext* c, const HkRenderParams* p) { c->s.params = *p;
 int32_t ok_clear(OkContext* c) {
     std::fill(c->s.pixel_rgb.begin(), c->s.pixel_rgb.end(), 0.0f);
     std::fill(c->s.pixel_weight_sum.begin(), c->s.pixel_weight_sum.end(), 0.0f);
+    std::fill(c->s.aux_albedo.begin(), c->s.aux_albedo.end(), 0.0f); std::fill(c->s.aux_normal.begin(), c->s.aux_normal.end(), 0.0f);
+    std::fill(c->s.aux_depth.begin(), c->s.aux_depth.end(), 0.0f);     // clear!(film), film.jl:343-346
+    return 0;
+}
+int32_t ok_fill_aux_buffers(OkContext* c, int32_t has_infinite_lights) { c->s.fill_aux_buffers(has_infinite_lights != 0); return 0; }
+int32_t ok_read_aux_buffers(OkContext* c, float* albedo, float* normal, float* depth) {
+    const size_t n = (size_t)c->s.params.width * c->s.params.height;
+    if (c->s.aux_depth.size() != n) return -1;
+    if (albedo) std::memcpy(albedo, c->s.aux_albedo.data(), 12 * n);
+    if (normal) std::memcpy(normal, c->s.aux_normal.data(), 12 * n);
+    if (depth) std::memcpy(depth, c->s.aux_depth.data(), 4 * n);
     return 0;
 }
 int32_t ok_render_samples_strided(OkContext* c, int32_t first, int32_t stride, int32_t count) {
@@ -201,6 +212,18 @@ int32_t ok_postprocess(OkContext* c, const HkPostprocess* P, float* out) {
             default: r = pp_clamp01(r); g = pp_clamp01(g); b = pp_clamp01(b); break;
         }
         if (P->apply_gamma) { r = std::pow(r, P->inv_gamma); g = std::pow(g, P->inv_gamma); b = std::pow(b, P->inv_gamma); }
+        if (P->mask_escaped) {     // AA depth mask, postprocess.jl:220-245: (row, col) = (py + 1, px + 1) of the (H, W) array, depth row flipped
+            if (s.aux_depth.size() != (size_t)W * H) return -1;
+            const int d_row = H - (py + 1) + 1, col = px + 1;
+            int escaped = 0, total = 0;
+            for (int dr = -1; dr <= 1; dr++)
+                for (int dc = -1; dc <= 1; dc++) {
+                    const int nr = d_row + dr, nc = col + dc;
+                    if (nr >= 1 && nr <= H && nc >= 1 && nc <= W) { escaped += std::isinf(s.aux_depth[(size_t)(nc - 1) * H + (nr - 1)]) ? 1 : 0; total++; }
+                }
+            const float alpha = (float)escaped / (float)total;
+            r = r * (1.0f - alpha) + P->background[0] * alpha; g = g * (1.0f - alpha) + P->background[1] * alpha; b = b * (1.0f - alpha) + P->background[2] * alpha;
+        }
         float* o = out + ((size_t)px * H + py) * 3;
         o[0] = r; o[1] = g; o[2] = b;
     }

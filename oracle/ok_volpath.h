@@ -107,6 +107,7 @@ struct Scene {
     struct RaySamples { float direct_uc; V2 direct_u; float indirect_uc; V2 indirect_u; float indirect_rr; };
     std::vector<RaySamples> pixel_samples;
     uint64_t rays_traced = 0;
+    std::vector<float> aux_albedo, aux_normal, aux_depth;      // film.albedo / normal / depth, (H, W) column-major (film.jl:410-488)
     std::string err;
 
     MatCtx matctx() const { return MatCtx{&T, &spectra}; }
@@ -197,6 +198,30 @@ struct Scene {
         pixel_L.assign(4 * n, 0.0f); pixel_rgb.assign(3 * n, 0.0f); pixel_weight_sum.assign(n, 0.0f);
         wavelengths.assign(4 * n, 0.0f); pdfs.assign(4 * n, 0.0f); filter_weight.assign(n, 0.0f);
         pixel_samples.assign(n, RaySamples());
+        aux_albedo.clear(); aux_normal.clear(); aux_depth.clear();
+    }
+    // aux_buffer_kernel!, film.jl:433-488: one centre-of-pixel primary ray per pixel, lens sample (0.5, 0.5).  si.core.n / si.core.p are
+    // Raycore's (source unavailable): taken as the geometric normal on the shading-normal side and o + d t, as VolPath's own
+    // vp_compute_surface_geometry does (intersection.jl:13-21, 158-182).
+    void fill_aux_buffers(bool has_infinite_lights) {
+        const int W = params.width, H = params.height;
+        const size_t n = (size_t)W * H;
+        aux_albedo.assign(3 * n, 0.0f); aux_normal.assign(3 * n, 0.0f); aux_depth.assign(n, 0.0f);
+        const float miss_depth = has_infinite_lights ? 1.0e30f : INF_F;
+        #pragma omp parallel for schedule(dynamic, 256)
+        for (int64_t idx = 0; idx < (int64_t)n; idx++) {
+            const int row = (int)(idx % H) + 1, col = (int)(idx / H) + 1;
+            Ray ray = camera_generate_ray(camera, V2((float)col + 0.5f, (float)row + 0.5f), V2(0.5f, 0.5f), 0.0f);
+            Hit h = closest_hit(ray.o, ray.d, INF_F);
+            if (h.hit) {
+                const float bary[3] = {1.0f - h.b1 - h.b2, h.b1, h.b2};
+                SurfGeom g = surface_geometry(h.prim, bary, ray.o, ray.d, h.t);
+                V3 v = g.pi - ray.o;
+                aux_normal[3 * idx] = g.n.x; aux_normal[3 * idx + 1] = g.n.y; aux_normal[3 * idx + 2] = g.n.z;
+                aux_depth[idx] = std::sqrt((v.x * v.x + v.y * v.y) + v.z * v.z);
+                aux_albedo[3 * idx] = aux_albedo[3 * idx + 1] = aux_albedo[3 * idx + 2] = 0.8f;
+            } else aux_depth[idx] = miss_depth;
+        }
     }
     void accumulate(int32_t pixel_index, const Spec& c) {   // spectral.jl:272-277
         size_t b = (size_t)(pixel_index - 1) * 4;

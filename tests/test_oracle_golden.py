@@ -316,3 +316,48 @@ def test_coated_diffuse_transmission_known_answers():
         # the pdf estimate is the reference's literal lerp(0.9, 1/4pi, sum) = 0.9 (1 - sum) + sum / 4pi (:2839): mostly ~0.9
         far = np.sign((x[:, 14:17] * x[:, 3:6]).sum(1)) != side_o
         assert np.median(o[far, 14]) > 0.5
+
+
+def test_aux_buffers_and_escaped_mask_on_the_oracle():
+    """fill_aux_buffers! (film.jl:410-488) and the escaped-ray mask of postprocess! (postprocess.jl:220-245): known answers on a
+    scene with closed-form geometry — a unit-normal floor plane seen from above: depth = camera height / cos(angle) on
+    hits, Inf (or 1e30 with has_infinite_lights) on misses, normal = +y, albedo 0.8; the mask turns fully escaped 3x3
+    neighbourhoods into the background colour and leaves fully covered ones untouched."""
+    s = H.Scene()
+    s.push(H.rect3((-1.0, -0.1, -1.6), (2.0, 0.1, 2.0)), H.MatteMaterial(Kd=(0.5, 0.5, 0.5)))      # top face at y = 0, off-centre in z
+    s.push(H.DirectionalLight((2, 2, 2), (0, -1, 0), legacy_rgbspectrum=True))      # only surfaces are lit: escaped rays stay black
+    s.sync()
+    film = H.Film((48, 32))
+    cam = H.PerspectiveCamera((0, 3, 0), (0, 0, 0), film, up=(0, 0, -1), fov=60.0)
+    vp = H.VolPath(samples=2, max_depth=2, backend=oracle_backend.make_backend())
+    vp(s, film, cam)
+    H.fill_aux_buffers(film, vp)
+    hit = np.isfinite(film.depth)
+    assert film.depth.shape == (32, 48) and film.normal.shape == (32, 48, 3) and 0.05 < hit.mean() < 0.9
+    assert np.isinf(film.depth[~hit]).all() and (film.albedo[~hit] == 0).all() and (film.normal[~hit] == 0).all()
+    assert np.allclose(film.albedo[hit], 0.8) and np.allclose(film.normal[hit], (0, 1, 0), atol=1e-6)
+    assert film.depth[hit].min() >= 3.0 - 1e-4 and film.depth[hit].max() < 3.0 * 1.6        # straight down = 3, slanted = 3 / cos
+    # depth row r is the raster row r (top = 1) while framebuffer row y is raster row H - y + 1 (volpath.jl:175-178): the lit
+    # pixels of the render are the vertically flipped hit mask
+    lit = film.framebuffer.sum(axis=2) > 0
+    assert (lit == hit[::-1, :]).mean() > 0.93 and (lit == hit).mean() < 0.8       # (the filter's 1.5-pixel footprint blurs the rim)
+    H.fill_aux_buffers(film, vp, has_infinite_lights=True)
+    assert np.isfinite(film.depth).all() and (film.depth[~hit] == np.float32(1e30)).all()
+    H.fill_aux_buffers(film, vp)
+    plain = H.postprocess(film, vp, tonemap=None, gamma=None).copy()
+    masked = H.postprocess(film, vp, tonemap=None, gamma=None, background=(0.25, 0.5, 0.75)).copy()
+    esc = ~hit[::-1, :]                                          # in framebuffer orientation
+    def grow(m):                                                 # 3x3 dilation
+        p = np.pad(m, 1, mode="constant"); out = np.zeros_like(m)
+        for dy in range(3):
+            for dx in range(3):
+                out |= p[dy:dy + m.shape[0], dx:dx + m.shape[1]]
+        return out
+    all_esc, none_esc = ~grow(~esc), ~grow(esc)
+    assert all_esc.any() and none_esc.any()
+    assert np.allclose(masked[all_esc], (0.25, 0.5, 0.75)) and np.array_equal(masked[none_esc], plain[none_esc])
+    edge = ~all_esc & ~none_esc
+    assert edge.any() and (np.abs(masked[edge] - plain[edge]).max(axis=1) > 0).mean() > 0.9       # anti-aliased rim
+    vp.clear()
+    assert (film.depth == film.depth).all()
+    vp.close()

@@ -357,8 +357,8 @@ IMAGE_CASES = [
     ("mix_materials", lambda: scenes.mix_spheres(24), (96, 72), 16, 6, "hashed:0.80"),
     ("coated_conductor", lambda: scenes.coated_conductor_spheres(24), (128, 72), 6, 6, "strict"),
     # every hit on the panels runs the LayeredBxDF walk (RNG seeded from direction bits), twice per crossing: per-pixel agreement is
-    # the lowest of the hashed class (0.80 measured at 8 spp), means agree to 0.1 %
-    ("coated_difftrans", lambda: scenes.coated_difftrans_panels(16), (96, 54), 16, 6, "hashed:0.75"),
+    # the lowest of the hashed class (0.77 measured at 16 spp), means agree to 0.1 %
+    ("coated_difftrans", lambda: scenes.coated_difftrans_panels(16), (96, 54), 16, 6, "hashed:0.70"),
     ("c3_small", lambda: scenes.c3_many_lights(300, 24), (96, 54), 4, 6, "strict"),
     ("c4_cloud_small", lambda: scenes.c4_cloud((32, 32, 16), "nanovdb", (8, 8, 8)), (64, 36), 4, 8, "hashed"),
     ("c4_grid_small", lambda: scenes.c4_cloud((32, 32, 16), "grid", (8, 8, 8)), (64, 36), 4, 8, "hashed"),
@@ -451,6 +451,46 @@ def test_postprocess_matches_oracle():
     vp.close(); ovp.close()
     wb = H.compute_white_balance_matrix(6504.0)       # D65's correlated colour temperature -> (almost) the identity
     assert np.abs(wb - np.eye(3)).max() < 5e-2
+
+
+def test_aux_buffers_and_escaped_mask_match_oracle():
+    """fill_aux_buffers! (film.jl:410-488) and postprocess!(background = ...) (postprocess.jl:220-245): albedo, normal and depth
+    of the centre-of-pixel primary rays are bit-exact against the oracle (same camera ray, same closest hit, sqrt / div only),
+    with and without has_infinite_lights, and so is the masked, tone-mapped image on the same accumulated film."""
+    import oracle_backend
+    for make, res in ((lambda: scenes.c1_spheres(16), (96, 64)), (lambda: scenes.c2_cat(32, 16), (80, 45))):
+        scene, camf = make()
+        film = H.Film(res); vp = H.VolPath(samples=2, max_depth=3)
+        vp(scene, film, camf(film))
+        ofilm = H.Film(res); ovp = H.VolPath(samples=2, max_depth=3, backend=oracle_backend.make_backend())
+        ovp._prepare(scene, ofilm, camf(ofilm)); ovp.clear()
+        rgb, w = vp.backend.read_accum()
+        oracle_backend.lib().ok_write_accum(ovp.backend.ctx, fp(rgb), fp(w))
+        with pytest.raises(RuntimeError, match="hk_fill_aux_buffers"):
+            H.postprocess(film, vp, background=(0, 0, 0))
+        for inf_lights in (False, True):
+            H.fill_aux_buffers(film, vp, inf_lights); H.fill_aux_buffers(ofilm, ovp, inf_lights)
+            for name in ("albedo", "normal", "depth"):
+                a, b = np.ascontiguousarray(getattr(film, name)), np.ascontiguousarray(getattr(ofilm, name))
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), f"film.{name} differs (has_infinite_lights={inf_lights})"
+            hit = film.albedo[..., 0] > 0
+            assert 0.05 < hit.mean() < 1.0 and np.isfinite(film.depth[hit]).all()
+            assert np.allclose(np.linalg.norm(film.normal[hit], axis=1), 1.0, atol=1e-5)
+            if (~hit).any():
+                assert (film.depth[~hit] == (np.float32(1e30) if inf_lights else np.inf)).all()
+        H.fill_aux_buffers(film, vp); H.fill_aux_buffers(ofilm, ovp)
+        for tm in (None, "aces"):
+            a = H.postprocess(film, vp, tonemap=tm, gamma=None, background=(0.1, 0.2, 0.9)).copy()
+            b = H.postprocess(ofilm, ovp, tonemap=tm, gamma=None, background=(0.1, 0.2, 0.9)).copy()
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+            plain = H.postprocess(film, vp, tonemap=tm, gamma=None).copy()
+            if np.isinf(film.depth).any():
+                assert not np.array_equal(a, plain)
+        vp.clear()
+        H_, W_ = film.depth.shape
+        z = np.zeros((W_, H_), f32); vp.backend.call("read_aux_buffers", None, None, fp(z))
+        assert (z == 0).all(), "clear!(film) resets the auxiliary buffers"
+        vp.close(); ovp.close()
 
 
 def test_uplift_cache_is_bitwise_invariant():
