@@ -34,6 +34,11 @@ class HkPostprocess(C.Structure):
                 ("mask_escaped", C.c_int32), ("background", c_f * 3)]
 
 
+class HkDenoiseConfig(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("sigma_color", c_f), ("sigma_normal", c_f), ("sigma_depth", c_f),
+                ("use_variance", C.c_int32)]
+
+
 class HkGeometry(C.Structure):
     _fields_ = [("positions", c_fp), ("normals", c_fp), ("tangents", c_fp), ("uvs", c_fp), ("indices", c_u32p),
                 ("tri_meta", c_u32p), ("n_verts", C.c_uint32), ("n_tris", C.c_uint32)]
@@ -119,7 +124,7 @@ HK_SYMBOLS = [
     "hk_abi_version", "hk_create", "hk_destroy", "hk_last_error", "hk_upload_tables", "hk_upload_geometry",
     "hk_upload_spectra", "hk_upload_materials", "hk_update_material", "hk_bounce_profile", "hk_upload_envmaps", "hk_upload_lights", "hk_upload_media",
     "hk_set_camera", "hk_set_filter", "hk_set_params", "hk_clear", "hk_render_samples", "hk_render_samples_strided",
-    "hk_read_film", "hk_read_film_async", "hk_read_film_wait", "hk_postprocess", "hk_fill_aux_buffers", "hk_read_aux_buffers", "hk_film_accum_dev", "hk_read_accum", "hk_write_accum", "hk_trace_closest",
+    "hk_read_film", "hk_read_film_async", "hk_read_film_wait", "hk_postprocess", "hk_fill_aux_buffers", "hk_read_aux_buffers", "hk_denoise", "hk_film_accum_dev", "hk_read_accum", "hk_write_accum", "hk_trace_closest",
     "hk_trace_closest_dev", "hk_trace_any", "hk_stats", "hk_synchronize", "hk_dev_alloc", "hk_dev_free",
     "hk_dev_upload", "hk_dev_download", "hk_set_profiling", "hk_stage_times", "hk_pinned_alloc", "hk_pinned_free",
 ]
@@ -144,6 +149,7 @@ def bind_common(lib, p):
     f("postprocess", [_VP, C.POINTER(HkPostprocess), c_fp])
     f("fill_aux_buffers", [_VP, C.c_int32])
     f("read_aux_buffers", [_VP, c_fp, c_fp, c_fp])
+    f("denoise", [_VP, C.POINTER(HkDenoiseConfig), c_fp, c_fp])
     if p == "hk_":
         f("read_film_async", [_VP, c_fp, C.POINTER(C.c_int32)])
         f("read_film_wait", [_VP, C.c_int32])

@@ -4,6 +4,7 @@
 #include "../../include/hikari_cuda.h"
 #include "../../include/hikari_cuda_testing.h"
 #include "hk_wavefront.cuh"
+#include "hk_denoise.cuh"
 #include "hk_bvh.h"
 #include <algorithm>
 #include <cstdio>
@@ -49,7 +50,7 @@ struct HkContext {
     DevBuf b_media;
     DevBuf b_f_func, b_f_mcdf, b_f_mfunc, b_f_ccdf;
     DevBuf b_state, b_counts, b_rays, b_film, b_scratch_u32, b_trace_ctr, b_readback;
-    DevBuf b_aux; size_t aux_pixels = 0;     // film.albedo [3n] | film.normal [3n] | film.depth [n], (H, W) column-major
+    DevBuf b_aux, b_denoise; size_t aux_pixels = 0;     // film.albedo [3n] | film.normal [3n] | film.depth [n], (H, W) column-major
     // pipelined read-out (hk_read_film_async): two device staging buffers, a copy stream, per-buffer events
     DevBuf b_readback_async[2]; cudaStream_t copy_stream = nullptr; cudaEvent_t ev_final[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     int async_next = 0; bool async_used[2] = {false, false};
@@ -769,6 +770,36 @@ int32_t hk_read_aux_buffers(HkContext* ctx, float* albedo, float* normal, float*
     if (albedo) CK(cudaMemcpyAsync(albedo, a, 12 * n, cudaMemcpyDeviceToHost, ctx->stream));
     if (normal) CK(cudaMemcpyAsync(normal, a + 3 * n, 12 * n, cudaMemcpyDeviceToHost, ctx->stream));
     if (depth) CK(cudaMemcpyAsync(depth, a + 6 * n, 4 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return HK_OK;
+}
+// denoise!(film; config), denoise.jl:301-372
+int32_t hk_denoise(HkContext* ctx, const HkDenoiseConfig* cfg, float* out_pp, float* out_fb) {
+    if (!ctx || !cfg || !out_pp) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    REQUIRE(ctx->have_params, "hk_set_params has not been called");
+    REQUIRE(cfg->iterations >= 0 && cfg->iterations <= 16, "denoise iterations out of range (0..16)");
+    const size_t n = (size_t)ctx->params.width * ctx->params.height;
+    REQUIRE(ctx->aux_pixels == n, "denoise needs film.normal / film.depth: call hk_fill_aux_buffers first");
+    const int W = ctx->params.width, H = ctx->params.height;
+    if (ctx->b_denoise.bytes != 28 * n) { CK(cudaStreamSynchronize(ctx->stream)); CK(ctx->b_denoise.alloc(28 * n)); }
+    float* buf_a = ctx->b_denoise.as<float>();            // film.framebuffer
+    float* buf_b = buf_a + 3 * n;                         // similar(film.framebuffer)
+    float* var = buf_a + 6 * n;
+    const float* aux = ctx->b_aux.as<float>();
+    const dim3 grid = grid_for(ctx, n, 256, 8);
+    k_film_finalize<<<grid, 256, 0, ctx->stream>>>(ctx->S.pixel_rgb, ctx->S.pixel_weight, buf_a, W, H);
+    if (cfg->use_variance) k_denoise_variance<<<grid, 256, 0, ctx->stream>>>(var, buf_a, W, H);
+    ctx->launches += cfg->use_variance ? 2 : 1;
+    for (int i = 1; i <= cfg->iterations; i++) {
+        DenoisePass P{W, H, 1 << (i - 1), cfg->sigma_color, cfg->sigma_normal, cfg->sigma_depth, cfg->use_variance ? 1 : 0};
+        if (i % 2 == 1) k_denoise_atrous<<<grid, 256, 0, ctx->stream>>>(buf_b, buf_a, aux + 3 * n, aux + 6 * n, var, P);
+        else k_denoise_atrous<<<grid, 256, 0, ctx->stream>>>(buf_a, buf_b, aux + 3 * n, aux + 6 * n, var, P);
+        ctx->launches++;
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_pp, cfg->iterations % 2 == 1 ? buf_b : buf_a, 12 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_fb && cfg->iterations >= 2) CK(cudaMemcpyAsync(out_fb, buf_a, 12 * n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return HK_OK;
 }

@@ -132,6 +132,8 @@ class Film:
     def clear(self):
         self.framebuffer[:] = 0
         self.iteration_index = 0
+        for a in getattr(self, "_aux_store", None) or ():       # clear!(film) also resets albedo / normal / depth, film.jl:343-346
+            a[...] = 0
 
 
 class FilmSensor:
@@ -214,6 +216,35 @@ def fill_aux_buffers(film, vp, has_infinite_lights=False):
     vp.backend.call("fill_aux_buffers", 1 if has_infinite_lights else 0)
     vp.backend.call("read_aux_buffers", _fp(film._aux_store[0]), _fp(film._aux_store[1]), _fp(film._aux_store[2]))
     return film
+
+
+class DenoiseConfig:
+    """src/denoise.jl:29-57"""
+
+    def __init__(self, iterations=5, sigma_color=4.0, sigma_normal=128.0, sigma_depth=1.0, use_variance=True):
+        self.iterations, self.use_variance = int(iterations), bool(use_variance)
+        self.sigma_color, self.sigma_normal, self.sigma_depth = float(sigma_color), float(sigma_normal), float(sigma_depth)
+
+
+def denoise(film, vp, config=None):
+    """denoise!(film; config), src/denoise.jl:301-372: edge-avoiding a-trous filter of the framebuffer guided by film.normal /
+    film.depth (fill_aux_buffers first); result in film.postprocess.  As in the reference, from two iterations on
+    film.framebuffer is left holding the last even pass (it is one of the two ping-pong buffers)."""
+    config = config if config is not None else DenoiseConfig()
+    c = A.HkDenoiseConfig(config.iterations, config.sigma_color, config.sigma_normal, config.sigma_depth, 1 if config.use_variance else 0)
+    w, h = film.resolution
+    if getattr(film, "_pp_store", None) is None:
+        film._pp_store = np.zeros((w, h, 3), dtype=f32)
+        film.postprocess = film._pp_store.transpose(1, 0, 2)
+    vp.backend.call("denoise", C.byref(c), _fp(film._pp_store), _fp(film._store))
+    return None
+
+
+def denoise_inplace(film, vp, config=None):
+    """denoise_inplace!(film; config), src/denoise.jl:379-383"""
+    denoise(film, vp, config)
+    film.framebuffer[:] = film.postprocess
+    return None
 
 
 class PerspectiveCamera:

@@ -363,6 +363,18 @@ int32_t hk_postprocess(HkContext* ctx, const HkPostprocess* params, float* out_r
  * hk_read_aux_buffers: any pointer may be NULL.                                                                  */
 int32_t hk_fill_aux_buffers(HkContext* ctx, int32_t has_infinite_lights);
 int32_t hk_read_aux_buffers(HkContext* ctx, float* albedo_hw3, float* normal_hw3, float* depth_hw);
+/* ---- denoise -------------------------------------------------------------------------------
+ * replaces: denoise!(film; config) (src/denoise.jl:301-372): 3x3 luminance variance of film.framebuffer when use_variance,
+ * then `iterations` edge-avoiding a-trous passes (step 1, 2, 4, ...) guided by film.normal / film.depth
+ * (hk_fill_aux_buffers first), result into film.postprocess.  The reference ping-pongs between film.framebuffer itself
+ * and a scratch copy, so from two iterations on it leaves the last even pass in film.framebuffer: pass
+ * out_framebuffer_hw3 (may be NULL) to receive that side effect (written only when iterations >= 2).           */
+typedef struct HkDenoiseConfig {     /* DenoiseConfig, denoise.jl:29-57; defaults 5, 4.0, 128.0, 1.0, true */
+    int32_t iterations;
+    float   sigma_color, sigma_normal, sigma_depth;
+    int32_t use_variance;
+} HkDenoiseConfig;
+int32_t hk_denoise(HkContext* ctx, const HkDenoiseConfig* config, float* out_postprocess_hw3, float* out_framebuffer_hw3);
 /* raw accumulators for the multi-GPU film reduce (pixel_rgb ‖ pixel_weight_sum, volpath-state.jl):
  * device pointer to [n*3] rgb sums followed by [n] weight sums, valid until the next hk_set_params. */
 int32_t hk_film_accum_dev(HkContext* ctx, float** out_accum_dev, uint64_t* out_count);

@@ -229,6 +229,85 @@ int32_t ok_postprocess(OkContext* c, const HkPostprocess* P, float* out) {
     }
     return 0;
 }
+int32_t ok_test_set_aux_depth(OkContext* c, const float* depth) {      // test hook: a synthetic film.depth ((H, W) column-major)
+    const size_t n = (size_t)c->s.params.width * c->s.params.height;
+    if (c->s.aux_depth.size() != n) return -1;
+    std::memcpy(c->s.aux_depth.data(), depth, 4 * n);
+    return 0;
+}
+// denoise!(film; config), src/denoise.jl:301-372 (weights :66-114, a-trous pass :123-207, variance :216-258); images (H, W) column-major
+static float dn_lum(float r, float g, float b) { return 0.2126f * r + 0.7152f * g + 0.0722f * b; }
+static float dn_max0(float x) { return x > 0.0f ? x : (x == x ? 0.0f : x); }      // Julia max(0f0, NaN) = NaN
+int32_t ok_denoise(OkContext* c, const HkDenoiseConfig* cfg, float* out_pp, float* out_fb) {
+    Scene& s = c->s;
+    const int W = s.params.width, H = s.params.height;
+    const size_t n = (size_t)W * H;
+    if (s.aux_depth.size() != n || cfg->iterations < 0) return -1;
+    std::vector<float> a(3 * n), b(3 * n), var(n, 0.0f);
+    for (size_t p = 0; p < n; p++) {      // film.framebuffer (vp_finalize_film_kernel!)
+        const size_t px = p % W, py = p / W;
+        const float ws = s.pixel_weight_sum[p];
+        float* o = a.data() + 3 * (px * H + py);
+        if (ws > 0.0f) { const float inv = 1.0f / ws; o[0] = s.pixel_rgb[3 * p] * inv; o[1] = s.pixel_rgb[3 * p + 1] * inv; o[2] = s.pixel_rgb[3 * p + 2] * inv; }
+        else o[0] = o[1] = o[2] = 0.0f;
+    }
+    if (cfg->use_variance) {
+        for (size_t idx = 0; idx < n; idx++) {
+            const int row = (int)(idx % H), col = (int)(idx / H);
+            float sl = 0.0f, sl2 = 0.0f; int count = 0;
+            for (int dy = -1; dy <= 1; dy++)
+                for (int dx = -1; dx <= 1; dx++) {
+                    const int qr = row + dy, qc = col + dx;
+                    if (qr >= 0 && qr < H && qc >= 0 && qc < W) {
+                        const float* p = a.data() + 3 * ((size_t)qc * H + qr);
+                        const float l = dn_lum(p[0], p[1], p[2]);
+                        sl += l; sl2 += l * l; count++;
+                    }
+                }
+            const float mean = sl / (float)count, mean_sq = sl2 / (float)count;
+            var[idx] = std::max(0.0f, mean_sq - mean * mean);
+        }
+    }
+    const float K[5] = {1.0f / 16.0f, 1.0f / 4.0f, 3.0f / 8.0f, 1.0f / 4.0f, 1.0f / 16.0f};
+    for (int it = 1; it <= cfg->iterations; it++) {
+        const int step = 1 << (it - 1);
+        const std::vector<float>& in = (it % 2 == 1) ? a : b;
+        std::vector<float>& out = (it % 2 == 1) ? b : a;
+        #pragma omp parallel for schedule(static)
+        for (int64_t idx = 0; idx < (int64_t)n; idx++) {
+            const int row = (int)(idx % H), col = (int)(idx / H);
+            const float rp = in[3 * idx], gp = in[3 * idx + 1], bp = in[3 * idx + 2];
+            const float lum_p = dn_lum(rp, gp, bp);
+            const float* np_ = s.aux_normal.data() + 3 * idx;
+            const float d_p = s.aux_depth[idx];
+            const float var_p = cfg->use_variance ? var[idx] : 0.0f;
+            float sr = 0.0f, sg = 0.0f, sb = 0.0f, sw = 0.0f;
+            for (int dyi = 0; dyi < 5; dyi++)
+                for (int dxi = 0; dxi < 5; dxi++) {
+                    int qr = row + (dyi - 2) * step, qc = col + (dxi - 2) * step;
+                    qr = std::min(std::max(qr, 0), H - 1); qc = std::min(std::max(qc, 0), W - 1);
+                    const size_t q = (size_t)qc * H + qr;
+                    const float rq = in[3 * q], gq = in[3 * q + 1], bq = in[3 * q + 2];
+                    const float lum_q = dn_lum(rq, gq, bq);
+                    const float* nq = s.aux_normal.data() + 3 * q;
+                    const float w_spatial = K[dxi] * K[dyi];
+                    const float es = var_p > 0.0f ? cfg->sigma_color * std::sqrt(var_p) + 1.0e-4f : cfg->sigma_color;
+                    const float w_color = std::exp(-std::fabs(lum_p - lum_q) / es);
+                    const float dotv = (np_[0] * nq[0] + np_[1] * nq[1]) + np_[2] * nq[2];
+                    const float w_norm = std::pow(dn_max0(dotv), cfg->sigma_normal);
+                    const float w_depth = std::exp(-std::fabs(d_p - s.aux_depth[q]) / (cfg->sigma_depth * (float)step + 1.0e-4f));
+                    const float w = w_spatial * w_color * w_norm * w_depth;
+                    sr += rq * w; sg += gq * w; sb += bq * w; sw += w;
+                }
+            float* o = out.data() + 3 * idx;
+            if (sw > 1.0e-6f) { const float inv = 1.0f / sw; o[0] = sr * inv; o[1] = sg * inv; o[2] = sb * inv; }
+            else { o[0] = rp; o[1] = gp; o[2] = bp; }
+        }
+    }
+    std::memcpy(out_pp, (cfg->iterations % 2 == 1 ? b : a).data(), 12 * n);
+    if (out_fb && cfg->iterations >= 2) std::memcpy(out_fb, a.data(), 12 * n);
+    return 0;
+}
 int32_t ok_read_accum(OkContext* c, float* rgb, float* w) {
     std::memcpy(rgb, c->s.pixel_rgb.data(), c->s.pixel_rgb.size() * 4);
     std::memcpy(w, c->s.pixel_weight_sum.data(), c->s.pixel_weight_sum.size() * 4);

@@ -361,3 +361,68 @@ def test_aux_buffers_and_escaped_mask_on_the_oracle():
     vp.clear()
     assert (film.depth == film.depth).all()
     vp.close()
+
+
+def _atrous_b3_reference(img, iterations):
+    """independent numpy statement of the un-weighted a-trous B3-spline filter with clamped borders (Dammertz et al. 2010)"""
+    k = np.array([1 / 16, 1 / 4, 3 / 8, 1 / 4, 1 / 16], np.float64)
+    out = img.astype(np.float64)
+    Hh, Ww = out.shape[:2]
+    for it in range(iterations):
+        step = 1 << it
+        acc = np.zeros_like(out)
+        for dy in range(5):
+            rows = np.clip(np.arange(Hh) + (dy - 2) * step, 0, Hh - 1)
+            for dx in range(5):
+                cols = np.clip(np.arange(Ww) + (dx - 2) * step, 0, Ww - 1)
+                acc += k[dy] * k[dx] * out[rows][:, cols]
+        out = acc
+    return out
+
+
+def test_denoise_known_answers_on_the_oracle():
+    """denoise! (src/denoise.jl): with every edge-stopping weight forced to 1 (flat normals and depth, sigma_color huge, no
+    variance) the filter must equal the plain a-trous B3-spline pyramid, restated here independently in numpy; iterations = 0
+    returns the framebuffer; a constant image is a fixed point; a depth step with a small sigma_depth stops the blur; and
+    the reference's side effect (film.framebuffer holds the last even pass from two iterations on) is reproduced."""
+    s = H.Scene()
+    s.push(H.rect3((-4.0, -0.1, -4.0), (8.0, 0.1, 8.0)), H.MatteMaterial(Kd=(0.5, 0.5, 0.5)))       # fills the view: normals (0,1,0)
+    s.push(H.DirectionalLight((2, 2, 2), (0, -1, 0), legacy_rgbspectrum=True))
+    s.sync()
+    film = H.Film((40, 28))
+    cam = H.PerspectiveCamera((0, 3, 0), (0, 0, 0), film, up=(0, 0, -1), fov=40.0)
+    vp = H.VolPath(samples=1, max_depth=2, backend=oracle_backend.make_backend())
+    vp(s, film, cam)
+    H.fill_aux_buffers(film, vp)
+    assert np.isfinite(film.depth).all() and np.allclose(film.normal, (0, 1, 0), atol=1e-6)
+    L = oracle_backend.lib()
+    w, h = film.resolution
+    rng = np.random.RandomState(2)
+    img = rng.uniform(0.0, 2.0, size=(h, w, 3)).astype(f32)                          # framebuffer[py, px]
+    def load(image):
+        rgb = np.ascontiguousarray(image.reshape(h * w, 3))                            # accumulator index p = py * W + px <- framebuffer[py, px]
+        L.ok_write_accum(vp.backend.ctx, fp(rgb), fp(np.ones(h * w, f32)))
+    load(img)
+    flat = H.DenoiseConfig(iterations=3, sigma_color=1e30, sigma_normal=128.0, sigma_depth=1e30, use_variance=False)
+    H.denoise(film, vp, H.DenoiseConfig(iterations=0)); assert np.array_equal(film.postprocess, img)
+    fb_before = film.framebuffer.copy()
+    H.denoise(film, vp, H.DenoiseConfig(iterations=1, sigma_color=1e30, sigma_depth=1e30, use_variance=False))
+    assert np.allclose(film.postprocess, _atrous_b3_reference(img, 1), rtol=2e-5, atol=1e-6) and np.array_equal(film.framebuffer, fb_before)
+    H.denoise(film, vp, flat)
+    assert np.allclose(film.postprocess, _atrous_b3_reference(img, 3), rtol=5e-5, atol=1e-6)
+    assert np.allclose(film.framebuffer, _atrous_b3_reference(img, 2), rtol=5e-5, atol=1e-6), "framebuffer = the last even pass"
+    const = np.full((h, w, 3), 0.37, f32); load(const)
+    H.denoise(film, vp, H.DenoiseConfig()); assert np.allclose(film.postprocess, 0.37, rtol=1e-6)
+    # default config on the noisy image: smoother (variance-guided), mean preserved to a few per cent
+    load(img); H.denoise(film, vp, H.DenoiseConfig())
+    assert film.postprocess.std() < 0.5 * img.std() and abs(film.postprocess.mean() - img.mean()) < 0.05 * img.mean()
+    # a depth edge: left half of the image a wall 1000 units nearer; sigma_depth = 1 keeps the halves apart
+    step_img = np.zeros((h, w, 3), f32); step_img[:, : w // 2] = 1.0
+    load(step_img)
+    d = np.ascontiguousarray(film._aux_store[2]); d[: w // 2, :] -= 1000.0            # storage is (W, H)
+    L.ok_test_set_aux_depth(vp.backend.ctx, fp(d))
+    H.denoise(film, vp, H.DenoiseConfig(iterations=4, sigma_color=1e30, sigma_depth=1.0, use_variance=False))
+    assert np.allclose(film.postprocess[:, : w // 2], 1.0, atol=1e-6) and np.allclose(film.postprocess[:, w // 2:], 0.0, atol=1e-6)
+    H.denoise(film, vp, H.DenoiseConfig(iterations=4, sigma_color=1e30, sigma_depth=1e30, use_variance=False))
+    assert 0.05 < film.postprocess[:, w // 2, 0].mean() < 0.95                         # without the depth stop the edge bleeds
+    vp.close()

@@ -493,6 +493,45 @@ def test_aux_buffers_and_escaped_mask_match_oracle():
         vp.close(); ovp.close()
 
 
+def test_denoise_matches_oracle():
+    """denoise! (src/denoise.jl:301-372) on the same accumulated film and the same auxiliary buffers: the a-trous passes use
+    expf / powf (x^128 on normal dot products), so CUDA and glibc agree to a few ulps of each weight: rtol 3e-4 on the image.
+    Also the reference's framebuffer side effect and the error path without aux buffers."""
+    import oracle_backend
+    scene, camf = scenes.c1_spheres(16)
+    res = (96, 64)
+    film = H.Film(res); vp = H.VolPath(samples=2, max_depth=4)
+    vp(scene, film, camf(film))
+    ofilm = H.Film(res); ovp = H.VolPath(samples=2, max_depth=4, backend=oracle_backend.make_backend())
+    ovp._prepare(scene, ofilm, camf(ofilm)); ovp.clear()
+    rgb, w = vp.backend.read_accum()
+    oracle_backend.lib().ok_write_accum(ovp.backend.ctx, fp(rgb), fp(w))
+    with pytest.raises(RuntimeError, match="hk_fill_aux_buffers"):
+        H.denoise(film, vp)
+    H.fill_aux_buffers(film, vp); H.fill_aux_buffers(ofilm, ovp)
+    noisy = film.framebuffer.copy()
+    ofilm.framebuffer[:] = noisy
+    for cfg in (H.DenoiseConfig(), H.DenoiseConfig(iterations=2, use_variance=False), H.DenoiseConfig(iterations=1, sigma_color=0.5, sigma_normal=16.0, sigma_depth=0.2),
+                H.DenoiseConfig(iterations=0)):
+        film.framebuffer[:] = noisy; ofilm.framebuffer[:] = noisy
+        H.denoise(film, vp, cfg); H.denoise(ofilm, ovp, cfg)
+        assert np.isfinite(film.postprocess).all()
+        np.testing.assert_allclose(film.postprocess, ofilm.postprocess, rtol=3e-4, atol=2e-6)
+        np.testing.assert_allclose(film.framebuffer, ofilm.framebuffer, rtol=3e-4, atol=2e-6)
+        if cfg.iterations >= 2:
+            assert not np.array_equal(film.framebuffer, noisy), "from two iterations on film.framebuffer holds the last even pass"
+        else:
+            assert np.array_equal(film.framebuffer, noisy)
+        if cfg.iterations == 5:
+            hit = np.isfinite(film.depth[::-1, :])
+            lum = lambda im: im @ np.array([0.2126, 0.7152, 0.0722])
+            # fewer high frequencies on the lit surfaces, same mean
+            hf = lambda im: np.abs(np.diff(lum(im), axis=1))[hit[:, 1:] & hit[:, :-1]].mean()
+            assert hf(film.postprocess) < 0.8 * hf(noisy)
+            assert abs(film.postprocess.mean() - noisy.mean()) < 0.05 * noisy.mean()
+    vp.close(); ovp.close()
+
+
 def test_uplift_cache_is_bitwise_invariant():
     """The upload-time uplift cache only moves rgb_to_spectrum of constant colours out of the shading kernels: renders
     with and without it must agree bit for bit (all material types + area / env lights + a medium)."""
