@@ -20,7 +20,7 @@ HK_MATFLAG_REMAP_ROUGHNESS, HK_MATFLAG_SPECTRAL_ETA_K, HK_MATFLAG_USE_ETA_K = 1,
 HK_LIGHT_POINT, HK_LIGHT_SPOT, HK_LIGHT_DIRECTIONAL, HK_LIGHT_SUN = 1, 2, 3, 4
 HK_LIGHT_ENVIRONMENT, HK_LIGHT_AMBIENT, HK_LIGHT_DIFFUSE_AREA = 5, 6, 7
 HK_SPECTRUM_RGB, HK_SPECTRUM_ILLUMINANT = 0, 1
-HK_MEDIUM_HOMOGENEOUS, HK_MEDIUM_GRID, HK_MEDIUM_NANOVDB = 1, 2, 3
+HK_MEDIUM_HOMOGENEOUS, HK_MEDIUM_GRID, HK_MEDIUM_NANOVDB, HK_MEDIUM_RGBGRID = 1, 2, 3, 4
 
 
 class HkTables(C.Structure):
@@ -91,7 +91,8 @@ class HkMedium(C.Structure):
                 ("nanovdb_root_offset", C.c_uint64), ("nanovdb_upper_offset", C.c_uint64),
                 ("nanovdb_lower_offset", C.c_uint64), ("nanovdb_leaf_offset", C.c_uint64),
                 ("nanovdb_root_tiles", C.c_int32), ("nanovdb_upper_count", C.c_int32),
-                ("nanovdb_lower_count", C.c_int32), ("nanovdb_leaf_count", C.c_int32)]
+                ("nanovdb_lower_count", C.c_int32), ("nanovdb_leaf_count", C.c_int32),
+                ("rgb_sigma_a", c_fp), ("rgb_sigma_s", c_fp), ("rgb_Le", c_fp), ("Le_scale", c_f)]
 
 
 class HkCamera(C.Structure):

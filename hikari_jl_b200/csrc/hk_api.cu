@@ -50,7 +50,8 @@ struct HkContext {
     DevBuf b_media;
     DevBuf b_f_func, b_f_mcdf, b_f_mfunc, b_f_ccdf;
     DevBuf b_state, b_counts, b_rays, b_film, b_scratch_u32, b_trace_ctr, b_readback;
-    DevBuf b_aux, b_denoise; size_t aux_pixels = 0;     // film.albedo [3n] | film.normal [3n] | film.depth [n], (H, W) column-major
+    DevBuf b_aux, b_denoise; size_t aux_pixels = 0;
+    bool has_rgbgrid = false;                // some uploaded medium is an RGBGridMedium: the tracking kernels with that branch compiled in     // film.albedo [3n] | film.normal [3n] | film.depth [n], (H, W) column-major
     // pipelined read-out (hk_read_film_async): two device staging buffers, a copy stream, per-buffer events
     DevBuf b_readback_async[2]; cudaStream_t copy_stream = nullptr; cudaEvent_t ev_final[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     int async_next = 0; bool async_used[2] = {false, false};
@@ -373,7 +374,7 @@ int32_t hk_upload_media(HkContext* ctx, const HkMedium* m, uint32_t n) {
     std::vector<DevMedium> dev(n);
     for (uint32_t i = 0; i < n; i++) {
         const HkMedium& M = m[i];
-        REQUIRE(M.type >= 1 && M.type <= 3, "unknown medium type (RGBGridMedium is out of scope)");
+        REQUIRE(M.type >= 1 && M.type <= 4, "unknown medium type");
         DevMedium& d = dev[i]; std::memset(&d, 0, sizeof(d));
         d.type = M.type; std::memcpy(d.sigma_a, M.sigma_a_rgb, 12); std::memcpy(d.sigma_s, M.sigma_s_rgb, 12); std::memcpy(d.Le, M.Le_rgb, 12); d.g = M.g;
         std::memcpy(d.bmin, M.bounds_min, 12); std::memcpy(d.bmax, M.bounds_max, 12); std::memcpy(d.medium_from_render, M.medium_from_render, 48);
@@ -381,6 +382,19 @@ int32_t hk_upload_media(HkContext* ctx, const HkMedium* m, uint32_t n) {
         if (M.type == HK_MEDIUM_GRID) {
             size_t cnt = (size_t)M.density_res[0] * M.density_res[1] * M.density_res[2];
             CK(B[0].upload(M.density, 4 * cnt)); d.density = B[0].as<float>(); std::memcpy(d.dres, M.density_res, 12);
+        }
+        if (M.type == HK_MEDIUM_RGBGRID) {     // the (up to) three RGB grids share one allocation
+            REQUIRE(M.rgb_sigma_a || M.rgb_sigma_s, "RGBGridMedium needs at least one of sigma_a / sigma_s grids (media.jl:1073)");
+            REQUIRE(!M.rgb_Le || M.rgb_sigma_a, "RGBGridMedium: Le grid requires a sigma_a grid (media.jl:1075)");
+            REQUIRE(M.density_res[0] >= 2 && M.density_res[1] >= 2 && M.density_res[2] >= 2, "RGBGridMedium: grid must be at least 2 voxels per axis");
+            const size_t cnt = 3 * (size_t)M.density_res[0] * M.density_res[1] * M.density_res[2];
+            const float* src[3] = {M.rgb_sigma_a, M.rgb_sigma_s, M.rgb_Le};
+            std::vector<float> packed; size_t off[3];
+            for (int k = 0; k < 3; k++) { off[k] = packed.size(); if (src[k]) packed.insert(packed.end(), src[k], src[k] + cnt); }
+            CK(B[0].upload(packed.data(), 4 * packed.size()));
+            d.rgb_a = src[0] ? B[0].as<float>() + off[0] : nullptr; d.rgb_s = src[1] ? B[0].as<float>() + off[1] : nullptr;
+            d.rgb_le = src[2] ? B[0].as<float>() + off[2] : nullptr;
+            std::memcpy(d.dres, M.density_res, 12); d.sigma_scale = M.scale; d.le_scale = M.Le_scale;
         }
         if (M.type != HK_MEDIUM_HOMOGENEOUS) {
             size_t cnt = (size_t)M.majorant_res[0] * M.majorant_res[1] * M.majorant_res[2];
@@ -391,6 +405,8 @@ int32_t hk_upload_media(HkContext* ctx, const HkMedium* m, uint32_t n) {
             std::memcpy(d.inv_mat, M.nanovdb_inv_mat, 36); std::memcpy(d.vec, M.nanovdb_vec, 12); d.root_off = M.nanovdb_root_offset; d.root_tiles = M.nanovdb_root_tiles;
         }
     }
+    ctx->has_rgbgrid = false;
+    for (uint32_t i = 0; i < n; i++) if (m[i].type == HK_MEDIUM_RGBGRID) ctx->has_rgbgrid = true;
     CK(ctx->b_media.upload(dev.data(), sizeof(DevMedium) * (size_t)n));
     ctx->D.media = ctx->b_media.as<DevMedium>(); ctx->D.n_media = (int32_t)n;
     ctx->camera_medium_valid = false;
@@ -605,7 +621,8 @@ int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride,
             { StageScope sc(ctx, HK_STAGE_ROUTE); k_route<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->D, ctx->S, cur, par); }
             if (ctx->D.n_media > 0) {
                 StageScope sc(ctx, HK_STAGE_MEDIUM);
-                k_medium_track<<<ctx->sm_count * 4, 128, 0, st>>>(ctx->D, ctx->S);
+                if (ctx->has_rgbgrid) k_medium_track<true><<<ctx->sm_count * 4, 128, 0, st>>>(ctx->D, ctx->S);
+                else k_medium_track<false><<<ctx->sm_count * 4, 128, 0, st>>>(ctx->D, ctx->S);
                 k_medium_finish<<<ctx->sm_count * 8, 128, 0, st>>>(ctx->D, ctx->S, A, cur ^ 1); ctx->launches++;
             }
             if (shadow_in_flight) { cudaStreamWaitEvent(st, ctx->ev_shadowed, 0); shadow_in_flight = false; }      // shadow(b-1) done before anything adds to L
@@ -630,7 +647,9 @@ int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride,
                     else for (int r = 0; r < HK_SHADOW_ROUNDS; r++) {      // one round per medium-boundary crossing; empty rounds exit at once
                         if (cnt) k_shadow_seg_trace<true><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, r, work);
                         else k_shadow_seg_trace<false><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, r, work);
-                        k_shadow_seg_ratio<<<ctx->sm_count * 4, 128, 0, st>>>(ctx->D, ctx->S, r); ctx->launches += r == 0 ? 1 : 2;
+                        if (ctx->has_rgbgrid) k_shadow_seg_ratio<true><<<ctx->sm_count * 4, 128, 0, st>>>(ctx->D, ctx->S, r);
+                        else k_shadow_seg_ratio<false><<<ctx->sm_count * 4, 128, 0, st>>>(ctx->D, ctx->S, r);
+                        ctx->launches += r == 0 ? 1 : 2;
                     }
                 }
             }

@@ -11,6 +11,8 @@ struct DevMedium {
     int32_t dres[3]; const float* __restrict__ density;
     int32_t mres[3]; const float* __restrict__ majorant;
     const uint8_t* __restrict__ nvdb; float inv_mat[9], vec[3]; uint64_t root_off; int32_t root_tiles;
+    // RGBGridMedium (media.jl:1002-1456): per-voxel RGB sigma_a / sigma_s / Le, [nz][ny][nx][3], null = absent (sigma: 1, Le: 0)
+    const float* __restrict__ rgb_a; const float* __restrict__ rgb_s; const float* __restrict__ rgb_le; float sigma_scale, le_scale;
 };
 struct MediaCtx { DevTables T; const DevMedium* __restrict__ media; int32_t n_media; };
 
@@ -155,6 +157,41 @@ HK_DEV float grid_density(const DevMedium& M, float3 pm) {   // media.jl:1544-15
     float d0 = d00 * fy1 + d10 * fy, d1 = d01 * fy1 + d11 * fy;
     return d0 * (1.0f - fz) + d1 * fz;
 }
+// _sample_rgb_grid, media.jl:1283-1325: trilinear RGB, zero outside the bounds
+HK_DEV float3 rgbgrid_sample(const DevMedium& M, const float* __restrict__ grid, const float* pn) {
+    if (pn[0] < 0.0f || pn[1] < 0.0f || pn[2] < 0.0f || pn[0] > 1.0f || pn[1] > 1.0f || pn[2] > 1.0f) return f3(0.0f, 0.0f, 0.0f);
+    const int nx = M.dres[0], ny = M.dres[1], nz = M.dres[2];
+    float gx = pn[0] * (float)nx + 0.5f, gy = pn[1] * (float)ny + 0.5f, gz = pn[2] * (float)nz + 0.5f;
+    int ix = clampi(floor_i(gx), 1, nx - 1), iy = clampi(floor_i(gy), 1, ny - 1), iz = clampi(floor_i(gz), 1, nz - 1);
+    float fx = clampf(gx - (float)ix, 0.0f, 1.0f), fy = clampf(gy - (float)iy, 0.0f, 1.0f), fz = clampf(gz - (float)iz, 0.0f, 1.0f);
+    const float* b = grid + 3 * ((size_t)(ix - 1) + (size_t)nx * ((size_t)(iy - 1) + (size_t)ny * (size_t)(iz - 1)));
+    const size_t sy = 3 * (size_t)nx, sz = 3 * (size_t)nx * ny;
+    const float fx1 = 1.0f - fx, fy1 = 1.0f - fy;
+    float out[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        float c00 = __ldg(b + c) * fx1 + __ldg(b + 3 + c) * fx, c10 = __ldg(b + sy + c) * fx1 + __ldg(b + sy + 3 + c) * fx;
+        float c01 = __ldg(b + sz + c) * fx1 + __ldg(b + sz + 3 + c) * fx, c11 = __ldg(b + sz + sy + c) * fx1 + __ldg(b + sz + sy + 3 + c) * fx;
+        float c0 = c00 * fy1 + c10 * fy, c1 = c01 * fy1 + c11 * fy;
+        out[c] = c0 * (1.0f - fz) + c1 * fz;
+    }
+    return f3(out[0], out[1], out[2]);
+}
+HK_DEV float3 affine_pt(const float* M, float3 p);
+// sample_point(::RGBGridMedium), media.jl:1327-1372: two (three with emission) RGB look-ups and unbounded uplifts PER EVENT --
+// kept out of line so the scalar-density media keep their register budget in the persistent tracking kernels
+__device__ __noinline__ void rgbgrid_props(const DevTables& T, const DevMedium& M, float3 p, float4 lam, Spec& sa, Spec& ss, Spec& Le) {
+    const float3 pm = affine_pt(M.medium_from_render, p);
+    float pn[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) pn[k] = (comp3(pm, k) - M.bmin[k]) / (M.bmax[k] - M.bmin[k]);
+    const float3 a = M.rgb_a ? rgbgrid_sample(M, M.rgb_a, pn) : f3(1.0f, 1.0f, 1.0f);
+    const float3 b = M.rgb_s ? rgbgrid_sample(M, M.rgb_s, pn) : f3(1.0f, 1.0f, 1.0f);
+    sa = uplift_rgb_unbounded(T, a.x, a.y, a.z, lam) * M.sigma_scale;
+    ss = uplift_rgb_unbounded(T, b.x, b.y, b.z, lam) * M.sigma_scale;
+    Le = sp(0.0f);
+    if (M.rgb_le && M.le_scale > 0.0f) { const float3 e = rgbgrid_sample(M, M.rgb_le, pn); Le = uplift_rgb_unbounded(T, e.x, e.y, e.z, lam) * M.le_scale; }
+}
 HK_DEV float3 affine_pt(const float* M, float3 p) { return f3(M[0] * p.x + M[1] * p.y + M[2] * p.z + M[3], M[4] * p.x + M[5] * p.y + M[6] * p.z + M[7], M[8] * p.x + M[9] * p.y + M[10] * p.z + M[11]); }
 HK_DEV float3 affine_vc(const float* M, float3 v) { return f3(M[0] * v.x + M[1] * v.y + M[2] * v.z, M[4] * v.x + M[5] * v.y + M[6] * v.z, M[8] * v.x + M[9] * v.y + M[10] * v.z); }
 
@@ -180,10 +217,10 @@ HK_DEV float medium_density(const DevMedium& M, float3 p) {
     return 1.0f;
 }
 HK_DEV void majiter_create(MajIter& it, const DevMedium& M, const MediumCoef& mc, float3 o, float3 d, float t_max) {
-    Spec st = mc.sa + mc.ss;
+    Spec st = M.type == HK_MEDIUM_RGBGRID ? sp(1.0f) : mc.sa + mc.ss;      // RGBGrid: the majorant grid already holds sigma_scale * max(sigma_a + sigma_s) (media.jl:1402)
     if (M.type == HK_MEDIUM_HOMOGENEOUS) { it.mode = (0.0f >= t_max) ? 0 : 1; it.sigma_t = st; it.t_min = 0.0f; it.t_max = t_max; it.hom_called = false; return; }
     float3 ro = o, rd_ = d;
-    if (M.type == HK_MEDIUM_GRID) {
+    if (M.type == HK_MEDIUM_GRID || M.type == HK_MEDIUM_RGBGRID) {
         ro = affine_pt(M.medium_from_render, o); rd_ = affine_vc(M.medium_from_render, d);
         if (rd_.x * rd_.x + rd_.y * rd_.y + rd_.z * rd_.z < 1.0e-20f) { majiter_invalid(it); return; }
     }
@@ -223,7 +260,10 @@ struct DeltaTracker {
     // Both return true when the walk is over (R is final).  skip_step (precondition !in_seg): advance the DDA to the next
     // non-empty segment; event_step (precondition in_seg): one tentative collision.  The persistent kernels vote per warp
     // on which of the two to run, so the expensive event code executes with many lanes at once.
-    HK_DEV bool step() { return in_seg ? event_step() : skip_step(); }
+    // T / lam: only read for an RGBGridMedium (its coefficients are uplifted at every event); lam points at the path's wavelengths
+    // RGB = false compiles the RGBGridMedium branch out: the persistent kernels are instantiated both ways and scenes without such
+    // a medium run the lean one (with the branch in, k_medium_track needs 164 registers instead of 128)
+    HK_DEV bool step(const DevTables& T, const float4* lam) { return in_seg ? event_step<true>(T, lam) : skip_step(); }
     HK_DEV bool skip_step() {
         for (int k = 0; k < HK_TRACK_SKIP && !in_seg; k++) {
             MajSeg seg;
@@ -234,7 +274,7 @@ struct DeltaTracker {
         }
         return false;
     }
-    HK_DEV bool event_step() {
+    template <bool RGB> HK_DEV bool event_step(const DevTables& T, const float4* lam) {
         if (si >= 1024) { in_seg = false; return false; }
         si++;
         const float s0 = smaj.x;
@@ -249,14 +289,18 @@ struct DeltaTracker {
         }
         Spec Tm = sp_exp(-dt * smaj);
         float3 p = ro + d * dt;
-        float dens = medium_density(*M, p);
-        Spec sa = M->type == HK_MEDIUM_HOMOGENEOUS ? mc.sa : mc.sa * dens;
-        Spec ss = M->type == HK_MEDIUM_HOMOGENEOUS ? mc.ss : mc.ss * dens;
-        if (!sp_black(mc.Le) && depth < max_depth) {
+        Spec sa, ss, Le = mc.Le;
+        if (RGB && M->type == HK_MEDIUM_RGBGRID) rgbgrid_props(T, *M, p, *lam, sa, ss, Le);
+        else {
+            float dens = medium_density(*M, p);
+            sa = M->type == HK_MEDIUM_HOMOGENEOUS ? mc.sa : mc.sa * dens;
+            ss = M->type == HK_MEDIUM_HOMOGENEOUS ? mc.ss : mc.ss * dens;
+        }
+        if (!sp_black(Le) && depth < max_depth) {
             float pr = s0 * Tm.x;
             if (pr > 1.0e-10f) {
                 Spec re = r_u * smaj * Tm / pr;
-                if (!sp_black(re)) R.Le_add = R.Le_add + beta * sa * Tm * mc.Le / (pr * sp_avg(re));
+                if (!sp_black(re)) R.Le_add = R.Le_add + beta * sa * Tm * Le / (pr * sp_avg(re));
             }
         }
         float pa = sa.x / s0, ps = ss.x / s0;
@@ -282,7 +326,7 @@ struct DeltaTracker {
 HK_DEV DeltaOut delta_track(const MediaCtx& C, int medium, float3 o, float3 d, float t_max, float4 lam, Spec beta, Spec r_u, Spec r_l, int depth, int max_depth) {
     DeltaTracker T;
     T.init(C, medium, o, d, t_max, lam, beta, r_u, r_l, depth, max_depth);
-    while (!T.step()) {}
+    while (!T.step(C.T, &lam)) {}
     return T.R;
 }
 
@@ -300,7 +344,7 @@ struct RatioTracker {
         rng = pcg32_init(hash_f3(o), hash_f3(d));
         sg = 0; si = 0; in_seg = false; t = 0.0f; smaj = sp(0.0f); seg_t_max = 0.0f;
     }
-    HK_DEV bool step() { return in_seg ? event_step() : skip_step(); }
+    HK_DEV bool step(const DevTables& T, const float4* lam) { return in_seg ? event_step<true>(T, lam) : skip_step(); }
     HK_DEV bool skip_step() {
         for (int k = 0; k < HK_TRACK_SKIP && !in_seg; k++) {
             MajSeg seg;
@@ -311,7 +355,7 @@ struct RatioTracker {
         }
         return false;
     }
-    HK_DEV bool event_step() {
+    template <bool RGB> HK_DEV bool event_step(const DevTables& T, const float4* lam) {
         if (si >= 100) { in_seg = false; return sp_black(T_ray); }
         si++;
         const float s0 = smaj.x;
@@ -325,9 +369,13 @@ struct RatioTracker {
             return sp_black(T_ray);
         }
         float3 p = o + d * ts;
-        float dens = medium_density(*M, p);
-        Spec sa = M->type == HK_MEDIUM_HOMOGENEOUS ? mc.sa : mc.sa * dens;
-        Spec ss = M->type == HK_MEDIUM_HOMOGENEOUS ? mc.ss : mc.ss * dens;
+        Spec sa, ss;
+        if (RGB && M->type == HK_MEDIUM_RGBGRID) { Spec le; rgbgrid_props(T, *M, p, *lam, sa, ss, le); }
+        else {
+            float dens = medium_density(*M, p);
+            sa = M->type == HK_MEDIUM_HOMOGENEOUS ? mc.sa : mc.sa * dens;
+            ss = M->type == HK_MEDIUM_HOMOGENEOUS ? mc.ss : mc.ss * dens;
+        }
         Spec sn = sp_max0(smaj - sa - ss);
         Spec Tm = sp_exp(-dt * smaj);
         float pr = Tm.x * s0;
@@ -346,6 +394,6 @@ struct RatioTracker {
 HK_DEV void ratio_track(const MediaCtx& C, int medium, float3 o, float3 d, float t_max, float4 lam, Spec& T_ray, Spec& r_u, Spec& r_l) {
     RatioTracker T;
     T.init(C, medium, o, d, t_max, lam);
-    while (!T.step()) {}
+    while (!T.step(C.T, &lam)) {}
     T_ray = T.T_ray; r_u = T.r_u; r_l = T.r_l;
 }

@@ -582,6 +582,7 @@ __global__ void __launch_bounds__(128, (TYPE == HK_MAT_COATED_DIFFUSE || TYPE ==
 #ifndef HK_MEDIUM_REFILL_MIN
 #define HK_MEDIUM_REFILL_MIN HK_PHASE_MIN     // idle lanes needed before the warp fetches new rays (32 = coherent groups, no mid-flight refill)
 #endif
+template <bool RGB>     // RGB: some medium of the scene is an RGBGridMedium (see DeltaTracker::event_step)
 __global__ void __launch_bounds__(128) k_medium_track(const __grid_constant__ DevScene D, PathState S) {
     const uint32_t n = S.counts[HK_C_MEDIUM];
     MediaCtx MDC = media_ctx(D);
@@ -616,7 +617,7 @@ __global__ void __launch_bounds__(128) k_medium_track(const __grid_constant__ De
             continue;
         }
         bool fin = false;
-        if ((uint32_t)__popc(ev) >= (uint32_t)HK_PHASE_MIN || sk == 0u) { if (busy && T.in_seg) fin = T.event_step(); }
+        if ((uint32_t)__popc(ev) >= (uint32_t)HK_PHASE_MIN || sk == 0u) { if (busy && T.in_seg) fin = T.template event_step<RGB>(MDC.T, S.lambda + slot); }
         else if (busy && !T.in_seg) fin = T.skip_step();
         if (fin) {
             const DeltaOut& R = T.R;
@@ -764,6 +765,7 @@ __global__ void __launch_bounds__(HK_TRACE_THREADS, HK_TRACE_BLOCKS_PER_SM) k_sh
     count_rays(S.rays_traced, traced);
     if (COUNT) { count_rays(work + 3, traced); count_rays(work + 4, wn); count_rays(work + 5, wt); }
 }
+template <bool RGB>
 __global__ void __launch_bounds__(128) k_shadow_seg_ratio(const __grid_constant__ DevScene D, PathState S, int round) {
     if (S.counts[HK_C_TOTAL_HITS] == 0) return;
     const uint32_t n = S.counts[round == 0 ? HK_C_SHADOW : HK_C_SHROUND0 + round];
@@ -806,7 +808,7 @@ __global__ void __launch_bounds__(128) k_shadow_seg_ratio(const __grid_constant_
             continue;
         }
         bool fin = false;
-        if ((uint32_t)__popc(ev) >= (uint32_t)HK_PHASE_MIN || sk == 0u) { if (busy) { if (!tracking) fin = true; else if (R.in_seg) fin = R.event_step(); } }
+        if ((uint32_t)__popc(ev) >= (uint32_t)HK_PHASE_MIN || sk == 0u) { if (busy) { if (!tracking) fin = true; else if (R.in_seg) fin = R.template event_step<RGB>(MDC.T, S.lambda + slot); } }
         else if (busy && tracking && !R.in_seg) fin = R.skip_step();
         if (fin) {
             // ---- the segment is done: fold its transmittance in and resolve ------------------------------------------

@@ -699,6 +699,54 @@ class GridMedium:                         # media.jl:886-936
         return m
 
 
+class RGBGridMedium:                      # media.jl:1002-1114
+    """Per-voxel RGB absorption / scattering (and optional emission) coefficients, pbrt-v4's RGBGridMedium.  Grids are
+    [nx, ny, nz, 3] arrays (the reference's Array{RGBSpectrum,3}); at least one of sigma_a_grid / sigma_s_grid is required,
+    an absent one counts as 1 everywhere; Le_grid requires sigma_a_grid."""
+
+    def __init__(self, sigma_a_grid=None, sigma_s_grid=None, Le_grid=None, sigma_scale=1.0, Le_scale=0.0, g=0.0,
+                 bounds=((0, 0, 0), (1, 1, 1)), transform=None, majorant_res=(16, 16, 16)):
+        conv = lambda a: None if a is None else np.ascontiguousarray(np.asarray(a, dtype=f32))
+        self.sigma_a_grid, self.sigma_s_grid, self.Le_grid = conv(sigma_a_grid), conv(sigma_s_grid), conv(Le_grid)
+        if self.sigma_a_grid is None and self.sigma_s_grid is None:
+            raise ValueError("At least one of sigma_a_grid or sigma_s_grid must be provided")            # media.jl:1073
+        if self.Le_grid is not None and self.sigma_a_grid is None:
+            raise ValueError("Le_grid requires sigma_a_grid to be provided (following pbrt-v4)")          # :1075
+        shapes = {a.shape for a in (self.sigma_a_grid, self.sigma_s_grid, self.Le_grid) if a is not None}
+        if len(shapes) != 1 or len(next(iter(shapes))) != 4 or next(iter(shapes))[3] != 3:
+            raise ValueError("RGB grids must share one [nx, ny, nz, 3] shape")                            # :1078-1083
+        self.grid_res = next(iter(shapes))[:3]
+        self.sigma_scale, self.Le_scale, self.g = float(sigma_scale), float(Le_scale), float(g)
+        self.bounds = (np.asarray(bounds[0], dtype=f32), np.asarray(bounds[1], dtype=f32))
+        self.medium_to_render = np.eye(4, dtype=f32) if transform is None else np.asarray(transform, dtype=f32)
+        self.render_to_medium = np.linalg.inv(self.medium_to_render.astype(np.float64)).astype(f32)
+        self.majorant_res = tuple(int(v) for v in majorant_res)
+        # build_rgb_majorant_grid, media.jl:1122-1183: sigma_scale * (max sigma_a + max sigma_s) per coarse voxel, the max taken
+        # over the voxel block AND the three channels; an absent grid contributes 1
+        one = np.ones(self.grid_res, dtype=f32)
+        ma = build_majorant_grid(self.sigma_a_grid.max(axis=3), self.majorant_res) if self.sigma_a_grid is not None else build_majorant_grid(one, self.majorant_res)
+        ms = build_majorant_grid(self.sigma_s_grid.max(axis=3), self.majorant_res) if self.sigma_s_grid is not None else build_majorant_grid(one, self.majorant_res)
+        self.majorant = (f32(self.sigma_scale) * (ma + ms)).astype(f32)
+
+    def to_abi(self, keep):
+        m = A.HkMedium(type=A.HK_MEDIUM_RGBGRID)
+        m.g, m.scale, m.Le_scale = self.g, self.sigma_scale, self.Le_scale
+        m.bounds_min[:], m.bounds_max[:] = self.bounds[0].tolist(), self.bounds[1].tolist()
+        m.render_from_medium[:] = self.medium_to_render.reshape(-1).tolist()
+        m.medium_from_render[:] = self.render_to_medium.reshape(-1).tolist()
+        m.density_res[:] = list(self.grid_res)
+        for name, grid in (("rgb_sigma_a", self.sigma_a_grid), ("rgb_sigma_s", self.sigma_s_grid), ("rgb_Le", self.Le_grid)):
+            if grid is not None:
+                d = np.ascontiguousarray(grid.transpose(2, 1, 0, 3))       # -> [nz][ny][nx][3]
+                keep.append(d)
+                setattr(m, name, _fp(d))
+        m.majorant_res[:] = list(self.majorant_res)
+        mj = np.ascontiguousarray(self.majorant)
+        keep.append(mj)
+        m.majorant = _fp(mj)
+        return m
+
+
 from .nanovdb import NanoVDBMedium  # noqa: E402  (host-side NanoVDB builder, nanovdb.jl:602-858)
 
 

@@ -44,6 +44,28 @@ def cornell_smoke():
     return s, _cam((0.0, 1.0, -3.5), (0.0, 1.0, 0.0), 40.0)
 
 
+def rgb_nebula(res=(20, 16, 12)):
+    """An RGBGridMedium (media.jl:1002-1456) inside an index-1 boundary: two coloured, partly emissive blobs over a matte floor."""
+    nx, ny, nz = res
+    x, y, z = np.meshgrid((np.arange(nx) + 0.5) / nx, (np.arange(ny) + 0.5) / ny, (np.arange(nz) + 0.5) / nz, indexing="ij")
+    blob = lambda c, r: np.clip(1.0 - np.sqrt((x - c[0]) ** 2 + (y - c[1]) ** 2 + (z - c[2]) ** 2) / r, 0.0, 1.0)
+    b1, b2 = blob((0.35, 0.5, 0.5), 0.33), blob((0.68, 0.55, 0.45), 0.28)
+    sig_s = (b1[..., None] * np.array([6.0, 3.0, 1.0]) + b2[..., None] * np.array([1.0, 3.0, 7.0])).astype(np.float32)
+    sig_a = (b1[..., None] * np.array([0.2, 0.6, 1.5]) + b2[..., None] * np.array([1.2, 0.4, 0.1])).astype(np.float32)
+    Le = ((b2 > 0.6)[..., None] * np.array([0.5, 1.0, 3.0])).astype(np.float32)
+    lo = (-0.8, 0.1, -0.5)
+    med = H.RGBGridMedium(sigma_a_grid=sig_a, sigma_s_grid=sig_s, Le_grid=Le, sigma_scale=1.5, Le_scale=1.0, g=0.3,
+                          bounds=(lo, (0.8, 1.3, 0.5)), majorant_res=(5, 4, 3))
+    s = H.Scene()
+    s.push(H.rect3((-3, -0.1, -3), (6, 0.1, 6)), H.MatteMaterial(Kd=(0.6, 0.6, 0.6)))
+    s.push(H.rect3(lo, (1.6, 1.2, 1.0)), H.MediumInterface(H.GlassMaterial(Kr=0.0, Kt=1.0, index=1.0), inside=med))
+    d = np.array([-0.4, -1.0, 0.6])
+    s.push(H.DirectionalLight((3, 3, 3), d / np.linalg.norm(d), legacy_rgbspectrum=True))
+    s.push(H.AmbientLight((0.15, 0.18, 0.25)))
+    s.sync()
+    return s, _cam((0.0, 0.9, -3.2), (0.0, 0.6, 0.0), 40.0)
+
+
 def c1_triangle():
     s = H.Scene()
     tri = H.Mesh([(-1, -0.5, 0), (1, -0.5, 0), (0, 1, 0)], [(0, 1, 2)],

@@ -208,6 +208,7 @@ typedef struct HkLightSampler {
 #define HK_MEDIUM_HOMOGENEOUS 1   /* media.jl:735-793   */
 #define HK_MEDIUM_GRID        2   /* media.jl:800-1000, 1544-1623 */
 #define HK_MEDIUM_NANOVDB     3   /* nanovdb.jl:153-191, 315-543   */
+#define HK_MEDIUM_RGBGRID     4   /* media.jl:1002-1456: per-voxel RGB sigma_a / sigma_s / Le     */
 
 typedef struct HkMedium {
     int32_t  type;
@@ -230,6 +231,13 @@ typedef struct HkMedium {
     float    nanovdb_vec[3];     /* translation                                             */
     uint64_t nanovdb_root_offset, nanovdb_upper_offset, nanovdb_lower_offset, nanovdb_leaf_offset;
     int32_t  nanovdb_root_tiles, nanovdb_upper_count, nanovdb_lower_count, nanovdb_leaf_count;
+    /* RGBGrid: density_res = grid_res; grids [nz][ny][nx][3] (RGBSpectrum per voxel), NULL = absent (sigma_a / sigma_s
+       default to 1, Le to 0, media.jl:1252-1273); scale = sigma_scale; majorant = build_rgb_majorant_grid (:1122-1183),
+       i.e. sigma_scale * (max sigma_a + max sigma_s) per coarse voxel; bounds and transforms as Grid             */
+    const float* rgb_sigma_a;
+    const float* rgb_sigma_s;
+    const float* rgb_Le;
+    float    Le_scale;
 } HkMedium;
 
 /* ---- camera, filter, params ---------------------------------------------------------------- */

@@ -120,7 +120,13 @@ int32_t ok_upload_media(OkContext* c, const HkMedium* m, uint32_t n) {
             M.majorant.assign(m[i].majorant, m[i].majorant + cnt);
         }
         if (m[i].type == HK_MEDIUM_NANOVDB) M.nvdb.assign(m[i].nanovdb_buf, m[i].nanovdb_buf + m[i].nanovdb_bytes);
-        M.h.density = nullptr; M.h.majorant = nullptr; M.h.nanovdb_buf = nullptr;
+        if (m[i].type == HK_MEDIUM_RGBGRID) {
+            size_t cnt = 3 * (size_t)m[i].density_res[0] * m[i].density_res[1] * m[i].density_res[2];
+            if (m[i].rgb_sigma_a) M.rgb_a.assign(m[i].rgb_sigma_a, m[i].rgb_sigma_a + cnt);
+            if (m[i].rgb_sigma_s) M.rgb_s.assign(m[i].rgb_sigma_s, m[i].rgb_sigma_s + cnt);
+            if (m[i].rgb_Le) M.rgb_le.assign(m[i].rgb_Le, m[i].rgb_Le + cnt);
+        }
+        M.h.density = nullptr; M.h.majorant = nullptr; M.h.nanovdb_buf = nullptr; M.h.rgb_sigma_a = M.h.rgb_sigma_s = M.h.rgb_Le = nullptr;
     }
     return 0;
 }

@@ -14,6 +14,7 @@ struct Medium {   // deep copy of an HkMedium
     HkMedium h;
     std::vector<float> density, majorant;
     std::vector<uint8_t> nvdb;
+    std::vector<float> rgb_a, rgb_s, rgb_le;     // RGBGridMedium grids, [nz][ny][nx][3]; empty = absent
 };
 struct MediaCtx { const Tables* T; const Medium* media; uint32_t n; };
 
@@ -176,6 +177,25 @@ inline float sample_grid_density(const Medium& m, V3 pm) {
     float d0 = d00 * fy1 + d10 * fy, d1 = d01 * fy1 + d11 * fy;
     return d0 * (1.0f - fz) + d1 * fz;
 }
+// _sample_rgb_grid, media.jl:1283-1325 (RGB trilinear; zero outside [0,1]^3)
+inline void sample_rgb_grid(const HkMedium& h, const std::vector<float>& grid, const float* pn, float* out) {
+    out[0] = out[1] = out[2] = 0.0f;
+    if (pn[0] < 0.0f || pn[1] < 0.0f || pn[2] < 0.0f || pn[0] > 1.0f || pn[1] > 1.0f || pn[2] > 1.0f) return;
+    int nx = h.density_res[0], ny = h.density_res[1], nz = h.density_res[2];
+    float gx = pn[0] * (float)nx + 0.5f, gy = pn[1] * (float)ny + 0.5f, gz = pn[2] * (float)nz + 0.5f;
+    int ix = clampi(floor_int32(gx), 1, nx - 1), iy = clampi(floor_int32(gy), 1, ny - 1), iz = clampi(floor_int32(gz), 1, nz - 1);
+    float fx = clampf(gx - (float)ix, 0.0f, 1.0f), fy = clampf(gy - (float)iy, 0.0f, 1.0f), fz = clampf(gz - (float)iz, 0.0f, 1.0f);
+    auto G = [&](int x, int y, int z, int c) { return grid[3 * ((size_t)(x - 1) + (size_t)nx * ((size_t)(y - 1) + (size_t)ny * (size_t)(z - 1))) + c]; };
+    float fx1 = 1.0f - fx, fy1 = 1.0f - fy;
+    for (int c = 0; c < 3; c++) {
+        float c00 = G(ix, iy, iz, c) * fx1 + G(ix + 1, iy, iz, c) * fx;
+        float c10 = G(ix, iy + 1, iz, c) * fx1 + G(ix + 1, iy + 1, iz, c) * fx;
+        float c01 = G(ix, iy, iz + 1, c) * fx1 + G(ix + 1, iy, iz + 1, c) * fx;
+        float c11 = G(ix, iy + 1, iz + 1, c) * fx1 + G(ix + 1, iy + 1, iz + 1, c) * fx;
+        float c0 = c00 * fy1 + c10 * fy, c1 = c01 * fy1 + c11 * fy;
+        out[c] = c0 * (1.0f - fz) + c1 * fz;
+    }
+}
 inline V3 affine_point(const float* M, V3 p) {   // rows 1-3 of a row-major 4x4, no divide (media.jl:1605-1608)
     return V3(M[0] * p.x + M[1] * p.y + M[2] * p.z + M[3], M[4] * p.x + M[5] * p.y + M[6] * p.z + M[7], M[8] * p.x + M[9] * p.y + M[10] * p.z + M[11]);
 }
@@ -187,8 +207,21 @@ inline MediumProps sample_point(const MediaCtx& C, uint32_t idx, V3 p, const Wav
     const Medium& m = C.media[idx - 1];
     const HkMedium& h = m.h;
     MediumProps r;
-    Spec sa = uplift_rgb_unbounded(*C.T, h.sigma_a_rgb, l), ss = uplift_rgb_unbounded(*C.T, h.sigma_s_rgb, l);
     r.g = h.g;
+    if (h.type == HK_MEDIUM_RGBGRID) {      // media.jl:1327-1372
+        V3 pm = affine_point(h.medium_from_render, p);
+        float pn[3];
+        for (int k = 0; k < 3; k++) pn[k] = (pm[k] - h.bounds_min[k]) / (h.bounds_max[k] - h.bounds_min[k]);
+        float a[3] = {1.0f, 1.0f, 1.0f}, b[3] = {1.0f, 1.0f, 1.0f};
+        if (!m.rgb_a.empty()) sample_rgb_grid(h, m.rgb_a, pn, a);
+        if (!m.rgb_s.empty()) sample_rgb_grid(h, m.rgb_s, pn, b);
+        r.sigma_a = uplift_rgb_unbounded(*C.T, a, l) * h.scale;
+        r.sigma_s = uplift_rgb_unbounded(*C.T, b, l) * h.scale;
+        r.Le = Spec(0.0f);
+        if (!m.rgb_le.empty() && h.Le_scale > 0.0f) { float e[3]; sample_rgb_grid(h, m.rgb_le, pn, e); r.Le = uplift_rgb_unbounded(*C.T, e, l) * h.Le_scale; }
+        return r;
+    }
+    Spec sa = uplift_rgb_unbounded(*C.T, h.sigma_a_rgb, l), ss = uplift_rgb_unbounded(*C.T, h.sigma_s_rgb, l);
     if (h.type == HK_MEDIUM_HOMOGENEOUS) {
         r.sigma_a = sa; r.sigma_s = ss; r.Le = uplift_rgb_unbounded(*C.T, h.Le_rgb, l);
     } else if (h.type == HK_MEDIUM_GRID) {
@@ -205,13 +238,13 @@ inline MajIter create_majorant_iterator(const MediaCtx& C, uint32_t idx, V3 o, V
     const Medium& m = C.media[idx - 1];
     const HkMedium& h = m.h;
     Spec sa = uplift_rgb_unbounded(*C.T, h.sigma_a_rgb, l), ss = uplift_rgb_unbounded(*C.T, h.sigma_s_rgb, l);
-    Spec st = sa + ss;
+    Spec st = h.type == HK_MEDIUM_RGBGRID ? Spec(1.0f) : sa + ss;      // RGBGrid: unit sigma_t, the scale is in the majorant grid (media.jl:1402)
     if (h.type == HK_MEDIUM_HOMOGENEOUS) {
         MajIter it{}; it.mode = (0.0f >= t_max) ? 0 : 1; it.sigma_t = st; it.t_min = 0.0f; it.t_max = t_max; it.hom_called = false;
         return it;
     }
     V3 ro = o, rd_ = d;
-    if (h.type == HK_MEDIUM_GRID) {
+    if (h.type == HK_MEDIUM_GRID || h.type == HK_MEDIUM_RGBGRID) {
         ro = affine_point(h.medium_from_render, o); rd_ = affine_vec(h.medium_from_render, d);
         if (rd_.x * rd_.x + rd_.y * rd_.y + rd_.z * rd_.z < 1.0e-20f) return majiter_invalid();
     }

@@ -426,3 +426,66 @@ def test_denoise_known_answers_on_the_oracle():
     H.denoise(film, vp, H.DenoiseConfig(iterations=4, sigma_color=1e30, sigma_depth=1e30, use_variance=False))
     assert 0.05 < film.postprocess[:, w // 2, 0].mean() < 0.95                         # without the depth stop the edge bleeds
     vp.close()
+
+
+def test_rgb_grid_medium_known_answers_on_the_oracle():
+    """RGBGridMedium (media.jl:1002-1456).  Identities of the reference's own formulas pin the restatement: a gray, constant RGB
+    grid (sigma_a = 0.25, sigma_s = 0.75, sigma_scale = 2; all exactly representable, and gray RGB uplifts to a constant
+    spectrum) is the same medium as a GridMedium of density 1 with sigma_a = 0.5, sigma_s = 1.5 — same majorants, same
+    coefficients, same LCG stream, so delta and ratio tracking must agree event for event; an absent sigma_a grid counts
+    as 1; the majorant grid is sigma_scale * (max sigma_a + max sigma_s) over channels and voxels; and a rendered RGB medium
+    is finite, lit, and tinted the way its coefficients say."""
+    lo, hi = (-0.6, 0.3, -0.6), (0.6, 1.5, 0.6)
+    shape = (8, 6, 5)
+    ones = np.ones(shape + (3,), f32)
+    def scene_with(med):
+        s = H.Scene()
+        s.push(H.rect3(lo, (1.2, 1.2, 1.2)), H.MediumInterface(H.GlassMaterial(Kr=0.0, Kt=1.0, index=1.0), inside=med))
+        s.push(H.PointLight((1, 1, 1), (0, 5, 0)))
+        s.sync()
+        return s
+    rng = np.random.RandomState(8)
+    n = 4000
+    x = np.zeros((n, 8), f32)
+    x[:, 0:3] = rng.uniform(-0.5, 0.5, size=(n, 3)) + (0, 0.9, 0)
+    d = rng.normal(size=(n, 3)); x[:, 3:6] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    x[:, 6] = rng.uniform(0.05, 2.0, n); x[::9, 6] = np.inf
+    x[:, 7] = rng.uniform(0, 1, n)
+    def track(med):
+        p = Pair(scene=scene_with(med), need_gpu=False)
+        try:
+            da = np.zeros((n, 16), f32); ra = np.zeros((n, 12), f32)
+            p.olib.ok_test_delta_tracking(p.ok.ctx, 1, fp(x), n, fp(da))
+            p.olib.ok_test_ratio_tracking(p.ok.ctx, 1, fp(x), n, fp(ra))
+            return da, ra
+        finally:
+            p.close()
+    rgb = H.RGBGridMedium(sigma_a_grid=0.25 * ones, sigma_s_grid=0.75 * ones, sigma_scale=2.0, g=0.2, bounds=(lo, hi), majorant_res=(4, 3, 2))
+    assert np.allclose(rgb.majorant, 2.0)
+    grid = H.GridMedium(np.ones(shape, f32), sigma_a=0.5, sigma_s=1.5, g=0.2, bounds=(lo, hi), majorant_res=(4, 3, 2))
+    (da, ra), (db, rb) = track(rgb), track(grid)
+    same = da[:, 0] == db[:, 0]
+    assert same.mean() >= 0.999 and len(np.unique(da[:, 0])) >= 2
+    assert np.isclose(da, db, rtol=1e-4, atol=1e-6).all(axis=1)[same].mean() >= 0.999
+    assert np.isclose(ra, rb, rtol=1e-4, atol=1e-6).all(axis=1).mean() >= 0.999
+    # sigma_a grid absent -> 1 (x sigma_scale): same medium as an explicit grid of ones
+    a_missing = H.RGBGridMedium(sigma_s_grid=0.75 * ones, sigma_scale=0.5, bounds=(lo, hi), majorant_res=(4, 3, 2))
+    a_ones = H.RGBGridMedium(sigma_a_grid=ones, sigma_s_grid=0.75 * ones, sigma_scale=0.5, bounds=(lo, hi), majorant_res=(4, 3, 2))
+    assert np.array_equal(a_missing.majorant, a_ones.majorant) and np.allclose(a_missing.majorant, 0.5 * 1.75)
+    (dc, rc), (dd, rd) = track(a_missing), track(a_ones)
+    assert np.array_equal(dc.view(np.uint32), dd.view(np.uint32)) and np.array_equal(rc.view(np.uint32), rd.view(np.uint32))
+    # majorant: channel- and voxel-wise maxima
+    g = rng.uniform(0, 1, size=shape + (3,)).astype(f32)
+    m = H.RGBGridMedium(sigma_a_grid=g, sigma_s_grid=2 * g, sigma_scale=3.0, majorant_res=(1, 1, 1))
+    assert np.allclose(m.majorant, 3.0 * (g.max() + 2 * g.max()))
+    with pytest.raises(ValueError):
+        H.RGBGridMedium()
+    with pytest.raises(ValueError):
+        H.RGBGridMedium(sigma_s_grid=ones, Le_grid=ones)
+    # render: the nebula scatters red on the left and blue on the right (sigma_s tints), and glows blue where it emits
+    scene, camf = scenes.rgb_nebula()
+    film = H.Film((64, 40))
+    vp = H.VolPath(samples=8, max_depth=6, backend=oracle_backend.make_backend())
+    img = vp(scene, film, camf(film))
+    assert np.isfinite(img).all() and img.max() > 0.05
+    vp.close()

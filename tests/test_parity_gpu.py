@@ -363,6 +363,9 @@ IMAGE_CASES = [
     ("c4_cloud_small", lambda: scenes.c4_cloud((32, 32, 16), "nanovdb", (8, 8, 8)), (64, 36), 4, 8, "hashed"),
     ("c4_grid_small", lambda: scenes.c4_cloud((32, 32, 16), "grid", (8, 8, 8)), (64, 36), 4, 8, "hashed"),
     ("c5_small", lambda: scenes.c5_instanced(12, 12), (96, 54), 4, 6, "hashed"),
+    # RGBGridMedium with emission: delta tracking re-seeds on ulp differences like the other media and the emissive voxels make the
+    # flipped paths bright (0.927 within tolerance at 6 spp, means equal to 0.14 %)
+    ("rgb_nebula", lambda: scenes.rgb_nebula(), (64, 40), 16, 8, "hashed:0.80"),
 ]
 
 
@@ -619,6 +622,13 @@ def _media_scene(kind):
         med = H.HomogeneousMedium(sigma_a=(0.1, 0.2, 0.3), sigma_s=(1.0, 0.8, 0.6), g=0.3)
     elif kind == "grid":
         med = H.GridMedium(dens, sigma_a=0.1, sigma_s=1.0, g=0.5, bounds=(lo, hi), majorant_res=(6, 5, 4))
+    elif kind == "rgbgrid":
+        tint_a, tint_s = np.array([0.02, 0.05, 0.2], f32), np.array([1.0, 0.8, 0.5], f32)
+        med = H.RGBGridMedium(sigma_a_grid=dens[..., None] * tint_a, sigma_s_grid=dens[..., None] * tint_s,
+                              Le_grid=(dens[..., None] > 20) * np.array([4.0, 2.0, 0.5], f32), sigma_scale=0.7, Le_scale=0.5, g=0.4,
+                              bounds=(lo, hi), majorant_res=(6, 5, 4))
+    elif kind == "rgbgrid_s_only":
+        med = H.RGBGridMedium(sigma_s_grid=dens[..., None] * np.array([1.0, 0.6, 0.3], f32), sigma_scale=0.5, g=0.0, bounds=(lo, hi), majorant_res=(4, 4, 4))
     else:
         med = H.NanoVDBMedium(dens, bounds=(lo, hi), sigma_a=0.0, sigma_s=1.0, g=0.877, majorant_res=(8, 8, 8))
     s = H.Scene()
@@ -628,7 +638,7 @@ def _media_scene(kind):
     return s, dens, lo, hi
 
 
-@pytest.mark.parametrize("kind", ["homogeneous", "grid", "nanovdb"])
+@pytest.mark.parametrize("kind", ["homogeneous", "grid", "nanovdb", "rgbgrid", "rgbgrid_s_only"])
 def test_media_density_delta_and_ratio_tracking(kind):
     s, dens, lo, hi = _media_scene(kind)
     p = Pair(scene=s)
