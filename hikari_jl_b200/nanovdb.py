@@ -147,8 +147,171 @@ def build_nanovdb_majorant_grid(data_xyz, meta, bounds, res=(64, 64, 64)):
     return np.ascontiguousarray(cur.transpose(2, 1, 0))
 
 
+# ---- .nvdb files (nanovdb.jl:1058-1170) -----------------------------------------------------------------------------
+# 0-based byte offsets of the fields the reference reads out of the NanoVDB GridData / TreeData headers (nanovdb.jl:9-32)
+GRIDDATA_SIZE, TREEDATA_SIZE = 672, 64
+MAP_INVMATF, MAP_VECF, WORLDBBOX = 296 + 36, 296 + 72, 560
+TREE_NODE_OFFSETS, TREE_NODE_COUNTS = GRIDDATA_SIZE, GRIDDATA_SIZE + 32
+
+
+def nanovdb_get_values(buf, meta, ijk):
+    """nanovdb_get_value (nanovdb.jl:315-388) for an [N, 3] array of index coordinates, vectorised: root tile by key, upper and
+    lower child masks / tables, leaf voxel; tile and background values where the tree has no child."""
+    ijk = np.asarray(ijk, dtype=np.int64)
+    xu, yu, zu = (ijk[:, k] & 0xFFFFFFFF for k in range(3))
+    b = np.frombuffer(buf, dtype=np.uint8) if not isinstance(buf, np.ndarray) else buf
+    rd = lambda off, dt: np.ascontiguousarray(b[np.asarray(off, dtype=np.int64)[:, None] + np.arange(np.dtype(dt).itemsize)]).view(dt)[:, 0]
+    root = int(meta["root_offset"])
+    n = len(ijk)
+    out = np.full(n, np.frombuffer(b[root + 28:root + 32].tobytes(), dtype=f32)[0], dtype=f32)       # background
+    key = ((zu >> 12) & 0x1FFFFF) | (((yu >> 12) & 0x1FFFFF) << 21) | (((xu >> 12) & 0x1FFFFF) << 42)
+    tile_off = np.full(n, -1, dtype=np.int64)
+    for i in range(int(meta["root_table_size"])):                      # linear search, first match wins (:331-339)
+        to = root + ROOT_HEADER + i * ROOT_TILE
+        k = int(np.frombuffer(b[to:to + 8].tobytes(), dtype=np.uint64)[0])
+        tile_off[(tile_off < 0) & (key == k)] = to
+    live = np.flatnonzero(tile_off >= 0)
+    if live.size == 0:
+        return out
+    child = rd(tile_off[live] + 8, np.int64)
+    out[live[child == 0]] = rd(tile_off[live[child == 0]] + 20, f32) if (child == 0).any() else out[live[child == 0]]
+    live, child = live[child != 0], child[child != 0]
+    if live.size == 0:
+        return out
+    upper = root + child
+    nu = (((xu[live] >> 7) & 31) << 10) | (((yu[live] >> 7) & 31) << 5) | ((zu[live] >> 7) & 31)
+    on = ((b[upper + 4128 + (nu >> 3)] >> (nu & 7)) & 1) != 0
+    if (~on).any():
+        out[live[~on]] = rd(upper[~on] + 8256 + nu[~on] * 8, f32)
+    live, upper, nu = live[on], upper[on], nu[on]
+    if live.size == 0:
+        return out
+    lower = upper + rd(upper + 8256 + nu * 8, np.int64)
+    nl = (((xu[live] >> 3) & 15) << 8) | (((yu[live] >> 3) & 15) << 4) | ((zu[live] >> 3) & 15)
+    on = ((b[lower + 544 + (nl >> 3)] >> (nl & 7)) & 1) != 0
+    if (~on).any():
+        out[live[~on]] = rd(lower[~on] + 1088 + nl[~on] * 8, f32)
+    live, lower, nl = live[on], lower[on], nl[on]
+    if live.size == 0:
+        return out
+    leaf = lower + rd(lower + 1088 + nl * 8, np.int64)
+    nf = ((ijk[live, 0] & 7) << 6) | ((ijk[live, 1] & 7) << 3) | (ijk[live, 2] & 7)
+    out[live] = rd(leaf + 96 + nf * 4, f32)
+    return out
+
+
+def extract_nanovdb_metadata(buf):
+    """nanovdb.jl:1109-1170; offsets returned 0-based."""
+    b = np.asarray(buf, dtype=np.uint8)
+    view = lambda off, dt, cnt: np.frombuffer(b[off:off + np.dtype(dt).itemsize * cnt].tobytes(), dtype=dt)
+    bbox = view(WORLDBBOX, np.float64, 6)
+    node_off, node_cnt = view(TREE_NODE_OFFSETS, np.uint64, 4), view(TREE_NODE_COUNTS, np.uint32, 3)
+    leaf_off, lower_off, upper_off, root_off = (GRIDDATA_SIZE + int(v) for v in node_off)
+    n_leaves = int(node_cnt[0])
+    origins = np.stack([view(leaf_off + i * LEAF_SIZE, np.int32, 3) for i in range(n_leaves)]) if n_leaves else np.zeros((0, 3), np.int32)
+    return dict(
+        world_min=tuple(f32(v) for v in bbox[:3]), world_max=tuple(f32(v) for v in bbox[3:]),
+        inv_mat=tuple(f32(v) for v in view(MAP_INVMATF, f32, 9)), vec=tuple(f32(v) for v in view(MAP_VECF, f32, 3)),
+        root_offset=root_off, upper_offset=upper_off, lower_offset=lower_off, leaf_offset=leaf_off,
+        leaf_count=n_leaves, lower_count=int(node_cnt[1]), upper_count=int(node_cnt[2]),
+        root_table_size=int(view(root_off + 24, np.uint32, 1)[0]),
+        index_min=tuple(int(v) for v in origins.min(axis=0)) if n_leaves else (2 ** 31 - 1,) * 3,
+        index_max=tuple(int(v) + LEAF_DIM for v in origins.max(axis=0)) if n_leaves else (-2 ** 31,) * 3)
+
+
+def parse_nanovdb_buffer(path):
+    """parse_nanovdb_buffer(filepath) (nanovdb.jl:1085-1107): find the zlib stream in the first 500 bytes of the file, inflate it,
+    read the metadata.  Returns (buffer np.uint8, metadata)."""
+    import zlib
+    raw = open(path, "rb").read()
+    start = -1
+    for i in range(min(500, len(raw) - 1)):
+        if raw[i] == 0x78 and raw[i + 1] in (0x01, 0x5E, 0x9C, 0xDA):
+            start = i
+            break
+    if start < 0:
+        raise ValueError("Could not find zlib header in NanoVDB file")
+    buf = np.frombuffer(zlib.decompressobj().decompress(raw[start:]), dtype=np.uint8).copy()
+    return buf, extract_nanovdb_metadata(buf)
+
+
+def write_nanovdb_file(path, tree_buf, meta, header=b"NanoVDB0" + bytes(56)):
+    """Test / export helper (no counterpart upstream): wrap a tree built by build_nanovdb_from_dense in GridData + TreeData headers
+    laid out as extract_nanovdb_metadata expects, zlib-compress, and prefix a small uncompressed file header."""
+    import zlib
+    tree = np.asarray(tree_buf, dtype=np.uint8)
+    # node sections as the builder lays them out: root | upper | lower | leaves, moved behind the two headers
+    shift = GRIDDATA_SIZE + TREEDATA_SIZE
+    out = np.zeros(shift + len(tree), dtype=np.uint8)
+    out[shift:] = tree
+    put = lambda off, arr: out.__setitem__(slice(off, off + arr.nbytes), np.frombuffer(arr.tobytes(), dtype=np.uint8))
+    inv = np.asarray(meta["inv_mat"], dtype=f32)
+    put(296, np.linalg.inv(inv.reshape(3, 3).astype(np.float64)).astype(f32).reshape(-1))
+    put(MAP_INVMATF, inv); put(MAP_VECF, np.asarray(meta["vec"], dtype=f32))
+    put(WORLDBBOX, np.asarray(list(meta["world_min"]) + list(meta["world_max"]), dtype=np.float64))
+    rel = lambda k: np.uint64(TREEDATA_SIZE + int(meta[k]))          # offsets are relative to the TreeData start
+    put(TREE_NODE_OFFSETS, np.array([rel("leaf_offset"), rel("lower_offset"), rel("upper_offset"), rel("root_offset")], dtype=np.uint64))
+    put(TREE_NODE_COUNTS, np.array([meta["leaf_count"], meta["lower_count"], meta["upper_count"]], dtype=np.uint32))
+    with open(path, "wb") as f:
+        f.write(header)
+        f.write(zlib.compress(out.tobytes(), 6))
+
+
+def build_nanovdb_majorant_grid_from_buffer(buf, meta, bounds, res=(64, 64, 64)):
+    """build_nanovdb_majorant_grid (nanovdb.jl:1174-1235) on a parsed buffer: per coarse cell, the maximum tree value over the index
+    box spanned by the cell's two corners (+- 1 voxel), clipped to the leaves' index range.  Returns [rz][ry][rx]."""
+    lo, hi = np.asarray(bounds[0], dtype=f32), np.asarray(bounds[1], dtype=f32)
+    diag = (hi - lo).astype(f32)
+    imin, imax = np.asarray(meta["index_min"], dtype=np.int64), np.asarray(meta["index_max"], dtype=np.int64)
+    ext = np.maximum(imax - imin + 1, 0)
+    dense = np.zeros(tuple(int(v) for v in ext), dtype=f32)
+    if dense.size:                                     # every voxel of the clip range, through the same look-up the device uses
+        gx, gy, gz = np.meshgrid(*(np.arange(imin[k], imax[k] + 1) for k in range(3)), indexing="ij")
+        coords = np.stack([gx.ravel(), gy.ravel(), gz.ravel()], axis=1)
+        vals = np.concatenate([nanovdb_get_values(buf, meta, coords[i:i + (1 << 20)]) for i in range(0, len(coords), 1 << 20)])
+        dense = vals.reshape(dense.shape)
+    M = np.asarray(meta["inv_mat"], dtype=f32).reshape(3, 3)
+    vec = np.asarray(meta["vec"], dtype=f32)
+    to_index = lambda p: (M @ (p - vec).astype(f32)).astype(f32)          # world_to_index_f_raw
+    out = np.zeros((res[2], res[1], res[0]), dtype=f32)
+    for iz in range(res[2]):
+        for iy in range(res[1]):
+            for ix in range(res[0]):
+                c = np.array([ix, iy, iz], dtype=f32)
+                p0 = (lo + diag * c / np.asarray(res, dtype=f32)).astype(f32)
+                p1 = (lo + diag * (c + f32(1)) / np.asarray(res, dtype=f32)).astype(f32)
+                i0, i1 = to_index(p0), to_index(p1)
+                n0 = np.maximum(np.floor(np.minimum(i0, i1) - f32(1)).astype(np.int64), imin) - imin
+                n1 = np.minimum(np.ceil(np.maximum(i0, i1) + f32(1)).astype(np.int64), imax) - imin
+                if (n1 >= n0).all():
+                    blk = dense[n0[0]:n1[0] + 1, n0[1]:n1[1] + 1, n0[2]:n1[2] + 1]
+                    out[iz, iy, ix] = max(f32(0), blk.max()) if blk.size else f32(0)
+    return out
+
+
 class NanoVDBMedium:
-    """NanoVDBMedium(data; bounds, σ_a, σ_s, g, majorant_res), nanovdb.jl:940-1000"""
+    """NanoVDBMedium(data; bounds, σ_a, σ_s, g, majorant_res), nanovdb.jl:940-1000; NanoVDBMedium.from_file = the
+    NanoVDBMedium(filepath; σ_a, σ_s, g, transform, majorant_res) constructor, :1320-1416"""
+
+    @classmethod
+    def from_file(cls, path, sigma_a=0.5, sigma_s=10.0, g=0.0, transform=None, majorant_res=(64, 64, 64)):
+        from .host import _rgb
+        self = cls.__new__(cls)
+        self.buffer, meta = parse_nanovdb_buffer(path)
+        T = np.eye(3, dtype=f32) if transform is None else np.asarray(transform, dtype=f32).reshape(3, 3)
+        inv_T = np.linalg.inv(T.astype(np.float64)).astype(f32)
+        # world -> medium -> index (:1357-1358).  `vec` is NOT rotated, as in the reference (its comment :1350-1355: "vec is in medium
+        # space ... for the bunny scene vec = (0,0,0), so this is fine")
+        combined = (np.asarray(meta["inv_mat"], dtype=f32).reshape(3, 3) @ inv_T).astype(f32)
+        wmin, wmax = np.asarray(meta["world_min"], dtype=f32), np.asarray(meta["world_max"], dtype=f32)
+        corners = np.array([[(wmin, wmax)[(i >> 2) & 1][0], (wmin, wmax)[(i >> 1) & 1][1], (wmin, wmax)[i & 1][2]] for i in range(8)], dtype=f32)
+        cw = (corners @ T.T).astype(f32)
+        self.bounds = (cw.min(axis=0).astype(f32), cw.max(axis=0).astype(f32))
+        self.meta = dict(meta, inv_mat=tuple(f32(v) for v in combined.reshape(-1)))
+        self.majorant_res = tuple(int(v) for v in majorant_res)
+        self.majorant = np.ascontiguousarray(build_nanovdb_majorant_grid_from_buffer(self.buffer, self.meta, self.bounds, self.majorant_res))
+        self.sigma_a, self.sigma_s, self.g = _rgb(sigma_a), _rgb(sigma_s), float(g)
+        return self
 
     def __init__(self, data_xyz, bounds, sigma_a=0.0, sigma_s=1.0, g=0.0, majorant_res=(64, 64, 64)):
         from .host import _rgb

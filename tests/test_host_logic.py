@@ -191,3 +191,51 @@ def test_white_balance_matrix_and_sensor_defaults():
     assert float(sensor.exposure_time * sensor.iso / 100) == 1.0 and sensor.white_balance == 0
     with pytest.raises(ValueError):
         H.postprocess(H.Film((4, 4)), None, tonemap="nope")
+
+
+def test_nanovdb_file_round_trip(tmp_path):
+    """.nvdb reader (parse_nanovdb_buffer / extract_nanovdb_metadata, nanovdb.jl:1085-1170): a tree wrapped in GridData + TreeData
+    headers and zlib-compressed behind a file header reads back with the same node offsets (shifted by the headers), counts,
+    transform, bounding box and voxel values; the vectorised look-up equals the dense source inside and the background outside;
+    the majorant grid built from the parsed buffer equals the one built from the dense source; NanoVDBMedium.from_file composes a
+    medium-to-world rotation into the index transform and bounds (:1357-1383)."""
+    import numpy as np
+    from hikari_jl_b200 import nanovdb as N
+    rng = np.random.RandomState(1)
+    dens = rng.uniform(0, 1, size=(20, 14, 11)).astype(np.float32) ** 3 * 10
+    dens[dens < 2] = 0
+    lo, hi = (-0.5, 0.2, -0.4), (0.7, 1.1, 0.5)
+    buf, meta = N.build_nanovdb_from_dense(dens, list(lo), [hi[k] - lo[k] for k in range(3)])
+    ii = np.stack(np.meshgrid(np.arange(-3, 26), np.arange(-3, 18), np.arange(-2, 14), indexing="ij"), -1).reshape(-1, 3)
+    ref = np.zeros(len(ii), np.float32)
+    inb = (ii >= 0).all(1) & (ii[:, 0] < 20) & (ii[:, 1] < 14) & (ii[:, 2] < 11)
+    ref[inb] = dens[ii[inb, 0], ii[inb, 1], ii[inb, 2]]
+    assert np.array_equal(N.nanovdb_get_values(buf, meta, ii), ref)
+    far = np.array([[5000, 0, 0], [-70000, 3, 9]])                     # other root keys: background
+    assert (N.nanovdb_get_values(buf, meta, far) == 0).all()
+    path = str(tmp_path / "t.nvdb")
+    N.write_nanovdb_file(path, buf, meta)
+    raw = open(path, "rb").read()
+    assert raw[:7] == b"NanoVDB" and len(raw) < len(buf)               # compressed
+    b2, m2 = N.parse_nanovdb_buffer(path)
+    shift = N.GRIDDATA_SIZE + N.TREEDATA_SIZE
+    for k in ("root_offset", "upper_offset", "lower_offset", "leaf_offset"):
+        assert m2[k] == meta[k] + shift
+    for k in ("leaf_count", "lower_count", "upper_count", "root_table_size", "index_min", "index_max", "inv_mat", "vec", "world_min", "world_max"):
+        assert m2[k] == meta[k], k
+    assert np.array_equal(N.nanovdb_get_values(b2, m2, ii), ref)
+    bounds = (np.float32(lo), np.float32(hi))
+    assert np.array_equal(N.build_nanovdb_majorant_grid(dens, meta, bounds, (6, 5, 4)), N.build_nanovdb_majorant_grid_from_buffer(b2, m2, bounds, (6, 5, 4)))
+    with pytest.raises(ValueError):
+        bad = tmp_path / "bad.nvdb"; bad.write_bytes(bytes(600)); N.parse_nanovdb_buffer(str(bad))
+    med = H.NanoVDBMedium.from_file(path, majorant_res=(4, 4, 4))
+    assert np.allclose(med.bounds[0], lo, atol=1e-6) and np.allclose(med.bounds[1], hi, atol=1e-6) and med.sigma_s == (10.0, 10.0, 10.0)
+    rot = np.array([[0, -1, 0], [1, 0, 0], [0, 0, 1]], np.float32)     # 90 degrees about z: (x, y) -> (-y, x)
+    mr = H.NanoVDBMedium.from_file(path, transform=rot, majorant_res=(4, 4, 4))
+    assert np.allclose(mr.bounds[0], (-hi[1], lo[0], lo[2]), atol=1e-6) and np.allclose(mr.bounds[1], (-lo[1], hi[0], hi[2]), atol=1e-6)
+    M = np.array(mr.meta["inv_mat"], np.float32).reshape(3, 3)
+    p_world = rot @ np.array([0.1, 0.6, 0.0], np.float32)
+    assert np.allclose(M @ p_world, np.array(med.meta["inv_mat"], np.float32).reshape(3, 3) @ np.array([0.1, 0.6, 0.0], np.float32), atol=1e-4)
+    # the reference keeps `vec` un-rotated ("vec is in medium space ... for the bunny scene vec = 0, so this is fine", :1350-1355):
+    # restated as is, so for a grid with a non-zero vec the rotated medium samples a shifted window of the tree
+    assert mr.meta["vec"] == med.meta["vec"] and mr.majorant.max() > 0

@@ -673,6 +673,43 @@ def test_media_density_delta_and_ratio_tracking(kind):
         p.close()
 
 
+def test_nanovdb_file_medium_matches_in_memory_medium(tmp_path):
+    """A NanoVDB grid read back from a .nvdb file (zlib stream behind GridData / TreeData headers, nanovdb.jl:1085-1170) has its tree
+    at a non-zero offset of the buffer: density look-ups must be bit-exact against the oracle and equal to the in-memory medium's,
+    and so must delta / ratio tracking."""
+    from hikari_jl_b200 import nanovdb as N
+    s0, dens, lo, hi = _media_scene("nanovdb")
+    mem = H.NanoVDBMedium(dens, bounds=(lo, hi), sigma_a=0.0, sigma_s=1.0, g=0.877, majorant_res=(8, 8, 8))
+    path = str(tmp_path / "cloud.nvdb")
+    N.write_nanovdb_file(path, mem.buffer, mem.meta)
+    med = H.NanoVDBMedium.from_file(path, sigma_a=0.0, sigma_s=1.0, g=0.877, majorant_res=(8, 8, 8))
+    assert med.meta["root_offset"] > 0 and np.array_equal(med.majorant, mem.majorant)
+    s = H.Scene()
+    s.push(H.rect3(lo, (1.2, 1.2, 1.2)), H.MediumInterface(H.GlassMaterial(Kr=0.0, Kt=1.0, index=1.0), inside=med))
+    s.push(H.PointLight((1, 1, 1), (0, 5, 0)))
+    s.sync()
+    p, p0 = Pair(scene=s), Pair(scene=s0)
+    try:
+        rng = np.random.RandomState(6)
+        n = 20000
+        pts = rng.uniform(-0.8, 1.7, size=(n, 3)).astype(f32)
+        a = np.zeros(n, f32); b = np.zeros(n, f32); c = np.zeros(n, f32)
+        assert p.lib.hk_test_density(p.cu.ctx, 1, fp(pts), n, fp(a)) == 0
+        p.olib.ok_test_density(p.ok.ctx, 1, fp(pts), n, fp(b))
+        assert p0.lib.hk_test_density(p0.cu.ctx, 1, fp(pts), n, fp(c)) == 0
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and np.array_equal(a.view(np.uint32), c.view(np.uint32)) and (a > 0).sum() > 100
+        x = np.zeros((n, 8), f32)
+        x[:, 0:3] = rng.uniform(-0.5, 0.5, size=(n, 3)) + (0, 0.9, 0)
+        d = rng.normal(size=(n, 3)); x[:, 3:6] = d / np.linalg.norm(d, axis=1, keepdims=True)
+        x[:, 6] = rng.uniform(0.05, 2.0, n); x[:, 7] = rng.uniform(0, 1, n)
+        da = np.zeros((n, 16), f32); dc = np.zeros((n, 16), f32)
+        assert p.lib.hk_test_delta_tracking(p.cu.ctx, 1, fp(x), n, fp(da)) == 0
+        assert p0.lib.hk_test_delta_tracking(p0.cu.ctx, 1, fp(x), n, fp(dc)) == 0
+        assert np.array_equal(da.view(np.uint32), dc.view(np.uint32)), "same tree, same majorants: the file medium tracks like the in-memory one"
+    finally:
+        p.close(); p0.close()
+
+
 def test_nanovdb_matches_dense_grid():
     """config C4 note: the NanoVDB and Grid media built from the same field must agree."""
     s, dens, lo, hi = _media_scene("nanovdb")
