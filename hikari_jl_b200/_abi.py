@@ -46,7 +46,11 @@ class HkGeometry(C.Structure):
 
 class HkMaterial(C.Structure):
     _fields_ = [("type", C.c_int32), ("flags", C.c_uint32), ("rgb0", c_f * 3), ("rgb1", c_f * 3), ("rgb2", c_f * 4), ("f", c_f * 8),
-                ("spec", C.c_int32 * 2), ("ival", C.c_int32 * 2)]
+                ("spec", C.c_int32 * 2), ("ival", C.c_int32 * 2), ("tex", C.c_int32 * 4)]
+
+
+class HkTexture(C.Structure):
+    _fields_ = [("rgb", c_fp), ("h", C.c_int32), ("w", C.c_int32)]
 
 
 class HkMediumInterface(C.Structure):
@@ -123,7 +127,7 @@ class HkStats(C.Structure):
 # every symbol include/hikari_cuda.h declares (checked by tests/test_abi.py)
 HK_SYMBOLS = [
     "hk_abi_version", "hk_create", "hk_destroy", "hk_last_error", "hk_upload_tables", "hk_upload_geometry",
-    "hk_upload_spectra", "hk_upload_materials", "hk_update_material", "hk_bounce_profile", "hk_upload_envmaps", "hk_upload_lights", "hk_upload_media",
+    "hk_upload_spectra", "hk_upload_textures", "hk_upload_materials", "hk_update_material", "hk_bounce_profile", "hk_upload_envmaps", "hk_upload_lights", "hk_upload_media",
     "hk_set_camera", "hk_set_filter", "hk_set_params", "hk_clear", "hk_render_samples", "hk_render_samples_strided",
     "hk_read_film", "hk_read_film_async", "hk_read_film_wait", "hk_postprocess", "hk_fill_aux_buffers", "hk_read_aux_buffers", "hk_denoise", "hk_film_accum_dev", "hk_read_accum", "hk_write_accum", "hk_trace_closest",
     "hk_trace_closest_dev", "hk_trace_any", "hk_stats", "hk_synchronize", "hk_dev_alloc", "hk_dev_free",
@@ -154,6 +158,7 @@ def bind_common(lib, p):
     if p == "hk_":
         f("read_film_async", [_VP, c_fp, C.POINTER(C.c_int32)])
         f("read_film_wait", [_VP, C.c_int32])
+    f("upload_textures", [_VP, C.POINTER(HkTexture), C.c_uint32])
     f("upload_envmaps", [_VP, C.POINTER(HkEnvMap), C.c_uint32])
     f("upload_lights", [_VP, C.POINTER(HkLight), C.c_uint32, C.POINTER(HkLightSampler)])
     f("upload_media", [_VP, C.POINTER(HkMedium), C.c_uint32])

@@ -51,6 +51,7 @@ struct HkContext {
     DevBuf b_f_func, b_f_mcdf, b_f_mfunc, b_f_ccdf;
     DevBuf b_state, b_counts, b_rays, b_film, b_scratch_u32, b_trace_ctr, b_readback;
     DevBuf b_aux, b_denoise; size_t aux_pixels = 0;
+    DevBuf b_uvs, b_textures; std::vector<DevBuf> tex_bufs;
     bool has_rgbgrid = false;                // some uploaded medium is an RGBGridMedium: the tracking kernels with that branch compiled in     // film.albedo [3n] | film.normal [3n] | film.depth [n], (H, W) column-major
     // pipelined read-out (hk_read_film_async): two device staging buffers, a copy stream, per-buffer events
     DevBuf b_readback_async[2]; cudaStream_t copy_stream = nullptr; cudaEvent_t ev_final[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
@@ -150,6 +151,8 @@ int32_t hk_destroy(HkContext* ctx) {
     for (DevBuf* b : bufs) b->release();
     for (auto& b : ctx->env_bufs) b.release();
     for (auto& b : ctx->media_bufs) b.release();
+    for (auto& b : ctx->tex_bufs) b.release();
+    ctx->b_aux.release(); ctx->b_denoise.release(); ctx->b_uvs.release(); ctx->b_textures.release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (auto& s : ctx->shade_streams) if (s) cudaStreamDestroy(s);
@@ -255,6 +258,8 @@ int32_t hk_upload_geometry(HkContext* ctx, const HkGeometry* g) {
     CK(ctx->b_tris.upload(bvh.tris.data(), bvh.tris.size() * sizeof(HkBvhTri)));
     CK(ctx->b_pos.upload(g->positions, 12 * (size_t)g->n_verts));
     if (g->normals) CK(ctx->b_nrm.upload(g->normals, 12 * (size_t)g->n_verts)); else ctx->b_nrm.release();
+    if (g->uvs) CK(ctx->b_uvs.upload(g->uvs, 8 * (size_t)g->n_verts)); else ctx->b_uvs.release();
+    ctx->D.uvs = g->uvs ? ctx->b_uvs.as<float>() : nullptr;
     CK(ctx->b_idx.upload(g->indices, 12 * (size_t)g->n_tris));
     CK(ctx->b_meta.upload(g->tri_meta, 12 * (size_t)g->n_tris));
     ctx->D.bvh.nodes = ctx->b_nodes.as<float4>(); ctx->D.bvh.tris = ctx->b_tris.as<float4>(); ctx->D.bvh.one_bits = 0x3F800000u;
@@ -276,6 +281,32 @@ int32_t hk_upload_spectra(HkContext* ctx, const HkSpectra* s) {
     return HK_OK;
 }
 
+int32_t hk_upload_textures(HkContext* ctx, const HkTexture* t, uint32_t n) {
+    if (!ctx) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    REQUIRE(n == 0 || t, "textures missing");
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (auto& b : ctx->tex_bufs) b.release();
+    ctx->tex_bufs.clear(); ctx->tex_bufs.resize(n);
+    std::vector<HkTexture> dev(n);
+    for (uint32_t i = 0; i < n; i++) {
+        REQUIRE(t[i].rgb && t[i].h >= 1 && t[i].w >= 1, "texture needs data and a positive size");
+        CK(ctx->tex_bufs[i].upload(t[i].rgb, 12 * (size_t)t[i].h * t[i].w));
+        dev[i].rgb = ctx->tex_bufs[i].as<float>(); dev[i].h = t[i].h; dev[i].w = t[i].w;
+    }
+    CK(ctx->b_textures.upload(dev.data(), sizeof(HkTexture) * (size_t)n));
+    ctx->D.textures = n ? ctx->b_textures.as<HkTexture>() : nullptr; ctx->D.n_textures = (int32_t)n;
+    return HK_OK;
+}
+static int32_t mat_textures_ok(HkContext* ctx, const HkMaterial& m) {
+    for (int k = 0; k < 4; k++) {
+        if (m.tex[k] == 0) continue;
+        REQUIRE(k == 0 && m.type == HK_MAT_MATTE, "textured parameters are supported for MatteMaterial.Kd only (SURVEY 8f item 2)");
+        REQUIRE(m.tex[k] >= 1 && m.tex[k] <= ctx->D.n_textures, "material references a texture that has not been uploaded (hk_upload_textures first)");
+    }
+    return HK_OK;
+}
+static uint32_t host_shade_class(const HkMaterial& m) { return (m.type == HK_MAT_MATTE && m.tex[0] > 0) ? (uint32_t)HK_SHADE_MATTE_TEX : (uint32_t)m.type; }
 static bool mat_type_supported(int32_t t) { return (t >= 1 && t < HK_MAX_MAT_TYPES) || t == HK_MAT_MIX || t == HK_MAT_COATED_CONDUCTOR || t == HK_MAT_COATED_DIFFUSE_TRANSMISSION; }
 int32_t hk_upload_materials(HkContext* ctx, const HkMaterial* m, uint32_t nm, const HkMediumInterface* mi, uint32_t ni) {
     if (!ctx) return HK_ERR_INVALID;
@@ -284,8 +315,9 @@ int32_t hk_upload_materials(HkContext* ctx, const HkMaterial* m, uint32_t nm, co
     uint32_t present = 0; int32_t trans = 0;
     for (uint32_t i = 0; i < nm; i++) {
         REQUIRE(mat_type_supported(m[i].type), "unsupported material type");
+        { int32_t rc = mat_textures_ok(ctx, m[i]); if (rc != HK_OK) return rc; }
         if (m[i].type == HK_MAT_MIX) { REQUIRE(m[i].ival[0] >= 1 && (uint32_t)m[i].ival[0] <= nm && m[i].ival[1] >= 1 && (uint32_t)m[i].ival[1] <= nm, "MixMaterial references a missing material"); }
-        else present |= 1u << m[i].type;
+        else present |= 1u << host_shade_class(m[i]);
     }
     for (uint32_t i = 0; i < ni; i++) {
         REQUIRE(mi[i].material >= 1 && mi[i].material <= nm, "interface references a missing material");
@@ -294,7 +326,7 @@ int32_t hk_upload_materials(HkContext* ctx, const HkMaterial* m, uint32_t nm, co
     CK(ctx->b_mats.upload(m, sizeof(HkMaterial) * (size_t)nm)); CK(ctx->b_ifaces.upload(mi, sizeof(HkMediumInterface) * (size_t)ni));
     ctx->D.materials = ctx->b_mats.as<HkMaterial>(); ctx->D.interfaces = ctx->b_ifaces.as<HkMediumInterface>();
     ctx->D.any_medium_transition = trans; ctx->mat_types_present = present; ctx->n_interfaces = ni;
-    ctx->mat_types.resize(nm); for (uint32_t i = 0; i < nm; i++) ctx->mat_types[i] = m[i].type;
+    ctx->mat_types.resize(nm); for (uint32_t i = 0; i < nm; i++) ctx->mat_types[i] = m[i].type == HK_MAT_MIX ? HK_MAT_MIX : (int32_t)host_shade_class(m[i]);
     if (!ctx->b_spec_o.p) { uint32_t zero = 0; CK(ctx->b_spec_o.upload(&zero, 4)); ctx->D.spec_offsets = ctx->b_spec_o.as<uint32_t>(); }
     ctx->have_mats = true; ctx->camera_medium_valid = false;
     int32_t rc = refresh_uplift_cache(ctx);
@@ -309,11 +341,13 @@ int32_t hk_update_material(HkContext* ctx, uint32_t index, const HkMaterial* m) 
     REQUIRE(ctx->have_mats, "hk_upload_materials has not been called");
     REQUIRE(index >= 1 && index <= ctx->mat_types.size(), "material index out of range");
     REQUIRE(mat_type_supported(m->type), "unsupported material type");
+    { int32_t rc = mat_textures_ok(ctx, *m); if (rc != HK_OK) return rc; }
     if (m->type == HK_MAT_MIX) REQUIRE(m->ival[0] >= 1 && (size_t)m->ival[0] <= ctx->mat_types.size() && m->ival[1] >= 1 && (size_t)m->ival[1] <= ctx->mat_types.size(), "MixMaterial references a missing material");
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaMemcpy(ctx->b_mats.as<HkMaterial>() + (index - 1), m, sizeof(HkMaterial), cudaMemcpyHostToDevice));
-    const bool type_changed = ctx->mat_types[index - 1] != m->type;
-    ctx->mat_types[index - 1] = m->type;
+    const int32_t cls = m->type == HK_MAT_MIX ? HK_MAT_MIX : (int32_t)host_shade_class(*m);      // mat_types holds shading classes
+    const bool type_changed = ctx->mat_types[index - 1] != cls;
+    ctx->mat_types[index - 1] = cls;
     { int32_t rc = refresh_uplift_cache(ctx); if (rc != HK_OK) return rc; }
     if (type_changed) {
         uint32_t present = 0;
@@ -633,6 +667,7 @@ int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride,
             launch_shade<HK_MAT_CONDUCTOR>(ctx, A, cur ^ 1); launch_shade<HK_MAT_COATED_DIFFUSE>(ctx, A, cur ^ 1);
             launch_shade<HK_MAT_THIN_DIELECTRIC>(ctx, A, cur ^ 1); launch_shade<HK_MAT_DIFFUSE_TRANSMISSION>(ctx, A, cur ^ 1);
             launch_shade<HK_MAT_COATED_CONDUCTOR>(ctx, A, cur ^ 1); launch_shade<HK_MAT_COATED_DIFFUSE_TRANSMISSION>(ctx, A, cur ^ 1);
+            launch_shade<HK_SHADE_MATTE_TEX>(ctx, A, cur ^ 1);
             if (fork) for (int j = 0; j < ctx->shade_fork_slot; j++) cudaStreamWaitEvent(st, ctx->ev_join[j], 0);
             if (ctx->D.n_lights > 0) {
                 if (overlap_shadow) {

@@ -143,6 +143,26 @@ HK_DEV BsdfEval eval_matte(const MatCtx& C, const HkMaterial& m, float3 wo, floa
     Spec kd = mat_spec(C, m, 0, lam);
     return eval_make(kd / HK_PI, c / HK_PI);
 }
+// Matte with a textured Kd: the same two functions with the uplifted texel passed in (k_shade<HK_SHADE_MATTE_TEX>)
+HK_DEV BsdfSample sample_matte_kd(Spec kd, float sigma, float3 wo, float3 n, float2 u) {
+    float wn = dot3(wo, n);
+    if (fabsf(wn) < 1.0e-6f) return bsdf_none();
+    Frame fr = make_frame(n);
+    float3 lw = cosine_sample_hemisphere(u);
+    float ct = lw.z;
+    if (ct < 1.0e-6f) return bsdf_none();
+    if (wn < 0.0f) lw.z = -lw.z;
+    float3 wi = norm3(to_world(fr, lw));
+    Spec f = sigma > 0.0f ? kd * ((1.0f - 0.5f * sigma / (sigma + 0.33f)) / HK_PI) : kd * (1.0f / HK_PI);
+    return bsdf_make(wi, f, ct / HK_PI, false, 1.0f);
+}
+HK_DEV BsdfEval eval_matte_kd(Spec kd, float3 wo, float3 wi, float3 n) {
+    float ci = dot3(wi, n), co = dot3(wo, n);
+    if (ci * co < 0.0f) return eval_none();
+    float c = fabsf(ci);
+    if (c < 1.0e-6f) return eval_none();
+    return eval_make(kd / HK_PI, c / HK_PI);
+}
 // ---- Mirror :108-132 ---------------------------------------------------------------------------------------
 HK_DEV BsdfSample sample_mirror(const MatCtx& C, const HkMaterial& m, float3 wo, float3 n, float4 lam) {
     float wn = dot3(wo, n);

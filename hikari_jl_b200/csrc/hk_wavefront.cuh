@@ -31,8 +31,11 @@
 #define HK_C_CURSOR_SHADOW 7
 #define HK_C_HIT0 8            // + hit queue 0..7 of the material type: types 1..7 use queue = type, CoatedConductor (9) the spare queue 0
 #define HK_C_HIT1 56           // + (hit queue - 8): second bank, CoatedDiffuseTransmission (10) = queue 8
-#define HK_N_HIT_QUEUES 9
-#define HK_TYPE_QUEUE(t) ((t) == HK_MAT_COATED_CONDUCTOR ? 0 : (t) == HK_MAT_COATED_DIFFUSE_TRANSMISSION ? 8 : (t))
+#define HK_N_HIT_QUEUES 10
+// shading class = the material type, except a MatteMaterial with a textured Kd, which gets its own class, queue and k_shade
+// instantiation (the constant-parameter kernels stay free of texture code)
+#define HK_SHADE_MATTE_TEX 11
+#define HK_TYPE_QUEUE(t) ((t) == HK_MAT_COATED_CONDUCTOR ? 0 : (t) == HK_MAT_COATED_DIFFUSE_TRANSMISSION ? 8 : (t) == HK_SHADE_MATTE_TEX ? 9 : (t))
 #define HK_HIT_COUNTER(q) ((q) < 8 ? HK_C_HIT0 + (q) : HK_C_HIT1 + (q) - 8)
 #define HK_N_QUEUE_COUNTERS 16 // the counters above (what hk_bounce_profile reports)
 #define HK_C_CURSOR_MEDIUM 16  // k_medium_track work cursor
@@ -68,7 +71,10 @@ struct DevScene {
     int32_t width, height, max_depth, regularize;
     float max_component_value;
     SobolParams sobol;
+    // textured parameters (appended last: the members above keep their offsets in the kernel parameter block)
+    const float* __restrict__ uvs; const HkTexture* __restrict__ textures; int32_t n_textures;
 };
+HK_DEV uint32_t shade_class(const HkMaterial& m) { return (m.type == HK_MAT_MATTE && m.tex[0] > 0) ? (uint32_t)HK_SHADE_MATTE_TEX : (uint32_t)m.type; }
 struct PathState {
     float4 *ray_a, *ray_b, *hit, *lambda, *lpdf, *beta, *r_u, *r_l, *L;
     uint32_t* flags; float* fweight;
@@ -168,6 +174,33 @@ HK_DEV Surf surface_at(const DevScene& D, uint32_t prim0, float b1, float b2, fl
     s.iface = __ldg(D.tri_meta + 3 * (size_t)prim0);
     s.arealight = __ldg(D.tri_meta + 3 * (size_t)prim0 + 2);
     return s;
+}
+// Kd of a textured MatteMaterial at a hit: uv = barycentric interpolation of the vertex uvs (intersection.jl:28-37), bilinear
+// texel of the (h, w) column-major image with v flipped and clamped indices (_sample_texture_bilinear, texture-ref.jl:160-190),
+// clamp to [0, 1] and uplift (spectral-eval.jl:57-60).  One uncached rgb_to_spectrum per hit.
+HK_DEV Spec textured_kd(const DevScene& D, const HkMaterial& m, uint32_t prim0, float b1, float b2, float4 lam) {
+    float u = 0.0f, v = 0.0f;
+    if (D.uvs) {
+        const uint32_t i0 = __ldg(D.indices + 3 * (size_t)prim0), i1 = __ldg(D.indices + 3 * (size_t)prim0 + 1), i2 = __ldg(D.indices + 3 * (size_t)prim0 + 2);
+        const float2 a = __ldg(reinterpret_cast<const float2*>(D.uvs) + i0), b = __ldg(reinterpret_cast<const float2*>(D.uvs) + i1), c = __ldg(reinterpret_cast<const float2*>(D.uvs) + i2);
+        const float w = 1.0f - b1 - b2;
+        u = w * a.x + b1 * b.x + b2 * c.x; v = w * a.y + b1 * b.y + b2 * c.y;
+    }
+    const HkTexture t = D.textures[m.tex[0] - 1];
+    const float px = u * (float)(t.w - 1) + 1.0f, py = (1.0f - v) * (float)(t.h - 1) + 1.0f;
+    const float flx = floorf(px), fly = floorf(py);
+    const int x0 = clampi(floor_i(px), 1, t.w), x1 = clampi(floor_i(px) + 1, 1, t.w), y0 = clampi(floor_i(py), 1, t.h), y1 = clampi(floor_i(py) + 1, 1, t.h);
+    const float fx = px - flx, fy = py - fly;
+    const float* T = t.rgb;
+    const size_t o00 = 3 * ((size_t)(x0 - 1) * t.h + (y0 - 1)), o10 = 3 * ((size_t)(x1 - 1) * t.h + (y0 - 1));
+    const size_t o01 = 3 * ((size_t)(x0 - 1) * t.h + (y1 - 1)), o11 = 3 * ((size_t)(x1 - 1) * t.h + (y1 - 1));
+    float rgb[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float c0 = __ldg(T + o00 + k) * (1.0f - fx) + __ldg(T + o10 + k) * fx, c1 = __ldg(T + o01 + k) * (1.0f - fx) + __ldg(T + o11 + k) * fx;
+        rgb[k] = clampf(c0 * (1.0f - fy) + c1 * fy, 0.0f, 1.0f);
+    }
+    return pre_bounded(make_pre_bounded(D.T, rgb[0], rgb[1], rgb[2]), lam);
 }
 HK_DEV float3 geometric_normal(const DevScene& D, uint32_t prim0) {
     const uint32_t i0 = __ldg(D.indices + 3 * (size_t)prim0), i1 = __ldg(D.indices + 3 * (size_t)prim0 + 1), i2 = __ldg(D.indices + 3 * (size_t)prim0 + 2);
@@ -365,19 +398,19 @@ HK_DEV int hit_queue_id(const DevScene& D, const PathState& S, uint32_t slot, ui
         const uint32_t mi = __ldg(D.tri_meta + 3 * (size_t)prim0);
         const uint32_t res = resolve_mix_material(D.materials, D.interfaces[mi - 1].material, o + d * t_hit, -d);
         S.res_mat[slot] = res;
-        mtype = (uint32_t)D.materials[res - 1].type;
+        mtype = shade_class(D.materials[res - 1]);
         if (mtype == HK_MAT_MIX) return -1;            // a mix chain deeper than 8 levels: the reference would shade a MixMaterial (undefined); dropped
     }
     return HK_HIT_COUNTER((int)HK_TYPE_QUEUE(mtype));
 }
 
-// writes the material type (1..7) of every BVH triangle into the spare word of its record (HitRec)
+// writes the shading class (material type; 11 = textured matte) of every BVH triangle into the spare word of its record (HitRec)
 __global__ void __launch_bounds__(256) k_patch_tri_types(float4* __restrict__ tris, uint32_t n_tris, const uint32_t* __restrict__ tri_meta,
                                                           const HkMediumInterface* __restrict__ interfaces, const HkMaterial* __restrict__ materials) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_tris; i += gridDim.x * blockDim.x) {
         const uint32_t prim0 = __float_as_uint(tris[3 * (size_t)i].w);
         const uint32_t mi = tri_meta[3 * (size_t)prim0];
-        const uint32_t type = (uint32_t)materials[interfaces[mi - 1].material - 1].type;
+        const uint32_t type = shade_class(materials[interfaces[mi - 1].material - 1]);
         tris[3 * (size_t)i + 1].w = __uint_as_float(type & 0xFu);
     }
 }
@@ -486,6 +519,8 @@ __global__ void __launch_bounds__(128, (TYPE == HK_MAT_COATED_DIFFUSE || TYPE ==
             const HkMediumInterface mi = D.interfaces[sf.iface - 1];
             const HkMaterial& mat = D.materials[(D.materials[mi.material - 1].type == HK_MAT_MIX ? S.res_mat[slot] : mi.material) - 1];
             const float4 lam = S.lambda[slot];
+            Spec kd_tex = sp(0.0f);
+            if (TYPE == HK_SHADE_MATTE_TEX) kd_tex = textured_kd(D, mat, prim0, hr.z, hr.w, lam);
             const Spec beta = S.beta[slot], r_u = S.r_u[slot], r_l = S.r_l[slot];
             const uint32_t fl = S.flags[slot];
             const int depth = HK_FLAG_DEPTH(fl);
@@ -521,7 +556,7 @@ __global__ void __launch_bounds__(128, (TYPE == HK_MAT_COATED_DIFFUSE || TYPE ==
                     float2 direct_u = zsobol_2d(D.sobol, px, py, sidx, bdim + 3, HK_SOBOL_SLOT_BOUNCE(depth, 1), pix);
                     LightSample ls = sample_light(LC, D.lights[li - 1], sf.pi, lam, direct_u);
                     if (ls.pdf > 0.0f && !sp_black(ls.Li)) {
-                        BsdfEval be = eval_bsdf<TYPE>(MC, mat, wo, ls.wi, sf.ns, lam);
+                        BsdfEval be = TYPE == HK_SHADE_MATTE_TEX ? eval_matte_kd(kd_tex, wo, ls.wi, sf.ns) : eval_bsdf<TYPE>(MC, mat, wo, ls.wi, sf.ns, lam);
                         if (!sp_black(be.f)) {
                             float ct = fabsf(dot3(ls.wi, sf.ns));
                             Spec Ld = beta * be.f * ls.Li * ct;
@@ -548,7 +583,8 @@ __global__ void __launch_bounds__(128, (TYPE == HK_MAT_COATED_DIFFUSE || TYPE ==
                 float indirect_uc = zsobol_1d(D.sobol, px, py, sidx, bdim + 4, HK_SOBOL_SLOT_BOUNCE(depth, 2), pix);
                 float2 indirect_u = zsobol_2d(D.sobol, px, py, sidx, bdim + 6, HK_SOBOL_SLOT_BOUNCE(depth, 3), pix);
                 const bool reg = D.regularize && (fl & HK_FLAG_ANYNS);
-                BsdfSample bs = sample_bsdf<TYPE>(MC, mat, wo, sf.ns, lam, indirect_u, indirect_uc, reg);
+                BsdfSample bs = TYPE == HK_SHADE_MATTE_TEX ? sample_matte_kd(kd_tex, mat.f[0], wo, sf.ns, indirect_u)
+                                                           : sample_bsdf<TYPE>(MC, mat, wo, sf.ns, lam, indirect_u, indirect_uc, reg);
                 if (bs.pdf > 0.0f && !sp_black(bs.f)) {
                     float ct = fabsf(dot3(bs.wi, sf.ns));
                     Spec nb = bs.specular ? beta * bs.f : beta * bs.f * ct / bs.pdf;

@@ -428,15 +428,29 @@ class MixMaterial(Material):
 Mix = MixMaterial
 
 
+class Texture:
+    """src/textures/basic.jl: Texture(data) over an (h, w) image of RGB values — data[y, x] as in the reference, row 1 at v = 1.
+    Stored column-major like the Julia matrix, so the bytes handed to hk_upload_textures are the reference's own."""
+
+    def __init__(self, data_hw3):
+        d = np.asarray(data_hw3, dtype=f32)
+        assert d.ndim == 3 and d.shape[2] == 3, "RGB texture: [h, w, 3]"
+        self.h, self.w = int(d.shape[0]), int(d.shape[1])
+        self.data = np.ascontiguousarray(d.transpose(1, 0, 2))       # [x][y][3] = column-major (h, w)
+
+
 class MatteMaterial(Material):            # uber-material.jl:180-183, 256
     type = A.HK_MAT_MATTE
 
     def __init__(self, Kd=0.5, sigma=0.0):
-        self.Kd, self.sigma = _rgb(Kd), float(sigma)
+        self.Kd, self.sigma = (Kd if isinstance(Kd, Texture) else _rgb(Kd)), float(sigma)
 
     def to_abi(self, scene):
         m = A.HkMaterial(type=self.type)
-        m.rgb0[:] = self.Kd
+        if isinstance(self.Kd, Texture):
+            m.tex[0] = scene._texture_id(self.Kd)                     # a TextureRef in the reference (texture-ref.jl:196-199)
+        else:
+            m.rgb0[:] = self.Kd
         m.f[0] = self.sigma
         return m
 
@@ -981,6 +995,11 @@ class Scene:
     def _spectrum_id(self, s):
         return self._index_of(self._spectra, s)
 
+    def _texture_id(self, t):
+        if not hasattr(self, "_textures"):
+            self._textures = []
+        return self._index_of(self._textures, t)
+
     def _envmap_id(self, light):
         return self._index_of(self._envmaps, light)
 
@@ -1158,8 +1177,11 @@ class Backend:
                          None if s.uvs is None else _fp(s.uvs), s.indices.ctypes.data_as(A.c_u32p),
                          s.tri_meta.ctypes.data_as(A.c_u32p), len(s.positions), len(s.indices))
         self.call("upload_geometry", C.byref(g))
-        # materials first (registers spectra ids), then spectra
+        # materials first (registers spectra and texture ids), then spectra and textures, then the material upload
+        scene._textures = []
         mats = (A.HkMaterial * max(1, len(scene.materials)))(*[m.to_abi(scene) for m in scene.materials])
+        texs = (A.HkTexture * max(1, len(scene._textures)))(*[A.HkTexture(_fp(t.data), t.h, t.w) for t in scene._textures])
+        self.call("upload_textures", texs, len(scene._textures))
         lam = np.concatenate([sp.lambdas for sp in scene._spectra]) if scene._spectra else np.zeros(0, f32)
         val = np.concatenate([sp.values for sp in scene._spectra]) if scene._spectra else np.zeros(0, f32)
         offs = np.cumsum([0] + [len(sp.lambdas) for sp in scene._spectra]).astype(np.uint32)

@@ -44,6 +44,31 @@ def cornell_smoke():
     return s, _cam((0.0, 1.0, -3.5), (0.0, 1.0, 0.0), 40.0)
 
 
+def textured_spheres(tess=24):
+    """MatteMaterial with a textured Kd (TextureRef + bilinear eval_tex, texture-ref.jl:72-190): a checker floor, a striped sphere,
+    a sphere whose texture has values outside [0, 1] (clamped after filtering), one reached through a MixMaterial, and a plain
+    matte sphere on the constant-parameter path next to them."""
+    rng = np.random.RandomState(3)
+    yy, xx = np.meshgrid(np.arange(16), np.arange(16), indexing="ij")
+    checker = np.where(((yy // 2 + xx // 2) % 2)[..., None] == 0, np.array([0.85, 0.8, 0.7]), np.array([0.15, 0.2, 0.45])).astype(np.float32)
+    stripes = np.zeros((8, 32, 3), np.float32); stripes[..., 0] = (np.arange(32) % 4 < 2) * 0.9; stripes[..., 1] = np.linspace(0.1, 0.9, 8)[:, None]; stripes[..., 2] = 0.3
+    wild = rng.uniform(-0.5, 1.6, size=(5, 7, 3)).astype(np.float32)
+    s = H.Scene()
+    floor = H.Mesh([(-5, -0.9, -5), (5, -0.9, -5), (5, -0.9, 5), (-5, -0.9, 5)], [(0, 2, 1), (0, 3, 2)],
+                   normals=[(0, 1, 0)] * 4, uvs=[(-0.2, -0.2), (1.2, -0.2), (1.2, 1.2), (-0.2, 1.2)])       # uv beyond [0, 1]: indices clamp
+    s.push(floor, H.MatteMaterial(Kd=H.Texture(checker)))
+    s.push(H.uv_sphere((-1.6, 0.0, 0.0), 0.75, tess, tess), H.MatteMaterial(Kd=H.Texture(stripes), sigma=20.0))
+    s.push(H.uv_sphere((0.0, 0.0, 0.0), 0.75, tess, tess), H.MatteMaterial(Kd=H.Texture(wild)))
+    s.push(H.uv_sphere((1.6, 0.0, 0.0), 0.75, tess, tess),
+           H.MixMaterial((H.MirrorMaterial(Kr=0.9), H.MatteMaterial(Kd=H.Texture(checker[:4, :6].copy()))), amount=1.0))
+    s.push(H.uv_sphere((0.0, 1.3, 0.0), 0.4, tess, tess), H.MatteMaterial(Kd=(0.2, 0.7, 0.3)))
+    d = np.array([-1.0, -1.5, -0.5])
+    s.push(H.DirectionalLight((3, 3, 3), d / np.linalg.norm(d), legacy_rgbspectrum=True))
+    s.push(H.AmbientLight((0.3, 0.35, 0.4)))
+    s.sync()
+    return s, _cam((0, 1.6, 4.5), (0, 0.2, 0), 40.0)
+
+
 def rgb_nebula(res=(20, 16, 12)):
     """An RGBGridMedium (media.jl:1002-1456) inside an index-1 boundary: two coloured, partly emissive blobs over a matte floor."""
     nx, ny, nz = res

@@ -78,10 +78,20 @@ typedef struct HkGeometry {
     uint32_t        n_tris;
 } HkGeometry;
 
+/* ---- textures -----------------------------------------------------------------------------
+ * replaces: the texture arrays a Raycore.TextureRef points at (src/textures/texture-ref.jl:50-76).  RGB float images in the
+ * reference's own memory order, an (h, w) column-major matrix: texel (row y, column x), 0-based, at rgb[3 * (x * h + y)].
+ * Sampled bilinearly at the hit's interpolated uv exactly as _sample_texture_bilinear (:160-190): px = u (w-1) + 1,
+ * py = (1 - v)(h-1) + 1, indices clamped, no wrap.  Upload before the materials that reference them.           */
+typedef struct HkTexture {
+    const float* rgb;
+    int32_t      h, w;
+} HkTexture;
+
 /* ---- materials ----------------------------------------------------------------------------
  * replaces: scene.materials (MultiTypeSet) + scene.media_interfaces (src/scene.jl:21-28,
- * src/materials/medium-interface.jl:78-82).  Only constant-valued parameters are in scope this
- * round (TextureRef parameters: SURVEY §8f item 2).                                            */
+ * src/materials/medium-interface.jl:78-82).  Parameters are constants, except MatteMaterial.Kd which may be a
+ * texture (tex[0]); other TextureRef parameters and alpha: SURVEY §8f item 2.                                 */
 #define HK_MAT_MATTE                1   /* src/materials/spectral-eval.jl:42-101, 371-397      */
 #define HK_MAT_MIRROR               2   /* :108-132                                            */
 #define HK_MAT_GLASS                3   /* :140-198, 407-413                                   */
@@ -119,6 +129,8 @@ typedef struct HkMaterial {
                         /* Mix: f0 = amount (constant texture); ival0 / ival1 = 1-based material1 / material2;
                            the SetKeys hashed by mix_hash_float (mix-material.jl:114-158): spec0 / spec1 = vec_idx of
                            material1 / material2, flags = type_idx1 | type_idx2 << 8                             */
+    int32_t  tex[4];    /* 1-based ids into the uploaded textures replacing rgb0 / rgb1 / rgb2 (0 = the constant); this round:
+                           tex[0] of a MatteMaterial (Kd); anything else is rejected at upload                        */
 } HkMaterial;
 
 typedef struct HkMediumInterface {   /* MediumInterfaceIdx, src/materials/medium-interface.jl:78-82 */
@@ -305,6 +317,7 @@ const char* hk_last_error(HkContext* ctx);
 int32_t hk_upload_tables(HkContext* ctx, const HkTables* tables);
 int32_t hk_upload_geometry(HkContext* ctx, const HkGeometry* geom);
 int32_t hk_upload_spectra(HkContext* ctx, const HkSpectra* spectra);
+int32_t hk_upload_textures(HkContext* ctx, const HkTexture* textures, uint32_t n_textures);
 int32_t hk_upload_materials(HkContext* ctx, const HkMaterial* materials, uint32_t n_materials,
                             const HkMediumInterface* interfaces, uint32_t n_interfaces);
 /* update_material!(scene, idx, new_material), src/scene.jl:109-112: replace one uploaded material in place (1-based

@@ -71,6 +71,14 @@ int32_t ok_upload_spectra(OkContext* c, const HkSpectra* sp) {
     s.spectra = HkSpectra{s.spec_lambdas.data(), s.spec_values.data(), s.spec_offsets.data(), sp->n_spectra};
     return 0;
 }
+int32_t ok_upload_textures(OkContext* c, const HkTexture* t, uint32_t n) {
+    TextureStore& S = c->s.textures;
+    S.rgb.clear(); S.h.clear(); S.w.clear();
+    for (uint32_t i = 0; i < n; i++) {
+        S.rgb.emplace_back(t[i].rgb, t[i].rgb + 3 * (size_t)t[i].h * t[i].w); S.h.push_back(t[i].h); S.w.push_back(t[i].w);
+    }
+    return 0;
+}
 int32_t ok_upload_materials(OkContext* c, const HkMaterial* m, uint32_t nm, const HkMediumInterface* mi, uint32_t ni) {
     c->s.materials.assign(m, m + nm); c->s.interfaces.assign(mi, mi + ni);
     if (c->s.spec_offsets.empty()) { c->s.spec_offsets.assign(1, 0); c->s.spectra = HkSpectra{nullptr, nullptr, c->s.spec_offsets.data(), 0}; }

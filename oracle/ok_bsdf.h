@@ -1,6 +1,7 @@
 // ok_bsdf.h — ORACLE (test infrastructure, NOT product code).
 // Spectral BSDF sample/eval per material, restating src/materials/spectral-eval.jl.
 #pragma once
+#include <vector>
 #include "ok_spectral.h"
 
 namespace ok {
@@ -12,10 +13,35 @@ struct BSDFSample {   // SpectralBSDFSample, spectral-eval.jl:18-27
 };
 struct BSDFEval { Spec f; float pdf; BSDFEval() : f(), pdf(0.0f) {} BSDFEval(Spec ff, float p) : f(ff), pdf(p) {} };
 
-struct MatCtx {   // what the reference passes around as (table, textures)
+struct TextureStore { std::vector<std::vector<float>> rgb; std::vector<int32_t> h, w; };
+struct MatCtx {   // what the reference passes around as (table, textures) + the TextureFilterContext's uv
     const Tables* T;
     const HkSpectra* spectra;
+    const TextureStore* textures = nullptr;
+    V2 uv = V2(0.0f, 0.0f);
 };
+// _sample_texture_bilinear, src/textures/texture-ref.jl:160-190, on an (h, w) column-major RGB image
+inline void sample_texture_bilinear(const TextureStore& S, int32_t id, V2 uv, float* out) {
+    const std::vector<float>& d = S.rgb[id - 1];
+    const int h = S.h[id - 1], w = S.w[id - 1];
+    const float ua0 = 1.0f - uv.y, ua1 = uv.x;                       // uv_adj = (1 - v, u)
+    const float px = ua1 * (float)(w - 1) + 1.0f, py = ua0 * (float)(h - 1) + 1.0f;
+    int x0 = (int)std::floor(px), y0 = (int)std::floor(py);
+    int x1 = x0 + 1, y1 = y0 + 1;
+    x0 = clampi(x0, 1, w); x1 = clampi(x1, 1, w); y0 = clampi(y0, 1, h); y1 = clampi(y1, 1, h);
+    const float fx = px - std::floor(px), fy = py - std::floor(py);
+    auto at = [&](int y, int x, int c) { return d[3 * ((size_t)(x - 1) * h + (y - 1)) + c]; };
+    for (int c = 0; c < 3; c++) {
+        const float c0 = at(y0, x0, c) * (1.0f - fx) + at(y0, x1, c) * fx;
+        const float c1 = at(y1, x0, c) * (1.0f - fx) + at(y1, x1, c) * fx;
+        out[c] = c0 * (1.0f - fy) + c1 * fy;
+    }
+}
+// eval_tex(textures, mat.Kd, tfc) for a MatteMaterial: the constant, or the bilinear texel at the hit's uv (texture-ref.jl:72-80)
+inline void matte_kd_rgb(const MatCtx& C, const HkMaterial& m, float* kd) {
+    if (m.tex[0] > 0 && C.textures) sample_texture_bilinear(*C.textures, m.tex[0], C.uv, kd);
+    else { kd[0] = m.rgb0[0]; kd[1] = m.rgb0[1]; kd[2] = m.rgb0[2]; }
+}
 
 // src/reflection/bxdf.jl:67-90
 inline float fresnel_dielectric(float cos_i, float eta) {
@@ -141,7 +167,7 @@ inline Spec eval_ior_spectral(const MatCtx& C, const HkMaterial& m, int which, c
 inline BSDFSample sample_matte(const MatCtx& C, const HkMaterial& m, V3 wo, V3 n, const Wavelengths& l, V2 u, float /*rng*/, bool /*reg*/) {
     float wo_dot_n = dot(wo, n);
     if (std::fabs(wo_dot_n) < 1.0e-6f) return BSDFSample();
-    float kd[3]; clamp_rgb01(m.rgb0, kd);
+    float kd_raw[3], kd[3]; matte_kd_rgb(C, m, kd_raw); clamp_rgb01(kd_raw, kd);
     float sigma = m.f[0];
     Spec kd_s = uplift_rgb(*C.T, kd, l);
     V3 t, b; coordinate_system(n, t, b);
@@ -164,7 +190,7 @@ inline BSDFEval eval_matte(const MatCtx& C, const HkMaterial& m, V3 wo, V3 wi, V
     if (ci * co < 0.0f) return BSDFEval();
     float c = std::fabs(ci);
     if (c < 1.0e-6f) return BSDFEval();
-    float kd[3]; clamp_rgb01(m.rgb0, kd);
+    float kd_raw[3], kd[3]; matte_kd_rgb(C, m, kd_raw); clamp_rgb01(kd_raw, kd);
     Spec kd_s = uplift_rgb(*C.T, kd, l);
     return BSDFEval(kd_s / PI_F, c / PI_F);
 }

@@ -110,7 +110,9 @@ struct Scene {
     std::vector<float> aux_albedo, aux_normal, aux_depth;      // film.albedo / normal / depth, (H, W) column-major (film.jl:410-488)
     std::string err;
 
-    MatCtx matctx() const { return MatCtx{&T, &spectra}; }
+    TextureStore textures;
+    MatCtx matctx() const { MatCtx c; c.T = &T; c.spectra = &spectra; c.textures = &textures; return c; }
+    MatCtx matctx_at(V2 uv) const { MatCtx c = matctx(); c.uv = uv; return c; }      // the TextureFilterContext of one hit
     LightCtx lightctx() const { return LightCtx{&T, lights.data(), (uint32_t)lights.size(), envmaps.data(), (uint32_t)envmaps.size(), &sampler}; }
     MediaCtx mediactx() const { return MediaCtx{&T, media.data(), (uint32_t)media.size()}; }
 
@@ -585,7 +587,7 @@ inline void Scene::render_sample(int32_t sample_idx) {
                     if (li < 1 || li > num_lights || pmf <= 0.0f) continue;
                     LightSample ls = sample_light(LC, lights[li - 1], w.g.pi, w.lambda, smp.direct_u);
                     if (!(ls.pdf > 0.0f && !is_black(ls.Li))) continue;
-                    BSDFEval be = eval_material(MC, materials[w.material - 1], w.wo, ls.wi, w.g.ns, w.lambda);
+                    BSDFEval be = eval_material(matctx_at(w.g.uv), materials[w.material - 1], w.wo, ls.wi, w.g.ns, w.lambda);
                     if (is_black(be.f)) continue;
                     // compute_direct_lighting_spectral, lights.jl:535-600
                     float ct = std::fabs(dot(ls.wi, w.g.ns));
@@ -621,7 +623,7 @@ inline void Scene::render_sample(int32_t sample_idx) {
                 if (new_depth >= params.max_depth) continue;
                 const RaySamples& smp = pixel_samples[w.pixel_index - 1];
                 bool regularize = params.regularize && w.any_non_specular;
-                BSDFSample s = sample_material(MC, materials[w.material - 1], w.wo, w.g.ns, w.lambda, smp.indirect_u, smp.indirect_uc, regularize);
+                BSDFSample s = sample_material(matctx_at(w.g.uv), materials[w.material - 1], w.wo, w.g.ns, w.lambda, smp.indirect_u, smp.indirect_uc, regularize);
                 if (!(s.pdf > 0.0f && !is_black(s.f))) continue;
                 float ct = std::fabs(dot(s.wi, w.g.ns));
                 Spec nb = s.is_specular ? w.beta * s.f : w.beta * s.f * ct / s.pdf;

@@ -34,7 +34,7 @@ def test_library_loads_and_exports_every_declared_symbol():
 
 def test_struct_sizes_match_header_layout():
     # sizes computed from the header by hand; a drift between ctypes and C would corrupt every upload
-    assert C.sizeof(A.HkMaterial) == 4 + 4 + 12 + 12 + 16 + 32 + 8 + 8
+    assert C.sizeof(A.HkMaterial) == 4 + 4 + 12 + 12 + 16 + 32 + 16 + 8 + 8
     assert C.sizeof(A.HkLightBVHNode) == 64
     assert C.sizeof(A.HkMediumInterface) == 12
     assert C.sizeof(A.HkRenderParams) == 44

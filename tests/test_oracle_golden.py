@@ -489,3 +489,44 @@ def test_rgb_grid_medium_known_answers_on_the_oracle():
     img = vp(scene, film, camf(film))
     assert np.isfinite(img).all() and img.max() > 0.05
     vp.close()
+
+
+def test_textured_matte_known_answers_on_the_oracle():
+    """MatteMaterial.Kd as a texture (eval_tex -> _sample_texture_bilinear, texture-ref.jl:72-190): known answers of the reference's
+    formula on a 2x3 image — px = u (w-1) + 1, py = (1-v)(h-1) + 1, so (u, v) = (0, 1) is data[1, 1], (1, 0) is data[h, w], the
+    centre is the mean of the four middle texels, and uv outside [0, 1] clamps to the border; then clamp to [0, 1] and uplift
+    (a gray texel uplifts to a constant spectrum, so f = Kd / pi exactly)."""
+    tex = np.zeros((2, 3, 3), f32)
+    tex[0, 0] = 0.2; tex[0, 1] = 0.4; tex[0, 2] = 0.6          # row 1 (v = 1): gray levels
+    tex[1, 0] = 0.8; tex[1, 1] = 1.4; tex[1, 2] = -0.3         # row 2 (v = 0): 1.4 and -0.3 clamp to 1 and 0
+    mat = H.MatteMaterial(Kd=H.Texture(tex))
+    def kd_at(u, v):
+        # a one-triangle scene whose three vertices all carry the same uv: every hit evaluates the texture there
+        s = H.Scene()
+        s.push(H.Mesh([(0, 0, 0), (1, 0, 0), (0, 1, 0)], [(0, 1, 2)], uvs=[(u, v)] * 3), mat)
+        s.push(H.DirectionalLight((np.pi,) * 3, (0, 0, -1), legacy_rgbspectrum=True))
+        s.sync()
+        film = H.Film((8, 8))
+        cam = H.PerspectiveCamera((0.25, 0.25, 2.0), (0.25, 0.25, 0.0), film, fov=5.0)
+        vp = H.VolPath(samples=4, max_depth=1, backend=oracle_backend.make_backend())
+        img = vp(s, film, cam)
+        vp.close()
+        return img[3:5, 3:5].mean(axis=(0, 1))                   # depth 1, light along the normal: L = Kd / pi * pi * 1 -> Kd (gray)
+    base = kd_at(0.0, 1.0)
+    assert np.allclose(base / base[1], [base[0] / base[1], 1.0, base[2] / base[1]])
+    rel = lambda u, v: kd_at(u, v)[1] / base[1] * 0.2             # in units where data[1, 1] = 0.2
+    assert abs(rel(0.0, 1.0) - 0.2) < 1e-6
+    assert abs(rel(1.0, 1.0) - 0.6) < 2e-3 and abs(rel(0.5, 1.0) - 0.4) < 2e-3
+    assert abs(rel(0.0, 0.0) - 0.8) < 2e-3
+    assert abs(rel(0.5, 0.0) - 1.0) < 4e-3                        # 1.4 clamps to 1
+    assert rel(1.0, 0.0) < 1e-3                                   # -0.3 clamps to 0
+    assert abs(rel(0.25, 1.0) - 0.3) < 2e-3                       # halfway between 0.2 and 0.4
+    assert abs(rel(0.25, 0.5) - 0.5 * (0.3 + 0.5 * (0.8 + 1.4))) < 4e-3      # bilinear BEFORE the clamp: (0.3 + 1.1) / 2 = 0.7
+    assert abs(rel(-3.0, 7.0) - 0.2) < 2e-3 and abs(rel(0.0, -2.0) - 0.8) < 2e-3      # no wrap: clamped indices
+    # and the whole textured scene renders on the oracle
+    scene, camf = scenes.textured_spheres(12)
+    film = H.Film((64, 36))
+    vp = H.VolPath(samples=2, max_depth=3, backend=oracle_backend.make_backend())
+    img = vp(scene, film, camf(film))
+    assert np.isfinite(img).all() and img.max() > 0.05
+    vp.close()

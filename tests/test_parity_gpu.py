@@ -359,6 +359,7 @@ IMAGE_CASES = [
     # every hit on the panels runs the LayeredBxDF walk (RNG seeded from direction bits), twice per crossing: per-pixel agreement is
     # the lowest of the hashed class (0.77 measured at 16 spp), means agree to 0.1 %
     ("coated_difftrans", lambda: scenes.coated_difftrans_panels(16), (96, 54), 16, 6, "hashed:0.70"),
+    ("textured_matte", lambda: scenes.textured_spheres(20), (128, 72), 4, 5, "strict"),
     ("c3_small", lambda: scenes.c3_many_lights(300, 24), (96, 54), 4, 6, "strict"),
     ("c4_cloud_small", lambda: scenes.c4_cloud((32, 32, 16), "nanovdb", (8, 8, 8)), (64, 36), 4, 8, "hashed"),
     ("c4_grid_small", lambda: scenes.c4_cloud((32, 32, 16), "grid", (8, 8, 8)), (64, 36), 4, 8, "hashed"),
@@ -738,6 +739,10 @@ def test_error_paths_return_status_codes_not_crashes():
     bad = A.HkMaterial(type=99)
     iface = A.HkMediumInterface(1, 0, 0)
     assert lib.hk_upload_materials(ctx, C.byref(bad), 1, C.byref(iface), 1) < 0 and b"unsupported material" in lib.hk_last_error(ctx)
+    texm = A.HkMaterial(type=A.HK_MAT_MATTE); texm.tex[0] = 3
+    assert lib.hk_upload_materials(ctx, C.byref(texm), 1, C.byref(iface), 1) < 0 and b"hk_upload_textures" in lib.hk_last_error(ctx)
+    texg = A.HkMaterial(type=A.HK_MAT_GLASS); texg.tex[1] = 1
+    assert lib.hk_upload_materials(ctx, C.byref(texg), 1, C.byref(iface), 1) < 0 and b"MatteMaterial.Kd only" in lib.hk_last_error(ctx)
     mix = A.HkMaterial(type=A.HK_MAT_MIX); mix.ival[0] = 1; mix.ival[1] = 7
     assert lib.hk_upload_materials(ctx, C.byref(mix), 1, C.byref(iface), 1) < 0 and b"MixMaterial" in lib.hk_last_error(ctx)
     p = A.HkRenderParams(0, 10, 5, 1, 1, 10.0, 0, 12, 15, 0, 1)
