@@ -248,9 +248,16 @@ def analytic_sky(res=512, sun_dir=(1, 2, 9), turbidity=3.0):
     return sky.astype(f32), sd
 
 
-def c3_many_lights(n_emitters=10000, sphere_tess=128, seed=1234):
+def c3_many_lights(n_emitters=10000, sphere_tess=128, seed=1234, sky_model="analytic"):
+    """sky_model = "hosek": the reference's own sunsky_to_envlight bake (hikari_jl_b200/sunsky.py); "analytic" (default, what the
+    round-1 C3 numbers were measured with): the smooth stand-in above in the same layout."""
     s = H.Scene()
-    sky, sd = analytic_sky(512)
+    if sky_model == "hosek":
+        from . import sunsky
+        sky, sd = sunsky.sunsky_sky_data((1, 2, 9), turbidity=3.0, ground_enabled=False, resolution=512)
+        sd = sd.astype(np.float64)
+    else:
+        sky, sd = analytic_sky(512)
     s.push(H.EnvironmentLight(H.EnvironmentMap(sky), scale=tuple([float(f32(1.0) / f32(10567.0))] * 3)))
     s.push(H.SunLight((5.0, 4.75, 4.25), -sd))
     s.push(H.uv_sphere((0, 0, 0), 1.0, sphere_tess, sphere_tess), H.GlassMaterial(index=1.5))

@@ -239,3 +239,55 @@ def test_nanovdb_file_round_trip(tmp_path):
     # the reference keeps `vec` un-rotated ("vec is in medium space ... for the bunny scene vec = 0, so this is fine", :1350-1355):
     # restated as is, so for a grid with a non-zero vec the rotated medium samples a shifted window of the tree
     assert mr.meta["vec"] == med.meta["vec"] and mr.majorant.max() > 0
+
+
+def test_hosek_wilkie_sky_bake():
+    """sunsky_to_envlight (src/lights/sun_sky.jl): the published Hosek-Wilkie dataset (11 bands x [2 albedos][10 turbidities][6 control
+    points][9 coefficients]) and the bake.  Upstream holds no vector for it (and cannot run here), so this pins the structure the
+    model's own formulas imply: Bernstein interpolation reproduces the dataset's end control points at elevation 0 and 90 degrees,
+    turbidity / albedo blending is linear, spectral radiance is linear between bands and zero outside 320-720 nm, the sky is
+    symmetric about the sun's azimuth, bluer at the zenith than towards the horizon, brightens towards the sun, and the returned
+    lights carry the reference's scales (env 1 / 10567, sun 5 (1, 0.95, 0.85) from the sun's direction)."""
+    import numpy as np
+    from hikari_jl_b200 import sunsky as S
+    cfg, rad = S._dataset()
+    assert cfg.shape == (11, 1080) and rad.shape == (11, 120) and np.isfinite(cfg).all() and np.isfinite(rad).all()
+    d = cfg[4].reshape(2, 10, 6, 9)
+    assert np.allclose(S._cook(cfg[4], 9, 3.0, 0.0, 0.0), d[0, 2, 0]) and np.allclose(S._cook(cfg[4], 9, 3.0, 1.0, np.pi / 2), d[1, 2, 5])
+    a, b, m = (S._cook(cfg[4], 9, t, 0.25, 0.7) for t in (3.0, 4.0, 3.5))
+    assert np.allclose(m, 0.5 * (a + b))
+    a, b, m = (S._cook(rad[4], 1, 3.0, al, 0.7) for al in (0.0, 1.0, 0.5))
+    assert np.allclose(m, 0.5 * (a + b))
+    assert np.allclose(S._cook(cfg[4], 9, 10.0, 0.0, 0.3), S._bernstein5((0.3 / (np.pi / 2)) ** (1 / 3), np.moveaxis(d[0, 9], 0, -1)))      # turbidity 10: no upper neighbour (:52)
+    st = S.HosekState(3.0, 0.5, 1.0)
+    th, ga = np.array([0.3, 0.9, 1.4]), np.array([0.5, 0.2, 1.1])
+    r480, r520, r500 = (S.hosek_spectral_radiance(st, th, ga, w) for w in (480.0, 520.0, 500.0))
+    assert (r480 > 0).all() and np.allclose(r500, 0.5 * (r480 + r520))
+    assert (S.hosek_spectral_radiance(st, th, ga, 300.0) == 0).all() and (S.hosek_spectral_radiance(st, th, ga, 800.0) == 0).all()
+    sky, sd = S.sunsky_sky_data((0.0, 1.0, 0.6), turbidity=3.0, ground_enabled=False, resolution=64)
+    assert sky.shape == (64, 64, 3) and sky.dtype == np.float32 and np.isfinite(sky).all() and sky.min() >= 0 and sky.max() > 0.05
+    c = (np.arange(64, dtype=np.float32) + 0.5) / 64
+    U, V = np.meshgrid(c, c, indexing="xy")
+    wi = S.equal_area_square_to_sphere(U, V)
+    assert np.allclose(np.linalg.norm(wi, axis=-1), 1.0, atol=1e-5)
+    assert np.allclose(sky, sky[:, ::-1], rtol=2e-4, atol=1e-6)                     # sun in the y-z plane: mirror symmetry in x (u -> 1 - u)
+    up = wi[..., 2] > 0
+    zen, hor = sky[wi[..., 2] > 0.9].mean(0), sky[up & (wi[..., 2] < 0.15)].mean(0)
+    assert zen[2] / zen[0] > hor[2] / hor[0] > 1.0                                   # blue sky, bluer overhead
+    cg = (wi * sd).sum(-1)
+    assert sky[up & (cg > 0.97)].mean() > sky[up & (cg < 0.0)].mean()               # aureole
+    g, _ = S.sunsky_sky_data((0.0, 1.0, 0.6), ground_albedo=(0.3, 0.2, 0.1), resolution=32)
+    c32 = (np.arange(32, dtype=np.float32) + 0.5) / 32
+    w32 = S.equal_area_square_to_sphere(*np.meshgrid(c32, c32, indexing="xy"))
+    assert np.allclose(g[w32[..., 2] <= 0], np.float32([0.09, 0.06, 0.03]))          # ground_albedo * 0.3 (:398-401)
+    env, sun = S.sunsky_to_envlight((1, 2, 9), intensity=2.0, turbidity=3.0, ground_enabled=False, resolution=32)
+    assert np.allclose(env.scale, 2.0 / 10567.0) and env.env_map.data.shape == (32, 32, 3)
+    n = np.array([1, 2, 9], np.float64); n /= np.linalg.norm(n)
+    assert isinstance(sun, H.SunLight)
+    # the C3 scene builds and renders with the baked sky on the oracle
+    scene, camf = scenes.c3_many_lights(40, 12, sky_model="hosek")
+    film = H.Film((48, 27))
+    vp = H.VolPath(samples=2, max_depth=4, backend=oracle_backend.make_backend())
+    img = vp(scene, film, camf(film))
+    assert np.isfinite(img).all() and img.max() > 0
+    vp.close()
