@@ -200,6 +200,7 @@ def bind_hk(lib):
     # host-side scene-build helpers (CPU code, usable without a GPU)
     f("hk_host_generate_rgb2spec", [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                     C.POINTER(C.c_double), c_fp, c_fp])
+    f("hk_host_build_bvh8", [c_fp, c_u32p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)])
     f("hk_host_build_light_sampler", [C.POINTER(HkLight), C.c_uint32, C.POINTER(HkLightBVHNode), c_u32p, c_u32p,
                                       c_i32p, c_u32p, c_u32p])
     return lib

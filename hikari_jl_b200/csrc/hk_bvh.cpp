@@ -294,3 +294,16 @@ void hk_build_bvh8(const float* positions, const uint32_t* indices, uint32_t n_t
         out.nodes[cur.out_idx] = node;
     }
 }
+
+// Host-only entry point (no GPU needed): build the BVH8 of a triangle soup and hand back its node / triangle arrays, so the
+// builder's invariants can be tested on the CPU (tests/test_host_logic.py).  Returns the sizes; copies only when they fit.
+extern "C" int32_t hk_host_build_bvh8(const float* positions, const uint32_t* indices, uint32_t n_tris, void* out_nodes, uint64_t nodes_cap,
+                                      void* out_tris, uint64_t tris_cap, uint64_t* n_nodes, uint64_t* n_out_tris) {
+    if (!positions || !indices || !n_nodes || !n_out_tris) return -1;
+    HkBvh bvh;
+    hk_build_bvh8(positions, indices, n_tris, bvh);
+    *n_nodes = bvh.nodes.size(); *n_out_tris = bvh.tris.size();
+    if (out_nodes && nodes_cap >= bvh.nodes.size()) std::memcpy(out_nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(HkBvhNode));
+    if (out_tris && tris_cap >= bvh.tris.size()) std::memcpy(out_tris, bvh.tris.data(), bvh.tris.size() * sizeof(HkBvhTri));
+    return 0;
+}

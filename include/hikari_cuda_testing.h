@@ -62,6 +62,10 @@ int32_t hk_host_generate_rgb2spec(int32_t res, const double* cie_x, const double
                                   const double* d65_normalised, float* out_scale, float* out_coeffs);
 int32_t hk_host_build_light_sampler(const HkLight* lights, uint32_t n_lights, HkLightBVHNode* out_nodes, uint32_t* out_n_nodes,
                                     uint32_t* out_trails, int32_t* out_infinite, uint32_t* out_n_infinite, uint32_t* out_n_bvh);
+/* the BVH8 builder on its own (csrc/hk_bvh.cpp; replaces Raycore's accel build): nodes are 80-byte HkBvhNode records, triangles
+ * 48-byte HkBvhTri records (csrc/hk_bvh.h).  Always returns the sizes; copies when the capacities (in records) suffice. */
+int32_t hk_host_build_bvh8(const float* positions, const uint32_t* indices, uint32_t n_tris, void* out_nodes, uint64_t nodes_cap,
+                           void* out_tris, uint64_t tris_cap, uint64_t* n_nodes, uint64_t* n_out_tris);
 #ifdef __cplusplus
 }
 #endif

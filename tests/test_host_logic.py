@@ -291,3 +291,95 @@ def test_hosek_wilkie_sky_bake():
     img = vp(scene, film, camf(film))
     assert np.isfinite(img).all() and img.max() > 0
     vp.close()
+
+
+def _build_bvh8(positions, faces):
+    lib = A.load_library()
+    pos = np.ascontiguousarray(positions, dtype=np.float32); idx = np.ascontiguousarray(faces, dtype=np.uint32)
+    nn, nt = C.c_uint64(), C.c_uint64()
+    assert lib.hk_host_build_bvh8(fp(pos), idx.ctypes.data_as(A.c_u32p), len(idx), None, 0, None, 0, C.byref(nn), C.byref(nt)) == 0
+    nodes = np.zeros((nn.value, 80), np.uint8); tris = np.zeros((nt.value, 12), np.float32)
+    assert lib.hk_host_build_bvh8(fp(pos), idx.ctypes.data_as(A.c_u32p), len(idx), nodes.ctypes.data, nn.value, tris.ctypes.data, nt.value,
+                                  C.byref(nn), C.byref(nt)) == 0
+    return nodes, tris
+
+
+def _check_bvh8(positions, faces):
+    """Structural invariants the traversal kernel relies on (csrc/hk_bvh.h): every triangle stored exactly once with its own vertices;
+    per node <= 8 children, internal children contiguous from child_base in slot order, leaf children of 1..3 triangles located by the
+    unary counts in `trivalid`; and — what makes closest hit exact — the 8-bit quantised box of every child slot, decoded the way the
+    kernel does (p + q * 2^(e-127)), CONTAINS every triangle below that child."""
+    positions = np.asarray(positions, np.float32); faces = np.asarray(faces, np.uint32)
+    nodes, tris = _build_bvh8(positions, faces)
+    n = len(faces)
+    prim = tris.view(np.uint32)[:, 3]
+    assert len(tris) == n and np.array_equal(np.sort(prim), np.arange(n)), "every triangle exactly once"
+    v0, v1, v2 = (positions[faces[prim, k]] for k in range(3))
+    assert np.array_equal(tris[:, 0:3], v0) and np.array_equal(tris[:, 4:7], v1 - v0) and np.array_equal(tris[:, 8:11], v2 - v0)
+    tri_lo, tri_hi = np.minimum(np.minimum(v0, v1), v2), np.maximum(np.maximum(v0, v1), v2)      # per stored triangle
+    p = nodes[:, 0:12].copy().view(np.float32)
+    e = nodes[:, 12:15].astype(np.int32); imask = nodes[:, 15]
+    child_base, tri_base, trivalid = (nodes[:, o:o + 4].copy().view(np.uint32)[:, 0] for o in (16, 20, 24))
+    qlo = nodes[:, 32:56].reshape(-1, 3, 8).astype(np.float32); qhi = nodes[:, 56:80].reshape(-1, 3, 8).astype(np.float32)
+    scale = (e.astype(np.uint32) << 23).view(np.float32)                                         # 2^(e-127), as the kernel builds it
+    seen_nodes, seen_tris = np.zeros(len(nodes), bool), np.zeros(n, bool)
+    seen_nodes[0] = True
+    n_children = []
+
+    def visit(ni):
+        """returns (lo, hi) of everything below node ni"""
+        lo, hi = np.full(3, np.inf, np.float32), np.full(3, -np.inf, np.float32)
+        nint, kids = 0, 0
+        for s in range(8):
+            cnt = bin((int(trivalid[ni]) >> (3 * s)) & 7).count("1")
+            internal = (imask[ni] >> s) & 1
+            assert not (internal and cnt), "a slot is a node or a leaf, not both"
+            if not internal and not cnt:
+                continue
+            kids += 1
+            if internal:
+                ci = int(child_base[ni]) + nint; nint += 1
+                assert not seen_nodes[ci], "node referenced twice"
+                seen_nodes[ci] = True
+                clo, chi = visit(ci)
+            else:
+                assert ((int(trivalid[ni]) >> (3 * s)) & 7) in (1, 3, 7), "unary triangle count"
+                first = int(tri_base[ni]) + bin(int(trivalid[ni]) & ((1 << (3 * s)) - 1)).count("1")
+                ids = np.arange(first, first + cnt)
+                assert not seen_tris[ids].any(); seen_tris[ids] = True
+                assert (np.diff(prim[ids].astype(np.int64)) > 0).all(), "leaf triangles in increasing primitive order (tie-break relies on ids, not order, but the layout is deterministic)"
+                clo, chi = tri_lo[ids].min(axis=0), tri_hi[ids].max(axis=0)
+            blo = p[ni] + qlo[ni, :, s] * scale[ni]; bhi = p[ni] + qhi[ni, :, s] * scale[ni]
+            assert (blo <= clo).all() and (bhi >= chi).all(), f"quantised box of node {ni} slot {s} does not contain its subtree"
+            lo, hi = np.minimum(lo, clo), np.maximum(hi, chi)
+        n_children.append(kids)
+        assert 1 <= kids <= 8
+        return lo, hi
+
+    import sys
+    sys.setrecursionlimit(10000)
+    visit(0)
+    assert seen_nodes.all() and seen_tris.all(), "no orphan nodes or triangles"
+    return len(nodes), float(np.mean(n_children))
+
+
+def test_bvh8_builder_invariants():
+    rng = np.random.RandomState(0)
+    # random soup
+    c = rng.uniform(-3, 3, size=(3000, 1, 3)); soup = (c + rng.normal(scale=0.15, size=(3000, 3, 3))).reshape(-1, 3)
+    nn, avg = _check_bvh8(soup, np.arange(9000).reshape(-1, 3))
+    assert avg > 5.0, f"SAH-optimal collapse should fill the 8-wide nodes (got {avg:.2f} children per node)"
+    # a tessellated mesh (shared vertices, coherent), plus a flat axis-aligned floor (zero extent on one axis)
+    m = H.uv_sphere((0.3, -0.2, 1.0), 0.8, 40, 40)
+    _check_bvh8(m.positions, m.faces)
+    f = H.rect3((-5, -1, -5), (10, 0.0, 10))
+    _check_bvh8(f.positions, f.faces)
+    # coincident duplicates, degenerate (zero-area) triangles, a huge dynamic range of sizes, and the one-triangle scene
+    tri = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    dup = np.concatenate([tri] * 7 + [np.zeros((3, 3), np.float32), tri * 1e-4 + 5, tri * 1e4 - 7e3])
+    _check_bvh8(dup, np.arange(len(dup)).reshape(-1, 3))
+    assert _check_bvh8(tri, [[0, 1, 2]])[0] == 1
+    # every sizable instance again, a few thousand elongated slivers (stress for the quantiser's conservative rounding)
+    a = rng.uniform(-1, 1, size=(2000, 3)); d = rng.normal(size=(2000, 3)) * rng.uniform(1e-3, 2.0, size=(2000, 1))
+    sl = np.stack([a, a + d, a + d + rng.normal(scale=1e-4, size=(2000, 3))], 1).reshape(-1, 3)
+    _check_bvh8(sl, np.arange(6000).reshape(-1, 3))
