@@ -52,6 +52,13 @@
 #define HK_C_SHCUR_RATIO 44    // + r: work cursor of the ratio-tracking pass of shadow round r
 #define HK_SHADOW_ROUNDS 10    // trace_shadow_transmittance: at most 10 segments (intersection.jl:302-406)
 #define HK_N_COUNTERS 64
+static_assert(HK_C_SHROUND0 + HK_SHADOW_ROUNDS < HK_C_SHCUR_TRACE && HK_C_SHCUR_TRACE + HK_SHADOW_ROUNDS < HK_C_SHCUR_RATIO &&
+              HK_C_SHCUR_RATIO + HK_SHADOW_ROUNDS < HK_C_HIT1, "shadow-round counters overlap the second bank of hit-queue counters");
+static_assert(HK_HIT_COUNTER(7) == 15 && HK_HIT_COUNTER(8) == HK_C_HIT1 && HK_HIT_COUNTER(HK_N_HIT_QUEUES - 1) < HK_N_COUNTERS,
+              "hit-queue counters must stay inside the counter block");
+static_assert(HK_TYPE_QUEUE(HK_MAT_COATED_CONDUCTOR) == 0 && HK_TYPE_QUEUE(HK_MAT_COATED_DIFFUSE_TRANSMISSION) == 8 &&
+              HK_TYPE_QUEUE(HK_SHADE_MATTE_TEX) == 9 && HK_TYPE_QUEUE(HK_MAT_DIFFUSE_TRANSMISSION) == 7 && HK_SHADE_MATTE_TEX < 16,
+              "every shading class needs its own hit queue and must fit the 4-bit type field of the hit record");
 
 struct DevScene {
     DevTables T;
