@@ -79,8 +79,10 @@ typedef struct HkGeometry {
 } HkGeometry;
 
 /* ---- textures -----------------------------------------------------------------------------
- * replaces: the texture arrays a Raycore.TextureRef points at (src/textures/texture-ref.jl:50-76).  RGB float images in the
- * reference's own memory order, an (h, w) column-major matrix: texel (row y, column x), 0-based, at rgb[3 * (x * h + y)].
+ * replaces: the texture arrays a Raycore.TextureRef points at (src/textures/texture-ref.jl:50-76).  Packed RGB float images
+ * (the reference's RGBSpectrum texels are r, g, b, alpha: the caller drops alpha, which must be 1 — alpha-tested surfaces are
+ * SURVEY 8f item 2) in the reference's memory order, an (h, w) column-major matrix: texel (row y, column x), 0-based, at
+ * rgb[3 * (x * h + y)].
  * Sampled bilinearly at the hit's interpolated uv exactly as _sample_texture_bilinear (:160-190): px = u (w-1) + 1,
  * py = (1 - v)(h-1) + 1, indices clamped, no wrap.  Upload before the materials that reference them.           */
 typedef struct HkTexture {
