@@ -434,7 +434,11 @@ class Texture:
 
     def __init__(self, data_hw3):
         d = np.asarray(data_hw3, dtype=f32)
-        assert d.ndim == 3 and d.shape[2] == 3, "RGB texture: [h, w, 3]"
+        assert d.ndim == 3 and d.shape[2] in (3, 4), "RGB(A) texture: [h, w, 3] or [h, w, 4]"
+        if d.shape[2] == 4:      # the reference's RGBSpectrum texels carry alpha (spectrum.jl:62-70)
+            if not (d[..., 3] == 1).all():
+                raise NotImplementedError("alpha-tested surfaces (alpha < 1 in a Kd texture, intersection.jl:221-266) are not supported yet")
+            d = d[..., :3]
         self.h, self.w = int(d.shape[0]), int(d.shape[1])
         self.data = np.ascontiguousarray(d.transpose(1, 0, 2))       # [x][y][3] = column-major (h, w)
 
