@@ -435,9 +435,10 @@ class Texture:
     def __init__(self, data_hw3):
         d = np.asarray(data_hw3, dtype=f32)
         assert d.ndim == 3 and d.shape[2] in (3, 4), "RGB(A) texture: [h, w, 3] or [h, w, 4]"
-        if d.shape[2] == 4:      # the reference's RGBSpectrum texels carry alpha (spectrum.jl:62-70)
+        self.alpha = None        # the reference's RGBSpectrum texels carry alpha as their 4th float (spectrum.jl:62-70)
+        if d.shape[2] == 4:
             if not (d[..., 3] == 1).all():
-                raise NotImplementedError("alpha-tested surfaces (alpha < 1 in a Kd texture, intersection.jl:221-266) are not supported yet")
+                self.alpha = np.ascontiguousarray(d[..., 3].T)        # column-major (h, w), like the colours
             d = d[..., :3]
         self.h, self.w = int(d.shape[0]), int(d.shape[1])
         self.data = np.ascontiguousarray(d.transpose(1, 0, 2))       # [x][y][3] = column-major (h, w)
@@ -1186,6 +1187,11 @@ class Backend:
         mats = (A.HkMaterial * max(1, len(scene.materials)))(*[m.to_abi(scene) for m in scene.materials])
         texs = (A.HkTexture * max(1, len(scene._textures)))(*[A.HkTexture(_fp(t.data), t.h, t.w) for t in scene._textures])
         self.call("upload_textures", texs, len(scene._textures))
+        for k, t in enumerate(scene._textures):
+            if t.alpha is not None:
+                if self.prefix == "hk_":       # the CUDA path fails loudly instead of rendering the surface opaque
+                    raise NotImplementedError("alpha-tested surfaces (alpha < 1 in a Kd texture, intersection.jl:221-266, 349-372) are not supported by the CUDA path yet")
+                self.lib.ok_test_upload_texture_alpha(self.ctx, k + 1, _fp(t.alpha))       # oracle-only test hook
         lam = np.concatenate([sp.lambdas for sp in scene._spectra]) if scene._spectra else np.zeros(0, f32)
         val = np.concatenate([sp.values for sp in scene._spectra]) if scene._spectra else np.zeros(0, f32)
         offs = np.cumsum([0] + [len(sp.lambdas) for sp in scene._spectra]).astype(np.uint32)

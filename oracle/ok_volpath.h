@@ -111,6 +111,17 @@ struct Scene {
     std::string err;
 
     TextureStore textures;
+    std::vector<std::vector<float>> tex_alpha;      // per texture: alpha plane (h, w) column-major, empty = opaque (the 4th float of the reference's RGBSpectrum texels)
+    // get_surface_alpha (spectral-eval.jl:3882-3888): alpha of the POINT-sampled Kd texel of a MatteMaterial (_sample_texture_data,
+    // textures/basic.jl:19-25), 1 for every other material (a MixMaterial included)
+    float surface_alpha(uint32_t material, V2 uv) const {
+        const HkMaterial& m = materials[material - 1];
+        if (m.type != HK_MAT_MATTE || m.tex[0] <= 0 || (size_t)m.tex[0] > tex_alpha.size() || tex_alpha[m.tex[0] - 1].empty()) return 1.0f;
+        const int h = textures.h[m.tex[0] - 1], w = textures.w[m.tex[0] - 1];
+        int row = (int)(1.0f + (float)(h - 1) * (1.0f - uv.y)), col = (int)(1.0f + (float)(w - 1) * uv.x);      // unsafe_trunc
+        row = clampi(row, 1, h); col = clampi(col, 1, w);
+        return tex_alpha[m.tex[0] - 1][(size_t)(col - 1) * h + (row - 1)];
+    }
     MatCtx matctx() const { MatCtx c; c.T = &T; c.spectra = &spectra; c.textures = &textures; return c; }
     MatCtx matctx_at(V2 uv) const { MatCtx c = matctx(); c.uv = uv; return c; }      // the TextureFilterContext of one hit
     LightCtx lightctx() const { return LightCtx{&T, lights.data(), (uint32_t)lights.size(), envmaps.data(), (uint32_t)envmaps.size(), &sampler}; }
@@ -328,7 +339,21 @@ inline void Scene::trace_shadow(const ShadowWork& work) {
         bool entering = dot(dir, n) < 0.0f;
         bool transmissive = mi.inside != mi.outside;
         if (!transmissive) {
-            // alpha is 1 for every constant-parameter material in scope (spectral-eval.jl:3882-3888)
+            // stochastic alpha pass-through (:349-372): same hash-seeded test as the trace kernel; the medium is unchanged
+            const float bary_a[3] = {1.0f - h.b1 - h.b2, h.b1, h.b2};
+            const float alpha = surface_alpha(mi.material, uv_bary(h.prim, bary_a));
+            if (alpha < 1.0f) {
+                PCG32 arng = pcg32_init(pbrt_hash(o), pbrt_hash(dir));
+                if (pcg32_f32(arng) > alpha) {
+                    if (cur != 0) {
+                        Spec sT, su, sl; transmittance_ratio_tracking(MC, cur, o, dir, h.t, work.lambda, sT, su, sl);
+                        T_ray = T_ray * sT; tr_u = tr_u * su; tr_l = tr_l * sl;
+                    }
+                    o = o + dir * (h.t + 1.0e-4f);
+                    t_rem = t_rem - h.t - 1.0e-4f;
+                    continue;
+                }
+            }
             T_ray = Spec(0.0f); tr_u = Spec(1.0f); tr_l = Spec(1.0f); visible = false; done = true; break;
         }
         if (cur != 0) {
@@ -435,8 +460,27 @@ inline void Scene::render_sample(int32_t sample_idx) {
                 o_med[i].valid = true; o_med[i].v = m;
                 continue;
             }
-            // vacuum: the alpha loop (:224-266) terminates on its first iteration because every
-            // constant-parameter material has alpha == 1 (spectral-eval.jl:3882-3888)
+            // vacuum: the alpha loop (:221-266).  Alpha-killed surfaces are skipped without consuming depth: the ray restarts 1e-4 behind
+            // the surface, at most 16 times; a ray that is still being skipped after that is absorbed.
+            Ray ray = w.ray;
+            bool absorbed = false;
+            for (int pass = 0; h.hit; pass++) {
+                const HkMediumInterface& mi_a = interfaces[tri_meta[3 * (size_t)h.prim] - 1];
+                const float bary_a[3] = {1.0f - h.b1 - h.b2, h.b1, h.b2};
+                const float alpha = surface_alpha(mi_a.material, uv_bary(h.prim, bary_a));
+                if (!(alpha < 1.0f)) break;
+                PCG32 arng = pcg32_init(pbrt_hash(ray.o), pbrt_hash(ray.d));
+                if (!(pcg32_f32(arng) > alpha)) break;                           // kept: a regular surface hit
+                if (pass == 15) { absorbed = true; break; }                      // the 16th iteration also asked to continue
+                V3 pi_a = ray.o + ray.d * h.t;
+                V3 n_a = geometric_normal(h.prim);
+                V3 off = dot(ray.d, n_a) > 0.0f ? n_a : -n_a;
+                ray = Ray{pi_a + off * 1.0e-4f, ray.d, INF_F, 0.0f};
+                h = closest_hit(ray.o, ray.d, ray.t_max);
+                #pragma omp atomic
+                rays_traced++;
+            }
+            if (absorbed) continue;
             if (!h.hit) {
                 EscapedWork e{w.ray.d, w.lambda, w.pixel_index, w.beta, w.r_u, w.r_l, w.depth, w.specular_bounce, w.prev_p, w.prev_n};
                 o_esc[i].valid = true; o_esc[i].v = e;
@@ -446,7 +490,7 @@ inline void Scene::render_sample(int32_t sample_idx) {
             const HkMediumInterface& mi = interfaces[meta[0] - 1];
             float bary[3] = {1.0f - h.b1 - h.b2, h.b1, h.b2};
             HitSurfaceWork hs;
-            hs.ray = w.ray; hs.g = surface_geometry(h.prim, bary, w.ray.o, w.ray.d, h.t);
+            hs.ray = w.ray; hs.g = surface_geometry(h.prim, bary, ray.o, ray.d, h.t);
             hs.material = mi.material; hs.iface = mi; hs.face_idx = meta[1];
             hs.bary[0] = bary[0]; hs.bary[1] = bary[1]; hs.bary[2] = bary[2];
             hs.arealight_flat_idx = meta[2]; hs.triangle_area = tri_area(h.prim);

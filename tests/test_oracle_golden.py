@@ -530,3 +530,53 @@ def test_textured_matte_known_answers_on_the_oracle():
     img = vp(scene, film, camf(film))
     assert np.isfinite(img).all() and img.max() > 0.05
     vp.close()
+
+
+def test_alpha_tested_surfaces_on_the_oracle():
+    """Alpha pass-through (intersection.jl:221-266 for camera / bounce rays, :349-372 for shadow rays; get_surface_alpha = alpha of the
+    point-sampled Kd texel of a MatteMaterial, spectral-eval.jl:3882-3888).  ORACLE ONLY so far: the CUDA path refuses such textures.
+    Known answers: alpha = 1 is the opaque render bit for bit; alpha = 0 makes the quad vanish (the floor behind it shows, lit, with
+    no shadow — up to the 1e-4 restart offsets); alpha = 0.5 lets about half of the rays through, decided per ray by the hash of its
+    origin and direction, so a repeated render is identical; only MatteMaterial has alpha."""
+    def scene_with(alpha, material="matte"):
+        s = H.Scene()
+        s.push(H.rect3((-4, -1.0, -4), (8, 0.1, 8)), H.MatteMaterial(Kd=(0.7, 0.7, 0.7)))
+        tex = np.zeros((4, 4, 4), f32); tex[..., :3] = (0.9, 0.2, 0.2); tex[..., 3] = alpha
+        quad = H.Mesh([(-1, 0.2, -1), (1, 0.2, -1), (1, 0.2, 1), (-1, 0.2, 1)], [(0, 2, 1), (0, 3, 2)], normals=[(0, 1, 0)] * 4,
+                      uvs=[(0, 0), (1, 0), (1, 1), (0, 1)])
+        s.push(quad, H.MatteMaterial(Kd=H.Texture(tex)) if material == "matte" else H.MatteMaterial(Kd=(0.9, 0.2, 0.2)))
+        s.push(H.DirectionalLight((3, 3, 3), (0, -1, 0), legacy_rgbspectrum=True))
+        s.sync()
+        return s
+    def render(scene):
+        film = H.Film((48, 48))
+        cam = H.PerspectiveCamera((0, 6, 0.001), (0, 0, 0), film, fov=40.0)
+        vp = H.VolPath(samples=8, max_depth=3, backend=oracle_backend.make_backend())
+        img = vp(scene, film, cam).copy()
+        rays = oracle_backend.lib().ok_rays_traced(vp.backend.ctx)
+        vp.close()
+        return img, rays
+    opaque, r1 = render(scene_with(1.0))
+    plain, r1b = render(scene_with(1.0, material="const"))
+    assert np.allclose(opaque, plain, rtol=1e-5, atol=1e-7) and r1 == r1b    # alpha == 1 everywhere: an opaque quad (the bilinear filter rounds 0.9 by an ulp)
+    gone, r0 = render(scene_with(0.0))
+    floor_only = H.Scene()
+    floor_only.push(H.rect3((-4, -1.0, -4), (8, 0.1, 8)), H.MatteMaterial(Kd=(0.7, 0.7, 0.7)))
+    floor_only.push(H.DirectionalLight((3, 3, 3), (0, -1, 0), legacy_rgbspectrum=True)); floor_only.sync()
+    bare, rb = render(floor_only)
+    assert np.allclose(gone, bare, rtol=1e-3, atol=1e-4) and r0 > rb          # same picture, more rays (every pass-through is a re-trace)
+    centre = (slice(18, 30), slice(18, 30))
+    assert opaque[centre][..., 0].mean() > 2 * opaque[centre][..., 1].mean()    # the red quad
+    assert abs(gone[centre][..., 0].mean() - gone[centre][..., 1].mean()) < 1e-3   # gray floor, unshadowed
+    half, rh = render(scene_with(0.5))
+    half2, _ = render(scene_with(0.5))
+    assert np.array_equal(half, half2)                                         # hash-seeded: deterministic
+    mix = half[centre].mean(axis=(0, 1)); a, b = opaque[centre].mean(axis=(0, 1)), gone[centre].mean(axis=(0, 1))
+    # half of the camera rays stop on the quad (a); the other half reach the floor, where half of the shadow rays are blocked: 0.5 a + 0.25 b
+    expect = 0.5 * a[1] + 0.25 * b[1]
+    assert abs(mix[1] - expect) < 0.08 * b[1], (mix[1], expect)
+    assert rb < rh < r0 + (r0 - rb)
+    # the CUDA path refuses instead of rendering the quad opaque
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        film = H.Film((8, 8)); cam = H.PerspectiveCamera((0, 6, 0.001), (0, 0, 0), film, fov=40.0)
+        H.VolPath(samples=1, max_depth=2)(scene_with(0.5), film, cam)
