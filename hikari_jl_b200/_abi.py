@@ -16,7 +16,7 @@ HK_MAT_COATED_DIFFUSE, HK_MAT_THIN_DIELECTRIC, HK_MAT_DIFFUSE_TRANSMISSION = 5, 
 HK_MAT_MIX = 8
 HK_MAT_COATED_CONDUCTOR = 9
 HK_MAT_COATED_DIFFUSE_TRANSMISSION = 10
-HK_MATFLAG_REMAP_ROUGHNESS, HK_MATFLAG_SPECTRAL_ETA_K, HK_MATFLAG_USE_ETA_K = 1, 2, 4
+HK_MATFLAG_REMAP_ROUGHNESS, HK_MATFLAG_SPECTRAL_ETA_K, HK_MATFLAG_USE_ETA_K, HK_MATFLAG_VERTEX_COLORS = 1, 2, 4, 8
 HK_LIGHT_POINT, HK_LIGHT_SPOT, HK_LIGHT_DIRECTIONAL, HK_LIGHT_SUN = 1, 2, 3, 4
 HK_LIGHT_ENVIRONMENT, HK_LIGHT_AMBIENT, HK_LIGHT_DIFFUSE_AREA = 5, 6, 7
 HK_SPECTRUM_RGB, HK_SPECTRUM_ILLUMINANT = 0, 1

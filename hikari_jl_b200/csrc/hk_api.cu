@@ -299,6 +299,7 @@ int32_t hk_upload_textures(HkContext* ctx, const HkTexture* t, uint32_t n) {
     return HK_OK;
 }
 static int32_t mat_textures_ok(HkContext* ctx, const HkMaterial& m) {
+    REQUIRE(m.type == HK_MAT_MIX || !(m.flags & HK_MATFLAG_VERTEX_COLORS), "VertexColorTexture parameters are not supported yet (SURVEY 8f item 2)");
     for (int k = 0; k < 4; k++) {
         if (m.tex[k] == 0) continue;
         REQUIRE(k == 0 && m.type == HK_MAT_MATTE, "textured parameters are supported for MatteMaterial.Kd only (SURVEY 8f item 2)");

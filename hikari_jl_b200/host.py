@@ -444,6 +444,17 @@ class Texture:
         self.data = np.ascontiguousarray(d.transpose(1, 0, 2))       # [x][y][3] = column-major (h, w)
 
 
+class VertexColorTexture(Texture):
+    """src/textures/basic.jl:43-46: three corner colours per face, face_colors[n_faces, 3, 3] (face, corner, rgb); evaluated by
+    barycentric interpolation with the hit's face index (texture-ref.jl:240-245).  Stored as the reference's (3, n_faces) matrix."""
+
+    def __init__(self, face_colors):
+        d = np.asarray(face_colors, dtype=f32)
+        assert d.ndim == 3 and d.shape[1:] == (3, 3), "face_colors: [n_faces, 3 corners, 3]"
+        self.h, self.w, self.alpha = 3, int(d.shape[0]), None
+        self.data = np.ascontiguousarray(d)                          # [face][corner][3] = column-major (3, n_faces)
+
+
 class MatteMaterial(Material):            # uber-material.jl:180-183, 256
     type = A.HK_MAT_MATTE
 
@@ -454,6 +465,8 @@ class MatteMaterial(Material):            # uber-material.jl:180-183, 256
         m = A.HkMaterial(type=self.type)
         if isinstance(self.Kd, Texture):
             m.tex[0] = scene._texture_id(self.Kd)                     # a TextureRef in the reference (texture-ref.jl:196-199)
+            if isinstance(self.Kd, VertexColorTexture):
+                m.flags |= A.HK_MATFLAG_VERTEX_COLORS
         else:
             m.rgb0[:] = self.Kd
         m.f[0] = self.sigma
@@ -1187,6 +1200,8 @@ class Backend:
         mats = (A.HkMaterial * max(1, len(scene.materials)))(*[m.to_abi(scene) for m in scene.materials])
         texs = (A.HkTexture * max(1, len(scene._textures)))(*[A.HkTexture(_fp(t.data), t.h, t.w) for t in scene._textures])
         self.call("upload_textures", texs, len(scene._textures))
+        if self.prefix == "hk_" and any(isinstance(t, VertexColorTexture) for t in scene._textures):
+            raise NotImplementedError("VertexColorTexture parameters (texture-ref.jl:240-245) are not supported by the CUDA path yet")
         for k, t in enumerate(scene._textures):
             if t.alpha is not None:
                 if self.prefix == "hk_":       # the CUDA path fails loudly instead of rendering the surface opaque

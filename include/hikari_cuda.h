@@ -110,6 +110,9 @@ typedef struct HkTexture {
 
 #define HK_MATFLAG_REMAP_ROUGHNESS  1u
 #define HK_MATFLAG_SPECTRAL_ETA_K   2u  /* conductor eta/k are piecewise-linear spectra (ids in spec[]) */
+#define HK_MATFLAG_VERTEX_COLORS    8u  /* tex[0] is a VertexColorTexture (src/textures/basic.jl:43-46, texture-ref.jl:240-245): a (3, n_faces)
+                                           table of per-face corner colours = an HkTexture with h = 3, w = n_faces, evaluated as
+                                           sum_k data[k, face] * bary[k].  Not built on the CUDA path yet: refused at upload  */
 #define HK_MATFLAG_USE_ETA_K        4u  /* CoatedConductor: rgb0 / rgb1 (or spec[]) are eta / k; clear = rgb0 is the
                                            artist reflectance (use_eta_k, coated-conductor.jl:98)                   */
 

@@ -19,6 +19,7 @@ struct MatCtx {   // what the reference passes around as (table, textures) + the
     const HkSpectra* spectra;
     const TextureStore* textures = nullptr;
     V2 uv = V2(0.0f, 0.0f);
+    uint32_t face_idx = 0; float bary[3] = {0.0f, 0.0f, 0.0f};      // TextureFilterContext.face_idx / bary (vertex colours)
 };
 // _sample_texture_bilinear, src/textures/texture-ref.jl:160-190, on an (h, w) column-major RGB image
 inline void sample_texture_bilinear(const TextureStore& S, int32_t id, V2 uv, float* out) {
@@ -39,7 +40,13 @@ inline void sample_texture_bilinear(const TextureStore& S, int32_t id, V2 uv, fl
 }
 // eval_tex(textures, mat.Kd, tfc) for a MatteMaterial: the constant, or the bilinear texel at the hit's uv (texture-ref.jl:72-80)
 inline void matte_kd_rgb(const MatCtx& C, const HkMaterial& m, float* kd) {
-    if (m.tex[0] > 0 && C.textures) sample_texture_bilinear(*C.textures, m.tex[0], C.uv, kd);
+    if (m.tex[0] > 0 && C.textures && (m.flags & HK_MATFLAG_VERTEX_COLORS)) {
+        // eval_tex(::VertexColorTexture, tfc), texture-ref.jl:240-245: data[1, fi] b1 + data[2, fi] b2 + data[3, fi] b3 on a (3, n_faces) table
+        const std::vector<float>& d = C.textures->rgb[m.tex[0] - 1];
+        const size_t base = 9 * (size_t)(C.face_idx - 1);
+        for (int c = 0; c < 3; c++) kd[c] = d[base + c] * C.bary[0] + d[base + 3 + c] * C.bary[1] + d[base + 6 + c] * C.bary[2];
+    }
+    else if (m.tex[0] > 0 && C.textures) sample_texture_bilinear(*C.textures, m.tex[0], C.uv, kd);
     else { kd[0] = m.rgb0[0]; kd[1] = m.rgb0[1]; kd[2] = m.rgb0[2]; }
 }
 

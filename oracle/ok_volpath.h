@@ -123,7 +123,9 @@ struct Scene {
         return tex_alpha[m.tex[0] - 1][(size_t)(col - 1) * h + (row - 1)];
     }
     MatCtx matctx() const { MatCtx c; c.T = &T; c.spectra = &spectra; c.textures = &textures; return c; }
-    MatCtx matctx_at(V2 uv) const { MatCtx c = matctx(); c.uv = uv; return c; }      // the TextureFilterContext of one hit
+    MatCtx matctx_at(V2 uv, uint32_t face_idx, const float* bary) const {                // the TextureFilterContext of one hit
+        MatCtx c = matctx(); c.uv = uv; c.face_idx = face_idx; c.bary[0] = bary[0]; c.bary[1] = bary[1]; c.bary[2] = bary[2]; return c;
+    }
     LightCtx lightctx() const { return LightCtx{&T, lights.data(), (uint32_t)lights.size(), envmaps.data(), (uint32_t)envmaps.size(), &sampler}; }
     MediaCtx mediactx() const { return MediaCtx{&T, media.data(), (uint32_t)media.size()}; }
 
@@ -631,7 +633,7 @@ inline void Scene::render_sample(int32_t sample_idx) {
                     if (li < 1 || li > num_lights || pmf <= 0.0f) continue;
                     LightSample ls = sample_light(LC, lights[li - 1], w.g.pi, w.lambda, smp.direct_u);
                     if (!(ls.pdf > 0.0f && !is_black(ls.Li))) continue;
-                    BSDFEval be = eval_material(matctx_at(w.g.uv), materials[w.material - 1], w.wo, ls.wi, w.g.ns, w.lambda);
+                    BSDFEval be = eval_material(matctx_at(w.g.uv, w.face_idx, w.bary), materials[w.material - 1], w.wo, ls.wi, w.g.ns, w.lambda);
                     if (is_black(be.f)) continue;
                     // compute_direct_lighting_spectral, lights.jl:535-600
                     float ct = std::fabs(dot(ls.wi, w.g.ns));
@@ -667,7 +669,7 @@ inline void Scene::render_sample(int32_t sample_idx) {
                 if (new_depth >= params.max_depth) continue;
                 const RaySamples& smp = pixel_samples[w.pixel_index - 1];
                 bool regularize = params.regularize && w.any_non_specular;
-                BSDFSample s = sample_material(matctx_at(w.g.uv), materials[w.material - 1], w.wo, w.g.ns, w.lambda, smp.indirect_u, smp.indirect_uc, regularize);
+                BSDFSample s = sample_material(matctx_at(w.g.uv, w.face_idx, w.bary), materials[w.material - 1], w.wo, w.g.ns, w.lambda, smp.indirect_u, smp.indirect_uc, regularize);
                 if (!(s.pdf > 0.0f && !is_black(s.f))) continue;
                 float ct = std::fabs(dot(s.wi, w.g.ns));
                 Spec nb = s.is_specular ? w.beta * s.f : w.beta * s.f * ct / s.pdf;

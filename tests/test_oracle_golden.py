@@ -580,3 +580,38 @@ def test_alpha_tested_surfaces_on_the_oracle():
     with pytest.raises((NotImplementedError, RuntimeError)):
         film = H.Film((8, 8)); cam = H.PerspectiveCamera((0, 6, 0.001), (0, 0, 0), film, fov=40.0)
         H.VolPath(samples=1, max_depth=2)(scene_with(0.5), film, cam)
+
+
+def test_vertex_color_texture_on_the_oracle():
+    """VertexColorTexture as MatteMaterial.Kd (textures/basic.jl:43-46, texture-ref.jl:240-245): Kd = sum_k face_colors[k, face] * bary[k].
+    ORACLE ONLY so far (the CUDA path refuses it).  Known answers: three equal corner colours are that constant colour (same image as
+    the constant material up to the rounding of b0 + b1 + b2); per-face colours select by TriangleMeta.primitive_index; corner colours
+    interpolate linearly across a triangle."""
+    quad = lambda: H.Mesh([(-1, -1, 0), (1, -1, 0), (1, 1, 0), (-1, 1, 0)], [(0, 1, 2), (0, 2, 3)], normals=[(0, 0, 1)] * 4)
+    def render(kd):
+        s = H.Scene()
+        s.push(quad(), H.MatteMaterial(Kd=kd))
+        s.push(H.DirectionalLight((np.pi,) * 3, (0, 0, -1), legacy_rgbspectrum=True))
+        s.sync()
+        film = H.Film((32, 32))
+        cam = H.PerspectiveCamera((0, 0, 4), (0, 0, 0), film, fov=35.0)
+        vp = H.VolPath(samples=4, max_depth=1, backend=oracle_backend.make_backend())
+        img = vp(s, film, cam).copy()
+        vp.close()
+        return img
+    const = render((0.5, 0.5, 0.5))
+    same = render(H.VertexColorTexture(np.full((2, 3, 3), 0.5, f32)))
+    assert np.allclose(same, const, rtol=1e-5) and const.max() > 0.1
+    fc = np.zeros((2, 3, 3), f32); fc[0] = 0.8; fc[1] = 0.2                    # face 1 light gray, face 2 dark gray
+    two = render(H.VertexColorTexture(fc))
+    # the quad's diagonal runs from (-1,-1) to (1,1): face 1 = lower right (x > y), face 2 = upper left; framebuffer row 0 is the top
+    lower_right, upper_left = two[22:26, 20:24].mean(), two[6:10, 8:12].mean()
+    assert abs(lower_right / upper_left - 4.0) < 0.1, (lower_right, upper_left)
+    grad = np.zeros((2, 3, 3), f32); grad[0, 1] = 1.0; grad[1, :] = 0.0          # face 1: only corner 2 (vertex (1,-1)) is white
+    g = render(H.VertexColorTexture(grad))
+    near, mid = g[25, 25].mean(), g[21, 21].mean()                                # towards the (1,-1) corner the colour rises linearly
+    assert near > mid > 0 and g[6:10, 8:12].max() == 0
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        film = H.Film((8, 8)); cam = H.PerspectiveCamera((0, 0, 4), (0, 0, 0), film, fov=35.0)
+        s = H.Scene(); s.push(quad(), H.MatteMaterial(Kd=H.VertexColorTexture(fc))); s.push(H.PointLight((1, 1, 1), (0, 0, 3))); s.sync()
+        H.VolPath(samples=1, max_depth=2)(s, film, cam)
