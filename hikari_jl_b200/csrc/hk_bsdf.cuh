@@ -85,7 +85,7 @@ HK_DEV float3 tr_sample_wm(float3 w, float2 u, float ax, float ay) {
     float3 t1 = wh.z < 0.99999f ? norm3(cross3(f3(0, 0, 1), wh)) : f3(1, 0, 0);
     float3 t2 = cross3(wh, t1);
     float r = sqrtf(u.x), phi = 2.0f * HK_PI * u.y;
-    float px = r * cosf(phi), py = r * sinf(phi);
+    float px = r * dm_cosf(phi), py = r * dm_sinf(phi);
     float h = sqrtf(1.0f - px * px);
     py = lerpf(h, py, 0.5f * (1.0f + wh.z));
     float pz = sqrtf(fmaxf(0.0f, 1.0f - px * px - py * py));

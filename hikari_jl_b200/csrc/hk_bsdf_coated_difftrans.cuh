@@ -72,7 +72,7 @@ HK_DEV BsdfSample sample_coated_difftrans(const MatCtx& C, const HkMaterial& m, 
         }
         if (w.z == 0.0f) return bsdf_none();
         if (P.has_medium) {
-            float dz = -logf(1.0f - pcg32_f32(rng)) / (1.0f / fabsf(w.z));
+            float dz = -dm_logf(1.0f - pcg32_f32(rng)) / (1.0f / fabsf(w.z));
             float zp = w.z > 0.0f ? z + dz : z - dz;
             if (zp == z) return bsdf_none();
             if (0.0f < zp && zp < P.thickness) {
@@ -176,7 +176,7 @@ HK_DEV BsdfEval eval_coated_difftrans(const MatCtx& C, const HkMaterial& m, floa
                 beta = beta / (1.0f - q);
             }
             if (P.has_medium) {
-                float dz = -logf(1.0f - pcg32_f32(rng)) / (1.0f / fabsf(w.z));
+                float dz = -dm_logf(1.0f - pcg32_f32(rng)) / (1.0f / fabsf(w.z));
                 float zp = w.z > 0.0f ? z + dz : z - dz;
                 if (zp == z) continue;
                 if (0.0f < zp && zp < th) {

@@ -14,7 +14,7 @@ struct IfaceSample { Spec f; float3 wi; float pdf; float eta; bool reflection, s
 HK_DEV IfaceSample iface_invalid() { IfaceSample s; s.f = sp(0.0f); s.wi = f3(0, 0, 0); s.pdf = 0.0f; s.eta = 1.0f; s.reflection = false; s.specular = false; s.valid = false; return s; }
 HK_DEV IfaceSample iface_make(Spec f, float3 wi, float pdf, bool refl, bool spec, float eta) { IfaceSample s; s.f = f; s.wi = wi; s.pdf = pdf; s.eta = eta; s.reflection = refl; s.specular = spec; s.valid = true; return s; }
 
-HK_DEV float layer_tr(float thickness, float3 w) { return fabsf(thickness) <= 1.1920929e-7f ? 1.0f : expf(-fabsf(thickness / w.z)); }   // :837-840
+HK_DEV float layer_tr(float thickness, float3 w) { return fabsf(thickness) <= 1.1920929e-7f ? 1.0f : dm_expf(-fabsf(thickness / w.z)); }   // :837-840
 HK_DEV float hg_phase(float g, float c) {                                                                                                // :879-883
     float g2 = g * g, d = 1.0f + g2 - 2.0f * g * c;
     return (1.0f - g2) / (4.0f * HK_PI * d * sqrtf(fmaxf(1.0e-10f, d)));
@@ -25,7 +25,7 @@ HK_DEV float3 hg_sample_layer(float g, float3 wo, float2 u, float& p) {         
     else { float g2 = g * g; float q = (1.0f - g2) / (1.0f - g + 2.0f * g * u.x); c = clampf((1.0f + g2 - q * q) / (2.0f * g), -1.0f, 1.0f); }
     float s = sqrtf(fmaxf(0.0f, 1.0f - c * c)), phi = 2.0f * HK_PI * u.y;
     Frame fr = make_frame(-wo);
-    float3 wi = norm3(s * cosf(phi) * fr.t + s * sinf(phi) * fr.b + c * (-wo));
+    float3 wi = norm3(s * dm_cosf(phi) * fr.t + s * dm_sinf(phi) * fr.b + c * (-wo));
     p = hg_phase(g, c);
     return wi;
 }
@@ -175,7 +175,7 @@ HK_DEV BsdfSample sample_coated_diffuse(const MatCtx& C, const HkMaterial& m, fl
         }
         if (w.z == 0.0f) return bsdf_none();
         if (P.has_medium) {
-            float dz = -logf(1.0f - pcg32_f32(rng)) / (1.0f / fabsf(w.z));
+            float dz = -dm_logf(1.0f - pcg32_f32(rng)) / (1.0f / fabsf(w.z));
             float zp = w.z > 0.0f ? z + dz : z - dz;
             if (zp == z) return bsdf_none();
             if (0.0f < zp && zp < P.thickness) {
@@ -279,7 +279,7 @@ HK_DEV BsdfEval eval_coated_diffuse(const MatCtx& C, const HkMaterial& m, float3
                 beta = beta / (1.0f - q);
             }
             if (P.has_medium) {
-                float dz = -logf(1.0f - pcg32_f32(rng)) / (1.0f / fabsf(w.z));
+                float dz = -dm_logf(1.0f - pcg32_f32(rng)) / (1.0f / fabsf(w.z));
                 float zp = w.z > 0.0f ? z + dz : z - dz;
                 if (zp == z) continue;
                 if (0.0f < zp && zp < th) {

@@ -53,10 +53,10 @@ __global__ void __launch_bounds__(256) k_denoise_atrous(float* __restrict__ out,
                 const float lum_q = dn_lum(rq, gq, bq);
                 const float3 n_q = f3(normals[3 * q], normals[3 * q + 1], normals[3 * q + 2]);
                 const float w_spatial = K[dxi] * K[dyi];
-                const float w_color = expf(-fabsf(lum_p - lum_q) / es);
+                const float w_color = dm_expf(-fabsf(lum_p - lum_q) / es);
                 const float dotv = dot3(n_p, n_q);
-                const float w_norm = powf(dotv > 0.0f ? dotv : (dotv == dotv ? 0.0f : dotv), P.sigma_normal);       // max(0, dot) ^ sigma; a NaN dot stays NaN as in Julia
-                const float w_depth = expf(-fabsf(d_p - depth[q]) / ds);
+                const float w_norm = dm_powf(dotv > 0.0f ? dotv : (dotv == dotv ? 0.0f : dotv), P.sigma_normal);       // max(0, dot) ^ sigma; a NaN dot stays NaN as in Julia
+                const float w_depth = dm_expf(-fabsf(d_p - depth[q]) / ds);
                 const float w = w_spatial * w_color * w_norm * w_depth;
                 sr += rq * w; sg += gq * w; sb += bq * w; sw += w;
             }

@@ -42,7 +42,7 @@ HK_DEV float3 square_to_sphere(float2 p) {   // :133-160
     float r = 1.0f - fabsf(sd);
     float phi = (r == 0.0f ? 1.0f : (vp - up) / r + 1.0f) * HK_PI / 4.0f;
     float z = copysignf(1.0f - r * r, sd);
-    float cp = copysignf(cosf(phi), u), sn = copysignf(sinf(phi), v);
+    float cp = copysignf(dm_cosf(phi), u), sn = copysignf(dm_sinf(phi), v);
     float rc = r * sqrtf(2.0f - r * r);
     return f3(cp * rc, sn * rc, z);
 }
@@ -150,7 +150,7 @@ HK_DEV LightSample sample_light(const LightCtx& C, const HkLight& L, float3 p, f
         case HK_LIGHT_AMBIENT: {
             float z = 1.0f - 2.0f * u.x;
             float r = sqrtf(fmaxf(0.0f, 1.0f - z * z)), phi = 2.0f * HK_PI * u.y;
-            float3 wi = f3(r * cosf(phi), r * sinf(phi), z);
+            float3 wi = f3(r * dm_cosf(phi), r * dm_sinf(phi), z);
             s.Li = L.scale * light_spectrum(C.T, L, lam); s.wi = wi; s.pdf = 1.0f / (4.0f * HK_PI); s.p_light = p + 1.0e6f * wi; s.delta = false;
             return s;
         }

@@ -6,6 +6,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "hk_detmath.h"
 
 #define HK_DEV __device__ __forceinline__
 #define HK_PI 3.14159265358979323846f
@@ -56,7 +57,7 @@ HK_DEV Spec operator/(Spec a, Spec b) { return sp4(a.x / b.x, a.y / b.y, a.z / b
 HK_DEV Spec operator*(Spec a, float s) { return sp4(a.x * s, a.y * s, a.z * s, a.w * s); }
 HK_DEV Spec operator*(float s, Spec a) { return a * s; }
 HK_DEV Spec operator/(Spec a, float s) { return sp4(a.x / s, a.y / s, a.z / s, a.w / s); }
-HK_DEV Spec sp_exp(Spec a) { return sp4(expf(a.x), expf(a.y), expf(a.z), expf(a.w)); }
+HK_DEV Spec sp_exp(Spec a) { return sp4(dm_expf(a.x), dm_expf(a.y), dm_expf(a.z), dm_expf(a.w)); }
 HK_DEV Spec sp_neg(Spec a) { return sp4(-a.x, -a.y, -a.z, -a.w); }
 HK_DEV Spec sp_max0(Spec a) { return sp4(fmaxf(a.x, 0.0f), fmaxf(a.y, 0.0f), fmaxf(a.z, 0.0f), fmaxf(a.w, 0.0f)); }
 HK_DEV float sp_avg(Spec s) { return (((s.x + s.y) + s.z) + s.w) / 4.0f; }
@@ -68,10 +69,10 @@ HK_DEV float sp_get(Spec s, int i) { return i == 0 ? s.x : (i == 1 ? s.y : (i ==
 HK_DEV float visible_wavelengths_pdf(float l) {
     if (l < 360.0f || l > 830.0f) return 0.0f;
     float x = 0.0072f * (l - 538.0f);
-    float c = coshf(x);
+    float c = dm_coshf(x);
     return 0.0039398042f / (c * c);
 }
-HK_DEV float sample_visible_wavelength(float u) { return 538.0f - 138.888889f * atanhf(0.85691062f - 1.82750197f * u); }
+HK_DEV float sample_visible_wavelength(float u) { return 538.0f - 138.888889f * dm_atanhf(0.85691062f - 1.82750197f * u); }
 HK_DEV void sample_wavelengths_visible(float u, float4& lambda, float4& pdf) {
     float u2 = u + 0.25f; u2 = u2 >= 1.0f ? u2 - 1.0f : u2;
     float u3 = u + 0.5f;  u3 = u3 >= 1.0f ? u3 - 1.0f : u3;
@@ -282,7 +283,7 @@ HK_DEV float2 concentric_sample_disk(float2 u) {
     bool xl = fabsf(ox) > fabsf(oy);
     float r = xl ? ox : oy;
     float th = xl ? (oy / (ox + 1.0e-10f)) * HK_PI / 4.0f : HK_PI / 2.0f - (ox / (oy + 1.0e-10f)) * HK_PI / 4.0f;
-    return make_float2(r * cosf(th), r * sinf(th));
+    return make_float2(r * dm_cosf(th), r * dm_sinf(th));
 }
 HK_DEV float3 cosine_sample_hemisphere(float2 u) {
     float2 d = concentric_sample_disk(u);

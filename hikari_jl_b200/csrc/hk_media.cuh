@@ -23,7 +23,7 @@ HK_DEV float3 sample_hg(float g, float3 wo, float2 u, float& pdf) {             
     else { float g2 = g * g; float q = (1.0f - g2) / (1.0f - g + 2.0f * g * u.x); c = clampf((1.0f + g2 - q * q) / (2.0f * g), -1.0f, 1.0f); }
     float s = sqrtf(fmaxf(0.0f, 1.0f - c * c)), phi = 2.0f * HK_PI * u.y;
     Frame fr = make_frame(-wo);
-    float3 wi = norm3(s * cosf(phi) * fr.t + s * sinf(phi) * fr.b + c * (-wo));
+    float3 wi = norm3(s * dm_cosf(phi) * fr.t + s * dm_sinf(phi) * fr.b + c * (-wo));
     pdf = hg_p(g, c);
     return wi;
 }
@@ -279,7 +279,7 @@ struct DeltaTracker {
         si++;
         const float s0 = smaj.x;
         float u = lcg_next(rng);
-        float dt = -logf(fmaxf(1.0e-10f, 1.0f - u)) / s0;
+        float dt = -dm_logf(fmaxf(1.0e-10f, 1.0f - u)) / s0;
         float ts = t + dt;
         if (ts >= seg_t_max) {
             Spec Tm = sp_exp(-(seg_t_max - t) * smaj);
@@ -360,7 +360,7 @@ struct RatioTracker {
         si++;
         const float s0 = smaj.x;
         float u = pcg32_f32(rng);
-        float dt = -logf(fmaxf(1.0e-10f, 1.0f - u)) / s0;
+        float dt = -dm_logf(fmaxf(1.0e-10f, 1.0f - u)) / s0;
         float ts = t + dt;
         if (ts >= seg_t_max) {
             Spec Tm = sp_exp(-(seg_t_max - t) * smaj);

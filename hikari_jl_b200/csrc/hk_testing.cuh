@@ -4,6 +4,12 @@
 
 #define TK_LOOP(n) for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < (n); i += (uint64_t)gridDim.x * blockDim.x)
 
+__global__ void tk_detmath(int fn, const float* __restrict__ x, const float* __restrict__ y, uint64_t n, float* out) {
+    TK_LOOP(n) {
+        const float a = x[i], b = y ? y[i] : 0.0f;
+        out[i] = fn == 0 ? dm_expf(a) : fn == 1 ? dm_logf(a) : fn == 2 ? dm_sinf(a) : fn == 3 ? dm_cosf(a) : fn == 4 ? dm_coshf(a) : fn == 5 ? dm_atanhf(a) : fn == 6 ? dm_powf(a, b) : dm_log1pf(a);
+    }
+}
 __global__ void tk_sobol(SobolParams P, const int32_t* __restrict__ q, uint64_t n, float* o1, float* o2) {
     TK_LOOP(n) {
         const int32_t* e = q + 4 * i;
@@ -163,6 +169,14 @@ struct TkIO {
 #define TK_GRID(n) ((int)std::min<uint64_t>(((n) + 127) / 128 ? ((n) + 127) / 128 : 1, 148 * 16)), 128
 
 extern "C" {
+int32_t hk_test_detmath(HkContext* ctx, int32_t fn, const float* x, const float* y, uint64_t n, float* out) {
+    if (!ctx || !x || !out || fn < 0 || fn > 7 || (fn == 6 && !y)) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device); TkIO io(ctx);
+    void* dx = io.in(x, 4 * n); void* dy = y ? io.in(y, 4 * n) : nullptr; float* dout = (float*)io.out(4 * n);
+    if (io.rc) return io.rc;
+    tk_detmath<<<TK_GRID(n)>>>(fn, (const float*)dx, (const float*)dy, n, dout); ctx->launches++;
+    return io.get(out, dout, 4 * n);
+}
 int32_t hk_test_sobol(HkContext* ctx, const int32_t* q, uint64_t n, int32_t l2, int32_t nb4, uint32_t seed, float* o1, float* o2) {
     if (!ctx || !ctx->have_tables) return HK_ERR_INVALID;
     cudaSetDevice(ctx->device); TkIO io(ctx);

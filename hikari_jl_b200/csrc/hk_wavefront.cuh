@@ -956,7 +956,7 @@ HK_DEV float3 postprocess_pixel(const HkPostprocess& P, float3 c) {
         case HK_TONEMAP_FILMIC: r = pp_filmic(r); g = pp_filmic(g); b = pp_filmic(b); break;
         default: r = pp_clamp01(r); g = pp_clamp01(g); b = pp_clamp01(b); break;
     }
-    if (P.apply_gamma) { r = powf(r, P.inv_gamma); g = powf(g, P.inv_gamma); b = powf(b, P.inv_gamma); }
+    if (P.apply_gamma) { r = dm_powf(r, P.inv_gamma); g = dm_powf(g, P.inv_gamma); b = dm_powf(b, P.inv_gamma); }
     return f3(r, g, b);
 }
 // framebuffer = sum / weight -> postprocess_pixel, same (H, W) column-major layout as k_film_finalize.

@@ -79,55 +79,45 @@ class Film:
         # The reference's framebuffer is an (H, W) COLUMN-major RGB{Float32} matrix (film.jl:61-106): linear index
         # (px-1)*H + py.  The same bytes are a C-order (W, H, 3) array; `framebuffer` is the [py, px] view of it, so
         # hk_read_film writes straight into it.  The storage is page-locked when a CUDA device is present.
-        self._pinned = None
-        self._store = None
+        self._pins = []                                              # (lib, pointer) of every page-locked buffer this film owns
+        self._free = []                                              # host buffers neither displayed nor targeted by an un-waited read-out
+        self._store = self._new_store()
+        self.framebuffer = self._store.transpose(1, 0, 2)            # framebuffer[py, px] = RGB (a view)
+        self.iteration_index = 0
+
+    def _new_store(self):
+        w, h = self.resolution
+        store = None
         try:
             lib = A.load_library()
             p = C.c_void_p()
             if lib.hk_pinned_alloc(12 * w * h, C.byref(p)) == 0 and p.value:
-                self._pinned = (lib, p)
-                self._store = np.ctypeslib.as_array(C.cast(p, A.c_fp), shape=(w, h, 3))
+                self._pins.append((lib, p))
+                store = np.ctypeslib.as_array(C.cast(p, A.c_fp), shape=(w, h, 3))
         except Exception:
-            self._pinned = None
-        if self._store is None:
-            self._store = np.empty((w, h, 3), dtype=f32)
-        self._store[...] = 0
-        self.framebuffer = self._store.transpose(1, 0, 2)            # framebuffer[py, px] = RGB (a view)
-        self.iteration_index = 0
+            store = None
+        if store is None:
+            store = np.empty((w, h, 3), dtype=f32)
+        store[...] = 0
+        return store
 
-    def _other_store(self):
-        """second page-locked buffer for the pipelined read-out (Backend.read_film_async): the frame being displayed is
-        never the one being written"""
-        if getattr(self, "_store2", None) is None:
-            w, h = self.resolution
-            self._pinned2 = None
-            try:
-                lib = A.load_library()
-                p = C.c_void_p()
-                if lib.hk_pinned_alloc(12 * w * h, C.byref(p)) == 0 and p.value:
-                    self._pinned2 = (lib, p)
-                    self._store2 = np.ctypeslib.as_array(C.cast(p, A.c_fp), shape=(w, h, 3))
-            except Exception:
-                self._pinned2 = None
-            if getattr(self, "_store2", None) is None:
-                self._store2 = np.empty((w, h, 3), dtype=f32)
-            self._store2[...] = 0
-        return self._store2
+    def _acquire_store(self):
+        """A host buffer for one pipelined read-out (Backend.read_film_async): never the displayed one and never one that an
+        un-waited read-out still targets -- with two frames in flight plus the displayed frame that is three buffers
+        (include/hikari_cuda.h: 'the caller alternates host buffers'); they are allocated on demand and recycled by _show."""
+        return self._free.pop() if self._free else self._new_store()
 
     def _show(self, store):
         if store is not self._store:
-            self._store, self._store2 = store, self._store
-            if getattr(self, "_pinned2", None) is not None or getattr(self, "_pinned", None) is not None:
-                self._pinned, self._pinned2 = getattr(self, "_pinned2", None), getattr(self, "_pinned", None)
+            self._free.append(self._store)
+            self._store = store
             self.framebuffer = self._store.transpose(1, 0, 2)
 
     def __del__(self):
-        for name in ("_pinned", "_pinned2"):
-            if getattr(self, name, None):
-                lib, p = getattr(self, name)
-                lib.hk_pinned_free(p)
-                setattr(self, name, None)
-        self.framebuffer = None; self._store = None; self._store2 = None
+        for lib, p in getattr(self, "_pins", []):
+            lib.hk_pinned_free(p)
+        self._pins = []
+        self.framebuffer = None; self._store = None; self._free = []
 
     def clear(self):
         self.framebuffer[:] = 0
@@ -248,14 +238,18 @@ def denoise_inplace(film, vp, config=None):
 
 
 class PerspectiveCamera:
-    """src/camera/perspective.jl:41-91.  `screen_window=None` picks the aspect-correct window (shorter axis
-    spans [-1,1]); pass ((-1,-1),(1,1)) for the reference convenience constructor's literal window (:84)."""
+    """src/camera/perspective.jl:41-91.  `screen_window=None` is the reference convenience constructor's literal
+    [-1,1]^2 window (:84: non-square films are stretched, exactly as upstream); "aspect" picks the aspect-correct window
+    (shorter axis spans [-1,1]) that the full constructor is normally called with (examples/*.jl, RayMakie)."""
 
     def __init__(self, eyepos, lookat, film, up=(0, 1, 0), fov=55.0, lens_radius=0.0, focal_distance=1e6,
                  screen_window=None):
         w, h = film.resolution
         self.camera_to_world = look_at(eyepos, lookat, up)
         if screen_window is None:
+            screen_window = ((-1.0, -1.0), (1.0, 1.0))
+        elif isinstance(screen_window, str):
+            assert screen_window == "aspect"
             aspect = w / h
             screen_window = ((-aspect, -1.0), (aspect, 1.0)) if aspect >= 1 else ((-1.0, -1 / aspect), (1.0, 1 / aspect))
         (x0, y0), (x1, y1) = screen_window
@@ -822,6 +816,44 @@ class PointLight(_Light):
         return L
 
 
+class SpotLight(_Light):
+    """src/lights/spot.jl.  SpotLight(rgb, position, target, total_width, falloff_start; power=nothing) [:78-94: RGB ->
+    RGBIlluminantSpectrum, scale = 1 / spectrum_to_photometric, optional radiant power] or, with legacy_rgbspectrum=True,
+    SpotLight(position, target, i::RGBSpectrum, total_width, falloff_start, scale=1) [:49-56].  Angles in degrees; the cone
+    points along +z of the light's frame (_spotlight_transform, :104-121)."""
+    type = A.HK_LIGHT_SPOT
+
+    def __init__(self, rgb, position, target, total_width, falloff_start, power=None, legacy_rgbspectrum=False, scale=None):
+        self.rgb, self.position, self.target = _rgb(rgb), _v3(position), _v3(target)
+        self.total_width, self.falloff_start = f32(total_width), f32(falloff_start)
+        self.power, self.legacy, self.scale = power, legacy_rgbspectrum, scale
+        self.cos_total_width = f32(np.cos(np.deg2rad(self.total_width, dtype=f32), dtype=f32))
+        self.cos_falloff_start = f32(np.cos(np.deg2rad(self.falloff_start, dtype=f32), dtype=f32))
+        d = (self.target - self.position).astype(f32)
+        d = (d * (f32(1) / f32(np.sqrt(f32(np.dot(d, d)))))).astype(f32)
+        up = np.array([0, 1, 0], dtype=f32) if abs(d[1]) < f32(0.99) else np.array([1, 0, 0], dtype=f32)
+        x = np.cross(up, d).astype(f32)
+        x = (x * (f32(1) / f32(np.sqrt(f32(np.dot(x, x)))))).astype(f32)
+        y = np.cross(d, x).astype(f32)
+        rot = np.eye(4, dtype=f32)
+        rot[:3, 0], rot[:3, 1], rot[:3, 2] = x, y, d                # columns = where the local axes land in world space
+        w2l = np.linalg.inv(rot).astype(f32) @ translate(-self.position)
+        self.world_to_light = w2l.astype(f32)
+
+    def to_abi(self, scene):
+        L = A.HkLight(type=self.type)
+        self._spectrum(L, self.rgb, self.legacy)
+        if self.legacy:
+            L.scale = 1.0 if self.scale is None else float(self.scale)       # spot.jl:49-52: scale defaults to 1
+        elif self.power is not None:                                          # spot.jl:86-91
+            k_e = f32(2) * f32(np.pi) * ((f32(1) - self.cos_falloff_start) + (self.cos_falloff_start - self.cos_total_width) / f32(2))
+            L.scale = float(f32(L.scale) * (f32(self.power) / k_e))
+        L.position[:] = self.position.tolist()
+        L.cos_total_width, L.cos_falloff_start = float(self.cos_total_width), float(self.cos_falloff_start)
+        L.world_to_light[:] = self.world_to_light.reshape(-1).tolist()
+        return L
+
+
 class DirectionalLight(_Light):
     type = A.HK_LIGHT_DIRECTIONAL
     infinite = True
@@ -1279,10 +1311,11 @@ class Backend:
         out_hw3[...] = buf.transpose(1, 0, 2)
 
     def read_film_async(self, film):
-        """Enqueue finalize + device->host copy of the current film into the film's OTHER page-locked buffer and return a
-        handle at once (hk_read_film_async); wait_film(handle) makes that frame film.framebuffer."""
+        """Enqueue finalize + device->host copy of the current film into a page-locked buffer of the film that no displayed or
+        in-flight frame uses and return a handle at once (hk_read_film_async); wait_film(handle) makes that frame
+        film.framebuffer.  At most two read-outs may be in flight (the library's two staging buffers)."""
         assert film.resolution == (self.width, self.height)
-        store = film._other_store()
+        store = film._acquire_store()
         ticket = C.c_int32(-1)
         self.call("read_film_async", _fp(store), C.byref(ticket))
         return (ticket.value, store)

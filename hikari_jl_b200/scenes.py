@@ -19,7 +19,7 @@ f32 = np.float32
 
 
 def _cam(eye, look, fov):
-    return lambda film: H.PerspectiveCamera(eye, look, film, fov=fov)
+    return lambda film: H.PerspectiveCamera(eye, look, film, fov=fov, screen_window="aspect")
 
 
 def cornell_smoke():

@@ -357,8 +357,8 @@ int32_t hk_read_film_wait(HkContext* ctx, int32_t ticket);
 
 /* postprocess!(film; exposure, tonemap, gamma, white_point, sensor), src/postprocess.jl:187-357 -- fused into the film
  * read-out: framebuffer = sum / weight, then exposure, Bradford white balance, sensor imaging ratio, tone map, gamma.
- * Same (H, W) column-major RGB layout as hk_read_film.  The escaped-ray background mask needs the auxiliary depth
- * buffer (fill_aux_buffers!) and is not offered.                                                         */
+ * Same (H, W) column-major RGB layout as hk_read_film.  mask_escaped != 0 blends `background` over pixels whose
+ * film.depth is infinite (postprocess.jl:220-245, 3x3 anti-aliased); it needs hk_fill_aux_buffers first.            */
 #define HK_TONEMAP_NONE         0   /* linear clamp                          postprocess.jl:160-182 */
 #define HK_TONEMAP_REINHARD     1
 #define HK_TONEMAP_REINHARD_EXT 2

@@ -11,6 +11,9 @@
 extern "C" {
 #endif
 
+/* fn: 0 expf 1 logf 2 sinf 3 cosf 4 coshf 5 atanhf 6 powf(x, y) 7 log1pf of csrc/hk_detmath.h, evaluated on the DEVICE (y may be NULL
+ * unless fn == 6): must equal the host evaluation of the same header bit for bit */
+int32_t hk_test_detmath(HkContext* ctx, int32_t fn, const float* x, const float* y, uint64_t n, float* out);
 /* q[n][4] = (px, py, sample_idx, dim) -> zsobol_sample_1d / _2d (src/sampler/sobol.jl:269-309) */
 int32_t hk_test_sobol(HkContext* ctx, const int32_t* q, uint64_t n, int32_t log2_spp, int32_t n_base4_digits, uint32_t seed, float* out1d, float* out2d);
 /* ray [n_slots][8] and hit [n_slots][4] (t, prim1, b1, b2) state after the last pass: per slot, the closest hit of the

@@ -231,7 +231,7 @@ int32_t ok_postprocess(OkContext* c, const HkPostprocess* P, float* out) {
             case HK_TONEMAP_FILMIC: r = pp_filmic(r); g = pp_filmic(g); b = pp_filmic(b); break;
             default: r = pp_clamp01(r); g = pp_clamp01(g); b = pp_clamp01(b); break;
         }
-        if (P->apply_gamma) { r = std::pow(r, P->inv_gamma); g = std::pow(g, P->inv_gamma); b = std::pow(b, P->inv_gamma); }
+        if (P->apply_gamma) { r = dm_powf(r, P->inv_gamma); g = dm_powf(g, P->inv_gamma); b = dm_powf(b, P->inv_gamma); }
         if (P->mask_escaped) {     // AA depth mask, postprocess.jl:220-245: (row, col) = (py + 1, px + 1) of the (H, W) array, depth row flipped
             if (s.aux_depth.size() != (size_t)W * H) return -1;
             const int d_row = H - (py + 1) + 1, col = px + 1;
@@ -312,10 +312,10 @@ int32_t ok_denoise(OkContext* c, const HkDenoiseConfig* cfg, float* out_pp, floa
                     const float* nq = s.aux_normal.data() + 3 * q;
                     const float w_spatial = K[dxi] * K[dyi];
                     const float es = var_p > 0.0f ? cfg->sigma_color * std::sqrt(var_p) + 1.0e-4f : cfg->sigma_color;
-                    const float w_color = std::exp(-std::fabs(lum_p - lum_q) / es);
+                    const float w_color = dm_expf(-std::fabs(lum_p - lum_q) / es);
                     const float dotv = (np_[0] * nq[0] + np_[1] * nq[1]) + np_[2] * nq[2];
-                    const float w_norm = std::pow(dn_max0(dotv), cfg->sigma_normal);
-                    const float w_depth = std::exp(-std::fabs(d_p - s.aux_depth[q]) / (cfg->sigma_depth * (float)step + 1.0e-4f));
+                    const float w_norm = dm_powf(dn_max0(dotv), cfg->sigma_normal);
+                    const float w_depth = dm_expf(-std::fabs(d_p - s.aux_depth[q]) / (cfg->sigma_depth * (float)step + 1.0e-4f));
                     const float w = w_spatial * w_color * w_norm * w_depth;
                     sr += rq * w; sg += gq * w; sb += bq * w; sw += w;
                 }
@@ -366,6 +366,14 @@ int32_t ok_trace_closest(OkContext* c, const float* rays, uint64_t n, float* hit
 // batch entry points for per-function parity tests (each mirrors an hk_test_* kernel)
 // ---------------------------------------------------------------------------------------------
 // out[i] = zsobol 1d / 2d samples for (px,py,sample_idx,dim) quadruples; 2d writes 2 floats
+// fn: 0 expf 1 logf 2 sinf 3 cosf 4 coshf 5 atanhf 6 powf(x, y) 7 log1pf  (hk_detmath.h; the CUDA library runs the same source)
+int32_t ok_test_detmath(int32_t fn, const float* x, const float* y, uint64_t n, float* out) {
+    for (uint64_t i = 0; i < n; i++) {
+        const float a = x[i], b = y ? y[i] : 0.0f;
+        out[i] = fn == 0 ? dm_expf(a) : fn == 1 ? dm_logf(a) : fn == 2 ? dm_sinf(a) : fn == 3 ? dm_cosf(a) : fn == 4 ? dm_coshf(a) : fn == 5 ? dm_atanhf(a) : fn == 6 ? dm_powf(a, b) : dm_log1pf(a);
+    }
+    return 0;
+}
 int32_t ok_test_sobol(OkContext* c, const int32_t* q, uint64_t n, int32_t log2_spp, int32_t nb4, uint32_t seed, float* out1d, float* out2d) {
     SobolRNG r{c->s.T.sobol, log2_spp, nb4, seed, 0};
     #pragma omp parallel for

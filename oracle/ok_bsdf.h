@@ -144,8 +144,8 @@ inline V3 tr_sample_wm(V3 w, V2 u, float ax, float ay) {
     V3 t2 = cross(wh, t1);
     float r = std::sqrt(u.x);
     float phi = 2.0f * PI_F * u.y;
-    float px = r * std::cos(phi);
-    float py = r * std::sin(phi);
+    float px = r * dm_cosf(phi);
+    float py = r * dm_sinf(phi);
     float h = std::sqrt(1.0f - px * px);
     py = lerpf(h, py, 0.5f * (1.0f + wh.z));
     float pz = std::sqrt(std::max(0.0f, 1.0f - px * px - py * py));

@@ -7,11 +7,11 @@
 namespace ok {
 
 // spectral-eval.jl:823-825
-inline float sample_exponential(float u, float a) { return -std::log(1.0f - u) / a; }
+inline float sample_exponential(float u, float a) { return -dm_logf(1.0f - u) / a; }
 // spectral-eval.jl:837-840
 inline float layer_transmittance(float thickness, V3 w) {
     if (std::fabs(thickness) <= 1.1920929e-7f) return 1.0f;
-    return std::exp(-std::fabs(thickness / w.z));
+    return dm_expf(-std::fabs(thickness / w.z));
 }
 // spectral-eval.jl:879-883
 inline float hg_phase_pdf(float g, float cos_t) {
@@ -31,7 +31,7 @@ inline V3 sample_hg_phase_spectral(float g, V3 wo, V2 u, float& p_out) {
     float sin_t = std::sqrt(std::max(0.0f, 1.0f - cos_t * cos_t));
     float phi = 2.0f * PI_F * u.y;
     V3 t1, t2; coordinate_system(-wo, t1, t2);
-    V3 wi = sin_t * std::cos(phi) * t1 + sin_t * std::sin(phi) * t2 + cos_t * (-wo);
+    V3 wi = sin_t * dm_cosf(phi) * t1 + sin_t * dm_sinf(phi) * t2 + cos_t * (-wo);
     wi = normalize(wi);
     float g2 = g * g;
     float denom = 1.0f + g2 - 2.0f * g * cos_t;

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <algorithm>
 #include <limits>
+#include "../hikari_jl_b200/csrc/hk_detmath.h"   // the ONE f32 libm shared with the CUDA library (bit-identical transcendentals)
 
 namespace ok {
 
@@ -84,7 +85,7 @@ inline Spec operator*(const Spec& a, float s) { return Spec(a.v[0] * s, a.v[1] *
 inline Spec operator*(float s, const Spec& a) { return a * s; }   // spectral.jl:46  s*a = a*s
 inline Spec operator/(const Spec& a, float s) { return Spec(a.v[0] / s, a.v[1] / s, a.v[2] / s, a.v[3] / s); }
 inline Spec operator-(const Spec& a) { return Spec(-a.v[0], -a.v[1], -a.v[2], -a.v[3]); }
-inline Spec exp(const Spec& a) { return Spec(std::exp(a.v[0]), std::exp(a.v[1]), std::exp(a.v[2]), std::exp(a.v[3])); }
+inline Spec exp(const Spec& a) { return Spec(dm_expf(a.v[0]), dm_expf(a.v[1]), dm_expf(a.v[2]), dm_expf(a.v[3])); }
 // spectral.jl:63-65  sum(s.data)/N ; Julia sum of a 4-tuple = ((a+b)+c)+d
 inline float average(const Spec& s) { return (((s.v[0] + s.v[1]) + s.v[2]) + s.v[3]) / 4.0f; }
 inline float max_component(const Spec& s) { return std::max(std::max(std::max(s.v[0], s.v[1]), s.v[2]), s.v[3]); }
@@ -96,12 +97,12 @@ struct Wavelengths { float lambda[4]; float pdf[4]; };
 inline float visible_wavelengths_pdf(float lambda) {
     if (lambda < 360.0f || lambda > 830.0f) return 0.0f;
     float x = 0.0072f * (lambda - 538.0f);
-    float c = std::cosh(x);
+    float c = dm_coshf(x);
     return 0.0039398042f / (c * c);
 }
 // spectral.jl:210-213
 inline float sample_visible_wavelengths(float u) {
-    return 538.0f - 138.888889f * std::atanh(0.85691062f - 1.82750197f * u);
+    return 538.0f - 138.888889f * dm_atanhf(0.85691062f - 1.82750197f * u);
 }
 // spectral.jl:221-249
 inline Wavelengths sample_wavelengths_visible(float u) {
@@ -288,7 +289,7 @@ inline V2 concentric_sample_disk(V2 u) {
     bool xl = ax > ay;
     float r = xl ? ox : oy;
     float th = xl ? (oy / sx) * PI_F / 4.0f : PI_F / 2.0f - (ox / sy) * PI_F / 4.0f;
-    return V2(r * std::cos(th), r * std::sin(th));
+    return V2(r * dm_cosf(th), r * dm_sinf(th));
 }
 inline V3 cosine_sample_hemisphere(V2 u) {
     V2 d = concentric_sample_disk(u);

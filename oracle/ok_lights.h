@@ -45,8 +45,8 @@ inline V3 equal_area_square_to_sphere(V2 p) {
     float r = 1.0f - d;
     float phi = (r == 0.0f ? 1.0f : (vp - up) / r + 1.0f) * PI_F / 4.0f;
     float z = std::copysign(1.0f - r * r, sd);
-    float cp = std::copysign(std::cos(phi), u);
-    float sp = std::copysign(std::sin(phi), v);
+    float cp = std::copysign(dm_cosf(phi), u);
+    float sp = std::copysign(dm_sinf(phi), v);
     float rc = r * std::sqrt(2.0f - r * r);
     return V3(cp * rc, sp * rc, z);
 }
@@ -187,7 +187,7 @@ inline LightSample sample_light(const LightCtx& C, const HkLight& L, V3 p, const
             float z = 1.0f - 2.0f * u.x;
             float r = std::sqrt(std::max(0.0f, 1.0f - z * z));
             float phi = 2.0f * PI_F * u.y;
-            V3 wi(r * std::cos(phi), r * std::sin(phi), z);
+            V3 wi(r * dm_cosf(phi), r * dm_sinf(phi), z);
             float pdf = 1.0f / (4.0f * PI_F);
             V3 pl = p + 1.0e6f * wi;
             Spec Li = L.scale * sample_light_spectrum(T, L, l);

@@ -36,7 +36,7 @@ inline V3 sample_hg(float g, V3 wo, V2 u, float& pdf) {
     float s = std::sqrt(std::max(0.0f, 1.0f - c * c));
     float phi = 2.0f * PI_F * u.y;
     V3 t1, t2; coordinate_system(-wo, t1, t2);
-    V3 wi = normalize(s * std::cos(phi) * t1 + s * std::sin(phi) * t2 + c * (-wo));
+    V3 wi = normalize(s * dm_cosf(phi) * t1 + s * dm_sinf(phi) * t2 + c * (-wo));
     pdf = hg_p(g, c);
     return wi;
 }
@@ -293,7 +293,7 @@ inline DeltaResult delta_track(const MediaCtx& C, uint32_t medium, V3 o, V3 d, f
         bool seg_done = false;
         for (int si = 0; si < 1024 && !seg_done; si++) {
             float u = lcg_next(rng);
-            float dt = -std::log(std::max(1.0e-10f, 1.0f - u)) / smaj0;
+            float dt = -dm_logf(std::max(1.0e-10f, 1.0f - u)) / smaj0;
             float ts = t + dt;
             if (ts >= t_end) {
                 float dr = t_end - t;
@@ -357,7 +357,7 @@ inline void transmittance_ratio_tracking(const MediaCtx& C, uint32_t medium, V3 
         float t = seg.t_min, t_end = seg.t_max;
         for (int si = 0; si < 100; si++) {
             float u = pcg32_f32(rng);
-            float dt = -std::log(std::max(1.0e-10f, 1.0f - u)) / smaj0;
+            float dt = -dm_logf(std::max(1.0e-10f, 1.0f - u)) / smaj0;
             float ts = t + dt;
             if (ts >= t_end) {
                 float dr = t_end - t;

@@ -383,3 +383,99 @@ def test_bvh8_builder_invariants():
     a = rng.uniform(-1, 1, size=(2000, 3)); d = rng.normal(size=(2000, 3)) * rng.uniform(1e-3, 2.0, size=(2000, 1))
     sl = np.stack([a, a + d, a + d + rng.normal(scale=1e-4, size=(2000, 3))], 1).reshape(-1, 3)
     _check_bvh8(sl, np.arange(6000).reshape(-1, 3))
+
+
+def test_film_async_buffers_never_alias():
+    """Backend.read_film_async targets film._acquire_store(): never the displayed buffer, never one an un-waited read-out still
+    targets (two frames in flight used to share one host buffer)."""
+    film = H.Film((8, 4))
+    shown = film._store
+    a = film._acquire_store(); b = film._acquire_store()
+    assert a is not b and a is not shown and b is not shown
+    film._show(a)                                   # frame a displayed; the old displayed buffer becomes free
+    assert film.framebuffer.base is a or np.shares_memory(film.framebuffer, a)
+    c = film._acquire_store()                       # b is still pending: c must be neither a (displayed) nor b (in flight)
+    assert c is not a and c is not b
+    film._show(b); film._show(c)
+    d = film._acquire_store()
+    assert d is not c and (d is a or d is b or d is shown), "recycled buffers come from the free list"
+
+
+def _light_zoo(n_area, seed):
+    rng = np.random.RandomState(seed)
+    s = H.Scene()
+    s.push(H.rect3((-2, -0.1, -2), (4, 0.1, 4)), H.MatteMaterial())
+    s.push(H.PointLight((1, 1, 1), (3, 3, -1))); s.push(H.PointLight((5, 2, 5), (-3, 2, 0), legacy_rgbspectrum=True))
+    s.push(H.AmbientLight((0.5, 0.7, 1.0)))
+    s.push(H.SpotLight((40, 40, 40), (0, 3, 0), (0, 0, 0), 30.0, 20.0))
+    s.push(H.SpotLight((10, 30, 50), (2, 2, -1), (0.5, 0, 0.5), 60.0, 60.0))
+    s.push(H.SpotLight((3, 2, 1), (0, 4, 0), (0, 5, 0), 80.0, 10.0, legacy_rgbspectrum=True, scale=2.0))
+    s.push(H.DirectionalLight((2, 2, 2), (0, -1, 0.2)))
+    s.push(H.PointLight((0, 0, 0), (1, 1, 1)))                      # phi == 0: in neither list
+    for k in range(n_area):
+        c = rng.uniform(-1.5, 1.5, 3) + (0, 1.5, 0)
+        s.push(H.Mesh(c + rng.normal(scale=0.1, size=(3, 3)), [(0, 1, 2)]),
+               H.MediumInterface(H.MatteMaterial(Kd=0.0), emission=(tuple(rng.uniform(5, 50, 3)), 1.0, k % 3 == 0)))
+    s.sync()
+    return s
+
+
+@pytest.mark.parametrize("n_area,seed", [(0, 1), (1, 2), (37, 3), (150, 4)])
+def test_light_bvh_builder_matches_restatement(n_area, seed):
+    """csrc/host_lightbvh.cpp (the builder both back ends receive their light BVH from) against the independent restatement of
+    bvh-light-sampler.jl:237-466 + light-bounds.jl in oracle/ok_lightbvh.py: identical structure, floats to 1e-5."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import ok_lightbvh
+    sc = _light_zoo(n_area, seed)
+    synced = sc._synced
+    labi = [L.to_abi(sc) for L in synced.lights]
+    n = len(labi)
+    larr = (A.HkLight * n)(*labi)
+    nodes = (A.HkLightBVHNode * (2 * n))()
+    trails = np.zeros(n, dtype=np.uint32); inf = np.zeros(n, dtype=np.int32)
+    nn, ni, nb = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    assert A.load_library().hk_host_build_light_sampler(larr, n, nodes, C.byref(nn), trails.ctypes.data_as(A.c_u32p), inf.ctypes.data_as(A.c_i32p),
+                                                        C.byref(ni), C.byref(nb)) == 0
+    want = ok_lightbvh.build_light_sampler(labi)
+    assert nb.value == want["n_bvh"] == n - 3 and nn.value == len(want["nodes"]) == 2 * nb.value - 1
+    assert list(inf[:ni.value]) == want["infinite"] and ni.value == 2
+    assert np.array_equal(trails, want["trails"])
+    assert trails[7] == 0xFFFFFFFF, "a light without power is in neither the tree nor the infinite list"
+    for k in range(nn.value):
+        g, w = nodes[k], want["nodes"][k]
+        assert (g.is_leaf != 0) == w["leaf"] and g.child1_or_light_idx == w["child"], f"node {k}: structure differs"
+        assert (g.two_sided != 0) == w["two_sided"]
+        np.testing.assert_allclose(list(g.bounds_min) + list(g.bounds_max), list(w["lo"]) + list(w["hi"]), rtol=1e-6, atol=0)
+        np.testing.assert_allclose(list(g.w), list(w["w"]), rtol=0, atol=2e-5, err_msg=f"node {k} axis")
+        np.testing.assert_allclose([g.phi, g.cos_theta_o, g.cos_theta_e], [w["phi"], w["cos_o"], w["cos_e"]], rtol=1e-5, atol=2e-6, err_msg=f"node {k}")
+
+
+def test_spot_light_known_answers_on_the_oracle():
+    """SpotLight (src/lights/spot.jl, sample_light_spectral lights.jl:66-105): on the axis the radiance is scale * I / r^2, outside the
+    cone it is zero, inside the falloff band it is smoothstep-like delta^4; the transform puts the cone along target - position."""
+    s = H.Scene()
+    s.push(H.rect3((-2, -0.1, -2), (4, 0.1, 4)), H.MatteMaterial())
+    spot = H.SpotLight((8, 8, 8), (0, 2, 0), (0, 0, 0), 30.0, 20.0, legacy_rgbspectrum=True, scale=1.0)
+    s.push(spot)
+    s.sync()
+    assert abs(spot.cos_total_width - np.cos(np.radians(30.0))) < 1e-6 and abs(spot.cos_falloff_start - np.cos(np.radians(20.0))) < 1e-6
+    local_z = spot.world_to_light[:3, :3] @ np.array([0, -1, 0], dtype=f32)
+    np.testing.assert_allclose(local_z, [0, 0, 1], atol=1e-6)
+    p = Pair(scene=s, need_gpu=False)
+    try:
+        pts = np.array([[0, 0, 0], [0.3, 0, 0], [2.0 * np.tan(np.radians(25.0)), 0, 0], [2.0 * np.tan(np.radians(35.0)), 0, 0], [0, 4, 0]], dtype=f32)
+        x = np.zeros((len(pts), 10), f32); x[:, 0:3] = pts; x[:, 3:6] = (0, 1, 0); x[:, 6] = 0.37; x[:, 7] = 0.5
+        out = np.zeros((len(pts), 16), f32)
+        p.olib.ok_test_lights(p.ok.ctx, fp(x), len(pts), fp(out))
+        Li = out[:, 2:6]
+        assert (out[:, 0] == 1).all() and (out[:, 1] == 1.0).all()
+        assert (Li[0] > 0).all() and (Li[3] == 0).all() and (Li[4] == 0).all(), "inside the cone lit, outside (and behind) dark"
+        r2 = lambda q: float(np.sum((np.array([0, 2, 0]) - q) ** 2))
+        np.testing.assert_allclose(Li[1] * r2(pts[1]), Li[0] * r2(pts[0]), rtol=1e-5)          # both inside the full-intensity core
+        ct = np.cos(np.radians(25.0)); d = (ct - spot.cos_total_width) / (spot.cos_falloff_start - spot.cos_total_width)
+        np.testing.assert_allclose(Li[2] * r2(pts[2]), Li[0] * r2(pts[0]) * d ** 4, rtol=2e-3)
+        np.testing.assert_allclose(out[0, 6:9], [0, 1, 0], atol=1e-6); np.testing.assert_allclose(out[0, 10:13], [0, 2, 0], atol=1e-6)
+        assert out[0, 13] == 1.0                                                               # delta light
+    finally:
+        p.close()

@@ -74,3 +74,14 @@ def trace_both(pair, rays, brute=False):
     assert rc == 0, pair.lib.hk_last_error(pair.cu.ctx)
     pair.olib.ok_trace_closest(pair.ok.ctx, fp(rays), n, fp(h_ok), 1 if brute else 0)
     return h_cu, h_ok
+
+
+def assert_bits_equal(a, b, what, allow=0):
+    """Bit-for-bit equality of two f32 arrays (NaN == NaN whatever the payload); `allow` = rows that may differ."""
+    a = np.ascontiguousarray(a, dtype=f32); b = np.ascontiguousarray(b, dtype=f32)
+    same = (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))
+    rows = same.reshape(len(a), -1).all(axis=1)
+    bad = int((~rows).sum())
+    if bad > allow:
+        i = int(np.argmin(rows))
+        raise AssertionError(f"{what}: {bad} of {len(a)} records differ bitwise (allowed {allow}); first at {i}: {a.reshape(len(a), -1)[i]} vs {b.reshape(len(b), -1)[i]}")
