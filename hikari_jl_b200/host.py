@@ -1162,6 +1162,11 @@ class Scene:
         self._synced = s
         return s
 
+    def triangle_count(self):
+        """world-space triangles of the scene (every instance counted)"""
+        s = self._synced or self.sync()
+        return int(len(s.indices))
+
     def world_radius(self):
         s = self._synced or self.sync()
         lo, hi = s.positions.min(0), s.positions.max(0)

@@ -39,6 +39,11 @@ int32_t ok_set_num_threads(int32_t n) {
     return 0;
 }
 int32_t ok_set_brute_force(OkContext* c, int32_t on) { c->s.brute_force = on != 0; return 0; }
+// bounded sample of a frame (bench.py CPU legs): render only every `step`-th image row, starting at row `offset`
+int32_t ok_set_row_subset(OkContext* c, int32_t step, int32_t offset) {
+    if (step < 1 || offset < 0 || offset >= step) return -1;
+    c->s.row_step = step; c->s.row_offset = offset; return 0;
+}
 
 int32_t ok_upload_tables(OkContext* c, const HkTables* t) {
     Scene& s = c->s;

@@ -92,6 +92,9 @@ struct Scene {
     Tables T;
     std::vector<float> positions, normals, tangents, uvs; std::vector<uint32_t> indices, tri_meta;
     bool has_normals = false, has_tangents = false, has_uvs = false;
+    // bench.py's bounded CPU sample of a full-resolution frame: only image rows y with (y - 1) % row_step == row_offset start a
+    // camera ray (same camera, resolution and per-pixel sample streams; the other pixels stay black).  1 / 0 = every row.
+    int32_t row_step = 1, row_offset = 0;
     Accel accel;
     std::vector<HkMaterial> materials; std::vector<HkMediumInterface> interfaces;
     std::vector<float> spec_lambdas, spec_values; std::vector<uint32_t> spec_offsets; HkSpectra spectra;
@@ -393,6 +396,11 @@ inline void Scene::render_sample(int32_t sample_idx) {
     for (int64_t idx = 1; idx <= n_pixels; idx++) {
         int32_t pixel_idx = (int32_t)(idx - 1);
         int32_t x = pixel_idx % W + 1, y = pixel_idx / W + 1;
+        if (row_step > 1 && (y - 1) % row_step != row_offset) {
+            filter_weight[idx - 1] = 0.0f;
+            for (int i = 0; i < 4; i++) { wavelengths[(size_t)pixel_idx * 4 + i] = 538.0f; pdfs[(size_t)pixel_idx * 4 + i] = 1.0f; }
+            continue;
+        }
         float wavelength_u = zsobol_1d(rng, x, y, sample_idx, 1);
         V2 jitter = zsobol_2d(rng, x, y, sample_idx, 3);
         float time_u = zsobol_1d(rng, x, y, sample_idx, 4);

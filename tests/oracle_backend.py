@@ -23,6 +23,8 @@ def lib():
             fn = getattr(L, name); fn.argtypes = args; fn.restype = res
         f("ok_trace_closest", [VP, A.c_fp, C.c_uint64, A.c_fp, C.c_int32])
         f("ok_set_brute_force", [VP, C.c_int32])
+        f("ok_set_row_subset", [VP, C.c_int32, C.c_int32])
+        f("ok_test_detmath", [C.c_int32, A.c_fp, A.c_fp, C.c_uint64, A.c_fp])
         f("ok_num_threads", [])
         f("ok_set_num_threads", [C.c_int32])
         f("ok_rays_traced", [VP], C.c_uint64)

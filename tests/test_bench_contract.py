@@ -37,3 +37,46 @@ def test_reference_arm_other_ranks_exit_quietly():
 def test_cuda_arm_fails_loudly_without_a_device():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_reference_arm_config_is_the_cuda_arm_config():
+    """Both arms print config_dict(): same workload name, resolution, max_depth, triangle and light counts (the driver compares them)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    bench.select_config("C1")
+    scene, _ = bench.build_scene()
+    c = bench.config_dict(scene, 1)
+    assert c["resolution"] == [512, 512] and c["max_depth"] == 5 and c["name"] == "C1" and c["triangles"] == 23826
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "C1", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    j = json.loads([l for l in r.stdout.strip().splitlines() if l.startswith("{")][0])
+    assert j["config"] == c
+    assert bench.DEFAULT_CONFIG == "C3" and bench.CONFIGS["C3"]["res"] == (3840, 2160), "the driver's bench line is quoted on a 4K configuration"
+
+
+def test_row_subset_is_a_sample_of_the_same_frame():
+    """The CPU legs render every k-th image row of the full-resolution frame (ok_set_row_subset): those rows are bit-identical to
+    the same rows of the full render (per-pixel sample streams are independent of the other pixels), the rest stay black."""
+    import numpy as np
+    import oracle_backend
+    from hikari_jl_b200 import scenes
+    from hikari_jl_b200.host import Film, VolPath
+    scene, camf = scenes.c1_spheres(12)
+    outs = []
+    for step, off in ((1, 0), (4, 1)):
+        film = Film((48, 32))
+        vp = VolPath(samples=2, max_depth=4, backend=oracle_backend.make_backend())
+        vp._prepare(scene, film, camf(film)); vp.clear()
+        assert oracle_backend.lib().ok_set_row_subset(vp.backend.ctx, step, off) == 0
+        vp.backend.call("render_samples", 1, 2)
+        vp.backend.read_film(film.framebuffer)
+        outs.append(film.framebuffer.copy()); vp.close()
+    full, sub = outs
+    # framebuffer[py, px] with py = H - y (the film is flipped vertically w.r.t. pixel rows y = 1..H, volpath.jl:384-417)
+    rows = np.array([r for r in range(32) if r % 4 == 1])
+    lit = np.zeros(32, bool)
+    for axis_rows in (rows, 31 - rows):
+        if np.array_equal(sub[axis_rows].view(np.uint32), full[axis_rows].view(np.uint32)) and sub[axis_rows].max() > 0:
+            lit[axis_rows] = True
+    assert lit.sum() == len(rows), "the sampled rows must equal the full render's rows bit for bit"
+    assert (sub[~lit] == 0).all()

@@ -303,9 +303,10 @@ def test_light_sampling(kind):
         p.olib.ok_test_lights(p.ok.ctx, fp(x), n, fp(b))
         assert_bits_equal(a, b, f"light samples ({kind})")       # choice, pmf, Li, wi, pdf, p_light, pmf replay: one libm on both sides
         if kind == "spot":
-            lit = a[:, 2:6].max(axis=1) > 0
-            assert 0.05 < lit[np.isin(a[:, 0], (1, 2, 3, 4))].mean() < 0.95, "spot cones should light some points and not others"
+            # the light BVH gives a spot zero importance outside its cone (cos_theta_e, light-bounds.jl:248-270): every pick is lit,
+            # and which light is picked depends on where the point is
             assert set(np.unique(a[:, 0]).astype(int)) >= {1, 2, 3, 5}
+            assert (a[np.isin(a[:, 0], (1, 2, 3, 4)), 2:6].max(axis=1) > 0).mean() > 0.9
         # escaped rays
         e = np.zeros((n, 4), f32); e[:, :3] = x[:, 3:6]; e[::5, :3] = [0, 1, 0]; e[:, 3] = x[:, 6]
         ea = np.zeros((n, 5), f32); eb = np.zeros((n, 5), f32)
@@ -807,7 +808,7 @@ def test_pipelined_read_out_matches_blocking_read():
     assert va.backend.lib.hk_read_film_wait(va.backend.ctx, 5) < 0          # bad ticket
     # two read-outs in flight before the first wait, and the device left to finish BOTH copies before either is looked at: frame k
     # must still be frame k (round 1 sent both into the same host buffer)
-    va.clear()
+    va.clear(); film_a.iteration_index = 0
     h1 = va.render(scene, film_a, cam_a, count=1, read="async")
     h2 = va.render(scene, film_a, cam_a, count=1, read="async")
     assert h1[1] is not h2[1] and h1[1] is not film_a._store and h2[1] is not film_a._store
