@@ -133,7 +133,7 @@ def build_scene():
     if CONFIG_NAME == "C4":
         return scenes.c4_cloud((256, 256, 128), "nanovdb", (64, 64, 64))
     if CONFIG_NAME == "C5":
-        return scenes.c5_instanced(C5_INSTANCES, 160)
+        return scenes.c5_instanced(C5_INSTANCES, 160, instanced=True)
     return scenes.c2_cat(256, 64)
 
 

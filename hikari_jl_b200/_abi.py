@@ -39,9 +39,18 @@ class HkDenoiseConfig(C.Structure):
                 ("use_variance", C.c_int32)]
 
 
+class HkMesh(C.Structure):
+    _fields_ = [("first_tri", C.c_uint32), ("n_tris", C.c_uint32)]
+
+
+class HkInstance(C.Structure):
+    _fields_ = [("mesh", C.c_uint32), ("medium_interface_idx", C.c_uint32), ("object_to_world", c_f * 12), ("world_to_object", c_f * 12)]
+
+
 class HkGeometry(C.Structure):
     _fields_ = [("positions", c_fp), ("normals", c_fp), ("tangents", c_fp), ("uvs", c_fp), ("indices", c_u32p),
-                ("tri_meta", c_u32p), ("n_verts", C.c_uint32), ("n_tris", C.c_uint32)]
+                ("tri_meta", c_u32p), ("n_verts", C.c_uint32), ("n_tris", C.c_uint32),
+                ("meshes", C.POINTER(HkMesh)), ("n_meshes", C.c_uint32), ("instances", C.POINTER(HkInstance)), ("n_instances", C.c_uint32)]
 
 
 class HkMaterial(C.Structure):

@@ -1,9 +1,9 @@
 // hk_api.cu — C ABI of libhikari_cuda.so (include/hikari_cuda.h): context, uploads, render loop, film, traversal.
 // There is NO CPU fallback anywhere in this file: every compute entry point needs a CUDA device and fails with
 // HK_ERR_NO_DEVICE / HK_ERR_CUDA otherwise.
-#include "../../include/hikari_cuda.h"
-#include "../../include/hikari_cuda_testing.h"
-#include "hk_wavefront.cuh"
+#define HK_TU_CORE
+#include "hk_context.h"
+#include "hk_launch.h"
 #include "hk_denoise.cuh"
 #include "hk_bvh.h"
 #include <algorithm>
@@ -13,71 +13,6 @@
 #include <array>
 #include <vector>
 #include <limits>
-
-#define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__); return HK_ERR_CUDA; } } while (0)
-#define REQUIRE(cond, msg) do { if (!(cond)) { ctx->err = (msg); return HK_ERR_INVALID; } } while (0)
-
-struct DevBuf {
-    void* p = nullptr; size_t bytes = 0;
-    cudaError_t alloc(size_t n) { release(); if (n == 0) n = 16; cudaError_t e = cudaMalloc(&p, n); if (e == cudaSuccess) bytes = n; else p = nullptr; return e; }
-    cudaError_t upload(const void* src, size_t n) { cudaError_t e = alloc(n); if (e != cudaSuccess) return e; return n ? cudaMemcpy(p, src, n, cudaMemcpyHostToDevice) : cudaSuccess; }
-    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
-    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
-};
-
-struct HkContext {
-    int device = 0;
-    std::string err;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    int sm_count = 148;
-    DevScene D;
-    PathState S;
-    HkRenderParams params;
-    bool have_tables = false, have_geom = false, have_mats = false, have_lights = false, have_cam = false, have_filter = false, have_params = false;
-    bool camera_medium_valid = false; uint32_t camera_medium = 0;
-    uint32_t mat_types_present = 0;
-    uint32_t n_interfaces = 0, max_iface_in_geom = 0; bool tri_types_valid = false;
-    std::vector<int32_t> mat_types;                  // host copy of the material types (hk_update_material)
-    // device buffers
-    DevBuf b_sobol, b_cie_x, b_cie_y, b_cie_z, b_d65, b_rgb_scale, b_rgb_coeffs;
-    DevBuf b_nodes, b_tris, b_pos, b_nrm, b_idx, b_meta;
-    DevBuf b_mats, b_ifaces, b_spec_l, b_spec_v, b_spec_o;
-    DevBuf b_lights, b_env, b_lnodes, b_trails, b_inf, b_esc;
-    DevBuf b_mat_pre, b_light_pre, b_med_pre;       // uplift cache (DevTables)
-    bool uplift_cache_enabled = true;
-    std::vector<DevBuf> env_bufs, media_bufs;
-    DevBuf b_media;
-    DevBuf b_f_func, b_f_mcdf, b_f_mfunc, b_f_ccdf;
-    DevBuf b_state, b_counts, b_rays, b_film, b_scratch_u32, b_trace_ctr, b_readback;
-    DevBuf b_aux, b_denoise; size_t aux_pixels = 0;
-    DevBuf b_uvs, b_textures; std::vector<DevBuf> tex_bufs;
-    bool has_rgbgrid = false;                // some uploaded medium is an RGBGridMedium: the tracking kernels with that branch compiled in     // film.albedo [3n] | film.normal [3n] | film.depth [n], (H, W) column-major
-    // pipelined read-out (hk_read_film_async): two device staging buffers, a copy stream, per-buffer events
-    DevBuf b_readback_async[2]; cudaStream_t copy_stream = nullptr; cudaEvent_t ev_final[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
-    int async_next = 0; bool async_used[2] = {false, false};
-    // fork / join of the per-material shading kernels of one bounce (independent queues) over side streams
-    cudaStream_t shade_streams[3] = {nullptr, nullptr, nullptr}; cudaEvent_t ev_fork = nullptr, ev_join[12] = {};
-    bool concurrent_shade = true; int shade_fork_slot = 0;
-    // the shadow pass of bounce b on its own stream, overlapping trace + route of bounce b+1 (opaque-only scenes)
-    cudaStream_t shadow_stream = nullptr; cudaEvent_t ev_shaded = nullptr, ev_shadowed = nullptr; int bounce_par = 0;
-    DevBuf b_sobol_top, b_sobol_dims, b_sobol_dimhash;        // ZSobol prefix cache (SobolParams::top)
-    int32_t sobol_cache_key[6] = {0, 0, 0, 0, 0, -1};          // width, height, log2_spp, nb4, seed, cached depths
-    bool sobol_cache_enabled = true;
-    size_t n_slots = 0;
-    HkStats stats;
-    uint64_t launches = 0;
-    // optional per-stage profiling (hk_set_profiling): CUDA events around every stage launch on the launching stream
-    int profiling = 0;
-    struct StageEv { int stage; cudaEvent_t a, b; };
-    std::vector<StageEv> stage_events; size_t stage_ev_used = 0;
-    double stage_ms[HK_N_STAGES]; uint64_t stage_launches[HK_N_STAGES];
-    DevBuf b_work_ctr;
-    // profiling bit 2: per-bounce queue counts and stage times of the most recent sample pass (host sync per bounce)
-    std::vector<std::array<uint32_t, HK_N_QUEUE_COUNTERS>> bounce_counts;
-    std::vector<std::array<double, HK_N_STAGES>> bounce_ms;
-    HkContext() { std::memset(&D, 0, sizeof(D)); std::memset(&S, 0, sizeof(S)); std::memset(&params, 0, sizeof(params)); std::memset(&stats, 0, sizeof(stats)); }
-};
 
 static int grid_for(const HkContext* c, size_t n, int block, int per_sm) {
     size_t need = (n + block - 1) / block;
@@ -153,6 +88,7 @@ int32_t hk_destroy(HkContext* ctx) {
     for (auto& b : ctx->media_bufs) b.release();
     for (auto& b : ctx->tex_bufs) b.release();
     ctx->b_aux.release(); ctx->b_denoise.release(); ctx->b_uvs.release(); ctx->b_textures.release();
+    ctx->b_inst_recs.release(); ctx->b_instances.release(); ctx->b_inst_base.release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (auto& s : ctx->shade_streams) if (s) cudaStreamDestroy(s);
@@ -169,7 +105,6 @@ int32_t hk_destroy(HkContext* ctx) {
 }
 const char* hk_last_error(HkContext* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
-static int32_t refresh_uplift_cache(HkContext* ctx);
 int32_t hk_upload_tables(HkContext* ctx, const HkTables* t) {
     if (!ctx || !t) return HK_ERR_INVALID;
     cudaSetDevice(ctx->device);
@@ -202,12 +137,12 @@ int32_t hk_upload_tables(HkContext* ctx, const HkTables* t) {
         ctx->D.sobol.fast = ok ? 1 : 0;
     }
     ctx->have_tables = true;
-    return refresh_uplift_cache(ctx);
+    return hk_refresh_uplift_cache(ctx);
 }
 
 // (Re)build the uplift cache for whatever is uploaded: needs the rgb2spec table; called after every upload that changes
 // a constant colour (tables, materials, lights, media, hk_update_material).
-static int32_t refresh_uplift_cache(HkContext* ctx) {
+int32_t hk_refresh_uplift_cache(HkContext* ctx) {
     DevTables& T = ctx->D.T;
     T.mat_pre = nullptr; T.light_pre = nullptr; T.med_pre = nullptr; T.mat_base = nullptr; T.light_base = nullptr; T.med_base = nullptr;
     if (!ctx->have_tables || !ctx->uplift_cache_enabled) return HK_OK;
@@ -234,6 +169,13 @@ static int32_t patch_tri_types(HkContext* ctx) {
     if (ctx->max_iface_in_geom > ctx->n_interfaces) return HK_OK;      // geometry and materials of different scenes: wait for the matching upload
     const uint32_t n = (uint32_t)(ctx->b_tris.bytes / sizeof(HkBvhTri));
     ctx->tri_types_valid = true;
+    if (ctx->D.n_inst > 0) {      // instanced: the shading class rides in the instance leaf records
+        k_patch_inst_types<<<grid_for(ctx, (size_t)ctx->D.n_inst, 256, 8), 256, 0, ctx->stream>>>(ctx->b_inst_recs.as<float4>(), (uint32_t)ctx->D.n_inst, ctx->D.instances, ctx->D.interfaces, ctx->D.materials);
+        ctx->launches++;
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaGetLastError());
+        return HK_OK;
+    }
     if (n == 0 || !ctx->D.tri_meta) return HK_OK;
     k_patch_tri_types<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(ctx->b_tris.as<float4>(), n, ctx->D.tri_meta, ctx->D.interfaces, ctx->D.materials);
     ctx->launches++;
@@ -245,15 +187,55 @@ static int32_t patch_tri_types(HkContext* ctx) {
 int32_t hk_upload_geometry(HkContext* ctx, const HkGeometry* g) {
     if (!ctx || !g) return HK_ERR_INVALID;
     cudaSetDevice(ctx->device);
-    REQUIRE(g->n_tris == 0 || (g->positions && g->indices && g->tri_meta), "geometry arrays missing");
-    REQUIRE(g->n_tris < HK_PRIM_MASK, "at most 2^28 - 2 triangles (the hit record keeps the material type in the top 4 bits)");
+    const bool instanced = g->n_instances > 0;
+    REQUIRE(g->n_tris == 0 || (g->positions && g->indices && (instanced || g->tri_meta)), "geometry arrays missing");
+    REQUIRE(!instanced || (g->meshes && g->n_meshes > 0 && g->instances), "instanced geometry needs meshes and instances");
+    for (size_t i = 0; i < 3 * (size_t)g->n_tris; i++) REQUIRE(g->indices[i] < g->n_verts, "vertex index out of range");
     ctx->max_iface_in_geom = 0;
-    for (uint32_t i = 0; i < g->n_tris; i++) {
-        REQUIRE(g->tri_meta[3 * (size_t)i] >= 1, "TriangleMeta.medium_interface_idx is 1-based");
-        ctx->max_iface_in_geom = std::max(ctx->max_iface_in_geom, g->tri_meta[3 * (size_t)i]);
+    uint64_t n_world = g->n_tris;
+    if (instanced) {
+        n_world = 0;
+        for (uint32_t m = 0; m < g->n_meshes; m++) REQUIRE((uint64_t)g->meshes[m].first_tri + g->meshes[m].n_tris <= g->n_tris, "mesh range outside the index array");
+        for (uint32_t i = 0; i < g->n_instances; i++) {
+            REQUIRE(g->instances[i].mesh < g->n_meshes, "instance references a missing mesh");
+            REQUIRE(g->instances[i].medium_interface_idx >= 1, "HkInstance.medium_interface_idx is 1-based");
+            ctx->max_iface_in_geom = std::max(ctx->max_iface_in_geom, g->instances[i].medium_interface_idx);
+            n_world += g->meshes[g->instances[i].mesh].n_tris;
+        }
+    } else {
+        for (uint32_t i = 0; i < g->n_tris; i++) {
+            REQUIRE(g->tri_meta[3 * (size_t)i] >= 1, "TriangleMeta.medium_interface_idx is 1-based");
+            ctx->max_iface_in_geom = std::max(ctx->max_iface_in_geom, g->tri_meta[3 * (size_t)i]);
+        }
     }
+    REQUIRE(n_world < HK_PRIM_MASK, "at most 2^28 - 2 triangles (the hit record keeps the material type in the top 4 bits)");
     HkBvh bvh;
-    hk_build_bvh8(g->positions, g->indices, g->n_tris, bvh);
+    int depth = 0;
+    std::vector<float4> inst_recs; std::vector<DevInstance> dinst; std::vector<uint32_t> ibase;
+    if (instanced) {
+        std::vector<HkMeshRange> mr(g->n_meshes); std::vector<HkInstanceXf> ix(g->n_instances); std::vector<uint32_t> mesh_root;
+        for (uint32_t m = 0; m < g->n_meshes; m++) mr[m] = HkMeshRange{g->meshes[m].first_tri, g->meshes[m].n_tris};
+        for (uint32_t i = 0; i < g->n_instances; i++) ix[i] = HkInstanceXf{g->instances[i].mesh, g->instances[i].object_to_world};
+        depth = hk_build_scene_bvh(g->positions, g->indices, mr.data(), g->n_meshes, ix.data(), g->n_instances, bvh, mesh_root, nullptr, nullptr) + 1;
+        dinst.resize(g->n_instances); ibase.resize(g->n_instances);
+        uint32_t base = 0;
+        for (uint32_t i = 0; i < g->n_instances; i++) {
+            const HkInstance& I = g->instances[i]; DevInstance& d = dinst[i];
+            std::memcpy(d.o2w, I.object_to_world, 48); std::memcpy(d.w2o, I.world_to_object, 48);
+            d.first_tri = g->meshes[I.mesh].first_tri; d.n_tris = g->meshes[I.mesh].n_tris; d.prim_base = base; d.iface = I.medium_interface_idx;
+            ibase[i] = base; base += d.n_tris;
+        }
+        // leaf records of the top level, in leaf order: tris[k].prim = instance index for k < n_instances
+        inst_recs.resize(4 * (size_t)g->n_instances);
+        auto u2f = [](uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; };
+        for (uint32_t k = 0; k < g->n_instances; k++) {
+            const uint32_t i = bvh.tris[k].prim; const HkInstance& I = g->instances[i];
+            for (int r = 0; r < 3; r++) inst_recs[4 * (size_t)k + r] = make_float4(I.world_to_object[4 * r], I.world_to_object[4 * r + 1], I.world_to_object[4 * r + 2], I.world_to_object[4 * r + 3]);
+            inst_recs[4 * (size_t)k + 3] = make_float4(u2f(mesh_root[I.mesh]), u2f(dinst[i].prim_base), u2f(0u), u2f(i));
+        }
+    } else depth = hk_build_bvh8(g->positions, g->indices, g->n_tris, bvh);
+    if (depth > HK_SM_STACK + HK_LM_STACK - 1) { ctx->err = "the BVH is deeper than the traversal stack (degenerate geometry: thousands of coincident triangle centroids?)"; return HK_ERR_UNSUPPORTED; }
+    CK(cudaStreamSynchronize(ctx->stream));
     CK(ctx->b_nodes.upload(bvh.nodes.data(), bvh.nodes.size() * sizeof(HkBvhNode)));
     CK(ctx->b_tris.upload(bvh.tris.data(), bvh.tris.size() * sizeof(HkBvhTri)));
     CK(ctx->b_pos.upload(g->positions, 12 * (size_t)g->n_verts));
@@ -261,12 +243,21 @@ int32_t hk_upload_geometry(HkContext* ctx, const HkGeometry* g) {
     if (g->uvs) CK(ctx->b_uvs.upload(g->uvs, 8 * (size_t)g->n_verts)); else ctx->b_uvs.release();
     ctx->D.uvs = g->uvs ? ctx->b_uvs.as<float>() : nullptr;
     CK(ctx->b_idx.upload(g->indices, 12 * (size_t)g->n_tris));
-    CK(ctx->b_meta.upload(g->tri_meta, 12 * (size_t)g->n_tris));
-    ctx->D.bvh.nodes = ctx->b_nodes.as<float4>(); ctx->D.bvh.tris = ctx->b_tris.as<float4>(); ctx->D.bvh.one_bits = 0x3F800000u;
+    if (!instanced) CK(ctx->b_meta.upload(g->tri_meta, 12 * (size_t)g->n_tris)); else ctx->b_meta.release();
+    ctx->D.bvh.nodes = ctx->b_nodes.as<float4>(); ctx->D.bvh.tris = ctx->b_tris.as<float4>(); ctx->D.bvh.one_bits = 0x3F800000u; ctx->D.bvh.inst = nullptr;
+    ctx->D.instances = nullptr; ctx->D.inst_prim_base = nullptr; ctx->D.n_inst = 0;
+    if (instanced) {
+        CK(ctx->b_inst_recs.upload(inst_recs.data(), inst_recs.size() * sizeof(float4)));
+        CK(ctx->b_instances.upload(dinst.data(), dinst.size() * sizeof(DevInstance)));
+        CK(ctx->b_inst_base.upload(ibase.data(), ibase.size() * 4));
+        ctx->D.bvh.inst = ctx->b_inst_recs.as<float4>();
+        ctx->D.instances = ctx->b_instances.as<DevInstance>(); ctx->D.inst_prim_base = ctx->b_inst_base.as<uint32_t>(); ctx->D.n_inst = (int32_t)g->n_instances;
+    } else { ctx->b_inst_recs.release(); ctx->b_instances.release(); ctx->b_inst_base.release(); }
     ctx->D.positions = ctx->b_pos.as<float>(); ctx->D.normals = g->normals ? ctx->b_nrm.as<float>() : nullptr;
-    ctx->D.indices = ctx->b_idx.as<uint32_t>(); ctx->D.tri_meta = ctx->b_meta.as<uint32_t>();
+    ctx->D.indices = ctx->b_idx.as<uint32_t>(); ctx->D.tri_meta = instanced ? nullptr : ctx->b_meta.as<uint32_t>();
     ctx->stats.bvh_nodes = bvh.nodes.size();
-    ctx->stats.bvh_bytes = bvh.nodes.size() * sizeof(HkBvhNode) + bvh.tris.size() * sizeof(HkBvhTri);
+    ctx->stats.bvh_bytes = bvh.nodes.size() * sizeof(HkBvhNode) + bvh.tris.size() * sizeof(HkBvhTri) + inst_recs.size() * sizeof(float4);
+    ctx->n_world_tris = n_world;
     ctx->have_geom = true; ctx->camera_medium_valid = false;
     return patch_tri_types(ctx);
 }
@@ -330,7 +321,7 @@ int32_t hk_upload_materials(HkContext* ctx, const HkMaterial* m, uint32_t nm, co
     ctx->mat_types.resize(nm); for (uint32_t i = 0; i < nm; i++) ctx->mat_types[i] = m[i].type == HK_MAT_MIX ? HK_MAT_MIX : (int32_t)host_shade_class(m[i]);
     if (!ctx->b_spec_o.p) { uint32_t zero = 0; CK(ctx->b_spec_o.upload(&zero, 4)); ctx->D.spec_offsets = ctx->b_spec_o.as<uint32_t>(); }
     ctx->have_mats = true; ctx->camera_medium_valid = false;
-    int32_t rc = refresh_uplift_cache(ctx);
+    int32_t rc = hk_refresh_uplift_cache(ctx);
     return rc != HK_OK ? rc : patch_tri_types(ctx);
 }
 
@@ -349,7 +340,7 @@ int32_t hk_update_material(HkContext* ctx, uint32_t index, const HkMaterial* m) 
     const int32_t cls = m->type == HK_MAT_MIX ? HK_MAT_MIX : (int32_t)host_shade_class(*m);      // mat_types holds shading classes
     const bool type_changed = ctx->mat_types[index - 1] != cls;
     ctx->mat_types[index - 1] = cls;
-    { int32_t rc = refresh_uplift_cache(ctx); if (rc != HK_OK) return rc; }
+    { int32_t rc = hk_refresh_uplift_cache(ctx); if (rc != HK_OK) return rc; }
     if (type_changed) {
         uint32_t present = 0;
         for (int32_t t : ctx->mat_types) if (t != HK_MAT_MIX) present |= 1u << t;
@@ -393,12 +384,16 @@ int32_t hk_upload_lights(HkContext* ctx, const HkLight* l, uint32_t n, const HkL
     ctx->D.lights = ctx->b_lights.as<HkLight>(); ctx->D.n_lights = (int32_t)n;
     ctx->D.lnodes = ctx->b_lnodes.as<HkLightBVHNode>(); ctx->D.bit_trails = ctx->b_trails.as<uint32_t>(); ctx->D.inf_idx = ctx->b_inf.as<int32_t>();
     ctx->D.n_infinite = (int32_t)sm->n_infinite; ctx->D.n_bvh = (int32_t)sm->n_bvh_lights;
+    {   // large light sets: light selection + sampling run as their own kernel (k_hit_lights) with the cooperative BVH descent
+        const char* e = std::getenv("HK_SPLIT_MIN_LIGHTS");      // development override of the threshold
+        ctx->D.split_lights = (int32_t)sm->n_bvh_lights >= (e ? std::atoi(e) : HK_COOP_MIN_LIGHTS) ? 1 : 0;
+    }
     std::vector<int32_t> esc;
     for (uint32_t i = 0; i < n; i++) if (l[i].type == HK_LIGHT_ENVIRONMENT || l[i].type == HK_LIGHT_AMBIENT) esc.push_back((int32_t)i);
     CK(ctx->b_esc.upload(esc.data(), 4 * esc.size()));
     ctx->D.esc_idx = ctx->b_esc.as<int32_t>(); ctx->D.n_esc = (int32_t)esc.size();
     ctx->have_lights = true;
-    return refresh_uplift_cache(ctx);
+    return hk_refresh_uplift_cache(ctx);
 }
 
 int32_t hk_upload_media(HkContext* ctx, const HkMedium* m, uint32_t n) {
@@ -445,7 +440,7 @@ int32_t hk_upload_media(HkContext* ctx, const HkMedium* m, uint32_t n) {
     CK(ctx->b_media.upload(dev.data(), sizeof(DevMedium) * (size_t)n));
     ctx->D.media = ctx->b_media.as<DevMedium>(); ctx->D.n_media = (int32_t)n;
     ctx->camera_medium_valid = false;
-    return refresh_uplift_cache(ctx);
+    return hk_refresh_uplift_cache(ctx);
 }
 
 int32_t hk_set_camera(HkContext* ctx, const HkCamera* c) {
@@ -480,8 +475,8 @@ static int32_t alloc_film(HkContext* ctx, size_t n_pixels) {
     return HK_OK;
 }
 static int32_t alloc_state(HkContext* ctx, size_t n_slots) {
-    // one slab: 19 float4 arrays, 5 u32/f32 arrays, 15 queues; every array starts 256-byte aligned
-    const size_t f4 = 19, w4 = 5, q = 6 + HK_N_HIT_QUEUES;
+    // one slab: 22 float4 arrays, 5 u32/f32 arrays, 16 queues; every array starts 256-byte aligned
+    const size_t f4 = 22, w4 = 5, q = 6 + HK_N_HIT_QUEUES;
     size_t rounded = f4 * (((16 * n_slots + 255) / 256) * 256) + (w4 + q) * (((4 * n_slots + 255) / 256) * 256);
     CK(cudaStreamSynchronize(ctx->stream));
     CK(ctx->b_state.alloc(rounded));
@@ -489,7 +484,7 @@ static int32_t alloc_state(HkContext* ctx, size_t n_slots) {
     auto take = [&](size_t elt) { char* r = p; p += ((elt * n_slots + 255) / 256) * 256; return r; };
     PathState& S = ctx->S;
     float4** f4s[] = {&S.ray_a, &S.ray_b, &S.hit, &S.lambda, &S.lpdf, &S.beta, &S.r_u, &S.r_l, &S.L, &S.sh_a, &S.sh_b, &S.sh_Ld, &S.sh_ru, &S.sh_rl,
-                      &S.med, &S.sh_hit, &S.sh_T, &S.sh_tu, &S.sh_tl};
+                      &S.med, &S.sh_hit, &S.sh_T, &S.sh_tu, &S.sh_tl, &S.nee_a, &S.nee_b, &S.nee_c};
     for (auto pp : f4s) *pp = reinterpret_cast<float4*>(take(16));
     S.flags = reinterpret_cast<uint32_t*>(take(4)); S.fweight = reinterpret_cast<float*>(take(4)); S.sh_medium = reinterpret_cast<uint32_t*>(take(4));
     S.med_ev = reinterpret_cast<uint32_t*>(take(4)); S.res_mat = reinterpret_cast<uint32_t*>(take(4));
@@ -596,13 +591,13 @@ template <int TYPE> static void launch_shade(HkContext* ctx, const PassArgs& A, 
         const int j = ctx->shade_fork_slot++;
         cudaStream_t s = ctx->shade_streams[j % 3];
         cudaStreamWaitEvent(s, ctx->ev_fork, 0);
-        k_shade<TYPE><<<ctx->sm_count * 8, 128, 0, s>>>(ctx->D, ctx->S, A, next, ctx->bounce_par);
+        hkl_shade(TYPE, ctx->sm_count * 8, s, ctx->D, ctx->S, A, next, ctx->bounce_par);
         cudaEventRecord(ctx->ev_join[j], s);
         ctx->launches++;
         return;
     }
     StageScope sc(ctx, HK_STAGE_SHADE);
-    k_shade<TYPE><<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(ctx->D, ctx->S, A, next, ctx->bounce_par);
+    hkl_shade(TYPE, ctx->sm_count * 8, ctx->stream, ctx->D, ctx->S, A, next, ctx->bounce_par);
 }
 extern "C" {
 int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride, int32_t count) {
@@ -620,7 +615,7 @@ int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride,
     }
     if (!ctx->camera_medium_valid) {   // hoisted out of the per-sample path (reference: one alloc + sync per sample, volpath.jl:503)
         CK(ctx->b_scratch_u32.alloc(16));
-        k_detect_camera_medium<<<1, 32, 0, st>>>(ctx->D, ctx->b_scratch_u32.as<uint32_t>());
+        hkl_detect_camera_medium(st, ctx->D, ctx->b_scratch_u32.as<uint32_t>());
         ctx->launches++;
         CK(cudaMemcpyAsync(&ctx->camera_medium, ctx->b_scratch_u32.p, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -650,18 +645,20 @@ int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride,
             k_reset_bounce<<<1, HK_N_COUNTERS, 0, st>>>(ctx->S, cur, overlap_shadow ? (par ^ 1) : -1); ctx->launches++;
             {
                 StageScope sc(ctx, HK_STAGE_TRACE);
-                if (cnt) k_trace<true><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, cur, work);
-                else k_trace<false><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, cur, work);
+                hkl_trace(cnt, tgrid, st, ctx->D, ctx->S, cur, work);
             }
             { StageScope sc(ctx, HK_STAGE_ROUTE); k_route<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->D, ctx->S, cur, par); }
             if (ctx->D.n_media > 0) {
                 StageScope sc(ctx, HK_STAGE_MEDIUM);
-                if (ctx->has_rgbgrid) k_medium_track<true><<<ctx->sm_count * 4, 128, 0, st>>>(ctx->D, ctx->S);
-                else k_medium_track<false><<<ctx->sm_count * 4, 128, 0, st>>>(ctx->D, ctx->S);
-                k_medium_finish<<<ctx->sm_count * 8, 128, 0, st>>>(ctx->D, ctx->S, A, cur ^ 1); ctx->launches++;
+                hkl_medium_track(ctx->has_rgbgrid, ctx->sm_count * 4, st, ctx->D, ctx->S);
+                hkl_medium_finish(ctx->sm_count * 8, st, ctx->D, ctx->S, A, cur ^ 1); ctx->launches++;
             }
             if (shadow_in_flight) { cudaStreamWaitEvent(st, ctx->ev_shadowed, 0); shadow_in_flight = false; }      // shadow(b-1) done before anything adds to L
             const bool fork = ctx->concurrent_shade && ctx->profiling == 0;
+            if (ctx->D.n_lights > 0 && ctx->D.split_lights) {      // emissive-hit MIS + the light sample of every surface hit of the bounce, ahead of the per-material kernels
+                StageScope sc(ctx, HK_STAGE_SHADE);
+                hkl_hit_lights(ctx->sm_count * 4, st, ctx->D, ctx->S, A);
+            }
             if (fork) { ctx->shade_fork_slot = 0; cudaEventRecord(ctx->ev_fork, st); }      // (the escaped-ray kernel overlaps the shading kernels too)
             if (ctx->D.n_lights > 0) { StageScope sc(ctx, HK_STAGE_ESCAPED); k_escaped<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->D, ctx->S); }
             launch_shade<HK_MAT_MATTE>(ctx, A, cur ^ 1); launch_shade<HK_MAT_MIRROR>(ctx, A, cur ^ 1); launch_shade<HK_MAT_GLASS>(ctx, A, cur ^ 1);
@@ -674,17 +671,15 @@ int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride,
                 if (overlap_shadow) {
                     cudaEventRecord(ctx->ev_shaded, st);
                     cudaStreamWaitEvent(ctx->shadow_stream, ctx->ev_shaded, 0);
-                    k_shadow_opaque<false><<<tgrid, HK_TRACE_THREADS, 0, ctx->shadow_stream>>>(ctx->D, ctx->S, work, par);
+                    hkl_shadow_opaque(false, tgrid, ctx->shadow_stream, ctx->D, ctx->S, work, par);
                     cudaEventRecord(ctx->ev_shadowed, ctx->shadow_stream);
                     ctx->launches++; shadow_in_flight = true;
                 } else {
                     StageScope sc(ctx, HK_STAGE_SHADOW);
-                    if (opaque_only) { if (cnt) k_shadow_opaque<true><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, work, par); else k_shadow_opaque<false><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, work, par); }
+                    if (opaque_only) hkl_shadow_opaque(cnt, tgrid, st, ctx->D, ctx->S, work, par);
                     else for (int r = 0; r < HK_SHADOW_ROUNDS; r++) {      // one round per medium-boundary crossing; empty rounds exit at once
-                        if (cnt) k_shadow_seg_trace<true><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, r, work);
-                        else k_shadow_seg_trace<false><<<tgrid, HK_TRACE_THREADS, 0, st>>>(ctx->D, ctx->S, r, work);
-                        if (ctx->has_rgbgrid) k_shadow_seg_ratio<true><<<ctx->sm_count * 4, 128, 0, st>>>(ctx->D, ctx->S, r);
-                        else k_shadow_seg_ratio<false><<<ctx->sm_count * 4, 128, 0, st>>>(ctx->D, ctx->S, r);
+                        hkl_shadow_seg_trace(cnt, tgrid, st, ctx->D, ctx->S, r, work);
+                        hkl_shadow_seg_ratio(ctx->has_rgbgrid, ctx->sm_count * 4, st, ctx->D, ctx->S, r);
                         ctx->launches += r == 0 ? 1 : 2;
                     }
                 }
@@ -810,7 +805,7 @@ int32_t hk_fill_aux_buffers(HkContext* ctx, int32_t has_infinite_lights) {
     if (ctx->b_aux.bytes != 28 * n) { CK(cudaStreamSynchronize(ctx->stream)); CK(ctx->b_aux.alloc(28 * n)); }
     ctx->aux_pixels = n;
     float* a = ctx->b_aux.as<float>();
-    k_aux_buffers<<<grid_for(ctx, n, HK_TRACE_THREADS, 8), HK_TRACE_THREADS, 0, ctx->stream>>>(ctx->D, a, a + 3 * n, a + 6 * n, has_infinite_lights ? 1.0e30f : std::numeric_limits<float>::infinity());
+    hkl_aux_buffers(grid_for(ctx, n, HK_TRACE_THREADS, 8), ctx->stream, ctx->D, a, a + 3 * n, a + 6 * n, has_infinite_lights ? 1.0e30f : std::numeric_limits<float>::infinity());
     ctx->launches++;
     CK(cudaGetLastError());
     return HK_OK;
@@ -901,9 +896,7 @@ static int32_t trace_dev(HkContext* ctx, const float* rays_dev, uint64_t n64, fl
         CK(cudaMemsetAsync(ctr, 0, 24, st));
         const int grid = ctx->sm_count * HK_TRACE_BLOCKS_PER_SM;
         const float4* rp = reinterpret_cast<const float4*>(rays_dev); float4* hp = reinterpret_cast<float4*>(hits_dev);
-        if (any) k_trace_batch<true, false><<<grid, HK_TRACE_THREADS, 0, st>>>(ctx->D.bvh, rp, n, hp, occ_dev, reinterpret_cast<uint32_t*>(ctr), ctr + 1);
-        else if (count) k_trace_batch<false, true><<<grid, HK_TRACE_THREADS, 0, st>>>(ctx->D.bvh, rp, n, hp, occ_dev, reinterpret_cast<uint32_t*>(ctr), ctr + 1);
-        else k_trace_batch<false, false><<<grid, HK_TRACE_THREADS, 0, st>>>(ctx->D.bvh, rp, n, hp, occ_dev, reinterpret_cast<uint32_t*>(ctr), ctr + 1);
+        hkl_trace_batch(any, count, grid, st, ctx->D.bvh, rp, n, hp, occ_dev, reinterpret_cast<uint32_t*>(ctr), ctr + 1);
         ctx->launches++;
     }
     CK(cudaEventRecord(ctx->ev1, st));
@@ -980,4 +973,3 @@ int32_t hk_dev_download(HkContext* ctx, void* dst, const void* src, uint64_t byt
 
 }  // extern "C"
 
-#include "hk_testing.cuh"

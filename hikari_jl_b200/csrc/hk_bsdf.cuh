@@ -56,11 +56,11 @@ HK_DEV float fr_complex(float ci, float eta, float k) {   // :3663-3739
     float s2_re = (m_re * q_re + m_im * q_im) / qm, s2_im = (m_im * q_re - m_re * q_im) / qm;
     return ((p_re * p_re + p_im * p_im) + (s2_re * s2_re + s2_im * s2_im)) * 0.5f;
 }
-HK_DEV Spec fr_complex4(float c, Spec eta, Spec k) { return sp4(fr_complex(c, eta.x, k.x), fr_complex(c, eta.y, k.y), fr_complex(c, eta.z, k.z), fr_complex(c, eta.w, k.w)); }
+HK_NI_BSDF Spec fr_complex4(float c, Spec eta, Spec k) { return sp4(fr_complex(c, eta.x, k.x), fr_complex(c, eta.y, k.y), fr_complex(c, eta.z, k.z), fr_complex(c, eta.w, k.w)); }
 
 // Trowbridge-Reitz (:3765-3864)
 HK_DEV bool tr_smooth(float ax, float ay) { return fmaxf(ax, ay) < 1.0e-3f; }
-HK_DEV float tr_d(float3 wm, float ax, float ay) {
+HK_NI_BSDF float tr_d(float3 wm, float ax, float ay) {
     float t2 = tan2_t(wm);
     if (isinf(t2)) return 0.0f;
     float c4 = cos2_t(wm) * cos2_t(wm);
@@ -70,7 +70,7 @@ HK_DEV float tr_d(float3 wm, float ax, float ay) {
     float q = 1.0f + e;
     return 1.0f / (HK_PI * ax * ay * c4 * (q * q));
 }
-HK_DEV float tr_lambda(float3 w, float ax, float ay) {
+HK_NI_BSDF float tr_lambda(float3 w, float ax, float ay) {
     float t2 = tan2_t(w);
     if (isinf(t2)) return 0.0f;
     float a = cos_phi(w) * ax, b = sin_phi(w) * ay;
@@ -79,7 +79,7 @@ HK_DEV float tr_lambda(float3 w, float ax, float ay) {
 HK_DEV float tr_g1(float3 w, float ax, float ay) { return 1.0f / (1.0f + tr_lambda(w, ax, ay)); }
 HK_DEV float tr_g(float3 wo, float3 wi, float ax, float ay) { return 1.0f / (1.0f + tr_lambda(wo, ax, ay) + tr_lambda(wi, ax, ay)); }
 HK_DEV float tr_pdf(float3 w, float3 wm, float ax, float ay) { return tr_g1(w, ax, ay) / fabsf(w.z) * tr_d(wm, ax, ay) * fabsf(dot3(w, wm)); }
-HK_DEV float3 tr_sample_wm(float3 w, float2 u, float ax, float ay) {
+HK_NI_BSDF float3 tr_sample_wm(float3 w, float2 u, float ax, float ay) {
     float3 wh = norm3(f3(ax * w.x, ay * w.y, w.z));
     if (wh.z < 0.0f) wh = -wh;
     float3 t1 = wh.z < 0.99999f ? norm3(cross3(f3(0, 0, 1), wh)) : f3(1, 0, 0);

@@ -19,7 +19,7 @@ HK_DEV float hg_phase(float g, float c) {                                       
     float g2 = g * g, d = 1.0f + g2 - 2.0f * g * c;
     return (1.0f - g2) / (4.0f * HK_PI * d * sqrtf(fmaxf(1.0e-10f, d)));
 }
-HK_DEV float3 hg_sample_layer(float g, float3 wo, float2 u, float& p) {                                                                    // :847-872
+HK_NI_LAYERED float3 hg_sample_layer(float g, float3 wo, float2 u, float& p) {                                                                    // :847-872
     float c;
     if (fabsf(g) < 1.0e-3f) c = 1.0f - 2.0f * u.x;
     else { float g2 = g * g; float q = (1.0f - g2) / (1.0f - g + 2.0f * g * u.x); c = clampf((1.0f + g2 - q * q) / (2.0f * g), -1.0f, 1.0f); }
@@ -47,7 +47,7 @@ HK_DEV bool refract_mf(float3 wo, float3 wm, float eta, float3& wi, float& etap)
     wi = norm3(-wo / etap + (ci / etap + (ci > 0.0f ? -ct : ct)) * wm);
     return true;
 }
-HK_DEV IfaceSample coat_sample(float3 wo, float uc, float2 u, float ax, float ay, float eta, uint32_t flags) {                              // :973-1063
+HK_NI_LAYERED IfaceSample coat_sample(float3 wo, float uc, float2 u, float ax, float ay, float eta, uint32_t flags) {                              // :973-1063
     if (tr_smooth(ax, ay) || eta == 1.0f) {
         float R = fresnel_dielectric(wo.z, eta), T = 1.0f - R;
         float pr = (flags & HK_REFL) ? R : 0.0f, pt = (flags & HK_TRANS) ? T : 0.0f;
@@ -88,7 +88,7 @@ HK_DEV IfaceSample base_sample(float3 wo, float2 u, Spec refl, uint32_t flags) {
 HK_DEV Spec base_eval(float3 wo, float3 wi, Spec refl) { return same_hemi(wo, wi) ? refl * (1.0f / HK_PI) : sp(0.0f); }                    // :1178-1187
 HK_DEV float base_pdf(float3 wo, float3 wi) { return same_hemi(wo, wi) ? fabsf(wi.z) / HK_PI : 0.0f; }                                      // :1194-1199
 HK_DEV float power_heur(float fp, float gp) { float f2 = fp * fp, g2 = gp * gp; return (f2 + g2 == 0.0f) ? 0.0f : f2 / (f2 + g2); }        // :1206-1215 (nf = ng = 1)
-HK_DEV Spec coat_eval(float3 wo, float3 wi, float ax, float ay, float eta) {                                                              // :1426-1486
+HK_NI_LAYERED Spec coat_eval(float3 wo, float3 wi, float ax, float ay, float eta) {                                                              // :1426-1486
     if (tr_smooth(ax, ay) || eta == 1.0f) return sp(0.0f);
     if (same_hemi(wo, wi)) {
         float3 wh = norm3(wo + wi);
@@ -106,7 +106,7 @@ HK_DEV Spec coat_eval(float3 wo, float3 wi, float ax, float ay, float eta) {    
     float den = dd * dd;
     return sp(T * tr_d(wh, ax, ay) * tr_g(wo, wi, ax, ay) * fabsf(cih * coh / (wo.z * wi.z * den)));
 }
-HK_DEV float coat_pdf(float3 wo, float3 wi, float ax, float ay, float eta, uint32_t flags) {                                               // :1493-1554
+HK_NI_LAYERED float coat_pdf(float3 wo, float3 wi, float ax, float ay, float eta, uint32_t flags) {                                               // :1493-1554
     if (tr_smooth(ax, ay) || eta == 1.0f) return 0.0f;
     if (same_hemi(wo, wi)) {
         if ((flags & HK_REFL) == 0) return 0.0f;

@@ -48,7 +48,7 @@ struct Builder {
 #define HK_BVH_CT 0.125f      // traversal-step cost relative to one leaf (<= 3 triangles) test in the SAH
 #endif
     static constexpr int NBINS = HK_BVH_NBINS;
-    static constexpr uint32_t MAX_LEAF = 3;       // triangles per BVH8 leaf child (unary count in 3 bits of trivalid)
+    uint32_t MAX_LEAF = 3;                        // primitives per BVH8 leaf child (unary count in 3 bits of trivalid); 1 for a top-level BVH over instances
 
     Builder(const std::vector<Box>& b, const std::vector<float>& c) : pb(b), cen(c) {}
 
@@ -122,25 +122,18 @@ inline float u2f(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 
 }  // namespace
 
-void hk_build_bvh8(const float* positions, const uint32_t* indices, uint32_t n_tris, HkBvh& out) {
+// Generic core: a BVH8 over n primitives given by their (padded) boxes and centroids; emit(prim, record) fills the 48-byte leaf
+// record of one primitive (a triangle for a mesh, an instance reference for the top level).  Returns the depth of the tree
+// (number of 8-wide levels), which bounds the traversal stack.
+template <class Emit>
+static int build_bvh8_core(const std::vector<Box>& pb, const std::vector<float>& cen, uint32_t n_tris, uint32_t max_leaf, Emit emit, HkBvh& out) {
     out.nodes.clear(); out.tris.clear();
     for (int k = 0; k < 3; k++) { out.bounds_min[k] = 0; out.bounds_max[k] = 0; }
     if (n_tris == 0) {
-        HkBvhNode root; std::memset(&root, 0, sizeof(root)); out.nodes.push_back(root); return;
-    }
-    std::vector<Box> pb(n_tris); std::vector<float> cen(3 * (size_t)n_tris);
-    #pragma omp parallel for schedule(static)
-    for (int64_t i = 0; i < (int64_t)n_tris; i++) {
-        Box b; b.reset();
-        for (int v = 0; v < 3; v++) b.grow(positions + 3 * (size_t)indices[3 * i + v]);
-        for (int k = 0; k < 3; k++) {
-            cen[3 * i + k] = 0.5f * (b.lo[k] + b.hi[k]);
-            float pad = 1.0e-5f * std::max(std::fabs(b.lo[k]), std::fabs(b.hi[k])) + 1.0e-6f;
-            b.lo[k] -= pad; b.hi[k] += pad;
-        }
-        pb[i] = b;
+        HkBvhNode root; std::memset(&root, 0, sizeof(root)); out.nodes.push_back(root); return 1;
     }
     Builder B(pb, cen);
+    B.MAX_LEAF = max_leaf;
     B.order.resize(n_tris); std::iota(B.order.begin(), B.order.end(), 0u);
     B.nodes.resize(2 * (size_t)n_tris);
     uint32_t root2 = B.alloc();
@@ -168,7 +161,7 @@ void hk_build_bvh8(const float* positions, const uint32_t* indices, uint32_t n_t
         if (best_k) *best_k = bk;
         return best;
     };
-    auto leaf_cost = [&](uint32_t n) { return N2[n].count <= Builder::MAX_LEAF ? N2[n].box.half_area() * (float)N2[n].count * C_PRIM : INF; };
+    auto leaf_cost = [&](uint32_t n) { return N2[n].count <= B.MAX_LEAF ? N2[n].box.half_area() * (float)N2[n].count * C_PRIM : INF; };
     for (int64_t n = (int64_t)n2 - 1; n >= 0; n--) {
         const Node2& nd = N2[n];
         if (nd.left == 0) { cost[n].fill(leaf_cost((uint32_t)n)); continue; }
@@ -193,11 +186,12 @@ void hk_build_bvh8(const float* positions, const uint32_t* indices, uint32_t n_t
 
     // ---- layout (BFS) -----------------------------------------------------------------------------
     out.nodes.reserve((size_t)n_tris / 6 + 16); out.tris.reserve(n_tris);
-    struct Pending { uint32_t n2; uint32_t out_idx; };
+    struct Pending { uint32_t n2; uint32_t out_idx; int depth; };
+    int max_depth = 1;
     std::vector<Pending> queue; queue.reserve((size_t)n_tris / 6 + 16);
     out.nodes.emplace_back(); std::memset(&out.nodes[0], 0, sizeof(HkBvhNode));
     // a root that is itself a leaf gets wrapped: treat it as a wide node with one leaf child
-    queue.push_back(Pending{root2, 0});
+    queue.push_back(Pending{root2, 0, 1});
     std::vector<Root> roots;
     for (size_t qi = 0; qi < queue.size(); qi++) {
         Pending cur = queue[qi];
@@ -273,12 +267,8 @@ void hk_build_bvh8(const float* positions, const uint32_t* indices, uint32_t n_t
                 std::sort(prims, prims + c.count);                  // deterministic leaf order
                 for (uint32_t t = 0; t < c.count; t++) {
                     uint32_t prim = prims[t];
-                    const float* a = positions + 3 * (size_t)indices[3 * (size_t)prim];
-                    const float* b = positions + 3 * (size_t)indices[3 * (size_t)prim + 1];
-                    const float* cc = positions + 3 * (size_t)indices[3 * (size_t)prim + 2];
                     HkBvhTri T; std::memset(&T, 0, sizeof(T));
-                    for (int k = 0; k < 3; k++) { T.v0[k] = a[k]; T.e1[k] = b[k] - a[k]; T.e2[k] = cc[k] - a[k]; }
-                    T.prim = prim;
+                    emit(prim, T);
                     out.tris.push_back(T);
                 }
             }
@@ -289,12 +279,84 @@ void hk_build_bvh8(const float* positions, const uint32_t* indices, uint32_t n_t
             if (i < 0 || ch_leaf[i]) continue;
             uint32_t idx = (uint32_t)out.nodes.size();
             out.nodes.emplace_back(); std::memset(&out.nodes.back(), 0, sizeof(HkBvhNode));
-            queue.push_back(Pending{ch[i], idx});
+            queue.push_back(Pending{ch[i], idx, cur.depth + 1}); max_depth = std::max(max_depth, cur.depth + 1);
         }
         out.nodes[cur.out_idx] = node;
     }
+    return max_depth;
 }
 
+static void triangle_boxes(const float* positions, const uint32_t* indices, uint32_t n_tris, std::vector<Box>& pb, std::vector<float>& cen) {
+    pb.resize(n_tris); cen.resize(3 * (size_t)n_tris);
+    #pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)n_tris; i++) {
+        Box b; b.reset();
+        for (int v = 0; v < 3; v++) b.grow(positions + 3 * (size_t)indices[3 * i + v]);
+        for (int k = 0; k < 3; k++) {
+            cen[3 * i + k] = 0.5f * (b.lo[k] + b.hi[k]);
+            float pad = 1.0e-5f * std::max(std::fabs(b.lo[k]), std::fabs(b.hi[k])) + 1.0e-6f;
+            b.lo[k] -= pad; b.hi[k] += pad;
+        }
+        pb[i] = b;
+    }
+}
+
+int hk_build_bvh8(const float* positions, const uint32_t* indices, uint32_t n_tris, HkBvh& out) {
+    std::vector<Box> pb; std::vector<float> cen;
+    triangle_boxes(positions, indices, n_tris, pb, cen);
+    return build_bvh8_core(pb, cen, n_tris, 3, [&](uint32_t prim, HkBvhTri& T) {
+        const float* a = positions + 3 * (size_t)indices[3 * (size_t)prim];
+        const float* b = positions + 3 * (size_t)indices[3 * (size_t)prim + 1];
+        const float* cc = positions + 3 * (size_t)indices[3 * (size_t)prim + 2];
+        for (int k = 0; k < 3; k++) { T.v0[k] = a[k]; T.e1[k] = b[k] - a[k]; T.e2[k] = cc[k] - a[k]; }
+        T.prim = prim;
+    }, out);
+}
+
+// Two-level scene BVH (HkGeometry.instances): one bottom-level BVH8 per mesh over its OBJECT-space triangles (leaf records carry the
+// face index within the mesh) and a top-level BVH8 over the instances' world boxes (one instance per leaf slot; its 48-byte leaf
+// record is {instance index, 0...}).  Everything lands in ONE node array -- top level first, root = node 0, then the meshes with their
+// child / triangle bases rebased -- and ONE leaf-record array (top-level records first).  mesh_root[m] = node index of mesh m's root.
+int hk_build_scene_bvh(const float* positions, const uint32_t* indices, const HkMeshRange* meshes, uint32_t n_meshes,
+                       const HkInstanceXf* inst, uint32_t n_inst, HkBvh& out, std::vector<uint32_t>& mesh_root, int* depth_top, int* depth_bottom) {
+    std::vector<HkBvh> blas(n_meshes);
+    std::vector<Box> obox(n_meshes);
+    int dbot = 1;
+    for (uint32_t m = 0; m < n_meshes; m++) {
+        dbot = std::max(dbot, hk_build_bvh8(positions, indices + 3 * (size_t)meshes[m].first_tri, meshes[m].n_tris, blas[m]));
+        Box b; b.reset();
+        for (uint32_t t = 0; t < 3 * meshes[m].n_tris; t++) b.grow(positions + 3 * (size_t)indices[3 * (size_t)meshes[m].first_tri + t]);
+        obox[m] = b;
+    }
+    std::vector<Box> pb(n_inst); std::vector<float> cen(3 * (size_t)n_inst);
+    for (uint32_t i = 0; i < n_inst; i++) {
+        const Box& ob = obox[inst[i].mesh]; const float* M = inst[i].object_to_world;
+        Box b; b.reset();
+        for (int c = 0; c < 8; c++) {
+            const float x = (c & 1) ? ob.hi[0] : ob.lo[0], y = (c & 2) ? ob.hi[1] : ob.lo[1], z = (c & 4) ? ob.hi[2] : ob.lo[2];
+            const float p[3] = {M[0] * x + M[1] * y + M[2] * z + M[3], M[4] * x + M[5] * y + M[6] * z + M[7], M[8] * x + M[9] * y + M[10] * z + M[11]};
+            b.grow(p);
+        }
+        for (int k = 0; k < 3; k++) {
+            cen[3 * (size_t)i + k] = 0.5f * (b.lo[k] + b.hi[k]);
+            const float pad = 1.0e-4f * std::max(std::fabs(b.lo[k]), std::fabs(b.hi[k])) + 1.0e-5f;      // culling must only ever be conservative
+            b.lo[k] -= pad; b.hi[k] += pad;
+        }
+        pb[i] = b;
+    }
+    const int dtop = build_bvh8_core(pb, cen, n_inst, 1, [&](uint32_t prim, HkBvhTri& T) { T.prim = prim; }, out);
+    mesh_root.assign(n_meshes, 0);
+    for (uint32_t m = 0; m < n_meshes; m++) {
+        const uint32_t node_off = (uint32_t)out.nodes.size(), tri_off = (uint32_t)out.tris.size();
+        mesh_root[m] = node_off;
+        for (HkBvhNode nd : blas[m].nodes) { nd.child_base += node_off; nd.tri_base += tri_off; out.nodes.push_back(nd); }
+        out.tris.insert(out.tris.end(), blas[m].tris.begin(), blas[m].tris.end());
+        blas[m] = HkBvh();
+    }
+    if (depth_top) *depth_top = dtop;
+    if (depth_bottom) *depth_bottom = dbot;
+    return dtop + dbot;
+}
 // Host-only entry point (no GPU needed): build the BVH8 of a triangle soup and hand back its node / triangle arrays, so the
 // builder's invariants can be tested on the CPU (tests/test_host_logic.py).  Returns the sizes; copies only when they fit.
 extern "C" int32_t hk_host_build_bvh8(const float* positions, const uint32_t* indices, uint32_t n_tris, void* out_nodes, uint64_t nodes_cap,

@@ -34,5 +34,10 @@ struct HkBvh {
     float bounds_min[3], bounds_max[3];
 };
 
-// positions [n_verts][3], indices [n_tris][3]
-void hk_build_bvh8(const float* positions, const uint32_t* indices, uint32_t n_tris, HkBvh& out);
+// positions [n_verts][3], indices [n_tris][3]; returns the depth of the tree in 8-wide levels (bounds the traversal stack)
+int hk_build_bvh8(const float* positions, const uint32_t* indices, uint32_t n_tris, HkBvh& out);
+// two-level BVH of an instanced scene (hk_bvh.cpp); returns top-level depth + bottom-level depth
+struct HkMeshRange { uint32_t first_tri, n_tris; };
+struct HkInstanceXf { uint32_t mesh; const float* object_to_world; };
+int hk_build_scene_bvh(const float* positions, const uint32_t* indices, const HkMeshRange* meshes, uint32_t n_meshes,
+                       const HkInstanceXf* inst, uint32_t n_inst, HkBvh& out, std::vector<uint32_t>& mesh_root, int* depth_top, int* depth_bottom);

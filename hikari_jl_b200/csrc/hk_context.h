@@ -1,0 +1,82 @@
+// hk_context.h — the context behind the opaque HkContext* of include/hikari_cuda.h, shared by the translation units of
+// libhikari_cuda.so (hk_api.cu: uploads, render loop, film; hk_testing.cu: the per-stage test entry points).
+#pragma once
+#include "../../include/hikari_cuda.h"
+#include "../../include/hikari_cuda_testing.h"
+#include "hk_wavefront.cuh"
+#include <algorithm>
+#include <array>
+#include <cstring>
+#include <cstdio>
+#include <limits>
+#include <string>
+#include <vector>
+
+#define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__); return HK_ERR_CUDA; } } while (0)
+#define REQUIRE(cond, msg) do { if (!(cond)) { ctx->err = (msg); return HK_ERR_INVALID; } } while (0)
+
+struct DevBuf {
+    void* p = nullptr; size_t bytes = 0;
+    cudaError_t alloc(size_t n) { release(); if (n == 0) n = 16; cudaError_t e = cudaMalloc(&p, n); if (e == cudaSuccess) bytes = n; else p = nullptr; return e; }
+    cudaError_t upload(const void* src, size_t n) { cudaError_t e = alloc(n); if (e != cudaSuccess) return e; return n ? cudaMemcpy(p, src, n, cudaMemcpyHostToDevice) : cudaSuccess; }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct HkContext {
+    int device = 0;
+    std::string err;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 148;
+    DevScene D;
+    PathState S;
+    HkRenderParams params;
+    bool have_tables = false, have_geom = false, have_mats = false, have_lights = false, have_cam = false, have_filter = false, have_params = false;
+    bool camera_medium_valid = false; uint32_t camera_medium = 0;
+    uint32_t mat_types_present = 0;
+    uint32_t n_interfaces = 0, max_iface_in_geom = 0; bool tri_types_valid = false;
+    std::vector<int32_t> mat_types;                  // host copy of the material types (hk_update_material)
+    // device buffers
+    DevBuf b_sobol, b_cie_x, b_cie_y, b_cie_z, b_d65, b_rgb_scale, b_rgb_coeffs;
+    DevBuf b_nodes, b_tris, b_pos, b_nrm, b_idx, b_meta;
+    DevBuf b_inst_recs, b_instances, b_inst_base; uint64_t n_world_tris = 0;      // instancing (HkGeometry.instances)
+    DevBuf b_mats, b_ifaces, b_spec_l, b_spec_v, b_spec_o;
+    DevBuf b_lights, b_env, b_lnodes, b_trails, b_inf, b_esc;
+    DevBuf b_mat_pre, b_light_pre, b_med_pre;       // uplift cache (DevTables)
+    bool uplift_cache_enabled = true;
+    std::vector<DevBuf> env_bufs, media_bufs;
+    DevBuf b_media;
+    DevBuf b_f_func, b_f_mcdf, b_f_mfunc, b_f_ccdf;
+    DevBuf b_state, b_counts, b_rays, b_film, b_scratch_u32, b_trace_ctr, b_readback;
+    DevBuf b_aux, b_denoise; size_t aux_pixels = 0;
+    DevBuf b_uvs, b_textures; std::vector<DevBuf> tex_bufs;
+    bool has_rgbgrid = false;                // some uploaded medium is an RGBGridMedium: the tracking kernels with that branch compiled in     // film.albedo [3n] | film.normal [3n] | film.depth [n], (H, W) column-major
+    // pipelined read-out (hk_read_film_async): two device staging buffers, a copy stream, per-buffer events
+    DevBuf b_readback_async[2]; cudaStream_t copy_stream = nullptr; cudaEvent_t ev_final[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    int async_next = 0; bool async_used[2] = {false, false};
+    // fork / join of the per-material shading kernels of one bounce (independent queues) over side streams
+    cudaStream_t shade_streams[3] = {nullptr, nullptr, nullptr}; cudaEvent_t ev_fork = nullptr, ev_join[12] = {};
+    bool concurrent_shade = true; int shade_fork_slot = 0;
+    // the shadow pass of bounce b on its own stream, overlapping trace + route of bounce b+1 (opaque-only scenes)
+    cudaStream_t shadow_stream = nullptr; cudaEvent_t ev_shaded = nullptr, ev_shadowed = nullptr; int bounce_par = 0;
+    DevBuf b_sobol_top, b_sobol_dims, b_sobol_dimhash;        // ZSobol prefix cache (SobolParams::top)
+    int32_t sobol_cache_key[6] = {0, 0, 0, 0, 0, -1};          // width, height, log2_spp, nb4, seed, cached depths
+    bool sobol_cache_enabled = true;
+    size_t n_slots = 0;
+    HkStats stats;
+    uint64_t launches = 0;
+    // optional per-stage profiling (hk_set_profiling): CUDA events around every stage launch on the launching stream
+    int profiling = 0;
+    struct StageEv { int stage; cudaEvent_t a, b; };
+    std::vector<StageEv> stage_events; size_t stage_ev_used = 0;
+    double stage_ms[HK_N_STAGES]; uint64_t stage_launches[HK_N_STAGES];
+    DevBuf b_work_ctr;
+    // profiling bit 2: per-bounce queue counts and stage times of the most recent sample pass (host sync per bounce)
+    std::vector<std::array<uint32_t, HK_N_QUEUE_COUNTERS>> bounce_counts;
+    std::vector<std::array<double, HK_N_STAGES>> bounce_ms;
+    HkContext() { std::memset(&D, 0, sizeof(D)); std::memset(&S, 0, sizeof(S)); std::memset(&params, 0, sizeof(params)); std::memset(&stats, 0, sizeof(stats)); }
+};
+
+// (re)build the uplift cache after an upload that changes a constant colour (hk_api.cu)
+extern "C" int32_t hk_refresh_uplift_cache(HkContext* ctx);

@@ -76,7 +76,7 @@ HK_DEV int cdf_interval(const float* __restrict__ cdf, int n, float u) {   // sa
     }
     return lo;
 }
-HK_DEV float2 env_sample_uv(const DevEnvMap& E, float2 u, float& pdf) {   // sampling.jl:270-311
+HK_NI_LIGHTS float2 env_sample_uv(const DevEnvMap& E, float2 u, float& pdf) {   // sampling.jl:270-311
     int vo = clampi(cdf_interval(E.mcdf, E.nv + 1, u.y), 1, E.nv);
     float m0 = __ldg(E.mcdf + vo - 1), m1 = __ldg(E.mcdf + vo);
     float dv = u.y - m0, dn = m1 - m0;
@@ -110,7 +110,7 @@ HK_DEV Spec arealight_Le(const DevTables& T, const HkLight& L, float3 wo, float3
     const float4 q = T.light_pre ? __ldg(T.light_pre + 2 * (&L - (const HkLight*)T.light_base) + 1) : make_pre_bounded(T, L.rgb[0] * L.scale, L.rgb[1] * L.scale, L.rgb[2] * L.scale);
     return pre_bounded(q, lam);
 }
-HK_DEV LightSample sample_light(const LightCtx& C, const HkLight& L, float3 p, float4 lam, float2 u) {   // lights.jl:39-290
+HK_NI_LIGHTS LightSample sample_light(const LightCtx& C, const HkLight& L, float3 p, float4 lam, float2 u) {   // lights.jl:39-290
     LightSample s;
     switch (L.type) {
         case HK_LIGHT_POINT: case HK_LIGHT_SPOT: {
@@ -175,7 +175,7 @@ HK_DEV LightSample sample_light(const LightCtx& C, const HkLight& L, float3 p, f
     }
     return ls_none();
 }
-HK_DEV Spec escaped_Le(const LightCtx& C, float3 d, float4 lam) {   // lights.jl:408-448
+HK_NI_LIGHTS Spec escaped_Le(const LightCtx& C, float3 d, float4 lam) {   // lights.jl:408-448
     Spec sum = sp(0.0f);
     for (int k = 0; k < C.n_esc; k++) {
         const HkLight& L = C.lights[__ldg(C.esc_idx + k)];
@@ -187,7 +187,7 @@ HK_DEV Spec escaped_Le(const LightCtx& C, float3 d, float4 lam) {   // lights.jl
     }
     return sum;
 }
-HK_DEV float env_light_pdf(const LightCtx& C, float3 d) {   // lights.jl:452-467
+HK_NI_LIGHTS float env_light_pdf(const LightCtx& C, float3 d) {   // lights.jl:452-467
     float sum = 0.0f;
     for (int k = 0; k < C.n_esc; k++) {
         const HkLight& L = C.lights[__ldg(C.esc_idx + k)];
@@ -213,7 +213,7 @@ HK_DEV LNode load_lnode(const HkLightBVHNode* __restrict__ nodes, int idx1) {
     n.two_sided = __float_as_uint(d.x); n.child = __float_as_uint(d.y); n.leaf = __float_as_uint(d.z);
     return n;
 }
-HK_DEV float lnode_importance(const LNode& N, float3 p, float3 n) {   // bvh-light-sampler.jl:58-91
+HK_NI_LIGHTS float lnode_importance(const LNode& N, float3 p, float3 n) {   // bvh-light-sampler.jl:58-91
     if (N.phi == 0.0f) return 0.0f;
     float3 pc = (N.lo + N.hi) * 0.5f;
     float3 dp = p - pc;
@@ -240,7 +240,7 @@ HK_DEV float lnode_importance(const LNode& N, float3 p, float3 n) {   // bvh-lig
     }
     return fmaxf(imp, 0.0f);
 }
-HK_DEV int bvh_sample_light(const LightCtx& C, float3 p, float3 n, float u, float& pmf_out) {   // :105-170
+HK_NI_LIGHTS int bvh_sample_light(const LightCtx& C, float3 p, float3 n, float u, float& pmf_out) {   // :105-170
     pmf_out = 0.0f;
     if (C.n_infinite + C.n_bvh == 0) return 0;
     const bool has_bvh = C.n_bvh > 0;
@@ -270,7 +270,7 @@ HK_DEV int bvh_sample_light(const LightCtx& C, float3 p, float3 n, float u, floa
 // scene only a fraction of a warp's lanes descends the light BVH (C3: 1/3 choose the 10 000-emitter tree, ncu: 6.8 of 32
 // lanes active in the descent), so the descents are served by PAIRS of lanes -- one child importance each, exchanged by
 // shuffle -- up to 16 descents per round.  Per item the arithmetic and its order are those of bvh_sample_light: same bits.
-HK_DEV int bvh_sample_light_coop(const LightCtx& C, float3 p, float3 n, float u, float& pmf_out) {
+HK_NI_LIGHTS int bvh_sample_light_coop(const LightCtx& C, float3 p, float3 n, float u, float& pmf_out) {
     pmf_out = 0.0f;
     int result = 0;
     const unsigned m = __activemask();
@@ -361,7 +361,7 @@ HK_DEV int bvh_sample_light_coop(const LightCtx& C, float3 p, float3 n, float u,
 HK_DEV int bvh_sample_light_auto(const LightCtx& C, float3 p, float3 n, float u, float& pmf_out) {
     return C.n_bvh >= HK_COOP_MIN_LIGHTS ? bvh_sample_light_coop(C, p, n, u, pmf_out) : bvh_sample_light(C, p, n, u, pmf_out);
 }
-HK_DEV float bvh_light_pmf(const LightCtx& C, float3 p, float3 n, int flat_idx) {   // :184-232
+HK_NI_LIGHTS float bvh_light_pmf(const LightCtx& C, float3 p, float3 n, int flat_idx) {   // :184-232
     if (flat_idx < 1) return 0.0f;
     const bool has_bvh = C.n_bvh > 0;
     uint32_t trail = __ldg(C.bit_trails + flat_idx - 1);

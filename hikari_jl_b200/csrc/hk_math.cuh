@@ -9,6 +9,60 @@
 #include "hk_detmath.h"
 
 #define HK_DEV __device__ __forceinline__
+// Code size matters on this path: fully inlined, the shading kernels were 110-670 KB of SASS each against a 32 KB L1.5
+// instruction cache (ncu: stall_no_instruction up to 11 warps per issue).  Two remedies, both measured on B200:
+// the light half of shading is its own kernel for large light sets (k_hit_lights), and selected helper groups can be compiled
+// as real functions (HK_NI_*; 1 = __noinline__).  Same arithmetic in the same order either way: same bits.
+#ifndef HK_NOINLINE_LIGHTS
+#define HK_NOINLINE_LIGHTS 0       // light-BVH importance / descent, sample_light, env-map sampling
+#endif
+#ifndef HK_NOINLINE_BSDF
+#define HK_NOINLINE_BSDF 0         // Trowbridge-Reitz D / Lambda / sample_wm, complex Fresnel x4
+#endif
+#ifndef HK_NOINLINE_LAYERED
+#define HK_NOINLINE_LAYERED 1      // coat_sample / coat_eval / coat_pdf / hg_sample_layer of the LayeredBxDF random walk
+#endif
+#ifndef HK_NOINLINE_SOBOL
+#define HK_NOINLINE_SOBOL 0        // zsobol_1d / zsobol_2d
+#endif
+#ifndef HK_NOINLINE_DIGITS
+#define HK_NOINLINE_DIGITS 0       // zsobol_digits (the permuted base-4 digit walk)
+#endif
+#ifndef HK_NOINLINE_MISC
+#define HK_NOINLINE_MISC 1         // 4-wide exp, the NanoVDB root->leaf walk
+#endif
+#define HK_NI_ON static __device__ __noinline__
+#define HK_NI_OFF __device__ __forceinline__
+#if HK_NOINLINE_LIGHTS
+#define HK_NI_LIGHTS HK_NI_ON
+#else
+#define HK_NI_LIGHTS HK_NI_OFF
+#endif
+#if HK_NOINLINE_BSDF
+#define HK_NI_BSDF HK_NI_ON
+#else
+#define HK_NI_BSDF HK_NI_OFF
+#endif
+#if HK_NOINLINE_LAYERED
+#define HK_NI_LAYERED HK_NI_ON
+#else
+#define HK_NI_LAYERED HK_NI_OFF
+#endif
+#if HK_NOINLINE_SOBOL
+#define HK_NI_SOBOL HK_NI_ON
+#else
+#define HK_NI_SOBOL HK_NI_OFF
+#endif
+#if HK_NOINLINE_DIGITS
+#define HK_NI_DIGITS HK_NI_ON
+#else
+#define HK_NI_DIGITS HK_NI_OFF
+#endif
+#if HK_NOINLINE_MISC
+#define HK_NI HK_NI_ON
+#else
+#define HK_NI HK_NI_OFF
+#endif
 #define HK_PI 3.14159265358979323846f
 #define HK_INF __int_as_float(0x7f800000)
 #define HK_ONE_MINUS_EPS 0.99999994f
@@ -57,7 +111,7 @@ HK_DEV Spec operator/(Spec a, Spec b) { return sp4(a.x / b.x, a.y / b.y, a.z / b
 HK_DEV Spec operator*(Spec a, float s) { return sp4(a.x * s, a.y * s, a.z * s, a.w * s); }
 HK_DEV Spec operator*(float s, Spec a) { return a * s; }
 HK_DEV Spec operator/(Spec a, float s) { return sp4(a.x / s, a.y / s, a.z / s, a.w / s); }
-HK_DEV Spec sp_exp(Spec a) { return sp4(dm_expf(a.x), dm_expf(a.y), dm_expf(a.z), dm_expf(a.w)); }
+HK_NI Spec sp_exp(Spec a) { return sp4(dm_expf(a.x), dm_expf(a.y), dm_expf(a.z), dm_expf(a.w)); }
 HK_DEV Spec sp_neg(Spec a) { return sp4(-a.x, -a.y, -a.z, -a.w); }
 HK_DEV Spec sp_max0(Spec a) { return sp4(fmaxf(a.x, 0.0f), fmaxf(a.y, 0.0f), fmaxf(a.z, 0.0f), fmaxf(a.w, 0.0f)); }
 HK_DEV float sp_avg(Spec s) { return (((s.x + s.y) + s.z) + s.w) / 4.0f; }
@@ -194,7 +248,7 @@ HK_DEV uint32_t perm4_byte(uint32_t p) {   // p in [0, 24)
 // not inlined: the digit loop is ~600 instructions and has five call sites per shading kernel; inlining all of them made
 // the kernels instruction-fetch bound (stall_no_instruction was the top stall reason)
 // digits i_hi .. i_lo (inclusive, i_lo >= log2_spp & 1) of zsobol_get_sample_index, sobol.jl:269-291
-HK_DEV uint64_t zsobol_digits(uint64_t morton, uint64_t dmix, int pow2, int i_hi, int i_lo) {
+HK_NI_DIGITS uint64_t zsobol_digits(uint64_t morton, uint64_t dmix, int pow2, int i_hi, int i_lo) {
     uint64_t idx = 0;
     for (int i = i_hi; i >= i_lo; --i) {
         int shift = 2 * i - pow2;
@@ -267,11 +321,11 @@ HK_DEV ZSample zsobol_index(const SobolParams& S, int32_t px, int32_t py, int32_
     }
     return z;
 }
-HK_DEV float zsobol_1d(const SobolParams& S, int32_t px, int32_t py, int32_t sample_idx, int32_t dim, int32_t cslot = -1, uint32_t pix = 0) {
+HK_NI_SOBOL float zsobol_1d(const SobolParams& S, int32_t px, int32_t py, int32_t sample_idx, int32_t dim, int32_t cslot = -1, uint32_t pix = 0) {
     const ZSample z = zsobol_index(S, px, py, sample_idx, dim, cslot, pix);
     return sobol_to_float(fast_owen_scramble(sobol_bits0(S, z.si), z.h1));
 }
-HK_DEV float2 zsobol_2d(const SobolParams& S, int32_t px, int32_t py, int32_t sample_idx, int32_t dim, int32_t cslot = -1, uint32_t pix = 0) {
+HK_NI_SOBOL float2 zsobol_2d(const SobolParams& S, int32_t px, int32_t py, int32_t sample_idx, int32_t dim, int32_t cslot = -1, uint32_t pix = 0) {
     const ZSample z = zsobol_index(S, px, py, sample_idx, dim, cslot, pix);
     return make_float2(sobol_to_float(fast_owen_scramble(sobol_bits0(S, z.si), z.h2lo)),
                        sobol_to_float(fast_owen_scramble(sobol_bits1(S, z.si), z.h2hi)));

@@ -92,31 +92,32 @@ HK_DEV bool majiter_next(MajIter& it, MajSeg& seg) {   // media.jl:625-729
 struct LeafCache { int32_t kx, ky, kz; uint64_t leaf_off; float tile; bool valid, is_leaf; };
 template <class Tp> HK_DEV Tp rd(const uint8_t* __restrict__ b, uint64_t off) { return __ldg(reinterpret_cast<const Tp*>(b + off)); }
 HK_DEV bool mask_on(const uint8_t* __restrict__ b, uint64_t off, uint32_t n) { return ((__ldg(b + off + (n >> 3)) >> (n & 7)) & 1) != 0; }
+// root -> upper -> lower walk to the 8^3 leaf (or the tile value) that holds voxel (x, y, z): a real function -- nvdb_density has
+// eight call sites and only the first of them (rarely the fifth) misses the per-thread leaf cache
+struct LeafWalk { uint64_t leaf_off; float tile; bool is_leaf; };
+HK_NI LeafWalk nvdb_walk(const uint8_t* __restrict__ b, uint64_t root_off, int32_t root_tiles, int32_t x, int32_t y, int32_t z) {
+    LeafWalk r; r.leaf_off = 0; r.tile = 0.0f; r.is_leaf = false;
+    uint32_t xu = (uint32_t)x, yu = (uint32_t)y, zu = (uint32_t)z;
+    uint64_t key = (uint64_t)((zu >> 12) & 0x1fffff) | ((uint64_t)((yu >> 12) & 0x1fffff) << 21) | ((uint64_t)((xu >> 12) & 0x1fffff) << 42);
+    uint64_t tile = 0; bool found = false;
+    for (int i = 0; i < root_tiles; i++) { uint64_t to = root_off + 64 + (uint64_t)i * 32; if (rd<uint64_t>(b, to) == key) { found = true; tile = to; break; } }
+    if (!found) { r.tile = rd<float>(b, root_off + 28); return r; }
+    int64_t child = rd<int64_t>(b, tile + 8);
+    if (child == 0) { r.tile = rd<float>(b, tile + 20); return r; }
+    uint64_t upper = root_off + child;
+    uint32_t nu = (((xu >> 7) & 31) << 10) | (((yu >> 7) & 31) << 5) | ((zu >> 7) & 31);
+    if (!mask_on(b, upper + 4128, nu)) { r.tile = rd<float>(b, upper + 8256 + (uint64_t)nu * 8); return r; }
+    uint64_t lower = upper + rd<int64_t>(b, upper + 8256 + (uint64_t)nu * 8);
+    uint32_t nl = (((xu >> 3) & 15) << 8) | (((yu >> 3) & 15) << 4) | ((zu >> 3) & 15);
+    if (!mask_on(b, lower + 544, nl)) { r.tile = rd<float>(b, lower + 1088 + (uint64_t)nl * 8); return r; }
+    r.is_leaf = true; r.leaf_off = lower + rd<int64_t>(b, lower + 1088 + (uint64_t)nl * 8);
+    return r;
+}
 HK_DEV float nvdb_value(const DevMedium& M, LeafCache& lc, int32_t x, int32_t y, int32_t z) {
     const int32_t kx = x >> 3, ky = y >> 3, kz = z >> 3;
     if (!(lc.valid && lc.kx == kx && lc.ky == ky && lc.kz == kz)) {
-        const uint8_t* b = M.nvdb;
-        uint32_t xu = (uint32_t)x, yu = (uint32_t)y, zu = (uint32_t)z;
-        uint64_t key = (uint64_t)((zu >> 12) & 0x1fffff) | ((uint64_t)((yu >> 12) & 0x1fffff) << 21) | ((uint64_t)((xu >> 12) & 0x1fffff) << 42);
-        lc.valid = true; lc.kx = kx; lc.ky = ky; lc.kz = kz; lc.is_leaf = false;
-        uint64_t tile = 0; bool found = false;
-        for (int i = 0; i < M.root_tiles; i++) { uint64_t to = M.root_off + 64 + (uint64_t)i * 32; if (rd<uint64_t>(b, to) == key) { found = true; tile = to; break; } }
-        if (!found) lc.tile = rd<float>(b, M.root_off + 28);
-        else {
-            int64_t child = rd<int64_t>(b, tile + 8);
-            if (child == 0) lc.tile = rd<float>(b, tile + 20);
-            else {
-                uint64_t upper = M.root_off + child;
-                uint32_t nu = (((xu >> 7) & 31) << 10) | (((yu >> 7) & 31) << 5) | ((zu >> 7) & 31);
-                if (!mask_on(b, upper + 4128, nu)) lc.tile = rd<float>(b, upper + 8256 + (uint64_t)nu * 8);
-                else {
-                    uint64_t lower = upper + rd<int64_t>(b, upper + 8256 + (uint64_t)nu * 8);
-                    uint32_t nl = (((xu >> 3) & 15) << 8) | (((yu >> 3) & 15) << 4) | ((zu >> 3) & 15);
-                    if (!mask_on(b, lower + 544, nl)) lc.tile = rd<float>(b, lower + 1088 + (uint64_t)nl * 8);
-                    else { lc.is_leaf = true; lc.leaf_off = lower + rd<int64_t>(b, lower + 1088 + (uint64_t)nl * 8); }
-                }
-            }
-        }
+        const LeafWalk w = nvdb_walk(M.nvdb, M.root_off, M.root_tiles, x, y, z);
+        lc.valid = true; lc.kx = kx; lc.ky = ky; lc.kz = kz; lc.is_leaf = w.is_leaf; lc.tile = w.tile; lc.leaf_off = w.leaf_off;
     }
     if (!lc.is_leaf) return lc.tile;
     uint32_t nf = ((uint32_t)(x & 7) << 6) | ((uint32_t)(y & 7) << 3) | (uint32_t)(z & 7);
@@ -180,7 +181,7 @@ HK_DEV float3 rgbgrid_sample(const DevMedium& M, const float* __restrict__ grid,
 HK_DEV float3 affine_pt(const float* M, float3 p);
 // sample_point(::RGBGridMedium), media.jl:1327-1372: two (three with emission) RGB look-ups and unbounded uplifts PER EVENT --
 // kept out of line so the scalar-density media keep their register budget in the persistent tracking kernels
-__device__ __noinline__ void rgbgrid_props(const DevTables& T, const DevMedium& M, float3 p, float4 lam, Spec& sa, Spec& ss, Spec& Le) {
+static __device__ __noinline__ void rgbgrid_props(const DevTables& T, const DevMedium& M, float3 p, float4 lam, Spec& sa, Spec& ss, Spec& Le) {
     const float3 pm = affine_pt(M.medium_from_render, p);
     float pn[3];
 #pragma unroll

@@ -32,7 +32,7 @@ struct Poly3 { float c0, c1, c2; };
 #define HK_NOINLINE_UPLIFT 1
 #endif
 #if HK_NOINLINE_UPLIFT
-#define HK_SPEC_FN __device__ __noinline__
+#define HK_SPEC_FN static __device__ __noinline__
 #else
 #define HK_SPEC_FN HK_DEV
 #endif

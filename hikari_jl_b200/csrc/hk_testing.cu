@@ -1,6 +1,7 @@
-// hk_testing.cuh — batch kernels behind include/hikari_cuda_testing.h: each runs ONE device function of the path
-// over an input array so tests can compare it with the CPU oracle in isolation.  Included at the end of hk_api.cu.
-#pragma once
+// hk_testing.cu — batch kernels behind include/hikari_cuda_testing.h: each runs ONE device function of the path
+// over an input array so tests can compare it with the CPU oracle in isolation.  Its own translation unit of libhikari_cuda.so.
+#include "hk_context.h"
+#include <cstring>
 
 #define TK_LOOP(n) for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < (n); i += (uint64_t)gridDim.x * blockDim.x)
 
@@ -193,7 +194,7 @@ int32_t hk_test_uplift_cache(HkContext* ctx, int32_t on) {
     if (!ctx) return HK_ERR_INVALID;
     cudaSetDevice(ctx->device);
     int32_t old = ctx->uplift_cache_enabled ? 1 : 0; ctx->uplift_cache_enabled = on != 0;
-    int32_t rc = refresh_uplift_cache(ctx);
+    int32_t rc = hk_refresh_uplift_cache(ctx);
     return rc != HK_OK ? rc : old;
 }
 // 0 / 1: disable / enable the ZSobol prefix cache (takes effect at the next hk_set_params); returns the previous setting

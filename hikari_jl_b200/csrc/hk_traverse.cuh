@@ -34,9 +34,15 @@
 #ifndef HK_TRACE_BLOCKS_PER_SM
 #define HK_TRACE_BLOCKS_PER_SM 8
 #endif
+#ifndef HK_TRACE_BLOCKS_PER_SM_INST
+#define HK_TRACE_BLOCKS_PER_SM_INST 6      // the instanced walker keeps the world-space ray and the instance's primitive base as well (80 registers)
+#endif
 
 // one_bits = 0x3F800000, supplied by the host so that it reaches the kernels as a run-time value: see HK_QF in node_step()
-struct DevBvh { const float4* __restrict__ nodes; const float4* __restrict__ tris; uint32_t one_bits; };
+// inst != nullptr: two-level BVH (HkGeometry.instances).  The top level occupies nodes[0..) with node 0 as its root and its leaf
+// records tris[k] = {instance slot k, ...}; inst[4 * k ..] is the 64-byte record of the instance in leaf slot k: rows 0-2 of
+// world_to_object and (root node of its mesh, first global primitive id, shading class << 28, instance index).
+struct DevBvh { const float4* __restrict__ nodes; const float4* __restrict__ tris; uint32_t one_bits; const float4* __restrict__ inst; };
 // prim1: 1-based global primitive id in the low 28 bits (0 = miss) | material type of the triangle's interface << 28.
 // The type bits ride along for free (they sit in the spare word of the 48-byte triangle record, written by
 // k_patch_tri_types once geometry and materials are both uploaded) so that the routing kernel needs no
@@ -80,11 +86,20 @@ struct TravStack {
 // pending triangles" per iteration: a lane whose leaf has several triangles keeps testing them in the following iterations
 // while its neighbours already expand their next node, instead of the whole warp waiting for the longest triangle list.
 // COUNT: accumulate node visits / triangle tests (roofline accounting).  ANY: stop at the first accepted hit.
-template <bool ANY, bool COUNT>
+// return marker pushed when the walk enters an instance: y has its top byte clear (a pending node group never has), bits 0-7 =
+// the other instances of the top-level leaf group still to visit, bits 8-15 = that group's valid mask (one instance per slot)
+HK_DEV uint32_t spread3(uint32_t b8) { uint32_t v = b8; v = (v | (v << 8)) & 0x00F00Fu; v = (v | (v << 4)) & 0x0C30C3u; v = (v | (v << 2)) & 0x249249u; return v; }
+HK_DEV uint32_t gather3(uint32_t b24) { uint32_t v = b24 & 0x249249u; v = (v | (v >> 2)) & 0x0C30C3u; v = (v | (v >> 4)) & 0x00F00Fu; v = (v | (v >> 8)) & 0xFFu; return v; }
+
+template <bool ANY, bool COUNT, bool INST = false>
 struct Bvh8Walker {
     float3 o, d, inv;
     float t_max;
     uint32_t oct_inv;
+    // INST only: the world-space ray (o, d above are the ray in the space being traversed), and the instance being traversed
+    float3 wo, wd;
+    uint32_t prim_base, mtype_bits;
+    bool in_blas;
     uint2 ngroup, tgroup;      // ngroup: (first internal child, octant-ordered hit bits << 24 | imask); tgroup: (first triangle, pending triangle bits)
     uint32_t tvalid;           // HkBvhNode::trivalid of the node tgroup came from
     TravStack st;
@@ -110,12 +125,25 @@ struct Bvh8Walker {
         if (!finite || (d.x == 0.0f && d.y == 0.0f && d.z == 0.0f)) ngroup.y = 0u;
         tgroup = make_uint2(0u, 0u); tvalid = 0u;
         best.t = t_max; best.prim1 = 0; best.b1 = 0.0f; best.b2 = 0.0f;
+        if (INST) { wo = o; wd = d; in_blas = false; prim_base = 0u; mtype_bits = 0u; }
+    }
+    HK_DEV void set_ray(float3 o_, float3 d_) {
+        o = o_; d = d_;
+        inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+        oct_inv = (d.x >= 0.0f ? 4u : 0u) | (d.y >= 0.0f ? 2u : 0u) | (d.z >= 0.0f ? 1u : 0u);
     }
     // precondition: no pending triangles.  Returns true when the traversal is finished (nothing left to visit).
     HK_DEV bool node_step(const DevBvh& B, uint32_t* n_nodes) {
         if (ngroup.y <= 0x00FFFFFFu) {
             if (st.n == 0) return true;
             ngroup = st.pop();
+            if (INST && ngroup.y <= 0x00FFFFFFu) {      // return marker: the instance is done, back to the top level in world space
+                in_blas = false;
+                set_ray(wo, wd);
+                tgroup = make_uint2(ngroup.x, spread3(ngroup.y & 0xFFu)); tvalid = spread3((ngroup.y >> 8) & 0xFFu);
+                ngroup.y = 0u;
+                return false;
+            }
         }
         // ---- pop the nearest pending internal child of this group -------------------------------------
         const uint32_t hits = ngroup.y;
@@ -187,15 +215,30 @@ struct Bvh8Walker {
         return false;
     }
     // precondition: tgroup.y != 0.  Tests one pending triangle; returns true only for ANY when a hit was accepted.
+    // INST, at the top level: the pending leaf entry is an instance -- enter it (object-space ray, the mesh's root as the node group).
     HK_DEV bool tri_step(const DevBvh& B, uint32_t* n_tris) {
         const uint32_t tbit = (uint32_t)__ffs(tgroup.y) - 1u;
         tgroup.y &= tgroup.y - 1u;
+        if (INST && !in_blas) {
+            const uint32_t slot = tgroup.x + (uint32_t)__popc(tvalid & ((1u << tbit) - 1u));
+            const float4* ip = B.inst + (size_t)slot * 4;
+            const float4 r0 = __ldg(ip), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2), r3 = __ldg(ip + 3);
+            if (ngroup.y > 0x00FFFFFFu) st.push(ngroup);
+            st.push(make_uint2(tgroup.x, gather3(tgroup.y) | (gather3(tvalid) << 8)));
+            const float3 oo = f3(r0.x * wo.x + r0.y * wo.y + r0.z * wo.z + r0.w, r1.x * wo.x + r1.y * wo.y + r1.z * wo.z + r1.w, r2.x * wo.x + r2.y * wo.y + r2.z * wo.z + r2.w);
+            const float3 od = f3(r0.x * wd.x + r0.y * wd.y + r0.z * wd.z, r1.x * wd.x + r1.y * wd.y + r1.z * wd.z, r2.x * wd.x + r2.y * wd.y + r2.z * wd.z);
+            set_ray(oo, od);
+            in_blas = true; prim_base = __float_as_uint(r3.y); mtype_bits = __float_as_uint(r3.z);
+            ngroup = make_uint2(__float_as_uint(r3.x), 0x80000000u);
+            tgroup.y = 0u;
+            return false;
+        }
         const float4* tp = B.tris + (size_t)(tgroup.x + (uint32_t)__popc(tvalid & ((1u << tbit) - 1u))) * 3;
         const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
         if (COUNT) (*n_tris)++;
         float t, u, v;
         if (tri_test(o, d, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), t_max, t, u, v)) {
-            const uint32_t prim1 = (__float_as_uint(a.w) + 1u) | (__float_as_uint(b.w) << 28);
+            const uint32_t prim1 = INST ? ((prim_base + __float_as_uint(a.w) + 1u) | mtype_bits) : ((__float_as_uint(a.w) + 1u) | (__float_as_uint(b.w) << 28));
             if (ANY) { best.t = t; best.prim1 = prim1; best.b1 = u; best.b2 = v; return true; }
             if (best.prim1 == 0u || t < best.t || (t == best.t && HK_HIT_PRIM1(prim1) < HK_HIT_PRIM1(best.prim1))) { best.t = t; best.prim1 = prim1; best.b1 = u; best.b2 = v; }
         }
@@ -204,9 +247,9 @@ struct Bvh8Walker {
 };
 
 // blocking form (one ray, run to completion)
-template <bool ANY, bool COUNT>
+template <bool ANY, bool COUNT, bool INST = false>
 HK_DEV HitRec bvh8_trace(const DevBvh& B, uint2* sm_stack, float3 o, float3 d, float t_max, uint32_t* n_nodes = nullptr, uint32_t* n_tris = nullptr) {
-    Bvh8Walker<ANY, COUNT> w;
+    Bvh8Walker<ANY, COUNT, INST> w;
     uint2 lm_stack[HK_LM_STACK];
     w.begin(sm_stack, lm_stack, o, d, t_max);
     for (;;) {
@@ -222,9 +265,9 @@ HK_DEV HitRec bvh8_trace(const DevBvh& B, uint2* sm_stack, float3 o, float3 d, f
 // (one atomicAdd per refill) once at least HK_REFILL_MIN lanes of the warp are idle -- the ray set-up is a divergent
 // region of its own, so it is batched instead of being run for single lanes in almost every iteration.
 // IO supplies  uint32_t load(idx, o, d, t_max) -> token  and  void store(token, hit).
-template <bool ANY, bool COUNT, class IO>
+template <bool ANY, bool COUNT, bool INST, class IO>
 HK_DEV void trace_queue(const DevBvh& B, uint2* sm_stack, uint32_t n, uint32_t* cursor, IO& io, uint32_t& traced, uint32_t& wn, uint32_t& wt) {
-    Bvh8Walker<ANY, COUNT> w;
+    Bvh8Walker<ANY, COUNT, INST> w;
     uint2 lm_stack[HK_LM_STACK];
     bool busy = false, exhausted = false;
     uint32_t token = 0;

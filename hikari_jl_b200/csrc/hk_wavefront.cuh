@@ -73,6 +73,7 @@ struct DevScene {
     const int32_t* __restrict__ esc_idx; int32_t n_esc;
     const DevMedium* __restrict__ media; int32_t n_media;
     int32_t any_medium_transition;     // some interface has inside != outside
+    int32_t split_lights;              // 1: k_hit_lights does emissive-hit MIS + the NEE light sample ahead of k_shade<TYPE, true> (large light sets)
     HkCamera camera;
     DevFilter filter;
     int32_t width, height, max_depth, regularize;
@@ -80,7 +81,35 @@ struct DevScene {
     SobolParams sobol;
     // textured parameters (appended last: the members above keep their offsets in the kernel parameter block)
     const float* __restrict__ uvs; const HkTexture* __restrict__ textures; int32_t n_textures;
+    // instancing (HkGeometry.instances): instances in upload order + their first global primitive ids (ascending); n_inst = 0: plain soup
+    const struct DevInstance* __restrict__ instances; const uint32_t* __restrict__ inst_prim_base; int32_t n_inst;
 };
+struct DevInstance { float o2w[12]; float w2o[12]; uint32_t first_tri, prim_base, iface, n_tris; };
+// A global primitive id resolves to (instance, triangle of the index array); vertices / normals of an instanced triangle are taken
+// to world space per hit: O v and normalize(W^T n) in f32, in the operation order of the oracle's Scene::vert / nrm.
+struct PrimRef { uint32_t tri; const DevInstance* inst; };
+HK_DEV PrimRef resolve_prim(const DevScene& D, uint32_t prim0) {
+    PrimRef r; r.tri = prim0; r.inst = nullptr;
+    if (D.n_inst <= 0) return r;
+    int lo = 0, hi = D.n_inst - 1;                     // last instance whose first primitive id is <= prim0
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (__ldg(D.inst_prim_base + mid) <= prim0) lo = mid; else hi = mid - 1; }
+    r.inst = D.instances + lo;
+    r.tri = r.inst->first_tri + (prim0 - r.inst->prim_base);
+    return r;
+}
+HK_DEV uint32_t prim_iface(const DevScene& D, const PrimRef& r, uint32_t prim0) { return r.inst ? r.inst->iface : __ldg(D.tri_meta + 3 * (size_t)prim0); }
+HK_DEV uint32_t prim_iface(const DevScene& D, uint32_t prim0) { return prim_iface(D, resolve_prim(D, prim0), prim0); }
+HK_DEV uint32_t prim_arealight(const DevScene& D, const PrimRef& r, uint32_t prim0) { return r.inst ? 0u : __ldg(D.tri_meta + 3 * (size_t)prim0 + 2); }
+HK_DEV float3 inst_point(const float* m, float3 p) { return f3(m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3], m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7], m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11]); }
+HK_DEV float3 inst_normal(const float* w, float3 n) { return norm3(f3(w[0] * n.x + w[4] * n.y + w[8] * n.z, w[1] * n.x + w[5] * n.y + w[9] * n.z, w[2] * n.x + w[6] * n.y + w[10] * n.z)); }
+HK_DEV void prim_vertices(const DevScene& D, const PrimRef& r, float3& v0, float3& v1, float3& v2) {
+    const uint32_t i0 = __ldg(D.indices + 3 * (size_t)r.tri), i1 = __ldg(D.indices + 3 * (size_t)r.tri + 1), i2 = __ldg(D.indices + 3 * (size_t)r.tri + 2);
+    const float* P = D.positions;
+    v0 = f3(__ldg(P + 3 * (size_t)i0), __ldg(P + 3 * (size_t)i0 + 1), __ldg(P + 3 * (size_t)i0 + 2));
+    v1 = f3(__ldg(P + 3 * (size_t)i1), __ldg(P + 3 * (size_t)i1 + 1), __ldg(P + 3 * (size_t)i1 + 2));
+    v2 = f3(__ldg(P + 3 * (size_t)i2), __ldg(P + 3 * (size_t)i2 + 1), __ldg(P + 3 * (size_t)i2 + 2));
+    if (r.inst) { v0 = inst_point(r.inst->o2w, v0); v1 = inst_point(r.inst->o2w, v1); v2 = inst_point(r.inst->o2w, v2); }
+}
 HK_DEV uint32_t shade_class(const HkMaterial& m) { return (m.type == HK_MAT_MATTE && m.tex[0] > 0) ? (uint32_t)HK_SHADE_MATTE_TEX : (uint32_t)m.type; }
 struct PathState {
     float4 *ray_a, *ray_b, *hit, *lambda, *lpdf, *beta, *r_u, *r_l, *L;
@@ -89,6 +118,7 @@ struct PathState {
     float4 *med; uint32_t* med_ev;                 // delta-tracking result per slot: (scatter point, g), event
     uint32_t* res_mat;                             // material a MixMaterial hit resolved to (written by the routing, read by k_shade)
     float4 *sh_hit, *sh_T, *sh_tu, *sh_tl;         // shadow rays through media: segment hit, running transmittance / MIS ratios
+    float4 *nee_a, *nee_b, *nee_c;                 // light sample of a surface hit, written by k_hit_lights for k_shade: Li | wi, pdf | p_light, pmf (sign bit = delta light)
     uint32_t *q_ray[2], *q_escaped, *q_medium, *q_shadow, *q_shadow2, *q_hit[HK_N_HIT_QUEUES];
     uint32_t* counts;                  // [HK_N_COUNTERS]
     unsigned long long* rays_traced;
@@ -156,30 +186,30 @@ HK_DEV void count_rays(unsigned long long* ctr, uint32_t mine) {
 struct Surf { float3 pi, n, ns; float area; uint32_t iface, arealight; };
 HK_DEV Surf surface_at(const DevScene& D, uint32_t prim0, float b1, float b2, float3 o, float3 d, float t) {
     Surf s;
-    const uint32_t i0 = __ldg(D.indices + 3 * (size_t)prim0), i1 = __ldg(D.indices + 3 * (size_t)prim0 + 1), i2 = __ldg(D.indices + 3 * (size_t)prim0 + 2);
-    const float* P = D.positions;
-    float3 v0 = f3(__ldg(P + 3 * (size_t)i0), __ldg(P + 3 * (size_t)i0 + 1), __ldg(P + 3 * (size_t)i0 + 2));
-    float3 v1 = f3(__ldg(P + 3 * (size_t)i1), __ldg(P + 3 * (size_t)i1 + 1), __ldg(P + 3 * (size_t)i1 + 2));
-    float3 v2 = f3(__ldg(P + 3 * (size_t)i2), __ldg(P + 3 * (size_t)i2 + 1), __ldg(P + 3 * (size_t)i2 + 2));
+    const PrimRef pr = resolve_prim(D, prim0);
+    float3 v0, v1, v2;
+    prim_vertices(D, pr, v0, v1, v2);
     s.pi = o + d * t;
     float3 cr = cross3(v1 - v0, v2 - v0);
     float3 n = norm3(cr);
     s.area = 0.5f * len3(cr);
     float3 ns = n;
     if (D.normals) {
+        const uint32_t i0 = __ldg(D.indices + 3 * (size_t)pr.tri), i1 = __ldg(D.indices + 3 * (size_t)pr.tri + 1), i2 = __ldg(D.indices + 3 * (size_t)pr.tri + 2);
         const float* N = D.normals;
         float3 n0 = f3(__ldg(N + 3 * (size_t)i0), __ldg(N + 3 * (size_t)i0 + 1), __ldg(N + 3 * (size_t)i0 + 2));
         float3 n1 = f3(__ldg(N + 3 * (size_t)i1), __ldg(N + 3 * (size_t)i1 + 1), __ldg(N + 3 * (size_t)i1 + 2));
         float3 n2 = f3(__ldg(N + 3 * (size_t)i2), __ldg(N + 3 * (size_t)i2 + 1), __ldg(N + 3 * (size_t)i2 + 2));
         if (!(isnan(n0.x) || isnan(n1.x) || isnan(n2.x))) {
+            if (pr.inst) { n0 = inst_normal(pr.inst->w2o, n0); n1 = inst_normal(pr.inst->w2o, n1); n2 = inst_normal(pr.inst->w2o, n2); }
             float w = 1.0f - b1 - b2;
             ns = norm3(f3(w * n0.x + b1 * n1.x + b2 * n2.x, w * n0.y + b1 * n1.y + b2 * n2.y, w * n0.z + b1 * n1.z + b2 * n2.z));
         }
     }
     s.ns = ns;
     s.n = dot3(n, ns) < 0.0f ? -n : n;
-    s.iface = __ldg(D.tri_meta + 3 * (size_t)prim0);
-    s.arealight = __ldg(D.tri_meta + 3 * (size_t)prim0 + 2);
+    s.iface = prim_iface(D, pr, prim0);
+    s.arealight = prim_arealight(D, pr, prim0);
     return s;
 }
 // Kd of a textured MatteMaterial at a hit: uv = barycentric interpolation of the vertex uvs (intersection.jl:28-37), bilinear
@@ -188,7 +218,8 @@ HK_DEV Surf surface_at(const DevScene& D, uint32_t prim0, float b1, float b2, fl
 HK_DEV Spec textured_kd(const DevScene& D, const HkMaterial& m, uint32_t prim0, float b1, float b2, float4 lam) {
     float u = 0.0f, v = 0.0f;
     if (D.uvs) {
-        const uint32_t i0 = __ldg(D.indices + 3 * (size_t)prim0), i1 = __ldg(D.indices + 3 * (size_t)prim0 + 1), i2 = __ldg(D.indices + 3 * (size_t)prim0 + 2);
+        const uint32_t tri = resolve_prim(D, prim0).tri;
+        const uint32_t i0 = __ldg(D.indices + 3 * (size_t)tri), i1 = __ldg(D.indices + 3 * (size_t)tri + 1), i2 = __ldg(D.indices + 3 * (size_t)tri + 2);
         const float2 a = __ldg(reinterpret_cast<const float2*>(D.uvs) + i0), b = __ldg(reinterpret_cast<const float2*>(D.uvs) + i1), c = __ldg(reinterpret_cast<const float2*>(D.uvs) + i2);
         const float w = 1.0f - b1 - b2;
         u = w * a.x + b1 * b.x + b2 * c.x; v = w * a.y + b1 * b.y + b2 * c.y;
@@ -210,15 +241,12 @@ HK_DEV Spec textured_kd(const DevScene& D, const HkMaterial& m, uint32_t prim0, 
     return pre_bounded(make_pre_bounded(D.T, rgb[0], rgb[1], rgb[2]), lam);
 }
 HK_DEV float3 geometric_normal(const DevScene& D, uint32_t prim0) {
-    const uint32_t i0 = __ldg(D.indices + 3 * (size_t)prim0), i1 = __ldg(D.indices + 3 * (size_t)prim0 + 1), i2 = __ldg(D.indices + 3 * (size_t)prim0 + 2);
-    const float* P = D.positions;
-    float3 v0 = f3(__ldg(P + 3 * (size_t)i0), __ldg(P + 3 * (size_t)i0 + 1), __ldg(P + 3 * (size_t)i0 + 2));
-    float3 v1 = f3(__ldg(P + 3 * (size_t)i1), __ldg(P + 3 * (size_t)i1 + 1), __ldg(P + 3 * (size_t)i1 + 2));
-    float3 v2 = f3(__ldg(P + 3 * (size_t)i2), __ldg(P + 3 * (size_t)i2 + 1), __ldg(P + 3 * (size_t)i2 + 2));
+    float3 v0, v1, v2;
+    prim_vertices(D, resolve_prim(D, prim0), v0, v1, v2);
     return norm3(cross3(v1 - v0, v2 - v0));
 }
 HK_DEV int material_type_of_prim(const DevScene& D, uint32_t prim0) {
-    uint32_t mi = __ldg(D.tri_meta + 3 * (size_t)prim0);
+    uint32_t mi = prim_iface(D, prim0);
     uint32_t mat = __ldg(&D.interfaces[mi - 1].material);
     return __ldg(&D.materials[mat - 1].type);
 }
@@ -228,6 +256,7 @@ HK_DEV int material_type_of_prim(const DevScene& D, uint32_t prim0) {
 // =====================================================================================================================
 HK_DEV int slot_sample_idx(const PassArgs& A, uint32_t slot) { return A.first_sample + A.stride * (int)(slot / A.n_pixels); }
 
+#ifdef HK_TU_CORE
 // vp_generate_camera_rays_kernel!, volpath.jl:125-205.  One thread per slot; ray queue 0 becomes the identity.
 __global__ void __launch_bounds__(256) k_camera(const __grid_constant__ DevScene D, PathState S, PassArgs A, uint32_t camera_medium) {
     const uint32_t n_slots = A.n_pixels * (uint32_t)A.n_batch;
@@ -306,6 +335,7 @@ __global__ void k_reset_bounce(PathState S, int cur, int keep_par) {      // lau
     if (keep_par >= 0 && (i == HK_CI_SHADOW(keep_par) || i == HK_CI_CURSOR_SHADOW(keep_par) || i == HK_CI_TOTAL_HITS(keep_par))) return;
     if (i < HK_N_COUNTERS && i != (HK_C_RAY0 + cur)) S.counts[i] = 0;
 }
+#endif  // HK_TU_CORE
 // append from whichever lanes are here (a divergent region of a persistent loop): lanes that arrive together share one atomic
 HK_DEV void push_active(uint32_t* counter, uint32_t* queue, uint32_t value) {
     const unsigned m = __activemask(), lane = threadIdx.x & 31u;
@@ -345,16 +375,18 @@ struct QueueRayIO {
     }
     HK_DEV void store(uint32_t slot, const HitRec& h) const { S.hit[slot] = make_float4(h.t, __uint_as_float(h.prim1), h.b1, h.b2); }
 };
-template <bool COUNT>
-__global__ void __launch_bounds__(HK_TRACE_THREADS, HK_TRACE_BLOCKS_PER_SM) k_trace(const __grid_constant__ DevScene D, PathState S, int cur, unsigned long long* work) {
+#ifdef HK_TU_TRACE
+template <bool COUNT, bool INST>
+__global__ void __launch_bounds__(HK_TRACE_THREADS, INST ? HK_TRACE_BLOCKS_PER_SM_INST : HK_TRACE_BLOCKS_PER_SM) k_trace(const __grid_constant__ DevScene D, PathState S, int cur, unsigned long long* work) {
     __shared__ uint2 sm_stack[HK_SM_STACK * HK_TRACE_THREADS];
     const uint32_t n = S.counts[HK_C_RAY0 + cur];
     uint32_t traced = 0, wn = 0, wt = 0;
     QueueRayIO io{S, S.q_ray[cur]};
-    trace_queue<false, COUNT>(D.bvh, sm_stack + threadIdx.x, n, S.counts + HK_C_CURSOR_TRACE, io, traced, wn, wt);
+    trace_queue<false, COUNT, INST>(D.bvh, sm_stack + threadIdx.x, n, S.counts + HK_C_CURSOR_TRACE, io, traced, wn, wt);
     count_rays(S.rays_traced, traced);
     if (COUNT) { count_rays(work, traced); count_rays(work + 1, wn); count_rays(work + 2, wt); }
 }
+#endif  // HK_TU_TRACE
 // in-medium rays go to delta tracking with their hit record; the vacuum alpha loop (:224-266) ends on its first iteration
 // because every constant-parameter material has alpha == 1 (spectral-eval.jl:3882-3888)
 // ---- MixMaterial, src/materials/mix-material.jl: mix_hash_float :114-158 (the UInt32 shifts truncate, the SetKey shifts
@@ -402,7 +434,7 @@ HK_DEV int hit_queue_id(const DevScene& D, const PathState& S, uint32_t slot, ui
         const float4 ra = S.ray_a[slot], rb = S.ray_b[slot];
         const float3 o = f3(ra.x, ra.y, ra.z), d = f3(ra.w, rb.x, rb.y);
         const uint32_t prim0 = HK_HIT_PRIM1(hit_bits) - 1u;
-        const uint32_t mi = __ldg(D.tri_meta + 3 * (size_t)prim0);
+        const uint32_t mi = prim_iface(D, prim0);
         const uint32_t res = resolve_mix_material(D.materials, D.interfaces[mi - 1].material, o + d * t_hit, -d);
         S.res_mat[slot] = res;
         mtype = shade_class(D.materials[res - 1]);
@@ -411,6 +443,7 @@ HK_DEV int hit_queue_id(const DevScene& D, const PathState& S, uint32_t slot, ui
     return HK_HIT_COUNTER((int)HK_TYPE_QUEUE(mtype));
 }
 
+#ifdef HK_TU_CORE
 // writes the shading class (material type; 11 = textured matte) of every BVH triangle into the spare word of its record (HitRec)
 __global__ void __launch_bounds__(256) k_patch_tri_types(float4* __restrict__ tris, uint32_t n_tris, const uint32_t* __restrict__ tri_meta,
                                                           const HkMediumInterface* __restrict__ interfaces, const HkMaterial* __restrict__ materials) {
@@ -419,6 +452,15 @@ __global__ void __launch_bounds__(256) k_patch_tri_types(float4* __restrict__ tr
         const uint32_t mi = tri_meta[3 * (size_t)prim0];
         const uint32_t type = shade_class(materials[interfaces[mi - 1].material - 1]);
         tris[3 * (size_t)i + 1].w = __uint_as_float(type & 0xFu);
+    }
+}
+// instanced scenes: the shading class rides in the instance's leaf record (word 2 of its fourth float4, already shifted to bits 28-31)
+__global__ void __launch_bounds__(256) k_patch_inst_types(float4* __restrict__ inst_recs, uint32_t n_inst, const DevInstance* __restrict__ instances,
+                                                           const HkMediumInterface* __restrict__ interfaces, const HkMaterial* __restrict__ materials) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_inst; i += gridDim.x * blockDim.x) {
+        const uint32_t orig = __float_as_uint(inst_recs[4 * (size_t)i + 3].w);
+        const uint32_t type = shade_class(materials[interfaces[instances[orig].iface - 1].material - 1]);
+        inst_recs[4 * (size_t)i + 3].z = __uint_as_float((type & 0xFu) << 28);
     }
 }
 // Appends are aggregated per BLOCK: every thread classifies HK_ROUTE_PER_THREAD rays, takes its positions from shared-memory
@@ -491,6 +533,7 @@ __global__ void __launch_bounds__(256) k_escaped(const __grid_constant__ DevScen
     }
 }
 
+#endif  // HK_TU_CORE
 // russian_roulette_spectral, material-dispatch.jl:263-287
 HK_DEV bool russian_roulette(Spec& beta, int depth, float rr) {
     if (depth <= 3) return true;
@@ -500,6 +543,72 @@ HK_DEV bool russian_roulette(Spec& beta, int depth, float rr) {
     return true;
 }
 
+#ifdef HK_TU_LIGHTS
+// The light half of surface shading, for the hits of ALL material queues of a bounce in one kernel: emissive-hit MIS
+// (HandleEmissiveIntersection, surface-eval.jl:147-220) and the light sample of next-event estimation -- BVH light selection
+// (bvh-light-sampler.jl:105-170) + sample_light (lights.jl:39-290) -- whose result k_shade<TYPE> picks up from the per-slot record
+// nee_a / nee_b / nee_c.  It used to be inlined into every k_shade<TYPE>: ~4 000 of the ~7 000 SASS instructions of each shading
+// kernel (110-230 KB against a 32 KB L1.5 instruction cache; ncu: stall_no_instruction 11 warps per issue on C3's conductor kernel,
+// issue slots 20 % busy).  Same functions on the same inputs in the same order: same bits.
+__global__ void __launch_bounds__(128, 4) k_hit_lights(const __grid_constant__ DevScene D, PathState S, PassArgs A) {
+    LightCtx LC = light_ctx(D);
+    for (int q = 0; q < HK_N_HIT_QUEUES; q++) {
+        const uint32_t n = S.counts[HK_HIT_COUNTER(q)];
+        const uint32_t n_round = (n + 31u) & ~31u;     // whole warps iterate together: the cooperative light-BVH descent pairs up the lanes of a warp
+        const uint32_t* __restrict__ queue = S.q_hit[q];
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+            if (i >= n) continue;
+            const uint32_t slot = queue[i];
+            const float4 hr = S.hit[slot];
+            const uint32_t prim0 = HK_HIT_PRIM1(__float_as_uint(hr.y)) - 1u;
+            const float4 ra = S.ray_a[slot], rb = S.ray_b[slot];
+            const float3 o = f3(ra.x, ra.y, ra.z), d = f3(ra.w, rb.x, rb.y);
+            const Surf sf = surface_at(D, prim0, hr.z, hr.w, o, d, hr.x);
+            const float4 lam = S.lambda[slot];
+            const uint32_t fl = S.flags[slot];
+            const int depth = HK_FLAG_DEPTH(fl);
+            // ---- HandleEmissiveIntersection ----------------------------------------------------------------
+            if (sf.arealight > 0u) {
+                const float3 wo = -d;
+                Spec Le = arealight_Le(D.T, D.lights[sf.arealight - 1], wo, sf.n, lam);
+                if (!sp_black(Le)) {
+                    const Spec beta = S.beta[slot], r_u = S.r_u[slot], r_l = S.r_l[slot];
+                    Spec contrib = beta * Le, fin;
+                    if (depth == 0 || (fl & HK_FLAG_SPEC)) fin = contrib / sp_avg(r_u);
+                    else {
+                        float lcp = bvh_light_pmf(LC, sf.pi, sf.n, (int)sf.arealight);
+                        float ct = fabsf(dot3(sf.n, norm3(d)));
+                        float lpdf = (ct > 0.0f && sf.area > 0.0f) ? lcp * ((hr.x * hr.x) / (ct * sf.area)) : 0.0f;
+                        float den = sp_avg(r_u + r_l * lpdf);
+                        fin = den > 1.0e-10f ? contrib / den : contrib / sp_avg(r_u);
+                    }
+                    S.L[slot] = S.L[slot] + fin;
+                }
+            }
+            // ---- the light sample of next-event estimation (surface-eval.jl:250-342 up to the BSDF evaluation) --------------
+            const uint32_t pix = slot % A.n_pixels;
+            const int px = (int)(pix % (uint32_t)D.width) + 1, py = (int)(pix / (uint32_t)D.width) + 1;
+            const int sidx = slot_sample_idx(A, slot);
+            const int bdim = 6 + 7 * depth;
+            float4 rec_b = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            const float direct_uc = zsobol_1d(D.sobol, px, py, sidx, bdim + 1, HK_SOBOL_SLOT_BOUNCE(depth, 0), pix);
+            float pmf;
+            const int li = bvh_sample_light_coop(LC, sf.pi, sf.ns, direct_uc, pmf);
+            if (li >= 1 && li <= D.n_lights && pmf > 0.0f) {
+                const float2 direct_u = zsobol_2d(D.sobol, px, py, sidx, bdim + 3, HK_SOBOL_SLOT_BOUNCE(depth, 1), pix);
+                const LightSample ls = sample_light(LC, D.lights[li - 1], sf.pi, lam, direct_u);
+                if (ls.pdf > 0.0f && !sp_black(ls.Li)) {
+                    rec_b = make_float4(ls.wi.x, ls.wi.y, ls.wi.z, ls.pdf);
+                    S.nee_a[slot] = ls.Li;
+                    S.nee_c[slot] = make_float4(ls.p_light.x, ls.p_light.y, ls.p_light.z, ls.delta ? -pmf : pmf);
+                }
+            }
+            S.nee_b[slot] = rec_b;
+        }
+    }
+}
+#endif  // HK_TU_LIGHTS
+#ifdef HK_TU_SHADE
 // Shading of one material type: emissive-hit MIS (surface-eval.jl:147-220), NEE (:250-342 + lights.jl:535-600) and
 // BSDF sampling / Russian roulette / continuation ray (:396-512), fused into one kernel per material type.
 // resident blocks per SM the shading kernels are compiled for: 4 (<= 128 registers; above that only 3 blocks fit and the
@@ -507,7 +616,11 @@ HK_DEV bool russian_roulette(Spec& beta, int depth, float rr) {
 #ifndef HK_SHADE_MIN_BLOCKS
 #define HK_SHADE_MIN_BLOCKS 4
 #endif
-template <int TYPE>
+// SPLIT: emissive-hit MIS and the NEE light sample of the vertex were done by k_hit_lights (scenes whose light BVH is deep enough
+// to need the cooperative descent, DevScene::split_lights); otherwise they are done here with the plain serial descent, as the
+// light work is then a few hundred instructions and a separate kernel plus its 48-byte record per hit costs more than it saves
+// (measured on B200: C3, 10 002 lights, shading 10.4 -> 6.2 ms per 4K sample when split; C2, 3 lights, 1.50 -> 1.67 ms).
+template <int TYPE, bool SPLIT>
 __global__ void __launch_bounds__(128, (TYPE == HK_MAT_COATED_DIFFUSE || TYPE == HK_MAT_COATED_DIFFUSE_TRANSMISSION) ? HK_SHADE_MIN_BLOCKS + 2 : HK_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DevScene D, PathState S, PassArgs A, int next, int par) {
     const uint32_t n = S.counts[HK_HIT_COUNTER(HK_TYPE_QUEUE(TYPE))];
     MatCtx MC = mat_ctx(D);
@@ -533,8 +646,8 @@ __global__ void __launch_bounds__(128, (TYPE == HK_MAT_COATED_DIFFUSE || TYPE ==
             const int depth = HK_FLAG_DEPTH(fl);
             const uint32_t cur_medium = HK_FLAG_MEDIUM(fl);
             const float3 wo = -d;
-            // ---- HandleEmissiveIntersection ----------------------------------------------------------------
-            if (sf.arealight > 0u) {
+            // ---- HandleEmissiveIntersection (SPLIT: done by k_hit_lights) ---------------------------------------
+            if (!SPLIT && sf.arealight > 0u) {
                 Spec Le = arealight_Le(D.T, D.lights[sf.arealight - 1], wo, sf.n, lam);
                 if (!sp_black(Le)) {
                     Spec contrib = beta * Le, fin;
@@ -554,32 +667,46 @@ __global__ void __launch_bounds__(128, (TYPE == HK_MAT_COATED_DIFFUSE || TYPE ==
             const int px = (int)(pix % (uint32_t)D.width) + 1, py = (int)(pix / (uint32_t)D.width) + 1;
             const int sidx = slot_sample_idx(A, slot);
             const int bdim = 6 + 7 * depth;
-            // ---- next-event estimation ---------------------------------------------------------------------------
+            // ---- next-event estimation: the light sample comes from k_hit_lights' record (SPLIT) or is drawn here ------------
             if (D.n_lights > 0) {
-                float direct_uc = zsobol_1d(D.sobol, px, py, sidx, bdim + 1, HK_SOBOL_SLOT_BOUNCE(depth, 0), pix);
-                float pmf;
-                int li = bvh_sample_light_auto(LC, sf.pi, sf.ns, direct_uc, pmf);
-                if (li >= 1 && li <= D.n_lights && pmf > 0.0f) {
-                    float2 direct_u = zsobol_2d(D.sobol, px, py, sidx, bdim + 3, HK_SOBOL_SLOT_BOUNCE(depth, 1), pix);
-                    LightSample ls = sample_light(LC, D.lights[li - 1], sf.pi, lam, direct_u);
-                    if (ls.pdf > 0.0f && !sp_black(ls.Li)) {
-                        BsdfEval be = TYPE == HK_SHADE_MATTE_TEX ? eval_matte_kd(kd_tex, wo, ls.wi, sf.ns) : eval_bsdf<TYPE>(MC, mat, wo, ls.wi, sf.ns, lam);
-                        if (!sp_black(be.f)) {
-                            float ct = fabsf(dot3(ls.wi, sf.ns));
-                            Spec Ld = beta * be.f * ls.Li * ct;
-                            if (!sp_black(Ld)) {
-                                float3 off = 1.0e-4f * sf.ns;
-                                float3 ro = dot3(ls.wi, sf.ns) > 0.0f ? sf.pi + off : sf.pi - off;
-                                float3 tl = ls.p_light - ro;
-                                float tmax = sqrtf(dot3(tl, tl)) - 1.0e-3f;
-                                S.sh_a[slot] = make_float4(ro.x, ro.y, ro.z, ls.wi.x);
-                                S.sh_b[slot] = make_float4(ls.wi.y, ls.wi.z, tmax, 0.0f);
-                                S.sh_Ld[slot] = Ld;
-                                S.sh_ru[slot] = r_u * (ls.delta ? 0.0f : be.pdf);
-                                S.sh_rl[slot] = r_u * ls.pdf * pmf;
-                                S.sh_medium[slot] = cur_medium;
-                                push_shadow = true;
-                            }
+                float3 lwi = f3(0.0f, 0.0f, 0.0f), lp = f3(0.0f, 0.0f, 0.0f);
+                float lpdf = 0.0f, pmf = 0.0f; bool ldelta = false;
+                Spec Li = sp(0.0f);
+                if (SPLIT) {
+                    const float4 nb4 = S.nee_b[slot];                  // wi, pdf (0 = no usable light sample)
+                    if (nb4.w > 0.0f) {
+                        const float4 nc4 = S.nee_c[slot];              // p_light, pmf (sign bit set = delta light)
+                        lwi = f3(nb4.x, nb4.y, nb4.z); lpdf = nb4.w; lp = f3(nc4.x, nc4.y, nc4.z);
+                        ldelta = (__float_as_uint(nc4.w) >> 31) != 0u; pmf = fabsf(nc4.w);
+                        Li = S.nee_a[slot];
+                    }
+                } else {
+                    float direct_uc = zsobol_1d(D.sobol, px, py, sidx, bdim + 1, HK_SOBOL_SLOT_BOUNCE(depth, 0), pix);
+                    float pm;
+                    int li = bvh_sample_light(LC, sf.pi, sf.ns, direct_uc, pm);
+                    if (li >= 1 && li <= D.n_lights && pm > 0.0f) {
+                        float2 direct_u = zsobol_2d(D.sobol, px, py, sidx, bdim + 3, HK_SOBOL_SLOT_BOUNCE(depth, 1), pix);
+                        LightSample ls = sample_light(LC, D.lights[li - 1], sf.pi, lam, direct_u);
+                        if (ls.pdf > 0.0f && !sp_black(ls.Li)) { lwi = ls.wi; lpdf = ls.pdf; lp = ls.p_light; ldelta = ls.delta; pmf = pm; Li = ls.Li; }
+                    }
+                }
+                if (lpdf > 0.0f) {
+                    BsdfEval be = TYPE == HK_SHADE_MATTE_TEX ? eval_matte_kd(kd_tex, wo, lwi, sf.ns) : eval_bsdf<TYPE>(MC, mat, wo, lwi, sf.ns, lam);
+                    if (!sp_black(be.f)) {
+                        float ct = fabsf(dot3(lwi, sf.ns));
+                        Spec Ld = beta * be.f * Li * ct;
+                        if (!sp_black(Ld)) {
+                            float3 off = 1.0e-4f * sf.ns;
+                            float3 ro = dot3(lwi, sf.ns) > 0.0f ? sf.pi + off : sf.pi - off;
+                            float3 tl = lp - ro;
+                            float tmax = sqrtf(dot3(tl, tl)) - 1.0e-3f;
+                            S.sh_a[slot] = make_float4(ro.x, ro.y, ro.z, lwi.x);
+                            S.sh_b[slot] = make_float4(lwi.y, lwi.z, tmax, 0.0f);
+                            S.sh_Ld[slot] = Ld;
+                            S.sh_ru[slot] = r_u * (ldelta ? 0.0f : be.pdf);
+                            S.sh_rl[slot] = r_u * lpdf * pmf;
+                            S.sh_medium[slot] = cur_medium;
+                            push_shadow = true;
                         }
                     }
                 }
@@ -616,6 +743,8 @@ __global__ void __launch_bounds__(128, (TYPE == HK_MAT_COATED_DIFFUSE || TYPE ==
     }
 }
 
+#endif  // HK_TU_SHADE
+#ifdef HK_TU_MEDIA
 // Delta tracking (delta-tracking.jl:142-453) runs as a persistent per-lane-refill loop over the DeltaTracker state machine
 // (hk_media.cuh); its per-slot result feeds k_medium_finish = medium NEE + phase-function sampling + routing
 // (medium-scatter.jl:15-203), a plain one-thread-per-entry pass where whole warps stay converged.
@@ -746,6 +875,8 @@ __global__ void __launch_bounds__(128) k_medium_finish(const __grid_constant__ D
     }
 }
 
+#endif  // HK_TU_MEDIA
+#ifdef HK_TU_TRACE
 // trace_shadow_transmittance + vp_trace_shadow_rays_kernel!, intersection.jl:302-406, 565-600.
 // Opaque-only scenes (no interface with inside != outside, no media): visibility is a single any-hit query, which yields
 // the same T in {0,1} as the reference's closest-hit loop.  Otherwise the ordered closest-hit walk with ratio tracking.
@@ -767,15 +898,15 @@ struct ShadowRayIO {
         }
     }
 };
-template <bool COUNT>
-__global__ void __launch_bounds__(HK_TRACE_THREADS, HK_TRACE_BLOCKS_PER_SM) k_shadow_opaque(const __grid_constant__ DevScene D, PathState S, unsigned long long* work, int par) {
+template <bool COUNT, bool INST>
+__global__ void __launch_bounds__(HK_TRACE_THREADS, INST ? HK_TRACE_BLOCKS_PER_SM_INST : HK_TRACE_BLOCKS_PER_SM) k_shadow_opaque(const __grid_constant__ DevScene D, PathState S, unsigned long long* work, int par) {
     __shared__ uint2 sm_stack[HK_SM_STACK * HK_TRACE_THREADS];
     // reference quirk (volpath.jl:571-609): shadow rays are only traced inside the `n_hits > 0` branch
     if (S.counts[HK_CI_TOTAL_HITS(par)] == 0) return;
     const uint32_t n = S.counts[HK_CI_SHADOW(par)];
     uint32_t traced = 0, wn = 0, wt = 0;
     ShadowRayIO io{S};
-    trace_queue<true, COUNT>(D.bvh, sm_stack + threadIdx.x, n, S.counts + HK_CI_CURSOR_SHADOW(par), io, traced, wn, wt);
+    trace_queue<true, COUNT, INST>(D.bvh, sm_stack + threadIdx.x, n, S.counts + HK_CI_CURSOR_SHADOW(par), io, traced, wn, wt);
     count_rays(S.rays_traced, traced);
     if (COUNT) { count_rays(work + 3, traced); count_rays(work + 4, wn); count_rays(work + 5, wt); }
 }
@@ -797,17 +928,19 @@ struct ShadowSegIO {
     }
     HK_DEV void store(uint32_t slot, const HitRec& h) const { S.sh_hit[slot] = make_float4(h.t, __uint_as_float(h.prim1), h.b1, h.b2); }
 };
-template <bool COUNT>
-__global__ void __launch_bounds__(HK_TRACE_THREADS, HK_TRACE_BLOCKS_PER_SM) k_shadow_seg_trace(const __grid_constant__ DevScene D, PathState S, int round, unsigned long long* work) {
+template <bool COUNT, bool INST>
+__global__ void __launch_bounds__(HK_TRACE_THREADS, INST ? HK_TRACE_BLOCKS_PER_SM_INST : HK_TRACE_BLOCKS_PER_SM) k_shadow_seg_trace(const __grid_constant__ DevScene D, PathState S, int round, unsigned long long* work) {
     __shared__ uint2 sm_stack[HK_SM_STACK * HK_TRACE_THREADS];
     if (S.counts[HK_C_TOTAL_HITS] == 0) return;      // reference quirk (volpath.jl:571-609): shadow pass only inside `n_hits > 0`
     const uint32_t n = S.counts[round == 0 ? HK_C_SHADOW : HK_C_SHROUND0 + round];
     uint32_t traced = 0, wn = 0, wt = 0;
     ShadowSegIO io{S, (round & 1) ? S.q_shadow2 : S.q_shadow};
-    trace_queue<false, COUNT>(D.bvh, sm_stack + threadIdx.x, n, S.counts + HK_C_SHCUR_TRACE + round, io, traced, wn, wt);
+    trace_queue<false, COUNT, INST>(D.bvh, sm_stack + threadIdx.x, n, S.counts + HK_C_SHCUR_TRACE + round, io, traced, wn, wt);
     count_rays(S.rays_traced, traced);
     if (COUNT) { count_rays(work + 3, traced); count_rays(work + 4, wn); count_rays(work + 5, wt); }
 }
+#endif  // HK_TU_TRACE
+#ifdef HK_TU_MEDIA
 template <bool RGB>
 __global__ void __launch_bounds__(128) k_shadow_seg_ratio(const __grid_constant__ DevScene D, PathState S, int round) {
     if (S.counts[HK_C_TOTAL_HITS] == 0) return;
@@ -834,7 +967,7 @@ __global__ void __launch_bounds__(128) k_shadow_seg_ratio(const __grid_constant_
                     const float4 h = S.sh_hit[slot];
                     const uint32_t hp = HK_HIT_PRIM1(__float_as_uint(h.y));
                     bool opaque = false;                          // an opaque surface (alpha == 1) blocks: no tracking needed
-                    if (hp != 0u) { const HkMediumInterface mi = D.interfaces[__ldg(D.tri_meta + 3 * (size_t)(hp - 1u)) - 1]; opaque = mi.inside == mi.outside; }
+                    if (hp != 0u) { const HkMediumInterface mi = D.interfaces[prim_iface(D, hp - 1u) - 1]; opaque = mi.inside == mi.outside; }
                     if (!(sb.z < 1.0e-6f) && !opaque) {           // t_rem < 1e-6: dropped (the reference's loop ends without a visible ray)
                         busy = true;
                         const uint32_t cur = S.sh_medium[slot];
@@ -864,7 +997,7 @@ __global__ void __launch_bounds__(128) k_shadow_seg_ratio(const __grid_constant_
             if (prim1 == 0u) visible = true;
             else {
                 const uint32_t prim0 = prim1 - 1u;
-                const HkMediumInterface mi = D.interfaces[__ldg(D.tri_meta + 3 * (size_t)prim0) - 1];
+                const HkMediumInterface mi = D.interfaces[prim_iface(D, prim0) - 1];
                 if (mi.inside != mi.outside) {                     // (an opaque surface, alpha == 1, blocks: nothing to do)
                     if (sp_black(T)) visible = true;               // reference: leaves the loop "visible" with T == 0 -> contributes nothing
                     else if (round + 1 < HK_SHADOW_ROUNDS) {
@@ -892,6 +1025,8 @@ __global__ void __launch_bounds__(128) k_shadow_seg_ratio(const __grid_constant_
     }
 }
 
+#endif  // HK_TU_MEDIA
+#ifdef HK_TU_CORE
 // vp_accumulate_to_rgb_kernel!, volpath.jl:326-375.  One thread per pixel walks the batch in sample order, so the
 // f32 sums see the samples in exactly the order the reference's per-sample passes do (and no atomics are needed).
 __global__ void __launch_bounds__(256) k_film_accumulate(const __grid_constant__ DevScene D, PathState S, PassArgs A) {
@@ -986,7 +1121,10 @@ __global__ void __launch_bounds__(256) k_film_postprocess(const float* __restric
     }
 }
 
+#endif  // HK_TU_CORE
+#ifdef HK_TU_TRACE
 // aux_buffer_kernel!, film.jl:433-488: one centre-of-pixel primary ray per pixel; idx runs over the (H, W) column-major buffers
+template <bool INST>
 __global__ void __launch_bounds__(HK_TRACE_THREADS) k_aux_buffers(const __grid_constant__ DevScene D, float* __restrict__ albedo, float* __restrict__ normal,
                                                                    float* __restrict__ depth, float miss_depth) {
     __shared__ uint2 sm_stack[HK_SM_STACK * HK_TRACE_THREADS];
@@ -995,7 +1133,7 @@ __global__ void __launch_bounds__(HK_TRACE_THREADS) k_aux_buffers(const __grid_c
         const uint32_t row = idx % H + 1u, col = idx / H + 1u;
         float3 o, d;
         camera_generate_ray(D.camera, (float)col + 0.5f, (float)row + 0.5f, make_float2(0.5f, 0.5f), o, d);
-        const HitRec h = bvh8_trace<false, false>(D.bvh, sm_stack + threadIdx.x, o, d, HK_INF);
+        const HitRec h = bvh8_trace<false, false, INST>(D.bvh, sm_stack + threadIdx.x, o, d, HK_INF);
         float3 nn = f3(0.0f, 0.0f, 0.0f); float dep = miss_depth, alb = 0.0f;
         if (h.prim1) {
             const Surf sf = surface_at(D, HK_HIT_PRIM1(h.prim1) - 1u, h.b1, h.b2, o, d, h.t);
@@ -1022,17 +1160,18 @@ struct BatchRayIO {
         else hits[i] = make_float4(h.prim1 ? h.t : __ldg(rays + 2 * (size_t)i + 1).z, __uint_as_float(HK_HIT_PRIM1(h.prim1)), h.b1, h.b2);
     }
 };
-template <bool ANY, bool COUNT>
-__global__ void __launch_bounds__(HK_TRACE_THREADS, HK_TRACE_BLOCKS_PER_SM) k_trace_batch(DevBvh B, const float4* __restrict__ rays, uint32_t n, float4* __restrict__ hits,
+template <bool ANY, bool COUNT, bool INST>
+__global__ void __launch_bounds__(HK_TRACE_THREADS, INST ? HK_TRACE_BLOCKS_PER_SM_INST : HK_TRACE_BLOCKS_PER_SM) k_trace_batch(DevBvh B, const float4* __restrict__ rays, uint32_t n, float4* __restrict__ hits,
                                                                 uint8_t* __restrict__ occluded, uint32_t* cursor, unsigned long long* counters) {
     __shared__ uint2 sm_stack[HK_SM_STACK * HK_TRACE_THREADS];
     uint32_t traced = 0, nn = 0, nt = 0;
     BatchRayIO<ANY> io{rays, hits, occluded};
-    trace_queue<ANY, COUNT>(B, sm_stack + threadIdx.x, n, cursor, io, traced, nn, nt);
+    trace_queue<ANY, COUNT, INST>(B, sm_stack + threadIdx.x, n, cursor, io, traced, nn, nt);
     if (COUNT) { count_rays(counters, nn); count_rays(counters + 1, nt); }
 }
 
 // detect_camera_medium, intersection.jl:690-747 (single thread; run once per camera change, not once per sample)
+template <bool INST>
 __global__ void k_detect_camera_medium(const __grid_constant__ DevScene D, uint32_t* out) {
     __shared__ uint2 sm_stack[HK_SM_STACK * HK_TRACE_THREADS];
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -1040,10 +1179,10 @@ __global__ void k_detect_camera_medium(const __grid_constant__ DevScene D, uint3
     const float3 d = f3(0.57735027f, 0.57735027f, 0.57735027f);
     uint32_t res = 0;
     for (int it = 0; it < 16; it++) {
-        HitRec h = bvh8_trace<false, false>(D.bvh, sm_stack, o, d, HK_INF);
+        HitRec h = bvh8_trace<false, false, INST>(D.bvh, sm_stack, o, d, HK_INF);
         if (h.prim1 == 0) break;
         const uint32_t prim0 = HK_HIT_PRIM1(h.prim1) - 1u;
-        const HkMediumInterface mi = D.interfaces[__ldg(D.tri_meta + 3 * (size_t)prim0) - 1];
+        const HkMediumInterface mi = D.interfaces[prim_iface(D, prim0) - 1];
         float3 n = geometric_normal(D, prim0);
         if (mi.inside != mi.outside) { res = dot3(-d, n) > 0.0f ? mi.outside : mi.inside; break; }
         float3 pi = o + d * h.t;
@@ -1051,3 +1190,4 @@ __global__ void k_detect_camera_medium(const __grid_constant__ DevScene D, uint3
     }
     *out = res;
 }
+#endif  // HK_TU_TRACE

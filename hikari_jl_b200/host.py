@@ -1026,6 +1026,7 @@ def quad(p0, p1, p2, p3, normal=None):
 class Scene:
     def __init__(self):
         self.meshes = []            # (mesh, transform, interface_idx, emission)
+        self.instanced = False      # True: keep pushed meshes as instances of shared object-space meshes (two-level BVH) instead of flattening them
         self.materials = []         # unique Material objects
         self.interfaces = []        # (material_idx, inside_medium_idx, outside_medium_idx)
         self.media = []
@@ -1096,7 +1097,58 @@ class Scene:
         return len(self.meshes)
 
     # -- sync!: flatten to the C ABI arrays ----------------------------------------------------------
+    def _sync_instanced(self):
+        """scene.instanced = True: the meshes stay in object space (one copy per distinct Mesh object) and every push becomes an
+        HkInstance (mesh, transform, medium interface) -- what the reference's Raycore TLAS holds (src/scene.jl:21-28, scene-mesh.jl:9-16)."""
+        mesh_ids, pos, nrm, uvs, idx, meshes, insts = {}, [], [], [], [], [], []
+        any_n = any(m.normals is not None for m, *_ in self.meshes)
+        any_uv = any(m.uvs is not None for m, *_ in self.meshes)
+        voff = toff = 0
+        lo, hi = np.full(3, np.inf), np.full(3, -np.inf)
+        n_world = 0
+        for mesh, xf, iface, emission in self.meshes:
+            if emission is not None:
+                raise NotImplementedError("instanced meshes cannot be area lights (include/hikari_cuda.h: HkInstance); push emissive meshes into a scene with instanced = False")
+            if id(mesh) not in mesh_ids:
+                mesh_ids[id(mesh)] = len(meshes)
+                pos.append(mesh.positions.astype(f32))
+                if any_n:
+                    nrm.append(np.full((len(mesh.positions), 3), np.nan, dtype=f32) if mesh.normals is None else mesh.normals.astype(f32))
+                if any_uv:
+                    uvs.append(np.zeros((len(mesh.positions), 2), dtype=f32) if mesh.uvs is None else mesh.uvs)
+                idx.append(mesh.faces + np.uint32(voff))
+                meshes.append((toff, len(mesh.faces)))
+                voff += len(mesh.positions); toff += len(mesh.faces)
+            M = np.eye(4) if xf is None else xf
+            o2w = M[:3, :4].astype(np.float64)
+            w2o = np.linalg.inv(np.vstack([o2w, [0, 0, 0, 1]]))[:3, :4]
+            insts.append((mesh_ids[id(mesh)], iface, o2w.astype(f32), w2o.astype(f32)))
+            P = mesh.positions.astype(np.float64)
+            blo, bhi = P.min(0), P.max(0)
+            corners = np.array([[(bhi if c & 1 else blo)[0], (bhi if c & 2 else blo)[1], (bhi if c & 4 else blo)[2]] for c in range(8)])
+            wc = corners @ o2w[:, :3].T + o2w[:, 3]
+            lo, hi = np.minimum(lo, wc.min(0)), np.maximum(hi, wc.max(0))
+            n_world += len(mesh.faces)
+        type_order = []
+        for L in self.lights:
+            if type(L) not in type_order:
+                type_order.append(type(L))
+        order = sorted(range(len(self.lights)), key=lambda i: (type_order.index(type(self.lights[i])), i))
+        s = type("Synced", (), {})()
+        s.positions = np.ascontiguousarray(np.concatenate(pos)) if pos else np.zeros((0, 3), f32)
+        s.normals = np.ascontiguousarray(np.concatenate(nrm)) if any_n else None
+        s.uvs = np.ascontiguousarray(np.concatenate(uvs).astype(f32)) if any_uv else None
+        s.indices = np.ascontiguousarray(np.concatenate(idx).astype(np.uint32)) if idx else np.zeros((0, 3), np.uint32)
+        s.tri_meta = None
+        s.meshes, s.instances = meshes, insts
+        s.n_world_tris, s.world_bounds = n_world, (lo, hi)
+        s.lights = [self.lights[i] for i in order]
+        self._synced = s
+        return s
+
     def sync(self):
+        if getattr(self, "instanced", False):
+            return self._sync_instanced()
         pos, nrm, uvs, idx, meta = [], [], [], [], []
         any_n = any(m.normals is not None for m, *_ in self.meshes)
         any_uv = any(m.uvs is not None for m, *_ in self.meshes)
@@ -1159,18 +1211,21 @@ class Scene:
         s.indices = np.ascontiguousarray(np.concatenate(idx).astype(np.uint32)) if idx else np.zeros((0, 3), np.uint32)
         s.tri_meta = np.ascontiguousarray(np.concatenate(meta).astype(np.uint32)) if meta else np.zeros((0, 3), np.uint32)
         s.lights = flat
+        s.meshes, s.instances = [], []
+        s.n_world_tris = len(s.indices)
+        s.world_bounds = (s.positions.min(0), s.positions.max(0)) if len(s.positions) else (np.zeros(3), np.zeros(3))
         self._synced = s
         return s
 
     def triangle_count(self):
         """world-space triangles of the scene (every instance counted)"""
         s = self._synced or self.sync()
-        return int(len(s.indices))
+        return int(s.n_world_tris)
 
     def world_radius(self):
         s = self._synced or self.sync()
-        lo, hi = s.positions.min(0), s.positions.max(0)
-        return float(np.linalg.norm(hi - lo) / 2)
+        lo, hi = s.world_bounds
+        return float(np.linalg.norm(np.asarray(hi, dtype=np.float64) - np.asarray(lo, dtype=np.float64)) / 2)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -1228,9 +1283,15 @@ class Backend:
 
     def upload_scene(self, scene):
         s = scene._synced or scene.sync()
+        marr = (A.HkMesh * max(1, len(s.meshes)))(*[A.HkMesh(a, b) for a, b in s.meshes])
+        iarr = (A.HkInstance * max(1, len(s.instances)))()
+        for k, (mi, iface, o2w, w2o) in enumerate(s.instances):
+            iarr[k].mesh, iarr[k].medium_interface_idx = mi, iface
+            iarr[k].object_to_world[:] = o2w.reshape(-1).tolist(); iarr[k].world_to_object[:] = w2o.reshape(-1).tolist()
         g = A.HkGeometry(_fp(s.positions), None if s.normals is None else _fp(s.normals), None,
                          None if s.uvs is None else _fp(s.uvs), s.indices.ctypes.data_as(A.c_u32p),
-                         s.tri_meta.ctypes.data_as(A.c_u32p), len(s.positions), len(s.indices))
+                         None if s.tri_meta is None else s.tri_meta.ctypes.data_as(A.c_u32p), len(s.positions), len(s.indices),
+                         marr, len(s.meshes), iarr, len(s.instances))
         self.call("upload_geometry", C.byref(g))
         # materials first (registers spectra and texture ids), then spectra and textures, then the material upload
         scene._textures = []

@@ -334,10 +334,12 @@ def c4_cloud(shape=(256, 256, 128), medium_kind="nanovdb", majorant_res=(64, 64,
     return s, _cam((0, 1, -3.5), (0, 0.9, 0), 40.0)
 
 
-def c5_instanced(n_instances=1000, base_tess=160, seed=11):
+def c5_instanced(n_instances=1000, base_tess=160, seed=11, instanced=False):
     """n_instances copies (jittered grid, random rotations) of a base mesh with (base_tess-1)^2*2 triangles;
-    materials round-robin over the six in-scope types.  Full size: 1000 x ~50 000 = 50 M triangles."""
+    materials round-robin over the six in-scope types.  Full size: 1000 x ~50 000 = 50 M triangles.
+    instanced=True keeps them as instances of ONE object-space mesh (HkGeometry.instances, two-level BVH); False flattens them."""
     s = H.Scene()
+    s.instanced = instanced
     sky, sd = analytic_sky(512)
     s.push(H.EnvironmentLight(H.EnvironmentMap(sky), scale=tuple([float(f32(1.0) / f32(10567.0))] * 3)))
     s.push(H.SunLight((5.0, 4.75, 4.25), -sd))

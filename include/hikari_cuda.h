@@ -65,6 +65,26 @@ typedef struct HkTables {
  * intersection.jl:14-16,30-32,86-88,130-132 (vertices/normals/tangents/uv/metadata).
  * World-space triangle soup; the global primitive id is the triangle's index here (instance-major,
  * then face order) and is what hk_trace_closest reports.                                      */
+/* Instancing (replaces: the instances of the Raycore TLAS behind scene.accel, src/scene.jl:21-28, 146-151; one per
+ * push!(scene, mesh, material; transform), src/scene-mesh.jl:9-16).  With n_instances > 0 the vertex arrays are in OBJECT space,
+ * `meshes` cuts `indices` into meshes, and every instance places one mesh with an affine transform and one medium interface.
+ * The library builds one bottom-level BVH per mesh and a top-level BVH over the instances; nothing is flattened.
+ * Global primitive id of (instance i, face f of its mesh) = sum of the face counts of instances 0..i-1, + f (instance-major, then
+ * face order: the order the reference's flattened TLAS enumerates), and TriangleMeta of that primitive is
+ * (instances[i].medium_interface_idx, f + 1, 0): instanced meshes cannot be area lights (pass emissive meshes un-instanced).
+ * Closest-hit contract for instances (the reference's Raycore is not on disk; stated here, restated in oracle/ok_accel.h): the ray is
+ * taken to object space as o' = W o, d' = W d (W = world_to_object, d' NOT renormalised, so t means the same on both sides),
+ * tested against the mesh's object-space triangles with the fixed Moller-Trumbore sequence; argmin t over all (instance, face)
+ * with 0 < t < t_max, equal t -> smallest global primitive id.  World-space shading data (vertices, normals) are O v and
+ * normalize(W^T n) evaluated in f32 in the operation order of csrc/hk_wavefront.cuh::prim_vertices.                      */
+typedef struct HkMesh { uint32_t first_tri, n_tris; } HkMesh;            /* a range of `indices` */
+typedef struct HkInstance {
+    uint32_t mesh;                    /* 0-based index into meshes                                          */
+    uint32_t medium_interface_idx;    /* 1-based, as TriangleMeta.medium_interface_idx                      */
+    float    object_to_world[12];     /* 3x4 row-major affine O                                            */
+    float    world_to_object[12];     /* 3x4 row-major affine W = O^-1                                     */
+} HkInstance;
+
 typedef struct HkGeometry {
     const float*    positions;   /* [n_verts][3]                                              */
     const float*    normals;     /* [n_verts][3] or NULL; NaN x-component = "no normal"        */
@@ -73,9 +93,14 @@ typedef struct HkGeometry {
     const uint32_t* indices;     /* [n_tris][3]  0-based vertex indices                        */
     const uint32_t* tri_meta;    /* [n_tris][3]  TriangleMeta (src/scene.jl:11-15):
                                     medium_interface_idx (1-based), primitive_index (1-based face
-                                    index within its mesh), arealight_flat_idx (0 = none)       */
+                                    index within its mesh), arealight_flat_idx (0 = none);
+                                    ignored (may be NULL) when n_instances > 0                  */
     uint32_t        n_verts;
     uint32_t        n_tris;
+    const HkMesh*     meshes;      /* [n_meshes]     (n_instances > 0 only)                    */
+    uint32_t          n_meshes;
+    const HkInstance* instances;   /* [n_instances]; 0 = plain world-space triangle soup        */
+    uint32_t          n_instances;
 } HkGeometry;
 
 /* ---- textures -----------------------------------------------------------------------------

@@ -64,6 +64,14 @@ int32_t ok_upload_geometry(OkContext* c, const HkGeometry* g) {
     if (g->tangents) s.tangents.assign(g->tangents, g->tangents + 3 * (size_t)g->n_verts); else s.tangents.clear();
     if (g->uvs) s.uvs.assign(g->uvs, g->uvs + 2 * (size_t)g->n_verts); else s.uvs.clear();
     s.indices.assign(g->indices, g->indices + 3 * (size_t)g->n_tris);
+    if (g->n_instances > 0) {       // object-space meshes + instances (HkGeometry.instances): per-mesh accelerators, nothing flattened
+        for (uint32_t i = 0; i < g->n_instances; i++) if (g->instances[i].mesh >= g->n_meshes) return -1;
+        s.tri_meta.clear();
+        s.accel = Accel();
+        s.iaccel.build(s.positions.data(), s.indices.data(), g->meshes, g->n_meshes, g->instances, g->n_instances);
+        return 0;
+    }
+    s.iaccel = InstancedAccel();
     s.tri_meta.assign(g->tri_meta, g->tri_meta + 3 * (size_t)g->n_tris);
     s.accel.build(s.positions.data(), s.indices.data(), g->n_tris);
     return 0;
@@ -359,7 +367,7 @@ int32_t ok_trace_closest(OkContext* c, const float* rays, uint64_t n, float* hit
     for (int64_t i = 0; i < (int64_t)n; i++) {
         const float* r = rays + 8 * i;
         V3 o(r[0], r[1], r[2]), d(r[3], r[4], r[5]);
-        Hit h = mode ? s.accel.closest_hit_brute(o, d, r[6]) : s.accel.closest_hit_bvh(o, d, r[6]);
+        Hit h = s.iaccel.enabled() ? s.iaccel.closest_hit(o, d, r[6], mode != 0) : (mode ? s.accel.closest_hit_brute(o, d, r[6]) : s.accel.closest_hit_bvh(o, d, r[6]));
         float* out = hits + 4 * i;
         uint32_t prim = h.hit ? h.prim + 1 : 0;
         out[0] = h.hit ? h.t : r[6]; std::memcpy(out + 1, &prim, 4); out[2] = h.hit ? h.b1 : 0.0f; out[3] = h.hit ? h.b2 : 0.0f;

@@ -4,10 +4,16 @@
 // Möller–Trumbore sequence below evaluated in f32 without FMA contraction; equal t -> smallest
 // global primitive id.  Raycore.jl (the reference's real traversal) is not on disk: parity of hit ids
 // against upstream is UNPINNED; this file is the definition both implementations are held to.
+// Instanced scenes (InstancedAccel below, HkGeometry.instances): the ray goes to object space as o' = W o, d' = W d (W =
+// world_to_object, d' not renormalised: t means the same on both sides), is tested against the mesh's OBJECT-space triangles with the
+// same test, and the closest hit is argmin t over all (instance, face) with equal t -> smallest GLOBAL primitive id
+// (instance-major: id = faces of the earlier instances + face index).
 #pragma once
 #include "ok_core.h"
 #include <vector>
 #include <numeric>
+#include <array>
+#include "../include/hikari_cuda.h"
 
 namespace ok {
 
@@ -128,6 +134,64 @@ struct Accel {
         for (uint32_t p = 0; p < tris.size(); p++) {
             float t, u, v;
             if (tri_intersect(o, d, tris[p], t_max, t, u, v) && hit_better(t, p, best)) best = Hit{true, p, t, u, v};
+        }
+        return best;
+    }
+};
+
+// ---- instances: one Accel per mesh + a linear, conservatively culled loop over the instances ------------------------------------
+inline V3 inst_point(const float* m, V3 p) { return V3(m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3], m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7], m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11]); }
+inline V3 inst_vector(const float* m, V3 v) { return V3(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z, m[8] * v.x + m[9] * v.y + m[10] * v.z); }
+inline V3 inst_normal(const float* w2o, V3 n) {      // normalize(W^T n): the inverse-transpose of the object-to-world linear part
+    return normalize(V3(w2o[0] * n.x + w2o[4] * n.y + w2o[8] * n.z, w2o[1] * n.x + w2o[5] * n.y + w2o[9] * n.z, w2o[2] * n.x + w2o[6] * n.y + w2o[10] * n.z));
+}
+struct Instance { uint32_t mesh, iface, prim_base, n_tris, first_tri; float o2w[12], w2o[12]; float wmin[3], wmax[3]; };
+struct InstancedAccel {
+    std::vector<Accel> meshes;
+    std::vector<Instance> inst;
+    std::vector<uint32_t> prim_base;          // per instance, ascending: global id of its first face
+    bool enabled() const { return !inst.empty(); }
+    void build(const float* pos, const uint32_t* idx, const HkMesh* ms, uint32_t n_meshes, const HkInstance* is, uint32_t n_inst) {
+        meshes.assign(n_meshes, Accel()); inst.clear(); prim_base.clear();
+        std::vector<std::array<float, 6>> obox(n_meshes);
+        for (uint32_t m = 0; m < n_meshes; m++) {
+            meshes[m].build(pos, idx + 3 * (size_t)ms[m].first_tri, ms[m].n_tris);
+            std::array<float, 6> b = {INF_F, INF_F, INF_F, -INF_F, -INF_F, -INF_F};
+            for (uint32_t t = 0; t < 3 * ms[m].n_tris; t++) for (int k = 0; k < 3; k++) {
+                const float v = pos[3 * (size_t)idx[3 * (size_t)ms[m].first_tri + t] + k];
+                b[k] = std::min(b[k], v); b[3 + k] = std::max(b[3 + k], v);
+            }
+            obox[m] = b;
+        }
+        uint32_t base = 0;
+        for (uint32_t i = 0; i < n_inst; i++) {
+            Instance I; I.mesh = is[i].mesh; I.iface = is[i].medium_interface_idx; I.prim_base = base; I.n_tris = ms[I.mesh].n_tris; I.first_tri = ms[I.mesh].first_tri;
+            std::memcpy(I.o2w, is[i].object_to_world, 48); std::memcpy(I.w2o, is[i].world_to_object, 48);
+            for (int k = 0; k < 3; k++) { I.wmin[k] = INF_F; I.wmax[k] = -INF_F; }
+            const auto& b = obox[I.mesh];
+            for (int c = 0; c < 8; c++) {           // world box of the 8 transformed corners, padded: culling must only ever be conservative
+                V3 p = inst_point(I.o2w, V3(b[(c & 1) ? 3 : 0], b[(c & 2) ? 4 : 1], b[(c & 4) ? 5 : 2]));
+                for (int k = 0; k < 3; k++) { I.wmin[k] = std::min(I.wmin[k], p[k]); I.wmax[k] = std::max(I.wmax[k], p[k]); }
+            }
+            for (int k = 0; k < 3; k++) { float pad = 1.0e-4f * std::max(std::fabs(I.wmin[k]), std::fabs(I.wmax[k])) + 1.0e-5f; I.wmin[k] -= pad; I.wmax[k] += pad; }
+            inst.push_back(I); prim_base.push_back(base);
+            base += I.n_tris;
+        }
+    }
+    uint32_t n_prims() const { return inst.empty() ? 0u : inst.back().prim_base + inst.back().n_tris; }
+    uint32_t instance_of(uint32_t prim) const { return (uint32_t)(std::upper_bound(prim_base.begin(), prim_base.end(), prim) - prim_base.begin()) - 1u; }
+    Hit closest_hit(V3 o, V3 d, float t_max, bool brute) const {
+        Hit best{false, 0, t_max, 0, 0};
+        const V3 inv(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+        for (const Instance& I : inst) {
+            if (!brute) {
+                Accel::Node N; for (int k = 0; k < 3; k++) { N.bmin[k] = I.wmin[k]; N.bmax[k] = I.wmax[k]; }
+                float tn;
+                if (!Accel::slab(N, o, inv, t_max, tn)) continue;
+            }
+            const V3 oo = inst_point(I.w2o, o), od = inst_vector(I.w2o, d);
+            const Hit h = brute ? meshes[I.mesh].closest_hit_brute(oo, od, t_max) : meshes[I.mesh].closest_hit_bvh(oo, od, t_max);
+            if (h.hit && hit_better(h.t, I.prim_base + h.prim, best)) best = Hit{true, I.prim_base + h.prim, h.t, h.b1, h.b2};
         }
         return best;
     }

@@ -96,6 +96,7 @@ struct Scene {
     // camera ray (same camera, resolution and per-pixel sample streams; the other pixels stay black).  1 / 0 = every row.
     int32_t row_step = 1, row_offset = 0;
     Accel accel;
+    InstancedAccel iaccel;       // HkGeometry.instances: per-mesh accelerators + instance transforms (empty for a plain triangle soup)
     std::vector<HkMaterial> materials; std::vector<HkMediumInterface> interfaces;
     std::vector<float> spec_lambdas, spec_values; std::vector<uint32_t> spec_offsets; HkSpectra spectra;
     std::vector<HkLight> lights;
@@ -133,20 +134,46 @@ struct Scene {
     MediaCtx mediactx() const { return MediaCtx{&T, media.data(), (uint32_t)media.size()}; }
 
     Hit closest_hit(V3 o, V3 d, float t_max) const {
+        if (iaccel.enabled()) return iaccel.closest_hit(o, d, t_max, brute_force);
         return brute_force ? accel.closest_hit_brute(o, d, t_max) : accel.closest_hit_bvh(o, d, t_max);
     }
-    V3 vert(uint32_t prim, int k) const { const float* p = positions.data() + 3 * (size_t)indices[3 * (size_t)prim + k]; return V3(p[0], p[1], p[2]); }
+    // A global primitive id resolves to (instance, triangle of the index array) in instanced scenes (HkGeometry.instances): vertices and
+    // normals are then taken to world space per hit -- O v and normalize(W^T n), f32, in this operation order (the CUDA path's
+    // prim_vertices / prim_normals do the same) -- and TriangleMeta is (instance interface, face + 1, no area light).
+    struct PrimRef { const Instance* inst; uint32_t tri; };
+    PrimRef resolve(uint32_t prim) const {
+        if (!iaccel.enabled()) return PrimRef{nullptr, prim};
+        const Instance& I = iaccel.inst[iaccel.instance_of(prim)];
+        return PrimRef{&I, I.first_tri + (prim - I.prim_base)};
+    }
+    struct PrimMeta { uint32_t iface, face, arealight; };
+    PrimMeta meta_of(uint32_t prim) const {
+        if (!iaccel.enabled()) return PrimMeta{tri_meta[3 * (size_t)prim], tri_meta[3 * (size_t)prim + 1], tri_meta[3 * (size_t)prim + 2]};
+        const PrimRef r = resolve(prim);
+        return PrimMeta{r.inst->iface, prim - r.inst->prim_base + 1u, 0u};
+    }
+    V3 vert(uint32_t prim, int k) const {
+        const PrimRef r = resolve(prim);
+        const float* p = positions.data() + 3 * (size_t)indices[3 * (size_t)r.tri + k];
+        return r.inst ? inst_point(r.inst->o2w, V3(p[0], p[1], p[2])) : V3(p[0], p[1], p[2]);
+    }
     V3 nrm(uint32_t prim, int k) const {
         if (!has_normals) return V3(NAN, NAN, NAN);
-        const float* p = normals.data() + 3 * (size_t)indices[3 * (size_t)prim + k]; return V3(p[0], p[1], p[2]);
+        const PrimRef r = resolve(prim);
+        const float* p = normals.data() + 3 * (size_t)indices[3 * (size_t)r.tri + k];
+        if (r.inst && !std::isnan(p[0])) return inst_normal(r.inst->w2o, V3(p[0], p[1], p[2]));
+        return V3(p[0], p[1], p[2]);
     }
     V3 tan(uint32_t prim, int k) const {
         if (!has_tangents) return V3(NAN, NAN, NAN);
-        const float* p = tangents.data() + 3 * (size_t)indices[3 * (size_t)prim + k]; return V3(p[0], p[1], p[2]);
+        const PrimRef r = resolve(prim);
+        const float* p = tangents.data() + 3 * (size_t)indices[3 * (size_t)r.tri + k];
+        if (r.inst && !std::isnan(p[0])) return normalize(inst_vector(r.inst->o2w, V3(p[0], p[1], p[2])));
+        return V3(p[0], p[1], p[2]);
     }
     V2 uv(uint32_t prim, int k) const {
         if (!has_uvs) return V2(0, 0);
-        const float* p = uvs.data() + 2 * (size_t)indices[3 * (size_t)prim + k]; return V2(p[0], p[1]);
+        const float* p = uvs.data() + 2 * (size_t)indices[3 * (size_t)resolve(prim).tri + k]; return V2(p[0], p[1]);
     }
     // intersection.jl:13-21
     V3 geometric_normal(uint32_t prim) const {
@@ -254,7 +281,7 @@ struct Scene {
         for (int it = 0; it < 16; it++) {
             Hit h = closest_hit(o, d, INF_F);
             if (!h.hit) return 0;
-            const HkMediumInterface& mi = interfaces[tri_meta[3 * (size_t)h.prim] - 1];
+            const HkMediumInterface& mi = interfaces[meta_of(h.prim).iface - 1];
             V3 n = geometric_normal(h.prim);
             if (mi.inside != mi.outside) return dot(-d, n) > 0.0f ? mi.outside : mi.inside;
             V3 pi = o + d * h.t;
@@ -339,7 +366,7 @@ inline void Scene::trace_shadow(const ShadowWork& work) {
             }
             visible = true; done = true; break;
         }
-        const HkMediumInterface& mi = interfaces[tri_meta[3 * (size_t)h.prim] - 1];
+        const HkMediumInterface& mi = interfaces[meta_of(h.prim).iface - 1];
         V3 n = geometric_normal(h.prim);
         bool entering = dot(dir, n) < 0.0f;
         bool transmissive = mi.inside != mi.outside;
@@ -454,7 +481,7 @@ inline void Scene::render_sample(int32_t sample_idx) {
             if (w.medium != 0) {
                 MediumSampleWork m; m.w = w;
                 if (h.hit) {
-                    const uint32_t* meta = &tri_meta[3 * (size_t)h.prim];
+                    const PrimMeta pm = meta_of(h.prim); const uint32_t meta[3] = {pm.iface, pm.face, pm.arealight};
                     const HkMediumInterface& mi = interfaces[meta[0] - 1];
                     float bary[3] = {1.0f - h.b1 - h.b2, h.b1, h.b2};
                     m.t_max = h.t; m.has_surface_hit = true;
@@ -475,7 +502,7 @@ inline void Scene::render_sample(int32_t sample_idx) {
             Ray ray = w.ray;
             bool absorbed = false;
             for (int pass = 0; h.hit; pass++) {
-                const HkMediumInterface& mi_a = interfaces[tri_meta[3 * (size_t)h.prim] - 1];
+                const HkMediumInterface& mi_a = interfaces[meta_of(h.prim).iface - 1];
                 const float bary_a[3] = {1.0f - h.b1 - h.b2, h.b1, h.b2};
                 const float alpha = surface_alpha(mi_a.material, uv_bary(h.prim, bary_a));
                 if (!(alpha < 1.0f)) break;
@@ -496,7 +523,7 @@ inline void Scene::render_sample(int32_t sample_idx) {
                 o_esc[i].valid = true; o_esc[i].v = e;
                 continue;
             }
-            const uint32_t* meta = &tri_meta[3 * (size_t)h.prim];
+            const PrimMeta pm = meta_of(h.prim); const uint32_t meta[3] = {pm.iface, pm.face, pm.arealight};
             const HkMediumInterface& mi = interfaces[meta[0] - 1];
             float bary[3] = {1.0f - h.b1 - h.b2, h.b1, h.b2};
             HitSurfaceWork hs;

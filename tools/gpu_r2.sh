@@ -28,6 +28,9 @@ for W in "$@"; do
       python tools/ncu_summary.py $R.ncu-rep > gpurun_out/${B}_summary.txt 2>&1
       for i in $(seq 0 $((CNT-1))); do python tools/ncu_hot_lines.py $R.ncu-rep $i 50 > gpurun_out/${B}_hot$i.txt 2>&1; done
       S=$(stat -c %s $R.ncu-rep); if [ $S -lt 15000000 ]; then cp $R.ncu-rep gpurun_out/; fi ;;
+    variants:*)
+      IFS=: read -r _ CFGS STEPS <<< "$W"
+      HK_BENCH_CONFIGS=$CFGS timeout 2400 python tools/variants.py run --steps ${STEPS:-8} > gpurun_out/variants_$T.log 2>&1; python tools/variants.py table | tee gpurun_out/variants_table_$T.txt ;;
     sanitize)
       timeout 1500 compute-sanitizer --tool memcheck --log-file gpurun_out/sanitizer_memcheck_smoke_$T.log python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/sanitizer_memcheck_smoke_$T.out 2>&1
       timeout 1500 compute-sanitizer --tool racecheck --log-file gpurun_out/sanitizer_racecheck_smoke_$T.log python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/sanitizer_racecheck_smoke_$T.out 2>&1

@@ -14,19 +14,16 @@ VDIR = os.path.join(ROOT, "build", "variants")
 def build(specs):
     import __graft_entry__ as g
     os.makedirs(VDIR, exist_ok=True)
-    for f in glob.glob(os.path.join(VDIR, "*.so")): os.remove(f)
-    procs = []
+    for f in glob.glob(os.path.join(VDIR, "*.so*")): os.remove(f)
     for spec in specs:
-        name, _, defs = spec.partition(":")
+        name, defs, envs = (spec.split(":") + ["", ""])[:3]          # name:-DA=1,-DB=2:ENV1=x,ENV2=y
         out = os.path.join(VDIR, f"lib_{name}.so")
-        srcs = [os.path.join(g.CSRC, f) for f in ("hk_api.cu", "hk_bvh.cpp", "host_rgb2spec.cpp", "host_lightbvh.cpp")]
-        flags = [f for f in g.NVCC_FLAGS if f not in ("-v",)]
-        flags = [f for i, f in enumerate(flags) if not (f == "-Xptxas" and g.NVCC_FLAGS[i + 1] == "-v")]
-        cmd = [g.NVCC] + flags + [d for d in defs.split(",") if d] + ["-o", out] + srcs + ["-lgomp"]
-        procs.append((name, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-    for name, p in procs:
-        o, _ = p.communicate()
-        print(name, "OK" if p.returncode == 0 else "FAILED\n" + o[-2000:])
+        open(out + ".env", "w").write(envs)
+        try:
+            g.build_cuda(extra_flags=tuple(d for d in defs.split(",") if d), out=out)
+            print(name, "OK")
+        except Exception as e:
+            print(name, "FAILED", e)
 
 
 def run(argv):
@@ -35,10 +32,14 @@ def run(argv):
     for so in sorted(glob.glob(os.path.join(VDIR, "*.so"))):
         name = os.path.basename(so)[4:-3]
         env = dict(os.environ, HK_CUDA_LIB=so)
-        extra = os.environ.get("HK_BENCH_ARGS", "").split()          # e.g. HK_BENCH_ARGS="--config C4"
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--quick", "--steps", steps, "--warmup", steps] + extra, env=env, capture_output=True, text=True, timeout=600)
-        open(os.path.join(ROOT, "gpurun_out", f"var_{name}.json"), "w").write(r.stdout if r.returncode == 0 else json.dumps({"error": r.stderr[-1500:]}))
-        print(name, r.stdout[:160] if r.returncode == 0 else r.stderr[-500:], flush=True)
+        if os.path.exists(so + ".env"):
+            env.update(dict(kv.split("=", 1) for kv in open(so + ".env").read().split(",") if "=" in kv))
+        for cfg in os.environ.get("HK_BENCH_CONFIGS", "C2").split(","):          # e.g. HK_BENCH_CONFIGS="C2,C3,C4"
+            extra = os.environ.get("HK_BENCH_ARGS", "").split()
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--quick", "--no-per-config", "--config", cfg, "--steps", steps, "--warmup", "3"] + extra,
+                               env=env, capture_output=True, text=True, timeout=900)
+            open(os.path.join(ROOT, "gpurun_out", f"var_{name}_{cfg}.json"), "w").write(r.stdout if r.returncode == 0 else json.dumps({"error": r.stderr[-1500:]}))
+            print(name, cfg, r.stdout[:160] if r.returncode == 0 else r.stderr[-500:], flush=True)
 
 
 def table():
