@@ -59,7 +59,7 @@ class HkMaterial(C.Structure):
 
 
 class HkTexture(C.Structure):
-    _fields_ = [("rgb", c_fp), ("h", C.c_int32), ("w", C.c_int32)]
+    _fields_ = [("rgb", c_fp), ("h", C.c_int32), ("w", C.c_int32), ("alpha", c_fp)]
 
 
 class HkMediumInterface(C.Structure):
@@ -138,7 +138,7 @@ HK_SYMBOLS = [
     "hk_abi_version", "hk_create", "hk_destroy", "hk_last_error", "hk_upload_tables", "hk_upload_geometry",
     "hk_upload_spectra", "hk_upload_textures", "hk_upload_materials", "hk_update_material", "hk_bounce_profile", "hk_upload_envmaps", "hk_upload_lights", "hk_upload_media",
     "hk_set_camera", "hk_set_filter", "hk_set_params", "hk_clear", "hk_render_samples", "hk_render_samples_strided",
-    "hk_read_film", "hk_read_film_async", "hk_read_film_wait", "hk_postprocess", "hk_fill_aux_buffers", "hk_read_aux_buffers", "hk_denoise", "hk_film_accum_dev", "hk_read_accum", "hk_write_accum", "hk_trace_closest",
+    "hk_read_film", "hk_read_film_async", "hk_read_film_wait", "hk_read_film_dev", "hk_set_stream", "hk_postprocess", "hk_postprocess_dev", "hk_fill_aux_buffers", "hk_read_aux_buffers", "hk_denoise", "hk_film_accum_dev", "hk_read_accum", "hk_write_accum", "hk_trace_closest",
     "hk_trace_closest_dev", "hk_trace_any", "hk_stats", "hk_synchronize", "hk_dev_alloc", "hk_dev_free",
     "hk_dev_upload", "hk_dev_download", "hk_set_profiling", "hk_stage_times", "hk_pinned_alloc", "hk_pinned_free",
 ]
@@ -197,6 +197,9 @@ def bind_hk(lib):
     f("hk_trace_any", [_VP, c_fp, C.c_uint64, c_u8p])
     f("hk_stats", [_VP, C.POINTER(HkStats)])
     f("hk_synchronize", [_VP])
+    f("hk_read_film_dev", [_VP, _VP])
+    f("hk_postprocess_dev", [_VP, C.POINTER(HkPostprocess), _VP])
+    f("hk_set_stream", [_VP, _VP])
     f("hk_dev_alloc", [_VP, C.c_uint64, C.POINTER(_VP)])
     f("hk_dev_free", [_VP, _VP])
     f("hk_dev_upload", [_VP, _VP, _VP, C.c_uint64])

@@ -59,7 +59,8 @@ int32_t hk_create(int32_t device, HkContext** out) {
     ctx->device = device;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return HK_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return HK_ERR_CUDA; }
+    ctx->stream = ctx->own_stream;
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
     for (auto& s : ctx->shade_streams) if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { s = nullptr; ctx->concurrent_shade = false; }
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
@@ -99,7 +100,7 @@ int32_t hk_destroy(HkContext* ctx) {
     for (auto& e : ctx->ev_join) if (e) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) { if (ctx->ev_final[i]) cudaEventDestroy(ctx->ev_final[i]); if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]); ctx->b_readback_async[i].release(); }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);      // (a caller-supplied stream is the caller's to destroy)
     delete ctx;
     return HK_OK;
 }
@@ -280,17 +281,26 @@ int32_t hk_upload_textures(HkContext* ctx, const HkTexture* t, uint32_t n) {
     for (auto& b : ctx->tex_bufs) b.release();
     ctx->tex_bufs.clear(); ctx->tex_bufs.resize(n);
     std::vector<HkTexture> dev(n);
+    bool any_alpha = false;
     for (uint32_t i = 0; i < n; i++) {
         REQUIRE(t[i].rgb && t[i].h >= 1 && t[i].w >= 1, "texture needs data and a positive size");
-        CK(ctx->tex_bufs[i].upload(t[i].rgb, 12 * (size_t)t[i].h * t[i].w));
+        const size_t texels = (size_t)t[i].h * t[i].w;
+        if (t[i].alpha) {      // colours and the alpha plane share one allocation
+            std::vector<float> packed(4 * texels);
+            std::memcpy(packed.data(), t[i].rgb, 12 * texels); std::memcpy(packed.data() + 3 * texels, t[i].alpha, 4 * texels);
+            CK(ctx->tex_bufs[i].upload(packed.data(), 16 * texels));
+            any_alpha = true;
+        } else CK(ctx->tex_bufs[i].upload(t[i].rgb, 12 * texels));
         dev[i].rgb = ctx->tex_bufs[i].as<float>(); dev[i].h = t[i].h; dev[i].w = t[i].w;
+        dev[i].alpha = t[i].alpha ? ctx->tex_bufs[i].as<float>() + 3 * texels : nullptr;
     }
+    ctx->D.has_alpha = any_alpha ? 1 : 0;
     CK(ctx->b_textures.upload(dev.data(), sizeof(HkTexture) * (size_t)n));
     ctx->D.textures = n ? ctx->b_textures.as<HkTexture>() : nullptr; ctx->D.n_textures = (int32_t)n;
     return HK_OK;
 }
 static int32_t mat_textures_ok(HkContext* ctx, const HkMaterial& m) {
-    REQUIRE(m.type == HK_MAT_MIX || !(m.flags & HK_MATFLAG_VERTEX_COLORS), "VertexColorTexture parameters are not supported yet (SURVEY 8f item 2)");
+    REQUIRE(m.type == HK_MAT_MIX || !(m.flags & HK_MATFLAG_VERTEX_COLORS) || (m.type == HK_MAT_MATTE && m.tex[0] > 0), "VertexColorTexture is supported for MatteMaterial.Kd only");
     for (int k = 0; k < 4; k++) {
         if (m.tex[k] == 0) continue;
         REQUIRE(k == 0 && m.type == HK_MAT_MATTE, "textured parameters are supported for MatteMaterial.Kd only (SURVEY 8f item 2)");
@@ -476,7 +486,7 @@ static int32_t alloc_film(HkContext* ctx, size_t n_pixels) {
 }
 static int32_t alloc_state(HkContext* ctx, size_t n_slots) {
     // one slab: 22 float4 arrays, 5 u32/f32 arrays, 16 queues; every array starts 256-byte aligned
-    const size_t f4 = 22, w4 = 5, q = 6 + HK_N_HIT_QUEUES;
+    const size_t f4 = 22, w4 = 5, q = 8 + HK_N_HIT_QUEUES;
     size_t rounded = f4 * (((16 * n_slots + 255) / 256) * 256) + (w4 + q) * (((4 * n_slots + 255) / 256) * 256);
     CK(cudaStreamSynchronize(ctx->stream));
     CK(ctx->b_state.alloc(rounded));
@@ -491,6 +501,7 @@ static int32_t alloc_state(HkContext* ctx, size_t n_slots) {
     S.q_ray[0] = reinterpret_cast<uint32_t*>(take(4)); S.q_ray[1] = reinterpret_cast<uint32_t*>(take(4));
     S.q_escaped = reinterpret_cast<uint32_t*>(take(4)); S.q_medium = reinterpret_cast<uint32_t*>(take(4)); S.q_shadow = reinterpret_cast<uint32_t*>(take(4));
     S.q_shadow2 = reinterpret_cast<uint32_t*>(take(4));
+    S.q_alpha[0] = reinterpret_cast<uint32_t*>(take(4)); S.q_alpha[1] = reinterpret_cast<uint32_t*>(take(4));
     for (int t = 0; t < HK_N_HIT_QUEUES; t++) S.q_hit[t] = reinterpret_cast<uint32_t*>(take(4));
     S.counts = ctx->b_counts.as<uint32_t>();
     S.rays_traced = reinterpret_cast<unsigned long long*>(ctx->b_counts.as<char>() + sizeof(uint32_t) * HK_N_COUNTERS);
@@ -561,10 +572,16 @@ int32_t hk_set_params(HkContext* ctx, const HkRenderParams* p) {
     size_t n_pixels = (size_t)p->width * p->height;
     // the pool itself is sized on demand by hk_render_samples* (a caller that renders one sample per call never
     // allocates more than one sample's worth)
-    int32_t rc = alloc_film(ctx, n_pixels);
-    if (rc != HK_OK) return rc;
-    ctx->aux_pixels = 0;                 // film.albedo / normal / depth belong to the previous film
-    ctx->b_state.release(); ctx->n_slots = 0;
+    // a call that only changes integrator parameters (max_depth, regularize, clamp, samples in flight) keeps what the film has
+    // accumulated, like the reference, whose render! reads the VolPath fields on every call (volpath.jl:445-520)
+    int32_t rc = HK_OK;
+    if (!ctx->have_params || ctx->b_film.bytes != 16 * n_pixels + 64) {
+        rc = alloc_film(ctx, n_pixels);
+        if (rc != HK_OK) return rc;
+        ctx->aux_pixels = 0;                 // film.albedo / normal / depth belong to the previous film
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->b_state.release(); ctx->n_slots = 0;
+    }
     rc = build_sobol_cache(ctx);
     if (rc != HK_OK) return rc;
     ctx->have_params = true;
@@ -621,7 +638,7 @@ int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride,
         CK(cudaStreamSynchronize(st));
         ctx->camera_medium_valid = true;
     }
-    const bool opaque_only = !ctx->D.any_medium_transition && ctx->D.n_media == 0;
+    const bool opaque_only = !ctx->D.any_medium_transition && ctx->D.n_media == 0 && !ctx->D.has_alpha;      // (an alpha-tested surface can let a shadow ray through: the segment walk)
     const bool cnt = (ctx->profiling & 2) != 0;
     unsigned long long* work = ctx->b_work_ctr.as<unsigned long long>();
     const int tgrid = ctx->sm_count * HK_TRACE_BLOCKS_PER_SM;
@@ -645,9 +662,13 @@ int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride,
             k_reset_bounce<<<1, HK_N_COUNTERS, 0, st>>>(ctx->S, cur, overlap_shadow ? (par ^ 1) : -1); ctx->launches++;
             {
                 StageScope sc(ctx, HK_STAGE_TRACE);
-                hkl_trace(cnt, tgrid, st, ctx->D, ctx->S, cur, work);
+                hkl_trace(cnt, tgrid, st, ctx->D, ctx->S, cur, 0, work);
             }
-            { StageScope sc(ctx, HK_STAGE_ROUTE); k_route<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->D, ctx->S, cur, par); }
+            { StageScope sc(ctx, HK_STAGE_ROUTE); k_route<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->D, ctx->S, cur, par, 0); }
+            if (ctx->D.has_alpha) for (int r = 1; r < HK_ALPHA_ROUNDS; r++) {      // alpha-tested surfaces: re-trace the rays whose hit was skipped (empty rounds exit at once)
+                { StageScope sc(ctx, HK_STAGE_TRACE); hkl_trace(cnt, tgrid, st, ctx->D, ctx->S, cur, r, work); }
+                { StageScope sc(ctx, HK_STAGE_ROUTE); k_route<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->D, ctx->S, cur, par, r); }
+            }
             if (ctx->D.n_media > 0) {
                 StageScope sc(ctx, HK_STAGE_MEDIUM);
                 hkl_medium_track(ctx->has_rgbgrid, ctx->sm_count * 4, st, ctx->D, ctx->S);
@@ -748,6 +769,28 @@ int32_t hk_read_film(HkContext* ctx, float* out) {
     CK(cudaStreamSynchronize(ctx->stream));
     return HK_OK;
 }
+int32_t hk_read_film_dev(HkContext* ctx, float* out_dev) {
+    if (!ctx || !out_dev) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    REQUIRE(ctx->have_params, "hk_set_params has not been called");
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, out_dev) != cudaSuccess || (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged)) {
+        cudaGetLastError(); ctx->err = "hk_read_film_dev needs a device pointer (use hk_read_film for host memory)"; return HK_ERR_INVALID;
+    }
+    const size_t n = (size_t)ctx->params.width * ctx->params.height;
+    k_film_finalize<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(ctx->S.pixel_rgb, ctx->S.pixel_weight, out_dev, ctx->params.width, ctx->params.height);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return HK_OK;
+}
+int32_t hk_set_stream(HkContext* ctx, void* cuda_stream) {
+    if (!ctx) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->copy_stream) CK(cudaStreamSynchronize(ctx->copy_stream));
+    ctx->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return HK_OK;
+}
 // Pipelined read-out for progressive display: finalize into one of two staging buffers on the render stream, copy it to the
 // (pinned) host buffer on a separate stream, and return at once -- the next hk_render_samples can be enqueued while the
 // DMA runs.  hk_read_film_wait(ticket) blocks until that frame has landed.  At most two frames in flight.
@@ -793,6 +836,23 @@ int32_t hk_postprocess(HkContext* ctx, const HkPostprocess* p, float* out) {
     ctx->launches++;
     CK(cudaMemcpyAsync(out, ctx->b_readback.p, 12 * n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return HK_OK;
+}
+int32_t hk_postprocess_dev(HkContext* ctx, const HkPostprocess* p, float* out_dev) {
+    if (!ctx || !p || !out_dev) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    REQUIRE(ctx->have_params, "hk_set_params has not been called");
+    REQUIRE(p->tonemap_mode >= HK_TONEMAP_NONE && p->tonemap_mode <= HK_TONEMAP_FILMIC, "unknown tonemap mode");
+    const size_t n = (size_t)ctx->params.width * ctx->params.height;
+    REQUIRE(!p->mask_escaped || ctx->aux_pixels == n, "postprocess with a background needs film.depth: call hk_fill_aux_buffers first");
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, out_dev) != cudaSuccess || (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged)) {
+        cudaGetLastError(); ctx->err = "hk_postprocess_dev needs a device pointer"; return HK_ERR_INVALID;
+    }
+    k_film_postprocess<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(ctx->S.pixel_rgb, ctx->S.pixel_weight, out_dev, ctx->params.width, ctx->params.height, *p,
+                                                                           p->mask_escaped ? ctx->b_aux.as<float>() + 6 * n : nullptr);
+    ctx->launches++;
+    CK(cudaGetLastError());
     return HK_OK;
 }
 // fill_aux_buffers!(film, scene, camera; has_infinite_lights), film.jl:410-431

@@ -26,7 +26,8 @@ struct DevBuf {
 struct HkContext {
     int device = 0;
     std::string err;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;              // the render stream: own_stream, or the caller's (hk_set_stream)
+    cudaStream_t own_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int sm_count = 148;
     DevScene D;

@@ -9,8 +9,8 @@
     else { if (b) kernel<false, true><<<HK_UNPACK cfg>>>args; else kernel<false, false><<<HK_UNPACK cfg>>>args; } } while (0)
 #define HK_UNPACK(...) __VA_ARGS__
 
-void hkl_trace(bool count, int grid, cudaStream_t st, const DevScene& D, const PathState& S, int cur, unsigned long long* work) {
-    HK_DISPATCH2(count, D.bvh.inst != nullptr, k_trace, (grid, HK_TRACE_THREADS, 0, st), (D, S, cur, work));
+void hkl_trace(bool count, int grid, cudaStream_t st, const DevScene& D, const PathState& S, int cur, int round, unsigned long long* work) {
+    HK_DISPATCH2(count, D.bvh.inst != nullptr, k_trace, (grid, HK_TRACE_THREADS, 0, st), (D, S, cur, round, work));
 }
 void hkl_shadow_opaque(bool count, int grid, cudaStream_t st, const DevScene& D, const PathState& S, unsigned long long* work, int par) {
     HK_DISPATCH2(count, D.bvh.inst != nullptr, k_shadow_opaque, (grid, HK_TRACE_THREADS, 0, st), (D, S, work, par));

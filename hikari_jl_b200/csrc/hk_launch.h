@@ -5,7 +5,7 @@
 #include "hk_wavefront.cuh"
 
 // hk_k_trace.cu (BVH8 traversal kernels)
-void hkl_trace(bool count, int grid, cudaStream_t st, const DevScene& D, const PathState& S, int cur, unsigned long long* work);
+void hkl_trace(bool count, int grid, cudaStream_t st, const DevScene& D, const PathState& S, int cur, int round, unsigned long long* work);
 void hkl_shadow_opaque(bool count, int grid, cudaStream_t st, const DevScene& D, const PathState& S, unsigned long long* work, int par);
 void hkl_shadow_seg_trace(bool count, int grid, cudaStream_t st, const DevScene& D, const PathState& S, int round, unsigned long long* work);
 void hkl_trace_batch(bool any, bool count, int grid, cudaStream_t st, const DevBvh& B, const float4* rays, uint32_t n, float4* hits, uint8_t* occluded,

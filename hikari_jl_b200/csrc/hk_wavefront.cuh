@@ -51,9 +51,15 @@
 #define HK_C_SHCUR_TRACE 32    // + r: work cursor of the closest-hit pass of shadow round r
 #define HK_C_SHCUR_RATIO 44    // + r: work cursor of the ratio-tracking pass of shadow round r
 #define HK_SHADOW_ROUNDS 10    // trace_shadow_transmittance: at most 10 segments (intersection.jl:302-406)
-#define HK_N_COUNTERS 64
+#define HK_N_COUNTERS 128
+// alpha-tested surfaces (intersection.jl:221-266): round r = 1..15 of the trace stage re-traces the rays whose hit was skipped in
+// round r-1 (round 0 = the bounce's own trace); the two retrace queues ping-pong by round parity
+#define HK_ALPHA_ROUNDS 16
+#define HK_C_ALPHA_N0 64       // + r: rays queued for retrace round r
+#define HK_C_ALPHA_CUR0 80     // + r: work cursor of retrace round r
 static_assert(HK_C_SHROUND0 + HK_SHADOW_ROUNDS < HK_C_SHCUR_TRACE && HK_C_SHCUR_TRACE + HK_SHADOW_ROUNDS < HK_C_SHCUR_RATIO &&
               HK_C_SHCUR_RATIO + HK_SHADOW_ROUNDS < HK_C_HIT1, "shadow-round counters overlap the second bank of hit-queue counters");
+static_assert(HK_C_ALPHA_N0 + HK_ALPHA_ROUNDS <= HK_C_ALPHA_CUR0 && HK_C_ALPHA_CUR0 + HK_ALPHA_ROUNDS <= HK_N_COUNTERS && HK_C_ALPHA_N0 > HK_C_HIT1 + 1, "alpha-round counters");
 static_assert(HK_HIT_COUNTER(7) == 15 && HK_HIT_COUNTER(8) == HK_C_HIT1 && HK_HIT_COUNTER(HK_N_HIT_QUEUES - 1) < HK_N_COUNTERS,
               "hit-queue counters must stay inside the counter block");
 static_assert(HK_TYPE_QUEUE(HK_MAT_COATED_CONDUCTOR) == 0 && HK_TYPE_QUEUE(HK_MAT_COATED_DIFFUSE_TRANSMISSION) == 8 &&
@@ -83,6 +89,7 @@ struct DevScene {
     const float* __restrict__ uvs; const HkTexture* __restrict__ textures; int32_t n_textures;
     // instancing (HkGeometry.instances): instances in upload order + their first global primitive ids (ascending); n_inst = 0: plain soup
     const struct DevInstance* __restrict__ instances; const uint32_t* __restrict__ inst_prim_base; int32_t n_inst;
+    int32_t has_alpha;                 // some uploaded texture carries an alpha plane: the trace / shadow stages run their pass-through rounds
 };
 struct DevInstance { float o2w[12]; float w2o[12]; uint32_t first_tri, prim_base, iface, n_tris; };
 // A global primitive id resolves to (instance, triangle of the index array); vertices / normals of an instanced triangle are taken
@@ -119,7 +126,7 @@ struct PathState {
     uint32_t* res_mat;                             // material a MixMaterial hit resolved to (written by the routing, read by k_shade)
     float4 *sh_hit, *sh_T, *sh_tu, *sh_tl;         // shadow rays through media: segment hit, running transmittance / MIS ratios
     float4 *nee_a, *nee_b, *nee_c;                 // light sample of a surface hit, written by k_hit_lights for k_shade: Li | wi, pdf | p_light, pmf (sign bit = delta light)
-    uint32_t *q_ray[2], *q_escaped, *q_medium, *q_shadow, *q_shadow2, *q_hit[HK_N_HIT_QUEUES];
+    uint32_t *q_ray[2], *q_escaped, *q_medium, *q_shadow, *q_shadow2, *q_hit[HK_N_HIT_QUEUES], *q_alpha[2];
     uint32_t* counts;                  // [HK_N_COUNTERS]
     unsigned long long* rays_traced;
     unsigned long long* path_vertices;  // surface hits routed + medium scatter events (HkStats::path_vertices)
@@ -215,16 +222,50 @@ HK_DEV Surf surface_at(const DevScene& D, uint32_t prim0, float b1, float b2, fl
 // Kd of a textured MatteMaterial at a hit: uv = barycentric interpolation of the vertex uvs (intersection.jl:28-37), bilinear
 // texel of the (h, w) column-major image with v flipped and clamped indices (_sample_texture_bilinear, texture-ref.jl:160-190),
 // clamp to [0, 1] and uplift (spectral-eval.jl:57-60).  One uncached rgb_to_spectrum per hit.
-HK_DEV Spec textured_kd(const DevScene& D, const HkMaterial& m, uint32_t prim0, float b1, float b2, float4 lam) {
-    float u = 0.0f, v = 0.0f;
-    if (D.uvs) {
-        const uint32_t tri = resolve_prim(D, prim0).tri;
-        const uint32_t i0 = __ldg(D.indices + 3 * (size_t)tri), i1 = __ldg(D.indices + 3 * (size_t)tri + 1), i2 = __ldg(D.indices + 3 * (size_t)tri + 2);
-        const float2 a = __ldg(reinterpret_cast<const float2*>(D.uvs) + i0), b = __ldg(reinterpret_cast<const float2*>(D.uvs) + i1), c = __ldg(reinterpret_cast<const float2*>(D.uvs) + i2);
-        const float w = 1.0f - b1 - b2;
-        u = w * a.x + b1 * b.x + b2 * c.x; v = w * a.y + b1 * b.y + b2 * c.y;
-    }
+// uv of a hit = barycentric interpolation of the vertex uvs, (0, 0) without uvs (vp_compute_uv_barycentric, intersection.jl:28-37)
+HK_DEV float2 hit_uv(const DevScene& D, uint32_t tri, float b1, float b2) {
+    if (!D.uvs) return make_float2(0.0f, 0.0f);
+    const uint32_t i0 = __ldg(D.indices + 3 * (size_t)tri), i1 = __ldg(D.indices + 3 * (size_t)tri + 1), i2 = __ldg(D.indices + 3 * (size_t)tri + 2);
+    const float2 a = __ldg(reinterpret_cast<const float2*>(D.uvs) + i0), b = __ldg(reinterpret_cast<const float2*>(D.uvs) + i1), c = __ldg(reinterpret_cast<const float2*>(D.uvs) + i2);
+    const float w = 1.0f - b1 - b2;
+    return make_float2(w * a.x + b1 * b.x + b2 * c.x, w * a.y + b1 * b.y + b2 * c.y);
+}
+// get_surface_alpha (spectral-eval.jl:3882-3888): alpha of the POINT-sampled Kd texel of a MatteMaterial (_sample_texture_data,
+// textures/basic.jl:19-25: idx = trunc(1 + (size - 1) (1 - v, u)), clamped), 1 for every other material (a MixMaterial included)
+HK_DEV float surface_alpha(const DevScene& D, uint32_t prim0, float b1, float b2) {
+    const PrimRef pr = resolve_prim(D, prim0);
+    const HkMaterial& m = D.materials[D.interfaces[prim_iface(D, pr, prim0) - 1].material - 1];
+    if (m.type != HK_MAT_MATTE || m.tex[0] <= 0 || (m.flags & HK_MATFLAG_VERTEX_COLORS)) return 1.0f;
     const HkTexture t = D.textures[m.tex[0] - 1];
+    if (!t.alpha) return 1.0f;
+    const float2 uv = hit_uv(D, pr.tri, b1, b2);
+    const int row = clampi((int)(1.0f + (float)(t.h - 1) * (1.0f - uv.y)), 1, t.h), col = clampi((int)(1.0f + (float)(t.w - 1) * uv.x), 1, t.w);
+    return __ldg(t.alpha + (size_t)(col - 1) * t.h + (row - 1));
+}
+// the stochastic alpha test both the trace stage and the shadow rays use (intersection.jl:241-243, 355-358): a PCG32 stream seeded
+// from the bits of the ray, so the same ray always gets the same decision
+HK_DEV bool alpha_skips(const DevScene& D, uint32_t prim0, float b1, float b2, float3 o, float3 d) {
+    const float alpha = surface_alpha(D, prim0, b1, b2);
+    if (!(alpha < 1.0f)) return false;
+    Pcg32 rng = pcg32_init(hash_f3(o), hash_f3(d));
+    return pcg32_f32(rng) > alpha;
+}
+HK_DEV Spec textured_kd(const DevScene& D, const HkMaterial& m, uint32_t prim0, float b1, float b2, float4 lam) {
+    const PrimRef pr = resolve_prim(D, prim0);
+    const HkTexture t = D.textures[m.tex[0] - 1];
+    if (m.flags & HK_MATFLAG_VERTEX_COLORS) {
+        // eval_tex(::VertexColorTexture, tfc), texture-ref.jl:240-245: data[1, fi] b1 + data[2, fi] b2 + data[3, fi] b3 over a (3, n_faces)
+        // table of per-face corner colours; fi = TriangleMeta.primitive_index (the face within its mesh)
+        const uint32_t face = pr.inst ? prim0 - pr.inst->prim_base + 1u : __ldg(D.tri_meta + 3 * (size_t)prim0 + 1);
+        const float* T = t.rgb + 9 * (size_t)(face - 1u);
+        const float w0 = 1.0f - b1 - b2;
+        float rgb[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) rgb[k] = clampf(__ldg(T + k) * w0 + __ldg(T + 3 + k) * b1 + __ldg(T + 6 + k) * b2, 0.0f, 1.0f);
+        return pre_bounded(make_pre_bounded(D.T, rgb[0], rgb[1], rgb[2]), lam);
+    }
+    const float2 uv = hit_uv(D, pr.tri, b1, b2);
+    const float u = uv.x, v = uv.y;
     const float px = u * (float)(t.w - 1) + 1.0f, py = (1.0f - v) * (float)(t.h - 1) + 1.0f;
     const float flx = floorf(px), fly = floorf(py);
     const int x0 = clampi(floor_i(px), 1, t.w), x1 = clampi(floor_i(px) + 1, 1, t.w), y0 = clampi(floor_i(py), 1, t.h), y1 = clampi(floor_i(py) + 1, 1, t.h);
@@ -356,6 +397,7 @@ HK_DEV uint32_t claim_for_idle(uint32_t* cursor, unsigned idle) {
 }
 
 HK_DEV uint32_t* queue_of(const PathState& S, int qid) {
+    if (qid >= HK_C_ALPHA_N0) return S.q_alpha[(qid - HK_C_ALPHA_N0) & 1];
     if (qid == HK_C_MEDIUM) return S.q_medium;
     if (qid == HK_C_ESCAPED) return S.q_escaped;
     if (qid >= HK_C_HIT1) return S.q_hit[8 + qid - HK_C_HIT1];
@@ -377,12 +419,13 @@ struct QueueRayIO {
 };
 #ifdef HK_TU_TRACE
 template <bool COUNT, bool INST>
-__global__ void __launch_bounds__(HK_TRACE_THREADS, INST ? HK_TRACE_BLOCKS_PER_SM_INST : HK_TRACE_BLOCKS_PER_SM) k_trace(const __grid_constant__ DevScene D, PathState S, int cur, unsigned long long* work) {
+__global__ void __launch_bounds__(HK_TRACE_THREADS, INST ? HK_TRACE_BLOCKS_PER_SM_INST : HK_TRACE_BLOCKS_PER_SM) k_trace(const __grid_constant__ DevScene D, PathState S, int cur, int round, unsigned long long* work) {
     __shared__ uint2 sm_stack[HK_SM_STACK * HK_TRACE_THREADS];
-    const uint32_t n = S.counts[HK_C_RAY0 + cur];
+    // round > 0: a retrace round of the alpha loop (rays whose previous hit was skipped, restarted just behind that surface)
+    const uint32_t n = S.counts[round == 0 ? HK_C_RAY0 + cur : HK_C_ALPHA_N0 + round];
     uint32_t traced = 0, wn = 0, wt = 0;
-    QueueRayIO io{S, S.q_ray[cur]};
-    trace_queue<false, COUNT, INST>(D.bvh, sm_stack + threadIdx.x, n, S.counts + HK_C_CURSOR_TRACE, io, traced, wn, wt);
+    QueueRayIO io{S, round == 0 ? S.q_ray[cur] : S.q_alpha[round & 1]};
+    trace_queue<false, COUNT, INST>(D.bvh, sm_stack + threadIdx.x, n, S.counts + (round == 0 ? HK_C_CURSOR_TRACE : HK_C_ALPHA_CUR0 + round), io, traced, wn, wt);
     count_rays(S.rays_traced, traced);
     if (COUNT) { count_rays(work, traced); count_rays(work + 1, wn); count_rays(work + 2, wt); }
 }
@@ -443,6 +486,20 @@ HK_DEV int hit_queue_id(const DevScene& D, const PathState& S, uint32_t slot, ui
     return HK_HIT_COUNTER((int)HK_TYPE_QUEUE(mtype));
 }
 
+// the alpha test of a routed hit; on a skip the slot's ray restarts behind the surface (same direction, t_max = Inf)
+HK_DEV bool route_alpha_skip(const DevScene& D, const PathState& S, uint32_t slot, uint32_t hit_bits, float t_hit) {
+    const float4 hr = S.hit[slot];
+    const float4 ra = S.ray_a[slot], rb = S.ray_b[slot];
+    const float3 o = f3(ra.x, ra.y, ra.z), d = f3(ra.w, rb.x, rb.y);
+    const uint32_t prim0 = HK_HIT_PRIM1(hit_bits) - 1u;
+    if (!alpha_skips(D, prim0, hr.z, hr.w, o, d)) return false;
+    const float3 pi = o + d * t_hit;
+    const float3 n = geometric_normal(D, prim0);
+    const float3 no = pi + (dot3(d, n) > 0.0f ? n : -n) * 1.0e-4f;
+    S.ray_a[slot] = make_float4(no.x, no.y, no.z, d.x);
+    S.ray_b[slot] = make_float4(d.y, d.z, HK_INF, 0.0f);
+    return true;
+}
 #ifdef HK_TU_CORE
 // writes the shading class (material type; 11 = textured matte) of every BVH triangle into the spare word of its record (HitRec)
 __global__ void __launch_bounds__(256) k_patch_tri_types(float4* __restrict__ tris, uint32_t n_tris, const uint32_t* __restrict__ tri_meta,
@@ -467,11 +524,14 @@ __global__ void __launch_bounds__(256) k_patch_inst_types(float4* __restrict__ i
 // counters, and one thread per queue then reserves the block's range with a single global atomicAdd (1 per queue per 1024
 // rays).  With warp-level aggregation alone the ~0.5 M same-address atomics per sample were what the kernel waited for.
 #define HK_ROUTE_PER_THREAD 4
-__global__ void __launch_bounds__(256) k_route(const __grid_constant__ DevScene D, PathState S, int cur, int par) {
+// round: 0 = the rays of the bounce; r > 0 = the rays re-traced in alpha round r.  A hit on an alpha-tested surface that the
+// stochastic test skips (vp_trace_rays_kernel!, intersection.jl:221-266) restarts its ray 1e-4 behind the surface and queues it
+// for round r + 1 -- no depth consumed; a ray still being skipped in the 16th round is absorbed.
+__global__ void __launch_bounds__(256) k_route(const __grid_constant__ DevScene D, PathState S, int cur, int par, int round) {
     __shared__ uint32_t s_cnt[HK_N_COUNTERS], s_base[HK_N_COUNTERS];
-    const uint32_t n = S.counts[HK_C_RAY0 + cur];
+    const uint32_t n = S.counts[round == 0 ? HK_C_RAY0 + cur : HK_C_ALPHA_N0 + round];
     const uint32_t chunk = 256u * HK_ROUTE_PER_THREAD;
-    const uint32_t* __restrict__ q = S.q_ray[cur];
+    const uint32_t* __restrict__ q = round == 0 ? S.q_ray[cur] : S.q_alpha[round & 1];
     for (uint32_t c0 = blockIdx.x * chunk; c0 < n; c0 += gridDim.x * chunk) {
         if (threadIdx.x < HK_N_COUNTERS) s_cnt[threadIdx.x] = 0;
         __syncthreads();
@@ -486,6 +546,7 @@ __global__ void __launch_bounds__(256) k_route(const __grid_constant__ DevScene 
                 const uint32_t hb = __float_as_uint(hty.y);
                 if (D.n_media > 0 && HK_FLAG_MEDIUM(S.flags[slot[r]]) != 0) qid[r] = HK_C_MEDIUM;
                 else if (HK_HIT_PRIM1(hb) == 0) qid[r] = HK_C_ESCAPED;
+                else if (D.has_alpha && HK_HIT_MTYPE(hb) == HK_SHADE_MATTE_TEX && route_alpha_skip(D, S, slot[r], hb, hty.x)) qid[r] = round + 1 < HK_ALPHA_ROUNDS ? HK_C_ALPHA_N0 + round + 1 : -1;
                 else qid[r] = hit_queue_id(D, S, slot[r], hb, hty.x);
             }
         }
@@ -950,7 +1011,7 @@ __global__ void __launch_bounds__(128) k_shadow_seg_ratio(const __grid_constant_
     MediaCtx MDC = media_ctx(D);
     RatioTracker R;
     R.in_seg = false;
-    bool busy = false, exhausted = false, tracking = false;
+    bool busy = false, exhausted = false, tracking = false, apass = false;
     uint32_t slot = 0;
     for (;;) {
         // same phase vote as k_medium_track; a lane whose segment needs no tracking (vacuum) resolves in the event phase
@@ -959,15 +1020,24 @@ __global__ void __launch_bounds__(128) k_shadow_seg_ratio(const __grid_constant_
         const unsigned sk = ~(idle | ev);
         if (idle == 0xFFFFFFFFu && exhausted) break;
         if (!exhausted && ((uint32_t)__popc(idle) >= (uint32_t)HK_MEDIUM_REFILL_MIN || (ev | sk) == 0u)) {
+            bool past_end = false;      // only a claim beyond the queue's end means the queue is exhausted: a claimed ray that is dropped
+                                        // below (blocked by an opaque surface, t_remaining < 1e-6) leaves its lane idle with work still queued
             if (!busy) {
                 const uint32_t idx = claim_for_idle(S.counts + HK_C_SHCUR_RATIO + round, idle);
+                past_end = idx >= n;
                 if (idx < n) {
                     slot = q[idx];
                     const float4 sa = S.sh_a[slot], sb = S.sh_b[slot];
                     const float4 h = S.sh_hit[slot];
                     const uint32_t hp = HK_HIT_PRIM1(__float_as_uint(h.y));
                     bool opaque = false;                          // an opaque surface (alpha == 1) blocks: no tracking needed
-                    if (hp != 0u) { const HkMediumInterface mi = D.interfaces[prim_iface(D, hp - 1u) - 1]; opaque = mi.inside == mi.outside; }
+                    apass = false;                                // ... unless the stochastic alpha test lets the ray through (intersection.jl:349-372)
+                    if (hp != 0u) {
+                        const HkMediumInterface mi = D.interfaces[prim_iface(D, hp - 1u) - 1]; opaque = mi.inside == mi.outside;
+                        if (opaque && D.has_alpha && !(sb.z < 1.0e-6f) && HK_HIT_MTYPE(__float_as_uint(h.y)) == HK_SHADE_MATTE_TEX) {
+                            apass = alpha_skips(D, hp - 1u, h.z, h.w, f3(sa.x, sa.y, sa.z), f3(sa.w, sb.x, sb.y)); opaque = !apass;
+                        }
+                    }
                     if (!(sb.z < 1.0e-6f) && !opaque) {           // t_rem < 1e-6: dropped (the reference's loop ends without a visible ray)
                         busy = true;
                         const uint32_t cur = S.sh_medium[slot];
@@ -980,7 +1050,7 @@ __global__ void __launch_bounds__(128) k_shadow_seg_ratio(const __grid_constant_
                     }
                 }
             }
-            exhausted = __any_sync(0xFFFFFFFFu, !busy);
+            exhausted = __any_sync(0xFFFFFFFFu, past_end);
             continue;
         }
         bool fin = false;
@@ -998,14 +1068,14 @@ __global__ void __launch_bounds__(128) k_shadow_seg_ratio(const __grid_constant_
             else {
                 const uint32_t prim0 = prim1 - 1u;
                 const HkMediumInterface mi = D.interfaces[prim_iface(D, prim0) - 1];
-                if (mi.inside != mi.outside) {                     // (an opaque surface, alpha == 1, blocks: nothing to do)
-                    if (sp_black(T)) visible = true;               // reference: leaves the loop "visible" with T == 0 -> contributes nothing
-                    else if (round + 1 < HK_SHADOW_ROUNDS) {
+                if (mi.inside != mi.outside || apass) {            // (an opaque surface, alpha == 1, blocks: nothing to do)
+                    if (!apass && sp_black(T)) visible = true;     // reference: leaves the loop "visible" with T == 0 -> contributes nothing
+                    else if (round + 1 < HK_SHADOW_ROUNDS) {       // (an alpha pass-through continues whatever T is, medium unchanged)
                         const float4 sa = S.sh_a[slot], sb = S.sh_b[slot];
                         const float3 o = f3(sa.x, sa.y, sa.z), d = f3(sa.w, sb.x, sb.y);
                         const bool entering = dot3(d, geometric_normal(D, prim0)) < 0.0f;
                         const float3 no = o + d * (h.x + 1.0e-4f);
-                        S.sh_medium[slot] = entering ? mi.inside : mi.outside;
+                        if (!apass) S.sh_medium[slot] = entering ? mi.inside : mi.outside;
                         S.sh_a[slot] = make_float4(no.x, no.y, no.z, d.x);
                         S.sh_b[slot] = make_float4(sb.x, sb.y, sb.z - h.x - 1.0e-4f, 0.0f);
                         S.sh_T[slot] = T; S.sh_tu[slot] = tu; S.sh_tl[slot] = tl;

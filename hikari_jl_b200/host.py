@@ -1296,15 +1296,9 @@ class Backend:
         # materials first (registers spectra and texture ids), then spectra and textures, then the material upload
         scene._textures = []
         mats = (A.HkMaterial * max(1, len(scene.materials)))(*[m.to_abi(scene) for m in scene.materials])
-        texs = (A.HkTexture * max(1, len(scene._textures)))(*[A.HkTexture(_fp(t.data), t.h, t.w) for t in scene._textures])
+        texs = (A.HkTexture * max(1, len(scene._textures)))(*[A.HkTexture(_fp(t.data), t.h, t.w, None if getattr(t, "alpha", None) is None else _fp(t.alpha))
+                                                             for t in scene._textures])
         self.call("upload_textures", texs, len(scene._textures))
-        if self.prefix == "hk_" and any(isinstance(t, VertexColorTexture) for t in scene._textures):
-            raise NotImplementedError("VertexColorTexture parameters (texture-ref.jl:240-245) are not supported by the CUDA path yet")
-        for k, t in enumerate(scene._textures):
-            if t.alpha is not None:
-                if self.prefix == "hk_":       # the CUDA path fails loudly instead of rendering the surface opaque
-                    raise NotImplementedError("alpha-tested surfaces (alpha < 1 in a Kd texture, intersection.jl:221-266, 349-372) are not supported by the CUDA path yet")
-                self.lib.ok_test_upload_texture_alpha(self.ctx, k + 1, _fp(t.alpha))       # oracle-only test hook
         lam = np.concatenate([sp.lambdas for sp in scene._spectra]) if scene._spectra else np.zeros(0, f32)
         val = np.concatenate([sp.values for sp in scene._spectra]) if scene._spectra else np.zeros(0, f32)
         offs = np.cumsum([0] + [len(sp.lambdas) for sp in scene._spectra]).astype(np.uint32)
@@ -1418,15 +1412,20 @@ class VolPath:
         w, h = film.resolution
         s = scene._synced or scene.sync()
         key = (id(s), w, h, len(s.lights))
+        pkey = (w, h, self.max_depth, self.samples_per_pixel, self.regularize, self.max_component_value, self.material_coherence,
+                self.sample_batch, id(self.filter_sampler_data))
         if self.backend is None:
             self.backend = Backend()
         if self.state != key:
             b = self.backend
             b.upload_tables()
             b.upload_scene(scene)
-            b.set_filter(self.filter_sampler_data)
-            b.set_params(self, w, h, self.sample_batch)
             self.state = key
+            self._params_key = None
+        if getattr(self, "_params_key", None) != pkey:      # the reference reads the VolPath fields on every render! call
+            self.backend.set_filter(self.filter_sampler_data)
+            self.backend.set_params(self, w, h, self.sample_batch)
+            self._params_key = pkey
         self.backend.set_camera(camera)
 
     def update_material(self, scene, interface_idx, new_material):
@@ -1434,10 +1433,22 @@ class VolPath:
         `interface_idx` (what push! returned) in place; the prepared backend gets the one struct, not the scene."""
         mi, _, _ = scene.interfaces[interface_idx - 1]
         assert not isinstance(new_material, MixMaterial), "replace the sub-materials of a mix, not the mix slot"
+        old_material = scene.materials[mi - 1]
         scene.materials[mi - 1] = new_material
+        # a MixMaterial that blends the replaced material must follow it: its ABI record holds the sub-material's index and
+        # SetKey (type, index within type), which the mix hash consumes (mix-material.jl:114-158)
+        mixes = [k for k, m in enumerate(scene.materials) if isinstance(m, MixMaterial) and any(sub is old_material for sub in m.materials)]
+        for k in mixes:
+            m = scene.materials[k]
+            m.materials = tuple(new_material if sub is old_material else sub for sub in m.materials)
         if self.backend is not None and self.state is not None:
             abi = new_material.to_abi(scene)
             self.backend.call("update_material", mi, C.byref(abi))
+            if type(new_material) is not type(old_material):
+                mixes = [k for k, m in enumerate(scene.materials) if isinstance(m, MixMaterial)]      # set keys of every type may have shifted
+            for k in mixes:
+                abi = scene.materials[k].to_abi(scene)
+                self.backend.call("update_material", k + 1, C.byref(abi))
 
     def wait_film(self, film, handle):
         """Block until the frame requested with render(..., read="async") is film.framebuffer."""

@@ -69,6 +69,67 @@ def textured_spheres(tess=24):
     return s, _cam((0, 1.6, 4.5), (0, 0.2, 0), 40.0)
 
 
+def alpha_foliage(fog=False, n_cards=24, seed=9):
+    """Alpha-tested surfaces (intersection.jl:221-266, 349-372): a stack of "leaf" cards whose MatteMaterial.Kd texture carries an alpha
+    plane (opaque discs on a transparent background, plus a fractional-alpha rim), over a matte floor, seen against the light so that
+    camera rays, bounce rays AND shadow rays all meet several cards in a row.  One card sits behind a MixMaterial (alpha 1 there,
+    whatever its texture says) and one is plain opaque.  fog=True puts the cards inside a homogeneous medium bounded by an index-1.5
+    glass box, so shadow rays that pass a card ratio-track up to it (the medium is unchanged by an alpha pass-through)."""
+    rng = np.random.RandomState(seed)
+    yy, xx = np.meshgrid(np.arange(32), np.arange(32), indexing="ij")
+    r = np.hypot(yy - 15.5, xx - 15.5)
+    leaf = np.zeros((32, 32, 4), np.float32)
+    leaf[..., 0] = 0.15 + 0.1 * (yy % 4 < 2); leaf[..., 1] = 0.55 + 0.2 * (xx % 8 < 4); leaf[..., 2] = 0.12
+    leaf[..., 3] = np.clip((14.0 - r) / 4.0, 0.0, 1.0)                 # opaque core, a rim of fractional alpha, transparent corners
+    half = leaf.copy(); half[..., :3] = (0.8, 0.3, 0.2); half[..., 3] = 0.5
+    s = H.Scene()
+    s.push(H.rect3((-5, -1.0, -5), (10, 0.1, 10)), H.MatteMaterial(Kd=(0.6, 0.6, 0.6)))
+    leaf_mat, half_mat = H.MatteMaterial(Kd=H.Texture(leaf)), H.MatteMaterial(Kd=H.Texture(half), sigma=15.0)
+    mixed = H.MixMaterial((H.MatteMaterial(Kd=H.Texture(half.copy())), H.MatteMaterial(Kd=(0.2, 0.2, 0.7))), amount=0.5)
+    for i in range(n_cards):
+        c = np.array([rng.uniform(-1.4, 1.4), rng.uniform(-0.5, 1.6), rng.uniform(-1.2, 1.2)])
+        ax = rng.normal(size=3); ax /= np.linalg.norm(ax)
+        R = H.rotation_matrix(rng.uniform(0, 360), ax).astype(np.float64)[:3, :3]
+        hs = rng.uniform(0.35, 0.7)
+        corners = [c + R @ np.array(v) * hs for v in ((-1, -1, 0), (1, -1, 0), (1, 1, 0), (-1, 1, 0))]
+        n = R @ np.array((0.0, 0.0, 1.0))
+        card = H.Mesh([tuple(v) for v in corners], [(0, 1, 2), (0, 2, 3)], normals=[tuple(n)] * 4, uvs=[(0, 0), (1, 0), (1, 1), (0, 1)])
+        mat = mixed if i == 3 else (H.MatteMaterial(Kd=(0.7, 0.6, 0.2)) if i == 5 else (half_mat if i % 4 == 1 else leaf_mat))
+        s.push(card, mat)
+    if fog:
+        medium = H.HomogeneousMedium(sigma_a=0.02, sigma_s=0.25, Le=0.0, g=0.2)
+        s.push(H.rect3((-2.2, -0.85, -2.0), (4.4, 3.2, 4.0)), H.MediumInterface(H.GlassMaterial(Kr=0.0, Kt=1.0, index=1.0), inside=medium, outside=None))
+    d = np.array([0.3, -1.0, 0.5])
+    s.push(H.DirectionalLight((4, 4, 4), d / np.linalg.norm(d), legacy_rgbspectrum=True))
+    s.push(H.PointLight((20, 20, 20), (0.5, 2.6, -1.0), legacy_rgbspectrum=True, scale=1.0))
+    s.push(H.AmbientLight((0.25, 0.3, 0.4)))
+    s.sync()
+    return s, _cam((0.0, 1.2, -5.0), (0.0, 0.4, 0.0), 40.0)
+
+
+def vertex_color_meshes(tess=10):
+    """VertexColorTexture as MatteMaterial.Kd (textures/basic.jl:43-46, texture-ref.jl:240-245): per-face corner colours interpolated
+    with the hit's barycentrics, indexed by TriangleMeta.primitive_index -- on two meshes (so the face index restarts), one of them
+    placed by a transform, next to a constant-colour sphere."""
+    rng = np.random.RandomState(4)
+    s = H.Scene()
+    s.push(H.rect3((-5, -1.0, -5), (10, 0.1, 10)), H.MatteMaterial(Kd=(0.7, 0.7, 0.7)))
+    for x in (-1.3, 1.3):
+        m = H.uv_sphere((x, 0.2, 0.0), 0.9, tess, tess)
+        fc = rng.uniform(-0.1, 1.2, size=(len(m.faces), 3, 3)).astype(np.float32)        # outside [0, 1]: clamped after interpolation
+        if x < 0:
+            s.push(m, H.MatteMaterial(Kd=H.VertexColorTexture(fc)))
+        else:
+            M = np.eye(4); M[:3, :3] = H.rotation_matrix(30.0, (0, 1, 0)).astype(np.float64)[:3, :3] * 0.9; M[:3, 3] = (0.1, 0.3, 0.2)
+            s.push(m, H.MatteMaterial(Kd=H.VertexColorTexture(fc), sigma=10.0), transform=M)
+    s.push(H.uv_sphere((0.0, 1.5, 0.3), 0.4, tess, tess), H.MatteMaterial(Kd=(0.2, 0.7, 0.3)))
+    d = np.array([-0.6, -1.0, 0.8])
+    s.push(H.DirectionalLight((3, 3, 3), d / np.linalg.norm(d), legacy_rgbspectrum=True))
+    s.push(H.AmbientLight((0.3, 0.35, 0.4)))
+    s.sync()
+    return s, _cam((0, 1.6, -4.5), (0, 0.2, 0), 40.0)
+
+
 def rgb_nebula(res=(20, 16, 12)):
     """An RGBGridMedium (media.jl:1002-1456) inside an index-1 boundary: two coloured, partly emissive blobs over a matte floor."""
     nx, ny, nz = res

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define HK_ABI_VERSION 1
+#define HK_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------------------------ */
 #define HK_OK                 0
@@ -104,21 +104,26 @@ typedef struct HkGeometry {
 } HkGeometry;
 
 /* ---- textures -----------------------------------------------------------------------------
- * replaces: the texture arrays a Raycore.TextureRef points at (src/textures/texture-ref.jl:50-76).  Packed RGB float images
- * (the reference's RGBSpectrum texels are r, g, b, alpha: the caller drops alpha, which must be 1 — alpha-tested surfaces are
- * SURVEY 8f item 2) in the reference's memory order, an (h, w) column-major matrix: texel (row y, column x), 0-based, at
- * rgb[3 * (x * h + y)].
- * Sampled bilinearly at the hit's interpolated uv exactly as _sample_texture_bilinear (:160-190): px = u (w-1) + 1,
- * py = (1 - v)(h-1) + 1, indices clamped, no wrap.  Upload before the materials that reference them.           */
+ * replaces: the texture arrays a Raycore.TextureRef points at (src/textures/texture-ref.jl:50-76).  The reference's RGBSpectrum
+ * texels are r, g, b, alpha (spectrum.jl:62-70); the caller splits them into a packed RGB image and an optional alpha plane, both
+ * in the reference's memory order, an (h, w) column-major matrix: texel (row y, column x), 0-based, at rgb[3 * (x * h + y)] and
+ * alpha[x * h + y].
+ * Colours are sampled bilinearly at the hit's interpolated uv exactly as _sample_texture_bilinear (:160-190): px = u (w-1) + 1,
+ * py = (1 - v)(h-1) + 1, indices clamped, no wrap.  alpha (null = opaque everywhere) makes the surfaces of a MatteMaterial whose Kd is
+ * this texture alpha-tested: get_surface_alpha (spectral-eval.jl:3882-3888) point-samples it (_sample_texture_data,
+ * textures/basic.jl:19-25) and the trace / shadow stages skip the surface when pcg32(hash(o), hash(d)) > alpha, without consuming
+ * depth (intersection.jl:221-266, 349-372).  A VertexColorTexture (HK_MATFLAG_VERTEX_COLORS) is passed as h = 3, w = n_faces.
+ * Upload before the materials that reference them.                                                              */
 typedef struct HkTexture {
     const float* rgb;
     int32_t      h, w;
+    const float* alpha;
 } HkTexture;
 
 /* ---- materials ----------------------------------------------------------------------------
  * replaces: scene.materials (MultiTypeSet) + scene.media_interfaces (src/scene.jl:21-28,
- * src/materials/medium-interface.jl:78-82).  Parameters are constants, except MatteMaterial.Kd which may be a
- * texture (tex[0]); other TextureRef parameters and alpha: SURVEY §8f item 2.                                 */
+ * src/materials/medium-interface.jl:78-82).  Parameters are constants, except MatteMaterial.Kd which may be an image
+ * texture (with or without alpha) or a VertexColorTexture (tex[0]).                                           */
 #define HK_MAT_MATTE                1   /* src/materials/spectral-eval.jl:42-101, 371-397      */
 #define HK_MAT_MIRROR               2   /* :108-132                                            */
 #define HK_MAT_GLASS                3   /* :140-198, 407-413                                   */
@@ -137,7 +142,7 @@ typedef struct HkTexture {
 #define HK_MATFLAG_SPECTRAL_ETA_K   2u  /* conductor eta/k are piecewise-linear spectra (ids in spec[]) */
 #define HK_MATFLAG_VERTEX_COLORS    8u  /* tex[0] is a VertexColorTexture (src/textures/basic.jl:43-46, texture-ref.jl:240-245): a (3, n_faces)
                                            table of per-face corner colours = an HkTexture with h = 3, w = n_faces, evaluated as
-                                           sum_k data[k, face] * bary[k].  Not built on the CUDA path yet: refused at upload  */
+                                           sum_k data[k, face] * bary[k] with face = TriangleMeta.primitive_index (MatteMaterial.Kd) */
 #define HK_MATFLAG_USE_ETA_K        4u  /* CoatedConductor: rgb0 / rgb1 (or spec[]) are eta / k; clear = rgb0 is the
                                            artist reflectance (use_eta_k, coated-conductor.jl:98)                   */
 
@@ -379,6 +384,17 @@ int32_t hk_read_film(HkContext* ctx, float* out_rgb_hw_colmajor);
  * most in flight; the caller alternates two host buffers.                                                         */
 int32_t hk_read_film_async(HkContext* ctx, float* out_rgb_hw_colmajor_pinned, int32_t* out_ticket);
 int32_t hk_read_film_wait(HkContext* ctx, int32_t ticket);
+/* Zero-copy read-out: the reference takes its GPU path when film.framebuffer is a device array
+ * (KA.get_backend(film.framebuffer), volpath.jl:453) and vp_finalize_film_kernel! writes straight into it (:384-417).
+ * out_dev is a DEVICE pointer to H*W RGB{Float32} in the same (H, W) column-major layout (a CuArray's pointer); the
+ * finalize kernel writes it on the render stream and the call returns without a host synchronisation
+ * (hk_synchronize, or stream order on a caller-supplied stream, orders later reads).                              */
+int32_t hk_read_film_dev(HkContext* ctx, float* out_dev_rgb_hw_colmajor);
+/* All rendering, read-out and upload-side kernels of `ctx` are enqueued on ONE stream.  By default the library owns it;
+ * hk_set_stream makes it the caller's (a cudaStream_t passed as void*; NULL = back to the library's own stream), which is
+ * how the Julia host orders hk_render_samples / hk_read_film_dev against its own CUDA.jl work without device-wide
+ * synchronisation.  The previous stream is drained first.  The stream must outlive the context or be reset first.  */
+int32_t hk_set_stream(HkContext* ctx, void* cuda_stream);
 
 /* postprocess!(film; exposure, tonemap, gamma, white_point, sensor), src/postprocess.jl:187-357 -- fused into the film
  * read-out: framebuffer = sum / weight, then exposure, Bradford white balance, sensor imaging ratio, tone map, gamma.
@@ -405,6 +421,8 @@ typedef struct HkPostprocess {
     float   background[3];
 } HkPostprocess;
 int32_t hk_postprocess(HkContext* ctx, const HkPostprocess* params, float* out_rgb_hw_colmajor);
+/* same into a DEVICE buffer (film.postprocess as a device array), no host synchronisation */
+int32_t hk_postprocess_dev(HkContext* ctx, const HkPostprocess* params, float* out_dev_rgb_hw_colmajor);
 /* ---- auxiliary buffers ---------------------------------------------------------------------
  * replaces: fill_aux_buffers!(film, scene, camera; has_infinite_lights) (src/film.jl:410-431, kernel :433-488):
  * one primary ray per pixel through the pixel centre (lens sample (0.5, 0.5)); writes film.albedo (0.8 on a hit,

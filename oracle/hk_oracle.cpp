@@ -89,13 +89,8 @@ int32_t ok_upload_textures(OkContext* c, const HkTexture* t, uint32_t n) {
     S.rgb.clear(); S.h.clear(); S.w.clear(); c->s.tex_alpha.assign(n, std::vector<float>());
     for (uint32_t i = 0; i < n; i++) {
         S.rgb.emplace_back(t[i].rgb, t[i].rgb + 3 * (size_t)t[i].h * t[i].w); S.h.push_back(t[i].h); S.w.push_back(t[i].w);
+        if (t[i].alpha) c->s.tex_alpha[i].assign(t[i].alpha, t[i].alpha + (size_t)t[i].h * t[i].w);      // HkTexture::alpha, (h, w) column-major
     }
-    return 0;
-}
-// test hook (oracle only, until the CUDA path grows the alpha loop): the alpha plane of texture `id` (1-based), (h, w) column-major
-int32_t ok_test_upload_texture_alpha(OkContext* c, uint32_t id, const float* alpha) {
-    if (id < 1 || id > c->s.textures.rgb.size()) return -1;
-    c->s.tex_alpha[id - 1].assign(alpha, alpha + (size_t)c->s.textures.h[id - 1] * c->s.textures.w[id - 1]);
     return 0;
 }
 int32_t ok_upload_materials(OkContext* c, const HkMaterial* m, uint32_t nm, const HkMediumInterface* mi, uint32_t ni) {

@@ -49,7 +49,6 @@ def lib():
         f("ok_fr_complex", [C.c_float, C.c_float, C.c_float], C.c_float)
         f("ok_write_accum", [VP, A.c_fp, A.c_fp])
         f("ok_test_set_aux_depth", [VP, A.c_fp])
-        f("ok_test_upload_texture_alpha", [VP, C.c_uint32, A.c_fp])
         f("ok_mix_hash_float", [A.c_fp, A.c_fp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32], C.c_float)
         _lib = L
     return _lib

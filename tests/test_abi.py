@@ -29,7 +29,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert not missing, f"declared in include/*.h but not exported: {missing}"
     for s in A.HK_SYMBOLS:
         assert s in syms, f"{s} listed in _abi.HK_SYMBOLS but not declared in the header"
-    assert lib.hk_abi_version() == 1
+    assert lib.hk_abi_version() == 2
 
 
 def test_struct_sizes_match_header_layout():

@@ -532,9 +532,9 @@ def test_textured_matte_known_answers_on_the_oracle():
     vp.close()
 
 
-def test_alpha_tested_surfaces_on_the_oracle():
+def test_alpha_tested_surfaces_known_answers():
     """Alpha pass-through (intersection.jl:221-266 for camera / bounce rays, :349-372 for shadow rays; get_surface_alpha = alpha of the
-    point-sampled Kd texel of a MatteMaterial, spectral-eval.jl:3882-3888).  ORACLE ONLY so far: the CUDA path refuses such textures.
+    point-sampled Kd texel of a MatteMaterial, spectral-eval.jl:3882-3888), pinned on the oracle; the CUDA path is compared with it in tests/test_parity_gpu.py.
     Known answers: alpha = 1 is the opaque render bit for bit; alpha = 0 makes the quad vanish (the floor behind it shows, lit, with
     no shadow — up to the 1e-4 restart offsets); alpha = 0.5 lets about half of the rays through, decided per ray by the hash of its
     origin and direction, so a repeated render is identical; only MatteMaterial has alpha."""
@@ -576,15 +576,11 @@ def test_alpha_tested_surfaces_on_the_oracle():
     expect = 0.5 * a[1] + 0.25 * b[1]
     assert abs(mix[1] - expect) < 0.08 * b[1], (mix[1], expect)
     assert rb < rh < r0 + (r0 - rb)
-    # the CUDA path refuses instead of rendering the quad opaque
-    with pytest.raises((NotImplementedError, RuntimeError)):
-        film = H.Film((8, 8)); cam = H.PerspectiveCamera((0, 6, 0.001), (0, 0, 0), film, fov=40.0)
-        H.VolPath(samples=1, max_depth=2)(scene_with(0.5), film, cam)
 
 
-def test_vertex_color_texture_on_the_oracle():
+def test_vertex_color_texture_known_answers():
     """VertexColorTexture as MatteMaterial.Kd (textures/basic.jl:43-46, texture-ref.jl:240-245): Kd = sum_k face_colors[k, face] * bary[k].
-    ORACLE ONLY so far (the CUDA path refuses it).  Known answers: three equal corner colours are that constant colour (same image as
+    Pinned on the oracle here (CUDA vs oracle: tests/test_parity_gpu.py).  Known answers: three equal corner colours are that constant colour (same image as
     the constant material up to the rounding of b0 + b1 + b2); per-face colours select by TriangleMeta.primitive_index; corner colours
     interpolate linearly across a triangle."""
     quad = lambda: H.Mesh([(-1, -1, 0), (1, -1, 0), (1, 1, 0), (-1, 1, 0)], [(0, 1, 2), (0, 2, 3)], normals=[(0, 0, 1)] * 4)
@@ -611,7 +607,3 @@ def test_vertex_color_texture_on_the_oracle():
     g = render(H.VertexColorTexture(grad))
     near, mid = g[25, 25].mean(), g[21, 21].mean()                                # towards the (1,-1) corner the colour rises linearly
     assert near > mid > 0 and g[6:10, 8:12].max() == 0
-    with pytest.raises((NotImplementedError, RuntimeError)):
-        film = H.Film((8, 8)); cam = H.PerspectiveCamera((0, 0, 4), (0, 0, 0), film, fov=35.0)
-        s = H.Scene(); s.push(quad(), H.MatteMaterial(Kd=H.VertexColorTexture(fc))); s.push(H.PointLight((1, 1, 1), (0, 0, 3))); s.sync()
-        H.VolPath(samples=1, max_depth=2)(s, film, cam)

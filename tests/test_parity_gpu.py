@@ -157,7 +157,7 @@ def test_instanced_closest_hit_bit_exact():
     s = _instanced_scene()
     p = Pair(scene=s)
     try:
-        assert s.triangle_count() > 10000
+        assert s.triangle_count() > 9000
         rays = np.concatenate([random_rays(30000, 11, lo=-3.0, hi=3.0), random_rays(10000, 12, lo=-2.0, hi=2.0, tmax=1.5)])
         rays[:64, 3:6] = [0, -1, 0]; rays[64:128, 3:6] = [1, 0, 0]               # axis-parallel directions
         h_cu, h_ok = trace_both(p, rays, brute=False)
@@ -447,6 +447,9 @@ IMAGE_CASES = [
     ("spot_and_lens", spot_and_lens, (96, 64), 4, 4),
     ("instanced_zoo", lambda: (_instanced_scene(30), scenes._cam((0, 2.5, 6), (0, 0, 0), 45.0)), (96, 64), 4, 6),
     ("c5_small_instanced", lambda: scenes.c5_instanced(12, 12, instanced=True), (96, 54), 4, 6),
+    ("alpha_foliage", lambda: scenes.alpha_foliage(), (96, 72), 8, 5),
+    ("alpha_foliage_in_fog", lambda: scenes.alpha_foliage(fog=True), (96, 72), 8, 5),
+    ("vertex_colors", lambda: scenes.vertex_color_meshes(), (96, 64), 4, 4),
 ]
 
 
@@ -472,6 +475,23 @@ def test_sample_batching_is_bitwise_invariant():
         outs.append(vp(scene, film, camf(film)).copy())
         vp.close()
     assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+
+
+def test_media_render_beyond_one_wave_of_persistent_lanes():
+    """More shadow rays than the persistent tracking kernels have lanes (148 SMs x 4 blocks x 128 threads = 75 776): lanes must
+    keep claiming work after a claimed shadow ray was dropped (blocked by an opaque surface).  A dropped ray used to mark the queue
+    exhausted, which left queue entries unprocessed once every lane had more than one claim to make: full-size C4 renders were
+    not deterministic.  Image vs the oracle (strict), equal ray counts, and bitwise equal for 1 and 2 samples in flight."""
+    make = lambda: scenes.c4_cloud((32, 32, 16), "nanovdb", (8, 8, 8))
+    scene, camf = make()
+    a, b, rays_c, rays_o = _render_pair(scene, camf, (384, 216), 2, 6, batch=2)
+    frac, rrmse = image_close(a, b)
+    exact = float((a.view(np.uint32) == b.view(np.uint32)).mean())
+    print(f"c4_cloud 384x216 batch 2: within_tol={frac:.5f} bit_identical={exact:.5f} rays {rays_c} vs {rays_o}")
+    assert frac >= 0.999 and rrmse <= 0.01 and rays_c == rays_o
+    film = H.Film((384, 216)); vp = H.VolPath(samples=2, max_depth=6, sample_batch=1)
+    a1 = vp(scene, film, camf(film)).copy(); vp.close()
+    assert np.array_equal(a.view(np.uint32), a1.view(np.uint32))
 
 
 def test_sobol_prefix_cache_is_bitwise_invariant():
