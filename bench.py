@@ -289,8 +289,13 @@ def measure(args, rank, world, local, dist, torch, full):
         e2e_steps = max(3, min(steps, 8))
         vp.clear(); film.iteration_index = 0
         if dist: dist.barrier()
-        for _ in range(2):               # untimed: page-locked host buffers, copy stream and staging buffers come into being here
-            vp.wait_film(film, vp.render(scene, film, cam, count=1, read="async"))
+        pending = None                   # untimed, in the SAME pipelined pattern as the timed loop: the three page-locked host buffers (displayed +
+        for _ in range(4):               # two in flight), the copy stream and the two staging buffers all come into being here, not in the timed region
+            handle = vp.render(scene, film, cam, count=1, read="async")
+            if pending is not None:
+                vp.wait_film(film, pending)
+            pending = handle
+        vp.wait_film(film, pending)
         vp.clear(); film.iteration_index = 0
         B.call("synchronize")
         if dist: dist.barrier()

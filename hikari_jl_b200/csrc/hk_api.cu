@@ -87,6 +87,7 @@ int32_t hk_destroy(HkContext* ctx) {
     for (DevBuf* b : bufs) b->release();
     for (auto& b : ctx->env_bufs) b.release();
     for (auto& b : ctx->media_bufs) b.release();
+    for (auto& b : ctx->mask_bufs) b.release();
     for (auto& b : ctx->tex_bufs) b.release();
     ctx->b_aux.release(); ctx->b_denoise.release(); ctx->b_uvs.release(); ctx->b_textures.release();
     ctx->b_inst_recs.release(); ctx->b_instances.release(); ctx->b_inst_base.release();
@@ -410,6 +411,7 @@ int32_t hk_upload_media(HkContext* ctx, const HkMedium* m, uint32_t n) {
     if (!ctx) return HK_ERR_INVALID;
     cudaSetDevice(ctx->device);
     for (auto& b : ctx->media_bufs) b.release();
+    for (auto& b : ctx->mask_bufs) b.release();
     ctx->media_bufs.clear(); ctx->media_bufs.resize(3 * (size_t)n);
     std::vector<DevMedium> dev(n);
     for (uint32_t i = 0; i < n; i++) {
@@ -447,6 +449,23 @@ int32_t hk_upload_media(HkContext* ctx, const HkMedium* m, uint32_t n) {
     }
     ctx->has_rgbgrid = false;
     for (uint32_t i = 0; i < n; i++) if (m[i].type == HK_MEDIUM_RGBGRID) ctx->has_rgbgrid = true;
+    // empty-cell masks of the majorant grids, built on the device from the uploaded grids (one bit per cell); the first one that fits
+    // HK_SMEM_MASK_WORDS is the one the tracking kernels stage in shared memory
+    ctx->D.smem_mask_medium = 0; ctx->D.smem_mask_words = 0;
+    ctx->mask_bufs.clear(); ctx->mask_bufs.resize(n);
+    for (uint32_t i = 0; i < n; i++) {
+        if (m[i].type == HK_MEDIUM_HOMOGENEOUS) continue;
+        const size_t cells = (size_t)m[i].majorant_res[0] * m[i].majorant_res[1] * m[i].majorant_res[2];
+        const size_t words = (cells + 31) / 32;
+        CK(ctx->mask_bufs[i].alloc(4 * words));
+        k_majorant_mask<<<grid_for(ctx, words, 256, 8), 256, 0, ctx->stream>>>(dev[i].majorant, (uint32_t)cells, ctx->mask_bufs[i].as<uint32_t>());
+        ctx->launches++;
+        dev[i].maj_empty = ctx->mask_bufs[i].as<uint32_t>();
+        if (ctx->D.smem_mask_medium == 0 && words <= HK_SMEM_MASK_WORDS && !std::getenv("HK_NO_SMEM_MASK")) { ctx->D.smem_mask_medium = (int32_t)i + 1; ctx->D.smem_mask_words = (uint32_t)words; }
+    }
+    if (std::getenv("HK_NO_EMPTY_MASK")) { for (auto& d : dev) d.maj_empty = nullptr; ctx->D.smem_mask_medium = 0; ctx->D.smem_mask_words = 0; }      // development A/B
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
     CK(ctx->b_media.upload(dev.data(), sizeof(DevMedium) * (size_t)n));
     ctx->D.media = ctx->b_media.as<DevMedium>(); ctx->D.n_media = (int32_t)n;
     ctx->camera_medium_valid = false;
@@ -641,7 +660,7 @@ int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride,
     const bool opaque_only = !ctx->D.any_medium_transition && ctx->D.n_media == 0 && !ctx->D.has_alpha;      // (an alpha-tested surface can let a shadow ray through: the segment walk)
     const bool cnt = (ctx->profiling & 2) != 0;
     unsigned long long* work = ctx->b_work_ctr.as<unsigned long long>();
-    const int tgrid = ctx->sm_count * HK_TRACE_BLOCKS_PER_SM;
+    const int tgrid = ctx->sm_count * (ctx->D.bvh.inst ? HK_TRACE_BLOCKS_PER_SM_INST : HK_TRACE_BLOCKS_PER_SM);      // persistent: one resident wave
     CK(cudaEventRecord(ctx->ev0, st));
     int32_t done = 0;
     while (done < count) {

@@ -5,13 +5,13 @@
 
 bool hkl_shade_1(int type, int grid, cudaStream_t st, const DevScene& D, const PathState& S, const PassArgs& A, int next, int par) {
     switch (type) {
-        case HK_MAT_MATTE: if (D.split_lights) k_shade<HK_MAT_MATTE, true><<<grid, 128, 0, st>>>(D, S, A, next, par); else k_shade<HK_MAT_MATTE, false><<<grid, 128, 0, st>>>(D, S, A, next, par); return true;
-        case HK_MAT_MIRROR: if (D.split_lights) k_shade<HK_MAT_MIRROR, true><<<grid, 128, 0, st>>>(D, S, A, next, par); else k_shade<HK_MAT_MIRROR, false><<<grid, 128, 0, st>>>(D, S, A, next, par); return true;
-        case HK_MAT_GLASS: if (D.split_lights) k_shade<HK_MAT_GLASS, true><<<grid, 128, 0, st>>>(D, S, A, next, par); else k_shade<HK_MAT_GLASS, false><<<grid, 128, 0, st>>>(D, S, A, next, par); return true;
-        case HK_MAT_CONDUCTOR: if (D.split_lights) k_shade<HK_MAT_CONDUCTOR, true><<<grid, 128, 0, st>>>(D, S, A, next, par); else k_shade<HK_MAT_CONDUCTOR, false><<<grid, 128, 0, st>>>(D, S, A, next, par); return true;
-        case HK_SHADE_MATTE_TEX: if (D.split_lights) k_shade<HK_SHADE_MATTE_TEX, true><<<grid, 128, 0, st>>>(D, S, A, next, par); else k_shade<HK_SHADE_MATTE_TEX, false><<<grid, 128, 0, st>>>(D, S, A, next, par); return true;
-        case HK_MAT_THIN_DIELECTRIC: if (D.split_lights) k_shade<HK_MAT_THIN_DIELECTRIC, true><<<grid, 128, 0, st>>>(D, S, A, next, par); else k_shade<HK_MAT_THIN_DIELECTRIC, false><<<grid, 128, 0, st>>>(D, S, A, next, par); return true;
-        case HK_MAT_DIFFUSE_TRANSMISSION: if (D.split_lights) k_shade<HK_MAT_DIFFUSE_TRANSMISSION, true><<<grid, 128, 0, st>>>(D, S, A, next, par); else k_shade<HK_MAT_DIFFUSE_TRANSMISSION, false><<<grid, 128, 0, st>>>(D, S, A, next, par); return true;
+        case HK_MAT_MATTE: launch_shade_class<HK_MAT_MATTE>(grid, st, D, S, A, next, par); return true;
+        case HK_MAT_MIRROR: launch_shade_class<HK_MAT_MIRROR>(grid, st, D, S, A, next, par); return true;
+        case HK_MAT_GLASS: launch_shade_class<HK_MAT_GLASS>(grid, st, D, S, A, next, par); return true;
+        case HK_MAT_CONDUCTOR: launch_shade_class<HK_MAT_CONDUCTOR>(grid, st, D, S, A, next, par); return true;
+        case HK_SHADE_MATTE_TEX: launch_shade_class<HK_SHADE_MATTE_TEX>(grid, st, D, S, A, next, par); return true;
+        case HK_MAT_THIN_DIELECTRIC: launch_shade_class<HK_MAT_THIN_DIELECTRIC>(grid, st, D, S, A, next, par); return true;
+        case HK_MAT_DIFFUSE_TRANSMISSION: launch_shade_class<HK_MAT_DIFFUSE_TRANSMISSION>(grid, st, D, S, A, next, par); return true;
         default: return false;
     }
 }

@@ -5,8 +5,8 @@
 
 bool hkl_shade_2(int type, int grid, cudaStream_t st, const DevScene& D, const PathState& S, const PassArgs& A, int next, int par) {
     switch (type) {
-        case HK_MAT_COATED_DIFFUSE: if (D.split_lights) k_shade<HK_MAT_COATED_DIFFUSE, true><<<grid, 128, 0, st>>>(D, S, A, next, par); else k_shade<HK_MAT_COATED_DIFFUSE, false><<<grid, 128, 0, st>>>(D, S, A, next, par); return true;
-        case HK_MAT_COATED_CONDUCTOR: if (D.split_lights) k_shade<HK_MAT_COATED_CONDUCTOR, true><<<grid, 128, 0, st>>>(D, S, A, next, par); else k_shade<HK_MAT_COATED_CONDUCTOR, false><<<grid, 128, 0, st>>>(D, S, A, next, par); return true;
+        case HK_MAT_COATED_DIFFUSE: launch_shade_class<HK_MAT_COATED_DIFFUSE>(grid, st, D, S, A, next, par); return true;
+        case HK_MAT_COATED_CONDUCTOR: launch_shade_class<HK_MAT_COATED_CONDUCTOR>(grid, st, D, S, A, next, par); return true;
         default: return false;
     }
 }

@@ -5,7 +5,7 @@
 
 bool hkl_shade_3(int type, int grid, cudaStream_t st, const DevScene& D, const PathState& S, const PassArgs& A, int next, int par) {
     switch (type) {
-        case HK_MAT_COATED_DIFFUSE_TRANSMISSION: if (D.split_lights) k_shade<HK_MAT_COATED_DIFFUSE_TRANSMISSION, true><<<grid, 128, 0, st>>>(D, S, A, next, par); else k_shade<HK_MAT_COATED_DIFFUSE_TRANSMISSION, false><<<grid, 128, 0, st>>>(D, S, A, next, par); return true;
+        case HK_MAT_COATED_DIFFUSE_TRANSMISSION: launch_shade_class<HK_MAT_COATED_DIFFUSE_TRANSMISSION>(grid, st, D, S, A, next, par); return true;
         default: return false;
     }
 }

@@ -13,8 +13,15 @@ struct DevMedium {
     const uint8_t* __restrict__ nvdb; float inv_mat[9], vec[3]; uint64_t root_off; int32_t root_tiles;
     // RGBGridMedium (media.jl:1002-1456): per-voxel RGB sigma_a / sigma_s / Le, [nz][ny][nx][3], null = absent (sigma: 1, Le: 0)
     const float* __restrict__ rgb_a; const float* __restrict__ rgb_s; const float* __restrict__ rgb_le; float sigma_scale, le_scale;
+    // one bit per majorant cell, set when the cell's majorant is exactly 0 (built on the device at upload, k_majorant_mask): such a
+    // cell yields sigma_maj = sigma_t * 0 = 0 < 1e-10 for every wavelength, i.e. the tracking loops skip it -- the DDA can step over it
+    // without fetching the grid value.  Bit i = cell x + rx (y + ry z).
+    const uint32_t* __restrict__ maj_empty;
 };
-struct MediaCtx { DevTables T; const DevMedium* __restrict__ media; int32_t n_media; };
+// smem_mask: the tracking kernels stage the empty-cell mask of ONE medium (smem_medium, 1-based; the first grid medium whose mask fits)
+// in shared memory; other media read theirs from global memory
+struct MediaCtx { DevTables T; const DevMedium* __restrict__ media; int32_t n_media; const uint32_t* smem_mask; int32_t smem_medium; };
+#define HK_SMEM_MASK_WORDS 8192      // 64^3 cells = 32 KB
 
 HK_DEV float hg_p(float g, float c) { float g2 = g * g, d = 1.0f + g2 - 2.0f * g * c; return (1.0f - g2) / (4.0f * HK_PI * d * sqrtf(d)); }   // media.jl:28-32
 HK_DEV float3 sample_hg(float g, float3 wo, float2 u, float& pdf) {                                                                            // media.jl:42-74
@@ -29,7 +36,7 @@ HK_DEV float3 sample_hg(float g, float3 wo, float2 u, float& pdf) {             
 }
 
 // ---- majorant iterator ----------------------------------------------------------------------------------------
-struct MajIter { int mode; Spec sigma_t; float t_min, t_max; bool hom_called; const float* __restrict__ grid; int res[3]; float next_t[3], delta_t[3]; int step[3], limit[3], voxel[3]; };
+struct MajIter { int mode; Spec sigma_t; float t_min, t_max; bool hom_called; const float* __restrict__ grid; const uint32_t* mask; int res[3]; float next_t[3], delta_t[3]; int step[3], limit[3], voxel[3]; };
 struct MajSeg { float t_min, t_max; Spec sigma_maj; };
 HK_DEV float jl_max(float a, float b) { return (a != a || b != b) ? __int_as_float(0x7fc00000) : fmaxf(a, b); }
 HK_DEV float jl_min(float a, float b) { return (a != a || b != b) ? __int_as_float(0x7fc00000) : fminf(a, b); }
@@ -64,6 +71,24 @@ HK_DEV void dda_init(MajIter& it, const DevMedium& M, float3 o, float3 d, float 
         it.voxel[k] = vox;
     }
     it.mode = t_min >= t_max ? 0 : 2;
+}
+// One DDA step over a cell whose majorant is known to be 0 (MajIter::mask): exactly the state changes of majiter_next() for that cell
+// -- same axis choice, same t_min = min(next_t, t_max), same incremental next_t += delta_t, same end-of-grid handling -- without the grid
+// fetch and without building the (unused) segment.  Returns 0: not applicable (no mask / cell not empty / iterator not in DDA mode):
+// take majiter_next();  1: stepped over one empty cell;  2: the iterator is exhausted (majiter_next would have returned false).
+HK_DEV int majiter_skip_empty(MajIter& it) {
+    if (it.mode != 2 || it.mask == nullptr) return 0;
+    const uint32_t cell = (uint32_t)(it.voxel[0] + it.res[0] * (it.voxel[1] + it.res[1] * it.voxel[2]));
+    if (((it.mask[cell >> 5] >> (cell & 31u)) & 1u) == 0u) return 0;
+    if (it.t_min >= it.t_max) { it.mode = 0; return 2; }
+    const int axis = (it.next_t[0] < it.next_t[1]) ? ((it.next_t[0] < it.next_t[2]) ? 0 : 2) : ((it.next_t[1] < it.next_t[2]) ? 1 : 2);
+    const float nt = axis == 0 ? it.next_t[0] : (axis == 1 ? it.next_t[1] : it.next_t[2]);
+    it.t_min = fminf(nt, it.t_max);
+    if (axis == 0) { it.voxel[0] += it.step[0]; it.next_t[0] += it.delta_t[0]; }
+    else if (axis == 1) { it.voxel[1] += it.step[1]; it.next_t[1] += it.delta_t[1]; }
+    else { it.voxel[2] += it.step[2]; it.next_t[2] += it.delta_t[2]; }
+    if (it.voxel[0] == it.limit[0] || it.voxel[1] == it.limit[1] || it.voxel[2] == it.limit[2]) { it.mode = 0; it.t_min = it.t_max; }
+    return 1;
 }
 HK_DEV bool majiter_next(MajIter& it, MajSeg& seg) {   // media.jl:625-729
     if (it.mode == 0) return false;
@@ -123,14 +148,16 @@ HK_DEV float nvdb_value(const DevMedium& M, LeafCache& lc, int32_t x, int32_t y,
     uint32_t nf = ((uint32_t)(x & 7) << 6) | ((uint32_t)(y & 7) << 3) | (uint32_t)(z & 7);
     return rd<float>(M.nvdb, lc.leaf_off + 96 + (uint64_t)nf * 4);
 }
-HK_DEV float nvdb_density(const DevMedium& M, float3 p) {
+// lc: the leaf that answered the previous look-up.  The trackers keep it across the events of a ray (consecutive events of a segment
+// fall into the same 8^3 leaf almost always, so the root -> upper -> lower walk -- four dependent loads -- runs once per leaf, not once
+// per event); a fresh cache (valid = false) gives the reference's literal behaviour.  Same values either way.
+HK_DEV float nvdb_density(const DevMedium& M, float3 p, LeafCache& lc) {
     float px = p.x - M.vec[0], py = p.y - M.vec[1], pz = p.z - M.vec[2];
     float gx = M.inv_mat[0] * px + M.inv_mat[1] * py + M.inv_mat[2] * pz;
     float gy = M.inv_mat[3] * px + M.inv_mat[4] * py + M.inv_mat[5] * pz;
     float gz = M.inv_mat[6] * px + M.inv_mat[7] * py + M.inv_mat[8] * pz;
     int ix = floor_i(gx), iy = floor_i(gy), iz = floor_i(gz);
     float fx = gx - (float)ix, fy = gy - (float)iy, fz = gz - (float)iz;
-    LeafCache lc; lc.valid = false;
     float v000 = nvdb_value(M, lc, ix, iy, iz), v001 = nvdb_value(M, lc, ix, iy, iz + 1);
     float v010 = nvdb_value(M, lc, ix, iy + 1, iz), v011 = nvdb_value(M, lc, ix, iy + 1, iz + 1);
     float v100 = nvdb_value(M, lc, ix + 1, iy, iz), v101 = nvdb_value(M, lc, ix + 1, iy, iz + 1);
@@ -212,12 +239,38 @@ HK_DEV MediumCoef medium_coef(const MediaCtx& C, const DevMedium& M, float4 lam)
     c.g = M.g;
     return c;
 }
-HK_DEV float medium_density(const DevMedium& M, float3 p) {
+HK_DEV float medium_density(const DevMedium& M, float3 p, LeafCache& lc) {
     if (M.type == HK_MEDIUM_GRID) return grid_density(M, affine_pt(M.medium_from_render, p));
-    if (M.type == HK_MEDIUM_NANOVDB) return nvdb_density(M, p);
+    if (M.type == HK_MEDIUM_NANOVDB) return nvdb_density(M, p, lc);
     return 1.0f;
 }
-HK_DEV void majiter_create(MajIter& it, const DevMedium& M, const MediumCoef& mc, float3 o, float3 d, float t_max) {
+HK_DEV float medium_density(const DevMedium& M, float3 p) { LeafCache lc; lc.valid = false; return medium_density(M, p, lc); }
+// The persistent tracking kernels keep each lane's LeafCache in SHARED memory between the events of its ray (lc_slot = the lane's
+// column of HK_LC_WORDS words, stride blockDim.x; word 0 = 0 invalidates it): consecutive events of a segment fall into the same 8^3
+// leaf almost always, so the root -> upper -> lower walk -- four dependent loads -- runs once per leaf instead of once per event,
+// without the cache's seven words living in registers for the whole walk (registers decide this kernel's occupancy).
+#define HK_LC_WORDS 7
+HK_DEV float medium_density_cached(const DevMedium& M, float3 p, uint32_t* lc_slot) {
+    if (M.type == HK_MEDIUM_GRID) return grid_density(M, affine_pt(M.medium_from_render, p));
+    if (M.type != HK_MEDIUM_NANOVDB) return 1.0f;
+    const unsigned st = blockDim.x;
+    LeafCache lc; lc.valid = false; lc.is_leaf = false; lc.kx = lc.ky = lc.kz = 0; lc.leaf_off = 0; lc.tile = 0.0f;
+    if (lc_slot != nullptr) {
+        const uint32_t fl = lc_slot[0];
+        lc.valid = (fl & 1u) != 0u; lc.is_leaf = (fl & 2u) != 0u;
+        lc.kx = (int32_t)lc_slot[st]; lc.ky = (int32_t)lc_slot[2 * st]; lc.kz = (int32_t)lc_slot[3 * st];
+        lc.leaf_off = (uint64_t)lc_slot[4 * st] | ((uint64_t)lc_slot[5 * st] << 32); lc.tile = __uint_as_float(lc_slot[6 * st]);
+    }
+    const float v = nvdb_density(M, p, lc);
+    if (lc_slot != nullptr) {
+        lc_slot[0] = (lc.valid ? 1u : 0u) | (lc.is_leaf ? 2u : 0u);
+        lc_slot[st] = (uint32_t)lc.kx; lc_slot[2 * st] = (uint32_t)lc.ky; lc_slot[3 * st] = (uint32_t)lc.kz;
+        lc_slot[4 * st] = (uint32_t)lc.leaf_off; lc_slot[5 * st] = (uint32_t)(lc.leaf_off >> 32); lc_slot[6 * st] = __float_as_uint(lc.tile);
+    }
+    return v;
+}
+HK_DEV void majiter_create(MajIter& it, const DevMedium& M, const MediumCoef& mc, float3 o, float3 d, float t_max, const uint32_t* mask = nullptr) {
+    it.mask = mask;
     Spec st = M.type == HK_MEDIUM_RGBGRID ? sp(1.0f) : mc.sa + mc.ss;      // RGBGrid: the majorant grid already holds sigma_scale * max(sigma_a + sigma_s) (media.jl:1402)
     if (M.type == HK_MEDIUM_HOMOGENEOUS) { it.mode = (0.0f >= t_max) ? 0 : 1; it.sigma_t = st; it.t_min = 0.0f; it.t_max = t_max; it.hom_called = false; return; }
     float3 ro = o, rd_ = d;
@@ -241,20 +294,35 @@ struct DeltaOut { int event; Spec beta, r_u, r_l; float3 p; float g; Spec Le_add
 // on its own ray and hand finished lanes a new one (k_medium_track) instead of idling until the longest walk of the warp
 // is done (ncu on C4: 7.9 of 32 lanes active in the one-ray-per-thread-to-completion form).  The arithmetic per ray, and
 // therefore every output bit, is that of the nested loops in delta-tracking.jl:142-453.
+// development statistics (-DHK_MEDIA_STATS): [0] rays set up, [1] empty cells stepped over, [2] cells fetched, [3] collision events,
+// [4] segment ends, [5] skip-phase iterations, [6] event-phase iterations (per warp), [7] event-phase lane-iterations
+#ifdef HK_MEDIA_STATS
+__device__ unsigned long long g_media_stats[16];
+#define HK_STAT(i, n) atomicAdd(&g_media_stats[i], (unsigned long long)(n))
+#else
+#define HK_STAT(i, n) ((void)0)
+#endif
 #ifndef HK_TRACK_SKIP
 #define HK_TRACK_SKIP 4
 #endif
+#ifndef HK_TRACK_SKIP_EMPTY
+#define HK_TRACK_SKIP_EMPTY 16
+#endif
+HK_DEV const uint32_t* medium_mask(const MediaCtx& C, int medium) {
+    if (medium == C.smem_medium) return C.smem_mask;
+    return C.media[medium - 1].maj_empty;
+}
 struct DeltaTracker {
     const DevMedium* M; MediumCoef mc; float3 o, d, ro; int depth, max_depth;
     uint64_t rng; MajIter it; Spec smaj; float seg_t_max, t; int sg, si; bool in_seg;
     Spec beta, r_u, r_l; DeltaOut R;
     HK_DEV void init(const MediaCtx& C, int medium, float3 o_, float3 d_, float t_max, float4 lam, Spec beta_, Spec r_u_, Spec r_l_, int depth_, int max_depth_) {
-        R.g = 0.0f; R.p = f3(0, 0, 0); R.Le_add = sp(0.0f); R.event = HK_EV_SURVIVED;
+        R.g = 0.0f; R.p = f3(0, 0, 0); R.Le_add = sp(0.0f); R.event = HK_EV_SURVIVED; HK_STAT(0, 1);
         M = &C.media[medium - 1];
         mc = medium_coef(C, *M, lam);
         o = o_; d = d_; depth = depth_; max_depth = max_depth_; beta = beta_; r_u = r_u_; r_l = r_l_;
         rng = lcg_init(o, d, t_max);
-        majiter_create(it, *M, mc, o, d, t_max);
+        majiter_create(it, *M, mc, o, d, t_max, medium_mask(C, medium));
         sg = 0; si = 0; in_seg = false; t = 0.0f; ro = o; smaj = sp(0.0f); seg_t_max = 0.0f;
     }
     HK_DEV bool finish(int ev, Spec b) { R.event = ev; R.beta = b; R.r_u = r_u; R.r_l = r_l; return true; }
@@ -268,14 +336,21 @@ struct DeltaTracker {
     HK_DEV bool skip_step() {
         for (int k = 0; k < HK_TRACK_SKIP && !in_seg; k++) {
             MajSeg seg;
-            if (sg >= 256 || !majiter_next(it, seg)) return finish(HK_EV_SURVIVED, beta);
-            sg++;
+            if (sg >= 256) return finish(HK_EV_SURVIVED, beta);
+            {   // cells known to be empty cost a DDA step only (up to HK_TRACK_SKIP_EMPTY of them per unit of work)
+                int r = 1;
+                for (int e = 0; e < HK_TRACK_SKIP_EMPTY && sg < 256 && (r = majiter_skip_empty(it)) == 1; e++) { sg++; HK_STAT(1, 1); }
+                if (r == 2 || sg >= 256) return finish(HK_EV_SURVIVED, beta);
+                if (r == 1) continue;
+            }
+            if (!majiter_next(it, seg)) return finish(HK_EV_SURVIVED, beta);
+            sg++; HK_STAT(2, 1);
             if (seg.sigma_maj.x < 1.0e-10f) continue;
             smaj = seg.sigma_maj; seg_t_max = seg.t_max; t = seg.t_min; ro = o + d * t; si = 0; in_seg = true;
         }
         return false;
     }
-    template <bool RGB> HK_DEV bool event_step(const DevTables& T, const float4* lam) {
+    template <bool RGB> HK_DEV bool event_step(const DevTables& T, const float4* lam, uint32_t* lc_slot = nullptr) {
         if (si >= 1024) { in_seg = false; return false; }
         si++;
         const float s0 = smaj.x;
@@ -283,17 +358,19 @@ struct DeltaTracker {
         float dt = -dm_logf(fmaxf(1.0e-10f, 1.0f - u)) / s0;
         float ts = t + dt;
         if (ts >= seg_t_max) {
+            HK_STAT(4, 1);
             Spec Tm = sp_exp(-(seg_t_max - t) * smaj);
             if (Tm.x > 1.0e-10f) { beta = beta * Tm / Tm.x; r_u = r_u * Tm / Tm.x; r_l = r_l * Tm / Tm.x; }
             in_seg = false;
             return false;
         }
+        HK_STAT(3, 1);
         Spec Tm = sp_exp(-dt * smaj);
         float3 p = ro + d * dt;
         Spec sa, ss, Le = mc.Le;
         if (RGB && M->type == HK_MEDIUM_RGBGRID) rgbgrid_props(T, *M, p, *lam, sa, ss, Le);
         else {
-            float dens = medium_density(*M, p);
+            float dens = medium_density_cached(*M, p, lc_slot);
             sa = M->type == HK_MEDIUM_HOMOGENEOUS ? mc.sa : mc.sa * dens;
             ss = M->type == HK_MEDIUM_HOMOGENEOUS ? mc.ss : mc.ss * dens;
         }
@@ -337,11 +414,11 @@ struct RatioTracker {
     Pcg32 rng; MajIter it; Spec smaj; float seg_t_max, t; int sg, si; bool in_seg;
     Spec T_ray, r_u, r_l;
     HK_DEV void init(const MediaCtx& C, int medium, float3 o_, float3 d_, float t_max, float4 lam) {
-        T_ray = sp(1.0f); r_u = sp(1.0f); r_l = sp(1.0f);
+        T_ray = sp(1.0f); r_u = sp(1.0f); r_l = sp(1.0f); HK_STAT(8, 1);
         M = &C.media[medium - 1];
         mc = medium_coef(C, *M, lam);
         o = o_; d = d_;
-        majiter_create(it, *M, mc, o, d, t_max);
+        majiter_create(it, *M, mc, o, d, t_max, medium_mask(C, medium));
         rng = pcg32_init(hash_f3(o), hash_f3(d));
         sg = 0; si = 0; in_seg = false; t = 0.0f; smaj = sp(0.0f); seg_t_max = 0.0f;
     }
@@ -349,14 +426,21 @@ struct RatioTracker {
     HK_DEV bool skip_step() {
         for (int k = 0; k < HK_TRACK_SKIP && !in_seg; k++) {
             MajSeg seg;
-            if (sg >= 256 || !majiter_next(it, seg)) return true;
-            sg++;
+            if (sg >= 256) return true;
+            {
+                int r = 1;
+                for (int e = 0; e < HK_TRACK_SKIP_EMPTY && sg < 256 && (r = majiter_skip_empty(it)) == 1; e++) { sg++; HK_STAT(9, 1); }
+                if (r == 2 || sg >= 256) return true;
+                if (r == 1) continue;
+            }
+            if (!majiter_next(it, seg)) return true;
+            sg++; HK_STAT(10, 1);
             if (seg.sigma_maj.x < 1.0e-10f) continue;
             smaj = seg.sigma_maj; seg_t_max = seg.t_max; t = seg.t_min; si = 0; in_seg = true;
         }
         return false;
     }
-    template <bool RGB> HK_DEV bool event_step(const DevTables& T, const float4* lam) {
+    template <bool RGB> HK_DEV bool event_step(const DevTables& T, const float4* lam, uint32_t* lc_slot = nullptr) {
         if (si >= 100) { in_seg = false; return sp_black(T_ray); }
         si++;
         const float s0 = smaj.x;
@@ -364,16 +448,18 @@ struct RatioTracker {
         float dt = -dm_logf(fmaxf(1.0e-10f, 1.0f - u)) / s0;
         float ts = t + dt;
         if (ts >= seg_t_max) {
+            HK_STAT(12, 1);
             Spec Tm = sp_exp(-(seg_t_max - t) * smaj);
             if (Tm.x > 1.0e-10f) { T_ray = T_ray * Tm / Tm.x; r_l = r_l * Tm / Tm.x; r_u = r_u * Tm / Tm.x; }
             in_seg = false;
             return sp_black(T_ray);
         }
+        HK_STAT(11, 1);
         float3 p = o + d * ts;
         Spec sa, ss;
         if (RGB && M->type == HK_MEDIUM_RGBGRID) { Spec le; rgbgrid_props(T, *M, p, *lam, sa, ss, le); }
         else {
-            float dens = medium_density(*M, p);
+            float dens = medium_density_cached(*M, p, lc_slot);
             sa = M->type == HK_MEDIUM_HOMOGENEOUS ? mc.sa : mc.sa * dens;
             ss = M->type == HK_MEDIUM_HOMOGENEOUS ? mc.ss : mc.ss * dens;
         }

@@ -35,7 +35,7 @@
 #define HK_TRACE_BLOCKS_PER_SM 8
 #endif
 #ifndef HK_TRACE_BLOCKS_PER_SM_INST
-#define HK_TRACE_BLOCKS_PER_SM_INST 6      // the instanced walker keeps the world-space ray and the instance's primitive base as well (80 registers)
+#define HK_TRACE_BLOCKS_PER_SM_INST 8      // (the instanced walker's world-space ray lives in shared memory; measured on C5: 6 blocks 14.1 ms, 7 13.5, 8 13.0)
 #endif
 
 // one_bits = 0x3F800000, supplied by the host so that it reaches the kernels as a run-time value: see HK_QF in node_step()
@@ -96,8 +96,12 @@ struct Bvh8Walker {
     float3 o, d, inv;
     float t_max;
     uint32_t oct_inv;
-    // INST only: the world-space ray (o, d above are the ray in the space being traversed), and the instance being traversed
-    float3 wo, wd;
+    // INST only: the world-space ray (o, d above are the ray in the space being traversed) and its inverse direction live in this
+    // lane's column of shared memory (wr[k * HK_TRACE_THREADS]: o 0-2, d 3-5, 1/d 6-8) -- they are only touched when the walk enters
+    // or leaves an instance, so they neither occupy nine registers for the whole walk nor cost three divisions per return to the
+    // top level (ncu on C5: the recomputed 1/d was 14 % of the kernel's samples, executed by 3.7 lanes) -- and the instance being
+    // traversed
+    float* wr;
     uint32_t prim_base, mtype_bits;
     bool in_blas;
     uint2 ngroup, tgroup;      // ngroup: (first internal child, octant-ordered hit bits << 24 | imask); tgroup: (first triangle, pending triangle bits)
@@ -105,7 +109,7 @@ struct Bvh8Walker {
     TravStack st;
     HitRec best;
 
-    HK_DEV void begin(uint2* sm_stack, uint2* lm_stack, float3 o_, float3 d_, float t_max_) {
+    HK_DEV void begin(uint2* sm_stack, uint2* lm_stack, float3 o_, float3 d_, float t_max_, float* wray = nullptr) {
         o = o_; d = d_; t_max = t_max_;
 #if HK_RCP_APPROX
         inv = f3(__frcp_approx(d.x), __frcp_approx(d.y), __frcp_approx(d.z));
@@ -125,7 +129,11 @@ struct Bvh8Walker {
         if (!finite || (d.x == 0.0f && d.y == 0.0f && d.z == 0.0f)) ngroup.y = 0u;
         tgroup = make_uint2(0u, 0u); tvalid = 0u;
         best.t = t_max; best.prim1 = 0; best.b1 = 0.0f; best.b2 = 0.0f;
-        if (INST) { wo = o; wd = d; in_blas = false; prim_base = 0u; mtype_bits = 0u; }
+        if (INST) {
+            wr = wray; in_blas = false; prim_base = 0u; mtype_bits = 0u;
+            wr[0] = o.x; wr[HK_TRACE_THREADS] = o.y; wr[2 * HK_TRACE_THREADS] = o.z; wr[3 * HK_TRACE_THREADS] = d.x; wr[4 * HK_TRACE_THREADS] = d.y; wr[5 * HK_TRACE_THREADS] = d.z;
+            wr[6 * HK_TRACE_THREADS] = inv.x; wr[7 * HK_TRACE_THREADS] = inv.y; wr[8 * HK_TRACE_THREADS] = inv.z;
+        }
     }
     HK_DEV void set_ray(float3 o_, float3 d_) {
         o = o_; d = d_;
@@ -139,7 +147,9 @@ struct Bvh8Walker {
             ngroup = st.pop();
             if (INST && ngroup.y <= 0x00FFFFFFu) {      // return marker: the instance is done, back to the top level in world space
                 in_blas = false;
-                set_ray(wo, wd);
+                o = f3(wr[0], wr[HK_TRACE_THREADS], wr[2 * HK_TRACE_THREADS]); d = f3(wr[3 * HK_TRACE_THREADS], wr[4 * HK_TRACE_THREADS], wr[5 * HK_TRACE_THREADS]);
+                inv = f3(wr[6 * HK_TRACE_THREADS], wr[7 * HK_TRACE_THREADS], wr[8 * HK_TRACE_THREADS]);
+                oct_inv = (d.x >= 0.0f ? 4u : 0u) | (d.y >= 0.0f ? 2u : 0u) | (d.z >= 0.0f ? 1u : 0u);
                 tgroup = make_uint2(ngroup.x, spread3(ngroup.y & 0xFFu)); tvalid = spread3((ngroup.y >> 8) & 0xFFu);
                 ngroup.y = 0u;
                 return false;
@@ -225,6 +235,7 @@ struct Bvh8Walker {
             const float4 r0 = __ldg(ip), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2), r3 = __ldg(ip + 3);
             if (ngroup.y > 0x00FFFFFFu) st.push(ngroup);
             st.push(make_uint2(tgroup.x, gather3(tgroup.y) | (gather3(tvalid) << 8)));
+            const float3 wo = f3(wr[0], wr[HK_TRACE_THREADS], wr[2 * HK_TRACE_THREADS]), wd = f3(wr[3 * HK_TRACE_THREADS], wr[4 * HK_TRACE_THREADS], wr[5 * HK_TRACE_THREADS]);
             const float3 oo = f3(r0.x * wo.x + r0.y * wo.y + r0.z * wo.z + r0.w, r1.x * wo.x + r1.y * wo.y + r1.z * wo.z + r1.w, r2.x * wo.x + r2.y * wo.y + r2.z * wo.z + r2.w);
             const float3 od = f3(r0.x * wd.x + r0.y * wd.y + r0.z * wd.z, r1.x * wd.x + r1.y * wd.y + r1.z * wd.z, r2.x * wd.x + r2.y * wd.y + r2.z * wd.z);
             set_ray(oo, od);
@@ -246,12 +257,14 @@ struct Bvh8Walker {
     }
 };
 
+// shared memory of a traversal kernel: the per-lane stack columns and, for the instanced walker, the per-lane world-space ray
+#define HK_TRACE_SMEM(INST) __shared__ uint2 sm_stack[HK_SM_STACK * HK_TRACE_THREADS]; __shared__ float sm_wray[(INST) ? 9 * HK_TRACE_THREADS : 1]
 // blocking form (one ray, run to completion)
 template <bool ANY, bool COUNT, bool INST = false>
-HK_DEV HitRec bvh8_trace(const DevBvh& B, uint2* sm_stack, float3 o, float3 d, float t_max, uint32_t* n_nodes = nullptr, uint32_t* n_tris = nullptr) {
+HK_DEV HitRec bvh8_trace(const DevBvh& B, uint2* sm_stack, float* sm_wray, float3 o, float3 d, float t_max, uint32_t* n_nodes = nullptr, uint32_t* n_tris = nullptr) {
     Bvh8Walker<ANY, COUNT, INST> w;
     uint2 lm_stack[HK_LM_STACK];
-    w.begin(sm_stack, lm_stack, o, d, t_max);
+    w.begin(sm_stack, lm_stack, o, d, t_max, sm_wray);
     for (;;) {
         if (w.node_step(B, n_nodes)) break;
         bool hit = false;
@@ -266,7 +279,7 @@ HK_DEV HitRec bvh8_trace(const DevBvh& B, uint2* sm_stack, float3 o, float3 d, f
 // region of its own, so it is batched instead of being run for single lanes in almost every iteration.
 // IO supplies  uint32_t load(idx, o, d, t_max) -> token  and  void store(token, hit).
 template <bool ANY, bool COUNT, bool INST, class IO>
-HK_DEV void trace_queue(const DevBvh& B, uint2* sm_stack, uint32_t n, uint32_t* cursor, IO& io, uint32_t& traced, uint32_t& wn, uint32_t& wt) {
+HK_DEV void trace_queue(const DevBvh& B, uint2* sm_stack, float* sm_wray, uint32_t n, uint32_t* cursor, IO& io, uint32_t& traced, uint32_t& wn, uint32_t& wt) {
     Bvh8Walker<ANY, COUNT, INST> w;
     uint2 lm_stack[HK_LM_STACK];
     bool busy = false, exhausted = false;
@@ -284,7 +297,7 @@ HK_DEV void trace_queue(const DevBvh& B, uint2* sm_stack, uint32_t n, uint32_t* 
                 if (idx < n) {
                     float3 o, d; float tm;
                     token = io.load(idx, o, d, tm);
-                    w.begin(sm_stack, lm_stack, o, d, tm);
+                    w.begin(sm_stack, lm_stack, o, d, tm, sm_wray);
                     busy = true; traced++;
                 }
             }

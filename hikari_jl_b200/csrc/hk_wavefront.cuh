@@ -90,6 +90,7 @@ struct DevScene {
     // instancing (HkGeometry.instances): instances in upload order + their first global primitive ids (ascending); n_inst = 0: plain soup
     const struct DevInstance* __restrict__ instances; const uint32_t* __restrict__ inst_prim_base; int32_t n_inst;
     int32_t has_alpha;                 // some uploaded texture carries an alpha plane: the trace / shadow stages run their pass-through rounds
+    int32_t smem_mask_medium; uint32_t smem_mask_words;      // medium (1-based, 0 = none) whose empty-cell mask the tracking kernels stage in shared memory
 };
 struct DevInstance { float o2w[12]; float w2o[12]; uint32_t first_tri, prim_base, iface, n_tris; };
 // A global primitive id resolves to (instance, triangle of the index array); vertices / normals of an instanced triangle are taken
@@ -144,7 +145,18 @@ HK_DEV LightCtx light_ctx(const DevScene& D) {
     LightCtx c; c.T = D.T; c.lights = D.lights; c.n_lights = D.n_lights; c.envmaps = D.envmaps; c.nodes = D.lnodes; c.bit_trails = D.bit_trails;
     c.inf_idx = D.inf_idx; c.n_infinite = D.n_infinite; c.n_bvh = D.n_bvh; c.esc_idx = D.esc_idx; c.n_esc = D.n_esc; return c;
 }
-HK_DEV MediaCtx media_ctx(const DevScene& D) { MediaCtx c; c.T = D.T; c.media = D.media; c.n_media = D.n_media; return c; }
+HK_DEV MediaCtx media_ctx(const DevScene& D) { MediaCtx c; c.T = D.T; c.media = D.media; c.n_media = D.n_media; c.smem_mask = nullptr; c.smem_medium = 0; return c; }
+// the persistent tracking kernels stage the empty-cell mask of DevScene::smem_mask_medium in shared memory (all threads of the block)
+HK_DEV MediaCtx media_ctx_staged(const DevScene& D, uint32_t* s_mask) {
+    MediaCtx c = media_ctx(D);
+    if (D.smem_mask_medium > 0) {
+        const uint32_t* __restrict__ g = D.media[D.smem_mask_medium - 1].maj_empty;
+        for (uint32_t i = threadIdx.x; i < D.smem_mask_words; i += blockDim.x) s_mask[i] = __ldg(g + i);
+        __syncthreads();
+        c.smem_mask = s_mask; c.smem_medium = D.smem_mask_medium;
+    }
+    return c;
+}
 
 // Warp-aggregated append to one of several queues: lanes that target the same queue elect a leader, which does a single
 // atomicAdd for the group.  Must be called by all 32 lanes (qid < 0 = nothing to push).
@@ -352,6 +364,15 @@ __global__ void __launch_bounds__(128) k_precompute_uplifts(DevTables T, const H
     }
 }
 
+// empty-cell mask of a majorant grid (DevMedium::maj_empty): one thread per 32 cells
+__global__ void __launch_bounds__(256) k_majorant_mask(const float* __restrict__ grid, uint32_t n_cells, uint32_t* __restrict__ mask) {
+    const uint32_t n_words = (n_cells + 31u) / 32u;
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += gridDim.x * blockDim.x) {
+        uint32_t bits = 0;
+        for (uint32_t b = 0; b < 32u; b++) { const uint32_t c = 32u * w + b; if (c < n_cells && grid[c] == 0.0f) bits |= 1u << b; }
+        mask[w] = bits;
+    }
+}
 // ZSobol prefix cache (SobolParams::top, hk_math.cuh): one pass per (resolution, seed), not per sample.
 // dims[slot] = the sampler dimension of cache slot `slot`.
 __global__ void __launch_bounds__(256) k_sobol_prefix(uint32_t* __restrict__ top, uint4* __restrict__ dimhash, const int32_t* __restrict__ dims, int32_t n_slots,
@@ -420,12 +441,12 @@ struct QueueRayIO {
 #ifdef HK_TU_TRACE
 template <bool COUNT, bool INST>
 __global__ void __launch_bounds__(HK_TRACE_THREADS, INST ? HK_TRACE_BLOCKS_PER_SM_INST : HK_TRACE_BLOCKS_PER_SM) k_trace(const __grid_constant__ DevScene D, PathState S, int cur, int round, unsigned long long* work) {
-    __shared__ uint2 sm_stack[HK_SM_STACK * HK_TRACE_THREADS];
+    HK_TRACE_SMEM(INST);
     // round > 0: a retrace round of the alpha loop (rays whose previous hit was skipped, restarted just behind that surface)
     const uint32_t n = S.counts[round == 0 ? HK_C_RAY0 + cur : HK_C_ALPHA_N0 + round];
     uint32_t traced = 0, wn = 0, wt = 0;
     QueueRayIO io{S, round == 0 ? S.q_ray[cur] : S.q_alpha[round & 1]};
-    trace_queue<false, COUNT, INST>(D.bvh, sm_stack + threadIdx.x, n, S.counts + (round == 0 ? HK_C_CURSOR_TRACE : HK_C_ALPHA_CUR0 + round), io, traced, wn, wt);
+    trace_queue<false, COUNT, INST>(D.bvh, sm_stack + threadIdx.x, sm_wray + threadIdx.x, n, S.counts + (round == 0 ? HK_C_CURSOR_TRACE : HK_C_ALPHA_CUR0 + round), io, traced, wn, wt);
     count_rays(S.rays_traced, traced);
     if (COUNT) { count_rays(work, traced); count_rays(work + 1, wn); count_rays(work + 2, wt); }
 }
@@ -681,8 +702,19 @@ __global__ void __launch_bounds__(128, 4) k_hit_lights(const __grid_constant__ D
 // to need the cooperative descent, DevScene::split_lights); otherwise they are done here with the plain serial descent, as the
 // light work is then a few hundred instructions and a separate kernel plus its 48-byte record per hit costs more than it saves
 // (measured on B200: C3, 10 002 lights, shading 10.4 -> 6.2 ms per 4K sample when split; C2, 3 lights, 1.50 -> 1.67 ms).
-template <int TYPE, bool SPLIT>
-__global__ void __launch_bounds__(128, (TYPE == HK_MAT_COATED_DIFFUSE || TYPE == HK_MAT_COATED_DIFFUSE_TRANSMISSION) ? HK_SHADE_MIN_BLOCKS + 2 : HK_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DevScene D, PathState S, PassArgs A, int next, int par) {
+// PART: 0 = the whole vertex in one kernel; 1 = emissive-hit MIS + next-event estimation only; 2 = BSDF sampling + continuation only.
+// The LayeredBxDF materials run as two kernels (1 then 2, same stream): their eval / pdf walks and their sampling walk are ~100 KB of
+// code each, and with both in one kernel the resident warps -- spread over all of it -- miss the instruction cache on almost every
+// fetch (ncu on C5: stall_no_instruction 45 warp-cycles per issue, issue slots 11 % busy).  Part 1 only reads what part 2 rewrites.
+#ifndef HK_SHADE_TWO_PARTS
+#define HK_SHADE_TWO_PARTS 1
+#endif
+#ifndef HK_SHADE_LAYERED_EXTRA_BLOCKS
+#define HK_SHADE_LAYERED_EXTRA_BLOCKS 2
+#endif
+#define HK_SHADE_IS_LAYERED(T) ((T) == HK_MAT_COATED_DIFFUSE || (T) == HK_MAT_COATED_DIFFUSE_TRANSMISSION)
+template <int TYPE, bool SPLIT, int PART>
+__global__ void __launch_bounds__(128, HK_SHADE_IS_LAYERED(TYPE) ? HK_SHADE_MIN_BLOCKS + HK_SHADE_LAYERED_EXTRA_BLOCKS : HK_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DevScene D, PathState S, PassArgs A, int next, int par) {
     const uint32_t n = S.counts[HK_HIT_COUNTER(HK_TYPE_QUEUE(TYPE))];
     MatCtx MC = mat_ctx(D);
     LightCtx LC = light_ctx(D);
@@ -708,7 +740,7 @@ __global__ void __launch_bounds__(128, (TYPE == HK_MAT_COATED_DIFFUSE || TYPE ==
             const uint32_t cur_medium = HK_FLAG_MEDIUM(fl);
             const float3 wo = -d;
             // ---- HandleEmissiveIntersection (SPLIT: done by k_hit_lights) ---------------------------------------
-            if (!SPLIT && sf.arealight > 0u) {
+            if (PART != 2 && !SPLIT && sf.arealight > 0u) {
                 Spec Le = arealight_Le(D.T, D.lights[sf.arealight - 1], wo, sf.n, lam);
                 if (!sp_black(Le)) {
                     Spec contrib = beta * Le, fin;
@@ -729,7 +761,7 @@ __global__ void __launch_bounds__(128, (TYPE == HK_MAT_COATED_DIFFUSE || TYPE ==
             const int sidx = slot_sample_idx(A, slot);
             const int bdim = 6 + 7 * depth;
             // ---- next-event estimation: the light sample comes from k_hit_lights' record (SPLIT) or is drawn here ------------
-            if (D.n_lights > 0) {
+            if (PART != 2 && D.n_lights > 0) {
                 float3 lwi = f3(0.0f, 0.0f, 0.0f), lp = f3(0.0f, 0.0f, 0.0f);
                 float lpdf = 0.0f, pmf = 0.0f; bool ldelta = false;
                 Spec Li = sp(0.0f);
@@ -774,7 +806,7 @@ __global__ void __launch_bounds__(128, (TYPE == HK_MAT_COATED_DIFFUSE || TYPE ==
             }
             // ---- BSDF sampling + continuation ----------------------------------------------------------------------
             const int new_depth = depth + 1;
-            if (new_depth < D.max_depth) {
+            if (PART != 1 && new_depth < D.max_depth) {
                 float indirect_uc = zsobol_1d(D.sobol, px, py, sidx, bdim + 4, HK_SOBOL_SLOT_BOUNCE(depth, 2), pix);
                 float2 indirect_u = zsobol_2d(D.sobol, px, py, sidx, bdim + 6, HK_SOBOL_SLOT_BOUNCE(depth, 3), pix);
                 const bool reg = D.regularize && (fl & HK_FLAG_ANYNS);
@@ -800,7 +832,18 @@ __global__ void __launch_bounds__(128, (TYPE == HK_MAT_COATED_DIFFUSE || TYPE ==
                 }
             }
         }
-        warp_push2(S.counts + HK_CI_SHADOW(par), S.q_shadow, push_shadow, S.counts + HK_C_RAY0 + next, S.q_ray[next], push_ray, slot);
+        if (PART == 0) warp_push2(S.counts + HK_CI_SHADOW(par), S.q_shadow, push_shadow, S.counts + HK_C_RAY0 + next, S.q_ray[next], push_ray, slot);
+        else if (PART == 1) warp_push1(S.counts + HK_CI_SHADOW(par), S.q_shadow, push_shadow, slot);
+        else warp_push1(S.counts + HK_C_RAY0 + next, S.q_ray[next], push_ray, slot);
+    }
+}
+// one shading class = one launch, or two for the LayeredBxDF materials
+template <int TYPE> static void launch_shade_class(int grid, cudaStream_t st, const DevScene& D, const PathState& S, const PassArgs& A, int next, int par) {
+    if constexpr (HK_SHADE_TWO_PARTS && HK_SHADE_IS_LAYERED(TYPE)) {
+        if (D.split_lights) { k_shade<TYPE, true, 1><<<grid, 128, 0, st>>>(D, S, A, next, par); k_shade<TYPE, true, 2><<<grid, 128, 0, st>>>(D, S, A, next, par); }
+        else { k_shade<TYPE, false, 1><<<grid, 128, 0, st>>>(D, S, A, next, par); k_shade<TYPE, false, 2><<<grid, 128, 0, st>>>(D, S, A, next, par); }
+    } else {
+        if (D.split_lights) k_shade<TYPE, true, 0><<<grid, 128, 0, st>>>(D, S, A, next, par); else k_shade<TYPE, false, 0><<<grid, 128, 0, st>>>(D, S, A, next, par);
     }
 }
 
@@ -812,13 +855,23 @@ __global__ void __launch_bounds__(128, (TYPE == HK_MAT_COATED_DIFFUSE || TYPE ==
 #ifndef HK_PHASE_MIN
 #define HK_PHASE_MIN 16
 #endif
+#ifndef HK_PHASE_POLICY
+#define HK_PHASE_POLICY 0      // 0: per-warp vote between the skip and the event phase; 1: both phases every iteration
+#endif
 #ifndef HK_MEDIUM_REFILL_MIN
 #define HK_MEDIUM_REFILL_MIN HK_PHASE_MIN     // idle lanes needed before the warp fetches new rays (32 = coherent groups, no mid-flight refill)
 #endif
+#ifndef HK_MEDIA_MIN_BLOCKS
+#define HK_MEDIA_MIN_BLOCKS 4      // 128 registers; measured on C4: 1 (150 registers, 3 blocks) -5 %, 5 (102 registers, spills) -11 %
+#endif
 template <bool RGB>     // RGB: some medium of the scene is an RGBGridMedium (see DeltaTracker::event_step)
-__global__ void __launch_bounds__(128) k_medium_track(const __grid_constant__ DevScene D, PathState S) {
+__global__ void __launch_bounds__(128, HK_MEDIA_MIN_BLOCKS) k_medium_track(const __grid_constant__ DevScene D, PathState S) {
+    extern __shared__ uint32_t s_mask[];
     const uint32_t n = S.counts[HK_C_MEDIUM];
-    MediaCtx MDC = media_ctx(D);
+    if (n == 0) return;
+    MediaCtx MDC = media_ctx_staged(D, s_mask);
+    uint32_t* lc_slot = s_mask + D.smem_mask_words + threadIdx.x;      // this lane's NanoVDB leaf cache (medium_density_cached)
+    lc_slot[0] = 0u;
     DeltaTracker T;
     T.in_seg = false;
     bool busy = false, exhausted = false;
@@ -843,6 +896,7 @@ __global__ void __launch_bounds__(128) k_medium_track(const __grid_constant__ De
                     const float t_max = HK_HIT_PRIM1(__float_as_uint(hr.y)) ? hr.x : HK_INF;
                     T.init(MDC, (int)HK_FLAG_MEDIUM(fl), f3(ra.x, ra.y, ra.z), f3(ra.w, rb.x, rb.y), t_max, S.lambda[slot], S.beta[slot], S.r_u[slot], S.r_l[slot],
                            HK_FLAG_DEPTH(fl), D.max_depth);
+                    lc_slot[0] = 0u;      // (another ray, possibly another medium)
                     busy = true;
                 }
             }
@@ -850,8 +904,18 @@ __global__ void __launch_bounds__(128) k_medium_track(const __grid_constant__ De
             continue;
         }
         bool fin = false;
-        if ((uint32_t)__popc(ev) >= (uint32_t)HK_PHASE_MIN || sk == 0u) { if (busy && T.in_seg) fin = T.template event_step<RGB>(MDC.T, S.lambda + slot); }
+#if HK_PHASE_POLICY == 1
+        // no vote: lanes outside a segment advance their DDA, then every lane inside a segment (the ones that just entered included)
+        // takes one collision event
+        if (busy && !T.in_seg) fin = T.skip_step();
+        if (busy && !fin && T.in_seg) fin = T.template event_step<RGB>(MDC.T, S.lambda + slot, lc_slot);
+#else
+#ifdef HK_MEDIA_STATS
+        if ((threadIdx.x & 31u) == 0u) { if ((uint32_t)__popc(ev) >= (uint32_t)HK_PHASE_MIN || sk == 0u) { HK_STAT(6, 1); HK_STAT(7, __popc(ev)); } else { HK_STAT(5, 1); HK_STAT(15, __popc(sk)); } }
+#endif
+        if ((uint32_t)__popc(ev) >= (uint32_t)HK_PHASE_MIN || sk == 0u) { if (busy && T.in_seg) fin = T.template event_step<RGB>(MDC.T, S.lambda + slot, lc_slot); }
         else if (busy && !T.in_seg) fin = T.skip_step();
+#endif
         if (fin) {
             const DeltaOut& R = T.R;
             if (!sp_black(R.Le_add)) S.L[slot] = S.L[slot] + R.Le_add;
@@ -961,13 +1025,13 @@ struct ShadowRayIO {
 };
 template <bool COUNT, bool INST>
 __global__ void __launch_bounds__(HK_TRACE_THREADS, INST ? HK_TRACE_BLOCKS_PER_SM_INST : HK_TRACE_BLOCKS_PER_SM) k_shadow_opaque(const __grid_constant__ DevScene D, PathState S, unsigned long long* work, int par) {
-    __shared__ uint2 sm_stack[HK_SM_STACK * HK_TRACE_THREADS];
+    HK_TRACE_SMEM(INST);
     // reference quirk (volpath.jl:571-609): shadow rays are only traced inside the `n_hits > 0` branch
     if (S.counts[HK_CI_TOTAL_HITS(par)] == 0) return;
     const uint32_t n = S.counts[HK_CI_SHADOW(par)];
     uint32_t traced = 0, wn = 0, wt = 0;
     ShadowRayIO io{S};
-    trace_queue<true, COUNT, INST>(D.bvh, sm_stack + threadIdx.x, n, S.counts + HK_CI_CURSOR_SHADOW(par), io, traced, wn, wt);
+    trace_queue<true, COUNT, INST>(D.bvh, sm_stack + threadIdx.x, sm_wray + threadIdx.x, n, S.counts + HK_CI_CURSOR_SHADOW(par), io, traced, wn, wt);
     count_rays(S.rays_traced, traced);
     if (COUNT) { count_rays(work + 3, traced); count_rays(work + 4, wn); count_rays(work + 5, wt); }
 }
@@ -991,24 +1055,28 @@ struct ShadowSegIO {
 };
 template <bool COUNT, bool INST>
 __global__ void __launch_bounds__(HK_TRACE_THREADS, INST ? HK_TRACE_BLOCKS_PER_SM_INST : HK_TRACE_BLOCKS_PER_SM) k_shadow_seg_trace(const __grid_constant__ DevScene D, PathState S, int round, unsigned long long* work) {
-    __shared__ uint2 sm_stack[HK_SM_STACK * HK_TRACE_THREADS];
+    HK_TRACE_SMEM(INST);
     if (S.counts[HK_C_TOTAL_HITS] == 0) return;      // reference quirk (volpath.jl:571-609): shadow pass only inside `n_hits > 0`
     const uint32_t n = S.counts[round == 0 ? HK_C_SHADOW : HK_C_SHROUND0 + round];
     uint32_t traced = 0, wn = 0, wt = 0;
     ShadowSegIO io{S, (round & 1) ? S.q_shadow2 : S.q_shadow};
-    trace_queue<false, COUNT, INST>(D.bvh, sm_stack + threadIdx.x, n, S.counts + HK_C_SHCUR_TRACE + round, io, traced, wn, wt);
+    trace_queue<false, COUNT, INST>(D.bvh, sm_stack + threadIdx.x, sm_wray + threadIdx.x, n, S.counts + HK_C_SHCUR_TRACE + round, io, traced, wn, wt);
     count_rays(S.rays_traced, traced);
     if (COUNT) { count_rays(work + 3, traced); count_rays(work + 4, wn); count_rays(work + 5, wt); }
 }
 #endif  // HK_TU_TRACE
 #ifdef HK_TU_MEDIA
 template <bool RGB>
-__global__ void __launch_bounds__(128) k_shadow_seg_ratio(const __grid_constant__ DevScene D, PathState S, int round) {
+__global__ void __launch_bounds__(128, HK_MEDIA_MIN_BLOCKS) k_shadow_seg_ratio(const __grid_constant__ DevScene D, PathState S, int round) {
     if (S.counts[HK_C_TOTAL_HITS] == 0) return;
     const uint32_t n = S.counts[round == 0 ? HK_C_SHADOW : HK_C_SHROUND0 + round];
     const uint32_t* __restrict__ q = (round & 1) ? S.q_shadow2 : S.q_shadow;
     uint32_t* q_next = (round & 1) ? S.q_shadow : S.q_shadow2;
-    MediaCtx MDC = media_ctx(D);
+    if (n == 0) return;
+    extern __shared__ uint32_t s_mask[];
+    MediaCtx MDC = media_ctx_staged(D, s_mask);
+    uint32_t* lc_slot = s_mask + D.smem_mask_words + threadIdx.x;
+    lc_slot[0] = 0u;
     RatioTracker R;
     R.in_seg = false;
     bool busy = false, exhausted = false, tracking = false, apass = false;
@@ -1046,6 +1114,7 @@ __global__ void __launch_bounds__(128) k_shadow_seg_ratio(const __grid_constant_
                         if (tracking) {
                             const float t_seg = hp ? h.x : sb.z;
                             R.init(MDC, (int)cur, f3(sa.x, sa.y, sa.z), f3(sa.w, sb.x, sb.y), t_seg, S.lambda[slot]);
+                            lc_slot[0] = 0u;
                         }
                     }
                 }
@@ -1054,8 +1123,16 @@ __global__ void __launch_bounds__(128) k_shadow_seg_ratio(const __grid_constant_
             continue;
         }
         bool fin = false;
-        if ((uint32_t)__popc(ev) >= (uint32_t)HK_PHASE_MIN || sk == 0u) { if (busy) { if (!tracking) fin = true; else if (R.in_seg) fin = R.template event_step<RGB>(MDC.T, S.lambda + slot); } }
+#if HK_PHASE_POLICY == 1
+        if (busy && tracking && !R.in_seg) fin = R.skip_step();
+        if (busy && !fin) { if (!tracking) fin = true; else if (R.in_seg) fin = R.template event_step<RGB>(MDC.T, S.lambda + slot, lc_slot); }
+#else
+#ifdef HK_MEDIA_STATS
+        if ((threadIdx.x & 31u) == 0u) { if ((uint32_t)__popc(ev) >= (uint32_t)HK_PHASE_MIN || sk == 0u) { HK_STAT(14, 1); HK_STAT(13, __popc(ev)); } }
+#endif
+        if ((uint32_t)__popc(ev) >= (uint32_t)HK_PHASE_MIN || sk == 0u) { if (busy) { if (!tracking) fin = true; else if (R.in_seg) fin = R.template event_step<RGB>(MDC.T, S.lambda + slot, lc_slot); } }
         else if (busy && tracking && !R.in_seg) fin = R.skip_step();
+#endif
         if (fin) {
             // ---- the segment is done: fold its transmittance in and resolve ------------------------------------------
             Spec T = sp(1.0f), tu = sp(1.0f), tl = sp(1.0f);
@@ -1197,13 +1274,13 @@ __global__ void __launch_bounds__(256) k_film_postprocess(const float* __restric
 template <bool INST>
 __global__ void __launch_bounds__(HK_TRACE_THREADS) k_aux_buffers(const __grid_constant__ DevScene D, float* __restrict__ albedo, float* __restrict__ normal,
                                                                    float* __restrict__ depth, float miss_depth) {
-    __shared__ uint2 sm_stack[HK_SM_STACK * HK_TRACE_THREADS];
+    HK_TRACE_SMEM(INST);
     const uint32_t n = (uint32_t)D.width * (uint32_t)D.height, H = (uint32_t)D.height;
     for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
         const uint32_t row = idx % H + 1u, col = idx / H + 1u;
         float3 o, d;
         camera_generate_ray(D.camera, (float)col + 0.5f, (float)row + 0.5f, make_float2(0.5f, 0.5f), o, d);
-        const HitRec h = bvh8_trace<false, false, INST>(D.bvh, sm_stack + threadIdx.x, o, d, HK_INF);
+        const HitRec h = bvh8_trace<false, false, INST>(D.bvh, sm_stack + threadIdx.x, sm_wray + threadIdx.x, o, d, HK_INF);
         float3 nn = f3(0.0f, 0.0f, 0.0f); float dep = miss_depth, alb = 0.0f;
         if (h.prim1) {
             const Surf sf = surface_at(D, HK_HIT_PRIM1(h.prim1) - 1u, h.b1, h.b2, o, d, h.t);
@@ -1233,23 +1310,23 @@ struct BatchRayIO {
 template <bool ANY, bool COUNT, bool INST>
 __global__ void __launch_bounds__(HK_TRACE_THREADS, INST ? HK_TRACE_BLOCKS_PER_SM_INST : HK_TRACE_BLOCKS_PER_SM) k_trace_batch(DevBvh B, const float4* __restrict__ rays, uint32_t n, float4* __restrict__ hits,
                                                                 uint8_t* __restrict__ occluded, uint32_t* cursor, unsigned long long* counters) {
-    __shared__ uint2 sm_stack[HK_SM_STACK * HK_TRACE_THREADS];
+    HK_TRACE_SMEM(INST);
     uint32_t traced = 0, nn = 0, nt = 0;
     BatchRayIO<ANY> io{rays, hits, occluded};
-    trace_queue<ANY, COUNT, INST>(B, sm_stack + threadIdx.x, n, cursor, io, traced, nn, nt);
+    trace_queue<ANY, COUNT, INST>(B, sm_stack + threadIdx.x, sm_wray + threadIdx.x, n, cursor, io, traced, nn, nt);
     if (COUNT) { count_rays(counters, nn); count_rays(counters + 1, nt); }
 }
 
 // detect_camera_medium, intersection.jl:690-747 (single thread; run once per camera change, not once per sample)
 template <bool INST>
 __global__ void k_detect_camera_medium(const __grid_constant__ DevScene D, uint32_t* out) {
-    __shared__ uint2 sm_stack[HK_SM_STACK * HK_TRACE_THREADS];
+    HK_TRACE_SMEM(INST);
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     float3 o = xf_point(D.camera.camera_to_world, f3(0, 0, 0));
     const float3 d = f3(0.57735027f, 0.57735027f, 0.57735027f);
     uint32_t res = 0;
     for (int it = 0; it < 16; it++) {
-        HitRec h = bvh8_trace<false, false, INST>(D.bvh, sm_stack, o, d, HK_INF);
+        HitRec h = bvh8_trace<false, false, INST>(D.bvh, sm_stack, sm_wray, o, d, HK_INF);
         if (h.prim1 == 0) break;
         const uint32_t prim0 = HK_HIT_PRIM1(h.prim1) - 1u;
         const HkMediumInterface mi = D.interfaces[prim_iface(D, prim0) - 1];

@@ -85,7 +85,7 @@ class Film:
         self.framebuffer = self._store.transpose(1, 0, 2)            # framebuffer[py, px] = RGB (a view)
         self.iteration_index = 0
 
-    def _new_store(self):
+    def _new_store(self, zero=True):
         w, h = self.resolution
         store = None
         try:
@@ -98,14 +98,15 @@ class Film:
             store = None
         if store is None:
             store = np.empty((w, h, 3), dtype=f32)
-        store[...] = 0
+        if zero:
+            store[...] = 0
         return store
 
     def _acquire_store(self):
         """A host buffer for one pipelined read-out (Backend.read_film_async): never the displayed one and never one that an
         un-waited read-out still targets -- with two frames in flight plus the displayed frame that is three buffers
         (include/hikari_cuda.h: 'the caller alternates host buffers'); they are allocated on demand and recycled by _show."""
-        return self._free.pop() if self._free else self._new_store()
+        return self._free.pop() if self._free else self._new_store(zero=False)      # (a read-out overwrites every byte)
 
     def _show(self, store):
         if store is not self._store:

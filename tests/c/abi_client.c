@@ -47,8 +47,7 @@ int main(int argc, char** argv) {
     CHECK(hk_upload_materials(ctx, &M, 1, &MI, 1));
     CHECK(hk_upload_media(ctx, NULL, 0));
     HkLight L; memset(&L, 0, sizeof(L));
-    L.type = HK_LIGHT_DIRECTIONAL; L.rgb[0] = L.rgb[1] = L.rgb[2] = 2.0f; L.scale = 1.0f / 10567.0f; L.dir[0] = 0; L.dir[1] = 0; L.dir[2] = 1.0f; /* towards the light */
-    L.world_radius = 3.0f;
+    L.type = HK_LIGHT_DIRECTIONAL; L.rgb[0] = L.rgb[1] = L.rgb[2] = 2.0f; L.scale = 1.0f / 10567.0f; L.direction[0] = 0; L.direction[1] = 0; L.direction[2] = -1.0f; /* travel direction */
     HkLightBVHNode nodes[2]; uint32_t trails[1]; int32_t inf[1]; uint32_t nn = 0, ni = 0, nb = 0;
     hk_host_build_light_sampler(&L, 1, nodes, &nn, trails, inf, &ni, &nb);
     HkLightSampler S = {nodes, nn, trails, inf, ni, nb};
@@ -66,7 +65,7 @@ int main(int argc, char** argv) {
         C.lens_radius = 0.0f; C.focal_distance = 1.0e6f;
     }
     CHECK(hk_set_camera(ctx, &C));
-    HkFilter F; memset(&F, 0, sizeof(F)); F.type = HK_FILTER_BOX; F.radius[0] = F.radius[1] = 0.5f;
+    HkFilter F; memset(&F, 0, sizeof(F)); F.type = 1; /* Box */ F.radius[0] = F.radius[1] = 0.5f;
     CHECK(hk_set_filter(ctx, &F));
     HkRenderParams P; memset(&P, 0, sizeof(P));
     P.width = W; P.height = H; P.max_depth = 3; P.samples_per_pixel = 4; P.regularize = 1; P.max_component_value = 10.0f;

@@ -50,3 +50,49 @@ def test_no_cpu_fallback_without_a_device():
     from hikari_jl_b200.host import Backend
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         Backend()
+
+
+def _build_c_client(tmp_path):
+    """gcc (C, not C++) compiles tests/c/abi_client.c against include/hikari_cuda.h and links libhikari_cuda.so"""
+    import subprocess
+    exe = str(tmp_path / "abi_client")
+    libdir = os.path.dirname(A.LIB_PATH)
+    cmd = ["gcc", "-std=c99", "-Wall", "-Werror", "-O1", "-I", os.path.join(ROOT, "include"), "-include", os.path.join(ROOT, "include", "hikari_cuda_testing.h"),
+           os.path.join(ROOT, "tests", "c", "abi_client.c"), "-o", exe, "-L", libdir, "-lhikari_cuda", "-lm", "-Wl,-rpath," + libdir]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def _write_tables(path):
+    import numpy as np
+    from hikari_jl_b200 import tables as T
+    t = T.load_tables()
+    scale, coeffs = T.get_srgb_table()
+    with open(path, "wb") as f:
+        f.write(np.int32(len(scale)).tobytes())
+        for k in ("sobol_matrices", "cie_x", "cie_y", "cie_z", "d65_values"):
+            f.write(np.ascontiguousarray(t[k]).tobytes())
+        f.write(np.ascontiguousarray(scale, dtype=np.float32).tobytes()); f.write(np.ascontiguousarray(coeffs, dtype=np.float32).tobytes())
+
+
+@pytest.mark.skipif(gpu_available(), reason="the no-GPU half of the C client")
+def test_c_client_compiles_links_and_fails_loudly_without_a_device(tmp_path):
+    import subprocess
+    A.load_library()
+    exe = _build_c_client(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("no-device abi=2"), (r.returncode, r.stdout, r.stderr)
+
+
+@pytest.mark.gpu
+def test_c_client_renders_through_the_c_abi(tmp_path):
+    """A C program (no Python, no ctypes) drives create -> uploads -> render -> host and device read-out -> destroy."""
+    import subprocess
+    A.load_library()
+    exe = _build_c_client(tmp_path)
+    tab = str(tmp_path / "tables.bin")
+    _write_tables(tab)
+    r = subprocess.run([exe, tab], capture_output=True, text=True)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0 and "dev_same=1" in r.stdout, (r.returncode, r.stdout, r.stderr)

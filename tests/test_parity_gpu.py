@@ -494,6 +494,38 @@ def test_media_render_beyond_one_wave_of_persistent_lanes():
     assert np.array_equal(a.view(np.uint32), a1.view(np.uint32))
 
 
+def test_caller_stream_and_device_framebuffer():
+    """The drop-in seam for a GPU-resident Film: hk_set_stream puts the whole render on the caller's cudaStream_t and hk_read_film_dev /
+    hk_postprocess_dev finalize straight into a caller device array (film.framebuffer / film.postprocess as CuArrays, volpath.jl:453,
+    384-417) without a host synchronisation.  Here the caller is torch: its stream, its tensors."""
+    import torch
+    scene, camf = scenes.c1_spheres(16)
+    film = H.Film((96, 64)); vp = H.VolPath(samples=4, max_depth=4)
+    ref = vp(scene, film, camf(film)).copy()                       # library stream, host read-out
+    lib, ctx = vp.backend.lib, vp.backend.ctx
+    st = torch.cuda.Stream()
+    fb = torch.zeros((96, 64, 3), dtype=torch.float32, device="cuda")      # (H, W) column-major == C-order (W, H, 3)
+    pp = torch.zeros_like(fb)
+    assert lib.hk_set_stream(ctx, C.c_void_p(st.cuda_stream)) == 0
+    vp.clear()
+    vp.backend.call("render_samples", 1, 4)
+    assert lib.hk_read_film_dev(ctx, C.c_void_p(fb.data_ptr())) == 0
+    P = A.HkPostprocess(exposure=1.0, tonemap_mode=0, inv_gamma=1.0, apply_gamma=0, white_point=4.0, imaging_ratio=1.0, apply_wb=0, mask_escaped=0)
+    assert lib.hk_postprocess_dev(ctx, C.byref(P), C.c_void_p(pp.data_ptr())) == 0
+    with torch.cuda.stream(st):
+        doubled = fb * 2.0                                         # consumer work ordered behind the render by the shared stream
+    st.synchronize()
+    got = fb.cpu().numpy().transpose(1, 0, 2)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    assert np.array_equal(doubled.cpu().numpy().transpose(1, 0, 2), 2.0 * ref)
+    assert np.allclose(pp.cpu().numpy().transpose(1, 0, 2), np.clip(ref, 0.0, 1.0))
+    assert lib.hk_read_film_dev(ctx, C.c_void_p(ref.ctypes.data)) < 0          # a host pointer is refused, not dereferenced
+    assert lib.hk_set_stream(ctx, None) == 0                        # back to the library's own stream
+    vp.clear(); vp.backend.call("render_samples", 1, 4); vp.backend.read_film(film)
+    assert np.array_equal(film.framebuffer.view(np.uint32), ref.view(np.uint32))
+    vp.close()
+
+
 def test_sobol_prefix_cache_is_bitwise_invariant():
     """The per-pixel ZSobol prefix cache (SobolParams::top) only moves work out of the sample loop: cached, uncached and
     partially cached (sample_idx >= 2^log2_spp takes the uncached path, the reference's Morton aliasing quirk) renders

@@ -7,6 +7,7 @@ import bench
 from hikari_jl_b200.host import Backend, Film, VolPath
 
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+if len(sys.argv) > 2: bench.select_config(sys.argv[2])      # python tools/bounce_profile.py <batch> <config>
 scene, camf = bench.build_scene()
 film = Film(bench.RES)
 vp = VolPath(samples=4096, max_depth=bench.MAX_DEPTH, sample_batch=batch, backend=Backend())
