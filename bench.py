@@ -243,7 +243,7 @@ def measure(args, rank, world, local, dist, torch, full):
     # flight, the warm-up is topped up to that number so that the path-state pool (allocated on demand) has its final size
     # and has been touched before the timed region starts.  The film is cleared afterwards: the timed region renders sample
     # indices the warm-up has not touched, so the film that is all-reduced holds exactly N x K distinct samples.
-    auto_batch = max(1, min(64, (32 << 20) // n))                      # HK_AUTO_SLOTS in hk_api.cu
+    auto_batch = max(1, min(64, (128 << 20) // n))                      # HK_AUTO_SLOTS in hk_api.cu
     batch_used = min(args.batch if args.batch > 0 else auto_batch, steps)
     warm = max(args.warmup, batch_used)
     B.call("render_samples_strided", sample_of(0), world, warm)

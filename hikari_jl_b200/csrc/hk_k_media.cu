@@ -19,5 +19,5 @@ void hkl_shadow_seg_ratio(bool rgb, int grid, cudaStream_t st, const DevScene& D
 
 #ifdef HK_MEDIA_STATS
 // development: print and reset the tracking statistics (hk_media.cuh)
-extern "C" void hk_dev_media_stats(unsigned long long* out16) { cudaDeviceSynchronize(); cudaMemcpyFromSymbol(out16, g_media_stats, sizeof(unsigned long long) * 16); unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_media_stats, z, sizeof(z)); }
+extern "C" void hk_dev_media_stats(unsigned long long* out16) { cudaDeviceSynchronize(); cudaMemcpyFromSymbol(out16, g_media_stats, sizeof(unsigned long long) * 32); unsigned long long z[32] = {0}; cudaMemcpyToSymbol(g_media_stats, z, sizeof(z)); }
 #endif

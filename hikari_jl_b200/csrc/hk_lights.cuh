@@ -14,7 +14,7 @@ struct LightCtx {
     DevTables T;
     const HkLight* __restrict__ lights; int32_t n_lights;
     const DevEnvMap* __restrict__ envmaps;
-    const HkLightBVHNode* __restrict__ nodes; const uint32_t* __restrict__ bit_trails; const int32_t* __restrict__ inf_idx;
+    const struct DevLNode* __restrict__ nodes; const uint32_t* __restrict__ bit_trails; const int32_t* __restrict__ inf_idx;
     int32_t n_infinite, n_bvh;
     // ascending indices of the lights an escaped ray can see (Environment, Ambient): the reference walks the whole light
     // tuple per escaped ray (lights.jl:408-467), which with 10 000 area lights (C3) is 10 002 type tests per ray
@@ -202,34 +202,47 @@ HK_NI_LIGHTS float env_light_pdf(const LightCtx& C, float3 d) {   // lights.jl:4
 // ---- BVH light sampler ----------------------------------------------------------------------------------
 HK_DEV float cos_sub_clamped(float sa, float ca, float sb, float cb) { return ca > cb ? 1.0f : ca * cb + sa * sb; }
 HK_DEV float sin_sub_clamped(float sa, float ca, float sb, float cb) { return ca > cb ? 0.0f : sa * cb - ca * sb; }
-// nodes are 64 bytes: four 16-byte loads
-struct LNode { float3 lo, hi, w; float phi, cos_o, cos_e; uint32_t two_sided, child, leaf; };
-HK_DEV LNode load_lnode(const HkLightBVHNode* __restrict__ nodes, int idx1) {
+// Device form of a light-BVH node (64 bytes, four 16-byte loads): everything node_importance needs that does NOT depend on the
+// shading point is evaluated once per upload (k_prepare_lnodes, the reference's own operations in the reference's order, so the
+// importance keeps its bits): the box centre, half its diagonal, the squared bounding-sphere radius and sin(theta_o).  The box
+// corners themselves are not needed after that.  [pc.xyz, half_diag] [w.xyz, phi] [cos_o, sin_o, cos_e, r2] [two_sided, child, leaf, -]
+struct DevLNode { float4 a, b, c, d; };
+struct LNode { float3 pc, w; float half_diag, phi, cos_o, sin_o, cos_e, r2; uint32_t two_sided, child, leaf; };
+HK_DEV DevLNode prepare_lnode(const HkLightBVHNode& N) {
+    const float3 lo = f3(N.bounds_min[0], N.bounds_min[1], N.bounds_min[2]), hi = f3(N.bounds_max[0], N.bounds_max[1], N.bounds_max[2]);
+    const float3 pc = (lo + hi) * 0.5f;
+    const float half_diag = len3(hi - lo) * 0.5f;
+    const float3 dr = hi - pc;
+    const float r2 = dot3(dr, dr);
+    const float so = sqrtf(fmaxf(0.0f, 1.0f - N.cos_theta_o * N.cos_theta_o));
+    DevLNode d;
+    d.a = make_float4(pc.x, pc.y, pc.z, half_diag); d.b = make_float4(N.w[0], N.w[1], N.w[2], N.phi);
+    d.c = make_float4(N.cos_theta_o, so, N.cos_theta_e, r2);
+    d.d = make_float4(__uint_as_float(N.two_sided), __uint_as_float(N.child1_or_light_idx), __uint_as_float(N.is_leaf), 0.0f);
+    return d;
+}
+HK_DEV LNode load_lnode(const DevLNode* __restrict__ nodes, int idx1) {
     const float4* q = reinterpret_cast<const float4*>(nodes + (idx1 - 1));
     float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
     LNode n;
-    n.lo = f3(a.x, a.y, a.z); n.hi = f3(a.w, b.x, b.y); n.w = f3(b.z, b.w, c.x);
-    n.phi = c.y; n.cos_o = c.z; n.cos_e = c.w;
+    n.pc = f3(a.x, a.y, a.z); n.half_diag = a.w; n.w = f3(b.x, b.y, b.z); n.phi = b.w;
+    n.cos_o = c.x; n.sin_o = c.y; n.cos_e = c.z; n.r2 = c.w;
     n.two_sided = __float_as_uint(d.x); n.child = __float_as_uint(d.y); n.leaf = __float_as_uint(d.z);
     return n;
 }
 HK_NI_LIGHTS float lnode_importance(const LNode& N, float3 p, float3 n) {   // bvh-light-sampler.jl:58-91
     if (N.phi == 0.0f) return 0.0f;
-    float3 pc = (N.lo + N.hi) * 0.5f;
-    float3 dp = p - pc;
+    float3 dp = p - N.pc;
     const float d2raw = dot3(dp, dp);
-    float d2 = fmaxf(d2raw, len3(N.hi - N.lo) * 0.5f);
+    float d2 = fmaxf(d2raw, N.half_diag);
     float3 wi = norm3(dp);
     float cw = dot3(N.w, wi);
     if (N.two_sided) cw = fabsf(cw);
     float sw = sqrtf(fmaxf(0.0f, 1.0f - cw * cw));
     // bound_subtended_directions (light-bounds.jl:96-109): only cosθ is needed
-    float3 dr = N.hi - pc;
-    float r2 = dot3(dr, dr);
-    float cb = d2raw < r2 ? -1.0f : sqrtf(fmaxf(0.0f, 1.0f - r2 / d2raw));
+    float cb = d2raw < N.r2 ? -1.0f : sqrtf(fmaxf(0.0f, 1.0f - N.r2 / d2raw));
     float sb = sqrtf(fmaxf(0.0f, 1.0f - cb * cb));
-    float so = sqrtf(fmaxf(0.0f, 1.0f - N.cos_o * N.cos_o));
-    float cx = cos_sub_clamped(sw, cw, so, N.cos_o), sx = sin_sub_clamped(sw, cw, so, N.cos_o);
+    float cx = cos_sub_clamped(sw, cw, N.sin_o, N.cos_o), sx = sin_sub_clamped(sw, cw, N.sin_o, N.cos_o);
     float cp = cos_sub_clamped(sx, cx, sb, cb);
     if (cp <= N.cos_e) return 0.0f;
     float imp = N.phi * cp / d2;
@@ -254,15 +267,18 @@ HK_NI_LIGHTS int bvh_sample_light(const LightCtx& C, float3 p, float3 n, float u
     float ub = C.n_infinite > 0 ? fminf((u - p_inf) / (1.0f - p_inf), 0.99999994f) : fminf(u, 0.99999994f);
     float pmf = 1.0f - p_inf;
     int ni = 1;
+    // (the node being expanded was loaded as a child one level up: its leaf flag / child index are carried over, not re-fetched)
+    uint32_t cur_leaf, cur_child;
+    { const LNode R = load_lnode(C.nodes, 1); cur_leaf = R.leaf; cur_child = R.child; }
     for (int it = 0; it < 64; it++) {
-        LNode N = load_lnode(C.nodes, ni);
-        if (N.leaf) { pmf_out = pmf; return (int)N.child; }
-        int c0i = ni + 1, c1i = (int)N.child;
-        float c0 = lnode_importance(load_lnode(C.nodes, c0i), p, n), c1 = lnode_importance(load_lnode(C.nodes, c1i), p, n);
+        if (cur_leaf) { pmf_out = pmf; return (int)cur_child; }
+        int c0i = ni + 1, c1i = (int)cur_child;
+        const LNode N0 = load_lnode(C.nodes, c0i), N1 = load_lnode(C.nodes, c1i);
+        float c0 = lnode_importance(N0, p, n), c1 = lnode_importance(N1, p, n);
         if (c0 == 0.0f && c1 == 0.0f) return 0;
         float p0 = c0 / (c0 + c1);
-        if (ub < p0) { pmf *= p0; ub = ub / p0; ni = c0i; }
-        else { pmf *= (1.0f - p0); ub = (ub - p0) / (1.0f - p0); ni = c1i; }
+        if (ub < p0) { pmf *= p0; ub = ub / p0; ni = c0i; cur_leaf = N0.leaf; cur_child = N0.child; }
+        else { pmf *= (1.0f - p0); ub = (ub - p0) / (1.0f - p0); ni = c1i; cur_leaf = N1.leaf; cur_child = N1.child; }
     }
     return 0;
 }
@@ -297,15 +313,17 @@ HK_NI_LIGHTS int bvh_sample_light_coop(const LightCtx& C, float3 p, float3 n, fl
     if (n_pairs == 0u) {        // a lone lane: plain descent
         if (need) {
             int ni = 1;
+            uint32_t cur_leaf, cur_child;
+            { const LNode R = load_lnode(C.nodes, 1); cur_leaf = R.leaf; cur_child = R.child; }
             for (int it = 0; it < 64; it++) {
-                LNode N = load_lnode(C.nodes, ni);
-                if (N.leaf) { pmf_out = pmf; return (int)N.child; }
-                int c0i = ni + 1, c1i = (int)N.child;
-                float c0 = lnode_importance(load_lnode(C.nodes, c0i), p, n), c1 = lnode_importance(load_lnode(C.nodes, c1i), p, n);
+                if (cur_leaf) { pmf_out = pmf; return (int)cur_child; }
+                int c0i = ni + 1, c1i = (int)cur_child;
+                const LNode N0 = load_lnode(C.nodes, c0i), N1 = load_lnode(C.nodes, c1i);
+                float c0 = lnode_importance(N0, p, n), c1 = lnode_importance(N1, p, n);
                 if (c0 == 0.0f && c1 == 0.0f) return 0;
                 float p0 = c0 / (c0 + c1);
-                if (ub < p0) { pmf *= p0; ub = ub / p0; ni = c0i; }
-                else { pmf *= (1.0f - p0); ub = (ub - p0) / (1.0f - p0); ni = c1i; }
+                if (ub < p0) { pmf *= p0; ub = ub / p0; ni = c0i; cur_leaf = N0.leaf; cur_child = N0.child; }
+                else { pmf *= (1.0f - p0); ub = (ub - p0) / (1.0f - p0); ni = c1i; cur_leaf = N1.leaf; cur_child = N1.child; }
             }
         }
         return 0;
@@ -322,23 +340,35 @@ HK_NI_LIGHTS int bvh_sample_light_coop(const LightCtx& C, float3 p, float3 n, fl
         int ni = 1, r_light = 0;
         float r_pmf = 0.0f;
         bool done = !active;
+        // the node being expanded was fetched one level up by one lane of the pair (as the child whose importance it evaluated): its
+        // leaf flag and child index travel by shuffle, so a level costs each lane ONE dependent node fetch, not two
+        uint32_t cur_leaf = 0u, cur_child = 0u;
+        if (active) { const LNode R = load_lnode(C.nodes, 1); cur_leaf = R.leaf; cur_child = R.child; }
         for (int it = 0; it < 64; it++) {
             if (__all_sync(m, done)) break;
             float mine = 0.0f;
             int c1i = 0;
+            uint32_t my_leaf = 0u, my_child = 0u;
             if (!done) {
-                const LNode N = load_lnode(C.nodes, ni);
-                if (N.leaf) { r_light = (int)N.child; r_pmf = bpmf; done = true; }
-                else { c1i = (int)N.child; mine = lnode_importance(load_lnode(C.nodes, child == 0u ? ni + 1 : c1i), bp, bn); }
+                if (cur_leaf) { r_light = (int)cur_child; r_pmf = bpmf; done = true; }
+                else {
+                    c1i = (int)cur_child;
+                    const LNode Nc = load_lnode(C.nodes, child == 0u ? ni + 1 : c1i);
+                    mine = lnode_importance(Nc, bp, bn); my_leaf = Nc.leaf; my_child = Nc.child;
+                }
             }
             const float other = __shfl_sync(m, mine, partner);
+            const uint32_t o_leaf = __shfl_sync(m, my_leaf, partner), o_child = __shfl_sync(m, my_child, partner);
             if (!done) {
                 const float c0 = child == 0u ? mine : other, c1 = child == 0u ? other : mine;
                 if (c0 == 0.0f && c1 == 0.0f) done = true;                       // result 0, pmf 0
                 else {
                     const float p0 = c0 / (c0 + c1);
-                    if (bub < p0) { bpmf *= p0; bub = bub / p0; ni = ni + 1; }
+                    const bool first = bub < p0;
+                    if (first) { bpmf *= p0; bub = bub / p0; ni = ni + 1; }
                     else { bpmf *= (1.0f - p0); bub = (bub - p0) / (1.0f - p0); ni = c1i; }
+                    const bool i_hold_it = first == (child == 0u);                // the chosen child is the one this lane fetched
+                    cur_leaf = i_hold_it ? my_leaf : o_leaf; cur_child = i_hold_it ? my_child : o_child;
                 }
             }
         }
@@ -369,14 +399,16 @@ HK_NI_LIGHTS float bvh_light_pmf(const LightCtx& C, float3 p, float3 n, int flat
     if (!has_bvh) return 0.0f;
     float pmf = 1.0f - (float)C.n_infinite / (float)(C.n_infinite + 1);
     int ni = 1;
+    uint32_t cur_leaf, cur_child;
+    { const LNode R = load_lnode(C.nodes, 1); cur_leaf = R.leaf; cur_child = R.child; }
     for (int it = 0; it < 64; it++) {
-        LNode N = load_lnode(C.nodes, ni);
-        if (N.leaf) return pmf;
-        int c0i = ni + 1, c1i = (int)N.child;
-        float c0 = lnode_importance(load_lnode(C.nodes, c0i), p, n), c1 = lnode_importance(load_lnode(C.nodes, c1i), p, n);
+        if (cur_leaf) return pmf;
+        int c0i = ni + 1, c1i = (int)cur_child;
+        const LNode N0 = load_lnode(C.nodes, c0i), N1 = load_lnode(C.nodes, c1i);
+        float c0 = lnode_importance(N0, p, n), c1 = lnode_importance(N1, p, n);
         float sc = c0 + c1;
         if (sc <= 0.0f) return 0.0f;
-        if ((trail & 1u) == 0) { pmf *= c0 / sc; ni = c0i; } else { pmf *= c1 / sc; ni = c1i; }
+        if ((trail & 1u) == 0) { pmf *= c0 / sc; ni = c0i; cur_leaf = N0.leaf; cur_child = N0.child; } else { pmf *= c1 / sc; ni = c1i; cur_leaf = N1.leaf; cur_child = N1.child; }
         trail >>= 1;
     }
     return pmf;

@@ -297,7 +297,7 @@ struct DeltaOut { int event; Spec beta, r_u, r_l; float3 p; float g; Spec Le_add
 // development statistics (-DHK_MEDIA_STATS): [0] rays set up, [1] empty cells stepped over, [2] cells fetched, [3] collision events,
 // [4] segment ends, [5] skip-phase iterations, [6] event-phase iterations (per warp), [7] event-phase lane-iterations
 #ifdef HK_MEDIA_STATS
-__device__ unsigned long long g_media_stats[16];
+__device__ unsigned long long g_media_stats[32];
 #define HK_STAT(i, n) atomicAdd(&g_media_stats[i], (unsigned long long)(n))
 #else
 #define HK_STAT(i, n) ((void)0)

@@ -75,7 +75,7 @@ struct DevScene {
     const float* __restrict__ spec_lambdas; const float* __restrict__ spec_values; const uint32_t* __restrict__ spec_offsets;
     const HkLight* __restrict__ lights; int32_t n_lights;
     const DevEnvMap* __restrict__ envmaps;
-    const HkLightBVHNode* __restrict__ lnodes; const uint32_t* __restrict__ bit_trails; const int32_t* __restrict__ inf_idx; int32_t n_infinite, n_bvh;
+    const DevLNode* __restrict__ lnodes; const uint32_t* __restrict__ bit_trails; const int32_t* __restrict__ inf_idx; int32_t n_infinite, n_bvh;
     const int32_t* __restrict__ esc_idx; int32_t n_esc;
     const DevMedium* __restrict__ media; int32_t n_media;
     int32_t any_medium_transition;     // some interface has inside != outside
@@ -372,6 +372,10 @@ __global__ void __launch_bounds__(256) k_majorant_mask(const float* __restrict__
         for (uint32_t b = 0; b < 32u; b++) { const uint32_t c = 32u * w + b; if (c < n_cells && grid[c] == 0.0f) bits |= 1u << b; }
         mask[w] = bits;
     }
+}
+// light-BVH nodes in their device form (DevLNode, hk_lights.cuh): the point-independent part of node_importance, once per upload
+__global__ void __launch_bounds__(256) k_prepare_lnodes(const HkLightBVHNode* __restrict__ in, uint32_t n, DevLNode* __restrict__ out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = prepare_lnode(in[i]);
 }
 // ZSobol prefix cache (SobolParams::top, hk_math.cuh): one pass per (resolution, seed), not per sample.
 // dims[slot] = the sampler dimension of cache slot `slot`.
@@ -875,6 +879,9 @@ __global__ void __launch_bounds__(128, HK_MEDIA_MIN_BLOCKS) k_medium_track(const
     DeltaTracker T;
     T.in_seg = false;
     bool busy = false, exhausted = false;
+#ifdef HK_MEDIA_STATS
+    bool had_seg = false;
+#endif
     uint32_t slot = 0;
     for (;;) {
         // Phase vote: the warp runs ONE of {refill, event, skip} per iteration, chosen so that the two expensive ones (ray
@@ -913,8 +920,19 @@ __global__ void __launch_bounds__(128, HK_MEDIA_MIN_BLOCKS) k_medium_track(const
 #ifdef HK_MEDIA_STATS
         if ((threadIdx.x & 31u) == 0u) { if ((uint32_t)__popc(ev) >= (uint32_t)HK_PHASE_MIN || sk == 0u) { HK_STAT(6, 1); HK_STAT(7, __popc(ev)); } else { HK_STAT(5, 1); HK_STAT(15, __popc(sk)); } }
 #endif
-        if ((uint32_t)__popc(ev) >= (uint32_t)HK_PHASE_MIN || sk == 0u) { if (busy && T.in_seg) fin = T.template event_step<RGB>(MDC.T, S.lambda + slot, lc_slot); }
+        if ((uint32_t)__popc(ev) >= (uint32_t)HK_PHASE_MIN || sk == 0u) {
+            if (busy && T.in_seg) {
+                fin = T.template event_step<RGB>(MDC.T, S.lambda + slot, lc_slot);
+#if HK_PHASE_POLICY == 2
+                if (!fin && !T.in_seg) fin = T.skip_step();      // the segment ended: move on to the next one right away (in a cloud it is the neighbouring cell), staying an event lane
+#endif
+            }
+        }
         else if (busy && !T.in_seg) fin = T.skip_step();
+#endif
+#ifdef HK_MEDIA_STATS
+        if (busy && T.in_seg) had_seg = true;
+        if (fin) { HK_STAT(had_seg ? 16 : 17, 1); had_seg = false; }
 #endif
         if (fin) {
             const DeltaOut& R = T.R;
@@ -1080,6 +1098,9 @@ __global__ void __launch_bounds__(128, HK_MEDIA_MIN_BLOCKS) k_shadow_seg_ratio(c
     RatioTracker R;
     R.in_seg = false;
     bool busy = false, exhausted = false, tracking = false, apass = false;
+#ifdef HK_MEDIA_STATS
+    bool had_seg = false;
+#endif
     uint32_t slot = 0;
     for (;;) {
         // same phase vote as k_medium_track; a lane whose segment needs no tracking (vacuum) resolves in the event phase
@@ -1130,8 +1151,22 @@ __global__ void __launch_bounds__(128, HK_MEDIA_MIN_BLOCKS) k_shadow_seg_ratio(c
 #ifdef HK_MEDIA_STATS
         if ((threadIdx.x & 31u) == 0u) { if ((uint32_t)__popc(ev) >= (uint32_t)HK_PHASE_MIN || sk == 0u) { HK_STAT(14, 1); HK_STAT(13, __popc(ev)); } }
 #endif
-        if ((uint32_t)__popc(ev) >= (uint32_t)HK_PHASE_MIN || sk == 0u) { if (busy) { if (!tracking) fin = true; else if (R.in_seg) fin = R.template event_step<RGB>(MDC.T, S.lambda + slot, lc_slot); } }
+        if ((uint32_t)__popc(ev) >= (uint32_t)HK_PHASE_MIN || sk == 0u) {
+            if (busy) {
+                if (!tracking) fin = true;
+                else if (R.in_seg) {
+                    fin = R.template event_step<RGB>(MDC.T, S.lambda + slot, lc_slot);
+#if HK_PHASE_POLICY == 2
+                    if (!fin && !R.in_seg) fin = R.skip_step();
+#endif
+                }
+            }
+        }
         else if (busy && tracking && !R.in_seg) fin = R.skip_step();
+#endif
+#ifdef HK_MEDIA_STATS
+        if (busy && tracking && R.in_seg) had_seg = true;
+        if (fin) { HK_STAT(!tracking ? 20 : (had_seg ? 18 : 19), 1); had_seg = false; }
 #endif
         if (fin) {
             // ---- the segment is done: fold its transmittance in and resolve ------------------------------------------
