@@ -391,7 +391,7 @@ def run_cuda(args):
                 row = line
             else:
                 select_config(name, args.c5_instances)
-                sub = argparse.Namespace(**vars(args)); sub.steps = min(args.steps, 8); sub.quick = True
+                sub = argparse.Namespace(**vars(args)); sub.steps = min(args.steps, 16); sub.quick = True
                 try:
                     row = measure(sub, 0, 1, local, None, torch, full=False)
                 except Exception as e:       # a config that cannot run (e.g. out of memory on a shared box) must not take the line down

@@ -71,13 +71,31 @@ int32_t hk_create(int32_t device, HkContext** out) {
     if (std::getenv("HK_SERIAL_SHADOW") && ctx->shadow_stream) { cudaStreamDestroy(ctx->shadow_stream); ctx->shadow_stream = nullptr; }
     if (ctx->b_counts.alloc(sizeof(uint32_t) * HK_N_COUNTERS + 64) != cudaSuccess || ctx->b_trace_ctr.alloc(64) != cudaSuccess || ctx->b_work_ctr.alloc(64) != cudaSuccess) { delete ctx; return HK_ERR_OOM; }
     cudaMemset(ctx->b_counts.p, 0, ctx->b_counts.bytes); cudaMemset(ctx->b_trace_ctr.p, 0, 64); cudaMemset(ctx->b_work_ctr.p, 0, 64);
+    if (ctx->b_scratch_u32.alloc(16) != cudaSuccess) { delete ctx; return HK_ERR_OOM; }
+    cudaMemset(ctx->b_scratch_u32.p, 0, 16);
     for (int i = 0; i < HK_N_STAGES; i++) { ctx->stage_ms[i] = 0; ctx->stage_launches[i] = 0; }
+    {   // the second render lane (frame pipelining); any failure just leaves it off
+        HkContext::AltLane& A = ctx->alt;
+        bool ok = cudaStreamCreateWithFlags(&A.stream, cudaStreamNonBlocking) == cudaSuccess;
+        for (auto& s : A.shade_streams) ok = ok && cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithFlags(&A.shadow_stream, cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaEventCreate(&A.ev0) == cudaSuccess && cudaEventCreate(&A.ev1) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&A.ev_fork, cudaEventDisableTiming) == cudaSuccess;
+        for (auto& e : A.ev_join) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&A.ev_shaded, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&A.ev_shadowed, cudaEventDisableTiming) == cudaSuccess;
+        for (auto& e : ctx->ev_lane_film) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&ctx->ev_film_touch, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && A.b_counts.alloc(sizeof(uint32_t) * HK_N_COUNTERS + 64) == cudaSuccess;
+        if (ok) cudaMemset(A.b_counts.p, 0, A.b_counts.bytes);
+        A.ready = ok && ctx->concurrent_shade && ctx->shadow_stream != nullptr && !std::getenv("HK_NO_FRAME_PIPELINE");
+        if (!ok) cudaGetLastError();
+    }
     *out = ctx;
     return HK_OK;
 }
 int32_t hk_destroy(HkContext* ctx) {
     if (!ctx) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device);
+    hk_enter(ctx);
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&ctx->b_sobol, &ctx->b_cie_x, &ctx->b_cie_y, &ctx->b_cie_z, &ctx->b_d65, &ctx->b_rgb_scale, &ctx->b_rgb_coeffs, &ctx->b_nodes, &ctx->b_tris,
                       &ctx->b_esc, &ctx->b_mat_pre, &ctx->b_light_pre, &ctx->b_med_pre, &ctx->b_sobol_top, &ctx->b_sobol_dims, &ctx->b_sobol_dimhash, &ctx->b_pos, &ctx->b_nrm, &ctx->b_idx, &ctx->b_meta, &ctx->b_mats, &ctx->b_ifaces, &ctx->b_spec_l, &ctx->b_spec_v, &ctx->b_spec_o, &ctx->b_lights,
@@ -101,6 +119,15 @@ int32_t hk_destroy(HkContext* ctx) {
     for (auto& e : ctx->ev_join) if (e) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) { if (ctx->ev_final[i]) cudaEventDestroy(ctx->ev_final[i]); if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]); ctx->b_readback_async[i].release(); }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    {   HkContext::AltLane& A = ctx->alt;
+        A.b_state.release(); A.b_counts.release();
+        if (A.stream) cudaStreamDestroy(A.stream);
+        for (auto& s2 : A.shade_streams) if (s2) cudaStreamDestroy(s2);
+        if (A.shadow_stream) cudaStreamDestroy(A.shadow_stream);
+        cudaEvent_t evs[] = {A.ev_fork, A.ev_shaded, A.ev_shadowed, A.ev0, A.ev1, ctx->ev_lane_film[0], ctx->ev_lane_film[1], ctx->ev_film_touch};
+        for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+        for (auto& e : A.ev_join) if (e) cudaEventDestroy(e);
+    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);      // (a caller-supplied stream is the caller's to destroy)
     delete ctx;
     return HK_OK;
@@ -109,7 +136,7 @@ const char* hk_last_error(HkContext* ctx) { return ctx ? ctx->err.c_str() : "nul
 
 int32_t hk_upload_tables(HkContext* ctx, const HkTables* t) {
     if (!ctx || !t) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device);
+    hk_enter(ctx);
     REQUIRE(t->rgb2spec_res >= 2, "rgb2spec_res must be >= 2");
     CK(ctx->b_sobol.upload(t->sobol_matrices, sizeof(uint32_t) * 1024 * 52));
     CK(ctx->b_cie_x.upload(t->cie_x, 4 * 471)); CK(ctx->b_cie_y.upload(t->cie_y, 4 * 471)); CK(ctx->b_cie_z.upload(t->cie_z, 4 * 471));
@@ -188,7 +215,7 @@ static int32_t patch_tri_types(HkContext* ctx) {
 
 int32_t hk_upload_geometry(HkContext* ctx, const HkGeometry* g) {
     if (!ctx || !g) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device);
+    hk_enter(ctx);
     const bool instanced = g->n_instances > 0;
     REQUIRE(g->n_tris == 0 || (g->positions && g->indices && (instanced || g->tri_meta)), "geometry arrays missing");
     REQUIRE(!instanced || (g->meshes && g->n_meshes > 0 && g->instances), "instanced geometry needs meshes and instances");
@@ -260,13 +287,13 @@ int32_t hk_upload_geometry(HkContext* ctx, const HkGeometry* g) {
     ctx->stats.bvh_nodes = bvh.nodes.size();
     ctx->stats.bvh_bytes = bvh.nodes.size() * sizeof(HkBvhNode) + bvh.tris.size() * sizeof(HkBvhTri) + inst_recs.size() * sizeof(float4);
     ctx->n_world_tris = n_world;
-    ctx->have_geom = true; ctx->camera_medium_valid = false;
+    ctx->have_geom = true; ctx->camera_version++;
     return patch_tri_types(ctx);
 }
 
 int32_t hk_upload_spectra(HkContext* ctx, const HkSpectra* s) {
     if (!ctx || !s) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device);
+    hk_enter(ctx);
     uint32_t n = s->n_spectra ? s->offsets[s->n_spectra] : 0;
     CK(ctx->b_spec_l.upload(s->lambdas, 4 * (size_t)n)); CK(ctx->b_spec_v.upload(s->values, 4 * (size_t)n));
     CK(ctx->b_spec_o.upload(s->offsets, 4 * ((size_t)s->n_spectra + 1)));
@@ -276,7 +303,7 @@ int32_t hk_upload_spectra(HkContext* ctx, const HkSpectra* s) {
 
 int32_t hk_upload_textures(HkContext* ctx, const HkTexture* t, uint32_t n) {
     if (!ctx) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device);
+    hk_enter(ctx);
     REQUIRE(n == 0 || t, "textures missing");
     CK(cudaStreamSynchronize(ctx->stream));
     for (auto& b : ctx->tex_bufs) b.release();
@@ -313,7 +340,7 @@ static uint32_t host_shade_class(const HkMaterial& m) { return (m.type == HK_MAT
 static bool mat_type_supported(int32_t t) { return (t >= 1 && t < HK_MAX_MAT_TYPES) || t == HK_MAT_MIX || t == HK_MAT_COATED_CONDUCTOR || t == HK_MAT_COATED_DIFFUSE_TRANSMISSION; }
 int32_t hk_upload_materials(HkContext* ctx, const HkMaterial* m, uint32_t nm, const HkMediumInterface* mi, uint32_t ni) {
     if (!ctx) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device);
+    hk_enter(ctx);
     REQUIRE(nm == 0 || m, "materials missing"); REQUIRE(ni == 0 || mi, "interfaces missing");
     uint32_t present = 0; int32_t trans = 0;
     for (uint32_t i = 0; i < nm; i++) {
@@ -331,7 +358,7 @@ int32_t hk_upload_materials(HkContext* ctx, const HkMaterial* m, uint32_t nm, co
     ctx->D.any_medium_transition = trans; ctx->mat_types_present = present; ctx->n_interfaces = ni;
     ctx->mat_types.resize(nm); for (uint32_t i = 0; i < nm; i++) ctx->mat_types[i] = m[i].type == HK_MAT_MIX ? HK_MAT_MIX : (int32_t)host_shade_class(m[i]);
     if (!ctx->b_spec_o.p) { uint32_t zero = 0; CK(ctx->b_spec_o.upload(&zero, 4)); ctx->D.spec_offsets = ctx->b_spec_o.as<uint32_t>(); }
-    ctx->have_mats = true; ctx->camera_medium_valid = false;
+    ctx->have_mats = true; ctx->camera_version++;
     int32_t rc = hk_refresh_uplift_cache(ctx);
     return rc != HK_OK ? rc : patch_tri_types(ctx);
 }
@@ -340,7 +367,7 @@ int32_t hk_upload_materials(HkContext* ctx, const HkMaterial* m, uint32_t nm, co
 // mode edits materials between frames); no re-upload of the scene.  index is 1-based into the uploaded material array.
 int32_t hk_update_material(HkContext* ctx, uint32_t index, const HkMaterial* m) {
     if (!ctx || !m) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device);
+    hk_enter(ctx);
     REQUIRE(ctx->have_mats, "hk_upload_materials has not been called");
     REQUIRE(index >= 1 && index <= ctx->mat_types.size(), "material index out of range");
     REQUIRE(mat_type_supported(m->type), "unsupported material type");
@@ -363,7 +390,7 @@ int32_t hk_update_material(HkContext* ctx, uint32_t index, const HkMaterial* m) 
 
 int32_t hk_upload_envmaps(HkContext* ctx, const HkEnvMap* maps, uint32_t n) {
     if (!ctx) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device);
+    hk_enter(ctx);
     for (auto& b : ctx->env_bufs) b.release();
     ctx->env_bufs.clear(); ctx->env_bufs.resize(6 * (size_t)n);
     std::vector<DevEnvMap> dev(n);
@@ -385,7 +412,7 @@ int32_t hk_upload_envmaps(HkContext* ctx, const HkEnvMap* maps, uint32_t n) {
 
 int32_t hk_upload_lights(HkContext* ctx, const HkLight* l, uint32_t n, const HkLightSampler* sm) {
     if (!ctx || !sm) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device);
+    hk_enter(ctx);
     REQUIRE(n == 0 || l, "lights missing");
     for (uint32_t i = 0; i < n; i++) REQUIRE(l[i].type >= 1 && l[i].type <= 7, "unknown light type");
     CK(ctx->b_lights.upload(l, sizeof(HkLight) * (size_t)n));
@@ -414,7 +441,7 @@ int32_t hk_upload_lights(HkContext* ctx, const HkLight* l, uint32_t n, const HkL
 
 int32_t hk_upload_media(HkContext* ctx, const HkMedium* m, uint32_t n) {
     if (!ctx) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device);
+    hk_enter(ctx);
     for (auto& b : ctx->media_bufs) b.release();
     for (auto& b : ctx->mask_bufs) b.release();
     ctx->media_bufs.clear(); ctx->media_bufs.resize(3 * (size_t)n);
@@ -473,18 +500,19 @@ int32_t hk_upload_media(HkContext* ctx, const HkMedium* m, uint32_t n) {
     CK(cudaGetLastError());
     CK(ctx->b_media.upload(dev.data(), sizeof(DevMedium) * (size_t)n));
     ctx->D.media = ctx->b_media.as<DevMedium>(); ctx->D.n_media = (int32_t)n;
-    ctx->camera_medium_valid = false;
+    ctx->camera_version++;
     return hk_refresh_uplift_cache(ctx);
 }
 
 int32_t hk_set_camera(HkContext* ctx, const HkCamera* c) {
     if (!ctx || !c) return HK_ERR_INVALID;
-    ctx->D.camera = *c; ctx->have_cam = true; ctx->camera_medium_valid = false;
+    if (!ctx->have_cam || std::memcmp(&ctx->D.camera, c, sizeof(HkCamera)) != 0) ctx->camera_version++;      // (an unchanged camera keeps its detected medium)
+    ctx->D.camera = *c; ctx->have_cam = true;
     return HK_OK;
 }
 int32_t hk_set_filter(HkContext* ctx, const HkFilter* f) {
     if (!ctx || !f) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device);
+    hk_enter(ctx);
     REQUIRE(f->type >= 1 && f->type <= 5, "unknown filter type");
     DevFilter& F = ctx->D.filter; std::memset(&F, 0, sizeof(F));
     F.type = f->type; F.rx = f->radius[0]; F.ry = f->radius[1]; F.nx = f->nx; F.ny = f->ny;
@@ -506,6 +534,7 @@ static int32_t alloc_film(HkContext* ctx, size_t n_pixels) {
     CK(ctx->b_film.alloc(16 * n_pixels + 64));
     CK(cudaMemset(ctx->b_film.p, 0, ctx->b_film.bytes));
     ctx->S.pixel_rgb = ctx->b_film.as<float>(); ctx->S.pixel_weight = ctx->b_film.as<float>() + 3 * n_pixels;
+    ctx->alt.S.pixel_rgb = ctx->S.pixel_rgb; ctx->alt.S.pixel_weight = ctx->S.pixel_weight;      // (the second render lane accumulates into the same film)
     return HK_OK;
 }
 static int32_t alloc_state(HkContext* ctx, size_t n_slots) {
@@ -579,7 +608,7 @@ static int32_t build_sobol_cache(HkContext* ctx) {
 
 int32_t hk_set_params(HkContext* ctx, const HkRenderParams* p) {
     if (!ctx || !p) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device);
+    hk_enter(ctx);
     REQUIRE(p->width > 0 && p->height > 0, "width/height must be positive");
     REQUIRE(p->max_depth >= 1 && p->max_depth <= 255, "max_depth must be in [1, 255]");
     ctx->params = *p;
@@ -607,6 +636,7 @@ int32_t hk_set_params(HkContext* ctx, const HkRenderParams* p) {
         ctx->aux_pixels = 0;                 // film.albedo / normal / depth belong to the previous film
         CK(cudaStreamSynchronize(ctx->stream));
         ctx->b_state.release(); ctx->n_slots = 0;
+        ctx->alt.b_state.release(); ctx->alt.n_slots = 0;
     }
     rc = build_sobol_cache(ctx);
     if (rc != HK_OK) return rc;
@@ -616,10 +646,11 @@ int32_t hk_set_params(HkContext* ctx, const HkRenderParams* p) {
 
 int32_t hk_clear(HkContext* ctx) {
     if (!ctx) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device);
+    hk_enter_film_async(ctx);
     REQUIRE(ctx->have_params, "hk_set_params has not been called");
     CK(cudaMemsetAsync(ctx->b_film.p, 0, ctx->b_film.bytes, ctx->stream));
     if (ctx->b_aux.p) CK(cudaMemsetAsync(ctx->b_aux.p, 0, ctx->b_aux.bytes, ctx->stream));      // clear!(film) also resets albedo / normal / depth
+    hk_film_touched(ctx);
     return HK_OK;
 }
 
@@ -645,24 +676,33 @@ template <int TYPE> static void launch_shade(HkContext* ctx, const PassArgs& A, 
 extern "C" {
 int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride, int32_t count) {
     if (!ctx) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device);
+    cudaSetDevice(ctx->device);      // (no host-side join of the render lanes here)
     REQUIRE(ctx->have_tables && ctx->have_geom && ctx->have_mats && ctx->have_lights && ctx->have_cam && ctx->have_filter && ctx->have_params,
             "render called before tables/geometry/materials/lights/camera/filter/params were all uploaded");
     REQUIRE(ctx->tri_types_valid, "geometry references medium interfaces that the uploaded material set does not have");
     REQUIRE(count >= 0 && stride >= 1 && first >= 1, "bad sample range");
     const size_t n_pixels = (size_t)ctx->params.width * ctx->params.height;
+    // frame pipelining: one-sample calls alternate between the two render lanes (hk_context.h)
+    const bool pipelined = count == 1 && ctx->alt.ready && ctx->frame_pipeline && ctx->profiling == 0 && ctx->stream == ctx->own_stream;
+    const int lane = pipelined ? ctx->next_lane : 0;
+    ctx->next_lane = pipelined ? (lane ^ 1) : 0;
+    if (!pipelined && ctx->lane_pending[1]) { cudaStreamSynchronize(ctx->alt.stream); ctx->lane_pending[1] = false; }      // a batched call: plain single-stream order
+    struct LaneGuard { HkContext* c; bool on; ~LaneGuard() { if (on) c->swap_lane(); } } lane_guard{ctx, lane == 1};
+    if (lane == 1) ctx->swap_lane();
+    ctx->last_lane = lane;
     cudaStream_t st = ctx->stream;
     {
         const size_t need = n_pixels * (size_t)std::max<int32_t>(1, std::min<int32_t>(ctx->params.sample_batch, count));
         if (ctx->n_slots < need) { int32_t rc = alloc_state(ctx, need); if (rc != HK_OK) return rc; }
     }
-    if (!ctx->camera_medium_valid) {   // hoisted out of the per-sample path (reference: one alloc + sync per sample, volpath.jl:503)
-        CK(ctx->b_scratch_u32.alloc(16));
-        hkl_detect_camera_medium(st, ctx->D, ctx->b_scratch_u32.as<uint32_t>());
+    // detect_camera_medium (intersection.jl:690-747), hoisted out of the per-sample path (reference: one alloc + host sync per sample,
+    // volpath.jl:503): re-run only when the camera or the scene changed, on this lane's stream, and its result stays on the device
+    // (k_camera reads it from there): no host round trip
+    uint32_t* cam_medium = ctx->b_scratch_u32.as<uint32_t>() + lane;
+    if (ctx->lane_cam_version[lane] != ctx->camera_version) {
+        hkl_detect_camera_medium(st, ctx->D, cam_medium);
         ctx->launches++;
-        CK(cudaMemcpyAsync(&ctx->camera_medium, ctx->b_scratch_u32.p, 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        ctx->camera_medium_valid = true;
+        ctx->lane_cam_version[lane] = ctx->camera_version;
     }
     const bool opaque_only = !ctx->D.any_medium_transition && ctx->D.n_media == 0 && !ctx->D.has_alpha;      // (an alpha-tested surface can let a shadow ray through: the segment walk)
     const bool cnt = (ctx->profiling & 2) != 0;
@@ -675,7 +715,7 @@ int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride,
         A.n_batch = std::min<int32_t>(ctx->params.sample_batch, count - done);
         A.first_sample = first + done * stride; A.stride = stride; A.n_pixels = (uint32_t)n_pixels;
         const size_t n_slots = n_pixels * (size_t)A.n_batch;
-        { StageScope sc(ctx, HK_STAGE_CAMERA); k_camera<<<grid_for(ctx, n_slots, 256, 8), 256, 0, st>>>(ctx->D, ctx->S, A, ctx->camera_medium); }
+        { StageScope sc(ctx, HK_STAGE_CAMERA); k_camera<<<grid_for(ctx, n_slots, 256, 8), 256, 0, st>>>(ctx->D, ctx->S, A, cam_medium); }
         int cur = 0;
         // Opaque-only scenes, stage timers off: the shadow pass of bounce b runs on its own stream and overlaps reset / trace /
         // route of bounce b+1 (it only reads the shadow records and adds to L; escaped / shading of b+1, which also add to L
@@ -740,7 +780,11 @@ int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride,
             cur ^= 1;
         }
         if (shadow_in_flight) cudaStreamWaitEvent(st, ctx->ev_shadowed, 0);      // the film pass reads L
+        // the film is summed in sample order: wait for the other lane's accumulation, and (second lane) for read-outs / clears of the film on the main stream
+        if (ctx->lane_pending[lane ^ 1]) cudaStreamWaitEvent(st, ctx->ev_lane_film[lane ^ 1], 0);
+        if (lane == 1 && ctx->film_touch_pending) cudaStreamWaitEvent(st, ctx->ev_film_touch, 0);
         { StageScope sc(ctx, HK_STAGE_FILM); k_film_accumulate<<<grid_for(ctx, n_pixels, 256, 8), 256, 0, st>>>(ctx->D, ctx->S, A); }
+        if (pipelined || ctx->lane_pending[1]) { cudaEventRecord(ctx->ev_lane_film[lane], st); ctx->lane_pending[lane] = true; }
         done += A.n_batch;
         if (ctx->profiling & 1) collect_stage_times(ctx);
     }
@@ -752,7 +796,7 @@ int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride,
 // profiling: bit 0 = time every stage launch with CUDA events, bit 1 = count traversal node visits / triangle tests
 int32_t hk_set_profiling(HkContext* ctx, int32_t mode) {
     if (!ctx) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device);
+    hk_enter(ctx);
     ctx->profiling = mode;
     for (int i = 0; i < HK_N_STAGES; i++) { ctx->stage_ms[i] = 0; ctx->stage_launches[i] = 0; }
     CK(cudaMemset(ctx->b_work_ctr.p, 0, 64));
@@ -760,7 +804,7 @@ int32_t hk_set_profiling(HkContext* ctx, int32_t mode) {
 }
 int32_t hk_stage_times(HkContext* ctx, double* out_ms, uint64_t* out_launches, uint64_t* out_work) {
     if (!ctx || !out_ms || !out_launches || !out_work) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device);
+    hk_enter(ctx);
     collect_stage_times(ctx);
     for (int i = 0; i < HK_N_STAGES; i++) { out_ms[i] = ctx->stage_ms[i]; out_launches[i] = ctx->stage_launches[i]; }
     CK(cudaMemcpy(out_work, ctx->b_work_ctr.p, 48, cudaMemcpyDeviceToHost));
@@ -778,14 +822,14 @@ int32_t hk_render_samples(HkContext* ctx, int32_t first, int32_t count) { return
 
 int32_t hk_synchronize(HkContext* ctx) {
     if (!ctx) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device);
+    hk_enter(ctx);
     CK(cudaStreamSynchronize(ctx->stream));
     return HK_OK;
 }
 
 int32_t hk_read_film(HkContext* ctx, float* out) {
     if (!ctx || !out) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device);
+    hk_enter(ctx);
     REQUIRE(ctx->have_params, "hk_set_params has not been called");
     const size_t n = (size_t)ctx->params.width * ctx->params.height;
     if (ctx->b_readback.bytes < 12 * n) CK(ctx->b_readback.alloc(12 * n));
@@ -797,7 +841,7 @@ int32_t hk_read_film(HkContext* ctx, float* out) {
 }
 int32_t hk_read_film_dev(HkContext* ctx, float* out_dev) {
     if (!ctx || !out_dev) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device);
+    hk_enter_film_async(ctx);
     REQUIRE(ctx->have_params, "hk_set_params has not been called");
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, out_dev) != cudaSuccess || (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged)) {
@@ -806,12 +850,13 @@ int32_t hk_read_film_dev(HkContext* ctx, float* out_dev) {
     const size_t n = (size_t)ctx->params.width * ctx->params.height;
     k_film_finalize<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(ctx->S.pixel_rgb, ctx->S.pixel_weight, out_dev, ctx->params.width, ctx->params.height);
     ctx->launches++;
+    hk_film_touched(ctx);
     CK(cudaGetLastError());
     return HK_OK;
 }
 int32_t hk_set_stream(HkContext* ctx, void* cuda_stream) {
     if (!ctx) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device);
+    hk_enter(ctx);
     CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->copy_stream) CK(cudaStreamSynchronize(ctx->copy_stream));
     ctx->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
@@ -822,7 +867,7 @@ int32_t hk_set_stream(HkContext* ctx, void* cuda_stream) {
 // DMA runs.  hk_read_film_wait(ticket) blocks until that frame has landed.  At most two frames in flight.
 int32_t hk_read_film_async(HkContext* ctx, float* out_pinned, int32_t* ticket) {
     if (!ctx || !out_pinned || !ticket) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device);
+    hk_enter_film_async(ctx);
     REQUIRE(ctx->have_params, "hk_set_params has not been called");
     const size_t n = (size_t)ctx->params.width * ctx->params.height;
     if (!ctx->copy_stream) {
@@ -834,6 +879,7 @@ int32_t hk_read_film_async(HkContext* ctx, float* out_pinned, int32_t* ticket) {
     if (ctx->async_used[k]) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[k], 0));      // the staging buffer's previous copy must be done
     k_film_finalize<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(ctx->S.pixel_rgb, ctx->S.pixel_weight, ctx->b_readback_async[k].as<float>(), ctx->params.width, ctx->params.height);
     ctx->launches++;
+    hk_film_touched(ctx);
     CK(cudaEventRecord(ctx->ev_final[k], ctx->stream));
     CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_final[k], 0));
     CK(cudaMemcpyAsync(out_pinned, ctx->b_readback_async[k].p, 12 * n, cudaMemcpyDeviceToHost, ctx->copy_stream));
@@ -851,7 +897,7 @@ int32_t hk_read_film_wait(HkContext* ctx, int32_t ticket) {
 }
 int32_t hk_postprocess(HkContext* ctx, const HkPostprocess* p, float* out) {
     if (!ctx || !p || !out) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device);
+    hk_enter(ctx);
     REQUIRE(ctx->have_params, "hk_set_params has not been called");
     REQUIRE(p->tonemap_mode >= HK_TONEMAP_NONE && p->tonemap_mode <= HK_TONEMAP_FILMIC, "unknown tonemap mode");
     const size_t n = (size_t)ctx->params.width * ctx->params.height;
@@ -866,7 +912,7 @@ int32_t hk_postprocess(HkContext* ctx, const HkPostprocess* p, float* out) {
 }
 int32_t hk_postprocess_dev(HkContext* ctx, const HkPostprocess* p, float* out_dev) {
     if (!ctx || !p || !out_dev) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device);
+    hk_enter_film_async(ctx);
     REQUIRE(ctx->have_params, "hk_set_params has not been called");
     REQUIRE(p->tonemap_mode >= HK_TONEMAP_NONE && p->tonemap_mode <= HK_TONEMAP_FILMIC, "unknown tonemap mode");
     const size_t n = (size_t)ctx->params.width * ctx->params.height;
@@ -878,13 +924,14 @@ int32_t hk_postprocess_dev(HkContext* ctx, const HkPostprocess* p, float* out_de
     k_film_postprocess<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(ctx->S.pixel_rgb, ctx->S.pixel_weight, out_dev, ctx->params.width, ctx->params.height, *p,
                                                                            p->mask_escaped ? ctx->b_aux.as<float>() + 6 * n : nullptr);
     ctx->launches++;
+    hk_film_touched(ctx);
     CK(cudaGetLastError());
     return HK_OK;
 }
 // fill_aux_buffers!(film, scene, camera; has_infinite_lights), film.jl:410-431
 int32_t hk_fill_aux_buffers(HkContext* ctx, int32_t has_infinite_lights) {
     if (!ctx) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device);
+    hk_enter(ctx);
     REQUIRE(ctx->have_params, "hk_set_params has not been called");
     REQUIRE(ctx->have_geom && ctx->have_cam, "geometry and camera must be uploaded before hk_fill_aux_buffers");
     const size_t n = (size_t)ctx->params.width * ctx->params.height;
@@ -898,7 +945,7 @@ int32_t hk_fill_aux_buffers(HkContext* ctx, int32_t has_infinite_lights) {
 }
 int32_t hk_read_aux_buffers(HkContext* ctx, float* albedo, float* normal, float* depth) {
     if (!ctx) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device);
+    hk_enter(ctx);
     REQUIRE(ctx->have_params, "hk_set_params has not been called");
     const size_t n = (size_t)ctx->params.width * ctx->params.height;
     REQUIRE(ctx->aux_pixels == n, "hk_fill_aux_buffers has not been called for this film size");
@@ -912,7 +959,7 @@ int32_t hk_read_aux_buffers(HkContext* ctx, float* albedo, float* normal, float*
 // denoise!(film; config), denoise.jl:301-372
 int32_t hk_denoise(HkContext* ctx, const HkDenoiseConfig* cfg, float* out_pp, float* out_fb) {
     if (!ctx || !cfg || !out_pp) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device);
+    hk_enter(ctx);
     REQUIRE(ctx->have_params, "hk_set_params has not been called");
     REQUIRE(cfg->iterations >= 0 && cfg->iterations <= 16, "denoise iterations out of range (0..16)");
     const size_t n = (size_t)ctx->params.width * ctx->params.height;
@@ -954,7 +1001,7 @@ int32_t hk_film_accum_dev(HkContext* ctx, float** out, uint64_t* count) {
 }
 int32_t hk_read_accum(HkContext* ctx, float* rgb, float* w) {
     if (!ctx || !rgb || !w) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device);
+    hk_enter(ctx);
     REQUIRE(ctx->have_params, "hk_set_params has not been called");
     const size_t n = (size_t)ctx->params.width * ctx->params.height;
     CK(cudaStreamSynchronize(ctx->stream));
@@ -963,7 +1010,7 @@ int32_t hk_read_accum(HkContext* ctx, float* rgb, float* w) {
 }
 int32_t hk_write_accum(HkContext* ctx, const float* rgb, const float* w) {
     if (!ctx || !rgb || !w) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device);
+    hk_enter(ctx);
     REQUIRE(ctx->have_params, "hk_set_params has not been called");
     const size_t n = (size_t)ctx->params.width * ctx->params.height;
     CK(cudaStreamSynchronize(ctx->stream));
@@ -995,13 +1042,13 @@ static int32_t trace_dev(HkContext* ctx, const float* rays_dev, uint64_t n64, fl
 }
 int32_t hk_trace_closest_dev(HkContext* ctx, const float* rays_dev, uint64_t n, float* hits_dev, int32_t repeat) {
     if (!ctx || !rays_dev || !hits_dev) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device);
+    hk_enter(ctx);
     REQUIRE(ctx->have_geom, "hk_upload_geometry has not been called");
     return trace_dev(ctx, rays_dev, n, hits_dev, nullptr, repeat < 1 ? 1 : repeat, false, false);
 }
 int32_t hk_trace_closest(HkContext* ctx, const float* rays, uint64_t n, float* hits) {
     if (!ctx || (n && (!rays || !hits))) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device);
+    hk_enter(ctx);
     REQUIRE(ctx->have_geom, "hk_upload_geometry has not been called");
     if (n == 0) return HK_OK;
     DevBuf r, h; CK(r.upload(rays, 32 * (size_t)n)); CK(h.alloc(16 * (size_t)n));
@@ -1012,7 +1059,7 @@ int32_t hk_trace_closest(HkContext* ctx, const float* rays, uint64_t n, float* h
 }
 int32_t hk_trace_any(HkContext* ctx, const float* rays, uint64_t n, uint8_t* occluded) {
     if (!ctx || (n && (!rays || !occluded))) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device);
+    hk_enter(ctx);
     REQUIRE(ctx->have_geom, "hk_upload_geometry has not been called");
     if (n == 0) return HK_OK;
     DevBuf r, o; CK(r.upload(rays, 32 * (size_t)n)); CK(o.alloc((size_t)n));
@@ -1024,7 +1071,7 @@ int32_t hk_trace_any(HkContext* ctx, const float* rays, uint64_t n, uint8_t* occ
 // traversal work counters for the roofline formula: node visits and triangle tests of one batch
 int32_t hk_test_trace_counts(HkContext* ctx, const float* rays, uint64_t n, uint64_t* out_nodes, uint64_t* out_tris) {
     if (!ctx || !rays || !out_nodes || !out_tris) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device);
+    hk_enter(ctx);
     REQUIRE(ctx->have_geom, "hk_upload_geometry has not been called");
     DevBuf r, h; CK(r.upload(rays, 32 * (size_t)n)); CK(h.alloc(16 * (size_t)n + 16));
     int32_t rc = trace_dev(ctx, r.as<float>(), n, h.as<float>(), nullptr, 1, false, true);
@@ -1038,24 +1085,27 @@ int32_t hk_test_trace_counts(HkContext* ctx, const float* rays, uint64_t n, uint
 
 int32_t hk_stats(HkContext* ctx, HkStats* out) {
     if (!ctx || !out) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device);
+    hk_enter(ctx);
     CK(cudaStreamSynchronize(ctx->stream));
     float ms = 0;
     if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->stats.last_render_ms = ms; else cudaGetLastError();
-    unsigned long long rt = 0;
+    if (ctx->last_lane == 1 && ctx->alt.ev0) { float m2 = 0; if (cudaEventElapsedTime(&m2, ctx->alt.ev0, ctx->alt.ev1) == cudaSuccess) ctx->stats.last_render_ms = m2; else cudaGetLastError(); }
+    unsigned long long rt = 0, rt2 = 0;
     if (ctx->S.rays_traced) cudaMemcpy(&rt, ctx->S.rays_traced, 8, cudaMemcpyDeviceToHost);
+    if (ctx->alt.S.rays_traced) cudaMemcpy(&rt2, ctx->alt.S.rays_traced, 8, cudaMemcpyDeviceToHost);
     *out = ctx->stats;
-    out->rays_traced = ctx->stats.rays_traced + rt;
-    { unsigned long long pv = 0; if (ctx->S.path_vertices) cudaMemcpy(&pv, ctx->S.path_vertices, 8, cudaMemcpyDeviceToHost); out->path_vertices = pv; }
+    out->rays_traced = ctx->stats.rays_traced + rt + rt2;
+    { unsigned long long pv = 0, pv2 = 0; if (ctx->S.path_vertices) cudaMemcpy(&pv, ctx->S.path_vertices, 8, cudaMemcpyDeviceToHost);
+      if (ctx->alt.S.path_vertices) cudaMemcpy(&pv2, ctx->alt.S.path_vertices, 8, cudaMemcpyDeviceToHost); out->path_vertices = pv + pv2; }
     out->kernel_launches = ctx->launches;
     out->queue_overflows = 0;
     return HK_OK;
 }
 
-int32_t hk_dev_alloc(HkContext* ctx, uint64_t bytes, void** out) { if (!ctx || !out) return HK_ERR_INVALID; cudaSetDevice(ctx->device); CK(cudaMalloc(out, bytes ? bytes : 16)); return HK_OK; }
-int32_t hk_dev_free(HkContext* ctx, void* p) { if (!ctx) return HK_ERR_INVALID; cudaSetDevice(ctx->device); CK(cudaFree(p)); return HK_OK; }
-int32_t hk_dev_upload(HkContext* ctx, void* dst, const void* src, uint64_t bytes) { if (!ctx) return HK_ERR_INVALID; cudaSetDevice(ctx->device); CK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice)); return HK_OK; }
-int32_t hk_dev_download(HkContext* ctx, void* dst, const void* src, uint64_t bytes) { if (!ctx) return HK_ERR_INVALID; cudaSetDevice(ctx->device); CK(cudaStreamSynchronize(ctx->stream)); CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost)); return HK_OK; }
+int32_t hk_dev_alloc(HkContext* ctx, uint64_t bytes, void** out) { if (!ctx || !out) return HK_ERR_INVALID; hk_enter(ctx); CK(cudaMalloc(out, bytes ? bytes : 16)); return HK_OK; }
+int32_t hk_dev_free(HkContext* ctx, void* p) { if (!ctx) return HK_ERR_INVALID; hk_enter(ctx); CK(cudaFree(p)); return HK_OK; }
+int32_t hk_dev_upload(HkContext* ctx, void* dst, const void* src, uint64_t bytes) { if (!ctx) return HK_ERR_INVALID; hk_enter(ctx); CK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice)); return HK_OK; }
+int32_t hk_dev_download(HkContext* ctx, void* dst, const void* src, uint64_t bytes) { if (!ctx) return HK_ERR_INVALID; hk_enter(ctx); CK(cudaStreamSynchronize(ctx->stream)); CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost)); return HK_OK; }
 
 }  // extern "C"
 

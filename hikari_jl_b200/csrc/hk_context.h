@@ -34,7 +34,7 @@ struct HkContext {
     PathState S;
     HkRenderParams params;
     bool have_tables = false, have_geom = false, have_mats = false, have_lights = false, have_cam = false, have_filter = false, have_params = false;
-    bool camera_medium_valid = false; uint32_t camera_medium = 0;
+    uint64_t camera_version = 1, lane_cam_version[2] = {0, 0};      // detect_camera_medium result per render lane (device-resident, b_scratch_u32[lane])
     uint32_t mat_types_present = 0;
     uint32_t n_interfaces = 0, max_iface_in_geom = 0; bool tri_types_valid = false;
     std::vector<int32_t> mat_types;                  // host copy of the material types (hk_update_material)
@@ -76,8 +76,46 @@ struct HkContext {
     // profiling bit 2: per-bounce queue counts and stage times of the most recent sample pass (host sync per bounce)
     std::vector<std::array<uint32_t, HK_N_QUEUE_COUNTERS>> bounce_counts;
     std::vector<std::array<double, HK_N_STAGES>> bounce_ms;
-    HkContext() { std::memset(&D, 0, sizeof(D)); std::memset(&S, 0, sizeof(S)); std::memset(&params, 0, sizeof(params)); std::memset(&stats, 0, sizeof(stats)); }
+    // ---- frame pipelining: a second render lane ----------------------------------------------------------------------------------
+    // One-sample hk_render_samples calls (the interactive render! loop: one sample + one read-out per frame) alternate between two
+    // lanes, each with its own path-state pool, counters, render stream, side streams and events, so that frame k+1's early bounces
+    // fill the GPU while frame k's deep bounces -- a few rays per stage, each stage a latency floor -- drain.  The film is shared; its
+    // accumulation order (sample order) and every read / clear of it are kept by events: ev_lane_film[l] = lane l's last
+    // k_film_accumulate, ev_film_touch = the last film read-out / clear on the main stream.  Only when the library owns the main stream.
+    struct AltLane {
+        PathState S; DevBuf b_state, b_counts; size_t n_slots = 0;
+        cudaStream_t stream = nullptr, shade_streams[3] = {nullptr, nullptr, nullptr}, shadow_stream = nullptr;
+        cudaEvent_t ev_fork = nullptr, ev_join[12] = {}, ev_shaded = nullptr, ev_shadowed = nullptr, ev0 = nullptr, ev1 = nullptr;
+        bool ready = false;
+    } alt;
+    cudaEvent_t ev_lane_film[2] = {nullptr, nullptr}, ev_film_touch = nullptr;
+    bool lane_pending[2] = {false, false}, film_touch_pending = false, frame_pipeline = true, in_alt = false;
+    int next_lane = 0, last_lane = 0;
+    // swap the main lane's per-pass resources with the second lane's (hk_render_samples* runs unchanged on whichever is current)
+    void swap_lane() {
+        std::swap(S, alt.S); std::swap(b_state, alt.b_state); std::swap(b_counts, alt.b_counts); std::swap(n_slots, alt.n_slots);
+        std::swap(stream, alt.stream); for (int i = 0; i < 3; i++) std::swap(shade_streams[i], alt.shade_streams[i]); std::swap(shadow_stream, alt.shadow_stream);
+        std::swap(ev_fork, alt.ev_fork); for (int i = 0; i < 12; i++) std::swap(ev_join[i], alt.ev_join[i]);
+        std::swap(ev_shaded, alt.ev_shaded); std::swap(ev_shadowed, alt.ev_shadowed); std::swap(ev0, alt.ev0); std::swap(ev1, alt.ev1);
+        in_alt = !in_alt;
+    }
+    HkContext() { std::memset(&D, 0, sizeof(D)); std::memset(&S, 0, sizeof(S)); std::memset(&alt.S, 0, sizeof(alt.S)); std::memset(&params, 0, sizeof(params)); std::memset(&stats, 0, sizeof(stats)); }
 };
+// entry-point prologue: select the device and wait (on the host) for the second render lane, so that everything but the render /
+// asynchronous read-out entry points sees the single-stream behaviour
+static inline void hk_enter(HkContext* ctx) {
+    cudaSetDevice(ctx->device);
+    if (ctx->lane_pending[1] && ctx->alt.stream) { cudaStreamSynchronize(ctx->alt.stream); ctx->lane_pending[1] = false; }
+}
+// the stream-ordered form for the asynchronous film readers / hk_clear on the main stream: the main stream waits for the second
+// lane's last film accumulation (which itself waited for everything before it)
+static inline void hk_enter_film_async(HkContext* ctx) {
+    cudaSetDevice(ctx->device);
+    if (ctx->lane_pending[1] && ctx->ev_lane_film[1]) cudaStreamWaitEvent(ctx->stream, ctx->ev_lane_film[1], 0);
+}
+static inline void hk_film_touched(HkContext* ctx) {      // after a film read-out / clear was enqueued on the main stream
+    if (ctx->ev_film_touch) { cudaEventRecord(ctx->ev_film_touch, ctx->stream); ctx->film_touch_pending = true; }
+}
 
 // (re)build the uplift cache after an upload that changes a constant colour (hk_api.cu)
 extern "C" int32_t hk_refresh_uplift_cache(HkContext* ctx);

@@ -172,7 +172,7 @@ struct TkIO {
 extern "C" {
 int32_t hk_test_detmath(HkContext* ctx, int32_t fn, const float* x, const float* y, uint64_t n, float* out) {
     if (!ctx || !x || !out || fn < 0 || fn > 7 || (fn == 6 && !y)) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device); TkIO io(ctx);
+    hk_enter(ctx); TkIO io(ctx);
     void* dx = io.in(x, 4 * n); void* dy = y ? io.in(y, 4 * n) : nullptr; float* dout = (float*)io.out(4 * n);
     if (io.rc) return io.rc;
     tk_detmath<<<TK_GRID(n)>>>(fn, (const float*)dx, (const float*)dy, n, dout); ctx->launches++;
@@ -180,7 +180,7 @@ int32_t hk_test_detmath(HkContext* ctx, int32_t fn, const float* x, const float*
 }
 int32_t hk_test_sobol(HkContext* ctx, const int32_t* q, uint64_t n, int32_t l2, int32_t nb4, uint32_t seed, float* o1, float* o2) {
     if (!ctx || !ctx->have_tables) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device); TkIO io(ctx);
+    hk_enter(ctx); TkIO io(ctx);
     SobolParams P{ctx->D.T.sobol, l2, nb4, seed, ctx->D.sobol.fast, nullptr, nullptr, 0u, 0};
     void* dq = io.in(q, 16 * n); float* d1 = (float*)io.out(4 * n); float* d2 = (float*)io.out(8 * n);
     if (io.rc) return io.rc;
@@ -192,7 +192,7 @@ int32_t hk_test_sobol_mode(HkContext* ctx, int32_t fast) { if (!ctx) return HK_E
 // 0 / 1: disable / enable the uplift cache (DevTables::mat_pre ...); returns the previous setting.  Takes effect at once.
 int32_t hk_test_uplift_cache(HkContext* ctx, int32_t on) {
     if (!ctx) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device);
+    hk_enter(ctx);
     int32_t old = ctx->uplift_cache_enabled ? 1 : 0; ctx->uplift_cache_enabled = on != 0;
     int32_t rc = hk_refresh_uplift_cache(ctx);
     return rc != HK_OK ? rc : old;
@@ -201,7 +201,7 @@ int32_t hk_test_uplift_cache(HkContext* ctx, int32_t on) {
 int32_t hk_test_sobol_cache(HkContext* ctx, int32_t on) { if (!ctx) return HK_ERR_INVALID; int32_t old = ctx->sobol_cache_enabled ? 1 : 0; ctx->sobol_cache_enabled = on != 0; ctx->sobol_cache_key[5] = -1; return old; }
 int32_t hk_test_mix_hash(HkContext* ctx, const float* in, uint64_t n, float* out) {
     if (!ctx) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device); TkIO io(ctx);
+    hk_enter(ctx); TkIO io(ctx);
     void* di = io.in(in, 40 * n); float* dout = (float*)io.out(4 * n);
     if (io.rc) return io.rc;
     tk_mix_hash<<<TK_GRID(n)>>>((const float*)di, n, dout); ctx->launches++;
@@ -209,7 +209,7 @@ int32_t hk_test_mix_hash(HkContext* ctx, const float* in, uint64_t n, float* out
 }
 int32_t hk_test_hashes(HkContext* ctx, const float* v, uint64_t n, uint64_t* oh, uint64_t* om, float* op) {
     if (!ctx) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device); TkIO io(ctx);
+    hk_enter(ctx); TkIO io(ctx);
     void* dv = io.in(v, 12 * n); uint64_t* dh = (uint64_t*)io.out(8 * n); uint64_t* dm = (uint64_t*)io.out(8 * n); float* dp = (float*)io.out(8 * n);
     if (io.rc) return io.rc;
     tk_hashes<<<TK_GRID(n)>>>((const float*)dv, n, dh, dm, dp); ctx->launches++;
@@ -217,7 +217,7 @@ int32_t hk_test_hashes(HkContext* ctx, const float* v, uint64_t n, uint64_t* oh,
 }
 int32_t hk_test_wavelengths(HkContext* ctx, const float* u, uint64_t n, float* lam, float* pdf) {
     if (!ctx) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device); TkIO io(ctx);
+    hk_enter(ctx); TkIO io(ctx);
     void* du = io.in(u, 4 * n); float4* dl = (float4*)io.out(16 * n); float4* dp = (float4*)io.out(16 * n);
     if (io.rc) return io.rc;
     tk_wavelengths<<<TK_GRID(n)>>>((const float*)du, n, dl, dp); ctx->launches++;
@@ -225,7 +225,7 @@ int32_t hk_test_wavelengths(HkContext* ctx, const float* u, uint64_t n, float* l
 }
 int32_t hk_test_uplift(HkContext* ctx, int32_t kind, const float* rgb, const float* lam, uint64_t n, float* out, float* poly) {
     if (!ctx || !ctx->have_tables) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device); TkIO io(ctx);
+    hk_enter(ctx); TkIO io(ctx);
     void* dr = io.in(rgb, 12 * n); void* dl = io.in(lam, 16 * n); float4* dout = (float4*)io.out(16 * n); float* dpoly = (float*)io.out(12 * n);
     if (io.rc) return io.rc;
     tk_uplift<<<TK_GRID(n)>>>(ctx->D.T, kind, (const float*)dr, (const float4*)dl, n, dout, dpoly); ctx->launches++;
@@ -233,7 +233,7 @@ int32_t hk_test_uplift(HkContext* ctx, int32_t kind, const float* rgb, const flo
 }
 int32_t hk_test_spectral_to_rgb(HkContext* ctx, const float* L, const float* lam, const float* pdf, uint64_t n, float* xyz, float* rgb) {
     if (!ctx || !ctx->have_tables) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device); TkIO io(ctx);
+    hk_enter(ctx); TkIO io(ctx);
     void* dL = io.in(L, 16 * n); void* dl = io.in(lam, 16 * n); void* dp = io.in(pdf, 16 * n); float* dx = (float*)io.out(12 * n); float* dr = (float*)io.out(12 * n);
     if (io.rc) return io.rc;
     tk_spec2rgb<<<TK_GRID(n)>>>(ctx->D.T, (const float4*)dL, (const float4*)dl, (const float4*)dp, n, dx, dr); ctx->launches++;
@@ -241,7 +241,7 @@ int32_t hk_test_spectral_to_rgb(HkContext* ctx, const float* L, const float* lam
 }
 int32_t hk_test_filter(HkContext* ctx, const float* u, uint64_t n, float* out) {
     if (!ctx || !ctx->have_filter) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device); TkIO io(ctx);
+    hk_enter(ctx); TkIO io(ctx);
     void* du = io.in(u, 8 * n); float* dout = (float*)io.out(12 * n);
     if (io.rc) return io.rc;
     tk_filter<<<TK_GRID(n)>>>(ctx->D.filter, (const float*)du, n, dout); ctx->launches++;
@@ -249,7 +249,7 @@ int32_t hk_test_filter(HkContext* ctx, const float* u, uint64_t n, float* out) {
 }
 int32_t hk_test_camera_rays(HkContext* ctx, int32_t sample_idx, float* out) {
     if (!ctx || !ctx->have_tables || !ctx->have_cam || !ctx->have_filter || !ctx->have_params) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device); TkIO io(ctx);
+    hk_enter(ctx); TkIO io(ctx);
     uint64_t n = (uint64_t)ctx->params.width * ctx->params.height;
     float* dout = (float*)io.out(32 * n);
     if (io.rc) return io.rc;
@@ -258,7 +258,7 @@ int32_t hk_test_camera_rays(HkContext* ctx, int32_t sample_idx, float* out) {
 }
 int32_t hk_test_bsdf(HkContext* ctx, uint32_t mat, const float* in, uint64_t n, float* out) {
     if (!ctx || !ctx->have_tables || !ctx->have_mats) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device); TkIO io(ctx);
+    hk_enter(ctx); TkIO io(ctx);
     void* di = io.in(in, 68 * n); float* dout = (float*)io.out(64 * n);
     if (io.rc) return io.rc;
     tk_bsdf<<<TK_GRID(n)>>>(ctx->D, mat, (const float*)di, n, dout); ctx->launches++;
@@ -266,7 +266,7 @@ int32_t hk_test_bsdf(HkContext* ctx, uint32_t mat, const float* in, uint64_t n, 
 }
 int32_t hk_test_lights(HkContext* ctx, const float* in, uint64_t n, float* out) {
     if (!ctx || !ctx->have_tables || !ctx->have_lights) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device); TkIO io(ctx);
+    hk_enter(ctx); TkIO io(ctx);
     void* di = io.in(in, 40 * n); float* dout = (float*)io.out(64 * n);
     if (io.rc) return io.rc;
     tk_lights<<<TK_GRID(n)>>>(ctx->D, (const float*)di, n, dout); ctx->launches++;
@@ -274,7 +274,7 @@ int32_t hk_test_lights(HkContext* ctx, const float* in, uint64_t n, float* out) 
 }
 int32_t hk_test_escaped(HkContext* ctx, const float* in, uint64_t n, float* out) {
     if (!ctx || !ctx->have_tables || !ctx->have_lights) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device); TkIO io(ctx);
+    hk_enter(ctx); TkIO io(ctx);
     void* di = io.in(in, 16 * n); float* dout = (float*)io.out(20 * n);
     if (io.rc) return io.rc;
     tk_escaped<<<TK_GRID(n)>>>(ctx->D, (const float*)di, n, dout); ctx->launches++;
@@ -282,7 +282,7 @@ int32_t hk_test_escaped(HkContext* ctx, const float* in, uint64_t n, float* out)
 }
 int32_t hk_test_delta_tracking(HkContext* ctx, uint32_t medium, const float* in, uint64_t n, float* out) {
     if (!ctx || !ctx->have_tables || medium < 1 || (int32_t)medium > ctx->D.n_media) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device); TkIO io(ctx);
+    hk_enter(ctx); TkIO io(ctx);
     void* di = io.in(in, 32 * n); float* dout = (float*)io.out(64 * n);
     if (io.rc) return io.rc;
     tk_delta<<<TK_GRID(n)>>>(ctx->D, medium, (const float*)di, n, dout); ctx->launches++;
@@ -290,7 +290,7 @@ int32_t hk_test_delta_tracking(HkContext* ctx, uint32_t medium, const float* in,
 }
 int32_t hk_test_density(HkContext* ctx, uint32_t medium, const float* p, uint64_t n, float* out) {
     if (!ctx || medium < 1 || (int32_t)medium > ctx->D.n_media) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device); TkIO io(ctx);
+    hk_enter(ctx); TkIO io(ctx);
     void* dp = io.in(p, 12 * n); float* dout = (float*)io.out(4 * n);
     if (io.rc) return io.rc;
     tk_density<<<TK_GRID(n)>>>(ctx->D, medium, (const float*)dp, n, dout); ctx->launches++;
@@ -298,7 +298,7 @@ int32_t hk_test_density(HkContext* ctx, uint32_t medium, const float* p, uint64_
 }
 int32_t hk_test_ratio_tracking(HkContext* ctx, uint32_t medium, const float* in, uint64_t n, float* out) {
     if (!ctx || !ctx->have_tables || medium < 1 || (int32_t)medium > ctx->D.n_media) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device); TkIO io(ctx);
+    hk_enter(ctx); TkIO io(ctx);
     void* di = io.in(in, 32 * n); float* dout = (float*)io.out(48 * n);
     if (io.rc) return io.rc;
     tk_ratio<<<TK_GRID(n)>>>(ctx->D, medium, (const float*)di, n, dout); ctx->launches++;
@@ -307,26 +307,30 @@ int32_t hk_test_ratio_tracking(HkContext* ctx, uint32_t medium, const float* in,
 // rays [n_slots][8] = (o, d, t_max, 0) and hits [n_slots][4] = (t, prim1 bits, b1, b2) as the last pass left them: for
 // every slot the hit record is the closest hit of the LAST ray traced for that path (full-size traversal parity checks)
 int32_t hk_test_read_rays(HkContext* ctx, float* rays, float* hits, uint64_t n_slots) {
-    if (!ctx || !ctx->have_params || n_slots > ctx->n_slots || !rays || !hits) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device);
+    if (!ctx || !ctx->have_params || !rays || !hits) return HK_ERR_INVALID;
+    hk_enter(ctx);
     CK(cudaStreamSynchronize(ctx->stream));
+    const PathState& PS = ctx->last_lane == 1 ? ctx->alt.S : ctx->S;      // the lane that rendered last (frame pipelining)
+    if (n_slots > (ctx->last_lane == 1 ? ctx->alt.n_slots : ctx->n_slots)) return HK_ERR_INVALID;
     std::vector<float4> a(n_slots), b(n_slots);
-    CK(cudaMemcpy(a.data(), ctx->S.ray_a, 16 * n_slots, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(b.data(), ctx->S.ray_b, 16 * n_slots, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(a.data(), PS.ray_a, 16 * n_slots, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(b.data(), PS.ray_b, 16 * n_slots, cudaMemcpyDeviceToHost));
     for (uint64_t i = 0; i < n_slots; i++) {
         float* r = rays + 8 * i;
         r[0] = a[i].x; r[1] = a[i].y; r[2] = a[i].z; r[3] = a[i].w; r[4] = b[i].x; r[5] = b[i].y; r[6] = b[i].z; r[7] = 0.0f;
     }
-    CK(cudaMemcpy(hits, ctx->S.hit, 16 * n_slots, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hits, PS.hit, 16 * n_slots, cudaMemcpyDeviceToHost));
     uint32_t* hb = reinterpret_cast<uint32_t*>(hits);
     for (uint64_t i = 0; i < n_slots; i++) hb[4 * i + 1] &= HK_PRIM_MASK;
     return HK_OK;
 }
 int32_t hk_test_read_pass(HkContext* ctx, float* L, float* lam, float* pdf, float* fw, uint64_t n_slots) {
-    if (!ctx || !ctx->have_params || n_slots > ctx->n_slots) return HK_ERR_INVALID;
-    cudaSetDevice(ctx->device);
+    if (!ctx || !ctx->have_params) return HK_ERR_INVALID;
+    hk_enter(ctx);
     CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaMemcpy(L, ctx->S.L, 16 * n_slots, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(lam, ctx->S.lambda, 16 * n_slots, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(pdf, ctx->S.lpdf, 16 * n_slots, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(fw, ctx->S.fweight, 4 * n_slots, cudaMemcpyDeviceToHost));
+    const PathState& PS = ctx->last_lane == 1 ? ctx->alt.S : ctx->S;
+    if (n_slots > (ctx->last_lane == 1 ? ctx->alt.n_slots : ctx->n_slots)) return HK_ERR_INVALID;
+    CK(cudaMemcpy(L, PS.L, 16 * n_slots, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(lam, PS.lambda, 16 * n_slots, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(pdf, PS.lpdf, 16 * n_slots, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(fw, PS.fweight, 4 * n_slots, cudaMemcpyDeviceToHost));
     return HK_OK;
 }
 }  // extern "C"

@@ -311,7 +311,8 @@ HK_DEV int slot_sample_idx(const PassArgs& A, uint32_t slot) { return A.first_sa
 
 #ifdef HK_TU_CORE
 // vp_generate_camera_rays_kernel!, volpath.jl:125-205.  One thread per slot; ray queue 0 becomes the identity.
-__global__ void __launch_bounds__(256) k_camera(const __grid_constant__ DevScene D, PathState S, PassArgs A, uint32_t camera_medium) {
+__global__ void __launch_bounds__(256) k_camera(const __grid_constant__ DevScene D, PathState S, PassArgs A, const uint32_t* __restrict__ camera_medium_dev) {
+    const uint32_t camera_medium = __ldg(camera_medium_dev);      // detect_camera_medium's result, left on the device
     const uint32_t n_slots = A.n_pixels * (uint32_t)A.n_batch;
     for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_slots; slot += gridDim.x * blockDim.x) {
         const uint32_t pix = slot % A.n_pixels;
