@@ -1241,30 +1241,27 @@ def compute_zsobol_params(samples_per_pixel, width, height):
 
 
 class Backend:
-    """One loaded C-ABI library + prefix.  The product backend is libhikari_cuda.so ('hk_'); tests construct a
-    second Backend around the oracle library ('ok_') to feed it the identical flattened scene."""
+    """The product backend: libhikari_cuda.so behind the C ABI (include/hikari_cuda.h).  There is no CPU fallback: construction
+    fails when the library or a CUDA device is missing.  (tests/oracle_backend.py derives the oracle's backend from this class to
+    feed the checker the identical flattened scene; nothing in this module loads or calls the oracle.)"""
+    prefix = "hk_"
 
-    def __init__(self, lib=None, prefix="hk_", device=0):
-        self.lib = A.load_library() if lib is None else lib
-        self.prefix = prefix
+    def __init__(self, device=0):
+        self.lib = A.load_library()
         self.ctx = C.c_void_p()
-        if prefix == "hk_":
-            rc = self.lib.hk_create(device, C.byref(self.ctx))
-        else:
-            rc = getattr(self.lib, prefix + "create")(C.byref(self.ctx))
+        rc = self.lib.hk_create(device, C.byref(self.ctx))
         if rc != 0:
-            raise RuntimeError(f"{prefix}create failed with status {rc}: no usable CUDA device / library "
-                               "(there is no CPU fallback)")
+            raise RuntimeError(f"hk_create failed with status {rc}: no usable CUDA device / library (there is no CPU fallback)")
         self._keep = []
+
+    def _last_error(self):
+        e = self.lib.hk_last_error(self.ctx)
+        return e.decode() if e else ""
 
     def call(self, name, *args):
         rc = getattr(self.lib, self.prefix + name)(self.ctx, *args)
         if rc != 0:
-            msg = ""
-            if self.prefix == "hk_":
-                e = self.lib.hk_last_error(self.ctx)
-                msg = e.decode() if e else ""
-            raise RuntimeError(f"{self.prefix}{name} failed ({rc}): {msg}")
+            raise RuntimeError(f"{self.prefix}{name} failed ({rc}): {self._last_error()}")
         return rc
 
     def close(self):

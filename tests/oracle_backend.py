@@ -54,8 +54,25 @@ def lib():
     return _lib
 
 
+class OracleBackend(Backend):
+    """The checker behind the product's host-side flattening (Backend.upload_scene / set_params / read_film): same structs, the
+    ok_* entry points of oracle/libhikari_oracle.so instead of hk_*."""
+    prefix = "ok_"
+
+    def __init__(self):
+        self.lib = lib()
+        self.ctx = C.c_void_p()
+        rc = self.lib.ok_create(C.byref(self.ctx))
+        if rc != 0:
+            raise RuntimeError(f"ok_create failed with status {rc}")
+        self._keep = []
+
+    def _last_error(self):
+        return ""
+
+
 def make_backend():
-    return Backend(lib=lib(), prefix="ok_")
+    return OracleBackend()
 
 
 def fp(a):

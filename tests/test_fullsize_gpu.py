@@ -129,3 +129,41 @@ def test_c4_4k_cloud_rays_and_batching():
     vp1.close()
     assert np.isfinite(img2).all() and img2.max() > 0
     assert np.array_equal(img2.view(np.uint32), img1.view(np.uint32))
+
+
+def _oracle_rows(scene, camf, res, depth, step, offset):
+    """sample 1 of image rows py with py % step == offset, rendered by the oracle at the full resolution (ok_set_row_subset)"""
+    film = H.Film(res)
+    vp = H.VolPath(samples=4096, max_depth=depth, backend=oracle_backend.make_backend())
+    vp._prepare(scene, film, camf(film)); vp.clear()
+    oracle_backend.lib().ok_set_row_subset(vp.backend.ctx, step, offset)
+    vp.backend.call("render_samples", 1, 1)
+    vp.backend.read_film(film)
+    img = film.framebuffer.copy()
+    rays = oracle_backend.lib().ok_rays_traced(vp.backend.ctx)
+    vp.close()
+    return img[offset::step], rays
+
+
+@pytest.mark.parametrize("name", ["C3", "C4", "C5"])
+def test_full_size_pixels_against_the_oracle(name):
+    """Pixels of the FULL-SIZE configurations against the oracle: the CUDA path renders one sample of the whole 4K frame (1 000
+    instances / 10 002 lights / the 256x256x128 NanoVDB cloud at depth 32), the oracle renders the same sample for every 270th image
+    row at the same resolution (same scene, camera, sampler state: a pixel's sample stream does not depend on its neighbours), and those
+    rows must agree bit for bit."""
+    if name == "C3":
+        (scene, camf), depth = scenes.c3_many_lights(10000, 128), 12
+    elif name == "C4":
+        (scene, camf), depth = scenes.c4_cloud((256, 256, 128), "nanovdb", (64, 64, 64)), 32
+    else:
+        (scene, camf), depth = scenes.c5_instanced(1000, 160, instanced=True), 8
+    res, step, offset = (3840, 2160), 270, 133
+    vp, img = _render(scene, camf, res, depth, 1, 1, 1)
+    vp.close()
+    rows_o, _ = _oracle_rows(scene, camf, res, depth, step, offset)
+    rows_c = img[offset::step]
+    assert rows_c.shape == rows_o.shape == (8, 3840, 3)
+    assert np.isfinite(rows_o).all() and rows_o.max() > 0
+    same = (rows_c.view(np.uint32) == rows_o.view(np.uint32)).all(axis=2)
+    print(f"{name} full size: {same.mean():.6f} of {same.size} pixels bit-identical; mean {rows_c.mean():.6f} vs {rows_o.mean():.6f}")
+    assert same.all(), f"{(~same).sum()} of {same.size} full-size pixels differ from the oracle"
