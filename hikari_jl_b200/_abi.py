@@ -55,7 +55,7 @@ class HkGeometry(C.Structure):
 
 class HkMaterial(C.Structure):
     _fields_ = [("type", C.c_int32), ("flags", C.c_uint32), ("rgb0", c_f * 3), ("rgb1", c_f * 3), ("rgb2", c_f * 4), ("f", c_f * 8),
-                ("spec", C.c_int32 * 2), ("ival", C.c_int32 * 2), ("tex", C.c_int32 * 4)]
+                ("spec", C.c_int32 * 2), ("ival", C.c_int32 * 2), ("tex", C.c_int32 * 4), ("ftex", C.c_int32 * 8)]
 
 
 class HkTexture(C.Structure):

@@ -328,13 +328,28 @@ int32_t hk_upload_textures(HkContext* ctx, const HkTexture* t, uint32_t n) {
     return HK_OK;
 }
 static int32_t mat_textures_ok(HkContext* ctx, const HkMaterial& m) {
-    REQUIRE(m.type == HK_MAT_MIX || !(m.flags & HK_MATFLAG_VERTEX_COLORS) || (m.type == HK_MAT_MATTE && m.tex[0] > 0), "VertexColorTexture is supported for MatteMaterial.Kd only");
-    for (int k = 0; k < 4; k++) {
-        if (m.tex[k] == 0) continue;
-        REQUIRE(k == 0 && m.type == HK_MAT_MATTE, "textured parameters are supported for MatteMaterial.Kd only (SURVEY 8f item 2)");
-        REQUIRE(m.tex[k] >= 1 && m.tex[k] <= ctx->D.n_textures, "material references a texture that has not been uploaded (hk_upload_textures first)");
-    }
+    REQUIRE(!(m.flags & HK_MATFLAG_VERTEX_COLORS) || m.type == HK_MAT_MIX || (m.type == HK_MAT_MATTE && m.tex[0] > 0), "VertexColorTexture is supported for MatteMaterial.Kd only");
+    REQUIRE(m.tex[3] == 0, "HkMaterial.tex[3] is unused");
+    bool any = false;
+    for (int k = 0; k < 3; k++) if (m.tex[k] != 0) { any = true; REQUIRE(m.tex[k] >= 1 && m.tex[k] <= ctx->D.n_textures, "material references a texture that has not been uploaded (hk_upload_textures first)"); }
+    for (int k = 0; k < 8; k++) if (m.ftex[k] != 0) { any = true; REQUIRE(m.ftex[k] >= 1 && m.ftex[k] <= ctx->D.n_textures, "material references a texture that has not been uploaded (hk_upload_textures first)"); }
+    REQUIRE(!any || m.type != HK_MAT_MIX, "MixMaterial.amount cannot be a texture");
+    REQUIRE(!((m.flags & HK_MATFLAG_SPECTRAL_ETA_K) && (m.tex[0] != 0 || m.tex[1] != 0)), "eta / k are piecewise-linear spectra: they cannot be textured as well");
     return HK_OK;
+}
+// textured parameters other than Matte.Kd (that one is the HK_SHADE_MATTE_TEX class): host mirror of material_has_textures()
+static bool mat_has_param_textures(const HkMaterial& m) {
+    if (m.type == HK_MAT_MIX) return false;
+    bool any = (m.tex[0] > 0 && m.type != HK_MAT_MATTE) || m.tex[1] > 0 || m.tex[2] > 0;
+    for (int k = 0; k < 8; k++) any = any || m.ftex[k] > 0;
+    return any;
+}
+static uint32_t host_shade_class(const HkMaterial& m);
+static void refresh_tex_classes(HkContext* ctx, const HkMaterial* m, uint32_t nm) {
+    (void)m; (void)nm;
+    uint32_t bits = 0;
+    for (size_t i = 0; i < ctx->mat_textured.size(); i++) if (ctx->mat_textured[i] && ctx->mat_types[i] != HK_MAT_MIX) bits |= 1u << ctx->mat_types[i];
+    ctx->D.tex_classes = bits;
 }
 static uint32_t host_shade_class(const HkMaterial& m) { return (m.type == HK_MAT_MATTE && m.tex[0] > 0) ? (uint32_t)HK_SHADE_MATTE_TEX : (uint32_t)m.type; }
 static bool mat_type_supported(int32_t t) { return (t >= 1 && t < HK_MAX_MAT_TYPES) || t == HK_MAT_MIX || t == HK_MAT_COATED_CONDUCTOR || t == HK_MAT_COATED_DIFFUSE_TRANSMISSION; }
@@ -356,7 +371,10 @@ int32_t hk_upload_materials(HkContext* ctx, const HkMaterial* m, uint32_t nm, co
     CK(ctx->b_mats.upload(m, sizeof(HkMaterial) * (size_t)nm)); CK(ctx->b_ifaces.upload(mi, sizeof(HkMediumInterface) * (size_t)ni));
     ctx->D.materials = ctx->b_mats.as<HkMaterial>(); ctx->D.interfaces = ctx->b_ifaces.as<HkMediumInterface>();
     ctx->D.any_medium_transition = trans; ctx->mat_types_present = present; ctx->n_interfaces = ni;
+    ctx->mat_textured.assign(nm, 0);
+    for (uint32_t i = 0; i < nm; i++) ctx->mat_textured[i] = mat_has_param_textures(m[i]) ? 1 : 0;
     ctx->mat_types.resize(nm); for (uint32_t i = 0; i < nm; i++) ctx->mat_types[i] = m[i].type == HK_MAT_MIX ? HK_MAT_MIX : (int32_t)host_shade_class(m[i]);
+    refresh_tex_classes(ctx, m, nm);
     if (!ctx->b_spec_o.p) { uint32_t zero = 0; CK(ctx->b_spec_o.upload(&zero, 4)); ctx->D.spec_offsets = ctx->b_spec_o.as<uint32_t>(); }
     ctx->have_mats = true; ctx->camera_version++;
     int32_t rc = hk_refresh_uplift_cache(ctx);
@@ -378,6 +396,8 @@ int32_t hk_update_material(HkContext* ctx, uint32_t index, const HkMaterial* m) 
     const int32_t cls = m->type == HK_MAT_MIX ? HK_MAT_MIX : (int32_t)host_shade_class(*m);      // mat_types holds shading classes
     const bool type_changed = ctx->mat_types[index - 1] != cls;
     ctx->mat_types[index - 1] = cls;
+    ctx->mat_textured[index - 1] = mat_has_param_textures(*m) ? 1 : 0;
+    refresh_tex_classes(ctx, nullptr, 0);
     { int32_t rc = hk_refresh_uplift_cache(ctx); if (rc != HK_OK) return rc; }
     if (type_changed) {
         uint32_t present = 0;

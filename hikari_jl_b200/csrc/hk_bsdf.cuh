@@ -12,7 +12,9 @@ HK_DEV BsdfSample bsdf_make(float3 wi, Spec f, float pdf, bool spec, float eta) 
 HK_DEV BsdfEval eval_none() { BsdfEval e; e.f = sp(0.0f); e.pdf = 0.0f; return e; }
 HK_DEV BsdfEval eval_make(Spec f, float pdf) { BsdfEval e; e.f = f; e.pdf = pdf; return e; }
 
-struct MatCtx { DevTables T; const float* __restrict__ spec_lambdas; const float* __restrict__ spec_values; const uint32_t* __restrict__ spec_offsets; };
+// local: the material being shaded is a per-hit copy whose textured parameters were resolved at the hit (resolve_material_textures):
+// the per-material uplift cache does not apply to it
+struct MatCtx { DevTables T; const float* __restrict__ spec_lambdas; const float* __restrict__ spec_values; const uint32_t* __restrict__ spec_offsets; bool local; };
 
 HK_DEV float fresnel_dielectric(float ci, float eta) {   // bxdf.jl:67-90
     ci = clampf(ci, -1.0f, 1.0f);
@@ -108,7 +110,7 @@ HK_DEV float4 mat_pre_compute(const DevTables& T, const HkMaterial& m, int which
     return make_pre_bounded(T, c[0], c[1], c[2]);      // (rgb_to_spectrum clamps to [0,1] itself)
 }
 HK_DEV Spec mat_spec(const MatCtx& C, const HkMaterial& m, int which, float4 lam) {
-    const float4 q = C.T.mat_pre ? __ldg(C.T.mat_pre + 2 * (&m - (const HkMaterial*)C.T.mat_base) + which) : mat_pre_compute(C.T, m, which);
+    const float4 q = (C.T.mat_pre && !C.local) ? __ldg(C.T.mat_pre + 2 * (&m - (const HkMaterial*)C.T.mat_base) + which) : mat_pre_compute(C.T, m, which);
     return mat_pre_is_unbounded(m, which) ? pre_unbounded(q, lam) : pre_bounded(q, lam);
 }
 HK_DEV Spec ior_spectrum(const MatCtx& C, const HkMaterial& m, int which, float4 lambda) {   // :206-210

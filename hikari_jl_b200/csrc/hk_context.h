@@ -38,6 +38,7 @@ struct HkContext {
     uint32_t mat_types_present = 0;
     uint32_t n_interfaces = 0, max_iface_in_geom = 0; bool tri_types_valid = false;
     std::vector<int32_t> mat_types;                  // host copy of the material types (hk_update_material)
+    std::vector<uint8_t> mat_textured;               // per material: has textured parameters other than Matte.Kd (DevScene::tex_classes)
     // device buffers
     DevBuf b_sobol, b_cie_x, b_cie_y, b_cie_z, b_d65, b_rgb_scale, b_rgb_coeffs;
     DevBuf b_nodes, b_tris, b_pos, b_nrm, b_idx, b_meta;

@@ -91,6 +91,7 @@ struct DevScene {
     const struct DevInstance* __restrict__ instances; const uint32_t* __restrict__ inst_prim_base; int32_t n_inst;
     int32_t has_alpha;                 // some uploaded texture carries an alpha plane: the trace / shadow stages run their pass-through rounds
     int32_t smem_mask_medium; uint32_t smem_mask_words;      // medium (1-based, 0 = none) whose empty-cell mask the tracking kernels stage in shared memory
+    uint32_t tex_classes;              // bit c: some material of shading class c has textured parameters (its k_shade runs the TEX instantiation)
 };
 struct DevInstance { float o2w[12]; float w2o[12]; uint32_t first_tri, prim_base, iface, n_tris; };
 // A global primitive id resolves to (instance, triangle of the index array); vertices / normals of an instanced triangle are taken
@@ -140,7 +141,7 @@ struct PassArgs { int32_t first_sample, stride, n_batch; uint32_t n_pixels; };
 #define HK_FLAG_ANYNS 0x200u
 #define HK_FLAG_MEDIUM(f) ((f) >> 16)
 
-HK_DEV MatCtx mat_ctx(const DevScene& D) { MatCtx c; c.T = D.T; c.spec_lambdas = D.spec_lambdas; c.spec_values = D.spec_values; c.spec_offsets = D.spec_offsets; return c; }
+HK_DEV MatCtx mat_ctx(const DevScene& D) { MatCtx c; c.T = D.T; c.spec_lambdas = D.spec_lambdas; c.spec_values = D.spec_values; c.spec_offsets = D.spec_offsets; c.local = false; return c; }
 HK_DEV LightCtx light_ctx(const DevScene& D) {
     LightCtx c; c.T = D.T; c.lights = D.lights; c.n_lights = D.n_lights; c.envmaps = D.envmaps; c.nodes = D.lnodes; c.bit_trails = D.bit_trails;
     c.inf_idx = D.inf_idx; c.n_infinite = D.n_infinite; c.n_bvh = D.n_bvh; c.esc_idx = D.esc_idx; c.n_esc = D.n_esc; return c;
@@ -262,6 +263,21 @@ HK_DEV bool alpha_skips(const DevScene& D, uint32_t prim0, float b1, float b2, f
     Pcg32 rng = pcg32_init(hash_f3(o), hash_f3(d));
     return pcg32_f32(rng) > alpha;
 }
+// _sample_texture_bilinear (texture-ref.jl:160-190) on an (h, w) column-major RGB image: v flipped, clamped indices, no wrap, no clamp of the value
+HK_DEV void tex_bilinear(const HkTexture& t, float2 uv, float* rgb) {
+    const float px = uv.x * (float)(t.w - 1) + 1.0f, py = (1.0f - uv.y) * (float)(t.h - 1) + 1.0f;
+    const float flx = floorf(px), fly = floorf(py);
+    const int x0 = clampi(floor_i(px), 1, t.w), x1 = clampi(floor_i(px) + 1, 1, t.w), y0 = clampi(floor_i(py), 1, t.h), y1 = clampi(floor_i(py) + 1, 1, t.h);
+    const float fx = px - flx, fy = py - fly;
+    const float* T = t.rgb;
+    const size_t o00 = 3 * ((size_t)(x0 - 1) * t.h + (y0 - 1)), o10 = 3 * ((size_t)(x1 - 1) * t.h + (y0 - 1));
+    const size_t o01 = 3 * ((size_t)(x0 - 1) * t.h + (y1 - 1)), o11 = 3 * ((size_t)(x1 - 1) * t.h + (y1 - 1));
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float c0 = __ldg(T + o00 + k) * (1.0f - fx) + __ldg(T + o10 + k) * fx, c1 = __ldg(T + o01 + k) * (1.0f - fx) + __ldg(T + o11 + k) * fx;
+        rgb[k] = c0 * (1.0f - fy) + c1 * fy;
+    }
+}
 HK_DEV Spec textured_kd(const DevScene& D, const HkMaterial& m, uint32_t prim0, float b1, float b2, float4 lam) {
     const PrimRef pr = resolve_prim(D, prim0);
     const HkTexture t = D.textures[m.tex[0] - 1];
@@ -276,22 +292,34 @@ HK_DEV Spec textured_kd(const DevScene& D, const HkMaterial& m, uint32_t prim0, 
         for (int k = 0; k < 3; k++) rgb[k] = clampf(__ldg(T + k) * w0 + __ldg(T + 3 + k) * b1 + __ldg(T + 6 + k) * b2, 0.0f, 1.0f);
         return pre_bounded(make_pre_bounded(D.T, rgb[0], rgb[1], rgb[2]), lam);
     }
+    float rgb[3];
+    tex_bilinear(t, hit_uv(D, pr.tri, b1, b2), rgb);
+    return pre_bounded(make_pre_bounded(D.T, clampf(rgb[0], 0.0f, 1.0f), clampf(rgb[1], 0.0f, 1.0f), clampf(rgb[2], 0.0f, 1.0f)), lam);
+}
+// Textured parameters of any material (eval_tex(textures, mat.<param>, tfc) at every parameter read of spectral-eval.jl): a per-hit
+// copy of the material whose textured RGB / scalar parameters hold the texel values at the hit; everything downstream -- clamps,
+// `albedo == 0` tests, uplifts -- then treats them exactly like the constants they replace.  Out of line: constant-parameter
+// materials never get here.
+static __device__ __noinline__ void resolve_material_textures(const DevScene& D, const HkMaterial& g, uint32_t prim0, float b1, float b2, HkMaterial& out) {
+    out = g;
+    const PrimRef pr = resolve_prim(D, prim0);
     const float2 uv = hit_uv(D, pr.tri, b1, b2);
-    const float u = uv.x, v = uv.y;
-    const float px = u * (float)(t.w - 1) + 1.0f, py = (1.0f - v) * (float)(t.h - 1) + 1.0f;
-    const float flx = floorf(px), fly = floorf(py);
-    const int x0 = clampi(floor_i(px), 1, t.w), x1 = clampi(floor_i(px) + 1, 1, t.w), y0 = clampi(floor_i(py), 1, t.h), y1 = clampi(floor_i(py) + 1, 1, t.h);
-    const float fx = px - flx, fy = py - fly;
-    const float* T = t.rgb;
-    const size_t o00 = 3 * ((size_t)(x0 - 1) * t.h + (y0 - 1)), o10 = 3 * ((size_t)(x1 - 1) * t.h + (y0 - 1));
-    const size_t o01 = 3 * ((size_t)(x0 - 1) * t.h + (y1 - 1)), o11 = 3 * ((size_t)(x1 - 1) * t.h + (y1 - 1));
     float rgb[3];
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        const float c0 = __ldg(T + o00 + k) * (1.0f - fx) + __ldg(T + o10 + k) * fx, c1 = __ldg(T + o01 + k) * (1.0f - fx) + __ldg(T + o11 + k) * fx;
-        rgb[k] = clampf(c0 * (1.0f - fy) + c1 * fy, 0.0f, 1.0f);
+        if (g.tex[k] <= 0 || (k == 0 && g.type == HK_MAT_MATTE)) continue;      // (Matte.Kd: textured_kd, its own shading class)
+        tex_bilinear(D.textures[g.tex[k] - 1], uv, rgb);
+        float* dst = k == 0 ? out.rgb0 : (k == 1 ? out.rgb1 : out.rgb2);
+        dst[0] = rgb[0]; dst[1] = rgb[1]; dst[2] = rgb[2];
     }
-    return pre_bounded(make_pre_bounded(D.T, rgb[0], rgb[1], rgb[2]), lam);
+    for (int k = 0; k < 8; k++) {
+        if (g.ftex[k] <= 0) continue;
+        tex_bilinear(D.textures[g.ftex[k] - 1], uv, rgb);
+        out.f[k] = rgb[0];
+    }
+}
+HK_DEV bool material_has_textures(const HkMaterial& m) {
+    return ((m.tex[0] > 0 && m.type != HK_MAT_MATTE) | (m.tex[1] > 0) | (m.tex[2] > 0) | ((m.ftex[0] | m.ftex[1] | m.ftex[2] | m.ftex[3] | m.ftex[4] | m.ftex[5] | m.ftex[6] | m.ftex[7]) > 0)) != 0;
 }
 HK_DEV float3 geometric_normal(const DevScene& D, uint32_t prim0) {
     float3 v0, v1, v2;
@@ -718,7 +746,9 @@ __global__ void __launch_bounds__(128, 4) k_hit_lights(const __grid_constant__ D
 #define HK_SHADE_LAYERED_EXTRA_BLOCKS 2
 #endif
 #define HK_SHADE_IS_LAYERED(T) ((T) == HK_MAT_COATED_DIFFUSE || (T) == HK_MAT_COATED_DIFFUSE_TRANSMISSION)
-template <int TYPE, bool SPLIT, int PART>
+// TEX: some material of this class has textured parameters (HkMaterial.tex / ftex): this instantiation resolves them per hit into a
+// local copy of the material; classes without textured materials run the lean instantiation, which has no such code
+template <int TYPE, bool SPLIT, int PART, bool TEX>
 __global__ void __launch_bounds__(128, HK_SHADE_IS_LAYERED(TYPE) ? HK_SHADE_MIN_BLOCKS + HK_SHADE_LAYERED_EXTRA_BLOCKS : HK_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DevScene D, PathState S, PassArgs A, int next, int par) {
     const uint32_t n = S.counts[HK_HIT_COUNTER(HK_TYPE_QUEUE(TYPE))];
     MatCtx MC = mat_ctx(D);
@@ -735,7 +765,10 @@ __global__ void __launch_bounds__(128, HK_SHADE_IS_LAYERED(TYPE) ? HK_SHADE_MIN_
             const float3 o = f3(ra.x, ra.y, ra.z), d = f3(ra.w, rb.x, rb.y);
             const Surf sf = surface_at(D, prim0, hr.z, hr.w, o, d, hr.x);
             const HkMediumInterface mi = D.interfaces[sf.iface - 1];
-            const HkMaterial& mat = D.materials[(D.materials[mi.material - 1].type == HK_MAT_MIX ? S.res_mat[slot] : mi.material) - 1];
+            const HkMaterial& gmat = D.materials[(D.materials[mi.material - 1].type == HK_MAT_MIX ? S.res_mat[slot] : mi.material) - 1];
+            HkMaterial lmat;                                   // TEX: per-hit copy with the textured parameters resolved (only when there are any)
+            if (TEX) { MC.local = material_has_textures(gmat); if (MC.local) resolve_material_textures(D, gmat, prim0, hr.z, hr.w, lmat); }
+            const HkMaterial& mat = (TEX && MC.local) ? lmat : gmat;
             const float4 lam = S.lambda[slot];
             Spec kd_tex = sp(0.0f);
             if (TYPE == HK_SHADE_MATTE_TEX) kd_tex = textured_kd(D, mat, prim0, hr.z, hr.w, lam);
@@ -843,13 +876,17 @@ __global__ void __launch_bounds__(128, HK_SHADE_IS_LAYERED(TYPE) ? HK_SHADE_MIN_
     }
 }
 // one shading class = one launch, or two for the LayeredBxDF materials
-template <int TYPE> static void launch_shade_class(int grid, cudaStream_t st, const DevScene& D, const PathState& S, const PassArgs& A, int next, int par) {
+template <int TYPE, bool TEX> static void launch_shade_class_t(int grid, cudaStream_t st, const DevScene& D, const PathState& S, const PassArgs& A, int next, int par) {
     if constexpr (HK_SHADE_TWO_PARTS && HK_SHADE_IS_LAYERED(TYPE)) {
-        if (D.split_lights) { k_shade<TYPE, true, 1><<<grid, 128, 0, st>>>(D, S, A, next, par); k_shade<TYPE, true, 2><<<grid, 128, 0, st>>>(D, S, A, next, par); }
-        else { k_shade<TYPE, false, 1><<<grid, 128, 0, st>>>(D, S, A, next, par); k_shade<TYPE, false, 2><<<grid, 128, 0, st>>>(D, S, A, next, par); }
+        if (D.split_lights) { k_shade<TYPE, true, 1, TEX><<<grid, 128, 0, st>>>(D, S, A, next, par); k_shade<TYPE, true, 2, TEX><<<grid, 128, 0, st>>>(D, S, A, next, par); }
+        else { k_shade<TYPE, false, 1, TEX><<<grid, 128, 0, st>>>(D, S, A, next, par); k_shade<TYPE, false, 2, TEX><<<grid, 128, 0, st>>>(D, S, A, next, par); }
     } else {
-        if (D.split_lights) k_shade<TYPE, true, 0><<<grid, 128, 0, st>>>(D, S, A, next, par); else k_shade<TYPE, false, 0><<<grid, 128, 0, st>>>(D, S, A, next, par);
+        if (D.split_lights) k_shade<TYPE, true, 0, TEX><<<grid, 128, 0, st>>>(D, S, A, next, par); else k_shade<TYPE, false, 0, TEX><<<grid, 128, 0, st>>>(D, S, A, next, par);
     }
+}
+template <int TYPE> static void launch_shade_class(int grid, cudaStream_t st, const DevScene& D, const PathState& S, const PassArgs& A, int next, int par) {
+    if ((D.tex_classes >> TYPE) & 1u) launch_shade_class_t<TYPE, true>(grid, st, D, S, A, next, par);
+    else launch_shade_class_t<TYPE, false>(grid, st, D, S, A, next, par);
 }
 
 #endif  // HK_TU_SHADE

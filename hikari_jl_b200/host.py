@@ -429,7 +429,9 @@ class Texture:
 
     def __init__(self, data_hw3):
         d = np.asarray(data_hw3, dtype=f32)
-        assert d.ndim == 3 and d.shape[2] in (3, 4), "RGB(A) texture: [h, w, 3] or [h, w, 4]"
+        if d.ndim == 2:                                                  # Texture{Float32}: uploaded as r = g = b (HkMaterial.ftex reads the first channel)
+            d = np.repeat(d[..., None], 3, axis=2)
+        assert d.ndim == 3 and d.shape[2] in (3, 4), "RGB(A) texture: [h, w, 3] or [h, w, 4]; scalar texture: [h, w]"
         self.alpha = None        # the reference's RGBSpectrum texels carry alpha as their 4th float (spectrum.jl:62-70)
         if d.shape[2] == 4:
             if not (d[..., 3] == 1).all():
@@ -450,11 +452,36 @@ class VertexColorTexture(Texture):
         self.data = np.ascontiguousarray(d)                          # [face][corner][3] = column-major (3, n_faces)
 
 
+def _param_rgb(v):
+    """an RGB material parameter: a constant or a Texture (the reference's fields are `Texture, Raycore.TextureRef, or raw RGBSpectrum`)"""
+    return v if isinstance(v, Texture) else _rgb(v)
+
+
+def _put_rgb(m, scene, slot, v):
+    """HkMaterial.rgb<slot> = the constant, or HkMaterial.tex[slot] = the texture's id (eval_tex at the hit, texture-ref.jl:72-80)"""
+    if isinstance(v, Texture):
+        assert not isinstance(v, VertexColorTexture), "VertexColorTexture is supported for MatteMaterial.Kd only"
+        m.tex[slot] = scene._texture_id(v)
+    else:
+        (m.rgb0, m.rgb1, m.rgb2)[slot][0:3] = _rgb(v)
+
+
+def _param_f(v):
+    return v if isinstance(v, Texture) else float(v)
+
+
+def _put_f(m, scene, k, v):
+    if isinstance(v, Texture):
+        m.ftex[k] = scene._texture_id(v)
+    else:
+        m.f[k] = float(v)
+
+
 class MatteMaterial(Material):            # uber-material.jl:180-183, 256
     type = A.HK_MAT_MATTE
 
     def __init__(self, Kd=0.5, sigma=0.0):
-        self.Kd, self.sigma = (Kd if isinstance(Kd, Texture) else _rgb(Kd)), float(sigma)
+        self.Kd, self.sigma = (Kd if isinstance(Kd, Texture) else _rgb(Kd)), _param_f(sigma)
 
     def to_abi(self, scene):
         m = A.HkMaterial(type=self.type)
@@ -464,7 +491,7 @@ class MatteMaterial(Material):            # uber-material.jl:180-183, 256
                 m.flags |= A.HK_MATFLAG_VERTEX_COLORS
         else:
             m.rgb0[:] = self.Kd
-        m.f[0] = self.sigma
+        _put_f(m, scene, 0, self.sigma)
         return m
 
 
@@ -472,11 +499,11 @@ class MirrorMaterial(Material):           # :193-195, 275
     type = A.HK_MAT_MIRROR
 
     def __init__(self, Kr=0.9):
-        self.Kr = _rgb(Kr)
+        self.Kr = _param_rgb(Kr)
 
     def to_abi(self, scene):
         m = A.HkMaterial(type=self.type)
-        m.rgb0[:] = self.Kr
+        _put_rgb(m, scene, 0, self.Kr)
         return m
 
 
@@ -484,13 +511,13 @@ class GlassMaterial(Material):            # :209-216, 299
     type = A.HK_MAT_GLASS
 
     def __init__(self, Kr=1.0, Kt=1.0, index=1.5, u_roughness=0.0, v_roughness=0.0, remap_roughness=True):
-        self.Kr, self.Kt, self.index = _rgb(Kr), _rgb(Kt), float(index)
+        self.Kr, self.Kt, self.index = _param_rgb(Kr), _param_rgb(Kt), _param_f(index)
 
     def to_abi(self, scene):
         m = A.HkMaterial(type=self.type)
-        m.rgb0[:] = self.Kr
-        m.rgb1[:] = self.Kt
-        m.f[0] = self.index
+        _put_rgb(m, scene, 0, self.Kr)
+        _put_rgb(m, scene, 1, self.Kt)
+        _put_f(m, scene, 0, self.index)
         return m
 
 
@@ -506,12 +533,12 @@ class ConductorMaterial(Material):        # :378-384, 418-426
     def __init__(self, eta=(0.2, 0.2, 0.2), k=(3.9, 3.9, 3.9), roughness=0.1, reflectance=(1, 1, 1),
                  remap_roughness=True):
         self.eta, self.k = eta, k
-        self.roughness, self.reflectance, self.remap = float(roughness), _rgb(reflectance), bool(remap_roughness)
+        self.roughness, self.reflectance, self.remap = _param_f(roughness), _rgb(reflectance), bool(remap_roughness)
 
     def to_abi(self, scene):
         m = A.HkMaterial(type=self.type)
         m.flags = A.HK_MATFLAG_REMAP_ROUGHNESS if self.remap else 0
-        m.f[0] = self.roughness
+        _put_f(m, scene, 0, self.roughness)
         spectral = isinstance(self.eta, PiecewiseLinearSpectrum)
         assert spectral == isinstance(self.k, PiecewiseLinearSpectrum), "eta and k must both be spectra or both RGB"
         if spectral:
@@ -519,8 +546,8 @@ class ConductorMaterial(Material):        # :378-384, 418-426
             m.spec[0] = scene._spectrum_id(self.eta)
             m.spec[1] = scene._spectrum_id(self.k)
         else:
-            m.rgb0[:] = _rgb(self.eta)
-            m.rgb1[:] = _rgb(self.k)
+            _put_rgb(m, scene, 0, self.eta)
+            _put_rgb(m, scene, 1, self.k)
         return m
 
 
@@ -552,17 +579,18 @@ class CoatedDiffuseMaterial(Material):    # coated-diffuse.jl:98-127
 
     def __init__(self, reflectance=0.5, roughness=0.0, thickness=0.01, eta=1.5, albedo=0.0, g=0.0, max_depth=10,
                  n_samples=1, remap_roughness=True):
-        self.reflectance, self.albedo = _rgb(reflectance), _rgb(albedo)
+        self.reflectance, self.albedo = _param_rgb(reflectance), _param_rgb(albedo)
         self.u_rough, self.v_rough = (roughness if isinstance(roughness, tuple) else (roughness, roughness))
-        self.thickness, self.eta, self.g = float(thickness), float(eta), float(g)
+        self.thickness, self.eta, self.g = _param_f(thickness), float(eta), _param_f(g)
         self.max_depth, self.n_samples, self.remap = int(max_depth), int(n_samples), bool(remap_roughness)
 
     def to_abi(self, scene):
         m = A.HkMaterial(type=self.type)
         m.flags = A.HK_MATFLAG_REMAP_ROUGHNESS if self.remap else 0
-        m.rgb0[:] = self.reflectance
-        m.rgb1[:] = self.albedo
-        m.f[0], m.f[1], m.f[2], m.f[3], m.f[4] = float(self.u_rough), float(self.v_rough), self.thickness, self.eta, self.g
+        _put_rgb(m, scene, 0, self.reflectance)
+        _put_rgb(m, scene, 1, self.albedo)
+        for k, v in enumerate((self.u_rough, self.v_rough, self.thickness, self.eta, self.g)):
+            _put_f(m, scene, k, v)
         m.ival[0], m.ival[1] = self.max_depth, self.n_samples
         return m
 
@@ -574,11 +602,11 @@ class CoatedDiffuseTransmissionMaterial(CoatedDiffuseMaterial):   # coated-diffu
     def __init__(self, reflectance=0.5, transmittance=0.25, roughness=0.0, thickness=0.01, eta=1.5, albedo=0.0, g=0.0,
                  max_depth=10, n_samples=1, remap_roughness=True):
         super().__init__(reflectance, roughness, thickness, eta, albedo, g, max_depth, n_samples, remap_roughness)
-        self.transmittance = _rgb(transmittance)
+        self.transmittance = _param_rgb(transmittance)
 
     def to_abi(self, scene):
         m = super().to_abi(scene)
-        m.rgb2[0:3] = self.transmittance
+        _put_rgb(m, scene, 2, self.transmittance)
         return m
 
 
@@ -595,13 +623,13 @@ class CoatedConductorMaterial(Material):  # coated-conductor.jl:48-105 (struct),
                  remap_roughness=True):
         if conductor_eta is not None and conductor_k is None:
             raise ValueError("conductor_k must be provided when using conductor_eta")     # coated-conductor.jl:203-205
-        pair = lambda r: tuple(float(v) for v in r) if isinstance(r, tuple) else (float(r), float(r))
+        pair = lambda r: tuple(_param_f(v) for v in r) if isinstance(r, tuple) else (_param_f(r), _param_f(r))
         self.i_rough, self.c_rough = pair(interface_roughness), pair(conductor_roughness)
-        self.interface_eta, self.thickness, self.g = float(interface_eta), float(thickness), float(g)
+        self.interface_eta, self.thickness, self.g = float(interface_eta), _param_f(thickness), _param_f(g)
         self.use_eta_k = conductor_eta is not None
         self.conductor_eta, self.conductor_k = conductor_eta, conductor_k
-        self.reflectance = _rgb(1.0 if reflectance is None else reflectance)
-        self.albedo = _rgb(albedo)
+        self.reflectance = _param_rgb(1.0 if reflectance is None else reflectance)
+        self.albedo = _param_rgb(albedo)
         self.max_depth, self.n_samples, self.remap = int(max_depth), int(n_samples), bool(remap_roughness)
 
     def to_abi(self, scene):
@@ -615,13 +643,13 @@ class CoatedConductorMaterial(Material):  # coated-conductor.jl:48-105 (struct),
                 m.flags |= A.HK_MATFLAG_SPECTRAL_ETA_K
                 m.spec[0], m.spec[1] = scene._spectrum_id(self.conductor_eta), scene._spectrum_id(self.conductor_k)
             else:
-                m.rgb0[:] = _rgb(self.conductor_eta)
-                m.rgb1[:] = _rgb(self.conductor_k)
+                _put_rgb(m, scene, 0, self.conductor_eta)
+                _put_rgb(m, scene, 1, self.conductor_k)
         else:
-            m.rgb0[:] = self.reflectance
-        m.rgb2[0:3] = self.albedo
-        m.f[0], m.f[1], m.f[2], m.f[3], m.f[4] = self.i_rough[0], self.i_rough[1], self.thickness, self.interface_eta, self.g
-        m.f[5], m.f[6] = self.c_rough
+            _put_rgb(m, scene, 0, self.reflectance)
+        _put_rgb(m, scene, 2, self.albedo)
+        for k, v in enumerate((self.i_rough[0], self.i_rough[1], self.thickness, self.interface_eta, self.g, self.c_rough[0], self.c_rough[1])):
+            _put_f(m, scene, k, v)
         m.ival[0], m.ival[1] = self.max_depth, self.n_samples
         return m
 
@@ -645,12 +673,12 @@ class DiffuseTransmissionMaterial(Material):   # diffuse-transmission.jl:39-85
     type = A.HK_MAT_DIFFUSE_TRANSMISSION
 
     def __init__(self, reflectance=0.25, transmittance=0.25, scale=1.0):
-        self.reflectance, self.transmittance, self.scale = _rgb(reflectance), _rgb(transmittance), float(scale)
+        self.reflectance, self.transmittance, self.scale = _param_rgb(reflectance), _param_rgb(transmittance), float(scale)
 
     def to_abi(self, scene):
         m = A.HkMaterial(type=self.type)
-        m.rgb0[:] = self.reflectance
-        m.rgb1[:] = self.transmittance
+        _put_rgb(m, scene, 0, self.reflectance)
+        _put_rgb(m, scene, 1, self.transmittance)
         m.f[0] = self.scale
         return m
 

@@ -130,6 +130,42 @@ def vertex_color_meshes(tess=10):
     return s, _cam((0, 1.6, -4.5), (0, 0.2, 0), 40.0)
 
 
+def textured_parameters(tess=16, seed=6):
+    """Textures on every kind of material parameter (eval_tex(textures, mat.<param>, tfc) at each read in spectral-eval.jl):
+    RGB parameters (Mirror.Kr, Glass.Kr / Kt, Conductor eta / k, Coated* reflectance / albedo / transmittance, DiffuseTransmission
+    reflectance / transmittance) and scalar ones (Matte sigma, Glass index, Conductor roughness, coating roughness / thickness / g),
+    each on its own sphere or panel, plus constant-parameter neighbours on the cached-uplift path."""
+    rng = np.random.RandomState(seed)
+    def rgb_tex(h, w, lo, hi):
+        return H.Texture(rng.uniform(lo, hi, size=(h, w, 3)).astype(np.float32))
+    def f_tex(h, w, lo, hi):
+        return H.Texture(rng.uniform(lo, hi, size=(h, w)).astype(np.float32))
+    s = H.Scene()
+    floor = H.Mesh([(-6, -0.9, -6), (6, -0.9, -6), (6, -0.9, 6), (-6, -0.9, 6)], [(0, 2, 1), (0, 3, 2)], normals=[(0, 1, 0)] * 4, uvs=[(0, 0), (1, 0), (1, 1), (0, 1)])
+    s.push(floor, H.MatteMaterial(Kd=(0.6, 0.6, 0.6), sigma=f_tex(6, 6, 0.0, 40.0)))
+    mats = [
+        H.MirrorMaterial(Kr=rgb_tex(8, 8, 0.2, 1.0)),
+        H.GlassMaterial(Kr=rgb_tex(4, 6, 0.5, 1.0), Kt=rgb_tex(6, 4, 0.4, 1.0), index=f_tex(5, 5, 1.3, 1.7)),
+        H.ConductorMaterial(eta=rgb_tex(4, 4, 0.1, 1.5), k=rgb_tex(4, 4, 1.5, 4.0), roughness=f_tex(8, 8, 0.0, 0.4)),
+        H.CoatedDiffuseMaterial(reflectance=rgb_tex(8, 8, 0.1, 0.9), roughness=(f_tex(4, 4, 0.0, 0.3), 0.1), thickness=f_tex(4, 4, 0.005, 0.05),
+                                albedo=rgb_tex(4, 4, 0.0, 0.8), g=f_tex(4, 4, -0.5, 0.5), max_depth=8, n_samples=1),
+        H.DiffuseTransmissionMaterial(reflectance=rgb_tex(6, 6, 0.0, 0.6), transmittance=rgb_tex(6, 6, 0.0, 0.6), scale=1.2),
+        H.CoatedConductorMaterial(interface_roughness=f_tex(4, 4, 0.0, 0.2), reflectance=rgb_tex(8, 8, 0.3, 1.0), conductor_roughness=(0.05, f_tex(4, 4, 0.01, 0.2)),
+                                  thickness=0.02, albedo=rgb_tex(4, 4, 0.0, 0.5), g=0.1),
+        H.CoatedDiffuseTransmissionMaterial(reflectance=rgb_tex(4, 4, 0.1, 0.7), transmittance=rgb_tex(4, 4, 0.1, 0.7), roughness=0.1, albedo=0.0),
+        H.ConductorMaterial(eta=(0.2, 0.9, 1.1), k=(3.9, 2.4, 2.2), roughness=0.05),          # constant parameters: the cached path next to the textured one
+    ]
+    for i, m in enumerate(mats):
+        x, z = -3.0 + 2.0 * (i % 4), (-1.0 if i < 4 else 1.4)
+        s.push(H.uv_sphere((x, 0.0, z), 0.8, tess, tess), m)
+    d = np.array([-0.5, -1.0, 0.6])
+    s.push(H.DirectionalLight((3, 3, 3), d / np.linalg.norm(d), legacy_rgbspectrum=True))
+    s.push(H.PointLight((30, 30, 30), (0.0, 3.5, -3.0), legacy_rgbspectrum=True, scale=1.0))
+    s.push(H.AmbientLight((0.3, 0.35, 0.4)))
+    s.sync()
+    return s, _cam((0, 3.0, -7.0), (0, -0.2, 0), 40.0)
+
+
 def rgb_nebula(res=(20, 16, 12)):
     """An RGBGridMedium (media.jl:1002-1456) inside an index-1 boundary: two coloured, partly emissive blobs over a matte floor."""
     nx, ny, nz = res

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define HK_ABI_VERSION 2
+#define HK_ABI_VERSION 3
 
 /* ---- status codes ------------------------------------------------------------------------ */
 #define HK_OK                 0
@@ -122,8 +122,9 @@ typedef struct HkTexture {
 
 /* ---- materials ----------------------------------------------------------------------------
  * replaces: scene.materials (MultiTypeSet) + scene.media_interfaces (src/scene.jl:21-28,
- * src/materials/medium-interface.jl:78-82).  Parameters are constants, except MatteMaterial.Kd which may be an image
- * texture (with or without alpha) or a VertexColorTexture (tex[0]).                                           */
+ * src/materials/medium-interface.jl:78-82).  Every RGB and scalar parameter is a constant or a texture (tex[] / ftex[]);
+ * MatteMaterial.Kd may also carry alpha or be a VertexColorTexture.  Not texturable: MixMaterial.amount, the integer
+ * parameters, piecewise-linear eta / k spectra.                                                                  */
 #define HK_MAT_MATTE                1   /* src/materials/spectral-eval.jl:42-101, 371-397      */
 #define HK_MAT_MIRROR               2   /* :108-132                                            */
 #define HK_MAT_GLASS                3   /* :140-198, 407-413                                   */
@@ -164,8 +165,12 @@ typedef struct HkMaterial {
                         /* Mix: f0 = amount (constant texture); ival0 / ival1 = 1-based material1 / material2;
                            the SetKeys hashed by mix_hash_float (mix-material.jl:114-158): spec0 / spec1 = vec_idx of
                            material1 / material2, flags = type_idx1 | type_idx2 << 8                             */
-    int32_t  tex[4];    /* 1-based ids into the uploaded textures replacing rgb0 / rgb1 / rgb2 (0 = the constant); this round:
-                           tex[0] of a MatteMaterial (Kd); anything else is rejected at upload                        */
+    int32_t  tex[4];    /* 1-based ids into the uploaded textures replacing rgb0 / rgb1 / rgb2 (0 = the constant; tex[3] unused):
+                           eval_tex(textures, mat.<param>, tfc) of the reference (spectral-eval.jl, texture-ref.jl:72-80) =
+                           the bilinear texel at the hit's uv, substituted for the constant before anything else is done
+                           with it.  HK_MATFLAG_VERTEX_COLORS: tex[0] of a MatteMaterial is a VertexColorTexture          */
+    int32_t  ftex[8];   /* the same for the scalar parameters f[0..7] (sigma, roughness, thickness, g, index, ...): the first
+                           channel of the texture (a Texture{Float32} is uploaded as r = g = b)                            */
 } HkMaterial;
 
 typedef struct HkMediumInterface {   /* MediumInterfaceIdx, src/materials/medium-interface.jl:78-82 */

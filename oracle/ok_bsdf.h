@@ -300,7 +300,27 @@ namespace ok {
 // ---------------------------------------------------------------------------------------------
 // Dispatch  src/integrators/physical-wavefront/material-dispatch.jl:23-53
 // ---------------------------------------------------------------------------------------------
-inline BSDFSample sample_material(const MatCtx& C, const HkMaterial& m, V3 wo, V3 ns, const Wavelengths& l, V2 u, float rng, bool regularize) {
+// eval_tex(textures, mat.<param>, tfc) at every parameter read of spectral-eval.jl: a per-hit copy of the material with its textured
+// RGB / scalar parameters replaced by the bilinear texel at the hit's uv (HkMaterial.tex / ftex); Matte.Kd keeps its own path above
+inline HkMaterial resolve_material_textures(const MatCtx& C, const HkMaterial& g) {
+    HkMaterial out = g;
+    if (!C.textures) return out;
+    float rgb[3];
+    for (int k = 0; k < 3; k++) {
+        if (g.tex[k] <= 0 || (k == 0 && g.type == HK_MAT_MATTE)) continue;
+        sample_texture_bilinear(*C.textures, g.tex[k], C.uv, rgb);
+        float* dst = k == 0 ? out.rgb0 : (k == 1 ? out.rgb1 : out.rgb2);
+        dst[0] = rgb[0]; dst[1] = rgb[1]; dst[2] = rgb[2];
+    }
+    for (int k = 0; k < 8; k++) {
+        if (g.ftex[k] <= 0) continue;
+        sample_texture_bilinear(*C.textures, g.ftex[k], C.uv, rgb);
+        out.f[k] = rgb[0];
+    }
+    return out;
+}
+inline BSDFSample sample_material(const MatCtx& C, const HkMaterial& m_in, V3 wo, V3 ns, const Wavelengths& l, V2 u, float rng, bool regularize) {
+    const HkMaterial m = resolve_material_textures(C, m_in);
     switch (m.type) {
         case HK_MAT_MATTE: return sample_matte(C, m, wo, ns, l, u, rng, regularize);
         case HK_MAT_MIRROR: return sample_mirror(C, m, wo, ns, l, u, rng, regularize);
@@ -314,7 +334,8 @@ inline BSDFSample sample_material(const MatCtx& C, const HkMaterial& m, V3 wo, V
     }
     return BSDFSample();
 }
-inline BSDFEval eval_material(const MatCtx& C, const HkMaterial& m, V3 wo, V3 wi, V3 ns, const Wavelengths& l) {
+inline BSDFEval eval_material(const MatCtx& C, const HkMaterial& m_in, V3 wo, V3 wi, V3 ns, const Wavelengths& l) {
+    const HkMaterial m = resolve_material_textures(C, m_in);
     switch (m.type) {
         case HK_MAT_MATTE: return eval_matte(C, m, wo, wi, ns, l);
         case HK_MAT_CONDUCTOR: return eval_conductor(C, m, wo, wi, ns, l);

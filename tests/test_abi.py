@@ -29,12 +29,12 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert not missing, f"declared in include/*.h but not exported: {missing}"
     for s in A.HK_SYMBOLS:
         assert s in syms, f"{s} listed in _abi.HK_SYMBOLS but not declared in the header"
-    assert lib.hk_abi_version() == 2
+    assert lib.hk_abi_version() == 3
 
 
 def test_struct_sizes_match_header_layout():
     # sizes computed from the header by hand; a drift between ctypes and C would corrupt every upload
-    assert C.sizeof(A.HkMaterial) == 4 + 4 + 12 + 12 + 16 + 32 + 16 + 8 + 8
+    assert C.sizeof(A.HkMaterial) == 4 + 4 + 12 + 12 + 16 + 32 + 8 + 8 + 16 + 32
     assert C.sizeof(A.HkLightBVHNode) == 64
     assert C.sizeof(A.HkMediumInterface) == 12
     assert C.sizeof(A.HkRenderParams) == 44
@@ -82,7 +82,7 @@ def test_c_client_compiles_links_and_fails_loudly_without_a_device(tmp_path):
     A.load_library()
     exe = _build_c_client(tmp_path)
     r = subprocess.run([exe], capture_output=True, text=True)
-    assert r.returncode == 0 and r.stdout.startswith("no-device abi=2"), (r.returncode, r.stdout, r.stderr)
+    assert r.returncode == 0 and r.stdout.startswith("no-device abi=3"), (r.returncode, r.stdout, r.stderr)
 
 
 @pytest.mark.gpu

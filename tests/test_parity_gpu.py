@@ -450,6 +450,7 @@ IMAGE_CASES = [
     ("alpha_foliage", lambda: scenes.alpha_foliage(), (96, 72), 8, 5),
     ("alpha_foliage_in_fog", lambda: scenes.alpha_foliage(fog=True), (96, 72), 8, 5),
     ("vertex_colors", lambda: scenes.vertex_color_meshes(), (96, 64), 4, 4),
+    ("textured_parameters", lambda: scenes.textured_parameters(), (128, 72), 8, 6),
 ]
 
 
@@ -891,8 +892,12 @@ def test_error_paths_return_status_codes_not_crashes():
     assert lib.hk_upload_materials(ctx, C.byref(bad), 1, C.byref(iface), 1) < 0 and b"unsupported material" in lib.hk_last_error(ctx)
     texm = A.HkMaterial(type=A.HK_MAT_MATTE); texm.tex[0] = 3
     assert lib.hk_upload_materials(ctx, C.byref(texm), 1, C.byref(iface), 1) < 0 and b"hk_upload_textures" in lib.hk_last_error(ctx)
-    texg = A.HkMaterial(type=A.HK_MAT_GLASS); texg.tex[1] = 1
-    assert lib.hk_upload_materials(ctx, C.byref(texg), 1, C.byref(iface), 1) < 0 and b"MatteMaterial.Kd only" in lib.hk_last_error(ctx)
+    texg = A.HkMaterial(type=A.HK_MAT_GLASS); texg.ftex[0] = 1                 # a textured index, but no texture was uploaded
+    assert lib.hk_upload_materials(ctx, C.byref(texg), 1, C.byref(iface), 1) < 0 and b"hk_upload_textures" in lib.hk_last_error(ctx)
+    vc = A.HkMaterial(type=A.HK_MAT_GLASS); vc.flags = A.HK_MATFLAG_VERTEX_COLORS
+    assert lib.hk_upload_materials(ctx, C.byref(vc), 1, C.byref(iface), 1) < 0 and b"MatteMaterial.Kd only" in lib.hk_last_error(ctx)
+    tmix = A.HkMaterial(type=A.HK_MAT_MIX); tmix.ival[0] = 1; tmix.ival[1] = 1; tmix.ftex[0] = 1
+    assert lib.hk_upload_materials(ctx, C.byref(tmix), 1, C.byref(iface), 1) < 0
     mix = A.HkMaterial(type=A.HK_MAT_MIX); mix.ival[0] = 1; mix.ival[1] = 7
     assert lib.hk_upload_materials(ctx, C.byref(mix), 1, C.byref(iface), 1) < 0 and b"MixMaterial" in lib.hk_last_error(ctx)
     p = A.HkRenderParams(0, 10, 5, 1, 1, 10.0, 0, 12, 15, 0, 1)
