@@ -30,7 +30,7 @@ end
 struct HkTexture; rgb::Ptr{Float32}; h::Int32; w::Int32; alpha::Ptr{Float32}; end
 struct HkMaterial
     type::Int32; flags::UInt32; rgb0::NTuple{3,Float32}; rgb1::NTuple{3,Float32}; rgb2::NTuple{4,Float32}
-    f::NTuple{8,Float32}; spec::NTuple{2,Int32}; ival::NTuple{2,Int32}; tex::NTuple{4,Int32}
+    f::NTuple{8,Float32}; spec::NTuple{2,Int32}; ival::NTuple{2,Int32}; tex::NTuple{4,Int32}; ftex::NTuple{8,Int32}
 end
 struct HkMediumInterface; material::UInt32; inside::UInt32; outside::UInt32; end
 struct HkSpectra; lambdas::Ptr{Float32}; values::Ptr{Float32}; offsets::Ptr{UInt32}; n_spectra::UInt32; end
@@ -111,6 +111,7 @@ function context(vp::VolPath)
 end
 
 t3(v) = (Float32(v[1]), Float32(v[2]), Float32(v[3]))
+const z3 = (0f0, 0f0, 0f0)
 rgb3(s::Hikari.RGBSpectrum) = (s.c[1], s.c[2], s.c[3])                                  # spectrum.jl:61-70 (c[4] = alpha)
 rowmajor16(m) = ntuple(i -> Float32(m[(i - 1) ÷ 4 + 1, (i - 1) % 4 + 1]), 16)            # Mat4f is column-major; the ABI wants rows
 rowmajor12(m) = ntuple(i -> Float32(m[(i - 1) ÷ 4 + 1, (i - 1) % 4 + 1]), 12)
@@ -192,12 +193,14 @@ flat_id(F::Flat, k) = k.type_idx == 0 ? UInt32(0) : UInt32(F.offsets[k.type_idx]
 struct TexPool; list::Vector{HkTexture}; keep::Vector{Any}; ids::IdDict{Any,Int32}; end
 TexPool() = TexPool(HkTexture[], Any[], IdDict{Any,Int32}())
 # a Texture over a Matrix{RGBSpectrum} (textures/basic.jl:5-10): r, g, b packed to 3 floats and, when some alpha != 1, the alpha
-# plane; both keep the Matrix' (h, w) column-major order.  VertexColorTexture (basic.jl:43-46): its (3, n_faces) matrix as h = 3.
+# plane; a Texture over a Matrix{Float32}: r = g = b (HkMaterial.ftex reads the first channel); both keep the Matrix' (h, w)
+# column-major order.  VertexColorTexture (basic.jl:43-46): its (3, n_faces) matrix as h = 3.
+texel(s::Hikari.RGBSpectrum) = (s.c[1], s.c[2], s.c[3], s.c[4]); texel(v::Real) = (Float32(v), Float32(v), Float32(v), 1f0)
 function texture_id!(P::TexPool, t)
     get!(P.ids, t) do
         data = t.data; h, w = size(data)
         rgb = Vector{Float32}(undef, 3 * h * w); alpha = Vector{Float32}(undef, h * w)
-        for (k, s) in enumerate(data); rgb[3k - 2], rgb[3k - 1], rgb[3k] = s.c[1], s.c[2], s.c[3]; alpha[k] = s.c[4]; end
+        for (k, s) in enumerate(data); r, g, b, a = texel(s); rgb[3k - 2], rgb[3k - 1], rgb[3k] = r, g, b; alpha[k] = a; end
         has_alpha = any(!=(1f0), alpha)
         push!(P.keep, rgb); has_alpha && push!(P.keep, alpha)
         push!(P.list, HkTexture(pointer(rgb), h, w, has_alpha ? pointer(alpha) : C_NULL))
@@ -206,10 +209,6 @@ function texture_id!(P::TexPool, t)
 end
 isconst(t) = !(t isa Hikari.Texture) || t.isconst
 constval(t) = t isa Hikari.Texture ? t.constval : t                                        # raw value, or ConstTexture (basic.jl:11-14)
-f32c(t, what) = isconst(t) ? Float32(constval(t)) : error("hikari_cuda: textured $what is not supported (only MatteMaterial.Kd may be a texture)")
-rgbc(t, what) = isconst(t) ? rgb3(constval(t)) : error("hikari_cuda: textured $what is not supported (only MatteMaterial.Kd may be a texture)")
-z3 = (0f0, 0f0, 0f0); z4 = (0f0, 0f0, 0f0, 0f0)
-f8(xs...) = ntuple(i -> i <= length(xs) ? Float32(xs[i]) : 0f0, 8)
 
 struct SpecPool; lambdas::Vector{Float32}; values::Vector{Float32}; offsets::Vector{UInt32}; end
 SpecPool() = SpecPool(Float32[], Float32[], UInt32[0])
@@ -217,51 +216,76 @@ function spectrum_id!(S::SpecPool, s::Hikari.PiecewiseLinearSpectrum)           
     append!(S.lambdas, s.lambdas); append!(S.values, s.values); push!(S.offsets, length(S.lambdas)); Int32(length(S.offsets) - 1)
 end
 
-hk(m::Hikari.MatteMaterial, F, P, S) = begin                                                  # uber-material.jl:180-183
-    if m.Kd isa Hikari.Texture && !m.Kd.isconst
-        vc = m.Kd isa Hikari.VertexColorTexture
-        HkMaterial(HK_MAT.matte, vc ? MATFLAG_VERTEX_COLORS : UInt32(0), z3, z3, z4, f8(f32c(m.σ, "MatteMaterial.σ")), (0, 0), (0, 0), (texture_id!(P, m.Kd), 0, 0, 0))
-    else
-        HkMaterial(HK_MAT.matte, 0, rgbc(m.Kd, "Kd"), z3, z4, f8(f32c(m.σ, "MatteMaterial.σ")), (0, 0), (0, 0), (0, 0, 0, 0))
-    end
+# HkMaterial under construction.  Every RGB / scalar parameter of the reference is `Texture, TextureRef or a raw value`: a constant goes
+# into rgb<slot> / f[k], a texture into tex[slot] / ftex[k] (eval_tex at the hit on the device).  Slots per type: include/hikari_cuda.h.
+mutable struct MatB
+    type::Int32; flags::UInt32; rgb::Vector{NTuple{3,Float32}}; f::Vector{Float32}; spec::Vector{Int32}; ival::Vector{Int32}; tex::Vector{Int32}; ftex::Vector{Int32}
 end
-hk(m::Hikari.MirrorMaterial, F, P, S) = HkMaterial(HK_MAT.mirror, 0, rgbc(m.Kr, "MirrorMaterial.Kr"), z3, z4, f8(), (0, 0), (0, 0), (0, 0, 0, 0))                       # :193-194
-hk(m::Hikari.GlassMaterial, F, P, S) = HkMaterial(HK_MAT.glass, m.remap_roughness ? MATFLAG_REMAP : 0, rgbc(m.Kr, "GlassMaterial.Kr"), rgbc(m.Kt, "GlassMaterial.Kt"), z4,
-    f8(f32c(m.u_roughness, "u_roughness"), f32c(m.v_roughness, "v_roughness"), 0, f32c(m.index, "index")), (0, 0), (0, 0), (0, 0, 0, 0))                               # :209-215
-function hk(m::Hikari.ConductorMaterial, F, P, S)                                                                                                                     # :378-383
-    fl = m.remap_roughness ? MATFLAG_REMAP : UInt32(0)
-    r = f32c(m.roughness, "ConductorMaterial.roughness")
+MatB(type; flags=UInt32(0)) = MatB(type, flags, fill((0f0, 0f0, 0f0), 3), zeros(Float32, 8), zeros(Int32, 2), zeros(Int32, 2), zeros(Int32, 4), zeros(Int32, 8))
+rgb!(b::MatB, P, slot, v) = (isconst(v) ? (b.rgb[slot] = rgb3(constval(v))) : (b.tex[slot] = texture_id!(P, v)); b)
+f!(b::MatB, P, k, v) = (isconst(v) ? (b.f[k] = Float32(constval(v))) : (b.ftex[k] = texture_id!(P, v)); b)
+HkMaterial(b::MatB) = HkMaterial(b.type, b.flags, b.rgb[1], b.rgb[2], (b.rgb[3]..., 0f0), Tuple(b.f), Tuple(b.spec), Tuple(b.ival), Tuple(b.tex), Tuple(b.ftex))
+remap(m) = m.remap_roughness ? MATFLAG_REMAP : UInt32(0)
+
+function hk(m::Hikari.MatteMaterial, F, P, S)                                                 # uber-material.jl:180-183; f0 = sigma
+    b = MatB(HK_MAT.matte); rgb!(b, P, 1, m.Kd); f!(b, P, 1, m.σ)
+    m.Kd isa Hikari.VertexColorTexture && (b.flags |= MATFLAG_VERTEX_COLORS)
+    HkMaterial(b)
+end
+hk(m::Hikari.MirrorMaterial, F, P, S) = HkMaterial(rgb!(MatB(HK_MAT.mirror), P, 1, m.Kr))                                       # :193-194
+function hk(m::Hikari.GlassMaterial, F, P, S)                                                 # :209-215; f0 = index (the roughness fields are ignored by the spectral path)
+    b = MatB(HK_MAT.glass; flags=remap(m)); rgb!(b, P, 1, m.Kr); rgb!(b, P, 2, m.Kt); f!(b, P, 1, m.index); HkMaterial(b)
+end
+function hk(m::Hikari.ConductorMaterial, F, P, S)                                             # :378-383; f0 = roughness
+    b = MatB(HK_MAT.conductor; flags=remap(m)); f!(b, P, 1, m.roughness)
     if m.eta isa Hikari.PiecewiseLinearSpectrum
-        return HkMaterial(HK_MAT.conductor, fl | MATFLAG_SPECTRAL_ETA_K, z3, z3, z4, f8(r, r), (spectrum_id!(S, m.eta), spectrum_id!(S, m.k)), (0, 0), (0, 0, 0, 0))
+        b.flags |= MATFLAG_SPECTRAL_ETA_K; b.spec[1] = spectrum_id!(S, m.eta); b.spec[2] = spectrum_id!(S, m.k)
+    else
+        rgb!(b, P, 1, m.eta); rgb!(b, P, 2, m.k)
     end
-    HkMaterial(HK_MAT.conductor, fl, rgbc(m.eta, "eta"), rgbc(m.k, "k"), z4, f8(r, r), (0, 0), (0, 0), (0, 0, 0, 0))
+    HkMaterial(b)
 end
-coat_f(m) = f8(f32c(m.u_roughness, "u_roughness"), f32c(m.v_roughness, "v_roughness"), f32c(m.thickness, "thickness"), m.eta, f32c(m.g, "g"))
-hk(m::Hikari.CoatedDiffuseMaterial, F, P, S) = HkMaterial(HK_MAT.coated_diffuse, m.remap_roughness ? MATFLAG_REMAP : 0, rgbc(m.reflectance, "reflectance"), rgbc(m.albedo, "albedo"), z4,
-    coat_f(m), (0, 0), (m.max_depth, m.n_samples), (0, 0, 0, 0))                                                                                                        # coated-diffuse.jl:32-42
-hk(m::Hikari.CoatedDiffuseTransmissionMaterial, F, P, S) = HkMaterial(HK_MAT.coated_diffuse_transmission, m.remap_roughness ? MATFLAG_REMAP : 0, rgbc(m.reflectance, "reflectance"),
-    rgbc(m.albedo, "albedo"), (rgbc(m.transmittance, "transmittance")..., 0f0), coat_f(m), (0, 0), (m.max_depth, m.n_samples), (0, 0, 0, 0))                            # coated-diffuse-transmission.jl:12-23
-hk(m::Hikari.ThinDielectricMaterial, F, P, S) = HkMaterial(HK_MAT.thin_dielectric, 0, z3, z3, z4, f8(0, 0, 0, m.eta), (0, 0), (0, 0), (0, 0, 0, 0))                    # thin-dielectric.jl:45-46
-hk(m::Hikari.DiffuseTransmissionMaterial, F, P, S) = HkMaterial(HK_MAT.diffuse_transmission, 0, rgbc(m.reflectance, "reflectance"), rgbc(m.transmittance, "transmittance"), z4,
-    f8(m.scale), (0, 0), (0, 0), (0, 0, 0, 0))                                                                                                                          # diffuse-transmission.jl:39-42
-function hk(m::Hikari.CoatedConductorMaterial, F, P, S)                                                                                                               # coated-conductor.jl:48-76
-    fl = (m.remap_roughness ? MATFLAG_REMAP : UInt32(0)) | (m.use_eta_k ? MATFLAG_USE_ETA_K : UInt32(0))
-    f = f8(f32c(m.interface_u_roughness, "interface_u_roughness"), f32c(m.interface_v_roughness, "interface_v_roughness"), f32c(m.thickness, "thickness"), m.interface_eta,
-           f32c(m.g, "g"), f32c(m.conductor_u_roughness, "conductor_u_roughness"), f32c(m.conductor_v_roughness, "conductor_v_roughness"))
-    alb = (rgbc(m.albedo, "albedo")..., 0f0)
+function coat!(b, P, m)                                                                       # f0 / f1 = u / v roughness, f2 = thickness, f3 = eta, f4 = g
+    f!(b, P, 1, m.u_roughness); f!(b, P, 2, m.v_roughness); f!(b, P, 3, m.thickness); b.f[4] = m.eta; f!(b, P, 5, m.g)
+    b.ival[1] = m.max_depth; b.ival[2] = m.n_samples; b
+end
+function hk(m::Hikari.CoatedDiffuseMaterial, F, P, S)                                         # coated-diffuse.jl:32-42
+    b = MatB(HK_MAT.coated_diffuse; flags=remap(m)); rgb!(b, P, 1, m.reflectance); rgb!(b, P, 2, m.albedo); HkMaterial(coat!(b, P, m))
+end
+function hk(m::Hikari.CoatedDiffuseTransmissionMaterial, F, P, S)                             # coated-diffuse-transmission.jl:12-23
+    b = MatB(HK_MAT.coated_diffuse_transmission; flags=remap(m)); rgb!(b, P, 1, m.reflectance); rgb!(b, P, 2, m.albedo); rgb!(b, P, 3, m.transmittance); HkMaterial(coat!(b, P, m))
+end
+hk(m::Hikari.ThinDielectricMaterial, F, P, S) = (b = MatB(HK_MAT.thin_dielectric); b.f[1] = m.eta; HkMaterial(b))               # thin-dielectric.jl:45-46; f0 = eta
+function hk(m::Hikari.DiffuseTransmissionMaterial, F, P, S)                                   # diffuse-transmission.jl:39-42; f0 = scale
+    b = MatB(HK_MAT.diffuse_transmission); rgb!(b, P, 1, m.reflectance); rgb!(b, P, 2, m.transmittance); b.f[1] = m.scale; HkMaterial(b)
+end
+function hk(m::Hikari.CoatedConductorMaterial, F, P, S)                                       # coated-conductor.jl:48-76
+    b = MatB(HK_MAT.coated_conductor; flags=remap(m) | (m.use_eta_k ? MATFLAG_USE_ETA_K : UInt32(0)))
+    f!(b, P, 1, m.interface_u_roughness); f!(b, P, 2, m.interface_v_roughness); f!(b, P, 3, m.thickness); b.f[4] = m.interface_eta; f!(b, P, 5, m.g)
+    f!(b, P, 6, m.conductor_u_roughness); f!(b, P, 7, m.conductor_v_roughness)
+    rgb!(b, P, 3, m.albedo); b.ival[1] = m.max_depth; b.ival[2] = m.n_samples
     if m.use_eta_k
-        e, k = constval(m.conductor_eta), constval(m.conductor_k)
-        e isa Hikari.PiecewiseLinearSpectrum && return HkMaterial(HK_MAT.coated_conductor, fl | MATFLAG_SPECTRAL_ETA_K, z3, z3, alb, f, (spectrum_id!(S, e), spectrum_id!(S, k)), (m.max_depth, m.n_samples), (0, 0, 0, 0))
-        return HkMaterial(HK_MAT.coated_conductor, fl, rgb3(e), rgb3(k), alb, f, (0, 0), (m.max_depth, m.n_samples), (0, 0, 0, 0))
+        e, k = m.conductor_eta, m.conductor_k
+        if constval(e) isa Hikari.PiecewiseLinearSpectrum
+            b.flags |= MATFLAG_SPECTRAL_ETA_K; b.spec[1] = spectrum_id!(S, constval(e)); b.spec[2] = spectrum_id!(S, constval(k))
+        else
+            rgb!(b, P, 1, e); rgb!(b, P, 2, k)
+        end
+    else
+        rgb!(b, P, 1, m.reflectance)
     end
-    HkMaterial(HK_MAT.coated_conductor, fl, rgbc(m.reflectance, "reflectance"), z3, alb, f, (0, 0), (m.max_depth, m.n_samples), (0, 0, 0, 0))
+    HkMaterial(b)
 end
 # MixMaterial (mix-material.jl:39-99): the two sub-materials' SetKeys are stored in the material (material_indices); the mix hash
-# consumes their type_idx / vec_idx (mix_hash_float :114-158), the library needs their flat ids as well
-hk(m::Hikari.MixMaterial, F, P, S) = HkMaterial(HK_MAT.mix, UInt32(m.material_indices[1].type_idx) | (UInt32(m.material_indices[2].type_idx) << 8), z3, z3, z4,
-    f8(f32c(m.amount, "MixMaterial.amount")), (Int32(m.material_indices[1].vec_idx), Int32(m.material_indices[2].vec_idx)),
-    (Int32(flat_id(F, m.material_indices[1])), Int32(flat_id(F, m.material_indices[2]))), (0, 0, 0, 0))
-hk(m::Hikari.MediumInterface, F, P, S) = hk(m.material, F, P, S)                                                                                                       # medium-interface.jl:39-42
+# consumes their type_idx / vec_idx (mix_hash_float :114-158), the library needs their flat ids as well.  The amount must be constant.
+function hk(m::Hikari.MixMaterial, F, P, S)
+    isconst(m.amount) || error("hikari_cuda: a textured MixMaterial.amount is not supported")
+    k1, k2 = m.material_indices
+    b = MatB(HK_MAT.mix; flags=UInt32(k1.type_idx) | (UInt32(k2.type_idx) << 8)); b.f[1] = Float32(constval(m.amount))
+    b.spec[1] = k1.vec_idx; b.spec[2] = k2.vec_idx; b.ival[1] = flat_id(F, k1); b.ival[2] = flat_id(F, k2)
+    HkMaterial(b)
+end
+hk(m::Hikari.MediumInterface, F, P, S) = hk(m.material, F, P, S)                              # medium-interface.jl:39-42
 hk(m::Material, F, P, S) = error("hikari_cuda: material type $(typeof(m)) is not on the VolPath spectral path")
 
 function upload_materials!(c::Ctx, scene)
@@ -300,7 +324,7 @@ function hk(l::Hikari.EnvironmentLight, envs)                                   
 end
 function hk(l::Hikari.DiffuseAreaLight, envs)                                                                              # diffuse-area.jl:25-32
     v = ntuple(i -> Float32(l.vertices[(i - 1) ÷ 3 + 1][(i - 1) % 3 + 1]), 9); uv = ntuple(i -> Float32(l.uv[(i - 1) ÷ 2 + 1][(i - 1) % 2 + 1]), 6)
-    HkLight(7, 0, l.scale, rgbc(l.Le, "DiffuseAreaLight.Le"), z3, 0f0, z3, z3, 0, 0, Z16, v, t3(l.normal), l.area, uv, l.two_sided, 0)
+    HkLight(7, 0, l.scale, (isconst(l.Le) ? rgb3(constval(l.Le)) : error("hikari_cuda: a textured DiffuseAreaLight.Le is not supported")), z3, 0f0, z3, z3, 0, 0, Z16, v, t3(l.normal), l.area, uv, l.two_sided, 0)
 end
 
 function upload_lights!(c::Ctx, scene)
