@@ -111,7 +111,12 @@ HK_DEV Spec operator/(Spec a, Spec b) { return sp4(a.x / b.x, a.y / b.y, a.z / b
 HK_DEV Spec operator*(Spec a, float s) { return sp4(a.x * s, a.y * s, a.z * s, a.w * s); }
 HK_DEV Spec operator*(float s, Spec a) { return a * s; }
 HK_DEV Spec operator/(Spec a, float s) { return sp4(a.x / s, a.y / s, a.z / s, a.w / s); }
-HK_NI Spec sp_exp(Spec a) { return sp4(dm_expf(a.x), dm_expf(a.y), dm_expf(a.z), dm_expf(a.w)); }
+// (a grey medium has equal coefficients at the four wavelengths: one exponential then serves all of them -- same function, same
+// argument, same bits)
+HK_NI Spec sp_exp(Spec a) {
+    if (a.x == a.y && a.y == a.z && a.z == a.w) { const float e = dm_expf(a.x); return sp4(e, e, e, e); }
+    return sp4(dm_expf(a.x), dm_expf(a.y), dm_expf(a.z), dm_expf(a.w));
+}
 HK_DEV Spec sp_neg(Spec a) { return sp4(-a.x, -a.y, -a.z, -a.w); }
 HK_DEV Spec sp_max0(Spec a) { return sp4(fmaxf(a.x, 0.0f), fmaxf(a.y, 0.0f), fmaxf(a.z, 0.0f), fmaxf(a.w, 0.0f)); }
 HK_DEV float sp_avg(Spec s) { return (((s.x + s.y) + s.z) + s.w) / 4.0f; }

@@ -413,10 +413,14 @@ struct RatioTracker {
     const DevMedium* M; MediumCoef mc; float3 o, d;
     Pcg32 rng; MajIter it; Spec smaj; float seg_t_max, t; int sg, si; bool in_seg;
     Spec T_ray, r_u, r_l;
+    bool uni;      // grey medium: sigma_a / sigma_s are equal at the four wavelengths, so T_ray, r_u, r_l (which start at 1) stay equal in all
+                   // four components; the spectral arithmetic of an event is then done once and broadcast -- the same operations on the same
+                   // operands as each component would see, so the same bits, with 4 instead of 16 divisions per collision event
     HK_DEV void init(const MediaCtx& C, int medium, float3 o_, float3 d_, float t_max, float4 lam) {
         T_ray = sp(1.0f); r_u = sp(1.0f); r_l = sp(1.0f); HK_STAT(8, 1);
         M = &C.media[medium - 1];
         mc = medium_coef(C, *M, lam);
+        uni = M->type != HK_MEDIUM_RGBGRID && mc.sa.x == mc.sa.y && mc.sa.y == mc.sa.z && mc.sa.z == mc.sa.w && mc.ss.x == mc.ss.y && mc.ss.y == mc.ss.z && mc.ss.z == mc.ss.w;
         o = o_; d = d_;
         majiter_create(it, *M, mc, o, d, t_max, medium_mask(C, medium));
         rng = pcg32_init(hash_f3(o), hash_f3(d));
@@ -449,6 +453,12 @@ struct RatioTracker {
         float ts = t + dt;
         if (ts >= seg_t_max) {
             HK_STAT(12, 1);
+            if (uni) {
+                const float tm = dm_expf(-(seg_t_max - t) * smaj.x);
+                if (tm > 1.0e-10f) { T_ray = sp(T_ray.x * tm / tm); r_l = sp(r_l.x * tm / tm); r_u = sp(r_u.x * tm / tm); }
+                in_seg = false;
+                return T_ray.x == 0.0f;
+            }
             Spec Tm = sp_exp(-(seg_t_max - t) * smaj);
             if (Tm.x > 1.0e-10f) { T_ray = T_ray * Tm / Tm.x; r_l = r_l * Tm / Tm.x; r_u = r_u * Tm / Tm.x; }
             in_seg = false;
@@ -462,6 +472,23 @@ struct RatioTracker {
             float dens = medium_density_cached(*M, p, lc_slot);
             sa = M->type == HK_MEDIUM_HOMOGENEOUS ? mc.sa : mc.sa * dens;
             ss = M->type == HK_MEDIUM_HOMOGENEOUS ? mc.ss : mc.ss * dens;
+        }
+        if (uni) {
+            const float sn = fmaxf(smaj.x - sa.x - ss.x, 0.0f);
+            const float tm = dm_expf(-dt * smaj.x);
+            const float pr = tm * s0;
+            if (!(pr > 1.0e-10f)) { T_ray = sp(0.0f); return true; }
+            const float tr = T_ray.x * tm * sn / pr, rl = r_l.x * tm * smaj.x / pr, ru = r_u.x * tm * sn / pr;
+            T_ray = sp(tr); r_l = sp(rl); r_u = sp(ru);
+            const float sum = rl + ru;
+            const float q = tr / fmaxf(1.0e-10f, (((sum + sum) + sum) + sum) / 4.0f);      // sp_maxc(T_ray / max(1e-10, sp_avg(r_l + r_u)))
+            if (q < 0.05f) {
+                if (pcg32_f32(rng) < 0.75f) { T_ray = sp(0.0f); return true; }
+                T_ray = sp(tr / (1.0f - 0.75f));
+            }
+            if (T_ray.x == 0.0f) return true;
+            t = ts;
+            return false;
         }
         Spec sn = sp_max0(smaj - sa - ss);
         Spec Tm = sp_exp(-dt * smaj);
