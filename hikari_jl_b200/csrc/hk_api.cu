@@ -559,7 +559,7 @@ static int32_t alloc_film(HkContext* ctx, size_t n_pixels) {
 }
 static int32_t alloc_state(HkContext* ctx, size_t n_slots) {
     // one slab: 22 float4 arrays, 5 u32/f32 arrays, 16 queues; every array starts 256-byte aligned
-    const size_t f4 = 22, w4 = 5, q = 8 + HK_N_HIT_QUEUES;
+    const size_t f4 = 22, w4 = 5, q = 9 + HK_N_HIT_QUEUES;
     size_t rounded = f4 * (((16 * n_slots + 255) / 256) * 256) + (w4 + q) * (((4 * n_slots + 255) / 256) * 256);
     CK(cudaStreamSynchronize(ctx->stream));
     CK(ctx->b_state.alloc(rounded));
@@ -575,6 +575,7 @@ static int32_t alloc_state(HkContext* ctx, size_t n_slots) {
     S.q_escaped = reinterpret_cast<uint32_t*>(take(4)); S.q_medium = reinterpret_cast<uint32_t*>(take(4)); S.q_shadow = reinterpret_cast<uint32_t*>(take(4));
     S.q_shadow2 = reinterpret_cast<uint32_t*>(take(4));
     S.q_alpha[0] = reinterpret_cast<uint32_t*>(take(4)); S.q_alpha[1] = reinterpret_cast<uint32_t*>(take(4));
+    S.q_lbvh = reinterpret_cast<uint32_t*>(take(4));
     for (int t = 0; t < HK_N_HIT_QUEUES; t++) S.q_hit[t] = reinterpret_cast<uint32_t*>(take(4));
     S.counts = ctx->b_counts.as<uint32_t>();
     S.rays_traced = reinterpret_cast<unsigned long long*>(ctx->b_counts.as<char>() + sizeof(uint32_t) * HK_N_COUNTERS);
@@ -765,6 +766,7 @@ int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride,
             if (ctx->D.n_lights > 0 && ctx->D.split_lights) {      // emissive-hit MIS + the light sample of every surface hit of the bounce, ahead of the per-material kernels
                 StageScope sc(ctx, HK_STAGE_SHADE);
                 hkl_hit_lights(ctx->sm_count * 4, st, ctx->D, ctx->S, A);
+                if (HK_LIGHTS_COMPACT) { hkl_hit_lights_bvh(ctx->sm_count * 6, st, ctx->D, ctx->S, A); ctx->launches++; }
             }
             if (fork) { ctx->shade_fork_slot = 0; cudaEventRecord(ctx->ev_fork, st); }      // (the escaped-ray kernel overlaps the shading kernels too)
             if (ctx->D.n_lights > 0) { StageScope sc(ctx, HK_STAGE_ESCAPED); k_escaped<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->D, ctx->S); }

@@ -6,3 +6,8 @@
 void hkl_hit_lights(int grid, cudaStream_t st, const DevScene& D, const PathState& S, const PassArgs& A) {
     k_hit_lights<<<grid, 128, 0, st>>>(D, S, A);
 }
+void hkl_hit_lights_bvh(int grid, cudaStream_t st, const DevScene& D, const PathState& S, const PassArgs& A) {
+#if HK_LIGHTS_COMPACT
+    k_hit_lights_bvh<<<grid, 128, 0, st>>>(D, S, A);
+#endif
+}

@@ -18,6 +18,7 @@ void hkl_medium_finish(int grid, cudaStream_t st, const DevScene& D, const PathS
 void hkl_shadow_seg_ratio(bool rgb, int grid, cudaStream_t st, const DevScene& D, const PathState& S, int round);
 // hk_k_lights.cu (emissive-hit MIS + NEE light sample of every surface hit)
 void hkl_hit_lights(int grid, cudaStream_t st, const DevScene& D, const PathState& S, const PassArgs& A);
+void hkl_hit_lights_bvh(int grid, cudaStream_t st, const DevScene& D, const PathState& S, const PassArgs& A);
 // hk_k_shade_{1,2,3}.cu: each handles a subset of the shading classes and returns false for the others
 bool hkl_shade_1(int type, int grid, cudaStream_t st, const DevScene& D, const PathState& S, const PassArgs& A, int next, int par);
 bool hkl_shade_2(int type, int grid, cudaStream_t st, const DevScene& D, const PathState& S, const PassArgs& A, int next, int par);

@@ -286,13 +286,11 @@ HK_NI_LIGHTS int bvh_sample_light(const LightCtx& C, float3 p, float3 n, float u
 // scene only a fraction of a warp's lanes descends the light BVH (C3: 1/3 choose the 10 000-emitter tree, ncu: 6.8 of 32
 // lanes active in the descent), so the descents are served by PAIRS of lanes -- one child importance each, exchanged by
 // shuffle -- up to 16 descents per round.  Per item the arithmetic and its order are those of bvh_sample_light: same bits.
-HK_NI_LIGHTS int bvh_sample_light_coop(const LightCtx& C, float3 p, float3 n, float u, float& pmf_out) {
-    pmf_out = 0.0f;
+// the part of bvh_sample_light ahead of the tree (:105-125): an infinite light is picked uniformly (returns its index, pmf_out set), or
+// the light BVH must be descended (need = true; ub = the remapped sample, pmf = the probability of having chosen the tree)
+HK_DEV int light_select_prologue(const LightCtx& C, float u, float& pmf_out, bool& need, float& ub, float& pmf) {
+    pmf_out = 0.0f; need = false; ub = 0.0f; pmf = 0.0f;
     int result = 0;
-    const unsigned m = __activemask();
-    const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
-    bool need = false;
-    float ub = 0.0f, pmf = 0.0f;
     if (C.n_infinite + C.n_bvh != 0) {
         const bool has_bvh = C.n_bvh > 0;
         const float p_inf = (float)C.n_infinite / (float)(C.n_infinite + (has_bvh ? 1 : 0));
@@ -306,6 +304,18 @@ HK_NI_LIGHTS int bvh_sample_light_coop(const LightCtx& C, float3 p, float3 n, fl
             pmf = 1.0f - p_inf;
         }
     }
+    return result;
+}
+HK_NI_LIGHTS int bvh_descend_coop(const LightCtx& C, float3 p, float3 n, bool need, float ub, float pmf, int result, float& pmf_out);
+HK_NI_LIGHTS int bvh_sample_light_coop(const LightCtx& C, float3 p, float3 n, float u, float& pmf_out) {
+    bool need; float ub, pmf;
+    const int result = light_select_prologue(C, u, pmf_out, need, ub, pmf);
+    return bvh_descend_coop(C, p, n, need, ub, pmf, result, pmf_out);
+}
+// the descent for the lanes that arrive together with need = true (the others pass their `result` / pmf_out through)
+HK_NI_LIGHTS int bvh_descend_coop(const LightCtx& C, float3 p, float3 n, bool need, float ub, float pmf, int result, float& pmf_out) {
+    const unsigned m = __activemask();
+    const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
     unsigned todo = __ballot_sync(m, need);
     if (todo == 0u) return result;
     const unsigned n_helpers = (unsigned)__popc(m), hidx = (unsigned)__popc(m & lt);

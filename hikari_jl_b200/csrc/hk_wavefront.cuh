@@ -57,6 +57,10 @@
 #define HK_ALPHA_ROUNDS 16
 #define HK_C_ALPHA_N0 64       // + r: rays queued for retrace round r
 #define HK_C_ALPHA_CUR0 80     // + r: work cursor of retrace round r
+#define HK_C_LBVH 96           // hits of the bounce whose light sample falls on the light BVH (k_hit_lights -> k_hit_lights_bvh)
+#ifndef HK_LIGHTS_COMPACT
+#define HK_LIGHTS_COMPACT 1
+#endif
 static_assert(HK_C_SHROUND0 + HK_SHADOW_ROUNDS < HK_C_SHCUR_TRACE && HK_C_SHCUR_TRACE + HK_SHADOW_ROUNDS < HK_C_SHCUR_RATIO &&
               HK_C_SHCUR_RATIO + HK_SHADOW_ROUNDS < HK_C_HIT1, "shadow-round counters overlap the second bank of hit-queue counters");
 static_assert(HK_C_ALPHA_N0 + HK_ALPHA_ROUNDS <= HK_C_ALPHA_CUR0 && HK_C_ALPHA_CUR0 + HK_ALPHA_ROUNDS <= HK_N_COUNTERS && HK_C_ALPHA_N0 > HK_C_HIT1 + 1, "alpha-round counters");
@@ -128,7 +132,7 @@ struct PathState {
     uint32_t* res_mat;                             // material a MixMaterial hit resolved to (written by the routing, read by k_shade)
     float4 *sh_hit, *sh_T, *sh_tu, *sh_tl;         // shadow rays through media: segment hit, running transmittance / MIS ratios
     float4 *nee_a, *nee_b, *nee_c;                 // light sample of a surface hit, written by k_hit_lights for k_shade: Li | wi, pdf | p_light, pmf (sign bit = delta light)
-    uint32_t *q_ray[2], *q_escaped, *q_medium, *q_shadow, *q_shadow2, *q_hit[HK_N_HIT_QUEUES], *q_alpha[2];
+    uint32_t *q_ray[2], *q_escaped, *q_medium, *q_shadow, *q_shadow2, *q_hit[HK_N_HIT_QUEUES], *q_alpha[2], *q_lbvh;
     uint32_t* counts;                  // [HK_N_COUNTERS]
     unsigned long long* rays_traced;
     unsigned long long* path_vertices;  // surface hits routed + medium scatter events (HkStats::path_vertices)
@@ -672,8 +676,10 @@ __global__ void __launch_bounds__(128, 4) k_hit_lights(const __grid_constant__ D
         const uint32_t n_round = (n + 31u) & ~31u;     // whole warps iterate together: the cooperative light-BVH descent pairs up the lanes of a warp
         const uint32_t* __restrict__ queue = S.q_hit[q];
         for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
-            if (i >= n) continue;
-            const uint32_t slot = queue[i];
+            bool push_lbvh = false;
+            uint32_t slot = 0;
+            if (i < n) {
+            slot = queue[i];
             const float4 hr = S.hit[slot];
             const uint32_t prim0 = HK_HIT_PRIM1(__float_as_uint(hr.y)) - 1u;
             const float4 ra = S.ray_a[slot], rb = S.ray_b[slot];
@@ -708,7 +714,17 @@ __global__ void __launch_bounds__(128, 4) k_hit_lights(const __grid_constant__ D
             float4 rec_b = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             const float direct_uc = zsobol_1d(D.sobol, px, py, sidx, bdim + 1, HK_SOBOL_SLOT_BOUNCE(depth, 0), pix);
             float pmf;
+#if HK_LIGHTS_COMPACT
+            // hits whose sample falls on the light BVH are queued for k_hit_lights_bvh, where every lane of a warp descends (here only
+            // the fraction 1 / (n_infinite + 1) of a warp's lanes would: ncu on C3, 13 of 32 lanes in the descent): the hit point, the
+            // shading normal and the remapped sample / tree probability wait in the vertex's light-sample record
+            bool need; float ub, tree_p;
+            const int li = light_select_prologue(LC, direct_uc, pmf, need, ub, tree_p);
+            if (need) { S.nee_a[slot] = make_float4(sf.pi.x, sf.pi.y, sf.pi.z, ub); S.nee_c[slot] = make_float4(sf.ns.x, sf.ns.y, sf.ns.z, tree_p); }
+            push_lbvh = need;
+#else
             const int li = bvh_sample_light_coop(LC, sf.pi, sf.ns, direct_uc, pmf);
+#endif
             if (li >= 1 && li <= D.n_lights && pmf > 0.0f) {
                 const float2 direct_u = zsobol_2d(D.sobol, px, py, sidx, bdim + 3, HK_SOBOL_SLOT_BOUNCE(depth, 1), pix);
                 const LightSample ls = sample_light(LC, D.lights[li - 1], sf.pi, lam, direct_u);
@@ -719,9 +735,56 @@ __global__ void __launch_bounds__(128, 4) k_hit_lights(const __grid_constant__ D
                 }
             }
             S.nee_b[slot] = rec_b;
+            }
+#if HK_LIGHTS_COMPACT
+            warp_push1(S.counts + HK_C_LBVH, S.q_lbvh, push_lbvh, slot);
+#else
+            (void)push_lbvh;
+#endif
         }
     }
 }
+#if HK_LIGHTS_COMPACT
+// The light-BVH descents of a bounce, compacted: every lane of a warp owns one queued hit, so the pair-of-lanes descent runs with all
+// 16 pairs busy, twice per 32 hits (bvh_descend_coop).  Then sample_light for the light that was picked, as k_hit_lights does for the
+// infinite lights.  Same functions on the same operands: same bits.
+__global__ void __launch_bounds__(128, 6) k_hit_lights_bvh(const __grid_constant__ DevScene D, PathState S, PassArgs A) {
+    LightCtx LC = light_ctx(D);
+    const uint32_t n = S.counts[HK_C_LBVH];
+    const uint32_t n_round = (n + 31u) & ~31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        const bool valid = i < n;
+        uint32_t slot = 0;
+        float3 p = f3(0.0f, 0.0f, 0.0f), ns = f3(0.0f, 0.0f, 0.0f);
+        float ub = 0.0f, tree_p = 0.0f;
+        if (valid) {
+            slot = S.q_lbvh[i];
+            const float4 a = S.nee_a[slot], c = S.nee_c[slot];
+            p = f3(a.x, a.y, a.z); ub = a.w; ns = f3(c.x, c.y, c.z); tree_p = c.w;
+        }
+        float pmf = 0.0f;
+        const int li = bvh_descend_coop(LC, p, ns, valid, ub, tree_p, 0, pmf);
+        if (valid) {
+            float4 rec_b = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (li >= 1 && li <= D.n_lights && pmf > 0.0f) {
+                const uint32_t pix = slot % A.n_pixels;
+                const int px = (int)(pix % (uint32_t)D.width) + 1, py = (int)(pix / (uint32_t)D.width) + 1;
+                const int sidx = slot_sample_idx(A, slot);
+                const int depth = HK_FLAG_DEPTH(S.flags[slot]);
+                const int bdim = 6 + 7 * depth;
+                const float2 direct_u = zsobol_2d(D.sobol, px, py, sidx, bdim + 3, HK_SOBOL_SLOT_BOUNCE(depth, 1), pix);
+                const LightSample ls = sample_light(LC, D.lights[li - 1], p, S.lambda[slot], direct_u);
+                if (ls.pdf > 0.0f && !sp_black(ls.Li)) {
+                    rec_b = make_float4(ls.wi.x, ls.wi.y, ls.wi.z, ls.pdf);
+                    S.nee_a[slot] = ls.Li;
+                    S.nee_c[slot] = make_float4(ls.p_light.x, ls.p_light.y, ls.p_light.z, ls.delta ? -pmf : pmf);
+                }
+            }
+            S.nee_b[slot] = rec_b;
+        }
+    }
+}
+#endif
 #endif  // HK_TU_LIGHTS
 #ifdef HK_TU_SHADE
 // Shading of one material type: emissive-hit MIS (surface-eval.jl:147-220), NEE (:250-342 + lights.jl:535-600) and
