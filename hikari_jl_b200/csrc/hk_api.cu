@@ -66,6 +66,7 @@ int32_t hk_create(int32_t device, HkContext** out) {
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     for (auto& e : ctx->ev_join) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     if (std::getenv("HK_SERIAL_SHADE")) ctx->concurrent_shade = false;
+    ctx->sort_rays = std::getenv("HK_SORT_RAYS") != nullptr;      // off: measured no gain (profiles/r02_sort_rays_ab.txt)
     if (cudaStreamCreateWithFlags(&ctx->shadow_stream, cudaStreamNonBlocking) != cudaSuccess) ctx->shadow_stream = nullptr;
     cudaEventCreateWithFlags(&ctx->ev_shaded, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_shadowed, cudaEventDisableTiming);
     if (std::getenv("HK_SERIAL_SHADOW") && ctx->shadow_stream) { cudaStreamDestroy(ctx->shadow_stream); ctx->shadow_stream = nullptr; }
@@ -747,6 +748,7 @@ int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride,
             const int par = overlap_shadow ? (depth & 1) : 0;
             ctx->bounce_par = par;
             k_reset_bounce<<<1, HK_N_COUNTERS, 0, st>>>(ctx->S, cur, overlap_shadow ? (par ^ 1) : -1); ctx->launches++;
+            if (depth >= 1 && ctx->sort_rays) { StageScope sc(ctx, HK_STAGE_ROUTE); k_sort_rays<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->S, cur); }      // (primary rays are coherent as generated)
             {
                 StageScope sc(ctx, HK_STAGE_TRACE);
                 hkl_trace(cnt, tgrid, st, ctx->D, ctx->S, cur, 0, work);

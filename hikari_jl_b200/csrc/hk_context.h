@@ -60,6 +60,7 @@ struct HkContext {
     // fork / join of the per-material shading kernels of one bounce (independent queues) over side streams
     cudaStream_t shade_streams[3] = {nullptr, nullptr, nullptr}; cudaEvent_t ev_fork = nullptr, ev_join[12] = {};
     bool concurrent_shade = true; int shade_fork_slot = 0;
+    bool sort_rays = false;                  // HK_SORT_RAYS=1: regroup the continuation-ray queue by direction octant before each trace (k_sort_rays); measured: no gain
     // the shadow pass of bounce b on its own stream, overlapping trace + route of bounce b+1 (opaque-only scenes)
     cudaStream_t shadow_stream = nullptr; cudaEvent_t ev_shaded = nullptr, ev_shadowed = nullptr; int bounce_par = 0;
     DevBuf b_sobol_top, b_sobol_dims, b_sobol_dimhash;        // ZSobol prefix cache (SobolParams::top)

@@ -627,6 +627,47 @@ __global__ void __launch_bounds__(256) k_route(const __grid_constant__ DevScene 
     }
 }
 
+// Ray-queue ordering for traversal coherence: continuation rays leave the shading kernels in hit-queue order -- neighbouring origins,
+// unrelated directions.  Each block regroups its tile of HK_SORT_TILE queue entries by direction octant, in place (a counting sort in
+// shared memory): the lanes of a traversal warp then walk the same children in the same order far more often.  Queue order has no
+// effect on any result (every slot is independent; the film is summed per slot in sample order).
+#ifndef HK_SORT_TILE
+#define HK_SORT_TILE 2048
+#endif
+__global__ void __launch_bounds__(256) k_sort_rays(PathState S, int cur) {
+    __shared__ uint32_t s_slot[HK_SORT_TILE];
+    __shared__ uint8_t s_oct[HK_SORT_TILE];
+    __shared__ uint32_t s_cnt[8], s_off[8];
+    const uint32_t n = S.counts[HK_C_RAY0 + cur];
+    uint32_t* __restrict__ q = S.q_ray[cur];
+    for (uint32_t t0 = blockIdx.x * HK_SORT_TILE; t0 < n; t0 += gridDim.x * HK_SORT_TILE) {
+        if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        uint32_t pos[HK_SORT_TILE / 256];
+#pragma unroll
+        for (int k = 0; k < HK_SORT_TILE / 256; k++) {
+            const uint32_t j = k * 256u + threadIdx.x, i = t0 + j;
+            pos[k] = 0;
+            if (i < n) {
+                const uint32_t slot = q[i];
+                const float dx = S.ray_a[slot].w; const float2 dyz = *reinterpret_cast<const float2*>(&S.ray_b[slot]);
+                const uint32_t oct = (dx >= 0.0f ? 4u : 0u) | (dyz.x >= 0.0f ? 2u : 0u) | (dyz.y >= 0.0f ? 1u : 0u);
+                s_slot[j] = slot; s_oct[j] = (uint8_t)oct;
+                pos[k] = atomicAdd(&s_cnt[oct], 1u);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { uint32_t a = 0; for (int o = 0; o < 8; o++) { s_off[o] = a; a += s_cnt[o]; } }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < HK_SORT_TILE / 256; k++) {
+            const uint32_t j = k * 256u + threadIdx.x, i = t0 + j;
+            if (i < n) q[t0 + s_off[s_oct[j]] + pos[k]] = s_slot[j];
+        }
+        __syncthreads();
+    }
+}
+
 // vp_handle_escaped_rays_kernel!, intersection.jl:622-668
 __global__ void __launch_bounds__(256) k_escaped(const __grid_constant__ DevScene D, PathState S) {
     const uint32_t n = S.counts[HK_C_ESCAPED];
