@@ -1,6 +1,9 @@
 // hk_k_shade_3.cu — translation unit 3 of 3 of the per-material shading kernels (hk_wavefront.cuh, HK_TU_SHADE): k_shade<TYPE> for
 // HK_MAT_COATED_DIFFUSE_TRANSMISSION.
 #define HK_TU_SHADE
+// the coated / layered kernels are several times the 32 KB instruction cache: the light-sampling helpers are real functions here
+// (measured on C5: shading 15.9 -> 12.8 ms; in the small kernels of hk_k_shade_1.cu the same switch costs 13-16 %)
+#define HK_NOINLINE_LIGHTS 1
 #include "hk_launch.h"
 
 bool hkl_shade_3(int type, int grid, cudaStream_t st, const DevScene& D, const PathState& S, const PassArgs& A, int next, int par) {

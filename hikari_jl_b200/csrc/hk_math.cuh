@@ -110,7 +110,15 @@ HK_DEV Spec operator*(Spec a, Spec b) { return sp4(a.x * b.x, a.y * b.y, a.z * b
 HK_DEV Spec operator/(Spec a, Spec b) { return sp4(a.x / b.x, a.y / b.y, a.z / b.z, a.w / b.w); }
 HK_DEV Spec operator*(Spec a, float s) { return sp4(a.x * s, a.y * s, a.z * s, a.w * s); }
 HK_DEV Spec operator*(float s, Spec a) { return a * s; }
+#ifndef HK_NOINLINE_SPDIV
+#define HK_NOINLINE_SPDIV 0        // Spec / float (four IEEE divisions, ~40 instructions per call site)
+#endif
+#if HK_NOINLINE_SPDIV
+static __device__ __noinline__ Spec sp_div_f(Spec a, float s) { return sp4(a.x / s, a.y / s, a.z / s, a.w / s); }
+HK_DEV Spec operator/(Spec a, float s) { return sp_div_f(a, s); }
+#else
 HK_DEV Spec operator/(Spec a, float s) { return sp4(a.x / s, a.y / s, a.z / s, a.w / s); }
+#endif
 // (a grey medium has equal coefficients at the four wavelengths: one exponential then serves all of them -- same function, same
 // argument, same bits)
 HK_NI Spec sp_exp(Spec a) {

@@ -21,6 +21,8 @@ def build(specs):
         open(out + ".env", "w").write(envs)
         try:
             g.build_cuda(extra_flags=tuple(d for d in defs.split(",") if d), out=out)
+            for d in glob.glob(os.path.join(ROOT, "build", "obj_*")):      # the variant's objects are not needed once it is linked (and gpurun snapshots are size-limited)
+                import shutil; shutil.rmtree(d, ignore_errors=True)
             print(name, "OK")
         except Exception as e:
             print(name, "FAILED", e)
