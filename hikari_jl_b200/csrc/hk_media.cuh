@@ -288,6 +288,17 @@ HK_DEV void majiter_create(MajIter& it, const DevMedium& M, const MediumCoef& mc
 #define HK_EV_ABSORBED 0
 #define HK_EV_SCATTER 1
 #define HK_EV_SURVIVED 2
+// ray set-up of the trackers as a real function (to shrink the skip / event loop below the 32 KB instruction cache): tried and dropped --
+// a member function that is not inlined takes `this` by address, which puts the whole tracker state (~100 words) in local memory
+// (C4: 308 -> 262 Msamples/s)
+#ifndef HK_NOINLINE_MEDIA_INIT
+#define HK_NOINLINE_MEDIA_INIT 0
+#endif
+#if HK_NOINLINE_MEDIA_INIT
+#define HK_MEDIA_INIT __device__ __noinline__
+#else
+#define HK_MEDIA_INIT HK_DEV
+#endif
 struct DeltaOut { int event; Spec beta, r_u, r_l; float3 p; float g; Spec Le_add; };
 // Delta tracking as a state machine: step() performs ONE unit of work -- advance the majorant DDA to the next non-empty
 // segment (skipping up to HK_TRACK_SKIP empty cells) or ONE tentative collision -- so a persistent warp can keep every lane
@@ -316,7 +327,7 @@ struct DeltaTracker {
     const DevMedium* M; MediumCoef mc; float3 o, d, ro; int depth, max_depth;
     uint64_t rng; MajIter it; Spec smaj; float seg_t_max, t; int sg, si; bool in_seg;
     Spec beta, r_u, r_l; DeltaOut R;
-    HK_DEV void init(const MediaCtx& C, int medium, float3 o_, float3 d_, float t_max, float4 lam, Spec beta_, Spec r_u_, Spec r_l_, int depth_, int max_depth_) {
+    HK_MEDIA_INIT void init(const MediaCtx& C, int medium, float3 o_, float3 d_, float t_max, float4 lam, Spec beta_, Spec r_u_, Spec r_l_, int depth_, int max_depth_) {
         R.g = 0.0f; R.p = f3(0, 0, 0); R.Le_add = sp(0.0f); R.event = HK_EV_SURVIVED; HK_STAT(0, 1);
         M = &C.media[medium - 1];
         mc = medium_coef(C, *M, lam);
@@ -416,7 +427,7 @@ struct RatioTracker {
     bool uni;      // grey medium: sigma_a / sigma_s are equal at the four wavelengths, so T_ray, r_u, r_l (which start at 1) stay equal in all
                    // four components; the spectral arithmetic of an event is then done once and broadcast -- the same operations on the same
                    // operands as each component would see, so the same bits, with 4 instead of 16 divisions per collision event
-    HK_DEV void init(const MediaCtx& C, int medium, float3 o_, float3 d_, float t_max, float4 lam) {
+    HK_MEDIA_INIT void init(const MediaCtx& C, int medium, float3 o_, float3 d_, float t_max, float4 lam) {
         T_ray = sp(1.0f); r_u = sp(1.0f); r_l = sp(1.0f); HK_STAT(8, 1);
         M = &C.media[medium - 1];
         mc = medium_coef(C, *M, lam);
