@@ -34,6 +34,12 @@
 #ifndef HK_TRACE_BLOCKS_PER_SM
 #define HK_TRACE_BLOCKS_PER_SM 8
 #endif
+#ifndef HK_TRI_HYBRID
+#define HK_TRI_HYBRID 0
+#endif
+#ifndef HK_TRI_VOTE
+#define HK_TRI_VOTE 0         // > 0: triangle tests wait until that many lanes of the warp have one pending
+#endif
 #ifndef HK_TRACE_BLOCKS_PER_SM_INST
 #define HK_TRACE_BLOCKS_PER_SM_INST 8      // (the instanced walker's world-space ray lives in shared memory; measured on C5: 6 blocks 14.1 ms, 7 13.5, 8 13.0)
 #endif
@@ -305,11 +311,32 @@ HK_DEV void trace_queue(const DevBvh& B, uint2* sm_stack, float* sm_wray, uint32
             exhausted = idle != 0u;          // a lane that found the queue empty
         }
         if (idle == 0xFFFFFFFFu) break;      // only reachable once the queue is exhausted
+#if HK_TRI_VOTE > 0 && HK_TRI_HYBRID
+        // node steps every iteration; the triangle tests of the warp wait until HK_TRI_VOTE lanes have one pending (or no lane took a node step)
+        bool fin = false, did_node = false;
+        if (busy && w.tgroup.y == 0u) { fin = w.node_step(B, &wn); did_node = true; }
+        const unsigned want_tri = __ballot_sync(0xFFFFFFFFu, busy && !fin && w.tgroup.y != 0u);
+        const unsigned nodes = __ballot_sync(0xFFFFFFFFu, did_node);
+        if ((uint32_t)__popc(want_tri) >= (uint32_t)HK_TRI_VOTE || nodes == 0u) { if (busy && !fin && w.tgroup.y != 0u) fin = w.tri_step(B, &wt); }
+        if (busy && fin) { io.store(token, w.best); busy = false; }
+#elif HK_TRI_VOTE > 0
+        // per-warp vote between the two kinds of unit work: triangle tests only run once HK_TRI_VOTE lanes have one pending (or no lane can
+        // take a node step), so their ~80 instructions are issued for many lanes at a time instead of ~7 of 32 in every iteration
+        const unsigned want_tri = __ballot_sync(0xFFFFFFFFu, busy && w.tgroup.y != 0u);
+        const unsigned want_node = __ballot_sync(0xFFFFFFFFu, busy && w.tgroup.y == 0u);
+        if (busy) {
+            bool fin = false;
+            if ((uint32_t)__popc(want_tri) >= (uint32_t)HK_TRI_VOTE || want_node == 0u) { if (w.tgroup.y != 0u) fin = w.tri_step(B, &wt); }
+            else if (w.tgroup.y == 0u) fin = w.node_step(B, &wn);
+            if (fin) { io.store(token, w.best); busy = false; }
+        }
+#else
         if (busy) {
             bool fin = false;
             if (w.tgroup.y == 0u) fin = w.node_step(B, &wn);
             if (!fin && w.tgroup.y != 0u) fin = w.tri_step(B, &wt);
             if (fin) { io.store(token, w.best); busy = false; }
         }
+#endif
     }
 }
