@@ -15,6 +15,8 @@ import argparse
 import ctypes as C
 import json
 import os
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")      # before anything creates the CUDA context (libhikari_cuda.so does the same on load;
+                                                                 # hk_api.cu: the render lanes need more than the default 8 hardware work queues)
 import subprocess
 import sys
 import threading
@@ -289,29 +291,26 @@ def measure(args, rank, world, local, dist, torch, full):
         e2e_steps = max(3, min(steps, 8))
         vp.clear(); film.iteration_index = 0
         if dist: dist.barrier()
-        pending = None                   # untimed, in the SAME pipelined pattern as the timed loop: the three page-locked host buffers (displayed +
-        for _ in range(4):               # two in flight), the copy stream and the two staging buffers all come into being here, not in the timed region
-            handle = vp.render(scene, film, cam, count=1, read="async")
-            if pending is not None:
-                vp.wait_film(film, pending)
-            pending = handle
-        vp.wait_film(film, pending)
-        vp.clear(); film.iteration_index = 0
+        depth = max(1, min(3, int(os.environ.get("HK_E2E_DEPTH", "3"))))      # read-outs left in flight while the next frame is enqueued
+        def display_loop(frames):        # progressive display loop: frame k's read-out (own stream) and frame k+1's render overlap frame k+2's
+            pending = []
+            for _ in range(frames):
+                pending.append(vp.render(scene, film, cam, count=1, read="async"))
+                if len(pending) > depth:
+                    vp.wait_film(film, pending.pop(0))
+            while pending:
+                vp.wait_film(film, pending.pop(0))      # every frame has landed in host memory before the loop returns
+        display_loop(6)                  # untimed, in the SAME pipelined pattern as the timed loop: the page-locked host buffers (displayed + in flight),
+        vp.clear(); film.iteration_index = 0      # the copy stream and the staging buffers all come into being here, not in the timed region
         B.call("synchronize")
         if dist: dist.barrier()
         t0 = time.perf_counter()
-        pending = None
-        for k in range(e2e_steps):       # progressive display loop: frame k's read-out (own stream) overlaps frame k+1's render
-            handle = vp.render(scene, film, cam, count=1, read="async")
-            if pending is not None:
-                vp.wait_film(film, pending)
-            pending = handle
-        vp.wait_film(film, pending)       # every one of the K frames has landed in host memory inside the timed region
+        display_loop(e2e_steps)
         e2e_dt = time.perf_counter() - t0
         if dist:
             te = torch.tensor([e2e_dt], device=f"cuda:{local}", dtype=torch.float64); dist.all_reduce(te, op=dist.ReduceOp.MAX); e2e_dt = float(te[0])
         e2e = {"value": world * n * e2e_steps / e2e_dt / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": C.sizeof(A.HkCamera), "d2h_bytes_per_step": 12 * n,
-               "steps": e2e_steps, "what": "per step: camera H2D, render!(vp, scene, film, camera) of one sample, framebuffer D2H into page-locked host memory (pipelined one frame deep: hk_read_film_async / _wait)",
+               "steps": e2e_steps, "what": "per step: camera H2D, render!(vp, scene, film, camera) of one sample, framebuffer D2H into page-locked host memory (pipelined: hk_read_film_async / _wait, " + str(depth) + " read-outs left in flight while the next frame is enqueued)",
                "scene_upload_s": t_upload}
     line = None
     if rank == 0:

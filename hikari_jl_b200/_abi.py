@@ -224,6 +224,11 @@ if os.environ.get("HK_CUDA_LIB"):      # development only: a tuning variant of t
     LIB_PATH = os.path.abspath(os.environ["HK_CUDA_LIB"])
 
 
+# The library's frame pipeline runs ~20 streams; the driver's default of 8 hardware work queues makes them serialise (hk_api.cu,
+# hk_on_load).  The variable is read when the CUDA context is created, so set it on import, unless the user chose a value.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+
 def load_library():
     """Load libhikari_cuda.so (built in-tree by __graft_entry__.build()).  Fails loudly when missing."""
     global _LIB

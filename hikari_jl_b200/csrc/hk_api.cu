@@ -2,6 +2,7 @@
 // There is NO CPU fallback anywhere in this file: every compute entry point needs a CUDA device and fails with
 // HK_ERR_NO_DEVICE / HK_ERR_CUDA otherwise.
 #define HK_TU_CORE
+#include <cstdlib>
 #include "hk_context.h"
 #include "hk_launch.h"
 #include "hk_denoise.cuh"
@@ -49,6 +50,13 @@ extern "C" {
 
 int32_t hk_abi_version(void) { return HK_ABI_VERSION; }
 
+// The frame pipeline (hk_context.h: HK_N_LANES) keeps ~20 streams busy.  The driver maps streams onto
+// CUDA_DEVICE_MAX_CONNECTIONS hardware work queues (default 8); streams that share a queue serialise, and with 8 the lanes
+// barely overlap (C3 4K, one sample per call: 808 Msamples/s with 8 queues, 1000 with 32; profiles/r02_e2e_lanes.txt).  The
+// variable is read when the CUDA context is created, so it is set when the library is LOADED, unless the host chose a value;
+// a host that initialises CUDA before loading the library sets it itself.
+__attribute__((constructor)) static void hk_on_load() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+
 int32_t hk_create(int32_t device, HkContext** out) {
     if (!out) return HK_ERR_INVALID;
     *out = nullptr;
@@ -75,21 +83,24 @@ int32_t hk_create(int32_t device, HkContext** out) {
     if (ctx->b_scratch_u32.alloc(16) != cudaSuccess) { delete ctx; return HK_ERR_OOM; }
     cudaMemset(ctx->b_scratch_u32.p, 0, 16);
     for (int i = 0; i < HK_N_STAGES; i++) { ctx->stage_ms[i] = 0; ctx->stage_launches[i] = 0; }
-    {   // the second render lane (frame pipelining); any failure just leaves it off
-        HkContext::AltLane& A = ctx->alt;
-        bool ok = cudaStreamCreateWithFlags(&A.stream, cudaStreamNonBlocking) == cudaSuccess;
-        for (auto& s : A.shade_streams) ok = ok && cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess;
-        ok = ok && cudaStreamCreateWithFlags(&A.shadow_stream, cudaStreamNonBlocking) == cudaSuccess;
-        ok = ok && cudaEventCreate(&A.ev0) == cudaSuccess && cudaEventCreate(&A.ev1) == cudaSuccess;
-        ok = ok && cudaEventCreateWithFlags(&A.ev_fork, cudaEventDisableTiming) == cudaSuccess;
-        for (auto& e : A.ev_join) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
-        ok = ok && cudaEventCreateWithFlags(&A.ev_shaded, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&A.ev_shadowed, cudaEventDisableTiming) == cudaSuccess;
+    {   // the extra render lanes (frame pipelining); any failure just leaves them off
+        bool ok = true;
+        for (auto& A : ctx->alts) {
+            ok = ok && cudaStreamCreateWithFlags(&A.stream, cudaStreamNonBlocking) == cudaSuccess;
+            for (auto& s : A.shade_streams) ok = ok && cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess;
+            ok = ok && cudaStreamCreateWithFlags(&A.shadow_stream, cudaStreamNonBlocking) == cudaSuccess;
+            ok = ok && cudaEventCreate(&A.ev0) == cudaSuccess && cudaEventCreate(&A.ev1) == cudaSuccess;
+            ok = ok && cudaEventCreateWithFlags(&A.ev_fork, cudaEventDisableTiming) == cudaSuccess;
+            for (auto& e : A.ev_join) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+            ok = ok && cudaEventCreateWithFlags(&A.ev_shaded, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&A.ev_shadowed, cudaEventDisableTiming) == cudaSuccess;
+            ok = ok && A.b_counts.alloc(sizeof(uint32_t) * HK_N_COUNTERS + 64) == cudaSuccess;
+            if (ok) cudaMemset(A.b_counts.p, 0, A.b_counts.bytes);
+        }
         for (auto& e : ctx->ev_lane_film) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&ctx->ev_film_touch, cudaEventDisableTiming) == cudaSuccess;
-        ok = ok && A.b_counts.alloc(sizeof(uint32_t) * HK_N_COUNTERS + 64) == cudaSuccess;
-        if (ok) cudaMemset(A.b_counts.p, 0, A.b_counts.bytes);
-        A.ready = ok && ctx->concurrent_shade && ctx->shadow_stream != nullptr && !std::getenv("HK_NO_FRAME_PIPELINE");
+        ctx->lanes_ready = ok && ctx->concurrent_shade && ctx->shadow_stream != nullptr && !std::getenv("HK_NO_FRAME_PIPELINE");
         if (!ok) cudaGetLastError();
+        if (const char* e = std::getenv("HK_LANE_MAX_COUNT")) ctx->lane_max_count = std::max(1, atoi(e));
     }
     *out = ctx;
     return HK_OK;
@@ -118,17 +129,19 @@ int32_t hk_destroy(HkContext* ctx) {
     if (ctx->ev_shaded) cudaEventDestroy(ctx->ev_shaded);
     if (ctx->ev_shadowed) cudaEventDestroy(ctx->ev_shadowed);
     for (auto& e : ctx->ev_join) if (e) cudaEventDestroy(e);
-    for (int i = 0; i < 2; i++) { if (ctx->ev_final[i]) cudaEventDestroy(ctx->ev_final[i]); if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]); ctx->b_readback_async[i].release(); }
+    for (int i = 0; i < HK_N_READOUTS; i++) { if (ctx->ev_final[i]) cudaEventDestroy(ctx->ev_final[i]); if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]); ctx->b_readback_async[i].release(); }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
-    {   HkContext::AltLane& A = ctx->alt;
+    for (auto& A : ctx->alts) {
         A.b_state.release(); A.b_counts.release();
         if (A.stream) cudaStreamDestroy(A.stream);
         for (auto& s2 : A.shade_streams) if (s2) cudaStreamDestroy(s2);
         if (A.shadow_stream) cudaStreamDestroy(A.shadow_stream);
-        cudaEvent_t evs[] = {A.ev_fork, A.ev_shaded, A.ev_shadowed, A.ev0, A.ev1, ctx->ev_lane_film[0], ctx->ev_lane_film[1], ctx->ev_film_touch};
+        cudaEvent_t evs[] = {A.ev_fork, A.ev_shaded, A.ev_shadowed, A.ev0, A.ev1};
         for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
         for (auto& e : A.ev_join) if (e) cudaEventDestroy(e);
     }
+    for (auto& e : ctx->ev_lane_film) if (e) cudaEventDestroy(e);
+    if (ctx->ev_film_touch) cudaEventDestroy(ctx->ev_film_touch);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);      // (a caller-supplied stream is the caller's to destroy)
     delete ctx;
     return HK_OK;
@@ -555,7 +568,7 @@ static int32_t alloc_film(HkContext* ctx, size_t n_pixels) {
     CK(ctx->b_film.alloc(16 * n_pixels + 64));
     CK(cudaMemset(ctx->b_film.p, 0, ctx->b_film.bytes));
     ctx->S.pixel_rgb = ctx->b_film.as<float>(); ctx->S.pixel_weight = ctx->b_film.as<float>() + 3 * n_pixels;
-    ctx->alt.S.pixel_rgb = ctx->S.pixel_rgb; ctx->alt.S.pixel_weight = ctx->S.pixel_weight;      // (the second render lane accumulates into the same film)
+    for (auto& A : ctx->alts) { A.S.pixel_rgb = ctx->S.pixel_rgb; A.S.pixel_weight = ctx->S.pixel_weight; }      // (the other render lanes accumulate into the same film)
     return HK_OK;
 }
 static int32_t alloc_state(HkContext* ctx, size_t n_slots) {
@@ -658,7 +671,7 @@ int32_t hk_set_params(HkContext* ctx, const HkRenderParams* p) {
         ctx->aux_pixels = 0;                 // film.albedo / normal / depth belong to the previous film
         CK(cudaStreamSynchronize(ctx->stream));
         ctx->b_state.release(); ctx->n_slots = 0;
-        ctx->alt.b_state.release(); ctx->alt.n_slots = 0;
+        for (auto& A : ctx->alts) { A.b_state.release(); A.n_slots = 0; }
     }
     rc = build_sobol_cache(ctx);
     if (rc != HK_OK) return rc;
@@ -705,12 +718,12 @@ int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride,
     REQUIRE(count >= 0 && stride >= 1 && first >= 1, "bad sample range");
     const size_t n_pixels = (size_t)ctx->params.width * ctx->params.height;
     // frame pipelining: one-sample calls alternate between the two render lanes (hk_context.h)
-    const bool pipelined = count == 1 && ctx->alt.ready && ctx->frame_pipeline && ctx->profiling == 0 && ctx->stream == ctx->own_stream;
+    const bool pipelined = count >= 1 && count <= ctx->lane_max_count && ctx->lanes_ready && ctx->frame_pipeline && ctx->profiling == 0 && ctx->stream == ctx->own_stream;
     const int lane = pipelined ? ctx->next_lane : 0;
-    ctx->next_lane = pipelined ? (lane ^ 1) : 0;
-    if (!pipelined && ctx->lane_pending[1]) { cudaStreamSynchronize(ctx->alt.stream); ctx->lane_pending[1] = false; }      // a batched call: plain single-stream order
-    struct LaneGuard { HkContext* c; bool on; ~LaneGuard() { if (on) c->swap_lane(); } } lane_guard{ctx, lane == 1};
-    if (lane == 1) ctx->swap_lane();
+    ctx->next_lane = pipelined ? (lane + 1) % HK_N_LANES : 0;
+    if (!pipelined) ctx->sync_alt_lanes();      // a batched call: plain single-stream order
+    struct LaneGuard { HkContext* c; int k; ~LaneGuard() { if (k > 0) c->swap_lane(k); } } lane_guard{ctx, lane};
+    if (lane > 0) ctx->swap_lane(lane);
     ctx->last_lane = lane;
     cudaStream_t st = ctx->stream;
     {
@@ -805,10 +818,10 @@ int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride,
         }
         if (shadow_in_flight) cudaStreamWaitEvent(st, ctx->ev_shadowed, 0);      // the film pass reads L
         // the film is summed in sample order: wait for the other lane's accumulation, and (second lane) for read-outs / clears of the film on the main stream
-        if (ctx->lane_pending[lane ^ 1]) cudaStreamWaitEvent(st, ctx->ev_lane_film[lane ^ 1], 0);
-        if (lane == 1 && ctx->film_touch_pending) cudaStreamWaitEvent(st, ctx->ev_film_touch, 0);
+        if (ctx->last_accum_lane >= 0 && ctx->last_accum_lane != lane && ctx->lane_pending[ctx->last_accum_lane]) cudaStreamWaitEvent(st, ctx->ev_lane_film[ctx->last_accum_lane], 0);
+        if (lane > 0 && ctx->film_touch_pending) cudaStreamWaitEvent(st, ctx->ev_film_touch, 0);
         { StageScope sc(ctx, HK_STAGE_FILM); k_film_accumulate<<<grid_for(ctx, n_pixels, 256, 8), 256, 0, st>>>(ctx->D, ctx->S, A); }
-        if (pipelined || ctx->lane_pending[1]) { cudaEventRecord(ctx->ev_lane_film[lane], st); ctx->lane_pending[lane] = true; }
+        if (pipelined || ctx->any_alt_pending()) { cudaEventRecord(ctx->ev_lane_film[lane], st); ctx->lane_pending[lane] = true; ctx->last_accum_lane = lane; }
         done += A.n_batch;
         if (ctx->profiling & 1) collect_stage_times(ctx);
     }
@@ -886,9 +899,9 @@ int32_t hk_set_stream(HkContext* ctx, void* cuda_stream) {
     ctx->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
     return HK_OK;
 }
-// Pipelined read-out for progressive display: finalize into one of two staging buffers on the render stream, copy it to the
-// (pinned) host buffer on a separate stream, and return at once -- the next hk_render_samples can be enqueued while the
-// DMA runs.  hk_read_film_wait(ticket) blocks until that frame has landed.  At most two frames in flight.
+// Pipelined read-out for progressive display: finalize into one of HK_N_READOUTS staging buffers on the render stream, copy it
+// to the (pinned) host buffer on a separate stream, and return at once -- the next hk_render_samples can be enqueued while the
+// DMA runs.  hk_read_film_wait(ticket) blocks until that frame has landed.  At most HK_N_READOUTS (4) frames in flight.
 int32_t hk_read_film_async(HkContext* ctx, float* out_pinned, int32_t* ticket) {
     if (!ctx || !out_pinned || !ticket) return HK_ERR_INVALID;
     hk_enter_film_async(ctx);
@@ -896,7 +909,7 @@ int32_t hk_read_film_async(HkContext* ctx, float* out_pinned, int32_t* ticket) {
     const size_t n = (size_t)ctx->params.width * ctx->params.height;
     if (!ctx->copy_stream) {
         CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; i++) { CK(cudaEventCreateWithFlags(&ctx->ev_final[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming)); }
+        for (int i = 0; i < HK_N_READOUTS; i++) { CK(cudaEventCreateWithFlags(&ctx->ev_final[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming)); }
     }
     const int k = ctx->async_next;
     if (ctx->b_readback_async[k].bytes < 12 * n) { CK(cudaStreamSynchronize(ctx->copy_stream)); CK(ctx->b_readback_async[k].alloc(12 * n)); ctx->async_used[k] = false; }
@@ -908,12 +921,12 @@ int32_t hk_read_film_async(HkContext* ctx, float* out_pinned, int32_t* ticket) {
     CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_final[k], 0));
     CK(cudaMemcpyAsync(out_pinned, ctx->b_readback_async[k].p, 12 * n, cudaMemcpyDeviceToHost, ctx->copy_stream));
     CK(cudaEventRecord(ctx->ev_copied[k], ctx->copy_stream));
-    ctx->async_used[k] = true; ctx->async_next = k ^ 1;
+    ctx->async_used[k] = true; ctx->async_next = (k + 1) % HK_N_READOUTS;
     *ticket = k;
     return HK_OK;
 }
 int32_t hk_read_film_wait(HkContext* ctx, int32_t ticket) {
-    if (!ctx || ticket < 0 || ticket > 1) return HK_ERR_INVALID;
+    if (!ctx || ticket < 0 || ticket >= HK_N_READOUTS) return HK_ERR_INVALID;
     cudaSetDevice(ctx->device);
     REQUIRE(ctx->copy_stream && ctx->async_used[ticket], "no asynchronous read-out with this ticket is in flight");
     CK(cudaEventSynchronize(ctx->ev_copied[ticket]));
@@ -1113,14 +1126,15 @@ int32_t hk_stats(HkContext* ctx, HkStats* out) {
     CK(cudaStreamSynchronize(ctx->stream));
     float ms = 0;
     if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->stats.last_render_ms = ms; else cudaGetLastError();
-    if (ctx->last_lane == 1 && ctx->alt.ev0) { float m2 = 0; if (cudaEventElapsedTime(&m2, ctx->alt.ev0, ctx->alt.ev1) == cudaSuccess) ctx->stats.last_render_ms = m2; else cudaGetLastError(); }
+    if (ctx->last_lane > 0 && ctx->alts[ctx->last_lane - 1].ev0) { float m2 = 0; if (cudaEventElapsedTime(&m2, ctx->alts[ctx->last_lane - 1].ev0, ctx->alts[ctx->last_lane - 1].ev1) == cudaSuccess) ctx->stats.last_render_ms = m2; else cudaGetLastError(); }
     unsigned long long rt = 0, rt2 = 0;
     if (ctx->S.rays_traced) cudaMemcpy(&rt, ctx->S.rays_traced, 8, cudaMemcpyDeviceToHost);
-    if (ctx->alt.S.rays_traced) cudaMemcpy(&rt2, ctx->alt.S.rays_traced, 8, cudaMemcpyDeviceToHost);
+    for (auto& A : ctx->alts) if (A.S.rays_traced) { unsigned long long x = 0; cudaMemcpy(&x, A.S.rays_traced, 8, cudaMemcpyDeviceToHost); rt2 += x; }
     *out = ctx->stats;
     out->rays_traced = ctx->stats.rays_traced + rt + rt2;
     { unsigned long long pv = 0, pv2 = 0; if (ctx->S.path_vertices) cudaMemcpy(&pv, ctx->S.path_vertices, 8, cudaMemcpyDeviceToHost);
-      if (ctx->alt.S.path_vertices) cudaMemcpy(&pv2, ctx->alt.S.path_vertices, 8, cudaMemcpyDeviceToHost); out->path_vertices = pv + pv2; }
+      for (auto& A : ctx->alts) if (A.S.path_vertices) { unsigned long long x = 0; cudaMemcpy(&x, A.S.path_vertices, 8, cudaMemcpyDeviceToHost); pv2 += x; }
+      out->path_vertices = pv + pv2; }
     out->kernel_launches = ctx->launches;
     out->queue_overflows = 0;
     return HK_OK;

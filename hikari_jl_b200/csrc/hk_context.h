@@ -34,7 +34,7 @@ struct HkContext {
     PathState S;
     HkRenderParams params;
     bool have_tables = false, have_geom = false, have_mats = false, have_lights = false, have_cam = false, have_filter = false, have_params = false;
-    uint64_t camera_version = 1, lane_cam_version[2] = {0, 0};      // detect_camera_medium result per render lane (device-resident, b_scratch_u32[lane])
+    uint64_t camera_version = 1, lane_cam_version[4] = {0, 0, 0, 0};      // detect_camera_medium result per render lane (device-resident, b_scratch_u32[lane])
     uint32_t mat_types_present = 0;
     uint32_t n_interfaces = 0, max_iface_in_geom = 0; bool tri_types_valid = false;
     std::vector<int32_t> mat_types;                  // host copy of the material types (hk_update_material)
@@ -55,8 +55,9 @@ struct HkContext {
     DevBuf b_uvs, b_textures; std::vector<DevBuf> tex_bufs;
     bool has_rgbgrid = false;                // some uploaded medium is an RGBGridMedium: the tracking kernels with that branch compiled in     // film.albedo [3n] | film.normal [3n] | film.depth [n], (H, W) column-major
     // pipelined read-out (hk_read_film_async): two device staging buffers, a copy stream, per-buffer events
-    DevBuf b_readback_async[2]; cudaStream_t copy_stream = nullptr; cudaEvent_t ev_final[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
-    int async_next = 0; bool async_used[2] = {false, false};
+#define HK_N_READOUTS 4                // asynchronous read-outs in flight (hk_read_film_async tickets 0..3)
+    DevBuf b_readback_async[HK_N_READOUTS]; cudaStream_t copy_stream = nullptr; cudaEvent_t ev_final[HK_N_READOUTS] = {}, ev_copied[HK_N_READOUTS] = {};
+    int async_next = 0; bool async_used[HK_N_READOUTS] = {};
     // fork / join of the per-material shading kernels of one bounce (independent queues) over side streams
     cudaStream_t shade_streams[3] = {nullptr, nullptr, nullptr}; cudaEvent_t ev_fork = nullptr, ev_join[12] = {};
     bool concurrent_shade = true; int shade_fork_slot = 0;
@@ -79,7 +80,7 @@ struct HkContext {
     std::vector<std::array<uint32_t, HK_N_QUEUE_COUNTERS>> bounce_counts;
     std::vector<std::array<double, HK_N_STAGES>> bounce_ms;
     // ---- frame pipelining: a second render lane ----------------------------------------------------------------------------------
-    // One-sample hk_render_samples calls (the interactive render! loop: one sample + one read-out per frame) alternate between two
+    // One-sample hk_render_samples calls (the interactive render! loop: one sample + one read-out per frame) rotate over HK_N_LANES
     // lanes, each with its own path-state pool, counters, render stream, side streams and events, so that frame k+1's early bounces
     // fill the GPU while frame k's deep bounces -- a few rays per stage, each stage a latency floor -- drain.  The film is shared; its
     // accumulation order (sample order) and every read / clear of it are kept by events: ev_lane_film[l] = lane l's last
@@ -88,32 +89,36 @@ struct HkContext {
         PathState S; DevBuf b_state, b_counts; size_t n_slots = 0;
         cudaStream_t stream = nullptr, shade_streams[3] = {nullptr, nullptr, nullptr}, shadow_stream = nullptr;
         cudaEvent_t ev_fork = nullptr, ev_join[12] = {}, ev_shaded = nullptr, ev_shadowed = nullptr, ev0 = nullptr, ev1 = nullptr;
-        bool ready = false;
-    } alt;
-    cudaEvent_t ev_lane_film[2] = {nullptr, nullptr}, ev_film_touch = nullptr;
-    bool lane_pending[2] = {false, false}, film_touch_pending = false, frame_pipeline = true, in_alt = false;
-    int next_lane = 0, last_lane = 0;
-    // swap the main lane's per-pass resources with the second lane's (hk_render_samples* runs unchanged on whichever is current)
-    void swap_lane() {
+    };
+#define HK_N_LANES 4                   // the main lane + three more: up to four one-sample frames in flight
+    AltLane alts[HK_N_LANES - 1];
+    bool lanes_ready = false;
+    cudaEvent_t ev_lane_film[HK_N_LANES] = {}, ev_film_touch = nullptr;
+    bool lane_pending[HK_N_LANES] = {}, film_touch_pending = false, frame_pipeline = true;
+    int next_lane = 0, last_lane = 0, last_accum_lane = -1, lane_max_count = 1;
+    // swap the main lane's per-pass resources with lane k's (hk_render_samples* runs unchanged on whichever is current)
+    void swap_lane(int k) {
+        AltLane& alt = alts[k - 1];
         std::swap(S, alt.S); std::swap(b_state, alt.b_state); std::swap(b_counts, alt.b_counts); std::swap(n_slots, alt.n_slots);
         std::swap(stream, alt.stream); for (int i = 0; i < 3; i++) std::swap(shade_streams[i], alt.shade_streams[i]); std::swap(shadow_stream, alt.shadow_stream);
         std::swap(ev_fork, alt.ev_fork); for (int i = 0; i < 12; i++) std::swap(ev_join[i], alt.ev_join[i]);
         std::swap(ev_shaded, alt.ev_shaded); std::swap(ev_shadowed, alt.ev_shadowed); std::swap(ev0, alt.ev0); std::swap(ev1, alt.ev1);
-        in_alt = !in_alt;
     }
-    HkContext() { std::memset(&D, 0, sizeof(D)); std::memset(&S, 0, sizeof(S)); std::memset(&alt.S, 0, sizeof(alt.S)); std::memset(&params, 0, sizeof(params)); std::memset(&stats, 0, sizeof(stats)); }
+    bool any_alt_pending() const { for (int l = 1; l < HK_N_LANES; l++) if (lane_pending[l]) return true; return false; }
+    void sync_alt_lanes() { for (int l = 1; l < HK_N_LANES; l++) if (lane_pending[l] && alts[l - 1].stream) { cudaStreamSynchronize(alts[l - 1].stream); lane_pending[l] = false; } }
+    HkContext() { std::memset(&D, 0, sizeof(D)); std::memset(&S, 0, sizeof(S)); for (auto& a : alts) std::memset(&a.S, 0, sizeof(a.S)); std::memset(&params, 0, sizeof(params)); std::memset(&stats, 0, sizeof(stats)); }
 };
 // entry-point prologue: select the device and wait (on the host) for the second render lane, so that everything but the render /
 // asynchronous read-out entry points sees the single-stream behaviour
 static inline void hk_enter(HkContext* ctx) {
     cudaSetDevice(ctx->device);
-    if (ctx->lane_pending[1] && ctx->alt.stream) { cudaStreamSynchronize(ctx->alt.stream); ctx->lane_pending[1] = false; }
+    ctx->sync_alt_lanes();
 }
 // the stream-ordered form for the asynchronous film readers / hk_clear on the main stream: the main stream waits for the second
 // lane's last film accumulation (which itself waited for everything before it)
 static inline void hk_enter_film_async(HkContext* ctx) {
     cudaSetDevice(ctx->device);
-    if (ctx->lane_pending[1] && ctx->ev_lane_film[1]) cudaStreamWaitEvent(ctx->stream, ctx->ev_lane_film[1], 0);
+    if (ctx->last_accum_lane > 0 && ctx->lane_pending[ctx->last_accum_lane]) cudaStreamWaitEvent(ctx->stream, ctx->ev_lane_film[ctx->last_accum_lane], 0);      // (each accumulation waited for the one before it)
 }
 static inline void hk_film_touched(HkContext* ctx) {      // after a film read-out / clear was enqueued on the main stream
     if (ctx->ev_film_touch) { cudaEventRecord(ctx->ev_film_touch, ctx->stream); ctx->film_touch_pending = true; }

@@ -310,8 +310,8 @@ int32_t hk_test_read_rays(HkContext* ctx, float* rays, float* hits, uint64_t n_s
     if (!ctx || !ctx->have_params || !rays || !hits) return HK_ERR_INVALID;
     hk_enter(ctx);
     CK(cudaStreamSynchronize(ctx->stream));
-    const PathState& PS = ctx->last_lane == 1 ? ctx->alt.S : ctx->S;      // the lane that rendered last (frame pipelining)
-    if (n_slots > (ctx->last_lane == 1 ? ctx->alt.n_slots : ctx->n_slots)) return HK_ERR_INVALID;
+    const PathState& PS = ctx->last_lane > 0 ? ctx->alts[ctx->last_lane - 1].S : ctx->S;      // the lane that rendered last (frame pipelining)
+    if (n_slots > (ctx->last_lane > 0 ? ctx->alts[ctx->last_lane - 1].n_slots : ctx->n_slots)) return HK_ERR_INVALID;
     std::vector<float4> a(n_slots), b(n_slots);
     CK(cudaMemcpy(a.data(), PS.ray_a, 16 * n_slots, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(b.data(), PS.ray_b, 16 * n_slots, cudaMemcpyDeviceToHost));
     for (uint64_t i = 0; i < n_slots; i++) {
@@ -327,8 +327,8 @@ int32_t hk_test_read_pass(HkContext* ctx, float* L, float* lam, float* pdf, floa
     if (!ctx || !ctx->have_params) return HK_ERR_INVALID;
     hk_enter(ctx);
     CK(cudaStreamSynchronize(ctx->stream));
-    const PathState& PS = ctx->last_lane == 1 ? ctx->alt.S : ctx->S;
-    if (n_slots > (ctx->last_lane == 1 ? ctx->alt.n_slots : ctx->n_slots)) return HK_ERR_INVALID;
+    const PathState& PS = ctx->last_lane > 0 ? ctx->alts[ctx->last_lane - 1].S : ctx->S;
+    if (n_slots > (ctx->last_lane > 0 ? ctx->alts[ctx->last_lane - 1].n_slots : ctx->n_slots)) return HK_ERR_INVALID;
     CK(cudaMemcpy(L, PS.L, 16 * n_slots, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(lam, PS.lambda, 16 * n_slots, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(pdf, PS.lpdf, 16 * n_slots, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(fw, PS.fweight, 4 * n_slots, cudaMemcpyDeviceToHost));
     return HK_OK;

@@ -104,7 +104,7 @@ class Film:
 
     def _acquire_store(self):
         """A host buffer for one pipelined read-out (Backend.read_film_async): never the displayed one and never one that an
-        un-waited read-out still targets -- with two frames in flight plus the displayed frame that is three buffers
+        un-waited read-out still targets -- with four frames in flight plus the displayed frame that is five buffers
         (include/hikari_cuda.h: 'the caller alternates host buffers'); they are allocated on demand and recycled by _show."""
         return self._free.pop() if self._free else self._new_store(zero=False)      # (a read-out overwrites every byte)
 
@@ -1399,7 +1399,7 @@ class Backend:
     def read_film_async(self, film):
         """Enqueue finalize + device->host copy of the current film into a page-locked buffer of the film that no displayed or
         in-flight frame uses and return a handle at once (hk_read_film_async); wait_film(handle) makes that frame
-        film.framebuffer.  At most two read-outs may be in flight (the library's two staging buffers)."""
+        film.framebuffer.  At most four read-outs may be in flight (the library's four staging buffers)."""
         assert film.resolution == (self.width, self.height)
         store = film._acquire_store()
         ticket = C.c_int32(-1)

@@ -385,8 +385,8 @@ int32_t hk_render_samples_strided(HkContext* ctx, int32_t first_sample_idx, int3
 int32_t hk_read_film(HkContext* ctx, float* out_rgb_hw_colmajor);
 /* Pipelined read-out for progressive display (library extension): finalize + device->host copy of the current film are
  * enqueued (copy on its own stream) and the call returns a ticket at once, so the next hk_render_samples overlaps the
- * DMA; hk_read_film_wait blocks until that frame is in `out` (page-locked memory: hk_pinned_alloc).  Two frames at
- * most in flight; the caller alternates two host buffers.                                                         */
+ * DMA; hk_read_film_wait blocks until that frame is in `out` (page-locked memory: hk_pinned_alloc).  Four frames
+ * at most in flight (a fifth call reuses the oldest ticket's staging, after its copy); one host buffer per frame in flight. */
 int32_t hk_read_film_async(HkContext* ctx, float* out_rgb_hw_colmajor_pinned, int32_t* out_ticket);
 int32_t hk_read_film_wait(HkContext* ctx, int32_t ticket);
 /* Zero-copy read-out: the reference takes its GPU path when film.framebuffer is a device array

@@ -16,6 +16,11 @@ import KernelAbstractions as KA
 
 const lib = "libhikari_cuda"                       # on the loader path (hikari_jl_b200/csrc/libhikari_cuda.so)
 
+# The library's frame pipeline needs more hardware work queues than the driver's default of 8 (INTEGRATION.md, "Frame pipelining");
+# the variable is read when the CUDA context is created, so this only helps when no context exists yet -- otherwise set it in
+# the shell / startup.jl.
+__init__() = (get!(ENV, "CUDA_DEVICE_MAX_CONNECTIONS", "32"); nothing)
+
 # ---- struct mirrors of include/hikari_cuda.h (isbits, C layout) ---------------------------------------------------------
 struct HkTables
     sobol_matrices::Ptr{UInt32}; cie_x::Ptr{Float32}; cie_y::Ptr{Float32}; cie_z::Ptr{Float32}; d65::Ptr{Float32}

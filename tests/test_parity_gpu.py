@@ -560,9 +560,9 @@ def test_caller_stream_and_device_framebuffer():
 
 
 def test_frame_pipelining_keeps_every_frame():
-    """The interactive loop (one sample + one read-out per render! call) alternates between two render lanes so that frame k+1
-    starts while frame k's deep bounces drain.  Every frame read out that way -- asynchronously, one frame in flight, as bench.py's
-    e2e loop does -- must be bit for bit the frame a strictly sequential loop reads, and the accumulated film that of ONE batched call."""
+    """The interactive loop (one sample + one read-out per render! call) rotates over three render lanes so that frames k+1 and k+2
+    start while frame k's deep bounces drain.  Every frame read out that way -- asynchronously, one or two frames in flight, as
+    bench.py's e2e loop does -- must be bit for bit the frame a strictly sequential loop reads, and the accumulated film that of ONE batched call."""
     for make, res, depth in ((scenes.cornell_smoke, (96, 96), 6), (lambda: scenes.c2_cat(32, 16), (160, 90), 8)):
         scene, camf = make()
         n_frames = 7
@@ -572,18 +572,19 @@ def test_frame_pipelining_keeps_every_frame():
             vp.render(scene, film, camf(film), count=1, read=True)
             seq.append(film.framebuffer.copy())
         vp.close()
-        film = H.Film(res); vp = H.VolPath(samples=64, max_depth=depth)
-        cam = camf(film)
-        pipe, pending = [], None
-        for k in range(n_frames):                                   # pipelined: frame k's read-out overlaps frame k+1's render
-            h = vp.render(scene, film, cam, count=1, read="async")
-            if pending is not None:
-                vp.wait_film(film, pending); pipe.append(film.framebuffer.copy())
-            pending = h
-        vp.wait_film(film, pending); pipe.append(film.framebuffer.copy())
-        vp.close()
-        for k in range(n_frames):
-            assert np.array_equal(seq[k].view(np.uint32), pipe[k].view(np.uint32)), f"frame {k} differs between the sequential and the pipelined loop"
+        for in_flight in (1, 2):                                    # read-outs left un-waited while the next frame is enqueued (bench.py: 2)
+            film = H.Film(res); vp = H.VolPath(samples=64, max_depth=depth)
+            cam = camf(film)
+            pipe, pending = [], []
+            for k in range(n_frames):                               # pipelined: frame k's read-out overlaps the renders of frames k+1, k+2
+                pending.append(vp.render(scene, film, cam, count=1, read="async"))
+                if len(pending) > in_flight:
+                    vp.wait_film(film, pending.pop(0)); pipe.append(film.framebuffer.copy())
+            while pending:
+                vp.wait_film(film, pending.pop(0)); pipe.append(film.framebuffer.copy())
+            vp.close()
+            for k in range(n_frames):
+                assert np.array_equal(seq[k].view(np.uint32), pipe[k].view(np.uint32)), f"frame {k} differs between the sequential and the pipelined loop ({in_flight} in flight)"
         film = H.Film(res); vp = H.VolPath(samples=64, max_depth=depth)
         vp._prepare(scene, film, camf(film)); vp.clear()
         vp.backend.call("render_samples", 1, n_frames); vp.backend.read_film(film)
