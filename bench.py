@@ -288,7 +288,7 @@ def measure(args, rank, world, local, dist, torch, full):
     if full:
         # ---- e2e: the interactive render! loop through the public API with HOST buffers: per step the camera is re-sent
         # (H2D), one sample pass runs and the framebuffer is read back (D2H) ------------------------------------------------
-        e2e_steps = max(3, min(steps, 8))
+        e2e_steps = max(3, steps)                      # the same K frames as the device-timed region
         vp.clear(); film.iteration_index = 0
         if dist: dist.barrier()
         depth = max(1, min(3, int(os.environ.get("HK_E2E_DEPTH", "3"))))      # read-outs left in flight while the next frame is enqueued
