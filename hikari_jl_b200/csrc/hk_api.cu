@@ -473,69 +473,111 @@ int32_t hk_upload_lights(HkContext* ctx, const HkLight* l, uint32_t n, const HkL
     return hk_refresh_uplift_cache(ctx);
 }
 
+// one medium: voxel buffers, majorant grid (uploaded, or built on the device when HkMedium.majorant is NULL: k_build_majorant) and
+// the empty-cell mask of the majorant grid (k_majorant_mask, one bit per cell)
+static int32_t upload_one_medium(HkContext* ctx, uint32_t i, const HkMedium& M, DevMedium& d) {
+    REQUIRE(M.type >= 1 && M.type <= 4, "unknown medium type");
+    std::memset(&d, 0, sizeof(d));
+    d.type = M.type; std::memcpy(d.sigma_a, M.sigma_a_rgb, 12); std::memcpy(d.sigma_s, M.sigma_s_rgb, 12); std::memcpy(d.Le, M.Le_rgb, 12); d.g = M.g;
+    std::memcpy(d.bmin, M.bounds_min, 12); std::memcpy(d.bmax, M.bounds_max, 12); std::memcpy(d.medium_from_render, M.medium_from_render, 48);
+    DevBuf* B = &ctx->media_bufs[3 * (size_t)i];
+    if (M.type == HK_MEDIUM_GRID) {
+        REQUIRE(M.density && M.density_res[0] >= 1 && M.density_res[1] >= 1 && M.density_res[2] >= 1, "GridMedium needs a density grid");
+        size_t cnt = (size_t)M.density_res[0] * M.density_res[1] * M.density_res[2];
+        CK(B[0].upload(M.density, 4 * cnt)); d.density = B[0].as<float>(); std::memcpy(d.dres, M.density_res, 12);
+    }
+    if (M.type == HK_MEDIUM_RGBGRID) {     // the (up to) three RGB grids share one allocation
+        REQUIRE(M.rgb_sigma_a || M.rgb_sigma_s, "RGBGridMedium needs at least one of sigma_a / sigma_s grids (media.jl:1073)");
+        REQUIRE(!M.rgb_Le || M.rgb_sigma_a, "RGBGridMedium: Le grid requires a sigma_a grid (media.jl:1075)");
+        REQUIRE(M.density_res[0] >= 2 && M.density_res[1] >= 2 && M.density_res[2] >= 2, "RGBGridMedium: grid must be at least 2 voxels per axis");
+        const size_t cnt = 3 * (size_t)M.density_res[0] * M.density_res[1] * M.density_res[2];
+        const float* src[3] = {M.rgb_sigma_a, M.rgb_sigma_s, M.rgb_Le};
+        std::vector<float> packed; size_t off[3];
+        for (int k = 0; k < 3; k++) { off[k] = packed.size(); if (src[k]) packed.insert(packed.end(), src[k], src[k] + cnt); }
+        CK(B[0].upload(packed.data(), 4 * packed.size()));
+        d.rgb_a = src[0] ? B[0].as<float>() + off[0] : nullptr; d.rgb_s = src[1] ? B[0].as<float>() + off[1] : nullptr;
+        d.rgb_le = src[2] ? B[0].as<float>() + off[2] : nullptr;
+        std::memcpy(d.dres, M.density_res, 12); d.sigma_scale = M.scale; d.le_scale = M.Le_scale;
+    }
+    if (M.type == HK_MEDIUM_NANOVDB) {
+        REQUIRE(M.nanovdb_buf && M.nanovdb_bytes > 0, "NanoVDBMedium needs its grid buffer");
+        CK(B[2].upload(M.nanovdb_buf, (size_t)M.nanovdb_bytes)); d.nvdb = B[2].as<uint8_t>();
+        std::memcpy(d.inv_mat, M.nanovdb_inv_mat, 36); std::memcpy(d.vec, M.nanovdb_vec, 12); d.root_off = M.nanovdb_root_offset; d.root_tiles = M.nanovdb_root_tiles;
+    }
+    ctx->mask_bufs[i].release();
+    if (M.type == HK_MEDIUM_HOMOGENEOUS) return HK_OK;
+    REQUIRE(M.majorant_res[0] >= 1 && M.majorant_res[1] >= 1 && M.majorant_res[2] >= 1, "majorant_res must be at least 1 per axis");
+    const size_t cells = (size_t)M.majorant_res[0] * M.majorant_res[1] * M.majorant_res[2];
+    REQUIRE(cells < (1ull << 31), "majorant grid too large");
+    std::memcpy(d.mres, M.majorant_res, 12);
+    if (M.majorant) { CK(B[1].upload(M.majorant, 4 * cells)); d.majorant = B[1].as<float>(); }
+    else {      // build_majorant_grid / build_rgb_majorant_grid / build_nanovdb_majorant_grid on the device
+        CK(B[1].alloc(4 * cells)); d.majorant = B[1].as<float>();
+        MajBuild P; std::memcpy(P.idx_min, M.nanovdb_index_min, 12); std::memcpy(P.idx_max, M.nanovdb_index_max, 12);
+        std::memcpy(P.bmin, M.bounds_min, 12); std::memcpy(P.bmax, M.bounds_max, 12);
+        k_build_majorant<<<(unsigned)cells, 128, 0, ctx->stream>>>(d, P, B[1].as<float>());
+        ctx->launches++;
+    }
+    const size_t words = (cells + 31) / 32;
+    CK(ctx->mask_bufs[i].alloc(4 * words));
+    k_majorant_mask<<<grid_for(ctx, words, 256, 8), 256, 0, ctx->stream>>>(d.majorant, (uint32_t)cells, ctx->mask_bufs[i].as<uint32_t>());
+    ctx->launches++;
+    d.maj_empty = ctx->mask_bufs[i].as<uint32_t>();
+    return HK_OK;
+}
+// after any change to ctx->media_host: which mask the tracking kernels stage in shared memory (the first one that fits
+// HK_SMEM_MASK_WORDS), the device copy of the records, the uplift cache
+static int32_t commit_media(HkContext* ctx) {
+    std::vector<DevMedium>& dev = ctx->media_host;
+    ctx->has_rgbgrid = false; ctx->D.smem_mask_medium = 0; ctx->D.smem_mask_words = 0;
+    for (size_t i = 0; i < dev.size(); i++) {
+        if (dev[i].type == HK_MEDIUM_RGBGRID) ctx->has_rgbgrid = true;
+        if (dev[i].type == HK_MEDIUM_HOMOGENEOUS) continue;
+        const size_t words = ((size_t)dev[i].mres[0] * dev[i].mres[1] * dev[i].mres[2] + 31) / 32;
+        if (ctx->D.smem_mask_medium == 0 && words <= HK_SMEM_MASK_WORDS && !std::getenv("HK_NO_SMEM_MASK")) { ctx->D.smem_mask_medium = (int32_t)i + 1; ctx->D.smem_mask_words = (uint32_t)words; }
+    }
+    std::vector<DevMedium> up = dev;
+    if (std::getenv("HK_NO_EMPTY_MASK")) { for (auto& d : up) d.maj_empty = nullptr; ctx->D.smem_mask_medium = 0; ctx->D.smem_mask_words = 0; }      // development A/B
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    CK(ctx->b_media.upload(up.data(), sizeof(DevMedium) * up.size()));
+    ctx->D.media = ctx->b_media.as<DevMedium>(); ctx->D.n_media = (int32_t)up.size();
+    ctx->camera_version++;
+    return hk_refresh_uplift_cache(ctx);
+}
 int32_t hk_upload_media(HkContext* ctx, const HkMedium* m, uint32_t n) {
-    if (!ctx) return HK_ERR_INVALID;
+    if (!ctx || (n > 0 && !m)) return HK_ERR_INVALID;
     hk_enter(ctx);
     for (auto& b : ctx->media_bufs) b.release();
     for (auto& b : ctx->mask_bufs) b.release();
     ctx->media_bufs.clear(); ctx->media_bufs.resize(3 * (size_t)n);
-    std::vector<DevMedium> dev(n);
-    for (uint32_t i = 0; i < n; i++) {
-        const HkMedium& M = m[i];
-        REQUIRE(M.type >= 1 && M.type <= 4, "unknown medium type");
-        DevMedium& d = dev[i]; std::memset(&d, 0, sizeof(d));
-        d.type = M.type; std::memcpy(d.sigma_a, M.sigma_a_rgb, 12); std::memcpy(d.sigma_s, M.sigma_s_rgb, 12); std::memcpy(d.Le, M.Le_rgb, 12); d.g = M.g;
-        std::memcpy(d.bmin, M.bounds_min, 12); std::memcpy(d.bmax, M.bounds_max, 12); std::memcpy(d.medium_from_render, M.medium_from_render, 48);
-        DevBuf* B = &ctx->media_bufs[3 * (size_t)i];
-        if (M.type == HK_MEDIUM_GRID) {
-            size_t cnt = (size_t)M.density_res[0] * M.density_res[1] * M.density_res[2];
-            CK(B[0].upload(M.density, 4 * cnt)); d.density = B[0].as<float>(); std::memcpy(d.dres, M.density_res, 12);
-        }
-        if (M.type == HK_MEDIUM_RGBGRID) {     // the (up to) three RGB grids share one allocation
-            REQUIRE(M.rgb_sigma_a || M.rgb_sigma_s, "RGBGridMedium needs at least one of sigma_a / sigma_s grids (media.jl:1073)");
-            REQUIRE(!M.rgb_Le || M.rgb_sigma_a, "RGBGridMedium: Le grid requires a sigma_a grid (media.jl:1075)");
-            REQUIRE(M.density_res[0] >= 2 && M.density_res[1] >= 2 && M.density_res[2] >= 2, "RGBGridMedium: grid must be at least 2 voxels per axis");
-            const size_t cnt = 3 * (size_t)M.density_res[0] * M.density_res[1] * M.density_res[2];
-            const float* src[3] = {M.rgb_sigma_a, M.rgb_sigma_s, M.rgb_Le};
-            std::vector<float> packed; size_t off[3];
-            for (int k = 0; k < 3; k++) { off[k] = packed.size(); if (src[k]) packed.insert(packed.end(), src[k], src[k] + cnt); }
-            CK(B[0].upload(packed.data(), 4 * packed.size()));
-            d.rgb_a = src[0] ? B[0].as<float>() + off[0] : nullptr; d.rgb_s = src[1] ? B[0].as<float>() + off[1] : nullptr;
-            d.rgb_le = src[2] ? B[0].as<float>() + off[2] : nullptr;
-            std::memcpy(d.dres, M.density_res, 12); d.sigma_scale = M.scale; d.le_scale = M.Le_scale;
-        }
-        if (M.type != HK_MEDIUM_HOMOGENEOUS) {
-            size_t cnt = (size_t)M.majorant_res[0] * M.majorant_res[1] * M.majorant_res[2];
-            CK(B[1].upload(M.majorant, 4 * cnt)); d.majorant = B[1].as<float>(); std::memcpy(d.mres, M.majorant_res, 12);
-        }
-        if (M.type == HK_MEDIUM_NANOVDB) {
-            CK(B[2].upload(M.nanovdb_buf, (size_t)M.nanovdb_bytes)); d.nvdb = B[2].as<uint8_t>();
-            std::memcpy(d.inv_mat, M.nanovdb_inv_mat, 36); std::memcpy(d.vec, M.nanovdb_vec, 12); d.root_off = M.nanovdb_root_offset; d.root_tiles = M.nanovdb_root_tiles;
-        }
-    }
-    ctx->has_rgbgrid = false;
-    for (uint32_t i = 0; i < n; i++) if (m[i].type == HK_MEDIUM_RGBGRID) ctx->has_rgbgrid = true;
-    // empty-cell masks of the majorant grids, built on the device from the uploaded grids (one bit per cell); the first one that fits
-    // HK_SMEM_MASK_WORDS is the one the tracking kernels stage in shared memory
-    ctx->D.smem_mask_medium = 0; ctx->D.smem_mask_words = 0;
     ctx->mask_bufs.clear(); ctx->mask_bufs.resize(n);
-    for (uint32_t i = 0; i < n; i++) {
-        if (m[i].type == HK_MEDIUM_HOMOGENEOUS) continue;
-        const size_t cells = (size_t)m[i].majorant_res[0] * m[i].majorant_res[1] * m[i].majorant_res[2];
-        const size_t words = (cells + 31) / 32;
-        CK(ctx->mask_bufs[i].alloc(4 * words));
-        k_majorant_mask<<<grid_for(ctx, words, 256, 8), 256, 0, ctx->stream>>>(dev[i].majorant, (uint32_t)cells, ctx->mask_bufs[i].as<uint32_t>());
-        ctx->launches++;
-        dev[i].maj_empty = ctx->mask_bufs[i].as<uint32_t>();
-        if (ctx->D.smem_mask_medium == 0 && words <= HK_SMEM_MASK_WORDS && !std::getenv("HK_NO_SMEM_MASK")) { ctx->D.smem_mask_medium = (int32_t)i + 1; ctx->D.smem_mask_words = (uint32_t)words; }
-    }
-    if (std::getenv("HK_NO_EMPTY_MASK")) { for (auto& d : dev) d.maj_empty = nullptr; ctx->D.smem_mask_medium = 0; ctx->D.smem_mask_words = 0; }      // development A/B
+    ctx->media_host.assign(n, DevMedium{});
+    for (uint32_t i = 0; i < n; i++) { int32_t rc = upload_one_medium(ctx, i, m[i], ctx->media_host[i]); if (rc != HK_OK) { ctx->media_host.clear(); ctx->D.n_media = 0; return rc; } }
+    return commit_media(ctx);
+}
+// In-place density update of ONE medium (build_majorant_grid! / build_rgb_majorant_grid!, media.jl:1185-1240, 1498-1530: the host
+// swaps the voxel data of a medium and rebuilds its majorant grid; everything else in the scene stays).  `index` is 1-based, the
+// record replaces the medium wholesale (same layout as hk_upload_media); its majorant is rebuilt on the device when m->majorant is NULL.
+int32_t hk_update_medium(HkContext* ctx, uint32_t index, const HkMedium* m) {
+    if (!ctx || !m) return HK_ERR_INVALID;
+    hk_enter(ctx);
+    REQUIRE(index >= 1 && index <= ctx->media_host.size(), "medium index out of range");
+    int32_t rc = upload_one_medium(ctx, index - 1, *m, ctx->media_host[index - 1]);
+    if (rc != HK_OK) return rc;
+    return commit_media(ctx);
+}
+// the majorant grid of medium `index` (1-based) as the device holds it, [rz][ry][rx] (uploaded or device-built)
+int32_t hk_read_majorant(HkContext* ctx, uint32_t index, float* out, uint64_t n_cells) {
+    if (!ctx || !out) return HK_ERR_INVALID;
+    hk_enter(ctx);
+    REQUIRE(index >= 1 && index <= ctx->media_host.size(), "medium index out of range");
+    const DevMedium& d = ctx->media_host[index - 1];
+    REQUIRE(d.type != HK_MEDIUM_HOMOGENEOUS, "a homogeneous medium has no majorant grid");
+    REQUIRE(n_cells == (uint64_t)d.mres[0] * d.mres[1] * d.mres[2], "n_cells does not match the medium's majorant_res");
     CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaGetLastError());
-    CK(ctx->b_media.upload(dev.data(), sizeof(DevMedium) * (size_t)n));
-    ctx->D.media = ctx->b_media.as<DevMedium>(); ctx->D.n_media = (int32_t)n;
-    ctx->camera_version++;
-    return hk_refresh_uplift_cache(ctx);
+    CK(cudaMemcpy(out, d.majorant, 4 * (size_t)n_cells, cudaMemcpyDeviceToHost));
+    return HK_OK;
 }
 
 int32_t hk_set_camera(HkContext* ctx, const HkCamera* c) {

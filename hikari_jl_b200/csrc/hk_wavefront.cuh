@@ -406,6 +406,72 @@ __global__ void __launch_bounds__(256) k_majorant_mask(const float* __restrict__
         mask[w] = bits;
     }
 }
+// Majorant grid of a grid / RGB grid / NanoVDB medium, built on the device from the uploaded voxels (HkMedium.majorant == NULL):
+//   GridMedium     build_majorant_grid          media.jl:1459-1496   max density over the voxels cell [i, i+1)/res maps to
+//   RGBGridMedium  build_rgb_majorant_grid      media.jl:1123-1183   sigma_scale * (max MaxValue(sigma_a) + max MaxValue(sigma_s)); absent grid = 1
+//   NanoVDBMedium  build_nanovdb_majorant_grid  nanovdb.jl:1174-1235 max tree value over the index box of the cell's two corners
+//                                                                    +- 1 voxel, clipped to [index_min, index_max]
+// One block per majorant cell; the threads stride over the cell's voxel box and the block reduces with Julia's NaN-propagating max
+// (a max is order independent, so the grid equals the serial loop's bit for bit).  The index ranges are the reference's: integer
+// floor / ceil of i*n/res (exact in integers), and for NanoVDB the cell corners in f32 with every product and sum rounded on its own.
+struct MajBuild { int32_t idx_min[3], idx_max[3]; float bmin[3], bmax[3]; };
+HK_DEV void maj_range(int i, int n, int r, int& a, int& b) {      // 0-based [a, b): max(1, floor(i n / r) + 1) .. min(n, ceil((i+1) n / r))
+    a = (int)(((long long)i * n) / r);
+    b = (int)((((long long)(i + 1)) * n + r - 1) / r); if (b > n) b = n;
+}
+__global__ void __launch_bounds__(128) k_build_majorant(DevMedium M, MajBuild P, float* __restrict__ out) {
+    __shared__ float red[2][4];
+    const int rx = M.mres[0], ry = M.mres[1];
+    const int cell = blockIdx.x, ix = cell % rx, iy = (cell / rx) % ry, iz = cell / (rx * ry);
+    float m0 = 0.0f, m1 = 0.0f;
+    if (M.type == HK_MEDIUM_NANOVDB) {
+        const int ci[3] = {ix, iy, iz};
+        float p0[3], p1[3], q0[3], q1[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float diag = __fsub_rn(P.bmax[k], P.bmin[k]), r = (float)M.mres[k];
+            p0[k] = __fsub_rn(__fadd_rn(P.bmin[k], __fdiv_rn(__fmul_rn(diag, (float)ci[k]), r)), M.vec[k]);
+            p1[k] = __fsub_rn(__fadd_rn(P.bmin[k], __fdiv_rn(__fmul_rn(diag, (float)(ci[k] + 1)), r)), M.vec[k]);
+        }
+        int lo[3], hi[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {      // world_to_index_f_raw, nanovdb.jl:1238-1246: (m1 px + m2 py) + m3 pz
+            q0[k] = __fadd_rn(__fadd_rn(__fmul_rn(M.inv_mat[3 * k], p0[0]), __fmul_rn(M.inv_mat[3 * k + 1], p0[1])), __fmul_rn(M.inv_mat[3 * k + 2], p0[2]));
+            q1[k] = __fadd_rn(__fadd_rn(__fmul_rn(M.inv_mat[3 * k], p1[0]), __fmul_rn(M.inv_mat[3 * k + 1], p1[1])), __fmul_rn(M.inv_mat[3 * k + 2], p1[2]));
+            lo[k] = max((int)floorf(__fsub_rn(fminf(q0[k], q1[k]), 1.0f)), P.idx_min[k]);
+            hi[k] = min((int)ceilf(__fadd_rn(fmaxf(q0[k], q1[k]), 1.0f)), P.idx_max[k]);
+        }
+        if (lo[0] <= hi[0] && lo[1] <= hi[1] && lo[2] <= hi[2]) {
+            const int ex = hi[0] - lo[0] + 1, ey = hi[1] - lo[1] + 1, ez = hi[2] - lo[2] + 1;
+            LeafCache lc; lc.valid = false;
+            for (int v = threadIdx.x; v < ex * ey * ez; v += blockDim.x) {      // z fastest: neighbouring threads share leaves
+                const int z = v % ez, y = (v / ez) % ey, x = v / (ez * ey);
+                m0 = jl_max(m0, nvdb_value(M, lc, lo[0] + x, lo[1] + y, lo[2] + z));
+            }
+        }
+    } else {
+        int x0, x1, y0, y1, z0, z1;
+        maj_range(ix, M.dres[0], M.mres[0], x0, x1); maj_range(iy, M.dres[1], M.mres[1], y0, y1); maj_range(iz, M.dres[2], M.mres[2], z0, z1);
+        const int ex = max(x1 - x0, 0), ey = max(y1 - y0, 0), ez = max(z1 - z0, 0);
+        for (int v = threadIdx.x; v < ex * ey * ez; v += blockDim.x) {
+            const int x = x0 + v % ex, y = y0 + (v / ex) % ey, z = z0 + v / (ex * ey);
+            const size_t at = (size_t)x + (size_t)M.dres[0] * ((size_t)y + (size_t)M.dres[1] * (size_t)z);
+            if (M.type == HK_MEDIUM_GRID) m0 = jl_max(m0, __ldg(M.density + at));
+            else {
+                if (M.rgb_a) m0 = jl_max(m0, jl_max(jl_max(__ldg(M.rgb_a + 3 * at), __ldg(M.rgb_a + 3 * at + 1)), __ldg(M.rgb_a + 3 * at + 2)));
+                if (M.rgb_s) m1 = jl_max(m1, jl_max(jl_max(__ldg(M.rgb_s + 3 * at), __ldg(M.rgb_s + 3 * at + 1)), __ldg(M.rgb_s + 3 * at + 2)));
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) { m0 = jl_max(m0, __shfl_xor_sync(0xFFFFFFFFu, m0, o)); m1 = jl_max(m1, __shfl_xor_sync(0xFFFFFFFFu, m1, o)); }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = m0; red[1][threadIdx.x >> 5] = m1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 4; w++) { m0 = jl_max(m0, red[0][w]); m1 = jl_max(m1, red[1][w]); }
+        if (M.type == HK_MEDIUM_RGBGRID) { if (!M.rgb_a) m0 = 1.0f; if (!M.rgb_s) m1 = 1.0f; m0 = __fmul_rn(M.sigma_scale, __fadd_rn(m0, m1)); }
+        out[cell] = m0;
+    }
+}
 // light-BVH nodes in their device form (DevLNode, hk_lights.cuh): the point-independent part of node_importance, once per upload
 __global__ void __launch_bounds__(256) k_prepare_lnodes(const HkLightBVHNode* __restrict__ in, uint32_t n, DevLNode* __restrict__ out) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = prepare_lnode(in[i]);

@@ -698,7 +698,7 @@ class HomogeneousMedium:                  # media.jl:735-750
     def __init__(self, sigma_a=0.01, sigma_s=1.0, Le=0.0, g=0.0):
         self.sigma_a, self.sigma_s, self.Le, self.g = _rgb(sigma_a), _rgb(sigma_s), _rgb(Le), float(g)
 
-    def to_abi(self, keep):
+    def to_abi(self, keep, device_majorant=False):
         m = A.HkMedium(type=A.HK_MEDIUM_HOMOGENEOUS)
         m.sigma_a_rgb[:], m.sigma_s_rgb[:], m.Le_rgb[:] = self.sigma_a, self.sigma_s, self.Le
         m.g, m.scale = self.g, 1.0
@@ -733,9 +733,17 @@ class GridMedium:                         # media.jl:886-936
         self.medium_to_render = np.eye(4, dtype=f32) if transform is None else np.asarray(transform, dtype=f32)
         self.render_to_medium = np.linalg.inv(self.medium_to_render.astype(np.float64)).astype(f32)
         self.majorant_res = tuple(int(v) for v in majorant_res)
-        self.majorant = build_majorant_grid(self.density, self.majorant_res)
+        self._majorant = None
 
-    def to_abi(self, keep):
+    @property
+    def majorant(self):
+        """build_majorant_grid on the host (numpy): what the oracle is handed, and what the device-built grid is tested against;
+        the CUDA back end builds its own from the uploaded voxels (HkMedium.majorant = NULL)"""
+        if self._majorant is None:
+            self._majorant = build_majorant_grid(self.density, self.majorant_res)
+        return self._majorant
+
+    def to_abi(self, keep, device_majorant=False):
         m = A.HkMedium(type=A.HK_MEDIUM_GRID)
         m.sigma_a_rgb[:], m.sigma_s_rgb[:], m.Le_rgb[:] = self.sigma_a, self.sigma_s, (0, 0, 0)
         m.g, m.scale = self.g, 1.0
@@ -748,9 +756,10 @@ class GridMedium:                         # media.jl:886-936
         keep.append(d)
         m.density = _fp(d)
         m.majorant_res[:] = list(self.majorant_res)
-        mj = np.ascontiguousarray(self.majorant)
-        keep.append(mj)
-        m.majorant = _fp(mj)
+        if not device_majorant:
+            mj = np.ascontiguousarray(self.majorant)
+            keep.append(mj)
+            m.majorant = _fp(mj)
         return m
 
 
@@ -776,14 +785,20 @@ class RGBGridMedium:                      # media.jl:1002-1114
         self.medium_to_render = np.eye(4, dtype=f32) if transform is None else np.asarray(transform, dtype=f32)
         self.render_to_medium = np.linalg.inv(self.medium_to_render.astype(np.float64)).astype(f32)
         self.majorant_res = tuple(int(v) for v in majorant_res)
-        # build_rgb_majorant_grid, media.jl:1122-1183: sigma_scale * (max sigma_a + max sigma_s) per coarse voxel, the max taken
-        # over the voxel block AND the three channels; an absent grid contributes 1
-        one = np.ones(self.grid_res, dtype=f32)
-        ma = build_majorant_grid(self.sigma_a_grid.max(axis=3), self.majorant_res) if self.sigma_a_grid is not None else build_majorant_grid(one, self.majorant_res)
-        ms = build_majorant_grid(self.sigma_s_grid.max(axis=3), self.majorant_res) if self.sigma_s_grid is not None else build_majorant_grid(one, self.majorant_res)
-        self.majorant = (f32(self.sigma_scale) * (ma + ms)).astype(f32)
+        self._majorant = None
 
-    def to_abi(self, keep):
+    @property
+    def majorant(self):
+        """build_rgb_majorant_grid, media.jl:1122-1183, on the host: sigma_scale * (max sigma_a + max sigma_s) per coarse voxel, the
+        max taken over the voxel block AND the three channels; an absent grid contributes 1"""
+        if self._majorant is None:
+            one = np.ones(self.grid_res, dtype=f32)
+            ma = build_majorant_grid(self.sigma_a_grid.max(axis=3), self.majorant_res) if self.sigma_a_grid is not None else build_majorant_grid(one, self.majorant_res)
+            ms = build_majorant_grid(self.sigma_s_grid.max(axis=3), self.majorant_res) if self.sigma_s_grid is not None else build_majorant_grid(one, self.majorant_res)
+            self._majorant = (f32(self.sigma_scale) * (ma + ms)).astype(f32)
+        return self._majorant
+
+    def to_abi(self, keep, device_majorant=False):
         m = A.HkMedium(type=A.HK_MEDIUM_RGBGRID)
         m.g, m.scale, m.Le_scale = self.g, self.sigma_scale, self.Le_scale
         m.bounds_min[:], m.bounds_max[:] = self.bounds[0].tolist(), self.bounds[1].tolist()
@@ -796,9 +811,10 @@ class RGBGridMedium:                      # media.jl:1002-1114
                 keep.append(d)
                 setattr(m, name, _fp(d))
         m.majorant_res[:] = list(self.majorant_res)
-        mj = np.ascontiguousarray(self.majorant)
-        keep.append(mj)
-        m.majorant = _fp(mj)
+        if not device_majorant:
+            mj = np.ascontiguousarray(self.majorant)
+            keep.append(mj)
+            m.majorant = _fp(mj)
         return m
 
 
@@ -1273,6 +1289,7 @@ class Backend:
     fails when the library or a CUDA device is missing.  (tests/oracle_backend.py derives the oracle's backend from this class to
     feed the checker the identical flattened scene; nothing in this module loads or calls the oracle.)"""
     prefix = "hk_"
+    device_majorant = True        # majorant grids are built on the device from the uploaded voxels (HkMedium.majorant = NULL)
 
     def __init__(self, device=0):
         self.lib = A.load_library()
@@ -1335,7 +1352,7 @@ class Backend:
         # media
         keep = []
         if scene.media:
-            med = (A.HkMedium * len(scene.media))(*[m.to_abi(keep) for m in scene.media])
+            med = (A.HkMedium * len(scene.media))(*[m.to_abi(keep, self.device_majorant) for m in scene.media])
             self.call("upload_media", med, len(scene.media))
         else:
             self.call("upload_media", None, 0)
@@ -1395,6 +1412,17 @@ class Backend:
         buf = np.empty((self.width, self.height, 3), dtype=f32)     # column-major (H,W) == C-order (W,H)
         self.call("read_film", _fp(buf))
         out_hw3[...] = buf.transpose(1, 0, 2)
+
+    def update_medium(self, medium_idx, medium):
+        keep = []
+        abi = medium.to_abi(keep, self.device_majorant)
+        self.call("update_medium", medium_idx, C.byref(abi))
+
+    def read_majorant(self, medium_idx, res):
+        """the majorant grid of medium `medium_idx` as the device holds it, [rz][ry][rx]"""
+        out = np.empty((res[2], res[1], res[0]), dtype=f32)
+        self.call("read_majorant", medium_idx, _fp(out), out.size)
+        return out
 
     def read_film_async(self, film):
         """Enqueue finalize + device->host copy of the current film into a page-locked buffer of the film that no displayed or
@@ -1475,6 +1503,14 @@ class VolPath:
             for k in mixes:
                 abi = scene.materials[k].to_abi(scene)
                 self.backend.call("update_material", k + 1, C.byref(abi))
+
+    def update_medium(self, scene, medium_idx, new_medium):
+        """The density-update path (build_majorant_grid! / build_rgb_majorant_grid!, media.jl:1498-1530, 1185-1240): replace medium
+        `medium_idx` (1-based, what push!(scene.media) made it) in place; the prepared backend gets that one medium -- voxels up,
+        majorant grid and empty-cell mask rebuilt on the device -- not the scene."""
+        scene.media[medium_idx - 1] = new_medium
+        if self.backend is not None and self.state is not None:
+            self.backend.update_medium(medium_idx, new_medium)
 
     def wait_film(self, film, handle):
         """Block until the frame requested with render(..., read="async") is film.framebuffer."""

@@ -272,7 +272,9 @@ def build_nanovdb_majorant_grid_from_buffer(buf, meta, bounds, res=(64, 64, 64))
         dense = vals.reshape(dense.shape)
     M = np.asarray(meta["inv_mat"], dtype=f32).reshape(3, 3)
     vec = np.asarray(meta["vec"], dtype=f32)
-    to_index = lambda p: (M @ (p - vec).astype(f32)).astype(f32)          # world_to_index_f_raw
+    def to_index(p):                                                       # world_to_index_f_raw (:1238-1246): (m1 px + m2 py) + m3 pz, f32
+        q = (p - vec).astype(f32)
+        return ((M[:, 0] * q[0] + M[:, 1] * q[1]).astype(f32) + M[:, 2] * q[2]).astype(f32)
     out = np.zeros((res[2], res[1], res[0]), dtype=f32)
     for iz in range(res[2]):
         for iy in range(res[1]):
@@ -309,7 +311,7 @@ class NanoVDBMedium:
         self.bounds = (cw.min(axis=0).astype(f32), cw.max(axis=0).astype(f32))
         self.meta = dict(meta, inv_mat=tuple(f32(v) for v in combined.reshape(-1)))
         self.majorant_res = tuple(int(v) for v in majorant_res)
-        self.majorant = np.ascontiguousarray(build_nanovdb_majorant_grid_from_buffer(self.buffer, self.meta, self.bounds, self.majorant_res))
+        self._majorant, self._dense = None, None
         self.sigma_a, self.sigma_s, self.g = _rgb(sigma_a), _rgb(sigma_s), float(g)
         return self
 
@@ -320,10 +322,21 @@ class NanoVDBMedium:
         extent = [float(v) for v in (self.bounds[1] - self.bounds[0])]
         self.buffer, self.meta = build_nanovdb_from_dense(data_xyz, origin, extent)
         self.majorant_res = tuple(int(v) for v in majorant_res)
-        self.majorant = build_nanovdb_majorant_grid(data_xyz, self.meta, self.bounds, self.majorant_res)
+        self._majorant, self._dense = None, np.asarray(data_xyz, dtype=f32)
         self.sigma_a, self.sigma_s, self.g = _rgb(sigma_a), _rgb(sigma_s), float(g)
 
-    def to_abi(self, keep):
+    @property
+    def majorant(self):
+        """build_nanovdb_majorant_grid on the host (numpy): what the oracle is handed, and what the device-built grid is tested
+        against; the CUDA back end builds its own from the uploaded tree (HkMedium.majorant = NULL)"""
+        if self._majorant is None:
+            if self._dense is not None:
+                self._majorant = build_nanovdb_majorant_grid(self._dense, self.meta, self.bounds, self.majorant_res)
+            else:
+                self._majorant = np.ascontiguousarray(build_nanovdb_majorant_grid_from_buffer(self.buffer, self.meta, self.bounds, self.majorant_res))
+        return self._majorant
+
+    def to_abi(self, keep, device_majorant=False):
         m = A.HkMedium(type=A.HK_MEDIUM_NANOVDB)
         m.sigma_a_rgb[:], m.sigma_s_rgb[:], m.Le_rgb[:] = self.sigma_a, self.sigma_s, (0, 0, 0)
         m.g, m.scale = self.g, 1.0
@@ -331,8 +344,11 @@ class NanoVDBMedium:
         ident = np.eye(4, dtype=f32).reshape(-1).tolist()
         m.render_from_medium[:], m.medium_from_render[:] = ident, ident
         m.majorant_res[:] = list(self.majorant_res)
-        keep.append(self.majorant)
-        m.majorant = self.majorant.ctypes.data_as(A.c_fp)
+        if not device_majorant:
+            keep.append(self.majorant)
+            m.majorant = self.majorant.ctypes.data_as(A.c_fp)
+        m.nanovdb_index_min[:] = [int(v) for v in self.meta["index_min"]]      # the clip range of the majorant build (nanovdb.jl:1137-1150)
+        m.nanovdb_index_max[:] = [int(v) for v in self.meta["index_max"]]
         keep.append(self.buffer)
         m.nanovdb_buf = self.buffer.ctypes.data_as(A.c_u8p)
         m.nanovdb_bytes = len(self.buffer)

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define HK_ABI_VERSION 3
+#define HK_ABI_VERSION 4
 
 /* ---- status codes ------------------------------------------------------------------------ */
 #define HK_OK                 0
@@ -290,6 +290,12 @@ typedef struct HkMedium {
     const float* rgb_sigma_s;
     const float* rgb_Le;
     float    Le_scale;
+    /* ABI v4.  majorant == NULL (Grid / RGBGrid / NanoVDB): the library builds the majorant grid on the device from the
+       uploaded voxels -- build_majorant_grid (media.jl:1459-1496), build_rgb_majorant_grid (:1123-1183),
+       build_nanovdb_majorant_grid (nanovdb.jl:1174-1235); the NanoVDB build clips its voxel boxes to
+       [nanovdb_index_min, nanovdb_index_max] = metadata.index_min / index_max (nanovdb.jl:1137-1150, :853).        */
+    int32_t  nanovdb_index_min[3];
+    int32_t  nanovdb_index_max[3];
 } HkMedium;
 
 /* ---- camera, filter, params ---------------------------------------------------------------- */
@@ -367,6 +373,12 @@ int32_t hk_upload_envmaps(HkContext* ctx, const HkEnvMap* maps, uint32_t n_maps)
 int32_t hk_upload_lights(HkContext* ctx, const HkLight* lights, uint32_t n_lights,
                          const HkLightSampler* sampler);
 int32_t hk_upload_media(HkContext* ctx, const HkMedium* media, uint32_t n_media);
+/* build_majorant_grid! / build_rgb_majorant_grid! (media.jl:1498-1530, 1185-1240): the host swapped the voxel data of ONE
+ * medium (1-based index).  The record replaces that medium wholesale, its majorant grid (majorant == NULL) and empty-cell
+ * mask are rebuilt on the device; geometry, materials, lights and the other media stay.                                */
+int32_t hk_update_medium(HkContext* ctx, uint32_t index, const HkMedium* medium);
+/* the majorant grid of medium `index` as the device holds it ([rz][ry][rx], n_cells = rx*ry*rz): uploaded or device-built */
+int32_t hk_read_majorant(HkContext* ctx, uint32_t index, float* out, uint64_t n_cells);
 int32_t hk_set_camera(HkContext* ctx, const HkCamera* camera);
 int32_t hk_set_filter(HkContext* ctx, const HkFilter* filter);
 /* replaces: VolPath(...) fields + state (re)allocation on resize, volpath.jl:466-482 */

@@ -22,6 +22,7 @@ const lib = "libhikari_cuda"                       # on the loader path (hikari_
 __init__() = (get!(ENV, "CUDA_DEVICE_MAX_CONNECTIONS", "32"); nothing)
 
 # ---- struct mirrors of include/hikari_cuda.h (isbits, C layout) ---------------------------------------------------------
+const z3_ = (0f0, 0f0, 0f0); const I16 = ntuple(i -> (i - 1) % 5 == 0 ? 1f0 : 0f0, 16)      # zero vector / row-major 4x4 identity
 struct HkTables
     sobol_matrices::Ptr{UInt32}; cie_x::Ptr{Float32}; cie_y::Ptr{Float32}; cie_z::Ptr{Float32}; d65::Ptr{Float32}
     rgb2spec_res::Int32; rgb2spec_scale::Ptr{Float32}; rgb2spec_coeffs::Ptr{Float32}
@@ -51,20 +52,25 @@ struct HkEnvMap
     marginal_func::Ptr{Float32}; marginal_cdf::Ptr{Float32}; marginal_func_int::Float32; nu::Int32; nv::Int32
 end
 struct HkLightBVHNode            # 64 bytes; written by bvh_nodes() below from Hikari.LightBVHNode (bvh-light-sampler.jl:21-56)
-    lo::NTuple{3,Float32}; hi::NTuple{3,Float32}; w::NTuple{3,Float32}; phi::Float32; cos_theta_o::Float32; cos_theta_e::Float32
-    two_sided::UInt32; child::UInt32; leaf::UInt32; pad::UInt32
+    bounds_min::NTuple{3,Float32}; bounds_max::NTuple{3,Float32}; w::NTuple{3,Float32}; phi::Float32; cos_theta_o::Float32; cos_theta_e::Float32
+    two_sided::UInt32; child1_or_light_idx::UInt32; is_leaf::UInt32; _pad::UInt32
 end
 struct HkLightSampler
     nodes::Ptr{HkLightBVHNode}; n_nodes::UInt32; light_to_bit_trail::Ptr{UInt32}; infinite_light_indices::Ptr{Int32}
     n_infinite::UInt32; n_bvh_lights::UInt32
 end
-struct HkMedium
-    type::Int32; sigma_a_rgb::NTuple{3,Float32}; sigma_s_rgb::NTuple{3,Float32}; Le_rgb::NTuple{3,Float32}; g::Float32
-    bounds_min::NTuple{3,Float32}; bounds_max::NTuple{3,Float32}; medium_from_render::NTuple{12,Float32}
-    density::Ptr{Float32}; density_res::NTuple{3,Int32}; majorant::Ptr{Float32}; majorant_res::NTuple{3,Int32}
-    nanovdb_buf::Ptr{UInt8}; nanovdb_bytes::UInt64; nanovdb_inv_mat::NTuple{9,Float32}; nanovdb_vec::NTuple{3,Float32}
-    nanovdb_root_offset::UInt64; nanovdb_root_tiles::Int32
-    rgb_sigma_a::Ptr{Float32}; rgb_sigma_s::Ptr{Float32}; rgb_Le::Ptr{Float32}; scale::Float32; Le_scale::Float32
+Base.@kwdef struct HkMedium          # field for field include/hikari_cuda.h (ABI v4, 416 bytes)
+    type::Int32; sigma_a_rgb::NTuple{3,Float32} = z3_; sigma_s_rgb::NTuple{3,Float32} = z3_; Le_rgb::NTuple{3,Float32} = z3_
+    scale::Float32 = 1f0; g::Float32 = 0f0; bounds_min::NTuple{3,Float32} = z3_; bounds_max::NTuple{3,Float32} = z3_
+    render_from_medium::NTuple{16,Float32} = I16; medium_from_render::NTuple{16,Float32} = I16
+    density_res::NTuple{3,Int32} = (0, 0, 0); density::Ptr{Float32} = C_NULL
+    majorant_res::NTuple{3,Int32} = (0, 0, 0); majorant::Ptr{Float32} = C_NULL      # NULL: built on the device (k_build_majorant)
+    nanovdb_buf::Ptr{UInt8} = C_NULL; nanovdb_bytes::UInt64 = 0
+    nanovdb_inv_mat::NTuple{9,Float32} = ntuple(_ -> 0f0, 9); nanovdb_vec::NTuple{3,Float32} = z3_
+    nanovdb_root_offset::UInt64 = 0; nanovdb_upper_offset::UInt64 = 0; nanovdb_lower_offset::UInt64 = 0; nanovdb_leaf_offset::UInt64 = 0
+    nanovdb_root_tiles::Int32 = 0; nanovdb_upper_count::Int32 = 0; nanovdb_lower_count::Int32 = 0; nanovdb_leaf_count::Int32 = 0
+    rgb_sigma_a::Ptr{Float32} = C_NULL; rgb_sigma_s::Ptr{Float32} = C_NULL; rgb_Le::Ptr{Float32} = C_NULL; Le_scale::Float32 = 0f0
+    nanovdb_index_min::NTuple{3,Int32} = (0, 0, 0); nanovdb_index_max::NTuple{3,Int32} = (0, 0, 0)
 end
 struct HkCamera
     raster_to_camera::NTuple{16,Float32}; camera_to_world::NTuple{16,Float32}; lens_radius::Float32; focal_distance::Float32
@@ -360,26 +366,31 @@ end
 # ---- media ----------------------------------------------------------------------------------------------------------------
 const NULLF = Ptr{Float32}(C_NULL)
 bmin(b) = t3(b.p_min); bmax(b) = t3(b.p_max)
-nomedium(type, σa, σs, Le, g) = (type, rgb3(σa), rgb3(σs), rgb3(Le), Float32(g))
-function hk(m::Hikari.HomogeneousMedium, keep)                                             # media.jl:762-766
-    HkMedium(1, rgb3(m.σ_a), rgb3(m.σ_s), rgb3(m.Le), m.g, z3, z3, ntuple(_ -> 0f0, 12), NULLF, (0, 0, 0), NULLF, (0, 0, 0), C_NULL, 0, Z9, z3, 0, 0, NULLF, NULLF, NULLF, 1f0, 0f0)
-end
+# Majorant grids are left to the library (majorant = NULL: built on the device from the voxels uploaded here, bit for bit the grid
+# build_majorant_grid / build_rgb_majorant_grid / build_nanovdb_majorant_grid produce); only their resolution is passed.
+hk(m::Hikari.HomogeneousMedium, keep) = HkMedium(type=1, sigma_a_rgb=rgb3(m.σ_a), sigma_s_rgb=rgb3(m.σ_s), Le_rgb=rgb3(m.Le), g=m.g)       # media.jl:762-766
 function hk(m::Hikari.GridMedium, keep)                                                    # media.jl:873-895 (density[x, y, z] is already x-fastest)
-    d = collect(Float32, m.density); mg = collect(Float32, m.majorant_grid.voxels); append!(keep, (d, mg))
-    HkMedium(2, rgb3(m.σ_a), rgb3(m.σ_s), z3, m.g, bmin(m.bounds), bmax(m.bounds), rowmajor12(m.render_to_medium), pointer(d), Tuple(m.density_res), pointer(mg), Tuple(m.majorant_grid.res),
-             C_NULL, 0, Z9, z3, 0, 0, NULLF, NULLF, NULLF, 1f0, 0f0)
+    d = collect(Float32, m.density); push!(keep, d)
+    HkMedium(type=2, sigma_a_rgb=rgb3(m.σ_a), sigma_s_rgb=rgb3(m.σ_s), g=m.g, bounds_min=bmin(m.bounds), bounds_max=bmax(m.bounds),
+             render_from_medium=rowmajor16(m.medium_to_render), medium_from_render=rowmajor16(m.render_to_medium),
+             density_res=Tuple(Int32.(m.density_res)), density=pointer(d), majorant_res=Tuple(Int32.(m.majorant_grid.res)))
 end
-function hk(m::Hikari.NanoVDBMedium, keep)                                                 # nanovdb.jl:153-175; byte offsets become 0-based
-    buf = collect(UInt8, m.buffer); mg = collect(Float32, m.majorant_grid.voxels); append!(keep, (buf, mg))
-    HkMedium(3, rgb3(m.σ_a), rgb3(m.σ_s), z3, m.g, bmin(m.bounds), bmax(m.bounds), ntuple(i -> i in (1, 6, 11) ? 1f0 : 0f0, 12), NULLF, (0, 0, 0), pointer(mg), Tuple(m.majorant_grid.res),
-             pointer(buf), length(buf), m.inv_mat, m.vec, UInt64(m.root_offset - 1), m.root_table_size, NULLF, NULLF, NULLF, 1f0, 0f0)
+function hk(m::Hikari.NanoVDBMedium, keep)                                                 # nanovdb.jl:153-182; byte offsets become 0-based
+    buf = collect(UInt8, m.buffer); push!(keep, buf)
+    HkMedium(type=3, sigma_a_rgb=rgb3(m.σ_a), sigma_s_rgb=rgb3(m.σ_s), g=m.g, bounds_min=bmin(m.bounds), bounds_max=bmax(m.bounds),
+             majorant_res=Tuple(Int32.(m.majorant_grid.res)), nanovdb_buf=pointer(buf), nanovdb_bytes=length(buf), nanovdb_inv_mat=m.inv_mat, nanovdb_vec=m.vec,
+             nanovdb_root_offset=m.root_offset - 1, nanovdb_upper_offset=m.upper_offset - 1, nanovdb_lower_offset=m.lower_offset - 1, nanovdb_leaf_offset=m.leaf_offset - 1,
+             nanovdb_root_tiles=m.root_table_size, nanovdb_upper_count=m.upper_count, nanovdb_lower_count=m.lower_count, nanovdb_leaf_count=m.leaf_count,
+             nanovdb_index_min=m.index_bbox_min, nanovdb_index_max=m.index_bbox_max)
 end
 function hk(m::Hikari.RGBGridMedium, keep)                                                 # media.jl:1002-1075
     pack(g) = g === nothing ? Float32[] : Float32[s.c[k] for s in g for k in 1:3]
-    a, s, e = pack(m.σ_a_grid), pack(m.σ_s_grid), pack(m.Le_grid); mg = collect(Float32, m.majorant_grid.voxels); append!(keep, (a, s, e, mg))
+    a, s, e = pack(m.σ_a_grid), pack(m.σ_s_grid), pack(m.Le_grid); append!(keep, (a, s, e))
     res = size(something(m.σ_a_grid, m.σ_s_grid))
-    HkMedium(4, z3, z3, z3, m.g, bmin(m.bounds), bmax(m.bounds), rowmajor12(m.render_to_medium), NULLF, Int32.(res), pointer(mg), Tuple(m.majorant_grid.res), C_NULL, 0, Z9, z3, 0, 0,
-             isempty(a) ? NULLF : pointer(a), isempty(s) ? NULLF : pointer(s), isempty(e) ? NULLF : pointer(e), m.sigma_scale, m.Le_scale)
+    HkMedium(type=4, g=m.g, scale=m.sigma_scale, Le_scale=m.Le_scale, bounds_min=bmin(m.bounds), bounds_max=bmax(m.bounds),
+             render_from_medium=rowmajor16(m.medium_to_render), medium_from_render=rowmajor16(m.render_to_medium),
+             density_res=Tuple(Int32.(res)), majorant_res=Tuple(Int32.(m.majorant_grid.res)),
+             rgb_sigma_a=isempty(a) ? NULLF : pointer(a), rgb_sigma_s=isempty(s) ? NULLF : pointer(s), rgb_Le=isempty(e) ? NULLF : pointer(e))
 end
 function upload_media!(c::Ctx, scene)
     keep = Any[]

@@ -58,6 +58,7 @@ class OracleBackend(Backend):
     """The checker behind the product's host-side flattening (Backend.upload_scene / set_params / read_film): same structs, the
     ok_* entry points of oracle/libhikari_oracle.so instead of hk_*."""
     prefix = "ok_"
+    device_majorant = False       # the checker is handed the host-built (numpy) majorant grids
 
     def __init__(self):
         self.lib = lib()

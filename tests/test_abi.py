@@ -29,7 +29,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert not missing, f"declared in include/*.h but not exported: {missing}"
     for s in A.HK_SYMBOLS:
         assert s in syms, f"{s} listed in _abi.HK_SYMBOLS but not declared in the header"
-    assert lib.hk_abi_version() == 3
+    assert lib.hk_abi_version() == 4
 
 
 def test_struct_sizes_match_header_layout():
@@ -37,6 +37,7 @@ def test_struct_sizes_match_header_layout():
     assert C.sizeof(A.HkMaterial) == 4 + 4 + 12 + 12 + 16 + 32 + 8 + 8 + 16 + 32
     assert C.sizeof(A.HkLightBVHNode) == 64
     assert C.sizeof(A.HkMediumInterface) == 12
+    assert C.sizeof(A.HkMedium) == 416      # ABI v4: + nanovdb_index_min / _max
     assert C.sizeof(A.HkRenderParams) == 44
     assert C.sizeof(A.HkLight) == 4 * (2 + 1 + 3 + 3 + 1 + 3 + 3 + 2 + 16 + 9 + 3 + 1 + 6 + 2)
 
@@ -82,7 +83,7 @@ def test_c_client_compiles_links_and_fails_loudly_without_a_device(tmp_path):
     A.load_library()
     exe = _build_c_client(tmp_path)
     r = subprocess.run([exe], capture_output=True, text=True)
-    assert r.returncode == 0 and r.stdout.startswith("no-device abi=3"), (r.returncode, r.stdout, r.stderr)
+    assert r.returncode == 0 and r.stdout.startswith("no-device abi=4"), (r.returncode, r.stdout, r.stderr)
 
 
 @pytest.mark.gpu
@@ -96,3 +97,58 @@ def test_c_client_renders_through_the_c_abi(tmp_path):
     r = subprocess.run([exe, tab], capture_output=True, text=True)
     print(r.stdout, r.stderr)
     assert r.returncode == 0 and "dev_same=1" in r.stdout, (r.returncode, r.stdout, r.stderr)
+
+
+def _julia_structs():
+    """struct mirrors of julia/HikariCUDA.jl: {name: [(field, julia type), ...]} in declaration order"""
+    lines = open(os.path.join(ROOT, "julia", "HikariCUDA.jl")).read().splitlines()
+    out, k = {}, 0
+    while k < len(lines):
+        one = re.match(r"^struct (Hk\w+);(.*); end\s*(#.*)?$", lines[k])
+        multi = re.match(r"^(?:Base\.@kwdef )?struct (Hk\w+)\s*(#.*)?$", lines[k])
+        if one:
+            name, body = one.group(1), one.group(2)
+        elif multi:
+            name, body = multi.group(1), ""
+            k += 1
+            while lines[k] != "end":
+                body += re.sub(r"#.*", "", lines[k]) + "\n"
+                k += 1
+        else:
+            k += 1
+            continue
+        fields = []
+        for part in re.split(r"[;\n]", body):
+            part = part.split(" = ")[0].strip()
+            if "::" in part:
+                f, t = part.split("::")
+                fields.append((f.strip(), t.strip()))
+        out[name] = fields
+        k += 1
+    return out
+
+
+def _julia_type_of(ct):
+    """the Julia spelling of a ctypes field type"""
+    scalars = {C.c_int32: "Int32", C.c_uint32: "UInt32", C.c_float: "Float32", C.c_uint64: "UInt64", C.c_int64: "Int64", C.c_uint8: "UInt8"}
+    if ct in scalars:
+        return scalars[ct]
+    if ct is C.c_void_p:
+        return "Ptr{Cvoid}"
+    if hasattr(ct, "_length_"):
+        return "NTuple{%d,%s}" % (ct._length_, _julia_type_of(ct._type_))
+    if hasattr(ct, "contents") or hasattr(ct, "_type_"):
+        inner = ct._type_
+        return "Ptr{%s}" % (inner.__name__ if issubclass(inner, C.Structure) else _julia_type_of(inner))
+    raise AssertionError(ct)
+
+
+def test_julia_struct_mirrors_match_the_ctypes_mirrors():
+    """julia/HikariCUDA.jl cannot be executed here, so its struct mirrors are checked textually: every Hk* struct it declares
+    has the fields of the ctypes mirror (which the C client test and every GPU test exercise), same names, order and types."""
+    js = _julia_structs()
+    assert len(js) >= 18, sorted(js)
+    for name, fields in js.items():
+        ct = getattr(A, name)
+        want = [(f, _julia_type_of(t)) for f, t in ct._fields_]
+        assert fields == want, f"{name}: julia {fields} != ctypes {want}"

@@ -895,6 +895,91 @@ def test_nanovdb_file_medium_matches_in_memory_medium(tmp_path):
         p.close(); p0.close()
 
 
+def _majorant_cases(tmp_path):
+    """media whose majorant grids exercise every branch of the three builders"""
+    from hikari_jl_b200 import nanovdb as N
+    rng = np.random.RandomState(21)
+    lo, hi = (-0.6, 0.3, -0.6), (0.6, 1.5, 0.6)
+    d1 = rng.uniform(0, 1, size=(24, 20, 16)).astype(f32) ** 3 * 30; d1[d1 < 3] = 0
+    d2 = rng.uniform(0, 2, size=(5, 3, 2)).astype(f32)                      # coarser than its majorant grid
+    d3 = rng.uniform(0, 1, size=(37, 29, 23)).astype(f32) ** 4 * 9; d3[d3 < 1] = 0      # nothing divides anything
+    ta, ts = np.array([0.02, 0.05, 0.2], f32), np.array([1.0, 0.8, 0.5], f32)
+    cases = [("grid 24x20x16 -> 6x5x4", H.GridMedium(d1, bounds=(lo, hi), majorant_res=(6, 5, 4))),
+             ("grid 5x3x2 -> 16^3 (majorant finer than the density)", H.GridMedium(d2, bounds=(lo, hi), majorant_res=(16, 16, 16))),
+             ("grid 37x29x23 -> 7x11x5", H.GridMedium(d3, bounds=(lo, hi), majorant_res=(7, 11, 5))),
+             ("grid -> 1x1x1", H.GridMedium(d3, bounds=(lo, hi), majorant_res=(1, 1, 1))),
+             ("rgb a+s", H.RGBGridMedium(sigma_a_grid=d1[..., None] * ta, sigma_s_grid=d1[..., None] * ts, sigma_scale=0.7, bounds=(lo, hi), majorant_res=(6, 5, 4))),
+             ("rgb s only (absent sigma_a counts as 1)", H.RGBGridMedium(sigma_s_grid=d3[..., None] * ts, sigma_scale=0.5, bounds=(lo, hi), majorant_res=(9, 4, 6))),
+             ("rgb a only", H.RGBGridMedium(sigma_a_grid=d3[..., None] * ta, sigma_scale=1.5, bounds=(lo, hi), majorant_res=(3, 3, 3))),
+             ("nanovdb 24x20x16 -> 8^3", H.NanoVDBMedium(d1, bounds=(lo, hi), majorant_res=(8, 8, 8))),
+             ("nanovdb 37x29x23 -> 13x7x64", H.NanoVDBMedium(d3, bounds=((-1.0, 0.0, 2.0), (0.37, 1.9, 2.5)), majorant_res=(13, 7, 64))),
+             ("nanovdb sparse 70^3 -> 16^3 (several leaves, empty regions)", None)]
+    sp = np.zeros((70, 70, 70), f32); sp[3:9, 40:66, 10:12] = rng.uniform(1, 5, size=(6, 26, 2)); sp[60:, :5, 33:41] = 2.5
+    cases[-1] = (cases[-1][0], H.NanoVDBMedium(sp, bounds=(lo, hi), majorant_res=(16, 16, 16)))
+    mem = cases[7][1]
+    path = str(tmp_path / "m.nvdb")
+    N.write_nanovdb_file(path, mem.buffer, mem.meta)
+    cases.append(("nanovdb from a .nvdb file (leaf-derived clip range, tree at an offset)", H.NanoVDBMedium.from_file(path, majorant_res=(8, 8, 8))))
+    rot = np.array([[0.8, -0.6, 0.0], [0.6, 0.8, 0.0], [0.0, 0.0, 1.0]], f32)
+    cases.append(("nanovdb from a file, rotated transform (full 3x3 world -> index)", H.NanoVDBMedium.from_file(path, transform=rot, majorant_res=(10, 9, 8))))
+    return cases
+
+
+def test_majorant_grids_built_on_the_device_equal_the_host_builders(tmp_path):
+    """build_majorant_grid (media.jl:1459-1496), build_rgb_majorant_grid (:1123-1183) and build_nanovdb_majorant_grid
+    (nanovdb.jl:1174-1235) run on the device at upload (HkMedium.majorant = NULL, k_build_majorant).  The grids the device holds
+    must equal, bit for bit, the host restatements the oracle is handed -- for resolutions that divide, do not divide and exceed the
+    density grid, absent RGB grids, sparse trees, a file-backed tree and a rotated index transform."""
+    cases = _majorant_cases(tmp_path)
+    s = H.Scene()
+    for _, med in cases:
+        s.push(H.rect3((0, 0, 0), (1, 1, 1)), H.MediumInterface(H.GlassMaterial(Kr=0.0, Kt=1.0, index=1.0), inside=med))
+    s.push(H.PointLight((1, 1, 1), (0, 5, 0)))
+    s.sync()
+    b = H.Backend()
+    try:
+        assert b.device_majorant
+        b.upload_tables(); b.upload_scene(s)
+        for k, (name, med) in enumerate(cases):
+            dev = b.read_majorant(s.media.index(med) + 1, med.majorant_res)
+            host = np.asarray(med.majorant, dtype=f32)
+            assert dev.shape == host.shape and (host > 0).any(), name
+            assert np.array_equal(dev.view(np.uint32), host.view(np.uint32)), f"{name}: {(dev != host).sum()} of {dev.size} cells differ"
+    finally:
+        b.close()
+
+
+def test_update_medium_replaces_one_medium_in_place():
+    """The density-update path (build_majorant_grid!, media.jl:1498-1530): hk_update_medium swaps the voxels of one medium and
+    rebuilds its majorant grid and empty-cell mask on the device.  The next frames must be the frames of a scene uploaded afresh
+    with the new medium, and of the oracle."""
+    for kind in ("grid", "nanovdb"):
+        scene, dens, lo, hi = _media_scene(kind)
+        cam = lambda film: H.PerspectiveCamera((0, 0.9, -3.0), (0, 0.9, 0), film, fov=40.0, screen_window="aspect")
+        new_d = np.roll(dens, 5, axis=0) * f32(0.5); new_d[:4] = 0
+        make = (lambda d: H.GridMedium(d, sigma_a=0.1, sigma_s=1.0, g=0.5, bounds=(lo, hi), majorant_res=(6, 5, 4))) if kind == "grid" else \
+               (lambda d: H.NanoVDBMedium(d, bounds=(lo, hi), sigma_a=0.0, sigma_s=1.0, g=0.877, majorant_res=(8, 8, 8)))
+        film = H.Film((48, 40)); vp = H.VolPath(samples=4, max_depth=6)
+        vp.render(scene, film, cam(film), count=2)
+        before = film.framebuffer.copy()
+        vp.update_medium(scene, 1, make(new_d))
+        dev = vp.backend.read_majorant(1, scene.media[0].majorant_res)
+        assert np.array_equal(dev.view(np.uint32), np.asarray(scene.media[0].majorant).view(np.uint32))
+        vp.clear(); film.iteration_index = 0
+        vp.render(scene, film, cam(film), count=2)
+        updated = film.framebuffer.copy()
+        vp.close()
+        assert not np.array_equal(before, updated)
+        film2 = H.Film((48, 40)); vp2 = H.VolPath(samples=4, max_depth=6)
+        vp2.render(scene, film2, cam(film2), count=2)          # the scene object now holds the new medium: a fresh upload
+        vp2.close()
+        assert np.array_equal(updated.view(np.uint32), film2.framebuffer.view(np.uint32)), kind
+        film3 = H.Film((48, 40)); vp3 = H.VolPath(samples=4, max_depth=6, backend=oracle_backend.make_backend())
+        vp3.render(scene, film3, cam(film3), count=2)
+        vp3.close()
+        assert np.array_equal(updated.view(np.uint32), film3.framebuffer.view(np.uint32)), f"{kind}: updated medium differs from the oracle"
+
+
 def test_nanovdb_matches_dense_grid():
     """config C4 note: the NanoVDB and Grid media built from the same field must agree."""
     s, dens, lo, hi = _media_scene("nanovdb")
