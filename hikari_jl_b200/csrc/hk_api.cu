@@ -347,7 +347,7 @@ static int32_t mat_textures_ok(HkContext* ctx, const HkMaterial& m) {
     bool any = false;
     for (int k = 0; k < 3; k++) if (m.tex[k] != 0) { any = true; REQUIRE(m.tex[k] >= 1 && m.tex[k] <= ctx->D.n_textures, "material references a texture that has not been uploaded (hk_upload_textures first)"); }
     for (int k = 0; k < 8; k++) if (m.ftex[k] != 0) { any = true; REQUIRE(m.ftex[k] >= 1 && m.ftex[k] <= ctx->D.n_textures, "material references a texture that has not been uploaded (hk_upload_textures first)"); }
-    REQUIRE(!any || m.type != HK_MAT_MIX, "MixMaterial.amount cannot be a texture");
+    if (m.type == HK_MAT_MIX) for (int k = 0; k < 3; k++) REQUIRE(m.tex[k] == 0, "a MixMaterial has no RGB parameters to texture");      // (ftex[0] = amount)
     REQUIRE(!((m.flags & HK_MATFLAG_SPECTRAL_ETA_K) && (m.tex[0] != 0 || m.tex[1] != 0)), "eta / k are piecewise-linear spectra: they cannot be textured as well");
     return HK_OK;
 }

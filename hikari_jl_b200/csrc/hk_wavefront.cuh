@@ -557,7 +557,7 @@ __global__ void __launch_bounds__(HK_TRACE_THREADS, INST ? HK_TRACE_BLOCKS_PER_S
 // in-medium rays go to delta tracking with their hit record; the vacuum alpha loop (:224-266) ends on its first iteration
 // because every constant-parameter material has alpha == 1 (spectral-eval.jl:3882-3888)
 // ---- MixMaterial, src/materials/mix-material.jl: mix_hash_float :114-158 (the UInt32 shifts truncate, the SetKey shifts
-// are 64-bit), choose_material :178-196 with a constant amount, resolve_mix_material :253-268 (<= 8 levels) ---------------
+// are 64-bit), choose_material :178-196, resolve_mix_material :253-268 (<= 8 levels) ---------------
 HK_DEV float mix_hash_float(float3 p, float3 wo, uint32_t type1, uint32_t vec1, uint32_t type2, uint32_t vec2) {
     uint64_t h = 0;
     h ^= (uint64_t)__float_as_uint(p.x);
@@ -579,11 +579,18 @@ HK_DEV float mix_hash_float(float3 p, float3 wo, uint32_t type1, uint32_t vec1, 
     h = mix_bits(h);
     return (float)(uint32_t)(h & 0xFFFFFFFFull) * 2.3283064365386963e-10f;
 }
-HK_DEV uint32_t resolve_mix_material(const HkMaterial* __restrict__ materials, uint32_t idx, float3 p, float3 wo) {
+// amount: the constant, or eval_tex(ctx, mix.amount, uv) = the bilinear texel at the hit's uv (choose_material :183)
+HK_DEV uint32_t resolve_mix_material(const DevScene& D, uint32_t idx, float3 p, float3 wo, uint32_t prim0, float b1, float b2) {
+    const HkMaterial* __restrict__ materials = D.materials;
+    bool have_uv = false; float2 uv = make_float2(0.0f, 0.0f);
     for (int it = 0; it < 8; it++) {
         const HkMaterial& m = materials[idx - 1];
         if (m.type != HK_MAT_MIX) return idx;
-        const float amt = m.f[0];
+        float amt = m.f[0];
+        if (m.ftex[0] > 0) {
+            if (!have_uv) { uv = hit_uv(D, resolve_prim(D, prim0).tri, b1, b2); have_uv = true; }
+            float rgb[3]; tex_bilinear(D.textures[m.ftex[0] - 1], uv, rgb); amt = rgb[0];
+        }
         if (amt <= 0.0f) idx = (uint32_t)m.ival[0];
         else if (amt >= 1.0f) idx = (uint32_t)m.ival[1];
         else {
@@ -602,7 +609,8 @@ HK_DEV int hit_queue_id(const DevScene& D, const PathState& S, uint32_t slot, ui
         const float3 o = f3(ra.x, ra.y, ra.z), d = f3(ra.w, rb.x, rb.y);
         const uint32_t prim0 = HK_HIT_PRIM1(hit_bits) - 1u;
         const uint32_t mi = prim_iface(D, prim0);
-        const uint32_t res = resolve_mix_material(D.materials, D.interfaces[mi - 1].material, o + d * t_hit, -d);
+        const float4 hr = S.hit[slot];      // (t, bits, b1, b2): the barycentrics are only needed for a textured amount
+        const uint32_t res = resolve_mix_material(D, D.interfaces[mi - 1].material, o + d * t_hit, -d, prim0, hr.z, hr.w);
         S.res_mat[slot] = res;
         mtype = shade_class(D.materials[res - 1]);
         if (mtype == HK_MAT_MIX) return -1;            // a mix chain deeper than 8 levels: the reference would shade a MixMaterial (undefined); dropped

@@ -399,18 +399,19 @@ class Material:
 
 class MixMaterial(Material):
     """src/materials/mix-material.jl:39-99: MixMaterial(materials=(m1, m2), amount=0.5).  Resolved to one of the two at
-    intersection time by a hash of (hit point, wo, SetKeys); `amount` is a constant here (textures: SURVEY 8f).
+    intersection time by a hash of (hit point, wo, SetKeys); `amount` is a constant or a Texture{Float32} evaluated at the hit's uv
+    (choose_material, mix-material.jl:178-196: `amt = eval_tex(ctx, mix.amount, uv)`).
     The reference takes the sub-materials' SetKeys explicitly (`material_indices`); the mirror derives them from the
     scene: type_idx = position of the material's type in first-push order, vec_idx = position within that type."""
     type = A.HK_MAT_MIX
 
     def __init__(self, materials, amount=0.5):
         assert len(materials) == 2 and all(isinstance(m, Material) for m in materials)
-        self.materials, self.amount = tuple(materials), float(amount)
+        self.materials, self.amount = tuple(materials), _param_f(amount)
 
     def to_abi(self, scene):
         m = A.HkMaterial(type=self.type)
-        m.f[0] = self.amount
+        _put_f(m, scene, 0, self.amount)
         keys = []
         for k, sub in enumerate(self.materials):
             m.ival[k] = scene._index_of(scene.materials, sub)

@@ -166,6 +166,30 @@ def textured_parameters(tess=16, seed=6):
     return s, _cam((0, 3.0, -7.0), (0, -0.2, 0), 40.0)
 
 
+def textured_mix(tess=24, seed=9):
+    """MixMaterial.amount as a Texture{Float32} (choose_material, mix-material.jl:183: amt = eval_tex(ctx, mix.amount, uv)): a
+    floor whose mix runs from all-matte (amount <= 0) through the hashed blend to all-mirror (amount >= 1) along u, a sphere
+    with a noisy amount, a nested mix whose inner amount is textured too, and a constant-amount neighbour."""
+    rng = np.random.RandomState(seed)
+    ramp = np.tile(np.linspace(-0.25, 1.25, 16, dtype=np.float32), (2, 1))          # [h, w]: varies along u, leaves [0, 1] at both ends
+    noise = rng.uniform(-0.2, 1.2, size=(12, 12)).astype(np.float32)
+    half = np.zeros((4, 4), np.float32); half[:2, :] = 1.0
+    s = H.Scene()
+    grey, mirror = H.MatteMaterial(Kd=(0.7, 0.7, 0.7)), H.MirrorMaterial(Kr=0.9)
+    red, blue, gold = H.MatteMaterial(Kd=(0.8, 0.2, 0.2)), H.MatteMaterial(Kd=(0.2, 0.3, 0.8)), H.Gold(roughness=0.1)
+    floor = H.Mesh([(-5, -0.9, -5), (5, -0.9, -5), (5, -0.9, 5), (-5, -0.9, 5)], [(0, 2, 1), (0, 3, 2)], normals=[(0, 1, 0)] * 4, uvs=[(0, 0), (1, 0), (1, 1), (0, 1)])
+    s.push(floor, H.MixMaterial((grey, mirror), amount=H.Texture(ramp)))
+    inner = H.MixMaterial((red, gold), amount=H.Texture(half))
+    s.push(H.uv_sphere((-1.8, 0.0, 0.0), 0.85, tess, tess), H.MixMaterial((blue, gold), amount=H.Texture(noise)))
+    s.push(H.uv_sphere((0.0, 0.0, 0.0), 0.85, tess, tess), H.MixMaterial((inner, blue), amount=H.Texture(noise.T.copy())))
+    s.push(H.uv_sphere((1.8, 0.0, 0.0), 0.85, tess, tess), H.MixMaterial((red, mirror), amount=0.5))
+    d = np.array([-0.6, -1.0, 0.5])
+    s.push(H.DirectionalLight((3, 3, 3), d / np.linalg.norm(d), legacy_rgbspectrum=True))
+    s.push(H.AmbientLight((0.25, 0.3, 0.35)))
+    s.sync()
+    return s, _cam((0, 2.2, -5.5), (0, -0.2, 0), 40.0)
+
+
 def rgb_nebula(res=(20, 16, 12)):
     """An RGBGridMedium (media.jl:1002-1456) inside an index-1 boundary: two coloured, partly emissive blobs over a matte floor."""
     nx, ny, nz = res

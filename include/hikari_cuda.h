@@ -123,8 +123,8 @@ typedef struct HkTexture {
 /* ---- materials ----------------------------------------------------------------------------
  * replaces: scene.materials (MultiTypeSet) + scene.media_interfaces (src/scene.jl:21-28,
  * src/materials/medium-interface.jl:78-82).  Every RGB and scalar parameter is a constant or a texture (tex[] / ftex[]);
- * MatteMaterial.Kd may also carry alpha or be a VertexColorTexture.  Not texturable: MixMaterial.amount, the integer
- * parameters, piecewise-linear eta / k spectra.                                                                  */
+ * MatteMaterial.Kd may also carry alpha or be a VertexColorTexture; MixMaterial.amount = f0 / ftex[0].  Not texturable: the
+ * integer parameters, piecewise-linear eta / k spectra.                                                                */
 #define HK_MAT_MATTE                1   /* src/materials/spectral-eval.jl:42-101, 371-397      */
 #define HK_MAT_MIRROR               2   /* :108-132                                            */
 #define HK_MAT_GLASS                3   /* :140-198, 407-413                                   */
@@ -162,7 +162,7 @@ typedef struct HkMaterial {
                                             f5/f6=conductor u/v roughness                              */
     int32_t  spec[2];   /* 1-based ids into the uploaded piecewise-linear spectra (eta, k); 0 = unused  */
     int32_t  ival[2];   /* CoatedDiffuse / CoatedConductor: ival0=max_depth ival1=n_samples             */
-                        /* Mix: f0 = amount (constant texture); ival0 / ival1 = 1-based material1 / material2;
+                        /* Mix: f0 / ftex[0] = amount (constant or texture, mix-material.jl:183); ival0 / ival1 = 1-based material1 / material2;
                            the SetKeys hashed by mix_hash_float (mix-material.jl:114-158): spec0 / spec1 = vec_idx of
                            material1 / material2, flags = type_idx1 | type_idx2 << 8                             */
     int32_t  tex[4];    /* 1-based ids into the uploaded textures replacing rgb0 / rgb1 / rgb2 (0 = the constant; tex[3] unused):

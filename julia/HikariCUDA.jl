@@ -288,11 +288,10 @@ function hk(m::Hikari.CoatedConductorMaterial, F, P, S)                         
     HkMaterial(b)
 end
 # MixMaterial (mix-material.jl:39-99): the two sub-materials' SetKeys are stored in the material (material_indices); the mix hash
-# consumes their type_idx / vec_idx (mix_hash_float :114-158), the library needs their flat ids as well.  The amount must be constant.
+# consumes their type_idx / vec_idx (mix_hash_float :114-158), the library needs their flat ids as well.  f0 / ftex[0] = amount (a constant, or a texture evaluated at the hit's uv, :183).
 function hk(m::Hikari.MixMaterial, F, P, S)
-    isconst(m.amount) || error("hikari_cuda: a textured MixMaterial.amount is not supported")
     k1, k2 = m.material_indices
-    b = MatB(HK_MAT.mix; flags=UInt32(k1.type_idx) | (UInt32(k2.type_idx) << 8)); b.f[1] = Float32(constval(m.amount))
+    b = MatB(HK_MAT.mix; flags=UInt32(k1.type_idx) | (UInt32(k2.type_idx) << 8)); f!(b, P, 1, m.amount)
     b.spec[1] = k1.vec_idx; b.spec[2] = k2.vec_idx; b.ival[1] = flat_id(F, k1); b.ival[2] = flat_id(F, k2)
     HkMaterial(b)
 end

@@ -296,8 +296,8 @@ struct Scene {
 };
 
 // ---- MixMaterial, src/materials/mix-material.jl ------------------------------------------------------
-// mix_hash_float :114-158 (the UInt32 shifts truncate, the SetKey shifts are 64-bit), choose_material :178-196 with a
-// constant `amount`, resolve_mix_material :253-268 (at most 8 levels).
+// mix_hash_float :114-158 (the UInt32 shifts truncate, the SetKey shifts are 64-bit), choose_material :178-196 (`amount` a
+// constant or a texture), resolve_mix_material :253-268 (at most 8 levels).
 inline float mix_hash_float(V3 p, V3 wo, uint32_t type1, uint32_t vec1, uint32_t type2, uint32_t vec2) {
     auto fb = [](float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; };
     uint64_t h = 0;
@@ -322,11 +322,12 @@ inline float mix_hash_float(V3 p, V3 wo, uint32_t type1, uint32_t vec1, uint32_t
     h ^= h >> 33;
     return (float)(uint32_t)(h & 0xFFFFFFFFull) * 2.3283064365386963e-10f;
 }
-inline uint32_t resolve_mix_material(const std::vector<HkMaterial>& materials, uint32_t idx, V3 p, V3 wo) {
+inline uint32_t resolve_mix_material(const std::vector<HkMaterial>& materials, const TextureStore& textures, uint32_t idx, V3 p, V3 wo, V2 uv) {
     for (int it = 0; it < 8; it++) {
         const HkMaterial& m = materials[idx - 1];
         if (m.type != HK_MAT_MIX) return idx;
-        const float amt = m.f[0];
+        float amt = m.f[0];
+        if (m.ftex[0] > 0) { float rgb[3]; sample_texture_bilinear(textures, m.ftex[0], uv, rgb); amt = rgb[0]; }      // amt = eval_tex(ctx, mix.amount, uv), :183
         if (amt <= 0.0f) idx = (uint32_t)m.ival[0];
         else if (amt >= 1.0f) idx = (uint32_t)m.ival[1];
         else {
@@ -629,7 +630,7 @@ inline void Scene::render_sample(int32_t sample_idx) {
             for (int64_t i = 0; i < n_hits; i++) {
                 const HitSurfaceWork& w = hit_surface_queue[i];
                 V3 wo = -w.ray.d;
-                uint32_t material_idx = resolve_mix_material(materials, w.material, w.g.pi, wo);   // mix-material.jl:253-268
+                uint32_t material_idx = resolve_mix_material(materials, textures, w.material, w.g.pi, wo, w.g.uv);   // mix-material.jl:253-268
                 if (w.arealight_flat_idx > 0) {
                     const HkLight& L = lights[w.arealight_flat_idx - 1];
                     Spec Le = arealight_Le(LC, L, wo, w.g.n, w.lambda);

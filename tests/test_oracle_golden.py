@@ -654,3 +654,35 @@ def test_textured_parameters_known_answers():
     img = vp(scene, film, camf(film))
     assert np.isfinite(img).all() and img.max() > 0.05
     vp.close()
+
+
+def test_textured_mix_amount_known_answers():
+    """MixMaterial.amount as a texture (choose_material, mix-material.jl:178-196), pinned on the oracle: a texture that is 0
+    everywhere renders exactly material 1, one that is 1 everywhere exactly material 2, a constant-valued 0.5 texture exactly the
+    constant amount 0.5 (0.5 (1 - f) + 0.5 f is exact), and a half-0 / half-1 texture shows material 1 on one side of the sphere
+    and material 2 on the other."""
+    red, blue = H.MatteMaterial(Kd=(0.8, 0.1, 0.1)), H.MatteMaterial(Kd=(0.1, 0.1, 0.8))
+    def render(mat):
+        s = H.Scene()
+        s.push(H.rect3((-4, -1.0, -4), (8, 0.1, 8)), H.MatteMaterial(Kd=(0.6, 0.6, 0.6)))
+        s.push(H.uv_sphere((0, 0.2, 0), 1.0, 16, 16), mat)
+        s.push(H.DirectionalLight((3, 3, 3), (-0.3, -1.0, 0.4), legacy_rgbspectrum=True)); s.push(H.AmbientLight((0.3, 0.3, 0.3)))
+        s.sync()
+        film = H.Film((48, 36))
+        vp = H.VolPath(samples=4, max_depth=4, backend=oracle_backend.make_backend())
+        img = vp(s, film, scenes._cam((0, 1.5, -4.5), (0, 0, 0), 40.0)(film)).copy()
+        vp.close()
+        return img
+    T1 = lambda v: H.Texture(np.full((4, 3), v, f32))
+    only_red, only_blue = render(H.MixMaterial((red, blue), amount=0.0)), render(H.MixMaterial((red, blue), amount=1.0))
+    assert np.array_equal(render(H.MixMaterial((red, blue), amount=T1(0.0))), only_red)
+    assert np.array_equal(render(H.MixMaterial((red, blue), amount=T1(1.0))), only_blue)
+    assert np.array_equal(render(H.MixMaterial((red, blue), amount=T1(-3.0))), only_red) and np.array_equal(render(H.MixMaterial((red, blue), amount=T1(7.0))), only_blue)
+    assert np.array_equal(render(H.MixMaterial((red, blue), amount=T1(0.5))), render(H.MixMaterial((red, blue), amount=0.5)))
+    assert not np.array_equal(only_red, only_blue)
+    split = np.zeros((2, 2), f32); split[:, 1] = 1.0                                   # u < 0.5: material 1, u > 0.5: material 2 (bilinear ramp between)
+    img = render(H.MixMaterial((red, blue), amount=H.Texture(split)))
+    sphere = (np.abs(only_red - only_blue).sum(axis=2) > 0.02)
+    like_red = np.isclose(img, only_red, rtol=1e-5, atol=1e-6).all(axis=2) & sphere
+    like_blue = np.isclose(img, only_blue, rtol=1e-5, atol=1e-6).all(axis=2) & sphere
+    assert like_red.sum() > 20 and like_blue.sum() > 20, (like_red.sum(), like_blue.sum(), sphere.sum())

@@ -452,6 +452,7 @@ IMAGE_CASES = [
     ("alpha_foliage_in_fog", lambda: scenes.alpha_foliage(fog=True), (96, 72), 8, 5),
     ("vertex_colors", lambda: scenes.vertex_color_meshes(), (96, 64), 4, 4),
     ("textured_parameters", lambda: scenes.textured_parameters(), (128, 72), 8, 6),
+    ("textured_mix", lambda: scenes.textured_mix(), (128, 72), 8, 6),
 ]
 
 
