@@ -118,6 +118,7 @@ int32_t hk_destroy(HkContext* ctx) {
     for (auto& b : ctx->env_bufs) b.release();
     for (auto& b : ctx->media_bufs) b.release();
     for (auto& b : ctx->mask_bufs) b.release();
+    for (auto& b : ctx->dense_bufs) b.release();
     for (auto& b : ctx->tex_bufs) b.release();
     ctx->b_aux.release(); ctx->b_denoise.release(); ctx->b_uvs.release(); ctx->b_textures.release();
     ctx->b_inst_recs.release(); ctx->b_instances.release(); ctx->b_inst_base.release();
@@ -504,6 +505,25 @@ static int32_t upload_one_medium(HkContext* ctx, uint32_t i, const HkMedium& M, 
         CK(B[2].upload(M.nanovdb_buf, (size_t)M.nanovdb_bytes)); d.nvdb = B[2].as<uint8_t>();
         std::memcpy(d.inv_mat, M.nanovdb_inv_mat, 36); std::memcpy(d.vec, M.nanovdb_vec, 12); d.root_off = M.nanovdb_root_offset; d.root_tiles = M.nanovdb_root_tiles;
     }
+    ctx->dense_bufs[i].release();
+    if (M.type == HK_MEDIUM_NANOVDB && !std::getenv("HK_NO_DENSE_MIRROR")) {
+        // dense mirror of the tree over [index_min, index_max] + 1 (the +1: the upper trilinear corner of the last voxel), when it fits
+        size_t cap = 2ull << 30;
+        if (const char* e = std::getenv("HK_DENSE_MIRROR_MAX_MB")) cap = (size_t)std::max(0, atoi(e)) << 20;
+        bool ok = true; size_t vox = 1;
+        for (int k = 0; k < 3; k++) {
+            const long long ext = (long long)M.nanovdb_index_max[k] - (long long)M.nanovdb_index_min[k] + 2;
+            ok = ok && ext >= 2 && ext < (1ll << 20);
+            if (ok) { d.dn_min[k] = M.nanovdb_index_min[k]; d.dn_ext[k] = (int32_t)ext; vox *= (size_t)ext; ok = vox <= (cap >> 2); }
+        }
+        if (ok) {
+            CK(ctx->dense_bufs[i].alloc(4 * vox));
+            d.dense = nullptr;      // (the fill itself walks the tree)
+            k_nvdb_densify<<<grid_for(ctx, vox, 256, 16), 256, 0, ctx->stream>>>(d, ctx->dense_bufs[i].as<float>());
+            ctx->launches++;
+            d.dense = ctx->dense_bufs[i].as<float>();
+        } else { d.dense = nullptr; for (int k = 0; k < 3; k++) d.dn_min[k] = d.dn_ext[k] = 0; }
+    }
     ctx->mask_bufs[i].release();
     if (M.type == HK_MEDIUM_HOMOGENEOUS) return HK_OK;
     REQUIRE(M.majorant_res[0] >= 1 && M.majorant_res[1] >= 1 && M.majorant_res[2] >= 1, "majorant_res must be at least 1 per axis");
@@ -550,8 +570,10 @@ int32_t hk_upload_media(HkContext* ctx, const HkMedium* m, uint32_t n) {
     hk_enter(ctx);
     for (auto& b : ctx->media_bufs) b.release();
     for (auto& b : ctx->mask_bufs) b.release();
+    for (auto& b : ctx->dense_bufs) b.release();
     ctx->media_bufs.clear(); ctx->media_bufs.resize(3 * (size_t)n);
     ctx->mask_bufs.clear(); ctx->mask_bufs.resize(n);
+    ctx->dense_bufs.clear(); ctx->dense_bufs.resize(n);
     ctx->media_host.assign(n, DevMedium{});
     for (uint32_t i = 0; i < n; i++) { int32_t rc = upload_one_medium(ctx, i, m[i], ctx->media_host[i]); if (rc != HK_OK) { ctx->media_host.clear(); ctx->D.n_media = 0; return rc; } }
     return commit_media(ctx);

@@ -1,6 +1,12 @@
 // hk_k_media.cu — translation unit of the participating-media kernels (hk_wavefront.cuh, HK_TU_MEDIA): k_medium_track,
 // k_medium_finish, k_shadow_seg_ratio.
 #define HK_TU_MEDIA
+// The tracking kernels are ~70 KB of SASS against a 32 KB instruction cache (ncu: no_instruction is their second largest stall).
+// Spec / float -- four IEEE divisions, ~40 instructions at each of ~14 call sites -- is a real function in this translation unit
+// (C4 +4 %; elsewhere inlining it is the faster choice, hk_math.cuh).
+#ifndef HK_NOINLINE_SPDIV
+#define HK_NOINLINE_SPDIV 1
+#endif
 #include "hk_launch.h"
 
 void hkl_medium_track(bool rgb, int grid, cudaStream_t st, const DevScene& D, const PathState& S) {

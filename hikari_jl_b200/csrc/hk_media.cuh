@@ -17,6 +17,10 @@ struct DevMedium {
     // cell yields sigma_maj = sigma_t * 0 = 0 < 1e-10 for every wavelength, i.e. the tracking loops skip it -- the DDA can step over it
     // without fetching the grid value.  Bit i = cell x + rx (y + ry z).
     const uint32_t* __restrict__ maj_empty;
+    // NanoVDB: a dense mirror of the tree's values over the index box [dn_min, dn_min + dn_ext) (built on the device at upload,
+    // k_nvdb_densify, when the box fits HK_DENSE_MIRROR_MAX; z fastest like the leaves).  Look-ups whose eight corners fall inside the
+    // box read the mirror -- the same values the root -> upper -> lower -> leaf walk returns -- everything else walks the tree.
+    const float* __restrict__ dense; int32_t dn_min[3], dn_ext[3];
 };
 // smem_mask: the tracking kernels stage the empty-cell mask of ONE medium (smem_medium, 1-based; the first grid medium whose mask fits)
 // in shared memory; other media read theirs from global memory
@@ -148,24 +152,47 @@ HK_DEV float nvdb_value(const DevMedium& M, LeafCache& lc, int32_t x, int32_t y,
     uint32_t nf = ((uint32_t)(x & 7) << 6) | ((uint32_t)(y & 7) << 3) | (uint32_t)(z & 7);
     return rd<float>(M.nvdb, lc.leaf_off + 96 + (uint64_t)nf * 4);
 }
-// lc: the leaf that answered the previous look-up.  The trackers keep it across the events of a ray (consecutive events of a segment
-// fall into the same 8^3 leaf almost always, so the root -> upper -> lower walk -- four dependent loads -- runs once per leaf, not once
-// per event); a fresh cache (valid = false) gives the reference's literal behaviour.  Same values either way.
-HK_DEV float nvdb_density(const DevMedium& M, float3 p, LeafCache& lc) {
+HK_DEV void nvdb_index(const DevMedium& M, float3 p, float& gx, float& gy, float& gz) {      // index-from-world (nanovdb.jl:400-412)
     float px = p.x - M.vec[0], py = p.y - M.vec[1], pz = p.z - M.vec[2];
-    float gx = M.inv_mat[0] * px + M.inv_mat[1] * py + M.inv_mat[2] * pz;
-    float gy = M.inv_mat[3] * px + M.inv_mat[4] * py + M.inv_mat[5] * pz;
-    float gz = M.inv_mat[6] * px + M.inv_mat[7] * py + M.inv_mat[8] * pz;
-    int ix = floor_i(gx), iy = floor_i(gy), iz = floor_i(gz);
-    float fx = gx - (float)ix, fy = gy - (float)iy, fz = gz - (float)iz;
-    float v000 = nvdb_value(M, lc, ix, iy, iz), v001 = nvdb_value(M, lc, ix, iy, iz + 1);
-    float v010 = nvdb_value(M, lc, ix, iy + 1, iz), v011 = nvdb_value(M, lc, ix, iy + 1, iz + 1);
-    float v100 = nvdb_value(M, lc, ix + 1, iy, iz), v101 = nvdb_value(M, lc, ix + 1, iy, iz + 1);
-    float v110 = nvdb_value(M, lc, ix + 1, iy + 1, iz), v111 = nvdb_value(M, lc, ix + 1, iy + 1, iz + 1);
+    gx = M.inv_mat[0] * px + M.inv_mat[1] * py + M.inv_mat[2] * pz;
+    gy = M.inv_mat[3] * px + M.inv_mat[4] * py + M.inv_mat[5] * pz;
+    gz = M.inv_mat[6] * px + M.inv_mat[7] * py + M.inv_mat[8] * pz;
+}
+HK_DEV float nvdb_lerp(float v000, float v001, float v010, float v011, float v100, float v101, float v110, float v111, float fx, float fy, float fz) {
     float fx1 = 1.0f - fx, fy1 = 1.0f - fy, fz1 = 1.0f - fz;
     float v00 = v000 * fz1 + v001 * fz, v01 = v010 * fz1 + v011 * fz, v10 = v100 * fz1 + v101 * fz, v11 = v110 * fz1 + v111 * fz;
     float v0 = v00 * fy1 + v01 * fy, v1 = v10 * fy1 + v11 * fy;
     return v0 * fx1 + v1 * fx;
+}
+// all eight trilinear corners of voxel (ix, iy, iz) inside the dense mirror?
+HK_DEV bool nvdb_in_mirror(const DevMedium& M, int ix, int iy, int iz) {
+    const uint32_t ux = (uint32_t)(ix - M.dn_min[0]), uy = (uint32_t)(iy - M.dn_min[1]), uz = (uint32_t)(iz - M.dn_min[2]);
+    return M.dense != nullptr && ux < (uint32_t)(M.dn_ext[0] - 1) && uy < (uint32_t)(M.dn_ext[1] - 1) && uz < (uint32_t)(M.dn_ext[2] - 1);
+}
+HK_DEV float nvdb_mirror_lerp(const DevMedium& M, int ix, int iy, int iz, float fx, float fy, float fz) {
+    const size_t sy = (size_t)M.dn_ext[2], sx = sy * (size_t)M.dn_ext[1];
+    const float* __restrict__ b = M.dense + (size_t)(ix - M.dn_min[0]) * sx + (size_t)(iy - M.dn_min[1]) * sy + (size_t)(iz - M.dn_min[2]);
+    return nvdb_lerp(__ldg(b), __ldg(b + 1), __ldg(b + sy), __ldg(b + sy + 1), __ldg(b + sx), __ldg(b + sx + 1), __ldg(b + sx + sy), __ldg(b + sx + sy + 1), fx, fy, fz);
+}
+// the eight corners through the tree (per-thread LeafCache: the corners share one root -> lower walk whenever they fall in one leaf)
+HK_DEV float nvdb_tree_lerp(const DevMedium& M, LeafCache& lc, int ix, int iy, int iz, float fx, float fy, float fz) {
+    float v000 = nvdb_value(M, lc, ix, iy, iz), v001 = nvdb_value(M, lc, ix, iy, iz + 1);
+    float v010 = nvdb_value(M, lc, ix, iy + 1, iz), v011 = nvdb_value(M, lc, ix, iy + 1, iz + 1);
+    float v100 = nvdb_value(M, lc, ix + 1, iy, iz), v101 = nvdb_value(M, lc, ix + 1, iy, iz + 1);
+    float v110 = nvdb_value(M, lc, ix + 1, iy + 1, iz), v111 = nvdb_value(M, lc, ix + 1, iy + 1, iz + 1);
+    return nvdb_lerp(v000, v001, v010, v011, v100, v101, v110, v111, fx, fy, fz);
+}
+// lc: the leaf that answered the previous look-up.  The trackers keep it across the events of a ray (consecutive events of a segment
+// fall into the same 8^3 leaf almost always, so the root -> upper -> lower walk -- four dependent loads -- runs once per leaf, not once
+// per event); a fresh cache (valid = false) gives the reference's literal behaviour.  Same values either way, and the same values from
+// the dense mirror.
+HK_DEV float nvdb_density(const DevMedium& M, float3 p, LeafCache& lc) {
+    float gx, gy, gz;
+    nvdb_index(M, p, gx, gy, gz);
+    int ix = floor_i(gx), iy = floor_i(gy), iz = floor_i(gz);
+    float fx = gx - (float)ix, fy = gy - (float)iy, fz = gz - (float)iz;
+    if (nvdb_in_mirror(M, ix, iy, iz)) return nvdb_mirror_lerp(M, ix, iy, iz, fx, fy, fz);
+    return nvdb_tree_lerp(M, lc, ix, iy, iz, fx, fy, fz);
 }
 HK_DEV float grid_density(const DevMedium& M, float3 pm) {   // media.jl:1544-1595
     float pn[3];
@@ -250,9 +277,9 @@ HK_DEV float medium_density(const DevMedium& M, float3 p) { LeafCache lc; lc.val
 // leaf almost always, so the root -> upper -> lower walk -- four dependent loads -- runs once per leaf instead of once per event,
 // without the cache's seven words living in registers for the whole walk (registers decide this kernel's occupancy).
 #define HK_LC_WORDS 7
-HK_DEV float medium_density_cached(const DevMedium& M, float3 p, uint32_t* lc_slot) {
-    if (M.type == HK_MEDIUM_GRID) return grid_density(M, affine_pt(M.medium_from_render, p));
-    if (M.type != HK_MEDIUM_NANOVDB) return 1.0f;
+// the tree path of medium_density_cached, out of line: with a dense mirror it only serves look-ups at the edge of / outside the tree's
+// index box, and its eight cached look-ups are several hundred instructions the tracking loops should not have to fetch around
+static __device__ __noinline__ float nvdb_density_tree_cached(const DevMedium& M, int ix, int iy, int iz, float fx, float fy, float fz, uint32_t* lc_slot) {
     const unsigned st = blockDim.x;
     LeafCache lc; lc.valid = false; lc.is_leaf = false; lc.kx = lc.ky = lc.kz = 0; lc.leaf_off = 0; lc.tile = 0.0f;
     if (lc_slot != nullptr) {
@@ -261,13 +288,23 @@ HK_DEV float medium_density_cached(const DevMedium& M, float3 p, uint32_t* lc_sl
         lc.kx = (int32_t)lc_slot[st]; lc.ky = (int32_t)lc_slot[2 * st]; lc.kz = (int32_t)lc_slot[3 * st];
         lc.leaf_off = (uint64_t)lc_slot[4 * st] | ((uint64_t)lc_slot[5 * st] << 32); lc.tile = __uint_as_float(lc_slot[6 * st]);
     }
-    const float v = nvdb_density(M, p, lc);
+    const float v = nvdb_tree_lerp(M, lc, ix, iy, iz, fx, fy, fz);
     if (lc_slot != nullptr) {
         lc_slot[0] = (lc.valid ? 1u : 0u) | (lc.is_leaf ? 2u : 0u);
         lc_slot[st] = (uint32_t)lc.kx; lc_slot[2 * st] = (uint32_t)lc.ky; lc_slot[3 * st] = (uint32_t)lc.kz;
         lc_slot[4 * st] = (uint32_t)lc.leaf_off; lc_slot[5 * st] = (uint32_t)(lc.leaf_off >> 32); lc_slot[6 * st] = __float_as_uint(lc.tile);
     }
     return v;
+}
+HK_DEV float medium_density_cached(const DevMedium& M, float3 p, uint32_t* lc_slot) {
+    if (M.type == HK_MEDIUM_GRID) return grid_density(M, affine_pt(M.medium_from_render, p));
+    if (M.type != HK_MEDIUM_NANOVDB) return 1.0f;
+    float gx, gy, gz;
+    nvdb_index(M, p, gx, gy, gz);
+    int ix = floor_i(gx), iy = floor_i(gy), iz = floor_i(gz);
+    float fx = gx - (float)ix, fy = gy - (float)iy, fz = gz - (float)iz;
+    if (nvdb_in_mirror(M, ix, iy, iz)) return nvdb_mirror_lerp(M, ix, iy, iz, fx, fy, fz);
+    return nvdb_density_tree_cached(M, ix, iy, iz, fx, fy, fz, lc_slot);
 }
 HK_DEV void majiter_create(MajIter& it, const DevMedium& M, const MediumCoef& mc, float3 o, float3 d, float t_max, const uint32_t* mask = nullptr) {
     it.mask = mask;

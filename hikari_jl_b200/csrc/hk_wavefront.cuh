@@ -472,6 +472,15 @@ __global__ void __launch_bounds__(128) k_build_majorant(DevMedium M, MajBuild P,
         out[cell] = m0;
     }
 }
+// dense mirror of a NanoVDB tree (DevMedium::dense): one thread per voxel of the index box, the value the tree walk returns
+__global__ void __launch_bounds__(256) k_nvdb_densify(DevMedium M, float* __restrict__ out) {
+    const size_t n = (size_t)M.dn_ext[0] * M.dn_ext[1] * M.dn_ext[2];
+    LeafCache lc; lc.valid = false;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int z = (int)(i % (size_t)M.dn_ext[2]), y = (int)((i / (size_t)M.dn_ext[2]) % (size_t)M.dn_ext[1]), x = (int)(i / ((size_t)M.dn_ext[2] * M.dn_ext[1]));
+        out[i] = nvdb_value(M, lc, M.dn_min[0] + x, M.dn_min[1] + y, M.dn_min[2] + z);
+    }
+}
 // light-BVH nodes in their device form (DevLNode, hk_lights.cuh): the point-independent part of node_importance, once per upload
 __global__ void __launch_bounds__(256) k_prepare_lnodes(const HkLightBVHNode* __restrict__ in, uint32_t n, DevLNode* __restrict__ out) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = prepare_lnode(in[i]);

@@ -981,6 +981,38 @@ def test_update_medium_replaces_one_medium_in_place():
         assert np.array_equal(updated.view(np.uint32), film3.framebuffer.view(np.uint32)), f"{kind}: updated medium differs from the oracle"
 
 
+def test_nanovdb_dense_mirror_and_tree_walk_agree(monkeypatch):
+    """NanoVDB look-ups read a dense mirror of the tree (built on the device at upload) when all eight trilinear corners fall inside
+    the tree's index box, and walk the tree otherwise.  Both paths must return the oracle's bits: densities at points inside, outside
+    and across the edge of the box, with the mirror on and with it switched off (HK_NO_DENSE_MIRROR), and delta tracking either way."""
+    s, dens, lo, hi = _media_scene("nanovdb")
+    rng = np.random.RandomState(16)
+    n = 30000
+    pts = rng.uniform(-0.9, 1.8, size=(n, 3)).astype(f32)
+    edge = rng.uniform(0.0, 1.0, size=(n // 3, 3)).astype(f32) * (np.array(hi, f32) - np.array(lo, f32)) + np.array(lo, f32)
+    edge[:, 0] = np.where(rng.uniform(size=n // 3) < 0.5, lo[0], hi[0]) + rng.uniform(-0.06, 0.06, size=n // 3)      # around two faces of the box
+    pts[: n // 3] = edge
+    x = np.zeros((n, 8), f32)
+    x[:, 0:3] = rng.uniform(-0.5, 0.5, size=(n, 3)) + (0, 0.9, 0)
+    d = rng.normal(size=(n, 3)); x[:, 3:6] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    x[:, 6] = rng.uniform(0.05, 2.0, n); x[:, 7] = rng.uniform(0, 1, n)
+    out = {}
+    for mirror in (True, False):
+        if mirror: monkeypatch.delenv("HK_NO_DENSE_MIRROR", raising=False)
+        else: monkeypatch.setenv("HK_NO_DENSE_MIRROR", "1")
+        p = Pair(scene=s)
+        try:
+            a = np.zeros(n, f32); b = np.zeros(n, f32); da = np.zeros((n, 16), f32)
+            assert p.lib.hk_test_density(p.cu.ctx, 1, fp(pts), n, fp(a)) == 0
+            p.olib.ok_test_density(p.ok.ctx, 1, fp(pts), n, fp(b))
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and (a > 0).sum() > 1000, f"mirror={mirror}"
+            assert p.lib.hk_test_delta_tracking(p.cu.ctx, 1, fp(x), n, fp(da)) == 0
+            out[mirror] = da
+        finally:
+            p.close()
+    assert np.array_equal(out[True].view(np.uint32), out[False].view(np.uint32))
+
+
 def test_nanovdb_matches_dense_grid():
     """config C4 note: the NanoVDB and Grid media built from the same field must agree."""
     s, dens, lo, hi = _media_scene("nanovdb")
