@@ -351,7 +351,9 @@ __device__ unsigned long long g_media_stats[32];
 #define HK_STAT(i, n) ((void)0)
 #endif
 #ifndef HK_TRACK_SKIP
+#ifndef HK_TRACK_SKIP
 #define HK_TRACK_SKIP 4
+#endif
 #endif
 #ifndef HK_TRACK_SKIP_EMPTY
 #define HK_TRACK_SKIP_EMPTY 16

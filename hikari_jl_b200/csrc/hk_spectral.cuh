@@ -172,8 +172,9 @@ HK_DEV float sample_tent(float u, float r) {
 }
 HK_DEV int filter_interval(const float* __restrict__ cdf, float u, int n) {   // filter.jl:727-741, 1-based result
     int lo = 1, hi = n + 1;
+    const int iters = 32 - __clz(n);      // >= ceil(log2(n)): the interval [lo, hi) is one entry wide by then, further rounds change nothing
 #pragma unroll 1
-    for (int it = 0; it < 20; it++) {
+    for (int it = 0; it < iters; it++) {
         int mid = (lo + hi) >> 1;
         bool c = __ldg(cdf + mid - 1) <= u;
         lo = c ? mid : lo; hi = c ? hi : mid;
