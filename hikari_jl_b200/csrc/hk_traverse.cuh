@@ -28,9 +28,18 @@
 #ifndef HK_NODE_PREFETCH
 #define HK_NODE_PREFETCH 0    // 1: L1-prefetch the node that will be visited next while this node's triangles are tested
 #endif
+// 1: MUFU.RCP (rcp.approx.ftz, <= 1 ulp) for the inverse direction instead of the IEEE division (~8 instructions and a slow-path call per
+// component, paid at every instance entry of the two-level walk: 7 % of k_trace's samples on C5 at 4-8 active lanes).  The inverse
+// direction feeds the slab tests only -- both the slope A = inv * scale and the offset b = -o * inv of an axis use the SAME value, so an
+// approximate reciprocal scales every slab distance of that axis by (1 +- 1 ulp) and nothing else; the far-side inflation below grows
+// from 6 to 10 ulp to cover it.  Hits are decided by the exact triangle test, so primitive ids / t / barycentrics stay bit-exact
+// (brute-force tests, image parity).  C5 trace 12.63 -> 12.17 ms/step, C3 2.33 -> 2.29, C2 1.055 -> 1.037.
 #ifndef HK_RCP_APPROX
-#define HK_RCP_APPROX 0       // 1: MUFU.RCP for the inverse direction (slab tests only)
+#define HK_RCP_APPROX 1
 #endif
+// far slab distance inflation: 6 ulp cover the rounding of the IEEE reciprocal and the two FMAs of a slab test; the approximate
+// reciprocal (<= 1 ulp off, both on the near and the far side) gets 10
+#define HK_SLAB_INFLATE (HK_RCP_APPROX ? 1.0000012f : 1.0000007f)
 #ifndef HK_TRACE_BLOCKS_PER_SM
 #define HK_TRACE_BLOCKS_PER_SM 8
 #endif
@@ -143,7 +152,11 @@ struct Bvh8Walker {
     }
     HK_DEV void set_ray(float3 o_, float3 d_) {
         o = o_; d = d_;
+#if HK_RCP_APPROX
+        inv = f3(__frcp_approx(d.x), __frcp_approx(d.y), __frcp_approx(d.z));
+#else
         inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+#endif
         oct_inv = (d.x >= 0.0f ? 4u : 0u) | (d.y >= 0.0f ? 2u : 0u) | (d.z >= 0.0f ? 1u : 0u);
     }
     // precondition: no pending triangles.  Returns true when the traversal is finished (nothing left to visit).
@@ -210,7 +223,7 @@ struct Bvh8Walker {
             const float tz0 = __fmaf_rn(HK_QF(i < 4 ? nz0 : nz1, k), Az, bzn), tz1 = __fmaf_rn(HK_QF(i < 4 ? fz0 : fz1, k), Az, bzf);
             // fmaxf/fminf drop NaNs (inf - inf when a direction component is zero): that axis is left unconstrained
             const float tn = fmaxf(fmaxf(tx0, ty0), fmaxf(tz0, 0.0f));
-            const float tf = fminf(fminf(tx1, ty1), fminf(tz1, tlim)) * 1.0000007f;
+            const float tf = fminf(fminf(tx1, ty1), fminf(tz1, tlim)) * HK_SLAB_INFLATE;
             if (tn <= tf) hits8 |= 1u << i;
         }
 #undef HK_QF
