@@ -291,7 +291,7 @@ def measure(args, rank, world, local, dist, torch, full):
         e2e_steps = max(3, steps)                      # the same K frames as the device-timed region
         vp.clear(); film.iteration_index = 0
         if dist: dist.barrier()
-        depth = max(1, min(3, int(os.environ.get("HK_E2E_DEPTH", "3"))))      # read-outs left in flight while the next frame is enqueued
+        depth = max(1, min(7, int(os.environ.get("HK_E2E_DEPTH", "3"))))      # read-outs left in flight while the next frame is enqueued
         def display_loop(frames):        # progressive display loop: frame k's read-out (own stream) and frame k+1's render overlap frame k+2's
             pending = []
             for _ in range(frames):

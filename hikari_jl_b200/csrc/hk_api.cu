@@ -80,8 +80,8 @@ int32_t hk_create(int32_t device, HkContext** out) {
     if (std::getenv("HK_SERIAL_SHADOW") && ctx->shadow_stream) { cudaStreamDestroy(ctx->shadow_stream); ctx->shadow_stream = nullptr; }
     if (ctx->b_counts.alloc(sizeof(uint32_t) * HK_N_COUNTERS + 64) != cudaSuccess || ctx->b_trace_ctr.alloc(64) != cudaSuccess || ctx->b_work_ctr.alloc(64) != cudaSuccess) { delete ctx; return HK_ERR_OOM; }
     cudaMemset(ctx->b_counts.p, 0, ctx->b_counts.bytes); cudaMemset(ctx->b_trace_ctr.p, 0, 64); cudaMemset(ctx->b_work_ctr.p, 0, 64);
-    if (ctx->b_scratch_u32.alloc(16) != cudaSuccess) { delete ctx; return HK_ERR_OOM; }
-    cudaMemset(ctx->b_scratch_u32.p, 0, 16);
+    if (ctx->b_scratch_u32.alloc(64) != cudaSuccess) { delete ctx; return HK_ERR_OOM; }
+    cudaMemset(ctx->b_scratch_u32.p, 0, 64);
     for (int i = 0; i < HK_N_STAGES; i++) { ctx->stage_ms[i] = 0; ctx->stage_launches[i] = 0; }
     {   // the extra render lanes (frame pipelining); any failure just leaves them off
         bool ok = true;
@@ -881,9 +881,9 @@ int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride,
             cur ^= 1;
         }
         if (shadow_in_flight) cudaStreamWaitEvent(st, ctx->ev_shadowed, 0);      // the film pass reads L
-        // the film is summed in sample order: wait for the other lane's accumulation, and (second lane) for read-outs / clears of the film on the main stream
+        // the film is summed in sample order: wait for the previous frame's accumulation, and for read-outs / clears of the film (main or copy stream)
         if (ctx->last_accum_lane >= 0 && ctx->last_accum_lane != lane && ctx->lane_pending[ctx->last_accum_lane]) cudaStreamWaitEvent(st, ctx->ev_lane_film[ctx->last_accum_lane], 0);
-        if (lane > 0 && ctx->film_touch_pending) cudaStreamWaitEvent(st, ctx->ev_film_touch, 0);
+        if (ctx->film_touch_pending) cudaStreamWaitEvent(st, ctx->ev_film_touch, 0);      // (a no-op when the event was recorded on this stream)
         { StageScope sc(ctx, HK_STAGE_FILM); k_film_accumulate<<<grid_for(ctx, n_pixels, 256, 8), 256, 0, st>>>(ctx->D, ctx->S, A); }
         if (pipelined || ctx->any_alt_pending()) { cudaEventRecord(ctx->ev_lane_film[lane], st); ctx->lane_pending[lane] = true; ctx->last_accum_lane = lane; }
         done += A.n_batch;
@@ -963,28 +963,35 @@ int32_t hk_set_stream(HkContext* ctx, void* cuda_stream) {
     ctx->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
     return HK_OK;
 }
-// Pipelined read-out for progressive display: finalize into one of HK_N_READOUTS staging buffers on the render stream, copy it
-// to the (pinned) host buffer on a separate stream, and return at once -- the next hk_render_samples can be enqueued while the
-// DMA runs.  hk_read_film_wait(ticket) blocks until that frame has landed.  At most HK_N_READOUTS (4) frames in flight.
+// Pipelined read-out for progressive display: finalize into one of HK_N_READOUTS staging buffers and copy it to the (pinned) host
+// buffer, both on the library's copy stream, and return at once -- the next hk_render_samples calls can be enqueued while the DMA
+// runs.  The finalize is ordered after everything enqueued on the render stream so far and after the last lane's film accumulation;
+// it does NOT sit in the render stream: there the main lane's next frame would queue behind it and wait for every frame in flight
+// (with three read-outs in flight the loop is bound by the host's wait for the oldest frame and the two placements measure the
+// same, 958-975 Msamples/s on C3; profiles/r02_e2e_lanes.txt).  Later accumulations / film readers wait for ev_film_touch.  hk_read_film_wait(ticket) blocks until that frame has landed.  At most HK_N_READOUTS (4) frames in flight.
 int32_t hk_read_film_async(HkContext* ctx, float* out_pinned, int32_t* ticket) {
     if (!ctx || !out_pinned || !ticket) return HK_ERR_INVALID;
-    hk_enter_film_async(ctx);
+    cudaSetDevice(ctx->device);
     REQUIRE(ctx->have_params, "hk_set_params has not been called");
+    REQUIRE(ctx->ev_film_touch != nullptr, "the context has no film events (creation failed)");
     const size_t n = (size_t)ctx->params.width * ctx->params.height;
     if (!ctx->copy_stream) {
         CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         for (int i = 0; i < HK_N_READOUTS; i++) { CK(cudaEventCreateWithFlags(&ctx->ev_final[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming)); }
     }
+    cudaStream_t fs = ctx->copy_stream;
     const int k = ctx->async_next;
-    if (ctx->b_readback_async[k].bytes < 12 * n) { CK(cudaStreamSynchronize(ctx->copy_stream)); CK(ctx->b_readback_async[k].alloc(12 * n)); ctx->async_used[k] = false; }
-    if (ctx->async_used[k]) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[k], 0));      // the staging buffer's previous copy must be done
-    k_film_finalize<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(ctx->S.pixel_rgb, ctx->S.pixel_weight, ctx->b_readback_async[k].as<float>(), ctx->params.width, ctx->params.height);
+    if (ctx->b_readback_async[k].bytes < 12 * n) { CK(cudaStreamSynchronize(fs)); CK(ctx->b_readback_async[k].alloc(12 * n)); ctx->async_used[k] = false; }
+    CK(cudaEventRecord(ctx->ev_final[k], ctx->stream));      // everything on the render stream so far (earlier frames, clears, batched calls) ...
+    CK(cudaStreamWaitEvent(fs, ctx->ev_final[k], 0));
+    if (ctx->last_accum_lane > 0 && ctx->lane_pending[ctx->last_accum_lane]) CK(cudaStreamWaitEvent(fs, ctx->ev_lane_film[ctx->last_accum_lane], 0));      // ... and the last accumulation
+    if (ctx->film_touch_pending) CK(cudaStreamWaitEvent(fs, ctx->ev_film_touch, 0));
+    // (the staging buffer's previous copy ran earlier on this same stream)
+    k_film_finalize<<<grid_for(ctx, n, 256, 8), 256, 0, fs>>>(ctx->S.pixel_rgb, ctx->S.pixel_weight, ctx->b_readback_async[k].as<float>(), ctx->params.width, ctx->params.height);
     ctx->launches++;
-    hk_film_touched(ctx);
-    CK(cudaEventRecord(ctx->ev_final[k], ctx->stream));
-    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_final[k], 0));
-    CK(cudaMemcpyAsync(out_pinned, ctx->b_readback_async[k].p, 12 * n, cudaMemcpyDeviceToHost, ctx->copy_stream));
-    CK(cudaEventRecord(ctx->ev_copied[k], ctx->copy_stream));
+    CK(cudaEventRecord(ctx->ev_film_touch, fs)); ctx->film_touch_pending = true;
+    CK(cudaMemcpyAsync(out_pinned, ctx->b_readback_async[k].p, 12 * n, cudaMemcpyDeviceToHost, fs));
+    CK(cudaEventRecord(ctx->ev_copied[k], fs));
     ctx->async_used[k] = true; ctx->async_next = (k + 1) % HK_N_READOUTS;
     *ticket = k;
     return HK_OK;

@@ -34,7 +34,7 @@ struct HkContext {
     PathState S;
     HkRenderParams params;
     bool have_tables = false, have_geom = false, have_mats = false, have_lights = false, have_cam = false, have_filter = false, have_params = false;
-    uint64_t camera_version = 1, lane_cam_version[4] = {0, 0, 0, 0};      // detect_camera_medium result per render lane (device-resident, b_scratch_u32[lane])
+    uint64_t camera_version = 1, lane_cam_version[8] = {};      // detect_camera_medium result per render lane (device-resident, b_scratch_u32[lane])
     uint32_t mat_types_present = 0;
     uint32_t n_interfaces = 0, max_iface_in_geom = 0; bool tri_types_valid = false;
     std::vector<int32_t> mat_types;                  // host copy of the material types (hk_update_material)
@@ -55,7 +55,9 @@ struct HkContext {
     DevBuf b_uvs, b_textures; std::vector<DevBuf> tex_bufs;
     bool has_rgbgrid = false;                // some uploaded medium is an RGBGridMedium: the tracking kernels with that branch compiled in     // film.albedo [3n] | film.normal [3n] | film.depth [n], (H, W) column-major
     // pipelined read-out (hk_read_film_async): two device staging buffers, a copy stream, per-buffer events
+#ifndef HK_N_READOUTS
 #define HK_N_READOUTS 4                // asynchronous read-outs in flight (hk_read_film_async tickets 0..3)
+#endif
     DevBuf b_readback_async[HK_N_READOUTS]; cudaStream_t copy_stream = nullptr; cudaEvent_t ev_final[HK_N_READOUTS] = {}, ev_copied[HK_N_READOUTS] = {};
     int async_next = 0; bool async_used[HK_N_READOUTS] = {};
     // fork / join of the per-material shading kernels of one bounce (independent queues) over side streams
@@ -90,7 +92,9 @@ struct HkContext {
         cudaStream_t stream = nullptr, shade_streams[3] = {nullptr, nullptr, nullptr}, shadow_stream = nullptr;
         cudaEvent_t ev_fork = nullptr, ev_join[12] = {}, ev_shaded = nullptr, ev_shadowed = nullptr, ev0 = nullptr, ev1 = nullptr;
     };
-#define HK_N_LANES 4                   // the main lane + three more: up to four one-sample frames in flight
+#ifndef HK_N_LANES
+#define HK_N_LANES 4                   // the main lane + three more: up to four one-sample frames in flight (at most 8)
+#endif
     AltLane alts[HK_N_LANES - 1];
     bool lanes_ready = false;
     cudaEvent_t ev_lane_film[HK_N_LANES] = {}, ev_film_touch = nullptr;
@@ -113,12 +117,14 @@ struct HkContext {
 static inline void hk_enter(HkContext* ctx) {
     cudaSetDevice(ctx->device);
     ctx->sync_alt_lanes();
+    if (ctx->film_touch_pending) cudaStreamWaitEvent(ctx->stream, ctx->ev_film_touch, 0);      // an asynchronous read-out's finalize runs on the copy stream
 }
 // the stream-ordered form for the asynchronous film readers / hk_clear on the main stream: the main stream waits for the second
 // lane's last film accumulation (which itself waited for everything before it)
 static inline void hk_enter_film_async(HkContext* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->last_accum_lane > 0 && ctx->lane_pending[ctx->last_accum_lane]) cudaStreamWaitEvent(ctx->stream, ctx->ev_lane_film[ctx->last_accum_lane], 0);      // (each accumulation waited for the one before it)
+    if (ctx->film_touch_pending) cudaStreamWaitEvent(ctx->stream, ctx->ev_film_touch, 0);
 }
 static inline void hk_film_touched(HkContext* ctx) {      // after a film read-out / clear was enqueued on the main stream
     if (ctx->ev_film_touch) { cudaEventRecord(ctx->ev_film_touch, ctx->stream); ctx->film_touch_pending = true; }
