@@ -137,7 +137,7 @@ class HkStats(C.Structure):
 # every symbol include/hikari_cuda.h declares (checked by tests/test_abi.py)
 HK_SYMBOLS = [
     "hk_abi_version", "hk_create", "hk_destroy", "hk_last_error", "hk_upload_tables", "hk_upload_geometry",
-    "hk_upload_spectra", "hk_upload_textures", "hk_upload_materials", "hk_update_material", "hk_bounce_profile", "hk_upload_envmaps", "hk_upload_lights", "hk_upload_media", "hk_update_medium", "hk_read_majorant",
+    "hk_upload_spectra", "hk_upload_textures", "hk_upload_materials", "hk_update_material", "hk_bounce_profile", "hk_upload_envmaps", "hk_upload_lights", "hk_upload_media", "hk_update_medium", "hk_read_majorant", "hk_read_nanovdb",
     "hk_set_camera", "hk_set_filter", "hk_set_params", "hk_clear", "hk_render_samples", "hk_render_samples_strided",
     "hk_read_film", "hk_read_film_async", "hk_read_film_wait", "hk_read_film_dev", "hk_set_stream", "hk_postprocess", "hk_postprocess_dev", "hk_fill_aux_buffers", "hk_read_aux_buffers", "hk_denoise", "hk_film_accum_dev", "hk_read_accum", "hk_write_accum", "hk_trace_closest",
     "hk_trace_closest_dev", "hk_trace_any", "hk_stats", "hk_synchronize", "hk_dev_alloc", "hk_dev_free",
@@ -175,6 +175,7 @@ def bind_common(lib, p):
     if p == "hk_":
         f("update_medium", [_VP, C.c_uint32, C.POINTER(HkMedium)])
         f("read_majorant", [_VP, C.c_uint32, c_fp, C.c_uint64])
+        f("read_nanovdb", [_VP, C.c_uint32, c_u8p, C.c_uint64, C.POINTER(C.c_uint64)])
     f("set_camera", [_VP, C.POINTER(HkCamera)])
     f("set_filter", [_VP, C.POINTER(HkFilter)])
     f("set_params", [_VP, C.POINTER(HkRenderParams)])

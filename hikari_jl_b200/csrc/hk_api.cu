@@ -500,10 +500,25 @@ static int32_t upload_one_medium(HkContext* ctx, uint32_t i, const HkMedium& M, 
         d.rgb_le = src[2] ? B[0].as<float>() + off[2] : nullptr;
         std::memcpy(d.dres, M.density_res, 12); d.sigma_scale = M.scale; d.le_scale = M.Le_scale;
     }
+    int32_t idx_min[3], idx_max[3];      // NanoVDB: the index range of the leaves (majorant build, dense mirror)
+    std::memcpy(idx_min, M.nanovdb_index_min, 12); std::memcpy(idx_max, M.nanovdb_index_max, 12);
     if (M.type == HK_MEDIUM_NANOVDB) {
-        REQUIRE(M.nanovdb_buf && M.nanovdb_bytes > 0, "NanoVDBMedium needs its grid buffer");
-        CK(B[2].upload(M.nanovdb_buf, (size_t)M.nanovdb_bytes)); d.nvdb = B[2].as<uint8_t>();
-        std::memcpy(d.inv_mat, M.nanovdb_inv_mat, 36); std::memcpy(d.vec, M.nanovdb_vec, 12); d.root_off = M.nanovdb_root_offset; d.root_tiles = M.nanovdb_root_tiles;
+        if (M.nanovdb_buf) {
+            REQUIRE(M.nanovdb_bytes > 0, "NanoVDBMedium needs its grid buffer");
+            CK(B[2].upload(M.nanovdb_buf, (size_t)M.nanovdb_bytes)); d.nvdb = B[2].as<uint8_t>();
+            d.root_off = M.nanovdb_root_offset; d.root_tiles = M.nanovdb_root_tiles;
+        } else {      // build_nanovdb_from_dense (nanovdb.jl:602-858) on the device, from the dense volume in `density`
+            REQUIRE(M.density && M.density_res[0] >= 1 && M.density_res[1] >= 1 && M.density_res[2] >= 1, "NanoVDBMedium needs its grid buffer, or a dense volume (density, density_res) to build it from");
+            const size_t cnt = (size_t)M.density_res[0] * M.density_res[1] * M.density_res[2];
+            CK(B[0].upload(M.density, 4 * cnt));
+            HkNvdbBuilt nb;
+            const int32_t rc = hk_nvdb_build_dense(ctx, B[0].as<float>(), M.density_res, 0.0f, B[2], nb);
+            B[0].release();
+            if (rc != HK_OK) return rc;
+            d.nvdb = B[2].as<uint8_t>(); d.root_off = nb.root_off; d.root_tiles = nb.n_up;
+            std::memcpy(idx_min, nb.idx_min, 12); std::memcpy(idx_max, nb.idx_max, 12);
+        }
+        std::memcpy(d.inv_mat, M.nanovdb_inv_mat, 36); std::memcpy(d.vec, M.nanovdb_vec, 12);
     }
     ctx->dense_bufs[i].release();
     if (M.type == HK_MEDIUM_NANOVDB && !std::getenv("HK_NO_DENSE_MIRROR")) {
@@ -512,9 +527,9 @@ static int32_t upload_one_medium(HkContext* ctx, uint32_t i, const HkMedium& M, 
         if (const char* e = std::getenv("HK_DENSE_MIRROR_MAX_MB")) cap = (size_t)std::max(0, atoi(e)) << 20;
         bool ok = true; size_t vox = 1;
         for (int k = 0; k < 3; k++) {
-            const long long ext = (long long)M.nanovdb_index_max[k] - (long long)M.nanovdb_index_min[k] + 2;
+            const long long ext = (long long)idx_max[k] - (long long)idx_min[k] + 2;
             ok = ok && ext >= 2 && ext < (1ll << 20);
-            if (ok) { d.dn_min[k] = M.nanovdb_index_min[k]; d.dn_ext[k] = (int32_t)ext; vox *= (size_t)ext; ok = vox <= (cap >> 2); }
+            if (ok) { d.dn_min[k] = idx_min[k]; d.dn_ext[k] = (int32_t)ext; vox *= (size_t)ext; ok = vox <= (cap >> 2); }
         }
         if (ok) {
             CK(ctx->dense_bufs[i].alloc(4 * vox));
@@ -533,7 +548,7 @@ static int32_t upload_one_medium(HkContext* ctx, uint32_t i, const HkMedium& M, 
     if (M.majorant) { CK(B[1].upload(M.majorant, 4 * cells)); d.majorant = B[1].as<float>(); }
     else {      // build_majorant_grid / build_rgb_majorant_grid / build_nanovdb_majorant_grid on the device
         CK(B[1].alloc(4 * cells)); d.majorant = B[1].as<float>();
-        MajBuild P; std::memcpy(P.idx_min, M.nanovdb_index_min, 12); std::memcpy(P.idx_max, M.nanovdb_index_max, 12);
+        MajBuild P; std::memcpy(P.idx_min, idx_min, 12); std::memcpy(P.idx_max, idx_max, 12);
         std::memcpy(P.bmin, M.bounds_min, 12); std::memcpy(P.bmax, M.bounds_max, 12);
         k_build_majorant<<<(unsigned)cells, 128, 0, ctx->stream>>>(d, P, B[1].as<float>());
         ctx->launches++;
@@ -588,6 +603,21 @@ int32_t hk_update_medium(HkContext* ctx, uint32_t index, const HkMedium* m) {
     int32_t rc = upload_one_medium(ctx, index - 1, *m, ctx->media_host[index - 1]);
     if (rc != HK_OK) return rc;
     return commit_media(ctx);
+}
+// the NanoVDB buffer of medium `index` (1-based) as the device holds it (uploaded or device-built): *bytes = its size; copied to `out`
+// when out != NULL and capacity suffices
+int32_t hk_read_nanovdb(HkContext* ctx, uint32_t index, uint8_t* out, uint64_t capacity, uint64_t* bytes) {
+    if (!ctx || !bytes) return HK_ERR_INVALID;
+    hk_enter(ctx);
+    REQUIRE(index >= 1 && index <= ctx->media_host.size(), "medium index out of range");
+    REQUIRE(ctx->media_host[index - 1].type == HK_MEDIUM_NANOVDB, "not a NanoVDB medium");
+    const DevBuf& T = ctx->media_bufs[3 * (size_t)(index - 1) + 2];
+    *bytes = T.bytes;
+    if (!out) return HK_OK;
+    REQUIRE(capacity >= T.bytes, "buffer too small for the NanoVDB tree");
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(out, T.p, T.bytes, cudaMemcpyDeviceToHost));
+    return HK_OK;
 }
 // the majorant grid of medium `index` (1-based) as the device holds it, [rz][ry][rx] (uploaded or device-built)
 int32_t hk_read_majorant(HkContext* ctx, uint32_t index, float* out, uint64_t n_cells) {

@@ -130,5 +130,9 @@ static inline void hk_film_touched(HkContext* ctx) {      // after a film read-o
     if (ctx->ev_film_touch) { cudaEventRecord(ctx->ev_film_touch, ctx->stream); ctx->film_touch_pending = true; }
 }
 
+// build_nanovdb_from_dense on the device (hk_nvdb_build.cu): offsets / counts of the tree it wrote
+struct HkNvdbBuilt { uint64_t bytes, root_off, upper_off, lower_off, leaf_off; int32_t n_up, n_low, n_leaf; int32_t idx_min[3], idx_max[3]; };
+int32_t hk_nvdb_build_dense(HkContext* ctx, const float* dens_dev, const int32_t res[3], float background, DevBuf& tree, HkNvdbBuilt& out);
+
 // (re)build the uplift cache after an upload that changes a constant colour (hk_api.cu)
 extern "C" int32_t hk_refresh_uplift_cache(HkContext* ctx);

@@ -1419,6 +1419,14 @@ class Backend:
         abi = medium.to_abi(keep, self.device_majorant)
         self.call("update_medium", medium_idx, C.byref(abi))
 
+    def read_nanovdb(self, medium_idx):
+        """the NanoVDB buffer of medium `medium_idx` as the device holds it (uploaded, or built on the device from the dense volume)"""
+        n = C.c_uint64(0)
+        self.call("read_nanovdb", medium_idx, None, 0, C.byref(n))
+        out = np.empty(n.value, dtype=np.uint8)
+        self.call("read_nanovdb", medium_idx, out.ctypes.data_as(A.c_u8p), out.size, C.byref(n))
+        return out
+
     def read_majorant(self, medium_idx, res):
         """the majorant grid of medium `medium_idx` as the device holds it, [rz][ry][rx]"""
         out = np.empty((res[2], res[1], res[0]), dtype=f32)

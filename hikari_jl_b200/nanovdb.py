@@ -299,6 +299,7 @@ class NanoVDBMedium:
     def from_file(cls, path, sigma_a=0.5, sigma_s=10.0, g=0.0, transform=None, majorant_res=(64, 64, 64)):
         from .host import _rgb
         self = cls.__new__(cls)
+        self._built = None
         self.buffer, meta = parse_nanovdb_buffer(path)
         T = np.eye(3, dtype=f32) if transform is None else np.asarray(transform, dtype=f32).reshape(3, 3)
         inv_T = np.linalg.inv(T.astype(np.float64)).astype(f32)
@@ -318,12 +319,45 @@ class NanoVDBMedium:
     def __init__(self, data_xyz, bounds, sigma_a=0.0, sigma_s=1.0, g=0.0, majorant_res=(64, 64, 64)):
         from .host import _rgb
         self.bounds = (np.asarray(bounds[0], dtype=f32), np.asarray(bounds[1], dtype=f32))
-        origin = [float(v) for v in self.bounds[0]]
-        extent = [float(v) for v in (self.bounds[1] - self.bounds[0])]
-        self.buffer, self.meta = build_nanovdb_from_dense(data_xyz, origin, extent)
         self.majorant_res = tuple(int(v) for v in majorant_res)
-        self._majorant, self._dense = None, np.asarray(data_xyz, dtype=f32)
+        self._majorant, self._dense = None, np.ascontiguousarray(np.asarray(data_xyz, dtype=f32))
+        self._built = None                 # (buffer, meta) of the host builder, made on first use
         self.sigma_a, self.sigma_s, self.g = _rgb(sigma_a), _rgb(sigma_s), float(g)
+
+    def _host_tree(self):
+        """build_nanovdb_from_dense on the host (numpy): what the oracle is handed, what a .nvdb file is written from, and what the
+        device-built tree is compared with byte for byte; the CUDA back end builds its own from the dense volume (nanovdb_buf = NULL)"""
+        if self._built is None:
+            origin = [float(v) for v in self.bounds[0]]
+            extent = [float(v) for v in (self.bounds[1] - self.bounds[0])]
+            self._built = build_nanovdb_from_dense(self._dense, origin, extent)
+        return self._built
+
+    @property
+    def buffer(self):
+        return self._host_tree()[0]
+
+    @buffer.setter
+    def buffer(self, b):                   # (from_file: the parsed file buffer)
+        self._built = (b, (self._built or (None, None))[1])
+
+    @property
+    def meta(self):
+        return self._host_tree()[1]
+
+    @meta.setter
+    def meta(self, m):
+        self._built = ((self._built or (None, None))[0], m)
+
+    def _index_transform(self):
+        """inv_mat / vec of a tree built from the dense volume (build_nanovdb_from_dense's map: voxel centres at origin + (i + 1/2) d),
+        without building the tree"""
+        nx, ny, nz = self._dense.shape
+        ext = [float(v) for v in (self.bounds[1] - self.bounds[0])]
+        org = [float(v) for v in self.bounds[0]]
+        dx, dy, dz = ext[0] / nx, ext[1] / ny, ext[2] / nz
+        return ((f32(1 / dx), f32(0), f32(0), f32(0), f32(1 / dy), f32(0), f32(0), f32(0), f32(1 / dz)),
+                (f32(org[0] + dx / 2), f32(org[1] + dy / 2), f32(org[2] + dz / 2)))
 
     @property
     def majorant(self):
@@ -347,6 +381,15 @@ class NanoVDBMedium:
         if not device_majorant:
             keep.append(self.majorant)
             m.majorant = self.majorant.ctypes.data_as(A.c_fp)
+        if device_majorant and self._dense is not None:      # the CUDA back end: tree, majorant grid and dense mirror are all built on the device
+            d = np.ascontiguousarray(self._dense.transpose(2, 1, 0))      # -> [nz][ny][nx]
+            keep.append(d)
+            m.density = d.ctypes.data_as(A.c_fp)
+            m.density_res[:] = list(self._dense.shape)
+            inv_mat, vec = self._index_transform()
+            m.nanovdb_inv_mat[:] = [float(v) for v in inv_mat]
+            m.nanovdb_vec[:] = [float(v) for v in vec]
+            return m
         m.nanovdb_index_min[:] = [int(v) for v in self.meta["index_min"]]      # the clip range of the majorant build (nanovdb.jl:1137-1150)
         m.nanovdb_index_max[:] = [int(v) for v in self.meta["index_max"]]
         keep.append(self.buffer)

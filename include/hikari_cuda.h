@@ -296,6 +296,9 @@ typedef struct HkMedium {
        [nanovdb_index_min, nanovdb_index_max] = metadata.index_min / index_max (nanovdb.jl:1137-1150, :853).        */
     int32_t  nanovdb_index_min[3];
     int32_t  nanovdb_index_max[3];
+    /* NanoVDB with nanovdb_buf == NULL: the tree is built on the device from the dense volume in density / density_res
+       ([nz][ny][nx], background 0) -- build_nanovdb_from_dense (nanovdb.jl:602-858): same bytes as the host builder's buffer;
+       nanovdb_inv_mat / nanovdb_vec are still the caller's, offsets / counts / index range are the library's                */
 } HkMedium;
 
 /* ---- camera, filter, params ---------------------------------------------------------------- */
@@ -377,6 +380,9 @@ int32_t hk_upload_media(HkContext* ctx, const HkMedium* media, uint32_t n_media)
  * medium (1-based index).  The record replaces that medium wholesale, its majorant grid (majorant == NULL) and empty-cell
  * mask are rebuilt on the device; geometry, materials, lights and the other media stay.                                */
 int32_t hk_update_medium(HkContext* ctx, uint32_t index, const HkMedium* medium);
+/* the NanoVDB buffer of medium `index` as the device holds it (uploaded, or built on the device from a dense volume): *bytes = its
+ * size; copied to `out` when out != NULL and capacity >= *bytes (e.g. to write a .nvdb file)                                */
+int32_t hk_read_nanovdb(HkContext* ctx, uint32_t index, uint8_t* out, uint64_t capacity, uint64_t* bytes);
 /* the majorant grid of medium `index` as the device holds it ([rz][ry][rx], n_cells = rx*ry*rz): uploaded or device-built */
 int32_t hk_read_majorant(HkContext* ctx, uint32_t index, float* out, uint64_t n_cells);
 int32_t hk_set_camera(HkContext* ctx, const HkCamera* camera);

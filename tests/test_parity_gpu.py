@@ -981,6 +981,52 @@ def test_update_medium_replaces_one_medium_in_place():
         assert np.array_equal(updated.view(np.uint32), film3.framebuffer.view(np.uint32)), f"{kind}: updated medium differs from the oracle"
 
 
+def test_nanovdb_tree_built_on_the_device():
+    """build_nanovdb_from_dense (nanovdb.jl:602-858) runs on the device when a NanoVDBMedium is uploaded as a dense volume
+    (HkMedium.nanovdb_buf = NULL; hk_nvdb_build.cu).  The buffer the device holds must be byte for byte the host builder's -- root
+    header and tiles, upper / lower masks and child tables, leaf headers, value masks, min / max and values -- for partially filled
+    leaves, empty regions, several lower nodes (an axis > 128 voxels) and several upper nodes (an axis > 4096 voxels)."""
+    rng = np.random.RandomState(33)
+    vols = []
+    d = rng.uniform(0, 1, size=(24, 20, 16)).astype(f32) ** 3 * 30; d[d < 3] = 0; vols.append(("24x20x16", d))
+    d = rng.uniform(0, 1, size=(37, 29, 23)).astype(f32) ** 4 * 9; d[d < 1] = 0; vols.append(("37x29x23 (partial leaves)", d))
+    d = np.zeros((70, 70, 70), f32); d[3:9, 40:66, 10:12] = rng.uniform(1, 5, size=(6, 26, 2)); d[60:, :5, 33:41] = 2.5; vols.append(("sparse 70^3", d))
+    d = np.zeros((300, 40, 150), f32); d[5, 5, 5] = 1; d[130:140, 10:30, 120:149] = rng.uniform(0.5, 2, size=(10, 20, 29)); d[299, 39, 149] = 7; vols.append(("300x40x150 (3 x 1 x 2 lower nodes)", d))
+    d = np.zeros((4104, 8, 9), f32); d[0, 0, 0] = 1; d[4097:4104, 2:7, 1:9] = rng.uniform(1, 2, size=(7, 5, 8)); vols.append(("4104x8x9 (two upper nodes)", d))
+    d = np.full((9, 9, 9), -1.5, f32); d[4, 4, 4] = 0; vols.append(("negative values, one background voxel", d))
+    s = H.Scene()
+    meds = []
+    for name, d in vols:
+        ext = tuple(float(n) / 32 for n in d.shape)
+        med = H.NanoVDBMedium(d, bounds=((0, 0, 0), ext), majorant_res=(4, 4, 4))
+        meds.append(med)
+        s.push(H.rect3((0, 0, 0), (1, 1, 1)), H.MediumInterface(H.GlassMaterial(Kr=0.0, Kt=1.0, index=1.0), inside=med))
+    s.push(H.PointLight((1, 1, 1), (0, 5, 0)))
+    s.sync()
+    b = H.Backend()
+    try:
+        b.upload_tables(); b.upload_scene(s)
+        for (name, d), med in zip(vols, meds):
+            k = s.media.index(med) + 1
+            dev = b.read_nanovdb(k)
+            host = np.asarray(med.buffer)
+            assert dev.size == host.size, f"{name}: {dev.size} bytes on the device, {host.size} from the host builder"
+            diff = np.nonzero(dev != host)[0]
+            assert diff.size == 0, f"{name}: {diff.size} bytes differ, first at offset {diff[:5]}"
+            assert np.array_equal(b.read_majorant(k, med.majorant_res).view(np.uint32), np.asarray(med.majorant).view(np.uint32)), name
+    finally:
+        b.close()
+    with pytest.raises(RuntimeError, match="no active voxels"):      # the host builder raises ValueError for the same input
+        s2 = H.Scene()
+        s2.push(H.rect3((0, 0, 0), (1, 1, 1)), H.MediumInterface(H.GlassMaterial(Kr=0.0, Kt=1.0, index=1.0), inside=H.NanoVDBMedium(np.zeros((8, 8, 8), f32), bounds=((0, 0, 0), (1, 1, 1)))))
+        s2.push(H.PointLight((1, 1, 1), (0, 5, 0))); s2.sync()
+        b2 = H.Backend()
+        try:
+            b2.upload_tables(); b2.upload_scene(s2)
+        finally:
+            b2.close()
+
+
 def test_nanovdb_dense_mirror_and_tree_walk_agree(monkeypatch):
     """NanoVDB look-ups read a dense mirror of the tree (built on the device at upload) when all eight trilinear corners fall inside
     the tree's index box, and walk the tree otherwise.  Both paths must return the oracle's bits: densities at points inside, outside
