@@ -78,7 +78,14 @@ HK_DEV float3 operator/(float3 a, float s) { return f3(a.x / s, a.y / s, a.z / s
 HK_DEV float dot3(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 HK_DEV float3 cross3(float3 a, float3 b) { return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 HK_DEV float len3(float3 a) { return sqrtf(dot3(a, a)); }
+#ifndef HK_NOINLINE_VEC
+#define HK_NOINLINE_VEC 0          // norm3 (an IEEE square root and an IEEE division: ~25 instructions and two slow-path calls per call site)
+#endif
+#if HK_NOINLINE_VEC
+static __device__ __noinline__ float3 norm3(float3 a) { float inv = 1.0f / len3(a); return f3(inv * a.x, inv * a.y, inv * a.z); }
+#else
 HK_DEV float3 norm3(float3 a) { float inv = 1.0f / len3(a); return f3(inv * a.x, inv * a.y, inv * a.z); }
+#endif
 HK_DEV float comp3(float3 a, int k) { return k == 0 ? a.x : (k == 1 ? a.y : a.z); }
 HK_DEV float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
 HK_DEV int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
