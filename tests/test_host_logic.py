@@ -479,3 +479,46 @@ def test_spot_light_known_answers_on_the_oracle():
         assert out[0, 13] == 1.0                                                               # delta light
     finally:
         p.close()
+
+
+def test_media_flatten_for_the_device_builders():
+    """What the CUDA back end is handed when the device builds the scene-side structures (ABI v4): a dense volume and NULL tree /
+    majorant pointers; what the oracle is handed: the host-built tree and majorant grid.  The host builders only run when asked."""
+    import ctypes as C
+    from hikari_jl_b200 import _abi as A
+    rng = np.random.RandomState(2)
+    d = rng.uniform(0, 1, size=(12, 10, 9)).astype(np.float32); d[d < 0.6] = 0
+    lo, hi = (-1.0, 0.0, 2.0), (2.0, 1.0, 3.5)
+    nv = H.NanoVDBMedium(d, bounds=(lo, hi), sigma_s=2.0, majorant_res=(4, 3, 2))
+    assert nv._built is None and nv._majorant is None
+    keep = []
+    m = nv.to_abi(keep, True)                                   # device_majorant / device build
+    assert nv._built is None and nv._majorant is None, "the device path must not run the host builders"
+    assert not m.nanovdb_buf and not m.majorant and m.nanovdb_bytes == 0
+    assert list(m.density_res) == [12, 10, 9] and list(m.majorant_res) == [4, 3, 2]
+    up = np.ctypeslib.as_array(m.density, shape=(9, 10, 12))                       # [nz][ny][nx]
+    assert np.array_equal(up, d.transpose(2, 1, 0))
+    keep2 = []
+    mo = nv.to_abi(keep2, False)                                # the oracle's view: host tree + host majorant
+    assert mo.nanovdb_buf and mo.majorant and mo.nanovdb_bytes == len(nv.buffer) > 0
+    # the index transform handed to the device equals the one the host builder derives
+    assert [float(v) for v in m.nanovdb_inv_mat] == [float(v) for v in nv.meta["inv_mat"]]
+    assert [float(v) for v in m.nanovdb_vec] == [float(v) for v in nv.meta["vec"]]
+    assert list(mo.nanovdb_index_min) == [int(v) for v in nv.meta["index_min"]] and list(mo.nanovdb_index_max) == [int(v) for v in nv.meta["index_max"]]
+    g = H.GridMedium(d, bounds=(lo, hi), majorant_res=(5, 4, 3))
+    assert g._majorant is None
+    mg = g.to_abi([], True)
+    assert g._majorant is None and not mg.majorant and mg.density
+    assert g.to_abi([], False).majorant and g.majorant.shape == (3, 4, 5)
+    r = H.RGBGridMedium(sigma_s_grid=d[..., None] * np.array([1.0, 0.5, 0.25], np.float32), sigma_scale=2.0, bounds=(lo, hi), majorant_res=(2, 2, 2))
+    assert not r.to_abi([], True).majorant and r._majorant is None
+    mj = r.majorant                                             # absent sigma_a grid counts as 1: 2 * (1 + max sigma_s)
+    assert mj.shape == (2, 2, 2) and np.isclose(mj.max(), 2.0 * (1.0 + d.max()), rtol=1e-6)
+    # a textured MixMaterial.amount goes to ftex[0], a constant one to f[0]
+    s = H.Scene()
+    a, b = H.MatteMaterial(Kd=(0.5, 0.5, 0.5)), H.MirrorMaterial(Kr=0.9)
+    s.push(H.rect3((0, 0, 0), (1, 1, 1)), H.MixMaterial((a, b), amount=H.Texture(np.full((2, 2), 0.25, np.float32))))
+    s.push(H.rect3((2, 0, 0), (1, 1, 1)), H.MixMaterial((a, b), amount=0.75))
+    s.push(H.PointLight((1, 1, 1), (0, 5, 0))); s.sync()
+    mixes = [mm.to_abi(s) for mm in s.materials if isinstance(mm, H.MixMaterial)]
+    assert mixes[0].ftex[0] >= 1 and mixes[0].f[0] == 0.0 and mixes[1].ftex[0] == 0 and mixes[1].f[0] == 0.75
