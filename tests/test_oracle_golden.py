@@ -686,3 +686,58 @@ def test_textured_mix_amount_known_answers():
     like_red = np.isclose(img, only_red, rtol=1e-5, atol=1e-6).all(axis=2) & sphere
     like_blue = np.isclose(img, only_blue, rtol=1e-5, atol=1e-6).all(axis=2) & sphere
     assert like_red.sum() > 20 and like_blue.sum() > 20, (like_red.sum(), like_blue.sum(), sphere.sum())
+
+
+def test_physical_known_answers_on_the_oracle():
+    """Closed-form radiometry the whole path has to reproduce, whatever the reading of the Julia source (the CUDA path is bit-identical
+    to the oracle, so these pin it as well):
+      * Lambert's law: a matte surface lit head-on by a directional light of irradiance E shows E rho / pi;
+      * a matte sphere in a uniform environment shows rho x the environment (light sampling + BSDF sampling + their MIS weights sum to
+        one) -- and under an AmbientLight it shows rho (3/2 - ln 5 / 8): the reference gives escaped rays a light pdf of 0 for every
+        light type but EnvironmentLight (lights.jl:450-458) while its light samples are MIS-weighted (a quirk kept bit for bit);
+      * furnace: a clear glass sphere (Kr = Kt = 1) in a uniform environment is invisible, a mirror of reflectance Kr shows Kr;
+      * Beer-Lambert: an absorbing slab of thickness d in front of a uniform background shows exp(-sigma_a d)."""
+    def render(s, cam, res=(32, 32), spp=64, depth=8):
+        film = H.Film(res)
+        vp = H.VolPath(samples=spp, max_depth=depth, backend=oracle_backend.make_backend())
+        img = vp(s, film, cam(film)).copy()
+        vp.close()
+        return img
+    near = scenes._cam((0, 0, -4), (0, 0, 0), 30.0)
+    far = scenes._cam((0, 0, -40), (0, 0, 0), 0.2)                 # a pencil of parallel rays at the sphere's pole
+    env = lambda: H.EnvironmentLight(H.EnvironmentMap(np.ones((8, 8, 3), f32)), scale=(1 / 10567.0,) * 3)      # ~1 after the D65 normalisation
+    # Lambert's law
+    for rho in (0.5, 0.18):
+        s = H.Scene(); s.push(H.uv_sphere((0, 0, 0), 1.0, 64, 64), H.MatteMaterial(Kd=(rho,) * 3))
+        s.push(H.DirectionalLight((1, 1, 1), (0, 0, 1), legacy_rgbspectrum=True)); s.sync()
+        c = render(s, far, depth=2)[14:18, 14:18].mean()
+        assert abs(c / (rho / np.pi) - 1) < 3e-3, (rho, c, rho / np.pi)
+    # uniform environment: MIS weights sum to one
+    for rho in (0.25, 0.8):
+        s = H.Scene(); s.push(H.uv_sphere((0, 0, 0), 1.0, 48, 48), H.MatteMaterial(Kd=(rho,) * 3)); s.push(env()); s.sync()
+        img = render(s, near, depth=2, spp=256)
+        bg = img[0:3, 0:3].mean()
+        assert abs(bg - 1) < 5e-3, bg
+        assert abs(img[12:20, 12:20].mean() / bg / rho - 1) < 1.5e-2, (rho, img[12:20, 12:20].mean() / bg)
+    # AmbientLight: the reference's escaped-ray pdf of 0
+    quirk = 1.5 - np.log(5.0) / 8.0
+    for rho in (0.5, 0.8):
+        s = H.Scene(); s.push(H.uv_sphere((0, 0, 0), 1.0, 48, 48), H.MatteMaterial(Kd=(rho,) * 3)); s.push(H.AmbientLight((1, 1, 1))); s.sync()
+        img = render(s, near, depth=2, spp=256)
+        assert abs(img[12:20, 12:20].mean() / img[0:3, 0:3].mean() / (rho * quirk) - 1) < 1.5e-2, (rho, img[12:20, 12:20].mean())
+    # furnace
+    s = H.Scene(); s.push(H.uv_sphere((0, 0, 0), 1.0, 48, 48), H.GlassMaterial(Kr=1.0, Kt=1.0, index=1.5)); s.push(H.AmbientLight((1, 1, 1))); s.sync()
+    img = render(s, near, depth=40)
+    assert abs(img[10:22, 10:22].mean() / img[0:3, 0:3].mean() - 1) < 1e-2
+    s = H.Scene(); s.push(H.uv_sphere((0, 0, 0), 1.0, 48, 48), H.MirrorMaterial(Kr=(0.5,) * 3)); s.push(H.AmbientLight((1, 1, 1))); s.sync()
+    img = render(s, near, depth=10)
+    assert abs(img[12:20, 12:20].mean() / img[0:3, 0:3].mean() - 0.5) < 5e-3
+    # Beer-Lambert
+    wide = scenes._cam((0, 0, -40), (0, 0, 0), 3.0)
+    for sa, dz in ((1.0, 0.5), (2.0, 0.75), (0.25, 2.0)):
+        s = H.Scene()
+        med = H.HomogeneousMedium(sigma_a=(sa,) * 3, sigma_s=(0, 0, 0), g=0.0)
+        s.push(H.rect3((-2, -2, -dz / 2), (4, 4, dz)), H.MediumInterface(H.GlassMaterial(Kr=0.0, Kt=1.0, index=1.0), inside=med))
+        s.push(H.AmbientLight((1, 1, 1))); s.sync()
+        t = render(s, wide, depth=8, spp=512).mean() / 1.0006      # (the ambient background renders as 1.0006)
+        assert abs(t / np.exp(-sa * dz) - 1) < 1e-2, (sa, dz, t, np.exp(-sa * dz))
