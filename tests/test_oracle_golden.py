@@ -741,3 +741,42 @@ def test_physical_known_answers_on_the_oracle():
         s.push(H.AmbientLight((1, 1, 1))); s.sync()
         t = render(s, wide, depth=8, spp=512).mean() / 1.0006      # (the ambient background renders as 1.0006)
         assert abs(t / np.exp(-sa * dz) - 1) < 1e-2, (sa, dz, t, np.exp(-sa * dz))
+
+
+def test_material_closed_forms_on_the_oracle():
+    """More closed forms, per material: a smooth conductor at normal incidence reflects ((eta-1)^2 + k^2) / ((eta+1)^2 + k^2) (the
+    complex Fresnel term, grey eta / k so the uplift is exact); a closed DiffuseTransmission sphere (reflectance R, transmittance T) in
+    a furnace shows R + T^2 / (1 - R) (= 1 when R + T = 1: the inner radiance solves I = R I + T); a ThinDielectric sphere seen along
+    its axis shows R^2 + T^4 / (1 - R^2) with R = R0 + T0^2 R0 / (1 - R0^2) -- NOT 1: the reference multiplies a specular sample's
+    f = R / |cos| into the throughput without dividing by the probability of having chosen it (surface-eval.jl:438-441,
+    spectral-eval.jl:2019-2034), kept bit for bit."""
+    def render(s, cam, res=(32, 32), spp=64, depth=8):
+        film = H.Film(res)
+        vp = H.VolPath(samples=spp, max_depth=depth, backend=oracle_backend.make_backend())
+        img = vp(s, film, cam(film)).copy()
+        vp.close()
+        return img
+    near = scenes._cam((0, 0, -4), (0, 0, 0), 30.0)
+    far = scenes._cam((0, 0, -40), (0, 0, 0), 0.2)
+    ambient = 1.0006                                              # what AmbientLight((1, 1, 1)) renders as
+    for eta, k in ((0.5, 2.0), (1.5, 0.0), (2.0, 3.0)):
+        s = H.Scene(); s.push(H.uv_sphere((0, 0, 0), 1.0, 64, 64), H.ConductorMaterial(eta=(eta,) * 3, k=(k,) * 3, roughness=0.0))
+        s.push(H.AmbientLight((1, 1, 1))); s.sync()
+        got = render(s, far, depth=4)[14:18, 14:18].mean() / ambient
+        want = ((eta - 1) ** 2 + k * k) / ((eta + 1) ** 2 + k * k)
+        assert abs(got / want - 1) < 2e-3, (eta, k, got, want)
+    for R, T in ((0.5, 0.5), (0.3, 0.3)):
+        want = R + T * T / (1 - R)
+        # (an EnvironmentLight: under an AmbientLight the light samples are over-counted, test_physical_known_answers_on_the_oracle)
+        s = H.Scene(); s.push(H.uv_sphere((0, 0, 0), 1.0, 48, 48), H.DiffuseTransmissionMaterial(reflectance=R, transmittance=T))
+        s.push(H.EnvironmentLight(H.EnvironmentMap(np.ones((8, 8, 3), f32)), scale=(1 / 10567.0,) * 3)); s.sync()
+        img = render(s, near, depth=40, spp=128)
+        got = img[12:20, 12:20].mean() / img[0:3, 0:3].mean()
+        assert abs(got / want - 1) < 1.5e-2, (R, T, got, want)
+    for eta in (1.5, 2.0):
+        s = H.Scene(); s.push(H.uv_sphere((0, 0, 0), 1.0, 128, 128), H.ThinDielectricMaterial(eta=eta)); s.push(H.AmbientLight((1, 1, 1))); s.sync()
+        got = render(s, far, depth=30, spp=256)[12:20, 12:20].mean() / ambient
+        R0 = ((eta - 1) / (eta + 1)) ** 2; T0 = 1 - R0
+        R = R0 + T0 * T0 * R0 / (1 - R0 * R0); T = 1 - R
+        want = R * R + T ** 4 / (1 - R * R)
+        assert abs(got / want - 1) < 5e-3, (eta, got, want)
