@@ -780,3 +780,36 @@ def test_material_closed_forms_on_the_oracle():
         R = R0 + T0 * T0 * R0 / (1 - R0 * R0); T = 1 - R
         want = R * R + T ** 4 / (1 - R * R)
         assert abs(got / want - 1) < 5e-3, (eta, got, want)
+
+
+def test_area_light_closed_form_on_the_oracle():
+    """A small square emitter of radiance L over a matte floor: the floor point below it shows rho / pi * L * integral(cos^2 / r^2 dA)
+    -- light-BVH selection of the emissive triangles, their area -> solid-angle pdf, the light sample and the emissive hit of the
+    BSDF-sampled ray with their MIS weights, all in one number.  L is taken from the same render (the emitter seen directly): the
+    reference clamps an area light's RGB to [0, 1] before the uplift (arealight_Le -> uplift_rgb, diffuse-area.jl:54-66,
+    rgb2spec.jl:83-87), so Le = 60 and Le = 100 both emit the unit spectrum."""
+    def render(s, cam, res=(16, 16), spp=512, depth=2):
+        film = H.Film(res)      # (no firefly clamp: the emitter seen directly is ~130 RGB units, max_component_value defaults to 10)
+        vp = H.VolPath(samples=spp, max_depth=depth, max_component_value=1.0e6, backend=oracle_backend.make_backend())
+        img = vp(s, film, cam(film)).copy()
+        vp.close()
+        return img
+    rho = 0.5
+    seen = []
+    for side, h, Le in ((0.2, 2.0, 100.0), (0.4, 3.0, 60.0), (1.0, 1.5, 2.0)):
+        s = H.Scene()
+        s.push(H.Mesh([(-5, 0, -5), (5, 0, -5), (5, 0, 5), (-5, 0, 5)], [(0, 2, 1), (0, 3, 2)]), H.MatteMaterial(Kd=(rho,) * 3))
+        a = side / 2
+        s.push(H.Mesh([(-a, h, -a), (a, h, -a), (a, h, a), (-a, h, a)], [(0, 1, 2), (0, 2, 3)]),
+               H.MediumInterface(H.MatteMaterial(Kd=(0, 0, 0)), emission=((Le, Le, Le), 1.0, True)))
+        s.sync()
+        floor = render(s, scenes._cam((20.0, 20.0, 0.0), (0, 0, 0), 0.05)).mean(axis=(0, 1))
+        direct = render(s, scenes._cam((0.0, h + 20.0, 0.001), (0, h, 0), 0.02), spp=16).mean(axis=(0, 1))      # the emitter from above
+        xs = (np.arange(400) + 0.5) / 400 * side - a
+        X, Z = np.meshgrid(xs, xs)
+        r2 = X * X + Z * Z + h * h
+        form = np.sum((h * h / r2) / r2) * (side / 400) ** 2
+        got = floor / direct
+        assert np.allclose(got, rho / np.pi * form, rtol=1.5e-2), (side, h, Le, got, rho / np.pi * form)
+        seen.append(direct)
+    assert np.allclose(seen[0], seen[1], rtol=1e-3) and np.allclose(seen[0], seen[2], rtol=1e-3), "Le >= 1 is clamped to the unit spectrum"
