@@ -691,7 +691,8 @@ def test_textured_mix_amount_known_answers():
 def test_physical_known_answers_on_the_oracle():
     """Closed-form radiometry the whole path has to reproduce, whatever the reading of the Julia source (the CUDA path is bit-identical
     to the oracle, so these pin it as well):
-      * Lambert's law: a matte surface lit head-on by a directional light of irradiance E shows E rho / pi;
+      * Lambert's law: a matte surface lit head-on by a directional light of irradiance E shows E rho / pi; under a point light of
+        intensity I it shows rho / pi * I cos(theta) / r^2;
       * a matte sphere in a uniform environment shows rho x the environment (light sampling + BSDF sampling + their MIS weights sum to
         one) -- and under an AmbientLight it shows rho (3/2 - ln 5 / 8): the reference gives escaped rays a light pdf of 0 for every
         light type but EnvironmentLight (lights.jl:450-458) while its light samples are MIS-weighted (a quirk kept bit for bit);
@@ -712,6 +713,13 @@ def test_physical_known_answers_on_the_oracle():
         s.push(H.DirectionalLight((1, 1, 1), (0, 0, 1), legacy_rgbspectrum=True)); s.sync()
         c = render(s, far, depth=2)[14:18, 14:18].mean()
         assert abs(c / (rho / np.pi) - 1) < 3e-3, (rho, c, rho / np.pi)
+    # inverse-square law and the cosine: a point light of intensity I at height h above a matte floor, seen below it and off to the side
+    for I, h, x in ((3.0, 2.0, 0.0), (3.0, 2.0, 1.5), (1.0, 0.7, 0.0)):
+        s = H.Scene(); s.push(H.Mesh([(-5, 0, -5), (5, 0, -5), (5, 0, 5), (-5, 0, 5)], [(0, 2, 1), (0, 3, 2)]), H.MatteMaterial(Kd=(0.5,) * 3))
+        s.push(H.PointLight((I, I, I), (0, h, 0))); s.sync()
+        c = render(s, scenes._cam((x + 20.0, 20.0, 0.0), (x, 0, 0), 0.05), res=(16, 16), depth=2).mean()
+        r2 = h * h + x * x
+        assert abs(c / (0.5 / np.pi * I * (h / np.sqrt(r2)) / r2) - 1) < 4e-3, (I, h, x, c)
     # uniform environment: MIS weights sum to one
     for rho in (0.25, 0.8):
         s = H.Scene(); s.push(H.uv_sphere((0, 0, 0), 1.0, 48, 48), H.MatteMaterial(Kd=(rho,) * 3)); s.push(env()); s.sync()
