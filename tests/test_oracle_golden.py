@@ -821,3 +821,36 @@ def test_area_light_closed_form_on_the_oracle():
         assert np.allclose(got, rho / np.pi * form, rtol=1.5e-2), (side, h, Le, got, rho / np.pi * form)
         seen.append(direct)
     assert np.allclose(seen[0], seen[1], rtol=1e-3) and np.allclose(seen[0], seen[2], rtol=1e-3), "Le >= 1 is clamped to the unit spectrum"
+
+
+def test_environment_map_closed_form_on_the_oracle():
+    """A matte surface (normal n) under an environment that is 1 on the hemisphere around an axis a and 0 elsewhere receives
+    E = pi (1 + n.a) / 2, so it shows rho (1 + n.a) / 2: the equal-area octahedral mapping in both directions, the luminance
+    Distribution2D (sampling and pdf, with the 4 pi Jacobian), the bilinear look-up of escaped rays and the MIS between the two have to
+    agree for that to come out -- for axes towards, away from, across and oblique to the normal."""
+    def dirs(res):                                              # environment_map.jl:133-160, texel centres -> directions
+        u = (np.arange(res) + 0.5) / res
+        U, V = np.meshgrid(u, u, indexing="xy")
+        uu, vv = 2 * U - 1, 2 * V - 1
+        up, vp = np.abs(uu), np.abs(vv)
+        sd = 1 - (up + vp)
+        r = 1 - np.abs(sd)
+        phi = np.where(r == 0, 1.0, (vp - up) / np.where(r == 0, 1, r) + 1.0) * np.pi / 4
+        z = np.copysign(1 - r * r, sd)
+        cx, sy = np.copysign(np.cos(phi), uu), np.copysign(np.sin(phi), vv)
+        rc = r * np.sqrt(2 - r * r)
+        return np.stack([cx * rc, sy * rc, z], -1)
+    rho, d = 0.5, dirs(256)
+    n = np.array([0.0, 0.0, -1.0])                              # the pole of the sphere the camera looks at
+    far = scenes._cam((0, 0, -40), (0, 0, 0), 0.2)
+    for a in ((0, 0, -1), (0, 0, 1), (0, 1, 0), (0.6, 0, -0.8), (0, 0.6, -0.8), (0.6, 0, 0.8), (-0.6, 0, -0.8)):
+        a = np.array(a, float)
+        env = np.repeat((d @ a > 0).astype(f32)[..., None], 3, axis=2)
+        s = H.Scene()
+        s.push(H.uv_sphere((0, 0, 0), 1.0, 64, 64), H.MatteMaterial(Kd=(rho,) * 3))
+        s.push(H.EnvironmentLight(H.EnvironmentMap(env), scale=(1 / 10567.0,) * 3)); s.sync()
+        film = H.Film((16, 16))
+        vp = H.VolPath(samples=256, max_depth=2, backend=oracle_backend.make_backend())
+        got = vp(s, film, far(film)).mean()
+        vp.close()
+        assert abs(got - rho * (1 + n @ a) / 2) < 4e-3, (a, got, rho * (1 + n @ a) / 2)
