@@ -1151,3 +1151,13 @@ def test_pipelined_read_out_matches_blocking_read():
     va.wait_film(film_a, h2); f2 = film_a.framebuffer.copy()
     assert np.array_equal(f1.view(np.uint32), want[0].view(np.uint32)) and np.array_equal(f2.view(np.uint32), want[1].view(np.uint32))
     va.close(); vb.close()
+
+
+@pytest.mark.parametrize("check", ["check_physical_known_answers", "check_material_closed_forms", "check_area_light_closed_form",
+                                   "check_environment_map_closed_form"])
+def test_closed_form_radiometry_on_the_gpu(check):
+    """The closed forms the oracle is pinned by (tests/closed_forms.py: Lambert, inverse square, furnaces, Beer-Lambert, conductor
+    Fresnel, diffuse-transmission furnace, area-light form factor, hemispherical environment -- and the reference's quirks next to
+    them), rendered by the CUDA library itself: physics the product has to reproduce whatever the oracle says."""
+    import closed_forms
+    getattr(closed_forms, check)(lambda: None)                  # backend=None: VolPath creates the product's CUDA back end
