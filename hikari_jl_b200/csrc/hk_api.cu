@@ -590,8 +590,11 @@ int32_t hk_upload_media(HkContext* ctx, const HkMedium* m, uint32_t n) {
     ctx->mask_bufs.clear(); ctx->mask_bufs.resize(n);
     ctx->dense_bufs.clear(); ctx->dense_bufs.resize(n);
     ctx->media_host.assign(n, DevMedium{});
+    ctx->media_ok = false;
     for (uint32_t i = 0; i < n; i++) { int32_t rc = upload_one_medium(ctx, i, m[i], ctx->media_host[i]); if (rc != HK_OK) { ctx->media_host.clear(); ctx->D.n_media = 0; return rc; } }
-    return commit_media(ctx);
+    const int32_t rc = commit_media(ctx);
+    ctx->media_ok = rc == HK_OK;
+    return rc;
 }
 // In-place density update of ONE medium (build_majorant_grid! / build_rgb_majorant_grid!, media.jl:1185-1240, 1498-1530: the host
 // swaps the voxel data of a medium and rebuilds its majorant grid; everything else in the scene stays).  `index` is 1-based, the
@@ -600,9 +603,12 @@ int32_t hk_update_medium(HkContext* ctx, uint32_t index, const HkMedium* m) {
     if (!ctx || !m) return HK_ERR_INVALID;
     hk_enter(ctx);
     REQUIRE(index >= 1 && index <= ctx->media_host.size(), "medium index out of range");
+    ctx->media_ok = false;      // (a failure below may have released buffers the device records still point to)
     int32_t rc = upload_one_medium(ctx, index - 1, *m, ctx->media_host[index - 1]);
     if (rc != HK_OK) return rc;
-    return commit_media(ctx);
+    rc = commit_media(ctx);
+    ctx->media_ok = rc == HK_OK;
+    return rc;
 }
 // the NanoVDB buffer of medium `index` (1-based) as the device holds it (uploaded or device-built): *bytes = its size; copied to `out`
 // when out != NULL and capacity suffices
@@ -809,6 +815,7 @@ int32_t hk_render_samples_strided(HkContext* ctx, int32_t first, int32_t stride,
     REQUIRE(ctx->have_tables && ctx->have_geom && ctx->have_mats && ctx->have_lights && ctx->have_cam && ctx->have_filter && ctx->have_params,
             "render called before tables/geometry/materials/lights/camera/filter/params were all uploaded");
     REQUIRE(ctx->tri_types_valid, "geometry references medium interfaces that the uploaded material set does not have");
+    REQUIRE(ctx->media_ok, "the last media upload / update failed: upload the media again before rendering");
     REQUIRE(count >= 0 && stride >= 1 && first >= 1, "bad sample range");
     const size_t n_pixels = (size_t)ctx->params.width * ctx->params.height;
     // frame pipelining: one-sample calls alternate between the two render lanes (hk_context.h)

@@ -48,6 +48,7 @@ struct HkContext {
     DevBuf b_mat_pre, b_light_pre, b_med_pre;       // uplift cache (DevTables)
     bool uplift_cache_enabled = true;
     std::vector<DevBuf> env_bufs, media_bufs, mask_bufs, dense_bufs;
+    bool media_ok = true;                            // false while / after a media upload that failed half-way: render refuses until media are uploaded again
     DevBuf b_media; std::vector<DevMedium> media_host;      // host copy of the device records (hk_update_medium)
     DevBuf b_f_func, b_f_mcdf, b_f_mfunc, b_f_ccdf;
     DevBuf b_state, b_counts, b_rays, b_film, b_scratch_u32, b_trace_ctr, b_readback;
