@@ -152,3 +152,29 @@ def test_julia_struct_mirrors_match_the_ctypes_mirrors():
         ct = getattr(A, name)
         want = [(f, _julia_type_of(t)) for f, t in ct._fields_]
         assert fields == want, f"{name}: julia {fields} != ctypes {want}"
+
+
+def test_ctypes_mirrors_match_the_header_field_by_field(tmp_path):
+    """Every struct of include/hikari_cuda.h against its ctypes mirror: a generated C program prints sizeof and offsetof of every field
+    the mirror names (gcc against the real header), and the numbers must equal ctypes' -- names, order, padding and sizes."""
+    import subprocess
+    structs = [n for n in dir(A) if n.startswith("Hk") and isinstance(getattr(A, n), type) and issubclass(getattr(A, n), C.Structure)]
+    assert len(structs) >= 18
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "hikari_cuda.h"', 'int main(void) {']
+    want = []
+    for n in sorted(structs):
+        ct = getattr(A, n)
+        src.append(f'  printf("%zu\\n", sizeof({n}));')
+        want.append((n, "sizeof", C.sizeof(ct)))
+        for f, _ in ct._fields_:
+            src.append(f'  printf("%zu\\n", offsetof({n}, {f}));')
+            want.append((n, f, getattr(ct, f).offset))
+    src += ['  return 0;', '}']
+    cfile, exe = tmp_path / "layout.c", tmp_path / "layout"
+    cfile.write_text("\n".join(src))
+    r = subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(cfile), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()]
+    assert len(got) == len(want)
+    bad = [(n, f, w, g) for (n, f, w), g in zip(want, got) if w != g]
+    assert not bad, f"ctypes vs C layout (struct, field, ctypes, C): {bad[:8]}"
