@@ -178,3 +178,45 @@ def test_ctypes_mirrors_match_the_header_field_by_field(tmp_path):
     assert len(got) == len(want)
     bad = [(n, f, w, g) for (n, f, w), g in zip(want, got) if w != g]
     assert not bad, f"ctypes vs C layout (struct, field, ctypes, C): {bad[:8]}"
+
+
+def _split_top_level(s):
+    """split on commas that are not inside (), {} or []"""
+    out, depth, cur = [], 0, ""
+    for ch in s:
+        if ch in "({[":
+            depth += 1
+        elif ch in ")}]":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur.strip()); cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur.strip())
+    return out
+
+
+def test_julia_ccalls_match_the_header_prototypes():
+    """Every ccall of julia/HikariCUDA.jl names an entry point the header declares, with as many argument types as the C prototype
+    has parameters, Int32 as the return type of the status-returning calls, and pointer / scalar kinds that agree position by
+    position (Ptr / Ref / Cstring for C pointers; Int32 / UInt32 / UInt64 / Float32 for the scalars)."""
+    hdr = open(os.path.join(ROOT, "include", "hikari_cuda.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"^\s*([A-Za-z_][\w \*]*?)\b(hk_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.M | re.S):
+        ret, name, params = m.group(1).strip(), m.group(2), m.group(3).strip()
+        plist = [] if params in ("", "void") else _split_top_level(params)
+        protos[name] = (ret, ["*" in p for p in plist])
+    jl = open(os.path.join(ROOT, "julia", "HikariCUDA.jl")).read()
+    calls = re.findall(r"ccall\(\(:(hk_[a-z0-9_]+), lib\), (\w+), \(((?:[^()]|\([^()]*\))*?)\)", jl)
+    assert len(calls) >= 25, len(calls)
+    for name, ret, types in calls:
+        assert name in protos, f"{name}: not declared in include/hikari_cuda.h"
+        cret, cptr = protos[name]
+        tl = [t for t in _split_top_level(types) if t]
+        assert len(tl) == len(cptr), f"{name}: ccall passes {len(tl)} arguments {tl}, the header declares {len(cptr)}"
+        assert (ret == "Int32") == (cret == "int32_t"), f"{name}: return type {ret} vs {cret}"
+        for k, (t, is_ptr) in enumerate(zip(tl, cptr)):
+            j_ptr = t.startswith(("Ptr{", "Ref{")) or t == "Cstring"
+            assert j_ptr == is_ptr, f"{name}: argument {k + 1} is {t} in the ccall, {'a pointer' if is_ptr else 'a scalar'} in the header"
