@@ -727,3 +727,105 @@ def test_environment_map_closed_form_on_the_oracle():
     Distribution2D (sampling and pdf, with the 4 pi Jacobian), the bilinear look-up of escaped rays and the MIS between the two have to
     agree for that to come out -- for axes towards, away from, across and oblique to the normal."""
     closed_forms.check_environment_map_closed_form(oracle_backend.make_backend)
+
+def test_rough_conductor_against_the_published_microfacet_formulas():
+    """The oracle's ConductorMaterial eval / pdf / sample against an independent numpy restatement of the published Trowbridge-Reitz
+    model (pbrt-v4 sec. 9.6: D, Lambda, G1, G, the visible-normal pdf, complex Fresnel): f = D F G / (4 cos_i cos_o),
+    pdf = G1(wo) D(wm) / (4 cos_o), written from the formulas and not from the oracle's code; the sampled direction must reproduce
+    f and pdf through the same formulas, and the cosine-weighted estimator f cos / pdf of the samples must average to the
+    directional albedo obtained by numerical integration of f cos over the hemisphere."""
+    rng = np.random.RandomState(11)
+    n = 6000
+    eta, kk, rough = 0.5, 2.0, 0.25
+    alpha = np.sqrt(rough)                                      # roughness_to_alpha, reflection/microfacet.jl:83-85
+    def hemi(k):
+        v = rng.normal(size=(k, 3)); v[:, 2] = np.abs(v[:, 2]) + 0.02
+        return v / np.linalg.norm(v, axis=1, keepdims=True)
+    x = np.zeros((n, 17), f32)
+    x[:, 0:3] = hemi(n); x[:, 3:6] = (0, 0, 1)
+    x[:, 6:10] = rng.uniform(380, 780, size=(n, 4))
+    x[:, 10:13] = rng.uniform(0, 1, size=(n, 3))
+    x[:, 14:17] = hemi(n)
+    o = _oracle_bsdf([H.ConductorMaterial(eta=(eta,) * 3, k=(kk,) * 3, roughness=rough)], x)[0].astype(np.float64)
+
+    def D(wm):
+        c2 = wm[:, 2] ** 2; t2 = (1 - c2) / c2
+        return 1.0 / (np.pi * alpha * alpha * c2 * c2 * (1 + t2 / (alpha * alpha)) ** 2)
+    def Lam(w):
+        c2 = w[:, 2] ** 2; t2 = (1 - c2) / c2
+        return (np.sqrt(1 + alpha * alpha * t2) - 1) / 2
+    def fresnel_complex(c):
+        e = eta + 1j * kk
+        s2 = 1 - c * c
+        st2 = s2 / (e * e)
+        ct = np.sqrt(1 - st2)
+        rp = (e * c - ct) / (e * c + ct); rs = (c - e * ct) / (c + e * ct)
+        return (np.abs(rp) ** 2 + np.abs(rs) ** 2) / 2
+    def model(wo, wi):
+        wm = wo + wi; wm /= np.linalg.norm(wm, axis=1, keepdims=True)
+        F = fresnel_complex(np.abs(np.sum(wo * wm, axis=1)))
+        G = 1 / (1 + Lam(wo) + Lam(wi))
+        f = D(wm) * F * G / (4 * wi[:, 2] * wo[:, 2])
+        pdf = D(wm) / (1 + Lam(wo)) / (4 * wo[:, 2])            # G1(wo) / cos_o * D * |wo.wm| / (4 |wo.wm|)
+        return f, pdf
+    wo, wi = x[:, 0:3].astype(np.float64), x[:, 14:17].astype(np.float64)
+    f, pdf = model(wo, wi)
+    # record layout (hikari_cuda_testing.h): sample wi [0:3], f[4] [3:7], pdf [7], specular [8], eta_scale [9]; eval f[4] [10:14], pdf [14]
+    assert np.allclose(o[:, 10], f, rtol=2e-3, atol=1e-5) and np.allclose(o[:, 13], f, rtol=2e-3, atol=1e-5), np.abs(o[:, 10] / f - 1).max()
+    assert np.allclose(o[:, 14], pdf, rtol=2e-3, atol=1e-5), np.abs(o[:, 14] / pdf - 1).max()
+    ok = o[:, 7] > 0                                            # valid samples (reflected above the surface)
+    assert ok.mean() > 0.8                                      # (grazing wo: some visible normals reflect below the horizon)
+    swi = o[ok, 0:3]
+    fs, ps = model(wo[ok], swi)
+    assert np.allclose(o[ok, 3], fs, rtol=5e-3, atol=1e-5) and np.allclose(o[ok, 7], ps, rtol=5e-3, atol=1e-5)
+    # the samples are DISTRIBUTED like the pdf they report: for a fixed wo, E[cos / pdf] = pi, E[1 / pdf] = 2 pi and E[f cos / pdf] = the
+    # directional albedo (numerical quadrature of the model); invalid samples (reflected below the horizon) count as 0
+    m = 100000
+    for c in (0.95, 0.55):
+        y = np.zeros((m, 17), f32)
+        y[:, 0:3] = (np.sqrt(1 - c * c), 0, c); y[:, 3:6] = (0, 0, 1); y[:, 6:10] = (450, 550, 650, 700)
+        y[:, 10:13] = rng.uniform(0, 1, size=(m, 3)); y[:, 14:17] = (0, 0, 1)
+        q = _oracle_bsdf([H.ConductorMaterial(eta=(eta,) * 3, k=(kk,) * 3, roughness=rough)], y)[0].astype(np.float64)
+        v = q[:, 7] > 0
+        th, ph = np.meshgrid((np.arange(400) + 0.5) / 400 * np.pi / 2, (np.arange(800) + 0.5) / 800 * 2 * np.pi, indexing="ij")
+        wq = np.stack([np.sin(th) * np.cos(ph), np.sin(th) * np.sin(ph), np.cos(th)], -1).reshape(-1, 3)
+        fq, _ = model(np.repeat(y[:1, 0:3].astype(np.float64), len(wq), axis=0), wq)
+        albedo = np.sum(fq * wq[:, 2] * np.sin(th).reshape(-1)) * (np.pi / 2 / 400) * (2 * np.pi / 800)
+        assert abs((q[v, 2] / q[v, 7]).sum() / m / np.pi - 1) < 1e-2
+        assert abs((1 / q[v, 7]).sum() / m / (2 * np.pi) - 1) < 1.5e-2
+        assert abs((q[v, 3] * q[v, 2] / q[v, 7]).sum() / m / albedo - 1) < 1e-2, (c, albedo)
+
+
+def test_glass_sampling_obeys_fresnel_and_snell():
+    """GlassMaterial samples (spectral-eval.jl:140-198) against first principles: for a fixed angle of incidence the fraction of
+    reflected samples is the unpolarised Fresnel reflectance, reflected directions mirror wo, refracted ones obey Snell's law
+    (sin theta_t = sin theta_i / eta, same plane of incidence), from outside and from inside (total internal reflection beyond the
+    critical angle)."""
+    rng = np.random.RandomState(4)
+    m, eta = 40000, 1.5
+    def fresnel(ci, e):
+        s2t = (1 - ci * ci) / (e * e)
+        if s2t >= 1:
+            return 1.0
+        ct = np.sqrt(1 - s2t)
+        rp = (e * ci - ct) / (e * ci + ct); rs = (ci - e * ct) / (ci + e * ct)
+        return (rp * rp + rs * rs) / 2
+    for cz in (0.95, 0.6, 0.25, -0.9, -0.5):                    # cz < 0: wo below the surface = the ray travels inside the glass
+        x = np.zeros((m, 17), f32)
+        sx = np.sqrt(1 - cz * cz)
+        x[:, 0:3] = (sx, 0, cz); x[:, 3:6] = (0, 0, 1); x[:, 6:10] = (450, 550, 650, 700)
+        x[:, 10:13] = rng.uniform(0, 1, size=(m, 3)); x[:, 14:17] = (0, 0, 1)
+        o = _oracle_bsdf([H.GlassMaterial(Kr=1.0, Kt=1.0, index=eta)], x)[0].astype(np.float64)
+        ok = o[:, 7] > 0
+        assert ok.all() and (o[:, 8] == 1).all()                # always a valid, specular sample
+        refl = np.sign(o[:, 2]) == np.sign(cz)
+        e = eta if cz > 0 else 1 / eta
+        F = fresnel(abs(cz), e)
+        assert abs(refl.mean() - F) < 4 * np.sqrt(max(F * (1 - F), 1e-4) / m) + 1e-3, (cz, refl.mean(), F)
+        assert np.allclose(o[refl, 0:3], (-sx, 0, cz), atol=2e-6)                       # mirror direction
+        if F < 1:
+            st = sx / e
+            want = (-st, 0.0, -np.sign(cz) * np.sqrt(1 - st * st))
+            assert np.allclose(o[~refl, 0:3], want, atol=2e-6), (cz, o[~refl, 0:3][0], want)
+        else:
+            assert refl.all()
