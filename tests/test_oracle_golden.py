@@ -829,3 +829,26 @@ def test_glass_sampling_obeys_fresnel_and_snell():
             assert np.allclose(o[~refl, 0:3], want, atol=2e-6), (cz, o[~refl, 0:3][0], want)
         else:
             assert refl.all()
+
+
+def test_visible_wavelength_sampling_is_the_inverse_cdf_of_its_pdf():
+    """sample_visible_wavelengths / visible_wavelengths_pdf (spectral.jl:192-249, pbrt-v4's SampleVisibleWavelengths): the pdf
+    0.0039398042 / cosh^2(0.0072 (lambda - 538)) integrates to 1 over [360, 830] nm, the sampled lambda(u) is monotone and is the
+    inverse of the pdf's CDF, and the three rotated hero wavelengths sit at u + k/4 (mod 1)."""
+    olib = oracle_backend.lib()
+    if True:                                                                    # (kept as a block: the hook needs no context)
+        n = 4001
+        u = np.linspace(0.0, 1.0, n, endpoint=False).astype(f32)
+        lam = np.zeros((n, 4), f32); pdf = np.zeros((n, 4), f32)
+        olib.ok_test_wavelengths(fp(u), n, fp(lam), fp(pdf))
+        l0, p0 = lam[:, 0].astype(np.float64), pdf[:, 0].astype(np.float64)
+        assert l0.min() >= 360.0 and l0.max() <= 830.0 and (np.diff(l0) > 0).all()
+        assert np.allclose(p0, 0.0039398042 / np.cosh(0.0072 * (l0 - 538.0)) ** 2, rtol=2e-5)
+        grid = np.linspace(360.0, 830.0, 200001)
+        dens = 0.0039398042 / np.cosh(0.0072 * (grid - 538.0)) ** 2
+        cdf = np.concatenate([[0.0], np.cumsum((dens[1:] + dens[:-1]) / 2 * np.diff(grid))])
+        assert abs(cdf[-1] - 1.0) < 2e-4                                        # normalised over the visible range
+        assert np.allclose(np.interp(l0, grid, cdf) / cdf[-1], u, atol=3e-4)    # lambda(u) = CDF^-1(u)
+        for k in (1, 2, 3):                                                     # the other hero wavelengths: u + k / 4, wrapped
+            uk = np.mod(u.astype(np.float64) + k / 4.0, 1.0)
+            assert np.allclose(np.interp(lam[:, k].astype(np.float64), grid, cdf) / cdf[-1], uk, atol=3e-4)
